@@ -1,0 +1,222 @@
+// blas.cu -- level BLAS-1, region copies (the FillBoundary data movers) and
+// reductions.  Stand-ins for amrex::MultiFab::{setVal,Copy,Saxpy,Xpay,Multiply,
+// Divide,mult,norm0,sum} and the pack/unpack loops inside FabArray::FillBoundary
+// (IAMR call sites: NSB.cpp:1387,1429,4408, MacProj.cpp:1126-1127,
+// Projection.cpp:273,338, Diffusion.cpp:202).
+#include "kernels.h"
+
+namespace ix {
+namespace k {
+namespace {
+
+constexpr int TX = 128;
+constexpr int TY = 2;
+
+inline dim3 grid_for(const Bx& bx, int nzc) { return dim3(cdiv(bx.nx(), TX), cdiv(bx.ny(), TY), nzc); }
+#define IDX3(bx)                                                     \
+  const int nz_ = bx.hi[2] - bx.lo[2] + 1;                            \
+  const int k = bx.lo[2] + (int)(blockIdx.z % nz_);                   \
+  const int n = (int)(blockIdx.z / nz_);                              \
+  const int j = bx.lo[1] + blockIdx.y * TY + threadIdx.y;             \
+  const int i = bx.lo[0] + blockIdx.x * TX + threadIdx.x;             \
+  if (j > bx.hi[1] || i > bx.hi[0]) return;
+
+__global__ void setval_kernel(Bx bx, V4 d, double v) { IDX3(bx) d(i, j, k, n) = v; }
+__global__ void copy_kernel(Bx bx, V4 d, C4 s) { IDX3(bx) d(i, j, k, n) = s(i, j, k, n); }
+__global__ void lincomb_kernel(Bx bx, V4 d, double a, C4 x, double b, C4 y) {
+  IDX3(bx) d(i, j, k, n) = a * x(i, j, k, n) + b * y(i, j, k, n);
+}
+__global__ void mult_kernel(Bx bx, V4 d, C4 s, int sn) { IDX3(bx) d(i, j, k, n) *= s(i, j, k, sn > 1 ? n : 0); }
+__global__ void div_kernel(Bx bx, V4 d, C4 s, int sn) { IDX3(bx) d(i, j, k, n) /= s(i, j, k, sn > 1 ? n : 0); }
+__global__ void scale_kernel(Bx bx, V4 d, double c) { IDX3(bx) d(i, j, k, n) *= c; }
+__global__ void addc_kernel(Bx bx, V4 d, double c) { IDX3(bx) d(i, j, k, n) += c; }
+__global__ void copy_shift_kernel(Bx bx, V4 d, C4 s, int s0, int s1, int s2) {
+  IDX3(bx) d(i, j, k, n) = s(i + s0, j + s1, k + s2, n);
+}
+__global__ void pack_kernel(Bx bx, double* buf, C4 s) {
+  IDX3(bx)
+  const int64_t nx = bx.hi[0] - bx.lo[0] + 1, ny = bx.hi[1] - bx.lo[1] + 1;
+  buf[(i - bx.lo[0]) + nx * ((j - bx.lo[1]) + ny * ((k - bx.lo[2]) + (int64_t)nz_ * n))] = s(i, j, k, n);
+}
+__global__ void unpack_kernel(Bx bx, V4 d, const double* buf) {
+  IDX3(bx)
+  const int64_t nx = bx.hi[0] - bx.lo[0] + 1, ny = bx.hi[1] - bx.lo[1] + 1;
+  d(i, j, k, n) = buf[(i - bx.lo[0]) + nx * ((j - bx.lo[1]) + ny * ((k - bx.lo[2]) + (int64_t)nz_ * n))];
+}
+
+#if defined(IX_EMUL)
+// tests-only serial stand-ins for the cooperative reduction kernels below
+static void reduce_serial(Bx bx, C4 src, int ncomp, int op, double* result) {
+  for (int n = 0; n < ncomp; ++n) {
+    double acc = result[n];
+    for (int k = bx.lo[2]; k <= bx.hi[2]; ++k)
+      for (int j = bx.lo[1]; j <= bx.hi[1]; ++j)
+        for (int i = bx.lo[0]; i <= bx.hi[0]; ++i) {
+          const double v = src(i, j, k, n);
+          acc = (op == 0) ? acc + v : (op == 1 ? fmin(acc, v) : fmax(acc, fabs(v)));
+        }
+    result[n] = acc;
+  }
+}
+static void dot_serial(Bx bx, C4 x, C4 y, C4 mask, double* result) {
+  double acc = 0.0;
+  for (int k = bx.lo[2]; k <= bx.hi[2]; ++k)
+    for (int j = bx.lo[1]; j <= bx.hi[1]; ++j)
+      for (int i = bx.lo[0]; i <= bx.hi[0]; ++i) {
+        double v = x(i, j, k) * y(i, j, k);
+        if (mask.ok()) v *= mask(i, j, k);
+        acc += v;
+      }
+  *result += acc;
+}
+#else
+// ---- reductions ----------------------------------------------------------
+// Grid-stride over (j,k) rows; warp-shuffle + smem block reduce; one atomic per
+// CTA.  max/min use the monotone bit pattern of non-negative / ordered doubles
+// through atomicMax/atomicMin on (unsigned) long long; sum uses atomicAdd.
+IX_D double warp_red(double v, int op) {
+  for (int o = 16; o > 0; o >>= 1) {
+    const double t = __shfl_xor_sync(0xffffffffu, v, o);
+    v = (op == 0) ? v + t : (op == 1 ? fmin(v, t) : fmax(v, t));
+  }
+  return v;
+}
+
+IX_D void atomic_fmax_nonneg(double* addr, double v) {  // v >= 0
+  atomicMax(reinterpret_cast<unsigned long long*>(addr), (unsigned long long)__double_as_longlong(v));
+}
+IX_D void atomic_fmin(double* addr, double v) {
+  // generic CAS loop (rare path: one per CTA)
+  unsigned long long* a = reinterpret_cast<unsigned long long*>(addr);
+  unsigned long long old = *a, assumed;
+  do {
+    assumed = old;
+    if (__longlong_as_double((long long)assumed) <= v) break;
+    old = atomicCAS(a, assumed, (unsigned long long)__double_as_longlong(v));
+  } while (assumed != old);
+}
+
+constexpr int RT = 256;
+
+__global__ void __launch_bounds__(RT) reduce_kernel(Bx bx, C4 src, int op, double* result) {
+  const int n = blockIdx.y;
+  const int nx = bx.nx(), ny = bx.ny(), nz = bx.nz();
+  const int64_t nrows = (int64_t)ny * nz;
+  double acc = (op == 0) ? 0.0 : (op == 1 ? 1.0e300 : 0.0);
+  const int lane_x = threadIdx.x & 63;
+  const int rsub = threadIdx.x >> 6;  // 4 rows per CTA pass
+  for (int64_t r = (int64_t)blockIdx.x * 4 + rsub; r < nrows; r += (int64_t)gridDim.x * 4) {
+    const int j = bx.lo[1] + (int)(r % ny);
+    const int k = bx.lo[2] + (int)(r / ny);
+    for (int ii = lane_x; ii < nx; ii += 64) {
+      const double v = src(bx.lo[0] + ii, j, k, n);
+      acc = (op == 0) ? acc + v : (op == 1 ? fmin(acc, v) : fmax(acc, fabs(v)));
+    }
+  }
+  __shared__ double sm[RT / 32];
+  acc = warp_red(acc, op);
+  if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    double v = (threadIdx.x < RT / 32) ? sm[threadIdx.x] : ((op == 0) ? 0.0 : (op == 1 ? 1.0e300 : 0.0));
+    v = warp_red(v, op);
+    if (threadIdx.x == 0) {
+      if (op == 0) atomicAdd(result + n, v);
+      else if (op == 1) atomic_fmin(result + n, v);
+      else atomic_fmax_nonneg(result + n, v);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(RT) dot_kernel(Bx bx, C4 x, C4 y, C4 mask, double* result) {
+  const int nx = bx.nx(), ny = bx.ny(), nz = bx.nz();
+  const int64_t nrows = (int64_t)ny * nz;
+  double acc = 0.0;
+  const int lane_x = threadIdx.x & 63;
+  const int rsub = threadIdx.x >> 6;
+  for (int64_t r = (int64_t)blockIdx.x * 4 + rsub; r < nrows; r += (int64_t)gridDim.x * 4) {
+    const int j = bx.lo[1] + (int)(r % ny);
+    const int k = bx.lo[2] + (int)(r / ny);
+    for (int ii = lane_x; ii < nx; ii += 64) {
+      const int i = bx.lo[0] + ii;
+      double v = x(i, j, k) * y(i, j, k);
+      if (mask.ok()) v *= mask(i, j, k);
+      acc += v;
+    }
+  }
+  __shared__ double sm[RT / 32];
+  acc = warp_red(acc, 0);
+  if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    double v = (threadIdx.x < RT / 32) ? sm[threadIdx.x] : 0.0;
+    v = warp_red(v, 0);
+    if (threadIdx.x == 0) atomicAdd(result, v);
+  }
+}
+
+#endif  // IX_EMUL
+
+__global__ void reduce_init_kernel(double* r, int n, int op) {
+  if ((int)threadIdx.x < n) r[threadIdx.x] = (op == 1) ? 1.0e300 : 0.0;
+}
+
+}  // namespace
+
+#define LAUNCH3(kern, bx, ncomp, s, ...)                                                  \
+  do {                                                                                    \
+    if (!(bx).ok() || (ncomp) <= 0) return IAMRX_OK;                                      \
+    IX_LAUNCH(kern, grid_for(bx, (bx).nz() * (ncomp)), dim3(TX, TY, 1), 0, s, bx, __VA_ARGS__);  \
+    return check_launch(#kern);                                                           \
+  } while (0)
+
+int setval(const Bx& bx, V4 dst, int ncomp, double val, cudaStream_t s) { LAUNCH3(setval_kernel, bx, ncomp, s, dst, val); }
+int copy(const Bx& bx, V4 dst, C4 src, int ncomp, cudaStream_t s) { LAUNCH3(copy_kernel, bx, ncomp, s, dst, src); }
+int lincomb(const Bx& bx, V4 dst, double a, C4 x, double b, C4 y, int ncomp, cudaStream_t s) {
+  LAUNCH3(lincomb_kernel, bx, ncomp, s, dst, a, x, b, y);
+}
+int mult(const Bx& bx, V4 dst, C4 src, int ncomp, int sn, cudaStream_t s) { LAUNCH3(mult_kernel, bx, ncomp, s, dst, src, sn); }
+int divide(const Bx& bx, V4 dst, C4 src, int ncomp, int sn, cudaStream_t s) { LAUNCH3(div_kernel, bx, ncomp, s, dst, src, sn); }
+int scale(const Bx& bx, V4 dst, double c, int ncomp, cudaStream_t s) { LAUNCH3(scale_kernel, bx, ncomp, s, dst, c); }
+int addconst(const Bx& bx, V4 dst, double c, int ncomp, cudaStream_t s) { LAUNCH3(addc_kernel, bx, ncomp, s, dst, c); }
+int copy_shift(const Bx& bx, V4 dst, C4 src, int s0, int s1, int s2, int ncomp, cudaStream_t s) {
+  LAUNCH3(copy_shift_kernel, bx, ncomp, s, dst, src, s0, s1, s2);
+}
+int pack(const Bx& bx, double* buf, C4 src, int ncomp, cudaStream_t s) { LAUNCH3(pack_kernel, bx, ncomp, s, buf, src); }
+int unpack(const Bx& bx, V4 dst, const double* buf, int ncomp, cudaStream_t s) { LAUNCH3(unpack_kernel, bx, ncomp, s, dst, buf); }
+
+int reduce_init(double* result, int n, int op, cudaStream_t s) {
+  IX_LAUNCH(reduce_init_kernel, 1, 32, 0, s, result, n, op);
+  return check_launch("reduce_init");
+}
+
+int reduce(const Bx& bx, C4 src, int ncomp, int op, double* result, cudaStream_t s) {
+  if (!bx.ok()) return IAMRX_OK;
+  const int64_t nrows = (int64_t)bx.ny() * bx.nz();
+  int nb = (int)((nrows + 3) / 4);
+  if (nb > 148 * 8) nb = 148 * 8;
+  if (nb < 1) nb = 1;
+#if defined(IX_EMUL)
+  (void)nb; reduce_serial(bx, src, ncomp, op, result);
+#else
+  IX_LAUNCH(reduce_kernel, dim3(nb, ncomp, 1), RT, 0, s, bx, src, op, result);
+#endif
+  return check_launch("reduce");
+}
+
+int reduce_dot(const Bx& bx, C4 x, C4 y, C4 mask, double* result, cudaStream_t s) {
+  if (!bx.ok()) return IAMRX_OK;
+  const int64_t nrows = (int64_t)bx.ny() * bx.nz();
+  int nb = (int)((nrows + 3) / 4);
+  if (nb > 148 * 8) nb = 148 * 8;
+  if (nb < 1) nb = 1;
+#if defined(IX_EMUL)
+  (void)nb; dot_serial(bx, x, y, mask, result);
+#else
+  IX_LAUNCH(dot_kernel, nb, RT, 0, s, bx, x, y, mask, result);
+#endif
+  return check_launch("reduce_dot");
+}
+
+}  // namespace k
+}  // namespace ix

@@ -1,0 +1,69 @@
+// godunov_math.h -- per-point arithmetic of the Godunov (PLM) advection path,
+// shared by the staged kernels in godunov.cu and the fused tile kernel.
+//
+// Restates AMReX-Hydro's hydro_godunov_plm / hydro_godunov_edge_state_3D /
+// hydro_godunov_extrap_vel_to_faces_3D / hydro_godunov_corner_couple and
+// AMReX_Slopes_K (4th-order limited slopes), which IAMR reaches through
+// Godunov::ExtrapVelToFaces (NavierStokesBase.cpp:4487-4491) and
+// HydroUtils::ComputeFluxesOnBoxFromState (NavierStokesBase.cpp:4701-4717).
+// Those sources are not vendored in the reference tree (Exec/Make.IAMR:15-19);
+// the formulas are the published algorithm (Almgren et al., JCP 142 (1998);
+// SURVEY.md Appendix A.2-A.5).  Periodic / interior faces only in this round.
+#pragma once
+#include "common.h"
+
+namespace ix {
+namespace gd {
+
+constexpr double SMALL_VEL = 1.0e-8;
+
+template <int D> struct E {  // unit offset of direction D
+  static constexpr int x = (D == 0), y = (D == 1), z = (D == 2);
+};
+
+template <int D, class A>
+IX_HD double sh(const A& a, int i, int j, int k, int o) {  // a(idx + o*e_D)
+  return a(i + o * E<D>::x, j + o * E<D>::y, k + o * E<D>::z);
+}
+
+IX_HD double lim2(double dlft, double drgt) {  // limited 2nd-order difference
+  const double dcen = 0.5 * (dlft + drgt);
+  const double dsgn = copysign(1.0, dcen);
+  const double slop = 2.0 * fmin(fabs(dlft), fabs(drgt));
+  const double dlim = (dlft * drgt >= 0.0) ? slop : 0.0;
+  return dsgn * fmin(dlim, fabs(dcen));
+}
+
+// 4th-order limited slope of q along D at cell (i,j,k) (amrex_calc_?slope, order 4)
+template <int D, class A>
+IX_HD double slope4(const A& q, int i, int j, int k) {
+  const double qm2 = sh<D>(q, i, j, k, -2), qm = sh<D>(q, i, j, k, -1), q0 = q(i, j, k);
+  const double qp = sh<D>(q, i, j, k, 1), qp2 = sh<D>(q, i, j, k, 2);
+  const double dxl = lim2(qm - qm2, q0 - qm);
+  const double dxr = lim2(qp - q0, qp2 - qp);
+  const double dlft = q0 - qm, drgt = qp - q0;
+  const double dcen = 0.5 * (dlft + drgt);
+  const double dsgn = copysign(1.0, dcen);
+  const double slop = 2.0 * fmin(fabs(dlft), fabs(drgt));
+  const double dlim = (dlft * drgt >= 0.0) ? slop : 0.0;
+  return dsgn * fmin(dlim, fabs((4.0 / 3.0) * dcen - (1.0 / 6.0) * (dxl + dxr)));
+}
+
+// upwind the pair (lo, hi) with a given face velocity (ComputeEdgeState /
+// transverse states of ExtrapVelToFaces)
+IX_HD double upwind(double lo, double hi, double vel) {
+  const double st = (vel >= 0.0) ? lo : hi;
+  const double fu = (fabs(vel) < SMALL_VEL) ? 0.0 : 1.0;
+  return fu * st + (1.0 - fu) * 0.5 * (hi + lo);
+}
+
+// Riemann upwinding of a normal velocity by itself (u_ad and the final u_mac of
+// ExtrapVelToFaces)
+IX_HD double riemann(double lo, double hi) {
+  const double st = ((lo + hi) >= 0.0) ? lo : hi;
+  const bool ltm = ((lo <= 0.0 && hi >= 0.0) || (fabs(lo + hi) < SMALL_VEL));
+  return ltm ? 0.0 : st;
+}
+
+}  // namespace gd
+}  // namespace ix

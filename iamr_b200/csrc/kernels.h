@@ -1,0 +1,117 @@
+// kernels.h -- internal C++ interface of the CUDA kernels (one level below the
+// C ABI in include/iamrx.h).  All functions are asynchronous on `s` and return
+// an IAMRX_* status.
+#pragma once
+#include "common.h"
+
+namespace ix {
+namespace k {
+
+struct Abec {
+  double a, b;      // scalars (setScalars)
+  C4 acoef;         // may be null if a == 0
+  C4 bx, by, bz;    // face coefficients; bncomp comps
+  int bncomp;       // 1 or ncomp
+  double dxinv[3];
+};
+
+// --- cell-centred ABec (abec.cu) -----------------------------------------
+int abec_gsrb(const Bx& bx, V4 phi, C4 rhs, const Abec& op, double omega, int redblack,
+              int ncomp, cudaStream_t s);
+// out = L phi (rhs null) or rhs - L phi
+int abec_apply(const Bx& bx, V4 out, C4 phi, C4 rhs, const Abec& op, int ncomp, cudaStream_t s);
+// face flux_d = -b * beta_d * dphi/dx_d on faces of bx (MLABecLaplacian FFlux)
+int abec_flux(const Bx& bx, V4 fx, V4 fy, V4 fz, C4 phi, const Abec& op, int comp, cudaStream_t s);
+// crse = mean of 2x2x2 fine (MLCellLinOp restriction / average_down)
+int cc_restrict(const Bx& cbx, V4 crse, C4 fine, int ncomp, cudaStream_t s);
+// fine += crse(i/2,j/2,k/2) (MLCellLinOp piecewise-constant interpolation)
+int cc_prolong_add(const Bx& fbx, V4 fine, C4 crse, int ncomp, cudaStream_t s);
+// crse face coefficient = mean of the 4 fine faces (average_down_faces)
+int face_restrict(const Bx& cfbx, int dir, V4 crse, C4 fine, int ncomp, cudaStream_t s);
+// beta_d = scale / (0.5*(rho(i-1)+rho(i))) (average_cellcenter_to_face + invert)
+int rho_to_beta(const Bx& fbx, int dir, V4 beta, C4 rho, double scale, cudaStream_t s);
+// div = fac * sum_d (u_d(i+1)-u_d(i))*dxinv[d]   (computeDivergence)
+int mac_divergence(const Bx& bx, V4 div, C4 u, C4 v, C4 w, const double dxinv[3], double fac,
+                   C4 minus_rhs, cudaStream_t s);
+// u_d -= b*beta_d*(phi(i)-phi(i-1))*dxinv[d]   (umac += getFluxes)
+int mac_update(const Bx& bx, V4 u, V4 v, V4 w, C4 phi, const Abec& op, cudaStream_t s);
+// tensor cross terms: out += b*div(F_cross(eta, vel))
+int tensor_cross(const Bx& bx, V4 out, C4 vel, C4 ex, C4 ey, C4 ez, double b,
+                 const double dxinv[3], cudaStream_t s);
+
+// --- BLAS-1 style level ops (blas.cu) ------------------------------------
+int setval(const Bx& bx, V4 dst, int ncomp, double val, cudaStream_t s);
+int copy(const Bx& bx, V4 dst, C4 src, int ncomp, cudaStream_t s);
+// dst = a*x + b*y  (x or y may alias dst)
+int lincomb(const Bx& bx, V4 dst, double a, C4 x, double b, C4 y, int ncomp, cudaStream_t s);
+// dst *= c*src  / dst = dst / src etc.
+int mult(const Bx& bx, V4 dst, C4 src, int ncomp, int src_ncomp, cudaStream_t s);
+int divide(const Bx& bx, V4 dst, C4 src, int ncomp, int src_ncomp, cudaStream_t s);
+int scale(const Bx& bx, V4 dst, double c, int ncomp, cudaStream_t s);
+int addconst(const Bx& bx, V4 dst, double c, int ncomp, cudaStream_t s);
+// region copy with index shift: dst(i,j,k) = src(i+s0, j+s1, k+s2) over bx
+int copy_shift(const Bx& bx, V4 dst, C4 src, int s0, int s1, int s2, int ncomp, cudaStream_t s);
+// pack / unpack a region to a contiguous buffer (halo exchange)
+int pack(const Bx& bx, double* buf, C4 src, int ncomp, cudaStream_t s);
+int unpack(const Bx& bx, V4 dst, const double* buf, int ncomp, cudaStream_t s);
+// reductions into device scalars: result[n] op= reduce over bx of comp n
+// op: 0 sum, 1 min, 2 max|x| (norm0).  `result` must be initialised by the caller
+// (reduce_init).  Deterministic order is NOT guaranteed for sum.
+int reduce_init(double* result, int n, int op, cudaStream_t s);
+int reduce(const Bx& bx, C4 src, int ncomp, int op, double* result, cudaStream_t s);
+int reduce_dot(const Bx& bx, C4 x, C4 y, C4 mask, double* result, cudaStream_t s);
+
+// --- Godunov advection (godunov.cu) --------------------------------------
+struct AdvGeom { double dx[3]; double dt; };
+int extrap_vel_to_faces(const Bx& bx, C4 vel, C4 force, V4 umac, V4 vmac, V4 wmac,
+                        const AdvGeom& g, int forces_in_trans, cudaStream_t s);
+struct AofsArgs {
+  V4 aofs;           // ncomp
+  C4 S, force, divu; // S: ncomp, 3 ghosts; force: ncomp 1 ghost (may be null); divu may be null
+  C4 umac, vmac, wmac;
+  C4 uflx, vflx, wflx;  // flux velocities (== umac.. unless sync)
+  V4 fx, fy, fz, xed, yed, zed;  // optional outputs
+  int ncomp;
+  int iconserv[8];
+  int forces_in_trans, is_velocity, is_sync, write_fluxes;
+};
+int compute_aofs(const Bx& bx, const AofsArgs& a, const AdvGeom& g, cudaStream_t s);
+
+// --- nodal Laplacian (nodal.cu) ------------------------------------------
+int nodal_divu(const Bx& nbx, V4 rhs, C4 vel, const double dxinv[3], cudaStream_t s);
+int nodal_adotx(const Bx& nbx, V4 out, C4 phi, C4 rhs, C4 sig, const double dxinv[3], cudaStream_t s);
+int nodal_gs_color(const Bx& nbx, V4 phi, C4 rhs, C4 sig, const double dxinv[3], int color,
+                   cudaStream_t s);
+int nodal_jacobi(const Bx& nbx, V4 out, C4 phi, C4 rhs, C4 sig, const double dxinv[3], double omega,
+                 cudaStream_t s);
+int nodal_restrict(const Bx& cnbx, V4 crse, C4 fine, cudaStream_t s);
+int nodal_interp_add(const Bx& fnbx, V4 fine, C4 crse, cudaStream_t s);
+int nodal_mknewu(const Bx& bx, V4 vel, V4 gp, int increment_gp, C4 phi, C4 sig,
+                 const double dxinv[3], cudaStream_t s);
+
+// --- pointwise IAMR glue (pointwise.cu) -----------------------------------
+// tf = (tf + visc - gp)/rho   (NSB.cpp:4466-4470, 3460-3466); divide optional
+int force_assemble(const Bx& bx, V4 tf, C4 visc, C4 gp, C4 rho, double grav, int ncomp, int add_gp,
+                   int div_rho, cudaStream_t s);
+// scalar forcing: tf = tf/rho + visc (nonconservative) or tf + visc (NS.cpp:774-804)
+// velocity update NSB.cpp:3607-3626
+int vel_update(const Bx& bx, V4 unew, C4 uold, C4 aofs, C4 gp, C4 rhohalf, double grav, double dt,
+               cudaStream_t s);
+// scalar update NSB.cpp:2761-2765 / 2887-2896 (no forcing in supported configs)
+int scal_update(const Bx& bx, V4 snew, C4 sold, C4 aofs, double dt, int ncomp, cudaStream_t s);
+// floor NSB.cpp:4530-4534
+int floor_small(const Bx& bx, V4 f, int ncomp, cudaStream_t s);
+// first-order extrapolation of the 1-cell ghost shell from the valid region for cells
+// OUTSIDE `domain` in non-periodic directions (Extrapolater::FirstOrderExtrap, NS.cpp:2047).
+int average_face_to_cc(const Bx& bx, V4 cc, C4 u, C4 v, C4 w, cudaStream_t s);
+// prob_init.cpp initial conditions
+int init_prob(const Bx& bx, V4 state, int probtype, const double* params, const iamrx_geom& g,
+              cudaStream_t s);
+// diffusion rhs: unew *= rho; rhs += unew (Diffusion.cpp:821-831)
+int diff_rhs(const Bx& bx, V4 rhs, V4 unew, C4 rho, int ncomp, cudaStream_t s);
+// level_project pre: u = u/dt + gp/rho  (Projection.cpp:273,296-300); sigma = 1/rho
+int proj_pre(const Bx& bx, V4 u, C4 gp, C4 rho, double dt_inv, int add_gp, cudaStream_t s);
+int invert(const Bx& bx, V4 sig, C4 rho, cudaStream_t s);
+
+}  // namespace k
+}  // namespace ix

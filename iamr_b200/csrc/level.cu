@@ -1,0 +1,540 @@
+// level.cu -- see level.h.  Memory pool, NCCL communicator (dlopen'd so the
+// library loads on CPU-only hosts), FillBoundary plan + batched copy kernel,
+// local multifabs and level-wide helpers.
+#include "level.h"
+#include <dlfcn.h>
+#include <algorithm>
+#include <mutex>
+
+namespace ix {
+
+// ---------------------------------------------------------------------------
+// errors / accounting
+// ---------------------------------------------------------------------------
+static thread_local std::string g_err;
+static std::mutex g_err_mu;
+static std::string g_err_shared;
+void set_error(const std::string& s) {
+  std::lock_guard<std::mutex> lk(g_err_mu);
+  g_err_shared = s;
+}
+const char* last_error_cstr() {
+  std::lock_guard<std::mutex> lk(g_err_mu);
+  g_err = g_err_shared;
+  return g_err.c_str();
+}
+std::atomic<int64_t> g_launches{0};
+
+bool device_ok() {
+  static int state = -1;
+  if (state < 0) {
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    state = (e == cudaSuccess && n > 0) ? 1 : 0;
+    if (e != cudaSuccess) cudaGetLastError();
+  }
+  return state == 1;
+}
+
+// ---------------------------------------------------------------------------
+// device pool
+// ---------------------------------------------------------------------------
+namespace {
+struct Pool {
+  std::multimap<size_t, double*> free_;
+  std::map<double*, size_t> size_;
+  size_t total = 0;
+  std::mutex mu;
+};
+Pool& pool() { static Pool p; return p; }
+size_t round_up(size_t n) {
+  // bucket to 1/8 octave to get reuse across slightly different shapes
+  size_t b = 512;
+  while (b < n) b <<= 1;
+  size_t step = b / 16;
+  if (step == 0) return b;
+  size_t r = ((n + step - 1) / step) * step;
+  return r;
+}
+}  // namespace
+
+double* dev_alloc(size_t nd) {
+  Pool& P = pool();
+  std::lock_guard<std::mutex> lk(P.mu);
+  size_t want = round_up(nd ? nd : 1);
+  auto it = P.free_.lower_bound(want);
+  if (it != P.free_.end() && it->first <= want + want / 8) {
+    double* p = it->second;
+    P.free_.erase(it);
+    return p;
+  }
+  double* p = nullptr;
+  cudaError_t e = cudaMalloc(&p, want * sizeof(double));
+  if (e != cudaSuccess) {
+    // release cached blocks and retry once
+    for (auto& kv : P.free_) { cudaFree(kv.second); P.total -= kv.first * 8; P.size_.erase(kv.second); }
+    P.free_.clear();
+    e = cudaMalloc(&p, want * sizeof(double));
+    if (e != cudaSuccess) { set_error(std::string("cudaMalloc: ") + cudaGetErrorString(e)); return nullptr; }
+  }
+  P.size_[p] = want;
+  P.total += want * 8;
+  return p;
+}
+void dev_free(double* p) {
+  if (!p) return;
+  Pool& P = pool();
+  std::lock_guard<std::mutex> lk(P.mu);
+  auto it = P.size_.find(p);
+  if (it == P.size_.end()) return;
+  P.free_.insert({it->second, p});
+}
+void dev_pool_release() {
+  Pool& P = pool();
+  std::lock_guard<std::mutex> lk(P.mu);
+  for (auto& kv : P.free_) { cudaFree(kv.second); P.total -= kv.first * 8; P.size_.erase(kv.second); }
+  P.free_.clear();
+}
+size_t dev_pool_bytes() { return pool().total; }
+
+// ---------------------------------------------------------------------------
+// communicator (NCCL through dlopen)
+// ---------------------------------------------------------------------------
+namespace {
+typedef int (*nccl_uid_fn)(void*);
+typedef int (*nccl_init_fn)(void**, int, /*ncclUniqueId by value*/ struct Uid128, int);
+struct Uid128 { char b[128]; };
+typedef int (*nccl_init_fn2)(void**, int, Uid128, int);
+typedef int (*nccl_destroy_fn)(void*);
+typedef int (*nccl_group_fn)(void);
+typedef int (*nccl_sendrecv_fn)(void*, size_t, int, int, void*, cudaStream_t);
+typedef int (*nccl_send_fn)(const void*, size_t, int, int, void*, cudaStream_t);
+typedef int (*nccl_allreduce_fn)(const void*, void*, size_t, int, int, void*, cudaStream_t);
+typedef const char* (*nccl_errstr_fn)(int);
+
+struct Nccl {
+  void* h = nullptr;
+  nccl_uid_fn uid = nullptr;
+  nccl_init_fn2 init = nullptr;
+  nccl_destroy_fn destroy = nullptr;
+  nccl_group_fn gstart = nullptr, gend = nullptr;
+  nccl_send_fn send = nullptr;
+  nccl_sendrecv_fn recv = nullptr;
+  nccl_allreduce_fn allreduce = nullptr;
+  nccl_errstr_fn errstr = nullptr;
+  bool load() {
+    if (h) return true;
+    const char* names[] = {"libnccl.so.2", "libnccl.so"};
+    for (const char* n : names) { h = dlopen(n, RTLD_NOW | RTLD_GLOBAL); if (h) break; }
+    if (!h) { set_error(std::string("dlopen libnccl failed: ") + dlerror()); return false; }
+    uid = (nccl_uid_fn)dlsym(h, "ncclGetUniqueId");
+    init = (nccl_init_fn2)dlsym(h, "ncclCommInitRank");
+    destroy = (nccl_destroy_fn)dlsym(h, "ncclCommDestroy");
+    gstart = (nccl_group_fn)dlsym(h, "ncclGroupStart");
+    gend = (nccl_group_fn)dlsym(h, "ncclGroupEnd");
+    send = (nccl_send_fn)dlsym(h, "ncclSend");
+    recv = (nccl_sendrecv_fn)dlsym(h, "ncclRecv");
+    allreduce = (nccl_allreduce_fn)dlsym(h, "ncclAllReduce");
+    errstr = (nccl_errstr_fn)dlsym(h, "ncclGetErrorString");
+    if (!uid || !init || !gstart || !gend || !send || !recv || !allreduce) {
+      set_error("libnccl: missing symbols"); return false;
+    }
+    return true;
+  }
+};
+Nccl& nccl() { static Nccl n; return n; }
+constexpr int NCCL_FLOAT64 = 8;  // ncclDouble
+constexpr int NCCL_SUM = 0, NCCL_MAX = 2, NCCL_MIN = 3;
+#define IX_NCCL(call)                                                                    \
+  do {                                                                                   \
+    int r_ = (call);                                                                     \
+    if (r_ != 0) {                                                                       \
+      set_error(std::string(#call) + ": " + (nccl().errstr ? nccl().errstr(r_) : "nccl error")); \
+      return IAMRX_ERR_COMM;                                                             \
+    }                                                                                    \
+  } while (0)
+}  // namespace
+
+Comm& comm() { static Comm c; return c; }
+
+int comm_unique_id(unsigned char uid[128]) {
+  if (!nccl().load()) return IAMRX_ERR_COMM;
+  IX_NCCL(nccl().uid(uid));
+  return IAMRX_OK;
+}
+int comm_init(int rank, int nranks, const unsigned char uid[128]) {
+  Comm& c = comm();
+  c.rank = rank; c.nranks = nranks;
+  if (nranks <= 1) return IAMRX_OK;
+  if (!nccl().load()) return IAMRX_ERR_COMM;
+  Uid128 u; memcpy(u.b, uid, 128);
+  IX_NCCL(nccl().init(&c.nccl, nranks, u, rank));
+  return IAMRX_OK;
+}
+int comm_finalize() {
+  Comm& c = comm();
+  if (c.nccl) { nccl().destroy(c.nccl); c.nccl = nullptr; }
+  c.rank = 0; c.nranks = 1;
+  return IAMRX_OK;
+}
+int comm_allreduce(double* dev, int n, int op, cudaStream_t s) {
+  Comm& c = comm();
+  if (c.nranks <= 1) return IAMRX_OK;
+  const int nop = (op == 0) ? NCCL_SUM : (op == 1 ? NCCL_MIN : NCCL_MAX);
+  IX_NCCL(nccl().allreduce(dev, dev, (size_t)n, NCCL_FLOAT64, nop, c.nccl, s));
+  return IAMRX_OK;
+}
+int comm_exchange(const std::vector<int>& peers, const std::vector<double*>& sbuf,
+                  const std::vector<int64_t>& scount, const std::vector<double*>& rbuf,
+                  const std::vector<int64_t>& rcount, cudaStream_t s) {
+  Comm& c = comm();
+  if (c.nranks <= 1 || peers.empty()) return IAMRX_OK;
+  IX_NCCL(nccl().gstart());
+  for (size_t i = 0; i < peers.size(); ++i) {
+    if (scount[i] > 0) IX_NCCL(nccl().send(sbuf[i], (size_t)scount[i], NCCL_FLOAT64, peers[i], c.nccl, s));
+    if (rcount[i] > 0) IX_NCCL(nccl().recv(rbuf[i], (size_t)rcount[i], NCCL_FLOAT64, peers[i], c.nccl, s));
+  }
+  IX_NCCL(nccl().gend());
+  return IAMRX_OK;
+}
+
+// ---------------------------------------------------------------------------
+// batched copy kernel: grid = (chunks, ndesc); each CTA walks rows of its
+// descriptor's region with x fastest.
+// ---------------------------------------------------------------------------
+namespace k {
+namespace {
+constexpr int CB_T = 256;
+constexpr int CB_CHUNKS = 24;
+
+__global__ void __launch_bounds__(CB_T)
+copy_batch_kernel(const CopyDesc* __restrict__ desc, FabTable dst, FabTable src, double* buf, int ncomp,
+                  int64_t bstride) {
+  const CopyDesc d = desc[blockIdx.y];
+  const int nx = d.hi[0] - d.lo[0] + 1, ny = d.hi[1] - d.lo[1] + 1, nz = d.hi[2] - d.lo[2] + 1;
+  const int64_t npts = (int64_t)nx * ny * nz;
+  const int64_t total = npts * ncomp;
+  for (int64_t t = (int64_t)blockIdx.x * CB_T + threadIdx.x; t < total; t += (int64_t)gridDim.x * CB_T) {
+    const int n = (int)(t / npts);
+    const int64_t r = t - (int64_t)n * npts;
+    const int ii = (int)(r % nx);
+    const int jj = (int)((r / nx) % ny);
+    const int kk = (int)(r / ((int64_t)nx * ny));
+    const int i = d.lo[0] + ii, j = d.lo[1] + jj, k = d.lo[2] + kk;
+    if (d.kind == 0) {
+      const double v = src.p[d.src][(i + d.sh[0] - src.lo[d.src][0]) + (j + d.sh[1] - src.lo[d.src][1]) * src.js[d.src] +
+                                    (k + d.sh[2] - src.lo[d.src][2]) * src.ks[d.src] + n * src.ns[d.src]];
+      dst.p[d.dst][(i - dst.lo[d.dst][0]) + (j - dst.lo[d.dst][1]) * dst.js[d.dst] +
+                   (k - dst.lo[d.dst][2]) * dst.ks[d.dst] + n * dst.ns[d.dst]] = v;
+    } else if (d.kind == 1) {  // pack: region given in src index space
+      buf[d.bufoff * ncomp + n * npts + r + 0 * bstride] =
+          src.p[d.src][(i - src.lo[d.src][0]) + (j - src.lo[d.src][1]) * src.js[d.src] +
+                       (k - src.lo[d.src][2]) * src.ks[d.src] + n * src.ns[d.src]];
+    } else {  // unpack
+      dst.p[d.dst][(i - dst.lo[d.dst][0]) + (j - dst.lo[d.dst][1]) * dst.js[d.dst] +
+                   (k - dst.lo[d.dst][2]) * dst.ks[d.dst] + n * dst.ns[d.dst]] =
+          buf[d.bufoff * ncomp + n * npts + r];
+    }
+  }
+}
+}  // namespace
+
+int copy_batch(const CopyDesc* d_desc, int ndesc, const FabTable& dst, const FabTable& src, double* buf,
+               int ncomp, int64_t bstride, cudaStream_t s) {
+  if (ndesc <= 0) return IAMRX_OK;
+  IX_LAUNCH(copy_batch_kernel, dim3(CB_CHUNKS, ndesc, 1), CB_T, 0, s, d_desc, dst, src, buf, ncomp, bstride);
+  return check_launch("copy_batch");
+}
+}  // namespace k
+
+// ---------------------------------------------------------------------------
+// FillBoundary plan
+// ---------------------------------------------------------------------------
+FBPlan::~FBPlan() {
+  if (d_local) cudaFree(d_local);
+  if (d_send) cudaFree(d_send);
+  if (d_recv) cudaFree(d_recv);
+}
+
+// subtract box `b` from `a`: returns up to 6 disjoint boxes covering a \ b
+static void box_diff(const Bx& a, const Bx& b, std::vector<Bx>& out) {
+  Bx isect = intersect(a, b);
+  if (!isect.ok()) { out.push_back(a); return; }
+  Bx rest = a;
+  for (int d = 2; d >= 0; --d) {  // peel z, then y, then x so x-rows stay long
+    if (rest.lo[d] < isect.lo[d]) { Bx p = rest; p.hi[d] = isect.lo[d] - 1; out.push_back(p); rest.lo[d] = isect.lo[d]; }
+    if (rest.hi[d] > isect.hi[d]) { Bx p = rest; p.lo[d] = isect.hi[d] + 1; out.push_back(p); rest.hi[d] = isect.hi[d]; }
+  }
+}
+
+void build_fb_regions(const Level& L, int ixtype, int ng, std::vector<int>& dst_box,
+                      std::vector<int>& src_box, std::vector<Bx>& region, std::vector<int>& shift3) {
+  const int nb = (int)L.boxes.size();
+  int plen[3];
+  for (int d = 0; d < 3; ++d) plen[d] = L.geom.domain.hi[d] - L.geom.domain.lo[d] + 1;
+  for (int bi = 0; bi < nb; ++bi) {
+    const Bx vdst = ixbox(L.boxes[bi], ixtype);
+    const Bx gdst = grow(vdst, ng);
+    // ghost region = gdst \ vdst, as disjoint pieces
+    std::vector<Bx> todo;
+    box_diff(gdst, vdst, todo);
+    // Candidate sources in a fixed order: (box index, shift).  The first source
+    // covering a point wins; pieces already filled are removed, so every ghost
+    // point is written exactly once (deterministic for face/nodal overlaps).
+    for (int bj = 0; bj < nb && !todo.empty(); ++bj) {
+      const Bx vsrc = ixbox(L.boxes[bj], ixtype);
+      for (int sz = -1; sz <= 1; ++sz) for (int sy = -1; sy <= 1; ++sy) for (int sx = -1; sx <= 1; ++sx) {
+        const int sh[3] = {sx, sy, sz};
+        bool okp = true;
+        for (int d = 0; d < 3; ++d) if (sh[d] != 0 && !L.geom.periodic[d]) okp = false;
+        if (!okp) continue;
+        if (bj == bi && sx == 0 && sy == 0 && sz == 0) continue;
+        Bx s = vsrc;  // source valid box shifted INTO dst index space
+        for (int d = 0; d < 3; ++d) { s.lo[d] += sh[d] * plen[d]; s.hi[d] += sh[d] * plen[d]; }
+        std::vector<Bx> next;
+        for (const Bx& piece : todo) {
+          Bx is = intersect(piece, s);
+          if (!is.ok()) { next.push_back(piece); continue; }
+          dst_box.push_back(bi); src_box.push_back(bj); region.push_back(is);
+          for (int d = 0; d < 3; ++d) shift3.push_back(-sh[d] * plen[d]);  // src = dst + shift
+          box_diff(piece, is, next);
+        }
+        todo.swap(next);
+        if (todo.empty()) break;
+      }
+    }
+  }
+}
+
+static CopyDesc* upload(const std::vector<CopyDesc>& v) {
+  if (v.empty()) return nullptr;
+  CopyDesc* d = nullptr;
+  cudaMalloc(&d, v.size() * sizeof(CopyDesc));
+  cudaMemcpy(d, v.data(), v.size() * sizeof(CopyDesc), cudaMemcpyHostToDevice);
+  return d;
+}
+
+FBPlan& Level::plan(int ixtype, int ng) {
+  auto key = std::make_pair(ixtype, ng);
+  auto it = plans.find(key);
+  if (it != plans.end()) return *it->second;
+  auto P = std::make_unique<FBPlan>();
+  P->ixtype = ixtype; P->ng = ng;
+  std::vector<int> db, sb, sh; std::vector<Bx> rg;
+  build_fb_regions(*this, ixtype, ng, db, sb, rg, sh);
+  const int me = comm().rank;
+  std::vector<int> g2l(boxes.size(), -1);
+  for (int il = 0; il < nlocal(); ++il) g2l[local[il]] = il;
+  std::map<int, std::vector<CopyDesc>> sendm, recvm;
+  std::map<int, int64_t> soff, roff;
+  for (size_t r = 0; r < rg.size(); ++r) {
+    const int od = owner[db[r]], os = owner[sb[r]];
+    if (od != me && os != me) continue;
+    CopyDesc d{};
+    for (int q = 0; q < 3; ++q) { d.lo[q] = rg[r].lo[q]; d.hi[q] = rg[r].hi[q]; d.sh[q] = sh[3 * r + q]; }
+    const int64_t npts = rg[r].npts();
+    if (od == me && os == me) {
+      d.kind = 0; d.dst = g2l[db[r]]; d.src = g2l[sb[r]];
+      P->local.push_back(d);
+    } else if (os == me) {  // I send: region expressed in src index space
+      d.kind = 1; d.src = g2l[sb[r]]; d.dst = -1;
+      for (int q = 0; q < 3; ++q) { d.lo[q] += d.sh[q]; d.hi[q] += d.sh[q]; d.sh[q] = 0; }
+      d.bufoff = soff[od]; soff[od] += npts;
+      sendm[od].push_back(d);
+    } else {  // I receive
+      d.kind = 2; d.dst = g2l[db[r]]; d.src = -1;
+      d.bufoff = roff[os]; roff[os] += npts;
+      recvm[os].push_back(d);
+    }
+  }
+  // peers: union of send/recv ranks, ascending
+  std::vector<int> peers;
+  for (auto& kv : sendm) peers.push_back(kv.first);
+  for (auto& kv : recvm) peers.push_back(kv.first);
+  std::sort(peers.begin(), peers.end());
+  peers.erase(std::unique(peers.begin(), peers.end()), peers.end());
+  P->peers = peers;
+  std::vector<CopyDesc> all_send, all_recv;
+  int64_t so = 0, ro = 0;
+  for (int p : peers) {
+    P->send_off.push_back(so); P->recv_off.push_back(ro);
+    P->send_pts.push_back(soff.count(p) ? soff[p] : 0);
+    P->recv_pts.push_back(roff.count(p) ? roff[p] : 0);
+    for (CopyDesc d : sendm[p]) { d.bufoff += so; all_send.push_back(d); }
+    for (CopyDesc d : recvm[p]) { d.bufoff += ro; all_recv.push_back(d); }
+    so += P->send_pts.back(); ro += P->recv_pts.back();
+  }
+  P->send_total = so; P->recv_total = ro;
+  P->d_local = upload(P->local);
+  P->d_send = upload(all_send); P->n_send = (int)all_send.size();
+  P->d_recv = upload(all_recv); P->n_recv = (int)all_recv.size();
+  FBPlan& ref = *P;
+  plans[key] = std::move(P);
+  return ref;
+}
+
+// ---------------------------------------------------------------------------
+// MF
+// ---------------------------------------------------------------------------
+MF& MF::operator=(MF&& o) noexcept {
+  if (this != &o) {
+    clear();
+    lev = o.lev; ixtype = o.ixtype; ncomp = o.ncomp; ng = o.ng;
+    fabs = std::move(o.fabs); owned = std::move(o.owned);
+    o.lev = nullptr; o.fabs.clear(); o.owned.clear();
+  }
+  return *this;
+}
+
+void MF::define(Level* L, int ixtype_, int ncomp_, int ng_) {
+  clear();
+  lev = L; ixtype = ixtype_; ncomp = ncomp_; ng = ng_;
+  fabs.resize(L->nlocal());
+  owned.resize(L->nlocal(), nullptr);
+  for (int il = 0; il < L->nlocal(); ++il) {
+    const Bx g = grow(ixbox(L->lbox(il), ixtype), ng);
+    // x rows padded so the first VALID cell of every row sits on a 128-byte line
+    const int pad = (16 - (ng % 16)) % 16;
+    const int64_t js = ((int64_t)(pad + g.nx()) + 15) / 16 * 16;
+    const int64_t ks = js * g.ny();
+    const int64_t ns = ks * g.nz();
+    double* base = dev_alloc((size_t)(ns * ncomp + 32));
+    owned[il] = base;
+    iamrx_fab& f = fabs[il];
+    // dev_alloc blocks come from cudaMalloc (256-byte aligned)
+    f.p = base ? base + pad : nullptr;
+    for (int d = 0; d < 3; ++d) { f.lo[d] = g.lo[d]; f.hi[d] = g.hi[d]; }
+    f.jstride = js; f.kstride = ks; f.nstride = ns; f.ncomp = ncomp; f.pad_ = 0;
+  }
+}
+
+void MF::alias(Level* L, int ixtype_, int ncomp_, int ng_, const iamrx_fab* f) {
+  clear();
+  lev = L; ixtype = ixtype_; ncomp = ncomp_; ng = ng_;
+  fabs.assign(f, f + L->nlocal());
+  owned.assign(L->nlocal(), nullptr);
+}
+
+void MF::clear() {
+  for (double* p : owned) if (p) dev_free(p);
+  owned.clear(); fabs.clear(); lev = nullptr;
+}
+
+static void fill_table(FabTable& t, const MF& m, int comp) {
+  for (int il = 0; il < m.n() && il < FabTable::MAXF; ++il) {
+    const iamrx_fab& f = m.fabs[il];
+    t.p[il] = f.p + (int64_t)comp * f.nstride;
+    for (int d = 0; d < 3; ++d) t.lo[il][d] = f.lo[d];
+    t.js[il] = f.jstride; t.ks[il] = f.kstride; t.ns[il] = f.nstride;
+  }
+}
+
+#define IX_TRY(call) do { int rc_ = (call); if (rc_ != IAMRX_OK) return rc_; } while (0)
+
+int mf_setval(MF& m, double v, int comp, int ncomp, int ng, cudaStream_t s) {
+  for (int il = 0; il < m.n(); ++il) IX_TRY(k::setval(m.gbox(il, ng), m.v(il, comp), ncomp, v, s));
+  return IAMRX_OK;
+}
+int mf_copy(MF& dst, const MF& src, int scomp, int dcomp, int ncomp, int ng, cudaStream_t s) {
+  for (int il = 0; il < dst.n(); ++il)
+    IX_TRY(k::copy(dst.gbox(il, ng), dst.v(il, dcomp), src.c(il, scomp), ncomp, s));
+  return IAMRX_OK;
+}
+int mf_lincomb(MF& dst, int dcomp, double a, const MF& x, int xcomp, double b, const MF& y, int ycomp,
+               int ncomp, int ng, cudaStream_t s) {
+  for (int il = 0; il < dst.n(); ++il)
+    IX_TRY(k::lincomb(dst.gbox(il, ng), dst.v(il, dcomp), a, x.c(il, xcomp), b, y.c(il, ycomp), ncomp, s));
+  return IAMRX_OK;
+}
+int mf_scale(MF& m, double c, int comp, int ncomp, int ng, cudaStream_t s) {
+  for (int il = 0; il < m.n(); ++il) IX_TRY(k::scale(m.gbox(il, ng), m.v(il, comp), c, ncomp, s));
+  return IAMRX_OK;
+}
+
+int mf_fill_boundary(MF& m, int comp, int ncomp, int ng, cudaStream_t s) {
+  if (ng <= 0 || m.n() == 0) return IAMRX_OK;
+  if (m.n() > FabTable::MAXF) { set_error("mf_fill_boundary: too many local boxes"); return IAMRX_ERR_ARG; }
+  Level& L = *m.lev;
+  FBPlan& P = L.plan(m.ixtype, ng);
+  FabTable t; fill_table(t, m, comp);
+  if (P.peers.empty()) {
+    return k::copy_batch(P.d_local, (int)P.local.size(), t, t, nullptr, ncomp, 0, s);
+  }
+  double* sbuf = dev_alloc((size_t)(P.send_total * ncomp + 1));
+  double* rbuf = dev_alloc((size_t)(P.recv_total * ncomp + 1));
+  if (!sbuf || !rbuf) return IAMRX_ERR_CUDA;
+  IX_TRY(k::copy_batch(P.d_send, P.n_send, t, t, sbuf, ncomp, 0, s));
+  std::vector<double*> sb, rb; std::vector<int64_t> sc, rc;
+  for (size_t i = 0; i < P.peers.size(); ++i) {
+    sb.push_back(sbuf + P.send_off[i] * ncomp); rb.push_back(rbuf + P.recv_off[i] * ncomp);
+    sc.push_back(P.send_pts[i] * ncomp); rc.push_back(P.recv_pts[i] * ncomp);
+  }
+  IX_TRY(comm_exchange(P.peers, sb, sc, rb, rc, s));
+  IX_TRY(k::copy_batch(P.d_local, (int)P.local.size(), t, t, nullptr, ncomp, 0, s));
+  IX_TRY(k::copy_batch(P.d_recv, P.n_recv, t, t, rbuf, ncomp, 0, s));
+  dev_free(sbuf); dev_free(rbuf);  // stream-ordered reuse: same stream
+  return IAMRX_OK;
+}
+
+// ---- reductions ---------------------------------------------------------
+namespace {
+struct RedScratch {
+  double* d = nullptr;
+  double* h = nullptr;
+  RedScratch() {}
+  int init() {
+    if (d) return IAMRX_OK;
+    if (cudaMalloc(&d, 64 * sizeof(double)) != cudaSuccess) return IAMRX_ERR_CUDA;
+    if (cudaMallocHost(&h, 64 * sizeof(double)) != cudaSuccess) return IAMRX_ERR_CUDA;
+    return IAMRX_OK;
+  }
+};
+RedScratch& red() { static RedScratch r; return r; }
+}  // namespace
+
+static Bx unique_box(const MF& m, int il) {
+  // points of box il not shared with a higher-index neighbour: drop the upper
+  // node/face layer unless it lies on a non-periodic domain boundary.
+  Bx b = m.vbox(il);
+  const Level& L = *m.lev;
+  for (int d = 0; d < 3; ++d) {
+    const bool nodal_d = (m.ixtype == IX_NODE) || (m.ixtype == IX_XFACE + d);
+    if (!nodal_d) continue;
+    const bool at_dom_hi = (L.lbox(il).hi[d] == L.geom.domain.hi[d]);
+    if (!(at_dom_hi && !L.geom.periodic[d])) b.hi[d] -= 1;
+  }
+  return b;
+}
+
+static int reduce_common(const MF& m, int comp, int ncomp, int op, double* out, cudaStream_t s,
+                         bool uniq) {
+  RedScratch& R = red();
+  IX_TRY(R.init());
+  IX_TRY(k::reduce_init(R.d, ncomp, op, s));
+  for (int il = 0; il < m.n(); ++il)
+    IX_TRY(k::reduce(uniq ? unique_box(m, il) : m.vbox(il), m.c(il, comp), ncomp, op, R.d, s));
+  IX_TRY(comm_allreduce(R.d, ncomp, op, s));
+  IX_CUDA(cudaMemcpyAsync(R.h, R.d, ncomp * sizeof(double), cudaMemcpyDeviceToHost, s));
+  IX_CUDA(cudaStreamSynchronize(s));
+  for (int n = 0; n < ncomp; ++n) out[n] = R.h[n];
+  return IAMRX_OK;
+}
+
+int mf_norminf_each(const MF& m, int comp, int ncomp, double* out, cudaStream_t s) {
+  return reduce_common(m, comp, ncomp, 2, out, s, false);
+}
+int mf_norminf(const MF& m, int comp, int ncomp, double* out, cudaStream_t s) {
+  double tmp[16];
+  IX_TRY(reduce_common(m, comp, ncomp, 2, tmp, s, false));
+  double r = 0; for (int n = 0; n < ncomp; ++n) r = std::max(r, tmp[n]);
+  *out = r;
+  return IAMRX_OK;
+}
+int mf_sum(const MF& m, int comp, double* out, cudaStream_t s, bool unique_nodes) {
+  return reduce_common(m, comp, 1, 0, out, s, unique_nodes);
+}
+int mf_min(const MF& m, int comp, double* out, cudaStream_t s) {
+  return reduce_common(m, comp, 1, 1, out, s, false);
+}
+
+}  // namespace ix

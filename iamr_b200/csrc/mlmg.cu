@@ -1,0 +1,385 @@
+// mlmg.cu -- see mlmg.h.  V-cycle drivers; every arithmetic step is one of the
+// kernels in abec.cu / nodal.cu / blas.cu launched over the rank's local boxes.
+#include "mlmg.h"
+#include <algorithm>
+#include <cmath>
+#include <cstdlib>
+
+namespace ix {
+
+#define IX_TRY(call) do { int rc_ = (call); if (rc_ != IAMRX_OK) return rc_; } while (0)
+
+std::unique_ptr<Level> make_level(const iamrx_geom& g, const std::vector<Bx>& boxes,
+                                  const std::vector<int>& owner) {
+  auto L = std::make_unique<Level>();
+  L->geom = g;
+  L->boxes = boxes;
+  L->owner = owner;
+  L->domain = mkbx(g.domain);
+  const int me = comm().rank;
+  for (size_t i = 0; i < boxes.size(); ++i) {
+    if (owner[i] == me) L->local.push_back((int)i);
+    L->ncells_global += boxes[i].npts();
+  }
+  for (int d = 0; d < 3; ++d) L->dxinv[d] = 1.0 / g.dx[d];
+  return L;
+}
+
+std::unique_ptr<Level> coarsen_level(const Level& f, int min_width) {
+  std::vector<Bx> cb;
+  for (const Bx& b : f.boxes) {
+    Bx c;
+    for (int d = 0; d < 3; ++d) {
+      const int n = b.hi[d] - b.lo[d] + 1;
+      if ((n % 2) != 0 || (b.lo[d] % 2) != 0 || n / 2 < min_width) return nullptr;
+      c.lo[d] = b.lo[d] / 2;
+      c.hi[d] = c.lo[d] + n / 2 - 1;
+    }
+    cb.push_back(c);
+  }
+  iamrx_geom g = f.geom;
+  for (int d = 0; d < 3; ++d) {
+    const int n = f.geom.domain.hi[d] - f.geom.domain.lo[d] + 1;
+    if ((n % 2) != 0 || (f.geom.domain.lo[d] % 2) != 0) return nullptr;
+    g.domain.lo[d] = f.geom.domain.lo[d] / 2;
+    g.domain.hi[d] = g.domain.lo[d] + n / 2 - 1;
+    g.dx[d] = 2.0 * f.geom.dx[d];
+  }
+  return make_level(g, cb, f.owner);
+}
+
+static bool all_periodic(const Level& L) {
+  return L.geom.periodic[0] && L.geom.periodic[1] && L.geom.periodic[2];
+}
+
+// ===========================================================================
+// CellMG
+// ===========================================================================
+CellMG::CellMG(Level* fine, int ncomp, bool tensor, int max_coarsening)
+    : ncomp_(ncomp), tensor_(tensor) {
+  iamrx_mg_info_default(&info_);
+  lv_.emplace_back();
+  lv_[0].lev = fine;
+  Level* cur = fine;
+  for (int l = 1; l <= max_coarsening; ++l) {
+    auto c = coarsen_level(*cur, 2);
+    if (!c) break;
+    lv_.emplace_back();
+    lv_.back().lev_owned = std::move(c);
+    lv_.back().lev = lv_.back().lev_owned.get();
+    cur = lv_.back().lev;
+  }
+  for (auto& L : lv_) {
+    for (int d = 0; d < 3; ++d) L.dxinv[d] = L.lev->dxinv[d];
+    L.cor.define(L.lev, IX_CELL, ncomp_, 1);
+    L.res.define(L.lev, IX_CELL, ncomp_, 0);
+    L.rescor.define(L.lev, IX_CELL, ncomp_, 0);
+  }
+}
+
+k::Abec CellMG::op_at(int l, int il) const {
+  const MGLevelCell& L = lv_[l];
+  k::Abec op;
+  op.a = a_; op.b = b_;
+  op.acoef = (a_ != 0.0 && L.acoef.ok()) ? L.acoef.c(il) : C4{};
+  op.bx = L.b[0].c(il); op.by = L.b[1].c(il); op.bz = L.b[2].c(il);
+  op.bncomp = tensor_ ? ncomp_ : 1;
+  for (int d = 0; d < 3; ++d) op.dxinv[d] = L.dxinv[d];
+  return op;
+}
+
+int CellMG::set_coeffs(const MF* acoef, const MF* bx, const MF* by, const MF* bz, cudaStream_t s) {
+  const MF* bin[3] = {bx, by, bz};
+  for (int d = 0; d < 3; ++d) eta_[d] = bin[d];
+  const int bn = tensor_ ? ncomp_ : 1;
+  // level 0
+  {
+    MGLevelCell& L = lv_[0];
+    if (a_ != 0.0 && acoef) {
+      if (!L.acoef.ok()) L.acoef.define(L.lev, IX_CELL, 1, 0);
+      IX_TRY(mf_copy(L.acoef, *acoef, 0, 0, 1, 0, s));
+    }
+    for (int d = 0; d < 3; ++d) {
+      if (!L.b[d].ok()) L.b[d].define(L.lev, IX_XFACE + d, bn, 0);
+      for (int c = 0; c < bn; ++c) {
+        const double fac = (tensor_ && c == d) ? (4.0 / 3.0) : 1.0;
+        IX_TRY(mf_lincomb(L.b[d], c, fac, *bin[d], 0, 0.0, *bin[d], 0, 1, 0, s));
+      }
+    }
+  }
+  for (size_t l = 1; l < lv_.size(); ++l) {
+    MGLevelCell& C = lv_[l];
+    MGLevelCell& F = lv_[l - 1];
+    if (a_ != 0.0 && acoef) {
+      if (!C.acoef.ok()) C.acoef.define(C.lev, IX_CELL, 1, 0);
+      for (int il = 0; il < C.acoef.n(); ++il)
+        IX_TRY(k::cc_restrict(C.acoef.vbox(il), C.acoef.v(il), F.acoef.c(il), 1, s));
+    }
+    for (int d = 0; d < 3; ++d) {
+      if (!C.b[d].ok()) C.b[d].define(C.lev, IX_XFACE + d, bn, 0);
+      for (int il = 0; il < C.b[d].n(); ++il)
+        IX_TRY(k::face_restrict(C.b[d].vbox(il), d, C.b[d].v(il), F.b[d].c(il), bn, s));
+    }
+  }
+  singular_ = (a_ == 0.0) && all_periodic(*lv_[0].lev);
+  return IAMRX_OK;
+}
+
+int CellMG::smooth(int l, MF& phi, const MF& rhs, int nsweeps, bool /*zero_init*/, cudaStream_t s) {
+  MGLevelCell& L = lv_[l];
+  for (int sw = 0; sw < nsweeps; ++sw) {
+    for (int rb = 0; rb < 2; ++rb) {
+      IX_TRY(mf_fill_boundary(phi, 0, ncomp_, 1, s));
+      for (int il = 0; il < phi.n(); ++il)
+        IX_TRY(k::abec_gsrb(phi.vbox(il), phi.v(il), rhs.c(il), op_at(l, il), info_.omega, rb, ncomp_, s));
+    }
+  }
+  (void)L;
+  return IAMRX_OK;
+}
+
+int CellMG::residual(int l, MF& out, MF& phi, const MF& rhs, bool with_cross, cudaStream_t s) {
+  IX_TRY(mf_fill_boundary(phi, 0, ncomp_, 1, s));
+  for (int il = 0; il < phi.n(); ++il) {
+    IX_TRY(k::abec_apply(phi.vbox(il), out.v(il), phi.c(il), rhs.c(il), op_at(l, il), ncomp_, s));
+    if (tensor_ && l == 0 && with_cross)
+      IX_TRY(k::tensor_cross(phi.vbox(il), out.v(il), phi.c(il), eta_[0]->c(il), eta_[1]->c(il),
+                             eta_[2]->c(il), -b_, lv_[0].dxinv, s));
+  }
+  return IAMRX_OK;
+}
+
+int CellMG::apply(MF& out, MF& phi, cudaStream_t s) {
+  IX_TRY(mf_fill_boundary(phi, 0, ncomp_, 1, s));
+  for (int il = 0; il < phi.n(); ++il) {
+    IX_TRY(k::abec_apply(phi.vbox(il), out.v(il), phi.c(il), C4{}, op_at(0, il), ncomp_, s));
+    if (tensor_)
+      IX_TRY(k::tensor_cross(phi.vbox(il), out.v(il), phi.c(il), eta_[0]->c(il), eta_[1]->c(il),
+                             eta_[2]->c(il), b_, lv_[0].dxinv, s));
+  }
+  return IAMRX_OK;
+}
+
+int CellMG::make_solvable(int l, MF& rhs, cudaStream_t s) {
+  for (int c = 0; c < ncomp_; ++c) {
+    double sum = 0;
+    IX_TRY(mf_sum(rhs, c, &sum, s));
+    const double mean = sum / (double)lv_[l].lev->ncells_global;
+    for (int il = 0; il < rhs.n(); ++il) IX_TRY(k::addconst(rhs.vbox(il), rhs.v(il, c), -mean, 1, s));
+  }
+  return IAMRX_OK;
+}
+
+int CellMG::vcycle(cudaStream_t s) {
+  const int nl = (int)lv_.size();
+  for (int l = 0; l < nl - 1; ++l) {
+    MGLevelCell& L = lv_[l];
+    IX_TRY(mf_setval(L.cor, 0.0, 0, ncomp_, 1, s));
+    IX_TRY(smooth(l, L.cor, L.res, info_.nu1, true, s));
+    IX_TRY(residual(l, L.rescor, L.cor, L.res, false, s));
+    MGLevelCell& C = lv_[l + 1];
+    for (int il = 0; il < C.res.n(); ++il)
+      IX_TRY(k::cc_restrict(C.res.vbox(il), C.res.v(il), L.rescor.c(il), ncomp_, s));
+  }
+  {
+    MGLevelCell& B = lv_[nl - 1];
+    IX_TRY(mf_setval(B.cor, 0.0, 0, ncomp_, 1, s));
+    if (singular_ && nl > 1) IX_TRY(make_solvable(nl - 1, B.res, s));
+    IX_TRY(smooth(nl - 1, B.cor, B.res, nl == 1 ? info_.nu1 + info_.nu2 : info_.bottom_sweeps, true, s));
+  }
+  for (int l = nl - 2; l >= 0; --l) {
+    MGLevelCell& L = lv_[l];
+    MGLevelCell& C = lv_[l + 1];
+    for (int il = 0; il < L.cor.n(); ++il)
+      IX_TRY(k::cc_prolong_add(L.cor.vbox(il), L.cor.v(il), C.cor.c(il), ncomp_, s));
+    IX_TRY(smooth(l, L.cor, L.res, info_.nu2, false, s));
+  }
+  return IAMRX_OK;
+}
+
+int CellMG::solve(MF& sol, const MF& rhs_in, iamrx_mg_info* info, cudaStream_t s) {
+  if (info) info_ = *info;
+  MGLevelCell& L0 = lv_[0];
+  MF rhs(L0.lev, IX_CELL, ncomp_, 0);
+  IX_TRY(mf_copy(rhs, rhs_in, 0, 0, ncomp_, 0, s));
+  if (singular_) IX_TRY(make_solvable(0, rhs, s));
+  double rhsnorm = 0, resnorm0 = 0, resnorm = 0;
+  IX_TRY(mf_norminf(rhs, 0, ncomp_, &rhsnorm, s));
+  IX_TRY(residual(0, L0.res, sol, rhs, true, s));
+  IX_TRY(mf_norminf(L0.res, 0, ncomp_, &resnorm0, s));
+  const double maxnorm = std::max(rhsnorm, resnorm0);
+  const double target = std::max(info_.atol, info_.rtol * maxnorm);
+  resnorm = resnorm0;
+  int iters = 0;
+  int rc = IAMRX_OK;
+  if (!(resnorm0 <= target)) {
+    rc = info_.max_iter;  // pessimistic: not converged
+    for (iters = 1; iters <= info_.max_iter; ++iters) {
+      IX_TRY(vcycle(s));
+      IX_TRY(mf_lincomb(sol, 0, 1.0, sol, 0, 1.0, L0.cor, 0, ncomp_, 0, s));
+      IX_TRY(residual(0, L0.res, sol, rhs, true, s));
+      IX_TRY(mf_norminf(L0.res, 0, ncomp_, &resnorm, s));
+      if (info_.verbose > 1)
+        fprintf(stderr, "[iamrx] CellMG iter %d resnorm %.6e (target %.3e)\n", iters, resnorm, target);
+      if (!(resnorm == resnorm)) { set_error("CellMG: NaN residual"); rc = IAMRX_ERR_NAN; break; }
+      if (resnorm <= target) { rc = IAMRX_OK; break; }
+    }
+  }
+  IX_TRY(mf_fill_boundary(sol, 0, ncomp_, 1, s));  // setFinalFillBC(true)
+  if (info_.verbose > 0)
+    fprintf(stderr, "[iamrx] CellMG: %d iters, res0 %.3e -> %.3e (rhs %.3e, levels %d)\n", iters, resnorm0,
+            resnorm, rhsnorm, nlevels());
+  if (info) { info->iters = iters; info->resnorm0 = resnorm0; info->resnorm = resnorm; info->rhsnorm = rhsnorm; }
+  if (rc > 0) set_error("CellMG: failed to converge");
+  return rc;
+}
+
+// ===========================================================================
+// NodeMG
+// ===========================================================================
+NodeMG::NodeMG(Level* fine, int max_coarsening) {
+  iamrx_mg_info_default(&info_);
+  lv_.emplace_back();
+  lv_[0].lev = fine;
+  Level* cur = fine;
+  for (int l = 1; l <= max_coarsening; ++l) {
+    auto c = coarsen_level(*cur, 2);
+    if (!c) break;
+    lv_.emplace_back();
+    lv_.back().lev_owned = std::move(c);
+    lv_.back().lev = lv_.back().lev_owned.get();
+    cur = lv_.back().lev;
+  }
+  for (auto& L : lv_) {
+    for (int d = 0; d < 3; ++d) L.dxinv[d] = L.lev->dxinv[d];
+    L.sigma.define(L.lev, IX_CELL, 1, 1);
+    L.cor.define(L.lev, IX_NODE, 1, 1);
+    L.res.define(L.lev, IX_NODE, 1, 1);
+    L.rescor.define(L.lev, IX_NODE, 1, 1);
+  }
+}
+
+int NodeMG::set_sigma(const MF& sigma, cudaStream_t s) {
+  IX_TRY(mf_setval(lv_[0].sigma, 0.0, 0, 1, 1, s));
+  IX_TRY(mf_copy(lv_[0].sigma, sigma, 0, 0, 1, 0, s));
+  IX_TRY(mf_fill_boundary(lv_[0].sigma, 0, 1, 1, s));
+  for (size_t l = 1; l < lv_.size(); ++l) {
+    MGLevelNode& C = lv_[l];
+    MGLevelNode& F = lv_[l - 1];
+    IX_TRY(mf_setval(C.sigma, 0.0, 0, 1, 1, s));
+    for (int il = 0; il < C.sigma.n(); ++il)
+      IX_TRY(k::cc_restrict(C.sigma.vbox(il), C.sigma.v(il), F.sigma.c(il), 1, s));
+    IX_TRY(mf_fill_boundary(C.sigma, 0, 1, 1, s));
+  }
+  return IAMRX_OK;
+}
+
+static int nodal_smoother_kind() {
+  static int kind = -1;
+  if (kind < 0) {
+    const char* e = getenv("IAMRX_NODAL_SMOOTHER");
+    kind = (e && e[0] == 'j') ? 1 : 0;  // 0 = 8-colour Gauss-Seidel, 1 = damped Jacobi
+  }
+  return kind;
+}
+
+int NodeMG::smooth(int l, MF& phi, const MF& rhs, int nsweeps, cudaStream_t s) {
+  MGLevelNode& L = lv_[l];
+  if (nodal_smoother_kind() == 1) {
+    MF tmp(L.lev, IX_NODE, 1, 1);
+    for (int sw = 0; sw < 2 * nsweeps; ++sw) {
+      IX_TRY(mf_fill_boundary(phi, 0, 1, 1, s));
+      for (int il = 0; il < phi.n(); ++il)
+        IX_TRY(k::nodal_jacobi(phi.vbox(il), tmp.v(il), phi.c(il), rhs.c(il), L.sigma.c(il), L.dxinv,
+                               2.0 / 3.0, s));
+      IX_TRY(mf_copy(phi, tmp, 0, 0, 1, 0, s));
+    }
+    return IAMRX_OK;
+  }
+  for (int sw = 0; sw < nsweeps; ++sw) {
+    for (int color = 0; color < 8; ++color) {
+      IX_TRY(mf_fill_boundary(phi, 0, 1, 1, s));
+      for (int il = 0; il < phi.n(); ++il)
+        IX_TRY(k::nodal_gs_color(phi.vbox(il), phi.v(il), rhs.c(il), L.sigma.c(il), L.dxinv, color, s));
+    }
+  }
+  return IAMRX_OK;
+}
+
+int NodeMG::residual(int l, MF& out, MF& phi, const MF& rhs, cudaStream_t s) {
+  MGLevelNode& L = lv_[l];
+  IX_TRY(mf_fill_boundary(phi, 0, 1, 1, s));
+  for (int il = 0; il < phi.n(); ++il)
+    IX_TRY(k::nodal_adotx(phi.vbox(il), out.v(il), phi.c(il), rhs.c(il), L.sigma.c(il), L.dxinv, s));
+  return IAMRX_OK;
+}
+
+int NodeMG::vcycle(cudaStream_t s) {
+  const int nl = (int)lv_.size();
+  for (int l = 0; l < nl - 1; ++l) {
+    MGLevelNode& L = lv_[l];
+    IX_TRY(mf_setval(L.cor, 0.0, 0, 1, 1, s));
+    IX_TRY(smooth(l, L.cor, L.res, info_.nu1, s));
+    IX_TRY(residual(l, L.rescor, L.cor, L.res, s));
+    IX_TRY(mf_fill_boundary(L.rescor, 0, 1, 1, s));
+    MGLevelNode& C = lv_[l + 1];
+    for (int il = 0; il < C.res.n(); ++il)
+      IX_TRY(k::nodal_restrict(C.res.vbox(il), C.res.v(il), L.rescor.c(il), s));
+  }
+  {
+    MGLevelNode& B = lv_[nl - 1];
+    IX_TRY(mf_setval(B.cor, 0.0, 0, 1, 1, s));
+    IX_TRY(smooth(nl - 1, B.cor, B.res, nl == 1 ? info_.nu1 + info_.nu2 : info_.bottom_sweeps, s));
+  }
+  for (int l = nl - 2; l >= 0; --l) {
+    MGLevelNode& L = lv_[l];
+    MGLevelNode& C = lv_[l + 1];
+    for (int il = 0; il < L.cor.n(); ++il)
+      IX_TRY(k::nodal_interp_add(L.cor.vbox(il), L.cor.v(il), C.cor.c(il), s));
+    IX_TRY(smooth(l, L.cor, L.res, info_.nu2, s));
+  }
+  return IAMRX_OK;
+}
+
+int NodeMG::solve(MF& phi, MF& rhs, iamrx_mg_info* info, cudaStream_t s) {
+  if (info) info_ = *info;
+  MGLevelNode& L0 = lv_[0];
+  Level& lev = *L0.lev;
+  if (all_periodic(lev)) {  // singular: make rhs solvable (subtract the mean over unique nodes)
+    double sum = 0;
+    IX_TRY(mf_sum(rhs, 0, &sum, s, true));
+    const double mean = sum / (double)lev.ncells_global;  // #unique nodes == #cells when periodic
+    for (int il = 0; il < rhs.n(); ++il) IX_TRY(k::addconst(rhs.vbox(il), rhs.v(il), -mean, 1, s));
+  }
+  double rhsnorm = 0, resnorm0 = 0, resnorm = 0;
+  IX_TRY(mf_norminf(rhs, 0, 1, &rhsnorm, s));
+  IX_TRY(residual(0, L0.res, phi, rhs, s));
+  IX_TRY(mf_norminf(L0.res, 0, 1, &resnorm0, s));
+  const double maxnorm = std::max(rhsnorm, resnorm0);
+  const double target = std::max(info_.atol, info_.rtol * maxnorm);
+  resnorm = resnorm0;
+  int iters = 0;
+  int rc = IAMRX_OK;
+  if (!(resnorm0 <= target)) {
+    rc = info_.max_iter;
+    for (iters = 1; iters <= info_.max_iter; ++iters) {
+      IX_TRY(vcycle(s));
+      IX_TRY(mf_lincomb(phi, 0, 1.0, phi, 0, 1.0, L0.cor, 0, 1, 0, s));
+      IX_TRY(residual(0, L0.res, phi, rhs, s));
+      IX_TRY(mf_norminf(L0.res, 0, 1, &resnorm, s));
+      if (info_.verbose > 1)
+        fprintf(stderr, "[iamrx] NodeMG iter %d resnorm %.6e (target %.3e)\n", iters, resnorm, target);
+      if (!(resnorm == resnorm)) { set_error("NodeMG: NaN residual"); rc = IAMRX_ERR_NAN; break; }
+      if (resnorm <= target) { rc = IAMRX_OK; break; }
+    }
+  }
+  IX_TRY(mf_fill_boundary(phi, 0, 1, 1, s));
+  if (info_.verbose > 0)
+    fprintf(stderr, "[iamrx] NodeMG: %d iters, res0 %.3e -> %.3e (rhs %.3e, levels %d)\n", iters, resnorm0,
+            resnorm, rhsnorm, nlevels());
+  if (info) { info->iters = iters; info->resnorm0 = resnorm0; info->resnorm = resnorm; info->rhsnorm = rhsnorm; }
+  if (rc > 0) set_error("NodeMG: failed to converge");
+  return rc;
+}
+
+}  // namespace ix

@@ -1,0 +1,80 @@
+// mlmg.h -- geometric multigrid drivers (host orchestration).
+//   CellMG : (a*alpha - b div beta grad) on cell centres, ncomp components,
+//            optional MLTensorOp cross terms at the finest level.
+//   NodeMG : div(sigma grad) on nodes (Q1 finite elements).
+// Host-side restatement of the subset of AMReX MLMG / MLABecLaplacian /
+// MLTensorOp / MLNodeLaplacian that IAMR drives (MacProj.cpp:1084-1184,
+// Projection.cpp:2385-2567, Diffusion.cpp:207-957); SURVEY.md Appendix A.6-A.9.
+#pragma once
+#include "level.h"
+
+namespace ix {
+
+struct MGLevelCell {
+  std::unique_ptr<Level> lev_owned;  // coarse levels own their Level
+  Level* lev = nullptr;
+  MF acoef;            // 1 comp, 0 ghost (only if a != 0)
+  MF b[3];             // face coefs, bncomp comps
+  MF cor, res, rescor; // ncomp
+  double dxinv[3];
+};
+
+class CellMG {
+ public:
+  // fine-level coefficient MFs are referenced, not copied (caller keeps them alive)
+  CellMG(Level* fine, int ncomp, bool tensor, int max_coarsening);
+  int set_scalars(double a, double b) { a_ = a; b_ = b; return 0; }
+  // acoef: cell MF (1 comp); eta[d]: face MFs with 1 comp.  For tensor the solver
+  // builds per-component b = eta * (1 + 1/3 delta_{c,d}) (4/3 on the diagonal).
+  int set_coeffs(const MF* acoef, const MF* bx, const MF* by, const MF* bz, cudaStream_t s);
+  int apply(MF& out, MF& phi, cudaStream_t s);   // out = L(phi) incl. cross terms; fills phi ghosts
+  int solve(MF& sol, const MF& rhs, iamrx_mg_info* info, cudaStream_t s);
+  int nlevels() const { return (int)lv_.size(); }
+  const MF& bcoef(int d) const { return lv_[0].b[d]; }
+  double bscalar() const { return b_; }
+  k::Abec op_at(int mglev, int il) const;
+
+ private:
+  int smooth(int l, MF& phi, const MF& rhs, int nsweeps, bool zero_init, cudaStream_t s);
+  int residual(int l, MF& out, MF& phi, const MF& rhs, bool with_cross, cudaStream_t s);
+  int vcycle(cudaStream_t s);
+  int make_solvable(int l, MF& rhs, cudaStream_t s);
+  std::vector<MGLevelCell> lv_;
+  int ncomp_;
+  bool tensor_;
+  double a_ = 0, b_ = 1;
+  bool singular_ = false;
+  const MF* eta_[3] = {nullptr, nullptr, nullptr};
+  iamrx_mg_info info_;
+};
+
+struct MGLevelNode {
+  std::unique_ptr<Level> lev_owned;
+  Level* lev = nullptr;
+  MF sigma;            // cell, 1 ghost
+  MF cor, res, rescor; // nodal, 1 ghost
+  double dxinv[3];
+};
+
+class NodeMG {
+ public:
+  NodeMG(Level* fine, int max_coarsening);
+  int set_sigma(const MF& sigma, cudaStream_t s);  // copies + coarsens
+  int solve(MF& phi, MF& rhs, iamrx_mg_info* info, cudaStream_t s);
+  int nlevels() const { return (int)lv_.size(); }
+  const MF& sigma0() const { return lv_[0].sigma; }
+
+ private:
+  int smooth(int l, MF& phi, const MF& rhs, int nsweeps, cudaStream_t s);
+  int residual(int l, MF& out, MF& phi, const MF& rhs, cudaStream_t s);
+  int vcycle(cudaStream_t s);
+  std::vector<MGLevelNode> lv_;
+  iamrx_mg_info info_;
+};
+
+// coarsen a level by 2 (all boxes must be coarsenable); nullptr if not possible
+std::unique_ptr<Level> coarsen_level(const Level& f, int min_width);
+std::unique_ptr<Level> make_level(const iamrx_geom& g, const std::vector<Bx>& boxes,
+                                  const std::vector<int>& owner);
+
+}  // namespace ix

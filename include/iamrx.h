@@ -1,0 +1,335 @@
+/*
+ * iamrx.h -- C ABI of the B200-native IAMR hot path (libiamrx.so).
+ *
+ * Everything that crosses this boundary is POD: raw DEVICE pointers, index
+ * boxes, strides, scalars and a cudaStream_t passed as void*.  No torch, no
+ * AMReX, no C++ types.  The layout of a field is the one AMReX's Array4 uses
+ * (x unit-stride, then y, then z, component outermost, ghost cells inside the
+ * allocation) with the three strides made explicit, so that an adapter inside
+ * IAMR can forward `MultiFab::array(mfi)` ({p, begin, end, jstride, kstride,
+ * nstride, ncomp}) without a copy.
+ *
+ * Each entry point names the reference call it stands in for
+ * (/root/reference = AMReX-Fluids/IAMR @ f46ba59; "NSB.cpp" =
+ * Source/NavierStokesBase.cpp, "NS.cpp" = Source/NavierStokes.cpp).  The
+ * arithmetic of those calls lives in AMReX / AMReX-Hydro, which the reference
+ * does not vendor (Exec/Make.IAMR:15-19,36-37); see DESIGN.md "Oracle".
+ *
+ * Error convention (reference: amrex::Abort on bad configuration, "MLMG failed
+ * to converge" abort): every function returns int, 0 = ok, <0 = bad argument /
+ * CUDA error (iamrx_last_error() gives text), >0 = solver did not converge
+ * (value = iterations done).  Nothing throws across the boundary.  There is no
+ * CPU fallback: without a usable CUDA device every compute entry returns
+ * IAMRX_ERR_NO_DEVICE.
+ */
+#ifndef IAMRX_H_
+#define IAMRX_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define IAMRX_OK 0
+#define IAMRX_ERR_ARG (-1)
+#define IAMRX_ERR_CUDA (-2)
+#define IAMRX_ERR_NO_DEVICE (-3)
+#define IAMRX_ERR_COMM (-4)
+#define IAMRX_ERR_NAN (-5)
+
+/* Index-space box, inclusive bounds (amrex::Box smallEnd/bigEnd). */
+typedef struct iamrx_box {
+  int lo[3];
+  int hi[3];
+} iamrx_box;
+
+/* One FArrayBox / Array4 view.  `lo`/`hi` bound the ALLOCATED region
+ * (valid + ghost) in the index space of the field's own centring; element
+ * (i,j,k,n) lives at p[(i-lo[0]) + (j-lo[1])*jstride + (k-lo[2])*kstride +
+ * n*nstride]. */
+typedef struct iamrx_fab {
+  double* p;
+  int lo[3];
+  int hi[3];
+  int64_t jstride;
+  int64_t kstride;
+  int64_t nstride;
+  int ncomp;
+  int pad_;
+} iamrx_fab;
+
+/* amrex::Geometry subset: domain box (cell indices), mesh spacing, periodicity
+ * (NS_setup.cpp / inputs `geometry.is_periodic`). */
+typedef struct iamrx_geom {
+  iamrx_box domain;
+  double dx[3];
+  double prob_lo[3];
+  int periodic[3];
+  int pad_;
+} iamrx_geom;
+
+/* amrex::BCType math codes used by BCRec (Source/NS_BC.H:7-55). */
+enum {
+  IAMRX_BC_INT_DIR = 0,      /* interior / periodic */
+  IAMRX_BC_REFLECT_ODD = -1,
+  IAMRX_BC_REFLECT_EVEN = 1,
+  IAMRX_BC_FOEXTRAP = 2,
+  IAMRX_BC_EXT_DIR = 3,
+  IAMRX_BC_HOEXTRAP = 4
+};
+
+/* amrex::LinOpBCType subset (MacProj.cpp:1187-1208, Projection.cpp:2436-2464,
+ * Diffusion.cpp:1900-1938). */
+enum {
+  IAMRX_LINOP_PERIODIC = 0,
+  IAMRX_LINOP_DIRICHLET = 1,
+  IAMRX_LINOP_NEUMANN = 2
+};
+
+/* flags of iamrx_compute_aofs_box (arguments of
+ * HydroUtils::ComputeFluxesOnBoxFromState, NSB.cpp:4701-4717) */
+enum {
+  IAMRX_ADV_PPM = 1,               /* godunov_use_ppm (not implemented: returns ERR_ARG) */
+  IAMRX_ADV_FORCES_IN_TRANS = 2,   /* godunov.use_forces_in_trans, NSB.cpp:556 */
+  IAMRX_ADV_IS_VELOCITY = 4,
+  IAMRX_ADV_WRITE_FLUXES = 8,      /* also store area-weighted fluxes + edge states */
+  IAMRX_ADV_IS_SYNC = 16           /* aofs -= update, fluxes from U_corr (NSB.cpp:4834) */
+};
+
+const char* iamrx_last_error(void);
+int iamrx_version(void);
+/* number of kernels this library has launched since load (bench.py's
+ * `gpu_launches`), and reset. */
+int64_t iamrx_launch_count(void);
+void iamrx_launch_count_reset(void);
+int iamrx_device_ok(void);
+
+/* ------------------------------------------------------------------------
+ * 1. Per-box kernels (one FArrayBox at a time, async on `stream`).
+ * ---------------------------------------------------------------------- */
+
+/* MLABecLaplacian red-black Gauss-Seidel colour pass on `bx`
+ * (AMReX MLABecLaplacian::Fsmooth, reached from every mlmg.solve in
+ * MacProj.cpp:1179, Diffusion.cpp:567,923):
+ *   phi += omega/(gamma) * (rhs - (a*alpha*phi - b*div(beta grad phi)))
+ * for cells with (i+j+k+redblack) even.  Ghost cells of phi must be filled.
+ * acoef may be NULL when a == 0.  ncomp components share bx/by/bz unless
+ * bcoef fabs carry ncomp components (MLTensorOp). */
+int iamrx_abec_gsrb_box(const iamrx_box* bx, iamrx_fab* phi, const iamrx_fab* rhs,
+                        double a, double b, const iamrx_fab* acoef,
+                        const iamrx_fab* bcoef_x, const iamrx_fab* bcoef_y,
+                        const iamrx_fab* bcoef_z, const double dxinv[3],
+                        double omega, int redblack, int ncomp, void* stream);
+
+/* MLABecLaplacian::Fapply / residual: out = L(phi) (rhs == NULL) or
+ * out = rhs - L(phi).  (mlmg.apply Diffusion.cpp:768,1757; residuals inside
+ * every solve.) */
+int iamrx_abec_apply_box(const iamrx_box* bx, iamrx_fab* out, const iamrx_fab* phi,
+                         const iamrx_fab* rhs, double a, double b,
+                         const iamrx_fab* acoef, const iamrx_fab* bcoef_x,
+                         const iamrx_fab* bcoef_y, const iamrx_fab* bcoef_z,
+                         const double dxinv[3], int ncomp, void* stream);
+
+/* MLTensorOp cross terms: out += b * div(cross-flux(eta, vel))
+ * (MLTensorOp::apply after the ABec part; Diffusion.cpp:715-768,1708-1757).
+ * vel has 3 components and filled ghost cells including edges/corners. */
+int iamrx_tensor_cross_box(const iamrx_box* bx, iamrx_fab* out, const iamrx_fab* vel,
+                           const iamrx_fab* eta_x, const iamrx_fab* eta_y,
+                           const iamrx_fab* eta_z, double b, const double dxinv[3],
+                           void* stream);
+
+/* Godunov::ExtrapVelToFaces (NSB.cpp:4487-4491), PLM, one box:
+ * vel (3 comps, 3 ghost cells filled), force (3 comps, 1 ghost) ->
+ * umac/vmac/wmac on the faces of bx. bc_lo/bc_hi: 3 comps x 3 dirs math BC
+ * codes (only IAMRX_BC_INT_DIR, i.e. periodic / interior, is implemented in
+ * this round). */
+int iamrx_extrap_vel_to_faces_box(const iamrx_box* bx, const iamrx_fab* vel,
+                                  const iamrx_fab* force, iamrx_fab* umac,
+                                  iamrx_fab* vmac, iamrx_fab* wmac,
+                                  const iamrx_geom* geom, double dt, int flags,
+                                  void* stream);
+
+/* NavierStokesBase::ComputeAofs body for one box (NSB.cpp:4661-4845):
+ * ComputeFluxesOnBoxFromState (Godunov edge states + fluxes) ->
+ * ComputeDivergence(mult=-1) -> ComputeConvectiveTerm -> aofs = -update.
+ * S: ncomp comps, 3 ghosts.  force: ncomp comps, 1 ghost.  divu may be NULL
+ * (== 0).  umac..wmac: MAC velocities with 1 ghost face layer.  fx,fy,fz /
+ * xed,yed,zed may be NULL unless IAMRX_ADV_WRITE_FLUXES. */
+int iamrx_compute_aofs_box(const iamrx_box* bx, iamrx_fab* aofs, int aofs_comp,
+                           const iamrx_fab* S, int s_comp, int ncomp,
+                           const iamrx_fab* force, int f_comp, const iamrx_fab* divu,
+                           const iamrx_fab* umac, const iamrx_fab* vmac,
+                           const iamrx_fab* wmac, iamrx_fab* fx, iamrx_fab* fy,
+                           iamrx_fab* fz, iamrx_fab* xed, iamrx_fab* yed,
+                           iamrx_fab* zed, const int* iconserv,
+                           const iamrx_geom* geom, double dt, int flags, void* stream);
+
+/* MLNodeLaplacian pieces on one box of NODES (Projection.cpp:2512-2542,
+ * NSB.cpp:4106-4118).  sigma is cell-centred with 1 ghost cell. */
+int iamrx_nodal_divu_box(const iamrx_box* nbx, iamrx_fab* rhs, const iamrx_fab* vel,
+                         const double dxinv[3], void* stream);
+int iamrx_nodal_adotx_box(const iamrx_box* nbx, iamrx_fab* out, const iamrx_fab* phi,
+                          const iamrx_fab* rhs, const iamrx_fab* sigma,
+                          const double dxinv[3], void* stream);
+int iamrx_nodal_gs_box(const iamrx_box* nbx, iamrx_fab* phi, const iamrx_fab* rhs,
+                       const iamrx_fab* sigma, const double dxinv[3], int color,
+                       void* stream);
+/* vel -= sigma*grad(phi); gp = grad(phi) (cell-centred average of the four
+ * parallel edge differences) -- NodalProjector::project tail + getGradPhi,
+ * MLNodeLaplacian::compGrad (NSB.cpp:4118). Either of vel / gp may be NULL. */
+int iamrx_nodal_mknewu_box(const iamrx_box* bx, iamrx_fab* vel, iamrx_fab* gp,
+                           const iamrx_fab* phi, const iamrx_fab* sigma,
+                           const double dxinv[3], void* stream);
+
+/* ------------------------------------------------------------------------
+ * 2. Level objects: a BoxArray + DistributionMapping of one AMR level,
+ *    sharded one-rank-per-GPU.
+ * ---------------------------------------------------------------------- */
+typedef struct iamrx_level_s* iamrx_level_t;
+typedef struct iamrx_ns_s* iamrx_ns_t;
+
+/* Communicator.  rank/nranks from the launcher; `nccl_uid` = 128-byte
+ * ncclUniqueId created on rank 0 with iamrx_comm_unique_id and broadcast by
+ * the caller (torch.distributed in this repo; MPI_Bcast in IAMR).  nranks==1
+ * needs no uid and loads no NCCL. */
+int iamrx_comm_unique_id(unsigned char uid[128]);
+int iamrx_comm_init(int rank, int nranks, const unsigned char uid[128]);
+int iamrx_comm_finalize(void);
+int iamrx_comm_rank(void);
+int iamrx_comm_size(void);
+/* ParallelDescriptor::ReduceReal{Min,Max,Sum} on n doubles in DEVICE memory. */
+int iamrx_allreduce(double* dev_buf, int n, int op /*0 sum,1 min,2 max*/, void* stream);
+
+/* Level = Geometry + BoxArray + owner rank of each box (DistributionMapping). */
+int iamrx_level_create(const iamrx_geom* geom, int nboxes, const iamrx_box* boxes,
+                       const int* owner, iamrx_level_t* out);
+int iamrx_level_destroy(iamrx_level_t lev);
+int iamrx_level_num_local(iamrx_level_t lev);
+int iamrx_level_local_box(iamrx_level_t lev, int ilocal, iamrx_box* out, int* global_index);
+
+/* ------------------------------------------------------------------------
+ * 3. Operators on a level (what Source/MacProj.cpp, Projection.cpp and
+ *    Diffusion.cpp call).  Field arguments are arrays of iamrx_fab, one per
+ *    LOCAL box in level order; the caller owns all field memory.
+ * ---------------------------------------------------------------------- */
+
+/* FabArray::FillBoundary(periodicity) on cell (ixtype 0), face-d (1+d) or
+ * nodal (4) data (NSB.cpp:1171, MacProj.cpp:1127, Projection.cpp:338). */
+int iamrx_fill_boundary(iamrx_level_t lev, iamrx_fab* fabs, int ixtype, int ncomp,
+                        int ngrow, void* stream);
+
+typedef struct iamrx_mg_info {
+  double rtol;
+  double atol;
+  int max_iter;          /* MLMG::setMaxIter, default 200 */
+  int max_coarsening;    /* LPInfo::setMaxCoarseningLevel */
+  int nu1, nu2;          /* pre/post smooths (AMReX default 2,2) */
+  int bottom_sweeps;     /* smoother bottom solve sweeps */
+  int verbose;
+  double omega;          /* GSRB over-relaxation (AMReX abec_gsrb: 1.15) */
+  /* out */
+  int iters;
+  int pad_;
+  double resnorm0;
+  double resnorm;
+  double rhsnorm;
+} iamrx_mg_info;
+
+void iamrx_mg_info_default(iamrx_mg_info* info);
+
+/* MacProj::mlmg_mac_solve (MacProj.cpp:1084-1184) = Hydro::MacProjector
+ * {ctor, setDomainBC, project}: beta_d = (1/rhs_scale)/avg(rho) on faces,
+ * solve -div(beta grad phi) = -(div(umac) - rhs), umac -= beta grad phi.
+ * rho: cell fabs with >=1 ghost (filled); umac[d]: face fabs; phi: cell fab,
+ * 1 ghost; rhs may be NULL (divu == 0). */
+int iamrx_mac_project(iamrx_level_t lev, iamrx_fab* umac, iamrx_fab* vmac,
+                      iamrx_fab* wmac, const iamrx_fab* rho, const iamrx_fab* rhs,
+                      iamrx_fab* phi, double rhs_scale, const int lobc[3],
+                      const int hibc[3], iamrx_mg_info* info, void* stream);
+
+/* Projection::doMLMGNodalProjection (Projection.cpp:2385-2567) =
+ * Hydro::NodalProjector{ctor, setDomainBC, project, getGradPhi}: solve
+ * div(sigma grad phi) = div(vel) on nodes, vel -= sigma grad phi,
+ * gp (=|+=) grad phi.  vel: 3 comps >=1 ghost; sigma: 1 comp 1 ghost;
+ * phi: nodal 1 ghost (initial guess in, solution out); gp: 3 comps. */
+int iamrx_nodal_project(iamrx_level_t lev, iamrx_fab* vel, const iamrx_fab* sigma,
+                        iamrx_fab* phi, iamrx_fab* gp, int increment_gp,
+                        const int lobc[3], const int hibc[3], iamrx_mg_info* info,
+                        void* stream);
+
+/* Diffusion: MLABecLaplacian / MLTensorOp solve and apply
+ * (Diffusion.cpp:327-567, 715-768, 858-923, 1708-1757).
+ *   (a*acoef - b*div(eta grad))soln = rhs   [+ tensor cross terms if tensor]
+ * eta_[xyz]: face fabs, 1 comp.  soln: ncomp comps (3 if tensor), 1 ghost. */
+int iamrx_diffusion_apply(iamrx_level_t lev, int tensor, int ncomp, iamrx_fab* out,
+                          iamrx_fab* soln, double a, double b, const iamrx_fab* acoef,
+                          const iamrx_fab* eta_x, const iamrx_fab* eta_y,
+                          const iamrx_fab* eta_z, void* stream);
+int iamrx_diffusion_solve(iamrx_level_t lev, int tensor, int ncomp, iamrx_fab* soln,
+                          const iamrx_fab* rhs, double a, double b,
+                          const iamrx_fab* acoef, const iamrx_fab* eta_x,
+                          const iamrx_fab* eta_y, const iamrx_fab* eta_z,
+                          iamrx_mg_info* info, void* stream);
+
+/* ------------------------------------------------------------------------
+ * 4. The level time step: NavierStokes::advance (NS.cpp:543-691) and the
+ *    start-up sequence NavierStokes::post_init (NS.cpp:1254-1432) for a
+ *    single-level periodic problem.  This is the caller of sections 1-3 in
+ *    this repo (the host driver that IAMR's own NavierStokes class is in the
+ *    reference).
+ * ---------------------------------------------------------------------- */
+typedef struct iamrx_ns_params {
+  double cfl;            /* ns.cfl */
+  double visc_coef;      /* ns.vel_visc_coef */
+  double scal_diff_coef; /* ns.scal_diff_coefs (tracer) */
+  double be_cn_theta;    /* ns.be_cn_theta, NSB.cpp:124 */
+  double change_max;     /* ns.change_max, NSB.cpp:101 */
+  double init_shrink;    /* ns.init_shrink */
+  double fixed_dt;       /* ns.fixed_dt (<=0: off) */
+  double gravity;        /* ns.gravity */
+  double visc_tol;       /* ns.visc_tol, NSB.cpp:122 */
+  double mac_tol, mac_abs_tol;     /* MacProj.cpp:49-51 */
+  double proj_tol, proj_abs_tol;   /* Projection.cpp:19-21 */
+  int init_iter;         /* ns.init_iter, NSB.cpp:98 */
+  int init_vel_iter;     /* ns.init_vel_iter, NSB.cpp:99 */
+  int do_init_proj;
+  int use_forces_in_trans;
+  int verbose;
+  int conservative_tracer; /* ns.do_cons_trac */
+  int mg_verbose;
+  int pad_;
+} iamrx_ns_params;
+
+void iamrx_ns_params_default(iamrx_ns_params* p);
+
+int iamrx_ns_create(iamrx_level_t lev, const iamrx_ns_params* p, iamrx_ns_t* out);
+int iamrx_ns_destroy(iamrx_ns_t ns);
+/* prob_init: probtype 11 TaylorGreen (prob_init.cpp:509-560) with (a,b,c,
+ * velocity_factor, density) ; probtype 5 DoubleShearLayer-like 3-D variant and
+ * a variable-density HIT-like synthetic field are selected by `probtype`. */
+int iamrx_ns_init_prob(iamrx_ns_t ns, int probtype, const double* prob_params, int nparams);
+/* NavierStokes::post_init: initial velocity projection, initial dt, initial
+ * pressure iterations. Returns dt for the first step in *dt0. */
+int iamrx_ns_post_init(iamrx_ns_t ns, double* dt0);
+/* One coarse time step: computeNewDt (unless dt>0 is forced) + advance.
+ * *dt_io: in = forced dt or <=0; out = dt used. */
+int iamrx_ns_step(iamrx_ns_t ns, double* dt_io);
+double iamrx_ns_time(iamrx_ns_t ns);
+int iamrx_ns_nstep(iamrx_ns_t ns);
+/* State access: which = 0 State_new (u,v,w,rho,tracer; 1 ghost), 1 Press_new
+ * (nodal, 1 ghost), 2 Gradp_new (3 comps, 1 ghost), 3 State_old,
+ * 4..6 u_mac (face x,y,z), 7 aofs. */
+int iamrx_ns_field(iamrx_ns_t ns, int which, int ilocal, iamrx_fab* out);
+/* Host-buffer variant of one step (the e2e path): copies the caller's HOST
+ * valid-region state (5 comps, no ghosts, box order = local boxes) to the
+ * device, advances, copies the new state back.  Both copies are inside. */
+int iamrx_ns_step_host(iamrx_ns_t ns, const double* const* host_state_in,
+                       double* const* host_state_out, double* dt_io);
+/* solver statistics of the last step: iterations of {mac, visc, nodal}. */
+int iamrx_ns_last_iters(iamrx_ns_t ns, int iters[3]);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* IAMRX_H_ */
