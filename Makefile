@@ -28,7 +28,7 @@ EMUL_OBJS := $(patsubst iamr_b200/csrc/%.cu,tests/emul/_build/%.o,$(SRCS))
 emul: tests/emul/_build/libiamrx_emul.so
 tests/emul/_build/%.o: iamr_b200/csrc/%.cu $(HDRS) tests/emul/cuda_emul.h
 	@mkdir -p tests/emul/_build
-	$(CXX) -x c++ -std=c++17 -O2 -fopenmp -fPIC -DIX_EMUL -Itests/emul -Wall -Wno-unused-function -Wno-unknown-pragmas -c $< -o $@
+	$(CXX) -x c++ -std=c++17 -O2 -fopenmp -fPIC -ftls-model=initial-exec -DIX_EMUL -Itests/emul -Wall -Wno-unused-function -Wno-unknown-pragmas -c $< -o $@
 tests/emul/_build/libiamrx_emul.so: $(EMUL_OBJS) tests/emul/cuda_emul.cpp
 	$(CXX) -std=c++17 -O2 -fopenmp -fPIC -shared -DIX_EMUL -Itests/emul -o $@ $(EMUL_OBJS) tests/emul/cuda_emul.cpp -ldl
 

@@ -41,7 +41,7 @@ constexpr int GS_TX = 64;
 constexpr int GS_TY = 4;
 
 __global__ void __launch_bounds__(GS_TX* GS_TY)
-gsrb_kernel(Bx bx, V4 phi, C4 rhs, AbecDev op, double omega, int redblack, int nz) {
+gsrb_kernel(Bx bx, V4 phi, C4 rhs, IX_KARG(AbecDev) op, double omega, int redblack, int nz) {
   const int kz = blockIdx.z % nz;
   const int n = blockIdx.z / nz;
   const int k = bx.lo[2] + kz;
@@ -71,7 +71,7 @@ constexpr int AP_TX = 128;
 constexpr int AP_TY = 2;
 
 __global__ void __launch_bounds__(AP_TX* AP_TY)
-apply_kernel(Bx bx, V4 out, C4 phi, C4 rhs, AbecDev op, int nz) {
+apply_kernel(Bx bx, V4 out, C4 phi, C4 rhs, IX_KARG(AbecDev) op, int nz) {
   const int kz = blockIdx.z % nz;
   const int n = blockIdx.z / nz;
   const int k = bx.lo[2] + kz;
@@ -90,7 +90,7 @@ apply_kernel(Bx bx, V4 out, C4 phi, C4 rhs, AbecDev op, int nz) {
   out(i, j, k, n) = rhs.ok() ? (rhs(i, j, k, n) - y) : y;
 }
 
-__global__ void flux_kernel(Bx bx, V4 fx, V4 fy, V4 fz, C4 phi, AbecDev op, double fxs, double fys,
+__global__ void flux_kernel(Bx bx, V4 fx, V4 fy, V4 fz, C4 phi, IX_KARG(AbecDev) op, double fxs, double fys,
                             double fzs, int comp) {
   const int k = bx.lo[2] + blockIdx.z;
   const int j = bx.lo[1] + blockIdx.y * AP_TY + threadIdx.y;
@@ -169,7 +169,7 @@ __global__ void mac_div_kernel(Bx bx, V4 div, C4 u, C4 v, C4 w, double fx, doubl
   div(i, j, k) = d;
 }
 
-__global__ void mac_update_kernel(Bx bx, V4 u, V4 v, V4 w, C4 phi, AbecDev op, double sx, double sy,
+__global__ void mac_update_kernel(Bx bx, V4 u, V4 v, V4 w, C4 phi, IX_KARG(AbecDev) op, double sx, double sy,
                                   double sz) {
   const int k = bx.lo[2] + blockIdx.z;
   const int j = bx.lo[1] + blockIdx.y * AP_TY + threadIdx.y;

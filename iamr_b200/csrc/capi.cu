@@ -1,0 +1,357 @@
+// capi.cu -- the extern "C" surface of libiamrx (include/iamrx.h), sections 0-3:
+// diagnostics, per-box kernels, communicator, level objects, FillBoundary and
+// the level solvers (MAC projection, nodal projection, diffusion).  Section 4
+// (the NavierStokes::advance driver) lives in ns.cu.
+//
+// Every entry point validates its arguments, refuses to run without a CUDA
+// device (there is no CPU path) and converts the POD views to the internal
+// V4/C4 types; nothing throws across the boundary.
+#include "mlmg.h"
+#include "solvers.h"
+
+using namespace ix;
+
+namespace ix {
+const char* last_error_cstr();
+int comm_unique_id(unsigned char uid[128]);
+int comm_init(int rank, int nranks, const unsigned char uid[128]);
+int comm_finalize();
+}  // namespace ix
+
+struct iamrx_level_s {
+  std::unique_ptr<Level> lev;
+  LevelSolvers solvers;
+};
+
+#define IX_TRY(call) do { int rc_ = (call); if (rc_ != IAMRX_OK) return rc_; } while (0)
+#define IX_GUARD_BEGIN try {
+#define IX_GUARD_END                                                            \
+  } catch (const std::exception& e) {                                           \
+    ix::set_error(std::string("exception: ") + e.what());                       \
+    return IAMRX_ERR_ARG;                                                       \
+  } catch (...) {                                                               \
+    ix::set_error("unknown exception");                                         \
+    return IAMRX_ERR_ARG;                                                       \
+  }
+
+static inline cudaStream_t S(void* s) { return (cudaStream_t)s; }
+
+static k::Abec make_abec(double a, double b, const iamrx_fab* acoef, const iamrx_fab* bx,
+                         const iamrx_fab* by, const iamrx_fab* bz, const double dxinv[3], int ncomp) {
+  k::Abec op;
+  op.a = a; op.b = b;
+  op.acoef = cview(acoef);
+  op.bx = cview(bx); op.by = cview(by); op.bz = cview(bz);
+  op.bncomp = (bx && bx->ncomp >= ncomp && ncomp > 1) ? ncomp : 1;
+  for (int d = 0; d < 3; ++d) op.dxinv[d] = dxinv[d];
+  return op;
+}
+
+extern "C" {
+
+const char* iamrx_last_error(void) { return ix::last_error_cstr(); }
+int iamrx_version(void) { return 100; }
+int64_t iamrx_launch_count(void) { return g_launches.load(); }
+void iamrx_launch_count_reset(void) { g_launches.store(0); }
+int iamrx_device_ok(void) { return device_ok() ? 1 : 0; }
+
+// ---------------------------------------------------------------------------
+// 1. per-box kernels
+// ---------------------------------------------------------------------------
+int iamrx_abec_gsrb_box(const iamrx_box* bx, iamrx_fab* phi, const iamrx_fab* rhs, double a, double b,
+                        const iamrx_fab* acoef, const iamrx_fab* bcoef_x, const iamrx_fab* bcoef_y,
+                        const iamrx_fab* bcoef_z, const double dxinv[3], double omega, int redblack,
+                        int ncomp, void* stream) {
+  IX_NEED_DEVICE();
+  IX_ARG(bx && phi && rhs && bcoef_x && bcoef_y && bcoef_z && dxinv, "null argument");
+  IX_ARG(a == 0.0 || (acoef && acoef->p), "acoef required when a != 0");
+  IX_ARG(ncomp >= 1 && ncomp <= phi->ncomp, "ncomp");
+  return k::abec_gsrb(mkbx(*bx), view(phi), cview(rhs), make_abec(a, b, acoef, bcoef_x, bcoef_y, bcoef_z, dxinv, ncomp),
+                      omega, redblack, ncomp, S(stream));
+}
+
+int iamrx_abec_apply_box(const iamrx_box* bx, iamrx_fab* out, const iamrx_fab* phi, const iamrx_fab* rhs,
+                         double a, double b, const iamrx_fab* acoef, const iamrx_fab* bcoef_x,
+                         const iamrx_fab* bcoef_y, const iamrx_fab* bcoef_z, const double dxinv[3],
+                         int ncomp, void* stream) {
+  IX_NEED_DEVICE();
+  IX_ARG(bx && out && phi && bcoef_x && bcoef_y && bcoef_z && dxinv, "null argument");
+  IX_ARG(a == 0.0 || (acoef && acoef->p), "acoef required when a != 0");
+  return k::abec_apply(mkbx(*bx), view(out), cview(phi), cview(rhs),
+                       make_abec(a, b, acoef, bcoef_x, bcoef_y, bcoef_z, dxinv, ncomp), ncomp, S(stream));
+}
+
+int iamrx_tensor_cross_box(const iamrx_box* bx, iamrx_fab* out, const iamrx_fab* vel, const iamrx_fab* eta_x,
+                           const iamrx_fab* eta_y, const iamrx_fab* eta_z, double b, const double dxinv[3],
+                           void* stream) {
+  IX_NEED_DEVICE();
+  IX_ARG(bx && out && vel && eta_x && eta_y && eta_z && dxinv, "null argument");
+  IX_ARG(vel->ncomp >= 3 && out->ncomp >= 3, "tensor operator needs 3 components");
+  return k::tensor_cross(mkbx(*bx), view(out), cview(vel), cview(eta_x), cview(eta_y), cview(eta_z), b, dxinv,
+                         S(stream));
+}
+
+int iamrx_extrap_vel_to_faces_box(const iamrx_box* bx, const iamrx_fab* vel, const iamrx_fab* force,
+                                  iamrx_fab* umac, iamrx_fab* vmac, iamrx_fab* wmac, const iamrx_geom* geom,
+                                  double dt, int flags, void* stream) {
+  IX_NEED_DEVICE();
+  IX_ARG(bx && vel && umac && vmac && wmac && geom, "null argument");
+  IX_ARG(vel->ncomp >= 3, "vel needs 3 components");
+  IX_ARG(!(flags & IAMRX_ADV_PPM), "Godunov_PPM is not implemented (ns.advection_scheme = Godunov_PLM only)");
+  k::AdvGeom g;
+  for (int d = 0; d < 3; ++d) g.dx[d] = geom->dx[d];
+  g.dt = dt;
+  return k::extrap_vel_to_faces(mkbx(*bx), cview(vel), cview(force), view(umac), view(vmac), view(wmac), g,
+                                (flags & IAMRX_ADV_FORCES_IN_TRANS) ? 1 : 0, S(stream));
+}
+
+int iamrx_compute_aofs_box(const iamrx_box* bx, iamrx_fab* aofs, int aofs_comp, const iamrx_fab* Sf, int s_comp,
+                           int ncomp, const iamrx_fab* force, int f_comp, const iamrx_fab* divu,
+                           const iamrx_fab* umac, const iamrx_fab* vmac, const iamrx_fab* wmac, iamrx_fab* fx,
+                           iamrx_fab* fy, iamrx_fab* fz, iamrx_fab* xed, iamrx_fab* yed, iamrx_fab* zed,
+                           const int* iconserv, const iamrx_geom* geom, double dt, int flags, void* stream) {
+  IX_NEED_DEVICE();
+  IX_ARG(bx && aofs && Sf && umac && vmac && wmac && iconserv && geom, "null argument");
+  IX_ARG(ncomp >= 1 && ncomp <= 8, "ncomp must be in [1,8]");
+  IX_ARG(!(flags & IAMRX_ADV_PPM), "Godunov_PPM is not implemented (ns.advection_scheme = Godunov_PLM only)");
+  const bool wf = (flags & IAMRX_ADV_WRITE_FLUXES) != 0;
+  IX_ARG(!wf || (fx && fy && fz && xed && yed && zed), "flux/edge outputs required with WRITE_FLUXES");
+  k::AofsArgs a{};
+  a.aofs = view(aofs, aofs_comp);
+  a.S = cview(Sf, s_comp);
+  a.force = cview(force, f_comp);
+  a.divu = cview(divu);
+  a.umac = cview(umac); a.vmac = cview(vmac); a.wmac = cview(wmac);
+  a.uflx = a.umac; a.vflx = a.vmac; a.wflx = a.wmac;
+  if (wf) { a.fx = view(fx); a.fy = view(fy); a.fz = view(fz); a.xed = view(xed); a.yed = view(yed); a.zed = view(zed); }
+  a.ncomp = ncomp;
+  for (int n = 0; n < ncomp; ++n) a.iconserv[n] = iconserv[n];
+  a.forces_in_trans = (flags & IAMRX_ADV_FORCES_IN_TRANS) ? 1 : 0;
+  a.is_velocity = (flags & IAMRX_ADV_IS_VELOCITY) ? 1 : 0;
+  a.is_sync = (flags & IAMRX_ADV_IS_SYNC) ? 1 : 0;
+  a.write_fluxes = wf ? 1 : 0;
+  k::AdvGeom g;
+  for (int d = 0; d < 3; ++d) g.dx[d] = geom->dx[d];
+  g.dt = dt;
+  return k::compute_aofs(mkbx(*bx), a, g, S(stream));
+}
+
+int iamrx_nodal_divu_box(const iamrx_box* nbx, iamrx_fab* rhs, const iamrx_fab* vel, const double dxinv[3],
+                         void* stream) {
+  IX_NEED_DEVICE();
+  IX_ARG(nbx && rhs && vel && dxinv, "null argument");
+  return k::nodal_divu(mkbx(*nbx), view(rhs), cview(vel), dxinv, S(stream));
+}
+int iamrx_nodal_adotx_box(const iamrx_box* nbx, iamrx_fab* out, const iamrx_fab* phi, const iamrx_fab* rhs,
+                          const iamrx_fab* sigma, const double dxinv[3], void* stream) {
+  IX_NEED_DEVICE();
+  IX_ARG(nbx && out && phi && sigma && dxinv, "null argument");
+  return k::nodal_adotx(mkbx(*nbx), view(out), cview(phi), cview(rhs), cview(sigma), dxinv, S(stream));
+}
+int iamrx_nodal_gs_box(const iamrx_box* nbx, iamrx_fab* phi, const iamrx_fab* rhs, const iamrx_fab* sigma,
+                       const double dxinv[3], int color, void* stream) {
+  IX_NEED_DEVICE();
+  IX_ARG(nbx && phi && rhs && sigma && dxinv, "null argument");
+  IX_ARG(color >= 0 && color < 8, "colour must be in [0,8)");
+  return k::nodal_gs_color(mkbx(*nbx), view(phi), cview(rhs), cview(sigma), dxinv, color, S(stream));
+}
+int iamrx_nodal_mknewu_box(const iamrx_box* bx, iamrx_fab* vel, iamrx_fab* gp, const iamrx_fab* phi,
+                           const iamrx_fab* sigma, const double dxinv[3], void* stream) {
+  IX_NEED_DEVICE();
+  IX_ARG(bx && phi && dxinv, "null argument");
+  IX_ARG(!vel || sigma, "sigma required to update vel");
+  return k::nodal_mknewu(mkbx(*bx), view(vel), view(gp), 0, cview(phi), cview(sigma), dxinv, S(stream));
+}
+
+// ---------------------------------------------------------------------------
+// 2. communicator + level
+// ---------------------------------------------------------------------------
+int iamrx_comm_unique_id(unsigned char uid[128]) { return comm_unique_id(uid); }
+int iamrx_comm_init(int rank, int nranks, const unsigned char uid[128]) {
+  IX_ARG(nranks >= 1 && rank >= 0 && rank < nranks, "rank/nranks");
+  IX_ARG(nranks == 1 || uid, "uid required for nranks > 1");
+  return comm_init(rank, nranks, uid);
+}
+int iamrx_comm_finalize(void) { return comm_finalize(); }
+int iamrx_comm_rank(void) { return comm().rank; }
+int iamrx_comm_size(void) { return comm().nranks; }
+int iamrx_allreduce(double* dev_buf, int n, int op, void* stream) {
+  IX_NEED_DEVICE();
+  IX_ARG(dev_buf && n > 0 && op >= 0 && op <= 2, "allreduce arguments");
+  return comm_allreduce(dev_buf, n, op, S(stream));
+}
+
+int iamrx_level_create(const iamrx_geom* geom, int nboxes, const iamrx_box* boxes, const int* owner,
+                       iamrx_level_t* out) {
+  IX_GUARD_BEGIN
+  IX_ARG(geom && boxes && out && nboxes > 0, "null argument");
+  std::vector<Bx> bxs; std::vector<int> own;
+  const Bx dom = mkbx(geom->domain);
+  for (int i = 0; i < nboxes; ++i) {
+    Bx b = mkbx(boxes[i]);
+    IX_ARG(b.ok(), "empty box");
+    IX_ARG(intersect(b, dom).npts() == b.npts(), "box outside the domain");
+    for (int j = 0; j < i; ++j) IX_ARG(!intersect(b, bxs[j]).ok(), "boxes overlap");
+    bxs.push_back(b);
+    const int o = owner ? owner[i] : 0;
+    IX_ARG(o >= 0 && o < comm().nranks, "owner rank out of range");
+    own.push_back(o);
+  }
+  for (int d = 0; d < 3; ++d) IX_ARG(geom->dx[d] > 0.0, "dx must be positive");
+  auto* h = new iamrx_level_s();
+  h->lev = make_level(*geom, bxs, own);
+  *out = h;
+  return IAMRX_OK;
+  IX_GUARD_END
+}
+int iamrx_level_destroy(iamrx_level_t lev) {
+  delete lev;
+  return IAMRX_OK;
+}
+int iamrx_level_num_local(iamrx_level_t lev) { return lev ? lev->lev->nlocal() : IAMRX_ERR_ARG; }
+int iamrx_level_local_box(iamrx_level_t lev, int il, iamrx_box* out, int* gi) {
+  IX_ARG(lev && out && il >= 0 && il < lev->lev->nlocal(), "local box index");
+  const Bx& b = lev->lev->lbox(il);
+  for (int d = 0; d < 3; ++d) { out->lo[d] = b.lo[d]; out->hi[d] = b.hi[d]; }
+  if (gi) *gi = lev->lev->local[il];
+  return IAMRX_OK;
+}
+
+// test hook: the FillBoundary copy plan of a level as plain arrays (pure host
+// logic; works without a device).  Returns the number of regions; fills up to
+// `cap` entries of dst_box/src_box, 6 ints per region, 3 ints per shift.
+int iamrx_debug_fb_plan(iamrx_level_t lev, int ixtype, int ng, int cap, int* dst_box, int* src_box,
+                        int* region6, int* shift3) {
+  IX_GUARD_BEGIN
+  IX_ARG(lev, "null level");
+  std::vector<int> db, sb, sh; std::vector<Bx> rg;
+  build_fb_regions(*lev->lev, ixtype, ng, db, sb, rg, sh);
+  const int n = (int)rg.size();
+  for (int r = 0; r < n && r < cap; ++r) {
+    if (dst_box) dst_box[r] = db[r];
+    if (src_box) src_box[r] = sb[r];
+    if (region6) for (int d = 0; d < 3; ++d) { region6[6 * r + d] = rg[r].lo[d]; region6[6 * r + 3 + d] = rg[r].hi[d]; }
+    if (shift3) for (int d = 0; d < 3; ++d) shift3[3 * r + d] = sh[3 * r + d];
+  }
+  return n;
+  IX_GUARD_END
+}
+
+// ---------------------------------------------------------------------------
+// 3. level operators
+// ---------------------------------------------------------------------------
+int iamrx_fill_boundary(iamrx_level_t lev, iamrx_fab* fabs, int ixtype, int ncomp, int ngrow, void* stream) {
+  IX_GUARD_BEGIN
+  IX_NEED_DEVICE();
+  IX_ARG(lev && fabs && ixtype >= 0 && ixtype <= 4 && ncomp >= 1 && ngrow >= 0, "fill_boundary arguments");
+  MF m; m.alias(lev->lev.get(), ixtype, ncomp, ngrow, fabs);
+  return mf_fill_boundary(m, 0, ncomp, ngrow, S(stream));
+  IX_GUARD_END
+}
+
+void iamrx_mg_info_default(iamrx_mg_info* info) {
+  if (!info) return;
+  memset(info, 0, sizeof(*info));
+  info->rtol = 1.0e-12;
+  info->atol = 1.0e-16;
+  info->max_iter = 200;
+  info->max_coarsening = 100;
+  info->nu1 = 2; info->nu2 = 2;
+  info->bottom_sweeps = 8;
+  info->verbose = 0;
+  info->omega = 1.0;
+}
+
+static int check_periodic_bc(const Level& L, const int lobc[3], const int hibc[3]) {
+  for (int d = 0; d < 3; ++d) {
+    const int lo = lobc ? lobc[d] : IAMRX_LINOP_PERIODIC, hi = hibc ? hibc[d] : IAMRX_LINOP_PERIODIC;
+    if (L.geom.periodic[d]) {
+      IX_ARG(lo == IAMRX_LINOP_PERIODIC && hi == IAMRX_LINOP_PERIODIC, "periodic direction needs periodic BC");
+    } else {
+      IX_ARG(false, "only periodic domain boundaries are implemented in this round");
+    }
+  }
+  return IAMRX_OK;
+}
+
+int iamrx_mac_project(iamrx_level_t lev, iamrx_fab* umac, iamrx_fab* vmac, iamrx_fab* wmac,
+                      const iamrx_fab* rho, const iamrx_fab* rhs, iamrx_fab* phi, double rhs_scale,
+                      const int lobc[3], const int hibc[3], iamrx_mg_info* info, void* stream) {
+  IX_GUARD_BEGIN
+  IX_NEED_DEVICE();
+  IX_ARG(lev && umac && vmac && wmac && rho && phi, "null argument");
+  IX_ARG(rhs_scale != 0.0, "rhs_scale");
+  Level* L = lev->lev.get();
+  IX_TRY(check_periodic_bc(*L, lobc, hibc));
+  iamrx_fab* um[3] = {umac, vmac, wmac};
+  MF U[3];
+  for (int d = 0; d < 3; ++d) U[d].alias(L, IX_XFACE + d, 1, 0, um[d]);
+  MF Rho; Rho.alias(L, IX_CELL, 1, 1, rho);
+  MF Phi; Phi.alias(L, IX_CELL, 1, 1, phi);
+  MF Rhs; if (rhs) Rhs.alias(L, IX_CELL, 1, 0, rhs);
+  return mac_project(*L, lev->solvers, U, Rho, rhs ? &Rhs : nullptr, Phi, rhs_scale, info, S(stream));
+  IX_GUARD_END
+}
+
+int iamrx_nodal_project(iamrx_level_t lev, iamrx_fab* vel, const iamrx_fab* sigma, iamrx_fab* phi,
+                        iamrx_fab* gp, int increment_gp, const int lobc[3], const int hibc[3],
+                        iamrx_mg_info* info, void* stream) {
+  IX_GUARD_BEGIN
+  IX_NEED_DEVICE();
+  IX_ARG(lev && vel && sigma && phi, "null argument");
+  Level* L = lev->lev.get();
+  IX_TRY(check_periodic_bc(*L, lobc, hibc));
+  MF Vel; Vel.alias(L, IX_CELL, 3, 1, vel);
+  MF Sig; Sig.alias(L, IX_CELL, 1, 0, sigma);
+  MF Phi; Phi.alias(L, IX_NODE, 1, 1, phi);
+  MF Gp; if (gp) Gp.alias(L, IX_CELL, 3, 0, gp);
+  return nodal_project(*L, lev->solvers, Vel, Sig, Phi, gp ? &Gp : nullptr, increment_gp, info, S(stream));
+  IX_GUARD_END
+}
+
+int iamrx_diffusion_apply(iamrx_level_t lev, int tensor, int ncomp, iamrx_fab* out, iamrx_fab* soln, double a,
+                          double b, const iamrx_fab* acoef, const iamrx_fab* eta_x, const iamrx_fab* eta_y,
+                          const iamrx_fab* eta_z, void* stream) {
+  IX_GUARD_BEGIN
+  IX_NEED_DEVICE();
+  IX_ARG(lev && out && soln && eta_x && eta_y && eta_z, "null argument");
+  IX_ARG(!tensor || ncomp == 3, "tensor operator needs ncomp == 3");
+  IX_ARG(a == 0.0 || acoef, "acoef required when a != 0");
+  Level* L = lev->lev.get();
+  MF Out; Out.alias(L, IX_CELL, ncomp, 0, out);
+  MF Sol; Sol.alias(L, IX_CELL, ncomp, 1, soln);
+  MF A; if (acoef) A.alias(L, IX_CELL, 1, 0, acoef);
+  MF E[3];
+  const iamrx_fab* e[3] = {eta_x, eta_y, eta_z};
+  for (int d = 0; d < 3; ++d) E[d].alias(L, IX_XFACE + d, 1, 0, e[d]);
+  return diffusion_apply(*L, lev->solvers, tensor != 0, ncomp, Out, Sol, a, b, acoef ? &A : nullptr, E, S(stream));
+  IX_GUARD_END
+}
+
+int iamrx_diffusion_solve(iamrx_level_t lev, int tensor, int ncomp, iamrx_fab* soln, const iamrx_fab* rhs,
+                          double a, double b, const iamrx_fab* acoef, const iamrx_fab* eta_x,
+                          const iamrx_fab* eta_y, const iamrx_fab* eta_z, iamrx_mg_info* info, void* stream) {
+  IX_GUARD_BEGIN
+  IX_NEED_DEVICE();
+  IX_ARG(lev && soln && rhs && eta_x && eta_y && eta_z, "null argument");
+  IX_ARG(!tensor || ncomp == 3, "tensor operator needs ncomp == 3");
+  IX_ARG(a == 0.0 || acoef, "acoef required when a != 0");
+  Level* L = lev->lev.get();
+  MF Sol; Sol.alias(L, IX_CELL, ncomp, 1, soln);
+  MF Rhs; Rhs.alias(L, IX_CELL, ncomp, 0, rhs);
+  MF A; if (acoef) A.alias(L, IX_CELL, 1, 0, acoef);
+  MF E[3];
+  const iamrx_fab* e[3] = {eta_x, eta_y, eta_z};
+  for (int d = 0; d < 3; ++d) E[d].alias(L, IX_XFACE + d, 1, 0, e[d]);
+  return diffusion_solve(*L, lev->solvers, tensor != 0, ncomp, Sol, Rhs, a, b, acoef ? &A : nullptr, E, info,
+                         S(stream));
+  IX_GUARD_END
+}
+
+}  // extern "C"
+
+// accessors used by ns.cu
+namespace ix {
+Level* level_of(iamrx_level_t h) { return h ? h->lev.get() : nullptr; }
+LevelSolvers* solvers_of(iamrx_level_t h) { return h ? &h->solvers : nullptr; }
+}  // namespace ix

@@ -15,6 +15,8 @@
 #else
 #include <cuda_runtime.h>
 #define IX_LAUNCH(kern, grid, block, smem, stream, ...) kern<<<grid, block, smem, stream>>>(__VA_ARGS__)
+// large by-value kernel parameter (the host emulation build passes it by reference)
+#define IX_KARG(T) T
 #endif
 #include "../../include/iamrx.h"
 

@@ -90,28 +90,27 @@ int nodal_mknewu(const Bx& bx, V4 vel, V4 gp, int increment_gp, C4 phi, C4 sig,
                  const double dxinv[3], cudaStream_t s);
 
 // --- pointwise IAMR glue (pointwise.cu) -----------------------------------
-// tf = (tf + visc - gp)/rho   (NSB.cpp:4466-4470, 3460-3466); divide optional
-int force_assemble(const Bx& bx, V4 tf, C4 visc, C4 gp, C4 rho, double grav, int ncomp, int add_gp,
-                   int div_rho, cudaStream_t s);
-// scalar forcing: tf = tf/rho + visc (nonconservative) or tf + visc (NS.cpp:774-804)
-// velocity update NSB.cpp:3607-3626
-int vel_update(const Bx& bx, V4 unew, C4 uold, C4 aofs, C4 gp, C4 rhohalf, double grav, double dt,
-               cudaStream_t s);
-// scalar update NSB.cpp:2761-2765 / 2887-2896 (no forcing in supported configs)
-int scal_update(const Bx& bx, V4 snew, C4 sold, C4 aofs, double dt, int ncomp, cudaStream_t s);
-// floor NSB.cpp:4530-4534
+// floor NSB.cpp:4530-4534: |v| > 1e-20 ? v : 0
 int floor_small(const Bx& bx, V4 f, int ncomp, cudaStream_t s);
-// first-order extrapolation of the 1-cell ghost shell from the valid region for cells
-// OUTSIDE `domain` in non-periodic directions (Extrapolater::FirstOrderExtrap, NS.cpp:2047).
-int average_face_to_cc(const Bx& bx, V4 cc, C4 u, C4 v, C4 w, cudaStream_t s);
-// prob_init.cpp initial conditions
-int init_prob(const Bx& bx, V4 state, int probtype, const double* params, const iamrx_geom& g,
-              cudaStream_t s);
+// velocity forcing: tf_n = getForce_n + visc_n - gp_n, optionally / rho
+// (NSB.cpp:4456-4470, 3445-3466, 1411-1424); getForce = NS_getForce.cpp:117-141
+// (buoyancy grav*rho on the z component when |grav| > 1e-4).  visc / gp may be null.
+int force_vel(const Bx& bx, V4 tf, C4 visc, C4 gp, C4 rho, double grav, int div_rho, cudaStream_t s);
+// velocity update NSB.cpp:3607-3626 (do_mom_diff = 0):
+//   unew = uold - dt*aofs + dt*(getForce(rho_half) - gp)/rho_half
+int vel_update(const Bx& bx, V4 unew, C4 uold, C4 aofs, C4 gp, C4 rhohalf, double grav, double dt,
+               int zero_force, cudaStream_t s);
+// scalar update NSB.cpp:2761-2765 / 2887-2896 with the default (zero) scalar forcing
+int scal_update(const Bx& bx, V4 snew, C4 sold, C4 aofs, double dt, int ncomp, cudaStream_t s);
 // diffusion rhs: unew *= rho; rhs += unew (Diffusion.cpp:821-831)
 int diff_rhs(const Bx& bx, V4 rhs, V4 unew, C4 rho, int ncomp, cudaStream_t s);
-// level_project pre: u = u/dt + gp/rho  (Projection.cpp:273,296-300); sigma = 1/rho
-int proj_pre(const Bx& bx, V4 u, C4 gp, C4 rho, double dt_inv, int add_gp, cudaStream_t s);
+// level_project pre: u = u*dt_inv + gp/rho  (Projection.cpp:273,296-300)
+int proj_pre(const Bx& bx, V4 u, C4 gp, C4 rho, double dt_inv, cudaStream_t s);
+// scaleVar: sig = 1/rho (Projection.cpp:1327-1349)
 int invert(const Bx& bx, V4 sig, C4 rho, cudaStream_t s);
+// prob_init.cpp initial conditions (state: u,v,w,rho,tracer) on bx
+int init_prob(const Bx& bx, V4 state, int probtype, const double* params, int nparams,
+              const iamrx_geom& g, cudaStream_t s);
 
 }  // namespace k
 }  // namespace ix

@@ -208,9 +208,9 @@ constexpr int CB_T = 256;
 constexpr int CB_CHUNKS = 24;
 
 __global__ void __launch_bounds__(CB_T)
-copy_batch_kernel(const CopyDesc* __restrict__ desc, FabTable dst, FabTable src, double* buf, int ncomp,
+copy_batch_kernel(const CopyDesc* __restrict__ desc, IX_KARG(FabTable) dst, IX_KARG(FabTable) src, double* buf, int ncomp,
                   int64_t bstride) {
-  const CopyDesc d = desc[blockIdx.y];
+  const CopyDesc& d = desc[blockIdx.y];
   const int nx = d.hi[0] - d.lo[0] + 1, ny = d.hi[1] - d.lo[1] + 1, nz = d.hi[2] - d.lo[2] + 1;
   const int64_t npts = (int64_t)nx * ny * nz;
   const int64_t total = npts * ncomp;
@@ -239,10 +239,14 @@ copy_batch_kernel(const CopyDesc* __restrict__ desc, FabTable dst, FabTable src,
 }
 }  // namespace
 
-int copy_batch(const CopyDesc* d_desc, int ndesc, const FabTable& dst, const FabTable& src, double* buf,
-               int ncomp, int64_t bstride, cudaStream_t s) {
+int copy_batch(const CopyDesc* d_desc, int ndesc, int64_t max_pts, const FabTable& dst, const FabTable& src,
+               double* buf, int ncomp, int64_t bstride, cudaStream_t s) {
   if (ndesc <= 0) return IAMRX_OK;
-  IX_LAUNCH(copy_batch_kernel, dim3(CB_CHUNKS, ndesc, 1), CB_T, 0, s, d_desc, dst, src, buf, ncomp, bstride);
+  // chunks per region: enough CTAs to cover the largest region 4 points per thread, at most CB_CHUNKS
+  int64_t chunks = (max_pts * ncomp + 4 * CB_T - 1) / (4 * CB_T);
+  if (chunks < 1) chunks = 1;
+  if (chunks > CB_CHUNKS) chunks = CB_CHUNKS;
+  IX_LAUNCH(copy_batch_kernel, dim3((unsigned)chunks, ndesc, 1), CB_T, 0, s, d_desc, dst, src, buf, ncomp, bstride);
   return check_launch("copy_batch");
 }
 }  // namespace k
@@ -365,6 +369,9 @@ FBPlan& Level::plan(int ixtype, int ng) {
     so += P->send_pts.back(); ro += P->recv_pts.back();
   }
   P->send_total = so; P->recv_total = ro;
+  for (const CopyDesc& d : P->local) P->max_local = std::max<int64_t>(P->max_local, (int64_t)(d.hi[0] - d.lo[0] + 1) * (d.hi[1] - d.lo[1] + 1) * (d.hi[2] - d.lo[2] + 1));
+  for (const CopyDesc& d : all_send) P->max_send = std::max<int64_t>(P->max_send, (int64_t)(d.hi[0] - d.lo[0] + 1) * (d.hi[1] - d.lo[1] + 1) * (d.hi[2] - d.lo[2] + 1));
+  for (const CopyDesc& d : all_recv) P->max_recv = std::max<int64_t>(P->max_recv, (int64_t)(d.hi[0] - d.lo[0] + 1) * (d.hi[1] - d.lo[1] + 1) * (d.hi[2] - d.lo[2] + 1));
   P->d_local = upload(P->local);
   P->d_send = upload(all_send); P->n_send = (int)all_send.size();
   P->d_recv = upload(all_recv); P->n_recv = (int)all_recv.size();
@@ -458,20 +465,20 @@ int mf_fill_boundary(MF& m, int comp, int ncomp, int ng, cudaStream_t s) {
   FBPlan& P = L.plan(m.ixtype, ng);
   FabTable t; fill_table(t, m, comp);
   if (P.peers.empty()) {
-    return k::copy_batch(P.d_local, (int)P.local.size(), t, t, nullptr, ncomp, 0, s);
+    return k::copy_batch(P.d_local, (int)P.local.size(), P.max_local, t, t, nullptr, ncomp, 0, s);
   }
   double* sbuf = dev_alloc((size_t)(P.send_total * ncomp + 1));
   double* rbuf = dev_alloc((size_t)(P.recv_total * ncomp + 1));
   if (!sbuf || !rbuf) return IAMRX_ERR_CUDA;
-  IX_TRY(k::copy_batch(P.d_send, P.n_send, t, t, sbuf, ncomp, 0, s));
+  IX_TRY(k::copy_batch(P.d_send, P.n_send, P.max_send, t, t, sbuf, ncomp, 0, s));
   std::vector<double*> sb, rb; std::vector<int64_t> sc, rc;
   for (size_t i = 0; i < P.peers.size(); ++i) {
     sb.push_back(sbuf + P.send_off[i] * ncomp); rb.push_back(rbuf + P.recv_off[i] * ncomp);
     sc.push_back(P.send_pts[i] * ncomp); rc.push_back(P.recv_pts[i] * ncomp);
   }
   IX_TRY(comm_exchange(P.peers, sb, sc, rb, rc, s));
-  IX_TRY(k::copy_batch(P.d_local, (int)P.local.size(), t, t, nullptr, ncomp, 0, s));
-  IX_TRY(k::copy_batch(P.d_recv, P.n_recv, t, t, rbuf, ncomp, 0, s));
+  IX_TRY(k::copy_batch(P.d_local, (int)P.local.size(), P.max_local, t, t, nullptr, ncomp, 0, s));
+  IX_TRY(k::copy_batch(P.d_recv, P.n_recv, P.max_recv, t, t, rbuf, ncomp, 0, s));
   dev_free(sbuf); dev_free(rbuf);  // stream-ordered reuse: same stream
   return IAMRX_OK;
 }

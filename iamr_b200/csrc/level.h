@@ -59,7 +59,7 @@ struct FabTable {  // passed by value to the batched copy kernel
 };
 
 namespace k {
-int copy_batch(const CopyDesc* d_desc, int ndesc, const FabTable& dst, const FabTable& src,
+int copy_batch(const CopyDesc* d_desc, int ndesc, int64_t max_pts, const FabTable& dst, const FabTable& src,
                double* buf, int ncomp, int64_t buf_comp_stride, cudaStream_t s);
 }
 
@@ -74,6 +74,7 @@ struct FBPlan {
   CopyDesc* d_send = nullptr; int n_send = 0;
   CopyDesc* d_recv = nullptr; int n_recv = 0;
   int64_t send_total = 0, recv_total = 0;         // points per component, all peers
+  int64_t max_local = 0, max_send = 0, max_recv = 0;  // largest region (points) per list: sizes the copy grid
   std::vector<int64_t> send_off, recv_off;
   ~FBPlan();
 };

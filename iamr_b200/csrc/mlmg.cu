@@ -88,7 +88,8 @@ k::Abec CellMG::op_at(int l, int il) const {
   return op;
 }
 
-int CellMG::set_coeffs(const MF* acoef, const MF* bx, const MF* by, const MF* bz, cudaStream_t s) {
+int CellMG::set_coeffs(const MF* acoef, const MF* bx, const MF* by, const MF* bz, cudaStream_t s,
+                       bool finest_only) {
   const MF* bin[3] = {bx, by, bz};
   for (int d = 0; d < 3; ++d) eta_[d] = bin[d];
   const int bn = tensor_ ? ncomp_ : 1;
@@ -107,7 +108,7 @@ int CellMG::set_coeffs(const MF* acoef, const MF* bx, const MF* by, const MF* bz
       }
     }
   }
-  for (size_t l = 1; l < lv_.size(); ++l) {
+  for (size_t l = 1; l < lv_.size() && !finest_only; ++l) {
     MGLevelCell& C = lv_[l];
     MGLevelCell& F = lv_[l - 1];
     if (a_ != 0.0 && acoef) {

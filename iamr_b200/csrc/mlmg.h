@@ -26,7 +26,8 @@ class CellMG {
   int set_scalars(double a, double b) { a_ = a; b_ = b; return 0; }
   // acoef: cell MF (1 comp); eta[d]: face MFs with 1 comp.  For tensor the solver
   // builds per-component b = eta * (1 + 1/3 delta_{c,d}) (4/3 on the diagonal).
-  int set_coeffs(const MF* acoef, const MF* bx, const MF* by, const MF* bz, cudaStream_t s);
+  int set_coeffs(const MF* acoef, const MF* bx, const MF* by, const MF* bz, cudaStream_t s,
+                 bool finest_only = false);
   int apply(MF& out, MF& phi, cudaStream_t s);   // out = L(phi) incl. cross terms; fills phi ghosts
   int solve(MF& sol, const MF& rhs, iamrx_mg_info* info, cudaStream_t s);
   int nlevels() const { return (int)lv_.size(); }

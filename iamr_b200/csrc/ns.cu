@@ -1,0 +1,508 @@
+// ns.cu -- the level time step: a host-side restatement of the operator sequence
+// of NavierStokes::advance (Source/NavierStokes.cpp:543-691) and of the start-up
+// sequence NavierStokes::post_init (NavierStokes.cpp:1254-1432) for a single-level
+// periodic problem, calling the level solvers (solvers.h) and kernels (kernels.h).
+// This is the caller of the hot path in this repository -- the role IAMR's own
+// NavierStokes / NavierStokesBase classes play in the reference.  Each step names
+// the reference lines it mirrors.
+#include <algorithm>
+#include <cmath>
+#include "solvers.h"
+
+namespace ix {
+Level* level_of(iamrx_level_t h);
+LevelSolvers* solvers_of(iamrx_level_t h);
+}  // namespace ix
+
+using namespace ix;
+
+#define IX_TRY(call) do { int rc_ = (call); if (rc_ != IAMRX_OK) return rc_; } while (0)
+// solver calls return >0 on non-convergence: treat as failure of the step ("MLMG failed to converge" aborts)
+#define IX_SOLVE(call) do { int rc_ = (call); if (rc_ != IAMRX_OK) return rc_; } while (0)
+
+enum { Xvel = 0, Yvel = 1, Zvel = 2, Density = 3, Tracer = 4, NUM_STATE = 5, NUM_SCALARS = 2 };
+
+struct iamrx_ns_s {
+  iamrx_level_t hlev = nullptr;
+  Level* L = nullptr;
+  LevelSolvers* sv = nullptr;
+  iamrx_ns_params p{};
+  cudaStream_t s = nullptr;
+
+  MF S_old, S_new;      // u,v,w,rho,tracer ; 1 ghost (NavierStokesBase.H:741)
+  MF P_old, P_new;      // nodal, 1 ghost (NS_setup.cpp:329-334)
+  MF Gp_old, Gp_new;    // 3 comps, 1 ghost (NS_setup.cpp:339-360)
+  MF umac[3];           // face MFs, 1 ghost (NSB.cpp:663-675)
+  MF aofs;              // NUM_STATE comps (NSB.cpp:680)
+  MF rho_ptime, rho_ctime, rho_half;  // 1 ghost
+  MF Umf, Smf;          // FillPatched copies, 3 ghosts (NSB.cpp:4399,4435; nghost_state :4539-4552)
+  MF visc, force;       // 3 comps, 1 ghost (nghost_force, NavierStokesBase.H:810)
+  MF sforce;            // scalar forcing, 2 comps, 1 ghost
+  MF eta[3];            // face viscosity (getViscosity, NS.cpp:2120-)
+  MF soln, rhs3, tmp3;  // diffusion work: Soln (1 ghost), Rhs
+  MF sig;               // 1/rho_half, 1 ghost
+  MF mac_phi;           // 1 ghost
+  MF tf0;               // estTimeStep forces, 0 ghost
+
+  double time = 0.0, dt_level = 0.0, dt_min = 1.0e100;
+  int nstep = 0;
+  bool initial_step = false, initial_iter = false;
+  int it_mac = 0, it_visc = 0, it_nodal = 0;
+  double* stage = nullptr; size_t stage_n = 0;  // host<->device staging for step_host
+
+  bool diffusive_vel() const { return p.visc_coef > 0.0; }
+};
+
+namespace {
+
+int fillpatch(iamrx_ns_s& ns, MF& dst, const MF& src, int scomp, int ncomp) {
+  // single-level periodic FillPatch = copy of the valid region + FillBoundary
+  IX_TRY(mf_copy(dst, src, scomp, 0, ncomp, 0, ns.s));
+  return mf_fill_boundary(dst, 0, ncomp, dst.ng, ns.s);
+}
+
+iamrx_mg_info mg_info(const iamrx_ns_s& ns, double rtol, double atol) {
+  iamrx_mg_info mi;
+  iamrx_mg_info_default(&mi);
+  mi.rtol = rtol; mi.atol = atol; mi.verbose = ns.p.mg_verbose;
+  return mi;
+}
+
+// NavierStokes::getViscTerms for velocity (NS.cpp:1960-2049) ->
+// Diffusion::getTensorViscTerms (Diffusion.cpp:1655-1777): visc = div(tau(U^n)), a=0, b=-1,
+// then FillBoundary on the grow cell (NS.cpp:2046; FirstOrderExtrap is a no-op when periodic)
+int get_visc_terms(iamrx_ns_s& ns, MF& visc, const MF& S) {
+  if (!ns.diffusive_vel()) return mf_setval(visc, 0.0, 0, 3, 1, ns.s);
+  IX_TRY(fillpatch(ns, ns.soln, S, Xvel, 3));
+  IX_TRY(diffusion_apply(*ns.L, *ns.sv, true, 3, visc, ns.soln, 0.0, -1.0, nullptr, ns.eta, ns.s));
+  return mf_fill_boundary(visc, 0, 3, 1, ns.s);
+}
+
+// velocity forcing on the 1-ghost box: tf = (getForce + visc - gp)/rho  (NSB.cpp:4456-4470 == 3445-3466)
+int vel_forcing(iamrx_ns_s& ns) {
+  for (int il = 0; il < ns.force.n(); ++il)
+    IX_TRY(k::force_vel(ns.force.gbox(il, 1), ns.force.v(il), ns.visc.c(il), ns.Gp_old.c(il), ns.Smf.c(il, 0),
+                        ns.p.gravity, 1, ns.s));
+  return IAMRX_OK;
+}
+
+// NavierStokesBase::predict_velocity (NSB.cpp:4376-4512)
+int predict_velocity(iamrx_ns_s& ns, double dt, double* dt_test) {
+  Level& L = *ns.L;
+  IX_TRY(fillpatch(ns, ns.Umf, ns.S_old, Xvel, 3));                       // :4399
+  for (int il = 0; il < ns.Umf.n(); ++il) IX_TRY(k::floor_small(ns.Umf.gbox(il, 3), ns.Umf.v(il), 3, ns.s));  // :4403
+  double umax[3];
+  IX_TRY(mf_norminf_each(ns.Umf, 0, 3, umax, ns.s));                       // :4408 (ghosts are periodic images)
+  double cflmax = 0.0;
+  for (int d = 0; d < 3; ++d) cflmax = std::max(cflmax, dt * umax[d] / L.geom.dx[d]);
+  const double tempdt = (cflmax == 0.0) ? ns.p.change_max : std::min(ns.p.change_max, ns.p.cfl / cflmax);  // :4413
+  if (ns.p.be_cn_theta != 1.0) IX_TRY(get_visc_terms(ns, ns.visc, ns.S_old));   // :4426-4433
+  else IX_TRY(mf_setval(ns.visc, 0.0, 0, 3, 1, ns.s));
+  IX_TRY(fillpatch(ns, ns.Smf, ns.S_old, Density, NUM_SCALARS));           // :4435
+  IX_TRY(vel_forcing(ns));                                                 // :4456-4470
+  k::AdvGeom g; for (int d = 0; d < 3; ++d) g.dx[d] = L.geom.dx[d]; g.dt = dt;
+  for (int il = 0; il < ns.Umf.n(); ++il)                                  // :4487-4491
+    IX_TRY(k::extrap_vel_to_faces(L.lbox(il), ns.Umf.c(il), ns.force.c(il), ns.umac[0].v(il), ns.umac[1].v(il),
+                                  ns.umac[2].v(il), g, ns.p.use_forces_in_trans, ns.s));
+  *dt_test = dt * tempdt;                                                  // :4511
+  return IAMRX_OK;
+}
+
+// NavierStokesBase::mac_project (NSB.cpp:2070-2109) -> MacProj::mac_project (MacProj.cpp:225-353)
+// + create_umac_grown (NSB.cpp:1068-1311; single level: FillPatchSingleLevel == periodic FillBoundary)
+int mac_project_step(iamrx_ns_s& ns, double dt) {
+  IX_TRY(mf_setval(ns.mac_phi, 0.0, 0, 1, 1, ns.s));                       // MacProj.cpp:253
+  iamrx_mg_info mi = mg_info(ns, ns.p.mac_tol, ns.p.mac_abs_tol);
+  IX_SOLVE(mac_project(*ns.L, *ns.sv, ns.umac, ns.rho_ptime, nullptr, ns.mac_phi, 2.0 / dt, &mi, ns.s));  // :272,294
+  ns.it_mac = mi.iters;
+  for (int d = 0; d < 3; ++d) IX_TRY(mf_fill_boundary(ns.umac[d], 0, 1, 1, ns.s));  // NSB.cpp:1102
+  return IAMRX_OK;
+}
+
+int compute_aofs(iamrx_ns_s& ns, int state_comp, int ncomp, const MF& Sq, const MF* forcing, bool is_velocity,
+                 double dt) {
+  // NavierStokesBase::ComputeAofs (NSB.cpp:4555-4591 wrapper, :4594-4845 body)
+  Level& L = *ns.L;
+  k::AdvGeom g; for (int d = 0; d < 3; ++d) g.dx[d] = L.geom.dx[d]; g.dt = dt;
+  for (int il = 0; il < ns.aofs.n(); ++il) {
+    k::AofsArgs a{};
+    a.aofs = ns.aofs.v(il, state_comp);
+    a.S = Sq.c(il);
+    a.force = forcing ? forcing->c(il) : C4{};
+    a.divu = C4{};  // have_divu == 0: getDivCond returns zeros (NSB.cpp:1577-1590)
+    a.umac = ns.umac[0].c(il); a.vmac = ns.umac[1].c(il); a.wmac = ns.umac[2].c(il);
+    a.uflx = a.umac; a.vflx = a.vmac; a.wflx = a.wmac;
+    a.ncomp = ncomp;
+    for (int n = 0; n < ncomp; ++n) {
+      const int sc = state_comp + n;
+      // advectionType: NS_setup.cpp:285-320 (velocity non-conservative unless do_mom_diff,
+      // density conservative, tracer per do_cons_trac)
+      a.iconserv[n] = (sc == Density) ? 1 : (sc == Tracer ? (ns.p.conservative_tracer ? 1 : 0) : 0);
+    }
+    a.forces_in_trans = ns.p.use_forces_in_trans;
+    a.is_velocity = is_velocity ? 1 : 0;
+    IX_TRY(k::compute_aofs(L.lbox(il), a, g, ns.s));
+  }
+  return IAMRX_OK;
+}
+
+// NavierStokesBase::velocity_advection (NSB.cpp:3358-3470), do_mom_diff == 0
+int velocity_advection(iamrx_ns_s& ns, double dt) {
+  IX_TRY(fillpatch(ns, ns.Umf, ns.S_old, Xvel, 3));   // :3382 (a fresh, un-floored copy)
+  // visc_terms (:3429) and the total forcing (:3445-3466) repeat predict_velocity's
+  // arithmetic on the same inputs; ns.force still holds exactly those values.
+  return compute_aofs(ns, Xvel, 3, ns.Umf, &ns.force, true, dt);  // :3469
+}
+
+// NavierStokes::scalar_advection (NS.cpp:698-812)
+int scalar_advection(iamrx_ns_s& ns, double dt) {
+  for (int il = 0; il < ns.Smf.n(); ++il) IX_TRY(k::floor_small(ns.Smf.gbox(il, 3), ns.Smf.v(il), NUM_SCALARS, ns.s));  // :722
+  IX_TRY(mf_setval(ns.sforce, 0.0, 0, NUM_SCALARS, 1, ns.s));  // getForce: zero scalar forcing; visc terms zero (:738-805)
+  return compute_aofs(ns, Density, NUM_SCALARS, ns.Smf, &ns.sforce, false, dt);  // :811
+}
+
+// Diffusion::diffuse_tensor_velocity (Diffusion.cpp:650-957), rho_flag = 1
+int velocity_diffusion_update(iamrx_ns_s& ns, double dt) {
+  if (!ns.diffusive_vel()) return IAMRX_OK;
+  Level& L = *ns.L;
+  const double theta = ns.p.be_cn_theta;
+  if (theta != 1.0) {
+    IX_TRY(fillpatch(ns, ns.soln, ns.S_old, Xvel, 3));  // :742
+    IX_TRY(diffusion_apply(L, *ns.sv, true, 3, ns.rhs3, ns.soln, 0.0, -(1.0 - theta) * dt, nullptr, ns.eta, ns.s));  // :702-768
+  } else {
+    IX_TRY(mf_setval(ns.rhs3, 0.0, 0, 3, 0, ns.s));
+  }
+  for (int il = 0; il < ns.rhs3.n(); ++il)  // :821-831
+    IX_TRY(k::diff_rhs(L.lbox(il), ns.rhs3.v(il), ns.S_new.v(il, Xvel), ns.rho_half.c(il), 3, ns.s));
+  // tolerances: visc_tol, get_scaled_abs_tol (Diffusion.cpp:193-204, :846-847)
+  double nrm[3];
+  IX_TRY(mf_norminf_each(ns.rhs3, 0, 3, nrm, ns.s));
+  const double tol_abs = ns.p.visc_tol * (nrm[0] + nrm[1] + nrm[2]) / 3.0;
+  IX_TRY(fillpatch(ns, ns.soln, ns.S_new, Xvel, 3));  // :885 initial guess = new-time state
+  iamrx_mg_info mi = mg_info(ns, ns.p.visc_tol, tol_abs);
+  IX_SOLVE(diffusion_solve(L, *ns.sv, true, 3, ns.soln, ns.rhs3, 1.0, theta * dt, &ns.rho_half, ns.eta, &mi, ns.s));  // :895-923
+  ns.it_visc = mi.iters;
+  return mf_copy(ns.S_new, ns.soln, 0, Xvel, 3, 1, ns.s);  // :928
+}
+
+// NavierStokesBase::initial_velocity_diffusion_update (NSB.cpp:3658-3749)
+int initial_velocity_diffusion_update(iamrx_ns_s& ns, double dt) {
+  if (!ns.diffusive_vel()) return IAMRX_OK;
+  Level& L = *ns.L;
+  if (ns.p.be_cn_theta != 1.0) IX_TRY(get_visc_terms(ns, ns.visc, ns.S_old));
+  else IX_TRY(mf_setval(ns.visc, 0.0, 0, 3, 1, ns.s));
+  for (int il = 0; il < ns.tf0.n(); ++il) {
+    // force = (getForce(rho_old) + visc - gp)/rho_half - aofs ; u_new = u_old + dt*force
+    IX_TRY(k::force_vel(L.lbox(il), ns.tf0.v(il), ns.visc.c(il), ns.Gp_old.c(il), ns.S_old.c(il, Density),
+                        ns.p.gravity, 0, ns.s));
+    IX_TRY(k::divide(L.lbox(il), ns.tf0.v(il), ns.rho_half.c(il), 3, 1, ns.s));
+    IX_TRY(k::lincomb(L.lbox(il), ns.tf0.v(il), 1.0, ns.tf0.c(il), -1.0, ns.aofs.c(il, Xvel), 3, ns.s));
+    IX_TRY(k::lincomb(L.lbox(il), ns.S_new.v(il, Xvel), 1.0, ns.S_old.c(il, Xvel), dt, ns.tf0.c(il), 3, ns.s));
+  }
+  return IAMRX_OK;
+}
+
+// Projection::level_project (Projection.cpp:166-450) + doMLMGNodalProjection (:2385-2567)
+int level_project(iamrx_ns_s& ns, double dt) {
+  Level& L = *ns.L;
+  IX_TRY(mf_setval(ns.P_new, 0.0, 0, 1, 1, ns.s));   // :247-256
+  for (int il = 0; il < ns.S_new.n(); ++il)          // :273, :296-300
+    IX_TRY(k::proj_pre(L.lbox(il), ns.S_new.v(il, Xvel), ns.Gp_old.c(il), ns.rho_half.c(il), 1.0 / dt, ns.s));
+  for (int il = 0; il < ns.sig.n(); ++il)            // scaleVar :332, :1327-1349
+    IX_TRY(k::invert(L.lbox(il), ns.sig.v(il), ns.rho_half.c(il), ns.s));
+  MF vel; vel.alias(&L, IX_CELL, 3, 1, ns.S_new.fabs.data());  // comps 0..2 of the state
+  iamrx_mg_info mi = mg_info(ns, ns.p.proj_tol, ns.p.proj_abs_tol);
+  IX_SOLVE(nodal_project(L, *ns.sv, vel, ns.sig, ns.P_new, &ns.Gp_new, 0, &mi, ns.s));  // :392 ; Gp = grad phi :2542-2563
+  ns.it_nodal = mi.iters;
+  IX_TRY(mf_fill_boundary(ns.Gp_new, 0, 3, 1, ns.s));  // :2565
+  return mf_scale(ns.S_new, dt, Xvel, 3, 0, ns.s);     // :438 (rescaleVar :434 restores rho_half: ns.sig is separate)
+}
+
+// NavierStokes::advance (NS.cpp:543-691)
+int advance(iamrx_ns_s& ns, double time, double dt, double* dt_test) {
+  (void)time;
+  Level& L = *ns.L;
+  // advance_setup (NSB.cpp:613-741): swap time levels, rho at the previous time
+  std::swap(ns.S_old, ns.S_new);
+  std::swap(ns.P_old, ns.P_new);
+  std::swap(ns.Gp_old, ns.Gp_new);
+  IX_TRY(fillpatch(ns, ns.rho_ptime, ns.S_old, Density, 1));   // make_rho_prev_time :703
+  IX_TRY(predict_velocity(ns, dt, dt_test));                   // NS.cpp:585
+  IX_TRY(mac_project_step(ns, dt));                            // :589-597
+  IX_TRY(velocity_advection(ns, dt));                          // :606
+  IX_TRY(scalar_advection(ns, dt));                            // :613
+  for (int il = 0; il < ns.S_new.n(); ++il)                    // scalar_update(rho) :617 -> NSB.cpp:2761-2765
+    IX_TRY(k::scal_update(L.lbox(il), ns.S_new.v(il, Density), ns.S_old.c(il, Density), ns.aofs.c(il, Density), dt, 1, ns.s));
+  IX_TRY(fillpatch(ns, ns.rho_ctime, ns.S_new, Density, 1));   // make_rho_curr_time :618
+  for (int il = 0; il < ns.S_new.n(); ++il)                    // scalar_update(tracer) :627 -> NSB.cpp:2887-2896
+    IX_TRY(k::scal_update(L.lbox(il), ns.S_new.v(il, Tracer), ns.S_old.c(il, Tracer), ns.aofs.c(il, Tracer), dt, 1, ns.s));
+  // velocity_update :645 -> NSB.cpp:3487: rho_half (:1561-1565), advection update (:3523-3655), diffusion
+  IX_TRY(mf_lincomb(ns.rho_half, 0, 0.5, ns.rho_ptime, 0, 0.5, ns.rho_ctime, 0, 1, 1, ns.s));
+  for (int il = 0; il < ns.S_new.n(); ++il)
+    IX_TRY(k::vel_update(L.lbox(il), ns.S_new.v(il, Xvel), ns.S_old.c(il, Xvel), ns.aofs.c(il, Xvel), ns.Gp_old.c(il),
+                         ns.rho_half.c(il), ns.p.gravity, dt, (ns.initial_iter && ns.diffusive_vel()) ? 1 : 0, ns.s));
+  if (!ns.initial_iter) IX_TRY(velocity_diffusion_update(ns, dt));
+  else IX_TRY(initial_velocity_diffusion_update(ns, dt));
+  if (!ns.initial_step) IX_TRY(level_project(ns, dt));         // :650-670
+  return IAMRX_OK;
+}
+
+// NavierStokesBase::estTimeStep (NSB.cpp:1353-1500)
+int est_time_step(iamrx_ns_s& ns, double* out) {
+  if (ns.p.fixed_dt > 0.0) { *out = ns.p.fixed_dt; return IAMRX_OK; }
+  Level& L = *ns.L;
+  const double small = 1.0e-8;
+  double estdt = 1.0e20;
+  double umax[3], fmax[3];
+  IX_TRY(mf_norminf_each(ns.S_new, Xvel, 3, umax, ns.s));
+  for (int il = 0; il < ns.tf0.n(); ++il)
+    IX_TRY(k::force_vel(L.lbox(il), ns.tf0.v(il), C4{}, ns.Gp_new.c(il), ns.S_new.c(il, Density), ns.p.gravity, 1, ns.s));
+  IX_TRY(mf_norminf_each(ns.tf0, 0, 3, fmax, ns.s));
+  for (int d = 0; d < 3; ++d) {
+    if (umax[d] > small) estdt = std::min(estdt, L.geom.dx[d] / umax[d]);
+    if (fmax[d] > small) estdt = std::min(estdt, std::sqrt(2.0 * L.geom.dx[d] / fmax[d]));
+  }
+  if (estdt < 1.0e20) estdt *= ns.p.cfl;
+  else { set_error("estTimeStep: zero velocity and forcing; set fixed_dt"); return IAMRX_ERR_ARG; }
+  *out = estdt;
+  return IAMRX_OK;
+}
+
+int project_simple(iamrx_ns_s& ns, MF& vel, const MF& sigma, MF& phi, MF* gp, int incr, int* iters) {
+  iamrx_mg_info mi = mg_info(ns, ns.p.proj_tol, ns.p.proj_abs_tol);
+  IX_SOLVE(nodal_project(*ns.L, *ns.sv, vel, sigma, phi, gp, incr, &mi, ns.s));
+  if (iters) *iters = mi.iters;
+  return IAMRX_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+void iamrx_ns_params_default(iamrx_ns_params* p) {
+  if (!p) return;
+  memset(p, 0, sizeof(*p));
+  p->cfl = 0.7;
+  p->visc_coef = 0.0;
+  p->scal_diff_coef = 0.0;
+  p->be_cn_theta = 0.5;   // NSB.cpp:124
+  p->change_max = 1.1;    // NSB.cpp:101
+  p->init_shrink = 1.0;
+  p->fixed_dt = -1.0;
+  p->gravity = 0.0;
+  p->visc_tol = 1.0e-10;  // NSB.cpp:122
+  p->mac_tol = 1.0e-12; p->mac_abs_tol = 1.0e-16;    // MacProj.cpp:49-51
+  p->proj_tol = 1.0e-12; p->proj_abs_tol = 1.0e-16;  // Projection.cpp:19-21
+  p->init_iter = 2;       // NSB.cpp:98
+  p->init_vel_iter = 1;   // NSB.cpp:99
+  p->do_init_proj = 1;
+  p->use_forces_in_trans = 0;
+  p->verbose = 0;
+  p->conservative_tracer = 0;
+  p->mg_verbose = 0;
+}
+
+int iamrx_ns_create(iamrx_level_t lev, const iamrx_ns_params* p, iamrx_ns_t* out) {
+  IX_NEED_DEVICE();
+  IX_ARG(lev && p && out, "null argument");
+  IX_ARG(p->cfl > 0.0 && p->cfl <= 1.0, "ns.cfl must be in (0,1]");
+  IX_ARG(p->be_cn_theta >= 0.5 && p->be_cn_theta <= 1.0, "ns.be_cn_theta must be in [0.5,1] (NSB.cpp:506-508)");
+  IX_ARG(p->visc_coef >= 0.0, "ns.vel_visc_coef must be >= 0 (NS.cpp:2077)");
+  IX_ARG(p->scal_diff_coef == 0.0, "tracer diffusion (ns.scal_diff_coefs > 0) is not implemented in the step driver");
+  Level* L = level_of(lev);
+  for (int d = 0; d < 3; ++d) IX_ARG(L->geom.periodic[d], "only fully periodic domains are implemented in this round");
+  auto* ns = new iamrx_ns_s();
+  ns->hlev = lev; ns->L = L; ns->sv = solvers_of(lev); ns->p = *p;
+  ns->S_old.define(L, IX_CELL, NUM_STATE, 1); ns->S_new.define(L, IX_CELL, NUM_STATE, 1);
+  ns->P_old.define(L, IX_NODE, 1, 1); ns->P_new.define(L, IX_NODE, 1, 1);
+  ns->Gp_old.define(L, IX_CELL, 3, 1); ns->Gp_new.define(L, IX_CELL, 3, 1);
+  for (int d = 0; d < 3; ++d) ns->umac[d].define(L, IX_XFACE + d, 1, 1);
+  ns->aofs.define(L, IX_CELL, NUM_STATE, 0);
+  ns->rho_ptime.define(L, IX_CELL, 1, 1); ns->rho_ctime.define(L, IX_CELL, 1, 1); ns->rho_half.define(L, IX_CELL, 1, 1);
+  ns->Umf.define(L, IX_CELL, 3, 3); ns->Smf.define(L, IX_CELL, NUM_SCALARS, 3);
+  ns->visc.define(L, IX_CELL, 3, 1); ns->force.define(L, IX_CELL, 3, 1); ns->sforce.define(L, IX_CELL, NUM_SCALARS, 1);
+  for (int d = 0; d < 3; ++d) ns->eta[d].define(L, IX_XFACE + d, 1, 0);
+  ns->soln.define(L, IX_CELL, 3, 1); ns->rhs3.define(L, IX_CELL, 3, 0);
+  ns->sig.define(L, IX_CELL, 1, 1); ns->mac_phi.define(L, IX_CELL, 1, 1); ns->tf0.define(L, IX_CELL, 3, 0);
+  cudaStream_t s = ns->s;
+  MF* all[] = {&ns->S_old, &ns->S_new, &ns->P_old, &ns->P_new, &ns->Gp_old, &ns->Gp_new, &ns->umac[0], &ns->umac[1],
+               &ns->umac[2], &ns->aofs, &ns->rho_ptime, &ns->rho_ctime, &ns->rho_half, &ns->Umf, &ns->Smf, &ns->visc,
+               &ns->force, &ns->sforce, &ns->soln, &ns->rhs3, &ns->sig, &ns->mac_phi, &ns->tf0};
+  for (MF* m : all) {
+    for (int il = 0; il < m->n(); ++il) if (!m->fabs[il].p) { delete ns; return IAMRX_ERR_CUDA; }
+    int rc = mf_setval(*m, 0.0, 0, m->ncomp, m->ng, s);
+    if (rc) { delete ns; return rc; }
+  }
+  for (int d = 0; d < 3; ++d) {  // constant viscosity on faces (NS.cpp:2062-2117 calcViscosity/getViscosity)
+    int rc = mf_setval(ns->eta[d], p->visc_coef, 0, 1, 0, s);
+    if (rc) { delete ns; return rc; }
+  }
+  *out = ns;
+  return IAMRX_OK;
+}
+
+int iamrx_ns_destroy(iamrx_ns_t ns) {
+  if (ns && ns->stage) cudaFreeHost(ns->stage);
+  delete ns;
+  return IAMRX_OK;
+}
+
+int iamrx_ns_init_prob(iamrx_ns_t ns, int probtype, const double* prob_params, int nparams) {
+  IX_NEED_DEVICE();
+  IX_ARG(ns && prob_params && nparams >= 0, "null argument");
+  IX_ARG(probtype == 11 || probtype == 100 || probtype == 5, "probtype must be 11 (TaylorGreen), 5 (DoubleShearLayer) or 100");
+  IX_ARG((probtype == 5) ? nparams >= 6 : nparams >= 5, "too few prob parameters");
+  Level& L = *ns->L;
+  // NavierStokes::initData (NS.cpp:335-460): S_new from prob_init, P_new = 0, Gp = 0
+  for (int il = 0; il < ns->S_new.n(); ++il)
+    IX_TRY(k::init_prob(L.lbox(il), ns->S_new.v(il), probtype, prob_params, nparams, L.geom, ns->s));
+  IX_TRY(mf_fill_boundary(ns->S_new, 0, NUM_STATE, 1, ns->s));
+  IX_TRY(mf_setval(ns->P_new, 0.0, 0, 1, 1, ns->s));
+  IX_TRY(mf_setval(ns->P_old, 0.0, 0, 1, 1, ns->s));
+  IX_TRY(mf_setval(ns->Gp_new, 0.0, 0, 3, 1, ns->s));
+  IX_TRY(mf_setval(ns->Gp_old, 0.0, 0, 3, 1, ns->s));
+  ns->time = 0.0; ns->nstep = 0; ns->dt_level = 0.0; ns->dt_min = 1.0e100;
+  return IAMRX_OK;
+}
+
+// NavierStokes::post_init (NS.cpp:1254-1303): post_init_state (NSB.cpp:2369-2439),
+// post_init_estDT (NSB.cpp:2307-2366), post_init_press (NS.cpp:1306-1432)
+int iamrx_ns_post_init(iamrx_ns_t nsp, double* dt0) {
+  IX_NEED_DEVICE();
+  IX_ARG(nsp, "null argument");
+  iamrx_ns_s& ns = *nsp;
+  Level& L = *ns.L;
+  // --- initialVelocityProject (Projection.cpp:615-838): sigma = 1, P/Gp reset to 0 afterwards
+  if (ns.p.do_init_proj) {
+    for (int it = 0; it < ns.p.init_vel_iter; ++it) {
+      IX_TRY(mf_setval(ns.P_old, 0.0, 0, 1, 1, ns.s));
+      IX_TRY(mf_setval(ns.sig, 1.0, 0, 1, 1, ns.s));
+      MF vel; vel.alias(&L, IX_CELL, 3, 1, ns.S_new.fabs.data());
+      IX_TRY(project_simple(ns, vel, ns.sig, ns.P_old, nullptr, 0, nullptr));
+      IX_TRY(mf_setval(ns.P_old, 0.0, 0, 1, 1, ns.s));
+      IX_TRY(mf_setval(ns.P_new, 0.0, 0, 1, 1, ns.s));
+      IX_TRY(mf_setval(ns.Gp_old, 0.0, 0, 3, 1, ns.s));
+      IX_TRY(mf_setval(ns.Gp_new, 0.0, 0, 3, 1, ns.s));
+    }
+  }
+  ns.initial_step = true;  // NSB.cpp:2403
+  // --- post_init_estDT: dt_init = init_shrink * estTimeStep
+  double est = 0.0;
+  IX_TRY(est_time_step(ns, &est));
+  const double dt_init = ns.p.init_shrink * est;
+  const double dt_save = dt_init;
+  // --- post_init_press: init_iter x { advance ; initialSyncProject ; resetState }
+  if (ns.p.init_iter > 0) {
+    ns.initial_iter = true;
+    for (int iter = 0; iter < ns.p.init_iter; ++iter) {
+      double dt_test = 0.0;
+      IX_TRY(advance(ns, ns.time, dt_init, &dt_test));   // NS.cpp:1348-1351
+      // initialSyncProject (Projection.cpp:970-1185): vel = (U_new - U_old)/dt, sigma = 1/rho_half,
+      // phi = P_old (zeroed scratch), Gp_new += grad phi, P_new += phi
+      IX_TRY(mf_setval(ns.P_old, 0.0, 0, 1, 1, ns.s));
+      for (int il = 0; il < ns.S_new.n(); ++il)
+        IX_TRY(k::lincomb(L.lbox(il), ns.S_new.v(il, Xvel), 1.0 / dt_init, ns.S_new.c(il, Xvel), -1.0 / dt_init,
+                          ns.S_old.c(il, Xvel), 3, ns.s));
+      for (int il = 0; il < ns.sig.n(); ++il) IX_TRY(k::invert(L.lbox(il), ns.sig.v(il), ns.rho_half.c(il), ns.s));
+      MF vel; vel.alias(&L, IX_CELL, 3, 1, ns.S_new.fabs.data());
+      IX_TRY(project_simple(ns, vel, ns.sig, ns.P_old, &ns.Gp_new, 1, &ns.it_nodal));
+      IX_TRY(mf_lincomb(ns.P_new, 0, 1.0, ns.P_new, 0, 1.0, ns.P_old, 0, 1, 1, ns.s));  // :1166-1170
+      IX_TRY(mf_fill_boundary(ns.Gp_new, 0, 3, 1, ns.s));
+      // resetState (NSB.cpp:2643-2680): State new := the time-n state; P, Gp old := new
+      std::swap(ns.S_old, ns.S_new);
+      IX_TRY(mf_copy(ns.P_old, ns.P_new, 0, 0, 1, 1, ns.s));
+      IX_TRY(mf_copy(ns.Gp_old, ns.Gp_new, 0, 0, 3, 1, ns.s));
+      ns.initial_iter = false;  // NS.cpp:1405
+    }
+  }
+  ns.initial_step = false;  // NS.cpp:1408
+  ns.dt_level = dt_save;
+  ns.dt_min = 1.0e100;
+  if (dt0) *dt0 = dt_save;
+  return IAMRX_OK;
+}
+
+// Amr::coarseTimeStep for one level: computeNewDt (NSB.cpp:945-1036) unless a dt is
+// forced, advance, bookkeeping of dt_min (Amr::timeStep)
+int iamrx_ns_step(iamrx_ns_t nsp, double* dt_io) {
+  IX_NEED_DEVICE();
+  IX_ARG(nsp, "null argument");
+  iamrx_ns_s& ns = *nsp;
+  double dt = (dt_io && *dt_io > 0.0) ? *dt_io : -1.0;
+  if (dt <= 0.0) {
+    if (ns.p.fixed_dt > 0.0) dt = ns.p.fixed_dt;
+    else if (ns.nstep == 0 && ns.dt_level > 0.0) dt = ns.dt_level;  // computeInitialDt: dt from post_init
+    else {
+      double est = 0.0;
+      IX_TRY(est_time_step(ns, &est));
+      dt = std::min(ns.dt_min, est);
+      if (ns.dt_level > 0.0) dt = std::min(dt, ns.p.change_max * ns.dt_level);
+    }
+  }
+  double dt_test = 0.0;
+  IX_TRY(advance(ns, ns.time, dt, &dt_test));
+  ns.dt_min = dt_test;
+  ns.dt_level = dt;
+  ns.time += dt;
+  ns.nstep += 1;
+  if (dt_io) *dt_io = dt;
+  if (ns.p.verbose)
+    fprintf(stderr, "[iamrx] step %d time %.6e dt %.6e iters mac/visc/nodal %d/%d/%d\n", ns.nstep, ns.time, dt, ns.it_mac,
+            ns.it_visc, ns.it_nodal);
+  return IAMRX_OK;
+}
+
+double iamrx_ns_time(iamrx_ns_t ns) { return ns ? ns->time : 0.0; }
+int iamrx_ns_nstep(iamrx_ns_t ns) { return ns ? ns->nstep : 0; }
+
+int iamrx_ns_field(iamrx_ns_t ns, int which, int il, iamrx_fab* out) {
+  IX_ARG(ns && out, "null argument");
+  IX_ARG(il >= 0 && il < ns->L->nlocal(), "local box index");
+  MF* m = nullptr;
+  switch (which) {
+    case 0: m = &ns->S_new; break;
+    case 1: m = &ns->P_new; break;
+    case 2: m = &ns->Gp_new; break;
+    case 3: m = &ns->S_old; break;
+    case 4: case 5: case 6: m = &ns->umac[which - 4]; break;
+    case 7: m = &ns->aofs; break;
+    default: IX_ARG(false, "field selector");
+  }
+  *out = m->fabs[il];
+  return IAMRX_OK;
+}
+
+int iamrx_ns_step_host(iamrx_ns_t nsp, const double* const* host_in, double* const* host_out, double* dt_io) {
+  IX_NEED_DEVICE();
+  IX_ARG(nsp && host_in && host_out, "null argument");
+  iamrx_ns_s& ns = *nsp;
+  Level& L = *ns.L;
+  size_t maxpts = 0;
+  for (int il = 0; il < L.nlocal(); ++il) maxpts = std::max(maxpts, (size_t)L.lbox(il).npts());
+  const size_t need = maxpts * NUM_STATE;
+  double* dbuf = dev_alloc(need);
+  if (!dbuf) return IAMRX_ERR_CUDA;
+  for (int il = 0; il < L.nlocal(); ++il) {
+    const size_t n = (size_t)L.lbox(il).npts() * NUM_STATE;
+    IX_CUDA(cudaMemcpyAsync(dbuf, host_in[il], n * sizeof(double), cudaMemcpyHostToDevice, ns.s));
+    IX_TRY(k::unpack(L.lbox(il), ns.S_new.v(il), dbuf, NUM_STATE, ns.s));
+  }
+  int rc = iamrx_ns_step(nsp, dt_io);
+  if (rc != IAMRX_OK) { dev_free(dbuf); return rc; }
+  for (int il = 0; il < L.nlocal(); ++il) {
+    const size_t n = (size_t)L.lbox(il).npts() * NUM_STATE;
+    IX_TRY(k::pack(L.lbox(il), dbuf, ns.S_new.c(il), NUM_STATE, ns.s));
+    IX_CUDA(cudaMemcpyAsync(host_out[il], dbuf, n * sizeof(double), cudaMemcpyDeviceToHost, ns.s));
+  }
+  IX_CUDA(cudaStreamSynchronize(ns.s));
+  dev_free(dbuf);
+  return IAMRX_OK;
+}
+
+int iamrx_ns_last_iters(iamrx_ns_t ns, int iters[3]) {
+  IX_ARG(ns && iters, "null argument");
+  iters[0] = ns->it_mac; iters[1] = ns->it_visc; iters[2] = ns->it_nodal;
+  return IAMRX_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,145 @@
+// pointwise.cu -- the small streaming kernels IAMR itself contributes to the hot
+// path: forcing assembly, state updates, projection scaling and
+// the problem initial conditions.  Each cites the amrex::ParallelFor lambda in
+// the reference it stands in for; the arithmetic is restated, not copied.
+#include "kernels.h"
+
+namespace ix {
+namespace k {
+namespace {
+
+constexpr int TX = 128;
+constexpr int TY = 2;
+inline dim3 grid_for(const Bx& bx, int nzc) { return dim3(cdiv(bx.nx(), TX), cdiv(bx.ny(), TY), nzc); }
+#define IDX3(bx)                                                     \
+  const int nz_ = bx.hi[2] - bx.lo[2] + 1;                            \
+  const int k = bx.lo[2] + (int)(blockIdx.z % nz_);                   \
+  const int n = (int)(blockIdx.z / nz_);                              \
+  const int j = bx.lo[1] + blockIdx.y * TY + threadIdx.y;             \
+  const int i = bx.lo[0] + blockIdx.x * TX + threadIdx.x;             \
+  if (j > bx.hi[1] || i > bx.hi[0]) return;
+
+__global__ void floor_kernel(Bx bx, V4 f) {
+  IDX3(bx)
+  const double v = f(i, j, k, n);
+  f(i, j, k, n) = (fabs(v) > 1.0e-20) ? v : 0.0;
+}
+
+IX_D double ext_force(int n, double grav, double rho) {  // NS_getForce.cpp:117-141
+  return (n == 2 && fabs(grav) > 1.0e-4) ? grav * rho : 0.0;
+}
+
+__global__ void force_vel_kernel(Bx bx, V4 tf, C4 visc, C4 gp, C4 rho, double grav, int div_rho) {
+  IDX3(bx)
+  const double r = rho(i, j, k);
+  double f = ext_force(n, grav, r);
+  if (visc.ok()) f += visc(i, j, k, n);
+  if (gp.ok()) f -= gp(i, j, k, n);
+  if (div_rho) f /= r;
+  tf(i, j, k, n) = f;
+}
+
+__global__ void vel_update_kernel(Bx bx, V4 unew, C4 uold, C4 aofs, C4 gp, C4 rh, double grav, double dt,
+                                  int zero_force) {
+  IDX3(bx)
+  const double r = rh(i, j, k);
+  const double force = zero_force ? 0.0 : ext_force(n, grav, r);
+  unew(i, j, k, n) = uold(i, j, k, n) - dt * aofs(i, j, k, n) + dt * force / r - dt * gp(i, j, k, n) / r;
+}
+
+__global__ void scal_update_kernel(Bx bx, V4 snew, C4 sold, C4 aofs, double dt) {
+  IDX3(bx)
+  snew(i, j, k, n) = sold(i, j, k, n) - dt * aofs(i, j, k, n);
+}
+
+__global__ void diff_rhs_kernel(Bx bx, V4 rhs, V4 unew, C4 rho) {
+  IDX3(bx)
+  const double u = unew(i, j, k, n) * rho(i, j, k);
+  unew(i, j, k, n) = u;
+  rhs(i, j, k, n) += u;
+}
+
+__global__ void proj_pre_kernel(Bx bx, V4 u, C4 gp, C4 rho, double dt_inv) {
+  IDX3(bx)
+  u(i, j, k, n) = u(i, j, k, n) * dt_inv + gp(i, j, k, n) / rho(i, j, k);
+}
+
+__global__ void invert_kernel(Bx bx, V4 sig, C4 rho) {
+  IDX3(bx)
+  sig(i, j, k, n) = 1.0 / rho(i, j, k, n);
+}
+
+struct ProbParams { double v[16]; int n; };
+
+// prob_init.cpp: probtype 11 TaylorGreen (:509-560); probtype 5 DoubleShearLayer
+// (:346-405, direction 1, extended uniformly in z); probtype 100 = synthetic
+// variable-density Taylor-Green used by the HIT-like weak-scaling configuration.
+__global__ void init_kernel(Bx bx, V4 st, int probtype, ProbParams pp, iamrx_geom g) {
+  IDX3(bx)
+  (void)n;
+  const double twopi = 2.0 * 3.14159265358979323846264338327950288;
+  const double x = g.prob_lo[0] + (i - g.domain.lo[0] + 0.5) * g.dx[0];
+  const double y = g.prob_lo[1] + (j - g.domain.lo[1] + 0.5) * g.dx[1];
+  const double z = g.prob_lo[2] + (k - g.domain.lo[2] + 0.5) * g.dx[2];
+  if (probtype == 11 || probtype == 100) {
+    const double a = pp.v[0], b = pp.v[1], c = pp.v[2], vx = pp.v[3], dens = pp.v[4];
+    st(i, j, k, 0) = vx * sin(a * twopi * x) * cos(b * twopi * y) * cos(c * twopi * z);
+    st(i, j, k, 1) = -vx * cos(a * twopi * x) * sin(b * twopi * y) * cos(c * twopi * z);
+    st(i, j, k, 2) = 0.0;
+    double rho = dens;
+    if (probtype == 100) rho = dens * (1.0 + 0.5 * sin(twopi * x) * sin(twopi * y) * sin(twopi * z));
+    st(i, j, k, 3) = rho;
+    st(i, j, k, 4) = (dens * vx * vx / 16.0) * (2.0 + cos(2.0 * c * twopi * z)) *
+                     (cos(2.0 * a * twopi * x) + cos(2.0 * b * twopi * y));
+  } else if (probtype == 5) {
+    // DoubleShearLayer, direction = 1 (shear layer in y): params = density, interface_width,
+    // blob_x, blob_y, blob_z, blob_radius
+    const double dens = pp.v[0], width = pp.v[1] > 0.0 ? pp.v[1] : 1.0;
+    const double pi = 0.5 * twopi;
+    st(i, j, k, 0) = -0.05 * sin(pi * y);
+    st(i, j, k, 1) = tanh(30.0 * (0.5 - fabs(x)) / width);
+    st(i, j, k, 2) = 0.0;
+    st(i, j, k, 3) = dens;
+    const double bx0 = pp.v[2], by0 = pp.v[3], bz0 = pp.v[4], br = pp.v[5];
+    const double d = sqrt((x - bx0) * (x - bx0) + (y - by0) * (y - by0) + (z - bz0) * (z - bz0));
+    st(i, j, k, 4) = (d < br) ? 1.0 : 0.0;
+  }
+}
+
+}  // namespace
+
+#define LAUNCH3(kern, bx, ncomp, s, ...)                                                  \
+  do {                                                                                    \
+    if (!(bx).ok() || (ncomp) <= 0) return IAMRX_OK;                                      \
+    IX_LAUNCH(kern, grid_for(bx, (bx).nz() * (ncomp)), dim3(TX, TY, 1), 0, s, bx, __VA_ARGS__);  \
+    return check_launch(#kern);                                                           \
+  } while (0)
+
+int floor_small(const Bx& bx, V4 f, int ncomp, cudaStream_t s) { LAUNCH3(floor_kernel, bx, ncomp, s, f); }
+int force_vel(const Bx& bx, V4 tf, C4 visc, C4 gp, C4 rho, double grav, int div_rho, cudaStream_t s) {
+  LAUNCH3(force_vel_kernel, bx, 3, s, tf, visc, gp, rho, grav, div_rho);
+}
+int vel_update(const Bx& bx, V4 unew, C4 uold, C4 aofs, C4 gp, C4 rhohalf, double grav, double dt, int zero_force,
+               cudaStream_t s) {
+  LAUNCH3(vel_update_kernel, bx, 3, s, unew, uold, aofs, gp, rhohalf, grav, dt, zero_force);
+}
+int scal_update(const Bx& bx, V4 snew, C4 sold, C4 aofs, double dt, int ncomp, cudaStream_t s) {
+  LAUNCH3(scal_update_kernel, bx, ncomp, s, snew, sold, aofs, dt);
+}
+int diff_rhs(const Bx& bx, V4 rhs, V4 unew, C4 rho, int ncomp, cudaStream_t s) {
+  LAUNCH3(diff_rhs_kernel, bx, ncomp, s, rhs, unew, rho);
+}
+int proj_pre(const Bx& bx, V4 u, C4 gp, C4 rho, double dt_inv, cudaStream_t s) {
+  LAUNCH3(proj_pre_kernel, bx, 3, s, u, gp, rho, dt_inv);
+}
+int invert(const Bx& bx, V4 sig, C4 rho, cudaStream_t s) { LAUNCH3(invert_kernel, bx, 1, s, sig, rho); }
+int init_prob(const Bx& bx, V4 state, int probtype, const double* params, int nparams, const iamrx_geom& g,
+              cudaStream_t s) {
+  ProbParams pp{};
+  pp.n = nparams < 16 ? nparams : 16;
+  for (int q = 0; q < pp.n; ++q) pp.v[q] = params[q];
+  LAUNCH3(init_kernel, bx, 1, s, state, probtype, pp, g);
+}
+
+}  // namespace k
+}  // namespace ix

@@ -58,7 +58,8 @@ inline cudaError_t cudaDeviceSynchronize() { return cudaSuccess; }
 // shared memory / shuffles carry an `#ifdef IX_EMUL` serial body instead.
 template <class F>
 inline void ix_emul_launch(dim3 g, dim3 b, F&& f) {
-#pragma omp parallel for collapse(2) schedule(static)
+  const size_t work_ = (size_t)g.x * g.y * g.z * b.x * b.y * b.z;
+#pragma omp parallel for collapse(2) schedule(static) if (work_ > 65536)
   for (unsigned bz = 0; bz < g.z; ++bz)
     for (unsigned by = 0; by < g.y; ++by) {
       gridDim = g; blockDim = b;
@@ -73,5 +74,6 @@ inline void ix_emul_launch(dim3 g, dim3 b, F&& f) {
       }
     }
 }
+#define IX_KARG(T) const T&
 #define IX_LAUNCH(kern, grid, block, smem, stream, ...) \
   ix_emul_launch(dim3(grid), dim3(block), [&]() { kern(__VA_ARGS__); })
