@@ -1,0 +1,1262 @@
+// oracle.cpp -- TEST INFRASTRUCTURE, NOT PRODUCT.  See oracle.h for scope and the
+// "parity unpinned" statement.  CPU restatement of the IAMR hot path on one fully
+// periodic box.  Every function cites the reference call site it follows
+// (/root/reference = AMReX-Fluids/IAMR @ f46ba59; NSB.cpp =
+// Source/NavierStokesBase.cpp, NS.cpp = Source/NavierStokes.cpp) and, where the
+// arithmetic lives in the un-vendored AMReX / AMReX-Hydro, the upstream routine it
+// restates.
+//
+// Implementation notes: fields are stored with ghost layers and refreshed by an
+// explicit periodic fill, loops run over the interior with plain indexing (OpenMP
+// over k).  The Godunov part is written the way AMReX-Hydro stages it (Im/Ip ->
+// lo/hi -> upwinded edge -> corner-coupled -> final), i.e. deliberately NOT the
+// way the CUDA kernels are organised.
+#include "oracle.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <memory>
+#include <vector>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+namespace {
+
+struct Arr {
+  int n[3] = {0, 0, 0}, ng = 0, nc = 0;
+  long sj = 0, sk = 0, sc = 0;
+  std::vector<double> d;
+  Arr() {}
+  Arr(const int n_[3], int nc_, int ng_) { define(n_, nc_, ng_); }
+  void define(const int n_[3], int nc_, int ng_) {
+    for (int q = 0; q < 3; ++q) n[q] = n_[q];
+    nc = nc_; ng = ng_;
+    sj = n[0] + 2 * ng; sk = sj * (n[1] + 2 * ng); sc = sk * (n[2] + 2 * ng);
+    d.assign((size_t)sc * nc, 0.0);
+  }
+  inline double& operator()(int i, int j, int k, int c = 0) { return d[(i + ng) + (j + ng) * sj + (k + ng) * sk + c * sc]; }
+  inline double operator()(int i, int j, int k, int c = 0) const { return d[(i + ng) + (j + ng) * sj + (k + ng) * sk + c * sc]; }
+  void setval(double v) { std::fill(d.begin(), d.end(), v); }
+  // FabArray::FillBoundary(periodicity) for a single box covering the domain
+  void fill_periodic() {
+    if (ng == 0) return;
+    for (int c = 0; c < nc; ++c) {
+#pragma omp parallel for
+      for (int k = 0; k < n[2]; ++k)
+        for (int j = 0; j < n[1]; ++j)
+          for (int g = 1; g <= ng; ++g) { (*this)(-g, j, k, c) = (*this)(n[0] - g, j, k, c); (*this)(n[0] - 1 + g, j, k, c) = (*this)(g - 1, j, k, c); }
+#pragma omp parallel for
+      for (int k = 0; k < n[2]; ++k)
+        for (int g = 1; g <= ng; ++g)
+          for (int i = -ng; i < n[0] + ng; ++i) { (*this)(i, -g, k, c) = (*this)(i, n[1] - g, k, c); (*this)(i, n[1] - 1 + g, k, c) = (*this)(i, g - 1, k, c); }
+      for (int g = 1; g <= ng; ++g) {
+#pragma omp parallel for
+        for (int j = -ng; j < n[1] + ng; ++j)
+          for (int i = -ng; i < n[0] + ng; ++i) { (*this)(i, j, -g, c) = (*this)(i, j, n[2] - g, c); (*this)(i, j, n[2] - 1 + g, c) = (*this)(i, j, g - 1, c); }
+      }
+    }
+  }
+  void load(const double* src, int c0 = 0, int ncopy = -1) {  // dense [c][k][j][i] -> interior
+    if (ncopy < 0) ncopy = nc;
+    for (int c = 0; c < ncopy; ++c)
+#pragma omp parallel for
+      for (int k = 0; k < n[2]; ++k)
+        for (int j = 0; j < n[1]; ++j)
+          for (int i = 0; i < n[0]; ++i) (*this)(i, j, k, c0 + c) = src[i + (long)n[0] * (j + (long)n[1] * (k + (long)n[2] * c))];
+  }
+  void store(double* dst, int c0 = 0, int ncopy = -1) const {
+    if (ncopy < 0) ncopy = nc;
+    for (int c = 0; c < ncopy; ++c)
+#pragma omp parallel for
+      for (int k = 0; k < n[2]; ++k)
+        for (int j = 0; j < n[1]; ++j)
+          for (int i = 0; i < n[0]; ++i) dst[i + (long)n[0] * (j + (long)n[1] * (k + (long)n[2] * c))] = (*this)(i, j, k, c0 + c);
+  }
+  void copy_from(const Arr& s, int sc0, int dc0, int ncopy) {  // interior only
+    for (int c = 0; c < ncopy; ++c)
+#pragma omp parallel for
+      for (int k = 0; k < n[2]; ++k)
+        for (int j = 0; j < n[1]; ++j)
+          for (int i = 0; i < n[0]; ++i) (*this)(i, j, k, dc0 + c) = s(i, j, k, sc0 + c);
+  }
+  double norminf(int c) const {
+    double m = 0.0;
+#pragma omp parallel for reduction(max : m)
+    for (int k = 0; k < n[2]; ++k)
+      for (int j = 0; j < n[1]; ++j)
+        for (int i = 0; i < n[0]; ++i) m = std::max(m, std::fabs((*this)(i, j, k, c)));
+    return m;
+  }
+  double sum(int c) const {
+    double s = 0.0;
+#pragma omp parallel for reduction(+ : s)
+    for (int k = 0; k < n[2]; ++k)
+      for (int j = 0; j < n[1]; ++j)
+        for (int i = 0; i < n[0]; ++i) s += (*this)(i, j, k, c);
+    return s;
+  }
+  long ncells() const { return (long)n[0] * n[1] * n[2]; }
+};
+
+#define FOR_CELLS(A, i, j, k)                 \
+  _Pragma("omp parallel for") for (int k = 0; k < (A).n[2]; ++k) \
+    for (int j = 0; j < (A).n[1]; ++j)        \
+      for (int i = 0; i < (A).n[0]; ++i)
+
+// ===========================================================================
+// MLABecLaplacian  (AMReX MLABecLap_3D_K.H: mlabeclap_adotx / abec_gsrb; A.6)
+//   L phi = a*alpha*phi - b * sum_d [ beta_d(i+1)(phi(i+1)-phi(i)) - beta_d(i)(phi(i)-phi(i-1)) ] / h_d^2
+// ===========================================================================
+struct AbecOp {
+  double a = 0, b = 1;
+  const Arr* alpha = nullptr;
+  const Arr* beta[3] = {nullptr, nullptr, nullptr};  // face arrays with >= 1 ghost (filled)
+  int bncomp = 1;
+  double dxinv[3];
+};
+
+void abec_apply(const AbecOp& op, Arr& phi, Arr& out, int ncomp) {  // phi ghosts are filled here
+  phi.fill_periodic();
+  const double hx = op.b * op.dxinv[0] * op.dxinv[0], hy = op.b * op.dxinv[1] * op.dxinv[1], hz = op.b * op.dxinv[2] * op.dxinv[2];
+  for (int c = 0; c < ncomp; ++c) {
+    const int cb = op.bncomp > 1 ? c : 0;
+    const Arr &bx = *op.beta[0], &by = *op.beta[1], &bz = *op.beta[2];
+    FOR_CELLS(out, i, j, k) {
+      const double p = phi(i, j, k, c);
+      double y = -hx * (bx(i + 1, j, k, cb) * (phi(i + 1, j, k, c) - p) - bx(i, j, k, cb) * (p - phi(i - 1, j, k, c)))
+                 - hy * (by(i, j + 1, k, cb) * (phi(i, j + 1, k, c) - p) - by(i, j, k, cb) * (p - phi(i, j - 1, k, c)))
+                 - hz * (bz(i, j, k + 1, cb) * (phi(i, j, k + 1, c) - p) - bz(i, j, k, cb) * (p - phi(i, j, k - 1, c)));
+      if (op.a != 0.0) y += op.a * (*op.alpha)(i, j, k) * p;
+      out(i, j, k, c) = y;
+    }
+  }
+}
+
+// one colour of red-black Gauss-Seidel (abec_gsrb): cells with (i+j+k+redblack) even
+void abec_gsrb(const AbecOp& op, Arr& phi, const Arr& rhs, int ncomp, double omega, int redblack) {
+  phi.fill_periodic();
+  const double hx = op.b * op.dxinv[0] * op.dxinv[0], hy = op.b * op.dxinv[1] * op.dxinv[1], hz = op.b * op.dxinv[2] * op.dxinv[2];
+  for (int c = 0; c < ncomp; ++c) {
+    const int cb = op.bncomp > 1 ? c : 0;
+    const Arr &bx = *op.beta[0], &by = *op.beta[1], &bz = *op.beta[2];
+#pragma omp parallel for
+    for (int k = 0; k < phi.n[2]; ++k)
+      for (int j = 0; j < phi.n[1]; ++j) {
+        const int ioff = (j + k + redblack) & 1;
+        for (int i = ioff; i < phi.n[0]; i += 2) {
+          double gamma = hx * (bx(i, j, k, cb) + bx(i + 1, j, k, cb)) + hy * (by(i, j, k, cb) + by(i, j + 1, k, cb)) +
+                         hz * (bz(i, j, k, cb) + bz(i, j, k + 1, cb));
+          if (op.a != 0.0) gamma += op.a * (*op.alpha)(i, j, k);
+          const double rho = hx * (bx(i, j, k, cb) * phi(i - 1, j, k, c) + bx(i + 1, j, k, cb) * phi(i + 1, j, k, c)) +
+                             hy * (by(i, j, k, cb) * phi(i, j - 1, k, c) + by(i, j + 1, k, cb) * phi(i, j + 1, k, c)) +
+                             hz * (bz(i, j, k, cb) * phi(i, j, k - 1, c) + bz(i, j, k + 1, cb) * phi(i, j, k + 1, c));
+          const double res = rhs(i, j, k, c) - (gamma * phi(i, j, k, c) - rho);
+          phi(i, j, k, c) += omega / gamma * res;
+        }
+      }
+  }
+}
+
+// MLTensorOp cross terms (AMReX MLTensor_3D_K.H mltensor_cross_terms_f{x,y,z} with kappa = 0; A.8):
+// out += bscalar * div(F), F_x = (-eta*(-2/3)(dv/dy+dw/dz), -eta du/dy, -eta du/dz) on x-faces, etc.
+void tensor_cross(const double dxinv[3], double bscalar, const Arr& ex, const Arr& ey, const Arr& ez, Arr& vel, Arr& out) {
+  vel.fill_periodic();
+  const double dxi = dxinv[0], dyi = dxinv[1], dzi = dxinv[2];
+  Arr fx(vel.n, 3, 1), fy(vel.n, 3, 1), fz(vel.n, 3, 1);
+  FOR_CELLS(out, i, j, k) {
+    auto ddy_x = [&](int c) { return (vel(i, j + 1, k, c) + vel(i - 1, j + 1, k, c) - vel(i, j - 1, k, c) - vel(i - 1, j - 1, k, c)) * (0.25 * dyi); };
+    auto ddz_x = [&](int c) { return (vel(i, j, k + 1, c) + vel(i - 1, j, k + 1, c) - vel(i, j, k - 1, c) - vel(i - 1, j, k - 1, c)) * (0.25 * dzi); };
+    auto ddx_y = [&](int c) { return (vel(i + 1, j, k, c) + vel(i + 1, j - 1, k, c) - vel(i - 1, j, k, c) - vel(i - 1, j - 1, k, c)) * (0.25 * dxi); };
+    auto ddz_y = [&](int c) { return (vel(i, j, k + 1, c) + vel(i, j - 1, k + 1, c) - vel(i, j, k - 1, c) - vel(i, j - 1, k - 1, c)) * (0.25 * dzi); };
+    auto ddx_z = [&](int c) { return (vel(i + 1, j, k, c) + vel(i + 1, j, k - 1, c) - vel(i - 1, j, k, c) - vel(i - 1, j, k - 1, c)) * (0.25 * dxi); };
+    auto ddy_z = [&](int c) { return (vel(i, j + 1, k, c) + vel(i, j + 1, k - 1, c) - vel(i, j - 1, k, c) - vel(i, j - 1, k - 1, c)) * (0.25 * dyi); };
+    const double twoThirds = 2.0 / 3.0;
+    {
+      const double mu = ex(i, j, k);
+      fx(i, j, k, 0) = -mu * (-twoThirds * (ddy_x(1) + ddz_x(2)));
+      fx(i, j, k, 1) = -mu * ddy_x(0);
+      fx(i, j, k, 2) = -mu * ddz_x(0);
+    }
+    {
+      const double mu = ey(i, j, k);
+      fy(i, j, k, 0) = -mu * ddx_y(1);
+      fy(i, j, k, 1) = -mu * (-twoThirds * (ddx_y(0) + ddz_y(2)));
+      fy(i, j, k, 2) = -mu * ddz_y(1);
+    }
+    {
+      const double mu = ez(i, j, k);
+      fz(i, j, k, 0) = -mu * ddx_z(2);
+      fz(i, j, k, 1) = -mu * ddy_z(2);
+      fz(i, j, k, 2) = -mu * (-twoThirds * (ddx_z(0) + ddy_z(1)));
+    }
+  }
+  fx.fill_periodic(); fy.fill_periodic(); fz.fill_periodic();
+  for (int c = 0; c < 3; ++c) {
+    FOR_CELLS(out, i, j, k) {
+      out(i, j, k, c) += bscalar * (dxi * (fx(i + 1, j, k, c) - fx(i, j, k, c)) + dyi * (fy(i, j + 1, k, c) - fy(i, j, k, c)) +
+                                    dzi * (fz(i, j, k + 1, c) - fz(i, j, k, c)));
+    }
+  }
+}
+
+// ===========================================================================
+// Cell-centred geometric multigrid (AMReX MLMG V-cycle, A.7; MLCellLinOp restriction =
+// mean of 8 children, interpolation = piecewise-constant add; coefficient coarsening =
+// average_down (alpha) / average_down_faces (beta))
+// ===========================================================================
+struct CellMG {
+  struct Lev { int n[3]; double dxinv[3]; Arr alpha, beta[3], cor, res, rescor; };
+  std::vector<Lev> lv;
+  int ncomp, bncomp;
+  bool tensor;
+  double a = 0, b = 1;
+  const Arr* eta[3] = {nullptr, nullptr, nullptr};
+  orc_mg mg;
+  bool singular = false;
+
+  CellMG(const int n[3], const double dx[3], int ncomp_, bool tensor_, int max_coarsening) : ncomp(ncomp_), tensor(tensor_) {
+    bncomp = tensor ? ncomp : 1;
+    orc_mg_default(&mg);
+    int cur[3] = {n[0], n[1], n[2]};
+    double h[3] = {dx[0], dx[1], dx[2]};
+    for (int l = 0; l <= max_coarsening; ++l) {
+      lv.emplace_back();
+      Lev& L = lv.back();
+      for (int d = 0; d < 3; ++d) { L.n[d] = cur[d]; L.dxinv[d] = 1.0 / h[d]; }
+      L.cor.define(cur, ncomp, 1); L.res.define(cur, ncomp, 0); L.rescor.define(cur, ncomp, 0);
+      bool ok = true;
+      for (int d = 0; d < 3; ++d) if (cur[d] % 2 != 0 || cur[d] / 2 < 2) ok = false;
+      if (!ok) break;
+      for (int d = 0; d < 3; ++d) { cur[d] /= 2; h[d] *= 2.0; }
+    }
+  }
+  AbecOp op(int l) const {
+    AbecOp o; o.a = a; o.b = b; o.alpha = (a != 0.0) ? &lv[l].alpha : nullptr;
+    for (int d = 0; d < 3; ++d) { o.beta[d] = &lv[l].beta[d]; o.dxinv[d] = lv[l].dxinv[d]; }
+    o.bncomp = bncomp;
+    return o;
+  }
+  void set_coeffs(const Arr* alpha, const Arr* e[3]) {
+    for (int d = 0; d < 3; ++d) eta[d] = e[d];
+    Lev& F = lv[0];
+    if (a != 0.0 && alpha) { F.alpha.define(F.n, 1, 0); F.alpha.copy_from(*alpha, 0, 0, 1); }
+    for (int d = 0; d < 3; ++d) {
+      F.beta[d].define(F.n, bncomp, 1);
+      for (int c = 0; c < bncomp; ++c) {
+        const double fac = (tensor && c == d) ? 4.0 / 3.0 : 1.0;  // MLTensorOp: (4/3)eta + kappa on the normal component
+        Arr& B = F.beta[d]; const Arr& E = *e[d];
+        FOR_CELLS(B, i, j, k) B(i, j, k, c) = fac * E(i, j, k);
+      }
+      F.beta[d].fill_periodic();
+    }
+    for (size_t l = 1; l < lv.size(); ++l) {
+      Lev& C = lv[l]; Lev& Fi = lv[l - 1];
+      if (a != 0.0 && alpha) {
+        C.alpha.define(C.n, 1, 0);
+        Arr& ca = C.alpha; const Arr& fa = Fi.alpha;
+        FOR_CELLS(ca, i, j, k) {
+          double s = 0; for (int dk = 0; dk < 2; ++dk) for (int dj = 0; dj < 2; ++dj) for (int di = 0; di < 2; ++di) s += fa(2 * i + di, 2 * j + dj, 2 * k + dk);
+          ca(i, j, k) = 0.125 * s;
+        }
+      }
+      for (int d = 0; d < 3; ++d) {
+        C.beta[d].define(C.n, bncomp, 1);
+        Arr& cb = C.beta[d]; const Arr& fb = Fi.beta[d];
+        for (int c = 0; c < bncomp; ++c) {
+          FOR_CELLS(cb, i, j, k) {
+            const int ii = 2 * i, jj = 2 * j, kk = 2 * k;
+            double s;
+            if (d == 0) s = fb(ii, jj, kk, c) + fb(ii, jj + 1, kk, c) + fb(ii, jj, kk + 1, c) + fb(ii, jj + 1, kk + 1, c);
+            else if (d == 1) s = fb(ii, jj, kk, c) + fb(ii + 1, jj, kk, c) + fb(ii, jj, kk + 1, c) + fb(ii + 1, jj, kk + 1, c);
+            else s = fb(ii, jj, kk, c) + fb(ii + 1, jj, kk, c) + fb(ii, jj + 1, kk, c) + fb(ii + 1, jj + 1, kk, c);
+            cb(i, j, k, c) = 0.25 * s;
+          }
+        }
+        cb.fill_periodic();
+      }
+    }
+    singular = (a == 0.0);  // all-periodic: the operator annihilates constants
+  }
+  void smooth(int l, Arr& phi, const Arr& rhs, int nsweeps) {
+    const AbecOp o = op(l);
+    for (int s = 0; s < nsweeps; ++s)
+      for (int rb = 0; rb < 2; ++rb) abec_gsrb(o, phi, rhs, ncomp, mg.omega, rb);
+  }
+  void residual(int l, Arr& out, Arr& phi, const Arr& rhs, bool cross) {
+    abec_apply(op(l), phi, out, ncomp);
+    if (tensor && l == 0 && cross) tensor_cross(lv[0].dxinv, b, *eta[0], *eta[1], *eta[2], phi, out);
+    for (int c = 0; c < ncomp; ++c) { FOR_CELLS(out, i, j, k) out(i, j, k, c) = rhs(i, j, k, c) - out(i, j, k, c); }
+  }
+  void apply(Arr& out, Arr& phi) {
+    abec_apply(op(0), phi, out, ncomp);
+    if (tensor) tensor_cross(lv[0].dxinv, b, *eta[0], *eta[1], *eta[2], phi, out);
+  }
+  void make_solvable(Arr& r) {
+    for (int c = 0; c < ncomp; ++c) {
+      const double mean = r.sum(c) / (double)r.ncells();
+      FOR_CELLS(r, i, j, k) r(i, j, k, c) -= mean;
+    }
+  }
+  void vcycle() {
+    const int nl = (int)lv.size();
+    for (int l = 0; l < nl - 1; ++l) {
+      Lev& L = lv[l];
+      L.cor.setval(0.0);
+      smooth(l, L.cor, L.res, mg.nu1);
+      residual(l, L.rescor, L.cor, L.res, false);
+      Arr& cr = lv[l + 1].res; const Arr& fr = L.rescor;
+      for (int c = 0; c < ncomp; ++c) {
+        FOR_CELLS(cr, i, j, k) {
+          double s = 0; for (int dk = 0; dk < 2; ++dk) for (int dj = 0; dj < 2; ++dj) for (int di = 0; di < 2; ++di) s += fr(2 * i + di, 2 * j + dj, 2 * k + dk, c);
+          cr(i, j, k, c) = 0.125 * s;
+        }
+      }
+    }
+    Lev& B = lv[nl - 1];
+    B.cor.setval(0.0);
+    if (singular && nl > 1) make_solvable(B.res);
+    smooth(nl - 1, B.cor, B.res, nl == 1 ? mg.nu1 + mg.nu2 : mg.bottom_sweeps);
+    for (int l = nl - 2; l >= 0; --l) {
+      Arr& fc = lv[l].cor; const Arr& cc = lv[l + 1].cor;
+      for (int c = 0; c < ncomp; ++c) { FOR_CELLS(fc, i, j, k) fc(i, j, k, c) += cc(i / 2, j / 2, k / 2, c); }
+      smooth(l, fc, lv[l].res, mg.nu2);
+    }
+  }
+  int solve(Arr& sol, const Arr& rhs_in) {
+    Arr rhs(lv[0].n, ncomp, 0);
+    rhs.copy_from(rhs_in, 0, 0, ncomp);
+    if (singular) make_solvable(rhs);
+    double rhsnorm = 0; for (int c = 0; c < ncomp; ++c) rhsnorm = std::max(rhsnorm, rhs.norminf(c));
+    Arr& res = lv[0].res;
+    residual(0, res, sol, rhs, true);
+    double r0 = 0; for (int c = 0; c < ncomp; ++c) r0 = std::max(r0, res.norminf(c));
+    const double target = std::max(mg.atol, mg.rtol * std::max(rhsnorm, r0));
+    double r = r0; int it = 0; int rc = 0;
+    if (!(r0 <= target)) {
+      rc = mg.max_iter;
+      for (it = 1; it <= mg.max_iter; ++it) {
+        vcycle();
+        Arr& cor = lv[0].cor;
+        for (int c = 0; c < ncomp; ++c) { FOR_CELLS(sol, i, j, k) sol(i, j, k, c) += cor(i, j, k, c); }
+        residual(0, res, sol, rhs, true);
+        r = 0; for (int c = 0; c < ncomp; ++c) r = std::max(r, res.norminf(c));
+        if (r <= target) { rc = 0; break; }
+      }
+    }
+    sol.fill_periodic();
+    mg.iters = it; mg.resnorm0 = r0; mg.resnorm = r; mg.rhsnorm = rhsnorm;
+    return rc;
+  }
+};
+
+// ===========================================================================
+// MLNodeLaplacian (A.9): Q1 finite elements, one sigma per cell.  The operator is
+// assembled here from the element stiffness matrices (1-D stiffness x 1-D mass
+// tensor products) instead of a hand-expanded 27-point formula:
+//   (A phi)_node = -(1/vol) * sum_{8 cells} sigma_cell * sum_{corners m} K_cell[node,m] phi_m
+// ===========================================================================
+struct Q1 {
+  double K[8][8];  // element stiffness / volume, corners ordered (cx + 2cy + 4cz)
+  explicit Q1(const double dxinv[3]) {
+    const double S[2][2] = {{1, -1}, {-1, 1}};         // 1-D stiffness * h
+    const double M[2][2] = {{2. / 6, 1. / 6}, {1. / 6, 2. / 6}};  // 1-D mass / h
+    for (int a = 0; a < 8; ++a)
+      for (int b = 0; b < 8; ++b) {
+        const int ax = a & 1, ay = (a >> 1) & 1, az = a >> 2, bx = b & 1, by = (b >> 1) & 1, bz = b >> 2;
+        K[a][b] = dxinv[0] * dxinv[0] * S[ax][bx] * M[ay][by] * M[az][bz] + dxinv[1] * dxinv[1] * M[ax][bx] * S[ay][by] * M[az][bz] +
+                  dxinv[2] * dxinv[2] * M[ax][bx] * M[ay][by] * S[az][bz];
+      }
+  }
+};
+
+// returns A*phi at node (i,j,k) and the diagonal coefficient; sig has ghosts filled
+inline double nodal_ax(const Q1& q, const Arr& sig, const Arr& phi, int i, int j, int k, double& diag) {
+  double y = 0.0; diag = 0.0;
+  for (int cz = 0; cz < 2; ++cz) for (int cy = 0; cy < 2; ++cy) for (int cx = 0; cx < 2; ++cx) {
+    // cell whose corner (cx,cy,cz) is this node
+    const int ci = i - cx, cj = j - cy, ck = k - cz;
+    const double s = sig(ci, cj, ck);
+    const int a = cx + 2 * cy + 4 * cz;
+    for (int m = 0; m < 8; ++m) {
+      const int mx = m & 1, my = (m >> 1) & 1, mz = m >> 2;
+      y -= s * q.K[a][m] * phi(ci + mx, cj + my, ck + mz);
+    }
+    diag -= s * q.K[a][a];
+  }
+  return y;
+}
+
+void nodal_adotx(const double dxinv[3], Arr& sig, Arr& phi, Arr& out) {
+  phi.fill_periodic();
+  const Q1 q(dxinv);
+  FOR_CELLS(out, i, j, k) { double dg; out(i, j, k) = nodal_ax(q, sig, phi, i, j, k, dg); }
+}
+
+// multi-colour Gauss-Seidel: colour = (i&1) + 2(j&1) + 4(k&1); nodes of one colour are
+// mutually uncoupled under the 27-point stencil (even n per direction)
+void nodal_gs(const double dxinv[3], Arr& sig, const Arr& rhs, int color, Arr& phi) {
+  phi.fill_periodic();
+  const Q1 q(dxinv);
+  const int c0 = color & 1, c1 = (color >> 1) & 1, c2 = (color >> 2) & 1;
+#pragma omp parallel for
+  for (int k = c2; k < phi.n[2]; k += 2)
+    for (int j = c1; j < phi.n[1]; j += 2)
+      for (int i = c0; i < phi.n[0]; i += 2) {
+        double dg; const double y = nodal_ax(q, sig, phi, i, j, k, dg);
+        phi(i, j, k) += (rhs(i, j, k) - y) / dg;
+      }
+}
+
+// FE divergence of a piecewise-constant velocity (NodalProjector computeRHS / mlndlap_divu)
+void nodal_divu(const double dxinv[3], Arr& vel, Arr& rhs) {
+  vel.fill_periodic();
+  FOR_CELLS(rhs, i, j, k) {
+    double r = 0.0;
+    for (int cz = 0; cz < 2; ++cz) for (int cy = 0; cy < 2; ++cy) for (int cx = 0; cx < 2; ++cx) {
+      const int ci = i - cx, cj = j - cy, ck = k - cz;
+      r += 0.25 * ((cx ? -1.0 : 1.0) * dxinv[0] * vel(ci, cj, ck, 0) + (cy ? -1.0 : 1.0) * dxinv[1] * vel(ci, cj, ck, 1) +
+                   (cz ? -1.0 : 1.0) * dxinv[2] * vel(ci, cj, ck, 2));
+    }
+    rhs(i, j, k) = r;
+  }
+}
+
+// cell-centred gradient of nodal phi (mlndlap_mknewu / compGrad): mean of the 4 parallel edge differences
+void nodal_grad(const double dxinv[3], Arr& phi, Arr& g) {
+  phi.fill_periodic();
+  FOR_CELLS(g, i, j, k) {
+    double gx = 0, gy = 0, gz = 0;
+    for (int b = 0; b < 2; ++b) for (int a = 0; a < 2; ++a) {
+      gx += phi(i + 1, j + a, k + b) - phi(i, j + a, k + b);
+      gy += phi(i + a, j + 1, k + b) - phi(i + a, j, k + b);
+      gz += phi(i + a, j + b, k + 1) - phi(i + a, j + b, k);
+    }
+    g(i, j, k, 0) = 0.25 * dxinv[0] * gx; g(i, j, k, 1) = 0.25 * dxinv[1] * gy; g(i, j, k, 2) = 0.25 * dxinv[2] * gz;
+  }
+}
+
+struct NodeMG {
+  struct Lev { int n[3]; double dxinv[3]; Arr sig, cor, res, rescor; };
+  std::vector<Lev> lv;
+  orc_mg mg;
+  NodeMG(const int n[3], const double dx[3], int max_coarsening) {
+    orc_mg_default(&mg);
+    int cur[3] = {n[0], n[1], n[2]}; double h[3] = {dx[0], dx[1], dx[2]};
+    for (int l = 0; l <= max_coarsening; ++l) {
+      lv.emplace_back();
+      Lev& L = lv.back();
+      for (int d = 0; d < 3; ++d) { L.n[d] = cur[d]; L.dxinv[d] = 1.0 / h[d]; }
+      L.sig.define(cur, 1, 1); L.cor.define(cur, 1, 1); L.res.define(cur, 1, 1); L.rescor.define(cur, 1, 1);
+      bool ok = true;
+      for (int d = 0; d < 3; ++d) if (cur[d] % 2 != 0 || cur[d] / 2 < 2) ok = false;
+      if (!ok) break;
+      for (int d = 0; d < 3; ++d) { cur[d] /= 2; h[d] *= 2.0; }
+    }
+  }
+  void set_sigma(const Arr& s) {
+    lv[0].sig.copy_from(s, 0, 0, 1); lv[0].sig.fill_periodic();
+    for (size_t l = 1; l < lv.size(); ++l) {  // coarse sigma = mean of the 8 children
+      Arr& c = lv[l].sig; const Arr& f = lv[l - 1].sig;
+      FOR_CELLS(c, i, j, k) {
+        double t = 0; for (int dk = 0; dk < 2; ++dk) for (int dj = 0; dj < 2; ++dj) for (int di = 0; di < 2; ++di) t += f(2 * i + di, 2 * j + dj, 2 * k + dk);
+        c(i, j, k) = 0.125 * t;
+      }
+      c.fill_periodic();
+    }
+  }
+  void smooth(int l, Arr& phi, const Arr& rhs, int ns) {
+    for (int s = 0; s < ns; ++s) for (int c = 0; c < 8; ++c) nodal_gs(lv[l].dxinv, lv[l].sig, rhs, c, phi);
+  }
+  void residual(int l, Arr& out, Arr& phi, const Arr& rhs) {
+    nodal_adotx(lv[l].dxinv, lv[l].sig, phi, out);
+    FOR_CELLS(out, i, j, k) out(i, j, k) = rhs(i, j, k) - out(i, j, k);
+  }
+  void vcycle() {
+    const int nl = (int)lv.size();
+    for (int l = 0; l < nl - 1; ++l) {
+      Lev& L = lv[l];
+      L.cor.setval(0.0);
+      smooth(l, L.cor, L.res, mg.nu1);
+      residual(l, L.rescor, L.cor, L.res);
+      L.rescor.fill_periodic();
+      Arr& cr = lv[l + 1].res; const Arr& fr = L.rescor;
+      FOR_CELLS(cr, i, j, k) {  // full weighting (1,2,1)^3 / 64
+        double s = 0;
+        for (int dk = -1; dk <= 1; ++dk) for (int dj = -1; dj <= 1; ++dj) for (int di = -1; di <= 1; ++di)
+          s += (double)((di ? 1 : 2) * (dj ? 1 : 2) * (dk ? 1 : 2)) * fr(2 * i + di, 2 * j + dj, 2 * k + dk);
+        cr(i, j, k) = s / 64.0;
+      }
+    }
+    Lev& B = lv[nl - 1];
+    B.cor.setval(0.0);
+    smooth(nl - 1, B.cor, B.res, nl == 1 ? mg.nu1 + mg.nu2 : mg.bottom_sweeps);
+    for (int l = nl - 2; l >= 0; --l) {
+      Arr& fc = lv[l].cor; Arr& cc = lv[l + 1].cor;
+      cc.fill_periodic();
+      FOR_CELLS(fc, i, j, k) {  // trilinear interpolation
+        const int ic = i / 2, jc = j / 2, kc = k / 2, ox = i & 1, oy = j & 1, oz = k & 1;
+        double s = 0;
+        for (int dk = 0; dk <= oz; ++dk) for (int dj = 0; dj <= oy; ++dj) for (int di = 0; di <= ox; ++di) s += cc(ic + di, jc + dj, kc + dk);
+        fc(i, j, k) += s / (double)((1 + ox) * (1 + oy) * (1 + oz));
+      }
+      smooth(l, fc, lv[l].res, mg.nu2);
+    }
+  }
+  int solve(Arr& phi, Arr& rhs) {
+    {  // periodic => singular: remove the mean of the rhs
+      const double mean = rhs.sum(0) / (double)rhs.ncells();
+      FOR_CELLS(rhs, i, j, k) rhs(i, j, k) -= mean;
+    }
+    const double rhsnorm = rhs.norminf(0);
+    Arr& res = lv[0].res;
+    residual(0, res, phi, rhs);
+    const double r0 = res.norminf(0);
+    const double target = std::max(mg.atol, mg.rtol * std::max(rhsnorm, r0));
+    double r = r0; int it = 0; int rc = 0;
+    if (!(r0 <= target)) {
+      rc = mg.max_iter;
+      for (it = 1; it <= mg.max_iter; ++it) {
+        vcycle();
+        Arr& cor = lv[0].cor;
+        FOR_CELLS(phi, i, j, k) phi(i, j, k) += cor(i, j, k);
+        residual(0, res, phi, rhs);
+        r = res.norminf(0);
+        if (r <= target) { rc = 0; break; }
+      }
+    }
+    phi.fill_periodic();
+    mg.iters = it; mg.resnorm0 = r0; mg.resnorm = r; mg.rhsnorm = rhsnorm;
+    return rc;
+  }
+};
+
+// ===========================================================================
+// Godunov PLM (AMReX-Hydro hydro_godunov_plm.cpp, hydro_godunov_edge_state_3D.cpp,
+// hydro_godunov_extrap_vel_to_faces_3D.cpp, hydro_godunov_corner_couple.H,
+// AMReX_Slopes_K.H; A.2-A.5), periodic boundaries only.
+// ===========================================================================
+const double small_vel = 1.0e-8;
+
+inline double limited2(double dl, double dr) {  // 2nd-order monotonised central difference
+  const double dc = 0.5 * (dl + dr);
+  const double lim = (dl * dr >= 0.0) ? 2.0 * std::min(std::fabs(dl), std::fabs(dr)) : 0.0;
+  return std::copysign(1.0, dc) * std::min(lim, std::fabs(dc));
+}
+// amrex_calc_{x,y,z}slope, order 4: q values at i-2..i+2 along the direction
+inline double slope_order4(double qmm, double qm, double q0, double qp, double qpp) {
+  const double dfm = limited2(qm - qmm, q0 - qm);
+  const double dfp = limited2(qp - q0, qpp - qp);
+  const double dl = q0 - qm, dr = qp - q0, dc = 0.5 * (dl + dr);
+  const double lim = (dl * dr >= 0.0) ? 2.0 * std::min(std::fabs(dl), std::fabs(dr)) : 0.0;
+  const double d4 = 4.0 / 3.0 * dc - 1.0 / 6.0 * (dfp + dfm);
+  return std::copysign(1.0, dc) * std::min(lim, std::fabs(d4));
+}
+inline int e0(int d) { return d == 0; }
+inline int e1(int d) { return d == 1; }
+inline int e2(int d) { return d == 2; }
+
+inline double upwind_by(double lo, double hi, double vel) {  // ComputeEdgeState-style upwinding
+  const double st = (vel >= 0.0) ? lo : hi;
+  const double fu = (std::fabs(vel) < small_vel) ? 0.0 : 1.0;
+  return fu * st + (1.0 - fu) * 0.5 * (hi + lo);
+}
+inline double riemann_self(double lo, double hi) {  // normal velocity upwinded by itself
+  const double st = ((lo + hi) >= 0.0) ? lo : hi;
+  const bool ltm = ((lo <= 0.0 && hi >= 0.0) || (std::fabs(lo + hi) < small_vel));
+  return ltm ? 0.0 : st;
+}
+
+// loop over faces of direction-independent "grown by 1" range (all arrays have >= 1 ghost)
+#define FOR_G1(A, i, j, k)                                        \
+  _Pragma("omp parallel for") for (int k = -1; k <= (A).n[2]; ++k) \
+    for (int j = -1; j <= (A).n[1]; ++j)                          \
+      for (int i = -1; i <= (A).n[0]; ++i)
+
+// PLM traced states on d-faces for component c: lo = Ip(cell below), hi = Im(cell above).
+// trace velocity: umac on the face (edge state) or the cell-centred normal velocity (vel prediction).
+void plm_lohi(const Arr& q, int c, int d, double dtdx, const Arr* mac, const Arr* vcc, const Arr* f, int fc, bool fit, double dt,
+              Arr& lo, Arr& hi) {
+  Arr s(q.n, 1, 1);
+  // slopes on cells -1..n (what the faces 0..n of direction d touch); needs q on -3..n+2
+#pragma omp parallel for
+  for (int k = -1; k <= q.n[2]; ++k)
+    for (int j = -1; j <= q.n[1]; ++j)
+      for (int i = -1; i <= q.n[0]; ++i)
+        s(i, j, k) = slope_order4(q(i - 2 * e0(d), j - 2 * e1(d), k - 2 * e2(d), c), q(i - e0(d), j - e1(d), k - e2(d), c), q(i, j, k, c),
+                                  q(i + e0(d), j + e1(d), k + e2(d), c), q(i + 2 * e0(d), j + 2 * e1(d), k + 2 * e2(d), c));
+  // faces 0..n along d, -1..n in the transverse directions
+#pragma omp parallel for
+  for (int k = -1 + e2(d); k <= q.n[2]; ++k)
+    for (int j = -1 + e1(d); j <= q.n[1]; ++j)
+      for (int i = -1 + e0(d); i <= q.n[0]; ++i) {
+    const int im = i - e0(d), jm = j - e1(d), km = k - e2(d);
+    const double ul = mac ? (*mac)(i, j, k) : (*vcc)(im, jm, km, d);
+    const double uh = mac ? (*mac)(i, j, k) : (*vcc)(i, j, k, d);
+    double l = q(im, jm, km, c) + 0.5 * (1.0 - ul * dtdx) * s(im, jm, km);
+    double h = q(i, j, k, c) + 0.5 * (-1.0 - uh * dtdx) * s(i, j, k);
+    if (fit && f) { l += 0.5 * dt * (*f)(im, jm, km, fc); h += 0.5 * dt * (*f)(i, j, k, fc); }
+    lo(i, j, k) = l; hi(i, j, k) = h;
+  }
+}
+
+// Godunov_corner_couple_<d1><d2>: d1-face lo/hi states corrected with the d2-derivative of the
+// (already upwinded) d2-edge state, then upwinded with the d1 face velocity
+void corner_couple(const Arr& lo, const Arr& hi, int d1, int d2, double dt3dx, bool conserv, const Arr& q, int c, const Arr& mac2,
+                   const Arr& edge2, const Arr& mac1, Arr& out) {
+  const int n0 = q.n[0], n1 = q.n[1], n2 = q.n[2];
+#pragma omp parallel for
+  for (int k = -1 + e2(d2); k <= n2 - e2(d2); ++k)
+    for (int j = -1 + e1(d2); j <= n1 - e1(d2); ++j)
+      for (int i = -1 + e0(d2); i <= n0 - e0(d2); ++i) {
+        const int im = i - e0(d1), jm = j - e1(d1), km = k - e2(d1);
+        if (im < -1 || jm < -1 || km < -1) continue;
+        const int ip = e0(d2), jp = e1(d2), kp = e2(d2);
+        double l = lo(i, j, k) - dt3dx * (edge2(im + ip, jm + jp, km + kp) * mac2(im + ip, jm + jp, km + kp) - edge2(im, jm, km) * mac2(im, jm, km));
+        double h = hi(i, j, k) - dt3dx * (edge2(i + ip, j + jp, k + kp) * mac2(i + ip, j + jp, k + kp) - edge2(i, j, k) * mac2(i, j, k));
+        if (!conserv) {
+          l += dt3dx * q(im, jm, km, c) * (mac2(im + ip, jm + jp, km + kp) - mac2(im, jm, km));
+          h += dt3dx * q(i, j, k, c) * (mac2(i + ip, j + jp, k + kp) - mac2(i, j, k));
+        }
+        out(i, j, k) = upwind_by(l, h, mac1(i, j, k));
+      }
+}
+
+// HydroUtils::ComputeFluxesOnBoxFromState -> Godunov::ComputeEdgeState for one component:
+// fills the final edge states edge[d] (1 comp) on the low faces of every cell
+void edge_state_comp(const Arr& q, int c, const Arr* f, int fc, const Arr* divu, const Arr* mac[3], bool conserv, bool fit,
+                     const double dx[3], double dt, Arr* edge[3]) {
+  const int* n = q.n;
+  Arr lo[3], hi[3], ed[3];
+  for (int d = 0; d < 3; ++d) {
+    lo[d].define(n, 1, 2); hi[d].define(n, 1, 2); ed[d].define(n, 1, 2);
+    plm_lohi(q, c, d, dt / dx[d], mac[d], nullptr, f, fc, fit, dt, lo[d], hi[d]);
+    Arr& E = ed[d]; const Arr& M = *mac[d]; const Arr &L = lo[d], &H = hi[d];
+    FOR_G1(E, i, j, k) E(i, j, k) = upwind_by(L(i, j, k), H(i, j, k), M(i, j, k));
+  }
+  // six corner-coupled states cc[d1][d2] (d1-face state corrected by the d2 derivative)
+  Arr cc[3][3];
+  for (int d1 = 0; d1 < 3; ++d1)
+    for (int d2 = 0; d2 < 3; ++d2) {
+      if (d1 == d2) continue;
+      cc[d1][d2].define(n, 1, 2);
+      corner_couple(lo[d1], hi[d1], d1, d2, dt / (3.0 * dx[d2]), conserv, q, c, *mac[d2], ed[d2], *mac[d1], cc[d1][d2]);
+    }
+  for (int d = 0; d < 3; ++d) {
+    const int t1 = (d == 0) ? 1 : 0, t2 = (d == 2) ? 1 : 2;  // the two transverse directions
+    // transverse d/dt1 uses the t1-face state that was corrected by the t2 derivative, and vice versa
+    const Arr &A1 = cc[t1][t2], &A2 = cc[t2][t1], &M1 = *mac[t1], &M2 = *mac[t2], &M = *mac[d];
+    const double dtd1 = dt / dx[t1], dtd2 = dt / dx[t2];
+    Arr& E = *edge[d];
+    FOR_CELLS(E, i, j, k) {
+      double st[2];
+      for (int side = 0; side < 2; ++side) {  // 0: from the cell below (stl), 1: from the cell above (sth)
+        const int ci = i - (side == 0 ? e0(d) : 0), cj = j - (side == 0 ? e1(d) : 0), ck = k - (side == 0 ? e2(d) : 0);
+        const int i1 = ci + e0(t1), j1 = cj + e1(t1), k1 = ck + e2(t1), i2 = ci + e0(t2), j2 = cj + e1(t2), k2 = ck + e2(t2);
+        double s = (side == 0) ? lo[d](i, j, k) : hi[d](i, j, k);
+        if (conserv) {
+          s += -(0.5 * dtd1) * (A1(i1, j1, k1) * M1(i1, j1, k1) - A1(ci, cj, ck) * M1(ci, cj, ck))
+               - (0.5 * dtd2) * (A2(i2, j2, k2) * M2(i2, j2, k2) - A2(ci, cj, ck) * M2(ci, cj, ck))
+               + (0.5 * dtd1) * q(ci, cj, ck, c) * (M1(i1, j1, k1) - M1(ci, cj, ck))
+               + (0.5 * dtd2) * q(ci, cj, ck, c) * (M2(i2, j2, k2) - M2(ci, cj, ck));
+          if (divu) s -= 0.5 * dt * q(ci, cj, ck, c) * (*divu)(ci, cj, ck);
+        } else {
+          s += -(0.25 * dtd1) * (M1(i1, j1, k1) + M1(ci, cj, ck)) * (A1(i1, j1, k1) - A1(ci, cj, ck))
+               - (0.25 * dtd2) * (M2(i2, j2, k2) + M2(ci, cj, ck)) * (A2(i2, j2, k2) - A2(ci, cj, ck));
+        }
+        if (!fit && f) s += 0.5 * dt * (*f)(ci, cj, ck, fc);
+        st[side] = s;
+      }
+      E(i, j, k) = upwind_by(st[0], st[1], M(i, j, k));
+    }
+  }
+}
+
+// NavierStokesBase::ComputeAofs body, non-EB, !is_sync (NSB.cpp:4661-4845)
+void compute_aofs(const Arr& S, int ncomp, const Arr* force, const Arr* divu, Arr mac[3], const int* iconserv, bool fit,
+                  const double dx[3], double dt, Arr& aofs, int acomp, Arr* fl[3], Arr* eds[3]) {
+  const int* n = S.n;
+  const Arr* macp[3] = {&mac[0], &mac[1], &mac[2]};
+  const double area[3] = {dx[1] * dx[2], dx[0] * dx[2], dx[0] * dx[1]};
+  const double vol = dx[0] * dx[1] * dx[2];
+  for (int c = 0; c < ncomp; ++c) {
+    Arr ed[3] = {Arr(n, 1, 1), Arr(n, 1, 1), Arr(n, 1, 1)};
+    Arr* edp[3] = {&ed[0], &ed[1], &ed[2]};
+    edge_state_comp(S, c, force, c, divu, macp, iconserv[c] != 0, fit, dx, dt, edp);
+    Arr fx[3] = {Arr(n, 1, 1), Arr(n, 1, 1), Arr(n, 1, 1)};
+    for (int d = 0; d < 3; ++d) {
+      Arr& F = fx[d]; const Arr& E = ed[d]; const Arr& M = mac[d];
+      FOR_CELLS(F, i, j, k) F(i, j, k) = E(i, j, k) * M(i, j, k) * area[d];  // HydroUtils::ComputeFluxes, area-weighted (NSB.cpp:4651)
+      F.fill_periodic(); ed[d].fill_periodic();
+    }
+    const bool cons = iconserv[c] != 0;
+    FOR_CELLS(aofs, i, j, k) {
+      // ComputeDivergence(mult = -1, area-weighted fluxes) NSB.cpp:4753-4771
+      double upd = -((fx[0](i + 1, j, k) - fx[0](i, j, k)) + (fx[1](i, j + 1, k) - fx[1](i, j, k)) + (fx[2](i, j, k + 1) - fx[2](i, j, k))) / vol;
+      if (!cons) {  // ComputeConvectiveTerm NSB.cpp:4809-4820
+        const double divum = (mac[0](i + 1, j, k) - mac[0](i, j, k)) / dx[0] + (mac[1](i, j + 1, k) - mac[1](i, j, k)) / dx[1] +
+                             (mac[2](i, j, k + 1) - mac[2](i, j, k)) / dx[2];
+        const double qavg = (ed[0](i, j, k) + ed[0](i + 1, j, k) + ed[1](i, j, k) + ed[1](i, j + 1, k) + ed[2](i, j, k) + ed[2](i, j, k + 1)) / 6.0;
+        upd += qavg * divum;
+      }
+      aofs(i, j, k, acomp + c) = -upd;  // NSB.cpp:4840
+    }
+    for (int d = 0; d < 3; ++d) {
+      if (fl && fl[d]) fl[d]->copy_from(fx[d], 0, c, 1);
+      if (eds && eds[d]) eds[d]->copy_from(ed[d], 0, c, 1);
+    }
+  }
+}
+
+// Godunov::ExtrapVelToFaces (hydro_godunov_extrap_vel_to_faces_3D.cpp), PLM, periodic
+void extrap_vel_to_faces(const Arr& vel, const Arr* f, bool fit, const double dx[3], double dt, Arr umac[3]) {
+  const int* n = vel.n;
+  // traced states of every component on every face direction
+  Arr lo[3][3], hi[3][3];  // [dir][comp]
+  for (int d = 0; d < 3; ++d)
+    for (int c = 0; c < 3; ++c) {
+      lo[d][c].define(n, 1, 2); hi[d][c].define(n, 1, 2);
+      plm_lohi(vel, c, d, dt / dx[d], nullptr, &vel, f, c, fit, dt, lo[d][c], hi[d][c]);
+    }
+  // advective velocities (ComputeAdvectiveVel) and transverse edge states upwinded by them
+  Arr ad[3], ed[3][3];
+  for (int d = 0; d < 3; ++d) {
+    ad[d].define(n, 1, 2);
+    Arr& A = ad[d]; const Arr &L = lo[d][d], &H = hi[d][d];
+    FOR_G1(A, i, j, k) A(i, j, k) = riemann_self(L(i, j, k), H(i, j, k));
+    for (int c = 0; c < 3; ++c) {
+      ed[d][c].define(n, 1, 2);
+      Arr& E = ed[d][c]; const Arr &Lc = lo[d][c], &Hc = hi[d][c];
+      FOR_G1(E, i, j, k) E(i, j, k) = upwind_by(Lc(i, j, k), Hc(i, j, k), A(i, j, k));
+    }
+  }
+  for (int d = 0; d < 3; ++d) {
+    const int t1 = (d == 0) ? 1 : 0, t2 = (d == 2) ? 1 : 2;
+    Arr a1(n, 1, 2), a2(n, 1, 2);  // t1-face state of comp d corrected by t2, and t2-face state corrected by t1
+    corner_couple(lo[t1][d], hi[t1][d], t1, t2, dt / (3.0 * dx[t2]), false, vel, d, ad[t2], ed[t2][d], ad[t1], a1);
+    corner_couple(lo[t2][d], hi[t2][d], t2, t1, dt / (3.0 * dx[t1]), false, vel, d, ad[t1], ed[t1][d], ad[t2], a2);
+    const double dtd1 = dt / dx[t1], dtd2 = dt / dx[t2];
+    const Arr &M1 = ad[t1], &M2 = ad[t2];
+    Arr& U = umac[d];
+    FOR_CELLS(U, i, j, k) {
+      double st[2];
+      for (int side = 0; side < 2; ++side) {
+        const int ci = i - (side == 0 ? e0(d) : 0), cj = j - (side == 0 ? e1(d) : 0), ck = k - (side == 0 ? e2(d) : 0);
+        const int i1 = ci + e0(t1), j1 = cj + e1(t1), k1 = ck + e2(t1), i2 = ci + e0(t2), j2 = cj + e1(t2), k2 = ck + e2(t2);
+        double s = (side == 0) ? lo[d][d](i, j, k) : hi[d][d](i, j, k);
+        s += -(0.25 * dtd1) * (M1(i1, j1, k1) + M1(ci, cj, ck)) * (a1(i1, j1, k1) - a1(ci, cj, ck))
+             - (0.25 * dtd2) * (M2(i2, j2, k2) + M2(ci, cj, ck)) * (a2(i2, j2, k2) - a2(ci, cj, ck));
+        if (!fit && f) s += 0.5 * dt * (*f)(ci, cj, ck, d);
+        st[side] = s;
+      }
+      U(i, j, k) = riemann_self(st[0], st[1]);
+    }
+  }
+}
+
+// ===========================================================================
+// level solvers
+// ===========================================================================
+int mac_project(const int n[3], const double dx[3], Arr mac[3], Arr& rho, const Arr* rhs_in, Arr& phi, double rhs_scale, orc_mg* mgp) {
+  // beta = (1/rhs_scale)/avg(rho)  MacProj.cpp:1115-1127
+  rho.fill_periodic();
+  Arr beta[3];
+  for (int d = 0; d < 3; ++d) {
+    beta[d].define(n, 1, 1);
+    Arr& B = beta[d];
+    FOR_CELLS(B, i, j, k) B(i, j, k) = (1.0 / rhs_scale) / (0.5 * (rho(i - e0(d), j - e1(d), k - e2(d)) + rho(i, j, k)));
+    B.fill_periodic();
+    mac[d].fill_periodic();
+  }
+  CellMG mg(n, dx, 1, false, mgp ? mgp->max_coarsening : 100);
+  if (mgp) mg.mg = *mgp;
+  mg.a = 0.0; mg.b = 1.0;
+  const Arr* e[3] = {&beta[0], &beta[1], &beta[2]};
+  mg.set_coeffs(nullptr, e);
+  Arr rhs(n, 1, 0);
+  FOR_CELLS(rhs, i, j, k) {
+    double dv = (mac[0](i + 1, j, k) - mac[0](i, j, k)) / dx[0] + (mac[1](i, j + 1, k) - mac[1](i, j, k)) / dx[1] +
+                (mac[2](i, j, k + 1) - mac[2](i, j, k)) / dx[2];
+    rhs(i, j, k) = -dv + (rhs_in ? (*rhs_in)(i, j, k) : 0.0);
+  }
+  const int rc = mg.solve(phi, rhs);
+  if (mgp) *mgp = mg.mg;
+  for (int d = 0; d < 3; ++d) {  // umac -= beta grad phi
+    Arr& U = mac[d]; const Arr& B = beta[d];
+    FOR_CELLS(U, i, j, k) U(i, j, k) -= B(i, j, k) * (phi(i, j, k) - phi(i - e0(d), j - e1(d), k - e2(d))) / dx[d];
+    U.fill_periodic();
+  }
+  return rc;
+}
+
+int nodal_project(const int n[3], const double dx[3], Arr& vel, Arr& sigma, Arr& phi, Arr* gp, bool increment, orc_mg* mgp) {
+  const double dxinv[3] = {1.0 / dx[0], 1.0 / dx[1], 1.0 / dx[2]};
+  NodeMG mg(n, dx, mgp ? mgp->max_coarsening : 100);
+  if (mgp) mg.mg = *mgp;
+  mg.set_sigma(sigma);
+  Arr rhs(n, 1, 1);
+  nodal_divu(dxinv, vel, rhs);
+  const int rc = mg.solve(phi, rhs);
+  if (mgp) *mgp = mg.mg;
+  Arr g(n, 3, 0);
+  nodal_grad(dxinv, phi, g);
+  for (int c = 0; c < 3; ++c) {
+    FOR_CELLS(g, i, j, k) {
+      vel(i, j, k, c) -= sigma(i, j, k) * g(i, j, k, c);
+      if (gp) { if (increment) (*gp)(i, j, k, c) += g(i, j, k, c); else (*gp)(i, j, k, c) = g(i, j, k, c); }
+    }
+  }
+  return rc;
+}
+
+}  // namespace
+
+// ===========================================================================
+// NavierStokes::advance / post_init (single level, periodic)
+// ===========================================================================
+struct orc_ns {
+  int n[3]; double dx[3], prob_lo[3];
+  orc_ns_params p;
+  enum { Xvel = 0, Density = 3, Tracer = 4, NUM_STATE = 5 };
+  Arr S_old, S_new, P_old, P_new, Gp_old, Gp_new, umac[3], aofs, rho_p, rho_c, rho_half, eta[3];
+  double time = 0, dt_level = 0, dt_min = 1e100; int nstep = 0;
+  bool initial_step = false, initial_iter = false;
+  int it[3] = {0, 0, 0};
+  Arr force;  // velocity forcing from predict_velocity (1 ghost), reused by velocity_advection
+
+  orc_mg mg(double rtol, double atol) const { orc_mg m; orc_mg_default(&m); m.rtol = rtol; m.atol = atol; return m; }
+  bool diffusive() const { return p.visc_coef > 0.0; }
+
+  // getViscTerms -> getTensorViscTerms (Diffusion.cpp:1655-1777): a = 0, b = -1
+  void visc_terms(const Arr& S, Arr& visc) {
+    if (!diffusive()) { visc.setval(0.0); return; }
+    Arr u(n, 3, 1); u.copy_from(S, Xvel, 0, 3);
+    CellMG op(n, dx, 3, true, 0);
+    op.a = 0.0; op.b = -1.0;
+    const Arr* e[3] = {&eta[0], &eta[1], &eta[2]};
+    op.set_coeffs(nullptr, e);
+    op.apply(visc, u);
+    visc.fill_periodic();
+  }
+  double ext_force(int c, double rho) const { return (c == 2 && std::fabs(p.gravity) > 1.0e-4) ? p.gravity * rho : 0.0; }  // NS_getForce.cpp:117-141
+
+  int advance(double dt, double* dt_test) {
+    // advance_setup NSB.cpp:613-741
+    std::swap(S_old, S_new); std::swap(P_old, P_new); std::swap(Gp_old, Gp_new);
+    rho_p.copy_from(S_old, Density, 0, 1); rho_p.fill_periodic();
+    // ---- predict_velocity NSB.cpp:4376-4512
+    Arr Umf(n, 3, 3); Umf.copy_from(S_old, Xvel, 0, 3); Umf.fill_periodic();
+    for (double& v : Umf.d) v = (std::fabs(v) > 1.0e-20) ? v : 0.0;  // floor :4530-4534
+    double cflmax = 0.0;
+    for (int d = 0; d < 3; ++d) cflmax = std::max(cflmax, dt * Umf.norminf(d) / dx[d]);
+    const double tempdt = (cflmax == 0.0) ? p.change_max : std::min(p.change_max, p.cfl / cflmax);
+    Arr visc(n, 3, 1);
+    if (p.be_cn_theta != 1.0) visc_terms(S_old, visc); else visc.setval(0.0);
+    Arr Smf(n, 2, 3); Smf.copy_from(S_old, Density, 0, 2); Smf.fill_periodic();
+    Gp_old.fill_periodic();
+    force.define(n, 3, 1);
+    for (int c = 0; c < 3; ++c) {
+      FOR_G1(force, i, j, k) force(i, j, k, c) = (ext_force(c, Smf(i, j, k, 0)) + visc(i, j, k, c) - Gp_old(i, j, k, c)) / Smf(i, j, k, 0);  // :4466-4470
+    }
+    extrap_vel_to_faces(Umf, &force, p.use_forces_in_trans != 0, dx, dt, umac);  // :4487
+    *dt_test = dt * tempdt;
+    // ---- mac_project NS.cpp:589-597, MacProj.cpp:225-353
+    Arr mac_phi(n, 1, 1);
+    orc_mg m1 = mg(p.mac_tol, p.mac_abs_tol);
+    int rc = mac_project(n, dx, umac, rho_p, nullptr, mac_phi, 2.0 / dt, &m1);
+    it[0] = m1.iters;
+    if (rc) return rc;
+    // ---- velocity_advection NSB.cpp:3358-3470 (fresh un-floored FillPatch copy, same forcing)
+    Arr Umf2(n, 3, 3); Umf2.copy_from(S_old, Xvel, 0, 3); Umf2.fill_periodic();
+    const int ic_vel[3] = {0, 0, 0};
+    compute_aofs(Umf2, 3, &force, nullptr, umac, ic_vel, p.use_forces_in_trans != 0, dx, dt, aofs, Xvel, nullptr, nullptr);
+    // ---- scalar_advection NS.cpp:698-812
+    for (double& v : Smf.d) v = (std::fabs(v) > 1.0e-20) ? v : 0.0;
+    Arr sforce(n, 2, 1);
+    const int ic_scal[2] = {1, p.conservative_tracer ? 1 : 0};
+    compute_aofs(Smf, 2, &sforce, nullptr, umac, ic_scal, p.use_forces_in_trans != 0, dx, dt, aofs, Density, nullptr, nullptr);
+    // ---- scalar updates NSB.cpp:2761-2765, 2887-2896
+    FOR_CELLS(S_new, i, j, k) S_new(i, j, k, Density) = S_old(i, j, k, Density) - dt * aofs(i, j, k, Density);
+    rho_c.copy_from(S_new, Density, 0, 1); rho_c.fill_periodic();
+    FOR_CELLS(S_new, i, j, k) S_new(i, j, k, Tracer) = S_old(i, j, k, Tracer) - dt * aofs(i, j, k, Tracer);
+    // ---- velocity_update NSB.cpp:3487-3655
+    FOR_G1(rho_half, i, j, k) rho_half(i, j, k) = 0.5 * (rho_p(i, j, k) + rho_c(i, j, k));
+    const bool zero_force = initial_iter && diffusive();
+    for (int c = 0; c < 3; ++c) {
+      FOR_CELLS(S_new, i, j, k) {
+        const double r = rho_half(i, j, k);
+        const double frc = zero_force ? 0.0 : ext_force(c, r);
+        S_new(i, j, k, c) = S_old(i, j, k, c) - dt * aofs(i, j, k, c) + dt * frc / r - dt * Gp_old(i, j, k, c) / r;
+      }
+    }
+    if (!initial_iter) { rc = velocity_diffusion(dt); if (rc) return rc; }
+    else initial_velocity_diffusion(dt);
+    if (!initial_step) { rc = level_project(dt); if (rc) return rc; }
+    return 0;
+  }
+
+  // Diffusion::diffuse_tensor_velocity Diffusion.cpp:650-957
+  int velocity_diffusion(double dt) {
+    if (!diffusive()) return 0;
+    const double th = p.be_cn_theta;
+    const Arr* e[3] = {&eta[0], &eta[1], &eta[2]};
+    Arr rhs(n, 3, 0);
+    if (th != 1.0) {
+      Arr u(n, 3, 1); u.copy_from(S_old, Xvel, 0, 3);
+      CellMG ex(n, dx, 3, true, 0);
+      ex.a = 0.0; ex.b = -(1.0 - th) * dt;
+      ex.set_coeffs(nullptr, e);
+      ex.apply(rhs, u);
+    }
+    for (int c = 0; c < 3; ++c) {
+      FOR_CELLS(rhs, i, j, k) { S_new(i, j, k, c) *= rho_half(i, j, k); rhs(i, j, k, c) += S_new(i, j, k, c); }  // :821-831
+    }
+    const double tol_abs = p.visc_tol * (rhs.norminf(0) + rhs.norminf(1) + rhs.norminf(2)) / 3.0;  // get_scaled_abs_tol :193-204
+    Arr soln(n, 3, 1); soln.copy_from(S_new, Xvel, 0, 3);
+    CellMG im(n, dx, 3, true, 100);
+    im.mg = mg(p.visc_tol, tol_abs);
+    im.a = 1.0; im.b = th * dt;
+    im.set_coeffs(&rho_half, e);
+    const int rc = im.solve(soln, rhs);
+    it[1] = im.mg.iters;
+    S_new.copy_from(soln, 0, Xvel, 3);
+    return rc;
+  }
+  // NSB.cpp:3658-3749
+  void initial_velocity_diffusion(double dt) {
+    if (!diffusive()) return;
+    Arr visc(n, 3, 1);
+    if (p.be_cn_theta != 1.0) visc_terms(S_old, visc); else visc.setval(0.0);
+    for (int c = 0; c < 3; ++c) {
+      FOR_CELLS(S_new, i, j, k) {
+        double f = ext_force(c, S_old(i, j, k, Density)) + visc(i, j, k, c) - Gp_old(i, j, k, c);
+        f /= rho_half(i, j, k);
+        f -= aofs(i, j, k, c);
+        S_new(i, j, k, c) = S_old(i, j, k, c) + f * dt;
+      }
+    }
+  }
+  // Projection::level_project Projection.cpp:166-450
+  int level_project(double dt) {
+    P_new.setval(0.0);
+    Arr vel(n, 3, 1), sig(n, 1, 1);
+    for (int c = 0; c < 3; ++c) { FOR_CELLS(vel, i, j, k) vel(i, j, k, c) = S_new(i, j, k, c) * (1.0 / dt) + Gp_old(i, j, k, c) / rho_half(i, j, k); }
+    FOR_CELLS(sig, i, j, k) sig(i, j, k) = 1.0 / rho_half(i, j, k);
+    orc_mg m = mg(p.proj_tol, p.proj_abs_tol);
+    const int rc = nodal_project(n, dx, vel, sig, P_new, &Gp_new, false, &m);
+    it[2] = m.iters;
+    if (rc) return rc;
+    Gp_new.fill_periodic();
+    for (int c = 0; c < 3; ++c) { FOR_CELLS(vel, i, j, k) S_new(i, j, k, c) = vel(i, j, k, c) * dt; }
+    return 0;
+  }
+  // NSB.cpp:1353-1500
+  int est_time_step(double* out) {
+    if (p.fixed_dt > 0.0) { *out = p.fixed_dt; return 0; }
+    double est = 1.0e20;
+    for (int d = 0; d < 3; ++d) {
+      const double um = S_new.norminf(d);
+      double fm = 0.0;
+#pragma omp parallel for reduction(max : fm)
+      for (int k = 0; k < n[2]; ++k)
+        for (int j = 0; j < n[1]; ++j)
+          for (int i = 0; i < n[0]; ++i) {
+            const double r = S_new(i, j, k, Density);
+            fm = std::max(fm, std::fabs((ext_force(d, r) - Gp_new(i, j, k, d)) / r));
+          }
+      if (um > 1.0e-8) est = std::min(est, dx[d] / um);
+      if (fm > 1.0e-8) est = std::min(est, std::sqrt(2.0 * dx[d] / fm));
+    }
+    if (est >= 1.0e20) return -1;
+    *out = est * p.cfl;
+    return 0;
+  }
+};
+
+extern "C" {
+
+int orc_num_threads(void) {
+#ifdef _OPENMP
+  return omp_get_max_threads();
+#else
+  return 1;
+#endif
+}
+
+void orc_mg_default(orc_mg* m) {
+  m->rtol = 1e-12; m->atol = 1e-16; m->max_iter = 200; m->nu1 = 2; m->nu2 = 2; m->bottom_sweeps = 8; m->max_coarsening = 100;
+  m->omega = 1.0; m->iters = 0; m->resnorm0 = m->resnorm = m->rhsnorm = 0.0;
+}
+
+static void load_faces(const int n[3], const double* bx, const double* by, const double* bz, int bn, Arr b[3]) {
+  const double* src[3] = {bx, by, bz};
+  for (int d = 0; d < 3; ++d) { b[d].define(n, bn, 1); b[d].load(src[d]); b[d].fill_periodic(); }
+}
+
+void orc_abec_apply(const int n[3], const double dxinv[3], double a, double b, const double* alpha, const double* bx,
+                    const double* by, const double* bz, int ncomp, int bncomp, const double* phi, double* out) {
+  Arr be[3]; load_faces(n, bx, by, bz, bncomp, be);
+  Arr al; if (alpha) { al.define(n, 1, 0); al.load(alpha); }
+  Arr p(n, ncomp, 1), o(n, ncomp, 0); p.load(phi);
+  AbecOp op; op.a = a; op.b = b; op.alpha = alpha ? &al : nullptr; op.bncomp = bncomp;
+  for (int d = 0; d < 3; ++d) { op.beta[d] = &be[d]; op.dxinv[d] = dxinv[d]; }
+  abec_apply(op, p, o, ncomp);
+  o.store(out);
+}
+
+void orc_abec_gsrb(const int n[3], const double dxinv[3], double a, double b, const double* alpha, const double* bx,
+                   const double* by, const double* bz, int ncomp, int bncomp, const double* rhs, double omega, int redblack,
+                   double* phi) {
+  Arr be[3]; load_faces(n, bx, by, bz, bncomp, be);
+  Arr al; if (alpha) { al.define(n, 1, 0); al.load(alpha); }
+  Arr p(n, ncomp, 1), r(n, ncomp, 0); p.load(phi); r.load(rhs);
+  AbecOp op; op.a = a; op.b = b; op.alpha = alpha ? &al : nullptr; op.bncomp = bncomp;
+  for (int d = 0; d < 3; ++d) { op.beta[d] = &be[d]; op.dxinv[d] = dxinv[d]; }
+  abec_gsrb(op, p, r, ncomp, omega, redblack);
+  p.store(phi);
+}
+
+void orc_tensor_cross(const int n[3], const double dxinv[3], double b, const double* ex, const double* ey, const double* ez,
+                      const double* vel, double* out) {
+  Arr e[3]; load_faces(n, ex, ey, ez, 1, e);
+  Arr v(n, 3, 1), o(n, 3, 0); v.load(vel); o.load(out);
+  tensor_cross(dxinv, b, e[0], e[1], e[2], v, o);
+  o.store(out);
+}
+
+int orc_diffusion_solve(const int n[3], const double dx[3], int tensor, int ncomp, double a, double b, const double* alpha,
+                        const double* ex, const double* ey, const double* ez, const double* rhs, double* soln, orc_mg* mgp) {
+  Arr e[3]; load_faces(n, ex, ey, ez, 1, e);
+  Arr al; if (alpha) { al.define(n, 1, 0); al.load(alpha); }
+  CellMG mg(n, dx, ncomp, tensor != 0, mgp ? mgp->max_coarsening : 100);
+  if (mgp) mg.mg = *mgp;
+  mg.a = a; mg.b = b;
+  const Arr* ep[3] = {&e[0], &e[1], &e[2]};
+  mg.set_coeffs(alpha ? &al : nullptr, ep);
+  Arr s(n, ncomp, 1), r(n, ncomp, 0); s.load(soln); r.load(rhs);
+  const int rc = mg.solve(s, r);
+  if (mgp) *mgp = mg.mg;
+  s.store(soln);
+  return rc;
+}
+
+void orc_diffusion_apply(const int n[3], const double dx[3], int tensor, int ncomp, double a, double b, const double* alpha,
+                         const double* ex, const double* ey, const double* ez, const double* soln, double* out) {
+  Arr e[3]; load_faces(n, ex, ey, ez, 1, e);
+  Arr al; if (alpha) { al.define(n, 1, 0); al.load(alpha); }
+  CellMG mg(n, dx, ncomp, tensor != 0, 0);
+  mg.a = a; mg.b = b;
+  const Arr* ep[3] = {&e[0], &e[1], &e[2]};
+  mg.set_coeffs(alpha ? &al : nullptr, ep);
+  Arr s(n, ncomp, 1), o(n, ncomp, 0); s.load(soln);
+  mg.apply(o, s);
+  o.store(out);
+}
+
+int orc_mac_project(const int n[3], const double dx[3], double* umac, double* vmac, double* wmac, const double* rho,
+                    const double* rhs, double* phi, double rhs_scale, orc_mg* mg) {
+  Arr mac[3]; double* m[3] = {umac, vmac, wmac};
+  for (int d = 0; d < 3; ++d) { mac[d].define(n, 1, 1); mac[d].load(m[d]); }
+  Arr r(n, 1, 1), p(n, 1, 1), rh; r.load(rho); p.load(phi);
+  if (rhs) { rh.define(n, 1, 0); rh.load(rhs); }
+  const int rc = mac_project(n, dx, mac, r, rhs ? &rh : nullptr, p, rhs_scale, mg);
+  for (int d = 0; d < 3; ++d) mac[d].store(m[d]);
+  p.store(phi);
+  return rc;
+}
+
+void orc_nodal_divu(const int n[3], const double dxinv[3], const double* vel, double* rhs) {
+  Arr v(n, 3, 1), r(n, 1, 0); v.load(vel);
+  nodal_divu(dxinv, v, r);
+  r.store(rhs);
+}
+void orc_nodal_adotx(const int n[3], const double dxinv[3], const double* sigma, const double* phi, double* out) {
+  Arr s(n, 1, 1), p(n, 1, 1), o(n, 1, 0); s.load(sigma); s.fill_periodic(); p.load(phi);
+  nodal_adotx(dxinv, s, p, o);
+  o.store(out);
+}
+void orc_nodal_gs(const int n[3], const double dxinv[3], const double* sigma, const double* rhs, int color, double* phi) {
+  Arr s(n, 1, 1), p(n, 1, 1), r(n, 1, 0); s.load(sigma); s.fill_periodic(); p.load(phi); r.load(rhs);
+  nodal_gs(dxinv, s, r, color, p);
+  p.store(phi);
+}
+void orc_nodal_mknewu(const int n[3], const double dxinv[3], const double* sigma, const double* phi, double* vel, double* gp) {
+  Arr p(n, 1, 1), g(n, 3, 0); p.load(phi);
+  nodal_grad(dxinv, p, g);
+  if (gp) g.store(gp);
+  if (vel) {
+    Arr s(n, 1, 0), v(n, 3, 0); s.load(sigma); v.load(vel);
+    for (int c = 0; c < 3; ++c) { FOR_CELLS(v, i, j, k) v(i, j, k, c) -= s(i, j, k) * g(i, j, k, c); }
+    v.store(vel);
+  }
+}
+int orc_nodal_project(const int n[3], const double dx[3], double* vel, const double* sigma, double* phi, double* gp,
+                      int increment_gp, orc_mg* mg) {
+  Arr v(n, 3, 1), s(n, 1, 1), p(n, 1, 1), g(n, 3, 0); v.load(vel); s.load(sigma); p.load(phi);
+  if (gp && increment_gp) g.load(gp);
+  const int rc = nodal_project(n, dx, v, s, p, gp ? &g : nullptr, increment_gp != 0, mg);
+  v.store(vel); p.store(phi);
+  if (gp) g.store(gp);
+  return rc;
+}
+
+void orc_extrap_vel_to_faces(const int n[3], const double dx[3], double dt, const double* vel, const double* force,
+                             int forces_in_trans, double* umac, double* vmac, double* wmac) {
+  Arr v(n, 3, 3), f; v.load(vel); v.fill_periodic();
+  if (force) { f.define(n, 3, 1); f.load(force); f.fill_periodic(); }
+  Arr mac[3] = {Arr(n, 1, 1), Arr(n, 1, 1), Arr(n, 1, 1)};
+  extrap_vel_to_faces(v, force ? &f : nullptr, forces_in_trans != 0, dx, dt, mac);
+  mac[0].store(umac); mac[1].store(vmac); mac[2].store(wmac);
+}
+
+void orc_compute_aofs(const int n[3], const double dx[3], double dt, int ncomp, const double* S, const double* force,
+                      const double* divu, const double* umac, const double* vmac, const double* wmac, const int* iconserv,
+                      int forces_in_trans, double* aofs, double* fx, double* fy, double* fz, double* xed, double* yed, double* zed) {
+  Arr q(n, ncomp, 3), f, dv; q.load(S); q.fill_periodic();
+  if (force) { f.define(n, ncomp, 1); f.load(force); f.fill_periodic(); }
+  if (divu) { dv.define(n, 1, 1); dv.load(divu); dv.fill_periodic(); }
+  Arr mac[3]; const double* m[3] = {umac, vmac, wmac};
+  for (int d = 0; d < 3; ++d) { mac[d].define(n, 1, 1); mac[d].load(m[d]); mac[d].fill_periodic(); }
+  Arr a(n, ncomp, 0);
+  Arr fl[3], ed[3]; Arr* flp[3] = {nullptr, nullptr, nullptr}; Arr* edp[3] = {nullptr, nullptr, nullptr};
+  double* fo[3] = {fx, fy, fz}; double* eo[3] = {xed, yed, zed};
+  for (int d = 0; d < 3; ++d) {
+    if (fo[d]) { fl[d].define(n, ncomp, 0); flp[d] = &fl[d]; }
+    if (eo[d]) { ed[d].define(n, ncomp, 0); edp[d] = &ed[d]; }
+  }
+  compute_aofs(q, ncomp, force ? &f : nullptr, divu ? &dv : nullptr, mac, iconserv, forces_in_trans != 0, dx, dt, a, 0, flp, edp);
+  a.store(aofs);
+  for (int d = 0; d < 3; ++d) { if (fo[d]) fl[d].store(fo[d]); if (eo[d]) ed[d].store(eo[d]); }
+}
+
+void orc_ns_params_default(orc_ns_params* p) {
+  p->cfl = 0.7; p->visc_coef = 0.0; p->be_cn_theta = 0.5; p->change_max = 1.1; p->init_shrink = 1.0; p->fixed_dt = -1.0;
+  p->gravity = 0.0; p->visc_tol = 1e-10; p->mac_tol = 1e-12; p->mac_abs_tol = 1e-16; p->proj_tol = 1e-12; p->proj_abs_tol = 1e-16;
+  p->init_iter = 2; p->init_vel_iter = 1; p->do_init_proj = 1; p->use_forces_in_trans = 0; p->conservative_tracer = 0; p->verbose = 0;
+}
+
+orc_ns* orc_ns_create(const int n[3], const double prob_lo[3], const double prob_hi[3], const orc_ns_params* p) {
+  orc_ns* ns = new orc_ns();
+  for (int d = 0; d < 3; ++d) { ns->n[d] = n[d]; ns->prob_lo[d] = prob_lo[d]; ns->dx[d] = (prob_hi[d] - prob_lo[d]) / n[d]; }
+  ns->p = *p;
+  ns->S_old.define(n, 5, 1); ns->S_new.define(n, 5, 1); ns->P_old.define(n, 1, 1); ns->P_new.define(n, 1, 1);
+  ns->Gp_old.define(n, 3, 1); ns->Gp_new.define(n, 3, 1); ns->aofs.define(n, 5, 0);
+  ns->rho_p.define(n, 1, 1); ns->rho_c.define(n, 1, 1); ns->rho_half.define(n, 1, 1);
+  for (int d = 0; d < 3; ++d) { ns->umac[d].define(n, 1, 1); ns->eta[d].define(n, 1, 1); ns->eta[d].setval(p->visc_coef); }
+  return ns;
+}
+void orc_ns_destroy(orc_ns* ns) { delete ns; }
+
+void orc_ns_init_prob(orc_ns* ns, int probtype, const double* pp, int) {
+  // Source/prob/prob_init.cpp: 11 TaylorGreen :509-560, 5 DoubleShearLayer :346-405 (direction 1);
+  // 100 = synthetic variable-density Taylor-Green (not in the reference)
+  const double twopi = 2.0 * 3.14159265358979323846264338327950288;
+  Arr& S = ns->S_new;
+  const int* n = ns->n;
+#pragma omp parallel for
+  for (int k = 0; k < n[2]; ++k)
+    for (int j = 0; j < n[1]; ++j)
+      for (int i = 0; i < n[0]; ++i) {
+        const double x = ns->prob_lo[0] + (i + 0.5) * ns->dx[0], y = ns->prob_lo[1] + (j + 0.5) * ns->dx[1], z = ns->prob_lo[2] + (k + 0.5) * ns->dx[2];
+        if (probtype == 11 || probtype == 100) {
+          const double a = pp[0], b = pp[1], c = pp[2], vx = pp[3], dens = pp[4];
+          S(i, j, k, 0) = vx * std::sin(a * twopi * x) * std::cos(b * twopi * y) * std::cos(c * twopi * z);
+          S(i, j, k, 1) = -vx * std::cos(a * twopi * x) * std::sin(b * twopi * y) * std::cos(c * twopi * z);
+          S(i, j, k, 2) = 0.0;
+          S(i, j, k, 3) = (probtype == 100) ? dens * (1.0 + 0.5 * std::sin(twopi * x) * std::sin(twopi * y) * std::sin(twopi * z)) : dens;
+          S(i, j, k, 4) = (dens * vx * vx / 16.0) * (2.0 + std::cos(2.0 * c * twopi * z)) * (std::cos(2.0 * a * twopi * x) + std::cos(2.0 * b * twopi * y));
+        } else {
+          const double dens = pp[0], width = pp[1] > 0 ? pp[1] : 1.0, pi = 0.5 * twopi;
+          S(i, j, k, 0) = -0.05 * std::sin(pi * y);
+          S(i, j, k, 1) = std::tanh(30.0 * (0.5 - std::fabs(x)) / width);
+          S(i, j, k, 2) = 0.0;
+          S(i, j, k, 3) = dens;
+          const double dist = std::sqrt((x - pp[2]) * (x - pp[2]) + (y - pp[3]) * (y - pp[3]) + (z - pp[4]) * (z - pp[4]));
+          S(i, j, k, 4) = dist < pp[5] ? 1.0 : 0.0;
+        }
+      }
+  ns->P_new.setval(0); ns->P_old.setval(0); ns->Gp_new.setval(0); ns->Gp_old.setval(0);
+  ns->time = 0; ns->nstep = 0; ns->dt_level = 0; ns->dt_min = 1e100;
+}
+
+int orc_ns_post_init(orc_ns* ns, double* dt0) {
+  const int* n = ns->n;
+  if (ns->p.do_init_proj) {  // initialVelocityProject Projection.cpp:615-838 (sigma = 1)
+    for (int it = 0; it < ns->p.init_vel_iter; ++it) {
+      Arr vel(n, 3, 1), sig(n, 1, 1), phi(n, 1, 1);
+      vel.copy_from(ns->S_new, 0, 0, 3); sig.setval(1.0);
+      orc_mg m = ns->mg(ns->p.proj_tol, ns->p.proj_abs_tol);
+      const int rc = nodal_project(n, ns->dx, vel, sig, phi, nullptr, false, &m);
+      if (rc) return rc;
+      ns->S_new.copy_from(vel, 0, 0, 3);
+      ns->P_old.setval(0); ns->P_new.setval(0); ns->Gp_old.setval(0); ns->Gp_new.setval(0);
+    }
+  }
+  ns->initial_step = true;
+  double est = 0;
+  if (ns->est_time_step(&est)) return -1;
+  const double dt_init = ns->p.init_shrink * est;  // post_init_estDT NSB.cpp:2307-2366
+  if (ns->p.init_iter > 0) {  // post_init_press NS.cpp:1306-1432
+    ns->initial_iter = true;
+    for (int iter = 0; iter < ns->p.init_iter; ++iter) {
+      double dtt;
+      int rc = ns->advance(dt_init, &dtt);
+      if (rc) return rc;
+      // initialSyncProject Projection.cpp:970-1185
+      Arr vel(n, 3, 1), sig(n, 1, 1), phi(n, 1, 1);
+      for (int c = 0; c < 3; ++c) { FOR_CELLS(vel, i, j, k) vel(i, j, k, c) = ns->S_new(i, j, k, c) * (1.0 / dt_init) + (-1.0 / dt_init) * ns->S_old(i, j, k, c); }
+      FOR_CELLS(sig, i, j, k) sig(i, j, k) = 1.0 / ns->rho_half(i, j, k);
+      orc_mg m = ns->mg(ns->p.proj_tol, ns->p.proj_abs_tol);
+      rc = nodal_project(n, ns->dx, vel, sig, phi, &ns->Gp_new, true, &m);
+      ns->it[2] = m.iters;
+      if (rc) return rc;
+      { Arr& P = ns->P_new; FOR_G1(P, i, j, k) P(i, j, k) += phi(i, j, k); }
+      ns->Gp_new.fill_periodic();
+      std::swap(ns->S_old, ns->S_new);  // resetState NSB.cpp:2643-2680
+      ns->P_old = ns->P_new; ns->Gp_old = ns->Gp_new;
+      ns->initial_iter = false;
+    }
+  }
+  ns->initial_step = false;
+  ns->dt_level = dt_init; ns->dt_min = 1e100;
+  if (dt0) *dt0 = dt_init;
+  return 0;
+}
+
+int orc_ns_step(orc_ns* ns, double* dt_io) {
+  double dt = (dt_io && *dt_io > 0.0) ? *dt_io : -1.0;
+  if (dt <= 0.0) {
+    if (ns->p.fixed_dt > 0.0) dt = ns->p.fixed_dt;
+    else if (ns->nstep == 0 && ns->dt_level > 0.0) dt = ns->dt_level;
+    else {  // computeNewDt NSB.cpp:945-1036
+      double est; if (ns->est_time_step(&est)) return -1;
+      dt = std::min(ns->dt_min, est);
+      if (ns->dt_level > 0.0) dt = std::min(dt, ns->p.change_max * ns->dt_level);
+    }
+  }
+  double dtt = 0;
+  const int rc = ns->advance(dt, &dtt);
+  if (rc) return rc;
+  ns->dt_min = dtt; ns->dt_level = dt; ns->time += dt; ns->nstep++;
+  if (dt_io) *dt_io = dt;
+  return 0;
+}
+
+double orc_ns_time(const orc_ns* ns) { return ns->time; }
+
+void orc_ns_get(const orc_ns* ns, int which, double* out) {
+  switch (which) {
+    case 0: ns->S_new.store(out); break;
+    case 1: ns->P_new.store(out); break;
+    case 2: ns->Gp_new.store(out); break;
+    case 4: case 5: case 6: ns->umac[which - 4].store(out); break;
+    case 7: ns->aofs.store(out); break;
+    default: break;
+  }
+}
+void orc_ns_set_state(orc_ns* ns, const double* s) { ns->S_new.load(s); }
+void orc_ns_last_iters(const orc_ns* ns, int it[3]) { for (int q = 0; q < 3; ++q) it[q] = ns->it[q]; }
+
+}  // extern "C"

@@ -1,0 +1,216 @@
+"""ctypes binding of the CPU oracle (oracle/oracle.h).  TEST INFRASTRUCTURE: only tests/,
+__graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference leg import this."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+_SO = os.path.join(_ROOT, "oracle", "_build", "liboracle.so")
+
+
+class OrcMG(C.Structure):
+    _fields_ = [("rtol", C.c_double), ("atol", C.c_double), ("max_iter", C.c_int), ("nu1", C.c_int), ("nu2", C.c_int),
+                ("bottom_sweeps", C.c_int), ("max_coarsening", C.c_int), ("omega", C.c_double), ("iters", C.c_int),
+                ("resnorm0", C.c_double), ("resnorm", C.c_double), ("rhsnorm", C.c_double)]
+
+
+class OrcNSParams(C.Structure):
+    _fields_ = [("cfl", C.c_double), ("visc_coef", C.c_double), ("be_cn_theta", C.c_double), ("change_max", C.c_double),
+                ("init_shrink", C.c_double), ("fixed_dt", C.c_double), ("gravity", C.c_double), ("visc_tol", C.c_double),
+                ("mac_tol", C.c_double), ("mac_abs_tol", C.c_double), ("proj_tol", C.c_double), ("proj_abs_tol", C.c_double),
+                ("init_iter", C.c_int), ("init_vel_iter", C.c_int), ("do_init_proj", C.c_int), ("use_forces_in_trans", C.c_int),
+                ("conservative_tracer", C.c_int), ("verbose", C.c_int)]
+
+
+_lib = None
+
+
+def build():
+    subprocess.check_call(["make", "-s", "-C", os.path.join(_ROOT, "oracle")])
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(_SO):
+            build()
+        _lib = C.CDLL(_SO)
+        _lib.orc_ns_create.restype = C.c_void_p
+        _lib.orc_ns_time.restype = C.c_double
+        _lib.orc_ns_time.argtypes = [C.c_void_p]
+    return _lib
+
+
+def _p(a):
+    if a is None:
+        return None
+    assert a.dtype == np.float64 and a.flags["C_CONTIGUOUS"]
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def _i3(n):
+    return (C.c_int * 3)(*[int(v) for v in n])
+
+
+def _d3(x):
+    return (C.c_double * 3)(*[float(v) for v in x])
+
+
+def mg_default(**kw):
+    m = OrcMG()
+    lib().orc_mg_default(C.byref(m))
+    for k, v in kw.items():
+        setattr(m, k, v)
+    return m
+
+
+def _n_of(a):  # array [..., nz, ny, nx] -> (nx, ny, nz)
+    return (a.shape[-1], a.shape[-2], a.shape[-3])
+
+
+def abec_apply(dxinv, a, b, alpha, bx, by, bz, phi):
+    ncomp, bn = phi.shape[0], bx.shape[0]
+    out = np.empty_like(phi)
+    lib().orc_abec_apply(_i3(_n_of(phi)), _d3(dxinv), C.c_double(a), C.c_double(b), _p(alpha), _p(bx), _p(by), _p(bz),
+                         ncomp, bn, _p(phi), _p(out))
+    return out
+
+
+def abec_gsrb(dxinv, a, b, alpha, bx, by, bz, rhs, omega, redblack, phi):
+    ncomp, bn = phi.shape[0], bx.shape[0]
+    phi = phi.copy()
+    lib().orc_abec_gsrb(_i3(_n_of(phi)), _d3(dxinv), C.c_double(a), C.c_double(b), _p(alpha), _p(bx), _p(by), _p(bz),
+                        ncomp, bn, _p(rhs), C.c_double(omega), int(redblack), _p(phi))
+    return phi
+
+
+def tensor_cross(dxinv, b, ex, ey, ez, vel, out):
+    out = out.copy()
+    lib().orc_tensor_cross(_i3(_n_of(vel)), _d3(dxinv), C.c_double(b), _p(ex), _p(ey), _p(ez), _p(vel), _p(out))
+    return out
+
+
+def diffusion_solve(dx, tensor, a, b, alpha, ex, ey, ez, rhs, soln, mg=None):
+    mg = mg or mg_default()
+    soln = soln.copy()
+    rc = lib().orc_diffusion_solve(_i3(_n_of(rhs)), _d3(dx), int(tensor), rhs.shape[0], C.c_double(a), C.c_double(b),
+                                   _p(alpha), _p(ex), _p(ey), _p(ez), _p(rhs), _p(soln), C.byref(mg))
+    return soln, rc, mg
+
+
+def diffusion_apply(dx, tensor, a, b, alpha, ex, ey, ez, soln):
+    out = np.empty_like(soln)
+    lib().orc_diffusion_apply(_i3(_n_of(soln)), _d3(dx), int(tensor), soln.shape[0], C.c_double(a), C.c_double(b),
+                              _p(alpha), _p(ex), _p(ey), _p(ez), _p(soln), _p(out))
+    return out
+
+
+def mac_project(dx, umac, vmac, wmac, rho, rhs, phi, rhs_scale, mg=None):
+    mg = mg or mg_default()
+    u, v, w, phi = umac.copy(), vmac.copy(), wmac.copy(), phi.copy()
+    rc = lib().orc_mac_project(_i3(_n_of(rho)), _d3(dx), _p(u), _p(v), _p(w), _p(rho), _p(rhs), _p(phi),
+                               C.c_double(rhs_scale), C.byref(mg))
+    return u, v, w, phi, rc, mg
+
+
+def nodal_divu(dxinv, vel):
+    out = np.empty(vel.shape[1:], dtype=np.float64)
+    lib().orc_nodal_divu(_i3(_n_of(vel)), _d3(dxinv), _p(vel), _p(out))
+    return out
+
+
+def nodal_adotx(dxinv, sigma, phi):
+    out = np.empty_like(phi)
+    lib().orc_nodal_adotx(_i3(_n_of(phi)), _d3(dxinv), _p(sigma), _p(phi), _p(out))
+    return out
+
+
+def nodal_gs(dxinv, sigma, rhs, color, phi):
+    phi = phi.copy()
+    lib().orc_nodal_gs(_i3(_n_of(phi)), _d3(dxinv), _p(sigma), _p(rhs), int(color), _p(phi))
+    return phi
+
+
+def nodal_mknewu(dxinv, sigma, phi, vel):
+    vel = vel.copy()
+    gp = np.empty_like(vel)
+    lib().orc_nodal_mknewu(_i3(_n_of(phi)), _d3(dxinv), _p(sigma), _p(phi), _p(vel), _p(gp))
+    return vel, gp
+
+
+def nodal_project(dx, vel, sigma, phi, mg=None):
+    mg = mg or mg_default()
+    vel, phi = vel.copy(), phi.copy()
+    gp = np.zeros_like(vel)
+    rc = lib().orc_nodal_project(_i3(_n_of(sigma)), _d3(dx), _p(vel), _p(sigma), _p(phi), _p(gp), 0, C.byref(mg))
+    return vel, phi, gp, rc, mg
+
+
+def extrap_vel_to_faces(dx, dt, vel, force, fit=0):
+    shp = vel.shape[1:]
+    u, v, w = (np.empty(shp, dtype=np.float64) for _ in range(3))
+    lib().orc_extrap_vel_to_faces(_i3(_n_of(vel)), _d3(dx), C.c_double(dt), _p(vel), _p(force), int(fit), _p(u), _p(v), _p(w))
+    return u, v, w
+
+
+def compute_aofs(dx, dt, S, force, umac, vmac, wmac, iconserv, fit=0, divu=None, want_fluxes=False):
+    ncomp = S.shape[0]
+    aofs = np.empty_like(S)
+    ic = (C.c_int * ncomp)(*iconserv)
+    outs = [np.empty_like(S) for _ in range(6)] if want_fluxes else [None] * 6
+    lib().orc_compute_aofs(_i3(_n_of(S)), _d3(dx), C.c_double(dt), ncomp, _p(S), _p(force), _p(divu), _p(umac), _p(vmac),
+                           _p(wmac), ic, int(fit), _p(aofs), *[_p(o) for o in outs])
+    return (aofs, outs) if want_fluxes else aofs
+
+
+class OracleNS:
+    def __init__(self, n, prob_lo=(0, 0, 0), prob_hi=(1, 1, 1), **params):
+        self.n = tuple(n)
+        p = OrcNSParams()
+        lib().orc_ns_params_default(C.byref(p))
+        for k, v in params.items():
+            if not hasattr(p, k):
+                raise KeyError(k)
+            setattr(p, k, v)
+        self.h = C.c_void_p(lib().orc_ns_create(_i3(n), _d3(prob_lo), _d3(prob_hi), C.byref(p)))
+
+    def init_prob(self, probtype, params):
+        arr = (C.c_double * len(params))(*params)
+        lib().orc_ns_init_prob(self.h, probtype, arr, len(params))
+
+    def post_init(self):
+        dt = C.c_double(0)
+        rc = lib().orc_ns_post_init(self.h, C.byref(dt))
+        assert rc == 0, rc
+        return dt.value
+
+    def step(self, dt=-1.0):
+        d = C.c_double(dt)
+        rc = lib().orc_ns_step(self.h, C.byref(d))
+        assert rc == 0, rc
+        return d.value
+
+    def get(self, which):
+        nc = {0: 5, 1: 1, 2: 3, 4: 1, 5: 1, 6: 1, 7: 5}[which]
+        out = np.empty((nc, self.n[2], self.n[1], self.n[0]), dtype=np.float64)
+        lib().orc_ns_get(self.h, which, _p(out))
+        return out
+
+    def set_state(self, s):
+        lib().orc_ns_set_state(self.h, _p(np.ascontiguousarray(s)))
+
+    @property
+    def time(self):
+        return lib().orc_ns_time(self.h)
+
+    def last_iters(self):
+        it = (C.c_int * 3)()
+        lib().orc_ns_last_iters(self.h, it)
+        return tuple(it)
+
+    def close(self):
+        if self.h:
+            lib().orc_ns_destroy(self.h)
+            self.h = None
