@@ -19,7 +19,7 @@ build/%.o: iamr_b200/csrc/%.cu $(HDRS)
 	$(NVCC) $(NVFLAGS) -c $< -o $@
 
 $(LIB): $(OBJS)
-	$(NVCC) -shared $(ARCH) -o $@ $(OBJS) -lcudart -ldl
+	$(NVCC) -shared $(ARCH) -Xlinker -Bsymbolic -o $@ $(OBJS) -lcudart -ldl
 
 oracle:
 	$(MAKE) -C oracle
@@ -30,7 +30,7 @@ tests/emul/_build/%.o: iamr_b200/csrc/%.cu $(HDRS) tests/emul/cuda_emul.h
 	@mkdir -p tests/emul/_build
 	$(CXX) -x c++ -std=c++17 -O2 -fopenmp -fPIC -ftls-model=initial-exec -DIX_EMUL -Itests/emul -Wall -Wno-unused-function -Wno-unknown-pragmas -c $< -o $@
 tests/emul/_build/libiamrx_emul.so: $(EMUL_OBJS) tests/emul/cuda_emul.cpp
-	$(CXX) -std=c++17 -O2 -fopenmp -fPIC -shared -DIX_EMUL -Itests/emul -o $@ $(EMUL_OBJS) tests/emul/cuda_emul.cpp -ldl
+	$(CXX) -std=c++17 -O2 -fopenmp -fPIC -shared -Wl,-Bsymbolic -DIX_EMUL -Itests/emul -o $@ $(EMUL_OBJS) tests/emul/cuda_emul.cpp -ldl
 
 clean:
 	rm -rf build $(LIB) tests/emul/_build oracle/_build

@@ -87,6 +87,9 @@ SIGNATURES = {
     "iamrx_launch_count": (C.c_int64, []),
     "iamrx_launch_count_reset": (None, []),
     "iamrx_device_ok": (C.c_int, []),
+    "iamrx_prof_enable": (C.c_int, [C.c_int, C.c_int64]),
+    "iamrx_prof_reset": (None, []),
+    "iamrx_prof_report": (C.c_int, [C.c_int, _P(C.c_double), _P(C.c_int64), _P(C.c_double)]),
     "iamrx_abec_gsrb_box": (C.c_int, [_P(Box), _P(Fab), _P(Fab), C.c_double, C.c_double, _P(Fab), _P(Fab), _P(Fab),
                                       _P(Fab), _P(C.c_double), C.c_double, C.c_int, C.c_int, _vp]),
     "iamrx_abec_apply_box": (C.c_int, [_P(Box), _P(Fab), _P(Fab), _P(Fab), C.c_double, C.c_double, _P(Fab), _P(Fab),
@@ -104,7 +107,9 @@ SIGNATURES = {
     "iamrx_nodal_mknewu_box": (C.c_int, [_P(Box), _P(Fab), _P(Fab), _P(Fab), _P(Fab), _P(C.c_double), _vp]),
     "iamrx_comm_unique_id": (C.c_int, [C.c_char_p]),
     "iamrx_comm_init": (C.c_int, [C.c_int, C.c_int, C.c_char_p]),
+    "iamrx_comm_set_transport": (C.c_int, [C.c_int, C.c_int, _vp, _vp, _vp]),
     "iamrx_comm_finalize": (C.c_int, []),
+    "iamrx_debug_fb_plan": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, _P(C.c_int), _P(C.c_int), _P(C.c_int), _P(C.c_int)]),
     "iamrx_comm_rank": (C.c_int, []),
     "iamrx_comm_size": (C.c_int, []),
     "iamrx_allreduce": (C.c_int, [_vp, C.c_int, C.c_int, _vp]),
@@ -145,7 +150,7 @@ class Library:
             raise FileNotFoundError(
                 f"{path} not found: build it with `make` (nvcc, sm_100a). iamr_b200 has no CPU fallback.")
         self.path = path
-        self.dll = C.CDLL(path, mode=C.RTLD_GLOBAL)
+        self.dll = C.CDLL(path, mode=C.RTLD_LOCAL)
         for name, (res, args) in SIGNATURES.items():
             fn = getattr(self.dll, name)  # AttributeError if the ABI is incomplete
             fn.restype = res

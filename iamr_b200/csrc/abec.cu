@@ -268,6 +268,7 @@ inline dim3 grid_for(const Bx& bx, int tx, int ty, int nz_total) {
 int abec_gsrb(const Bx& bx, V4 phi, C4 rhs, const Abec& op, double omega, int redblack, int ncomp,
               cudaStream_t s) {
   if (!bx.ok()) return IAMRX_OK;
+  ProfScope prof_(IAMRX_PROF_ABEC_GSRB, bx.npts(), (double)bx.npts() * ncomp * (op.a != 0.0 ? 56.0 : 48.0), s);
   dim3 blk(GS_TX, GS_TY, 1);
   dim3 grd(cdiv(bx.nx() + 1, 2 * GS_TX), cdiv(bx.ny(), GS_TY), bx.nz() * ncomp);
   IX_LAUNCH(gsrb_kernel, grd, blk, 0, s, bx, phi, rhs, to_dev(op), omega, redblack, bx.nz());
@@ -276,6 +277,7 @@ int abec_gsrb(const Bx& bx, V4 phi, C4 rhs, const Abec& op, double omega, int re
 
 int abec_apply(const Bx& bx, V4 out, C4 phi, C4 rhs, const Abec& op, int ncomp, cudaStream_t s) {
   if (!bx.ok()) return IAMRX_OK;
+  ProfScope prof_(IAMRX_PROF_ABEC_APPLY, bx.npts(), (double)bx.npts() * ncomp * ((op.a != 0.0 ? 56.0 : 48.0) + (rhs.ok() ? 0.0 : -8.0)), s);
   IX_LAUNCH(apply_kernel, grid_for(bx, AP_TX, AP_TY, bx.nz() * ncomp), dim3(AP_TX, AP_TY, 1), 0, s, 
       bx, out, phi, rhs, to_dev(op), bx.nz());
   return check_launch("abec_apply");

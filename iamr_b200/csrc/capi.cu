@@ -16,6 +16,10 @@ const char* last_error_cstr();
 int comm_unique_id(unsigned char uid[128]);
 int comm_init(int rank, int nranks, const unsigned char uid[128]);
 int comm_finalize();
+int prof_enable(int on, int64_t min_points);
+void prof_reset();
+int prof_report(int kclass, double* total_ms, int64_t* launches, double* algo_bytes);
+int comm_set_transport(int rank, int nranks, iamrx_exchange_fn ex, iamrx_allreduce_fn ar, void* ctx);
 }  // namespace ix
 
 struct iamrx_level_s {
@@ -54,6 +58,12 @@ int iamrx_version(void) { return 100; }
 int64_t iamrx_launch_count(void) { return g_launches.load(); }
 void iamrx_launch_count_reset(void) { g_launches.store(0); }
 int iamrx_device_ok(void) { return device_ok() ? 1 : 0; }
+int iamrx_prof_enable(int on, int64_t min_points) { return prof_enable(on, min_points); }
+void iamrx_prof_reset(void) { prof_reset(); }
+int iamrx_prof_report(int kclass, double* total_ms, int64_t* launches, double* algo_bytes) {
+  IX_ARG(kclass >= 0 && kclass < IAMRX_PROF_NCLASS, "kernel class");
+  return prof_report(kclass, total_ms, launches, algo_bytes);
+}
 
 // ---------------------------------------------------------------------------
 // 1. per-box kernels
@@ -171,6 +181,11 @@ int iamrx_comm_init(int rank, int nranks, const unsigned char uid[128]) {
   IX_ARG(nranks >= 1 && rank >= 0 && rank < nranks, "rank/nranks");
   IX_ARG(nranks == 1 || uid, "uid required for nranks > 1");
   return comm_init(rank, nranks, uid);
+}
+int iamrx_comm_set_transport(int rank, int nranks, iamrx_exchange_fn exchange, iamrx_allreduce_fn allreduce, void* ctx) {
+  IX_ARG(nranks >= 1 && rank >= 0 && rank < nranks, "rank/nranks");
+  IX_ARG(nranks == 1 || (exchange && allreduce), "exchange and allreduce callbacks required for nranks > 1");
+  return comm_set_transport(rank, nranks, exchange, allreduce, ctx);
 }
 int iamrx_comm_finalize(void) { return comm_finalize(); }
 int iamrx_comm_rank(void) { return comm().rank; }

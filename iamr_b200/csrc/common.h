@@ -136,4 +136,12 @@ inline int check_launch(const char* what) {
 
 inline int cdiv(int a, int b) { return (a + b - 1) / b; }
 
+// ---- optional per-launch timing (iamrx_prof_*, see include/iamrx.h) ---------
+struct ProfScope {
+  int slot = -1;
+  cudaStream_t s;
+  ProfScope(int kclass, int64_t points, double algo_bytes, cudaStream_t s);
+  ~ProfScope();
+};
+
 }  // namespace ix

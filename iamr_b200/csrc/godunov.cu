@@ -443,6 +443,7 @@ struct ScratchOwner {
 
 int compute_aofs(const Bx& bx, const AofsArgs& a, const AdvGeom& g, cudaStream_t s) {
   if (!bx.ok()) return IAMRX_OK;
+  ProfScope prof_(IAMRX_PROF_AOFS, bx.npts(), (double)bx.npts() * (24.0 * a.ncomp + 32.0), s);
   ScratchOwner so;
   if (so.init(bx, A_N * a.ncomp) != IAMRX_OK) return IAMRX_ERR_CUDA;
   EsArgs e{};
@@ -475,6 +476,7 @@ int compute_aofs(const Bx& bx, const AofsArgs& a, const AdvGeom& g, cudaStream_t
 int extrap_vel_to_faces(const Bx& bx, C4 vel, C4 force, V4 umac, V4 vmac, V4 wmac, const AdvGeom& g,
                         int forces_in_trans, cudaStream_t s) {
   if (!bx.ok()) return IAMRX_OK;
+  ProfScope prof_(IAMRX_PROF_EXTRAP, bx.npts(), (double)bx.npts() * 72.0, s);
   ScratchOwner so;
   if (so.init(bx, B_N) != IAMRX_OK) return IAMRX_ERR_CUDA;
   EvArgs e{};

@@ -37,6 +37,75 @@ bool device_ok() {
 }
 
 // ---------------------------------------------------------------------------
+// per-launch timing
+// ---------------------------------------------------------------------------
+#if defined(IX_EMUL)
+ProfScope::ProfScope(int, int64_t, double, cudaStream_t s_) : s(s_) {}
+ProfScope::~ProfScope() {}
+int prof_enable(int, int64_t) { return IAMRX_OK; }
+void prof_reset() {}
+int prof_report(int, double* ms, int64_t* n, double* b) { if (ms) *ms = 0; if (n) *n = 0; if (b) *b = 0; return IAMRX_OK; }
+#else
+namespace {
+struct ProfRec { int kclass; cudaEvent_t e0, e1; double bytes; };
+struct Prof {
+  bool on = false;
+  int64_t min_points = 0;
+  std::vector<ProfRec> recs;
+  std::vector<cudaEvent_t> free_events;
+  std::mutex mu;
+  cudaEvent_t get() {
+    if (!free_events.empty()) { cudaEvent_t e = free_events.back(); free_events.pop_back(); return e; }
+    cudaEvent_t e; cudaEventCreate(&e); return e;
+  }
+};
+Prof& prof() { static Prof p; return p; }
+}  // namespace
+ProfScope::ProfScope(int kclass, int64_t points, double algo_bytes, cudaStream_t s_) : s(s_) {
+  Prof& P = prof();
+  if (!P.on || points < P.min_points) return;
+  std::lock_guard<std::mutex> lk(P.mu);
+  ProfRec r{kclass, P.get(), P.get(), algo_bytes};
+  cudaEventRecord(r.e0, s);
+  slot = (int)P.recs.size();
+  P.recs.push_back(r);
+}
+ProfScope::~ProfScope() {
+  if (slot < 0) return;
+  Prof& P = prof();
+  std::lock_guard<std::mutex> lk(P.mu);
+  cudaEventRecord(P.recs[slot].e1, s);
+}
+int prof_enable(int on, int64_t min_points) {
+  Prof& P = prof();
+  P.on = on != 0; P.min_points = min_points;
+  return IAMRX_OK;
+}
+void prof_reset() {
+  Prof& P = prof();
+  std::lock_guard<std::mutex> lk(P.mu);
+  for (auto& r : P.recs) { P.free_events.push_back(r.e0); P.free_events.push_back(r.e1); }
+  P.recs.clear();
+}
+int prof_report(int kclass, double* total_ms, int64_t* launches, double* algo_bytes) {
+  Prof& P = prof();
+  IX_CUDA(cudaDeviceSynchronize());
+  std::lock_guard<std::mutex> lk(P.mu);
+  double ms = 0, by = 0; int64_t n = 0;
+  for (auto& r : P.recs) {
+    if (r.kclass != kclass) continue;
+    float t = 0;
+    if (cudaEventElapsedTime(&t, r.e0, r.e1) != cudaSuccess) { cudaGetLastError(); continue; }
+    ms += t; by += r.bytes; n++;
+  }
+  if (total_ms) *total_ms = ms;
+  if (launches) *launches = n;
+  if (algo_bytes) *algo_bytes = by;
+  return IAMRX_OK;
+}
+#endif
+
+// ---------------------------------------------------------------------------
 // device pool
 // ---------------------------------------------------------------------------
 namespace {
@@ -171,8 +240,14 @@ int comm_init(int rank, int nranks, const unsigned char uid[128]) {
   IX_NCCL(nccl().init(&c.nccl, nranks, u, rank));
   return IAMRX_OK;
 }
+int comm_set_transport(int rank, int nranks, iamrx_exchange_fn ex, iamrx_allreduce_fn ar, void* ctx) {
+  Comm& c = comm();
+  c.rank = rank; c.nranks = nranks; c.ex = ex; c.ar = ar; c.ctx = ctx;
+  return IAMRX_OK;
+}
 int comm_finalize() {
   Comm& c = comm();
+  c.ex = nullptr; c.ar = nullptr; c.ctx = nullptr;
   if (c.nccl) { nccl().destroy(c.nccl); c.nccl = nullptr; }
   c.rank = 0; c.nranks = 1;
   return IAMRX_OK;
@@ -180,6 +255,11 @@ int comm_finalize() {
 int comm_allreduce(double* dev, int n, int op, cudaStream_t s) {
   Comm& c = comm();
   if (c.nranks <= 1) return IAMRX_OK;
+  if (c.ar) {
+    if (c.ar(c.ctx, dev, n, op, (void*)s) != 0) { set_error("host transport: allreduce failed"); return IAMRX_ERR_COMM; }
+    return IAMRX_OK;
+  }
+  if (!c.nccl) { set_error("communicator not initialised"); return IAMRX_ERR_COMM; }
   const int nop = (op == 0) ? NCCL_SUM : (op == 1 ? NCCL_MIN : NCCL_MAX);
   IX_NCCL(nccl().allreduce(dev, dev, (size_t)n, NCCL_FLOAT64, nop, c.nccl, s));
   return IAMRX_OK;
@@ -189,6 +269,13 @@ int comm_exchange(const std::vector<int>& peers, const std::vector<double*>& sbu
                   const std::vector<int64_t>& rcount, cudaStream_t s) {
   Comm& c = comm();
   if (c.nranks <= 1 || peers.empty()) return IAMRX_OK;
+  if (c.ex) {
+    if (c.ex(c.ctx, (int)peers.size(), peers.data(), sbuf.data(), scount.data(), rbuf.data(), rcount.data(), (void*)s) != 0) {
+      set_error("host transport: exchange failed"); return IAMRX_ERR_COMM;
+    }
+    return IAMRX_OK;
+  }
+  if (!c.nccl) { set_error("communicator not initialised"); return IAMRX_ERR_COMM; }
   IX_NCCL(nccl().gstart());
   for (size_t i = 0; i < peers.size(); ++i) {
     if (scount[i] > 0) IX_NCCL(nccl().send(sbuf[i], (size_t)scount[i], NCCL_FLOAT64, peers[i], c.nccl, s));

@@ -33,6 +33,10 @@ size_t dev_pool_bytes();
 struct Comm {
   int rank = 0, nranks = 1;
   void* nccl = nullptr;  // ncclComm_t
+  // host-supplied transport (iamrx_comm_set_transport); overrides NCCL when set
+  iamrx_exchange_fn ex = nullptr;
+  iamrx_allreduce_fn ar = nullptr;
+  void* ctx = nullptr;
 };
 Comm& comm();
 int comm_allreduce(double* dev, int n, int op, cudaStream_t s);

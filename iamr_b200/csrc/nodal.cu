@@ -171,6 +171,7 @@ int nodal_divu(const Bx& nbx, V4 rhs, C4 vel, const double dxinv[3], cudaStream_
 int nodal_adotx(const Bx& nbx, V4 out, C4 phi, C4 rhs, C4 sig, const double dxinv[3], cudaStream_t s) {
   if (!nbx.ok()) return IAMRX_OK;
   double f[3]; facs(dxinv, f);
+  ProfScope prof_(IAMRX_PROF_NODAL_ADOTX, nbx.npts(), (double)nbx.npts() * (rhs.ok() ? 32.0 : 24.0), s);
   IX_LAUNCH(adotx_kernel, grid_for(nbx), dim3(TX, TY, 1), 0, s, nbx, out, phi, rhs, sig, f[0], f[1], f[2]);
   return check_launch("nodal_adotx");
 }
@@ -194,6 +195,7 @@ int nodal_gs_color(const Bx& nbx, V4 phi, C4 rhs, C4 sig, const double dxinv[3],
     n[d] = (nbx.hi[d] >= o[d]) ? (nbx.hi[d] - o[d]) / 2 + 1 : 0;
     if (n[d] == 0) return IAMRX_OK;
   }
+  ProfScope prof_(IAMRX_PROF_NODAL_GS, nbx.npts(), (double)nbx.npts() * 4.0, s);  // 32 B/node/sweep over 8 colour passes
   dim3 grd(cdiv(n[0], TX), cdiv(n[1], TY), n[2]);
   IX_LAUNCH(gs_color_kernel, grd, dim3(TX, TY, 1), 0, s, nbx, phi, rhs, sig, f[0], f[1], f[2], o[0], o[1], o[2]);
   return check_launch("nodal_gs_color");

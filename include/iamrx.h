@@ -105,6 +105,24 @@ int64_t iamrx_launch_count(void);
 void iamrx_launch_count_reset(void);
 int iamrx_device_ok(void);
 
+/* Kernel timing for the roofline report (bench.py): when enabled, every launch of
+ * the listed kernel classes that covers >= min_points points is bracketed by CUDA
+ * events on its stream.  iamrx_prof_report synchronises and returns the summed
+ * device time, launch count and ALGORITHMIC bytes (per-kernel table)
+ * of one class since the last reset. */
+enum {
+  IAMRX_PROF_ABEC_GSRB = 0,   /* one colour pass of the ABec smoother */
+  IAMRX_PROF_NODAL_GS = 1,    /* one colour pass of the nodal smoother */
+  IAMRX_PROF_AOFS = 2,        /* ComputeAofs on one box (all stages) */
+  IAMRX_PROF_EXTRAP = 3,      /* ExtrapVelToFaces on one box (all stages) */
+  IAMRX_PROF_ABEC_APPLY = 4,  /* ABec apply / residual */
+  IAMRX_PROF_NODAL_ADOTX = 5, /* nodal apply / residual */
+  IAMRX_PROF_NCLASS = 6
+};
+int iamrx_prof_enable(int on, int64_t min_points);
+void iamrx_prof_reset(void);
+int iamrx_prof_report(int kclass, double* total_ms, int64_t* launches, double* algo_bytes);
+
 /* ------------------------------------------------------------------------
  * 1. Per-box kernels (one FArrayBox at a time, async on `stream`).
  * ---------------------------------------------------------------------- */
@@ -198,6 +216,17 @@ int iamrx_comm_init(int rank, int nranks, const unsigned char uid[128]);
 int iamrx_comm_finalize(void);
 int iamrx_comm_rank(void);
 int iamrx_comm_size(void);
+/* Host-supplied transport (optional alternative to iamrx_comm_init).  IAMR's ranks
+ * talk MPI through amrex::ParallelDescriptor; a host that owns the
+ * communicator registers its (GPU-aware) point-to-point exchange and all-reduce
+ * here instead of letting libiamrx open NCCL.  Buffers are DEVICE pointers;
+ * counts are in doubles; op as in iamrx_allreduce.  Return 0 on success. */
+typedef int (*iamrx_exchange_fn)(void* ctx, int npeers, const int* peers, double* const* sendbuf,
+                                 const int64_t* sendcount, double* const* recvbuf,
+                                 const int64_t* recvcount, void* stream);
+typedef int (*iamrx_allreduce_fn)(void* ctx, double* buf, int n, int op, void* stream);
+int iamrx_comm_set_transport(int rank, int nranks, iamrx_exchange_fn exchange,
+                             iamrx_allreduce_fn allreduce, void* ctx);
 /* ParallelDescriptor::ReduceReal{Min,Max,Sum} on n doubles in DEVICE memory. */
 int iamrx_allreduce(double* dev_buf, int n, int op /*0 sum,1 min,2 max*/, void* stream);
 
@@ -207,6 +236,12 @@ int iamrx_level_create(const iamrx_geom* geom, int nboxes, const iamrx_box* boxe
 int iamrx_level_destroy(iamrx_level_t lev);
 int iamrx_level_num_local(iamrx_level_t lev);
 int iamrx_level_local_box(iamrx_level_t lev, int ilocal, iamrx_box* out, int* global_index);
+
+/* Test hook (pure host logic, no device needed): the FillBoundary copy plan of a
+ * level.  Returns the number of regions; fills up to `cap` entries (6 ints per
+ * region lo/hi in destination index space, 3 ints per shift: src = dst + shift). */
+int iamrx_debug_fb_plan(iamrx_level_t lev, int ixtype, int ng, int cap, int* dst_box, int* src_box,
+                        int* region6, int* shift3);
 
 /* ------------------------------------------------------------------------
  * 3. Operators on a level (what Source/MacProj.cpp, Projection.cpp and

@@ -1,0 +1,105 @@
+"""Worker of tests/test_multirank.py: one rank of a world_size-2 gloo job driving the host
+emulation build of libiamrx through the host-transport hook (iamrx_comm_set_transport)."""
+import ctypes as C
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+import iamr_b200 as ix  # noqa: E402
+import orc  # noqa: E402
+from util import split_boxes, hash_uniform, to_fab, fab_array, stream_of  # noqa: E402
+
+EXCH = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_void_p), C.POINTER(C.c_int64),
+                   C.POINTER(C.c_void_p), C.POINTER(C.c_int64), C.c_void_p)
+ARED = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p)
+
+
+def _view(ptr, n):
+    return torch.from_numpy(np.ctypeslib.as_array((C.c_double * n).from_address(ptr)))
+
+
+def exchange(ctx, npeers, peers, sbuf, scount, rbuf, rcount, stream):
+    try:
+        reqs = []
+        for i in range(npeers):
+            if scount[i] > 0:
+                reqs.append(dist.isend(_view(sbuf[i], scount[i]), peers[i]))
+            if rcount[i] > 0:
+                reqs.append(dist.irecv(_view(rbuf[i], rcount[i]), peers[i]))
+        for r in reqs:
+            r.wait()
+        return 0
+    except Exception as e:  # noqa: BLE001
+        print("exchange failed:", e, flush=True)
+        return 1
+
+
+def allreduce(ctx, buf, n, op, stream):
+    try:
+        t = _view(buf, n)
+        dist.all_reduce(t, op={0: dist.ReduceOp.SUM, 1: dist.ReduceOp.MIN, 2: dist.ReduceOp.MAX}[op])
+        return 0
+    except Exception as e:  # noqa: BLE001
+        print("allreduce failed:", e, flush=True)
+        return 1
+
+
+def main():
+    rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    lib = ix.load(os.path.join(ROOT, "tests", "emul", "_build", "libiamrx_emul.so"))
+    ex, ar = EXCH(exchange), ARED(allreduce)
+    lib.check(lib.iamrx_comm_set_transport(rank, world, C.cast(ex, C.c_void_p), C.cast(ar, C.c_void_p), None))
+    assert lib.iamrx_comm_rank() == rank and lib.iamrx_comm_size() == world
+    n = (16, 16, 16)
+    boxes = split_boxes(n, (2, 2, 1))
+    owners = [0, 1, 1, 0]
+    g = ix.Geom.make(n)
+    lev = ix.Level(lib, g, boxes, owners)
+    mine = [i for i, o in enumerate(owners) if o == rank]
+    assert lev.num_local() == len(mine)
+
+    # 1. FillBoundary across ranks (cell ng=3, nodal ng=1) vs periodic wrap
+    for ixtype, ncomp, ng in ((ix.CELL, 2, 3), (ix.NODE, 1, 1), (ix.XFACE, 1, 1)):
+        dense = hash_uniform(11 + ixtype, (ncomp, n[2], n[1], n[0]))
+        pairs = [to_fab(dense, boxes[i], ng, ixtype, "cpu", fill_ghost=False) for i in mine]
+        want = [to_fab(dense, boxes[i], ng, ixtype, "cpu", fill_ghost=True)[0] for i in mine]
+        lib.check(lib.iamrx_fill_boundary(lev.h, fab_array([p[1] for p in pairs]), ixtype, ncomp, ng, stream_of("cpu")))
+        for (t, _), w in zip(pairs, want):
+            assert np.array_equal(t.numpy(), w.numpy()), (rank, ixtype)
+
+    # 2. the full step on 2 ranks vs the single-box oracle
+    kw = dict(visc_coef=1e-3, cfl=0.7, gravity=-0.5)
+    ns = ix.NavierStokes(lib, lev, "cpu", **kw)
+    o = orc.OracleNS(n, **kw)
+    pp = [1.0, 1.0, 1.0, 1.0, 1.0]
+    ns.init_prob(100, pp); o.init_prob(100, pp)
+    d1, d2 = ns.post_init(), o.post_init()
+    assert abs(d1 - d2) <= 1e-13 * d2
+    for _ in range(2):
+        a, b = ns.step(), o.step()
+        assert abs(a - b) <= 1e-12 * b
+    So = o.get(0)
+    err = 0.0
+    for il, gi in enumerate(mine):
+        lo, hi = boxes[gi]
+        t = ns.field(0, il).numpy()
+        err = max(err, np.abs(t - So[:, lo[2]:hi[2] + 1, lo[1]:hi[1] + 1, lo[0]:hi[0] + 1]).max())
+    assert err <= 1e-10, err
+    # 3. reductions agree across ranks
+    t = torch.tensor([err])
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    print(f"rank {rank} ok max_err {t.item():.3e}", flush=True)
+    ns.close(); lev.close()
+    lib.iamrx_comm_finalize()
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

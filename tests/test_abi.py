@@ -1,0 +1,78 @@
+"""The C-ABI shared library: loads without a GPU, exports every symbol include/iamrx.h
+declares, refuses to compute without a device (no CPU fallback), and the product package
+never touches the oracle."""
+import ctypes as C
+import os
+import re
+import subprocess
+
+import pytest
+
+import iamr_b200 as ix
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared():
+    hdr = open(os.path.join(ROOT, "include", "iamrx.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    names = set(re.findall(r"\b(iamrx_[a-z0-9_]+)\s*\(", hdr))
+    return {n for n in names if not n.endswith("_fn")}
+
+
+def test_library_exports_every_declared_symbol():
+    if not os.path.exists(ix.lib_path()):
+        subprocess.check_call(["make", "-s", "-j8", "-C", ROOT])
+    lib = ix.load()
+    names = _declared()
+    assert len(names) >= 40
+    for n in names:
+        assert hasattr(lib.dll, n), f"{n} declared in include/iamrx.h but not exported"
+    # and the binding knows all of them
+    assert names <= set(ix.binding.SIGNATURES)
+    assert lib.iamrx_version() >= 100
+
+
+def test_no_cpu_fallback():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    lib = ix.load()
+    assert lib.iamrx_device_ok() == 0
+    g = ix.Geom.make((8, 8, 8))
+    lev = ix.Level(lib, g, [((0, 0, 0), (7, 7, 7))])  # pure host object: allowed
+    p = ix.NSParams()
+    lib.iamrx_ns_params_default(C.byref(p))
+    h = C.c_void_p()
+    rc = lib.iamrx_ns_create(lev.h, C.byref(p), C.byref(h))
+    assert rc == -3 and b"no CPU fallback" in lib.iamrx_last_error()
+    rc = lib.iamrx_fill_boundary(lev.h, None, 0, 1, 1, None)
+    assert rc == -3
+    lev.close()
+
+
+def test_missing_library_fails_loudly(tmp_path):
+    with pytest.raises(FileNotFoundError):
+        ix.load(str(tmp_path / "libiamrx.so"))
+
+
+def test_product_never_references_oracle():
+    pkg = os.path.join(ROOT, "iamr_b200")
+    for dp, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".h", ".cpp")):
+                txt = open(os.path.join(dp, f), errors="ignore").read()
+                assert "liboracle" not in txt and "import orc" not in txt and "oracle/_build" not in txt, f
+    out = subprocess.run(["ldd", ix.lib_path()], capture_output=True, text=True).stdout
+    assert "oracle" not in out and "emul" not in out
+
+
+def test_level_argument_checks():
+    lib = ix.load()
+    g = ix.Geom.make((8, 8, 8))
+    with pytest.raises(ix.IamrxError):
+        ix.Level(lib, g, [((0, 0, 0), (7, 7, 7)), ((4, 4, 4), (7, 7, 7))])  # overlap
+    with pytest.raises(ix.IamrxError):
+        ix.Level(lib, g, [((0, 0, 0), (8, 7, 7))])  # outside the domain
+    with pytest.raises(ix.IamrxError):
+        ix.Level(lib, g, [((0, 0, 0), (7, 7, 7))], owners=[3])  # rank out of range

@@ -1,0 +1,271 @@
+"""Per-box kernels through the C ABI vs the CPU oracle on the same seeded inputs.
+Tolerances: these are single stencil evaluations in fp64; the two sides may differ only by
+FMA contraction / summation order, so max|diff| <= 1e-13 * scale is asserted."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import iamr_b200 as ix
+from util import (hash_uniform, smooth_field, split_boxes, to_fab, from_fabs, d3, box_of, stream_of, sync)
+
+N = (16, 12, 8)
+DX = (1.0 / 16, 1.0 / 12, 1.0 / 8)
+DXINV = tuple(1.0 / h for h in DX)
+RTOL = 1e-13
+
+
+def _coeffs(seed, n=N, ncomp=1):
+    nz, ny, nx = n[2], n[1], n[0]
+    bx = 1.0 + 0.5 * hash_uniform(seed + 1, (ncomp, nz, ny, nx))
+    by = 1.0 + 0.5 * hash_uniform(seed + 2, (ncomp, nz, ny, nx))
+    bz = 1.0 + 0.5 * hash_uniform(seed + 3, (ncomp, nz, ny, nx))
+    alpha = 1.5 + 0.5 * hash_uniform(seed + 4, (1, nz, ny, nx))
+    return alpha, bx, by, bz
+
+
+def _scale(a):
+    return max(1.0, float(np.abs(a).max()))
+
+
+@pytest.mark.parametrize("nb", [(1, 1, 1), (2, 2, 2)])
+@pytest.mark.parametrize("a,ncomp,bn", [(0.0, 1, 1), (1.0, 1, 1), (1.0, 3, 3)])
+def test_abec_gsrb_and_apply(backend, oracle, nb, a, ncomp, bn):
+    lib, dev = backend
+    b = 0.37
+    alpha, bx, by, bz = _coeffs(10, ncomp=bn)
+    phi = hash_uniform(1, (ncomp, N[2], N[1], N[0]))
+    rhs = hash_uniform(2, (ncomp, N[2], N[1], N[0]))
+    boxes = split_boxes(N, nb)
+    s = stream_of(dev)
+    for rb in (0, 1):
+        ref = oracle.abec_gsrb(DXINV, a, b, alpha if a else None, bx, by, bz, rhs, 1.15, rb, phi)
+        outs = []
+        for box in boxes:
+            tp, fp = to_fab(phi, box, 1, ix.CELL, dev)
+            tr, fr = to_fab(rhs, box, 0, ix.CELL, dev)
+            ta, fa = to_fab(alpha, box, 0, ix.CELL, dev)
+            tbx, fbx = to_fab(bx, box, 0, ix.XFACE, dev)
+            tby, fby = to_fab(by, box, 0, ix.YFACE, dev)
+            tbz, fbz = to_fab(bz, box, 0, ix.ZFACE, dev)
+            bb = box_of(*box)
+            lib.check(lib.iamrx_abec_gsrb_box(C.byref(bb), C.byref(fp), C.byref(fr), a, b, C.byref(fa) if a else None,
+                                              C.byref(fbx), C.byref(fby), C.byref(fbz), d3(DXINV), 1.15, rb, ncomp, s))
+            outs.append(tp)
+        sync(dev)
+        got, _ = from_fabs(outs, boxes, 1, ix.CELL, N, ncomp)
+        assert np.abs(got - ref).max() <= RTOL * _scale(ref) * 100  # division by gamma amplifies rounding
+        # cells of the other colour are untouched (bit-exact)
+        kk, jj, ii = np.meshgrid(np.arange(N[2]), np.arange(N[1]), np.arange(N[0]), indexing="ij")
+        other = ((ii + jj + kk + rb) % 2) == 1
+        assert np.array_equal(got[:, other], phi[:, other])
+    # apply and residual
+    ref = oracle.abec_apply(DXINV, a, b, alpha if a else None, bx, by, bz, phi)
+    for with_rhs in (False, True):
+        outs = []
+        for box in boxes:
+            tp, fp = to_fab(phi, box, 1, ix.CELL, dev)
+            to, fo = to_fab(np.zeros_like(phi), box, 0, ix.CELL, dev)
+            tr, fr = to_fab(rhs, box, 0, ix.CELL, dev)
+            ta, fa = to_fab(alpha, box, 0, ix.CELL, dev)
+            tbx, fbx = to_fab(bx, box, 0, ix.XFACE, dev)
+            tby, fby = to_fab(by, box, 0, ix.YFACE, dev)
+            tbz, fbz = to_fab(bz, box, 0, ix.ZFACE, dev)
+            bb = box_of(*box)
+            lib.check(lib.iamrx_abec_apply_box(C.byref(bb), C.byref(fo), C.byref(fp), C.byref(fr) if with_rhs else None, a, b,
+                                               C.byref(fa) if a else None, C.byref(fbx), C.byref(fby), C.byref(fbz),
+                                               d3(DXINV), ncomp, s))
+            outs.append(to)
+        sync(dev)
+        got, _ = from_fabs(outs, boxes, 0, ix.CELL, N, ncomp)
+        want = (rhs - ref) if with_rhs else ref
+        assert np.abs(got - want).max() <= RTOL * _scale(ref)
+
+
+def test_tensor_cross(backend, oracle):
+    lib, dev = backend
+    vel = smooth_field(N, 5, 3)
+    ex, ey, ez = (1.0 + 0.3 * hash_uniform(20 + d, (1, N[2], N[1], N[0])) for d in range(3))
+    out0 = hash_uniform(30, (3, N[2], N[1], N[0]))
+    ref = oracle.tensor_cross(DXINV, -0.8, ex, ey, ez, vel, out0)
+    boxes = split_boxes(N, (2, 1, 2))
+    outs = []
+    for box in boxes:
+        tv, fv = to_fab(vel, box, 1, ix.CELL, dev)
+        to, fo = to_fab(out0, box, 0, ix.CELL, dev)
+        te = [to_fab(e, box, 0, t, dev) for e, t in ((ex, ix.XFACE), (ey, ix.YFACE), (ez, ix.ZFACE))]
+        bb = box_of(*box)
+        lib.check(lib.iamrx_tensor_cross_box(C.byref(bb), C.byref(fo), C.byref(fv), C.byref(te[0][1]), C.byref(te[1][1]),
+                                             C.byref(te[2][1]), -0.8, d3(DXINV), stream_of(dev)))
+        outs.append(to)
+    sync(dev)
+    got, _ = from_fabs(outs, boxes, 0, ix.CELL, N, 3)
+    assert np.abs(got - ref).max() <= RTOL * _scale(ref)
+
+
+@pytest.mark.parametrize("nb", [(1, 1, 1), (2, 2, 1)])
+def test_nodal_kernels(backend, oracle, nb):
+    lib, dev = backend
+    sig = 1.0 + 0.5 * hash_uniform(40, (1, N[2], N[1], N[0]))
+    phi = hash_uniform(41, (1, N[2], N[1], N[0]))
+    rhs = hash_uniform(42, (1, N[2], N[1], N[0]))
+    vel = hash_uniform(43, (3, N[2], N[1], N[0]))
+    boxes = split_boxes(N, nb)
+    s = stream_of(dev)
+    # divergence
+    ref = oracle.nodal_divu(DXINV, vel)[None]
+    outs = []
+    for box in boxes:
+        tv, fv = to_fab(vel, box, 1, ix.CELL, dev)
+        tr, fr = to_fab(np.zeros_like(phi), box, 0, ix.NODE, dev)
+        nbx = box_of(box[0], tuple(h + 1 for h in box[1]))
+        lib.check(lib.iamrx_nodal_divu_box(C.byref(nbx), C.byref(fr), C.byref(fv), d3(DXINV), s))
+        outs.append(tr)
+    sync(dev)
+    got, dup = from_fabs(outs, boxes, 0, ix.NODE, N, 1)
+    assert dup == 0.0 and np.abs(got - ref).max() <= RTOL * _scale(ref)
+    # A*phi and residual
+    ref = oracle.nodal_adotx(DXINV, sig, phi)
+    for with_rhs in (False, True):
+        outs = []
+        for box in boxes:
+            tp, fp = to_fab(phi, box, 1, ix.NODE, dev)
+            ts, fs = to_fab(sig, box, 1, ix.CELL, dev)
+            tr, fr = to_fab(rhs, box, 0, ix.NODE, dev)
+            to, fo = to_fab(np.zeros_like(phi), box, 0, ix.NODE, dev)
+            nbx = box_of(box[0], tuple(h + 1 for h in box[1]))
+            lib.check(lib.iamrx_nodal_adotx_box(C.byref(nbx), C.byref(fo), C.byref(fp), C.byref(fr) if with_rhs else None,
+                                                C.byref(fs), d3(DXINV), s))
+            outs.append(to)
+        sync(dev)
+        got, dup = from_fabs(outs, boxes, 0, ix.NODE, N, 1)
+        want = (rhs - ref) if with_rhs else ref
+        assert dup == 0.0 and np.abs(got - want).max() <= RTOL * _scale(ref)
+    # Gauss-Seidel colours
+    for color in range(8):
+        ref = oracle.nodal_gs(DXINV, sig, rhs, color, phi)
+        outs = []
+        for box in boxes:
+            tp, fp = to_fab(phi, box, 1, ix.NODE, dev)
+            ts, fs = to_fab(sig, box, 1, ix.CELL, dev)
+            tr, fr = to_fab(rhs, box, 0, ix.NODE, dev)
+            nbx = box_of(box[0], tuple(h + 1 for h in box[1]))
+            lib.check(lib.iamrx_nodal_gs_box(C.byref(nbx), C.byref(fp), C.byref(fr), C.byref(fs), d3(DXINV), color, s))
+            outs.append(tp)
+        sync(dev)
+        got, dup = from_fabs(outs, boxes, 1, ix.NODE, N, 1)
+        assert dup == 0.0 and np.abs(got - ref).max() <= 1e-12 * _scale(ref)
+    # mknewu / gradient
+    vref, gref = oracle.nodal_mknewu(DXINV, sig, phi, vel)
+    ov, og = [], []
+    for box in boxes:
+        tp, fp = to_fab(phi, box, 1, ix.NODE, dev)
+        ts, fs = to_fab(sig, box, 1, ix.CELL, dev)
+        tv, fv = to_fab(vel, box, 1, ix.CELL, dev)
+        tg, fg = to_fab(np.zeros_like(vel), box, 0, ix.CELL, dev)
+        bb = box_of(*box)
+        lib.check(lib.iamrx_nodal_mknewu_box(C.byref(bb), C.byref(fv), C.byref(fg), C.byref(fp), C.byref(fs), d3(DXINV), s))
+        ov.append(tv); og.append(tg)
+    sync(dev)
+    gv, _ = from_fabs(ov, boxes, 1, ix.CELL, N, 3)
+    gg, _ = from_fabs(og, boxes, 0, ix.CELL, N, 3)
+    assert np.abs(gv - vref).max() <= RTOL * _scale(vref) and np.abs(gg - gref).max() <= RTOL * _scale(gref)
+
+
+def _adv_inputs(n, ncomp, seed):
+    vel = smooth_field(n, seed, 3, amp=0.4)
+    q = smooth_field(n, seed + 7, ncomp, amp=0.5) + 1.0
+    # sharpen one component so the limiters are active
+    q[0] += 0.3 * np.sign(smooth_field(n, seed + 9, 1)[0])
+    f = smooth_field(n, seed + 11, max(ncomp, 3), amp=0.2)
+    dx = tuple(1.0 / m for m in n)
+    # face velocities: average of cells + perturbation (not divergence free on purpose)
+    um = 0.5 * (vel[0] + np.roll(vel[0], 1, axis=2)) + 0.05 * smooth_field(n, seed + 1, 1)[0]
+    vm = 0.5 * (vel[1] + np.roll(vel[1], 1, axis=1)) + 0.05 * smooth_field(n, seed + 2, 1)[0]
+    wm = 0.5 * (vel[2] + np.roll(vel[2], 1, axis=0)) + 0.05 * smooth_field(n, seed + 3, 1)[0]
+    return vel, q, f, (um, vm, wm), dx
+
+
+@pytest.mark.parametrize("nb", [(1, 1, 1), (2, 2, 2)])
+@pytest.mark.parametrize("fit", [0, 1])
+def test_extrap_vel_to_faces(backend, oracle, nb, fit):
+    lib, dev = backend
+    n = (16, 16, 8)
+    vel, _, f, _, dx = _adv_inputs(n, 3, 100)
+    vel[2] += 0.2  # make sure every branch of the upwinding sees both signs
+    dt = 0.5 * min(dx) / np.abs(vel).max()
+    ref = oracle.extrap_vel_to_faces(dx, dt, vel, f[:3].copy(), fit)
+    g = ix.Geom.make(n)
+    boxes = split_boxes(n, nb)
+    outs = [[], [], []]
+    for box in boxes:
+        tv, fv = to_fab(vel, box, 3, ix.CELL, dev)
+        tf, ff = to_fab(f[:3], box, 1, ix.CELL, dev)
+        macs = [to_fab(np.zeros((1, n[2], n[1], n[0])), box, 1, t, dev) for t in (ix.XFACE, ix.YFACE, ix.ZFACE)]
+        bb = box_of(*box)
+        lib.check(lib.iamrx_extrap_vel_to_faces_box(C.byref(bb), C.byref(fv), C.byref(ff), C.byref(macs[0][1]),
+                                                    C.byref(macs[1][1]), C.byref(macs[2][1]), C.byref(g), dt,
+                                                    2 if fit else 0, stream_of(dev)))
+        for d in range(3):
+            outs[d].append(macs[d][0])
+    sync(dev)
+    for d, t in enumerate((ix.XFACE, ix.YFACE, ix.ZFACE)):
+        got, dup = from_fabs(outs[d], boxes, 1, t, n, 1)
+        assert dup == 0.0
+        assert np.abs(got[0] - ref[d]).max() <= RTOL * 10
+
+
+@pytest.mark.parametrize("nb", [(1, 1, 1), (2, 2, 2)])
+@pytest.mark.parametrize("ncomp,iconserv,fit", [(3, (0, 0, 0), 0), (2, (1, 0), 0), (2, (1, 1), 1)])
+def test_compute_aofs(backend, oracle, nb, ncomp, iconserv, fit):
+    lib, dev = backend
+    n = (16, 16, 8)
+    _, q, f, (um, vm, wm), dx = _adv_inputs(n, ncomp, 200)
+    dt = 0.5 * min(dx) / max(np.abs(um).max(), np.abs(vm).max(), np.abs(wm).max())
+    ref, (rfx, rfy, rfz, rxe, rye, rze) = oracle.compute_aofs(dx, dt, q, f[:ncomp].copy(), um, vm, wm, iconserv, fit, want_fluxes=True)
+    g = ix.Geom.make(n)
+    boxes = split_boxes(n, nb)
+    ic = (C.c_int * ncomp)(*iconserv)
+    out_a, out_f, out_e = [], [[], [], []], [[], [], []]
+    for box in boxes:
+        tq, fq = to_fab(q, box, 3, ix.CELL, dev)
+        tf, ff = to_fab(f[:ncomp], box, 1, ix.CELL, dev)
+        ta, fa = to_fab(np.zeros_like(q), box, 0, ix.CELL, dev)
+        macs = [to_fab(m[None], box, 1, t, dev) for m, t in ((um, ix.XFACE), (vm, ix.YFACE), (wm, ix.ZFACE))]
+        fl = [to_fab(np.zeros_like(q), box, 0, t, dev) for t in (ix.XFACE, ix.YFACE, ix.ZFACE)]
+        ed = [to_fab(np.zeros_like(q), box, 0, t, dev) for t in (ix.XFACE, ix.YFACE, ix.ZFACE)]
+        bb = box_of(*box)
+        flags = (2 if fit else 0) | 8
+        lib.check(lib.iamrx_compute_aofs_box(C.byref(bb), C.byref(fa), 0, C.byref(fq), 0, ncomp, C.byref(ff), 0, None,
+                                             C.byref(macs[0][1]), C.byref(macs[1][1]), C.byref(macs[2][1]),
+                                             C.byref(fl[0][1]), C.byref(fl[1][1]), C.byref(fl[2][1]),
+                                             C.byref(ed[0][1]), C.byref(ed[1][1]), C.byref(ed[2][1]),
+                                             ic, C.byref(g), dt, flags, stream_of(dev)))
+        out_a.append(ta)
+        for d in range(3):
+            out_f[d].append(fl[d][0]); out_e[d].append(ed[d][0])
+    sync(dev)
+    got, _ = from_fabs(out_a, boxes, 0, ix.CELL, n, ncomp)
+    scale = _scale(ref)
+    assert np.abs(got - ref).max() <= 1e-12 * scale
+    for d, (t, rf, re) in enumerate(((ix.XFACE, rfx, rxe), (ix.YFACE, rfy, rye), (ix.ZFACE, rfz, rze))):
+        gf, dup = from_fabs(out_f[d], boxes, 0, t, n, ncomp)
+        ge, dup2 = from_fabs(out_e[d], boxes, 0, t, n, ncomp)
+        assert dup == 0.0 and dup2 == 0.0
+        assert np.abs(ge - re).max() <= RTOL * 10 and np.abs(gf - rf).max() <= RTOL * 10
+
+
+def test_bad_arguments(backend):
+    lib, dev = backend
+    rc = lib.iamrx_abec_gsrb_box(None, None, None, 0.0, 1.0, None, None, None, None, None, 1.0, 0, 1, None)
+    assert rc == -1 and b"null" in lib.iamrx_last_error()
+    n = (8, 8, 8)
+    g = ix.Geom.make(n)
+    box = ((0, 0, 0), (7, 7, 7))
+    z = np.zeros((3, 8, 8, 8))
+    tv, fv = to_fab(z, box, 3, ix.CELL, dev)
+    macs = [to_fab(z[:1], box, 1, t, dev) for t in (ix.XFACE, ix.YFACE, ix.ZFACE)]
+    bb = box_of(*box)
+    rc = lib.iamrx_extrap_vel_to_faces_box(C.byref(bb), C.byref(fv), None, C.byref(macs[0][1]), C.byref(macs[1][1]),
+                                           C.byref(macs[2][1]), C.byref(g), 0.1, 1, stream_of(dev))
+    assert rc == -1 and b"PPM" in lib.iamrx_last_error()

@@ -1,0 +1,160 @@
+"""Pins the CPU oracle to what the reference itself offers for this path:
+ * the analytic decaying Taylor vortex (Tutorials/TaylorGreen/benchmarks/EXACT_3D.F:75,114-118;
+   ViscBench.cpp:143-236) -- 2nd-order convergence (Util/Convergence_scripts/multiRuns.py:34);
+ * the identities the reference prints: div(u_mac) ~ 0 after the MAC projection
+   (MacProj.cpp:792-846), conservation of MASS (NS.cpp:1076-1078);
+ * discrete properties of the operators (symmetry, null space, linearity).
+The reference ships no golden plotfiles (Test/README.md:23-29): at 1e-10 the oracle is
+"parity unpinned" against AMReX/AMReX-Hydro; see oracle/oracle.h."""
+import math
+
+import numpy as np
+import pytest
+
+from util import hash_uniform, smooth_field
+
+
+def _tg_error(oracle, n, t_end, nu=1e-3):
+    o = oracle.OracleNS((n, n, n), visc_coef=nu, cfl=0.7)
+    o.init_prob(11, [1.0, 1.0, 0.0, 1.0, 1.0])
+    o.post_init()
+    while o.time < t_end - 1e-12:
+        dt = o.step()
+        if o.time + dt > t_end:
+            o.step(t_end - o.time)
+            break
+    S = o.get(0)
+    x = (np.arange(n) + 0.5) / n
+    Z, Y, X = np.meshgrid(x, x, x, indexing="ij")
+    dec = math.exp(-8 * math.pi ** 2 * nu * o.time)
+    ue = np.sin(2 * math.pi * X) * np.cos(2 * math.pi * Y) * dec
+    ve = -np.cos(2 * math.pi * X) * np.sin(2 * math.pi * Y) * dec
+    err = max(np.sqrt(np.mean((S[0] - ue) ** 2)), np.sqrt(np.mean((S[1] - ve) ** 2)))
+    mass = S[3].sum() / n ** 3
+    w = np.abs(S[2]).max()
+    o.close()
+    return err, mass, w
+
+
+def test_taylor_vortex_second_order(oracle):
+    e16, m16, w16 = _tg_error(oracle, 16, 0.05)
+    e32, m32, w32 = _tg_error(oracle, 32, 0.05)
+    # L2 error (ViscBench's L2 norm) must drop by ~4x per refinement
+    rate = math.log2(e16 / e32)
+    assert 1.7 < rate < 3.2, (e16, e32, rate)
+    assert e32 < 2e-3
+    assert abs(m16 - 1.0) < 1e-13 and abs(m32 - 1.0) < 1e-13   # MASS conserved
+    assert w16 < 1e-13 and w32 < 1e-13                        # prob.c = 0: the flow stays 2-D
+
+
+def test_mac_projection_is_exact_and_idempotent(oracle):
+    n = (16, 16, 8)
+    dx = tuple(1.0 / m for m in n)
+    rho = 1.0 + 0.4 * smooth_field(n, 3, 1)
+    u, v, w = (smooth_field(n, 10 + d, 1)[0] for d in range(3))
+    mg = oracle.mg_default(rtol=1e-13)
+    pu, pv, pw, phi, rc, _ = oracle.mac_project(dx, u, v, w, rho, None, np.zeros_like(rho), 30.0, mg)
+    assert rc == 0
+    div = (np.roll(pu, -1, 2) - pu) / dx[0] + (np.roll(pv, -1, 1) - pv) / dx[1] + (np.roll(pw, -1, 0) - pw) / dx[2]
+    div0 = (np.roll(u, -1, 2) - u) / dx[0] + (np.roll(v, -1, 1) - v) / dx[1] + (np.roll(w, -1, 0) - w) / dx[2]
+    assert np.abs(div).max() < 1e-11 * np.abs(div0).max()
+    qu, qv, qw, phi2, rc, mg2 = oracle.mac_project(dx, pu, pv, pw, rho, None, np.zeros_like(rho), 30.0, oracle.mg_default(rtol=1e-13))
+    assert np.abs(qu - pu).max() < 1e-12  # idempotent
+
+
+def test_abec_operator_properties(oracle):
+    n = (8, 12, 16)
+    dxinv = (8.0, 12.0, 16.0)
+    shp = (1, n[2], n[1], n[0])
+    bx, by, bz = (1.0 + 0.5 * hash_uniform(s, shp) for s in (1, 2, 3))
+    al = 1.5 + 0.5 * hash_uniform(4, shp)
+    x, y = hash_uniform(5, shp), hash_uniform(6, shp)
+    A = lambda p: oracle.abec_apply(dxinv, 0.7, 0.3, al, bx, by, bz, p)
+    assert abs((x * A(y)).sum() - (y * A(x)).sum()) < 1e-9 * abs((x * A(y)).sum())        # self-adjoint
+    assert np.abs(A(2.0 * x + y) - (2.0 * A(x) + A(y))).max() < 1e-10                      # linear
+    L = lambda p: oracle.abec_apply(dxinv, 0.0, 1.0, None, bx, by, bz, p)
+    assert np.abs(L(np.ones(shp))).max() < 1e-11                                           # constants in the null space
+    # GSRB: a full red+black sweep of the exact solution is a fixed point; residual decreases otherwise
+    rhs = A(x)
+    p = x.copy()
+    for rb in (0, 1):
+        p = oracle.abec_gsrb(dxinv, 0.7, 0.3, al, bx, by, bz, rhs, 1.0, rb, p)
+    assert np.abs(p - x).max() < 1e-12
+    p = np.zeros(shp)
+    r0 = np.abs(rhs - A(p)).max()
+    for sweep in range(10):
+        for rb in (0, 1):
+            p = oracle.abec_gsrb(dxinv, 0.7, 0.3, al, bx, by, bz, rhs, 1.0, rb, p)
+    assert np.abs(rhs - A(p)).max() < 0.5 * r0
+
+
+def test_tensor_operator_matches_analytic_divergence_of_stress(oracle):
+    # constant eta: div(eta (grad u + grad u^T) - 2/3 eta div u I) evaluated on smooth data, O(h^2)
+    errs = []
+    for m in (16, 32):
+        n = (m, m, m)
+        dx = (1.0 / m,) * 3
+        x = (np.arange(m) + 0.5) / m
+        Z, Y, X = np.meshgrid(x, x, x, indexing="ij")
+        tp = 2 * np.pi
+        u = np.stack([np.sin(tp * X) * np.cos(tp * Y), np.sin(tp * Y) * np.cos(tp * Z), np.sin(tp * Z) * np.cos(tp * X)])
+        eta = np.full((1, m, m, m), 0.3)
+        out = oracle.diffusion_apply(dx, 1, 0.0, -1.0, None, eta, eta, eta, u)
+        # analytic: eta*(lap u + (1/3) grad(div u))
+        lap = np.stack([-2 * tp ** 2 * u[0], -2 * tp ** 2 * u[1], -2 * tp ** 2 * u[2]])
+        gd = -tp ** 2 * np.stack([np.sin(tp * X) * (np.cos(tp * Y) + np.cos(tp * Z)),
+                                  np.sin(tp * Y) * (np.cos(tp * X) + np.cos(tp * Z)),
+                                  np.sin(tp * Z) * (np.cos(tp * Y) + np.cos(tp * X))])
+        exact = 0.3 * (lap + gd / 3.0)
+        errs.append(np.abs(out - exact).max() / np.abs(exact).max())
+    assert errs[1] < 0.3 * errs[0] and errs[1] < 5e-3, errs
+
+
+def test_nodal_operator_properties(oracle):
+    n = (8, 8, 12)
+    dxinv = (8.0, 8.0, 12.0)
+    shp = (1, n[2], n[1], n[0])
+    sig = 1.0 + 0.5 * hash_uniform(7, shp)
+    x, y = hash_uniform(8, shp), hash_uniform(9, shp)
+    A = lambda p: oracle.nodal_adotx(dxinv, sig, p)
+    assert np.abs(A(np.ones(shp))).max() < 1e-10
+    assert abs((x * A(y)).sum() - (y * A(x)).sum()) < 1e-9 * abs((x * A(y)).sum())
+    assert (x * A(x)).sum() < 0.0   # div(sigma grad) is negative semi-definite
+    # FE divergence and gradient are (negative) adjoints: <phi, D v> = -<G phi, v>
+    v = hash_uniform(10, (3,) + shp[1:])
+    d = oracle.nodal_divu(dxinv, v)
+    _, g = oracle.nodal_mknewu(dxinv, np.ones(shp), x, np.zeros_like(v))
+    assert abs((x[0] * d).sum() + (g * v).sum()) < 1e-9 * abs((g * v).sum())
+
+
+def test_advection_properties(oracle):
+    n = (16, 16, 8)
+    dx = tuple(1.0 / m for m in n)
+    rho = np.ones((1, n[2], n[1], n[0]))
+    u, v, w = (0.5 * smooth_field(n, 20 + d, 1)[0] for d in range(3))
+    pu, pv, pw, *_ = oracle.mac_project(dx, u, v, w, rho, None, np.zeros_like(rho), 1.0, oracle.mg_default(rtol=1e-13))
+    dt = 0.4 * min(dx) / max(np.abs(pu).max(), np.abs(pv).max(), np.abs(pw).max())
+    q = np.concatenate([np.full((1, n[2], n[1], n[0]), 3.0), 1.0 + 0.5 * smooth_field(n, 30, 1)])
+    f = np.zeros_like(q)
+    # constant field, divergence-free u_mac: the convective form preserves it exactly
+    a = oracle.compute_aofs(dx, dt, q, f, pu, pv, pw, (0, 1))
+    assert np.abs(a[0]).max() < 1e-9
+    # the conservative form does so only up to the O(dt^2) corner-coupling terms in 3-D (flux-form
+    # corner coupling without the q*div add-back) ...
+    a3 = oracle.compute_aofs(dx, dt, q, f, pu, pv, pw, (1, 0))
+    a3h = oracle.compute_aofs(dx, 0.5 * dt, q, f, pu, pv, pw, (1, 0))
+    assert np.abs(a3h[0]).max() < 0.3 * np.abs(a3[0]).max()
+    # ... and exactly when the flow is z-invariant (the Taylor vortex of inputs.3d.taylorgreen)
+    u2, v2 = (np.repeat(x[:1], n[2], axis=0) for x in (u, v))
+    qu, qv, qw, *_ = oracle.mac_project(dx, u2, v2, np.zeros_like(u2), rho, None, np.zeros_like(rho), 1.0, oracle.mg_default(rtol=1e-13))
+    a2 = oracle.compute_aofs(dx, dt, q, f, qu, qv, qw, (1, 0))
+    assert np.abs(a2[0]).max() < 1e-9
+    # conservative update telescopes: sum(aofs) == 0
+    assert abs(a[1].sum()) < 1e-9 * np.abs(a[1]).sum()
+    # uniform translation u=(c,0,0), dt = dx/c: first-order upwind limit reproduces an exact shift
+    c = 0.7
+    uu = np.full_like(pu, c); zz = np.zeros_like(pu)
+    dt1 = dx[0] / c
+    qq = 1.0 + 0.5 * smooth_field(n, 31, 1)
+    a = oracle.compute_aofs(dx, dt1, qq, np.zeros_like(qq), uu, zz, zz, (1,))
+    assert np.abs((qq - dt1 * a) - np.roll(qq, 1, axis=3)).max() < 1e-12

@@ -1,0 +1,138 @@
+"""The level time step (NavierStokes::advance / post_init restated in ns.cu) against the oracle,
+the analytic Taylor vortex, and size-independent invariants."""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+import iamr_b200 as ix
+from util import split_boxes
+
+
+def _assemble(ns, which, boxes, n, ncomp, ext=(0, 0, 0)):
+    out = np.zeros((ncomp, n[2], n[1], n[0]))
+    for il, (lo, hi) in enumerate(boxes):
+        t = ns.field(which, il).cpu().numpy()
+        nz, ny, nx = (hi[2] - lo[2] + 1, hi[1] - lo[1] + 1, hi[0] - lo[0] + 1)
+        out[:, lo[2]:hi[2] + 1, lo[1]:hi[1] + 1, lo[0]:hi[0] + 1] = t[:, :nz, :ny, :nx]
+    return out
+
+
+@pytest.mark.parametrize("nb", [(1, 1, 1), (2, 2, 2)])
+@pytest.mark.parametrize("probtype,pp,extra", [
+    (11, [1.0, 1.0, 0.0, 1.0, 1.0], {}),                       # TaylorGreen, inputs.3d.taylorgreen (prob.c = 0)
+    (100, [1.0, 1.0, 1.0, 1.0, 1.0], {"gravity": -0.5}),       # 3-D variable density + buoyancy
+    (5, [1.0, 1.0, 0.0, 0.0, 0.0, 0.4], {"conservative_tracer": 1}),  # DoubleShearLayer IC, conservative tracer
+])
+def test_step_matches_oracle(backend, oracle, nb, probtype, pp, extra):
+    """Velocity / pressure L-inf parity <= 1e-10 (north_star tolerance) over init + 3 steps."""
+    lib, dev = backend
+    n = (16, 16, 16)
+    lo, hi = ((-1.0, -1.0, -1.0), (1.0, 1.0, 1.0)) if probtype == 5 else ((0, 0, 0), (1, 1, 1))
+    g = ix.Geom.make(n, lo, hi)
+    boxes = split_boxes(n, nb)
+    lev = ix.Level(lib, g, boxes)
+    kw = dict(visc_coef=1e-3, cfl=0.7)
+    kw.update(extra)
+    ns = ix.NavierStokes(lib, lev, dev, **kw)
+    o = oracle.OracleNS(n, lo, hi, **kw)
+    ns.init_prob(probtype, pp); o.init_prob(probtype, pp)
+    d1, d2 = ns.post_init(), o.post_init()
+    assert abs(d1 - d2) <= 1e-13 * d2
+    for step in range(3):
+        a, b = ns.step(), o.step()
+        assert abs(a - b) <= 1e-12 * b
+        S, So = _assemble(ns, 0, boxes, n, 5), o.get(0)
+        P, Po = _assemble(ns, 1, boxes, n, 1), o.get(1)
+        G, Go = _assemble(ns, 2, boxes, n, 3), o.get(2)
+        assert np.abs(S - So).max() <= 1e-10
+        assert np.abs(G - Go).max() <= 1e-9
+        assert np.abs((P - P.mean()) - (Po - Po.mean())).max() <= 1e-9
+    if nb == (1, 1, 1):
+        assert ns.last_iters() == o.last_iters()
+    ns.close(); o.close(); lev.close()
+
+
+def test_step_host_roundtrip(backend):
+    """The host-buffer entry (e2e path) gives the same state as the device-resident step."""
+    lib, dev = backend
+    n = (16, 16, 16)
+    g = ix.Geom.make(n)
+    boxes = split_boxes(n, (2, 1, 1))
+    lev = ix.Level(lib, g, boxes)
+    a = ix.NavierStokes(lib, lev, dev, visc_coef=1e-3)
+    b = ix.NavierStokes(lib, lev, dev, visc_coef=1e-3)
+    for ns in (a, b):
+        ns.init_prob(11, [1.0, 1.0, 1.0, 1.0, 1.0])
+        ns.post_init()
+    hin = [a.field(0, il).cpu().contiguous() for il in range(len(boxes))]
+    hout = [torch.empty_like(t) for t in hin]
+    dt = a.step()
+    dtb = b.step_host(hin, hout)
+    assert dt == dtb
+    for il in range(len(boxes)):
+        assert np.array_equal(hout[il].numpy(), a.field(0, il).cpu().numpy())
+    a.close(); b.close(); lev.close()
+
+
+def test_create_rejects_unsupported_configurations(backend):
+    lib, dev = backend
+    g = ix.Geom.make((8, 8, 8), periodic=(1, 1, 0))
+    lev = ix.Level(lib, g, [((0, 0, 0), (7, 7, 7))])
+    with pytest.raises(ix.IamrxError, match="periodic"):
+        ix.NavierStokes(lib, lev, dev)
+    lev.close()
+    g = ix.Geom.make((8, 8, 8))
+    lev = ix.Level(lib, g, [((0, 0, 0), (7, 7, 7))])
+    with pytest.raises(ix.IamrxError, match="be_cn_theta"):
+        ix.NavierStokes(lib, lev, dev, be_cn_theta=0.2)
+    lev.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n", [64, 128])
+def test_taylor_green_analytic_gpu(cuda_lib, n):
+    """inputs.3d.taylorgreen on the GPU vs the analytic vortex: L2 error O(h^2)."""
+    lib, dev = cuda_lib, "cuda:0"
+    g = ix.Geom.make((n, n, n))
+    lev = ix.Level(lib, g, [((0, 0, 0), (n - 1, n - 1, n - 1))])
+    ns = ix.NavierStokes(lib, lev, dev, visc_coef=1e-4, cfl=0.7)
+    ns.init_prob(11, [1.0, 1.0, 0.0, 1.0, 1.0])
+    ns.post_init()
+    while ns.time < 0.05:
+        ns.step()
+    S = ns.field(0)
+    x = (torch.arange(n, dtype=torch.float64, device=dev) + 0.5) / n
+    X, Y = x.view(1, 1, n), x.view(1, n, 1)
+    dec = math.exp(-8 * math.pi ** 2 * 1e-4 * ns.time)
+    ue = torch.sin(2 * math.pi * X) * torch.cos(2 * math.pi * Y) * dec
+    err = ((S[0] - ue) ** 2).mean().sqrt().item()
+    assert err < 1.2e-3 * (64.0 / n) ** 2, err
+    assert S[2].abs().max().item() < 1e-12
+    assert abs(S[3].mean().item() - 1.0) < 1e-13
+    ns.close(); lev.close()
+
+
+@pytest.mark.gpu
+def test_invariants_at_full_size_gpu(cuda_lib):
+    """BASELINE.json config[1] size (256^3): properties that need no oracle run --
+    u_mac divergence-free to the MAC tolerance, mass and tracer-mass conservation, symmetry."""
+    lib, dev = cuda_lib, "cuda:0"
+    n = 256
+    g = ix.Geom.make((n, n, n))
+    lev = ix.Level(lib, g, [((0, 0, 0), (n - 1, n - 1, n - 1))])
+    ns = ix.NavierStokes(lib, lev, dev, visc_coef=1e-4, cfl=0.7, conservative_tracer=1)
+    ns.init_prob(100, [1.0, 1.0, 1.0, 1.0, 1.0])
+    S0 = ns.field(0).clone()
+    ns.post_init()
+    for _ in range(2):
+        ns.step()
+    S = ns.field(0)
+    u, v, w = (ns.field(4 + d)[0] for d in range(3))
+    div = (u[:, :, 1:] - u[:, :, :-1] + v[:, 1:, :] - v[:, :-1, :] + w[1:, :, :] - w[:-1, :, :]) * n
+    assert div.abs().max().item() < 1e-9 * (u.abs().max().item() * n)
+    for c in (3, 4):  # conservative scalars: sum preserved to rounding
+        assert abs((S[c].sum() - S0[c].sum()).item()) < 1e-10 * S0[c].abs().sum().item()
+    assert torch.isfinite(S).all()
+    ns.close(); lev.close()
