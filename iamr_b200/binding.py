@@ -89,6 +89,8 @@ SIGNATURES = {
     "iamrx_device_ok": (C.c_int, []),
     "iamrx_prof_enable": (C.c_int, [C.c_int, C.c_int64]),
     "iamrx_prof_reset": (None, []),
+    "iamrx_prof_all": (C.c_int, [C.c_int]),
+    "iamrx_prof_dump": (C.c_int, [C.c_char_p, C.c_int]),
     "iamrx_prof_report": (C.c_int, [C.c_int, _P(C.c_double), _P(C.c_int64), _P(C.c_double)]),
     "iamrx_abec_gsrb_box": (C.c_int, [_P(Box), _P(Fab), _P(Fab), C.c_double, C.c_double, _P(Fab), _P(Fab), _P(Fab),
                                       _P(Fab), _P(C.c_double), C.c_double, C.c_int, C.c_int, _vp]),

@@ -41,7 +41,7 @@ constexpr int GS_TX = 64;
 constexpr int GS_TY = 4;
 
 __global__ void __launch_bounds__(GS_TX* GS_TY)
-gsrb_kernel(Bx bx, V4 phi, C4 rhs, IX_KARG(AbecDev) op, double omega, int redblack, int nz) {
+gsrb_kernel(Bx bx, V4 phi, C4 rhs, IX_KARG(AbecDev) op, double omega, int redblack, int nz, int wm) {
   const int kz = blockIdx.z % nz;
   const int n = blockIdx.z / nz;
   const int k = bx.lo[2] + kz;
@@ -59,9 +59,13 @@ gsrb_kernel(Bx bx, V4 phi, C4 rhs, IX_KARG(AbecDev) op, double omega, int redbla
   const double p0 = phi(i, j, k, n);
   double gamma = op.dhx * (bxm + bxp) + op.dhy * (bym + byp) + op.dhz * (bzm + bzp);
   if (op.a != 0.0) gamma += op.a * op.acoef(i, j, k);
-  const double rho = op.dhx * (bxm * phi(i - 1, j, k, n) + bxp * phi(i + 1, j, k, n)) +
-                     op.dhy * (bym * phi(i, j - 1, k, n) + byp * phi(i, j + 1, k, n)) +
-                     op.dhz * (bzm * phi(i, j, k - 1, n) + bzp * phi(i, j, k + 1, n));
+  // periodic wrap inside the kernel when the box spans the domain (no ghost fill needed)
+  const int im = ((wm & 1) && i == bx.lo[0]) ? bx.hi[0] : i - 1, ip = ((wm & 1) && i == bx.hi[0]) ? bx.lo[0] : i + 1;
+  const int jm = ((wm & 2) && j == bx.lo[1]) ? bx.hi[1] : j - 1, jp = ((wm & 2) && j == bx.hi[1]) ? bx.lo[1] : j + 1;
+  const int km = ((wm & 4) && k == bx.lo[2]) ? bx.hi[2] : k - 1, kp = ((wm & 4) && k == bx.hi[2]) ? bx.lo[2] : k + 1;
+  const double rho = op.dhx * (bxm * phi(im, j, k, n) + bxp * phi(ip, j, k, n)) +
+                     op.dhy * (bym * phi(i, jm, k, n) + byp * phi(i, jp, k, n)) +
+                     op.dhz * (bzm * phi(i, j, km, n) + bzp * phi(i, j, kp, n));
   const double res = rhs(i, j, k, n) - (gamma * p0 - rho);
   phi(i, j, k, n) = p0 + omega / gamma * res;
 }
@@ -71,7 +75,7 @@ constexpr int AP_TX = 128;
 constexpr int AP_TY = 2;
 
 __global__ void __launch_bounds__(AP_TX* AP_TY)
-apply_kernel(Bx bx, V4 out, C4 phi, C4 rhs, IX_KARG(AbecDev) op, int nz) {
+apply_kernel(Bx bx, V4 out, C4 phi, C4 rhs, IX_KARG(AbecDev) op, int nz, int wm) {
   const int kz = blockIdx.z % nz;
   const int n = blockIdx.z / nz;
   const int k = bx.lo[2] + kz;
@@ -80,12 +84,15 @@ apply_kernel(Bx bx, V4 out, C4 phi, C4 rhs, IX_KARG(AbecDev) op, int nz) {
   if (j > bx.hi[1] || i > bx.hi[0]) return;
   const int nb = (op.bncomp > 1) ? n : 0;
   const double p0 = phi(i, j, k, n);
-  double y = -op.dhx * (op.bx(i + 1, j, k, nb) * (phi(i + 1, j, k, n) - p0) -
-                        op.bx(i, j, k, nb) * (p0 - phi(i - 1, j, k, n))) -
-             op.dhy * (op.by(i, j + 1, k, nb) * (phi(i, j + 1, k, n) - p0) -
-                       op.by(i, j, k, nb) * (p0 - phi(i, j - 1, k, n))) -
-             op.dhz * (op.bz(i, j, k + 1, nb) * (phi(i, j, k + 1, n) - p0) -
-                       op.bz(i, j, k, nb) * (p0 - phi(i, j, k - 1, n)));
+  const int im = ((wm & 1) && i == bx.lo[0]) ? bx.hi[0] : i - 1, ip = ((wm & 1) && i == bx.hi[0]) ? bx.lo[0] : i + 1;
+  const int jm = ((wm & 2) && j == bx.lo[1]) ? bx.hi[1] : j - 1, jp = ((wm & 2) && j == bx.hi[1]) ? bx.lo[1] : j + 1;
+  const int km = ((wm & 4) && k == bx.lo[2]) ? bx.hi[2] : k - 1, kp = ((wm & 4) && k == bx.hi[2]) ? bx.lo[2] : k + 1;
+  double y = -op.dhx * (op.bx(i + 1, j, k, nb) * (phi(ip, j, k, n) - p0) -
+                        op.bx(i, j, k, nb) * (p0 - phi(im, j, k, n))) -
+             op.dhy * (op.by(i, j + 1, k, nb) * (phi(i, jp, k, n) - p0) -
+                       op.by(i, j, k, nb) * (p0 - phi(i, jm, k, n))) -
+             op.dhz * (op.bz(i, j, k + 1, nb) * (phi(i, j, kp, n) - p0) -
+                       op.bz(i, j, k, nb) * (p0 - phi(i, j, km, n)));
   if (op.a != 0.0) y += op.a * op.acoef(i, j, k) * p0;
   out(i, j, k, n) = rhs.ok() ? (rhs(i, j, k, n) - y) : y;
 }
@@ -266,20 +273,20 @@ inline dim3 grid_for(const Bx& bx, int tx, int ty, int nz_total) {
 }  // namespace
 
 int abec_gsrb(const Bx& bx, V4 phi, C4 rhs, const Abec& op, double omega, int redblack, int ncomp,
-              cudaStream_t s) {
+              cudaStream_t s, int wrapmask) {
   if (!bx.ok()) return IAMRX_OK;
   ProfScope prof_(IAMRX_PROF_ABEC_GSRB, bx.npts(), (double)bx.npts() * ncomp * (op.a != 0.0 ? 56.0 : 48.0), s);
   dim3 blk(GS_TX, GS_TY, 1);
   dim3 grd(cdiv(bx.nx() + 1, 2 * GS_TX), cdiv(bx.ny(), GS_TY), bx.nz() * ncomp);
-  IX_LAUNCH(gsrb_kernel, grd, blk, 0, s, bx, phi, rhs, to_dev(op), omega, redblack, bx.nz());
+  IX_LAUNCH(gsrb_kernel, grd, blk, 0, s, bx, phi, rhs, to_dev(op), omega, redblack, bx.nz(), wrapmask);
   return check_launch("abec_gsrb");
 }
 
-int abec_apply(const Bx& bx, V4 out, C4 phi, C4 rhs, const Abec& op, int ncomp, cudaStream_t s) {
+int abec_apply(const Bx& bx, V4 out, C4 phi, C4 rhs, const Abec& op, int ncomp, cudaStream_t s, int wrapmask) {
   if (!bx.ok()) return IAMRX_OK;
   ProfScope prof_(IAMRX_PROF_ABEC_APPLY, bx.npts(), (double)bx.npts() * ncomp * ((op.a != 0.0 ? 56.0 : 48.0) + (rhs.ok() ? 0.0 : -8.0)), s);
   IX_LAUNCH(apply_kernel, grid_for(bx, AP_TX, AP_TY, bx.nz() * ncomp), dim3(AP_TX, AP_TY, 1), 0, s, 
-      bx, out, phi, rhs, to_dev(op), bx.nz());
+      bx, out, phi, rhs, to_dev(op), bx.nz(), wrapmask);
   return check_launch("abec_apply");
 }
 

@@ -98,7 +98,9 @@ IX_D void atomic_fmin(double* addr, double v) {
 
 constexpr int RT = 256;
 
-__global__ void __launch_bounds__(RT) reduce_kernel(Bx bx, C4 src, int op, double* result) {
+// op == 0 (sum) writes one partial per CTA into `partials` (summed in a fixed order by
+// reduce_final_kernel: bit-reproducible run to run); min / max go straight to `result`.
+__global__ void __launch_bounds__(RT) reduce_kernel(Bx bx, C4 src, int op, double* result, double* partials) {
   const int n = blockIdx.y;
   const int nx = bx.nx(), ny = bx.ny(), nz = bx.nz();
   const int64_t nrows = (int64_t)ny * nz;
@@ -121,11 +123,25 @@ __global__ void __launch_bounds__(RT) reduce_kernel(Bx bx, C4 src, int op, doubl
     double v = (threadIdx.x < RT / 32) ? sm[threadIdx.x] : ((op == 0) ? 0.0 : (op == 1 ? 1.0e300 : 0.0));
     v = warp_red(v, op);
     if (threadIdx.x == 0) {
-      if (op == 0) atomicAdd(result + n, v);
+      if (op == 0) partials[(size_t)n * gridDim.x + blockIdx.x] = v;
       else if (op == 1) atomic_fmin(result + n, v);
       else atomic_fmax_nonneg(result + n, v);
     }
   }
+}
+
+__global__ void __launch_bounds__(RT) reduce_final_kernel(const double* partials, int nb, double* result) {
+  const int n = blockIdx.x;
+  double acc = 0.0;
+  for (int b = threadIdx.x; b < nb; b += RT) acc += partials[(size_t)n * nb + b];
+  __shared__ double sm[RT];
+  sm[threadIdx.x] = acc;
+  __syncthreads();
+  for (int o = RT / 2; o > 0; o >>= 1) {
+    if ((int)threadIdx.x < o) sm[threadIdx.x] += sm[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) result[n] += sm[0];
 }
 
 __global__ void __launch_bounds__(RT) dot_kernel(Bx bx, C4 x, C4 y, C4 mask, double* result) {
@@ -199,7 +215,17 @@ int reduce(const Bx& bx, C4 src, int ncomp, int op, double* result, cudaStream_t
 #if defined(IX_EMUL)
   (void)nb; reduce_serial(bx, src, ncomp, op, result);
 #else
-  IX_LAUNCH(reduce_kernel, dim3(nb, ncomp, 1), RT, 0, s, bx, src, op, result);
+  static double* partials = nullptr;  // 148*8 CTAs x up to 16 components
+  if (!partials && cudaMalloc(&partials, sizeof(double) * 148 * 8 * 16) != cudaSuccess) {
+    set_error("reduce: cudaMalloc failed"); return IAMRX_ERR_CUDA;
+  }
+  if (ncomp > 16) { set_error("reduce: ncomp > 16"); return IAMRX_ERR_ARG; }
+  IX_LAUNCH(reduce_kernel, dim3(nb, ncomp, 1), RT, 0, s, bx, src, op, result, partials);
+  if (op == 0) {
+    int rc = check_launch("reduce");
+    if (rc) return rc;
+    IX_LAUNCH(reduce_final_kernel, ncomp, RT, 0, s, partials, nb, result);
+  }
 #endif
   return check_launch("reduce");
 }

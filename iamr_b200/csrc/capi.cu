@@ -17,6 +17,8 @@ int comm_unique_id(unsigned char uid[128]);
 int comm_init(int rank, int nranks, const unsigned char uid[128]);
 int comm_finalize();
 int prof_enable(int on, int64_t min_points);
+int prof_all(int on);
+int prof_dump(char* buf, int cap);
 void prof_reset();
 int prof_report(int kclass, double* total_ms, int64_t* launches, double* algo_bytes);
 int comm_set_transport(int rank, int nranks, iamrx_exchange_fn ex, iamrx_allreduce_fn ar, void* ctx);
@@ -60,6 +62,8 @@ void iamrx_launch_count_reset(void) { g_launches.store(0); }
 int iamrx_device_ok(void) { return device_ok() ? 1 : 0; }
 int iamrx_prof_enable(int on, int64_t min_points) { return prof_enable(on, min_points); }
 void iamrx_prof_reset(void) { prof_reset(); }
+int iamrx_prof_all(int on) { return prof_all(on); }
+int iamrx_prof_dump(char* buf, int cap) { return prof_dump(buf, cap); }
 int iamrx_prof_report(int kclass, double* total_ms, int64_t* launches, double* algo_bytes) {
   IX_ARG(kclass >= 0 && kclass < IAMRX_PROF_NCLASS, "kernel class");
   return prof_report(kclass, total_ms, launches, algo_bytes);

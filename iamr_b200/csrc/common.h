@@ -14,7 +14,13 @@
 #include "cuda_emul.h"
 #else
 #include <cuda_runtime.h>
-#define IX_LAUNCH(kern, grid, block, smem, stream, ...) kern<<<grid, block, smem, stream>>>(__VA_ARGS__)
+namespace ix { struct KernelTimer { int slot; void* s; KernelTimer(const char* name, void* stream); ~KernelTimer(); }; }
+// every launch goes through here; KernelTimer is a no-op unless iamrx_prof_all(1) was called
+#define IX_LAUNCH(kern, grid, block, smem, stream, ...)                      \
+  do {                                                                       \
+    ix::KernelTimer kt_(#kern, (void*)(stream));                             \
+    kern<<<grid, block, smem, stream>>>(__VA_ARGS__);                        \
+  } while (0)
 // large by-value kernel parameter (the host emulation build passes it by reference)
 #define IX_KARG(T) T
 #endif

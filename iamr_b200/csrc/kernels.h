@@ -16,10 +16,13 @@ struct Abec {
 };
 
 // --- cell-centred ABec (abec.cu) -----------------------------------------
+// wrapmask bit d: bx spans the periodic domain in direction d -> neighbours are read with
+// periodic wrap inside the kernel and phi's ghost cells in that direction are not touched.
 int abec_gsrb(const Bx& bx, V4 phi, C4 rhs, const Abec& op, double omega, int redblack,
-              int ncomp, cudaStream_t s);
+              int ncomp, cudaStream_t s, int wrapmask = 0);
 // out = L phi (rhs null) or rhs - L phi
-int abec_apply(const Bx& bx, V4 out, C4 phi, C4 rhs, const Abec& op, int ncomp, cudaStream_t s);
+int abec_apply(const Bx& bx, V4 out, C4 phi, C4 rhs, const Abec& op, int ncomp, cudaStream_t s,
+               int wrapmask = 0);
 // face flux_d = -b * beta_d * dphi/dx_d on faces of bx (MLABecLaplacian FFlux)
 int abec_flux(const Bx& bx, V4 fx, V4 fy, V4 fz, C4 phi, const Abec& op, int comp, cudaStream_t s);
 // crse = mean of 2x2x2 fine (MLCellLinOp restriction / average_down)
@@ -79,9 +82,10 @@ int compute_aofs(const Bx& bx, const AofsArgs& a, const AdvGeom& g, cudaStream_t
 
 // --- nodal Laplacian (nodal.cu) ------------------------------------------
 int nodal_divu(const Bx& nbx, V4 rhs, C4 vel, const double dxinv[3], cudaStream_t s);
-int nodal_adotx(const Bx& nbx, V4 out, C4 phi, C4 rhs, C4 sig, const double dxinv[3], cudaStream_t s);
+int nodal_adotx(const Bx& nbx, V4 out, C4 phi, C4 rhs, C4 sig, const double dxinv[3], cudaStream_t s,
+                int wrapmask = 0);
 int nodal_gs_color(const Bx& nbx, V4 phi, C4 rhs, C4 sig, const double dxinv[3], int color,
-                   cudaStream_t s);
+                   cudaStream_t s, int wrapmask = 0);
 int nodal_jacobi(const Bx& nbx, V4 out, C4 phi, C4 rhs, C4 sig, const double dxinv[3], double omega,
                  cudaStream_t s);
 int nodal_restrict(const Bx& cnbx, V4 crse, C4 fine, cudaStream_t s);

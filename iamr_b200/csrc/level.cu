@@ -45,6 +45,8 @@ ProfScope::~ProfScope() {}
 int prof_enable(int, int64_t) { return IAMRX_OK; }
 void prof_reset() {}
 int prof_report(int, double* ms, int64_t* n, double* b) { if (ms) *ms = 0; if (n) *n = 0; if (b) *b = 0; return IAMRX_OK; }
+int prof_all(int) { return IAMRX_OK; }
+int prof_dump(char* buf, int cap) { if (buf && cap > 0) buf[0] = 0; return 0; }
 #else
 namespace {
 struct ProfRec { int kclass; cudaEvent_t e0, e1; double bytes; };
@@ -75,6 +77,51 @@ ProfScope::~ProfScope() {
   Prof& P = prof();
   std::lock_guard<std::mutex> lk(P.mu);
   cudaEventRecord(P.recs[slot].e1, s);
+}
+// --- all-kernel timing by name (iamrx_prof_all / iamrx_prof_dump) ---
+namespace {
+struct NameRec { const char* name; cudaEvent_t e0, e1; };
+struct ProfAll { bool on = false; std::vector<NameRec> recs; };
+ProfAll& profall() { static ProfAll p; return p; }
+}  // namespace
+KernelTimer::KernelTimer(const char* name, void* stream) : slot(-1), s(stream) {
+  ProfAll& A = profall();
+  if (!A.on) return;
+  Prof& P = prof();
+  std::lock_guard<std::mutex> lk(P.mu);
+  NameRec r{name, P.get(), P.get()};
+  cudaEventRecord(r.e0, (cudaStream_t)s);
+  slot = (int)A.recs.size();
+  A.recs.push_back(r);
+}
+KernelTimer::~KernelTimer() {
+  if (slot < 0) return;
+  cudaEventRecord(profall().recs[slot].e1, (cudaStream_t)s);
+}
+int prof_all(int on) { profall().on = on != 0; return IAMRX_OK; }
+int prof_dump(char* buf, int cap) {
+  ProfAll& A = profall();
+  Prof& P = prof();
+  IX_CUDA(cudaDeviceSynchronize());
+  std::map<std::string, std::pair<double, int64_t>> agg;
+  {
+    std::lock_guard<std::mutex> lk(P.mu);
+    for (auto& r : A.recs) {
+      float t = 0;
+      if (cudaEventElapsedTime(&t, r.e0, r.e1) == cudaSuccess) { agg[r.name].first += t; agg[r.name].second++; }
+      else cudaGetLastError();
+      P.free_events.push_back(r.e0); P.free_events.push_back(r.e1);
+    }
+    A.recs.clear();
+  }
+  std::string out;
+  for (auto& kv : agg) {
+    char line[256];
+    snprintf(line, sizeof(line), "%s %lld %.6f\n", kv.first.c_str(), (long long)kv.second.second, kv.second.first);
+    out += line;
+  }
+  if (buf && cap > 0) { strncpy(buf, out.c_str(), (size_t)cap - 1); buf[cap - 1] = 0; }
+  return (int)out.size();
 }
 int prof_enable(int on, int64_t min_points) {
   Prof& P = prof();

@@ -96,6 +96,19 @@ struct Level {
   int nlocal() const { return (int)local.size(); }
   const Bx& lbox(int il) const { return boxes[local[il]]; }
   FBPlan& plan(int ixtype, int ng);
+  // bit d set iff local box il spans the whole periodic domain in direction d: its periodic
+  // neighbour is the box itself and kernels can wrap indices instead of reading ghost cells
+  int wrapmask(int il) const {
+    int m = 0;
+    for (int d = 0; d < 3; ++d)
+      if (geom.periodic[d] && lbox(il).lo[d] == domain.lo[d] && lbox(il).hi[d] == domain.hi[d]) m |= (1 << d);
+    return m;
+  }
+  // true when every local box wraps in all three directions (ghost fills can be skipped)
+  bool all_wrap() const {
+    for (int il = 0; il < nlocal(); ++il) if (wrapmask(il) != 7) return false;
+    return true;
+  }
 };
 
 // Build the list of (dst box, src box, periodic shift, region) ghost copies for

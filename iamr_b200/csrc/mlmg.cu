@@ -128,21 +128,25 @@ int CellMG::set_coeffs(const MF* acoef, const MF* bx, const MF* by, const MF* bz
 
 int CellMG::smooth(int l, MF& phi, const MF& rhs, int nsweeps, bool /*zero_init*/, cudaStream_t s) {
   MGLevelCell& L = lv_[l];
+  // a box that spans the periodic domain wraps its neighbour indices inside the kernel:
+  // no ghost fill (and no extra launch) per colour
+  const bool wrap = L.lev->all_wrap();
   for (int sw = 0; sw < nsweeps; ++sw) {
     for (int rb = 0; rb < 2; ++rb) {
-      IX_TRY(mf_fill_boundary(phi, 0, ncomp_, 1, s));
+      if (!wrap) IX_TRY(mf_fill_boundary(phi, 0, ncomp_, 1, s));
       for (int il = 0; il < phi.n(); ++il)
-        IX_TRY(k::abec_gsrb(phi.vbox(il), phi.v(il), rhs.c(il), op_at(l, il), info_.omega, rb, ncomp_, s));
+        IX_TRY(k::abec_gsrb(phi.vbox(il), phi.v(il), rhs.c(il), op_at(l, il), info_.omega, rb, ncomp_, s, wrap ? 7 : 0));
     }
   }
-  (void)L;
   return IAMRX_OK;
 }
 
 int CellMG::residual(int l, MF& out, MF& phi, const MF& rhs, bool with_cross, cudaStream_t s) {
-  IX_TRY(mf_fill_boundary(phi, 0, ncomp_, 1, s));
+  const bool cross = tensor_ && l == 0 && with_cross;  // the cross terms read edge/corner ghosts
+  const bool wrap = lv_[l].lev->all_wrap() && !cross;
+  if (!wrap) IX_TRY(mf_fill_boundary(phi, 0, ncomp_, 1, s));
   for (int il = 0; il < phi.n(); ++il) {
-    IX_TRY(k::abec_apply(phi.vbox(il), out.v(il), phi.c(il), rhs.c(il), op_at(l, il), ncomp_, s));
+    IX_TRY(k::abec_apply(phi.vbox(il), out.v(il), phi.c(il), rhs.c(il), op_at(l, il), ncomp_, s, wrap ? 7 : 0));
     if (tensor_ && l == 0 && with_cross)
       IX_TRY(k::tensor_cross(phi.vbox(il), out.v(il), phi.c(il), eta_[0]->c(il), eta_[1]->c(il),
                              eta_[2]->c(il), -b_, lv_[0].dxinv, s));
@@ -286,6 +290,7 @@ static int nodal_smoother_kind() {
 
 int NodeMG::smooth(int l, MF& phi, const MF& rhs, int nsweeps, cudaStream_t s) {
   MGLevelNode& L = lv_[l];
+  const bool wrap = L.lev->all_wrap();
   if (nodal_smoother_kind() == 1) {
     MF tmp(L.lev, IX_NODE, 1, 1);
     for (int sw = 0; sw < 2 * nsweeps; ++sw) {
@@ -299,9 +304,9 @@ int NodeMG::smooth(int l, MF& phi, const MF& rhs, int nsweeps, cudaStream_t s) {
   }
   for (int sw = 0; sw < nsweeps; ++sw) {
     for (int color = 0; color < 8; ++color) {
-      IX_TRY(mf_fill_boundary(phi, 0, 1, 1, s));
+      if (!wrap) IX_TRY(mf_fill_boundary(phi, 0, 1, 1, s));
       for (int il = 0; il < phi.n(); ++il)
-        IX_TRY(k::nodal_gs_color(phi.vbox(il), phi.v(il), rhs.c(il), L.sigma.c(il), L.dxinv, color, s));
+        IX_TRY(k::nodal_gs_color(phi.vbox(il), phi.v(il), rhs.c(il), L.sigma.c(il), L.dxinv, color, s, wrap ? 7 : 0));
     }
   }
   return IAMRX_OK;
@@ -309,9 +314,10 @@ int NodeMG::smooth(int l, MF& phi, const MF& rhs, int nsweeps, cudaStream_t s) {
 
 int NodeMG::residual(int l, MF& out, MF& phi, const MF& rhs, cudaStream_t s) {
   MGLevelNode& L = lv_[l];
-  IX_TRY(mf_fill_boundary(phi, 0, 1, 1, s));
+  const bool wrap = L.lev->all_wrap();
+  if (!wrap) IX_TRY(mf_fill_boundary(phi, 0, 1, 1, s));
   for (int il = 0; il < phi.n(); ++il)
-    IX_TRY(k::nodal_adotx(phi.vbox(il), out.v(il), phi.c(il), rhs.c(il), L.sigma.c(il), L.dxinv, s));
+    IX_TRY(k::nodal_adotx(phi.vbox(il), out.v(il), phi.c(il), rhs.c(il), L.sigma.c(il), L.dxinv, s, wrap ? 7 : 0));
   return IAMRX_OK;
 }
 

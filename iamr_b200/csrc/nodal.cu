@@ -17,8 +17,9 @@ constexpr int TX = 64;
 constexpr int TY = 4;
 
 // A*phi at node (i,j,k) and the diagonal coefficient.
-IX_D double nodal_ax(C4 x, C4 sig, int i, int j, int k, double facx, double facy, double facz,
-                     double& s0) {
+// im/ip, jm/jp, km/kp: indices of the neighbouring NODES (i-1/i+1 ..., or their periodic images)
+IX_D double nodal_ax(C4 x, C4 sig, int i, int j, int k, int im, int ip, int jm, int jp, int km, int kp,
+                     double facx, double facy, double facz, double& s0) {
   const double s000 = sig(i - 1, j - 1, k - 1), s100 = sig(i, j - 1, k - 1);
   const double s010 = sig(i - 1, j, k - 1), s110 = sig(i, j, k - 1);
   const double s001 = sig(i - 1, j - 1, k), s101 = sig(i, j - 1, k);
@@ -32,24 +33,31 @@ IX_D double nodal_ax(C4 x, C4 sig, int i, int j, int k, double facx, double facy
   const double fm2xm2y4z = -2.0 * facx - 2.0 * facy + 4.0 * facz;
   s0 = (-4.0) * fxyz * (s000 + s100 + s010 + s110 + s001 + s101 + s011 + s111);
   double y = x(i, j, k) * s0;
-  y += fxyz * (x(i - 1, j - 1, k - 1) * s000 + x(i + 1, j - 1, k - 1) * s100 +
-               x(i - 1, j + 1, k - 1) * s010 + x(i + 1, j + 1, k - 1) * s110 +
-               x(i - 1, j - 1, k + 1) * s001 + x(i + 1, j - 1, k + 1) * s101 +
-               x(i - 1, j + 1, k + 1) * s011 + x(i + 1, j + 1, k + 1) * s111);
-  y += fmx2y2z * (x(i, j - 1, k - 1) * (s000 + s100) + x(i, j + 1, k - 1) * (s010 + s110) +
-                  x(i, j - 1, k + 1) * (s001 + s101) + x(i, j + 1, k + 1) * (s011 + s111));
-  y += f2xmy2z * (x(i - 1, j, k - 1) * (s000 + s010) + x(i + 1, j, k - 1) * (s100 + s110) +
-                  x(i - 1, j, k + 1) * (s001 + s011) + x(i + 1, j, k + 1) * (s101 + s111));
-  y += f2x2ymz * (x(i - 1, j - 1, k) * (s000 + s001) + x(i + 1, j - 1, k) * (s100 + s101) +
-                  x(i - 1, j + 1, k) * (s010 + s011) + x(i + 1, j + 1, k) * (s110 + s111));
-  y += f4xm2ym2z * (x(i - 1, j, k) * (s000 + s010 + s001 + s011) +
-                    x(i + 1, j, k) * (s100 + s110 + s101 + s111));
-  y += fm2x4ym2z * (x(i, j - 1, k) * (s000 + s100 + s001 + s101) +
-                    x(i, j + 1, k) * (s010 + s110 + s011 + s111));
-  y += fm2xm2y4z * (x(i, j, k - 1) * (s000 + s100 + s010 + s110) +
-                    x(i, j, k + 1) * (s001 + s101 + s011 + s111));
+  y += fxyz * (x(im, jm, km) * s000 + x(ip, jm, km) * s100 +
+               x(im, jp, km) * s010 + x(ip, jp, km) * s110 +
+               x(im, jm, kp) * s001 + x(ip, jm, kp) * s101 +
+               x(im, jp, kp) * s011 + x(ip, jp, kp) * s111);
+  y += fmx2y2z * (x(i, jm, km) * (s000 + s100) + x(i, jp, km) * (s010 + s110) +
+                  x(i, jm, kp) * (s001 + s101) + x(i, jp, kp) * (s011 + s111));
+  y += f2xmy2z * (x(im, j, km) * (s000 + s010) + x(ip, j, km) * (s100 + s110) +
+                  x(im, j, kp) * (s001 + s011) + x(ip, j, kp) * (s101 + s111));
+  y += f2x2ymz * (x(im, jm, k) * (s000 + s001) + x(ip, jm, k) * (s100 + s101) +
+                  x(im, jp, k) * (s010 + s011) + x(ip, jp, k) * (s110 + s111));
+  y += f4xm2ym2z * (x(im, j, k) * (s000 + s010 + s001 + s011) +
+                    x(ip, j, k) * (s100 + s110 + s101 + s111));
+  y += fm2x4ym2z * (x(i, jm, k) * (s000 + s100 + s001 + s101) +
+                    x(i, jp, k) * (s010 + s110 + s011 + s111));
+  y += fm2xm2y4z * (x(i, j, km) * (s000 + s100 + s010 + s110) +
+                    x(i, j, kp) * (s001 + s101 + s011 + s111));
   return y;
 }
+
+// neighbour node indices; with wrap bit d set the node box [lo, hi] carries the periodic
+// duplicate (node hi == node lo), so lo-1 -> hi-1 and hi+1 -> lo+1
+#define NWRAP(bx, wm)                                                                          \
+  const int im = (((wm) & 1) && i == bx.lo[0]) ? bx.hi[0] - 1 : i - 1, ip = (((wm) & 1) && i == bx.hi[0]) ? bx.lo[0] + 1 : i + 1; \
+  const int jm = (((wm) & 2) && j == bx.lo[1]) ? bx.hi[1] - 1 : j - 1, jp = (((wm) & 2) && j == bx.hi[1]) ? bx.lo[1] + 1 : j + 1; \
+  const int km = (((wm) & 4) && k == bx.lo[2]) ? bx.hi[2] - 1 : k - 1, kp = (((wm) & 4) && k == bx.hi[2]) ? bx.lo[2] + 1 : k + 1;
 
 #define NIDX(bx)                                                   \
   const int k = bx.lo[2] + blockIdx.z;                             \
@@ -58,10 +66,11 @@ IX_D double nodal_ax(C4 x, C4 sig, int i, int j, int k, double facx, double facy
   if (j > bx.hi[1] || i > bx.hi[0]) return;
 
 __global__ void __launch_bounds__(TX* TY)
-adotx_kernel(Bx bx, V4 out, C4 phi, C4 rhs, C4 sig, double facx, double facy, double facz) {
+adotx_kernel(Bx bx, V4 out, C4 phi, C4 rhs, C4 sig, double facx, double facy, double facz, int wm) {
   NIDX(bx)
   double s0;
-  const double y = nodal_ax(phi, sig, i, j, k, facx, facy, facz, s0);
+  NWRAP(bx, wm)
+  const double y = nodal_ax(phi, sig, i, j, k, im, ip, jm, jp, km, kp, facx, facy, facz, s0);
   out(i, j, k) = rhs.ok() ? (rhs(i, j, k) - y) : y;
 }
 
@@ -69,7 +78,8 @@ __global__ void __launch_bounds__(TX* TY)
 jacobi_kernel(Bx bx, V4 out, C4 phi, C4 rhs, C4 sig, double facx, double facy, double facz, double omega) {
   NIDX(bx)
   double s0;
-  const double y = nodal_ax(phi, sig, i, j, k, facx, facy, facz, s0);
+  NWRAP(bx, 0)
+  const double y = nodal_ax(phi, sig, i, j, k, im, ip, jm, jp, km, kp, facx, facy, facz, s0);
   out(i, j, k) = phi(i, j, k) + omega * (rhs(i, j, k) - y) / s0;
 }
 
@@ -77,14 +87,15 @@ jacobi_kernel(Bx bx, V4 out, C4 phi, C4 rhs, C4 sig, double facx, double facy, d
 // uncoupled under the 27-point stencil.
 __global__ void __launch_bounds__(TX* TY)
 gs_color_kernel(Bx bx, V4 phi, C4 rhs, C4 sig, double facx, double facy, double facz, int i0, int j0,
-                int k0) {
+                int k0, int wm) {
   const int k = k0 + 2 * blockIdx.z;
   const int j = j0 + 2 * (blockIdx.y * TY + threadIdx.y);
   const int i = i0 + 2 * (blockIdx.x * TX + threadIdx.x);
   if (k > bx.hi[2] || j > bx.hi[1] || i > bx.hi[0]) return;
   double s0;
   C4 x{phi.p, phi.l0, phi.l1, phi.l2, phi.js, phi.ks, phi.ns};
-  const double y = nodal_ax(x, sig, i, j, k, facx, facy, facz, s0);
+  NWRAP(bx, wm)
+  const double y = nodal_ax(x, sig, i, j, k, im, ip, jm, jp, km, kp, facx, facy, facz, s0);
   phi(i, j, k) += (rhs(i, j, k) - y) / s0;
 }
 
@@ -168,11 +179,11 @@ int nodal_divu(const Bx& nbx, V4 rhs, C4 vel, const double dxinv[3], cudaStream_
   return check_launch("nodal_divu");
 }
 
-int nodal_adotx(const Bx& nbx, V4 out, C4 phi, C4 rhs, C4 sig, const double dxinv[3], cudaStream_t s) {
+int nodal_adotx(const Bx& nbx, V4 out, C4 phi, C4 rhs, C4 sig, const double dxinv[3], cudaStream_t s, int wrapmask) {
   if (!nbx.ok()) return IAMRX_OK;
   double f[3]; facs(dxinv, f);
   ProfScope prof_(IAMRX_PROF_NODAL_ADOTX, nbx.npts(), (double)nbx.npts() * (rhs.ok() ? 32.0 : 24.0), s);
-  IX_LAUNCH(adotx_kernel, grid_for(nbx), dim3(TX, TY, 1), 0, s, nbx, out, phi, rhs, sig, f[0], f[1], f[2]);
+  IX_LAUNCH(adotx_kernel, grid_for(nbx), dim3(TX, TY, 1), 0, s, nbx, out, phi, rhs, sig, f[0], f[1], f[2], wrapmask);
   return check_launch("nodal_adotx");
 }
 
@@ -185,7 +196,7 @@ int nodal_jacobi(const Bx& nbx, V4 out, C4 phi, C4 rhs, C4 sig, const double dxi
 }
 
 int nodal_gs_color(const Bx& nbx, V4 phi, C4 rhs, C4 sig, const double dxinv[3], int color,
-                   cudaStream_t s) {
+                   cudaStream_t s, int wrapmask) {
   if (!nbx.ok()) return IAMRX_OK;
   double f[3]; facs(dxinv, f);
   const int c[3] = {color & 1, (color >> 1) & 1, (color >> 2) & 1};
@@ -197,7 +208,7 @@ int nodal_gs_color(const Bx& nbx, V4 phi, C4 rhs, C4 sig, const double dxinv[3],
   }
   ProfScope prof_(IAMRX_PROF_NODAL_GS, nbx.npts(), (double)nbx.npts() * 4.0, s);  // 32 B/node/sweep over 8 colour passes
   dim3 grd(cdiv(n[0], TX), cdiv(n[1], TY), n[2]);
-  IX_LAUNCH(gs_color_kernel, grd, dim3(TX, TY, 1), 0, s, nbx, phi, rhs, sig, f[0], f[1], f[2], o[0], o[1], o[2]);
+  IX_LAUNCH(gs_color_kernel, grd, dim3(TX, TY, 1), 0, s, nbx, phi, rhs, sig, f[0], f[1], f[2], o[0], o[1], o[2], wrapmask);
   return check_launch("nodal_gs_color");
 }
 

@@ -122,6 +122,11 @@ enum {
 int iamrx_prof_enable(int on, int64_t min_points);
 void iamrx_prof_reset(void);
 int iamrx_prof_report(int kclass, double* total_ms, int64_t* launches, double* algo_bytes);
+/* Time EVERY kernel launch by kernel name (CUDA events; adds two event records per
+ * launch while on).  iamrx_prof_dump synchronises, writes "name launches total_ms"
+ * lines into buf (truncated to cap) and clears the records; returns the full length. */
+int iamrx_prof_all(int on);
+int iamrx_prof_dump(char* buf, int cap);
 
 /* ------------------------------------------------------------------------
  * 1. Per-box kernels (one FArrayBox at a time, async on `stream`).
