@@ -10,6 +10,7 @@
 // All kernels are HBM-bound 7-point stencils: x is unit stride, threadIdx.x
 // runs along x, each CTA covers a (128 x 4) xy-strip of one z-plane so every
 // warp request is a contiguous 256-byte (GSRB: strided 512-byte) span.
+#include <cstdlib>
 #include "kernels.h"
 
 namespace ix {
@@ -40,7 +41,8 @@ inline AbecDev to_dev(const Abec& op) {
 constexpr int GS_TX = 64;
 constexpr int GS_TY = 4;
 
-__global__ void __launch_bounds__(GS_TX* GS_TY)
+template <int MINB>
+__global__ void __launch_bounds__(GS_TX* GS_TY, MINB)
 gsrb_kernel(Bx bx, V4 phi, C4 rhs, IX_KARG(AbecDev) op, double omega, int redblack, int nz, int wm) {
   const int kz = blockIdx.z % nz;
   const int n = blockIdx.z / nz;
@@ -53,21 +55,27 @@ gsrb_kernel(Bx bx, V4 phi, C4 rhs, IX_KARG(AbecDev) op, double omega, int redbla
   if (i > bx.hi[0]) return;
   const int nb = (op.bncomp > 1) ? n : 0;
 
-  const double bxm = op.bx(i, j, k, nb), bxp = op.bx(i + 1, j, k, nb);
-  const double bym = op.by(i, j, k, nb), byp = op.by(i, j + 1, k, nb);
-  const double bzm = op.bz(i, j, k, nb), bzp = op.bz(i, j, k + 1, nb);
-  const double p0 = phi(i, j, k, n);
+  // 32-bit element offsets from the cell's own address (one address computation per array)
+  const double* bxc = op.bx.p + nb * op.bx.ns + ((i - op.bx.l0) + (j - op.bx.l1) * op.bx.js + (k - op.bx.l2) * op.bx.ks);
+  const double* byc = op.by.p + nb * op.by.ns + ((i - op.by.l0) + (j - op.by.l1) * op.by.js + (k - op.by.l2) * op.by.ks);
+  const double* bzc = op.bz.p + nb * op.bz.ns + ((i - op.bz.l0) + (j - op.bz.l1) * op.bz.js + (k - op.bz.l2) * op.bz.ks);
+  const double bxm = bxc[0], bxp = bxc[1];
+  const double bym = byc[0], byp = byc[(int)op.by.js];
+  const double bzm = bzc[0], bzp = bzc[(int)op.bz.ks];
+  double* pc = phi.p + n * phi.ns + ((i - phi.l0) + (j - phi.l1) * phi.js + (k - phi.l2) * phi.ks);
+  const int pjs = (int)phi.js, pks = (int)phi.ks;
+  const double p0 = pc[0];
   double gamma = op.dhx * (bxm + bxp) + op.dhy * (bym + byp) + op.dhz * (bzm + bzp);
   if (op.a != 0.0) gamma += op.a * op.acoef(i, j, k);
   // periodic wrap inside the kernel when the box spans the domain (no ghost fill needed)
-  const int im = ((wm & 1) && i == bx.lo[0]) ? bx.hi[0] : i - 1, ip = ((wm & 1) && i == bx.hi[0]) ? bx.lo[0] : i + 1;
-  const int jm = ((wm & 2) && j == bx.lo[1]) ? bx.hi[1] : j - 1, jp = ((wm & 2) && j == bx.hi[1]) ? bx.lo[1] : j + 1;
-  const int km = ((wm & 4) && k == bx.lo[2]) ? bx.hi[2] : k - 1, kp = ((wm & 4) && k == bx.hi[2]) ? bx.lo[2] : k + 1;
-  const double rho = op.dhx * (bxm * phi(im, j, k, n) + bxp * phi(ip, j, k, n)) +
-                     op.dhy * (bym * phi(i, jm, k, n) + byp * phi(i, jp, k, n)) +
-                     op.dhz * (bzm * phi(i, j, km, n) + bzp * phi(i, j, kp, n));
+  const int oxm = ((wm & 1) && i == bx.lo[0]) ? bx.hi[0] - i : -1, oxp = ((wm & 1) && i == bx.hi[0]) ? bx.lo[0] - i : 1;
+  const int oym = (((wm & 2) && j == bx.lo[1]) ? bx.hi[1] - j : -1) * pjs, oyp = (((wm & 2) && j == bx.hi[1]) ? bx.lo[1] - j : 1) * pjs;
+  const int ozm = (((wm & 4) && k == bx.lo[2]) ? bx.hi[2] - k : -1) * pks, ozp = (((wm & 4) && k == bx.hi[2]) ? bx.lo[2] - k : 1) * pks;
+  const double rho = op.dhx * (bxm * pc[oxm] + bxp * pc[oxp]) +
+                     op.dhy * (bym * pc[oym] + byp * pc[oyp]) +
+                     op.dhz * (bzm * pc[ozm] + bzp * pc[ozp]);
   const double res = rhs(i, j, k, n) - (gamma * p0 - rho);
-  phi(i, j, k, n) = p0 + omega / gamma * res;
+  pc[0] = p0 + omega / gamma * res;
 }
 
 // ---- apply / residual ----------------------------------------------------
@@ -83,16 +91,18 @@ apply_kernel(Bx bx, V4 out, C4 phi, C4 rhs, IX_KARG(AbecDev) op, int nz, int wm)
   const int i = bx.lo[0] + blockIdx.x * AP_TX + threadIdx.x;
   if (j > bx.hi[1] || i > bx.hi[0]) return;
   const int nb = (op.bncomp > 1) ? n : 0;
-  const double p0 = phi(i, j, k, n);
-  const int im = ((wm & 1) && i == bx.lo[0]) ? bx.hi[0] : i - 1, ip = ((wm & 1) && i == bx.hi[0]) ? bx.lo[0] : i + 1;
-  const int jm = ((wm & 2) && j == bx.lo[1]) ? bx.hi[1] : j - 1, jp = ((wm & 2) && j == bx.hi[1]) ? bx.lo[1] : j + 1;
-  const int km = ((wm & 4) && k == bx.lo[2]) ? bx.hi[2] : k - 1, kp = ((wm & 4) && k == bx.hi[2]) ? bx.lo[2] : k + 1;
-  double y = -op.dhx * (op.bx(i + 1, j, k, nb) * (phi(ip, j, k, n) - p0) -
-                        op.bx(i, j, k, nb) * (p0 - phi(im, j, k, n))) -
-             op.dhy * (op.by(i, j + 1, k, nb) * (phi(i, jp, k, n) - p0) -
-                       op.by(i, j, k, nb) * (p0 - phi(i, jm, k, n))) -
-             op.dhz * (op.bz(i, j, k + 1, nb) * (phi(i, j, kp, n) - p0) -
-                       op.bz(i, j, k, nb) * (p0 - phi(i, j, km, n)));
+  const double* bxc = op.bx.p + nb * op.bx.ns + ((i - op.bx.l0) + (j - op.bx.l1) * op.bx.js + (k - op.bx.l2) * op.bx.ks);
+  const double* byc = op.by.p + nb * op.by.ns + ((i - op.by.l0) + (j - op.by.l1) * op.by.js + (k - op.by.l2) * op.by.ks);
+  const double* bzc = op.bz.p + nb * op.bz.ns + ((i - op.bz.l0) + (j - op.bz.l1) * op.bz.js + (k - op.bz.l2) * op.bz.ks);
+  const double* pc = phi.p + n * phi.ns + ((i - phi.l0) + (j - phi.l1) * phi.js + (k - phi.l2) * phi.ks);
+  const int pjs = (int)phi.js, pks = (int)phi.ks;
+  const double p0 = pc[0];
+  const int oxm = ((wm & 1) && i == bx.lo[0]) ? bx.hi[0] - i : -1, oxp = ((wm & 1) && i == bx.hi[0]) ? bx.lo[0] - i : 1;
+  const int oym = (((wm & 2) && j == bx.lo[1]) ? bx.hi[1] - j : -1) * pjs, oyp = (((wm & 2) && j == bx.hi[1]) ? bx.lo[1] - j : 1) * pjs;
+  const int ozm = (((wm & 4) && k == bx.lo[2]) ? bx.hi[2] - k : -1) * pks, ozp = (((wm & 4) && k == bx.hi[2]) ? bx.lo[2] - k : 1) * pks;
+  double y = -op.dhx * (bxc[1] * (pc[oxp] - p0) - bxc[0] * (p0 - pc[oxm])) -
+             op.dhy * (byc[(int)op.by.js] * (pc[oyp] - p0) - byc[0] * (p0 - pc[oym])) -
+             op.dhz * (bzc[(int)op.bz.ks] * (pc[ozp] - p0) - bzc[0] * (p0 - pc[ozm]));
   if (op.a != 0.0) y += op.a * op.acoef(i, j, k) * p0;
   out(i, j, k, n) = rhs.ok() ? (rhs(i, j, k, n) - y) : y;
 }
@@ -278,7 +288,10 @@ int abec_gsrb(const Bx& bx, V4 phi, C4 rhs, const Abec& op, double omega, int re
   ProfScope prof_(IAMRX_PROF_ABEC_GSRB, bx.npts(), (double)bx.npts() * ncomp * (op.a != 0.0 ? 56.0 : 48.0), s);
   dim3 blk(GS_TX, GS_TY, 1);
   dim3 grd(cdiv(bx.nx() + 1, 2 * GS_TX), cdiv(bx.ny(), GS_TY), bx.nz() * ncomp);
-  IX_LAUNCH(gsrb_kernel, grd, blk, 0, s, bx, phi, rhs, to_dev(op), omega, redblack, bx.nz(), wrapmask);
+  static int minb = -1;
+  if (minb < 0) { const char* e = getenv("IAMRX_GSRB_MINB"); minb = e ? atoi(e) : 6; }
+  if (minb >= 8) IX_LAUNCH(gsrb_kernel<8>, grd, blk, 0, s, bx, phi, rhs, to_dev(op), omega, redblack, bx.nz(), wrapmask);
+  else IX_LAUNCH(gsrb_kernel<6>, grd, blk, 0, s, bx, phi, rhs, to_dev(op), omega, redblack, bx.nz(), wrapmask);
   return check_launch("abec_gsrb");
 }
 

@@ -28,28 +28,32 @@ using namespace gd;
 constexpr int TX = 64;
 constexpr int TY = 4;
 
-struct Comp {  // one component of a C4 view as a 3-index callable
-  const double* p; int l0, l1, l2; int64_t js, ks;
-  IX_HD double operator()(int i, int j, int k) const { return p[(i - l0) + (j - l1) * js + (k - l2) * ks]; }
-};
-IX_HD Comp comp(const C4& v, int n) { return Comp{v.p + n * v.ns, v.l0, v.l1, v.l2, v.js, v.ks}; }
-
-// traced states on face (i,j,k) of direction D: lo from the cell below, hi from the
-// cell above.  ulo/uhi: the velocity used in the trace (cell-centred normal velocity
+// traced states on the D-face below the cell the cursor `q` sits on: lo from the cell below,
+// hi from this cell.  ulo/uhi: the velocity used in the trace (cell-centred normal velocity
 // for ExtrapVelToFaces, the MAC velocity of this face for ComputeEdgeState).
-template <int D, class Q>
-IX_D void trace(const Q& q, int i, int j, int k, double ulo, double uhi, double dtdx, double& lo, double& hi) {
-  const int im = i - E<D>::x, jm = j - E<D>::y, km = k - E<D>::z;
-  lo = q(im, jm, km) + 0.5 * (1.0 - ulo * dtdx) * slope4<D>(q, im, jm, km);
-  hi = q(i, j, k) + 0.5 * (-1.0 - uhi * dtdx) * slope4<D>(q, i, j, k);
+template <int D>
+IX_D void trace(const Cur& q, double ulo, double uhi, double dtdx, double& lo, double& hi) {
+  const Cur qm = below<D>(q);
+  lo = qm(0, 0, 0) + 0.5 * (1.0 - ulo * dtdx) * slope4c<D>(qm);
+  hi = q(0, 0, 0) + 0.5 * (-1.0 - uhi * dtdx) * slope4c<D>(q);
 }
 
 struct Scratch {  // all on the same grown index box, component-major
   double* p; int l0, l1, l2; int64_t js, ks, as;  // as = stride between arrays
-  IX_HD double& operator()(int a, int i, int j, int k) const {
-    return p[a * as + (i - l0) + (j - l1) * js + (k - l2) * ks];
-  }
 };
+// scratch cursor at (i,j,k): array a, relative offsets
+struct SCur {
+  double* p; int js, ks; int64_t as;
+  IX_D double& operator()(int a, int di, int dj, int dk) const { return p[a * as + (di + dj * js + dk * ks)]; }
+};
+IX_D SCur scur_at(const Scratch& s, int i, int j, int k) {
+  return SCur{s.p + ((i - s.l0) + (j - s.l1) * s.js + (k - s.l2) * s.ks), (int)s.js, (int)s.ks, s.as};
+}
+struct SArr {  // one scratch array of an SCur as a relative-offset callable
+  const double* p; int js, ks;
+  IX_D double operator()(int di, int dj, int dk) const { return p[di + dj * js + dk * ks]; }
+};
+IX_D SArr sarr(const SCur& s, int a) { return SArr{s.p + a * s.as, s.js, s.ks}; }
 
 #define GIDX(R)                                                \
   const int nz_ = R.hi[2] - R.lo[2] + 1;                      \
@@ -75,68 +79,73 @@ struct EsArgs {
 // scratch array ids per component: 0..2 edge x,y,z; 3..8 corner xy,xz,yx,yz,zx,zy; 9..11 flux
 enum { A_XE = 0, A_YE, A_ZE, A_XY, A_XZ, A_YX, A_YZ, A_ZX, A_ZY, A_FX, A_FY, A_FZ, A_N };
 
+// lo/hi on the D-face of the cursor's cell, traced with the MAC velocity `u` of that face
 template <int D>
-IX_D void es_lohi(const EsArgs& a, const Comp& q, const C4& mac, int n, int i, int j, int k, double dtdx,
-                  double& lo, double& hi) {
-  const double u = mac(i, j, k);
-  trace<D>(q, i, j, k, u, u, dtdx, lo, hi);
-  if (a.fit && a.force.ok()) {
-    lo += 0.5 * a.dt * a.force(i - E<D>::x, j - E<D>::y, k - E<D>::z, n);
-    hi += 0.5 * a.dt * a.force(i, j, k, n);
+IX_D void es_lohi(const EsArgs& a, const Cur& q, const Cur& f, double u, double dtdx, double& lo, double& hi) {
+  trace<D>(q, u, u, dtdx, lo, hi);
+  if (a.fit && f.ok()) {
+    lo += 0.5 * a.dt * along<D>(f, -1);
+    hi += 0.5 * a.dt * f(0, 0, 0);
   }
+}
+
+struct EsCur {  // the cursors one thread needs
+  Cur q, f, u, v, w;
+  SCur s;
+};
+IX_D EsCur es_cursors(const EsArgs& a, const Scratch& sc, int n, int i, int j, int k) {
+  return EsCur{cur_at(a.S, n, i, j, k), cur_at(a.force, n, i, j, k), cur_at(a.umac, 0, i, j, k),
+               cur_at(a.vmac, 0, i, j, k), cur_at(a.wmac, 0, i, j, k), scur_at(sc, i, j, k)};
 }
 
 __global__ void __launch_bounds__(TX* TY) es_edge_kernel(IX_KARG(EsArgs) a, IX_KARG(Scratch) sc, IX_KARG(Bx) R) {
   GIDX(R)
-  const Comp q = comp(a.S, n);
+  const EsCur c = es_cursors(a, sc, n, i, j, k);
   const Bx& b = a.bx;
+  const int o = A_N * n;
   const bool inx = i >= b.lo[0] - 1 && i <= b.hi[0] + 1, iny = j >= b.lo[1] - 1 && j <= b.hi[1] + 1,
              inz = k >= b.lo[2] - 1 && k <= b.hi[2] + 1;
   double lo, hi;
   if (i >= b.lo[0] && i <= b.hi[0] + 1 && iny && inz) {  // x-faces lo..hi+1
-    es_lohi<0>(a, q, a.umac, n, i, j, k, a.dtdx, lo, hi);
-    sc(A_N * n + A_XE, i, j, k) = upwind(lo, hi, a.umac(i, j, k));
+    const double u = c.u(0, 0, 0);
+    es_lohi<0>(a, c.q, c.f, u, a.dtdx, lo, hi);
+    c.s(o + A_XE, 0, 0, 0) = upwind(lo, hi, u);
   }
   if (j >= b.lo[1] && j <= b.hi[1] + 1 && inx && inz) {
-    es_lohi<1>(a, q, a.vmac, n, i, j, k, a.dtdy, lo, hi);
-    sc(A_N * n + A_YE, i, j, k) = upwind(lo, hi, a.vmac(i, j, k));
+    const double v = c.v(0, 0, 0);
+    es_lohi<1>(a, c.q, c.f, v, a.dtdy, lo, hi);
+    c.s(o + A_YE, 0, 0, 0) = upwind(lo, hi, v);
   }
   if (k >= b.lo[2] && k <= b.hi[2] + 1 && inx && iny) {
-    es_lohi<2>(a, q, a.wmac, n, i, j, k, a.dtdz, lo, hi);
-    sc(A_N * n + A_ZE, i, j, k) = upwind(lo, hi, a.wmac(i, j, k));
+    const double w = c.w(0, 0, 0);
+    es_lohi<2>(a, c.q, c.f, w, a.dtdz, lo, hi);
+    c.s(o + A_ZE, 0, 0, 0) = upwind(lo, hi, w);
   }
 }
 
-// corner coupling of the D1-face state at (i,j,k) with the derivative along D2
-// (Godunov_corner_couple_<d1><d2>): mac2/edge2 live on D2-faces.
-template <int D1, int D2, class Q, class M, class Ed>
-IX_D void corner(double& lo1, double& hi1, double lo, double hi, const Q& q, const M& mac2, const Ed& edge2,
-                 int i, int j, int k, double dt3dx, bool conserv) {
-  const int im = i - E<D1>::x, jm = j - E<D1>::y, km = k - E<D1>::z;  // cell below the face
-  const int ip = E<D2>::x, jp = E<D2>::y, kp = E<D2>::z;
-  const double mlo_p = mac2(im + ip, jm + jp, km + kp), mlo_m = mac2(im, jm, km);
-  const double mhi_p = mac2(i + ip, j + jp, k + kp), mhi_m = mac2(i, j, k);
-  lo1 = lo - dt3dx * (edge2(im + ip, jm + jp, km + kp) * mlo_p - edge2(im, jm, km) * mlo_m);
-  hi1 = hi - dt3dx * (edge2(i + ip, j + jp, k + kp) * mhi_p - edge2(i, j, k) * mhi_m);
+// corner coupling of the D1-face state with the derivative along D2
+// (Godunov_corner_couple_<d1><d2>): mac2/edge2 live on D2-faces; all offsets are relative
+// to the cell above the D1-face.
+template <int D1, int D2, class M, class Ed>
+IX_D void corner(double& lo1, double& hi1, double lo, double hi, const Cur& q, const M& mac2, const Ed& edge2,
+                 double dt3dx, bool conserv) {
+  const double mlo_p = rel2<D1, D2>(mac2, -1, 1), mlo_m = rel2<D1, D2>(mac2, -1, 0);
+  const double mhi_p = rel2<D1, D2>(mac2, 0, 1), mhi_m = mac2(0, 0, 0);
+  lo1 = lo - dt3dx * (rel2<D1, D2>(edge2, -1, 1) * mlo_p - rel2<D1, D2>(edge2, -1, 0) * mlo_m);
+  hi1 = hi - dt3dx * (rel2<D1, D2>(edge2, 0, 1) * mhi_p - edge2(0, 0, 0) * mhi_m);
   if (!conserv) {
-    lo1 += dt3dx * q(im, jm, km) * (mlo_p - mlo_m);
-    hi1 += dt3dx * q(i, j, k) * (mhi_p - mhi_m);
+    lo1 += dt3dx * along<D1>(q, -1) * (mlo_p - mlo_m);
+    hi1 += dt3dx * q(0, 0, 0) * (mhi_p - mhi_m);
   }
 }
-
-struct ScArr {  // one scratch array as a 3-index callable
-  const double* p; int l0, l1, l2; int64_t js, ks;
-  IX_HD double operator()(int i, int j, int k) const { return p[(i - l0) + (j - l1) * js + (k - l2) * ks]; }
-};
-IX_HD ScArr arr(const Scratch& s, int a) { return ScArr{s.p + a * s.as, s.l0, s.l1, s.l2, s.js, s.ks}; }
 
 __global__ void __launch_bounds__(TX* TY) es_corner_kernel(IX_KARG(EsArgs) a, IX_KARG(Scratch) sc, IX_KARG(Bx) R) {
   GIDX(R)
-  const Comp q = comp(a.S, n);
+  const EsCur c = es_cursors(a, sc, n, i, j, k);
   const Bx& b = a.bx;
   const bool cs = a.iconserv[n] != 0;
   const int o = A_N * n;
-  const ScArr xe = arr(sc, o + A_XE), ye = arr(sc, o + A_YE), ze = arr(sc, o + A_ZE);
+  const SArr xe = sarr(c.s, o + A_XE), ye = sarr(c.s, o + A_YE), ze = sarr(c.s, o + A_ZE);
   const bool cx = i <= b.hi[0], cy = j <= b.hi[1], cz = k <= b.hi[2];           // cell index inside bx (upper)
   const bool gx = i >= b.lo[0] - 1 && i <= b.hi[0] + 1, gy = j >= b.lo[1] - 1 && j <= b.hi[1] + 1,
              gz = k >= b.lo[2] - 1 && k <= b.hi[2] + 1;
@@ -145,77 +154,76 @@ __global__ void __launch_bounds__(TX* TY) es_corner_kernel(IX_KARG(EsArgs) a, IX
   double lo, hi, l1, h1;
   // x-faces
   if (fx && ((fy && cy && gz) || (gy && fz && cz))) {
-    es_lohi<0>(a, q, a.umac, n, i, j, k, a.dtdx, lo, hi);
+    const double u = c.u(0, 0, 0);
+    es_lohi<0>(a, c.q, c.f, u, a.dtdx, lo, hi);
     if (fy && cy && gz) {  // xy: needed for z-faces -> grown in z
-      corner<0, 1>(l1, h1, lo, hi, q, a.vmac, ye, i, j, k, a.dtdy / 3.0, cs);
-      sc(o + A_XY, i, j, k) = upwind(l1, h1, a.umac(i, j, k));
+      corner<0, 1>(l1, h1, lo, hi, c.q, c.v, ye, a.dtdy / 3.0, cs);
+      c.s(o + A_XY, 0, 0, 0) = upwind(l1, h1, u);
     }
     if (gy && fz && cz) {  // xz: needed for y-faces -> grown in y
-      corner<0, 2>(l1, h1, lo, hi, q, a.wmac, ze, i, j, k, a.dtdz / 3.0, cs);
-      sc(o + A_XZ, i, j, k) = upwind(l1, h1, a.umac(i, j, k));
+      corner<0, 2>(l1, h1, lo, hi, c.q, c.w, ze, a.dtdz / 3.0, cs);
+      c.s(o + A_XZ, 0, 0, 0) = upwind(l1, h1, u);
     }
   }
   // y-faces
   if (fy && ((fx && cx && gz) || (gx && fz && cz))) {
-    es_lohi<1>(a, q, a.vmac, n, i, j, k, a.dtdy, lo, hi);
+    const double v = c.v(0, 0, 0);
+    es_lohi<1>(a, c.q, c.f, v, a.dtdy, lo, hi);
     if (fx && cx && gz) {  // yx: needed for z-faces
-      corner<1, 0>(l1, h1, lo, hi, q, a.umac, xe, i, j, k, a.dtdx / 3.0, cs);
-      sc(o + A_YX, i, j, k) = upwind(l1, h1, a.vmac(i, j, k));
+      corner<1, 0>(l1, h1, lo, hi, c.q, c.u, xe, a.dtdx / 3.0, cs);
+      c.s(o + A_YX, 0, 0, 0) = upwind(l1, h1, v);
     }
     if (gx && fz && cz) {  // yz: needed for x-faces
-      corner<1, 2>(l1, h1, lo, hi, q, a.wmac, ze, i, j, k, a.dtdz / 3.0, cs);
-      sc(o + A_YZ, i, j, k) = upwind(l1, h1, a.vmac(i, j, k));
+      corner<1, 2>(l1, h1, lo, hi, c.q, c.w, ze, a.dtdz / 3.0, cs);
+      c.s(o + A_YZ, 0, 0, 0) = upwind(l1, h1, v);
     }
   }
   // z-faces
   if (fz && ((fx && cx && gy) || (gx && fy && cy))) {
-    es_lohi<2>(a, q, a.wmac, n, i, j, k, a.dtdz, lo, hi);
+    const double w = c.w(0, 0, 0);
+    es_lohi<2>(a, c.q, c.f, w, a.dtdz, lo, hi);
     if (fx && cx && gy) {  // zx: needed for y-faces
-      corner<2, 0>(l1, h1, lo, hi, q, a.umac, xe, i, j, k, a.dtdx / 3.0, cs);
-      sc(o + A_ZX, i, j, k) = upwind(l1, h1, a.wmac(i, j, k));
+      corner<2, 0>(l1, h1, lo, hi, c.q, c.u, xe, a.dtdx / 3.0, cs);
+      c.s(o + A_ZX, 0, 0, 0) = upwind(l1, h1, w);
     }
     if (gx && fy && cy) {  // zy: needed for x-faces
-      corner<2, 1>(l1, h1, lo, hi, q, a.vmac, ye, i, j, k, a.dtdy / 3.0, cs);
-      sc(o + A_ZY, i, j, k) = upwind(l1, h1, a.wmac(i, j, k));
+      corner<2, 1>(l1, h1, lo, hi, c.q, c.v, ye, a.dtdy / 3.0, cs);
+      c.s(o + A_ZY, 0, 0, 0) = upwind(l1, h1, w);
     }
   }
 }
 
 // transverse correction of the D-face state from the two corner-coupled arrays:
 // t1 lives on D1-faces, t2 on D2-faces (D1, D2 = the two transverse directions).
-template <int D, int D1, int D2, class Q>
-IX_D void transverse(double& stl, double& sth, const Q& q, const C4& mac1, const C4& mac2, const ScArr& t1,
-                     const ScArr& t2, int i, int j, int k, double dtd1, double dtd2, bool conserv) {
-  const int im = i - E<D>::x, jm = j - E<D>::y, km = k - E<D>::z;
-  const int i1 = E<D1>::x, j1 = E<D1>::y, k1 = E<D1>::z;
-  const int i2 = E<D2>::x, j2 = E<D2>::y, k2 = E<D2>::z;
+template <int D, int D1, int D2, class M1, class M2, class T1, class T2>
+IX_D void transverse(double& stl, double& sth, const Cur& q, const M1& mac1, const M2& mac2, const T1& t1, const T2& t2,
+                     double dtd1, double dtd2, bool conserv) {
+  // offsets: (a, b) = a*e_D + b*e_Dt ; the cell below the face is a = -1
+  const double m1lp = rel2<D, D1>(mac1, -1, 1), m1lm = rel2<D, D1>(mac1, -1, 0), m1hp = rel2<D, D1>(mac1, 0, 1), m1hm = mac1(0, 0, 0);
+  const double m2lp = rel2<D, D2>(mac2, -1, 1), m2lm = rel2<D, D2>(mac2, -1, 0), m2hp = rel2<D, D2>(mac2, 0, 1), m2hm = mac2(0, 0, 0);
+  const double t1lp = rel2<D, D1>(t1, -1, 1), t1lm = rel2<D, D1>(t1, -1, 0), t1hp = rel2<D, D1>(t1, 0, 1), t1hm = t1(0, 0, 0);
+  const double t2lp = rel2<D, D2>(t2, -1, 1), t2lm = rel2<D, D2>(t2, -1, 0), t2hp = rel2<D, D2>(t2, 0, 1), t2hm = t2(0, 0, 0);
   if (conserv) {
-    stl += -(0.5 * dtd1) * (t1(im + i1, jm + j1, km + k1) * mac1(im + i1, jm + j1, km + k1) - t1(im, jm, km) * mac1(im, jm, km))
-           - (0.5 * dtd2) * (t2(im + i2, jm + j2, km + k2) * mac2(im + i2, jm + j2, km + k2) - t2(im, jm, km) * mac2(im, jm, km))
-           + (0.5 * dtd1) * q(im, jm, km) * (mac1(im + i1, jm + j1, km + k1) - mac1(im, jm, km))
-           + (0.5 * dtd2) * q(im, jm, km) * (mac2(im + i2, jm + j2, km + k2) - mac2(im, jm, km));
-    sth += -(0.5 * dtd1) * (t1(i + i1, j + j1, k + k1) * mac1(i + i1, j + j1, k + k1) - t1(i, j, k) * mac1(i, j, k))
-           - (0.5 * dtd2) * (t2(i + i2, j + j2, k + k2) * mac2(i + i2, j + j2, k + k2) - t2(i, j, k) * mac2(i, j, k))
-           + (0.5 * dtd1) * q(i, j, k) * (mac1(i + i1, j + j1, k + k1) - mac1(i, j, k))
-           + (0.5 * dtd2) * q(i, j, k) * (mac2(i + i2, j + j2, k + k2) - mac2(i, j, k));
+    const double ql = along<D>(q, -1), qh = q(0, 0, 0);
+    stl += -(0.5 * dtd1) * (t1lp * m1lp - t1lm * m1lm) - (0.5 * dtd2) * (t2lp * m2lp - t2lm * m2lm)
+           + (0.5 * dtd1) * ql * (m1lp - m1lm) + (0.5 * dtd2) * ql * (m2lp - m2lm);
+    sth += -(0.5 * dtd1) * (t1hp * m1hp - t1hm * m1hm) - (0.5 * dtd2) * (t2hp * m2hp - t2hm * m2hm)
+           + (0.5 * dtd1) * qh * (m1hp - m1hm) + (0.5 * dtd2) * qh * (m2hp - m2hm);
   } else {
-    stl += -(0.25 * dtd1) * (mac1(im + i1, jm + j1, km + k1) + mac1(im, jm, km)) * (t1(im + i1, jm + j1, km + k1) - t1(im, jm, km))
-           - (0.25 * dtd2) * (mac2(im + i2, jm + j2, km + k2) + mac2(im, jm, km)) * (t2(im + i2, jm + j2, km + k2) - t2(im, jm, km));
-    sth += -(0.25 * dtd1) * (mac1(i + i1, j + j1, k + k1) + mac1(i, j, k)) * (t1(i + i1, j + j1, k + k1) - t1(i, j, k))
-           - (0.25 * dtd2) * (mac2(i + i2, j + j2, k + k2) + mac2(i, j, k)) * (t2(i + i2, j + j2, k + k2) - t2(i, j, k));
+    stl += -(0.25 * dtd1) * (m1lp + m1lm) * (t1lp - t1lm) - (0.25 * dtd2) * (m2lp + m2lm) * (t2lp - t2lm);
+    sth += -(0.25 * dtd1) * (m1hp + m1hm) * (t1hp - t1hm) - (0.25 * dtd2) * (m2hp + m2hm) * (t2hp - t2hm);
   }
 }
 
 template <int D>
-IX_D void es_finish(const EsArgs& a, const Comp& q, int n, int i, int j, int k, double& stl, double& sth) {
-  const int im = i - E<D>::x, jm = j - E<D>::y, km = k - E<D>::z;
-  if (a.iconserv[n] && a.divu.ok()) {
-    stl -= 0.5 * a.dt * q(im, jm, km) * a.divu(im, jm, km);
-    sth -= 0.5 * a.dt * q(i, j, k) * a.divu(i, j, k);
+IX_D void es_finish(const EsArgs& a, const Cur& q, const Cur& f, const Cur& dv, bool conserv, double& stl, double& sth) {
+  if (conserv && dv.ok()) {
+    stl -= 0.5 * a.dt * along<D>(q, -1) * along<D>(dv, -1);
+    sth -= 0.5 * a.dt * q(0, 0, 0) * dv(0, 0, 0);
   }
-  if (!a.fit && a.force.ok()) {
-    stl += 0.5 * a.dt * a.force(im, jm, km, n);
-    sth += 0.5 * a.dt * a.force(i, j, k, n);
+  if (!a.fit && f.ok()) {
+    stl += 0.5 * a.dt * along<D>(f, -1);
+    sth += 0.5 * a.dt * f(0, 0, 0);
   }
 }
 
@@ -226,42 +234,46 @@ struct EsOut {
 
 __global__ void __launch_bounds__(TX* TY) es_final_kernel(IX_KARG(EsArgs) a, IX_KARG(Scratch) sc, IX_KARG(EsOut) out, IX_KARG(Bx) R) {
   GIDX(R)
-  const Comp q = comp(a.S, n);
+  const EsCur c = es_cursors(a, sc, n, i, j, k);
+  const Cur dv = cur_at(a.divu, 0, i, j, k);
   const Bx& b = a.bx;
   const bool cs = a.iconserv[n] != 0;
   const int o = A_N * n;
   const bool cx = i <= b.hi[0], cy = j <= b.hi[1], cz = k <= b.hi[2];
   double stl, sth;
   if (cy && cz) {  // x-face
-    es_lohi<0>(a, q, a.umac, n, i, j, k, a.dtdx, stl, sth);
-    transverse<0, 1, 2>(stl, sth, q, a.vmac, a.wmac, arr(sc, o + A_YZ), arr(sc, o + A_ZY), i, j, k, a.dtdy, a.dtdz, cs);
-    es_finish<0>(a, q, n, i, j, k, stl, sth);
-    const double st = upwind(stl, sth, a.umac(i, j, k));
+    const double u = c.u(0, 0, 0);
+    es_lohi<0>(a, c.q, c.f, u, a.dtdx, stl, sth);
+    transverse<0, 1, 2>(stl, sth, c.q, c.v, c.w, sarr(c.s, o + A_YZ), sarr(c.s, o + A_ZY), a.dtdy, a.dtdz, cs);
+    es_finish<0>(a, c.q, c.f, dv, cs, stl, sth);
+    const double st = upwind(stl, sth, u);
     const double f = st * a.uflx(i, j, k) * out.ax;
-    sc(o + A_XE, i, j, k) = st;
-    sc(o + A_FX, i, j, k) = f;
+    c.s(o + A_XE, 0, 0, 0) = st;
+    c.s(o + A_FX, 0, 0, 0) = f;
     if (out.xed.ok()) out.xed(i, j, k, n) = st;
     if (out.fx.ok()) out.fx(i, j, k, n) = f;
   }
   if (cx && cz) {  // y-face
-    es_lohi<1>(a, q, a.vmac, n, i, j, k, a.dtdy, stl, sth);
-    transverse<1, 0, 2>(stl, sth, q, a.umac, a.wmac, arr(sc, o + A_XZ), arr(sc, o + A_ZX), i, j, k, a.dtdx, a.dtdz, cs);
-    es_finish<1>(a, q, n, i, j, k, stl, sth);
-    const double st = upwind(stl, sth, a.vmac(i, j, k));
+    const double v = c.v(0, 0, 0);
+    es_lohi<1>(a, c.q, c.f, v, a.dtdy, stl, sth);
+    transverse<1, 0, 2>(stl, sth, c.q, c.u, c.w, sarr(c.s, o + A_XZ), sarr(c.s, o + A_ZX), a.dtdx, a.dtdz, cs);
+    es_finish<1>(a, c.q, c.f, dv, cs, stl, sth);
+    const double st = upwind(stl, sth, v);
     const double f = st * a.vflx(i, j, k) * out.ay;
-    sc(o + A_YE, i, j, k) = st;
-    sc(o + A_FY, i, j, k) = f;
+    c.s(o + A_YE, 0, 0, 0) = st;
+    c.s(o + A_FY, 0, 0, 0) = f;
     if (out.yed.ok()) out.yed(i, j, k, n) = st;
     if (out.fy.ok()) out.fy(i, j, k, n) = f;
   }
   if (cx && cy) {  // z-face
-    es_lohi<2>(a, q, a.wmac, n, i, j, k, a.dtdz, stl, sth);
-    transverse<2, 0, 1>(stl, sth, q, a.umac, a.vmac, arr(sc, o + A_XY), arr(sc, o + A_YX), i, j, k, a.dtdx, a.dtdy, cs);
-    es_finish<2>(a, q, n, i, j, k, stl, sth);
-    const double st = upwind(stl, sth, a.wmac(i, j, k));
+    const double w = c.w(0, 0, 0);
+    es_lohi<2>(a, c.q, c.f, w, a.dtdz, stl, sth);
+    transverse<2, 0, 1>(stl, sth, c.q, c.u, c.v, sarr(c.s, o + A_XY), sarr(c.s, o + A_YX), a.dtdx, a.dtdy, cs);
+    es_finish<2>(a, c.q, c.f, dv, cs, stl, sth);
+    const double st = upwind(stl, sth, w);
     const double f = st * a.wflx(i, j, k) * out.az;
-    sc(o + A_ZE, i, j, k) = st;
-    sc(o + A_FZ, i, j, k) = f;
+    c.s(o + A_ZE, 0, 0, 0) = st;
+    c.s(o + A_FZ, 0, 0, 0) = f;
     if (out.zed.ok()) out.zed(i, j, k, n) = st;
     if (out.fz.ok()) out.fz(i, j, k, n) = f;
   }
@@ -271,15 +283,15 @@ __global__ void __launch_bounds__(TX* TY) es_final_kernel(IX_KARG(EsArgs) a, IX_
 __global__ void __launch_bounds__(TX* TY)
 es_div_kernel(IX_KARG(EsArgs) a, IX_KARG(Scratch) sc, V4 aofs, double volinv, double dxi, double dyi, double dzi, int is_sync, Bx R) {
   GIDX(R)
+  const SCur s = scur_at(sc, i, j, k);
   const int o = A_N * n;
-  double upd = -volinv * ((sc(o + A_FX, i + 1, j, k) - sc(o + A_FX, i, j, k)) +
-                          (sc(o + A_FY, i, j + 1, k) - sc(o + A_FY, i, j, k)) +
-                          (sc(o + A_FZ, i, j, k + 1) - sc(o + A_FZ, i, j, k)));
+  double upd = -volinv * ((s(o + A_FX, 1, 0, 0) - s(o + A_FX, 0, 0, 0)) + (s(o + A_FY, 0, 1, 0) - s(o + A_FY, 0, 0, 0)) +
+                          (s(o + A_FZ, 0, 0, 1) - s(o + A_FZ, 0, 0, 0)));
   if (!a.iconserv[n] && !is_sync) {
-    const double divum = dxi * (a.umac(i + 1, j, k) - a.umac(i, j, k)) + dyi * (a.vmac(i, j + 1, k) - a.vmac(i, j, k)) +
-                         dzi * (a.wmac(i, j, k + 1) - a.wmac(i, j, k));
-    double qb = sc(o + A_XE, i, j, k) + sc(o + A_XE, i + 1, j, k) + sc(o + A_YE, i, j, k) + sc(o + A_YE, i, j + 1, k) +
-                sc(o + A_ZE, i, j, k) + sc(o + A_ZE, i, j, k + 1);
+    const Cur u = cur_at(a.umac, 0, i, j, k), v = cur_at(a.vmac, 0, i, j, k), w = cur_at(a.wmac, 0, i, j, k);
+    const double divum = dxi * (u(1, 0, 0) - u(0, 0, 0)) + dyi * (v(0, 1, 0) - v(0, 0, 0)) + dzi * (w(0, 0, 1) - w(0, 0, 0));
+    double qb = s(o + A_XE, 0, 0, 0) + s(o + A_XE, 1, 0, 0) + s(o + A_YE, 0, 0, 0) + s(o + A_YE, 0, 1, 0) +
+                s(o + A_ZE, 0, 0, 0) + s(o + A_ZE, 0, 0, 1);
     qb /= 6.0;
     upd += qb * divum;
   }
@@ -301,57 +313,70 @@ struct EvArgs {
 enum { B_UAD = 0, B_VAD, B_WAD, B_XE_V, B_XE_W, B_YE_U, B_YE_W, B_ZE_U, B_ZE_V,
        B_YZ_U, B_ZY_U, B_XZ_V, B_ZX_V, B_XY_W, B_YX_W, B_N };
 
+struct EvCur {
+  Cur q[3], f[3];
+  SCur s;
+};
+IX_D EvCur ev_cursors(const EvArgs& a, const Scratch& sc, int i, int j, int k) {
+  EvCur c;
+  for (int n = 0; n < 3; ++n) { c.q[n] = cur_at(a.vel, n, i, j, k); c.f[n] = cur_at(a.force, n, i, j, k); }
+  c.s = scur_at(sc, i, j, k);
+  return c;
+}
+
+// lo/hi of component n on the D-face, traced with the cell-centred velocity component D
 template <int D>
-IX_D void ev_lohi(const EvArgs& a, int n, int i, int j, int k, double dtdx, double& lo, double& hi) {
-  const int im = i - E<D>::x, jm = j - E<D>::y, km = k - E<D>::z;
-  trace<D>(comp(a.vel, n), i, j, k, a.vel(im, jm, km, D), a.vel(i, j, k, D), dtdx, lo, hi);
-  if (a.fit && a.force.ok()) {
-    lo += 0.5 * a.dt * a.force(im, jm, km, n);
-    hi += 0.5 * a.dt * a.force(i, j, k, n);
+IX_D void ev_lohi(const EvArgs& a, const EvCur& c, int n, double dtdx, double& lo, double& hi) {
+  trace<D>(c.q[n], along<D>(c.q[D], -1), c.q[D](0, 0, 0), dtdx, lo, hi);
+  if (a.fit && c.f[n].ok()) {
+    lo += 0.5 * a.dt * along<D>(c.f[n], -1);
+    hi += 0.5 * a.dt * c.f[n](0, 0, 0);
   }
 }
 
 __global__ void __launch_bounds__(TX* TY) ev_edge_kernel(IX_KARG(EvArgs) a, IX_KARG(Scratch) sc, IX_KARG(Bx) R) {
   GIDX(R)
   (void)n;
+  const EvCur c = ev_cursors(a, sc, i, j, k);
   const Bx& b = a.bx;
   const bool inx = i >= b.lo[0] - 1 && i <= b.hi[0] + 1, iny = j >= b.lo[1] - 1 && j <= b.hi[1] + 1,
              inz = k >= b.lo[2] - 1 && k <= b.hi[2] + 1;
   double lo, hi;
   if (i >= b.lo[0] && i <= b.hi[0] + 1 && iny && inz) {
-    ev_lohi<0>(a, 0, i, j, k, a.dtdx, lo, hi);
+    ev_lohi<0>(a, c, 0, a.dtdx, lo, hi);
     const double uad = riemann(lo, hi);
-    sc(B_UAD, i, j, k) = uad;
-    ev_lohi<0>(a, 1, i, j, k, a.dtdx, lo, hi);
-    sc(B_XE_V, i, j, k) = upwind(lo, hi, uad);
-    ev_lohi<0>(a, 2, i, j, k, a.dtdx, lo, hi);
-    sc(B_XE_W, i, j, k) = upwind(lo, hi, uad);
+    c.s(B_UAD, 0, 0, 0) = uad;
+    ev_lohi<0>(a, c, 1, a.dtdx, lo, hi);
+    c.s(B_XE_V, 0, 0, 0) = upwind(lo, hi, uad);
+    ev_lohi<0>(a, c, 2, a.dtdx, lo, hi);
+    c.s(B_XE_W, 0, 0, 0) = upwind(lo, hi, uad);
   }
   if (j >= b.lo[1] && j <= b.hi[1] + 1 && inx && inz) {
-    ev_lohi<1>(a, 1, i, j, k, a.dtdy, lo, hi);
+    ev_lohi<1>(a, c, 1, a.dtdy, lo, hi);
     const double vad = riemann(lo, hi);
-    sc(B_VAD, i, j, k) = vad;
-    ev_lohi<1>(a, 0, i, j, k, a.dtdy, lo, hi);
-    sc(B_YE_U, i, j, k) = upwind(lo, hi, vad);
-    ev_lohi<1>(a, 2, i, j, k, a.dtdy, lo, hi);
-    sc(B_YE_W, i, j, k) = upwind(lo, hi, vad);
+    c.s(B_VAD, 0, 0, 0) = vad;
+    ev_lohi<1>(a, c, 0, a.dtdy, lo, hi);
+    c.s(B_YE_U, 0, 0, 0) = upwind(lo, hi, vad);
+    ev_lohi<1>(a, c, 2, a.dtdy, lo, hi);
+    c.s(B_YE_W, 0, 0, 0) = upwind(lo, hi, vad);
   }
   if (k >= b.lo[2] && k <= b.hi[2] + 1 && inx && iny) {
-    ev_lohi<2>(a, 2, i, j, k, a.dtdz, lo, hi);
+    ev_lohi<2>(a, c, 2, a.dtdz, lo, hi);
     const double wad = riemann(lo, hi);
-    sc(B_WAD, i, j, k) = wad;
-    ev_lohi<2>(a, 0, i, j, k, a.dtdz, lo, hi);
-    sc(B_ZE_U, i, j, k) = upwind(lo, hi, wad);
-    ev_lohi<2>(a, 1, i, j, k, a.dtdz, lo, hi);
-    sc(B_ZE_V, i, j, k) = upwind(lo, hi, wad);
+    c.s(B_WAD, 0, 0, 0) = wad;
+    ev_lohi<2>(a, c, 0, a.dtdz, lo, hi);
+    c.s(B_ZE_U, 0, 0, 0) = upwind(lo, hi, wad);
+    ev_lohi<2>(a, c, 1, a.dtdz, lo, hi);
+    c.s(B_ZE_V, 0, 0, 0) = upwind(lo, hi, wad);
   }
 }
 
 __global__ void __launch_bounds__(TX* TY) ev_corner_kernel(IX_KARG(EvArgs) a, IX_KARG(Scratch) sc, IX_KARG(Bx) R) {
   GIDX(R)
   (void)n;
+  const EvCur c = ev_cursors(a, sc, i, j, k);
   const Bx& b = a.bx;
-  const ScArr uad = arr(sc, B_UAD), vad = arr(sc, B_VAD), wad = arr(sc, B_WAD);
+  const SArr uad = sarr(c.s, B_UAD), vad = sarr(c.s, B_VAD), wad = sarr(c.s, B_WAD);
   const bool cx = i <= b.hi[0], cy = j <= b.hi[1], cz = k <= b.hi[2];
   const bool gx = i >= b.lo[0] - 1 && i <= b.hi[0] + 1, gy = j >= b.lo[1] - 1 && j <= b.hi[1] + 1,
              gz = k >= b.lo[2] - 1 && k <= b.hi[2] + 1;
@@ -360,67 +385,59 @@ __global__ void __launch_bounds__(TX* TY) ev_corner_kernel(IX_KARG(EvArgs) a, IX
   double lo, hi, l1, h1;
   // x-face states: comp 2 coupled with y (for wmac), comp 1 coupled with z (for vmac)
   if (fx && fy && cy && gz) {
-    ev_lohi<0>(a, 2, i, j, k, a.dtdx, lo, hi);
-    corner<0, 1>(l1, h1, lo, hi, comp(a.vel, 2), vad, arr(sc, B_YE_W), i, j, k, a.dtdy / 3.0, false);
-    sc(B_XY_W, i, j, k) = upwind(l1, h1, uad(i, j, k));
+    ev_lohi<0>(a, c, 2, a.dtdx, lo, hi);
+    corner<0, 1>(l1, h1, lo, hi, c.q[2], vad, sarr(c.s, B_YE_W), a.dtdy / 3.0, false);
+    c.s(B_XY_W, 0, 0, 0) = upwind(l1, h1, uad(0, 0, 0));
   }
   if (fx && gy && fz && cz) {
-    ev_lohi<0>(a, 1, i, j, k, a.dtdx, lo, hi);
-    corner<0, 2>(l1, h1, lo, hi, comp(a.vel, 1), wad, arr(sc, B_ZE_V), i, j, k, a.dtdz / 3.0, false);
-    sc(B_XZ_V, i, j, k) = upwind(l1, h1, uad(i, j, k));
+    ev_lohi<0>(a, c, 1, a.dtdx, lo, hi);
+    corner<0, 2>(l1, h1, lo, hi, c.q[1], wad, sarr(c.s, B_ZE_V), a.dtdz / 3.0, false);
+    c.s(B_XZ_V, 0, 0, 0) = upwind(l1, h1, uad(0, 0, 0));
   }
   // y-face states: comp 2 coupled with x (for wmac), comp 0 coupled with z (for umac)
   if (fy && fx && cx && gz) {
-    ev_lohi<1>(a, 2, i, j, k, a.dtdy, lo, hi);
-    corner<1, 0>(l1, h1, lo, hi, comp(a.vel, 2), uad, arr(sc, B_XE_W), i, j, k, a.dtdx / 3.0, false);
-    sc(B_YX_W, i, j, k) = upwind(l1, h1, vad(i, j, k));
+    ev_lohi<1>(a, c, 2, a.dtdy, lo, hi);
+    corner<1, 0>(l1, h1, lo, hi, c.q[2], uad, sarr(c.s, B_XE_W), a.dtdx / 3.0, false);
+    c.s(B_YX_W, 0, 0, 0) = upwind(l1, h1, vad(0, 0, 0));
   }
   if (fy && gx && fz && cz) {
-    ev_lohi<1>(a, 0, i, j, k, a.dtdy, lo, hi);
-    corner<1, 2>(l1, h1, lo, hi, comp(a.vel, 0), wad, arr(sc, B_ZE_U), i, j, k, a.dtdz / 3.0, false);
-    sc(B_YZ_U, i, j, k) = upwind(l1, h1, vad(i, j, k));
+    ev_lohi<1>(a, c, 0, a.dtdy, lo, hi);
+    corner<1, 2>(l1, h1, lo, hi, c.q[0], wad, sarr(c.s, B_ZE_U), a.dtdz / 3.0, false);
+    c.s(B_YZ_U, 0, 0, 0) = upwind(l1, h1, vad(0, 0, 0));
   }
   // z-face states: comp 1 coupled with x (for vmac), comp 0 coupled with y (for umac)
   if (fz && fx && cx && gy) {
-    ev_lohi<2>(a, 1, i, j, k, a.dtdz, lo, hi);
-    corner<2, 0>(l1, h1, lo, hi, comp(a.vel, 1), uad, arr(sc, B_XE_V), i, j, k, a.dtdx / 3.0, false);
-    sc(B_ZX_V, i, j, k) = upwind(l1, h1, wad(i, j, k));
+    ev_lohi<2>(a, c, 1, a.dtdz, lo, hi);
+    corner<2, 0>(l1, h1, lo, hi, c.q[1], uad, sarr(c.s, B_XE_V), a.dtdx / 3.0, false);
+    c.s(B_ZX_V, 0, 0, 0) = upwind(l1, h1, wad(0, 0, 0));
   }
   if (fz && gx && fy && cy) {
-    ev_lohi<2>(a, 0, i, j, k, a.dtdz, lo, hi);
-    corner<2, 1>(l1, h1, lo, hi, comp(a.vel, 0), vad, arr(sc, B_YE_U), i, j, k, a.dtdy / 3.0, false);
-    sc(B_ZY_U, i, j, k) = upwind(l1, h1, wad(i, j, k));
+    ev_lohi<2>(a, c, 0, a.dtdz, lo, hi);
+    corner<2, 1>(l1, h1, lo, hi, c.q[0], vad, sarr(c.s, B_YE_U), a.dtdy / 3.0, false);
+    c.s(B_ZY_U, 0, 0, 0) = upwind(l1, h1, wad(0, 0, 0));
   }
 }
 
 template <int D, int D1, int D2>
-IX_D double ev_final(const EvArgs& a, const Scratch& sc, int A1, int A2, int T1, int T2, int i, int j, int k,
-                     double dtdx, double dtd1, double dtd2) {
-  const int im = i - E<D>::x, jm = j - E<D>::y, km = k - E<D>::z;
-  const int i1 = E<D1>::x, j1 = E<D1>::y, k1 = E<D1>::z;
-  const int i2 = E<D2>::x, j2 = E<D2>::y, k2 = E<D2>::z;
-  const ScArr ad1 = arr(sc, A1), ad2 = arr(sc, A2), t1 = arr(sc, T1), t2 = arr(sc, T2);
+IX_D double ev_final(const EvArgs& a, const EvCur& c, int A1, int A2, int T1, int T2, double dtdx, double dtd1, double dtd2) {
   double stl, sth;
-  ev_lohi<D>(a, D, i, j, k, dtdx, stl, sth);
-  stl += -(0.25 * dtd1) * (ad1(im + i1, jm + j1, km + k1) + ad1(im, jm, km)) * (t1(im + i1, jm + j1, km + k1) - t1(im, jm, km))
-         - (0.25 * dtd2) * (ad2(im + i2, jm + j2, km + k2) + ad2(im, jm, km)) * (t2(im + i2, jm + j2, km + k2) - t2(im, jm, km));
-  sth += -(0.25 * dtd1) * (ad1(i + i1, j + j1, k + k1) + ad1(i, j, k)) * (t1(i + i1, j + j1, k + k1) - t1(i, j, k))
-         - (0.25 * dtd2) * (ad2(i + i2, j + j2, k + k2) + ad2(i, j, k)) * (t2(i + i2, j + j2, k + k2) - t2(i, j, k));
-  if (!a.fit && a.force.ok()) {
-    stl += 0.5 * a.dt * a.force(im, jm, km, D);
-    sth += 0.5 * a.dt * a.force(i, j, k, D);
-  }
+  ev_lohi<D>(a, c, D, dtdx, stl, sth);
+  double fl = 0.0, fh = 0.0;
+  if (!a.fit && c.f[D].ok()) { fl = 0.5 * a.dt * along<D>(c.f[D], -1); fh = 0.5 * a.dt * c.f[D](0, 0, 0); }
+  transverse<D, D1, D2>(stl, sth, c.q[D], sarr(c.s, A1), sarr(c.s, A2), sarr(c.s, T1), sarr(c.s, T2), dtd1, dtd2, false);
+  stl += fl; sth += fh;
   return riemann(stl, sth);
 }
 
 __global__ void __launch_bounds__(TX* TY) ev_final_kernel(IX_KARG(EvArgs) a, IX_KARG(Scratch) sc, V4 umac, V4 vmac, V4 wmac, IX_KARG(Bx) R) {
   GIDX(R)
   (void)n;
+  const EvCur c = ev_cursors(a, sc, i, j, k);
   const Bx& b = a.bx;
   const bool cx = i <= b.hi[0], cy = j <= b.hi[1], cz = k <= b.hi[2];
-  if (cy && cz) umac(i, j, k) = ev_final<0, 1, 2>(a, sc, B_VAD, B_WAD, B_YZ_U, B_ZY_U, i, j, k, a.dtdx, a.dtdy, a.dtdz);
-  if (cx && cz) vmac(i, j, k) = ev_final<1, 0, 2>(a, sc, B_UAD, B_WAD, B_XZ_V, B_ZX_V, i, j, k, a.dtdy, a.dtdx, a.dtdz);
-  if (cx && cy) wmac(i, j, k) = ev_final<2, 0, 1>(a, sc, B_UAD, B_VAD, B_XY_W, B_YX_W, i, j, k, a.dtdz, a.dtdx, a.dtdy);
+  if (cy && cz) umac(i, j, k) = ev_final<0, 1, 2>(a, c, B_VAD, B_WAD, B_YZ_U, B_ZY_U, a.dtdx, a.dtdy, a.dtdz);
+  if (cx && cz) vmac(i, j, k) = ev_final<1, 0, 2>(a, c, B_UAD, B_WAD, B_XZ_V, B_ZX_V, a.dtdy, a.dtdx, a.dtdz);
+  if (cx && cy) wmac(i, j, k) = ev_final<2, 0, 1>(a, c, B_UAD, B_VAD, B_XY_W, B_YX_W, a.dtdz, a.dtdx, a.dtdy);
 }
 
 struct ScratchOwner {

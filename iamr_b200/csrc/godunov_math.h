@@ -34,11 +34,9 @@ IX_HD double lim2(double dlft, double drgt) {  // limited 2nd-order difference
   return dsgn * fmin(dlim, fabs(dcen));
 }
 
-// 4th-order limited slope of q along D at cell (i,j,k) (amrex_calc_?slope, order 4)
-template <int D, class A>
-IX_HD double slope4(const A& q, int i, int j, int k) {
-  const double qm2 = sh<D>(q, i, j, k, -2), qm = sh<D>(q, i, j, k, -1), q0 = q(i, j, k);
-  const double qp = sh<D>(q, i, j, k, 1), qp2 = sh<D>(q, i, j, k, 2);
+// 4th-order limited slope from the five values q(i-2..i+2) along one direction
+// (amrex_calc_{x,y,z}slope, order 4)
+IX_HD double slope4_vals(double qm2, double qm, double q0, double qp, double qp2) {
   const double dxl = lim2(qm - qm2, q0 - qm);
   const double dxr = lim2(qp - q0, qp2 - qp);
   const double dlft = q0 - qm, drgt = qp - q0;
@@ -47,6 +45,39 @@ IX_HD double slope4(const A& q, int i, int j, int k) {
   const double slop = 2.0 * fmin(fabs(dlft), fabs(drgt));
   const double dlim = (dlft * drgt >= 0.0) ? slop : 0.0;
   return dsgn * fmin(dlim, fabs((4.0 / 3.0) * dcen - (1.0 / 6.0) * (dxl + dxr)));
+}
+
+// 4th-order limited slope of q along D at cell (i,j,k)
+template <int D, class A>
+IX_HD double slope4(const A& q, int i, int j, int k) {
+  return slope4_vals(sh<D>(q, i, j, k, -2), sh<D>(q, i, j, k, -1), q(i, j, k), sh<D>(q, i, j, k, 1), sh<D>(q, i, j, k, 2));
+}
+
+// Cursor: a read-only view of one component positioned at a fixed (i,j,k); neighbours are
+// addressed by small relative offsets, so the per-access index arithmetic is one 32-bit
+// add (the offsets are compile-time constants after inlining) instead of the 64-bit
+// (i-l0) + (j-l1)*js + (k-l2)*ks of the absolute views.
+struct Cur {
+  const double* p;
+  int js, ks;
+  IX_HD double operator()(int di, int dj, int dk) const { return p[di + dj * js + dk * ks]; }
+  IX_HD bool ok() const { return p != nullptr; }
+};
+template <class V>
+IX_HD Cur cur_at(const V& v, int n, int i, int j, int k) {
+  if (!v.p) return Cur{nullptr, 0, 0};
+  return Cur{v.p + n * v.ns + ((i - v.l0) + (j - v.l1) * v.js + (k - v.l2) * v.ks), (int)v.js, (int)v.ks};
+}
+template <int D> IX_HD Cur below(const Cur& c) {  // cursor moved one cell down along D
+  return Cur{c.p - (E<D>::x + E<D>::y * c.js + E<D>::z * c.ks), c.js, c.ks};
+}
+template <int D> IX_HD double along(const Cur& c, int o) { return c(o * E<D>::x, o * E<D>::y, o * E<D>::z); }
+// value at offset a*e_D1 + b*e_D2
+template <int D1, int D2, class C> IX_HD double rel2(const C& c, int a, int b) {
+  return c(a * E<D1>::x + b * E<D2>::x, a * E<D1>::y + b * E<D2>::y, a * E<D1>::z + b * E<D2>::z);
+}
+template <int D> IX_HD double slope4c(const Cur& q) {
+  return slope4_vals(along<D>(q, -2), along<D>(q, -1), q(0, 0, 0), along<D>(q, 1), along<D>(q, 2));
 }
 
 // upwind the pair (lo, hi) with a given face velocity (ComputeEdgeState /

@@ -7,6 +7,8 @@
 // (IAMR call sites Projection.cpp:2512-2542, NSB.cpp:4106-4118); the stencil is
 // the trilinear stiffness matrix with one sigma per cell, which
 // the oracle re-derives by element integration (oracle/oracle.cpp nodal_*).
+#include <cstdint>
+#include <cstdlib>
 #include "kernels.h"
 
 namespace ix {
@@ -17,13 +19,16 @@ constexpr int TX = 64;
 constexpr int TY = 4;
 
 // A*phi at node (i,j,k) and the diagonal coefficient.
-// im/ip, jm/jp, km/kp: indices of the neighbouring NODES (i-1/i+1 ..., or their periodic images)
-IX_D double nodal_ax(C4 x, C4 sig, int i, int j, int k, int im, int ip, int jm, int jp, int km, int kp,
-                     double facx, double facy, double facz, double& s0) {
-  const double s000 = sig(i - 1, j - 1, k - 1), s100 = sig(i, j - 1, k - 1);
-  const double s010 = sig(i - 1, j, k - 1), s110 = sig(i, j, k - 1);
-  const double s001 = sig(i - 1, j - 1, k), s101 = sig(i, j - 1, k);
-  const double s011 = sig(i - 1, j, k), s111 = sig(i, j, k);
+// A*phi at a node and the diagonal coefficient s0, written against two accessors so that the
+// one-thread-per-node kernels and the shared-memory tile kernels evaluate the SAME expression
+// (bit-identical results):  X(di,dj,dk) = phi at node offset (di,dj,dk) in {-1,0,1}^3,
+//                           S(di,dj,dk) = sigma of the cell at offset (di,dj,dk) in {-1,0}^3.
+template <class XA, class SA>
+IX_D double nodal_ax_rel(const XA& X, const SA& S, double facx, double facy, double facz, double& s0) {
+  const double s000 = S(-1, -1, -1), s100 = S(0, -1, -1);
+  const double s010 = S(-1, 0, -1), s110 = S(0, 0, -1);
+  const double s001 = S(-1, -1, 0), s101 = S(0, -1, 0);
+  const double s011 = S(-1, 0, 0), s111 = S(0, 0, 0);
   const double fxyz = facx + facy + facz;
   const double fmx2y2z = -facx + 2.0 * facy + 2.0 * facz;
   const double f2xmy2z = 2.0 * facx - facy + 2.0 * facz;
@@ -32,24 +37,35 @@ IX_D double nodal_ax(C4 x, C4 sig, int i, int j, int k, int im, int ip, int jm, 
   const double fm2x4ym2z = -2.0 * facx + 4.0 * facy - 2.0 * facz;
   const double fm2xm2y4z = -2.0 * facx - 2.0 * facy + 4.0 * facz;
   s0 = (-4.0) * fxyz * (s000 + s100 + s010 + s110 + s001 + s101 + s011 + s111);
-  double y = x(i, j, k) * s0;
-  y += fxyz * (x(im, jm, km) * s000 + x(ip, jm, km) * s100 +
-               x(im, jp, km) * s010 + x(ip, jp, km) * s110 +
-               x(im, jm, kp) * s001 + x(ip, jm, kp) * s101 +
-               x(im, jp, kp) * s011 + x(ip, jp, kp) * s111);
-  y += fmx2y2z * (x(i, jm, km) * (s000 + s100) + x(i, jp, km) * (s010 + s110) +
-                  x(i, jm, kp) * (s001 + s101) + x(i, jp, kp) * (s011 + s111));
-  y += f2xmy2z * (x(im, j, km) * (s000 + s010) + x(ip, j, km) * (s100 + s110) +
-                  x(im, j, kp) * (s001 + s011) + x(ip, j, kp) * (s101 + s111));
-  y += f2x2ymz * (x(im, jm, k) * (s000 + s001) + x(ip, jm, k) * (s100 + s101) +
-                  x(im, jp, k) * (s010 + s011) + x(ip, jp, k) * (s110 + s111));
-  y += f4xm2ym2z * (x(im, j, k) * (s000 + s010 + s001 + s011) +
-                    x(ip, j, k) * (s100 + s110 + s101 + s111));
-  y += fm2x4ym2z * (x(i, jm, k) * (s000 + s100 + s001 + s101) +
-                    x(i, jp, k) * (s010 + s110 + s011 + s111));
-  y += fm2xm2y4z * (x(i, j, km) * (s000 + s100 + s010 + s110) +
-                    x(i, j, kp) * (s001 + s101 + s011 + s111));
+  double y = X(0, 0, 0) * s0;
+  y += fxyz * (X(-1, -1, -1) * s000 + X(1, -1, -1) * s100 + X(-1, 1, -1) * s010 + X(1, 1, -1) * s110 +
+               X(-1, -1, 1) * s001 + X(1, -1, 1) * s101 + X(-1, 1, 1) * s011 + X(1, 1, 1) * s111);
+  y += fmx2y2z * (X(0, -1, -1) * (s000 + s100) + X(0, 1, -1) * (s010 + s110) +
+                  X(0, -1, 1) * (s001 + s101) + X(0, 1, 1) * (s011 + s111));
+  y += f2xmy2z * (X(-1, 0, -1) * (s000 + s010) + X(1, 0, -1) * (s100 + s110) +
+                  X(-1, 0, 1) * (s001 + s011) + X(1, 0, 1) * (s101 + s111));
+  y += f2x2ymz * (X(-1, -1, 0) * (s000 + s001) + X(1, -1, 0) * (s100 + s101) +
+                  X(-1, 1, 0) * (s010 + s011) + X(1, 1, 0) * (s110 + s111));
+  y += f4xm2ym2z * (X(-1, 0, 0) * (s000 + s010 + s001 + s011) + X(1, 0, 0) * (s100 + s110 + s101 + s111));
+  y += fm2x4ym2z * (X(0, -1, 0) * (s000 + s100 + s001 + s101) + X(0, 1, 0) * (s010 + s110 + s011 + s111));
+  y += fm2xm2y4z * (X(0, 0, -1) * (s000 + s100 + s010 + s110) + X(0, 0, 1) * (s001 + s101 + s011 + s111));
   return y;
+}
+
+// global-memory form: im/ip, jm/jp, km/kp are the neighbouring NODE indices (or their periodic
+// images).  Neighbours are addressed as 32-bit element offsets from the node's own address.
+IX_D double nodal_ax(C4 x, C4 sig, int i, int j, int k, int im, int ip, int jm, int jp, int km, int kp,
+                     double facx, double facy, double facz, double& s0) {
+  const double* xc = x.p + ((i - x.l0) + (j - x.l1) * x.js + (k - x.l2) * x.ks);
+  const int xjs = (int)x.js, xks = (int)x.ks;
+  const int oxm = im - i, oxp = ip - i, oym = (jm - j) * xjs, oyp = (jp - j) * xjs, ozm = (km - k) * xks, ozp = (kp - k) * xks;
+  auto X = [&](int di, int dj, int dk) {
+    return xc[(di < 0 ? oxm : (di > 0 ? oxp : 0)) + (dj < 0 ? oym : (dj > 0 ? oyp : 0)) + (dk < 0 ? ozm : (dk > 0 ? ozp : 0))];
+  };
+  const double* sc = sig.p + ((i - sig.l0) + (j - sig.l1) * sig.js + (k - sig.l2) * sig.ks);
+  const int sjs = (int)sig.js, sks = (int)sig.ks;
+  auto S = [&](int di, int dj, int dk) { return sc[di + dj * sjs + dk * sks]; };
+  return nodal_ax_rel(X, S, facx, facy, facz, s0);
 }
 
 // neighbour node indices; with wrap bit d set the node box [lo, hi] carries the periodic
@@ -85,7 +101,8 @@ jacobi_kernel(Bx bx, V4 out, C4 phi, C4 rhs, C4 sig, double facx, double facy, d
 
 // colour = cx + 2*cy + 4*cz; nodes with (i&1,j&1,k&1) == (cx,cy,cz) are mutually
 // uncoupled under the 27-point stencil.
-__global__ void __launch_bounds__(TX* TY)
+template <int MINB>
+__global__ void __launch_bounds__(TX* TY, MINB)
 gs_color_kernel(Bx bx, V4 phi, C4 rhs, C4 sig, double facx, double facy, double facz, int i0, int j0,
                 int k0, int wm) {
   const int k = k0 + 2 * blockIdx.z;
@@ -165,6 +182,179 @@ mknewu_kernel(Bx bx, V4 vel, V4 gp, int incr, C4 p, C4 sig, double facx, double 
   }
 }
 
+#if !defined(IX_EMUL)
+// ---- Gauss-Seidel colour pass with 128-bit loads + warp shuffles -------------------------------
+// The updated nodes of one colour are 2 apart in x, so a warp's scalar loads of phi(i-1), phi(i),
+// phi(i+1) each span 512 B and use half of every sector (ncu: 13 sectors/request, L1 tag stage the
+// busiest unit).  Here each lane issues ONE aligned 16-byte load per (row, plane) that returns its
+// own node and one x-neighbour; the other neighbour is the adjacent lane's second word (warp
+// shuffle).  Same for sigma.  27 + 8 scalar loads become 9 + 4 vector loads + shuffles.
+// The stencil is accumulated row by row:
+//   y = sum_{dj,dk} [ F1(dj,dk) (Sm xm + Sp xp) + F0(dj,dk) (Sm + Sp) x0 ]
+// with Sm/Sp = sums of sigma over the cells on the -x/+x side shared with row (dj,dk) and
+//   F(di,dj,dk) = -36 sum_d fac_d s_d prod_{e != d} m_e,  s = +1 (same node) / -1, m = 2/6 (same) / 1/6
+// (the Q1 element matrices; identical to the hand-expanded coefficients of nodal_ax_rel).
+IX_D double q1_factor(bool nx, bool ny, bool nz, double facx, double facy, double facz) {
+  const double sx = nx ? -1.0 : 1.0, sy = ny ? -1.0 : 1.0, sz = nz ? -1.0 : 1.0;
+  const double mx = nx ? 1.0 : 2.0, my = ny ? 1.0 : 2.0, mz = nz ? 1.0 : 2.0;  // x 1/6 each, folded into the -36
+  return -(facx * sx * my * mz + facy * sy * mx * mz + facz * sz * mx * my);
+}
+
+__global__ void __launch_bounds__(TX* TY)
+gs_color_vec_kernel(Bx bx, V4 phi, C4 rhs, C4 sig, double facx, double facy, double facz, int i0, int j0, int k0, int wm,
+                    int phi_pair_at_i, int sig_pair_at_i) {
+  const int k = k0 + 2 * blockIdx.z;
+  const int j = j0 + 2 * (blockIdx.y * TY + threadIdx.y);
+  const int i = i0 + 2 * (blockIdx.x * TX + threadIdx.x);
+  if (k > bx.hi[2] || j > bx.hi[1]) return;  // uniform per warp (a warp is 32 consecutive x of one row)
+  const bool valid = i <= bx.hi[0];
+  const int lane = threadIdx.x & 31;
+  const unsigned full = 0xffffffffu;
+  const bool next_valid = (i + 2) <= bx.hi[0];
+  const int ic = valid ? i : bx.hi[0];  // clamp so that address arithmetic stays in range for idle lanes
+  double* pc = phi.p + ((ic - phi.l0) + (j - phi.l1) * phi.js + (k - phi.l2) * phi.ks);
+  const int pjs = (int)phi.js, pks = (int)phi.ks;
+  const bool wx = (wm & 1) != 0;
+  const int oxm = (wx && ic == bx.lo[0]) ? (bx.hi[0] - 1 - ic) : -1, oxp = (wx && ic == bx.hi[0]) ? (bx.lo[0] + 1 - ic) : 1;
+  const int oy[3] = {(((wm & 2) && j == bx.lo[1]) ? bx.hi[1] - 1 - j : -1) * pjs, 0, (((wm & 2) && j == bx.hi[1]) ? bx.lo[1] + 1 - j : 1) * pjs};
+  const int oz[3] = {(((wm & 4) && k == bx.lo[2]) ? bx.hi[2] - 1 - k : -1) * pks, 0, (((wm & 4) && k == bx.hi[2]) ? bx.lo[2] + 1 - k : 1) * pks};
+  // sigma: cells (i-1, i) x (j-1, j) x (k-1, k)
+  const double* sc = sig.p + ((ic - sig.l0) + (j - sig.l1) * sig.js + (k - sig.l2) * sig.ks);
+  const int sjs = (int)sig.js, sks = (int)sig.ks;
+  double sm[2][2], sp[2][2];  // [dk+1][dj+1] for dj,dk in {-1,0}: sigma(i-1,..) and sigma(i,..)
+#pragma unroll
+  for (int b = 0; b < 2; ++b)
+#pragma unroll
+    for (int a = 0; a < 2; ++a) {
+      const double* sr = sc + (a - 1) * sjs + (b - 1) * sks;
+      if (sig_pair_at_i) {  // aligned pair = (i, i+1): own cell in .x, cell i-1 is the left lane's .y
+        double2 v = make_double2(0.0, 0.0);
+        if (valid) {  // the last column's pair would end one element past the sigma row
+          if (ic < bx.hi[0]) v = *reinterpret_cast<const double2*>(sr); else v.x = sr[0];
+        }
+        double left = __shfl_up_sync(full, v.y, 1);
+        if (lane == 0 && valid) left = sr[-1];
+        sp[b][a] = v.x; sm[b][a] = left;
+      } else {              // aligned pair = (i-1, i)
+        double2 v = make_double2(0.0, 0.0);
+        if (valid) v = *reinterpret_cast<const double2*>(sr - 1);
+        sm[b][a] = v.x; sp[b][a] = v.y;
+      }
+    }
+  double y = 0.0, x00 = 0.0, s0 = 0.0;
+#pragma unroll
+  for (int dk = -1; dk <= 1; ++dk)
+#pragma unroll
+    for (int dj = -1; dj <= 1; ++dj) {
+      // sigma sums over the cells shared with this row
+      double Sm = 0.0, Sp = 0.0;
+#pragma unroll
+      for (int b = 0; b < 2; ++b)
+#pragma unroll
+        for (int a = 0; a < 2; ++a) {
+          const bool use_a = (dj == 0) || (dj < 0 ? a == 0 : a == 1);
+          const bool use_b = (dk == 0) || (dk < 0 ? b == 0 : b == 1);
+          if (use_a && use_b) { Sm += sm[b][a]; Sp += sp[b][a]; }
+        }
+      const double* pr = pc + oy[dj + 1] + oz[dk + 1];
+      double xm, x0, xp;
+      if (phi_pair_at_i) {  // aligned pair = (i, i+1)
+        double2 v = make_double2(0.0, 0.0);
+        if (valid) v = *reinterpret_cast<const double2*>(pr);
+        x0 = v.x; xp = v.y;
+        xm = __shfl_up_sync(full, v.y, 1);
+        if (valid && (lane == 0)) xm = pr[oxm];
+        if (valid && wx && ic == bx.hi[0]) xp = pr[oxp];
+      } else {              // aligned pair = (i-1, i)
+        double2 v = make_double2(0.0, 0.0);
+        if (valid) v = *reinterpret_cast<const double2*>(pr - 1);
+        xm = v.x; x0 = v.y;
+        xp = __shfl_down_sync(full, v.x, 1);
+        if (valid && (lane == 31 || !next_valid)) xp = pr[oxp];
+        if (valid && wx && ic == bx.lo[0]) xm = pr[oxm];
+      }
+      const double F1 = q1_factor(true, dj != 0, dk != 0, facx, facy, facz);
+      const double F0 = q1_factor(false, dj != 0, dk != 0, facx, facy, facz);
+      if (dj == 0 && dk == 0) { s0 = F0 * (Sm + Sp); x00 = x0; y += F1 * (Sm * xm + Sp * xp) + s0 * x0; }
+      else y += F1 * (Sm * xm + Sp * xp) + F0 * (Sm + Sp) * x0;
+    }
+  if (valid) pc[0] = x00 + (rhs(i, j, k) - y) / s0;
+}
+#endif
+
+#if !defined(IX_EMUL)
+// ---- shared-memory tile kernels (27-point stencil) ------------------------------------------
+// One CTA = TXU x TYU updated nodes of one k-plane.  The phi tile (3 planes x (ST*TYU+1) rows x
+// (ST*TXU+1) columns) and the sigma tile (2 x ST*TYU x ST*TXU cells) are staged with cp.async
+// (8-byte LDGSTS: rows start at odd element offsets, so 16-byte copies are not possible), every
+// global element is requested once per CTA with full-row coalescing, and the 27+8 stencil reads
+// come from shared memory.  ST = 2: one Gauss-Seidel colour (updated nodes are 2 apart; the tile
+// is stored de-interleaved, even and odd columns apart, so that a warp's stride-2 reads are
+// contiguous in shared memory);  ST = 1: apply / residual over every node.
+namespace tile {
+constexpr int TXU = 64, TYU = 4;
+template <int ST> struct Geo {
+  static constexpr int NC = ST * (TXU - 1) + 3, NR = ST * (TYU - 1) + 3;  // nodes touched: first-1 .. last+1
+  static constexpr int PITCH = (ST == 2) ? 132 : 66;
+  static constexpr int SC = ST * (TXU - 1) + 2, SR = ST * (TYU - 1) + 2;  // cells touched by the updated nodes
+  IX_D static int col(int c) { return ST == 2 ? ((c & 1) * 66 + (c >> 1)) : c; }
+  IX_D static int scol(int c) { return ST == 2 ? ((c & 1) * (SC / 2) + (c >> 1)) : c; }
+};
+IX_D void cp_async8(double* smem_dst, const double* gsrc) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(gsrc) : "memory");
+}
+IX_D int wrap_node(int g, int lo, int hi, bool w) {  // node lo-1 == hi-1, node hi+1 == lo+1 when periodic
+  return w ? (g < lo ? hi - 1 : (g > hi ? lo + 1 : g)) : g;
+}
+
+template <int ST, bool GS>
+__global__ void __launch_bounds__(TXU* TYU)
+nodal_tile_kernel(Bx bx, V4 out, C4 phi, C4 rhs, C4 sig, double facx, double facy, double facz, int i0, int j0, int k0,
+                  int wm) {
+  using G = Geo<ST>;
+  __shared__ double sp[3][G::NR][G::PITCH];
+  __shared__ double ss[2][G::SR][G::SC];
+  const int tid = threadIdx.y * TXU + threadIdx.x;
+  const int ib = i0 + ST * TXU * (int)blockIdx.x, jb = j0 + ST * TYU * (int)blockIdx.y, k = k0 + ST * (int)blockIdx.z;
+  for (int e = tid; e < 3 * G::NR * G::PITCH; e += TXU * TYU) {
+    const int c = e % G::PITCH, rr = e / G::PITCH, r = rr % G::NR, p = rr / G::NR;
+    const int gi = ib - 1 + c, gj = jb - 1 + r, gk = k - 1 + p;
+    if (c < G::NC && gi <= bx.hi[0] + 1 && gj <= bx.hi[1] + 1)
+      cp_async8(&sp[p][r][G::col(c)], &phi.p[(wrap_node(gi, bx.lo[0], bx.hi[0], wm & 1) - phi.l0) +
+                                               (wrap_node(gj, bx.lo[1], bx.hi[1], wm & 2) - phi.l1) * phi.js +
+                                               (wrap_node(gk, bx.lo[2], bx.hi[2], wm & 4) - phi.l2) * phi.ks]);
+  }
+  for (int e = tid; e < 2 * G::SR * G::SC; e += TXU * TYU) {
+    const int c = e % G::SC, rr = e / G::SC, r = rr % G::SR, p = rr / G::SR;
+    const int ci = ib - 1 + c, cj = jb - 1 + r, ck = k - 1 + p;
+    if (ci <= bx.hi[0] && cj <= bx.hi[1])
+      cp_async8(&ss[p][r][G::scol(c)], &sig.p[(ci - sig.l0) + (cj - sig.l1) * sig.js + (ck - sig.l2) * sig.ks]);
+  }
+  asm volatile("cp.async.commit_group;" ::: "memory");
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+  __syncthreads();
+  const int i = ib + ST * (int)threadIdx.x, j = jb + ST * (int)threadIdx.y;
+  if (i > bx.hi[0] || j > bx.hi[1]) return;
+  const int c = 1 + ST * (int)threadIdx.x, r = 1 + ST * (int)threadIdx.y;
+  auto X = [&](int di, int dj, int dk) { return sp[1 + dk][r + dj][G::col(c + di)]; };
+  auto S = [&](int di, int dj, int dk) { return ss[1 + dk][r + dj][G::scol(c + di)]; };
+  double s0;
+  const double y = nodal_ax_rel(X, S, facx, facy, facz, s0);
+  if (GS) out(i, j, k) = X(0, 0, 0) + (rhs(i, j, k) - y) / s0;
+  else out(i, j, k) = rhs.ok() ? (rhs(i, j, k) - y) : y;
+}
+}  // namespace tile
+#endif
+
+// The tile kernels measured SLOWER than the one-thread-per-node kernels on B200 (nodal GS colour
+// pass at 257^3: 186 us vs 105 us; profiles/r01_notes.md), so they are opt-in (IAMRX_NODAL_TILE=1)
+// and kept for the parity tests and further tuning.
+inline bool use_tile_kernels() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("IAMRX_NODAL_TILE"); v = (e && e[0] == '1') ? 1 : 0; }
+  return v == 1;
+}
 inline dim3 grid_for(const Bx& bx) { return dim3(cdiv(bx.nx(), TX), cdiv(bx.ny(), TY), bx.nz()); }
 inline void facs(const double dxinv[3], double f[3]) {
   for (int d = 0; d < 3; ++d) f[d] = (1.0 / 36.0) * dxinv[d] * dxinv[d];
@@ -183,6 +373,15 @@ int nodal_adotx(const Bx& nbx, V4 out, C4 phi, C4 rhs, C4 sig, const double dxin
   if (!nbx.ok()) return IAMRX_OK;
   double f[3]; facs(dxinv, f);
   ProfScope prof_(IAMRX_PROF_NODAL_ADOTX, nbx.npts(), (double)nbx.npts() * (rhs.ok() ? 32.0 : 24.0), s);
+#if !defined(IX_EMUL)
+  if (use_tile_kernels() && nbx.nx() >= 32 && out.p != phi.p) {  // boxes wide enough to fill a CTA row
+    using namespace tile;
+    dim3 grd(cdiv(nbx.nx(), TXU), cdiv(nbx.ny(), TYU), nbx.nz());
+    IX_LAUNCH((nodal_tile_kernel<1, false>), grd, dim3(TXU, TYU, 1), 0, s, nbx, out, phi, rhs, sig, f[0], f[1], f[2],
+              nbx.lo[0], nbx.lo[1], nbx.lo[2], wrapmask);
+    return check_launch("nodal_adotx_tile");
+  }
+#endif
   IX_LAUNCH(adotx_kernel, grid_for(nbx), dim3(TX, TY, 1), 0, s, nbx, out, phi, rhs, sig, f[0], f[1], f[2], wrapmask);
   return check_launch("nodal_adotx");
 }
@@ -207,8 +406,36 @@ int nodal_gs_color(const Bx& nbx, V4 phi, C4 rhs, C4 sig, const double dxinv[3],
     if (n[d] == 0) return IAMRX_OK;
   }
   ProfScope prof_(IAMRX_PROF_NODAL_GS, nbx.npts(), (double)nbx.npts() * 4.0, s);  // 32 B/node/sweep over 8 colour passes
+#if !defined(IX_EMUL)
+  {
+    static int use_vec = -1;
+    if (use_vec < 0) { const char* e = getenv("IAMRX_GS_VEC"); use_vec = (e && e[0] == '0') ? 0 : 1; }
+    // 16-byte loads need even row / plane strides and 8-byte aligned bases whose parity we can read off
+    const bool ok = use_vec && n[0] >= 32 && (phi.js % 2 == 0) && (phi.ks % 2 == 0) && (sig.js % 2 == 0) && (sig.ks % 2 == 0);
+    if (ok) {
+      const uintptr_t a_phi = (uintptr_t)(phi.p + ((o[0] - phi.l0) + (o[1] - phi.l1) * phi.js + (o[2] - phi.l2) * phi.ks));
+      const uintptr_t a_sig = (uintptr_t)(sig.p + ((o[0] - sig.l0) + (o[1] - sig.l1) * sig.js + (o[2] - sig.l2) * sig.ks));
+      dim3 vg(cdiv(n[0], TX), cdiv(n[1], TY), n[2]);
+      IX_LAUNCH(gs_color_vec_kernel, vg, dim3(TX, TY, 1), 0, s, nbx, phi, rhs, sig, f[0], f[1], f[2], o[0], o[1], o[2], wrapmask,
+                (a_phi % 16 == 0) ? 1 : 0, (a_sig % 16 == 0) ? 1 : 0);
+      return check_launch("nodal_gs_vec");
+    }
+  }
+  if (use_tile_kernels() && n[0] >= 16) {
+    using namespace tile;
+    dim3 tg(cdiv(n[0], TXU), cdiv(n[1], TYU), n[2]);
+    C4 pin{phi.p, phi.l0, phi.l1, phi.l2, phi.js, phi.ks, phi.ns};
+    IX_LAUNCH((nodal_tile_kernel<2, true>), tg, dim3(TXU, TYU, 1), 0, s, nbx, phi, pin, rhs, sig, f[0], f[1], f[2],
+              o[0], o[1], o[2], wrapmask);
+    return check_launch("nodal_gs_tile");
+  }
+#endif
   dim3 grd(cdiv(n[0], TX), cdiv(n[1], TY), n[2]);
-  IX_LAUNCH(gs_color_kernel, grd, dim3(TX, TY, 1), 0, s, nbx, phi, rhs, sig, f[0], f[1], f[2], o[0], o[1], o[2], wrapmask);
+  static int minb = -1;  // resident CTAs per SM the kernel is compiled for (register cap): tuning knob
+  if (minb < 0) { const char* e = getenv("IAMRX_GS_MINB"); minb = e ? atoi(e) : 4; }
+  if (minb >= 5) IX_LAUNCH(gs_color_kernel<5>, grd, dim3(TX, TY, 1), 0, s, nbx, phi, rhs, sig, f[0], f[1], f[2], o[0], o[1], o[2], wrapmask);
+  else if (minb == 4) IX_LAUNCH(gs_color_kernel<4>, grd, dim3(TX, TY, 1), 0, s, nbx, phi, rhs, sig, f[0], f[1], f[2], o[0], o[1], o[2], wrapmask);
+  else IX_LAUNCH(gs_color_kernel<3>, grd, dim3(TX, TY, 1), 0, s, nbx, phi, rhs, sig, f[0], f[1], f[2], o[0], o[1], o[2], wrapmask);
   return check_launch("nodal_gs_color");
 }
 

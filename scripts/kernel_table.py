@@ -34,7 +34,8 @@ buf = C.create_string_buffer(1 << 16)
 lib.iamrx_prof_dump(buf, len(buf))
 rows = []
 for line in buf.value.decode().splitlines():
-    name, cnt, ms = line.split()
+    name, cnt, ms = line.rsplit(' ', 2)
+    name = name.replace(' ', '')
     rows.append((float(ms) / steps, int(cnt) // steps, name))
 rows.sort(reverse=True)
 tot = sum(r[0] for r in rows)

@@ -103,9 +103,13 @@ def test_tensor_cross(backend, oracle):
     assert np.abs(got - ref).max() <= RTOL * _scale(ref)
 
 
-@pytest.mark.parametrize("nb", [(1, 1, 1), (2, 2, 1)])
-def test_nodal_kernels(backend, oracle, nb):
+@pytest.mark.parametrize("nb,N", [((1, 1, 1), N), ((2, 2, 1), N), ((1, 1, 1), (72, 20, 12)), ((2, 1, 2), (136, 10, 8))])
+def test_nodal_kernels(backend, oracle, nb, N):
+    """The last two shapes are wide enough for the shared-memory tile kernels on the GPU
+    (partial tiles in x and y, boxes with and without neighbours)."""
     lib, dev = backend
+    DX = tuple(1.0 / m for m in N)
+    DXINV = tuple(1.0 / h for h in DX)
     sig = 1.0 + 0.5 * hash_uniform(40, (1, N[2], N[1], N[0]))
     phi = hash_uniform(41, (1, N[2], N[1], N[0]))
     rhs = hash_uniform(42, (1, N[2], N[1], N[0]))
