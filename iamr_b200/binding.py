@@ -106,6 +106,7 @@ SIGNATURES = {
     "iamrx_nodal_divu_box": (C.c_int, [_P(Box), _P(Fab), _P(Fab), _P(C.c_double), _vp]),
     "iamrx_nodal_adotx_box": (C.c_int, [_P(Box), _P(Fab), _P(Fab), _P(Fab), _P(Fab), _P(C.c_double), _vp]),
     "iamrx_nodal_gs_box": (C.c_int, [_P(Box), _P(Fab), _P(Fab), _P(Fab), _P(C.c_double), C.c_int, _vp]),
+    "iamrx_nodal_gs_sweep_box": (C.c_int, [_P(Box), _P(Fab), _P(Fab), _P(Fab), _P(Fab), _P(C.c_double), _vp]),
     "iamrx_nodal_mknewu_box": (C.c_int, [_P(Box), _P(Fab), _P(Fab), _P(Fab), _P(Fab), _P(C.c_double), _vp]),
     "iamrx_comm_unique_id": (C.c_int, [C.c_char_p]),
     "iamrx_comm_init": (C.c_int, [C.c_int, C.c_int, C.c_char_p]),

@@ -169,6 +169,15 @@ int iamrx_nodal_gs_box(const iamrx_box* nbx, iamrx_fab* phi, const iamrx_fab* rh
   IX_ARG(color >= 0 && color < 8, "colour must be in [0,8)");
   return k::nodal_gs_color(mkbx(*nbx), view(phi), cview(rhs), cview(sigma), dxinv, color, S(stream));
 }
+int iamrx_nodal_gs_sweep_box(const iamrx_box* nbx, iamrx_fab* phi_out, const iamrx_fab* phi_in, const iamrx_fab* rhs,
+                             const iamrx_fab* sigma, const double dxinv[3], void* stream) {
+  IX_NEED_DEVICE();
+  IX_ARG(nbx && phi_out && phi_in && rhs && sigma && dxinv, "null argument");
+  IX_ARG(phi_out->p != phi_in->p, "the fused sweep is out of place");
+  const Bx b = mkbx(*nbx);
+  for (int d = 0; d < 3; ++d) IX_ARG(((b.hi[d] - b.lo[d]) % 2) == 0 && b.hi[d] - b.lo[d] >= 2, "even number of cells per direction required");
+  return k::nodal_gs_sweep(b, view(phi_out), cview(phi_in), cview(rhs), cview(sigma), dxinv, S(stream));
+}
 int iamrx_nodal_mknewu_box(const iamrx_box* bx, iamrx_fab* vel, iamrx_fab* gp, const iamrx_fab* phi,
                            const iamrx_fab* sigma, const double dxinv[3], void* stream) {
   IX_NEED_DEVICE();

@@ -302,6 +302,20 @@ int NodeMG::smooth(int l, MF& phi, const MF& rhs, int nsweeps, cudaStream_t s) {
     }
     return IAMRX_OK;
   }
+  bool fused = wrap;
+  for (int il = 0; il < phi.n() && fused; ++il) fused = k::nodal_gs_sweep_ok(phi.vbox(il), 7);
+  if (fused) {
+    // out-of-place fused sweeps ping-pong between phi and a second buffer
+    if (!L.gs_tmp.ok()) L.gs_tmp.define(L.lev, IX_NODE, 1, 1);
+    MF* src = &phi; MF* dst = &L.gs_tmp;
+    for (int sw = 0; sw < nsweeps; ++sw) {
+      for (int il = 0; il < phi.n(); ++il)
+        IX_TRY(k::nodal_gs_sweep(phi.vbox(il), dst->v(il), src->c(il), rhs.c(il), L.sigma.c(il), L.dxinv, s));
+      std::swap(src, dst);
+    }
+    if (src != &phi) IX_TRY(mf_copy(phi, *src, 0, 0, 1, 0, s));
+    return IAMRX_OK;
+  }
   for (int sw = 0; sw < nsweeps; ++sw) {
     for (int color = 0; color < 8; ++color) {
       if (!wrap) IX_TRY(mf_fill_boundary(phi, 0, 1, 1, s));

@@ -54,6 +54,7 @@ struct MGLevelNode {
   Level* lev = nullptr;
   MF sigma;            // cell, 1 ghost
   MF cor, res, rescor; // nodal, 1 ghost
+  MF gs_tmp;           // second phi buffer of the out-of-place fused Gauss-Seidel sweep (lazy)
   double dxinv[3];
 };
 

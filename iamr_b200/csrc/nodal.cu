@@ -194,7 +194,7 @@ mknewu_kernel(Bx bx, V4 vel, V4 gp, int incr, C4 p, C4 sig, double facx, double 
 // with Sm/Sp = sums of sigma over the cells on the -x/+x side shared with row (dj,dk) and
 //   F(di,dj,dk) = -36 sum_d fac_d s_d prod_{e != d} m_e,  s = +1 (same node) / -1, m = 2/6 (same) / 1/6
 // (the Q1 element matrices; identical to the hand-expanded coefficients of nodal_ax_rel).
-IX_D double q1_factor(bool nx, bool ny, bool nz, double facx, double facy, double facz) {
+IX_HD double q1_factor(bool nx, bool ny, bool nz, double facx, double facy, double facz) {
   const double sx = nx ? -1.0 : 1.0, sy = ny ? -1.0 : 1.0, sz = nz ? -1.0 : 1.0;
   const double mx = nx ? 1.0 : 2.0, my = ny ? 1.0 : 2.0, mz = nz ? 1.0 : 2.0;  // x 1/6 each, folded into the -36
   return -(facx * sx * my * mz + facy * sy * mx * mz + facz * sz * mx * my);
@@ -347,6 +347,151 @@ nodal_tile_kernel(Bx bx, V4 out, C4 phi, C4 rhs, C4 sig, double facx, double fac
 }  // namespace tile
 #endif
 
+#if !defined(IX_EMUL)
+// ---- fused 8-colour Gauss-Seidel sweep (box spans the periodic domain) --------------------------
+// The colour order 0..7 (colour = cx + 2 cy + 4 cz) visits every EVEN plane (cz = 0, colours 0-3)
+// before any ODD plane (colours 4-7), and under the 27-point stencil an even plane only couples to
+// itself and to the two odd planes next to it.  So one sweep is two phases of mutually independent
+// planes: phase A updates all even planes from the old odd planes, phase B all odd planes from the
+// new even planes.  Inside a plane the four (cx, cy) colours are run back to back on a shared-memory
+// tile; the dependence of colour 3 on 2 on 1 on 0 reaches 3 nodes in x and 1 in y, so each CTA
+// recomputes that halo redundantly (identical arithmetic, identical values) instead of waiting for
+// its neighbours.  The sweep is out of place (phi_in -> phi_out) because neighbouring CTAs read each
+// other's plane-k halo.  Per sweep every phi/sigma/rhs element is fetched from HBM about 1.5x
+// (phi planes are read by both phases) instead of 8x by the colour-per-launch kernels.
+//
+// Tile: 56 x 14 updated nodes; loaded 64 columns x 17 rows x 3 planes of phi and 2 planes of sigma
+// (8-byte cp.async; columns stored de-interleaved, even | odd, so that the stride-2 accesses of one
+// colour are contiguous in shared memory).  One warp per tile row, one lane per node of the colour.
+namespace fused {
+constexpr int TXI = 56, TYI = 14, NC = 64, HALF = 32, NR = TYI + 4, NT = 256;
+
+IX_D int wrap_node_any(int g, int lo, int hi) {  // any distance; node hi duplicates node lo
+  if (g >= lo && g <= hi) return g;
+  const int n = hi - lo;
+  int m = (g - lo) % n;
+  if (m < 0) m += n;
+  return lo + m;
+}
+IX_D int wrap_cell_any(int c, int lo, int hi) {  // cells lo .. hi-1 (hi = node hi)
+  if (c >= lo && c < hi) return c;
+  const int n = hi - lo;
+  int m = (c - lo) % n;
+  if (m < 0) m += n;
+  return lo + m;
+}
+IX_D int col(int c) { return (c & 1) * HALF + (c >> 1); }
+
+struct Q1F { double f0c, f1c, f0j, f1j, f0k, f1k, f0jk, f1jk; };  // q1_factor by row kind
+
+template <int CX, int CY>
+IX_D void pass(double (*sp)[NR][NC], double (*ss)[NR][NC], int warp, int lane, double rhsv, const Q1F& q) {
+  // nodes of this colour that the later colours (and finally the 56 x 14 interior) depend on
+  constexpr int H0 = (CY == 0) ? 1 : 2;                         // first half-column index
+  constexpr int NH = (CY == 0) ? (CX == 0 ? 31 : 30) : (CX == 0 ? 29 : 28);
+  constexpr int NRW = (CY == 0) ? 8 : 7;
+  if (warp < NRW && lane < NH) {
+    const int h = H0 + lane;
+    const int ty = 2 + CY + 2 * warp;
+    // de-interleaved column slots of tx-1, tx, tx+1 for tx = 2h + CX
+    const int c0 = CX ? HALF + h : h;
+    const int cm = CX ? h : HALF + h - 1;
+    const int cp = CX ? h + 1 : HALF + h;
+    // A phi accumulated row by row (see gs_color_vec_kernel): for the row at offset (dj, dk)
+    //   F1(dj,dk) (Sm xm + Sp xp) + F0(dj,dk) (Sm + Sp) x0,  Sm / Sp = sigma summed over the cells on the
+    // -x / +x side that touch the row; rows of the same kind (centre, j-edge, k-edge, corner) share F.
+    // Same stencil as nodal_ax_rel with ~55 instead of ~95 fp64 operations (rounding differs in the last bits).
+    const double m00 = ss[0][ty - 1][cm], m01 = ss[0][ty][cm], m10 = ss[1][ty - 1][cm], m11 = ss[1][ty][cm];  // [dk+1][dj+1]
+    const double p00 = ss[0][ty - 1][c0], p01 = ss[0][ty][c0], p10 = ss[1][ty - 1][c0], p11 = ss[1][ty][c0];
+    const double mk0 = m00 + m01, mk1 = m10 + m11, mj0 = m00 + m10, mj1 = m01 + m11, mc = mk0 + mk1;
+    const double pk0 = p00 + p01, pk1 = p10 + p11, pj0 = p00 + p10, pj1 = p01 + p11, pc = pk0 + pk1;
+#define IXR(P, R) const double xm##P##R = sp[P][ty + R - 1][cm], x0##P##R = sp[P][ty + R - 1][c0], xp##P##R = sp[P][ty + R - 1][cp]
+    IXR(0, 0); IXR(0, 1); IXR(0, 2); IXR(1, 0); IXR(1, 1); IXR(1, 2); IXR(2, 0); IXR(2, 1); IXR(2, 2);
+#undef IXR
+    // corners (dj, dk != 0): one cell on each side
+    const double a1jk = m00 * xm00 + p00 * xp00 + m01 * xm02 + p01 * xp02 + m10 * xm20 + p10 * xp20 + m11 * xm22 + p11 * xp22;
+    const double a0jk = (m00 + p00) * x000 + (m01 + p01) * x002 + (m10 + p10) * x020 + (m11 + p11) * x022;
+    // k-edges (dj = 0, dk != 0) and j-edges (dj != 0, dk = 0): two cells on each side
+    const double a1k = mk0 * xm01 + pk0 * xp01 + mk1 * xm21 + pk1 * xp21;
+    const double a0k = (mk0 + pk0) * x001 + (mk1 + pk1) * x021;
+    const double a1j = mj0 * xm10 + pj0 * xp10 + mj1 * xm12 + pj1 * xp12;
+    const double a0j = (mj0 + pj0) * x010 + (mj1 + pj1) * x012;
+    const double a1c = mc * xm11 + pc * xp11;
+    const double s0 = q.f0c * (mc + pc);
+    const double y = s0 * x011 + q.f1c * a1c + q.f1j * a1j + q.f0j * a0j + q.f1k * a1k + q.f0k * a0k + q.f1jk * a1jk + q.f0jk * a0jk;
+    sp[1][ty][c0] = x011 + (rhsv - y) / s0;
+  }
+}
+
+__global__ void __launch_bounds__(NT, 4)
+gs_sweep_kernel(Bx bx, V4 out, C4 pin, C4 padj, C4 rhs, C4 sig, IX_KARG(Q1F) q, int k0) {
+  __shared__ double sp[3][NR][NC];
+  __shared__ double ss[2][NR][NC];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int X0 = (bx.lo[0] - (bx.lo[0] & 1)) + TXI * (int)blockIdx.x - 4;   // global node index of tile column 0
+  const int Y0 = (bx.lo[1] - (bx.lo[1] & 1)) + TYI * (int)blockIdx.y - 2;   // ... of tile row 0
+  const int k = k0 + 2 * (int)blockIdx.z;
+  const int km = (k == bx.lo[2]) ? bx.hi[2] - 1 : k - 1, kp = (k == bx.hi[2]) ? bx.lo[2] + 1 : k + 1;
+  // stage phi (rows 1..17 of three planes) and sigma (cell rows 1..16 of planes k-1, k): a thread
+  // always loads the same tile column, so the x wrap is done once
+  {
+    // lanes 0-15 of a warp take the even columns of its 32-column segment, lanes 16-31 the odd ones: each
+    // half-warp then writes 128 contiguous bytes of shared memory (no bank conflict in the de-interleaved
+    // layout) while the warp still reads one contiguous 256-byte global segment
+    const int c = (tid & 32) + 2 * (tid & 15) + ((tid >> 4) & 1), r0 = 1 + (tid >> 6), sc = col(c);
+    const int gi = wrap_node_any(X0 + c, bx.lo[0], bx.hi[0]);
+    const int ci = wrap_cell_any(X0 + c, bx.lo[0], bx.hi[0]);
+    const double* pk = pin.p + (gi - pin.l0) + (int64_t)(k - pin.l2) * pin.ks;
+    const double* pm = padj.p + (gi - padj.l0) + (int64_t)(km - padj.l2) * padj.ks;
+    const double* pp = padj.p + (gi - padj.l0) + (int64_t)(kp - padj.l2) * padj.ks;
+    const double* s0p = sig.p + (ci - sig.l0) + (int64_t)(wrap_cell_any(k - 1, bx.lo[2], bx.hi[2]) - sig.l2) * sig.ks;
+    const double* s1p = sig.p + (ci - sig.l0) + (int64_t)(wrap_cell_any(k, bx.lo[2], bx.hi[2]) - sig.l2) * sig.ks;
+    const int pjs = (int)pin.js, ajs = (int)padj.js, sjs = (int)sig.js;
+#pragma unroll
+    for (int m = 0; m < 5; ++m) {
+      const int r = r0 + 4 * m;
+      if (r <= 17) {
+        const int gj = wrap_node_any(Y0 + r, bx.lo[1], bx.hi[1]);
+        tile::cp_async8(&sp[0][r][sc], pm + (gj - padj.l1) * ajs);
+        tile::cp_async8(&sp[1][r][sc], pk + (gj - pin.l1) * pjs);
+        tile::cp_async8(&sp[2][r][sc], pp + (gj - padj.l1) * ajs);
+        if (r <= 16) {
+          const int cj = wrap_cell_any(Y0 + r, bx.lo[1], bx.hi[1]) - sig.l1;
+          tile::cp_async8(&ss[0][r][sc], s0p + cj * sjs);
+          tile::cp_async8(&ss[1][r][sc], s1p + cj * sjs);
+        }
+      }
+    }
+  }
+  asm volatile("cp.async.commit_group;" ::: "memory");
+  // right-hand sides of the (up to) four nodes this thread updates, one per colour
+  double rv[4];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const int cx = q & 1, cy = q >> 1;
+    const int h = (cy == 0 ? 1 : 2) + lane, ty = 2 + cy + 2 * warp;
+    const int gi = wrap_node_any(X0 + 2 * h + cx, bx.lo[0], bx.hi[0]), gj = wrap_node_any(Y0 + ty, bx.lo[1], bx.hi[1]);
+    rv[q] = (warp < 8 && ty < NR) ? rhs(gi, gj, k) : 0.0;
+  }
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+  __syncthreads();
+  pass<0, 0>(sp, ss, warp, lane, rv[0], q);
+  __syncthreads();
+  pass<1, 0>(sp, ss, warp, lane, rv[1], q);
+  __syncthreads();
+  pass<0, 1>(sp, ss, warp, lane, rv[2], q);
+  __syncthreads();
+  pass<1, 1>(sp, ss, warp, lane, rv[3], q);
+  __syncthreads();
+  for (int e = tid; e < TXI * TYI; e += NT) {
+    const int tx = 4 + e % TXI, ty = 2 + e / TXI;
+    const int gi = X0 + tx, gj = Y0 + ty;
+    if (gi >= bx.lo[0] && gi <= bx.hi[0] && gj >= bx.lo[1] && gj <= bx.hi[1]) out(gi, gj, k) = sp[1][ty][col(tx)];
+  }
+}
+}  // namespace fused
+#endif
+
 // The tile kernels measured SLOWER than the one-thread-per-node kernels on B200 (nodal GS colour
 // pass at 257^3: 186 us vs 105 us; profiles/r01_notes.md), so they are opt-in (IAMRX_NODAL_TILE=1)
 // and kept for the parity tests and further tuning.
@@ -437,6 +582,48 @@ int nodal_gs_color(const Bx& nbx, V4 phi, C4 rhs, C4 sig, const double dxinv[3],
   else if (minb == 4) IX_LAUNCH(gs_color_kernel<4>, grd, dim3(TX, TY, 1), 0, s, nbx, phi, rhs, sig, f[0], f[1], f[2], o[0], o[1], o[2], wrapmask);
   else IX_LAUNCH(gs_color_kernel<3>, grd, dim3(TX, TY, 1), 0, s, nbx, phi, rhs, sig, f[0], f[1], f[2], o[0], o[1], o[2], wrapmask);
   return check_launch("nodal_gs_color");
+}
+
+// One full 8-colour sweep, phi_in -> phi_out (different arrays), on a node box that spans the
+// periodic domain in all three directions with an even number of cells per direction.
+bool nodal_gs_sweep_ok(const Bx& nbx, int wrapmask) {
+  static int on = -1;
+  if (on < 0) { const char* e = getenv("IAMRX_NODAL_FUSED"); on = (e && e[0] == '0') ? 0 : 1; }
+  if (!on || wrapmask != 7) return false;
+  for (int d = 0; d < 3; ++d) if (((nbx.hi[d] - nbx.lo[d]) & 1) || nbx.hi[d] - nbx.lo[d] < 2) return false;
+  return true;
+}
+
+int nodal_gs_sweep(const Bx& nbx, V4 phi_out, C4 phi_in, C4 rhs, C4 sig, const double dxinv[3], cudaStream_t s) {
+  if (!nbx.ok()) return IAMRX_OK;
+  double f[3]; facs(dxinv, f);
+#if defined(IX_EMUL)
+  // host emulation (tests only): the same sweep as eight in-place colour passes on a copy
+  int rc = copy(nbx, phi_out, phi_in, 1, s);
+  for (int color = 0; color < 8 && rc == IAMRX_OK; ++color) rc = nodal_gs_color(nbx, phi_out, rhs, sig, dxinv, color, s, 7);
+  return rc;
+#else
+  using namespace fused;
+  ProfScope prof_(IAMRX_PROF_NODAL_GS, nbx.npts(), (double)nbx.npts() * 32.0, s);  // phi in + out, rhs, sigma
+  C4 pout{phi_out.p, phi_out.l0, phi_out.l1, phi_out.l2, phi_out.js, phi_out.ks, phi_out.ns};
+  Q1F q;
+  q.f0c = q1_factor(false, false, false, f[0], f[1], f[2]); q.f1c = q1_factor(true, false, false, f[0], f[1], f[2]);
+  q.f0j = q1_factor(false, true, false, f[0], f[1], f[2]);  q.f1j = q1_factor(true, true, false, f[0], f[1], f[2]);
+  q.f0k = q1_factor(false, false, true, f[0], f[1], f[2]);  q.f1k = q1_factor(true, false, true, f[0], f[1], f[2]);
+  q.f0jk = q1_factor(false, true, true, f[0], f[1], f[2]);  q.f1jk = q1_factor(true, true, true, f[0], f[1], f[2]);
+  const int gx = cdiv(nbx.hi[0] - (nbx.lo[0] - (nbx.lo[0] & 1)) + 1, TXI), gy = cdiv(nbx.hi[1] - (nbx.lo[1] - (nbx.lo[1] & 1)) + 1, TYI);
+  for (int cz = 0; cz < 2; ++cz) {
+    const int k0 = nbx.lo[2] + ((cz - nbx.lo[2]) & 1);
+    if (k0 > nbx.hi[2]) continue;
+    const int nk = (nbx.hi[2] - k0) / 2 + 1;
+    // phase A (even planes): neighbours = old odd planes; phase B (odd planes): neighbours = new even planes
+    IX_LAUNCH(gs_sweep_kernel, dim3(gx, gy, nk), dim3(NT, 1, 1), 0, s, nbx, phi_out, phi_in, cz == 0 ? phi_in : pout, rhs, sig,
+              q, k0);
+    const int rc = check_launch("nodal_gs_sweep");
+    if (rc != IAMRX_OK) return rc;
+  }
+  return IAMRX_OK;
+#endif
 }
 
 int nodal_restrict(const Bx& cnbx, V4 crse, C4 fine, cudaStream_t s) {

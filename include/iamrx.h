@@ -198,6 +198,15 @@ int iamrx_nodal_adotx_box(const iamrx_box* nbx, iamrx_fab* out, const iamrx_fab*
 int iamrx_nodal_gs_box(const iamrx_box* nbx, iamrx_fab* phi, const iamrx_fab* rhs,
                        const iamrx_fab* sigma, const double dxinv[3], int color,
                        void* stream);
+/* One full sweep of the 8-colour nodal Gauss-Seidel smoother (colours 0..7 in order, the
+ * MLNodeLaplacian GPU smoother reached from NodalProjector::project, Projection.cpp:2540),
+ * phi_in -> phi_out (two different fabs), for a node box that spans a fully periodic
+ * domain with an even number of cells per direction (node hi duplicates node lo; ghost
+ * nodes are not read).  Same result as eight iamrx_nodal_gs_box calls with periodic ghost
+ * fills in between, from two fused launches.  Other boxes: IAMRX_ERR_ARG. */
+int iamrx_nodal_gs_sweep_box(const iamrx_box* nbx, iamrx_fab* phi_out, const iamrx_fab* phi_in,
+                             const iamrx_fab* rhs, const iamrx_fab* sigma, const double dxinv[3],
+                             void* stream);
 /* vel -= sigma*grad(phi); gp = grad(phi) (cell-centred average of the four
  * parallel edge differences) -- NodalProjector::project tail + getGradPhi,
  * MLNodeLaplacian::compGrad (NSB.cpp:4118). Either of vel / gp may be NULL. */

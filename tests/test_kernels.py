@@ -176,6 +176,39 @@ def test_nodal_kernels(backend, oracle, nb, N):
     assert np.abs(gv - vref).max() <= RTOL * _scale(vref) and np.abs(gg - gref).max() <= RTOL * _scale(gref)
 
 
+@pytest.mark.parametrize("N", [(2, 2, 2), (4, 6, 2), (16, 16, 16), (72, 20, 12), (136, 10, 8), (58, 30, 6), (112, 28, 4)])
+def test_nodal_gs_fused_sweep(backend, oracle, N):
+    """Fused out-of-place 8-colour sweep on a single box spanning the periodic domain == eight
+    sequential colour passes of the oracle (shapes cover single/multiple/partial tiles and
+    domains smaller than the tile halo, where the halo wraps around several times)."""
+    lib, dev = backend
+    DXINV = tuple(float(m) for m in N)
+    sig = 1.0 + 0.5 * hash_uniform(50, (1, N[2], N[1], N[0]))
+    phi = hash_uniform(51, (1, N[2], N[1], N[0]))
+    rhs = hash_uniform(52, (1, N[2], N[1], N[0]))
+    ref = phi
+    for color in range(8):
+        ref = oracle.nodal_gs(DXINV, sig, rhs, color, ref)
+    box = ((0, 0, 0), tuple(m - 1 for m in N))
+    s = stream_of(dev)
+    tp, fp = to_fab(phi, box, 1, ix.NODE, dev, fill_ghost=False)   # ghost nodes must not be read
+    to, fo = to_fab(np.zeros_like(phi), box, 1, ix.NODE, dev)
+    ts, fs = to_fab(sig, box, 1, ix.CELL, dev)
+    tr, fr = to_fab(rhs, box, 0, ix.NODE, dev)
+    nbx = box_of(box[0], tuple(h + 1 for h in box[1]))
+    lib.check(lib.iamrx_nodal_gs_sweep_box(C.byref(nbx), C.byref(fo), C.byref(fp), C.byref(fr), C.byref(fs), d3(DXINV), s))
+    sync(dev)
+    got, dup = from_fabs([to], [box], 1, ix.NODE, N, 1)
+    assert dup == 0.0 and np.abs(got - ref).max() <= 1e-12 * _scale(ref)
+    # a second sweep back into the first buffer (ping-pong as the multigrid smoother does)
+    for color in range(8):
+        ref = oracle.nodal_gs(DXINV, sig, rhs, color, ref)
+    lib.check(lib.iamrx_nodal_gs_sweep_box(C.byref(nbx), C.byref(fp), C.byref(fo), C.byref(fr), C.byref(fs), d3(DXINV), s))
+    sync(dev)
+    got, dup = from_fabs([tp], [box], 1, ix.NODE, N, 1)
+    assert dup == 0.0 and np.abs(got - ref).max() <= 1e-12 * _scale(ref)
+
+
 def _adv_inputs(n, ncomp, seed):
     vel = smooth_field(n, seed, 3, amp=0.4)
     q = smooth_field(n, seed + 7, ncomp, amp=0.5) + 1.0
