@@ -144,6 +144,7 @@ int iamrx_compute_aofs_box(const iamrx_box* bx, iamrx_fab* aofs, int aofs_comp, 
   a.is_velocity = (flags & IAMRX_ADV_IS_VELOCITY) ? 1 : 0;
   a.is_sync = (flags & IAMRX_ADV_IS_SYNC) ? 1 : 0;
   a.write_fluxes = wf ? 1 : 0;
+  a.staged = (flags & IAMRX_ADV_STAGED) ? 1 : 0;
   k::AdvGeom g;
   for (int d = 0; d < 3; ++d) g.dx[d] = geom->dx[d];
   g.dt = dt;

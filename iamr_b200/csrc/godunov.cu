@@ -15,6 +15,7 @@
 // 4th-order slopes) rather than stored: 9 scratch arrays per component instead of 15.
 // Physical-boundary (ext_dir/hoextrap) edge treatment is not implemented: the C ABI
 // rejects non-periodic configurations before reaching these kernels.
+#include <cstdlib>
 #include "godunov_math.h"
 #include "kernels.h"
 #include "level.h"
@@ -440,6 +441,192 @@ __global__ void __launch_bounds__(TX* TY) ev_final_kernel(IX_KARG(EvArgs) a, IX_
   if (cx && cy) wmac(i, j, k) = ev_final<2, 0, 1>(a, c, B_UAD, B_VAD, B_XY_W, B_YX_W, a.dtdz, a.dtdx, a.dtdy);
 }
 
+#if !defined(IX_EMUL)
+// ===========================================================================
+// Fused ComputeAofs tile kernel
+// ===========================================================================
+// One CTA = one 8x8x8 tile of cells of ONE component; one thread = one "site" of the tile grown
+// by one cell (10^3 = 1000 sites, 1024 threads).  Every intermediate of the Godunov pipeline lives
+// in shared memory or registers; global memory sees q (tile grown by 3), the MAC velocities,
+// force/divu once per site, and the aofs (and optional flux / edge-state) stores.
+//
+// The algorithm is the staged one above, regrouped per CELL so that every stage exchanges one
+// value per site with its neighbours instead of re-deriving face quantities:
+//   site c traces to its two faces per direction:  L_d(c) -> face c+e_d (its "lo" state),
+//                                                  H_d(c) -> face c      (its "hi" state)
+//   stage 2  e_d(face c)  = upwind(L_d(c-e_d), H_d(c), mac_d(c))
+//   stage 3  T_d(c)       = e_d(c+e_d) mac_d(c+e_d) - e_d(c) mac_d(c) [- q (mac_d(c+e_d) - mac_d(c))]
+//            (the transverse derivative the corner coupling applies to BOTH faces next to cell c)
+//   stage 4  corner state d|t on face c = upwind(L_d(c-e_d) - dt/3dx_t T_t(c-e_d), H_d(c) - dt/3dx_t T_t(c), mac_d(c))
+//   stage 5  W_d(c) = transverse + divu + forcing correction of cell c for its two d-faces
+//   stage 6  final state on face c = upwind(L_d(c-e_d) - W_d(c-e_d), H_d(c) - W_d(c), mac_d(c))
+//   stage 7  aofs(c) from the six final face states
+// This is algebraically the staged pipeline; the grouping of the corner/transverse terms per cell
+// changes rounding in the last bits only.  Each 4th-order slope is evaluated once per site
+// (x1.95 halo redundancy for an 8^3 tile) instead of 18 times per cell in the staged kernels.
+namespace tile {
+constexpr int TB = 8, G = TB + 2, GG = G * G, NS = G * G * G;
+constexpr int QE = TB + 6, QQ = QE * QE, NQ = QE * QE * QE;
+constexpr int NT = 1024;
+constexpr int SMEM_BYTES = (NQ + 12 * NS) * (int)sizeof(double);
+
+__global__ void __launch_bounds__(NT, 1)
+aofs_tile_kernel(IX_KARG(EsArgs) a, IX_KARG(EsOut) out, V4 aofs, double volinv, double dxi, double dyi, double dzi,
+                 int is_sync, int ntz) {
+  extern __shared__ double sm[];
+  double* const Q = sm;
+  double* const AL = sm + NQ;       // L_x, L_y, L_z
+  double* const AE = AL + 3 * NS;   // edge states; then corner xy, xz, yx; then final states
+  double* const AT = AE + 3 * NS;   // T_x, T_y, T_z; then final lo states
+  double* const AC = AT + 3 * NS;   // corner yz, zx, zy
+  const int tid = threadIdx.x;
+  const int n = (int)blockIdx.z / ntz;
+  const int l0 = a.bx.lo[0] + TB * (int)blockIdx.x, l1 = a.bx.lo[1] + TB * (int)blockIdx.y,
+            l2 = a.bx.lo[2] + TB * ((int)blockIdx.z % ntz);
+  {  // stage 0: q on the tile grown by 3
+    const double* Sp = a.S.p + n * a.S.ns + ((l0 - 3 - a.S.l0) + (l1 - 3 - a.S.l1) * a.S.js + (l2 - 3 - a.S.l2) * a.S.ks);
+    const int js = (int)a.S.js, ks = (int)a.S.ks;
+    for (int e = tid; e < NQ; e += NT) {
+      const int x = e % QE, r = e / QE, y = r % QE, z = r / QE;
+      Q[e] = Sp[x + y * js + z * ks];
+    }
+  }
+  __syncthreads();
+  const bool act = tid < NS;
+  const int t = act ? tid : 0;
+  const int si = t % G, sj = (t / G) % G, sk = t / GG;
+  const int i = l0 - 1 + si, j = l1 - 1 + sj, k = l2 - 1 + sk;
+  const bool fx = act && si >= 1, fy = act && sj >= 1, fz = act && sk >= 1;          // low face is a face of the tile
+  const bool inx = fx && si <= TB, iny = fy && sj <= TB, inz = fz && sk <= TB;      // cell index inside the tile
+  const bool cs = a.iconserv[n] != 0;
+  const bool hasf = a.force.ok();
+  double q0 = 0, Hx = 0, Hy = 0, Hz = 0, um = 0, up = 0, vm = 0, vp = 0, wm = 0, wp = 0, fv = 0;
+  if (act) {  // stage 1: slopes and the six traced states of this cell
+    const int qi = (si + 2) + (sj + 2) * QE + (sk + 2) * QQ;
+    q0 = Q[qi];
+    const double sx = slope4_vals(Q[qi - 2], Q[qi - 1], q0, Q[qi + 1], Q[qi + 2]);
+    const double sy = slope4_vals(Q[qi - 2 * QE], Q[qi - QE], q0, Q[qi + QE], Q[qi + 2 * QE]);
+    const double sz = slope4_vals(Q[qi - 2 * QQ], Q[qi - QQ], q0, Q[qi + QQ], Q[qi + 2 * QQ]);
+    const Cur u = cur_at(a.umac, 0, i, j, k), v = cur_at(a.vmac, 0, i, j, k), w = cur_at(a.wmac, 0, i, j, k);
+    um = u(0, 0, 0); up = u(1, 0, 0); vm = v(0, 0, 0); vp = v(0, 1, 0); wm = w(0, 0, 0); wp = w(0, 0, 1);
+    if (hasf) fv = a.force(i, j, k, n);
+    double Lx = q0 + 0.5 * (1.0 - up * a.dtdx) * sx, Ly = q0 + 0.5 * (1.0 - vp * a.dtdy) * sy, Lz = q0 + 0.5 * (1.0 - wp * a.dtdz) * sz;
+    Hx = q0 + 0.5 * (-1.0 - um * a.dtdx) * sx; Hy = q0 + 0.5 * (-1.0 - vm * a.dtdy) * sy; Hz = q0 + 0.5 * (-1.0 - wm * a.dtdz) * sz;
+    if (a.fit && hasf) {
+      const double h = 0.5 * a.dt * fv;
+      Lx += h; Ly += h; Lz += h; Hx += h; Hy += h; Hz += h;
+    }
+    AL[t] = Lx; AL[NS + t] = Ly; AL[2 * NS + t] = Lz;
+  }
+  __syncthreads();
+  // stage 2: upwinded edge states on the low faces
+  double xe = 0, ye = 0, ze = 0;
+  if (fx) { xe = upwind(AL[t - 1], Hx, um); AE[t] = xe; }
+  if (fy) { ye = upwind(AL[NS + t - G], Hy, vm); AE[NS + t] = ye; }
+  if (fz) { ze = upwind(AL[2 * NS + t - GG], Hz, wm); AE[2 * NS + t] = ze; }
+  __syncthreads();
+  // stage 3: transverse derivative terms of this cell
+  if (inx) { double T = AE[t + 1] * up - xe * um; if (!cs) T -= q0 * (up - um); AT[t] = T; }
+  if (iny) { double T = AE[NS + t + G] * vp - ye * vm; if (!cs) T -= q0 * (vp - vm); AT[NS + t] = T; }
+  if (inz) { double T = AE[2 * NS + t + GG] * wp - ze * wm; if (!cs) T -= q0 * (wp - wm); AT[2 * NS + t] = T; }
+  __syncthreads();
+  {  // stage 4: corner-coupled states on the low faces
+    const double d3x = a.dtdx / 3.0, d3y = a.dtdy / 3.0, d3z = a.dtdz / 3.0;
+    if (fx) {
+      const double lo = AL[t - 1];
+      if (iny) AE[t] = upwind(lo - d3y * AT[NS + t - 1], Hx - d3y * AT[NS + t], um);                      // xy
+      if (inz) AE[NS + t] = upwind(lo - d3z * AT[2 * NS + t - 1], Hx - d3z * AT[2 * NS + t], um);         // xz
+    }
+    if (fy) {
+      const double lo = AL[NS + t - G];
+      if (inx) AE[2 * NS + t] = upwind(lo - d3x * AT[t - G], Hy - d3x * AT[t], vm);                      // yx
+      if (inz) AC[t] = upwind(lo - d3z * AT[2 * NS + t - G], Hy - d3z * AT[2 * NS + t], vm);              // yz
+    }
+    if (fz) {
+      const double lo = AL[2 * NS + t - GG];
+      if (inx) AC[NS + t] = upwind(lo - d3x * AT[t - GG], Hz - d3x * AT[t], wm);                          // zx
+      if (iny) AC[2 * NS + t] = upwind(lo - d3y * AT[NS + t - GG], Hz - d3y * AT[NS + t], wm);            // zy
+    }
+  }
+  __syncthreads();
+  {  // stage 5: transverse / divu / forcing correction of this cell, per direction
+    double base = 0.0;  // the part common to the three directions (es_finish)
+    if (cs && a.divu.ok() && act) base += 0.5 * a.dt * q0 * a.divu(i, j, k);
+    if (!a.fit && hasf) base -= 0.5 * a.dt * fv;
+    const double* XY = AE; const double* XZ = AE + NS; const double* YX = AE + 2 * NS;
+    const double* YZ = AC; const double* ZX = AC + NS; const double* ZY = AC + 2 * NS;
+    double Wx = base, Wy = base, Wz = base;
+    if (cs) {
+      if (iny && inz) Wx += (0.5 * a.dtdy) * (YZ[t + G] * vp - YZ[t] * vm) + (0.5 * a.dtdz) * (ZY[t + GG] * wp - ZY[t] * wm)
+                            - (0.5 * a.dtdy) * q0 * (vp - vm) - (0.5 * a.dtdz) * q0 * (wp - wm);
+      if (inx && inz) Wy += (0.5 * a.dtdx) * (XZ[t + 1] * up - XZ[t] * um) + (0.5 * a.dtdz) * (ZX[t + GG] * wp - ZX[t] * wm)
+                            - (0.5 * a.dtdx) * q0 * (up - um) - (0.5 * a.dtdz) * q0 * (wp - wm);
+      if (inx && iny) Wz += (0.5 * a.dtdx) * (XY[t + 1] * up - XY[t] * um) + (0.5 * a.dtdy) * (YX[t + G] * vp - YX[t] * vm)
+                            - (0.5 * a.dtdx) * q0 * (up - um) - (0.5 * a.dtdy) * q0 * (vp - vm);
+    } else {
+      if (iny && inz) Wx += (0.25 * a.dtdy) * (vp + vm) * (YZ[t + G] - YZ[t]) + (0.25 * a.dtdz) * (wp + wm) * (ZY[t + GG] - ZY[t]);
+      if (inx && inz) Wy += (0.25 * a.dtdx) * (up + um) * (XZ[t + 1] - XZ[t]) + (0.25 * a.dtdz) * (wp + wm) * (ZX[t + GG] - ZX[t]);
+      if (inx && iny) Wz += (0.25 * a.dtdx) * (up + um) * (XY[t + 1] - XY[t]) + (0.25 * a.dtdy) * (vp + vm) * (YX[t + G] - YX[t]);
+    }
+    if (iny && inz) { AT[t] = AL[t] - Wx; Hx -= Wx; }
+    if (inx && inz) { AT[NS + t] = AL[NS + t] - Wy; Hy -= Wy; }
+    if (inx && iny) { AT[2 * NS + t] = AL[2 * NS + t] - Wz; Hz -= Wz; }
+  }
+  __syncthreads();
+  // stage 6: final states on the low faces (AE is free again: the corner arrays were consumed in stage 5)
+  const bool same_flux_vel = (a.uflx.p == a.umac.p) && (a.vflx.p == a.vmac.p) && (a.wflx.p == a.wmac.p);
+  double ufm = um, ufp = up, vfm = vm, vfp = vp, wfm = wm, wfp = wp;
+  if (!same_flux_vel && act) {
+    const Cur u = cur_at(a.uflx, 0, i, j, k), v = cur_at(a.vflx, 0, i, j, k), w = cur_at(a.wflx, 0, i, j, k);
+    ufm = u(0, 0, 0); ufp = u(1, 0, 0); vfm = v(0, 0, 0); vfp = v(0, 1, 0); wfm = w(0, 0, 0); wfp = w(0, 0, 1);
+  }
+  double xs = 0, ys = 0, zs = 0;
+  if (fx && iny && inz) {
+    xs = upwind(AT[t - 1], Hx, um); AE[t] = xs;
+    if (si <= TB || i == a.bx.hi[0] + 1) {
+      if (out.xed.ok()) out.xed(i, j, k, n) = xs;
+      if (out.fx.ok()) out.fx(i, j, k, n) = xs * ufm * out.ax;
+    }
+  }
+  if (fy && inx && inz) {
+    ys = upwind(AT[NS + t - G], Hy, vm); AE[NS + t] = ys;
+    if (sj <= TB || j == a.bx.hi[1] + 1) {
+      if (out.yed.ok()) out.yed(i, j, k, n) = ys;
+      if (out.fy.ok()) out.fy(i, j, k, n) = ys * vfm * out.ay;
+    }
+  }
+  if (fz && inx && iny) {
+    zs = upwind(AT[2 * NS + t - GG], Hz, wm); AE[2 * NS + t] = zs;
+    if (sk <= TB || k == a.bx.hi[2] + 1) {
+      if (out.zed.ok()) out.zed(i, j, k, n) = zs;
+      if (out.fz.ok()) out.fz(i, j, k, n) = zs * wfm * out.az;
+    }
+  }
+  __syncthreads();
+  // stage 7: ComputeDivergence(mult = -1) + ComputeConvectiveTerm + sign
+  if (inx && iny && inz) {
+    const double xp = AE[t + 1], yp = AE[NS + t + G], zp = AE[2 * NS + t + GG];
+    double upd = -volinv * ((xp * ufp * out.ax - xs * ufm * out.ax) + (yp * vfp * out.ay - ys * vfm * out.ay) +
+                            (zp * wfp * out.az - zs * wfm * out.az));
+    if (!cs && !is_sync) {
+      const double divum = dxi * (up - um) + dyi * (vp - vm) + dzi * (wp - wm);
+      double qb = xs + xp + ys + yp + zs + zp;
+      qb /= 6.0;
+      upd += qb * divum;
+    }
+    if (is_sync) aofs(i, j, k, n) -= upd;
+    else aofs(i, j, k, n) = -upd;
+  }
+}
+
+inline bool aofs_tile_ok(const Bx& bx) {
+  static int on = -1;
+  if (on < 0) { const char* e = getenv("IAMRX_ADV_TILE"); on = (e && e[0] == '0') ? 0 : 1; }
+  return on && bx.nx() % TB == 0 && bx.ny() % TB == 0 && bx.nz() % TB == 0;
+}
+}  // namespace tile
+#endif
+
 struct ScratchOwner {
   double* p = nullptr;
   Scratch sc{};
@@ -461,8 +648,6 @@ struct ScratchOwner {
 int compute_aofs(const Bx& bx, const AofsArgs& a, const AdvGeom& g, cudaStream_t s) {
   if (!bx.ok()) return IAMRX_OK;
   ProfScope prof_(IAMRX_PROF_AOFS, bx.npts(), (double)bx.npts() * (24.0 * a.ncomp + 32.0), s);
-  ScratchOwner so;
-  if (so.init(bx, A_N * a.ncomp) != IAMRX_OK) return IAMRX_ERR_CUDA;
   EsArgs e{};
   e.bx = bx;
   e.S = a.S; e.force = a.force; e.divu = a.divu;
@@ -471,6 +656,25 @@ int compute_aofs(const Bx& bx, const AofsArgs& a, const AdvGeom& g, cudaStream_t
   for (int n = 0; n < 8; ++n) e.iconserv[n] = (n < a.ncomp) ? a.iconserv[n] : 0;
   e.fit = a.forces_in_trans;
   e.dt = g.dt; e.dtdx = g.dt / g.dx[0]; e.dtdy = g.dt / g.dx[1]; e.dtdz = g.dt / g.dx[2];
+  EsOut out{};
+  if (a.write_fluxes) { out.fx = a.fx; out.fy = a.fy; out.fz = a.fz; out.xed = a.xed; out.yed = a.yed; out.zed = a.zed; }
+  out.ax = g.dx[1] * g.dx[2]; out.ay = g.dx[0] * g.dx[2]; out.az = g.dx[0] * g.dx[1];
+#if !defined(IX_EMUL)
+  if (!a.staged && tile::aofs_tile_ok(bx)) {
+    static bool attr_set = false;
+    if (!attr_set) {
+      IX_CUDA(cudaFuncSetAttribute(tile::aofs_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tile::SMEM_BYTES));
+      attr_set = true;
+    }
+    const int ntz = bx.nz() / tile::TB;
+    IX_LAUNCH(tile::aofs_tile_kernel, dim3(bx.nx() / tile::TB, bx.ny() / tile::TB, ntz * a.ncomp), dim3(tile::NT, 1, 1),
+              tile::SMEM_BYTES, s, e, out, a.aofs, 1.0 / (g.dx[0] * g.dx[1] * g.dx[2]), 1.0 / g.dx[0], 1.0 / g.dx[1],
+              1.0 / g.dx[2], a.is_sync, ntz);
+    return check_launch("aofs_tile");
+  }
+#endif
+  ScratchOwner so;
+  if (so.init(bx, A_N * a.ncomp) != IAMRX_OK) return IAMRX_ERR_CUDA;
   Bx R1 = grow(bx, 1); R1.hi[0]++; R1.hi[1]++; R1.hi[2]++;
   IX_LAUNCH(es_edge_kernel, grid_for(R1, a.ncomp), dim3(TX, TY, 1), 0, s, e, so.sc, R1);
   int rc = check_launch("es_edge");
@@ -479,9 +683,6 @@ int compute_aofs(const Bx& bx, const AofsArgs& a, const AdvGeom& g, cudaStream_t
   rc = check_launch("es_corner");
   if (rc) return rc;
   Bx R2 = bx; R2.hi[0]++; R2.hi[1]++; R2.hi[2]++;
-  EsOut out{};
-  if (a.write_fluxes) { out.fx = a.fx; out.fy = a.fy; out.fz = a.fz; out.xed = a.xed; out.yed = a.yed; out.zed = a.zed; }
-  out.ax = g.dx[1] * g.dx[2]; out.ay = g.dx[0] * g.dx[2]; out.az = g.dx[0] * g.dx[1];
   IX_LAUNCH(es_final_kernel, grid_for(R2, a.ncomp), dim3(TX, TY, 1), 0, s, e, so.sc, out, R2);
   rc = check_launch("es_final");
   if (rc) return rc;

@@ -77,6 +77,7 @@ struct AofsArgs {
   int ncomp;
   int iconserv[8];
   int forces_in_trans, is_velocity, is_sync, write_fluxes;
+  int staged = 0;  // force the staged kernels
 };
 int compute_aofs(const Bx& bx, const AofsArgs& a, const AdvGeom& g, cudaStream_t s);
 

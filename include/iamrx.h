@@ -94,7 +94,9 @@ enum {
   IAMRX_ADV_FORCES_IN_TRANS = 2,   /* godunov.use_forces_in_trans, NSB.cpp:556 */
   IAMRX_ADV_IS_VELOCITY = 4,
   IAMRX_ADV_WRITE_FLUXES = 8,      /* also store area-weighted fluxes + edge states */
-  IAMRX_ADV_IS_SYNC = 16           /* aofs -= update, fluxes from U_corr (NSB.cpp:4834) */
+  IAMRX_ADV_IS_SYNC = 16,          /* aofs -= update, fluxes from U_corr (NSB.cpp:4834) */
+  IAMRX_ADV_STAGED = 32            /* use the staged (global-scratch) kernels instead of the fused tile
+                                      kernel: same algorithm, kept for cross-checks and partial tiles */
 };
 
 const char* iamrx_last_error(void);

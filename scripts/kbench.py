@@ -119,6 +119,10 @@ timeit("ComputeAofs 3 comps (velocity)",
        lambda: lib.check(lib.iamrx_compute_aofs_box(C.byref(bx), C.byref(fA), 0, C.byref(fS), 0, 3, C.byref(fF), 0, None, C.byref(fum[0]), C.byref(fum[1]),
                                                     C.byref(fum[2]), None, None, None, None, None, None, icons, C.byref(g), dt, ix.ADV_IS_VELOCITY if hasattr(ix, 'ADV_IS_VELOCITY') else 4, s)),
        104.0 * N, reps=5)
+timeit("ComputeAofs 3 comps staged kernels",
+       lambda: lib.check(lib.iamrx_compute_aofs_box(C.byref(bx), C.byref(fA), 0, C.byref(fS), 0, 3, C.byref(fF), 0, None, C.byref(fum[0]), C.byref(fum[1]),
+                                                    C.byref(fum[2]), None, None, None, None, None, None, icons, C.byref(g), dt, 4 | 32, s)),
+       104.0 * N, reps=3)
 tmac = [fab(tuple(m + (1 if d == q else 0) for q, m in enumerate(cells)), 1) for d in range(3)]
 fmac = [f for _, f in tmac]
 timeit("ExtrapVelToFaces",

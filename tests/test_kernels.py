@@ -252,9 +252,10 @@ def test_extrap_vel_to_faces(backend, oracle, nb, fit):
         assert np.abs(got[0] - ref[d]).max() <= RTOL * 10
 
 
-@pytest.mark.parametrize("nb", [(1, 1, 1), (2, 2, 2)])
+@pytest.mark.parametrize("nb", [(1, 1, 1), (2, 2, 2), (2, 2, 1)])
 @pytest.mark.parametrize("ncomp,iconserv,fit", [(3, (0, 0, 0), 0), (2, (1, 0), 0), (2, (1, 1), 1)])
 def test_compute_aofs(backend, oracle, nb, ncomp, iconserv, fit):
+    # (1,1,1) and (2,2,1): boxes are whole 8^3 tiles -> fused tile kernel on the GPU; (2,2,2): 8x8x4 boxes -> staged kernels
     lib, dev = backend
     n = (16, 16, 8)
     _, q, f, (um, vm, wm), dx = _adv_inputs(n, ncomp, 200)
@@ -290,6 +291,57 @@ def test_compute_aofs(backend, oracle, nb, ncomp, iconserv, fit):
         ge, dup2 = from_fabs(out_e[d], boxes, 0, t, n, ncomp)
         assert dup == 0.0 and dup2 == 0.0
         assert np.abs(ge - re).max() <= RTOL * 10 and np.abs(gf - rf).max() <= RTOL * 10
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("nb", [(1, 1, 1), (2, 1, 2)])
+@pytest.mark.parametrize("ncomp,iconserv,fit,sync_flag,with_divu", [
+    (3, (0, 0, 0), 0, 0, 0), (2, (1, 0), 1, 0, 1), (2, (1, 1), 0, 16, 1), (1, (0,), 1, 16, 0)])
+def test_compute_aofs_fused_tile_vs_staged_gpu(cuda_lib, nb, ncomp, iconserv, fit, sync_flag, with_divu):
+    """The fused shared-memory tile kernel (boxes made of whole 8^3 tiles) against the staged
+    global-scratch kernels (IAMRX_ADV_STAGED) on the same inputs: same algorithm regrouped per cell,
+    so only last-bit differences are allowed.  Covers divu, conservative comps, the sync sign and
+    the flux / edge-state outputs, which the oracle comparison above does not."""
+    lib, dev = cuda_lib, "cuda:0"
+    n = (32, 24, 16)
+    _, q, f, (um, vm, wm), dx = _adv_inputs(n, ncomp, 300)
+    divu = smooth_field(n, 77, 1, amp=0.3)
+    dt = 0.5 * min(dx) / max(np.abs(um).max(), np.abs(vm).max(), np.abs(wm).max())
+    g = ix.Geom.make(n)
+    boxes = split_boxes(n, nb)
+    ic = (C.c_int * ncomp)(*iconserv)
+    res = {}
+    for staged in (0, 32):
+        out_a, out_f, out_e = [], [[], [], []], [[], [], []]
+        for box in boxes:
+            tq, fq = to_fab(q, box, 3, ix.CELL, dev)
+            tf, ff = to_fab(f[:ncomp], box, 1, ix.CELL, dev)
+            td, fd = to_fab(divu, box, 1, ix.CELL, dev)
+            ta, fa = to_fab(0.25 * np.ones_like(q), box, 0, ix.CELL, dev)
+            macs = [to_fab(m[None], box, 1, t, dev) for m, t in ((um, ix.XFACE), (vm, ix.YFACE), (wm, ix.ZFACE))]
+            fl = [to_fab(np.zeros_like(q), box, 0, t, dev) for t in (ix.XFACE, ix.YFACE, ix.ZFACE)]
+            ed = [to_fab(np.zeros_like(q), box, 0, t, dev) for t in (ix.XFACE, ix.YFACE, ix.ZFACE)]
+            bb = box_of(*box)
+            flags = (2 if fit else 0) | 8 | sync_flag | staged
+            lib.check(lib.iamrx_compute_aofs_box(C.byref(bb), C.byref(fa), 0, C.byref(fq), 0, ncomp, C.byref(ff), 0,
+                                                 C.byref(fd) if with_divu else None,
+                                                 C.byref(macs[0][1]), C.byref(macs[1][1]), C.byref(macs[2][1]),
+                                                 C.byref(fl[0][1]), C.byref(fl[1][1]), C.byref(fl[2][1]),
+                                                 C.byref(ed[0][1]), C.byref(ed[1][1]), C.byref(ed[2][1]),
+                                                 ic, C.byref(g), dt, flags, stream_of(dev)))
+            out_a.append(ta)
+            for d in range(3):
+                out_f[d].append(fl[d][0]); out_e[d].append(ed[d][0])
+        sync(dev)
+        r = [from_fabs(out_a, boxes, 0, ix.CELL, n, ncomp)[0]]
+        for d, t in enumerate((ix.XFACE, ix.YFACE, ix.ZFACE)):
+            gf, dup = from_fabs(out_f[d], boxes, 0, t, n, ncomp)
+            ge, dup2 = from_fabs(out_e[d], boxes, 0, t, n, ncomp)
+            assert dup == 0.0 and dup2 == 0.0
+            r += [gf, ge]
+        res[staged] = r
+    for x, y in zip(res[0], res[32]):
+        assert np.abs(x - y).max() <= 1e-12 * _scale(y)
 
 
 def test_bad_arguments(backend):
