@@ -468,14 +468,32 @@ namespace tile {
 constexpr int TB = 8, G = TB + 2, GG = G * G, NS = G * G * G;
 constexpr int QE = TB + 6, QQ = QE * QE, NQ = QE * QE * QE;
 constexpr int NT = 1024;
-constexpr int SMEM_BYTES = (NQ + 12 * NS) * (int)sizeof(double);
+constexpr int PAD = 128;  // neighbour reads of unused sites may run up to GG past an array: keep them inside the allocation
+constexpr int SMEM_BYTES = (PAD + NQ + 12 * NS + PAD) * (int)sizeof(double);
 
+// upwind() as a select: identical value for finite inputs (fu is exactly 0 or 1 there), fewer DP instructions
+IX_D double upsel(double lo, double hi, double vel) {
+  return (fabs(vel) < SMALL_VEL) ? 0.5 * (hi + lo) : ((vel >= 0.0) ? lo : hi);
+}
+// 32-bit element offset of (i,j,k) in a view (host checks that every fab has < 2^31 elements)
+template <class V> IX_D int off32(const V& v, int i, int j, int k) {
+  return (i - v.l0) + (j - v.l1) * (int)v.js + (k - v.l2) * (int)v.ks;
+}
+IX_D void cp_async8(double* smem_dst, const double* gsrc) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(gsrc) : "memory");
+}
+
+// Stages 2-5 run WITHOUT per-site predicates: a site that does not need a quantity computes it anyway
+// from whatever its neighbours hold (possibly garbage, always inside the shared allocation).  Values that
+// reach a store are only ever derived from needed, fully defined quantities (the dependence cone of the
+// tile interior lies inside the site box), so the extra lanes cost nothing and the branches disappear.
 __global__ void __launch_bounds__(NT, 1)
 aofs_tile_kernel(IX_KARG(EsArgs) a, IX_KARG(EsOut) out, V4 aofs, double volinv, double dxi, double dyi, double dzi,
                  int is_sync, int ntz) {
-  extern __shared__ double sm[];
-  double* const Q = sm;
-  double* const AL = sm + NQ;       // L_x, L_y, L_z
+  extern __shared__ double sm_raw[];
+  double* const Q = sm_raw + PAD;
+  double* const AL = Q + NQ;        // L_x, L_y, L_z
   double* const AE = AL + 3 * NS;   // edge states; then corner xy, xz, yx; then final states
   double* const AT = AE + 3 * NS;   // T_x, T_y, T_z; then final lo states
   double* const AC = AT + 3 * NS;   // corner yz, zx, zy
@@ -483,33 +501,46 @@ aofs_tile_kernel(IX_KARG(EsArgs) a, IX_KARG(EsOut) out, V4 aofs, double volinv, 
   const int n = (int)blockIdx.z / ntz;
   const int l0 = a.bx.lo[0] + TB * (int)blockIdx.x, l1 = a.bx.lo[1] + TB * (int)blockIdx.y,
             l2 = a.bx.lo[2] + TB * ((int)blockIdx.z % ntz);
-  {  // stage 0: q on the tile grown by 3
-    const double* Sp = a.S.p + n * a.S.ns + ((l0 - 3 - a.S.l0) + (l1 - 3 - a.S.l1) * a.S.js + (l2 - 3 - a.S.l2) * a.S.ks);
+  {  // stage 0: q on the tile grown by 3, asynchronously (16 lanes per row of 14, 64 rows per pass)
+    const double* Sp = a.S.p + n * a.S.ns + off32(a.S, l0 - 3, l1 - 3, l2 - 3);
     const int js = (int)a.S.js, ks = (int)a.S.ks;
-    for (int e = tid; e < NQ; e += NT) {
-      const int x = e % QE, r = e / QE, y = r % QE, z = r / QE;
-      Q[e] = Sp[x + y * js + z * ks];
+    const int x = tid & 15, r0 = tid >> 4;
+    if (x < QE) {
+#pragma unroll
+      for (int m = 0; m < 4; ++m) {
+        const int r = r0 + 64 * m;
+        if (r < QQ) {
+          const int z = r / QE, y = r - z * QE;
+          cp_async8(&Q[x + r * QE], Sp + x + y * js + z * ks);
+        }
+      }
     }
+    asm volatile("cp.async.commit_group;" ::: "memory");
   }
-  __syncthreads();
   const bool act = tid < NS;
   const int t = act ? tid : 0;
-  const int si = t % G, sj = (t / G) % G, sk = t / GG;
+  const int sk = t / GG, sj = (t - sk * GG) / G, si = t - sk * GG - sj * G;
   const int i = l0 - 1 + si, j = l1 - 1 + sj, k = l2 - 1 + sk;
   const bool fx = act && si >= 1, fy = act && sj >= 1, fz = act && sk >= 1;          // low face is a face of the tile
   const bool inx = fx && si <= TB, iny = fy && sj <= TB, inz = fz && sk <= TB;      // cell index inside the tile
   const bool cs = a.iconserv[n] != 0;
   const bool hasf = a.force.ok();
-  double q0 = 0, Hx = 0, Hy = 0, Hz = 0, um = 0, up = 0, vm = 0, vp = 0, wm = 0, wp = 0, fv = 0;
-  if (act) {  // stage 1: slopes and the six traced states of this cell
+  // global inputs of this site (overlap the q staging)
+  const double* pu = a.umac.p + off32(a.umac, i, j, k);
+  const double* pv = a.vmac.p + off32(a.vmac, i, j, k);
+  const double* pw = a.wmac.p + off32(a.wmac, i, j, k);
+  const double um = pu[0], up = pu[1], vm = pv[0], vp = pv[(int)a.vmac.js], wm = pw[0], wp = pw[(int)a.wmac.ks];
+  const double fv = hasf ? a.force.p[n * a.force.ns + off32(a.force, i, j, k)] : 0.0;
+  const double dv = (cs && a.divu.ok()) ? a.divu.p[off32(a.divu, i, j, k)] : 0.0;
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+  __syncthreads();
+  double q0, Hx, Hy, Hz;
+  {  // stage 1: slopes and the six traced states of this cell
     const int qi = (si + 2) + (sj + 2) * QE + (sk + 2) * QQ;
     q0 = Q[qi];
     const double sx = slope4_vals(Q[qi - 2], Q[qi - 1], q0, Q[qi + 1], Q[qi + 2]);
     const double sy = slope4_vals(Q[qi - 2 * QE], Q[qi - QE], q0, Q[qi + QE], Q[qi + 2 * QE]);
     const double sz = slope4_vals(Q[qi - 2 * QQ], Q[qi - QQ], q0, Q[qi + QQ], Q[qi + 2 * QQ]);
-    const Cur u = cur_at(a.umac, 0, i, j, k), v = cur_at(a.vmac, 0, i, j, k), w = cur_at(a.wmac, 0, i, j, k);
-    um = u(0, 0, 0); up = u(1, 0, 0); vm = v(0, 0, 0); vp = v(0, 1, 0); wm = w(0, 0, 0); wp = w(0, 0, 1);
-    if (hasf) fv = a.force(i, j, k, n);
     double Lx = q0 + 0.5 * (1.0 - up * a.dtdx) * sx, Ly = q0 + 0.5 * (1.0 - vp * a.dtdy) * sy, Lz = q0 + 0.5 * (1.0 - wp * a.dtdz) * sz;
     Hx = q0 + 0.5 * (-1.0 - um * a.dtdx) * sx; Hy = q0 + 0.5 * (-1.0 - vm * a.dtdy) * sy; Hz = q0 + 0.5 * (-1.0 - wm * a.dtdz) * sz;
     if (a.fit && hasf) {
@@ -520,87 +551,62 @@ aofs_tile_kernel(IX_KARG(EsArgs) a, IX_KARG(EsOut) out, V4 aofs, double volinv, 
   }
   __syncthreads();
   // stage 2: upwinded edge states on the low faces
-  double xe = 0, ye = 0, ze = 0;
-  if (fx) { xe = upwind(AL[t - 1], Hx, um); AE[t] = xe; }
-  if (fy) { ye = upwind(AL[NS + t - G], Hy, vm); AE[NS + t] = ye; }
-  if (fz) { ze = upwind(AL[2 * NS + t - GG], Hz, wm); AE[2 * NS + t] = ze; }
+  const double lox = AL[t - 1], loy = AL[NS + t - G], loz = AL[2 * NS + t - GG];
+  const double xe = upsel(lox, Hx, um), ye = upsel(loy, Hy, vm), ze = upsel(loz, Hz, wm);
+  AE[t] = xe; AE[NS + t] = ye; AE[2 * NS + t] = ze;
   __syncthreads();
-  // stage 3: transverse derivative terms of this cell
-  if (inx) { double T = AE[t + 1] * up - xe * um; if (!cs) T -= q0 * (up - um); AT[t] = T; }
-  if (iny) { double T = AE[NS + t + G] * vp - ye * vm; if (!cs) T -= q0 * (vp - vm); AT[NS + t] = T; }
-  if (inz) { double T = AE[2 * NS + t + GG] * wp - ze * wm; if (!cs) T -= q0 * (wp - wm); AT[2 * NS + t] = T; }
-  __syncthreads();
-  {  // stage 4: corner-coupled states on the low faces
+  {  // stage 3: transverse derivative terms of this cell
+    double Tx = AE[t + 1] * up - xe * um, Ty = AE[NS + t + G] * vp - ye * vm, Tz = AE[2 * NS + t + GG] * wp - ze * wm;
+    if (!cs) { Tx -= q0 * (up - um); Ty -= q0 * (vp - vm); Tz -= q0 * (wp - wm); }
+    AT[t] = Tx; AT[NS + t] = Ty; AT[2 * NS + t] = Tz;
+    __syncthreads();
+    // stage 4: corner-coupled states on the low faces (AE is free: its last readers are behind the barrier)
     const double d3x = a.dtdx / 3.0, d3y = a.dtdy / 3.0, d3z = a.dtdz / 3.0;
-    if (fx) {
-      const double lo = AL[t - 1];
-      if (iny) AE[t] = upwind(lo - d3y * AT[NS + t - 1], Hx - d3y * AT[NS + t], um);                      // xy
-      if (inz) AE[NS + t] = upwind(lo - d3z * AT[2 * NS + t - 1], Hx - d3z * AT[2 * NS + t], um);         // xz
-    }
-    if (fy) {
-      const double lo = AL[NS + t - G];
-      if (inx) AE[2 * NS + t] = upwind(lo - d3x * AT[t - G], Hy - d3x * AT[t], vm);                      // yx
-      if (inz) AC[t] = upwind(lo - d3z * AT[2 * NS + t - G], Hy - d3z * AT[2 * NS + t], vm);              // yz
-    }
-    if (fz) {
-      const double lo = AL[2 * NS + t - GG];
-      if (inx) AC[NS + t] = upwind(lo - d3x * AT[t - GG], Hz - d3x * AT[t], wm);                          // zx
-      if (iny) AC[2 * NS + t] = upwind(lo - d3y * AT[NS + t - GG], Hz - d3y * AT[NS + t], wm);            // zy
-    }
+    AE[t] = upsel(lox - d3y * AT[NS + t - 1], Hx - d3y * Ty, um);                  // xy
+    AE[NS + t] = upsel(lox - d3z * AT[2 * NS + t - 1], Hx - d3z * Tz, um);         // xz
+    AE[2 * NS + t] = upsel(loy - d3x * AT[t - G], Hy - d3x * Tx, vm);             // yx
+    AC[t] = upsel(loy - d3z * AT[2 * NS + t - G], Hy - d3z * Tz, vm);             // yz
+    AC[NS + t] = upsel(loz - d3x * AT[t - GG], Hz - d3x * Tx, wm);                // zx
+    AC[2 * NS + t] = upsel(loz - d3y * AT[NS + t - GG], Hz - d3y * Ty, wm);       // zy
   }
   __syncthreads();
   {  // stage 5: transverse / divu / forcing correction of this cell, per direction
-    double base = 0.0;  // the part common to the three directions (es_finish)
-    if (cs && a.divu.ok() && act) base += 0.5 * a.dt * q0 * a.divu(i, j, k);
+    double base = 0.5 * a.dt * q0 * dv;  // es_finish terms, common to the three directions (dv = 0 unless conservative)
     if (!a.fit && hasf) base -= 0.5 * a.dt * fv;
     const double* XY = AE; const double* XZ = AE + NS; const double* YX = AE + 2 * NS;
     const double* YZ = AC; const double* ZX = AC + NS; const double* ZY = AC + 2 * NS;
-    double Wx = base, Wy = base, Wz = base;
+    double Wx, Wy, Wz;
     if (cs) {
-      if (iny && inz) Wx += (0.5 * a.dtdy) * (YZ[t + G] * vp - YZ[t] * vm) + (0.5 * a.dtdz) * (ZY[t + GG] * wp - ZY[t] * wm)
-                            - (0.5 * a.dtdy) * q0 * (vp - vm) - (0.5 * a.dtdz) * q0 * (wp - wm);
-      if (inx && inz) Wy += (0.5 * a.dtdx) * (XZ[t + 1] * up - XZ[t] * um) + (0.5 * a.dtdz) * (ZX[t + GG] * wp - ZX[t] * wm)
-                            - (0.5 * a.dtdx) * q0 * (up - um) - (0.5 * a.dtdz) * q0 * (wp - wm);
-      if (inx && iny) Wz += (0.5 * a.dtdx) * (XY[t + 1] * up - XY[t] * um) + (0.5 * a.dtdy) * (YX[t + G] * vp - YX[t] * vm)
-                            - (0.5 * a.dtdx) * q0 * (up - um) - (0.5 * a.dtdy) * q0 * (vp - vm);
+      Wx = base + (0.5 * a.dtdy) * (YZ[t + G] * vp - YZ[t] * vm) + (0.5 * a.dtdz) * (ZY[t + GG] * wp - ZY[t] * wm)
+           - (0.5 * a.dtdy) * q0 * (vp - vm) - (0.5 * a.dtdz) * q0 * (wp - wm);
+      Wy = base + (0.5 * a.dtdx) * (XZ[t + 1] * up - XZ[t] * um) + (0.5 * a.dtdz) * (ZX[t + GG] * wp - ZX[t] * wm)
+           - (0.5 * a.dtdx) * q0 * (up - um) - (0.5 * a.dtdz) * q0 * (wp - wm);
+      Wz = base + (0.5 * a.dtdx) * (XY[t + 1] * up - XY[t] * um) + (0.5 * a.dtdy) * (YX[t + G] * vp - YX[t] * vm)
+           - (0.5 * a.dtdx) * q0 * (up - um) - (0.5 * a.dtdy) * q0 * (vp - vm);
     } else {
-      if (iny && inz) Wx += (0.25 * a.dtdy) * (vp + vm) * (YZ[t + G] - YZ[t]) + (0.25 * a.dtdz) * (wp + wm) * (ZY[t + GG] - ZY[t]);
-      if (inx && inz) Wy += (0.25 * a.dtdx) * (up + um) * (XZ[t + 1] - XZ[t]) + (0.25 * a.dtdz) * (wp + wm) * (ZX[t + GG] - ZX[t]);
-      if (inx && iny) Wz += (0.25 * a.dtdx) * (up + um) * (XY[t + 1] - XY[t]) + (0.25 * a.dtdy) * (vp + vm) * (YX[t + G] - YX[t]);
+      Wx = base + (0.25 * a.dtdy) * (vp + vm) * (YZ[t + G] - YZ[t]) + (0.25 * a.dtdz) * (wp + wm) * (ZY[t + GG] - ZY[t]);
+      Wy = base + (0.25 * a.dtdx) * (up + um) * (XZ[t + 1] - XZ[t]) + (0.25 * a.dtdz) * (wp + wm) * (ZX[t + GG] - ZX[t]);
+      Wz = base + (0.25 * a.dtdx) * (up + um) * (XY[t + 1] - XY[t]) + (0.25 * a.dtdy) * (vp + vm) * (YX[t + G] - YX[t]);
     }
-    if (iny && inz) { AT[t] = AL[t] - Wx; Hx -= Wx; }
-    if (inx && inz) { AT[NS + t] = AL[NS + t] - Wy; Hy -= Wy; }
-    if (inx && iny) { AT[2 * NS + t] = AL[2 * NS + t] - Wz; Hz -= Wz; }
+    AT[t] = AL[t] - Wx; AT[NS + t] = AL[NS + t] - Wy; AT[2 * NS + t] = AL[2 * NS + t] - Wz;
+    Hx -= Wx; Hy -= Wy; Hz -= Wz;
   }
   __syncthreads();
   // stage 6: final states on the low faces (AE is free again: the corner arrays were consumed in stage 5)
   const bool same_flux_vel = (a.uflx.p == a.umac.p) && (a.vflx.p == a.vmac.p) && (a.wflx.p == a.wmac.p);
   double ufm = um, ufp = up, vfm = vm, vfp = vp, wfm = wm, wfp = wp;
-  if (!same_flux_vel && act) {
-    const Cur u = cur_at(a.uflx, 0, i, j, k), v = cur_at(a.vflx, 0, i, j, k), w = cur_at(a.wflx, 0, i, j, k);
-    ufm = u(0, 0, 0); ufp = u(1, 0, 0); vfm = v(0, 0, 0); vfp = v(0, 1, 0); wfm = w(0, 0, 0); wfp = w(0, 0, 1);
+  if (!same_flux_vel) {
+    const double* qu = a.uflx.p + off32(a.uflx, i, j, k);
+    const double* qv = a.vflx.p + off32(a.vflx, i, j, k);
+    const double* qw = a.wflx.p + off32(a.wflx, i, j, k);
+    ufm = qu[0]; ufp = qu[1]; vfm = qv[0]; vfp = qv[(int)a.vflx.js]; wfm = qw[0]; wfp = qw[(int)a.wflx.ks];
   }
-  double xs = 0, ys = 0, zs = 0;
-  if (fx && iny && inz) {
-    xs = upwind(AT[t - 1], Hx, um); AE[t] = xs;
-    if (si <= TB || i == a.bx.hi[0] + 1) {
-      if (out.xed.ok()) out.xed(i, j, k, n) = xs;
-      if (out.fx.ok()) out.fx(i, j, k, n) = xs * ufm * out.ax;
-    }
-  }
-  if (fy && inx && inz) {
-    ys = upwind(AT[NS + t - G], Hy, vm); AE[NS + t] = ys;
-    if (sj <= TB || j == a.bx.hi[1] + 1) {
-      if (out.yed.ok()) out.yed(i, j, k, n) = ys;
-      if (out.fy.ok()) out.fy(i, j, k, n) = ys * vfm * out.ay;
-    }
-  }
-  if (fz && inx && iny) {
-    zs = upwind(AT[2 * NS + t - GG], Hz, wm); AE[2 * NS + t] = zs;
-    if (sk <= TB || k == a.bx.hi[2] + 1) {
-      if (out.zed.ok()) out.zed(i, j, k, n) = zs;
-      if (out.fz.ok()) out.fz(i, j, k, n) = zs * wfm * out.az;
-    }
+  const double xs = upsel(AT[t - 1], Hx, um), ys = upsel(AT[NS + t - G], Hy, vm), zs = upsel(AT[2 * NS + t - GG], Hz, wm);
+  AE[t] = xs; AE[NS + t] = ys; AE[2 * NS + t] = zs;
+  if (out.xed.ok()) {  // optional outputs: every face is written by exactly one tile
+    if (fx && iny && inz && (si <= TB || i == a.bx.hi[0] + 1)) { out.xed(i, j, k, n) = xs; out.fx(i, j, k, n) = xs * ufm * out.ax; }
+    if (fy && inx && inz && (sj <= TB || j == a.bx.hi[1] + 1)) { out.yed(i, j, k, n) = ys; out.fy(i, j, k, n) = ys * vfm * out.ay; }
+    if (fz && inx && iny && (sk <= TB || k == a.bx.hi[2] + 1)) { out.zed(i, j, k, n) = zs; out.fz(i, j, k, n) = zs * wfm * out.az; }
   }
   __syncthreads();
   // stage 7: ComputeDivergence(mult = -1) + ComputeConvectiveTerm + sign
@@ -614,15 +620,23 @@ aofs_tile_kernel(IX_KARG(EsArgs) a, IX_KARG(EsOut) out, V4 aofs, double volinv, 
       qb /= 6.0;
       upd += qb * divum;
     }
-    if (is_sync) aofs(i, j, k, n) -= upd;
-    else aofs(i, j, k, n) = -upd;
+    double* pa = aofs.p + n * aofs.ns + off32(aofs, i, j, k);
+    if (is_sync) *pa -= upd;
+    else *pa = -upd;
   }
 }
 
-inline bool aofs_tile_ok(const Bx& bx) {
+inline bool fits32(const C4& v, const Bx& bx, int ng) {  // offsets of grow(bx, ng+1) fit in 32 bits
+  return !v.p || ((int64_t)(bx.nz() + 2 * ng + 2) * v.ks < (int64_t)1 << 31);
+}
+inline bool aofs_tile_ok(const Bx& bx, const AofsArgs& a) {
   static int on = -1;
   if (on < 0) { const char* e = getenv("IAMRX_ADV_TILE"); on = (e && e[0] == '0') ? 0 : 1; }
-  return on && bx.nx() % TB == 0 && bx.ny() % TB == 0 && bx.nz() % TB == 0;
+  if (!on || bx.nx() % TB || bx.ny() % TB || bx.nz() % TB) return false;
+  if (a.write_fluxes && !(a.fx.ok() && a.fy.ok() && a.fz.ok() && a.xed.ok() && a.yed.ok() && a.zed.ok())) return false;
+  return fits32(a.S, bx, 3) && fits32(a.force, bx, 1) && fits32(a.divu, bx, 1) && fits32(a.umac, bx, 1) && fits32(a.vmac, bx, 1) &&
+         fits32(a.wmac, bx, 1) && fits32(a.uflx, bx, 1) && fits32(a.vflx, bx, 1) && fits32(a.wflx, bx, 1) &&
+         fits32(C4{a.aofs.p, 0, 0, 0, a.aofs.js, a.aofs.ks, a.aofs.ns}, bx, 0);
 }
 }  // namespace tile
 #endif
@@ -660,7 +674,7 @@ int compute_aofs(const Bx& bx, const AofsArgs& a, const AdvGeom& g, cudaStream_t
   if (a.write_fluxes) { out.fx = a.fx; out.fy = a.fy; out.fz = a.fz; out.xed = a.xed; out.yed = a.yed; out.zed = a.zed; }
   out.ax = g.dx[1] * g.dx[2]; out.ay = g.dx[0] * g.dx[2]; out.az = g.dx[0] * g.dx[1];
 #if !defined(IX_EMUL)
-  if (!a.staged && tile::aofs_tile_ok(bx)) {
+  if (!a.staged && tile::aofs_tile_ok(bx, a)) {
     static bool attr_set = false;
     if (!attr_set) {
       IX_CUDA(cudaFuncSetAttribute(tile::aofs_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tile::SMEM_BYTES));
