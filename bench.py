@@ -36,6 +36,15 @@ TG = [1.0, 1.0, 0.0, 1.0, 1.0]   # prob.a, b, c, velocity_factor, density_ic (in
 RANK_GRID = {1: (1, 1, 1), 2: (2, 1, 1), 4: (2, 2, 1), 8: (2, 2, 2)}
 
 
+def ncu_traffic(kernel, box):
+    """DRAM bytes per launch of `kernel` from the committed ncu --set full capture (profiles/ncu_traffic.json)."""
+    try:
+        e = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))[kernel]
+        return e["dram_bytes_per_launch"] if e["box"] == box else None, e["source"]
+    except Exception:  # noqa: BLE001
+        return None, None
+
+
 def measured_peak():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -257,6 +266,7 @@ def run_ours(args):
 
     if rank == 0:
         peak, peak_src = measured_peak()
+        traffic, traffic_src = ncu_traffic("gsrb_kernel", nbox)
         t, nl, by = prof["abec_gsrb"]
         achieved = (by / 1e9) / (t * 1e-3) if t > 0 else 0.0
         secondary = {}
@@ -287,7 +297,8 @@ def run_ours(args):
                     "checksum_max_abs_u": checksum},
             "gpu_launches": launches,
             "roofline": {"bound": "hbm", "kernel": "gsrb_kernel (ABec red-black colour pass, finest two MG levels)",
-                         "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                         "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                         "traffic_note": f"DRAM bytes per finest-level launch ({nbox}^3, algorithmic {48 * nbox ** 3}); {traffic_src}",
                          "peak_source": peak_src, "launches_timed": nl, "ms_total": t,
                          "algorithmic_bytes": "48 B/cell/colour pass (a=0), 56 with alpha (SURVEY.md 8d)",
                          "other_kernels": secondary},
