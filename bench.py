@@ -264,6 +264,28 @@ def run_ours(args):
         e2e_value = cells_total * args.e2e_steps / e2e_s
         checksum = float(hin[0][0].abs().max())
 
+    if args.kernel_table:   # diagnostic: per-kernel device time of ONE extra step (rank 0, stderr); not part of any reported number
+        barrier()
+        lib.iamrx_prof_all(1)
+        t0 = time.perf_counter()
+        ns.step()
+        barrier()
+        wall_ms = (time.perf_counter() - t0) * 1e3
+        lib.iamrx_prof_all(0)
+        buf = C.create_string_buffer(1 << 16)
+        lib.iamrx_prof_dump(buf, len(buf))
+        if rank == 0:
+            rows = []
+            for ln in buf.value.decode().splitlines():
+                name, cnt, kms = ln.rsplit(' ', 2)
+                rows.append((float(kms), int(cnt), name.replace(' ', '')))
+            rows.sort(reverse=True)
+            tot = sum(r[0] for r in rows)
+            print(f"# kernel table, 1 step, {world} rank(s): wall {wall_ms:.2f} ms, sum of kernel times on rank 0 {tot:.2f} ms, "
+                  f"launches {sum(r[1] for r in rows)}", file=sys.stderr)
+            for kms, cnt, name in rows[:32]:
+                print(f"{name:28s} {cnt:7d} {kms:10.3f} ms {100 * kms / tot:5.1f}%", file=sys.stderr)
+
     if rank == 0:
         peak, peak_src = measured_peak()
         traffic, traffic_src = ncu_traffic("gsrb_kernel", nbox)
@@ -323,6 +345,7 @@ def main():
     ap.add_argument("--cpu-n", type=int, default=64, help="box size of the CPU sample")
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--kernel-table", action="store_true", help="diagnostic per-kernel table of one extra step on stderr")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -94,6 +94,8 @@ SIGNATURES = {
     "iamrx_prof_report": (C.c_int, [C.c_int, _P(C.c_double), _P(C.c_int64), _P(C.c_double)]),
     "iamrx_abec_gsrb_box": (C.c_int, [_P(Box), _P(Fab), _P(Fab), C.c_double, C.c_double, _P(Fab), _P(Fab), _P(Fab),
                                       _P(Fab), _P(C.c_double), C.c_double, C.c_int, C.c_int, _vp]),
+    "iamrx_abec_gsrb_sweep_box": (C.c_int, [_P(Box), _P(Fab), _P(Fab), _P(Fab), C.c_double, C.c_double, _P(Fab), _P(Fab),
+                                            _P(Fab), _P(Fab), _P(C.c_double), C.c_double, C.c_int, _vp]),
     "iamrx_abec_apply_box": (C.c_int, [_P(Box), _P(Fab), _P(Fab), _P(Fab), C.c_double, C.c_double, _P(Fab), _P(Fab),
                                        _P(Fab), _P(Fab), _P(C.c_double), C.c_int, _vp]),
     "iamrx_tensor_cross_box": (C.c_int, [_P(Box), _P(Fab), _P(Fab), _P(Fab), _P(Fab), _P(Fab), C.c_double,

@@ -11,6 +11,7 @@
 // runs along x, each CTA covers a (128 x 4) xy-strip of one z-plane so every
 // warp request is a contiguous 256-byte (GSRB: strided 512-byte) span.
 #include <cstdlib>
+#include <type_traits>
 #include "kernels.h"
 
 namespace ix {
@@ -276,6 +277,231 @@ tensor_cross_kernel(Bx bx, V4 out, C4 vel, C4 ex, C4 ey, C4 ez, double b, double
   for (int n = 0; n < 3; ++n) out(i, j, k, n) += b * acc[n];
 }
 
+#if !defined(IX_EMUL)
+// ---- fused red+black GSRB sweep (box spans the periodic domain) ------------------------------
+// One launch = one full sweep (colour `rb0` then the other), phi_in -> phi_out.  A CTA owns an xy tile
+// (<= 60 x 14 cells) and marches along z through a chunk of planes.  Per plane r it
+//   (1) red-updates plane r on the tile grown by one cell (the ring is recomputed redundantly by the
+//       neighbouring CTAs with identical arithmetic) from the OLD values of planes r-1, r, r+1 held in a
+//       4-slot shared-memory ring that cp.async fills one plane ahead, and stores the mixed plane
+//       (new red, old black) in a 3-slot ring;
+//   (2) black-updates plane r-1 on the tile from the mixed planes r-2, r-1, r and writes it out.
+// Every phi / rhs / coefficient element is read from HBM once per sweep (plus the tile halo, which
+// mostly hits L2) and phi is written once: 56 B/cell (48 + out) instead of 96 for two colour launches.
+// A thread owns the cell pair (2p, 2p+1) of one row for the whole march: it loads the coefficients of
+// both cells when the pair's plane is red-updated, uses the red cell's set at once and keeps the black
+// cell's set in registers for the black update one iteration later.  The update expression is the one
+// of gsrb_kernel, so the result is bit-identical to two colour passes.
+namespace sweep {
+constexpr int PX = 32;              // pairs per row: one warp
+constexpr int PW = 2 * PX;          // plane width in shared memory: tile + 2 cells on either side
+constexpr int TWMAX = PW - 4;       // 60
+constexpr int TY = 14;              // tile rows
+constexpr int PH = TY + 4;          // plane rows in shared memory
+constexpr int NW = TY + 2;          // warps: one per row of the red region
+constexpr int NT = 32 * NW;         // 512 threads
+constexpr int NP = 4, NM = 3;       // ring depths: old planes / mixed planes
+constexpr int PLANE = PW * PH;
+constexpr int SMEM_BYTES = (NP + NM) * PLANE * (int)sizeof(double);
+
+IX_D int wrapi(int g, int lo, int n) {  // periodic image in [lo, lo+n)
+  int m = (g - lo) % n;
+  if (m < 0) m += n;
+  return lo + m;
+}
+IX_D void cp_async8(double* smem_dst, const double* gsrc) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(gsrc) : "memory");
+}
+// shared-memory slot of plane column c: (c & 1) * PX + (c >> 1) -- even columns first, odd columns after them, so
+// that the stride-2 accesses of one colour (and of its x neighbours) are contiguous across a warp
+
+template <bool HASA>
+IX_D double relax(const AbecDev& op, double omega, double bxm, double bxp, double bym, double byp, double bzm, double bzp,
+                  double rh, double ac, double p0, double pxm, double pxp, double pym, double pyp, double pzm, double pzp) {
+  double gamma = op.dhx * (bxm + bxp) + op.dhy * (bym + byp) + op.dhz * (bzm + bzp);
+  if (HASA) gamma += op.a * ac;
+  const double rho = op.dhx * (bxm * pxm + bxp * pxp) + op.dhy * (bym * pym + byp * pyp) + op.dhz * (bzm * pzm + bzp * pzp);
+  const double res = rh - (gamma * p0 - rho);
+  return p0 + omega / gamma * res;
+}
+
+// raw coefficients of a cell pair on one plane: x faces 0,1,2; y faces (cell 0/1, lower/upper); z likewise; rhs; acoef
+struct Raw { double bx0, bx1, bx2, by00, by10, by01, by11, bz00, bz10, bz01, bz11, rh0, rh1, ac0, ac1; };
+// the coefficient set of cell F (0/1) of the pair
+#define IX_SET(w, F) ((F) ? (w).bx1 : (w).bx0), ((F) ? (w).bx2 : (w).bx1), ((F) ? (w).by10 : (w).by00), ((F) ? (w).by11 : (w).by01), \
+                     ((F) ? (w).bz10 : (w).bz00), ((F) ? (w).bz11 : (w).bz01), ((F) ? (w).rh1 : (w).rh0), ((F) ? (w).ac1 : (w).ac0)
+
+struct Ctx {      // per-thread constants of the march
+  double* P; double* M;
+  int c0, pr, twl;
+  bool pair_red, pair_blk;
+};
+
+// One plane of the march.  RF = which cell of the pair (0/1) belongs to the FIRST colour on plane r (compile-time:
+// it alternates from plane to plane and is warp-uniform, so the caller dispatches once and unrolls by two).
+//   cur : coefficients of plane r (loaded one plane ahead)
+//   kp  : coefficients of the second-colour cell of plane r-1 (cell RF of the pair as well: the colours swap between planes)
+struct Coef { double bxm, bxp, bym, byp, bzm, bzp, rh, ac; };
+template <bool HASA, int RF>
+IX_D void plane_step(const Ctx& t, const AbecDev& op, double omega, int rr, bool do_black, const Raw& cur, const Coef& kp, double* po) {
+  const double* Pm = t.P + ((rr - 1) & (NP - 1)) * PLANE;
+  const double* Pc = t.P + (rr & (NP - 1)) * PLANE;
+  const double* Pp = t.P + ((rr + 1) & (NP - 1)) * PLANE;
+  double* Mc = t.M + (rr % NM) * PLANE;
+  const int row = t.pr * PW;
+  // slots of the pair's two cells and of the x neighbours of cell RF
+  const int s_r = row + RF * PX + (t.c0 >> 1), s_b = row + (1 - RF) * PX + (t.c0 >> 1);
+  const int s_xm = RF ? s_b : s_b - 1, s_xp = RF ? s_b + 1 : s_b;   // columns cr-1 / cr+1 live in the other half
+  if (t.pair_red) {
+    // columns 0 and twl+3 are outside the red region: they are updated from whatever sits next to them, and nothing
+    // reads the result (the second colour only looks at columns 1 .. twl+2)
+    Mc[s_r] = relax<HASA>(op, omega, IX_SET(cur, RF), Pc[s_r], Pc[s_xm], Pc[s_xp], Pc[s_r - PW], Pc[s_r + PW], Pm[s_r], Pp[s_r]);
+    Mc[s_b] = Pc[s_b];
+  }
+  __syncthreads();
+  if (do_black && t.pair_blk) {  // second colour pass on plane r-1: its second-colour cell is cell RF of the pair
+    const double* Mm = t.M + ((rr - 2) % NM) * PLANE;
+    const double* Mk = t.M + ((rr - 1) % NM) * PLANE;
+    const double v = relax<HASA>(op, omega, kp.bxm, kp.bxp, kp.bym, kp.byp, kp.bzm, kp.bzp, kp.rh, kp.ac,
+                                 Mk[s_r], Mk[s_xm], Mk[s_xp], Mk[s_r - PW], Mk[s_r + PW], Mm[s_r], Mc[s_r]);
+    po[RF] = v;
+    po[1 - RF] = Mk[s_b];
+  }
+}
+
+template <bool HASA>
+__global__ void __launch_bounds__(NT, 1)
+gsrb_sweep_kernel(Bx bx, V4 out, C4 pin, C4 rhs, IX_KARG(AbecDev) op, double omega, int rb0, int tw, int th, int nzc, int nchunk) {
+  extern __shared__ double sm[];
+  Ctx t;
+  t.P = sm;                  // [NP][PH][PW] old values
+  t.M = sm + NP * PLANE;     // [NM][PH][PW] new first colour / old second colour
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int n = (int)blockIdx.z / nchunk, chunk = (int)blockIdx.z % nchunk;
+  const int nb = (op.bncomp > 1) ? n : 0;
+  const int nx = bx.nx(), ny = bx.ny(), nz = bx.nz();
+  const int x0 = bx.lo[0] + tw * (int)blockIdx.x, y0 = bx.lo[1] + th * (int)blockIdx.y;
+  const int twl = min(tw, bx.hi[0] + 1 - x0), thl = min(th, bx.hi[1] + 1 - y0);   // this tile's extent
+  const int kc0 = bx.lo[2] + nzc * chunk, nzl = min(nzc, bx.hi[2] + 1 - kc0);
+  // plane coordinates: column c <-> x = x0 - 2 + c (c = 0 .. twl+3), row pr <-> y = y0 - 2 + pr (pr = 0 .. thl+3)
+  const int c0 = 2 * lane, pr = warp + 1;
+  t.c0 = c0; t.pr = pr; t.twl = twl;
+  const bool col_ok = c0 <= twl + 3;          // pair inside the staged plane (twl even: both cells or none)
+  const int gx = wrapi(x0 - 2 + c0, bx.lo[0], nx);   // pairs never straddle the wrap (x0 - lo, nx even)
+  const int gy = wrapi(y0 - 2 + pr, bx.lo[1], ny);
+  // staging: each thread copies its own pair of row pr; warps 0 / 1 also copy rows 0 / thl+3
+  const int pr2 = (warp == 0) ? 0 : thl + 3;
+  const bool extra = col_ok && warp < 2;
+  const int gy2 = wrapi(y0 - 2 + pr2, bx.lo[1], ny);
+  const bool own = col_ok && pr <= thl + 3;
+  const int r0 = kc0 - 1, nred = nzl + 2;
+  // All plane addressing is incremental: a 32-bit element offset per array that advances by the array's plane
+  // stride and wraps with the periodic plane index (the host checks that every array has < 2^31 elements).
+  const double* pst1 = pin.p + n * pin.ns + (gx - pin.l0) + (gy - pin.l1) * (int)pin.js;
+  const double* pst2 = pin.p + n * pin.ns + (gx - pin.l0) + (gy2 - pin.l1) * (int)pin.js;
+  const int d1 = pr * PW + (c0 >> 1), d2 = pr2 * PW + (c0 >> 1);
+  const int pks = (int)pin.ks;
+  int gk_st = wrapi(r0 - 1, bx.lo[2], nz);   // plane being STAGED (two ahead of the plane being updated)
+  int ko_st = (gk_st - pin.l2) * pks;
+  int st_cnt = 3;                            // its ring counter (plane r0-1 <-> 3)
+  auto stage = [&]() {
+    double* dst = t.P + (st_cnt & (NP - 1)) * PLANE;
+    if (own) { cp_async8(dst + d1, pst1 + ko_st); cp_async8(dst + d1 + PX, pst1 + ko_st + 1); }
+    if (extra) { cp_async8(dst + d2, pst2 + ko_st); cp_async8(dst + d2 + PX, pst2 + ko_st + 1); }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    ++st_cnt;
+    const bool w = gk_st == bx.hi[2];
+    gk_st = w ? bx.lo[2] : gk_st + 1;
+    ko_st = w ? ko_st - (nz - 1) * pks : ko_st + pks;
+    if (own) asm volatile("prefetch.global.L2 [%0];" ::"l"(pst1 + ko_st));   // next plane to be staged -> L2
+  };
+  stage(); stage(); stage();
+  t.pair_red = col_ok && pr >= 1 && pr <= thl + 2 && c0 <= twl + 2;      // at least one cell of the pair in the red region
+  t.pair_blk = pr >= 2 && pr <= thl + 1 && c0 >= 2 && c0 + 1 <= twl + 1;   // pair inside the tile
+  const double* bxp_ = op.bx.p + nb * op.bx.ns + (gx - op.bx.l0) + (gy - op.bx.l1) * (int)op.bx.js;
+  const double* byp_ = op.by.p + nb * op.by.ns + (gx - op.by.l0) + (gy - op.by.l1) * (int)op.by.js;
+  const double* bzp_ = op.bz.p + nb * op.bz.ns + (gx - op.bz.l0) + (gy - op.bz.l1) * (int)op.bz.js;
+  const double* rhp_ = rhs.p + n * rhs.ns + (gx - rhs.l0) + (gy - rhs.l1) * (int)rhs.js;
+  const double* acp_ = HASA ? op.acoef.p + (gx - op.acoef.l0) + (gy - op.acoef.l1) * (int)op.acoef.js : nullptr;
+  double* outp_ = out.p + n * out.ns + (gx - out.l0) + (gy - out.l1) * (int)out.js;
+  const int byjs = (int)op.by.js;
+  const int bxks = (int)op.bx.ks, byks = (int)op.by.ks, bzks = (int)op.bz.ks, rhks = (int)rhs.ks, acks = HASA ? (int)op.acoef.ks : 0;
+  // coefficient loads run ONE PLANE AHEAD of the update (registers) and are preceded by an L2 prefetch TWO planes
+  // ahead, so that their HBM latency overlaps the updates; gk_ld = plane being loaded
+  int gk_ld = wrapi(r0, bx.lo[2], nz);
+  int kbx = (gk_ld - op.bx.l2) * bxks, kby = (gk_ld - op.by.l2) * byks, kbz = (gk_ld - op.bz.l2) * bzks, krh = (gk_ld - rhs.l2) * rhks;
+  int kac = HASA ? (gk_ld - op.acoef.l2) * acks : 0;
+  auto load_raw = [&](Raw& w, const Raw* below) {
+    const double* pbx = bxp_ + kbx;
+    const double* pby = byp_ + kby;
+    const double* pbz = bzp_ + kbz;
+    const double* prh = rhp_ + krh;
+    w.bx0 = pbx[0]; w.bx1 = pbx[1]; w.bx2 = pbx[2];
+    w.by00 = pby[0]; w.by10 = pby[1]; w.by01 = pby[byjs]; w.by11 = pby[byjs + 1];
+    if (below) { w.bz00 = below->bz01; w.bz10 = below->bz11; }   // the lower z faces are the upper ones of the plane below
+    else { w.bz00 = pbz[0]; w.bz10 = pbz[1]; }
+    w.bz01 = pbz[bzks]; w.bz11 = pbz[bzks + 1];
+    w.rh0 = prh[0]; w.rh1 = prh[1];
+    w.ac0 = 0.0; w.ac1 = 0.0;
+    if (HASA) { const double* pac = acp_ + kac; w.ac0 = pac[0]; w.ac1 = pac[1]; }
+    const bool wr = gk_ld == bx.hi[2];
+    gk_ld = wr ? bx.lo[2] : gk_ld + 1;
+    kbx = wr ? kbx - (nz - 1) * bxks : kbx + bxks;
+    kby = wr ? kby - (nz - 1) * byks : kby + byks;
+    kbz = wr ? kbz - (nz - 1) * bzks : kbz + bzks;
+    krh = wr ? krh - (nz - 1) * rhks : krh + rhks;
+    if (HASA) kac = wr ? kac - (nz - 1) * acks : kac + acks;
+    // the next plane's lines -> L2 (one 16-byte touch per pair covers the warp's 512-byte row segment)
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(bxp_ + kbx));
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(byp_ + kby));
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(bzp_ + kbz + bzks));
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(rhp_ + krh));
+    if (HASA) asm volatile("prefetch.global.L2 [%0];" ::"l"(acp_ + kac));
+  };
+  Raw A{}, B{};   // A: coefficients of even iterations' planes, B: of odd iterations' planes
+  if (t.pair_red) load_raw(A, nullptr);
+  // which cell of the pair is updated first on plane r0 (warp-uniform: 2*lane drops out of the parity)
+  const int f0 = (x0 - 2 + c0 + y0 - 2 + pr + rb0 + r0) & 1;
+  const int oks = (int)out.ks;
+  int gk_out = wrapi(r0 - 1, bx.lo[2], nz);   // plane r-1 of iteration kk (written from kk >= 2)
+  int ko_out = (gk_out - out.l2) * oks;
+  auto step = [&](auto rf_tag, int kk, const Raw& cur, Raw& nxt) {
+    constexpr int RF = decltype(rf_tag)::value;
+    // `nxt` still holds plane r-1: save the set its second-colour update needs before the prefetch of plane r+1 reuses it
+    const Coef kp = {IX_SET(nxt, RF)};
+    if (t.pair_red && kk + 1 < nred) load_raw(nxt, &cur);
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncthreads();
+    if (kk + 1 < nred) stage();
+    plane_step<HASA, RF>(t, op, omega, kk + 4, kk >= 2, cur, kp, outp_ + ko_out);
+    const bool w = gk_out == bx.hi[2];
+    gk_out = w ? bx.lo[2] : gk_out + 1;
+    ko_out = w ? ko_out - (nz - 1) * oks : ko_out + oks;
+  };
+  // iteration kk updates plane r0+kk with coefficients in A (kk even) / B (kk odd); the previous plane's set is the other one
+  if (f0 == 0) {
+    for (int kk = 0; kk < nred; kk += 2) {
+      step(std::integral_constant<int, 0>{}, kk, A, B);
+      if (kk + 1 < nred) step(std::integral_constant<int, 1>{}, kk + 1, B, A);
+    }
+  } else {
+    for (int kk = 0; kk < nred; kk += 2) {
+      step(std::integral_constant<int, 1>{}, kk, A, B);
+      if (kk + 1 < nred) step(std::integral_constant<int, 0>{}, kk + 1, B, A);
+    }
+  }
+}
+#undef IX_SET
+
+inline bool gsrb_sweep_ok(const Bx& bx, int wrapmask) {  // shape requirements of the fused sweep
+  if (wrapmask != 7) return false;
+  if ((int64_t)(bx.nx() + 18) * (bx.ny() + 2) * (bx.nz() + 2) * 3 >= ((int64_t)1 << 31)) return false;   // 32-bit plane offsets
+  return bx.nx() % 2 == 0 && bx.ny() % 2 == 0 && bx.nz() % 2 == 0 && bx.nx() >= 8 && bx.ny() >= 8 && bx.nz() >= 8;
+}
+}  // namespace sweep
+#endif
+
 inline dim3 grid_for(const Bx& bx, int tx, int ty, int nz_total) {
   return dim3(cdiv(bx.nx(), tx), cdiv(bx.ny(), ty), nz_total);
 }
@@ -293,6 +519,66 @@ int abec_gsrb(const Bx& bx, V4 phi, C4 rhs, const Abec& op, double omega, int re
   if (minb >= 8) IX_LAUNCH(gsrb_kernel<8>, grd, blk, 0, s, bx, phi, rhs, to_dev(op), omega, redblack, bx.nz(), wrapmask);
   else IX_LAUNCH(gsrb_kernel<6>, grd, blk, 0, s, bx, phi, rhs, to_dev(op), omega, redblack, bx.nz(), wrapmask);
   return check_launch("abec_gsrb");
+}
+
+// Measured on B200 (profiles/r01_notes.md): the fused sweep halves the DRAM traffic (832 MB vs 1590 MB per sweep at 256^3)
+// but its per-plane barriers leave it latency-bound at one CTA per SM -- 252 us vs 264 us for the two colour launches at
+// 256^3 and slower on the L2-resident coarser levels -- so the multigrid smoother uses it only on request
+// (IAMRX_GSRB_FUSED=1) until the coefficient planes are staged asynchronously as well.
+bool abec_gsrb_sweep_enabled() {
+  static int on = -1;
+  if (on < 0) { const char* e = getenv("IAMRX_GSRB_FUSED"); on = (e && e[0] == '1') ? 1 : 0; }
+  return on != 0;
+}
+
+bool abec_gsrb_sweep_ok(const Bx& bx, int wrapmask) {
+#if defined(IX_EMUL)
+  (void)bx;
+  return wrapmask == 7;
+#else
+  return sweep::gsrb_sweep_ok(bx, wrapmask);
+#endif
+}
+
+int abec_gsrb_sweep(const Bx& bx, V4 phi_out, C4 phi_in, C4 rhs, const Abec& op, double omega, int rb0, int ncomp, cudaStream_t s) {
+  if (!bx.ok()) return IAMRX_OK;
+#if defined(IX_EMUL)
+  // host emulation (tests only): the same sweep as two in-place colour passes on a copy
+  int rc = copy(bx, phi_out, phi_in, ncomp, s);
+  for (int rb = 0; rb < 2 && rc == IAMRX_OK; ++rb) rc = abec_gsrb(bx, phi_out, rhs, op, omega, rb0 ^ rb, ncomp, s, 7);
+  return rc;
+#else
+  using namespace sweep;
+  // algorithmic bytes as for two colour passes (SURVEY.md 8d counts no temporal blocking); the kernel moves about 56 B/cell
+  ProfScope prof_(IAMRX_PROF_ABEC_GSRB, bx.npts(), (double)bx.npts() * ncomp * 2.0 * (op.a != 0.0 ? 56.0 : 48.0), s);
+  static bool attr_set = false;
+  if (!attr_set) {
+    IX_CUDA(cudaFuncSetAttribute(gsrb_sweep_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    IX_CUDA(cudaFuncSetAttribute(gsrb_sweep_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    attr_set = true;
+  }
+  // even tile widths/heights that split the box evenly
+  const int ntx = cdiv(bx.nx(), TWMAX), nty = cdiv(bx.ny(), TY);
+  const int tw = 2 * cdiv(cdiv(bx.nx(), ntx), 2), th = 2 * cdiv(cdiv(bx.ny(), nty), 2);
+  const int gx = cdiv(bx.nx(), tw), gy = cdiv(bx.ny(), th);
+  // z chunks: fill whole waves of one CTA per SM (each chunk recomputes 2 extra red planes; >= 8 planes per chunk)
+  int nchunk = 1;
+  {
+    const int nxy = gx * gy * ncomp, nsm = 148;
+    double best = 1e30;
+    for (int c = 1; c <= bx.nz() / 8; ++c) {
+      const int nzc_ = cdiv(bx.nz(), c), cc = cdiv(bx.nz(), nzc_);
+      const double cost = (double)cdiv(nxy * cc, nsm) * (nzc_ + 2);   // waves x iterations per CTA
+      if (cost < best - 1e-9) { best = cost; nchunk = cc; }
+    }
+  }
+  const int nzc = cdiv(bx.nz(), nchunk);
+  nchunk = cdiv(bx.nz(), nzc);
+  const dim3 grd(gx, gy, nchunk * ncomp);
+  if (op.a != 0.0) IX_LAUNCH(gsrb_sweep_kernel<true>, grd, dim3(NT, 1, 1), SMEM_BYTES, s, bx, phi_out, phi_in, rhs, to_dev(op), omega, rb0, tw, th, nzc, nchunk);
+  else IX_LAUNCH(gsrb_sweep_kernel<false>, grd, dim3(NT, 1, 1), SMEM_BYTES, s, bx, phi_out, phi_in, rhs, to_dev(op), omega, rb0, tw, th, nzc, nchunk);
+  return check_launch("abec_gsrb_sweep");
+#endif
 }
 
 int abec_apply(const Bx& bx, V4 out, C4 phi, C4 rhs, const Abec& op, int ncomp, cudaStream_t s, int wrapmask) {

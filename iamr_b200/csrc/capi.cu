@@ -84,6 +84,20 @@ int iamrx_abec_gsrb_box(const iamrx_box* bx, iamrx_fab* phi, const iamrx_fab* rh
                       omega, redblack, ncomp, S(stream));
 }
 
+int iamrx_abec_gsrb_sweep_box(const iamrx_box* bx, iamrx_fab* phi_out, const iamrx_fab* phi_in, const iamrx_fab* rhs,
+                              double a, double b, const iamrx_fab* acoef, const iamrx_fab* bcoef_x,
+                              const iamrx_fab* bcoef_y, const iamrx_fab* bcoef_z, const double dxinv[3], double omega,
+                              int ncomp, void* stream) {
+  IX_NEED_DEVICE();
+  IX_ARG(bx && phi_out && phi_in && rhs && bcoef_x && bcoef_y && bcoef_z && dxinv, "null argument");
+  IX_ARG(phi_out->p != phi_in->p, "the fused sweep is out of place: phi_out and phi_in must differ");
+  IX_ARG(a == 0.0 || (acoef && acoef->p), "acoef required when a != 0");
+  IX_ARG(ncomp >= 1 && ncomp <= phi_in->ncomp && ncomp <= phi_out->ncomp, "ncomp");
+  IX_ARG(k::abec_gsrb_sweep_ok(mkbx(*bx), 7), "fused sweep needs even extents >= 8 in every direction");
+  return k::abec_gsrb_sweep(mkbx(*bx), view(phi_out), cview(phi_in), cview(rhs),
+                            make_abec(a, b, acoef, bcoef_x, bcoef_y, bcoef_z, dxinv, ncomp), omega, 0, ncomp, S(stream));
+}
+
 int iamrx_abec_apply_box(const iamrx_box* bx, iamrx_fab* out, const iamrx_fab* phi, const iamrx_fab* rhs,
                          double a, double b, const iamrx_fab* acoef, const iamrx_fab* bcoef_x,
                          const iamrx_fab* bcoef_y, const iamrx_fab* bcoef_z, const double dxinv[3],

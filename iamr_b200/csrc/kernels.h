@@ -20,6 +20,12 @@ struct Abec {
 // periodic wrap inside the kernel and phi's ghost cells in that direction are not touched.
 int abec_gsrb(const Bx& bx, V4 phi, C4 rhs, const Abec& op, double omega, int redblack,
               int ncomp, cudaStream_t s, int wrapmask = 0);
+// one full red-black sweep (colour rb0, then the other) phi_in -> phi_out (different arrays) on a box that spans
+// the periodic domain in all directions with even extents; abec_gsrb_sweep_ok tells whether the box qualifies
+bool abec_gsrb_sweep_ok(const Bx& bx, int wrapmask);
+bool abec_gsrb_sweep_enabled();  // multigrid uses the fused sweep only when IAMRX_GSRB_FUSED=1 (see abec.cu)
+int abec_gsrb_sweep(const Bx& bx, V4 phi_out, C4 phi_in, C4 rhs, const Abec& op, double omega, int rb0, int ncomp,
+                    cudaStream_t s);
 // out = L phi (rhs null) or rhs - L phi
 int abec_apply(const Bx& bx, V4 out, C4 phi, C4 rhs, const Abec& op, int ncomp, cudaStream_t s,
                int wrapmask = 0);

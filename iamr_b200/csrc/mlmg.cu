@@ -131,6 +131,20 @@ int CellMG::smooth(int l, MF& phi, const MF& rhs, int nsweeps, bool /*zero_init*
   // a box that spans the periodic domain wraps its neighbour indices inside the kernel:
   // no ghost fill (and no extra launch) per colour
   const bool wrap = L.lev->all_wrap();
+  bool fused = wrap && k::abec_gsrb_sweep_enabled();
+  for (int il = 0; il < phi.n() && fused; ++il) fused = k::abec_gsrb_sweep_ok(phi.vbox(il), 7);
+  if (fused) {
+    // one fused launch per sweep, out of place: ping-pong between phi and a second buffer
+    if (!L.gs_tmp.ok()) L.gs_tmp.define(L.lev, IX_CELL, ncomp_, 1);
+    MF* src = &phi; MF* dst = &L.gs_tmp;
+    for (int sw = 0; sw < nsweeps; ++sw) {
+      for (int il = 0; il < phi.n(); ++il)
+        IX_TRY(k::abec_gsrb_sweep(phi.vbox(il), dst->v(il), src->c(il), rhs.c(il), op_at(l, il), info_.omega, 0, ncomp_, s));
+      std::swap(src, dst);
+    }
+    if (src != &phi) IX_TRY(mf_copy(phi, *src, 0, 0, ncomp_, 0, s));
+    return IAMRX_OK;
+  }
   for (int sw = 0; sw < nsweeps; ++sw) {
     for (int rb = 0; rb < 2; ++rb) {
       if (!wrap) IX_TRY(mf_fill_boundary(phi, 0, ncomp_, 1, s));

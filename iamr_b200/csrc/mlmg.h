@@ -16,6 +16,7 @@ struct MGLevelCell {
   MF acoef;            // 1 comp, 0 ghost (only if a != 0)
   MF b[3];             // face coefs, bncomp comps
   MF cor, res, rescor; // ncomp
+  MF gs_tmp;           // second phi buffer of the out-of-place fused red-black sweep (lazy)
   double dxinv[3];
 };
 

@@ -147,6 +147,17 @@ int iamrx_abec_gsrb_box(const iamrx_box* bx, iamrx_fab* phi, const iamrx_fab* rh
                         const iamrx_fab* bcoef_z, const double dxinv[3],
                         double omega, int redblack, int ncomp, void* stream);
 
+/* One full red-black sweep (redblack 0, then 1) of the same smoother, phi_in -> phi_out (two
+ * different fabs), for a box that spans a fully periodic domain with even extents >= 8
+ * (neighbours wrap inside the kernel; ghost cells are not read).  Bit-identical to two
+ * iamrx_abec_gsrb_box passes with periodic ghost fills, in one fused launch that reads every
+ * array once.  Other boxes: IAMRX_ERR_ARG. */
+int iamrx_abec_gsrb_sweep_box(const iamrx_box* bx, iamrx_fab* phi_out, const iamrx_fab* phi_in,
+                              const iamrx_fab* rhs, double a, double b, const iamrx_fab* acoef,
+                              const iamrx_fab* bcoef_x, const iamrx_fab* bcoef_y,
+                              const iamrx_fab* bcoef_z, const double dxinv[3], double omega,
+                              int ncomp, void* stream);
+
 /* MLABecLaplacian::Fapply / residual: out = L(phi) (rhs == NULL) or
  * out = rhs - L(phi).  (mlmg.apply Diffusion.cpp:768,1757; residuals inside
  * every solve.) */

@@ -82,6 +82,46 @@ def test_abec_gsrb_and_apply(backend, oracle, nb, a, ncomp, bn):
         assert np.abs(got - want).max() <= RTOL * _scale(ref)
 
 
+@pytest.mark.parametrize("N3", [(8, 8, 8), (16, 12, 8), (72, 20, 12), (136, 10, 8), (60, 14, 24), (64, 30, 10)])
+@pytest.mark.parametrize("a,ncomp,bn", [(0.0, 1, 1), (1.0, 1, 1), (1.0, 3, 3)])
+def test_abec_gsrb_fused_sweep(backend, oracle, N3, a, ncomp, bn):
+    """One fused red+black launch (out of place, in-kernel periodic wrap, z-marching tiles) against two
+    oracle colour passes; sizes exercise partial tiles in x and y and several z chunks."""
+    lib, dev = backend
+    dxinv = tuple(float(m) for m in N3)
+    alpha, bx, by, bz = _coeffs(11, N3, bn)
+    nz, ny, nx = N3[2], N3[1], N3[0]
+    rhs = hash_uniform(21, (ncomp, nz, ny, nx))
+    phi = hash_uniform(22, (ncomp, nz, ny, nx))
+    b = 0.37
+    ref = phi
+    for sweep in range(2):
+        for rb in range(2):
+            ref = oracle.abec_gsrb(dxinv, a, b, alpha if a else None, bx, by, bz, rhs, 1.15, rb, ref)
+        if sweep == 0:
+            ref1 = ref
+    box = ((0, 0, 0), (nx - 1, ny - 1, nz - 1))
+    tp, fp = to_fab(phi, box, 1, ix.CELL, dev, fill_ghost=False)      # ghost cells must not be read
+    to, fo = to_fab(np.zeros_like(phi), box, 1, ix.CELL, dev)
+    tr, fr = to_fab(rhs, box, 0, ix.CELL, dev)
+    ta, fa = to_fab(alpha, box, 0, ix.CELL, dev)
+    tbx, fbx = to_fab(bx, box, 0, ix.XFACE, dev)
+    tby, fby = to_fab(by, box, 0, ix.YFACE, dev)
+    tbz, fbz = to_fab(bz, box, 0, ix.ZFACE, dev)
+    bb = box_of(*box)
+    s = stream_of(dev)
+    args = (C.byref(fr), a, b, C.byref(fa) if a else None, C.byref(fbx), C.byref(fby), C.byref(fbz), d3(dxinv), 1.15, ncomp, s)
+    lib.check(lib.iamrx_abec_gsrb_sweep_box(C.byref(bb), C.byref(fo), C.byref(fp), *args))
+    sync(dev)
+    got, _ = from_fabs([to], [box], 1, ix.CELL, N3, ncomp)
+    assert np.abs(got - ref1).max() <= RTOL * _scale(ref1)
+    # second sweep back into the first buffer (ping-pong as the multigrid smoother does)
+    lib.check(lib.iamrx_abec_gsrb_sweep_box(C.byref(bb), C.byref(fp), C.byref(fo), *args))
+    sync(dev)
+    got, _ = from_fabs([tp], [box], 1, ix.CELL, N3, ncomp)
+    assert np.abs(got - ref).max() <= RTOL * _scale(ref)
+
+
 def test_tensor_cross(backend, oracle):
     lib, dev = backend
     vel = smooth_field(N, 5, 3)
