@@ -33,7 +33,9 @@ METRIC = "cells-advanced/sec (fp64)"
 UNIT = "cells/s"
 NU, CFL = 1.0e-4, 0.7
 TG = [1.0, 1.0, 0.0, 1.0, 1.0]   # prob.a, b, c, velocity_factor, density_ic (inputs.3d.taylorgreen:107-109)
-RANK_GRID = {1: (1, 1, 1), 2: (2, 1, 1), 4: (2, 2, 1), 8: (2, 2, 2)}
+# weak scaling decomposes the domain into z slabs, one 256^3 box per rank: every box then spans the periodic domain in x
+# and y (neighbours wrap inside the kernels, no ghost traffic) and exchanges contiguous z planes with two neighbours
+RANK_GRID = {1: (1, 1, 1), 2: (1, 1, 2), 4: (1, 1, 4), 8: (1, 1, 8)}
 
 
 def ncu_traffic(kernel, box):

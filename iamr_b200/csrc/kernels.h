@@ -96,7 +96,11 @@ int nodal_gs_color(const Bx& nbx, V4 phi, C4 rhs, C4 sig, const double dxinv[3],
 // full 8-colour Gauss-Seidel sweep phi_in -> phi_out on a box that spans the periodic domain
 // (one fused launch per plane parity); nodal_gs_sweep_ok tells whether the box qualifies
 bool nodal_gs_sweep_ok(const Bx& nbx, int wrapmask);
-int nodal_gs_sweep(const Bx& nbx, V4 phi_out, C4 phi_in, C4 rhs, C4 sig, const double dxinv[3], cudaStream_t s);
+// wrapmask 7 (box spans the periodic domain) or 3 (slab: x, y wrapped, z neighbours read from filled ghost planes).
+// phase 0 = even planes (colours 0-3), 1 = odd planes (colours 4-7), -1 = both; with wrapmask 3 the caller exchanges
+// the z ghost planes of phi_out between the phases.
+int nodal_gs_sweep(const Bx& nbx, V4 phi_out, C4 phi_in, C4 rhs, C4 sig, const double dxinv[3], cudaStream_t s,
+                   int wrapmask = 7, int phase = -1);
 int nodal_jacobi(const Bx& nbx, V4 out, C4 phi, C4 rhs, C4 sig, const double dxinv[3], double omega,
                  cudaStream_t s);
 int nodal_restrict(const Bx& cnbx, V4 crse, C4 fine, cudaStream_t s);

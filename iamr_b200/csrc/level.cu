@@ -339,7 +339,7 @@ int comm_exchange(const std::vector<int>& peers, const std::vector<double*>& sbu
 namespace k {
 namespace {
 constexpr int CB_T = 256;
-constexpr int CB_CHUNKS = 24;
+constexpr int CB_CHUNKS = 1024;
 
 __global__ void __launch_bounds__(CB_T)
 copy_batch_kernel(const CopyDesc* __restrict__ desc, IX_KARG(FabTable) dst, IX_KARG(FabTable) src, double* buf, int ncomp,
@@ -347,27 +347,38 @@ copy_batch_kernel(const CopyDesc* __restrict__ desc, IX_KARG(FabTable) dst, IX_K
   const CopyDesc& d = desc[blockIdx.y];
   const int nx = d.hi[0] - d.lo[0] + 1, ny = d.hi[1] - d.lo[1] + 1, nz = d.hi[2] - d.lo[2] + 1;
   const int64_t npts = (int64_t)nx * ny * nz;
-  const int64_t total = npts * ncomp;
-  for (int64_t t = (int64_t)blockIdx.x * CB_T + threadIdx.x; t < total; t += (int64_t)gridDim.x * CB_T) {
-    const int n = (int)(t / npts);
-    const int64_t r = t - (int64_t)n * npts;
-    const int ii = (int)(r % nx);
-    const int jj = (int)((r / nx) % ny);
-    const int kk = (int)(r / ((int64_t)nx * ny));
-    const int i = d.lo[0] + ii, j = d.lo[1] + jj, k = d.lo[2] + kk;
-    if (d.kind == 0) {
-      const double v = src.p[d.src][(i + d.sh[0] - src.lo[d.src][0]) + (j + d.sh[1] - src.lo[d.src][1]) * src.js[d.src] +
-                                    (k + d.sh[2] - src.lo[d.src][2]) * src.ks[d.src] + n * src.ns[d.src]];
-      dst.p[d.dst][(i - dst.lo[d.dst][0]) + (j - dst.lo[d.dst][1]) * dst.js[d.dst] +
-                   (k - dst.lo[d.dst][2]) * dst.ks[d.dst] + n * dst.ns[d.dst]] = v;
-    } else if (d.kind == 1) {  // pack: region given in src index space
-      buf[d.bufoff * ncomp + n * npts + r + 0 * bstride] =
-          src.p[d.src][(i - src.lo[d.src][0]) + (j - src.lo[d.src][1]) * src.js[d.src] +
-                       (k - src.lo[d.src][2]) * src.ks[d.src] + n * src.ns[d.src]];
-    } else {  // unpack
-      dst.p[d.dst][(i - dst.lo[d.dst][0]) + (j - dst.lo[d.dst][1]) * dst.js[d.dst] +
-                   (k - dst.lo[d.dst][2]) * dst.ks[d.dst] + n * dst.ns[d.dst]] =
-          buf[d.bufoff * ncomp + n * npts + r];
+  (void)bstride;
+  // "rows": x lines of the region, or whole xy planes when the region is thin in x (x-face slabs), so that a
+  // CTA always sweeps a long contiguous-in-index run and the divisions are per row, not per point
+  const bool flat = nx < 32;
+  const int rowlen = flat ? nx * ny : nx;
+  const int nrows = (flat ? nz : ny * nz) * ncomp;
+  const int rpn = flat ? nz : ny * nz;   // rows per component
+  const double* sp = (d.kind != 2) ? src.p[d.src] : nullptr;
+  double* dp = (d.kind != 1) ? dst.p[d.dst] : nullptr;
+  // threads cover (row, position in row) jointly: RW = power of two >= rowlen (at most CB_T) lanes per row and
+  // CB_T / RW rows per CTA pass, so short rows do not serialise into one dependent load-store round trip each
+  int RW = 32;
+  while (RW < rowlen && RW < CB_T) RW <<= 1;
+  const int rpp = CB_T / RW;                       // rows per pass
+  const int tx = threadIdx.x & (RW - 1), ty = threadIdx.x / RW;
+  for (int row = blockIdx.x * rpp + ty; row < nrows; row += gridDim.x * rpp) {
+    const int n = row / rpn, rr = row - n * rpn;
+    const int kk = flat ? rr : rr / ny, jj0 = flat ? 0 : rr - kk * ny;
+    const int k = d.lo[2] + kk;
+    int64_t sbase = 0, dbase = 0;
+    if (d.kind != 2) sbase = (int64_t)(k + d.sh[2] - src.lo[d.src][2]) * src.ks[d.src] + (int64_t)n * src.ns[d.src] + (d.sh[0] + d.lo[0] - src.lo[d.src][0]) +
+                             (int64_t)(d.sh[1] + d.lo[1] + jj0 - src.lo[d.src][1]) * src.js[d.src];
+    if (d.kind != 1) dbase = (int64_t)(k - dst.lo[d.dst][2]) * dst.ks[d.dst] + (int64_t)n * dst.ns[d.dst] + (d.lo[0] - dst.lo[d.dst][0]) +
+                             (int64_t)(d.lo[1] + jj0 - dst.lo[d.dst][1]) * dst.js[d.dst];
+    const int64_t bbase = d.bufoff * ncomp + (int64_t)n * npts + (int64_t)kk * nx * ny + (int64_t)jj0 * nx;
+    const int sjs = (d.kind != 2) ? (int)src.js[d.src] : 0, djs = (d.kind != 1) ? (int)dst.js[d.dst] : 0;
+    for (int m = tx; m < rowlen; m += RW) {
+      int ii = m, jj = 0;
+      if (flat) { jj = m / nx; ii = m - jj * nx; }
+      const double v = (d.kind == 2) ? buf[bbase + m] : sp[sbase + ii + jj * sjs];
+      if (d.kind == 1) buf[bbase + m] = v;
+      else dp[dbase + ii + jj * djs] = v;
     }
   }
 }
@@ -376,8 +387,9 @@ copy_batch_kernel(const CopyDesc* __restrict__ desc, IX_KARG(FabTable) dst, IX_K
 int copy_batch(const CopyDesc* d_desc, int ndesc, int64_t max_pts, const FabTable& dst, const FabTable& src,
                double* buf, int ncomp, int64_t bstride, cudaStream_t s) {
   if (ndesc <= 0) return IAMRX_OK;
-  // chunks per region: enough CTAs to cover the largest region 4 points per thread, at most CB_CHUNKS
-  int64_t chunks = (max_pts * ncomp + 4 * CB_T - 1) / (4 * CB_T);
+  // CTAs per region: one point per thread of the largest region (all loads in flight at once: these copies are
+  // latency-, not bandwidth-bound), at most CB_CHUNKS
+  int64_t chunks = (max_pts * ncomp + CB_T - 1) / CB_T;
   if (chunks < 1) chunks = 1;
   if (chunks > CB_CHUNKS) chunks = CB_CHUNKS;
   IX_LAUNCH(copy_batch_kernel, dim3((unsigned)chunks, ndesc, 1), CB_T, 0, s, d_desc, dst, src, buf, ncomp, bstride);
@@ -452,14 +464,27 @@ static CopyDesc* upload(const std::vector<CopyDesc>& v) {
   return d;
 }
 
-FBPlan& Level::plan(int ixtype, int ng) {
-  auto key = std::make_pair(ixtype, ng);
+FBPlan& Level::plan(int ixtype, int ng, int skip) {
+  auto key = std::make_pair(ixtype, ng + 1024 * skip);
   auto it = plans.find(key);
   if (it != plans.end()) return *it->second;
   auto P = std::make_unique<FBPlan>();
   P->ixtype = ixtype; P->ng = ng;
   std::vector<int> db, sb, sh; std::vector<Bx> rg;
   build_fb_regions(*this, ixtype, ng, db, sb, rg, sh);
+  if (skip) {  // clip every region to the valid range of the skipped directions; drop what is left empty
+    std::vector<int> db2, sb2, sh2; std::vector<Bx> rg2;
+    for (size_t r = 0; r < rg.size(); ++r) {
+      const Bx v = ixbox(boxes[db[r]], ixtype);
+      Bx c = rg[r];
+      for (int d = 0; d < 3; ++d)
+        if (skip & (1 << d)) { c.lo[d] = std::max(c.lo[d], v.lo[d]); c.hi[d] = std::min(c.hi[d], v.hi[d]); }
+      if (!c.ok()) continue;
+      db2.push_back(db[r]); sb2.push_back(sb[r]); rg2.push_back(c);
+      for (int q = 0; q < 3; ++q) sh2.push_back(sh[3 * r + q]);
+    }
+    db.swap(db2); sb.swap(sb2); rg.swap(rg2); sh.swap(sh2);
+  }
   const int me = comm().rank;
   std::vector<int> g2l(boxes.size(), -1);
   for (int il = 0; il < nlocal(); ++il) g2l[local[il]] = il;
@@ -592,13 +617,14 @@ int mf_scale(MF& m, double c, int comp, int ncomp, int ng, cudaStream_t s) {
   return IAMRX_OK;
 }
 
-int mf_fill_boundary(MF& m, int comp, int ncomp, int ng, cudaStream_t s) {
-  if (ng <= 0 || m.n() == 0) return IAMRX_OK;
+int mf_fill_boundary(MF& m, int comp, int ncomp, int ng, cudaStream_t s, int skip) {
+  if (ng <= 0 || m.n() == 0 || skip == 7) return IAMRX_OK;
   if (m.n() > FabTable::MAXF) { set_error("mf_fill_boundary: too many local boxes"); return IAMRX_ERR_ARG; }
   Level& L = *m.lev;
-  FBPlan& P = L.plan(m.ixtype, ng);
+  FBPlan& P = L.plan(m.ixtype, ng, skip);
   FabTable t; fill_table(t, m, comp);
   if (P.peers.empty()) {
+    if (P.local.empty()) return IAMRX_OK;
     return k::copy_batch(P.d_local, (int)P.local.size(), P.max_local, t, t, nullptr, ncomp, 0, s);
   }
   double* sbuf = dev_alloc((size_t)(P.send_total * ncomp + 1));
@@ -611,7 +637,7 @@ int mf_fill_boundary(MF& m, int comp, int ncomp, int ng, cudaStream_t s) {
     sc.push_back(P.send_pts[i] * ncomp); rc.push_back(P.recv_pts[i] * ncomp);
   }
   IX_TRY(comm_exchange(P.peers, sb, sc, rb, rc, s));
-  IX_TRY(k::copy_batch(P.d_local, (int)P.local.size(), P.max_local, t, t, nullptr, ncomp, 0, s));
+  if (!P.local.empty()) IX_TRY(k::copy_batch(P.d_local, (int)P.local.size(), P.max_local, t, t, nullptr, ncomp, 0, s));
   IX_TRY(k::copy_batch(P.d_recv, P.n_recv, P.max_recv, t, t, rbuf, ncomp, 0, s));
   dev_free(sbuf); dev_free(rbuf);  // stream-ordered reuse: same stream
   return IAMRX_OK;

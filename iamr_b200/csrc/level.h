@@ -95,7 +95,9 @@ struct Level {
 
   int nlocal() const { return (int)local.size(); }
   const Bx& lbox(int il) const { return boxes[local[il]]; }
-  FBPlan& plan(int ixtype, int ng);
+  // skip: bit d set = no ghost cells are needed in direction d (kernels wrap indices there): regions are clipped to
+  // the valid range of direction d and dropped when empty
+  FBPlan& plan(int ixtype, int ng, int skip = 0);
   // bit d set iff local box il spans the whole periodic domain in direction d: its periodic
   // neighbour is the box itself and kernels can wrap indices instead of reading ghost cells
   int wrapmask(int il) const {
@@ -108,6 +110,15 @@ struct Level {
   bool all_wrap() const {
     for (int il = 0; il < nlocal(); ++il) if (wrapmask(il) != 7) return false;
     return true;
+  }
+  // directions in which EVERY box of the level (on any rank) spans the periodic domain: the same value on all ranks,
+  // so it can steer both the kernels (in-kernel wrap) and the exchange plan (no ghost traffic in those directions)
+  int level_wrapmask() const {
+    int m = 7;
+    for (const Bx& b : boxes)
+      for (int d = 0; d < 3; ++d)
+        if (!(geom.periodic[d] && b.lo[d] == domain.lo[d] && b.hi[d] == domain.hi[d])) m &= ~(1 << d);
+    return boxes.empty() ? 0 : m;
   }
 };
 
@@ -149,7 +160,7 @@ int mf_copy(MF& dst, const MF& src, int scomp, int dcomp, int ncomp, int ng, cud
 int mf_lincomb(MF& dst, int dcomp, double a, const MF& x, int xcomp, double b, const MF& y, int ycomp,
                int ncomp, int ng, cudaStream_t s);
 int mf_scale(MF& m, double c, int comp, int ncomp, int ng, cudaStream_t s);
-int mf_fill_boundary(MF& m, int comp, int ncomp, int ng, cudaStream_t s);
+int mf_fill_boundary(MF& m, int comp, int ncomp, int ng, cudaStream_t s, int skip = 0);
 // reductions over valid regions, all ranks (blocking: returns host value).
 // For face/nodal data shared points are counted once per owning box (norms only).
 int mf_norminf(const MF& m, int comp, int ncomp, double* out_host, cudaStream_t s);  // max over comps

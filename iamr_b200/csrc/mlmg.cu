@@ -130,7 +130,8 @@ int CellMG::smooth(int l, MF& phi, const MF& rhs, int nsweeps, bool /*zero_init*
   MGLevelCell& L = lv_[l];
   // a box that spans the periodic domain wraps its neighbour indices inside the kernel:
   // no ghost fill (and no extra launch) per colour
-  const bool wrap = L.lev->all_wrap();
+  const int wm = L.lev->level_wrapmask();   // directions wrapped inside the kernels: no ghost traffic there
+  const bool wrap = wm == 7;
   bool fused = wrap && k::abec_gsrb_sweep_enabled();
   for (int il = 0; il < phi.n() && fused; ++il) fused = k::abec_gsrb_sweep_ok(phi.vbox(il), 7);
   if (fused) {
@@ -147,9 +148,9 @@ int CellMG::smooth(int l, MF& phi, const MF& rhs, int nsweeps, bool /*zero_init*
   }
   for (int sw = 0; sw < nsweeps; ++sw) {
     for (int rb = 0; rb < 2; ++rb) {
-      if (!wrap) IX_TRY(mf_fill_boundary(phi, 0, ncomp_, 1, s));
+      if (!wrap) IX_TRY(mf_fill_boundary(phi, 0, ncomp_, 1, s, wm));
       for (int il = 0; il < phi.n(); ++il)
-        IX_TRY(k::abec_gsrb(phi.vbox(il), phi.v(il), rhs.c(il), op_at(l, il), info_.omega, rb, ncomp_, s, wrap ? 7 : 0));
+        IX_TRY(k::abec_gsrb(phi.vbox(il), phi.v(il), rhs.c(il), op_at(l, il), info_.omega, rb, ncomp_, s, wm));
     }
   }
   return IAMRX_OK;
@@ -157,10 +158,10 @@ int CellMG::smooth(int l, MF& phi, const MF& rhs, int nsweeps, bool /*zero_init*
 
 int CellMG::residual(int l, MF& out, MF& phi, const MF& rhs, bool with_cross, cudaStream_t s) {
   const bool cross = tensor_ && l == 0 && with_cross;  // the cross terms read edge/corner ghosts
-  const bool wrap = lv_[l].lev->all_wrap() && !cross;
-  if (!wrap) IX_TRY(mf_fill_boundary(phi, 0, ncomp_, 1, s));
+  const int wm = cross ? 0 : lv_[l].lev->level_wrapmask();
+  if (wm != 7) IX_TRY(mf_fill_boundary(phi, 0, ncomp_, 1, s, wm));
   for (int il = 0; il < phi.n(); ++il) {
-    IX_TRY(k::abec_apply(phi.vbox(il), out.v(il), phi.c(il), rhs.c(il), op_at(l, il), ncomp_, s, wrap ? 7 : 0));
+    IX_TRY(k::abec_apply(phi.vbox(il), out.v(il), phi.c(il), rhs.c(il), op_at(l, il), ncomp_, s, wm));
     if (tensor_ && l == 0 && with_cross)
       IX_TRY(k::tensor_cross(phi.vbox(il), out.v(il), phi.c(il), eta_[0]->c(il), eta_[1]->c(il),
                              eta_[2]->c(il), -b_, lv_[0].dxinv, s));
@@ -304,7 +305,8 @@ static int nodal_smoother_kind() {
 
 int NodeMG::smooth(int l, MF& phi, const MF& rhs, int nsweeps, cudaStream_t s) {
   MGLevelNode& L = lv_[l];
-  const bool wrap = L.lev->all_wrap();
+  const int wm = L.lev->level_wrapmask();   // directions wrapped inside the kernels: no ghost traffic there
+  const bool wrap = wm == 7;
   if (nodal_smoother_kind() == 1) {
     MF tmp(L.lev, IX_NODE, 1, 1);
     for (int sw = 0; sw < 2 * nsweeps; ++sw) {
@@ -316,25 +318,31 @@ int NodeMG::smooth(int l, MF& phi, const MF& rhs, int nsweeps, cudaStream_t s) {
     }
     return IAMRX_OK;
   }
-  bool fused = wrap;
-  for (int il = 0; il < phi.n() && fused; ++il) fused = k::nodal_gs_sweep_ok(phi.vbox(il), 7);
+  bool fused = true;
+  for (int il = 0; il < phi.n() && fused; ++il) fused = k::nodal_gs_sweep_ok(phi.vbox(il), wm);
   if (fused) {
-    // out-of-place fused sweeps ping-pong between phi and a second buffer
+    // out-of-place fused sweeps ping-pong between phi and a second buffer.  Slabs (x and y wrapped in the kernel, z
+    // exchanged): the even-plane phase reads the old odd ghost planes of `src`, the odd-plane phase the NEW even ghost
+    // planes of `dst` -- two plane exchanges per sweep instead of eight colour fills.
     if (!L.gs_tmp.ok()) L.gs_tmp.define(L.lev, IX_NODE, 1, 1);
     MF* src = &phi; MF* dst = &L.gs_tmp;
+    if (!wrap) IX_TRY(mf_fill_boundary(*src, 0, 1, 1, s, wm));
     for (int sw = 0; sw < nsweeps; ++sw) {
-      for (int il = 0; il < phi.n(); ++il)
-        IX_TRY(k::nodal_gs_sweep(phi.vbox(il), dst->v(il), src->c(il), rhs.c(il), L.sigma.c(il), L.dxinv, s));
+      for (int phase = 0; phase < 2; ++phase) {
+        for (int il = 0; il < phi.n(); ++il)
+          IX_TRY(k::nodal_gs_sweep(phi.vbox(il), dst->v(il), src->c(il), rhs.c(il), L.sigma.c(il), L.dxinv, s, wm, phase));
+        if (!wrap) IX_TRY(mf_fill_boundary(*dst, 0, 1, 1, s, wm));
+      }
       std::swap(src, dst);
     }
-    if (src != &phi) IX_TRY(mf_copy(phi, *src, 0, 0, 1, 0, s));
+    if (src != &phi) IX_TRY(mf_copy(phi, *src, 0, 0, 1, wrap ? 0 : 1, s));
     return IAMRX_OK;
   }
   for (int sw = 0; sw < nsweeps; ++sw) {
     for (int color = 0; color < 8; ++color) {
-      if (!wrap) IX_TRY(mf_fill_boundary(phi, 0, 1, 1, s));
+      if (!wrap) IX_TRY(mf_fill_boundary(phi, 0, 1, 1, s, wm));
       for (int il = 0; il < phi.n(); ++il)
-        IX_TRY(k::nodal_gs_color(phi.vbox(il), phi.v(il), rhs.c(il), L.sigma.c(il), L.dxinv, color, s, wrap ? 7 : 0));
+        IX_TRY(k::nodal_gs_color(phi.vbox(il), phi.v(il), rhs.c(il), L.sigma.c(il), L.dxinv, color, s, wm));
     }
   }
   return IAMRX_OK;
@@ -342,10 +350,10 @@ int NodeMG::smooth(int l, MF& phi, const MF& rhs, int nsweeps, cudaStream_t s) {
 
 int NodeMG::residual(int l, MF& out, MF& phi, const MF& rhs, cudaStream_t s) {
   MGLevelNode& L = lv_[l];
-  const bool wrap = L.lev->all_wrap();
-  if (!wrap) IX_TRY(mf_fill_boundary(phi, 0, 1, 1, s));
+  const int wm = L.lev->level_wrapmask();
+  if (wm != 7) IX_TRY(mf_fill_boundary(phi, 0, 1, 1, s, wm));
   for (int il = 0; il < phi.n(); ++il)
-    IX_TRY(k::nodal_adotx(phi.vbox(il), out.v(il), phi.c(il), rhs.c(il), L.sigma.c(il), L.dxinv, s, wrap ? 7 : 0));
+    IX_TRY(k::nodal_adotx(phi.vbox(il), out.v(il), phi.c(il), rhs.c(il), L.sigma.c(il), L.dxinv, s, wm));
   return IAMRX_OK;
 }
 

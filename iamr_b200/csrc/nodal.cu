@@ -424,14 +424,16 @@ IX_D void pass(double (*sp)[NR][NC], double (*ss)[NR][NC], int warp, int lane, d
 }
 
 __global__ void __launch_bounds__(NT, 4)
-gs_sweep_kernel(Bx bx, V4 out, C4 pin, C4 padj, C4 rhs, C4 sig, IX_KARG(Q1F) q, int k0) {
+gs_sweep_kernel(Bx bx, V4 out, C4 pin, C4 padj, C4 rhs, C4 sig, IX_KARG(Q1F) q, int k0, int zwrap) {
   __shared__ double sp[3][NR][NC];
   __shared__ double ss[2][NR][NC];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int X0 = (bx.lo[0] - (bx.lo[0] & 1)) + TXI * (int)blockIdx.x - 4;   // global node index of tile column 0
   const int Y0 = (bx.lo[1] - (bx.lo[1] & 1)) + TYI * (int)blockIdx.y - 2;   // ... of tile row 0
   const int k = k0 + 2 * (int)blockIdx.z;
-  const int km = (k == bx.lo[2]) ? bx.hi[2] - 1 : k - 1, kp = (k == bx.hi[2]) ? bx.lo[2] + 1 : k + 1;
+  // z neighbours: periodic images when the box spans the domain in z, else the (filled) ghost planes / ghost cells
+  const int km = (zwrap && k == bx.lo[2]) ? bx.hi[2] - 1 : k - 1, kp = (zwrap && k == bx.hi[2]) ? bx.lo[2] + 1 : k + 1;
+  const int ckm = zwrap ? wrap_cell_any(k - 1, bx.lo[2], bx.hi[2]) : k - 1, ckp = zwrap ? wrap_cell_any(k, bx.lo[2], bx.hi[2]) : k;
   // stage phi (rows 1..17 of three planes) and sigma (cell rows 1..16 of planes k-1, k): a thread
   // always loads the same tile column, so the x wrap is done once
   {
@@ -444,8 +446,8 @@ gs_sweep_kernel(Bx bx, V4 out, C4 pin, C4 padj, C4 rhs, C4 sig, IX_KARG(Q1F) q, 
     const double* pk = pin.p + (gi - pin.l0) + (int64_t)(k - pin.l2) * pin.ks;
     const double* pm = padj.p + (gi - padj.l0) + (int64_t)(km - padj.l2) * padj.ks;
     const double* pp = padj.p + (gi - padj.l0) + (int64_t)(kp - padj.l2) * padj.ks;
-    const double* s0p = sig.p + (ci - sig.l0) + (int64_t)(wrap_cell_any(k - 1, bx.lo[2], bx.hi[2]) - sig.l2) * sig.ks;
-    const double* s1p = sig.p + (ci - sig.l0) + (int64_t)(wrap_cell_any(k, bx.lo[2], bx.hi[2]) - sig.l2) * sig.ks;
+    const double* s0p = sig.p + (ci - sig.l0) + (int64_t)(ckm - sig.l2) * sig.ks;
+    const double* s1p = sig.p + (ci - sig.l0) + (int64_t)(ckp - sig.l2) * sig.ks;
     const int pjs = (int)pin.js, ajs = (int)padj.js, sjs = (int)sig.js;
 #pragma unroll
     for (int m = 0; m < 5; ++m) {
@@ -589,23 +591,28 @@ int nodal_gs_color(const Bx& nbx, V4 phi, C4 rhs, C4 sig, const double dxinv[3],
 bool nodal_gs_sweep_ok(const Bx& nbx, int wrapmask) {
   static int on = -1;
   if (on < 0) { const char* e = getenv("IAMRX_NODAL_FUSED"); on = (e && e[0] == '0') ? 0 : 1; }
-  if (!on || wrapmask != 7) return false;
+  if (!on || (wrapmask != 7 && wrapmask != 3)) return false;
   for (int d = 0; d < 3; ++d) if (((nbx.hi[d] - nbx.lo[d]) & 1) || nbx.hi[d] - nbx.lo[d] < 2) return false;
   return true;
 }
 
-int nodal_gs_sweep(const Bx& nbx, V4 phi_out, C4 phi_in, C4 rhs, C4 sig, const double dxinv[3], cudaStream_t s) {
+int nodal_gs_sweep(const Bx& nbx, V4 phi_out, C4 phi_in, C4 rhs, C4 sig, const double dxinv[3], cudaStream_t s, int wrapmask,
+                   int phase) {
   if (!nbx.ok()) return IAMRX_OK;
   double f[3]; facs(dxinv, f);
+  C4 pout{phi_out.p, phi_out.l0, phi_out.l1, phi_out.l2, phi_out.js, phi_out.ks, phi_out.ns};
 #if defined(IX_EMUL)
-  // host emulation (tests only): the same sweep as eight in-place colour passes on a copy
-  int rc = copy(nbx, phi_out, phi_in, 1, s);
-  for (int color = 0; color < 8 && rc == IAMRX_OK; ++color) rc = nodal_gs_color(nbx, phi_out, rhs, sig, dxinv, color, s, 7);
+  // host emulation (tests only): the same sweep as eight in-place colour passes on a copy (ghost planes of the
+  // exchanged direction included: the even-plane colours read them as old values)
+  int rc = IAMRX_OK;
+  if (phase != 1) rc = copy((wrapmask & 4) ? nbx : grow(nbx, 2, 1), phi_out, phi_in, 1, s);
+  const int c0 = (phase == 1) ? 4 : 0, c1 = (phase == 0) ? 4 : 8;
+  (void)pout;
+  for (int color = c0; color < c1 && rc == IAMRX_OK; ++color) rc = nodal_gs_color(nbx, phi_out, rhs, sig, dxinv, color, s, wrapmask);
   return rc;
 #else
   using namespace fused;
-  ProfScope prof_(IAMRX_PROF_NODAL_GS, nbx.npts(), (double)nbx.npts() * 32.0, s);  // phi in + out, rhs, sigma
-  C4 pout{phi_out.p, phi_out.l0, phi_out.l1, phi_out.l2, phi_out.js, phi_out.ks, phi_out.ns};
+  ProfScope prof_(IAMRX_PROF_NODAL_GS, nbx.npts(), (double)nbx.npts() * (phase < 0 ? 32.0 : 16.0), s);  // phi in + out, rhs, sigma
   Q1F q;
   q.f0c = q1_factor(false, false, false, f[0], f[1], f[2]); q.f1c = q1_factor(true, false, false, f[0], f[1], f[2]);
   q.f0j = q1_factor(false, true, false, f[0], f[1], f[2]);  q.f1j = q1_factor(true, true, false, f[0], f[1], f[2]);
@@ -613,12 +620,13 @@ int nodal_gs_sweep(const Bx& nbx, V4 phi_out, C4 phi_in, C4 rhs, C4 sig, const d
   q.f0jk = q1_factor(false, true, true, f[0], f[1], f[2]);  q.f1jk = q1_factor(true, true, true, f[0], f[1], f[2]);
   const int gx = cdiv(nbx.hi[0] - (nbx.lo[0] - (nbx.lo[0] & 1)) + 1, TXI), gy = cdiv(nbx.hi[1] - (nbx.lo[1] - (nbx.lo[1] & 1)) + 1, TYI);
   for (int cz = 0; cz < 2; ++cz) {
+    if (phase >= 0 && phase != cz) continue;
     const int k0 = nbx.lo[2] + ((cz - nbx.lo[2]) & 1);
     if (k0 > nbx.hi[2]) continue;
     const int nk = (nbx.hi[2] - k0) / 2 + 1;
     // phase A (even planes): neighbours = old odd planes; phase B (odd planes): neighbours = new even planes
     IX_LAUNCH(gs_sweep_kernel, dim3(gx, gy, nk), dim3(NT, 1, 1), 0, s, nbx, phi_out, phi_in, cz == 0 ? phi_in : pout, rhs, sig,
-              q, k0);
+              q, k0, (wrapmask & 4) ? 1 : 0);
     const int rc = check_launch("nodal_gs_sweep");
     if (rc != IAMRX_OK) return rc;
   }

@@ -9,10 +9,11 @@ import iamr_b200 as ix
 
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 256
 steps = int(sys.argv[2]) if len(sys.argv) > 2 else 3
+nzb = int(sys.argv[3]) if len(sys.argv) > 3 else 1   # number of z slabs (boxes) the domain is cut into, all on this GPU
 lib = ix.load()
 dev = 'cuda:0'
 g = ix.Geom.make((n, n, n))
-lev = ix.Level(lib, g, [((0, 0, 0), (n - 1, n - 1, n - 1))])
+lev = ix.Level(lib, g, [((0, 0, b * (n // nzb)), (n - 1, n - 1, (b + 1) * (n // nzb) - 1)) for b in range(nzb)])
 ns = ix.NavierStokes(lib, lev, dev, visc_coef=1e-4, cfl=0.7)
 ns.init_prob(11, [1.0, 1.0, 0.0, 1.0, 1.0])
 ns.post_init()
