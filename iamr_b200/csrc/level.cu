@@ -1,6 +1,7 @@
 // level.cu -- see level.h.  Memory pool, NCCL communicator (dlopen'd so the
 // library loads on CPU-only hosts), FillBoundary plan + batched copy kernel,
 // local multifabs and level-wide helpers.
+#include <cstdlib>
 #include "level.h"
 #include <dlfcn.h>
 #include <algorithm>
@@ -528,6 +529,20 @@ FBPlan& Level::plan(int ixtype, int ng, int skip) {
     so += P->send_pts.back(); ro += P->recv_pts.back();
   }
   P->send_total = so; P->recv_total = ro;
+  for (int p : peers) { P->send.push_back(sendm[p]); P->recv.push_back(recvm[p]); }
+  {
+    static int direct_on = -1;
+    if (direct_on < 0) { const char* e = getenv("IAMRX_FB_DIRECT"); direct_on = (e && e[0] == '0') ? 0 : 1; }
+    bool ok = direct_on && (skip & 3) == 3 && !peers.empty();
+    for (size_t r = 0; r < rg.size() && ok; ++r) {
+      const int od = owner[db[r]], os = owner[sb[r]];
+      if ((od != me && os != me) || (od == me && os == me)) continue;
+      const Bx vd = ixbox(boxes[db[r]], ixtype), vs = ixbox(boxes[sb[r]], ixtype);
+      for (int d = 0; d < 2; ++d)
+        if (sh[3 * r + d] != 0 || rg[r].lo[d] != vd.lo[d] || rg[r].hi[d] != vd.hi[d] || vs.lo[d] != vd.lo[d] || vs.hi[d] != vd.hi[d]) ok = false;
+    }
+    P->direct = ok;
+  }
   for (const CopyDesc& d : P->local) P->max_local = std::max<int64_t>(P->max_local, (int64_t)(d.hi[0] - d.lo[0] + 1) * (d.hi[1] - d.lo[1] + 1) * (d.hi[2] - d.lo[2] + 1));
   for (const CopyDesc& d : all_send) P->max_send = std::max<int64_t>(P->max_send, (int64_t)(d.hi[0] - d.lo[0] + 1) * (d.hi[1] - d.lo[1] + 1) * (d.hi[2] - d.lo[2] + 1));
   for (const CopyDesc& d : all_recv) P->max_recv = std::max<int64_t>(P->max_recv, (int64_t)(d.hi[0] - d.lo[0] + 1) * (d.hi[1] - d.lo[1] + 1) * (d.hi[2] - d.lo[2] + 1));
@@ -627,6 +642,31 @@ int mf_fill_boundary(MF& m, int comp, int ncomp, int ng, cudaStream_t s, int ski
     if (P.local.empty()) return IAMRX_OK;
     return k::copy_batch(P.d_local, (int)P.local.size(), P.max_local, t, t, nullptr, ncomp, 0, s);
   }
+  bool owned = true;
+  for (double* o : m.owned) if (!o) owned = false;
+  if (P.direct && owned && (int)m.owned.size() == m.n()) {
+    // whole z planes, identical layout on both sides: exchange them in place
+    std::vector<int> pl; std::vector<double*> sb, rb; std::vector<int64_t> sc, rc;
+    for (size_t i = 0; i < P.peers.size(); ++i) {
+      const size_t ns_ = P.send[i].size() * ncomp, nr_ = P.recv[i].size() * ncomp, ne = std::max(ns_, nr_);
+      for (size_t e = 0; e < ne; ++e) {
+        pl.push_back(P.peers[i]);
+        if (e < ns_) {
+          const CopyDesc& d = P.send[i][e / ncomp]; const iamrx_fab& f = m.fabs[d.src];
+          sb.push_back(f.p + (int64_t)(comp + (int)(e % ncomp)) * f.nstride + (int64_t)(d.lo[2] - f.lo[2]) * f.kstride - (f.p - m.owned[d.src]));
+          sc.push_back((int64_t)(d.hi[2] - d.lo[2] + 1) * f.kstride);
+        } else { sb.push_back(nullptr); sc.push_back(0); }
+        if (e < nr_) {
+          const CopyDesc& d = P.recv[i][e / ncomp]; const iamrx_fab& f = m.fabs[d.dst];
+          rb.push_back(f.p + (int64_t)(comp + (int)(e % ncomp)) * f.nstride + (int64_t)(d.lo[2] - f.lo[2]) * f.kstride - (f.p - m.owned[d.dst]));
+          rc.push_back((int64_t)(d.hi[2] - d.lo[2] + 1) * f.kstride);
+        } else { rb.push_back(nullptr); rc.push_back(0); }
+      }
+    }
+    IX_TRY(comm_exchange(pl, sb, sc, rb, rc, s));
+    if (!P.local.empty()) IX_TRY(k::copy_batch(P.d_local, (int)P.local.size(), P.max_local, t, t, nullptr, ncomp, 0, s));
+    return IAMRX_OK;
+  }
   double* sbuf = dev_alloc((size_t)(P.send_total * ncomp + 1));
   double* rbuf = dev_alloc((size_t)(P.recv_total * ncomp + 1));
   if (!sbuf || !rbuf) return IAMRX_ERR_CUDA;
@@ -640,6 +680,78 @@ int mf_fill_boundary(MF& m, int comp, int ncomp, int ng, cudaStream_t s, int ski
   if (!P.local.empty()) IX_TRY(k::copy_batch(P.d_local, (int)P.local.size(), P.max_local, t, t, nullptr, ncomp, 0, s));
   IX_TRY(k::copy_batch(P.d_recv, P.n_recv, P.max_recv, t, t, rbuf, ncomp, 0, s));
   dev_free(sbuf); dev_free(rbuf);  // stream-ordered reuse: same stream
+  return IAMRX_OK;
+}
+
+// ---- gather into a replicated level ---------------------------------------------------
+GatherPlan::~GatherPlan() {
+  if (d_pack) cudaFree(d_pack);
+  if (d_local) cudaFree(d_local);
+  if (d_unpack) cudaFree(d_unpack);
+}
+
+GatherPlan& Level::gather_plan(int ixtype) {
+  auto it = gplans.find(ixtype);
+  if (it != gplans.end()) return *it->second;
+  auto P = std::make_unique<GatherPlan>();
+  const int me = comm().rank;
+  std::vector<int> g2l(boxes.size(), -1);
+  for (int il = 0; il < nlocal(); ++il) g2l[local[il]] = il;
+  std::map<int, int64_t> roff;                 // points received so far per peer
+  std::map<int, std::vector<CopyDesc>> unp;
+  for (size_t b = 0; b < boxes.size(); ++b) {  // global box order on every rank: sender and receiver agree on the layout
+    const Bx v = ixbox(boxes[b], ixtype);
+    CopyDesc d{};
+    for (int q = 0; q < 3; ++q) { d.lo[q] = v.lo[q]; d.hi[q] = v.hi[q]; d.sh[q] = 0; }
+    const int64_t npts = v.npts();
+    if (owner[b] == me) {
+      d.kind = 0; d.dst = 0; d.src = g2l[b]; P->local.push_back(d);
+      d.kind = 1; d.dst = -1; d.bufoff = P->send_pts; P->send_pts += npts; P->pack.push_back(d);
+      P->max_local = std::max(P->max_local, npts);
+    } else {
+      d.kind = 2; d.dst = 0; d.src = -1; d.bufoff = roff[owner[b]]; roff[owner[b]] += npts;
+      unp[owner[b]].push_back(d);
+    }
+  }
+  P->max_pack = P->max_local;
+  int64_t ro = 0;
+  for (int p = 0; p < comm().nranks; ++p) {   // every other rank is a peer (it needs this rank's boxes even if it owns none)
+    if (p == me) continue;
+    P->peers.push_back(p);
+    P->recv_off.push_back(ro); P->recv_pts.push_back(roff.count(p) ? roff[p] : 0);
+    if (!unp.count(p)) continue;
+    for (CopyDesc d : unp[p]) {
+      d.bufoff += ro; P->unpack.push_back(d);
+      P->max_unpack = std::max<int64_t>(P->max_unpack, (int64_t)(d.hi[0] - d.lo[0] + 1) * (d.hi[1] - d.lo[1] + 1) * (d.hi[2] - d.lo[2] + 1));
+    }
+    ro += roff[p];
+  }
+  P->recv_total = ro;
+  P->d_pack = upload(P->pack); P->d_local = upload(P->local); P->d_unpack = upload(P->unpack);
+  GatherPlan& ref = *P;
+  gplans[ixtype] = std::move(P);
+  return ref;
+}
+
+int mf_gather_replicate(MF& dst, const MF& src, int ncomp, cudaStream_t s) {
+  if (dst.n() != 1 || src.n() > FabTable::MAXF) { set_error("mf_gather_replicate: bad layout"); return IAMRX_ERR_ARG; }
+  GatherPlan& P = src.lev->gather_plan(src.ixtype);
+  FabTable td; fill_table(td, dst, 0);
+  FabTable ts; fill_table(ts, src, 0);
+  if (!P.local.empty()) IX_TRY(k::copy_batch(P.d_local, (int)P.local.size(), P.max_local, td, ts, nullptr, ncomp, 0, s));
+  if (P.peers.empty()) return IAMRX_OK;
+  double* sbuf = dev_alloc((size_t)(P.send_pts * ncomp + 1));
+  double* rbuf = dev_alloc((size_t)(P.recv_total * ncomp + 1));
+  if (!sbuf || !rbuf) return IAMRX_ERR_CUDA;
+  if (!P.pack.empty()) IX_TRY(k::copy_batch(P.d_pack, (int)P.pack.size(), P.max_pack, td, ts, sbuf, ncomp, 0, s));
+  std::vector<double*> sb, rb; std::vector<int64_t> sc, rc;
+  for (size_t i = 0; i < P.peers.size(); ++i) {
+    sb.push_back(sbuf); sc.push_back(P.send_pts * ncomp);
+    rb.push_back(rbuf + P.recv_off[i] * ncomp); rc.push_back(P.recv_pts[i] * ncomp);
+  }
+  IX_TRY(comm_exchange(P.peers, sb, sc, rb, rc, s));
+  if (!P.unpack.empty()) IX_TRY(k::copy_batch(P.d_unpack, (int)P.unpack.size(), P.max_unpack, td, ts, rbuf, ncomp, 0, s));
+  dev_free(sbuf); dev_free(rbuf);
   return IAMRX_OK;
 }
 
@@ -680,7 +792,7 @@ static int reduce_common(const MF& m, int comp, int ncomp, int op, double* out, 
   IX_TRY(k::reduce_init(R.d, ncomp, op, s));
   for (int il = 0; il < m.n(); ++il)
     IX_TRY(k::reduce(uniq ? unique_box(m, il) : m.vbox(il), m.c(il, comp), ncomp, op, R.d, s));
-  IX_TRY(comm_allreduce(R.d, ncomp, op, s));
+  if (!m.lev->replicated) IX_TRY(comm_allreduce(R.d, ncomp, op, s));   // a replicated level holds the same data on every rank
   IX_CUDA(cudaMemcpyAsync(R.h, R.d, ncomp * sizeof(double), cudaMemcpyDeviceToHost, s));
   IX_CUDA(cudaStreamSynchronize(s));
   for (int n = 0; n < ncomp; ++n) out[n] = R.h[n];

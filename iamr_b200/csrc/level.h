@@ -80,7 +80,21 @@ struct FBPlan {
   int64_t send_total = 0, recv_total = 0;         // points per component, all peers
   int64_t max_local = 0, max_send = 0, max_recv = 0;  // largest region (points) per list: sizes the copy grid
   std::vector<int64_t> send_off, recv_off;
+  // every remote region is a stack of whole z planes (x, y skipped and spanned, shift in z only) between boxes of equal
+  // x-y shape: planes of MF-owned fabs are then contiguous and identical in layout on both sides, and are sent straight
+  // from / received straight into the arrays (no pack / unpack kernels)
+  bool direct = false;
   ~FBPlan();
+};
+
+// gather of a distributed level's data into a replicated single-box level (multigrid consolidation)
+struct GatherPlan {
+  std::vector<CopyDesc> pack, local, unpack;
+  CopyDesc* d_pack = nullptr; CopyDesc* d_local = nullptr; CopyDesc* d_unpack = nullptr;
+  std::vector<int> peers;
+  std::vector<int64_t> recv_off, recv_pts;   // points per component, per peer
+  int64_t send_pts = 0, recv_total = 0, max_pack = 0, max_local = 0, max_unpack = 0;
+  ~GatherPlan();
 };
 
 struct Level {
@@ -89,6 +103,11 @@ struct Level {
   std::vector<int> owner;  // rank of each box
   std::vector<int> local;  // global indices of the boxes this rank owns
   std::map<std::pair<int, int>, std::unique_ptr<FBPlan>> plans;
+  std::map<int, std::unique_ptr<GatherPlan>> gplans;   // by ixtype
+  // replicated level: ONE box covering the whole domain, held (and computed on) by every rank identically -- the
+  // consolidated coarse multigrid levels.  No ghost traffic, and reductions need no all-reduce.
+  bool replicated = false;
+  GatherPlan& gather_plan(int ixtype);
   double dxinv[3];
   Bx domain;
   int64_t ncells_global = 0;
@@ -161,6 +180,9 @@ int mf_lincomb(MF& dst, int dcomp, double a, const MF& x, int xcomp, double b, c
                int ncomp, int ng, cudaStream_t s);
 int mf_scale(MF& m, double c, int comp, int ncomp, int ng, cudaStream_t s);
 int mf_fill_boundary(MF& m, int comp, int ncomp, int ng, cudaStream_t s, int skip = 0);
+// dst (one box covering the domain, on a replicated level) <- valid regions of every box of src (a distributed level
+// of the same resolution): local boxes by a copy kernel, remote ones by an all-to-all of packed boxes
+int mf_gather_replicate(MF& dst, const MF& src, int ncomp, cudaStream_t s);
 // reductions over valid regions, all ranks (blocking: returns host value).
 // For face/nodal data shared points are counted once per owning box (norms only).
 int mf_norminf(const MF& m, int comp, int ncomp, double* out_host, cudaStream_t s);  // max over comps

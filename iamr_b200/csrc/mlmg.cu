@@ -45,7 +45,24 @@ std::unique_ptr<Level> coarsen_level(const Level& f, int min_width) {
     g.domain.hi[d] = g.domain.lo[d] + n / 2 - 1;
     g.dx[d] = 2.0 * f.geom.dx[d];
   }
-  return make_level(g, cb, f.owner);
+  auto L = make_level(g, cb, f.owner);
+  L->replicated = f.replicated;
+  return L;
+}
+
+std::unique_ptr<Level> consolidated_level(const Level& c) {
+  static int64_t thresh = -1;   // boxes of at most this many cells are consolidated (IAMRX_MG_CONSOLIDATE=0: never)
+  if (thresh < 0) { const char* e = getenv("IAMRX_MG_CONSOLIDATE"); thresh = e ? atoll(e) : 32 * 32 * 32; }
+  if (c.replicated || c.boxes.size() < 2 || thresh == 0) return nullptr;
+  for (const Bx& b : c.boxes) if (b.npts() > thresh) return nullptr;
+  int64_t covered = 0;
+  for (const Bx& b : c.boxes) covered += b.npts();
+  if (covered != mkbx(c.geom.domain).npts()) return nullptr;   // boxes must tile the domain
+  std::vector<Bx> one{mkbx(c.geom.domain)};
+  std::vector<int> own{comm().rank};
+  auto L = make_level(c.geom, one, own);
+  L->replicated = true;
+  return L;
 }
 
 static bool all_periodic(const Level& L) {
@@ -65,7 +82,12 @@ CellMG::CellMG(Level* fine, int ncomp, bool tensor, int max_coarsening)
     auto c = coarsen_level(*cur, 2);
     if (!c) break;
     lv_.emplace_back();
-    lv_.back().lev_owned = std::move(c);
+    if (auto r = consolidated_level(*c)) {   // from here down: one replicated box per rank, no ghost traffic
+      lv_.back().xfer_lev = std::move(c);
+      lv_.back().lev_owned = std::move(r);
+    } else {
+      lv_.back().lev_owned = std::move(c);
+    }
     lv_.back().lev = lv_.back().lev_owned.get();
     cur = lv_.back().lev;
   }
@@ -74,6 +96,7 @@ CellMG::CellMG(Level* fine, int ncomp, bool tensor, int max_coarsening)
     L.cor.define(L.lev, IX_CELL, ncomp_, 1);
     L.res.define(L.lev, IX_CELL, ncomp_, 0);
     L.rescor.define(L.lev, IX_CELL, ncomp_, 0);
+    if (L.xfer_lev) L.xfer.define(L.xfer_lev.get(), IX_CELL, ncomp_, 0);
   }
 }
 
@@ -113,13 +136,25 @@ int CellMG::set_coeffs(const MF* acoef, const MF* bx, const MF* by, const MF* bz
     MGLevelCell& F = lv_[l - 1];
     if (a_ != 0.0 && acoef) {
       if (!C.acoef.ok()) C.acoef.define(C.lev, IX_CELL, 1, 0);
-      for (int il = 0; il < C.acoef.n(); ++il)
-        IX_TRY(k::cc_restrict(C.acoef.vbox(il), C.acoef.v(il), F.acoef.c(il), 1, s));
+      if (C.xfer_lev) {   // restrict on the distributed layout, then gather into the replicated box
+        MF tmp(C.xfer_lev.get(), IX_CELL, 1, 0);
+        for (int il = 0; il < tmp.n(); ++il) IX_TRY(k::cc_restrict(tmp.vbox(il), tmp.v(il), F.acoef.c(il), 1, s));
+        IX_TRY(mf_gather_replicate(C.acoef, tmp, 1, s));
+      } else {
+        for (int il = 0; il < C.acoef.n(); ++il)
+          IX_TRY(k::cc_restrict(C.acoef.vbox(il), C.acoef.v(il), F.acoef.c(il), 1, s));
+      }
     }
     for (int d = 0; d < 3; ++d) {
       if (!C.b[d].ok()) C.b[d].define(C.lev, IX_XFACE + d, bn, 0);
-      for (int il = 0; il < C.b[d].n(); ++il)
-        IX_TRY(k::face_restrict(C.b[d].vbox(il), d, C.b[d].v(il), F.b[d].c(il), bn, s));
+      if (C.xfer_lev) {
+        MF tmp(C.xfer_lev.get(), IX_XFACE + d, bn, 0);
+        for (int il = 0; il < tmp.n(); ++il) IX_TRY(k::face_restrict(tmp.vbox(il), d, tmp.v(il), F.b[d].c(il), bn, s));
+        IX_TRY(mf_gather_replicate(C.b[d], tmp, bn, s));
+      } else {
+        for (int il = 0; il < C.b[d].n(); ++il)
+          IX_TRY(k::face_restrict(C.b[d].vbox(il), d, C.b[d].v(il), F.b[d].c(il), bn, s));
+      }
     }
   }
   singular_ = (a_ == 0.0) && all_periodic(*lv_[0].lev);
@@ -198,8 +233,14 @@ int CellMG::vcycle(cudaStream_t s) {
     IX_TRY(smooth(l, L.cor, L.res, info_.nu1, true, s));
     IX_TRY(residual(l, L.rescor, L.cor, L.res, false, s));
     MGLevelCell& C = lv_[l + 1];
-    for (int il = 0; il < C.res.n(); ++il)
-      IX_TRY(k::cc_restrict(C.res.vbox(il), C.res.v(il), L.rescor.c(il), ncomp_, s));
+    if (C.xfer_lev) {
+      for (int il = 0; il < C.xfer.n(); ++il)
+        IX_TRY(k::cc_restrict(C.xfer.vbox(il), C.xfer.v(il), L.rescor.c(il), ncomp_, s));
+      IX_TRY(mf_gather_replicate(C.res, C.xfer, ncomp_, s));
+    } else {
+      for (int il = 0; il < C.res.n(); ++il)
+        IX_TRY(k::cc_restrict(C.res.vbox(il), C.res.v(il), L.rescor.c(il), ncomp_, s));
+    }
   }
   {
     MGLevelCell& B = lv_[nl - 1];
@@ -211,7 +252,7 @@ int CellMG::vcycle(cudaStream_t s) {
     MGLevelCell& L = lv_[l];
     MGLevelCell& C = lv_[l + 1];
     for (int il = 0; il < L.cor.n(); ++il)
-      IX_TRY(k::cc_prolong_add(L.cor.vbox(il), L.cor.v(il), C.cor.c(il), ncomp_, s));
+      IX_TRY(k::cc_prolong_add(L.cor.vbox(il), L.cor.v(il), C.cor.c(C.xfer_lev ? 0 : il), ncomp_, s));   // replicated coarse box: read in place
     IX_TRY(smooth(l, L.cor, L.res, info_.nu2, false, s));
   }
   return IAMRX_OK;
@@ -266,7 +307,12 @@ NodeMG::NodeMG(Level* fine, int max_coarsening) {
     auto c = coarsen_level(*cur, 2);
     if (!c) break;
     lv_.emplace_back();
-    lv_.back().lev_owned = std::move(c);
+    if (auto r = consolidated_level(*c)) {   // from here down: one replicated box per rank, no ghost traffic
+      lv_.back().xfer_lev = std::move(c);
+      lv_.back().lev_owned = std::move(r);
+    } else {
+      lv_.back().lev_owned = std::move(c);
+    }
     lv_.back().lev = lv_.back().lev_owned.get();
     cur = lv_.back().lev;
   }
@@ -276,6 +322,7 @@ NodeMG::NodeMG(Level* fine, int max_coarsening) {
     L.cor.define(L.lev, IX_NODE, 1, 1);
     L.res.define(L.lev, IX_NODE, 1, 1);
     L.rescor.define(L.lev, IX_NODE, 1, 1);
+    if (L.xfer_lev) L.xfer.define(L.xfer_lev.get(), IX_NODE, 1, 1);
   }
 }
 
@@ -287,8 +334,14 @@ int NodeMG::set_sigma(const MF& sigma, cudaStream_t s) {
     MGLevelNode& C = lv_[l];
     MGLevelNode& F = lv_[l - 1];
     IX_TRY(mf_setval(C.sigma, 0.0, 0, 1, 1, s));
-    for (int il = 0; il < C.sigma.n(); ++il)
-      IX_TRY(k::cc_restrict(C.sigma.vbox(il), C.sigma.v(il), F.sigma.c(il), 1, s));
+    if (C.xfer_lev) {
+      MF tmp(C.xfer_lev.get(), IX_CELL, 1, 0);
+      for (int il = 0; il < tmp.n(); ++il) IX_TRY(k::cc_restrict(tmp.vbox(il), tmp.v(il), F.sigma.c(il), 1, s));
+      IX_TRY(mf_gather_replicate(C.sigma, tmp, 1, s));
+    } else {
+      for (int il = 0; il < C.sigma.n(); ++il)
+        IX_TRY(k::cc_restrict(C.sigma.vbox(il), C.sigma.v(il), F.sigma.c(il), 1, s));
+    }
     IX_TRY(mf_fill_boundary(C.sigma, 0, 1, 1, s));
   }
   return IAMRX_OK;
@@ -366,8 +419,14 @@ int NodeMG::vcycle(cudaStream_t s) {
     IX_TRY(residual(l, L.rescor, L.cor, L.res, s));
     IX_TRY(mf_fill_boundary(L.rescor, 0, 1, 1, s));
     MGLevelNode& C = lv_[l + 1];
-    for (int il = 0; il < C.res.n(); ++il)
-      IX_TRY(k::nodal_restrict(C.res.vbox(il), C.res.v(il), L.rescor.c(il), s));
+    if (C.xfer_lev) {
+      for (int il = 0; il < C.xfer.n(); ++il)
+        IX_TRY(k::nodal_restrict(C.xfer.vbox(il), C.xfer.v(il), L.rescor.c(il), s));
+      IX_TRY(mf_gather_replicate(C.res, C.xfer, 1, s));
+    } else {
+      for (int il = 0; il < C.res.n(); ++il)
+        IX_TRY(k::nodal_restrict(C.res.vbox(il), C.res.v(il), L.rescor.c(il), s));
+    }
   }
   {
     MGLevelNode& B = lv_[nl - 1];
@@ -378,7 +437,7 @@ int NodeMG::vcycle(cudaStream_t s) {
     MGLevelNode& L = lv_[l];
     MGLevelNode& C = lv_[l + 1];
     for (int il = 0; il < L.cor.n(); ++il)
-      IX_TRY(k::nodal_interp_add(L.cor.vbox(il), L.cor.v(il), C.cor.c(il), s));
+      IX_TRY(k::nodal_interp_add(L.cor.vbox(il), L.cor.v(il), C.cor.c(C.xfer_lev ? 0 : il), s));
     IX_TRY(smooth(l, L.cor, L.res, info_.nu2, s));
   }
   return IAMRX_OK;

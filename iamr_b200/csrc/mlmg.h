@@ -13,6 +13,10 @@ namespace ix {
 struct MGLevelCell {
   std::unique_ptr<Level> lev_owned;  // coarse levels own their Level
   Level* lev = nullptr;
+  // consolidation: this level is the first REPLICATED one (one box = the domain on every rank); xfer_lev is the
+  // distributed coarsening of the level above, where restrictions land before they are gathered
+  std::unique_ptr<Level> xfer_lev;
+  MF xfer;
   MF acoef;            // 1 comp, 0 ghost (only if a != 0)
   MF b[3];             // face coefs, bncomp comps
   MF cor, res, rescor; // ncomp
@@ -53,6 +57,8 @@ class CellMG {
 struct MGLevelNode {
   std::unique_ptr<Level> lev_owned;
   Level* lev = nullptr;
+  std::unique_ptr<Level> xfer_lev;   // see MGLevelCell
+  MF xfer;
   MF sigma;            // cell, 1 ghost
   MF cor, res, rescor; // nodal, 1 ghost
   MF gs_tmp;           // second phi buffer of the out-of-place fused Gauss-Seidel sweep (lazy)
@@ -77,6 +83,9 @@ class NodeMG {
 
 // coarsen a level by 2 (all boxes must be coarsenable); nullptr if not possible
 std::unique_ptr<Level> coarsen_level(const Level& f, int min_width);
+// consolidation policy: given the distributed coarsening `c` of a level, return the replicated single-box level that
+// should replace it (small boxes: ghost exchanges are pure latency there), or nullptr to stay distributed
+std::unique_ptr<Level> consolidated_level(const Level& c);
 std::unique_ptr<Level> make_level(const iamrx_geom& g, const std::vector<Bx>& boxes,
                                   const std::vector<int>& owner);
 
