@@ -49,6 +49,14 @@ struct iamrx_ns_s {
   bool initial_step = false, initial_iter = false;
   int it_mac = 0, it_visc = 0, it_nodal = 0;
   double* stage = nullptr; size_t stage_n = 0;  // host<->device staging for step_host
+  // step_host: the new density / tracer are final long before the velocity (diffusion solve + nodal projection still
+  // to come), so their device->host copy runs on a second stream underneath the rest of the step
+#if !defined(IX_EMUL)
+  cudaStream_t s2 = nullptr;
+  cudaEvent_t ev_scal = nullptr;
+#endif
+  double* early_out = nullptr;   // host destination of comps Density.. (single local box), or null
+  double* early_buf = nullptr;   // device staging of the packed scalars
 
   bool diffusive_vel() const { return p.visc_coef > 0.0; }
 };
@@ -236,6 +244,15 @@ int advance(iamrx_ns_s& ns, double time, double dt, double* dt_test) {
   IX_TRY(fillpatch(ns, ns.rho_ctime, ns.S_new, Density, 1));   // make_rho_curr_time :618
   for (int il = 0; il < ns.S_new.n(); ++il)                    // scalar_update(tracer) :627 -> NSB.cpp:2887-2896
     IX_TRY(k::scal_update(L.lbox(il), ns.S_new.v(il, Tracer), ns.S_old.c(il, Tracer), ns.aofs.c(il, Tracer), dt, 1, ns.s));
+#if !defined(IX_EMUL)
+  if (ns.early_out && ns.S_new.n() == 1) {   // scalars are final: pack + copy them out underneath the velocity solves
+    IX_CUDA(cudaEventRecord(ns.ev_scal, ns.s));
+    IX_CUDA(cudaStreamWaitEvent(ns.s2, ns.ev_scal, 0));
+    IX_TRY(k::pack(L.lbox(0), ns.early_buf, ns.S_new.c(0, Density), NUM_SCALARS, ns.s2));
+    IX_CUDA(cudaMemcpyAsync(ns.early_out, ns.early_buf, (size_t)L.lbox(0).npts() * NUM_SCALARS * sizeof(double),
+                            cudaMemcpyDeviceToHost, ns.s2));
+  }
+#endif
   // velocity_update :645 -> NSB.cpp:3487: rho_half (:1561-1565), advection update (:3523-3655), diffusion
   IX_TRY(mf_lincomb(ns.rho_half, 0, 0.5, ns.rho_ptime, 0, 0.5, ns.rho_ctime, 0, 1, 1, ns.s));
   for (int il = 0; il < ns.S_new.n(); ++il)
@@ -343,6 +360,9 @@ int iamrx_ns_create(iamrx_level_t lev, const iamrx_ns_params* p, iamrx_ns_t* out
 
 int iamrx_ns_destroy(iamrx_ns_t ns) {
   if (ns && ns->stage) cudaFreeHost(ns->stage);
+#if !defined(IX_EMUL)
+  if (ns && ns->s2) { cudaStreamDestroy(ns->s2); cudaEventDestroy(ns->ev_scal); }
+#endif
   delete ns;
   return IAMRX_OK;
 }
@@ -487,14 +507,38 @@ int iamrx_ns_step_host(iamrx_ns_t nsp, const double* const* host_in, double* con
     IX_CUDA(cudaMemcpyAsync(dbuf, host_in[il], n * sizeof(double), cudaMemcpyHostToDevice, ns.s));
     IX_TRY(k::unpack(L.lbox(il), ns.S_new.v(il), dbuf, NUM_STATE, ns.s));
   }
+  bool early = false;
+#if !defined(IX_EMUL)
+  early = L.nlocal() == 1 && !ns.initial_step && !ns.initial_iter;
+  if (early) {
+    if (!ns.s2) {
+      IX_CUDA(cudaStreamCreateWithFlags(&ns.s2, cudaStreamNonBlocking));
+      IX_CUDA(cudaEventCreateWithFlags(&ns.ev_scal, cudaEventDisableTiming));
+    }
+    ns.early_buf = dev_alloc(maxpts * NUM_SCALARS);
+    if (!ns.early_buf) { dev_free(dbuf); return IAMRX_ERR_CUDA; }
+    ns.early_out = host_out[0] + (size_t)L.lbox(0).npts() * Density;
+  }
+#endif
   int rc = iamrx_ns_step(nsp, dt_io);
-  if (rc != IAMRX_OK) { dev_free(dbuf); return rc; }
+  ns.early_out = nullptr;
+  if (rc != IAMRX_OK) {
+#if !defined(IX_EMUL)
+    if (early) { cudaStreamSynchronize(ns.s2); dev_free(ns.early_buf); }
+#endif
+    dev_free(dbuf);
+    return rc;
+  }
+  const int nout = early ? Density : NUM_STATE;   // velocity only when the scalars already left
   for (int il = 0; il < L.nlocal(); ++il) {
-    const size_t n = (size_t)L.lbox(il).npts() * NUM_STATE;
-    IX_TRY(k::pack(L.lbox(il), dbuf, ns.S_new.c(il), NUM_STATE, ns.s));
+    const size_t n = (size_t)L.lbox(il).npts() * nout;
+    IX_TRY(k::pack(L.lbox(il), dbuf, ns.S_new.c(il), nout, ns.s));
     IX_CUDA(cudaMemcpyAsync(host_out[il], dbuf, n * sizeof(double), cudaMemcpyDeviceToHost, ns.s));
   }
   IX_CUDA(cudaStreamSynchronize(ns.s));
+#if !defined(IX_EMUL)
+  if (early) { IX_CUDA(cudaStreamSynchronize(ns.s2)); dev_free(ns.early_buf); ns.early_buf = nullptr; }
+#endif
   dev_free(dbuf);
   return IAMRX_OK;
 }
