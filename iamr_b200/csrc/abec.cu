@@ -10,6 +10,7 @@
 // All kernels are HBM-bound 7-point stencils: x is unit stride, threadIdx.x
 // runs along x, each CTA covers a (128 x 4) xy-strip of one z-plane so every
 // warp request is a contiguous 256-byte (GSRB: strided 512-byte) span.
+#include <cstdint>
 #include <cstdlib>
 #include <type_traits>
 #include "kernels.h"
@@ -107,6 +108,56 @@ apply_kernel(Bx bx, V4 out, C4 phi, C4 rhs, IX_KARG(AbecDev) op, int nz, int wm)
   if (op.a != 0.0) y += op.a * op.acoef(i, j, k) * p0;
   out(i, j, k, n) = rhs.ok() ? (rhs(i, j, k, n) - y) : y;
 }
+
+#if !defined(IX_EMUL)
+// apply / residual, two cells per thread with 128-bit loads and stores (same expression per cell as apply_kernel:
+// bit-identical).  Needs an even x extent and 16-byte aligned cell pairs in every array (checked by the launcher).
+IX_D double2 ld2(const double* p) { return *reinterpret_cast<const double2*>(p); }
+template <bool HASA>
+__global__ void __launch_bounds__(AP_TX* AP_TY)
+apply2_kernel(Bx bx, V4 out, C4 phi, C4 rhs, IX_KARG(AbecDev) op, int nz, int wm) {
+  const int kz = blockIdx.z % nz;
+  const int n = blockIdx.z / nz;
+  const int k = bx.lo[2] + kz;
+  const int j = bx.lo[1] + blockIdx.y * AP_TY + threadIdx.y;
+  const int i = bx.lo[0] + 2 * (blockIdx.x * AP_TX + threadIdx.x);
+  if (j > bx.hi[1] || i > bx.hi[0]) return;
+  const int nb = (op.bncomp > 1) ? n : 0;
+  const double* bxc = op.bx.p + nb * op.bx.ns + ((i - op.bx.l0) + (j - op.bx.l1) * op.bx.js + (k - op.bx.l2) * op.bx.ks);
+  const double* byc = op.by.p + nb * op.by.ns + ((i - op.by.l0) + (j - op.by.l1) * op.by.js + (k - op.by.l2) * op.by.ks);
+  const double* bzc = op.bz.p + nb * op.bz.ns + ((i - op.bz.l0) + (j - op.bz.l1) * op.bz.js + (k - op.bz.l2) * op.bz.ks);
+  const double* pc = phi.p + n * phi.ns + ((i - phi.l0) + (j - phi.l1) * phi.js + (k - phi.l2) * phi.ks);
+  const int pjs = (int)phi.js, pks = (int)phi.ks;
+  const int oxm = ((wm & 1) && i == bx.lo[0]) ? bx.hi[0] - i : -1, oxp = ((wm & 1) && i + 1 == bx.hi[0]) ? bx.lo[0] - i : 2;
+  const int oym = (((wm & 2) && j == bx.lo[1]) ? bx.hi[1] - j : -1) * pjs, oyp = (((wm & 2) && j == bx.hi[1]) ? bx.lo[1] - j : 1) * pjs;
+  const int ozm = (((wm & 4) && k == bx.lo[2]) ? bx.hi[2] - k : -1) * pks, ozp = (((wm & 4) && k == bx.hi[2]) ? bx.lo[2] - k : 1) * pks;
+  const double2 p0 = ld2(pc), pym = ld2(pc + oym), pyp = ld2(pc + oyp), pzm = ld2(pc + ozm), pzp = ld2(pc + ozp);
+  const double pxm = pc[oxm], pxp = pc[oxp];
+  const double2 b01 = ld2(bxc); const double b2 = bxc[2];
+  const double2 bym = ld2(byc), byp = ld2(byc + (int)op.by.js), bzm = ld2(bzc), bzp = ld2(bzc + (int)op.bz.ks);
+  double y0 = -op.dhx * (b01.y * (p0.y - p0.x) - b01.x * (p0.x - pxm)) - op.dhy * (byp.x * (pyp.x - p0.x) - bym.x * (p0.x - pym.x)) -
+              op.dhz * (bzp.x * (pzp.x - p0.x) - bzm.x * (p0.x - pzm.x));
+  double y1 = -op.dhx * (b2 * (pxp - p0.y) - b01.y * (p0.y - p0.x)) - op.dhy * (byp.y * (pyp.y - p0.y) - bym.y * (p0.y - pym.y)) -
+              op.dhz * (bzp.y * (pzp.y - p0.y) - bzm.y * (p0.y - pzm.y));
+  if (HASA) {
+    const double2 ac = ld2(op.acoef.p + ((i - op.acoef.l0) + (j - op.acoef.l1) * op.acoef.js + (k - op.acoef.l2) * op.acoef.ks));
+    y0 += op.a * ac.x * p0.x; y1 += op.a * ac.y * p0.y;
+  }
+  double2 r;
+  if (rhs.ok()) {
+    const double2 rh = ld2(rhs.p + n * rhs.ns + ((i - rhs.l0) + (j - rhs.l1) * rhs.js + (k - rhs.l2) * rhs.ks));
+    r.x = rh.x - y0; r.y = rh.y - y1;
+  } else { r.x = y0; r.y = y1; }
+  *reinterpret_cast<double2*>(out.p + n * out.ns + ((i - out.l0) + (j - out.l1) * out.js + (k - out.l2) * out.ks)) = r;
+}
+
+// every (lo0 + 2m, j, k, n) element of the view is 16-byte aligned
+template <class V> inline bool pairs_aligned(const V& v, const Bx& bx) {
+  if (!v.p) return true;
+  const double* q = v.p + ((bx.lo[0] - v.l0) + (bx.lo[1] - v.l1) * v.js + (bx.lo[2] - v.l2) * v.ks);
+  return ((uintptr_t)q % 16 == 0) && v.js % 2 == 0 && v.ks % 2 == 0 && v.ns % 2 == 0;
+}
+#endif
 
 __global__ void flux_kernel(Bx bx, V4 fx, V4 fy, V4 fz, C4 phi, IX_KARG(AbecDev) op, double fxs, double fys,
                             double fzs, int comp) {
@@ -584,6 +635,15 @@ int abec_gsrb_sweep(const Bx& bx, V4 phi_out, C4 phi_in, C4 rhs, const Abec& op,
 int abec_apply(const Bx& bx, V4 out, C4 phi, C4 rhs, const Abec& op, int ncomp, cudaStream_t s, int wrapmask) {
   if (!bx.ok()) return IAMRX_OK;
   ProfScope prof_(IAMRX_PROF_ABEC_APPLY, bx.npts(), (double)bx.npts() * ncomp * ((op.a != 0.0 ? 56.0 : 48.0) + (rhs.ok() ? 0.0 : -8.0)), s);
+#if !defined(IX_EMUL)
+  if (bx.nx() % 2 == 0 && pairs_aligned(out, bx) && pairs_aligned(phi, bx) && pairs_aligned(rhs, bx) && pairs_aligned(op.acoef, bx) &&
+      pairs_aligned(op.bx, bx) && pairs_aligned(op.by, bx) && pairs_aligned(op.bz, bx)) {
+    const dim3 grd(cdiv(bx.nx() / 2, AP_TX), cdiv(bx.ny(), AP_TY), bx.nz() * ncomp);
+    if (op.a != 0.0) IX_LAUNCH(apply2_kernel<true>, grd, dim3(AP_TX, AP_TY, 1), 0, s, bx, out, phi, rhs, to_dev(op), bx.nz(), wrapmask);
+    else IX_LAUNCH(apply2_kernel<false>, grd, dim3(AP_TX, AP_TY, 1), 0, s, bx, out, phi, rhs, to_dev(op), bx.nz(), wrapmask);
+    return check_launch("abec_apply2");
+  }
+#endif
   IX_LAUNCH(apply_kernel, grid_for(bx, AP_TX, AP_TY, bx.nz() * ncomp), dim3(AP_TX, AP_TY, 1), 0, s, 
       bx, out, phi, rhs, to_dev(op), bx.nz(), wrapmask);
   return check_launch("abec_apply");
