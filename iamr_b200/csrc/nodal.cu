@@ -494,6 +494,85 @@ gs_sweep_kernel(Bx bx, V4 out, C4 pin, C4 padj, C4 rhs, C4 sig, IX_KARG(Q1F) q, 
 }  // namespace fused
 #endif
 
+#if !defined(IX_EMUL)
+// ---- z-marching apply / residual (27-point stencil, register window) -----------------------------
+// One thread owns a node column (i, j) and marches through KB planes keeping the three phi planes (3 x 3 values each)
+// and the two sigma planes (2 x 2 cells each) of the current node in registers: per node it loads ONE new phi plane
+// (9 values) and one new sigma plane (4 values) instead of 27 + 8, which takes the kernel off the L1 pipe.  The
+// arithmetic is the row form of fused::pass (same rounding as the fused smoother).
+namespace march {
+struct Pl { double v[3][3]; };   // [row j-1, j, j+1][column i-1, i, i+1]
+struct Sg { double m0, m1, p0, p1; };   // cells (i-1, j-1), (i-1, j), (i, j-1), (i, j) of one cell plane
+
+template <int KB, int MINB>
+__global__ void __launch_bounds__(TX* TY, MINB)
+adotx_march_kernel(Bx bx, V4 out, C4 phi, C4 rhs, C4 sig, IX_KARG(fused::Q1F) q, int wm, int nchunk) {
+  const int i = bx.lo[0] + blockIdx.x * TX + threadIdx.x;
+  const int j = bx.lo[1] + blockIdx.y * TY + threadIdx.y;
+  if (i > bx.hi[0] || j > bx.hi[1]) return;
+  const int kc0 = bx.lo[2] + KB * (int)blockIdx.z;
+  const int kc1 = min(kc0 + KB - 1, bx.hi[2]);
+  (void)nchunk;
+  // neighbour columns / rows (periodic images when the box spans the domain: node hi duplicates node lo)
+  const int im = ((wm & 1) && i == bx.lo[0]) ? bx.hi[0] - 1 : i - 1, ip = ((wm & 1) && i == bx.hi[0]) ? bx.lo[0] + 1 : i + 1;
+  const int jm = ((wm & 2) && j == bx.lo[1]) ? bx.hi[1] - 1 : j - 1, jp = ((wm & 2) && j == bx.hi[1]) ? bx.lo[1] + 1 : j + 1;
+  const int pjs = (int)phi.js, sjs = (int)sig.js;
+  const double* pcol = phi.p + (i - phi.l0);
+  const int ox[3] = {im - i, 0, ip - i};
+  const int oy[3] = {(jm - phi.l1) * pjs, (j - phi.l1) * pjs, (jp - phi.l1) * pjs};
+  const double* scol = sig.p + (i - sig.l0) + (j - sig.l1) * sjs;
+  auto zplane = [&](int k) {  // node plane index with periodic image
+    if (!(wm & 4)) return k;
+    return k < bx.lo[2] ? bx.hi[2] - 1 : (k > bx.hi[2] ? bx.lo[2] + 1 : k);
+  };
+  auto load_pl = [&](Pl& P, int k) {
+    const double* b = pcol + (int64_t)(zplane(k) - phi.l2) * phi.ks;
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+#pragma unroll
+      for (int c = 0; c < 3; ++c) P.v[r][c] = b[oy[r] + ox[c]];
+  };
+  auto load_sg = [&](Sg& S, int kcell) {  // cell plane kcell (ghost cells of sigma are filled)
+    const double* b = scol + (int64_t)(kcell - sig.l2) * sig.ks;
+    S.m0 = b[-1 - sjs]; S.m1 = b[-1]; S.p0 = b[-sjs]; S.p1 = b[0];
+  };
+  // coupling of a node with the plane above / below it through ONE cell layer S: U(X, S) is what plane X contributes to
+  // the node on the other side of layer S.  The lower plane's term is computed one iteration early (when that plane and
+  // its layer are both in registers) and carried as a scalar, so only two raw planes stay live -- which leaves room to
+  // load the NEXT plane and layer one iteration ahead of their use (the loop is latency-, not bandwidth-bound).
+  auto U = [&](const Pl& X, const Sg& S) {
+    const double mk = S.m0 + S.m1, pk = S.p0 + S.p1;
+    return q.f1jk * (S.m0 * X.v[0][0] + S.p0 * X.v[0][2] + S.m1 * X.v[2][0] + S.p1 * X.v[2][2]) +
+           q.f0jk * ((S.m0 + S.p0) * X.v[0][1] + (S.m1 + S.p1) * X.v[2][1]) + q.f1k * (mk * X.v[1][0] + pk * X.v[1][2]) +
+           q.f0k * (mk + pk) * X.v[1][1];
+  };
+  Pl B, C, D;
+  Sg S0, S1, S2;
+  {
+    Pl A;
+    load_pl(A, kc0 - 1); load_sg(S0, kc0 - 1);
+    load_pl(B, kc0); load_sg(S1, kc0);
+    load_pl(C, kc0 + 1);
+    D = C; S2 = S1;
+    double ua = U(A, S0);
+    for (int k = kc0; k <= kc1; ++k) {
+      if (k < kc1) { load_pl(D, k + 2); load_sg(S2, k + 1); }   // next iteration's plane and layer
+      const double mj0 = S0.m0 + S1.m0, mj1 = S0.m1 + S1.m1, pj0 = S0.p0 + S1.p0, pj1 = S0.p1 + S1.p1;
+      const double mc = mj0 + mj1, pc = pj0 + pj1;
+      const double a1j = mj0 * B.v[0][0] + pj0 * B.v[0][2] + mj1 * B.v[2][0] + pj1 * B.v[2][2];
+      const double a0j = (mj0 + pj0) * B.v[0][1] + (mj1 + pj1) * B.v[2][1];
+      const double a1c = mc * B.v[1][0] + pc * B.v[1][2];
+      const double s0 = q.f0c * (mc + pc);
+      const double y = s0 * B.v[1][1] + q.f1c * a1c + q.f1j * a1j + q.f0j * a0j + ua + U(C, S1);
+      out(i, j, k) = rhs.ok() ? (rhs(i, j, k) - y) : y;
+      ua = U(B, S1);          // plane k seen from node k+1 through layer k
+      B = C; C = D; S0 = S1; S1 = S2;
+    }
+  }
+}
+}  // namespace march
+#endif
+
 // The tile kernels measured SLOWER than the one-thread-per-node kernels on B200 (nodal GS colour
 // pass at 257^3: 186 us vs 105 us; profiles/r01_notes.md), so they are opt-in (IAMRX_NODAL_TILE=1)
 // and kept for the parity tests and further tuning.
@@ -527,6 +606,31 @@ int nodal_adotx(const Bx& nbx, V4 out, C4 phi, C4 rhs, C4 sig, const double dxin
     IX_LAUNCH((nodal_tile_kernel<1, false>), grd, dim3(TXU, TYU, 1), 0, s, nbx, out, phi, rhs, sig, f[0], f[1], f[2],
               nbx.lo[0], nbx.lo[1], nbx.lo[2], wrapmask);
     return check_launch("nodal_adotx_tile");
+  }
+#endif
+#if !defined(IX_EMUL)
+  {
+    static int on = -1;
+    if (on < 0) { const char* e = getenv("IAMRX_ADOTX_MARCH"); on = (e && e[0] == '0') ? 0 : 1; }
+    if (on && nbx.nz() >= 8 && out.p != phi.p) {
+      using namespace fused;
+      Q1F q;
+      q.f0c = q1_factor(false, false, false, f[0], f[1], f[2]); q.f1c = q1_factor(true, false, false, f[0], f[1], f[2]);
+      q.f0j = q1_factor(false, true, false, f[0], f[1], f[2]);  q.f1j = q1_factor(true, true, false, f[0], f[1], f[2]);
+      q.f0k = q1_factor(false, false, true, f[0], f[1], f[2]);  q.f1k = q1_factor(true, false, true, f[0], f[1], f[2]);
+      q.f0jk = q1_factor(false, true, true, f[0], f[1], f[2]);  q.f1jk = q1_factor(true, true, true, f[0], f[1], f[2]);
+      static int kb = -1, minb = -1;   // tuning knobs: planes per thread, resident CTAs per SM the kernel is compiled for
+      if (kb < 0) { const char* e = getenv("IAMRX_ADOTX_KB"); kb = e ? atoi(e) : 32; }
+      if (minb < 0) { const char* e = getenv("IAMRX_ADOTX_MINB"); minb = e ? atoi(e) : 2; }
+      const int KBv = (kb >= 32) ? 32 : 16;
+      const int nchunk = cdiv(nbx.nz(), KBv);
+      const dim3 grd(cdiv(nbx.nx(), TX), cdiv(nbx.ny(), TY), nchunk), blk(TX, TY, 1);
+      if (KBv == 32 && minb >= 3) IX_LAUNCH((march::adotx_march_kernel<32, 3>), grd, blk, 0, s, nbx, out, phi, rhs, sig, q, wrapmask, nchunk);
+      else if (KBv == 32) IX_LAUNCH((march::adotx_march_kernel<32, 2>), grd, blk, 0, s, nbx, out, phi, rhs, sig, q, wrapmask, nchunk);
+      else if (minb >= 3) IX_LAUNCH((march::adotx_march_kernel<16, 3>), grd, blk, 0, s, nbx, out, phi, rhs, sig, q, wrapmask, nchunk);
+      else IX_LAUNCH((march::adotx_march_kernel<16, 2>), grd, blk, 0, s, nbx, out, phi, rhs, sig, q, wrapmask, nchunk);
+      return check_launch("nodal_adotx_march");
+    }
   }
 #endif
   IX_LAUNCH(adotx_kernel, grid_for(nbx), dim3(TX, TY, 1), 0, s, nbx, out, phi, rhs, sig, f[0], f[1], f[2], wrapmask);
