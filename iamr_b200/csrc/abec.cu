@@ -347,13 +347,17 @@ namespace sweep {
 constexpr int PX = 32;              // pairs per row: one warp
 constexpr int PW = 2 * PX;          // plane width in shared memory: tile + 2 cells on either side
 constexpr int TWMAX = PW - 4;       // 60
-constexpr int TY = 14;              // tile rows
-constexpr int PH = TY + 4;          // plane rows in shared memory
-constexpr int NW = TY + 2;          // warps: one per row of the red region
-constexpr int NT = 32 * NW;         // 512 threads
 constexpr int NP = 4, NM = 3;       // ring depths: old planes / mixed planes
-constexpr int PLANE = PW * PH;
-constexpr int SMEM_BYTES = (NP + NM) * PLANE * (int)sizeof(double);
+// tile rows TY are a template parameter: 14 (16 warps, one CTA per SM) or 6 (8 warps, two CTAs per SM: two
+// independent barrier domains overlap each other's waits at the price of more halo rows)
+template <int TY> struct Cfg {
+  static constexpr int PH = TY + 4;          // plane rows in shared memory
+  static constexpr int NW = TY + 2;          // warps: one per row of the red region
+  static constexpr int NT = 32 * NW;
+  static constexpr int PLANE = PW * PH;
+  static constexpr int SMEM_BYTES = (NP + NM) * PLANE * (int)sizeof(double);
+  static constexpr int MINB = (TY <= 6) ? 2 : 1;
+};
 
 IX_D int wrapi(int g, int lo, int n) {  // periodic image in [lo, lo+n)
   int m = (g - lo) % n;
@@ -394,7 +398,7 @@ struct Ctx {      // per-thread constants of the march
 //   cur : coefficients of plane r (loaded one plane ahead)
 //   kp  : coefficients of the second-colour cell of plane r-1 (cell RF of the pair as well: the colours swap between planes)
 struct Coef { double bxm, bxp, bym, byp, bzm, bzp, rh, ac; };
-template <bool HASA, int RF>
+template <bool HASA, int RF, int PLANE>
 IX_D void plane_step(const Ctx& t, const AbecDev& op, double omega, int rr, bool do_black, const Raw& cur, const Coef& kp, double* po) {
   const double* Pm = t.P + ((rr - 1) & (NP - 1)) * PLANE;
   const double* Pc = t.P + (rr & (NP - 1)) * PLANE;
@@ -421,9 +425,10 @@ IX_D void plane_step(const Ctx& t, const AbecDev& op, double omega, int rr, bool
   }
 }
 
-template <bool HASA>
-__global__ void __launch_bounds__(NT, 1)
+template <bool HASA, int TY>
+__global__ void __launch_bounds__(Cfg<TY>::NT, Cfg<TY>::MINB)
 gsrb_sweep_kernel(Bx bx, V4 out, C4 pin, C4 rhs, IX_KARG(AbecDev) op, double omega, int rb0, int tw, int th, int nzc, int nchunk) {
+  constexpr int PLANE = Cfg<TY>::PLANE;
   extern __shared__ double sm[];
   Ctx t;
   t.P = sm;                  // [NP][PH][PW] old values
@@ -525,7 +530,7 @@ gsrb_sweep_kernel(Bx bx, V4 out, C4 pin, C4 rhs, IX_KARG(AbecDev) op, double ome
     asm volatile("cp.async.wait_group 0;" ::: "memory");
     __syncthreads();
     if (kk + 1 < nred) stage();
-    plane_step<HASA, RF>(t, op, omega, kk + 4, kk >= 2, cur, kp, outp_ + ko_out);
+    plane_step<HASA, RF, PLANE>(t, op, omega, kk + 4, kk >= 2, cur, kp, outp_ + ko_out);
     const bool w = gk_out == bx.hi[2];
     gk_out = w ? bx.lo[2] : gk_out + 1;
     ko_out = w ? ko_out - (nz - 1) * oks : ko_out + oks;
@@ -602,32 +607,39 @@ int abec_gsrb_sweep(const Bx& bx, V4 phi_out, C4 phi_in, C4 rhs, const Abec& op,
   using namespace sweep;
   // algorithmic bytes as for two colour passes (SURVEY.md 8d counts no temporal blocking); the kernel moves about 56 B/cell
   ProfScope prof_(IAMRX_PROF_ABEC_GSRB, bx.npts(), (double)bx.npts() * ncomp * 2.0 * (op.a != 0.0 ? 56.0 : 48.0), s);
+  static int ty = -1;   // tile rows: 14 (default) or 6 (IAMRX_GSRB_FUSED_TY)
+  if (ty < 0) { const char* e = getenv("IAMRX_GSRB_FUSED_TY"); ty = (e && atoi(e) == 6) ? 6 : 14; }
   static bool attr_set = false;
   if (!attr_set) {
-    IX_CUDA(cudaFuncSetAttribute(gsrb_sweep_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-    IX_CUDA(cudaFuncSetAttribute(gsrb_sweep_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    IX_CUDA(cudaFuncSetAttribute(gsrb_sweep_kernel<false, 14>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<14>::SMEM_BYTES));
+    IX_CUDA(cudaFuncSetAttribute(gsrb_sweep_kernel<true, 14>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<14>::SMEM_BYTES));
+    IX_CUDA(cudaFuncSetAttribute(gsrb_sweep_kernel<false, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<6>::SMEM_BYTES));
+    IX_CUDA(cudaFuncSetAttribute(gsrb_sweep_kernel<true, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<6>::SMEM_BYTES));
     attr_set = true;
   }
   // even tile widths/heights that split the box evenly
-  const int ntx = cdiv(bx.nx(), TWMAX), nty = cdiv(bx.ny(), TY);
+  const int ntx = cdiv(bx.nx(), TWMAX), nty = cdiv(bx.ny(), ty);
   const int tw = 2 * cdiv(cdiv(bx.nx(), ntx), 2), th = 2 * cdiv(cdiv(bx.ny(), nty), 2);
   const int gx = cdiv(bx.nx(), tw), gy = cdiv(bx.ny(), th);
-  // z chunks: fill whole waves of one CTA per SM (each chunk recomputes 2 extra red planes; >= 8 planes per chunk)
+  // z chunks: fill whole waves of resident CTAs (each chunk recomputes 2 extra red planes; >= 8 planes per chunk)
   int nchunk = 1;
   {
-    const int nxy = gx * gy * ncomp, nsm = 148;
+    const int nxy = gx * gy * ncomp, nslots = 148 * (ty == 6 ? 2 : 1);
     double best = 1e30;
     for (int c = 1; c <= bx.nz() / 8; ++c) {
       const int nzc_ = cdiv(bx.nz(), c), cc = cdiv(bx.nz(), nzc_);
-      const double cost = (double)cdiv(nxy * cc, nsm) * (nzc_ + 2);   // waves x iterations per CTA
+      const double cost = (double)cdiv(nxy * cc, nslots) * (nzc_ + 2);   // waves x iterations per CTA
       if (cost < best - 1e-9) { best = cost; nchunk = cc; }
     }
   }
   const int nzc = cdiv(bx.nz(), nchunk);
   nchunk = cdiv(bx.nz(), nzc);
   const dim3 grd(gx, gy, nchunk * ncomp);
-  if (op.a != 0.0) IX_LAUNCH(gsrb_sweep_kernel<true>, grd, dim3(NT, 1, 1), SMEM_BYTES, s, bx, phi_out, phi_in, rhs, to_dev(op), omega, rb0, tw, th, nzc, nchunk);
-  else IX_LAUNCH(gsrb_sweep_kernel<false>, grd, dim3(NT, 1, 1), SMEM_BYTES, s, bx, phi_out, phi_in, rhs, to_dev(op), omega, rb0, tw, th, nzc, nchunk);
+#define IX_SWEEP(HA, T) IX_LAUNCH((gsrb_sweep_kernel<HA, T>), grd, dim3(Cfg<T>::NT, 1, 1), Cfg<T>::SMEM_BYTES, s, bx, phi_out, phi_in, rhs, \
+                                  to_dev(op), omega, rb0, tw, th, nzc, nchunk)
+  if (ty == 6) { if (op.a != 0.0) IX_SWEEP(true, 6); else IX_SWEEP(false, 6); }
+  else { if (op.a != 0.0) IX_SWEEP(true, 14); else IX_SWEEP(false, 14); }
+#undef IX_SWEEP
   return check_launch("abec_gsrb_sweep");
 #endif
 }

@@ -27,6 +27,22 @@ if what == 'adotx':
     tphi, fphi = fab(nodes, 1); tout, fout = fab(nodes, 1); trhs, frhs = fab(nodes, 1); tsig, fsig = fab(cells, 1)
     fn = lambda: lib.check(lib.iamrx_nodal_adotx_box(C.byref(nbx), C.byref(fout), C.byref(fphi), C.byref(frhs), C.byref(fsig), d3(DXINV), s))
     nbytes = 32.0 * (n + 1) ** 3
+elif what in ('gsrb', 'gsrb_sweep'):
+    tp, fp = fab(cells, 1); tp2, fp2 = fab(cells, 1); tr, fr = fab(cells, 0)
+    tb = [fab(tuple(m + (1 if d == q else 0) for q, m in enumerate(cells)), 0) for d in range(3)]
+    for t, _ in tb:
+        t.add_(0.5)
+    fb = [f for _, f in tb]
+    bx = box_of((0, 0, 0), (n - 1, n - 1, n - 1))
+    if what == 'gsrb':
+        def fn():
+            for rb in range(2):
+                lib.check(lib.iamrx_abec_gsrb_box(C.byref(bx), C.byref(fp), C.byref(fr), 0.0, 1.0, None, C.byref(fb[0]), C.byref(fb[1]), C.byref(fb[2]),
+                                                  d3(DXINV), 1.15, rb, 1, s))
+    else:
+        fn = lambda: lib.check(lib.iamrx_abec_gsrb_sweep_box(C.byref(bx), C.byref(fp2), C.byref(fp), C.byref(fr), 0.0, 1.0, None, C.byref(fb[0]),
+                                                             C.byref(fb[1]), C.byref(fb[2]), d3(DXINV), 1.15, 1, s))
+    nbytes = 96.0 * n ** 3
 else:
     raise SystemExit("unknown kernel")
 for _ in range(3):
