@@ -488,9 +488,10 @@ IX_D void cp_async8(double* smem_dst, const double* gsrc) {
 // from whatever its neighbours hold (possibly garbage, always inside the shared allocation).  Values that
 // reach a store are only ever derived from needed, fully defined quantities (the dependence cone of the
 // tile interior lies inside the site box), so the extra lanes cost nothing and the branches disappear.
+template <bool SAMEFLUX>   // the flux velocities are the MAC velocities (everything but the sync call)
 __global__ void __launch_bounds__(NT, 1)
 aofs_tile_kernel(IX_KARG(EsArgs) a, IX_KARG(EsOut) out, V4 aofs, double volinv, double dxi, double dyi, double dzi,
-                 int is_sync, int ntz) {
+                 int is_sync, int ncomp) {
   extern __shared__ double sm_raw[];
   double* const Q = sm_raw + PAD;
   double* const AL = Q + NQ;        // L_x, L_y, L_z
@@ -498,12 +499,12 @@ aofs_tile_kernel(IX_KARG(EsArgs) a, IX_KARG(EsOut) out, V4 aofs, double volinv, 
   double* const AT = AE + 3 * NS;   // T_x, T_y, T_z; then final lo states
   double* const AC = AT + 3 * NS;   // corner yz, zx, zy
   const int tid = threadIdx.x;
-  const int n = (int)blockIdx.z / ntz;
-  const int l0 = a.bx.lo[0] + TB * (int)blockIdx.x, l1 = a.bx.lo[1] + TB * (int)blockIdx.y,
-            l2 = a.bx.lo[2] + TB * ((int)blockIdx.z % ntz);
-  {  // stage 0: q on the tile grown by 3, asynchronously (16 lanes per row of 14, 64 rows per pass)
-    const double* Sp = a.S.p + n * a.S.ns + off32(a.S, l0 - 3, l1 - 3, l2 - 3);
-    const int js = (int)a.S.js, ks = (int)a.S.ks;
+  const int l0 = a.bx.lo[0] + TB * (int)blockIdx.x, l1 = a.bx.lo[1] + TB * (int)blockIdx.y, l2 = a.bx.lo[2] + TB * (int)blockIdx.z;
+  // stage 0: q of one component on the tile grown by 3, asynchronously (16 lanes per row of 14, 64 rows per pass)
+  const int sjs = (int)a.S.js, sks = (int)a.S.ks;
+  const double* Sp0 = a.S.p + off32(a.S, l0 - 3, l1 - 3, l2 - 3);
+  auto stage_q = [&](int n) {
+    const double* Sp = Sp0 + n * a.S.ns;
     const int x = tid & 15, r0 = tid >> 4;
     if (x < QE) {
 #pragma unroll
@@ -511,27 +512,43 @@ aofs_tile_kernel(IX_KARG(EsArgs) a, IX_KARG(EsOut) out, V4 aofs, double volinv, 
         const int r = r0 + 64 * m;
         if (r < QQ) {
           const int z = r / QE, y = r - z * QE;
-          cp_async8(&Q[x + r * QE], Sp + x + y * js + z * ks);
+          cp_async8(&Q[x + r * QE], Sp + x + y * sjs + z * sks);
         }
       }
     }
     asm volatile("cp.async.commit_group;" ::: "memory");
-  }
+  };
+  stage_q(0);
   const bool act = tid < NS;
   const int t = act ? tid : 0;
   const int sk = t / GG, sj = (t - sk * GG) / G, si = t - sk * GG - sj * G;
   const int i = l0 - 1 + si, j = l1 - 1 + sj, k = l2 - 1 + sk;
   const bool fx = act && si >= 1, fy = act && sj >= 1, fz = act && sk >= 1;          // low face is a face of the tile
   const bool inx = fx && si <= TB, iny = fy && sj <= TB, inz = fz && sk <= TB;      // cell index inside the tile
-  const bool cs = a.iconserv[n] != 0;
   const bool hasf = a.force.ok();
-  // global inputs of this site (overlap the q staging)
+  // global inputs of this site that all components share (overlap the q staging): MAC and flux velocities, divu
   const double* pu = a.umac.p + off32(a.umac, i, j, k);
   const double* pv = a.vmac.p + off32(a.vmac, i, j, k);
   const double* pw = a.wmac.p + off32(a.wmac, i, j, k);
   const double um = pu[0], up = pu[1], vm = pv[0], vp = pv[(int)a.vmac.js], wm = pw[0], wp = pw[(int)a.wmac.ks];
-  const double fv = hasf ? a.force.p[n * a.force.ns + off32(a.force, i, j, k)] : 0.0;
-  const double dv = (cs && a.divu.ok()) ? a.divu.p[off32(a.divu, i, j, k)] : 0.0;
+  double ufm_ = 0, ufp_ = 0, vfm_ = 0, vfp_ = 0, wfm_ = 0, wfp_ = 0;
+  if (!SAMEFLUX) {
+    const double* qu = a.uflx.p + off32(a.uflx, i, j, k);
+    const double* qv = a.vflx.p + off32(a.vflx, i, j, k);
+    const double* qw = a.wflx.p + off32(a.wflx, i, j, k);
+    ufm_ = qu[0]; ufp_ = qu[1]; vfm_ = qv[0]; vfp_ = qv[(int)a.vflx.js]; wfm_ = qw[0]; wfp_ = qw[(int)a.wflx.ks];
+  }
+  const double ufm = SAMEFLUX ? um : ufm_, ufp = SAMEFLUX ? up : ufp_, vfm = SAMEFLUX ? vm : vfm_, vfp = SAMEFLUX ? vp : vfp_,
+               wfm = SAMEFLUX ? wm : wfm_, wfp = SAMEFLUX ? wp : wfp_;
+  const double dv0 = a.divu.ok() ? a.divu.p[off32(a.divu, i, j, k)] : 0.0;
+  const double* pf = hasf ? a.force.p + off32(a.force, i, j, k) : nullptr;
+  double fv_next = hasf ? pf[0] : 0.0;
+  // The CTA works through the components of its tile one after the other: the velocities above are loaded once, and
+  // the next component's q is staged (cp.async) underneath stages 2-7 of the current one (q is dead after stage 1).
+  for (int n = 0; n < ncomp; ++n) {
+  const bool cs = a.iconserv[n] != 0;
+  const double fv = fv_next;
+  const double dv = cs ? dv0 : 0.0;
   asm volatile("cp.async.wait_group 0;" ::: "memory");
   __syncthreads();
   double q0, Hx, Hy, Hz;
@@ -550,6 +567,10 @@ aofs_tile_kernel(IX_KARG(EsArgs) a, IX_KARG(EsOut) out, V4 aofs, double volinv, 
     AL[t] = Lx; AL[NS + t] = Ly; AL[2 * NS + t] = Lz;
   }
   __syncthreads();
+  if (n + 1 < ncomp) {   // q is consumed: stage the next component into the same buffer, fetch its force
+    stage_q(n + 1);
+    if (hasf) fv_next = pf[(n + 1) * a.force.ns];
+  }
   // stage 2: upwinded edge states on the low faces
   const double lox = AL[t - 1], loy = AL[NS + t - G], loz = AL[2 * NS + t - GG];
   const double xe = upsel(lox, Hx, um), ye = upsel(loy, Hy, vm), ze = upsel(loz, Hz, wm);
@@ -593,14 +614,6 @@ aofs_tile_kernel(IX_KARG(EsArgs) a, IX_KARG(EsOut) out, V4 aofs, double volinv, 
   }
   __syncthreads();
   // stage 6: final states on the low faces (AE is free again: the corner arrays were consumed in stage 5)
-  const bool same_flux_vel = (a.uflx.p == a.umac.p) && (a.vflx.p == a.vmac.p) && (a.wflx.p == a.wmac.p);
-  double ufm = um, ufp = up, vfm = vm, vfp = vp, wfm = wm, wfp = wp;
-  if (!same_flux_vel) {
-    const double* qu = a.uflx.p + off32(a.uflx, i, j, k);
-    const double* qv = a.vflx.p + off32(a.vflx, i, j, k);
-    const double* qw = a.wflx.p + off32(a.wflx, i, j, k);
-    ufm = qu[0]; ufp = qu[1]; vfm = qv[0]; vfp = qv[(int)a.vflx.js]; wfm = qw[0]; wfp = qw[(int)a.wflx.ks];
-  }
   const double xs = upsel(AT[t - 1], Hx, um), ys = upsel(AT[NS + t - G], Hy, vm), zs = upsel(AT[2 * NS + t - GG], Hz, wm);
   AE[t] = xs; AE[NS + t] = ys; AE[2 * NS + t] = zs;
   if (out.xed.ok()) {  // optional outputs: every face is written by exactly one tile
@@ -624,6 +637,7 @@ aofs_tile_kernel(IX_KARG(EsArgs) a, IX_KARG(EsOut) out, V4 aofs, double volinv, 
     if (is_sync) *pa -= upd;
     else *pa = -upd;
   }
+  }  // components
 }
 
 inline bool fits32(const C4& v, const Bx& bx, int ng) {  // offsets of grow(bx, ng+1) fit in 32 bits
@@ -677,13 +691,16 @@ int compute_aofs(const Bx& bx, const AofsArgs& a, const AdvGeom& g, cudaStream_t
   if (!a.staged && tile::aofs_tile_ok(bx, a)) {
     static bool attr_set = false;
     if (!attr_set) {
-      IX_CUDA(cudaFuncSetAttribute(tile::aofs_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tile::SMEM_BYTES));
+      IX_CUDA(cudaFuncSetAttribute(tile::aofs_tile_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, tile::SMEM_BYTES));
+      IX_CUDA(cudaFuncSetAttribute(tile::aofs_tile_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, tile::SMEM_BYTES));
       attr_set = true;
     }
-    const int ntz = bx.nz() / tile::TB;
-    IX_LAUNCH(tile::aofs_tile_kernel, dim3(bx.nx() / tile::TB, bx.ny() / tile::TB, ntz * a.ncomp), dim3(tile::NT, 1, 1),
-              tile::SMEM_BYTES, s, e, out, a.aofs, 1.0 / (g.dx[0] * g.dx[1] * g.dx[2]), 1.0 / g.dx[0], 1.0 / g.dx[1],
-              1.0 / g.dx[2], a.is_sync, ntz);
+    const dim3 grd(bx.nx() / tile::TB, bx.ny() / tile::TB, bx.nz() / tile::TB);
+    const bool same = (a.uflx.p == a.umac.p) && (a.vflx.p == a.vmac.p) && (a.wflx.p == a.wmac.p);
+    if (same) IX_LAUNCH(tile::aofs_tile_kernel<true>, grd, dim3(tile::NT, 1, 1), tile::SMEM_BYTES, s, e, out, a.aofs,
+                        1.0 / (g.dx[0] * g.dx[1] * g.dx[2]), 1.0 / g.dx[0], 1.0 / g.dx[1], 1.0 / g.dx[2], a.is_sync, a.ncomp);
+    else IX_LAUNCH(tile::aofs_tile_kernel<false>, grd, dim3(tile::NT, 1, 1), tile::SMEM_BYTES, s, e, out, a.aofs,
+                   1.0 / (g.dx[0] * g.dx[1] * g.dx[2]), 1.0 / g.dx[0], 1.0 / g.dx[1], 1.0 / g.dx[2], a.is_sync, a.ncomp);
     return check_launch("aofs_tile");
   }
 #endif
