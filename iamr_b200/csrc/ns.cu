@@ -43,6 +43,8 @@ struct iamrx_ns_s {
   MF sig;               // 1/rho_half, 1 ghost
   MF mac_phi;           // 1 ghost
   MF tf0;               // estTimeStep forces, 0 ghost
+  MF seta[3];           // tracer diffusivity on faces (getDiffusivity: constant ns.scal_diff_coefs, NS.cpp:2051-2119)
+  MF s1, r1, svisc, ones;  // tracer diffusion work: Soln (1 ghost), Rhs, visc term (1 ghost), alpha = 1
 
   double time = 0.0, dt_level = 0.0, dt_min = 1.0e100;
   int nstep = 0;
@@ -59,6 +61,8 @@ struct iamrx_ns_s {
   double* early_buf = nullptr;   // device staging of the packed scalars
 
   bool diffusive_vel() const { return p.visc_coef > 0.0; }
+  bool diffusive_tracer() const { return p.scal_diff_coef > 0.0; }      // is_diffusive[Tracer], NS_setup.cpp:292-295
+  int rho_flag() const { return p.conservative_tracer ? 2 : 0; }         // set_rho_flag(diffusionType[Tracer]), NS_setup.cpp:304-308
 };
 
 namespace {
@@ -165,8 +169,49 @@ int velocity_advection(iamrx_ns_s& ns, double dt) {
 // NavierStokes::scalar_advection (NS.cpp:698-812)
 int scalar_advection(iamrx_ns_s& ns, double dt) {
   for (int il = 0; il < ns.Smf.n(); ++il) IX_TRY(k::floor_small(ns.Smf.gbox(il, 3), ns.Smf.v(il), NUM_SCALARS, ns.s));  // :722
-  IX_TRY(mf_setval(ns.sforce, 0.0, 0, NUM_SCALARS, 1, ns.s));  // getForce: zero scalar forcing; visc terms zero (:738-805)
+  IX_TRY(mf_setval(ns.sforce, 0.0, 0, NUM_SCALARS, 1, ns.s));  // getForce: zero scalar forcing (:755-760)
+  if (ns.diffusive_tracer() && ns.p.be_cn_theta != 1.0) {
+    // getViscTerms (NS.cpp:2012-2048) -> Diffusion::getViscTerms (Diffusion.cpp:1540-1652): a = 0, b = -1 applied to S (rho_flag 0) or
+    // S/rho (rho_flag 2), FillBoundary; then tf = tf/rho + visc or tf + visc with a zero body force (NS.cpp:774-804)
+    Level& L = *ns.L;
+    IX_TRY(fillpatch(ns, ns.s1, ns.S_old, Tracer, 1));
+    if (ns.rho_flag() == 2)
+      for (int il = 0; il < ns.s1.n(); ++il) IX_TRY(k::divide(ns.s1.gbox(il, 1), ns.s1.v(il), ns.rho_ptime.c(il), 1, 1, ns.s));
+    IX_TRY(diffusion_apply(L, *ns.sv, false, 1, ns.svisc, ns.s1, 0.0, -1.0, nullptr, ns.seta, ns.s));
+    IX_TRY(mf_fill_boundary(ns.svisc, 0, 1, 1, ns.s));
+    IX_TRY(mf_copy(ns.sforce, ns.svisc, 0, Tracer - Density, 1, 1, ns.s));
+  }
   return compute_aofs(ns, Density, NUM_SCALARS, ns.Smf, &ns.sforce, false, dt);  // :811
+}
+
+// NavierStokes::scalar_diffusion_update (NS.cpp:858-1000) -> Diffusion::diffuse_scalar (Diffusion.cpp:207-600) for the tracer:
+// Crank-Nicolson with rho_flag 0 (S diffuses, alpha = 1) or 2 (S/rho diffuses, alpha = rho_new, result times rho_new)
+int tracer_diffusion_update(iamrx_ns_s& ns, double dt) {
+  if (!ns.diffusive_tracer()) return IAMRX_OK;
+  Level& L = *ns.L;
+  const double theta = ns.p.be_cn_theta;
+  const int rf = ns.rho_flag();
+  if (theta != 1.0) {   // :364-430: Rhs = (1-theta) dt div beta grad (old solution): a = 0, b = -(1-theta) dt
+    IX_TRY(fillpatch(ns, ns.s1, ns.S_old, Tracer, 1));
+    if (rf == 2)
+      for (int il = 0; il < ns.s1.n(); ++il) IX_TRY(k::divide(ns.s1.gbox(il, 1), ns.s1.v(il), ns.rho_ptime.c(il), 1, 1, ns.s));
+    IX_TRY(diffusion_apply(L, *ns.sv, false, 1, ns.r1, ns.s1, 0.0, -(1.0 - theta) * dt, nullptr, ns.seta, ns.s));
+  } else {
+    IX_TRY(mf_setval(ns.r1, 0.0, 0, 1, 0, ns.s));
+  }
+  IX_TRY(mf_lincomb(ns.r1, 0, 1.0, ns.r1, 0, 1.0, ns.S_new, Tracer, 1, 0, ns.s));   // :465-490 Rhs += S_new (no scaling for rho_flag 0, 2)
+  double nrm = 0.0;
+  IX_TRY(mf_norminf(ns.r1, 0, 1, &nrm, ns.s));
+  const double tol_abs = ns.p.visc_tol * nrm;   // get_scaled_abs_tol :193-204
+  IX_TRY(fillpatch(ns, ns.s1, ns.S_new, Tracer, 1));   // :520-540 initial guess = new state (/ rho_new)
+  if (rf == 2)
+    for (int il = 0; il < ns.s1.n(); ++il) IX_TRY(k::divide(ns.s1.gbox(il, 1), ns.s1.v(il), ns.rho_ctime.c(il), 1, 1, ns.s));
+  iamrx_mg_info mi = mg_info(ns, ns.p.visc_tol, tol_abs);
+  // computeAlpha (:1355-1395): alpha = 1 (rho_flag 0) or rho_new (rho_flag 2); a = 1, b = theta dt
+  IX_SOLVE(diffusion_solve(L, *ns.sv, false, 1, ns.s1, ns.r1, 1.0, theta * dt, rf == 2 ? &ns.rho_ctime : &ns.ones, ns.seta, &mi, ns.s));
+  if (rf == 2)   // :575-590
+    for (int il = 0; il < ns.s1.n(); ++il) IX_TRY(k::mult(L.lbox(il), ns.s1.v(il), ns.rho_ctime.c(il), 1, 1, ns.s));
+  return mf_copy(ns.S_new, ns.s1, 0, Tracer, 1, 0, ns.s);
 }
 
 // Diffusion::diffuse_tensor_velocity (Diffusion.cpp:650-957), rho_flag = 1
@@ -244,6 +289,7 @@ int advance(iamrx_ns_s& ns, double time, double dt, double* dt_test) {
   IX_TRY(fillpatch(ns, ns.rho_ctime, ns.S_new, Density, 1));   // make_rho_curr_time :618
   for (int il = 0; il < ns.S_new.n(); ++il)                    // scalar_update(tracer) :627 -> NSB.cpp:2887-2896
     IX_TRY(k::scal_update(L.lbox(il), ns.S_new.v(il, Tracer), ns.S_old.c(il, Tracer), ns.aofs.c(il, Tracer), dt, 1, ns.s));
+  IX_TRY(tracer_diffusion_update(ns, dt));                     // scalar_update -> scalar_diffusion_update NS.cpp:836-841
 #if !defined(IX_EMUL)
   if (ns.early_out && ns.S_new.n() == 1) {   // scalars are final: pack + copy them out underneath the velocity solves
     IX_CUDA(cudaEventRecord(ns.ev_scal, ns.s));
@@ -325,7 +371,7 @@ int iamrx_ns_create(iamrx_level_t lev, const iamrx_ns_params* p, iamrx_ns_t* out
   IX_ARG(p->cfl > 0.0 && p->cfl <= 1.0, "ns.cfl must be in (0,1]");
   IX_ARG(p->be_cn_theta >= 0.5 && p->be_cn_theta <= 1.0, "ns.be_cn_theta must be in [0.5,1] (NSB.cpp:506-508)");
   IX_ARG(p->visc_coef >= 0.0, "ns.vel_visc_coef must be >= 0 (NS.cpp:2077)");
-  IX_ARG(p->scal_diff_coef == 0.0, "tracer diffusion (ns.scal_diff_coefs > 0) is not implemented in the step driver");
+  IX_ARG(p->scal_diff_coef >= 0.0, "ns.scal_diff_coefs must be >= 0");
   Level* L = level_of(lev);
   for (int d = 0; d < 3; ++d) IX_ARG(L->geom.periodic[d], "only fully periodic domains are implemented in this round");
   auto* ns = new iamrx_ns_s();
@@ -341,6 +387,10 @@ int iamrx_ns_create(iamrx_level_t lev, const iamrx_ns_params* p, iamrx_ns_t* out
   for (int d = 0; d < 3; ++d) ns->eta[d].define(L, IX_XFACE + d, 1, 0);
   ns->soln.define(L, IX_CELL, 3, 1); ns->rhs3.define(L, IX_CELL, 3, 0);
   ns->sig.define(L, IX_CELL, 1, 1); ns->mac_phi.define(L, IX_CELL, 1, 1); ns->tf0.define(L, IX_CELL, 3, 0);
+  if (p->scal_diff_coef > 0.0) {
+    for (int d = 0; d < 3; ++d) ns->seta[d].define(L, IX_XFACE + d, 1, 0);
+    ns->s1.define(L, IX_CELL, 1, 1); ns->r1.define(L, IX_CELL, 1, 0); ns->svisc.define(L, IX_CELL, 1, 1); ns->ones.define(L, IX_CELL, 1, 1);
+  }
   cudaStream_t s = ns->s;
   MF* all[] = {&ns->S_old, &ns->S_new, &ns->P_old, &ns->P_new, &ns->Gp_old, &ns->Gp_new, &ns->umac[0], &ns->umac[1],
                &ns->umac[2], &ns->aofs, &ns->rho_ptime, &ns->rho_ctime, &ns->rho_half, &ns->Umf, &ns->Smf, &ns->visc,
@@ -352,6 +402,15 @@ int iamrx_ns_create(iamrx_level_t lev, const iamrx_ns_params* p, iamrx_ns_t* out
   }
   for (int d = 0; d < 3; ++d) {  // constant viscosity on faces (NS.cpp:2062-2117 calcViscosity/getViscosity)
     int rc = mf_setval(ns->eta[d], p->visc_coef, 0, 1, 0, s);
+    if (rc) { delete ns; return rc; }
+  }
+  if (p->scal_diff_coef > 0.0) {  // constant tracer diffusivity (calcDiffusivity/getDiffusivity NS.cpp:2084-2119); alpha = 1 for rho_flag 0
+    int rc = IAMRX_OK;
+    for (int d = 0; d < 3 && rc == IAMRX_OK; ++d) rc = mf_setval(ns->seta[d], p->scal_diff_coef, 0, 1, 0, s);
+    if (rc == IAMRX_OK) rc = mf_setval(ns->ones, 1.0, 0, 1, 1, s);
+    if (rc == IAMRX_OK) rc = mf_setval(ns->s1, 0.0, 0, 1, 1, s);
+    if (rc == IAMRX_OK) rc = mf_setval(ns->svisc, 0.0, 0, 1, 1, s);
+    if (rc == IAMRX_OK) rc = mf_setval(ns->r1, 0.0, 0, 1, 0, s);
     if (rc) { delete ns; return rc; }
   }
   *out = ns;

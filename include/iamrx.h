@@ -344,7 +344,9 @@ int iamrx_diffusion_solve(iamrx_level_t lev, int tensor, int ncomp, iamrx_fab* s
 typedef struct iamrx_ns_params {
   double cfl;            /* ns.cfl */
   double visc_coef;      /* ns.vel_visc_coef */
-  double scal_diff_coef; /* ns.scal_diff_coefs (tracer) */
+  double scal_diff_coef; /* ns.scal_diff_coefs of the tracer: > 0 adds its viscous term to the advection forcing and the
+                            Crank-Nicolson solve of NavierStokes::scalar_diffusion_update (NS.cpp:858-1000) ->
+                            Diffusion::diffuse_scalar (Diffusion.cpp:207-600), rho_flag 0 (tracer) / 2 (conservative tracer) */
   double be_cn_theta;    /* ns.be_cn_theta, NSB.cpp:124 */
   double change_max;     /* ns.change_max, NSB.cpp:101 */
   double init_shrink;    /* ns.init_shrink */

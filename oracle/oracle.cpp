@@ -825,9 +825,12 @@ struct orc_ns {
   bool initial_step = false, initial_iter = false;
   int it[3] = {0, 0, 0};
   Arr force;  // velocity forcing from predict_velocity (1 ghost), reused by velocity_advection
+  Arr seta[3];  // tracer diffusivity on faces (getDiffusivity: constant ns.scal_diff_coefs, NS.cpp:2051-2119)
 
   orc_mg mg(double rtol, double atol) const { orc_mg m; orc_mg_default(&m); m.rtol = rtol; m.atol = atol; return m; }
   bool diffusive() const { return p.visc_coef > 0.0; }
+  bool diffusive_tracer() const { return p.scal_diff_coef > 0.0; }   // is_diffusive[Tracer], NS_setup.cpp:292-295
+  int rho_flag() const { return p.conservative_tracer ? 2 : 0; }      // Diffusion::set_rho_flag of diffusionType[Tracer], NS_setup.cpp:304-308
 
   // getViscTerms -> getTensorViscTerms (Diffusion.cpp:1655-1777): a = 0, b = -1
   void visc_terms(const Arr& S, Arr& visc) {
@@ -875,12 +878,27 @@ struct orc_ns {
     // ---- scalar_advection NS.cpp:698-812
     for (double& v : Smf.d) v = (std::fabs(v) > 1.0e-20) ? v : 0.0;
     Arr sforce(n, 2, 1);
+    if (diffusive_tracer() && p.be_cn_theta != 1.0) {
+      // NavierStokes::getViscTerms (NS.cpp:2012-2048) -> Diffusion::getViscTerms (Diffusion.cpp:1540-1652): a = 0, b = -1 applied to
+      // S (rho_flag 0) or S/rho (rho_flag 2), then FillBoundary; tf = tf/rho + visc or tf + visc with zero body force (NS.cpp:774-804)
+      Arr s1(n, 1, 1); s1.copy_from(S_old, Tracer, 0, 1);
+      if (rho_flag() == 2) { FOR_CELLS(s1, i, j, k) s1(i, j, k) /= S_old(i, j, k, Density); }
+      CellMG op(n, dx, 1, false, 0);
+      op.a = 0.0; op.b = -1.0;
+      const Arr* e[3] = {&seta[0], &seta[1], &seta[2]};
+      op.set_coeffs(nullptr, e);
+      Arr sv(n, 1, 1);
+      op.apply(sv, s1);
+      sv.fill_periodic();
+      FOR_G1(sforce, i, j, k) sforce(i, j, k, 1) = sv(i, j, k);
+    }
     const int ic_scal[2] = {1, p.conservative_tracer ? 1 : 0};
     compute_aofs(Smf, 2, &sforce, nullptr, umac, ic_scal, p.use_forces_in_trans != 0, dx, dt, aofs, Density, nullptr, nullptr);
     // ---- scalar updates NSB.cpp:2761-2765, 2887-2896
     FOR_CELLS(S_new, i, j, k) S_new(i, j, k, Density) = S_old(i, j, k, Density) - dt * aofs(i, j, k, Density);
     rho_c.copy_from(S_new, Density, 0, 1); rho_c.fill_periodic();
     FOR_CELLS(S_new, i, j, k) S_new(i, j, k, Tracer) = S_old(i, j, k, Tracer) - dt * aofs(i, j, k, Tracer);
+    if (diffusive_tracer()) { rc = tracer_diffusion(dt); if (rc) return rc; }   // scalar_update -> scalar_diffusion_update NS.cpp:836-841
     // ---- velocity_update NSB.cpp:3487-3655
     FOR_G1(rho_half, i, j, k) rho_half(i, j, k) = 0.5 * (rho_p(i, j, k) + rho_c(i, j, k));
     const bool zero_force = initial_iter && diffusive();
@@ -895,6 +913,38 @@ struct orc_ns {
     else initial_velocity_diffusion(dt);
     if (!initial_step) { rc = level_project(dt); if (rc) return rc; }
     return 0;
+  }
+
+  // NavierStokes::scalar_diffusion_update (NS.cpp:858-1000) -> Diffusion::diffuse_scalar (Diffusion.cpp:207-600) for the tracer:
+  // Crank-Nicolson with rho_flag 0 (S diffuses, alpha = 1) or 2 (S/rho diffuses, alpha = rho_new, result times rho_new)
+  int tracer_diffusion(double dt) {
+    const double th = p.be_cn_theta;
+    const int rf = rho_flag();
+    const Arr* e[3] = {&seta[0], &seta[1], &seta[2]};
+    Arr rhs(n, 1, 0);
+    if (th != 1.0) {   // :364-430: Rhs = -(b) div beta grad (old solution), a = 0, b = -(1-theta) dt
+      Arr so(n, 1, 1); so.copy_from(S_old, Tracer, 0, 1);
+      if (rf == 2) { FOR_CELLS(so, i, j, k) so(i, j, k) /= S_old(i, j, k, Density); }
+      CellMG ex(n, dx, 1, false, 0);
+      ex.a = 0.0; ex.b = -(1.0 - th) * dt;
+      ex.set_coeffs(nullptr, e);
+      ex.apply(rhs, so);
+    }
+    FOR_CELLS(rhs, i, j, k) rhs(i, j, k) += S_new(i, j, k, Tracer);   // :465-490 (rho_flag 0 and 2: no scaling)
+    Arr soln(n, 1, 1), alpha(n, 1, 0);
+    FOR_CELLS(soln, i, j, k) {   // :520-540 initial guess = new state (/ rho_new), :1355-1395 computeAlpha
+      const double r = S_new(i, j, k, Density);
+      soln(i, j, k) = (rf == 2) ? S_new(i, j, k, Tracer) / r : S_new(i, j, k, Tracer);
+      alpha(i, j, k) = (rf == 2) ? r : 1.0;
+    }
+    const double tol_abs = p.visc_tol * rhs.norminf(0);   // get_scaled_abs_tol :193-204
+    CellMG im(n, dx, 1, false, 100);
+    im.mg = mg(p.visc_tol, tol_abs);
+    im.a = 1.0; im.b = th * dt;
+    im.set_coeffs(&alpha, e);
+    const int rc = im.solve(soln, rhs);
+    FOR_CELLS(soln, i, j, k) S_new(i, j, k, Tracer) = (rf == 2) ? soln(i, j, k) * S_new(i, j, k, Density) : soln(i, j, k);   // :575-590
+    return rc;
   }
 
   // Diffusion::diffuse_tensor_velocity Diffusion.cpp:650-957
@@ -1134,7 +1184,7 @@ void orc_compute_aofs(const int n[3], const double dx[3], double dt, int ncomp, 
 void orc_ns_params_default(orc_ns_params* p) {
   p->cfl = 0.7; p->visc_coef = 0.0; p->be_cn_theta = 0.5; p->change_max = 1.1; p->init_shrink = 1.0; p->fixed_dt = -1.0;
   p->gravity = 0.0; p->visc_tol = 1e-10; p->mac_tol = 1e-12; p->mac_abs_tol = 1e-16; p->proj_tol = 1e-12; p->proj_abs_tol = 1e-16;
-  p->init_iter = 2; p->init_vel_iter = 1; p->do_init_proj = 1; p->use_forces_in_trans = 0; p->conservative_tracer = 0; p->verbose = 0;
+  p->init_iter = 2; p->init_vel_iter = 1; p->do_init_proj = 1; p->use_forces_in_trans = 0; p->conservative_tracer = 0; p->verbose = 0; p->scal_diff_coef = 0.0;
 }
 
 orc_ns* orc_ns_create(const int n[3], const double prob_lo[3], const double prob_hi[3], const orc_ns_params* p) {
@@ -1144,7 +1194,7 @@ orc_ns* orc_ns_create(const int n[3], const double prob_lo[3], const double prob
   ns->S_old.define(n, 5, 1); ns->S_new.define(n, 5, 1); ns->P_old.define(n, 1, 1); ns->P_new.define(n, 1, 1);
   ns->Gp_old.define(n, 3, 1); ns->Gp_new.define(n, 3, 1); ns->aofs.define(n, 5, 0);
   ns->rho_p.define(n, 1, 1); ns->rho_c.define(n, 1, 1); ns->rho_half.define(n, 1, 1);
-  for (int d = 0; d < 3; ++d) { ns->umac[d].define(n, 1, 1); ns->eta[d].define(n, 1, 1); ns->eta[d].setval(p->visc_coef); }
+  for (int d = 0; d < 3; ++d) { ns->umac[d].define(n, 1, 1); ns->eta[d].define(n, 1, 1); ns->eta[d].setval(p->visc_coef); ns->seta[d].define(n, 1, 1); ns->seta[d].setval(p->scal_diff_coef); }
   return ns;
 }
 void orc_ns_destroy(orc_ns* ns) { delete ns; }

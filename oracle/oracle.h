@@ -86,6 +86,7 @@ typedef struct orc_ns_params {
   double cfl, visc_coef, be_cn_theta, change_max, init_shrink, fixed_dt, gravity, visc_tol;
   double mac_tol, mac_abs_tol, proj_tol, proj_abs_tol;
   int init_iter, init_vel_iter, do_init_proj, use_forces_in_trans, conservative_tracer, verbose;
+  double scal_diff_coef;   /* ns.scal_diff_coefs of the tracer (0: non-diffusive) */
 } orc_ns_params;
 void orc_ns_params_default(orc_ns_params* p);
 typedef struct orc_ns orc_ns;

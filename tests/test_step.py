@@ -24,6 +24,10 @@ def _assemble(ns, which, boxes, n, ncomp, ext=(0, 0, 0)):
     (11, [1.0, 1.0, 0.0, 1.0, 1.0], {}),                       # TaylorGreen, inputs.3d.taylorgreen (prob.c = 0)
     (100, [1.0, 1.0, 1.0, 1.0, 1.0], {"gravity": -0.5}),       # 3-D variable density + buoyancy
     (5, [1.0, 1.0, 0.0, 0.0, 0.0, 0.4], {"conservative_tracer": 1}),  # DoubleShearLayer IC, conservative tracer
+    # diffusive tracer (ns.scal_diff_coefs > 0): Diffusion::diffuse_scalar with rho_flag 0 (Laplacian_S) and 2 (Laplacian_SoverRho)
+    (100, [1.0, 1.0, 1.0, 1.0, 1.0], {"scal_diff_coef": 5e-3}),
+    (100, [1.0, 1.0, 1.0, 1.0, 1.0], {"scal_diff_coef": 5e-3, "conservative_tracer": 1, "gravity": -0.5}),
+    (5, [1.0, 1.0, 0.0, 0.0, 0.0, 0.4], {"scal_diff_coef": 2e-2, "be_cn_theta": 1.0}),   # backward Euler: no old-time term
 ])
 def test_step_matches_oracle(backend, oracle, nb, probtype, pp, extra):
     """Velocity / pressure L-inf parity <= 1e-10 (north_star tolerance) over init + 3 steps."""
