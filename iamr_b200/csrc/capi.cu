@@ -125,12 +125,11 @@ int iamrx_extrap_vel_to_faces_box(const iamrx_box* bx, const iamrx_fab* vel, con
   IX_NEED_DEVICE();
   IX_ARG(bx && vel && umac && vmac && wmac && geom, "null argument");
   IX_ARG(vel->ncomp >= 3, "vel needs 3 components");
-  IX_ARG(!(flags & IAMRX_ADV_PPM), "Godunov_PPM is not implemented (ns.advection_scheme = Godunov_PLM only)");
   k::AdvGeom g;
   for (int d = 0; d < 3; ++d) g.dx[d] = geom->dx[d];
   g.dt = dt;
   return k::extrap_vel_to_faces(mkbx(*bx), cview(vel), cview(force), view(umac), view(vmac), view(wmac), g,
-                                (flags & IAMRX_ADV_FORCES_IN_TRANS) ? 1 : 0, S(stream));
+                                (flags & IAMRX_ADV_FORCES_IN_TRANS) ? 1 : 0, S(stream), (flags & IAMRX_ADV_PPM) ? 1 : 0);
 }
 
 int iamrx_compute_aofs_box(const iamrx_box* bx, iamrx_fab* aofs, int aofs_comp, const iamrx_fab* Sf, int s_comp,
@@ -141,7 +140,6 @@ int iamrx_compute_aofs_box(const iamrx_box* bx, iamrx_fab* aofs, int aofs_comp, 
   IX_NEED_DEVICE();
   IX_ARG(bx && aofs && Sf && umac && vmac && wmac && iconserv && geom, "null argument");
   IX_ARG(ncomp >= 1 && ncomp <= 8, "ncomp must be in [1,8]");
-  IX_ARG(!(flags & IAMRX_ADV_PPM), "Godunov_PPM is not implemented (ns.advection_scheme = Godunov_PLM only)");
   const bool wf = (flags & IAMRX_ADV_WRITE_FLUXES) != 0;
   IX_ARG(!wf || (fx && fy && fz && xed && yed && zed), "flux/edge outputs required with WRITE_FLUXES");
   k::AofsArgs a{};
@@ -159,6 +157,7 @@ int iamrx_compute_aofs_box(const iamrx_box* bx, iamrx_fab* aofs, int aofs_comp, 
   a.is_sync = (flags & IAMRX_ADV_IS_SYNC) ? 1 : 0;
   a.write_fluxes = wf ? 1 : 0;
   a.staged = (flags & IAMRX_ADV_STAGED) ? 1 : 0;
+  a.ppm = (flags & IAMRX_ADV_PPM) ? 1 : 0;
   k::AdvGeom g;
   for (int d = 0; d < 3; ++d) g.dx[d] = geom->dx[d];
   g.dt = dt;

@@ -33,8 +33,16 @@ constexpr int TY = 4;
 // hi from this cell.  ulo/uhi: the velocity used in the trace (cell-centred normal velocity
 // for ExtrapVelToFaces, the MAC velocity of this face for ComputeEdgeState).
 template <int D>
-IX_D void trace(const Cur& q, double ulo, double uhi, double dtdx, double& lo, double& hi) {
+IX_D void trace(const Cur& q, double ulo, double uhi, double dtdx, double& lo, double& hi, int ppm = 0) {
   const Cur qm = below<D>(q);
+  if (ppm) {  // Godunov_PPM: lo = Ip of the cell below, hi = Im of this cell
+    double sm, sp;
+    ppm_parabola(along<D>(qm, -2), along<D>(qm, -1), qm(0, 0, 0), along<D>(qm, 1), along<D>(qm, 2), sm, sp);
+    lo = ppm_ip(qm(0, 0, 0), sm, sp, ulo, dtdx);
+    ppm_parabola(along<D>(q, -2), along<D>(q, -1), q(0, 0, 0), along<D>(q, 1), along<D>(q, 2), sm, sp);
+    hi = ppm_im(q(0, 0, 0), sm, sp, uhi, dtdx);
+    return;
+  }
   lo = qm(0, 0, 0) + 0.5 * (1.0 - ulo * dtdx) * slope4c<D>(qm);
   hi = q(0, 0, 0) + 0.5 * (-1.0 - uhi * dtdx) * slope4c<D>(q);
 }
@@ -74,6 +82,7 @@ struct EsArgs {
   C4 S, force, divu, umac, vmac, wmac, uflx, vflx, wflx;
   int iconserv[8];
   int fit;  // use_forces_in_trans
+  int ppm;  // Godunov_PPM instead of Godunov_PLM
   double dt, dtdx, dtdy, dtdz;
 };
 
@@ -83,7 +92,7 @@ enum { A_XE = 0, A_YE, A_ZE, A_XY, A_XZ, A_YX, A_YZ, A_ZX, A_ZY, A_FX, A_FY, A_F
 // lo/hi on the D-face of the cursor's cell, traced with the MAC velocity `u` of that face
 template <int D>
 IX_D void es_lohi(const EsArgs& a, const Cur& q, const Cur& f, double u, double dtdx, double& lo, double& hi) {
-  trace<D>(q, u, u, dtdx, lo, hi);
+  trace<D>(q, u, u, dtdx, lo, hi, a.ppm);
   if (a.fit && f.ok()) {
     lo += 0.5 * a.dt * along<D>(f, -1);
     hi += 0.5 * a.dt * f(0, 0, 0);
@@ -306,7 +315,7 @@ es_div_kernel(IX_KARG(EsArgs) a, IX_KARG(Scratch) sc, V4 aofs, double volinv, do
 struct EvArgs {
   Bx bx;
   C4 vel, force;
-  int fit;
+  int fit, ppm;
   double dt, dtdx, dtdy, dtdz;
 };
 // scratch ids: advective velocities 0..2; transverse edges: XE_V,XE_W (x-faces, comps 1,2),
@@ -328,7 +337,7 @@ IX_D EvCur ev_cursors(const EvArgs& a, const Scratch& sc, int i, int j, int k) {
 // lo/hi of component n on the D-face, traced with the cell-centred velocity component D
 template <int D>
 IX_D void ev_lohi(const EvArgs& a, const EvCur& c, int n, double dtdx, double& lo, double& hi) {
-  trace<D>(c.q[n], along<D>(c.q[D], -1), c.q[D](0, 0, 0), dtdx, lo, hi);
+  trace<D>(c.q[n], along<D>(c.q[D], -1), c.q[D](0, 0, 0), dtdx, lo, hi, a.ppm);
   if (a.fit && c.f[n].ok()) {
     lo += 0.5 * a.dt * along<D>(c.f[n], -1);
     hi += 0.5 * a.dt * c.f[n](0, 0, 0);
@@ -683,12 +692,13 @@ int compute_aofs(const Bx& bx, const AofsArgs& a, const AdvGeom& g, cudaStream_t
   e.uflx = a.uflx; e.vflx = a.vflx; e.wflx = a.wflx;
   for (int n = 0; n < 8; ++n) e.iconserv[n] = (n < a.ncomp) ? a.iconserv[n] : 0;
   e.fit = a.forces_in_trans;
+  e.ppm = a.ppm;
   e.dt = g.dt; e.dtdx = g.dt / g.dx[0]; e.dtdy = g.dt / g.dx[1]; e.dtdz = g.dt / g.dx[2];
   EsOut out{};
   if (a.write_fluxes) { out.fx = a.fx; out.fy = a.fy; out.fz = a.fz; out.xed = a.xed; out.yed = a.yed; out.zed = a.zed; }
   out.ax = g.dx[1] * g.dx[2]; out.ay = g.dx[0] * g.dx[2]; out.az = g.dx[0] * g.dx[1];
 #if !defined(IX_EMUL)
-  if (!a.staged && tile::aofs_tile_ok(bx, a)) {
+  if (!a.staged && !a.ppm && tile::aofs_tile_ok(bx, a)) {   // the tile kernel is PLM only
     static bool attr_set = false;
     if (!attr_set) {
       IX_CUDA(cudaFuncSetAttribute(tile::aofs_tile_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, tile::SMEM_BYTES));
@@ -723,13 +733,13 @@ int compute_aofs(const Bx& bx, const AofsArgs& a, const AdvGeom& g, cudaStream_t
 }
 
 int extrap_vel_to_faces(const Bx& bx, C4 vel, C4 force, V4 umac, V4 vmac, V4 wmac, const AdvGeom& g,
-                        int forces_in_trans, cudaStream_t s) {
+                        int forces_in_trans, cudaStream_t s, int ppm) {
   if (!bx.ok()) return IAMRX_OK;
   ProfScope prof_(IAMRX_PROF_EXTRAP, bx.npts(), (double)bx.npts() * 72.0, s);
   ScratchOwner so;
   if (so.init(bx, B_N) != IAMRX_OK) return IAMRX_ERR_CUDA;
   EvArgs e{};
-  e.bx = bx; e.vel = vel; e.force = force; e.fit = forces_in_trans;
+  e.bx = bx; e.vel = vel; e.force = force; e.fit = forces_in_trans; e.ppm = ppm;
   e.dt = g.dt; e.dtdx = g.dt / g.dx[0]; e.dtdy = g.dt / g.dx[1]; e.dtdz = g.dt / g.dx[2];
   Bx R1 = grow(bx, 1); R1.hi[0]++; R1.hi[1]++; R1.hi[2]++;
   IX_LAUNCH(ev_edge_kernel, grid_for(R1, 1), dim3(TX, TY, 1), 0, s, e, so.sc, R1);

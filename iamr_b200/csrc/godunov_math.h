@@ -80,6 +80,35 @@ template <int D> IX_HD double slope4c(const Cur& q) {
   return slope4_vals(along<D>(q, -2), along<D>(q, -1), q(0, 0, 0), along<D>(q, 1), along<D>(q, 2));
 }
 
+// ---- PPM (ns.advection_scheme = Godunov_PPM, NSB.cpp:552-554,4485; AMReX-Hydro hydro_godunov_ppm.H restated: van Leer
+// limited edge values, Colella-Woodward monotonisation) ----------------------------------------------------------
+IX_HD double vanleer(double s0, double sp1, double sm1) {
+  const double dsc = 0.5 * (sp1 - sm1), dsl = 2.0 * (s0 - sm1), dsr = 2.0 * (sp1 - s0);
+  return (dsl * dsr > 0.0) ? copysign(1.0, dsc) * fmin(fabs(dsc), fmin(fabs(dsl), fabs(dsr))) : 0.0;
+}
+// parabola edges (sm at the lower, sp at the upper face) of the cell whose five values along the direction are given
+IX_HD void ppm_parabola(double sm2, double sm1, double s0, double sp1, double sp2, double& sm, double& sp) {
+  const double d0 = vanleer(s0, sp1, sm1), dm = vanleer(sm1, s0, sm2), dp = vanleer(sp1, sp2, s0);
+  sm = 0.5 * (s0 + sm1) - (1.0 / 6.0) * (d0 - dm);
+  sm = fmin(fmax(sm, fmin(s0, sm1)), fmax(s0, sm1));
+  sp = 0.5 * (sp1 + s0) - (1.0 / 6.0) * (dp - d0);
+  sp = fmin(fmax(sp, fmin(s0, sp1)), fmax(s0, sp1));
+  if ((sp - s0) * (s0 - sm) <= 0.0) { sm = s0; sp = s0; }
+  else if (fabs(sp - s0) >= 2.0 * fabs(sm - s0)) sp = 3.0 * s0 - 2.0 * sm;
+  else if (fabs(sm - s0) >= 2.0 * fabs(sp - s0)) sm = 3.0 * s0 - 2.0 * sp;
+}
+// averages of the parabola over the domain of dependence of the upper (Ip) / lower (Im) face for trace velocity v
+IX_HD double ppm_ip(double s0, double sm, double sp, double v, double dtdx) {
+  if (!(v > SMALL_VEL)) return s0;
+  const double sg = fabs(v) * dtdx, s6 = 6.0 * s0 - 3.0 * (sm + sp);
+  return sp - 0.5 * sg * ((sp - sm) - (1.0 - (2.0 / 3.0) * sg) * s6);
+}
+IX_HD double ppm_im(double s0, double sm, double sp, double v, double dtdx) {
+  if (!(v < -SMALL_VEL)) return s0;
+  const double sg = fabs(v) * dtdx, s6 = 6.0 * s0 - 3.0 * (sm + sp);
+  return sm + 0.5 * sg * ((sp - sm) + (1.0 - (2.0 / 3.0) * sg) * s6);
+}
+
 // upwind the pair (lo, hi) with a given face velocity (ComputeEdgeState /
 // transverse states of ExtrapVelToFaces)
 IX_HD double upwind(double lo, double hi, double vel) {

@@ -73,7 +73,7 @@ int reduce_dot(const Bx& bx, C4 x, C4 y, C4 mask, double* result, cudaStream_t s
 // --- Godunov advection (godunov.cu) --------------------------------------
 struct AdvGeom { double dx[3]; double dt; };
 int extrap_vel_to_faces(const Bx& bx, C4 vel, C4 force, V4 umac, V4 vmac, V4 wmac,
-                        const AdvGeom& g, int forces_in_trans, cudaStream_t s);
+                        const AdvGeom& g, int forces_in_trans, cudaStream_t s, int ppm = 0);
 struct AofsArgs {
   V4 aofs;           // ncomp
   C4 S, force, divu; // S: ncomp, 3 ghosts; force: ncomp 1 ghost (may be null); divu may be null
@@ -84,6 +84,7 @@ struct AofsArgs {
   int iconserv[8];
   int forces_in_trans, is_velocity, is_sync, write_fluxes;
   int staged = 0;  // force the staged kernels
+  int ppm = 0;     // Godunov_PPM (staged kernels only)
 };
 int compute_aofs(const Bx& bx, const AofsArgs& a, const AdvGeom& g, cudaStream_t s);
 

@@ -115,7 +115,7 @@ int predict_velocity(iamrx_ns_s& ns, double dt, double* dt_test) {
   k::AdvGeom g; for (int d = 0; d < 3; ++d) g.dx[d] = L.geom.dx[d]; g.dt = dt;
   for (int il = 0; il < ns.Umf.n(); ++il)                                  // :4487-4491
     IX_TRY(k::extrap_vel_to_faces(L.lbox(il), ns.Umf.c(il), ns.force.c(il), ns.umac[0].v(il), ns.umac[1].v(il),
-                                  ns.umac[2].v(il), g, ns.p.use_forces_in_trans, ns.s));
+                                  ns.umac[2].v(il), g, ns.p.use_forces_in_trans, ns.s, ns.p.godunov_ppm));
   *dt_test = dt * tempdt;                                                  // :4511
   return IAMRX_OK;
 }
@@ -152,6 +152,7 @@ int compute_aofs(iamrx_ns_s& ns, int state_comp, int ncomp, const MF& Sq, const 
       a.iconserv[n] = (sc == Density) ? 1 : (sc == Tracer ? (ns.p.conservative_tracer ? 1 : 0) : 0);
     }
     a.forces_in_trans = ns.p.use_forces_in_trans;
+    a.ppm = ns.p.godunov_ppm;   // advection_scheme == Godunov_PPM (NSB.cpp:4609)
     a.is_velocity = is_velocity ? 1 : 0;
     IX_TRY(k::compute_aofs(L.lbox(il), a, g, ns.s));
   }
@@ -363,6 +364,7 @@ void iamrx_ns_params_default(iamrx_ns_params* p) {
   p->verbose = 0;
   p->conservative_tracer = 0;
   p->mg_verbose = 0;
+  p->godunov_ppm = 0;     // ns.advection_scheme = Godunov_PLM (NSB.cpp:169)
 }
 
 int iamrx_ns_create(iamrx_level_t lev, const iamrx_ns_params* p, iamrx_ns_t* out) {

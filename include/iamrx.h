@@ -90,7 +90,7 @@ enum {
 /* flags of iamrx_compute_aofs_box (arguments of
  * HydroUtils::ComputeFluxesOnBoxFromState, NSB.cpp:4701-4717) */
 enum {
-  IAMRX_ADV_PPM = 1,               /* godunov_use_ppm (not implemented: returns ERR_ARG) */
+  IAMRX_ADV_PPM = 1,               /* godunov_use_ppm: advection_scheme Godunov_PPM (NSB.cpp:552-554,4485); staged kernels */
   IAMRX_ADV_FORCES_IN_TRANS = 2,   /* godunov.use_forces_in_trans, NSB.cpp:556 */
   IAMRX_ADV_IS_VELOCITY = 4,
   IAMRX_ADV_WRITE_FLUXES = 8,      /* also store area-weighted fluxes + edge states */
@@ -362,7 +362,7 @@ typedef struct iamrx_ns_params {
   int verbose;
   int conservative_tracer; /* ns.do_cons_trac */
   int mg_verbose;
-  int pad_;
+  int godunov_ppm;       /* ns.advection_scheme = Godunov_PPM instead of the default Godunov_PLM (NSB.cpp:169,552-554) */
 } iamrx_ns_params;
 
 void iamrx_ns_params_default(iamrx_ns_params* p);

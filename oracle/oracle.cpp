@@ -575,6 +575,59 @@ inline double riemann_self(double lo, double hi) {  // normal velocity upwinded 
     for (int j = -1; j <= (A).n[1]; ++j)                          \
       for (int i = -1; i <= (A).n[0]; ++i)
 
+struct AdvOpt { bool fit; bool ppm; };   // godunov.use_forces_in_trans, advection_scheme == Godunov_PPM (NSB.cpp:4485)
+
+// PPM (AMReX-Hydro hydro_godunov_ppm.H, van Leer limited edges + Colella-Woodward monotonisation): parabola of one cell from
+// the five values along the direction; Im / Ip are its averages over the domain of dependence of the lower / upper face
+inline double vanleer(double s0, double sp1, double sm1) {
+  const double dsc = 0.5 * (sp1 - sm1), dsl = 2.0 * (s0 - sm1), dsr = 2.0 * (sp1 - s0);
+  return (dsl * dsr > 0.0) ? std::copysign(1.0, dsc) * std::min(std::fabs(dsc), std::min(std::fabs(dsl), std::fabs(dsr))) : 0.0;
+}
+inline void ppm_parabola(double sm2, double sm1, double s0, double sp1, double sp2, double& sm, double& sp) {
+  const double d0 = vanleer(s0, sp1, sm1), dm = vanleer(sm1, s0, sm2), dp = vanleer(sp1, sp2, s0);
+  sm = 0.5 * (s0 + sm1) - (1.0 / 6.0) * (d0 - dm);
+  sm = std::min(std::max(sm, std::min(s0, sm1)), std::max(s0, sm1));
+  sp = 0.5 * (sp1 + s0) - (1.0 / 6.0) * (dp - d0);
+  sp = std::min(std::max(sp, std::min(s0, sp1)), std::max(s0, sp1));
+  if ((sp - s0) * (s0 - sm) <= 0.0) { sm = s0; sp = s0; }
+  else if (std::fabs(sp - s0) >= 2.0 * std::fabs(sm - s0)) sp = 3.0 * s0 - 2.0 * sm;
+  else if (std::fabs(sm - s0) >= 2.0 * std::fabs(sp - s0)) sm = 3.0 * s0 - 2.0 * sp;
+}
+inline double ppm_ip(double s0, double sm, double sp, double v, double dtdx) {   // state sent to the UPPER face
+  if (!(v > small_vel)) return s0;
+  const double sg = std::fabs(v) * dtdx, s6 = 6.0 * s0 - 3.0 * (sm + sp);
+  return sp - 0.5 * sg * ((sp - sm) - (1.0 - (2.0 / 3.0) * sg) * s6);
+}
+inline double ppm_im(double s0, double sm, double sp, double v, double dtdx) {   // state sent to the LOWER face
+  if (!(v < -small_vel)) return s0;
+  const double sg = std::fabs(v) * dtdx, s6 = 6.0 * s0 - 3.0 * (sm + sp);
+  return sm + 0.5 * sg * ((sp - sm) + (1.0 - (2.0 / 3.0) * sg) * s6);
+}
+
+void ppm_lohi(const Arr& q, int c, int d, double dtdx, const Arr* mac, const Arr* vcc, const Arr* f, int fc, bool fit, double dt,
+              Arr& lo, Arr& hi) {
+  Arr pm(q.n, 1, 1), pp(q.n, 1, 1);   // parabola edges of cells -1..n
+#pragma omp parallel for
+  for (int k = -1; k <= q.n[2]; ++k)
+    for (int j = -1; j <= q.n[1]; ++j)
+      for (int i = -1; i <= q.n[0]; ++i)
+        ppm_parabola(q(i - 2 * e0(d), j - 2 * e1(d), k - 2 * e2(d), c), q(i - e0(d), j - e1(d), k - e2(d), c), q(i, j, k, c),
+                     q(i + e0(d), j + e1(d), k + e2(d), c), q(i + 2 * e0(d), j + 2 * e1(d), k + 2 * e2(d), c), pm(i, j, k), pp(i, j, k));
+#pragma omp parallel for
+  for (int k = -1 + e2(d); k <= q.n[2]; ++k)
+    for (int j = -1 + e1(d); j <= q.n[1]; ++j)
+      for (int i = -1 + e0(d); i <= q.n[0]; ++i) {
+    const int im = i - e0(d), jm = j - e1(d), km = k - e2(d);
+    // trace velocities: the MAC velocity of THIS face for both sides (edge states), or each cell's own velocity (prediction)
+    const double ul = mac ? (*mac)(i, j, k) : (*vcc)(im, jm, km, d);
+    const double uh = mac ? (*mac)(i, j, k) : (*vcc)(i, j, k, d);
+    double l = ppm_ip(q(im, jm, km, c), pm(im, jm, km), pp(im, jm, km), ul, dtdx);
+    double h = ppm_im(q(i, j, k, c), pm(i, j, k), pp(i, j, k), uh, dtdx);
+    if (fit && f) { l += 0.5 * dt * (*f)(im, jm, km, fc); h += 0.5 * dt * (*f)(i, j, k, fc); }
+    lo(i, j, k) = l; hi(i, j, k) = h;
+  }
+}
+
 // PLM traced states on d-faces for component c: lo = Ip(cell below), hi = Im(cell above).
 // trace velocity: umac on the face (edge state) or the cell-centred normal velocity (vel prediction).
 void plm_lohi(const Arr& q, int c, int d, double dtdx, const Arr* mac, const Arr* vcc, const Arr* f, int fc, bool fit, double dt,
@@ -626,13 +679,14 @@ void corner_couple(const Arr& lo, const Arr& hi, int d1, int d2, double dt3dx, b
 
 // HydroUtils::ComputeFluxesOnBoxFromState -> Godunov::ComputeEdgeState for one component:
 // fills the final edge states edge[d] (1 comp) on the low faces of every cell
-void edge_state_comp(const Arr& q, int c, const Arr* f, int fc, const Arr* divu, const Arr* mac[3], bool conserv, bool fit,
+void edge_state_comp(const Arr& q, int c, const Arr* f, int fc, const Arr* divu, const Arr* mac[3], bool conserv, AdvOpt opt,
                      const double dx[3], double dt, Arr* edge[3]) {
+  const bool fit = opt.fit;
   const int* n = q.n;
   Arr lo[3], hi[3], ed[3];
   for (int d = 0; d < 3; ++d) {
     lo[d].define(n, 1, 2); hi[d].define(n, 1, 2); ed[d].define(n, 1, 2);
-    plm_lohi(q, c, d, dt / dx[d], mac[d], nullptr, f, fc, fit, dt, lo[d], hi[d]);
+    (opt.ppm ? ppm_lohi : plm_lohi)(q, c, d, dt / dx[d], mac[d], nullptr, f, fc, fit, dt, lo[d], hi[d]);
     Arr& E = ed[d]; const Arr& M = *mac[d]; const Arr &L = lo[d], &H = hi[d];
     FOR_G1(E, i, j, k) E(i, j, k) = upwind_by(L(i, j, k), H(i, j, k), M(i, j, k));
   }
@@ -675,7 +729,7 @@ void edge_state_comp(const Arr& q, int c, const Arr* f, int fc, const Arr* divu,
 }
 
 // NavierStokesBase::ComputeAofs body, non-EB, !is_sync (NSB.cpp:4661-4845)
-void compute_aofs(const Arr& S, int ncomp, const Arr* force, const Arr* divu, Arr mac[3], const int* iconserv, bool fit,
+void compute_aofs(const Arr& S, int ncomp, const Arr* force, const Arr* divu, Arr mac[3], const int* iconserv, AdvOpt fit,
                   const double dx[3], double dt, Arr& aofs, int acomp, Arr* fl[3], Arr* eds[3]) {
   const int* n = S.n;
   const Arr* macp[3] = {&mac[0], &mac[1], &mac[2]};
@@ -711,14 +765,15 @@ void compute_aofs(const Arr& S, int ncomp, const Arr* force, const Arr* divu, Ar
 }
 
 // Godunov::ExtrapVelToFaces (hydro_godunov_extrap_vel_to_faces_3D.cpp), PLM, periodic
-void extrap_vel_to_faces(const Arr& vel, const Arr* f, bool fit, const double dx[3], double dt, Arr umac[3]) {
+void extrap_vel_to_faces(const Arr& vel, const Arr* f, AdvOpt opt, const double dx[3], double dt, Arr umac[3]) {
+  const bool fit = opt.fit;
   const int* n = vel.n;
   // traced states of every component on every face direction
   Arr lo[3][3], hi[3][3];  // [dir][comp]
   for (int d = 0; d < 3; ++d)
     for (int c = 0; c < 3; ++c) {
       lo[d][c].define(n, 1, 2); hi[d][c].define(n, 1, 2);
-      plm_lohi(vel, c, d, dt / dx[d], nullptr, &vel, f, c, fit, dt, lo[d][c], hi[d][c]);
+      (opt.ppm ? ppm_lohi : plm_lohi)(vel, c, d, dt / dx[d], nullptr, &vel, f, c, fit, dt, lo[d][c], hi[d][c]);
     }
   // advective velocities (ComputeAdvectiveVel) and transverse edge states upwinded by them
   Arr ad[3], ed[3][3];
@@ -863,7 +918,8 @@ struct orc_ns {
     for (int c = 0; c < 3; ++c) {
       FOR_G1(force, i, j, k) force(i, j, k, c) = (ext_force(c, Smf(i, j, k, 0)) + visc(i, j, k, c) - Gp_old(i, j, k, c)) / Smf(i, j, k, 0);  // :4466-4470
     }
-    extrap_vel_to_faces(Umf, &force, p.use_forces_in_trans != 0, dx, dt, umac);  // :4487
+    const AdvOpt aopt{p.use_forces_in_trans != 0, p.use_ppm != 0};
+    extrap_vel_to_faces(Umf, &force, aopt, dx, dt, umac);  // :4487
     *dt_test = dt * tempdt;
     // ---- mac_project NS.cpp:589-597, MacProj.cpp:225-353
     Arr mac_phi(n, 1, 1);
@@ -874,7 +930,7 @@ struct orc_ns {
     // ---- velocity_advection NSB.cpp:3358-3470 (fresh un-floored FillPatch copy, same forcing)
     Arr Umf2(n, 3, 3); Umf2.copy_from(S_old, Xvel, 0, 3); Umf2.fill_periodic();
     const int ic_vel[3] = {0, 0, 0};
-    compute_aofs(Umf2, 3, &force, nullptr, umac, ic_vel, p.use_forces_in_trans != 0, dx, dt, aofs, Xvel, nullptr, nullptr);
+    compute_aofs(Umf2, 3, &force, nullptr, umac, ic_vel, aopt, dx, dt, aofs, Xvel, nullptr, nullptr);
     // ---- scalar_advection NS.cpp:698-812
     for (double& v : Smf.d) v = (std::fabs(v) > 1.0e-20) ? v : 0.0;
     Arr sforce(n, 2, 1);
@@ -893,7 +949,7 @@ struct orc_ns {
       FOR_G1(sforce, i, j, k) sforce(i, j, k, 1) = sv(i, j, k);
     }
     const int ic_scal[2] = {1, p.conservative_tracer ? 1 : 0};
-    compute_aofs(Smf, 2, &sforce, nullptr, umac, ic_scal, p.use_forces_in_trans != 0, dx, dt, aofs, Density, nullptr, nullptr);
+    compute_aofs(Smf, 2, &sforce, nullptr, umac, ic_scal, aopt, dx, dt, aofs, Density, nullptr, nullptr);
     // ---- scalar updates NSB.cpp:2761-2765, 2887-2896
     FOR_CELLS(S_new, i, j, k) S_new(i, j, k, Density) = S_old(i, j, k, Density) - dt * aofs(i, j, k, Density);
     rho_c.copy_from(S_new, Density, 0, 1); rho_c.fill_periodic();
@@ -1157,7 +1213,7 @@ void orc_extrap_vel_to_faces(const int n[3], const double dx[3], double dt, cons
   Arr v(n, 3, 3), f; v.load(vel); v.fill_periodic();
   if (force) { f.define(n, 3, 1); f.load(force); f.fill_periodic(); }
   Arr mac[3] = {Arr(n, 1, 1), Arr(n, 1, 1), Arr(n, 1, 1)};
-  extrap_vel_to_faces(v, force ? &f : nullptr, forces_in_trans != 0, dx, dt, mac);
+  extrap_vel_to_faces(v, force ? &f : nullptr, AdvOpt{(forces_in_trans & 1) != 0, (forces_in_trans & 2) != 0}, dx, dt, mac);
   mac[0].store(umac); mac[1].store(vmac); mac[2].store(wmac);
 }
 
@@ -1176,7 +1232,7 @@ void orc_compute_aofs(const int n[3], const double dx[3], double dt, int ncomp, 
     if (fo[d]) { fl[d].define(n, ncomp, 0); flp[d] = &fl[d]; }
     if (eo[d]) { ed[d].define(n, ncomp, 0); edp[d] = &ed[d]; }
   }
-  compute_aofs(q, ncomp, force ? &f : nullptr, divu ? &dv : nullptr, mac, iconserv, forces_in_trans != 0, dx, dt, a, 0, flp, edp);
+  compute_aofs(q, ncomp, force ? &f : nullptr, divu ? &dv : nullptr, mac, iconserv, AdvOpt{(forces_in_trans & 1) != 0, (forces_in_trans & 2) != 0}, dx, dt, a, 0, flp, edp);
   a.store(aofs);
   for (int d = 0; d < 3; ++d) { if (fo[d]) fl[d].store(fo[d]); if (eo[d]) ed[d].store(eo[d]); }
 }
@@ -1184,7 +1240,7 @@ void orc_compute_aofs(const int n[3], const double dx[3], double dt, int ncomp, 
 void orc_ns_params_default(orc_ns_params* p) {
   p->cfl = 0.7; p->visc_coef = 0.0; p->be_cn_theta = 0.5; p->change_max = 1.1; p->init_shrink = 1.0; p->fixed_dt = -1.0;
   p->gravity = 0.0; p->visc_tol = 1e-10; p->mac_tol = 1e-12; p->mac_abs_tol = 1e-16; p->proj_tol = 1e-12; p->proj_abs_tol = 1e-16;
-  p->init_iter = 2; p->init_vel_iter = 1; p->do_init_proj = 1; p->use_forces_in_trans = 0; p->conservative_tracer = 0; p->verbose = 0; p->scal_diff_coef = 0.0;
+  p->init_iter = 2; p->init_vel_iter = 1; p->do_init_proj = 1; p->use_forces_in_trans = 0; p->conservative_tracer = 0; p->verbose = 0; p->scal_diff_coef = 0.0; p->use_ppm = 0;
 }
 
 orc_ns* orc_ns_create(const int n[3], const double prob_lo[3], const double prob_hi[3], const orc_ns_params* p) {

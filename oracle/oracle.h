@@ -71,7 +71,7 @@ void orc_nodal_mknewu(const int n[3], const double dxinv[3], const double* sigma
 /* Projection::doMLMGNodalProjection (Projection.cpp:2385-2567) */
 int orc_nodal_project(const int n[3], const double dx[3], double* vel, const double* sigma, double* phi,
                       double* gp, int increment_gp, orc_mg* mg);
-/* Godunov::ExtrapVelToFaces (NSB.cpp:4487-4491), PLM */
+/* Godunov::ExtrapVelToFaces (NSB.cpp:4487-4491); forces_in_trans is a flag word: bit 0 use_forces_in_trans, bit 1 PPM instead of PLM */
 void orc_extrap_vel_to_faces(const int n[3], const double dx[3], double dt, const double* vel,
                              const double* force, int forces_in_trans, double* umac, double* vmac,
                              double* wmac);
@@ -87,6 +87,7 @@ typedef struct orc_ns_params {
   double mac_tol, mac_abs_tol, proj_tol, proj_abs_tol;
   int init_iter, init_vel_iter, do_init_proj, use_forces_in_trans, conservative_tracer, verbose;
   double scal_diff_coef;   /* ns.scal_diff_coefs of the tracer (0: non-diffusive) */
+  int use_ppm, pad_;       /* ns.advection_scheme = Godunov_PPM (NSB.cpp:552-554, 4485) */
 } orc_ns_params;
 void orc_ns_params_default(orc_ns_params* p);
 typedef struct orc_ns orc_ns;

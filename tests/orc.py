@@ -21,7 +21,7 @@ class OrcNSParams(C.Structure):
                 ("init_shrink", C.c_double), ("fixed_dt", C.c_double), ("gravity", C.c_double), ("visc_tol", C.c_double),
                 ("mac_tol", C.c_double), ("mac_abs_tol", C.c_double), ("proj_tol", C.c_double), ("proj_abs_tol", C.c_double),
                 ("init_iter", C.c_int), ("init_vel_iter", C.c_int), ("do_init_proj", C.c_int), ("use_forces_in_trans", C.c_int),
-                ("conservative_tracer", C.c_int), ("verbose", C.c_int), ("scal_diff_coef", C.c_double)]
+                ("conservative_tracer", C.c_int), ("verbose", C.c_int), ("scal_diff_coef", C.c_double), ("use_ppm", C.c_int), ("pad_", C.c_int)]
 
 
 _lib = None
@@ -148,20 +148,20 @@ def nodal_project(dx, vel, sigma, phi, mg=None):
     return vel, phi, gp, rc, mg
 
 
-def extrap_vel_to_faces(dx, dt, vel, force, fit=0):
+def extrap_vel_to_faces(dx, dt, vel, force, fit=0, ppm=0):
     shp = vel.shape[1:]
     u, v, w = (np.empty(shp, dtype=np.float64) for _ in range(3))
-    lib().orc_extrap_vel_to_faces(_i3(_n_of(vel)), _d3(dx), C.c_double(dt), _p(vel), _p(force), int(fit), _p(u), _p(v), _p(w))
+    lib().orc_extrap_vel_to_faces(_i3(_n_of(vel)), _d3(dx), C.c_double(dt), _p(vel), _p(force), int(fit) | (2 if ppm else 0), _p(u), _p(v), _p(w))
     return u, v, w
 
 
-def compute_aofs(dx, dt, S, force, umac, vmac, wmac, iconserv, fit=0, divu=None, want_fluxes=False):
+def compute_aofs(dx, dt, S, force, umac, vmac, wmac, iconserv, fit=0, divu=None, want_fluxes=False, ppm=0):
     ncomp = S.shape[0]
     aofs = np.empty_like(S)
     ic = (C.c_int * ncomp)(*iconserv)
     outs = [np.empty_like(S) for _ in range(6)] if want_fluxes else [None] * 6
     lib().orc_compute_aofs(_i3(_n_of(S)), _d3(dx), C.c_double(dt), ncomp, _p(S), _p(force), _p(divu), _p(umac), _p(vmac),
-                           _p(wmac), ic, int(fit), _p(aofs), *[_p(o) for o in outs])
+                           _p(wmac), ic, int(fit) | (2 if ppm else 0), _p(aofs), *[_p(o) for o in outs])
     return (aofs, outs) if want_fluxes else aofs
 
 

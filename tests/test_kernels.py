@@ -264,14 +264,14 @@ def _adv_inputs(n, ncomp, seed):
 
 
 @pytest.mark.parametrize("nb", [(1, 1, 1), (2, 2, 2)])
-@pytest.mark.parametrize("fit", [0, 1])
-def test_extrap_vel_to_faces(backend, oracle, nb, fit):
+@pytest.mark.parametrize("fit,ppm", [(0, 0), (1, 0), (0, 1), (1, 1)])
+def test_extrap_vel_to_faces(backend, oracle, nb, fit, ppm):
     lib, dev = backend
     n = (16, 16, 8)
     vel, _, f, _, dx = _adv_inputs(n, 3, 100)
     vel[2] += 0.2  # make sure every branch of the upwinding sees both signs
     dt = 0.5 * min(dx) / np.abs(vel).max()
-    ref = oracle.extrap_vel_to_faces(dx, dt, vel, f[:3].copy(), fit)
+    ref = oracle.extrap_vel_to_faces(dx, dt, vel, f[:3].copy(), fit, ppm)
     g = ix.Geom.make(n)
     boxes = split_boxes(n, nb)
     outs = [[], [], []]
@@ -282,7 +282,7 @@ def test_extrap_vel_to_faces(backend, oracle, nb, fit):
         bb = box_of(*box)
         lib.check(lib.iamrx_extrap_vel_to_faces_box(C.byref(bb), C.byref(fv), C.byref(ff), C.byref(macs[0][1]),
                                                     C.byref(macs[1][1]), C.byref(macs[2][1]), C.byref(g), dt,
-                                                    2 if fit else 0, stream_of(dev)))
+                                                    (2 if fit else 0) | (1 if ppm else 0), stream_of(dev)))
         for d in range(3):
             outs[d].append(macs[d][0])
     sync(dev)
@@ -293,14 +293,15 @@ def test_extrap_vel_to_faces(backend, oracle, nb, fit):
 
 
 @pytest.mark.parametrize("nb", [(1, 1, 1), (2, 2, 2), (2, 2, 1)])
-@pytest.mark.parametrize("ncomp,iconserv,fit", [(3, (0, 0, 0), 0), (2, (1, 0), 0), (2, (1, 1), 1)])
-def test_compute_aofs(backend, oracle, nb, ncomp, iconserv, fit):
+@pytest.mark.parametrize("ncomp,iconserv,fit,ppm", [(3, (0, 0, 0), 0, 0), (2, (1, 0), 0, 0), (2, (1, 1), 1, 0),
+                                                    (3, (0, 0, 0), 0, 1), (2, (1, 0), 1, 1)])   # ppm: Godunov_PPM (staged kernels)
+def test_compute_aofs(backend, oracle, nb, ncomp, iconserv, fit, ppm):
     # (1,1,1) and (2,2,1): boxes are whole 8^3 tiles -> fused tile kernel on the GPU; (2,2,2): 8x8x4 boxes -> staged kernels
     lib, dev = backend
     n = (16, 16, 8)
     _, q, f, (um, vm, wm), dx = _adv_inputs(n, ncomp, 200)
     dt = 0.5 * min(dx) / max(np.abs(um).max(), np.abs(vm).max(), np.abs(wm).max())
-    ref, (rfx, rfy, rfz, rxe, rye, rze) = oracle.compute_aofs(dx, dt, q, f[:ncomp].copy(), um, vm, wm, iconserv, fit, want_fluxes=True)
+    ref, (rfx, rfy, rfz, rxe, rye, rze) = oracle.compute_aofs(dx, dt, q, f[:ncomp].copy(), um, vm, wm, iconserv, fit, want_fluxes=True, ppm=ppm)
     g = ix.Geom.make(n)
     boxes = split_boxes(n, nb)
     ic = (C.c_int * ncomp)(*iconserv)
@@ -313,7 +314,7 @@ def test_compute_aofs(backend, oracle, nb, ncomp, iconserv, fit):
         fl = [to_fab(np.zeros_like(q), box, 0, t, dev) for t in (ix.XFACE, ix.YFACE, ix.ZFACE)]
         ed = [to_fab(np.zeros_like(q), box, 0, t, dev) for t in (ix.XFACE, ix.YFACE, ix.ZFACE)]
         bb = box_of(*box)
-        flags = (2 if fit else 0) | 8
+        flags = (2 if fit else 0) | 8 | (1 if ppm else 0)
         lib.check(lib.iamrx_compute_aofs_box(C.byref(bb), C.byref(fa), 0, C.byref(fq), 0, ncomp, C.byref(ff), 0, None,
                                              C.byref(macs[0][1]), C.byref(macs[1][1]), C.byref(macs[2][1]),
                                              C.byref(fl[0][1]), C.byref(fl[1][1]), C.byref(fl[2][1]),
@@ -391,10 +392,10 @@ def test_bad_arguments(backend):
     n = (8, 8, 8)
     g = ix.Geom.make(n)
     box = ((0, 0, 0), (7, 7, 7))
-    z = np.zeros((3, 8, 8, 8))
-    tv, fv = to_fab(z, box, 3, ix.CELL, dev)
+    z = np.zeros((2, 8, 8, 8))
+    tv, fv = to_fab(z, box, 3, ix.CELL, dev)          # only 2 components: ExtrapVelToFaces needs all three velocities
     macs = [to_fab(z[:1], box, 1, t, dev) for t in (ix.XFACE, ix.YFACE, ix.ZFACE)]
     bb = box_of(*box)
     rc = lib.iamrx_extrap_vel_to_faces_box(C.byref(bb), C.byref(fv), None, C.byref(macs[0][1]), C.byref(macs[1][1]),
-                                           C.byref(macs[2][1]), C.byref(g), 0.1, 1, stream_of(dev))
-    assert rc == -1 and b"PPM" in lib.iamrx_last_error()
+                                           C.byref(macs[2][1]), C.byref(g), 0.1, 0, stream_of(dev))
+    assert rc == -1 and b"3 components" in lib.iamrx_last_error()

@@ -14,8 +14,8 @@ import pytest
 from util import hash_uniform, smooth_field
 
 
-def _tg_error(oracle, n, t_end, nu=1e-3):
-    o = oracle.OracleNS((n, n, n), visc_coef=nu, cfl=0.7)
+def _tg_error(oracle, n, t_end, nu=1e-3, **kw):
+    o = oracle.OracleNS((n, n, n), visc_coef=nu, cfl=0.7, **kw)
     o.init_prob(11, [1.0, 1.0, 0.0, 1.0, 1.0])
     o.post_init()
     while o.time < t_end - 1e-12:
@@ -183,3 +183,13 @@ def test_tracer_diffusion_properties(oracle):
         assert abs(S4.sum() - s0) <= 1e-12 * np.abs(S4).sum()   # the synthetic tracer has zero mean: absolute scale
     assert np.abs(res["off"][0] - res["zero"][0]).max() <= 1e-13   # same path (OpenMP reductions are not bit-reproducible)
     assert res["on"][0].var() < res["off"][0].var()
+
+
+def test_taylor_vortex_second_order_ppm(oracle):
+    """ns.advection_scheme = Godunov_PPM: the same analytic vortex (EXACT_3D.F), still second order."""
+    e16, m16, w16 = _tg_error(oracle, 16, 0.05, use_ppm=1)
+    e32, m32, w32 = _tg_error(oracle, 32, 0.05, use_ppm=1)
+    rate = math.log2(e16 / e32)
+    assert 1.7 < rate < 3.2, (e16, e32, rate)
+    assert e32 < 2e-3
+    assert abs(m32 - 1.0) < 1e-13 and w32 < 1e-13

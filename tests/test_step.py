@@ -28,6 +28,7 @@ def _assemble(ns, which, boxes, n, ncomp, ext=(0, 0, 0)):
     (100, [1.0, 1.0, 1.0, 1.0, 1.0], {"scal_diff_coef": 5e-3}),
     (100, [1.0, 1.0, 1.0, 1.0, 1.0], {"scal_diff_coef": 5e-3, "conservative_tracer": 1, "gravity": -0.5}),
     (5, [1.0, 1.0, 0.0, 0.0, 0.0, 0.4], {"scal_diff_coef": 2e-2, "be_cn_theta": 1.0}),   # backward Euler: no old-time term
+    (100, [1.0, 1.0, 1.0, 1.0, 1.0], {"godunov_ppm": 1, "gravity": -0.5}),               # ns.advection_scheme = Godunov_PPM
 ])
 def test_step_matches_oracle(backend, oracle, nb, probtype, pp, extra):
     """Velocity / pressure L-inf parity <= 1e-10 (north_star tolerance) over init + 3 steps."""
@@ -40,7 +41,8 @@ def test_step_matches_oracle(backend, oracle, nb, probtype, pp, extra):
     kw = dict(visc_coef=1e-3, cfl=0.7)
     kw.update(extra)
     ns = ix.NavierStokes(lib, lev, dev, **kw)
-    o = oracle.OracleNS(n, lo, hi, **kw)
+    okw = {("use_ppm" if k == "godunov_ppm" else k): v for k, v in kw.items()}
+    o = oracle.OracleNS(n, lo, hi, **okw)
     ns.init_prob(probtype, pp); o.init_prob(probtype, pp)
     d1, d2 = ns.post_init(), o.post_init()
     assert abs(d1 - d2) <= 1e-13 * d2
