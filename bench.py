@@ -313,7 +313,7 @@ def run_ours(args):
             "dtype": "f64", "data": "synthetic",
             "config": {"workload": f"TaylorGreen 3D {nbox}^3 per GPU single-level (Tutorials/TaylorGreen/inputs.3d.taylorgreen, "
                                    f"nu=1e-4, cfl=0.7, periodic), BASELINE.json configs[1]" + ("" if world == 1 else " weak-scaled"),
-                       "n_cell": list(ncell), "boxes": len(boxes), "box": nbox, "parallelism": f"one {nbox}^3 box per rank x{world}",
+                       "n_cell": list(ncell), "boxes": len(boxes), "box": nbox, "parallelism": f"one {nbox}^3 box per rank x{world}" + ("" if world == 1 else ", z slabs: x/y wrapped in-kernel, z ghost planes over NCCL, coarse multigrid levels replicated"),
                        "l2": "working set per kernel >> 126 MB L2 (one fp64 cell array = 134 MB)",
                        "mg_iters_last_step": {"mac": iters[-1][0], "visc": iters[-1][1], "nodal": iters[-1][2]}},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": state_bytes, "d2h_bytes_per_step": state_bytes,

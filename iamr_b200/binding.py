@@ -143,6 +143,7 @@ SIGNATURES = {
     "iamrx_ns_field": (C.c_int, [_vp, C.c_int, C.c_int, _P(Fab)]),
     "iamrx_ns_step_host": (C.c_int, [_vp, _P(_vp), _P(_vp), _P(C.c_double)]),
     "iamrx_ns_last_iters": (C.c_int, [_vp, _P(C.c_int)]),
+    "iamrx_ns_sum_integrated_quantities": (C.c_int, [_vp, _P(C.c_double)]),
 }
 
 
@@ -335,6 +336,12 @@ class NavierStokes:
         it = (C.c_int * 3)()
         self.lib.check(self.lib.iamrx_ns_last_iters(self.h, it))
         return tuple(it)
+
+    def sums(self):
+        """(MASS, TRAC, KINETIC ENERGY) as NavierStokes::sum_integrated_quantities prints them."""
+        out = (C.c_double * 3)()
+        self.lib.check(self.lib.iamrx_ns_sum_integrated_quantities(self.h, out))
+        return tuple(out)
 
     def close(self):
         if self.h:

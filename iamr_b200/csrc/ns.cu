@@ -610,4 +610,27 @@ int iamrx_ns_last_iters(iamrx_ns_t ns, int iters[3]) {
   return IAMRX_OK;
 }
 
+int iamrx_ns_sum_integrated_quantities(iamrx_ns_t nsp, double out[3]) {
+  IX_NEED_DEVICE();
+  IX_ARG(nsp && out, "null argument");
+  iamrx_ns_s& ns = *nsp;
+  Level& L = *ns.L;
+  const double vol = L.geom.dx[0] * L.geom.dx[1] * L.geom.dx[2];
+  double mass = 0.0, trac = 0.0, ke = 0.0;
+  IX_TRY(mf_sum(ns.S_new, Density, &mass, ns.s));
+  IX_TRY(mf_sum(ns.S_new, Tracer, &trac, ns.s));
+  // derkeng: 0.5 rho (u^2 + v^2 + w^2), built in the estTimeStep scratch from existing pointwise kernels
+  IX_TRY(mf_copy(ns.tf0, ns.S_new, Xvel, 0, 3, 0, ns.s));
+  for (int il = 0; il < ns.tf0.n(); ++il) {
+    const Bx& b = L.lbox(il);
+    IX_TRY(k::mult(b, ns.tf0.v(il), ns.tf0.c(il), 3, 3, ns.s));                                        // squares
+    IX_TRY(k::lincomb(b, ns.tf0.v(il, 0), 1.0, ns.tf0.c(il, 0), 1.0, ns.tf0.c(il, 1), 1, ns.s));
+    IX_TRY(k::lincomb(b, ns.tf0.v(il, 0), 1.0, ns.tf0.c(il, 0), 1.0, ns.tf0.c(il, 2), 1, ns.s));
+    IX_TRY(k::mult(b, ns.tf0.v(il, 0), ns.S_new.c(il, Density), 1, 1, ns.s));
+  }
+  IX_TRY(mf_sum(ns.tf0, 0, &ke, ns.s));
+  out[0] = mass * vol; out[1] = trac * vol; out[2] = 0.5 * ke * vol;
+  return IAMRX_OK;
+}
+
 }  // extern "C"

@@ -392,6 +392,10 @@ int iamrx_ns_step_host(iamrx_ns_t ns, const double* const* host_state_in,
                        double* const* host_state_out, double* dt_io);
 /* solver statistics of the last step: iterations of {mac, visc, nodal}. */
 int iamrx_ns_last_iters(iamrx_ns_t ns, int iters[3]);
+/* NavierStokes::sum_integrated_quantities (NS.cpp:1046-1080): volume-weighted sums of the new state over the level, all
+ * ranks: out = {MASS (density), TRAC (tracer), KINETIC ENERGY (derkeng: 0.5 rho |u|^2, NS_derive.cpp:266-300)} -- the
+ * numbers IAMR prints as "TIME= .. MASS= .." every ns.sum_interval steps. */
+int iamrx_ns_sum_integrated_quantities(iamrx_ns_t ns, double out[3]);
 
 #ifdef __cplusplus
 }
