@@ -60,6 +60,30 @@ def test_step_matches_oracle(backend, oracle, nb, probtype, pp, extra):
     ns.close(); o.close(); lev.close()
 
 
+@pytest.mark.parametrize("nb", [(1, 1, 2), (1, 1, 4), (1, 2, 1)])
+def test_step_slab_decompositions_match_oracle(backend, oracle, nb):
+    """Several boxes on ONE rank that each span the periodic domain in two directions (the bench.py slab layout, here with local
+    plane copies instead of NCCL): per-direction wrap masks, skip-mask ghost fills, the two-phase fused nodal sweep and the
+    consolidated coarse levels must reproduce the single-box oracle."""
+    lib, dev = backend
+    n = (16, 16, 16)
+    boxes = split_boxes(n, nb)
+    lev = ix.Level(lib, ix.Geom.make(n), boxes)
+    kw = dict(visc_coef=1e-3, cfl=0.7, gravity=-0.5)
+    ns = ix.NavierStokes(lib, lev, dev, **kw)
+    o = oracle.OracleNS(n, **kw)
+    pp = [1.0, 1.0, 1.0, 1.0, 1.0]
+    ns.init_prob(100, pp); o.init_prob(100, pp)
+    d1, d2 = ns.post_init(), o.post_init()
+    assert abs(d1 - d2) <= 1e-13 * d2
+    for step in range(2):
+        a, b = ns.step(), o.step()
+        assert abs(a - b) <= 1e-12 * b
+    assert np.abs(_assemble(ns, 0, boxes, n, 5) - o.get(0)).max() <= 1e-10
+    assert np.abs(_assemble(ns, 2, boxes, n, 3) - o.get(2)).max() <= 1e-9
+    ns.close(); o.close(); lev.close()
+
+
 @pytest.mark.parametrize("nb", [(1, 1, 1), (2, 1, 2)])
 def test_sum_integrated_quantities(backend, nb):
     """iamrx_ns_sum_integrated_quantities (NavierStokes::sum_integrated_quantities, NS.cpp:1046-1080) against the same sums taken
