@@ -116,7 +116,28 @@ def main():
         err2 = max(err2, np.abs(t - So[:, lo[2]:hi[2] + 1, lo[1]:hi[1] + 1, lo[0]:hi[0] + 1]).max())
     assert err2 <= 1e-10, err2
     o2.close()
-    # 4. reductions agree across ranks
+    ns.close(); lev.close()
+
+    # 4. the empty case: rank 1 owns NO boxes (both slabs on rank 0) -- it must still take part in every exchange,
+    #    gather and reduction and report the same dt and solver iterations
+    owners = [0, 0]
+    lev = ix.Level(lib, g, boxes, owners)
+    assert lev.num_local() == (2 if rank == 0 else 0)
+    ns = ix.NavierStokes(lib, lev, "cpu", **kw)
+    ns.init_prob(100, pp)
+    dts = [ns.post_init()] + [ns.step() for _ in range(2)]
+    o3 = orc.OracleNS(n, **kw)
+    o3.init_prob(100, pp)
+    dto = [o3.post_init()] + [o3.step() for _ in range(2)]
+    assert np.allclose(dts, dto, rtol=1e-12, atol=0)
+    if rank == 0:
+        So = o3.get(0)
+        for il, (lo, hi) in enumerate(boxes):
+            t = ns.field(0, il).numpy()
+            err2 = max(err2, np.abs(t - So[:, lo[2]:hi[2] + 1, lo[1]:hi[1] + 1, lo[0]:hi[0] + 1]).max())
+        assert err2 <= 1e-10, err2
+    o3.close()
+    # 5. reductions agree across ranks
     t = torch.tensor([max(err, err2)])
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     print(f"rank {rank} ok max_err {t.item():.3e}", flush=True)
