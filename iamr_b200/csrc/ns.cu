@@ -431,8 +431,9 @@ int iamrx_ns_destroy(iamrx_ns_t ns) {
 int iamrx_ns_init_prob(iamrx_ns_t ns, int probtype, const double* prob_params, int nparams) {
   IX_NEED_DEVICE();
   IX_ARG(ns && prob_params && nparams >= 0, "null argument");
-  IX_ARG(probtype == 11 || probtype == 100 || probtype == 5, "probtype must be 11 (TaylorGreen), 5 (DoubleShearLayer) or 100");
-  IX_ARG((probtype == 5) ? nparams >= 6 : nparams >= 5, "too few prob parameters");
+  IX_ARG(probtype == 11 || probtype == 100 || probtype == 5 || probtype == 20,
+         "probtype must be 11 (TaylorGreen), 5 (DoubleShearLayer), 20 (HIT) or 100");
+  IX_ARG((probtype == 5) ? nparams >= 6 : (probtype == 20 ? nparams >= 2 : nparams >= 5), "too few prob parameters");
   Level& L = *ns->L;
   // NavierStokes::initData (NS.cpp:335-460): S_new from prob_init, P_new = 0, Gp = 0
   for (int il = 0; il < ns->S_new.n(); ++il)

@@ -73,7 +73,7 @@ struct ProbParams { double v[16]; int n; };
 
 // prob_init.cpp: probtype 11 TaylorGreen (:509-560); probtype 5 DoubleShearLayer
 // (:346-405, direction 1, extended uniformly in z); probtype 100 = synthetic
-// variable-density Taylor-Green used by the HIT-like weak-scaling configuration.
+// variable-density Taylor-Green; probtype 20 = the HIT tutorial's initial condition.
 __global__ void init_kernel(Bx bx, V4 st, int probtype, ProbParams pp, iamrx_geom g) {
   IDX3(bx)
   (void)n;
@@ -103,6 +103,18 @@ __global__ void init_kernel(Bx bx, V4 st, int probtype, ProbParams pp, iamrx_geo
     const double bx0 = pp.v[2], by0 = pp.v[3], bz0 = pp.v[4], br = pp.v[5];
     const double d = sqrt((x - bx0) * (x - bx0) + (y - by0) * (y - by0) + (z - bz0) * (z - bz0));
     st(i, j, k, 4) = (d < br) ? 1.0 : 0.0;
+  } else if (probtype == 20) {
+    // HIT (Tutorials/HIT/prob_init.cpp:100-131): params = turb_scale, density [, amplitude of the synthetic density variation
+    // of BASELINE.json's "variable-density HIT"; 0 = the reference's constant density].  Lz is measured from prob_lo[1] as
+    // in the reference (:113).
+    const double ts = pp.v[0], dens = pp.v[1], vd = pp.n > 2 ? pp.v[2] : 0.0;
+    const double Lx = (g.domain.hi[0] - g.domain.lo[0] + 1) * g.dx[0], Ly = (g.domain.hi[1] - g.domain.lo[1] + 1) * g.dx[1];
+    const double Lz = g.prob_lo[2] + (g.domain.hi[2] - g.domain.lo[2] + 1) * g.dx[2] - g.prob_lo[1];
+    st(i, j, k, 0) = ts * cos(twopi * y / Ly) * cos(twopi * z / Lz);
+    st(i, j, k, 1) = ts * cos(twopi * x / Lx) * cos(twopi * z / Lz);
+    st(i, j, k, 2) = ts * cos(twopi * x / Lx) * cos(twopi * y / Ly);
+    st(i, j, k, 3) = dens * (1.0 + vd * sin(twopi * x / Lx) * sin(twopi * y / Ly) * sin(twopi * z / Lz));
+    st(i, j, k, 4) = 1.0;
   }
 }
 

@@ -369,9 +369,10 @@ void iamrx_ns_params_default(iamrx_ns_params* p);
 
 int iamrx_ns_create(iamrx_level_t lev, const iamrx_ns_params* p, iamrx_ns_t* out);
 int iamrx_ns_destroy(iamrx_ns_t ns);
-/* prob_init: probtype 11 TaylorGreen (prob_init.cpp:509-560) with (a,b,c,
- * velocity_factor, density) ; probtype 5 DoubleShearLayer-like 3-D variant and
- * a variable-density HIT-like synthetic field are selected by `probtype`. */
+/* prob_init: probtype 11 TaylorGreen (prob_init.cpp:509-560) with (a,b,c, velocity_factor, density); probtype 5
+ * DoubleShearLayer (:346-405, direction 1, uniform in z; density, interface_width, blob centre x y z, blob radius);
+ * probtype 20 the HIT tutorial's field (Tutorials/HIT/prob_init.cpp:100-131; turb_scale, density [, amplitude of a
+ * synthetic density variation]); probtype 100 a synthetic variable-density Taylor-Green field. */
 int iamrx_ns_init_prob(iamrx_ns_t ns, int probtype, const double* prob_params, int nparams);
 /* NavierStokes::post_init: initial velocity projection, initial dt, initial
  * pressure iterations. Returns dt for the first step in *dt0. */

@@ -1255,7 +1255,7 @@ orc_ns* orc_ns_create(const int n[3], const double prob_lo[3], const double prob
 }
 void orc_ns_destroy(orc_ns* ns) { delete ns; }
 
-void orc_ns_init_prob(orc_ns* ns, int probtype, const double* pp, int) {
+void orc_ns_init_prob(orc_ns* ns, int probtype, const double* pp, int npp) {
   // Source/prob/prob_init.cpp: 11 TaylorGreen :509-560, 5 DoubleShearLayer :346-405 (direction 1);
   // 100 = synthetic variable-density Taylor-Green (not in the reference)
   const double twopi = 2.0 * 3.14159265358979323846264338327950288;
@@ -1273,6 +1273,14 @@ void orc_ns_init_prob(orc_ns* ns, int probtype, const double* pp, int) {
           S(i, j, k, 2) = 0.0;
           S(i, j, k, 3) = (probtype == 100) ? dens * (1.0 + 0.5 * std::sin(twopi * x) * std::sin(twopi * y) * std::sin(twopi * z)) : dens;
           S(i, j, k, 4) = (dens * vx * vx / 16.0) * (2.0 + std::cos(2.0 * c * twopi * z)) * (std::cos(2.0 * a * twopi * x) + std::cos(2.0 * b * twopi * y));
+        } else if (probtype == 20) {   // Tutorials/HIT/prob_init.cpp:100-131 (+ optional synthetic density variation pp[2])
+          const double ts = pp[0], dens = pp[1], vd = npp > 2 ? pp[2] : 0.0;
+          const double Lx = n[0] * ns->dx[0], Ly = n[1] * ns->dx[1], Lz = ns->prob_lo[2] + n[2] * ns->dx[2] - ns->prob_lo[1];   // :113
+          S(i, j, k, 0) = ts * std::cos(twopi * y / Ly) * std::cos(twopi * z / Lz);
+          S(i, j, k, 1) = ts * std::cos(twopi * x / Lx) * std::cos(twopi * z / Lz);
+          S(i, j, k, 2) = ts * std::cos(twopi * x / Lx) * std::cos(twopi * y / Ly);
+          S(i, j, k, 3) = dens * (1.0 + vd * std::sin(twopi * x / Lx) * std::sin(twopi * y / Ly) * std::sin(twopi * z / Lz));
+          S(i, j, k, 4) = 1.0;
         } else {
           const double dens = pp[0], width = pp[1] > 0 ? pp[1] : 1.0, pi = 0.5 * twopi;
           S(i, j, k, 0) = -0.05 * std::sin(pi * y);

@@ -29,12 +29,15 @@ def _assemble(ns, which, boxes, n, ncomp, ext=(0, 0, 0)):
     (100, [1.0, 1.0, 1.0, 1.0, 1.0], {"scal_diff_coef": 5e-3, "conservative_tracer": 1, "gravity": -0.5}),
     (5, [1.0, 1.0, 0.0, 0.0, 0.0, 0.4], {"scal_diff_coef": 2e-2, "be_cn_theta": 1.0}),   # backward Euler: no old-time term
     (100, [1.0, 1.0, 1.0, 1.0, 1.0], {"godunov_ppm": 1, "gravity": -0.5}),               # ns.advection_scheme = Godunov_PPM
+    (20, [1.0, 1.0, 0.5], {}),   # Tutorials/HIT initial field on [-1/2, 1/2]^3 with the synthetic density variation (BASELINE configs[4])
 ])
 def test_step_matches_oracle(backend, oracle, nb, probtype, pp, extra):
     """Velocity / pressure L-inf parity <= 1e-10 (north_star tolerance) over init + 3 steps."""
     lib, dev = backend
     n = (16, 16, 16)
     lo, hi = ((-1.0, -1.0, -1.0), (1.0, 1.0, 1.0)) if probtype == 5 else ((0, 0, 0), (1, 1, 1))
+    if probtype == 20:
+        lo, hi = (-0.5, -0.5, -0.5), (0.5, 0.5, 0.5)   # inputs.3d.forced geometry
     g = ix.Geom.make(n, lo, hi)
     boxes = split_boxes(n, nb)
     lev = ix.Level(lib, g, boxes)
