@@ -122,6 +122,8 @@ int vel_update(const Bx& bx, V4 unew, C4 uold, C4 aofs, C4 gp, C4 rhohalf, doubl
                int zero_force, cudaStream_t s);
 // scalar update NSB.cpp:2761-2765 / 2887-2896 with the default (zero) scalar forcing
 int scal_update(const Bx& bx, V4 snew, C4 sold, C4 aofs, double dt, int ncomp, cudaStream_t s);
+// ns.do_scalminmax: Conservative / ConvectiveScalMinMax (NSB.cpp:2907-2935, 4256-4370); sold / rhoold need 1 filled ghost cell
+int scal_minmax(const Bx& bx, V4 snew, C4 rhonew, C4 sold, C4 rhoold, int conservative, cudaStream_t s);
 // diffusion rhs: unew *= rho; rhs += unew (Diffusion.cpp:821-831)
 int diff_rhs(const Bx& bx, V4 rhs, V4 unew, C4 rho, int ncomp, cudaStream_t s);
 // level_project pre: u = u*dt_inv + gp/rho  (Projection.cpp:273,296-300)

@@ -45,6 +45,7 @@ struct iamrx_ns_s {
   MF tf0;               // estTimeStep forces, 0 ghost
   MF seta[3];           // tracer diffusivity on faces (getDiffusivity: constant ns.scal_diff_coefs, NS.cpp:2051-2119)
   MF s1, r1, svisc, ones;  // tracer diffusion work: Soln (1 ghost), Rhs, visc term (1 ghost), alpha = 1
+  MF smm;                  // old scalars (density, tracer) with 1 filled ghost for ns.do_scalminmax
 
   double time = 0.0, dt_level = 0.0, dt_min = 1.0e100;
   int nstep = 0;
@@ -290,6 +291,12 @@ int advance(iamrx_ns_s& ns, double time, double dt, double* dt_test) {
   IX_TRY(fillpatch(ns, ns.rho_ctime, ns.S_new, Density, 1));   // make_rho_curr_time :618
   for (int il = 0; il < ns.S_new.n(); ++il)                    // scalar_update(tracer) :627 -> NSB.cpp:2887-2896
     IX_TRY(k::scal_update(L.lbox(il), ns.S_new.v(il, Tracer), ns.S_old.c(il, Tracer), ns.aofs.c(il, Tracer), dt, 1, ns.s));
+  if (ns.p.do_scalminmax) {                                    // NSB.cpp:2907-2935 (fresh FillPatch of the old scalars, 1 ghost)
+    IX_TRY(fillpatch(ns, ns.smm, ns.S_old, Density, NUM_SCALARS));
+    for (int il = 0; il < ns.S_new.n(); ++il)
+      IX_TRY(k::scal_minmax(L.lbox(il), ns.S_new.v(il, Tracer), ns.S_new.c(il, Density), ns.smm.c(il, Tracer - Density), ns.smm.c(il, 0),
+                            ns.p.conservative_tracer ? 1 : 0, ns.s));
+  }
   IX_TRY(tracer_diffusion_update(ns, dt));                     // scalar_update -> scalar_diffusion_update NS.cpp:836-841
 #if !defined(IX_EMUL)
   if (ns.early_out && ns.S_new.n() == 1) {   // scalars are final: pack + copy them out underneath the velocity solves
@@ -365,6 +372,7 @@ void iamrx_ns_params_default(iamrx_ns_params* p) {
   p->conservative_tracer = 0;
   p->mg_verbose = 0;
   p->godunov_ppm = 0;     // ns.advection_scheme = Godunov_PLM (NSB.cpp:169)
+  p->do_scalminmax = 0;   // NSB.cpp:140
 }
 
 int iamrx_ns_create(iamrx_level_t lev, const iamrx_ns_params* p, iamrx_ns_t* out) {
@@ -389,6 +397,7 @@ int iamrx_ns_create(iamrx_level_t lev, const iamrx_ns_params* p, iamrx_ns_t* out
   for (int d = 0; d < 3; ++d) ns->eta[d].define(L, IX_XFACE + d, 1, 0);
   ns->soln.define(L, IX_CELL, 3, 1); ns->rhs3.define(L, IX_CELL, 3, 0);
   ns->sig.define(L, IX_CELL, 1, 1); ns->mac_phi.define(L, IX_CELL, 1, 1); ns->tf0.define(L, IX_CELL, 3, 0);
+  if (p->do_scalminmax) ns->smm.define(L, IX_CELL, NUM_SCALARS, 1);
   if (p->scal_diff_coef > 0.0) {
     for (int d = 0; d < 3; ++d) ns->seta[d].define(L, IX_XFACE + d, 1, 0);
     ns->s1.define(L, IX_CELL, 1, 1); ns->r1.define(L, IX_CELL, 1, 0); ns->svisc.define(L, IX_CELL, 1, 1); ns->ones.define(L, IX_CELL, 1, 1);

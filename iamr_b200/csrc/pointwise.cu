@@ -47,6 +47,24 @@ __global__ void vel_update_kernel(Bx bx, V4 unew, C4 uold, C4 aofs, C4 gp, C4 rh
   unew(i, j, k, n) = uold(i, j, k, n) - dt * aofs(i, j, k, n) + dt * force / r - dt * gp(i, j, k, n) / r;
 }
 
+// NavierStokesBase::ConservativeScalMinMax / ConvectiveScalMinMax (NSB.cpp:4256-4370): clamp the new scalar (per unit mass when
+// conservative) to the range of the old one over the 3x3x3 neighbourhood.  smx starts from numeric_limits::min() (the smallest
+// POSITIVE double) exactly as in the reference.
+__global__ void scal_minmax_kernel(Bx bx, V4 snew, C4 rhonew, C4 sold, C4 rhoold, int conservative) {
+  IDX3(bx)
+  (void)n;
+  double smn = 1.7976931348623157e308, smx = 2.2250738585072014e-308;
+  for (int kk = -1; kk <= 1; ++kk)
+    for (int jj = -1; jj <= 1; ++jj)
+      for (int ii = -1; ii <= 1; ++ii) {
+        double v = sold(i + ii, j + jj, k + kk);
+        if (conservative) v /= rhoold(i + ii, j + jj, k + kk);
+        smn = fmin(smn, v); smx = fmax(smx, v);
+      }
+  if (conservative) snew(i, j, k) = fmin(fmax(snew(i, j, k) / rhonew(i, j, k), smn), smx) * rhonew(i, j, k);
+  else snew(i, j, k) = fmin(fmax(snew(i, j, k), smn), smx);
+}
+
 __global__ void scal_update_kernel(Bx bx, V4 snew, C4 sold, C4 aofs, double dt) {
   IDX3(bx)
   snew(i, j, k, n) = sold(i, j, k, n) - dt * aofs(i, j, k, n);
@@ -137,6 +155,9 @@ int vel_update(const Bx& bx, V4 unew, C4 uold, C4 aofs, C4 gp, C4 rhohalf, doubl
 }
 int scal_update(const Bx& bx, V4 snew, C4 sold, C4 aofs, double dt, int ncomp, cudaStream_t s) {
   LAUNCH3(scal_update_kernel, bx, ncomp, s, snew, sold, aofs, dt);
+}
+int scal_minmax(const Bx& bx, V4 snew, C4 rhonew, C4 sold, C4 rhoold, int conservative, cudaStream_t s) {
+  LAUNCH3(scal_minmax_kernel, bx, 1, s, snew, rhonew, sold, rhoold, conservative);
 }
 int diff_rhs(const Bx& bx, V4 rhs, V4 unew, C4 rho, int ncomp, cudaStream_t s) {
   LAUNCH3(diff_rhs_kernel, bx, ncomp, s, rhs, unew, rho);

@@ -363,6 +363,8 @@ typedef struct iamrx_ns_params {
   int conservative_tracer; /* ns.do_cons_trac */
   int mg_verbose;
   int godunov_ppm;       /* ns.advection_scheme = Godunov_PPM instead of the default Godunov_PLM (NSB.cpp:169,552-554) */
+  int do_scalminmax;     /* ns.do_scalminmax (NSB.cpp:140,2907-2935): clamp the advected tracer to the old 3x3x3 range */
+  int pad_;
 } iamrx_ns_params;
 
 void iamrx_ns_params_default(iamrx_ns_params* p);

@@ -17,6 +17,7 @@
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <limits>
 #include <memory>
 #include <vector>
 #ifdef _OPENMP
@@ -954,6 +955,20 @@ struct orc_ns {
     FOR_CELLS(S_new, i, j, k) S_new(i, j, k, Density) = S_old(i, j, k, Density) - dt * aofs(i, j, k, Density);
     rho_c.copy_from(S_new, Density, 0, 1); rho_c.fill_periodic();
     FOR_CELLS(S_new, i, j, k) S_new(i, j, k, Tracer) = S_old(i, j, k, Tracer) - dt * aofs(i, j, k, Tracer);
+    if (p.do_scalminmax) {   // NSB.cpp:2907-2935 -> Conservative / ConvectiveScalMinMax (:4256-4370) on an un-floored copy of the old scalars
+      Arr so(n, 2, 1); so.copy_from(S_old, Density, 0, 2); so.fill_periodic();
+      const bool cons = p.conservative_tracer != 0;
+      FOR_CELLS(S_new, i, j, k) {
+        double smn = std::numeric_limits<double>::max(), smx = std::numeric_limits<double>::min();   // sic: smallest positive value
+        for (int kk = -1; kk <= 1; ++kk) for (int jj = -1; jj <= 1; ++jj) for (int ii = -1; ii <= 1; ++ii) {
+          const double v = cons ? so(i + ii, j + jj, k + kk, 1) / so(i + ii, j + jj, k + kk, 0) : so(i + ii, j + jj, k + kk, 1);
+          smn = std::min(smn, v); smx = std::max(smx, v);
+        }
+        const double r = S_new(i, j, k, Density);
+        S_new(i, j, k, Tracer) = cons ? std::min(std::max(S_new(i, j, k, Tracer) / r, smn), smx) * r
+                                      : std::min(std::max(S_new(i, j, k, Tracer), smn), smx);
+      }
+    }
     if (diffusive_tracer()) { rc = tracer_diffusion(dt); if (rc) return rc; }   // scalar_update -> scalar_diffusion_update NS.cpp:836-841
     // ---- velocity_update NSB.cpp:3487-3655
     FOR_G1(rho_half, i, j, k) rho_half(i, j, k) = 0.5 * (rho_p(i, j, k) + rho_c(i, j, k));
@@ -1240,7 +1255,7 @@ void orc_compute_aofs(const int n[3], const double dx[3], double dt, int ncomp, 
 void orc_ns_params_default(orc_ns_params* p) {
   p->cfl = 0.7; p->visc_coef = 0.0; p->be_cn_theta = 0.5; p->change_max = 1.1; p->init_shrink = 1.0; p->fixed_dt = -1.0;
   p->gravity = 0.0; p->visc_tol = 1e-10; p->mac_tol = 1e-12; p->mac_abs_tol = 1e-16; p->proj_tol = 1e-12; p->proj_abs_tol = 1e-16;
-  p->init_iter = 2; p->init_vel_iter = 1; p->do_init_proj = 1; p->use_forces_in_trans = 0; p->conservative_tracer = 0; p->verbose = 0; p->scal_diff_coef = 0.0; p->use_ppm = 0;
+  p->init_iter = 2; p->init_vel_iter = 1; p->do_init_proj = 1; p->use_forces_in_trans = 0; p->conservative_tracer = 0; p->verbose = 0; p->scal_diff_coef = 0.0; p->use_ppm = 0; p->do_scalminmax = 0;
 }
 
 orc_ns* orc_ns_create(const int n[3], const double prob_lo[3], const double prob_hi[3], const orc_ns_params* p) {

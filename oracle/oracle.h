@@ -87,7 +87,8 @@ typedef struct orc_ns_params {
   double mac_tol, mac_abs_tol, proj_tol, proj_abs_tol;
   int init_iter, init_vel_iter, do_init_proj, use_forces_in_trans, conservative_tracer, verbose;
   double scal_diff_coef;   /* ns.scal_diff_coefs of the tracer (0: non-diffusive) */
-  int use_ppm, pad_;       /* ns.advection_scheme = Godunov_PPM (NSB.cpp:552-554, 4485) */
+  int use_ppm;             /* ns.advection_scheme = Godunov_PPM (NSB.cpp:552-554, 4485) */
+  int do_scalminmax;       /* ns.do_scalminmax (NSB.cpp:2907-2935) */
 } orc_ns_params;
 void orc_ns_params_default(orc_ns_params* p);
 typedef struct orc_ns orc_ns;

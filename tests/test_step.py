@@ -29,6 +29,8 @@ def _assemble(ns, which, boxes, n, ncomp, ext=(0, 0, 0)):
     (100, [1.0, 1.0, 1.0, 1.0, 1.0], {"scal_diff_coef": 5e-3, "conservative_tracer": 1, "gravity": -0.5}),
     (5, [1.0, 1.0, 0.0, 0.0, 0.0, 0.4], {"scal_diff_coef": 2e-2, "be_cn_theta": 1.0}),   # backward Euler: no old-time term
     (100, [1.0, 1.0, 1.0, 1.0, 1.0], {"godunov_ppm": 1, "gravity": -0.5}),               # ns.advection_scheme = Godunov_PPM
+    (5, [1.0, 1.0, 0.0, 0.0, 0.0, 0.4], {"do_scalminmax": 1}),                            # ConvectiveScalMinMax on the sharp blob
+    (5, [1.0, 1.0, 0.0, 0.0, 0.0, 0.4], {"do_scalminmax": 1, "conservative_tracer": 1}),   # ConservativeScalMinMax
     (20, [1.0, 1.0, 0.5], {}),   # Tutorials/HIT initial field on [-1/2, 1/2]^3 with the synthetic density variation (BASELINE configs[4])
 ])
 def test_step_matches_oracle(backend, oracle, nb, probtype, pp, extra):
