@@ -72,7 +72,7 @@ class NSParams(C.Structure):
                 ("mac_tol", C.c_double), ("mac_abs_tol", C.c_double), ("proj_tol", C.c_double),
                 ("proj_abs_tol", C.c_double), ("init_iter", C.c_int), ("init_vel_iter", C.c_int),
                 ("do_init_proj", C.c_int), ("use_forces_in_trans", C.c_int), ("verbose", C.c_int),
-                ("conservative_tracer", C.c_int), ("mg_verbose", C.c_int), ("godunov_ppm", C.c_int), ("do_scalminmax", C.c_int), ("pad_", C.c_int)]
+                ("conservative_tracer", C.c_int), ("mg_verbose", C.c_int), ("godunov_ppm", C.c_int), ("do_scalminmax", C.c_int), ("do_mom_diff", C.c_int)]
 
 
 _P = C.POINTER

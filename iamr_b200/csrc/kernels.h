@@ -116,10 +116,10 @@ int floor_small(const Bx& bx, V4 f, int ncomp, cudaStream_t s);
 // (NSB.cpp:4456-4470, 3445-3466, 1411-1424); getForce = NS_getForce.cpp:117-141
 // (buoyancy grav*rho on the z component when |grav| > 1e-4).  visc / gp may be null.
 int force_vel(const Bx& bx, V4 tf, C4 visc, C4 gp, C4 rho, double grav, int div_rho, cudaStream_t s);
-// velocity update NSB.cpp:3607-3626 (do_mom_diff = 0):
+// velocity update NSB.cpp:3607-3626; do_mom_diff when rho_old / rho_new are given (u_new = (rho_old u_old - dt aofs + dt f - dt gp) / rho_new):
 //   unew = uold - dt*aofs + dt*(getForce(rho_half) - gp)/rho_half
 int vel_update(const Bx& bx, V4 unew, C4 uold, C4 aofs, C4 gp, C4 rhohalf, double grav, double dt,
-               int zero_force, cudaStream_t s);
+               int zero_force, cudaStream_t s, C4 rho_old = C4{}, C4 rho_new = C4{});
 // scalar update NSB.cpp:2761-2765 / 2887-2896 with the default (zero) scalar forcing
 int scal_update(const Bx& bx, V4 snew, C4 sold, C4 aofs, double dt, int ncomp, cudaStream_t s);
 // ns.do_scalminmax: Conservative / ConvectiveScalMinMax (NSB.cpp:2907-2935, 4256-4370); sold / rhoold need 1 filled ghost cell

@@ -150,7 +150,7 @@ int compute_aofs(iamrx_ns_s& ns, int state_comp, int ncomp, const MF& Sq, const 
       const int sc = state_comp + n;
       // advectionType: NS_setup.cpp:285-320 (velocity non-conservative unless do_mom_diff,
       // density conservative, tracer per do_cons_trac)
-      a.iconserv[n] = (sc == Density) ? 1 : (sc == Tracer ? (ns.p.conservative_tracer ? 1 : 0) : 0);
+      a.iconserv[n] = (sc == Density) ? 1 : (sc == Tracer ? (ns.p.conservative_tracer ? 1 : 0) : (ns.p.do_mom_diff ? 1 : 0));
     }
     a.forces_in_trans = ns.p.use_forces_in_trans;
     a.ppm = ns.p.godunov_ppm;   // advection_scheme == Godunov_PPM (NSB.cpp:4609)
@@ -160,9 +160,18 @@ int compute_aofs(iamrx_ns_s& ns, int state_comp, int ncomp, const MF& Sq, const 
   return IAMRX_OK;
 }
 
-// NavierStokesBase::velocity_advection (NSB.cpp:3358-3470), do_mom_diff == 0
+// NavierStokesBase::velocity_advection (NSB.cpp:3358-3470)
 int velocity_advection(iamrx_ns_s& ns, double dt) {
   IX_TRY(fillpatch(ns, ns.Umf, ns.S_old, Xvel, 3));   // :3382 (a fresh, un-floored copy)
+  if (ns.p.do_mom_diff) {
+    // :3390-3414 the advected state is the momentum rho^n u^n on the 3-ghost box; :3459-3466 the forcing is NOT divided by rho.
+    // ns.Smf(0) is the old density with 3 filled ghosts (its floor at 1e-20 never bites a density); ns.visc still holds visc^n.
+    for (int il = 0; il < ns.Umf.n(); ++il) {
+      IX_TRY(k::mult(ns.Umf.gbox(il, 3), ns.Umf.v(il), ns.Smf.c(il, 0), 3, 1, ns.s));
+      IX_TRY(k::force_vel(ns.force.gbox(il, 1), ns.force.v(il), ns.visc.c(il), ns.Gp_old.c(il), ns.Smf.c(il, 0), ns.p.gravity, 0, ns.s));
+    }
+    return compute_aofs(ns, Xvel, 3, ns.Umf, &ns.force, true, dt);  // conservative: advectionType[Xvel..] (NS_setup.cpp:297-299)
+  }
   // visc_terms (:3429) and the total forcing (:3445-3466) repeat predict_velocity's
   // arithmetic on the same inputs; ns.force still holds exactly those values.
   return compute_aofs(ns, Xvel, 3, ns.Umf, &ns.force, true, dt);  // :3469
@@ -216,7 +225,7 @@ int tracer_diffusion_update(iamrx_ns_s& ns, double dt) {
   return mf_copy(ns.S_new, ns.s1, 0, Tracer, 1, 0, ns.s);
 }
 
-// Diffusion::diffuse_tensor_velocity (Diffusion.cpp:650-957), rho_flag = 1
+// Diffusion::diffuse_tensor_velocity (Diffusion.cpp:650-957), rho_flag = 1 (3 with do_mom_diff)
 int velocity_diffusion_update(iamrx_ns_s& ns, double dt) {
   if (!ns.diffusive_vel()) return IAMRX_OK;
   Level& L = *ns.L;
@@ -228,14 +237,17 @@ int velocity_diffusion_update(iamrx_ns_s& ns, double dt) {
     IX_TRY(mf_setval(ns.rhs3, 0.0, 0, 3, 0, ns.s));
   }
   for (int il = 0; il < ns.rhs3.n(); ++il)  // :821-831
-    IX_TRY(k::diff_rhs(L.lbox(il), ns.rhs3.v(il), ns.S_new.v(il, Xvel), ns.rho_half.c(il), 3, ns.s));
+    IX_TRY(k::diff_rhs(L.lbox(il), ns.rhs3.v(il), ns.S_new.v(il, Xvel),   // rho_flag 1: rho_half; 3 (do_mom_diff): the OLD density (:819)
+                       ns.p.do_mom_diff ? ns.S_old.c(il, Density) : ns.rho_half.c(il), 3, ns.s));
   // tolerances: visc_tol, get_scaled_abs_tol (Diffusion.cpp:193-204, :846-847)
   double nrm[3];
   IX_TRY(mf_norminf_each(ns.rhs3, 0, 3, nrm, ns.s));
   const double tol_abs = ns.p.visc_tol * (nrm[0] + nrm[1] + nrm[2]) / 3.0;
   IX_TRY(fillpatch(ns, ns.soln, ns.S_new, Xvel, 3));  // :885 initial guess = new-time state
   iamrx_mg_info mi = mg_info(ns, ns.p.visc_tol, tol_abs);
-  IX_SOLVE(diffusion_solve(L, *ns.sv, true, 3, ns.soln, ns.rhs3, 1.0, theta * dt, &ns.rho_half, ns.eta, &mi, ns.s));  // :895-923
+  // :893-897 alpha = rho_half (rho_flag 1) or the NEW density (rho_flag 3, NS.cpp:1016)
+  IX_SOLVE(diffusion_solve(L, *ns.sv, true, 3, ns.soln, ns.rhs3, 1.0, theta * dt, ns.p.do_mom_diff ? &ns.rho_ctime : &ns.rho_half, ns.eta,
+                           &mi, ns.s));  // :895-923
   ns.it_visc = mi.iters;
   return mf_copy(ns.S_new, ns.soln, 0, Xvel, 3, 1, ns.s);  // :928
 }
@@ -250,9 +262,16 @@ int initial_velocity_diffusion_update(iamrx_ns_s& ns, double dt) {
     // force = (getForce(rho_old) + visc - gp)/rho_half - aofs ; u_new = u_old + dt*force
     IX_TRY(k::force_vel(L.lbox(il), ns.tf0.v(il), ns.visc.c(il), ns.Gp_old.c(il), ns.S_old.c(il, Density),
                         ns.p.gravity, 0, ns.s));
-    IX_TRY(k::divide(L.lbox(il), ns.tf0.v(il), ns.rho_half.c(il), 3, 1, ns.s));
+    if (!ns.p.do_mom_diff) IX_TRY(k::divide(L.lbox(il), ns.tf0.v(il), ns.rho_half.c(il), 3, 1, ns.s));
     IX_TRY(k::lincomb(L.lbox(il), ns.tf0.v(il), 1.0, ns.tf0.c(il), -1.0, ns.aofs.c(il, Xvel), 3, ns.s));
-    IX_TRY(k::lincomb(L.lbox(il), ns.S_new.v(il, Xvel), 1.0, ns.S_old.c(il, Xvel), dt, ns.tf0.c(il), 3, ns.s));
+    if (ns.p.do_mom_diff) {   // :3743-3744 u_new = (force dt + u_old rho_old) / rho_new
+      IX_TRY(k::copy(L.lbox(il), ns.S_new.v(il, Xvel), ns.S_old.c(il, Xvel), 3, ns.s));
+      IX_TRY(k::mult(L.lbox(il), ns.S_new.v(il, Xvel), ns.S_old.c(il, Density), 3, 1, ns.s));
+      IX_TRY(k::lincomb(L.lbox(il), ns.S_new.v(il, Xvel), 1.0, ns.S_new.c(il, Xvel), dt, ns.tf0.c(il), 3, ns.s));
+      IX_TRY(k::divide(L.lbox(il), ns.S_new.v(il, Xvel), ns.S_new.c(il, Density), 3, 1, ns.s));
+    } else {
+      IX_TRY(k::lincomb(L.lbox(il), ns.S_new.v(il, Xvel), 1.0, ns.S_old.c(il, Xvel), dt, ns.tf0.c(il), 3, ns.s));
+    }
   }
   return IAMRX_OK;
 }
@@ -284,11 +303,12 @@ int advance(iamrx_ns_s& ns, double time, double dt, double* dt_test) {
   IX_TRY(fillpatch(ns, ns.rho_ptime, ns.S_old, Density, 1));   // make_rho_prev_time :703
   IX_TRY(predict_velocity(ns, dt, dt_test));                   // NS.cpp:585
   IX_TRY(mac_project_step(ns, dt));                            // :589-597
-  IX_TRY(velocity_advection(ns, dt));                          // :606
+  if (!ns.p.do_mom_diff) IX_TRY(velocity_advection(ns, dt));   // :606
   IX_TRY(scalar_advection(ns, dt));                            // :613
   for (int il = 0; il < ns.S_new.n(); ++il)                    // scalar_update(rho) :617 -> NSB.cpp:2761-2765
     IX_TRY(k::scal_update(L.lbox(il), ns.S_new.v(il, Density), ns.S_old.c(il, Density), ns.aofs.c(il, Density), dt, 1, ns.s));
   IX_TRY(fillpatch(ns, ns.rho_ctime, ns.S_new, Density, 1));   // make_rho_curr_time :618
+  if (ns.p.do_mom_diff) IX_TRY(velocity_advection(ns, dt));    // :622-623 momenta, once rho^{n+1} exists
   for (int il = 0; il < ns.S_new.n(); ++il)                    // scalar_update(tracer) :627 -> NSB.cpp:2887-2896
     IX_TRY(k::scal_update(L.lbox(il), ns.S_new.v(il, Tracer), ns.S_old.c(il, Tracer), ns.aofs.c(il, Tracer), dt, 1, ns.s));
   if (ns.p.do_scalminmax) {                                    // NSB.cpp:2907-2935 (fresh FillPatch of the old scalars, 1 ghost)
@@ -311,7 +331,8 @@ int advance(iamrx_ns_s& ns, double time, double dt, double* dt_test) {
   IX_TRY(mf_lincomb(ns.rho_half, 0, 0.5, ns.rho_ptime, 0, 0.5, ns.rho_ctime, 0, 1, 1, ns.s));
   for (int il = 0; il < ns.S_new.n(); ++il)
     IX_TRY(k::vel_update(L.lbox(il), ns.S_new.v(il, Xvel), ns.S_old.c(il, Xvel), ns.aofs.c(il, Xvel), ns.Gp_old.c(il),
-                         ns.rho_half.c(il), ns.p.gravity, dt, (ns.initial_iter && ns.diffusive_vel()) ? 1 : 0, ns.s));
+                         ns.rho_half.c(il), ns.p.gravity, dt, (ns.initial_iter && ns.diffusive_vel()) ? 1 : 0, ns.s,
+                         ns.p.do_mom_diff ? ns.S_old.c(il, Density) : C4{}, ns.p.do_mom_diff ? ns.S_new.c(il, Density) : C4{}));
   if (!ns.initial_iter) IX_TRY(velocity_diffusion_update(ns, dt));
   else IX_TRY(initial_velocity_diffusion_update(ns, dt));
   if (!ns.initial_step) IX_TRY(level_project(ns, dt));         // :650-670
@@ -373,6 +394,7 @@ void iamrx_ns_params_default(iamrx_ns_params* p) {
   p->mg_verbose = 0;
   p->godunov_ppm = 0;     // ns.advection_scheme = Godunov_PLM (NSB.cpp:169)
   p->do_scalminmax = 0;   // NSB.cpp:140
+  p->do_mom_diff = 0;     // NSB.cpp:167
 }
 
 int iamrx_ns_create(iamrx_level_t lev, const iamrx_ns_params* p, iamrx_ns_t* out) {

@@ -40,10 +40,15 @@ __global__ void force_vel_kernel(Bx bx, V4 tf, C4 visc, C4 gp, C4 rho, double gr
 }
 
 __global__ void vel_update_kernel(Bx bx, V4 unew, C4 uold, C4 aofs, C4 gp, C4 rh, double grav, double dt,
-                                  int zero_force) {
+                                  int zero_force, C4 rho_old, C4 rho_new) {
   IDX3(bx)
   const double r = rh(i, j, k);
   const double force = zero_force ? 0.0 : ext_force(n, grav, r);
+  if (rho_old.ok()) {  // do_mom_diff (NSB.cpp:3609-3616): momentum update, then back to velocity with the new density
+    const double m = uold(i, j, k, n) * rho_old(i, j, k) - dt * aofs(i, j, k, n) + dt * force - dt * gp(i, j, k, n);
+    unew(i, j, k, n) = m / rho_new(i, j, k);
+    return;
+  }
   unew(i, j, k, n) = uold(i, j, k, n) - dt * aofs(i, j, k, n) + dt * force / r - dt * gp(i, j, k, n) / r;
 }
 
@@ -150,8 +155,8 @@ int force_vel(const Bx& bx, V4 tf, C4 visc, C4 gp, C4 rho, double grav, int div_
   LAUNCH3(force_vel_kernel, bx, 3, s, tf, visc, gp, rho, grav, div_rho);
 }
 int vel_update(const Bx& bx, V4 unew, C4 uold, C4 aofs, C4 gp, C4 rhohalf, double grav, double dt, int zero_force,
-               cudaStream_t s) {
-  LAUNCH3(vel_update_kernel, bx, 3, s, unew, uold, aofs, gp, rhohalf, grav, dt, zero_force);
+               cudaStream_t s, C4 rho_old, C4 rho_new) {
+  LAUNCH3(vel_update_kernel, bx, 3, s, unew, uold, aofs, gp, rhohalf, grav, dt, zero_force, rho_old, rho_new);
 }
 int scal_update(const Bx& bx, V4 snew, C4 sold, C4 aofs, double dt, int ncomp, cudaStream_t s) {
   LAUNCH3(scal_update_kernel, bx, ncomp, s, snew, sold, aofs, dt);

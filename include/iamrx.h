@@ -364,7 +364,7 @@ typedef struct iamrx_ns_params {
   int mg_verbose;
   int godunov_ppm;       /* ns.advection_scheme = Godunov_PPM instead of the default Godunov_PLM (NSB.cpp:169,552-554) */
   int do_scalminmax;     /* ns.do_scalminmax (NSB.cpp:140,2907-2935): clamp the advected tracer to the old 3x3x3 range */
-  int pad_;
+  int do_mom_diff;       /* ns.do_mom_diff (NSB.cpp:167,3358-3470,3609-3616; NS.cpp:606-623,1016): advect and diffuse momentum rho*u */
 } iamrx_ns_params;
 
 void iamrx_ns_params_default(iamrx_ns_params* p);

@@ -928,10 +928,25 @@ struct orc_ns {
     int rc = mac_project(n, dx, umac, rho_p, nullptr, mac_phi, 2.0 / dt, &m1);
     it[0] = m1.iters;
     if (rc) return rc;
-    // ---- velocity_advection NSB.cpp:3358-3470 (fresh un-floored FillPatch copy, same forcing)
-    Arr Umf2(n, 3, 3); Umf2.copy_from(S_old, Xvel, 0, 3); Umf2.fill_periodic();
-    const int ic_vel[3] = {0, 0, 0};
-    compute_aofs(Umf2, 3, &force, nullptr, umac, ic_vel, aopt, dx, dt, aofs, Xvel, nullptr, nullptr);
+    // ---- velocity_advection NSB.cpp:3358-3470 (fresh un-floored FillPatch copy, same forcing); with do_mom_diff it runs AFTER
+    //      rho^{n+1} exists (NS.cpp:606-623), advects the momentum rho^n u^n conservatively and its forcing is not divided by rho
+    auto velocity_advection = [&]() {
+      Arr Umf2(n, 3, 3); Umf2.copy_from(S_old, Xvel, 0, 3); Umf2.fill_periodic();
+      if (p.do_mom_diff) {
+        Arr rho3(n, 1, 3); rho3.copy_from(S_old, Density, 0, 1); rho3.fill_periodic();
+        for (int c = 0; c < 3; ++c) {
+#pragma omp parallel for
+          for (int k = -3; k < n[2] + 3; ++k) for (int j = -3; j < n[1] + 3; ++j) for (int i = -3; i < n[0] + 3; ++i) Umf2(i, j, k, c) *= rho3(i, j, k);
+          FOR_G1(force, i, j, k) force(i, j, k, c) = ext_force(c, rho3(i, j, k)) + visc(i, j, k, c) - Gp_old(i, j, k, c);   // :3459-3466
+        }
+        const int ic_mom[3] = {1, 1, 1};   // NS_setup.cpp:297-299
+        compute_aofs(Umf2, 3, &force, nullptr, umac, ic_mom, aopt, dx, dt, aofs, Xvel, nullptr, nullptr);
+      } else {
+        const int ic_vel[3] = {0, 0, 0};
+        compute_aofs(Umf2, 3, &force, nullptr, umac, ic_vel, aopt, dx, dt, aofs, Xvel, nullptr, nullptr);
+      }
+    };
+    if (!p.do_mom_diff) velocity_advection();
     // ---- scalar_advection NS.cpp:698-812
     for (double& v : Smf.d) v = (std::fabs(v) > 1.0e-20) ? v : 0.0;
     Arr sforce(n, 2, 1);
@@ -954,6 +969,7 @@ struct orc_ns {
     // ---- scalar updates NSB.cpp:2761-2765, 2887-2896
     FOR_CELLS(S_new, i, j, k) S_new(i, j, k, Density) = S_old(i, j, k, Density) - dt * aofs(i, j, k, Density);
     rho_c.copy_from(S_new, Density, 0, 1); rho_c.fill_periodic();
+    if (p.do_mom_diff) velocity_advection();
     FOR_CELLS(S_new, i, j, k) S_new(i, j, k, Tracer) = S_old(i, j, k, Tracer) - dt * aofs(i, j, k, Tracer);
     if (p.do_scalminmax) {   // NSB.cpp:2907-2935 -> Conservative / ConvectiveScalMinMax (:4256-4370) on an un-floored copy of the old scalars
       Arr so(n, 2, 1); so.copy_from(S_old, Density, 0, 2); so.fill_periodic();
@@ -977,7 +993,10 @@ struct orc_ns {
       FOR_CELLS(S_new, i, j, k) {
         const double r = rho_half(i, j, k);
         const double frc = zero_force ? 0.0 : ext_force(c, r);
-        S_new(i, j, k, c) = S_old(i, j, k, c) - dt * aofs(i, j, k, c) + dt * frc / r - dt * Gp_old(i, j, k, c) / r;
+        if (p.do_mom_diff)   // NSB.cpp:3609-3616
+          S_new(i, j, k, c) = (S_old(i, j, k, c) * S_old(i, j, k, Density) - dt * aofs(i, j, k, c) + dt * frc - dt * Gp_old(i, j, k, c)) / S_new(i, j, k, Density);
+        else
+          S_new(i, j, k, c) = S_old(i, j, k, c) - dt * aofs(i, j, k, c) + dt * frc / r - dt * Gp_old(i, j, k, c) / r;
       }
     }
     if (!initial_iter) { rc = velocity_diffusion(dt); if (rc) return rc; }
@@ -1032,14 +1051,18 @@ struct orc_ns {
       ex.apply(rhs, u);
     }
     for (int c = 0; c < 3; ++c) {
-      FOR_CELLS(rhs, i, j, k) { S_new(i, j, k, c) *= rho_half(i, j, k); rhs(i, j, k, c) += S_new(i, j, k, c); }  // :821-831
+      FOR_CELLS(rhs, i, j, k) {   // :814-831: rho_flag 1 -> rho_half, rho_flag 3 (do_mom_diff, NS.cpp:1016) -> the OLD density
+        S_new(i, j, k, c) *= p.do_mom_diff ? S_old(i, j, k, Density) : rho_half(i, j, k);
+        rhs(i, j, k, c) += S_new(i, j, k, c);
+      }
     }
     const double tol_abs = p.visc_tol * (rhs.norminf(0) + rhs.norminf(1) + rhs.norminf(2)) / 3.0;  // get_scaled_abs_tol :193-204
     Arr soln(n, 3, 1); soln.copy_from(S_new, Xvel, 0, 3);
     CellMG im(n, dx, 3, true, 100);
     im.mg = mg(p.visc_tol, tol_abs);
     im.a = 1.0; im.b = th * dt;
-    im.set_coeffs(&rho_half, e);
+    Arr rho_n(n, 1, 0); rho_n.copy_from(S_new, Density, 0, 1);
+    im.set_coeffs(p.do_mom_diff ? &rho_n : &rho_half, e);   // :893-897 alpha = rho_half or (rho_flag 3) the NEW density
     const int rc = im.solve(soln, rhs);
     it[1] = im.mg.iters;
     S_new.copy_from(soln, 0, Xvel, 3);
@@ -1053,9 +1076,10 @@ struct orc_ns {
     for (int c = 0; c < 3; ++c) {
       FOR_CELLS(S_new, i, j, k) {
         double f = ext_force(c, S_old(i, j, k, Density)) + visc(i, j, k, c) - Gp_old(i, j, k, c);
-        f /= rho_half(i, j, k);
+        if (!p.do_mom_diff) f /= rho_half(i, j, k);
         f -= aofs(i, j, k, c);
-        S_new(i, j, k, c) = S_old(i, j, k, c) + f * dt;
+        if (p.do_mom_diff) S_new(i, j, k, c) = (f * dt + S_old(i, j, k, c) * S_old(i, j, k, Density)) / S_new(i, j, k, Density);   // :3743
+        else S_new(i, j, k, c) = S_old(i, j, k, c) + f * dt;
       }
     }
   }
@@ -1255,7 +1279,7 @@ void orc_compute_aofs(const int n[3], const double dx[3], double dt, int ncomp, 
 void orc_ns_params_default(orc_ns_params* p) {
   p->cfl = 0.7; p->visc_coef = 0.0; p->be_cn_theta = 0.5; p->change_max = 1.1; p->init_shrink = 1.0; p->fixed_dt = -1.0;
   p->gravity = 0.0; p->visc_tol = 1e-10; p->mac_tol = 1e-12; p->mac_abs_tol = 1e-16; p->proj_tol = 1e-12; p->proj_abs_tol = 1e-16;
-  p->init_iter = 2; p->init_vel_iter = 1; p->do_init_proj = 1; p->use_forces_in_trans = 0; p->conservative_tracer = 0; p->verbose = 0; p->scal_diff_coef = 0.0; p->use_ppm = 0; p->do_scalminmax = 0;
+  p->init_iter = 2; p->init_vel_iter = 1; p->do_init_proj = 1; p->use_forces_in_trans = 0; p->conservative_tracer = 0; p->verbose = 0; p->scal_diff_coef = 0.0; p->use_ppm = 0; p->do_scalminmax = 0; p->do_mom_diff = 0;
 }
 
 orc_ns* orc_ns_create(const int n[3], const double prob_lo[3], const double prob_hi[3], const orc_ns_params* p) {

@@ -89,6 +89,7 @@ typedef struct orc_ns_params {
   double scal_diff_coef;   /* ns.scal_diff_coefs of the tracer (0: non-diffusive) */
   int use_ppm;             /* ns.advection_scheme = Godunov_PPM (NSB.cpp:552-554, 4485) */
   int do_scalminmax;       /* ns.do_scalminmax (NSB.cpp:2907-2935) */
+  int do_mom_diff, pad_;   /* ns.do_mom_diff (NSB.cpp:3358-3470, 3609-3616; NS.cpp:606-623, 1016) */
 } orc_ns_params;
 void orc_ns_params_default(orc_ns_params* p);
 typedef struct orc_ns orc_ns;
