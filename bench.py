@@ -147,7 +147,7 @@ def run_reference(args):
         return
     n = args.cpu_n
     val, ms, cores = cpu_oracle_run(n, args.steps, args.warmup)
-    sample = (f"TaylorGreen {n}^3 single box (BASELINE.json configs[0] size), {args.steps} timed steps after "
+    sample = (f"TaylorGreen {n}^3 single box (bounded sample of the 256^3 workload), {args.steps} timed steps after "
               f"init + {args.warmup} warm-up, OpenMP on {cores} host threads")
     line = {
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
@@ -304,7 +304,7 @@ def run_ours(args):
         if world == 1 and not args.no_cpu_baseline:
             cpu_val, cpu_ms, cores = cpu_oracle_run(args.cpu_n, 2, 1)
             cpu = {"value": cpu_val, "unit": UNIT, "cores": cores, "kind": "port",
-                   "sample": f"TaylorGreen {args.cpu_n}^3 (BASELINE.json configs[0] size): 2 timed steps after init + 1 warm-up of "
+                   "sample": f"TaylorGreen {args.cpu_n}^3 (a bounded sample of the 256^3 workload; BASELINE.json configs[0] is 64^3): 2 timed steps after init + 1 warm-up of "
                              f"the CPU oracle (restatement of the IAMR path; the AMReX build cannot be produced offline), "
                              f"OpenMP on {cores} host threads"}
         line = {
@@ -344,7 +344,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--n", type=int, default=256, help="box size per GPU")
-    ap.add_argument("--cpu-n", type=int, default=64, help="box size of the CPU sample")
+    ap.add_argument("--cpu-n", type=int, default=128, help="box size of the CPU sample (128^3: ~10-30 s of host work)")
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--kernel-table", action="store_true", help="diagnostic per-kernel table of one extra step on stderr")
