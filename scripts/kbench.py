@@ -13,8 +13,10 @@ sys.path.insert(0, 'tests')
 import iamr_b200 as ix
 from util import box_of, d3, stream_of
 
-n = int(sys.argv[1]) if len(sys.argv) > 1 else 256
-reps = int(sys.argv[2]) if len(sys.argv) > 2 else 20
+spec = "--spec" in sys.argv     # SURVEY.md 8d inputs (hashed phi / rhs, sinusoidal rho, Taylor-Green velocities) instead of uniform noise
+argv = [a for a in sys.argv if a != "--spec"]
+n = int(argv[1]) if len(argv) > 1 else 256
+reps = int(argv[2]) if len(argv) > 2 else 20
 dev = 'cuda:0'
 lib = ix.load()
 s = stream_of(dev)
@@ -79,6 +81,14 @@ for t, _ in tb:
     t.add_(0.5)
 fb = [f for _, f in tb]
 ta, fa = fab(cells, 0)
+if spec:   # K1 of SURVEY.md 8d
+    sys.path.insert(0, 'scripts')
+    import spec_inputs as si
+    k1 = si.k1_gsrb(n, dev)
+    tp.copy_(si.ghosted(k1["phi"], 1)); tr.copy_(si.ghosted(k1["rhs"], 0)); ta.copy_(si.ghosted(k1["rho"], 0))
+    for d in range(3):
+        tb[d][0].copy_(si.ghosted(k1["beta"][d], 0, tuple(1 if q == d else 0 for q in range(3))))
+    del k1
 
 
 def gsrb(a):
@@ -115,6 +125,13 @@ fum = [f for _, f in tum]
 tA, fA = fab(cells, 0, 3)
 icons = (C.c_int * 3)(0, 0, 0)
 dt = 0.7 / n
+if spec:   # K2 of SURVEY.md 8d: Taylor-Green velocities at cell and face centres, zero forcing
+    import spec_inputs as si
+    k2 = si.k2_advection(n, dev)
+    tS.copy_(si.ghosted(k2["vel"], 3)); tF.zero_()
+    for d, key in enumerate(("umac", "vmac", "wmac")):
+        tum[d][0].copy_(si.ghosted(k2[key], 1, tuple(1 if q == d else 0 for q in range(3))))
+    del k2
 timeit("ComputeAofs 3 comps (velocity)",
        lambda: lib.check(lib.iamrx_compute_aofs_box(C.byref(bx), C.byref(fA), 0, C.byref(fS), 0, 3, C.byref(fF), 0, None, C.byref(fum[0]), C.byref(fum[1]),
                                                     C.byref(fum[2]), None, None, None, None, None, None, icons, C.byref(g), dt, ix.ADV_IS_VELOCITY if hasattr(ix, 'ADV_IS_VELOCITY') else 4, s)),
