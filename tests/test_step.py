@@ -257,3 +257,97 @@ def test_invariants_at_full_size_gpu(cuda_lib):
         assert abs((S[c].sum() - S0[c].sum()).item()) < 1e-10 * S0[c].abs().sum().item()
     assert torch.isfinite(S).all()
     ns.close(); lev.close()
+
+
+@pytest.mark.parametrize("theta", [0.5, 1.0])
+@pytest.mark.parametrize("cons", [0, 1])
+def test_tracer_diffusion_analytic_amplification(emul_lib, oracle, theta, cons):
+    """A known answer for Diffusion::diffuse_scalar: fluid at rest, uniform density, tracer = one Fourier mode.  One Crank-Nicolson
+    step multiplies the mode by (1 - (1-theta) dt beta lam) / (1 + theta dt beta lam), lam = the eigenvalue of the 7-point Laplacian
+    -- for the library (through the host-state entry, CPU emulation) and for the oracle alike."""
+    lib, dev = emul_lib, "cpu"
+    n = (16, 8, 8)
+    beta, rho0, dt = 3.0e-2, 1.7, 0.02
+    x = (np.arange(n[0]) + 0.5) / n[0]
+    y = (np.arange(n[1]) + 0.5) / n[1]
+    mode = np.sin(2 * np.pi * x)[None, None, :] * np.cos(2 * np.pi * y)[None, :, None] * np.ones((n[2], 1, 1))
+    S = np.zeros((5, n[2], n[1], n[0]))
+    S[3] = rho0
+    S[4] = (rho0 if cons else 1.0) * mode      # conservative tracer stores rho*q
+    hx, hy = 1.0 / n[0], 1.0 / n[1]
+    lam = (2 - 2 * np.cos(2 * np.pi * hx)) / hx ** 2 + (2 - 2 * np.cos(2 * np.pi * hy)) / hy ** 2
+    # rho_flag 0: (1 + th dt b lam) T' = (1 - (1-th) dt b lam) T ; rho_flag 2: q = S/rho diffuses with alpha = rho
+    bl = beta * lam / (rho0 if cons else 1.0)
+    amp = (1 - (1 - theta) * dt * bl) / (1 + theta * dt * bl)
+    kw = dict(visc_coef=0.0, scal_diff_coef=beta, be_cn_theta=theta, fixed_dt=dt, conservative_tracer=cons, do_init_proj=0, init_iter=0)
+    lev = ix.Level(lib, ix.Geom.make(n), [((0, 0, 0), (n[0] - 1, n[1] - 1, n[2] - 1))])
+    ns = ix.NavierStokes(lib, lev, dev, **kw)
+    ns.init_prob(11, [1.0, 1.0, 0.0, 0.0, rho0])   # velocity factor 0: fluid at rest (the state itself comes from the host buffer)
+    ns.post_init()
+    hin, hout = [torch.from_numpy(S.copy())], [torch.empty((5, n[2], n[1], n[0]), dtype=torch.float64)]
+    ns.step_host(hin, hout, dt)
+    got = hout[0].numpy()
+    assert np.abs(got[4] - amp * S[4]).max() <= 1e-9 * np.abs(S[4]).max()      # visc_tol = 1e-10 solve
+    assert np.abs(got[:3]).max() <= 1e-12 and np.abs(got[3] - rho0).max() <= 1e-13
+    o = oracle.OracleNS(n, **kw)
+    o.init_prob(11, [1.0, 1.0, 0.0, 0.0, rho0])
+    o.post_init()
+    o.set_state(S)
+    o.step(dt)
+    assert np.abs(o.get(0)[4] - amp * S[4]).max() <= 1e-9 * np.abs(S[4]).max()
+    ns.close(); o.close(); lev.close()
+
+
+@pytest.mark.parametrize("theta,mom", [(0.5, 0), (1.0, 0), (0.5, 1)])
+def test_viscous_shear_mode_analytic_amplification(emul_lib, oracle, theta, mom):
+    """A known answer for the whole step: the shear flow v = sin(2 pi x) is an exact steady solution of the discrete Euler step
+    (no advection, no divergence, no pressure gradient), so one step only applies Diffusion::diffuse_tensor_velocity: the mode is
+    multiplied by (1 - (1-theta) dt nu lam / rho) / (1 + theta dt nu lam / rho), lam = eigenvalue of the x second difference."""
+    lib, dev = emul_lib, "cpu"
+    n = (16, 8, 8)
+    nu, rho0, dt = 2.0e-2, 1.3, 0.01
+    x = (np.arange(n[0]) + 0.5) / n[0]
+    S = np.zeros((5, n[2], n[1], n[0]))
+    S[1] = 0.8 * np.sin(2 * np.pi * x)[None, None, :]
+    S[3] = rho0
+    S[4] = 1.0
+    hx = 1.0 / n[0]
+    lam = (2 - 2 * np.cos(2 * np.pi * hx)) / hx ** 2
+    amp = (1 - (1 - theta) * dt * nu * lam / rho0) / (1 + theta * dt * nu * lam / rho0)
+    kw = dict(visc_coef=nu, be_cn_theta=theta, fixed_dt=dt, do_init_proj=0, init_iter=0, do_mom_diff=mom)
+    lev = ix.Level(lib, ix.Geom.make(n), [((0, 0, 0), (n[0] - 1, n[1] - 1, n[2] - 1))])
+    ns = ix.NavierStokes(lib, lev, dev, **kw)
+    ns.init_prob(11, [1.0, 1.0, 0.0, 0.0, rho0])
+    ns.post_init()
+    hin, hout = [torch.from_numpy(S.copy())], [torch.empty((5, n[2], n[1], n[0]), dtype=torch.float64)]
+    ns.step_host(hin, hout, dt)
+    got = hout[0].numpy()
+    assert np.abs(got[1] - amp * S[1]).max() <= 2e-9
+    assert np.abs(got[0]).max() <= 1e-10 and np.abs(got[2]).max() <= 1e-10
+    o = oracle.OracleNS(n, **kw)
+    o.init_prob(11, [1.0, 1.0, 0.0, 0.0, rho0])
+    o.post_init()
+    o.set_state(S)
+    o.step(dt)
+    assert np.abs(o.get(0)[1] - amp * S[1]).max() <= 2e-9
+    ns.close(); o.close(); lev.close()
+
+
+@pytest.mark.parametrize("cons,ppm", [(0, 0), (0, 1)])
+def test_uniform_tracer_is_preserved(emul_lib, oracle, cons, ppm):
+    """Free-stream preservation: a uniform tracer (the HIT tutorial's initial tracer = 1) stays uniform under the full 3-D flow for the
+    convective form (ComputeConvectiveTerm cancels div(u_mac) term by term).  The conservative form does NOT have this property at
+    finite dt: its corner-coupled states carry the uncompensated -dt/3 S du_t/dx_t pieces (no `+ q (mac_p - mac_m)` term when
+    iconserv = 1), a feature of the algorithm that the oracle and the kernels share (1.4 % after three 16^3 steps)."""
+    lib, dev = emul_lib, "cpu"
+    n = (16, 16, 16)
+    kw = dict(visc_coef=1e-3, cfl=0.7, conservative_tracer=cons, godunov_ppm=ppm)
+    lev = ix.Level(lib, ix.Geom.make(n, (-0.5, -0.5, -0.5), (0.5, 0.5, 0.5)), [((0, 0, 0), (15, 15, 15))])
+    ns = ix.NavierStokes(lib, lev, dev, **kw)
+    ns.init_prob(20, [1.0, 1.0])      # constant density: rho * q is uniform too
+    ns.post_init()
+    for _ in range(3):
+        ns.step()
+    tr = ns.field(0, 0).numpy()[4]
+    assert np.abs(tr - 1.0).max() <= (1e-10 if cons else 1e-13)
+    ns.close(); lev.close()
