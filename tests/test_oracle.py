@@ -220,3 +220,35 @@ def test_aofs_converges_to_the_advective_derivative(oracle, ppm):
         errs.append(np.mean(np.abs(a - (u * qx + v * qy))))   # L1: the limiters drop to first order at the few smooth extrema
     rate = math.log2(errs[0] / errs[1])
     assert rate > 1.7, (errs, rate)
+
+
+@pytest.mark.parametrize("ppm", [0, 1])
+def test_extrap_vel_to_faces_is_second_order(oracle, ppm):
+    """ExtrapVelToFaces for dt -> 0: the predicted face-normal velocities tend to the cell-centred field evaluated at the face centres
+    with second-order accuracy (PLM and PPM), and the forcing enters as dt/2 * f."""
+    errs = []
+    tp = 2 * np.pi
+    for m in (32, 64):
+        dx = (1.0 / m,) * 3
+        xc = (np.arange(m) + 0.5) / m
+        xf = np.arange(m) / m
+
+        def field(x, y, z):
+            X, Y, Z = x[None, None, :], y[None, :, None], z[:, None, None]
+            return (0.6 + np.sin(tp * X) * np.cos(tp * Y) * np.cos(tp * Z), 0.5 - np.cos(tp * X) * np.sin(tp * Y) * np.cos(tp * Z),
+                    0.4 + 0.3 * np.sin(tp * (X + Z)) * np.cos(tp * Y))
+
+        vel = np.stack(field(xc, xc, xc))
+        f = np.zeros_like(vel)
+        um, vm, wm = oracle.extrap_vel_to_faces(dx, 1.0e-7, vel, f, 0, ppm)
+        e = [np.mean(np.abs(um - field(xf, xc, xc)[0])), np.mean(np.abs(vm - field(xc, xf, xc)[1])), np.mean(np.abs(wm - field(xc, xc, xf)[2]))]
+        errs.append(max(e))
+        if m == 32:   # forcing: d(umac)/d(f) = dt/2 exactly (the same dt/2 f on both sides of a face)
+            dt = 1.0e-3
+            f1 = np.zeros_like(vel); f1[0] = 2.0
+            u0 = oracle.extrap_vel_to_faces(dx, dt, vel, f, 0, ppm)[0]
+            u1 = oracle.extrap_vel_to_faces(dx, dt, vel, f1, 0, ppm)[0]
+            away = np.abs(u0) > 0.05      # away from the sign changes of u, where the Riemann switch itself moves with f
+            assert np.abs((u1 - u0) - 0.5 * dt * 2.0)[away].max() < 1e-9 and away.mean() > 0.9
+    rate = math.log2(errs[0] / errs[1])
+    assert rate > 1.7, (errs, rate)
