@@ -47,6 +47,26 @@ def ncu_traffic(kernel, box):
         return None, None
 
 
+# kernel class -> entry of profiles/ncu_traffic.json (ncu --set full summaries of the shipping kernels)
+NCU_KEY = {"nodal_gs": "gs_sweep_kernel", "compute_aofs": "aofs_tile_kernel", "extrap_vel": "ev_kernels",
+           "abec_apply": "apply2_kernel", "nodal_adotx": "adotx_march_kernel"}
+
+
+def ncu_entry(key):
+    try:
+        return json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json"))).get(key)
+    except Exception:  # noqa: BLE001
+        return None
+
+
+def fp64_peak():
+    """Measured DFMA-pipe rate (profiles/fp64_peak.json, written by scripts/fp64_peak.py on the B200), else None."""
+    try:
+        return json.load(open(os.path.join(ROOT, "profiles", "fp64_peak.json")))
+    except Exception:  # noqa: BLE001
+        return None
+
+
 def measured_peak():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -105,8 +125,11 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
-def domain_for(nranks, nbox):
-    gx, gy, gz = RANK_GRID[nranks]
+BLOCK_GRID = {1: (1, 1, 1), 2: (2, 1, 1), 4: (2, 2, 1), 8: (2, 2, 2)}
+
+
+def domain_for(nranks, nbox, decomp="slabs"):
+    gx, gy, gz = (RANK_GRID if decomp == "slabs" else BLOCK_GRID)[nranks]
     ncell = (gx * nbox, gy * nbox, gz * nbox)
     boxes, owners = [], []
     r = 0
@@ -124,38 +147,73 @@ def domain_for(nranks, nbox):
 # ---------------------------------------------------------------------------
 # CPU arm: the oracle timed on the host cores (cpu_baseline and --impl reference)
 # ---------------------------------------------------------------------------
-def cpu_oracle_run(n, steps, warmup):
+def host_threads():
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:  # noqa: BLE001
+        return os.cpu_count() or 1
+
+
+def cpu_oracle_run(n, steps, warmup, budget_s=None):
+    """TaylorGreen n^3 on the CPU oracle with ALL host threads (set explicitly: torchrun exports OMP_NUM_THREADS=1).
+    With a time budget the number of timed steps actually run is reduced (never below 1) so that the run ends in a few
+    minutes; the count is returned and reported."""
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import orc
+    orc.lib().orc_set_num_threads(host_threads())
+    t_start = time.perf_counter()
     o = orc.OracleNS((n, n, n), visc_coef=NU, cfl=CFL)
     o.init_prob(11, TG)
     o.post_init()
+    t_step = None
+    wdone = 0
     for _ in range(warmup):
+        t0 = time.perf_counter()
         o.step()
+        t_step = time.perf_counter() - t0
+        wdone += 1
+        if budget_s is not None and (time.perf_counter() - t_start) + 2 * t_step > budget_s:
+            break   # keep room for at least one timed step
+    if budget_s is not None and t_step is not None:
+        left = budget_s - (time.perf_counter() - t_start)
+        steps = max(1, min(steps, int(left / t_step)))
     t0 = time.perf_counter()
     for _ in range(steps):
         o.step()
     dt = time.perf_counter() - t0
     cores = orc.lib().orc_num_threads()
     o.close()
-    return n ** 3 * steps / dt, dt / steps * 1e3, cores
+    return n ** 3 * steps / dt, dt / steps * 1e3, cores, steps, wdone
+
+
+def workload_config(nbox, world, ncell, nboxes, decomp="slabs"):
+    par = f"one {nbox}^3 box per rank x{world}"
+    if world > 1:
+        par += (", z slabs: x/y wrapped in-kernel, z ghost planes over NCCL, coarse multigrid levels replicated" if decomp == "slabs"
+                else ", 3-D block decomposition: ghost shells over NCCL per smoother colour, coarse multigrid levels replicated")
+    return {"workload": f"TaylorGreen 3D {nbox}^3 per GPU single-level (Tutorials/TaylorGreen/inputs.3d.taylorgreen, "
+                        f"nu=1e-4, cfl=0.7, periodic), BASELINE.json configs[1]" + ("" if world == 1 else " weak-scaled"),
+            "n_cell": list(ncell), "boxes": nboxes, "box": nbox, "parallelism": par,
+            "l2": "working set per kernel >> 126 MB L2 (one fp64 cell array = 134 MB)"}
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    n = args.cpu_n
-    val, ms, cores = cpu_oracle_run(n, args.steps, args.warmup)
-    sample = (f"TaylorGreen {n}^3 single box (bounded sample of the 256^3 workload), {args.steps} timed steps after "
-              f"init + {args.warmup} warm-up, OpenMP on {cores} host threads")
+    n = args.cpu_n if args.cpu_n > 0 else args.n    # the SAME box as the GPU arm (256^3) unless overridden
+    budget = float(os.environ.get("IAMRX_REF_BUDGET_S", "300"))
+    val, ms, cores, steps_run, warm_run = cpu_oracle_run(n, args.steps, args.warmup, budget)
+    sample = (f"TaylorGreen {n}^3 single box = the GPU arm's per-GPU workload; {steps_run} timed steps (asked {args.steps}) after init + "
+              f"{warm_run} warm-up (asked {args.warmup}), bounded to ~{budget:.0f} s of host time; OpenMP on {cores} host threads; "
+              f"CPU restatement of the IAMR path (oracle/), not the AMReX build: AMReX/AMReX-Hydro are not vendored in the reference")
+    world = args.gpus
+    ncell, boxes, _, _ = domain_for(world, args.n, args.decomp)
+    cfg = workload_config(args.n, world, ncell, len(boxes), args.decomp)
     line = {
-        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "TaylorGreen 3D single-level (inputs.3d.taylorgreen), CPU sample of the 256^3/GPU workload",
-                   "n_cell": [n, n, n], "note": "CPU restatement of the IAMR path (oracle/), not the AMReX build: "
-                   "AMReX/AMReX-Hydro are not vendored in the reference and cannot be built offline"},
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": steps_run,
+        "warmup": warm_run, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic", "config": cfg,
         "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -166,6 +224,38 @@ def run_reference(args):
 # ---------------------------------------------------------------------------
 # GPU arm
 # ---------------------------------------------------------------------------
+def verify_multirank(lib, ix, dev, rank, world, decomp):
+    """Untimed parity leg of the N>1 run: a z-DEPENDENT variable-density field (probtype 100, c = 1) advanced on the
+    bench decomposition (one box per rank) and on the single-rank layout (the same boxes, all owned by rank 0); the two
+    must agree to rounding.  A wrong ghost plane / gather / reduction shows up here."""
+    import torch
+    import torch.distributed as dist
+    nb = 32
+    ncell, boxes, owners, prob_hi = domain_for(world, nb, decomp)
+    g = ix.Geom.make(ncell, (0.0, 0.0, 0.0), prob_hi)
+    pp = [1.0, 1.0, 1.0, 1.0, 1.0]
+    kw = dict(visc_coef=1e-3, cfl=0.7, gravity=-0.5)
+    states, dts = [], []
+    for own in (owners, [0] * len(boxes)):
+        lev = ix.Level(lib, g, boxes, own)
+        ns = ix.NavierStokes(lib, lev, dev, **kw)
+        ns.init_prob(100, pp)
+        d = [ns.post_init()] + [ns.step() for _ in range(2)]
+        torch.cuda.synchronize()
+        dts.append(d)
+        states.append([ns.field(0, il).clone() for il in range(lev.num_local())])
+        ns.close(); lev.close()
+    mine = states[0][0].contiguous()
+    gathered = [torch.empty_like(mine) for _ in range(world)]
+    dist.all_gather(gathered, mine)
+    err = 0.0
+    if rank == 0:
+        for r in range(world):
+            err = max(err, float((gathered[r] - states[1][r]).abs().max()))
+    return {"linf_state_vs_single_rank_layout": err, "field": "probtype 100 (z-dependent velocity and density), 2 steps after post_init",
+            "n_cell": list(ncell), "dt_equal": bool(max(abs(a - b) for a, b in zip(dts[0], dts[1])) <= 1e-12 * dts[1][0])}
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -192,12 +282,19 @@ def run_ours(args):
     if world not in RANK_GRID:
         raise SystemExit(f"unsupported --gpus {world}")
 
+    verify = verify_multirank(lib, ix, dev, rank, world, args.decomp) if (world > 1 and not args.no_verify) else None
+
     nbox = args.n
-    ncell, boxes, owners, prob_hi = domain_for(world, nbox)
+    ncell, boxes, owners, prob_hi = domain_for(world, nbox, args.decomp)
     g = ix.Geom.make(ncell, (0.0, 0.0, 0.0), prob_hi)
     lev = ix.Level(lib, g, boxes, owners)
-    ns = ix.NavierStokes(lib, lev, dev, visc_coef=NU, cfl=CFL)
-    ns.init_prob(11, TG)
+    hit = args.problem == "hit"
+    if hit:   # BASELINE.json configs[4]: Tutorials/HIT initial field, nu = 1e-4, proj_tol 1e-10 (inputs.3d.forced:129), synthetic variable density
+        ns = ix.NavierStokes(lib, lev, dev, visc_coef=NU, cfl=CFL, proj_tol=1e-10)
+        ns.init_prob(20, [1.0, 1.0, 0.5])
+    else:
+        ns = ix.NavierStokes(lib, lev, dev, visc_coef=NU, cfl=CFL)
+        ns.init_prob(11, TG)
     ns.post_init()
     cells_total = ncell[0] * ncell[1] * ncell[2]
 
@@ -213,7 +310,7 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return t.item()
 
-    # ---- device-resident steps ------------------------------------------------
+    # ---- device-resident steps: the headline pass runs WITHOUT per-launch event profiling ----------------------------
     for _ in range(args.warmup):
         ns.step()
     barrier()
@@ -221,8 +318,6 @@ def run_ours(args):
     if rank == 0:
         sampler.start()
     lib.iamrx_launch_count_reset()
-    lib.iamrx_prof_reset()
-    lib.iamrx_prof_enable(1, (nbox // 2) ** 3)   # time launches on the two finest multigrid levels
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     torch.cuda.cudart().cudaProfilerStart()   # ncu --profile-from-start off profiles only the timed steps
@@ -237,6 +332,16 @@ def run_ours(args):
     ms = max_over_ranks(e0.elapsed_time(e1))
     launches = lib.iamrx_launch_count()
     clocks = sampler.stop() if rank == 0 else None
+    value = cells_total * args.steps / (ms * 1e-3)
+
+    # ---- roofline pass: a few MORE steps of the same run with CUDA events around every launch of the tracked kernel
+    #      classes on the two finest multigrid levels (on the launching stream) --------------------------------------------
+    lib.iamrx_prof_reset()
+    lib.iamrx_prof_enable(1, (nbox // 2) ** 3)
+    barrier()
+    for _ in range(args.prof_steps):
+        ns.step()
+    barrier()
     lib.iamrx_prof_enable(0, 0)
     prof = {}
     for name, k in (("abec_gsrb", 0), ("nodal_gs", 1), ("compute_aofs", 2), ("extrap_vel", 3), ("abec_apply", 4), ("nodal_adotx", 5)):
@@ -244,7 +349,6 @@ def run_ours(args):
         lib.check(lib.iamrx_prof_report(k, C.byref(t), C.byref(nl), C.byref(by)))
         prof[name] = (t.value, nl.value, by.value)
     lib.iamrx_prof_reset()
-    value = cells_total * args.steps / (ms * 1e-3)
 
     # ---- end-to-end steps through the host-buffer entry ---------------------------
     nloc = lev.num_local()
@@ -285,7 +389,7 @@ def run_ours(args):
             tot = sum(r[0] for r in rows)
             print(f"# kernel table, 1 step, {world} rank(s): wall {wall_ms:.2f} ms, sum of kernel times on rank 0 {tot:.2f} ms, "
                   f"launches {sum(r[1] for r in rows)}", file=sys.stderr)
-            for kms, cnt, name in rows[:32]:
+            for kms, cnt, name in rows[:40]:
                 print(f"{name:28s} {cnt:7d} {kms:10.3f} ms {100 * kms / tot:5.1f}%", file=sys.stderr)
 
     if rank == 0:
@@ -293,29 +397,34 @@ def run_ours(args):
         traffic, traffic_src = ncu_traffic("gsrb_kernel", nbox)
         t, nl, by = prof["abec_gsrb"]
         achieved = (by / 1e9) / (t * 1e-3) if t > 0 else 0.0
+        fp64 = fp64_peak()
         secondary = {}
         for name in ("nodal_gs", "compute_aofs", "extrap_vel", "abec_apply", "nodal_adotx"):
             tt, nn, bb = prof[name]
             if tt > 0:
                 secondary[name] = {"achieved_gbs": (bb / 1e9) / (tt * 1e-3), "frac": (bb / 1e9) / (tt * 1e-3) / peak,
-                                   "launches": nn, "ms_total": tt}
-        cpu_val, cpu_ms, cores = (None, None, None)
+                                   "launches": nn, "ms_total": tt, "ms_per_step": tt / max(1, args.prof_steps)}
+                e = ncu_entry(NCU_KEY[name])
+                if e:   # committed ncu --set full summary of the same kernel: DRAM traffic and, for the Godunov kernels, the
+                    secondary[name]["ncu"] = e   # FP64-pipe utilisation (their second roofline; fp64_peak = measured DFMA rate)
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
-            cpu_val, cpu_ms, cores = cpu_oracle_run(args.cpu_n, 2, 1)
+            cn = args.cpu_n if args.cpu_n > 0 else 128
+            cpu_val, cpu_ms, cores, srun, wrun = cpu_oracle_run(cn, 2, 1)
             cpu = {"value": cpu_val, "unit": UNIT, "cores": cores, "kind": "port",
-                   "sample": f"TaylorGreen {args.cpu_n}^3 (a bounded sample of the 256^3 workload; BASELINE.json configs[0] is 64^3): 2 timed steps after init + 1 warm-up of "
+                   "sample": f"TaylorGreen {cn}^3 (a bounded sample of the 256^3 workload; --impl reference runs 256^3): {srun} timed steps after init + {wrun} warm-up of "
                              f"the CPU oracle (restatement of the IAMR path; the AMReX build cannot be produced offline), "
                              f"OpenMP on {cores} host threads"}
+        cfg = workload_config(nbox, world, ncell, len(boxes), args.decomp)
+        if hit:
+            cfg["workload"] = (f"HIT 3D {nbox}^3 per GPU single-level variable-density (Tutorials/HIT/prob_init.cpp:100-131 field, nu=1e-4, "
+                               f"proj_tol 1e-10, rho = 1 + 0.5 sin sin sin, forcing off), BASELINE.json configs[4]" + ("" if world == 1 else " weak-scaled"))
+        cfg["mg_iters_last_step"] = {"mac": iters[-1][0], "visc": iters[-1][1], "nodal": iters[-1][2]}
+        cfg["timing"] = "headline pass without per-launch events; roofline from a separate pass of %d steps" % args.prof_steps
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"TaylorGreen 3D {nbox}^3 per GPU single-level (Tutorials/TaylorGreen/inputs.3d.taylorgreen, "
-                                   f"nu=1e-4, cfl=0.7, periodic), BASELINE.json configs[1]" + ("" if world == 1 else " weak-scaled"),
-                       "n_cell": list(ncell), "boxes": len(boxes), "box": nbox, "parallelism": f"one {nbox}^3 box per rank x{world}" + ("" if world == 1 else ", z slabs: x/y wrapped in-kernel, z ghost planes over NCCL, coarse multigrid levels replicated"),
-                       "l2": "working set per kernel >> 126 MB L2 (one fp64 cell array = 134 MB)",
-                       "mg_iters_last_step": {"mac": iters[-1][0], "visc": iters[-1][1], "nodal": iters[-1][2]}},
+            "dtype": "f64", "data": "synthetic", "config": cfg,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": state_bytes, "d2h_bytes_per_step": state_bytes,
                     "steps": args.e2e_steps, "api": "iamrx_ns_step_host (pinned host state in, new state out)",
                     "checksum_max_abs_u": checksum},
@@ -323,11 +432,13 @@ def run_ours(args):
             "roofline": {"bound": "hbm", "kernel": "gsrb_kernel (ABec red-black colour pass, finest two MG levels)",
                          "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                          "traffic_note": f"DRAM bytes per finest-level launch ({nbox}^3, algorithmic {48 * nbox ** 3}); {traffic_src}",
-                         "peak_source": peak_src, "launches_timed": nl, "ms_total": t,
+                         "peak_source": peak_src, "launches_timed": nl, "ms_total": t, "ms_per_step": t / max(1, args.prof_steps),
                          "algorithmic_bytes": "48 B/cell/colour pass (a=0), 56 with alpha (SURVEY.md 8d)",
-                         "other_kernels": secondary},
+                         "fp64_peak": fp64, "other_kernels": secondary},
             "clocks": clocks,
         }
+        if verify is not None:
+            line["verify"] = verify
         if cpu:
             line["cpu_baseline"] = cpu
         print(json.dumps(line), flush=True)
@@ -344,7 +455,11 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--n", type=int, default=256, help="box size per GPU")
-    ap.add_argument("--cpu-n", type=int, default=128, help="box size of the CPU sample (128^3: ~10-30 s of host work)")
+    ap.add_argument("--cpu-n", type=int, default=0, help="box size of the CPU runs (0: --impl reference uses --n, the cpu_baseline leg 128)")
+    ap.add_argument("--decomp", default="slabs", choices=["slabs", "blocks"], help="weak-scaling decomposition: z slabs or 3-D blocks")
+    ap.add_argument("--problem", default="tg", choices=["tg", "hit"], help="tg: BASELINE configs[1]; hit: configs[4] (HIT, variable density)")
+    ap.add_argument("--prof-steps", type=int, default=3, help="steps of the separate roofline pass")
+    ap.add_argument("--no-verify", action="store_true", help="skip the untimed multi-rank parity leg")
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--kernel-table", action="store_true", help="diagnostic per-kernel table of one extra step on stderr")

@@ -57,6 +57,25 @@ class Geom(C.Structure):
         return g
 
 
+class BCRec(C.Structure):
+    """amrex::BCRec of one component: math BC codes (lo[3], hi[3])."""
+    _fields_ = [("lo", C.c_int * 3), ("hi", C.c_int * 3)]
+
+    @staticmethod
+    def make(lo, hi):
+        b = BCRec()
+        for d in range(3):
+            b.lo[d] = int(lo[d])
+            b.hi[d] = int(hi[d])
+        return b
+
+
+# amrex::BCType math codes (include/iamrx.h IAMRX_BC_*)
+BC_INT_DIR, BC_REFLECT_ODD, BC_REFLECT_EVEN, BC_FOEXTRAP, BC_EXT_DIR, BC_HOEXTRAP = 0, -1, 1, 2, 3, 4
+# iamrx_compute_aofs_box flags
+ADV_PPM, ADV_FORCES_IN_TRANS, ADV_IS_VELOCITY, ADV_WRITE_FLUXES, ADV_IS_SYNC, ADV_STAGED, ADV_KNOWN_EDGE_STATE = 1, 2, 4, 8, 16, 32, 64
+
+
 class MGInfo(C.Structure):
     _fields_ = [("rtol", C.c_double), ("atol", C.c_double), ("max_iter", C.c_int),
                 ("max_coarsening", C.c_int), ("nu1", C.c_int), ("nu2", C.c_int),
@@ -87,6 +106,7 @@ SIGNATURES = {
     "iamrx_launch_count": (C.c_int64, []),
     "iamrx_launch_count_reset": (None, []),
     "iamrx_device_ok": (C.c_int, []),
+    "iamrx_debug_fp64_peak": (C.c_int, [_P(C.c_double), _vp]),
     "iamrx_prof_enable": (C.c_int, [C.c_int, C.c_int64]),
     "iamrx_prof_reset": (None, []),
     "iamrx_prof_all": (C.c_int, [C.c_int]),
@@ -100,11 +120,12 @@ SIGNATURES = {
                                        _P(Fab), _P(Fab), _P(C.c_double), C.c_int, _vp]),
     "iamrx_tensor_cross_box": (C.c_int, [_P(Box), _P(Fab), _P(Fab), _P(Fab), _P(Fab), _P(Fab), C.c_double,
                                          _P(C.c_double), _vp]),
-    "iamrx_extrap_vel_to_faces_box": (C.c_int, [_P(Box), _P(Fab), _P(Fab), _P(Fab), _P(Fab), _P(Fab), _P(Geom),
+    "iamrx_extrap_vel_to_faces_box": (C.c_int, [_P(Box), _P(Fab), _P(Fab), _P(Fab), _P(Fab), _P(Fab), _P(BCRec), _P(Geom),
                                                 C.c_double, C.c_int, _vp]),
     "iamrx_compute_aofs_box": (C.c_int, [_P(Box), _P(Fab), C.c_int, _P(Fab), C.c_int, C.c_int, _P(Fab), C.c_int,
-                                         _P(Fab), _P(Fab), _P(Fab), _P(Fab), _P(Fab), _P(Fab), _P(Fab), _P(Fab),
-                                         _P(Fab), _P(Fab), _P(C.c_int), _P(Geom), C.c_double, C.c_int, _vp]),
+                                         _P(Fab), _P(Fab), _P(Fab), _P(Fab), _P(Fab), _P(Fab), _P(Fab),
+                                         _P(Fab), _P(Fab), _P(Fab), _P(Fab), _P(Fab), _P(Fab), _P(C.c_int), _P(BCRec),
+                                         _P(Geom), C.c_double, C.c_int, _vp]),
     "iamrx_nodal_divu_box": (C.c_int, [_P(Box), _P(Fab), _P(Fab), _P(C.c_double), _vp]),
     "iamrx_nodal_adotx_box": (C.c_int, [_P(Box), _P(Fab), _P(Fab), _P(Fab), _P(Fab), _P(C.c_double), _vp]),
     "iamrx_nodal_gs_box": (C.c_int, [_P(Box), _P(Fab), _P(Fab), _P(Fab), _P(C.c_double), C.c_int, _vp]),
@@ -126,6 +147,7 @@ SIGNATURES = {
     "iamrx_mg_info_default": (None, [_P(MGInfo)]),
     "iamrx_mac_project": (C.c_int, [_vp, _P(Fab), _P(Fab), _P(Fab), _P(Fab), _P(Fab), _P(Fab), C.c_double,
                                     _P(C.c_int), _P(C.c_int), _P(MGInfo), _vp]),
+    "iamrx_mac_get_fluxes": (C.c_int, [_vp, _P(Fab), _P(Fab), _P(Fab), _P(Fab), _vp]),
     "iamrx_nodal_project": (C.c_int, [_vp, _P(Fab), _P(Fab), _P(Fab), _P(Fab), C.c_int, _P(C.c_int), _P(C.c_int),
                                       _P(MGInfo), _vp]),
     "iamrx_diffusion_apply": (C.c_int, [_vp, C.c_int, C.c_int, _P(Fab), _P(Fab), C.c_double, C.c_double, _P(Fab),

@@ -244,5 +244,46 @@ int reduce_dot(const Bx& bx, C4 x, C4 y, C4 mask, double* result, cudaStream_t s
   return check_launch("reduce_dot");
 }
 
+
+#if !defined(IX_EMUL)
+// ---- diagnostic: measured FP64 pipe rate (the second roofline of the Godunov kernels; BASELINE.md asks for a measured,
+// not a nominal, DFMA rate).  Eight independent DFMA chains per thread, 256 threads, 8 CTAs per SM.
+namespace {
+__global__ void __launch_bounds__(256) dfma_peak_kernel(double* out, double a, double b, int iters) {
+  double x0 = threadIdx.x, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6, x7 = x0 + 7;
+  for (int i = 0; i < iters; ++i) {
+    x0 = fma(x0, a, b); x1 = fma(x1, a, b); x2 = fma(x2, a, b); x3 = fma(x3, a, b);
+    x4 = fma(x4, a, b); x5 = fma(x5, a, b); x6 = fma(x6, a, b); x7 = fma(x7, a, b);
+  }
+  if (x0 + x1 + x2 + x3 + x4 + x5 + x6 + x7 == 123.456) out[0] = x0;   // keep the chains alive
+}
+}  // namespace
+int fp64_peak(double* dp_ginstr_per_s, cudaStream_t s) {
+  double* d = nullptr;
+  IX_CUDA(cudaMalloc(&d, 8));
+  cudaEvent_t e0, e1;
+  IX_CUDA(cudaEventCreate(&e0)); IX_CUDA(cudaEventCreate(&e1));
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int iters = 1 << 15, blocks = sms * 8;
+  double best = 0.0;
+  for (int rep = 0; rep < 5; ++rep) {
+    IX_CUDA(cudaEventRecord(e0, s));
+    dfma_peak_kernel<<<blocks, 256, 0, s>>>(d, 0.999999, 1.0e-6, iters);
+    IX_CUDA(cudaEventRecord(e1, s));
+    IX_CUDA(cudaEventSynchronize(e1));
+    float ms = 0; cudaEventElapsedTime(&ms, e0, e1);
+    const double rate = (double)blocks * 256.0 * 8.0 * iters / (ms * 1e-3) / 1e9;
+    if (rep > 0 && rate > best) best = rate;
+  }
+  cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(d);
+  *dp_ginstr_per_s = best;
+  return check_launch("dfma_peak");
+}
+#else
+int fp64_peak(double* r, cudaStream_t) { *r = 0.0; return IAMRX_OK; }
+#endif
+
 }  // namespace k
 }  // namespace ix

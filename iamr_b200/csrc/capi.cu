@@ -60,6 +60,11 @@ int iamrx_version(void) { return 100; }
 int64_t iamrx_launch_count(void) { return g_launches.load(); }
 void iamrx_launch_count_reset(void) { g_launches.store(0); }
 int iamrx_device_ok(void) { return device_ok() ? 1 : 0; }
+int iamrx_debug_fp64_peak(double* dp_ginstr_per_s, void* stream) {
+  IX_NEED_DEVICE();
+  IX_ARG(dp_ginstr_per_s, "null argument");
+  return k::fp64_peak(dp_ginstr_per_s, (cudaStream_t)stream);
+}
 int iamrx_prof_enable(int on, int64_t min_points) { return prof_enable(on, min_points); }
 void iamrx_prof_reset(void) { prof_reset(); }
 int iamrx_prof_all(int on) { return prof_all(on); }
@@ -119,49 +124,102 @@ int iamrx_tensor_cross_box(const iamrx_box* bx, iamrx_fab* out, const iamrx_fab*
                          S(stream));
 }
 
+// does `f` (all of its allocation) cover box `need`?
+static bool covers(const iamrx_fab* f, const Bx& need) {
+  for (int d = 0; d < 3; ++d) if (f->lo[d] > need.lo[d] || f->hi[d] < need.hi[d]) return false;
+  return true;
+}
+static k::AdvBC make_advbc(const iamrx_bcrec* bc, int ncomp, const iamrx_geom* geom) {
+  k::AdvBC b{};
+  for (int d = 0; d < 3; ++d) { b.dlo[d] = geom->domain.lo[d]; b.dhi[d] = geom->domain.hi[d]; }
+  if (bc)
+    for (int n = 0; n < ncomp && n < 8; ++n)
+      for (int d = 0; d < 3; ++d) { b.lo[n][d] = bc[n].lo[d]; b.hi[n][d] = bc[n].hi[d]; }
+  return b;
+}
+static bool bc_codes_ok(const iamrx_bcrec* bc, int ncomp) {
+  if (!bc) return true;
+  for (int n = 0; n < ncomp; ++n)
+    for (int d = 0; d < 3; ++d)
+      for (int v : {bc[n].lo[d], bc[n].hi[d]})
+        if (v < IAMRX_BC_REFLECT_ODD || v > IAMRX_BC_HOEXTRAP) return false;
+  return true;
+}
+
 int iamrx_extrap_vel_to_faces_box(const iamrx_box* bx, const iamrx_fab* vel, const iamrx_fab* force,
-                                  iamrx_fab* umac, iamrx_fab* vmac, iamrx_fab* wmac, const iamrx_geom* geom,
-                                  double dt, int flags, void* stream) {
+                                  iamrx_fab* umac, iamrx_fab* vmac, iamrx_fab* wmac, const iamrx_bcrec* bcrec,
+                                  const iamrx_geom* geom, double dt, int flags, void* stream) {
   IX_NEED_DEVICE();
   IX_ARG(bx && vel && umac && vmac && wmac && geom, "null argument");
   IX_ARG(vel->ncomp >= 3, "vel needs 3 components");
+  IX_ARG(bc_codes_ok(bcrec, 3), "unknown BCRec code");
+  const Bx b = mkbx(*bx);
+  IX_ARG(covers(vel, grow(b, 3)), "vel must cover the box grown by 3 cells (nghost_state, NSB.cpp:4539-4552)");
+  IX_ARG(!force || !force->p || (force->ncomp >= 3 && covers(force, grow(b, 1))), "force must have 3 components on the box grown by 1");
+  IX_ARG(covers(umac, surrounding(b, 0)) && covers(vmac, surrounding(b, 1)) && covers(wmac, surrounding(b, 2)), "u_mac must cover the faces of the box");
   k::AdvGeom g;
   for (int d = 0; d < 3; ++d) g.dx[d] = geom->dx[d];
   g.dt = dt;
-  return k::extrap_vel_to_faces(mkbx(*bx), cview(vel), cview(force), view(umac), view(vmac), view(wmac), g,
-                                (flags & IAMRX_ADV_FORCES_IN_TRANS) ? 1 : 0, S(stream), (flags & IAMRX_ADV_PPM) ? 1 : 0);
+  const k::AdvBC abc = make_advbc(bcrec, 3, geom);
+  return k::extrap_vel_to_faces(b, cview(vel), cview(force), view(umac), view(vmac), view(wmac), g,
+                                (flags & IAMRX_ADV_FORCES_IN_TRANS) ? 1 : 0, S(stream), (flags & IAMRX_ADV_PPM) ? 1 : 0, &abc);
 }
 
 int iamrx_compute_aofs_box(const iamrx_box* bx, iamrx_fab* aofs, int aofs_comp, const iamrx_fab* Sf, int s_comp,
                            int ncomp, const iamrx_fab* force, int f_comp, const iamrx_fab* divu,
-                           const iamrx_fab* umac, const iamrx_fab* vmac, const iamrx_fab* wmac, iamrx_fab* fx,
+                           const iamrx_fab* umac, const iamrx_fab* vmac, const iamrx_fab* wmac,
+                           const iamrx_fab* uflux, const iamrx_fab* vflux, const iamrx_fab* wflux, iamrx_fab* fx,
                            iamrx_fab* fy, iamrx_fab* fz, iamrx_fab* xed, iamrx_fab* yed, iamrx_fab* zed,
-                           const int* iconserv, const iamrx_geom* geom, double dt, int flags, void* stream) {
+                           const int* iconserv, const iamrx_bcrec* bcrec, const iamrx_geom* geom, double dt, int flags,
+                           void* stream) {
   IX_NEED_DEVICE();
   IX_ARG(bx && aofs && Sf && umac && vmac && wmac && iconserv && geom, "null argument");
   IX_ARG(ncomp >= 1 && ncomp <= 8, "ncomp must be in [1,8]");
-  const bool wf = (flags & IAMRX_ADV_WRITE_FLUXES) != 0;
+  IX_ARG(aofs_comp >= 0 && aofs_comp + ncomp <= aofs->ncomp && s_comp >= 0 && s_comp + ncomp <= Sf->ncomp, "component range");
+  const bool wf = (flags & IAMRX_ADV_WRITE_FLUXES) != 0, known = (flags & IAMRX_ADV_KNOWN_EDGE_STATE) != 0;
   IX_ARG(!wf || (fx && fy && fz && xed && yed && zed), "flux/edge outputs required with WRITE_FLUXES");
+  IX_ARG(!known || (xed && yed && zed), "edge states required with KNOWN_EDGE_STATE");
+  IX_ARG((!uflux && !vflux && !wflux) || (uflux && vflux && wflux), "give all three flux velocities or none");
+  IX_ARG(bc_codes_ok(bcrec, ncomp), "unknown BCRec code");
+  const Bx b = mkbx(*bx);
+  IX_ARG(covers(Sf, known ? b : grow(b, 3)), "S must cover the box grown by 3 cells (nghost_state, NSB.cpp:4539-4552)");
+  IX_ARG(!force || !force->p || (f_comp >= 0 && f_comp + ncomp <= force->ncomp && covers(force, grow(b, 1))), "force must cover the box grown by 1");
+  IX_ARG(!divu || !divu->p || covers(divu, grow(b, 1)), "divu must cover the box grown by 1");
+  IX_ARG(covers(aofs, b), "aofs must cover the box");
+  const iamrx_fab* mv[3] = {umac, vmac, wmac};
+  const iamrx_fab* fv[3] = {uflux, vflux, wflux};
+  iamrx_fab* fo[3] = {fx, fy, fz};
+  iamrx_fab* eo[3] = {xed, yed, zed};
+  for (int d = 0; d < 3; ++d) {
+    // the transverse terms read the MAC velocities one cell outside the box in the other two directions
+    IX_ARG(covers(mv[d], known ? surrounding(b, d) : surrounding(grow(b, 1), d)), "MAC velocities need one ghost face layer around the box");
+    IX_ARG(!fv[d] || covers(fv[d], surrounding(b, d)), "flux velocities must cover the faces of the box");
+    IX_ARG(!(wf || known) || !fo[d] || (fo[d]->ncomp >= ncomp && covers(fo[d], surrounding(b, d))), "flux output must cover the faces of the box");
+    IX_ARG(!(wf || known) || !eo[d] || (eo[d]->ncomp >= ncomp && covers(eo[d], surrounding(b, d))), "edge states must cover the faces of the box");
+  }
   k::AofsArgs a{};
   a.aofs = view(aofs, aofs_comp);
   a.S = cview(Sf, s_comp);
   a.force = cview(force, f_comp);
   a.divu = cview(divu);
   a.umac = cview(umac); a.vmac = cview(vmac); a.wmac = cview(wmac);
-  a.uflx = a.umac; a.vflx = a.vmac; a.wflx = a.wmac;
-  if (wf) { a.fx = view(fx); a.fy = view(fy); a.fz = view(fz); a.xed = view(xed); a.yed = view(yed); a.zed = view(zed); }
+  // flux velocities: u_mac itself except in the sync call, where the fluxes are built with U_corr (NSB.cpp:4672-4677)
+  a.uflx = uflux ? cview(uflux) : a.umac; a.vflx = vflux ? cview(vflux) : a.vmac; a.wflx = wflux ? cview(wflux) : a.wmac;
+  if (wf || known) { a.fx = view(fx); a.fy = view(fy); a.fz = view(fz); a.xed = view(xed); a.yed = view(yed); a.zed = view(zed); }
   a.ncomp = ncomp;
   for (int n = 0; n < ncomp; ++n) a.iconserv[n] = iconserv[n];
   a.forces_in_trans = (flags & IAMRX_ADV_FORCES_IN_TRANS) ? 1 : 0;
   a.is_velocity = (flags & IAMRX_ADV_IS_VELOCITY) ? 1 : 0;
   a.is_sync = (flags & IAMRX_ADV_IS_SYNC) ? 1 : 0;
   a.write_fluxes = wf ? 1 : 0;
+  a.known_edge_state = known ? 1 : 0;
   a.staged = (flags & IAMRX_ADV_STAGED) ? 1 : 0;
   a.ppm = (flags & IAMRX_ADV_PPM) ? 1 : 0;
+  a.bc = make_advbc(bcrec, ncomp, geom);
   k::AdvGeom g;
   for (int d = 0; d < 3; ++d) g.dx[d] = geom->dx[d];
   g.dt = dt;
-  return k::compute_aofs(mkbx(*bx), a, g, S(stream));
+  return k::compute_aofs(b, a, g, S(stream));
 }
 
 int iamrx_nodal_divu_box(const iamrx_box* nbx, iamrx_fab* rhs, const iamrx_fab* vel, const double dxinv[3],
@@ -301,7 +359,7 @@ void iamrx_mg_info_default(iamrx_mg_info* info) {
   info->nu1 = 2; info->nu2 = 2;
   info->bottom_sweeps = 8;
   info->verbose = 0;
-  info->omega = 1.0;
+  info->omega = 1.15;   // AMReX abec_gsrb over-relaxation (AMReX_MLABecLap_3D_K.H); the UNVERIFIED-UPSTREAM table in DESIGN.md
 }
 
 static int check_periodic_bc(const Level& L, const int lobc[3], const int hibc[3]) {
@@ -332,6 +390,19 @@ int iamrx_mac_project(iamrx_level_t lev, iamrx_fab* umac, iamrx_fab* vmac, iamrx
   MF Phi; Phi.alias(L, IX_CELL, 1, 1, phi);
   MF Rhs; if (rhs) Rhs.alias(L, IX_CELL, 1, 0, rhs);
   return mac_project(*L, lev->solvers, U, Rho, rhs ? &Rhs : nullptr, Phi, rhs_scale, info, S(stream));
+  IX_GUARD_END
+}
+
+int iamrx_mac_get_fluxes(iamrx_level_t lev, iamrx_fab* fx, iamrx_fab* fy, iamrx_fab* fz, iamrx_fab* phi, void* stream) {
+  IX_GUARD_BEGIN
+  IX_NEED_DEVICE();
+  IX_ARG(lev && fx && fy && fz && phi, "null argument");
+  Level* L = lev->lev.get();
+  iamrx_fab* ff[3] = {fx, fy, fz};
+  MF F[3];
+  for (int d = 0; d < 3; ++d) F[d].alias(L, IX_XFACE + d, 1, 0, ff[d]);
+  MF Phi; Phi.alias(L, IX_CELL, 1, 1, phi);
+  return mac_get_fluxes(*L, lev->solvers, F, Phi, S(stream));
   IX_GUARD_END
 }
 

@@ -13,8 +13,9 @@
 //   diverg : -div(flux)/vol + qbar*div(umac) for non-conservative comps, sign -> aofs
 // The lo/hi traced states are recomputed from q where a later stage needs them (two
 // 4th-order slopes) rather than stored: 9 scratch arrays per component instead of 15.
-// Physical-boundary (ext_dir/hoextrap) edge treatment is not implemented: the C ABI
-// rejects non-periodic configurations before reaching these kernels.
+// Physical domain boundaries (BCRec per component, NSB.cpp:4489,4712): one-sided ext_dir / hoextrap slopes, the
+// Set{X,Y,Z}EdgeBCs rules after every stage and the outflow clipping of the final states (godunov_math.h) in the
+// staged kernels; the fused tile kernel handles boxes whose stencil stays away from non-interior boundaries.
 #include <cstdlib>
 #include "godunov_math.h"
 #include "kernels.h"
@@ -32,19 +33,32 @@ constexpr int TY = 4;
 // traced states on the D-face below the cell the cursor `q` sits on: lo from the cell below,
 // hi from this cell.  ulo/uhi: the velocity used in the trace (cell-centred normal velocity
 // for ExtrapVelToFaces, the MAC velocity of this face for ComputeEdgeState).
+// domain bounds + BCRec of every component (amrex::BCRec, NS_BC.H:7-55 via NavierStokesBase::fetchBCArray)
+struct BcAll {
+  int dlo[3], dhi[3];
+  int lo[8][3], hi[8][3];
+  int any;   // some side of some component is not int_dir: otherwise every boundary branch is skipped
+  IX_HD BcD dir(int n, int d) const { return BcD{lo[n][d], hi[n][d], dlo[d], dhi[d]}; }
+};
+template <int D> IX_HD int idx_of(int i, int j, int k) { return D == 0 ? i : (D == 1 ? j : k); }
+
 template <int D>
-IX_D void trace(const Cur& q, double ulo, double uhi, double dtdx, double& lo, double& hi, int ppm = 0) {
-  const Cur qm = below<D>(q);
+IX_D void trace(const Cur& q, double ulo, double uhi, double dtdx, double& lo, double& hi, int ppm, int c, const BcD* b) {
+  const Cur qm = below<D>(q);   // c = index along D of the cell the cursor sits on (== index of the face)
   if (ppm) {  // Godunov_PPM: lo = Ip of the cell below, hi = Im of this cell
     double sm, sp;
-    ppm_parabola(along<D>(qm, -2), along<D>(qm, -1), qm(0, 0, 0), along<D>(qm, 1), along<D>(qm, 2), sm, sp);
+    if (b) ppm_parabola_bc(along<D>(qm, -2), along<D>(qm, -1), qm(0, 0, 0), along<D>(qm, 1), along<D>(qm, 2), c - 1, *b, sm, sp);
+    else ppm_parabola(along<D>(qm, -2), along<D>(qm, -1), qm(0, 0, 0), along<D>(qm, 1), along<D>(qm, 2), sm, sp);
     lo = ppm_ip(qm(0, 0, 0), sm, sp, ulo, dtdx);
-    ppm_parabola(along<D>(q, -2), along<D>(q, -1), q(0, 0, 0), along<D>(q, 1), along<D>(q, 2), sm, sp);
+    if (b) ppm_parabola_bc(along<D>(q, -2), along<D>(q, -1), q(0, 0, 0), along<D>(q, 1), along<D>(q, 2), c, *b, sm, sp);
+    else ppm_parabola(along<D>(q, -2), along<D>(q, -1), q(0, 0, 0), along<D>(q, 1), along<D>(q, 2), sm, sp);
     hi = ppm_im(q(0, 0, 0), sm, sp, uhi, dtdx);
     return;
   }
-  lo = qm(0, 0, 0) + 0.5 * (1.0 - ulo * dtdx) * slope4c<D>(qm);
-  hi = q(0, 0, 0) + 0.5 * (-1.0 - uhi * dtdx) * slope4c<D>(q);
+  const double sl = b ? slope4_bc_vals(along<D>(qm, -2), along<D>(qm, -1), qm(0, 0, 0), along<D>(qm, 1), along<D>(qm, 2), c - 1, *b) : slope4c<D>(qm);
+  const double sh = b ? slope4_bc_vals(along<D>(q, -2), along<D>(q, -1), q(0, 0, 0), along<D>(q, 1), along<D>(q, 2), c, *b) : slope4c<D>(q);
+  lo = qm(0, 0, 0) + 0.5 * (1.0 - ulo * dtdx) * sl;
+  hi = q(0, 0, 0) + 0.5 * (-1.0 - uhi * dtdx) * sh;
 }
 
 struct Scratch {  // all on the same grown index box, component-major
@@ -83,20 +97,30 @@ struct EsArgs {
   int iconserv[8];
   int fit;  // use_forces_in_trans
   int ppm;  // Godunov_PPM instead of Godunov_PLM
+  int is_velocity;
   double dt, dtdx, dtdy, dtdz;
+  BcAll bc;
 };
 
 // scratch array ids per component: 0..2 edge x,y,z; 3..8 corner xy,xz,yx,yz,zx,zy; 9..11 flux
 enum { A_XE = 0, A_YE, A_ZE, A_XY, A_XZ, A_YX, A_YZ, A_ZX, A_ZY, A_FX, A_FY, A_FZ, A_N };
 
 // lo/hi on the D-face of the cursor's cell, traced with the MAC velocity `u` of that face
+// Set{X,Y,Z}EdgeBCs on the states of the D-face with index c for component n
+template <int D, class A>
+IX_D void edge_bc(const A& a, int n, const Cur& q, int c, double& lo, double& hi, bool normal_vel) {
+  if (!a.bc.any) return;
+  set_edge_bc(lo, hi, along<D>(q, -1), q(0, 0, 0), c, a.bc.dir(n, D), normal_vel);
+}
 template <int D>
-IX_D void es_lohi(const EsArgs& a, const Cur& q, const Cur& f, double u, double dtdx, double& lo, double& hi) {
-  trace<D>(q, u, u, dtdx, lo, hi, a.ppm);
+IX_D void es_lohi(const EsArgs& a, int n, int c, const Cur& q, const Cur& f, double u, double dtdx, double& lo, double& hi) {
+  const BcD b = a.bc.dir(n, D);
+  trace<D>(q, u, u, dtdx, lo, hi, a.ppm, c, a.bc.any ? &b : nullptr);
   if (a.fit && f.ok()) {
     lo += 0.5 * a.dt * along<D>(f, -1);
     hi += 0.5 * a.dt * f(0, 0, 0);
   }
+  edge_bc<D>(a, n, q, c, lo, hi, a.is_velocity && n == D);
 }
 
 struct EsCur {  // the cursors one thread needs
@@ -118,17 +142,17 @@ __global__ void __launch_bounds__(TX* TY) es_edge_kernel(IX_KARG(EsArgs) a, IX_K
   double lo, hi;
   if (i >= b.lo[0] && i <= b.hi[0] + 1 && iny && inz) {  // x-faces lo..hi+1
     const double u = c.u(0, 0, 0);
-    es_lohi<0>(a, c.q, c.f, u, a.dtdx, lo, hi);
+    es_lohi<0>(a, n, i, c.q, c.f, u, a.dtdx, lo, hi);
     c.s(o + A_XE, 0, 0, 0) = upwind(lo, hi, u);
   }
   if (j >= b.lo[1] && j <= b.hi[1] + 1 && inx && inz) {
     const double v = c.v(0, 0, 0);
-    es_lohi<1>(a, c.q, c.f, v, a.dtdy, lo, hi);
+    es_lohi<1>(a, n, j, c.q, c.f, v, a.dtdy, lo, hi);
     c.s(o + A_YE, 0, 0, 0) = upwind(lo, hi, v);
   }
   if (k >= b.lo[2] && k <= b.hi[2] + 1 && inx && iny) {
     const double w = c.w(0, 0, 0);
-    es_lohi<2>(a, c.q, c.f, w, a.dtdz, lo, hi);
+    es_lohi<2>(a, n, k, c.q, c.f, w, a.dtdz, lo, hi);
     c.s(o + A_ZE, 0, 0, 0) = upwind(lo, hi, w);
   }
 }
@@ -165,39 +189,48 @@ __global__ void __launch_bounds__(TX* TY) es_corner_kernel(IX_KARG(EsArgs) a, IX
   // x-faces
   if (fx && ((fy && cy && gz) || (gy && fz && cz))) {
     const double u = c.u(0, 0, 0);
-    es_lohi<0>(a, c.q, c.f, u, a.dtdx, lo, hi);
+    const bool nv = a.is_velocity && n == 0;
+    es_lohi<0>(a, n, i, c.q, c.f, u, a.dtdx, lo, hi);
     if (fy && cy && gz) {  // xy: needed for z-faces -> grown in z
       corner<0, 1>(l1, h1, lo, hi, c.q, c.v, ye, a.dtdy / 3.0, cs);
+      edge_bc<0>(a, n, c.q, i, l1, h1, nv);
       c.s(o + A_XY, 0, 0, 0) = upwind(l1, h1, u);
     }
     if (gy && fz && cz) {  // xz: needed for y-faces -> grown in y
       corner<0, 2>(l1, h1, lo, hi, c.q, c.w, ze, a.dtdz / 3.0, cs);
+      edge_bc<0>(a, n, c.q, i, l1, h1, nv);
       c.s(o + A_XZ, 0, 0, 0) = upwind(l1, h1, u);
     }
   }
   // y-faces
   if (fy && ((fx && cx && gz) || (gx && fz && cz))) {
     const double v = c.v(0, 0, 0);
-    es_lohi<1>(a, c.q, c.f, v, a.dtdy, lo, hi);
+    const bool nv = a.is_velocity && n == 1;
+    es_lohi<1>(a, n, j, c.q, c.f, v, a.dtdy, lo, hi);
     if (fx && cx && gz) {  // yx: needed for z-faces
       corner<1, 0>(l1, h1, lo, hi, c.q, c.u, xe, a.dtdx / 3.0, cs);
+      edge_bc<1>(a, n, c.q, j, l1, h1, nv);
       c.s(o + A_YX, 0, 0, 0) = upwind(l1, h1, v);
     }
     if (gx && fz && cz) {  // yz: needed for x-faces
       corner<1, 2>(l1, h1, lo, hi, c.q, c.w, ze, a.dtdz / 3.0, cs);
+      edge_bc<1>(a, n, c.q, j, l1, h1, nv);
       c.s(o + A_YZ, 0, 0, 0) = upwind(l1, h1, v);
     }
   }
   // z-faces
   if (fz && ((fx && cx && gy) || (gx && fy && cy))) {
     const double w = c.w(0, 0, 0);
-    es_lohi<2>(a, c.q, c.f, w, a.dtdz, lo, hi);
+    const bool nv = a.is_velocity && n == 2;
+    es_lohi<2>(a, n, k, c.q, c.f, w, a.dtdz, lo, hi);
     if (fx && cx && gy) {  // zx: needed for y-faces
       corner<2, 0>(l1, h1, lo, hi, c.q, c.u, xe, a.dtdx / 3.0, cs);
+      edge_bc<2>(a, n, c.q, k, l1, h1, nv);
       c.s(o + A_ZX, 0, 0, 0) = upwind(l1, h1, w);
     }
     if (gx && fy && cy) {  // zy: needed for x-faces
       corner<2, 1>(l1, h1, lo, hi, c.q, c.v, ye, a.dtdy / 3.0, cs);
+      edge_bc<2>(a, n, c.q, k, l1, h1, nv);
       c.s(o + A_ZY, 0, 0, 0) = upwind(l1, h1, w);
     }
   }
@@ -237,6 +270,16 @@ IX_D void es_finish(const EsArgs& a, const Cur& q, const Cur& f, const Cur& dv, 
   }
 }
 
+// boundary conditions of the final states: SetEdgeBCs, then the outflow rule (the normal velocity is not advected
+// INTO the domain through a foextrap / hoextrap face)
+template <int D>
+IX_D void es_final_bc(const EsArgs& a, int n, const Cur& q, int c, double mac, double& stl, double& sth) {
+  if (!a.bc.any) return;
+  const bool nv = a.is_velocity && n == D;
+  set_edge_bc(stl, sth, along<D>(q, -1), q(0, 0, 0), c, a.bc.dir(n, D), nv);
+  outflow_bc(stl, sth, c, a.bc.dir(n, D), nv && mac >= 0.0, nv && mac <= 0.0);
+}
+
 struct EsOut {
   V4 fx, fy, fz, xed, yed, zed;  // optional user outputs (area-weighted fluxes, edge states)
   double ax, ay, az;             // face areas
@@ -253,9 +296,10 @@ __global__ void __launch_bounds__(TX* TY) es_final_kernel(IX_KARG(EsArgs) a, IX_
   double stl, sth;
   if (cy && cz) {  // x-face
     const double u = c.u(0, 0, 0);
-    es_lohi<0>(a, c.q, c.f, u, a.dtdx, stl, sth);
+    es_lohi<0>(a, n, i, c.q, c.f, u, a.dtdx, stl, sth);
     transverse<0, 1, 2>(stl, sth, c.q, c.v, c.w, sarr(c.s, o + A_YZ), sarr(c.s, o + A_ZY), a.dtdy, a.dtdz, cs);
     es_finish<0>(a, c.q, c.f, dv, cs, stl, sth);
+    es_final_bc<0>(a, n, c.q, i, u, stl, sth);
     const double st = upwind(stl, sth, u);
     const double f = st * a.uflx(i, j, k) * out.ax;
     c.s(o + A_XE, 0, 0, 0) = st;
@@ -265,9 +309,10 @@ __global__ void __launch_bounds__(TX* TY) es_final_kernel(IX_KARG(EsArgs) a, IX_
   }
   if (cx && cz) {  // y-face
     const double v = c.v(0, 0, 0);
-    es_lohi<1>(a, c.q, c.f, v, a.dtdy, stl, sth);
+    es_lohi<1>(a, n, j, c.q, c.f, v, a.dtdy, stl, sth);
     transverse<1, 0, 2>(stl, sth, c.q, c.u, c.w, sarr(c.s, o + A_XZ), sarr(c.s, o + A_ZX), a.dtdx, a.dtdz, cs);
     es_finish<1>(a, c.q, c.f, dv, cs, stl, sth);
+    es_final_bc<1>(a, n, c.q, j, v, stl, sth);
     const double st = upwind(stl, sth, v);
     const double f = st * a.vflx(i, j, k) * out.ay;
     c.s(o + A_YE, 0, 0, 0) = st;
@@ -277,14 +322,40 @@ __global__ void __launch_bounds__(TX* TY) es_final_kernel(IX_KARG(EsArgs) a, IX_
   }
   if (cx && cy) {  // z-face
     const double w = c.w(0, 0, 0);
-    es_lohi<2>(a, c.q, c.f, w, a.dtdz, stl, sth);
+    es_lohi<2>(a, n, k, c.q, c.f, w, a.dtdz, stl, sth);
     transverse<2, 0, 1>(stl, sth, c.q, c.u, c.v, sarr(c.s, o + A_XY), sarr(c.s, o + A_YX), a.dtdx, a.dtdy, cs);
     es_finish<2>(a, c.q, c.f, dv, cs, stl, sth);
+    es_final_bc<2>(a, n, c.q, k, w, stl, sth);
     const double st = upwind(stl, sth, w);
     const double f = st * a.wflx(i, j, k) * out.az;
     c.s(o + A_ZE, 0, 0, 0) = st;
     c.s(o + A_FZ, 0, 0, 0) = f;
     if (out.zed.ok()) out.zed(i, j, k, n) = st;
+    if (out.fz.ok()) out.fz(i, j, k, n) = f;
+  }
+}
+
+// known_edge_state (MacProj.cpp:776-785 -> NSB.cpp:4708): the caller's edge states are taken as they are and only the
+// fluxes are formed: flux = edge * uflux * area (HydroUtils::ComputeFluxes)
+__global__ void __launch_bounds__(TX* TY) es_known_kernel(IX_KARG(EsArgs) a, IX_KARG(Scratch) sc, IX_KARG(EsOut) out, IX_KARG(Bx) R) {
+  GIDX(R)
+  const SCur s = scur_at(sc, i, j, k);
+  const Bx& b = a.bx;
+  const int o = A_N * n;
+  const bool cx = i <= b.hi[0], cy = j <= b.hi[1], cz = k <= b.hi[2];
+  if (cy && cz) {
+    const double st = out.xed(i, j, k, n), f = st * a.uflx(i, j, k) * out.ax;
+    s(o + A_XE, 0, 0, 0) = st; s(o + A_FX, 0, 0, 0) = f;
+    if (out.fx.ok()) out.fx(i, j, k, n) = f;
+  }
+  if (cx && cz) {
+    const double st = out.yed(i, j, k, n), f = st * a.vflx(i, j, k) * out.ay;
+    s(o + A_YE, 0, 0, 0) = st; s(o + A_FY, 0, 0, 0) = f;
+    if (out.fy.ok()) out.fy(i, j, k, n) = f;
+  }
+  if (cx && cy) {
+    const double st = out.zed(i, j, k, n), f = st * a.wflx(i, j, k) * out.az;
+    s(o + A_ZE, 0, 0, 0) = st; s(o + A_FZ, 0, 0, 0) = f;
     if (out.fz.ok()) out.fz(i, j, k, n) = f;
   }
 }
@@ -317,6 +388,7 @@ struct EvArgs {
   C4 vel, force;
   int fit, ppm;
   double dt, dtdx, dtdy, dtdz;
+  BcAll bc;
 };
 // scratch ids: advective velocities 0..2; transverse edges: XE_V,XE_W (x-faces, comps 1,2),
 // YE_U,YE_W, ZE_U,ZE_V; corner: YZ_U, ZY_U (for umac), XZ_V, ZX_V (vmac), XY_W, YX_W (wmac)
@@ -336,12 +408,14 @@ IX_D EvCur ev_cursors(const EvArgs& a, const Scratch& sc, int i, int j, int k) {
 
 // lo/hi of component n on the D-face, traced with the cell-centred velocity component D
 template <int D>
-IX_D void ev_lohi(const EvArgs& a, const EvCur& c, int n, double dtdx, double& lo, double& hi) {
-  trace<D>(c.q[n], along<D>(c.q[D], -1), c.q[D](0, 0, 0), dtdx, lo, hi, a.ppm);
+IX_D void ev_lohi(const EvArgs& a, const EvCur& c, int n, int ci, double dtdx, double& lo, double& hi) {
+  const BcD b = a.bc.dir(n, D);
+  trace<D>(c.q[n], along<D>(c.q[D], -1), c.q[D](0, 0, 0), dtdx, lo, hi, a.ppm, ci, a.bc.any ? &b : nullptr);
   if (a.fit && c.f[n].ok()) {
     lo += 0.5 * a.dt * along<D>(c.f[n], -1);
     hi += 0.5 * a.dt * c.f[n](0, 0, 0);
   }
+  edge_bc<D>(a, n, c.q[n], ci, lo, hi, n == D);
 }
 
 __global__ void __launch_bounds__(TX* TY) ev_edge_kernel(IX_KARG(EvArgs) a, IX_KARG(Scratch) sc, IX_KARG(Bx) R) {
@@ -353,30 +427,30 @@ __global__ void __launch_bounds__(TX* TY) ev_edge_kernel(IX_KARG(EvArgs) a, IX_K
              inz = k >= b.lo[2] - 1 && k <= b.hi[2] + 1;
   double lo, hi;
   if (i >= b.lo[0] && i <= b.hi[0] + 1 && iny && inz) {
-    ev_lohi<0>(a, c, 0, a.dtdx, lo, hi);
+    ev_lohi<0>(a, c, 0, i, a.dtdx, lo, hi);
     const double uad = riemann(lo, hi);
     c.s(B_UAD, 0, 0, 0) = uad;
-    ev_lohi<0>(a, c, 1, a.dtdx, lo, hi);
+    ev_lohi<0>(a, c, 1, i, a.dtdx, lo, hi);
     c.s(B_XE_V, 0, 0, 0) = upwind(lo, hi, uad);
-    ev_lohi<0>(a, c, 2, a.dtdx, lo, hi);
+    ev_lohi<0>(a, c, 2, i, a.dtdx, lo, hi);
     c.s(B_XE_W, 0, 0, 0) = upwind(lo, hi, uad);
   }
   if (j >= b.lo[1] && j <= b.hi[1] + 1 && inx && inz) {
-    ev_lohi<1>(a, c, 1, a.dtdy, lo, hi);
+    ev_lohi<1>(a, c, 1, j, a.dtdy, lo, hi);
     const double vad = riemann(lo, hi);
     c.s(B_VAD, 0, 0, 0) = vad;
-    ev_lohi<1>(a, c, 0, a.dtdy, lo, hi);
+    ev_lohi<1>(a, c, 0, j, a.dtdy, lo, hi);
     c.s(B_YE_U, 0, 0, 0) = upwind(lo, hi, vad);
-    ev_lohi<1>(a, c, 2, a.dtdy, lo, hi);
+    ev_lohi<1>(a, c, 2, j, a.dtdy, lo, hi);
     c.s(B_YE_W, 0, 0, 0) = upwind(lo, hi, vad);
   }
   if (k >= b.lo[2] && k <= b.hi[2] + 1 && inx && iny) {
-    ev_lohi<2>(a, c, 2, a.dtdz, lo, hi);
+    ev_lohi<2>(a, c, 2, k, a.dtdz, lo, hi);
     const double wad = riemann(lo, hi);
     c.s(B_WAD, 0, 0, 0) = wad;
-    ev_lohi<2>(a, c, 0, a.dtdz, lo, hi);
+    ev_lohi<2>(a, c, 0, k, a.dtdz, lo, hi);
     c.s(B_ZE_U, 0, 0, 0) = upwind(lo, hi, wad);
-    ev_lohi<2>(a, c, 1, a.dtdz, lo, hi);
+    ev_lohi<2>(a, c, 1, k, a.dtdz, lo, hi);
     c.s(B_ZE_V, 0, 0, 0) = upwind(lo, hi, wad);
   }
 }
@@ -395,47 +469,57 @@ __global__ void __launch_bounds__(TX* TY) ev_corner_kernel(IX_KARG(EvArgs) a, IX
   double lo, hi, l1, h1;
   // x-face states: comp 2 coupled with y (for wmac), comp 1 coupled with z (for vmac)
   if (fx && fy && cy && gz) {
-    ev_lohi<0>(a, c, 2, a.dtdx, lo, hi);
+    ev_lohi<0>(a, c, 2, i, a.dtdx, lo, hi);
     corner<0, 1>(l1, h1, lo, hi, c.q[2], vad, sarr(c.s, B_YE_W), a.dtdy / 3.0, false);
+    edge_bc<0>(a, 2, c.q[2], i, l1, h1, 2 == 0);
     c.s(B_XY_W, 0, 0, 0) = upwind(l1, h1, uad(0, 0, 0));
   }
   if (fx && gy && fz && cz) {
-    ev_lohi<0>(a, c, 1, a.dtdx, lo, hi);
+    ev_lohi<0>(a, c, 1, i, a.dtdx, lo, hi);
     corner<0, 2>(l1, h1, lo, hi, c.q[1], wad, sarr(c.s, B_ZE_V), a.dtdz / 3.0, false);
+    edge_bc<0>(a, 1, c.q[1], i, l1, h1, 1 == 0);
     c.s(B_XZ_V, 0, 0, 0) = upwind(l1, h1, uad(0, 0, 0));
   }
   // y-face states: comp 2 coupled with x (for wmac), comp 0 coupled with z (for umac)
   if (fy && fx && cx && gz) {
-    ev_lohi<1>(a, c, 2, a.dtdy, lo, hi);
+    ev_lohi<1>(a, c, 2, j, a.dtdy, lo, hi);
     corner<1, 0>(l1, h1, lo, hi, c.q[2], uad, sarr(c.s, B_XE_W), a.dtdx / 3.0, false);
+    edge_bc<1>(a, 2, c.q[2], j, l1, h1, 2 == 1);
     c.s(B_YX_W, 0, 0, 0) = upwind(l1, h1, vad(0, 0, 0));
   }
   if (fy && gx && fz && cz) {
-    ev_lohi<1>(a, c, 0, a.dtdy, lo, hi);
+    ev_lohi<1>(a, c, 0, j, a.dtdy, lo, hi);
     corner<1, 2>(l1, h1, lo, hi, c.q[0], wad, sarr(c.s, B_ZE_U), a.dtdz / 3.0, false);
+    edge_bc<1>(a, 0, c.q[0], j, l1, h1, 0 == 1);
     c.s(B_YZ_U, 0, 0, 0) = upwind(l1, h1, vad(0, 0, 0));
   }
   // z-face states: comp 1 coupled with x (for vmac), comp 0 coupled with y (for umac)
   if (fz && fx && cx && gy) {
-    ev_lohi<2>(a, c, 1, a.dtdz, lo, hi);
+    ev_lohi<2>(a, c, 1, k, a.dtdz, lo, hi);
     corner<2, 0>(l1, h1, lo, hi, c.q[1], uad, sarr(c.s, B_XE_V), a.dtdx / 3.0, false);
+    edge_bc<2>(a, 1, c.q[1], k, l1, h1, 1 == 2);
     c.s(B_ZX_V, 0, 0, 0) = upwind(l1, h1, wad(0, 0, 0));
   }
   if (fz && gx && fy && cy) {
-    ev_lohi<2>(a, c, 0, a.dtdz, lo, hi);
+    ev_lohi<2>(a, c, 0, k, a.dtdz, lo, hi);
     corner<2, 1>(l1, h1, lo, hi, c.q[0], vad, sarr(c.s, B_YE_U), a.dtdy / 3.0, false);
+    edge_bc<2>(a, 0, c.q[0], k, l1, h1, 0 == 2);
     c.s(B_ZY_U, 0, 0, 0) = upwind(l1, h1, wad(0, 0, 0));
   }
 }
 
 template <int D, int D1, int D2>
-IX_D double ev_final(const EvArgs& a, const EvCur& c, int A1, int A2, int T1, int T2, double dtdx, double dtd1, double dtd2) {
+IX_D double ev_final(const EvArgs& a, const EvCur& c, int ci, int A1, int A2, int T1, int T2, double dtdx, double dtd1, double dtd2) {
   double stl, sth;
-  ev_lohi<D>(a, c, D, dtdx, stl, sth);
+  ev_lohi<D>(a, c, D, ci, dtdx, stl, sth);
   double fl = 0.0, fh = 0.0;
   if (!a.fit && c.f[D].ok()) { fl = 0.5 * a.dt * along<D>(c.f[D], -1); fh = 0.5 * a.dt * c.f[D](0, 0, 0); }
   transverse<D, D1, D2>(stl, sth, c.q[D], sarr(c.s, A1), sarr(c.s, A2), sarr(c.s, T1), sarr(c.s, T2), dtd1, dtd2, false);
   stl += fl; sth += fh;
+  if (a.bc.any) {
+    set_edge_bc(stl, sth, along<D>(c.q[D], -1), c.q[D](0, 0, 0), ci, a.bc.dir(D, D), true);
+    outflow_bc(stl, sth, ci, a.bc.dir(D, D), true, true);
+  }
   return riemann(stl, sth);
 }
 
@@ -445,9 +529,9 @@ __global__ void __launch_bounds__(TX* TY) ev_final_kernel(IX_KARG(EvArgs) a, IX_
   const EvCur c = ev_cursors(a, sc, i, j, k);
   const Bx& b = a.bx;
   const bool cx = i <= b.hi[0], cy = j <= b.hi[1], cz = k <= b.hi[2];
-  if (cy && cz) umac(i, j, k) = ev_final<0, 1, 2>(a, c, B_VAD, B_WAD, B_YZ_U, B_ZY_U, a.dtdx, a.dtdy, a.dtdz);
-  if (cx && cz) vmac(i, j, k) = ev_final<1, 0, 2>(a, c, B_UAD, B_WAD, B_XZ_V, B_ZX_V, a.dtdy, a.dtdx, a.dtdz);
-  if (cx && cy) wmac(i, j, k) = ev_final<2, 0, 1>(a, c, B_UAD, B_VAD, B_XY_W, B_YX_W, a.dtdz, a.dtdx, a.dtdy);
+  if (cy && cz) umac(i, j, k) = ev_final<0, 1, 2>(a, c, i, B_VAD, B_WAD, B_YZ_U, B_ZY_U, a.dtdx, a.dtdy, a.dtdz);
+  if (cx && cz) vmac(i, j, k) = ev_final<1, 0, 2>(a, c, j, B_UAD, B_WAD, B_XZ_V, B_ZX_V, a.dtdy, a.dtdx, a.dtdz);
+  if (cx && cy) wmac(i, j, k) = ev_final<2, 0, 1>(a, c, k, B_UAD, B_VAD, B_XY_W, B_YX_W, a.dtdz, a.dtdx, a.dtdy);
 }
 
 #if !defined(IX_EMUL)
@@ -664,6 +748,21 @@ inline bool aofs_tile_ok(const Bx& bx, const AofsArgs& a) {
 }  // namespace tile
 #endif
 
+// AdvBC -> device form; `any` only if the stencil of `bx` (slopes reach the second cell, faces of the box grown by 1)
+// can see a non-interior boundary
+inline BcAll to_bcall(const AdvBC* bc, const Bx& bx, int ncomp) {
+  BcAll b{};
+  if (!bc) return b;
+  for (int d = 0; d < 3; ++d) { b.dlo[d] = bc->dlo[d]; b.dhi[d] = bc->dhi[d]; }
+  for (int n = 0; n < 8; ++n)
+    for (int d = 0; d < 3; ++d) {
+      b.lo[n][d] = bc->lo[n][d]; b.hi[n][d] = bc->hi[n][d];
+      if (n < ncomp && ((b.lo[n][d] != IAMRX_BC_INT_DIR && bx.lo[d] - 4 <= b.dlo[d]) || (b.hi[n][d] != IAMRX_BC_INT_DIR && bx.hi[d] + 4 >= b.dhi[d])))
+        b.any = 1;
+    }
+  return b;
+}
+
 struct ScratchOwner {
   double* p = nullptr;
   Scratch sc{};
@@ -693,12 +792,14 @@ int compute_aofs(const Bx& bx, const AofsArgs& a, const AdvGeom& g, cudaStream_t
   for (int n = 0; n < 8; ++n) e.iconserv[n] = (n < a.ncomp) ? a.iconserv[n] : 0;
   e.fit = a.forces_in_trans;
   e.ppm = a.ppm;
+  e.is_velocity = a.is_velocity;
+  e.bc = to_bcall(&a.bc, bx, a.ncomp);
   e.dt = g.dt; e.dtdx = g.dt / g.dx[0]; e.dtdy = g.dt / g.dx[1]; e.dtdz = g.dt / g.dx[2];
   EsOut out{};
-  if (a.write_fluxes) { out.fx = a.fx; out.fy = a.fy; out.fz = a.fz; out.xed = a.xed; out.yed = a.yed; out.zed = a.zed; }
+  if (a.write_fluxes || a.known_edge_state) { out.fx = a.fx; out.fy = a.fy; out.fz = a.fz; out.xed = a.xed; out.yed = a.yed; out.zed = a.zed; }
   out.ax = g.dx[1] * g.dx[2]; out.ay = g.dx[0] * g.dx[2]; out.az = g.dx[0] * g.dx[1];
 #if !defined(IX_EMUL)
-  if (!a.staged && !a.ppm && tile::aofs_tile_ok(bx, a)) {   // the tile kernel is PLM only
+  if (!a.staged && !a.ppm && !a.known_edge_state && !e.bc.any && tile::aofs_tile_ok(bx, a)) {   // the tile kernel: PLM, interior stencil
     static bool attr_set = false;
     if (!attr_set) {
       IX_CUDA(cudaFuncSetAttribute(tile::aofs_tile_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, tile::SMEM_BYTES));
@@ -717,29 +818,37 @@ int compute_aofs(const Bx& bx, const AofsArgs& a, const AdvGeom& g, cudaStream_t
   ScratchOwner so;
   if (so.init(bx, A_N * a.ncomp) != IAMRX_OK) return IAMRX_ERR_CUDA;
   Bx R1 = grow(bx, 1); R1.hi[0]++; R1.hi[1]++; R1.hi[2]++;
-  IX_LAUNCH(es_edge_kernel, grid_for(R1, a.ncomp), dim3(TX, TY, 1), 0, s, e, so.sc, R1);
-  int rc = check_launch("es_edge");
-  if (rc) return rc;
-  IX_LAUNCH(es_corner_kernel, grid_for(R1, a.ncomp), dim3(TX, TY, 1), 0, s, e, so.sc, R1);
-  rc = check_launch("es_corner");
-  if (rc) return rc;
   Bx R2 = bx; R2.hi[0]++; R2.hi[1]++; R2.hi[2]++;
-  IX_LAUNCH(es_final_kernel, grid_for(R2, a.ncomp), dim3(TX, TY, 1), 0, s, e, so.sc, out, R2);
-  rc = check_launch("es_final");
-  if (rc) return rc;
+  int rc = IAMRX_OK;
+  if (a.known_edge_state) {
+    IX_LAUNCH(es_known_kernel, grid_for(R2, a.ncomp), dim3(TX, TY, 1), 0, s, e, so.sc, out, R2);
+    rc = check_launch("es_known");
+    if (rc) return rc;
+  } else {
+    IX_LAUNCH(es_edge_kernel, grid_for(R1, a.ncomp), dim3(TX, TY, 1), 0, s, e, so.sc, R1);
+    rc = check_launch("es_edge");
+    if (rc) return rc;
+    IX_LAUNCH(es_corner_kernel, grid_for(R1, a.ncomp), dim3(TX, TY, 1), 0, s, e, so.sc, R1);
+    rc = check_launch("es_corner");
+    if (rc) return rc;
+    IX_LAUNCH(es_final_kernel, grid_for(R2, a.ncomp), dim3(TX, TY, 1), 0, s, e, so.sc, out, R2);
+    rc = check_launch("es_final");
+    if (rc) return rc;
+  }
   IX_LAUNCH(es_div_kernel, grid_for(bx, a.ncomp), dim3(TX, TY, 1), 0, s, e, so.sc, a.aofs,
             1.0 / (g.dx[0] * g.dx[1] * g.dx[2]), 1.0 / g.dx[0], 1.0 / g.dx[1], 1.0 / g.dx[2], a.is_sync, bx);
   return check_launch("es_div");
 }
 
 int extrap_vel_to_faces(const Bx& bx, C4 vel, C4 force, V4 umac, V4 vmac, V4 wmac, const AdvGeom& g,
-                        int forces_in_trans, cudaStream_t s, int ppm) {
+                        int forces_in_trans, cudaStream_t s, int ppm, const AdvBC* bc) {
   if (!bx.ok()) return IAMRX_OK;
   ProfScope prof_(IAMRX_PROF_EXTRAP, bx.npts(), (double)bx.npts() * 72.0, s);
   ScratchOwner so;
   if (so.init(bx, B_N) != IAMRX_OK) return IAMRX_ERR_CUDA;
   EvArgs e{};
   e.bx = bx; e.vel = vel; e.force = force; e.fit = forces_in_trans; e.ppm = ppm;
+  e.bc = to_bcall(bc, bx, 3);
   e.dt = g.dt; e.dtdx = g.dt / g.dx[0]; e.dtdy = g.dt / g.dx[1]; e.dtdz = g.dt / g.dx[2];
   Bx R1 = grow(bx, 1); R1.hi[0]++; R1.hi[1]++; R1.hi[2]++;
   IX_LAUNCH(ev_edge_kernel, grid_for(R1, 1), dim3(TX, TY, 1), 0, s, e, so.sc, R1);

@@ -8,7 +8,8 @@
 // HydroUtils::ComputeFluxesOnBoxFromState (NavierStokesBase.cpp:4701-4717).
 // Those sources are not vendored in the reference tree (Exec/Make.IAMR:15-19);
 // the formulas are the published algorithm (Almgren et al., JCP 142 (1998);
-// SURVEY.md Appendix A.2-A.5).  Periodic / interior faces only in this round.
+// SURVEY.md Appendix A.2-A.5).  Domain boundaries: the ext_dir / hoextrap one-sided slopes
+// (amrex_calc_*slope_extdir), the PPM boundary parabolas and hydro_bcs_K.H Set{X,Y,Z}EdgeBCs.
 #pragma once
 #include "common.h"
 
@@ -107,6 +108,101 @@ IX_HD double ppm_im(double s0, double sm, double sp, double v, double dtdx) {
   if (!(v < -SMALL_VEL)) return s0;
   const double sg = fabs(v) * dtdx, s6 = 6.0 * s0 - 3.0 * (sm + sp);
   return sm + 0.5 * sg * ((sp - sm) + (1.0 - (2.0 / 3.0) * sg) * s6);
+}
+
+
+// ---- physical domain boundaries ---------------------------------------------------------------------------------
+// Boundary description of ONE direction for one component: amrex::BCRec codes (IAMRX_BC_*) of the low / high side and
+// the domain's cell bounds in that direction.
+struct BcD { int lo, hi, dlo, dhi; };
+IX_HD bool bc_extdir_or_ho(int bc) { return bc == IAMRX_BC_EXT_DIR || bc == IAMRX_BC_HOEXTRAP; }
+IX_HD double lim_os(double dl, double dr, double d) {   // one-sided limiter of the boundary slopes (dl, dr carry the factor 2)
+  const double lim = (dl * dr >= 0.0) ? fmin(fabs(dl), fabs(dr)) : 0.0;
+  return copysign(1.0, d) * fmin(lim, fabs(d));
+}
+// amrex_calc_{x,y,z}slope_extdir, order 4, from the five values along the direction; c = index of the cell along the
+// direction.  Next to an ext_dir / hoextrap face the ghost value sits ON the face (Software.rst:206-213), hence the
+// one-sided 4-point formula in the first cell and the revised neighbour slope in the second.
+IX_HD double slope4_bc_vals(double qm2, double qm, double q0, double qp, double qp2, int c, const BcD& b) {
+  const bool edlo = bc_extdir_or_ho(b.lo), edhi = bc_extdir_or_ho(b.hi);
+  if (!(edlo && (c == b.dlo || c == b.dlo + 1)) && !(edhi && (c == b.dhi || c == b.dhi - 1)))
+    return slope4_vals(qm2, qm, q0, qp, qp2);
+  double dfm = lim2(qm - qm2, q0 - qm), dfp = lim2(qp - q0, qp2 - qp);
+  const double dlft = q0 - qm, drgt = qp - q0, dcen = 0.5 * (dlft + drgt), dsgn = copysign(1.0, dcen);
+  const double dlim = (dlft * drgt >= 0.0) ? 2.0 * fmin(fabs(dlft), fabs(drgt)) : 0.0;
+  double s = dsgn * fmin(dlim, fabs((4.0 / 3.0) * dcen - (1.0 / 6.0) * (dfp + dfm)));
+  if (edlo && c == b.dlo) {
+    s = lim_os(2.0 * (q0 - qm), 2.0 * (qp - q0), -(16.0 / 15.0) * qm + 0.5 * q0 + (2.0 / 3.0) * qp - 0.1 * qp2);
+  } else if (edlo && c == b.dlo + 1) {   // the slope of cell dlo, which enters dfm, is the one-sided one
+    dfm = lim_os(2.0 * (qm - qm2), 2.0 * (q0 - qm), -(16.0 / 15.0) * qm2 + 0.5 * qm + (2.0 / 3.0) * q0 - 0.1 * qp);
+    s = dsgn * fmin(dlim, fabs((4.0 / 3.0) * dcen - (1.0 / 6.0) * (dfp + dfm)));
+  }
+  if (edhi && c == b.dhi) {
+    s = lim_os(2.0 * (q0 - qm), 2.0 * (qp - q0), (16.0 / 15.0) * qp - 0.5 * q0 - (2.0 / 3.0) * qm + 0.1 * qm2);
+  } else if (edhi && c == b.dhi - 1) {
+    dfp = lim_os(2.0 * (qp - q0), 2.0 * (qp2 - qp), (16.0 / 15.0) * qp2 - 0.5 * qp - (2.0 / 3.0) * q0 + 0.1 * qm);
+    s = dsgn * fmin(dlim, fabs((4.0 / 3.0) * dcen - (1.0 / 6.0) * (dfp + dfm)));
+  }
+  return s;
+}
+// PPM parabola with the boundary treatment of hydro_godunov_ppm.H (SetXBCs): next to an ext_dir / hoextrap face the
+// boundary-side edge value is the face value itself and the other edge the one-sided cubic, clamped
+IX_HD double clamp2(double v, double a, double b) { return fmin(fmax(v, fmin(a, b)), fmax(a, b)); }
+IX_HD void ppm_parabola_bc(double sm2, double sm1, double s0, double sp1, double sp2, int c, const BcD& b,
+                           double& sm, double& sp) {
+  ppm_parabola(sm2, sm1, s0, sp1, sp2, sm, sp);
+  const bool edlo = bc_extdir_or_ho(b.lo), edhi = bc_extdir_or_ho(b.hi);
+  auto mono = [&](double& m, double& p) {
+    if ((p - s0) * (s0 - m) <= 0.0) { m = s0; p = s0; }
+    else if (fabs(p - s0) >= 2.0 * fabs(m - s0)) p = 3.0 * s0 - 2.0 * m;
+    else if (fabs(m - s0) >= 2.0 * fabs(p - s0)) m = 3.0 * s0 - 2.0 * p;
+  };
+  if (edlo && c == b.dlo) {          // sm1 is the face value
+    sp = clamp2(-0.2 * sm1 + 0.75 * s0 + 0.5 * sp1 - 0.05 * sp2, sp1, s0);
+    sm = sm1;
+  } else if (edlo && c == b.dlo + 1) {   // sm2 is the face value, sm1 the first cell
+    const double e1 = clamp2(-0.2 * sm2 + 0.75 * sm1 + 0.5 * s0 - 0.05 * sp1, s0, sm1);
+    const double d0 = vanleer(s0, sp1, sm1), dp = vanleer(sp1, sp2, s0);
+    const double e2 = clamp2(0.5 * (sp1 + s0) - (1.0 / 6.0) * (dp - d0), s0, sp1);
+    sm = e1; sp = e2; mono(sm, sp);
+  }
+  if (edhi && c == b.dhi) {
+    sm = clamp2(-0.2 * sp1 + 0.75 * s0 + 0.5 * sm1 - 0.05 * sm2, sm1, s0);
+    sp = sp1;
+  } else if (edhi && c == b.dhi - 1) {
+    const double e2 = clamp2(-0.2 * sp2 + 0.75 * sp1 + 0.5 * s0 - 0.05 * sm1, s0, sp1);
+    const double d0 = vanleer(s0, sp1, sm1), dm = vanleer(sm1, s0, sm2);
+    const double e1 = clamp2(0.5 * (s0 + sm1) - (1.0 / 6.0) * (d0 - dm), s0, sm1);
+    sm = e1; sp = e2; mono(sm, sp);
+  }
+}
+// hydro_bcs_K.H Set{X,Y,Z}EdgeBCs: boundary conditions on the traced states (lo, hi) of the face with index f along
+// the direction.  qbelow / qabove = the cell values either side of the face (the ghost value at an ext_dir face).
+// normal_vel: the component is the velocity normal to the face (is_velocity && n == dir): a Dirichlet face then pins
+// both states, otherwise the interior state may still carry information out of the domain.
+IX_HD void set_edge_bc(double& lo, double& hi, double qbelow, double qabove, int f, const BcD& b, bool normal_vel) {
+  if (f == b.dlo) {
+    if (b.lo == IAMRX_BC_EXT_DIR) { lo = qbelow; if (normal_vel) hi = lo; }
+    else if (b.lo == IAMRX_BC_FOEXTRAP || b.lo == IAMRX_BC_HOEXTRAP || b.lo == IAMRX_BC_REFLECT_EVEN) lo = hi;
+    else if (b.lo == IAMRX_BC_REFLECT_ODD) { lo = 0.0; hi = 0.0; }
+  } else if (f == b.dhi + 1) {
+    if (b.hi == IAMRX_BC_EXT_DIR) { hi = qabove; if (normal_vel) lo = hi; }
+    else if (b.hi == IAMRX_BC_FOEXTRAP || b.hi == IAMRX_BC_HOEXTRAP || b.hi == IAMRX_BC_REFLECT_EVEN) hi = lo;
+    else if (b.hi == IAMRX_BC_REFLECT_ODD) { lo = 0.0; hi = 0.0; }
+  }
+}
+// outflow faces (foextrap / hoextrap) of the final states: no inflow of the normal velocity through an outflow face.
+// `clip`: ExtrapVelToFaces always clips; ComputeEdgeState only for the normal velocity component when the MAC
+// velocity points into the domain.
+IX_HD void outflow_bc(double& lo, double& hi, int f, const BcD& b, bool clip_lo, bool clip_hi) {
+  if (f == b.dlo && (b.lo == IAMRX_BC_FOEXTRAP || b.lo == IAMRX_BC_HOEXTRAP)) {
+    if (clip_lo) hi = fmin(hi, 0.0);
+    lo = hi;
+  }
+  if (f == b.dhi + 1 && (b.hi == IAMRX_BC_FOEXTRAP || b.hi == IAMRX_BC_HOEXTRAP)) {
+    if (clip_hi) lo = fmax(lo, 0.0);
+    hi = lo;
+  }
 }
 
 // upwind the pair (lo, hi) with a given face velocity (ComputeEdgeState /

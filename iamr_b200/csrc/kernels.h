@@ -70,10 +70,23 @@ int reduce_init(double* result, int n, int op, cudaStream_t s);
 int reduce(const Bx& bx, C4 src, int ncomp, int op, double* result, cudaStream_t s);
 int reduce_dot(const Bx& bx, C4 x, C4 y, C4 mask, double* result, cudaStream_t s);
 
+// diagnostic: measured DFMA issue rate of the device in 1e9 instructions/s (thread-level; x2 = flop/s)
+int fp64_peak(double* dp_ginstr_per_s, cudaStream_t s);
+
 // --- Godunov advection (godunov.cu) --------------------------------------
 struct AdvGeom { double dx[3]; double dt; };
+// physical boundaries seen by the Godunov kernels: the domain's cell bounds and the BCRec (IAMRX_BC_* codes) of every
+// component; all-zero lo/hi (int_dir) = periodic / interior everywhere
+struct AdvBC {
+  int dlo[3], dhi[3];
+  int lo[8][3], hi[8][3];
+  bool interior() const {
+    for (int n = 0; n < 8; ++n) for (int d = 0; d < 3; ++d) if (lo[n][d] != IAMRX_BC_INT_DIR || hi[n][d] != IAMRX_BC_INT_DIR) return false;
+    return true;
+  }
+};
 int extrap_vel_to_faces(const Bx& bx, C4 vel, C4 force, V4 umac, V4 vmac, V4 wmac,
-                        const AdvGeom& g, int forces_in_trans, cudaStream_t s, int ppm = 0);
+                        const AdvGeom& g, int forces_in_trans, cudaStream_t s, int ppm = 0, const AdvBC* bc = nullptr);
 struct AofsArgs {
   V4 aofs;           // ncomp
   C4 S, force, divu; // S: ncomp, 3 ghosts; force: ncomp 1 ghost (may be null); divu may be null
@@ -85,6 +98,8 @@ struct AofsArgs {
   int forces_in_trans, is_velocity, is_sync, write_fluxes;
   int staged = 0;  // force the staged kernels
   int ppm = 0;     // Godunov_PPM (staged kernels only)
+  int known_edge_state = 0;   // xed/yed/zed are INPUTS: only fluxes, divergence and the convective term are formed
+  AdvBC bc{};      // zero-initialised = interior
 };
 int compute_aofs(const Bx& bx, const AofsArgs& a, const AdvGeom& g, cudaStream_t s);
 

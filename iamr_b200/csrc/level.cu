@@ -612,6 +612,16 @@ static void fill_table(FabTable& t, const MF& m, int comp) {
 
 #define IX_TRY(call) do { int rc_ = (call); if (rc_ != IAMRX_OK) return rc_; } while (0)
 
+namespace {
+struct DevBuf {   // pool block released on every exit path (stream-ordered reuse: one stream per rank)
+  double* p;
+  explicit DevBuf(size_t n) : p(dev_alloc(n)) {}
+  ~DevBuf() { dev_free(p); }
+  DevBuf(const DevBuf&) = delete;
+  DevBuf& operator=(const DevBuf&) = delete;
+};
+}  // namespace
+
 int mf_setval(MF& m, double v, int comp, int ncomp, int ng, cudaStream_t s) {
   for (int il = 0; il < m.n(); ++il) IX_TRY(k::setval(m.gbox(il, ng), m.v(il, comp), ncomp, v, s));
   return IAMRX_OK;
@@ -667,8 +677,8 @@ int mf_fill_boundary(MF& m, int comp, int ncomp, int ng, cudaStream_t s, int ski
     if (!P.local.empty()) IX_TRY(k::copy_batch(P.d_local, (int)P.local.size(), P.max_local, t, t, nullptr, ncomp, 0, s));
     return IAMRX_OK;
   }
-  double* sbuf = dev_alloc((size_t)(P.send_total * ncomp + 1));
-  double* rbuf = dev_alloc((size_t)(P.recv_total * ncomp + 1));
+  DevBuf sb_((size_t)(P.send_total * ncomp + 1)), rb_((size_t)(P.recv_total * ncomp + 1));
+  double* sbuf = sb_.p; double* rbuf = rb_.p;
   if (!sbuf || !rbuf) return IAMRX_ERR_CUDA;
   IX_TRY(k::copy_batch(P.d_send, P.n_send, P.max_send, t, t, sbuf, ncomp, 0, s));
   std::vector<double*> sb, rb; std::vector<int64_t> sc, rc;
@@ -679,7 +689,6 @@ int mf_fill_boundary(MF& m, int comp, int ncomp, int ng, cudaStream_t s, int ski
   IX_TRY(comm_exchange(P.peers, sb, sc, rb, rc, s));
   if (!P.local.empty()) IX_TRY(k::copy_batch(P.d_local, (int)P.local.size(), P.max_local, t, t, nullptr, ncomp, 0, s));
   IX_TRY(k::copy_batch(P.d_recv, P.n_recv, P.max_recv, t, t, rbuf, ncomp, 0, s));
-  dev_free(sbuf); dev_free(rbuf);  // stream-ordered reuse: same stream
   return IAMRX_OK;
 }
 
@@ -740,8 +749,8 @@ int mf_gather_replicate(MF& dst, const MF& src, int ncomp, cudaStream_t s) {
   FabTable ts; fill_table(ts, src, 0);
   if (!P.local.empty()) IX_TRY(k::copy_batch(P.d_local, (int)P.local.size(), P.max_local, td, ts, nullptr, ncomp, 0, s));
   if (P.peers.empty()) return IAMRX_OK;
-  double* sbuf = dev_alloc((size_t)(P.send_pts * ncomp + 1));
-  double* rbuf = dev_alloc((size_t)(P.recv_total * ncomp + 1));
+  DevBuf sb_((size_t)(P.send_pts * ncomp + 1)), rb_((size_t)(P.recv_total * ncomp + 1));
+  double* sbuf = sb_.p; double* rbuf = rb_.p;
   if (!sbuf || !rbuf) return IAMRX_ERR_CUDA;
   if (!P.pack.empty()) IX_TRY(k::copy_batch(P.d_pack, (int)P.pack.size(), P.max_pack, td, ts, sbuf, ncomp, 0, s));
   std::vector<double*> sb, rb; std::vector<int64_t> sc, rc;
@@ -751,7 +760,6 @@ int mf_gather_replicate(MF& dst, const MF& src, int ncomp, cudaStream_t s) {
   }
   IX_TRY(comm_exchange(P.peers, sb, sc, rb, rc, s));
   if (!P.unpack.empty()) IX_TRY(k::copy_batch(P.d_unpack, (int)P.unpack.size(), P.max_unpack, td, ts, rbuf, ncomp, 0, s));
-  dev_free(sbuf); dev_free(rbuf);
   return IAMRX_OK;
 }
 

@@ -168,7 +168,7 @@ int CellMG::smooth(int l, MF& phi, const MF& rhs, int nsweeps, bool /*zero_init*
   const int wm = L.lev->level_wrapmask();   // directions wrapped inside the kernels: no ghost traffic there
   const bool wrap = wm == 7;
   bool fused = wrap && k::abec_gsrb_sweep_enabled();
-  for (int il = 0; il < phi.n() && fused; ++il) fused = k::abec_gsrb_sweep_ok(phi.vbox(il), 7);
+  for (size_t b = 0; b < L.lev->boxes.size() && fused; ++b) fused = k::abec_gsrb_sweep_ok(L.lev->boxes[b], 7);
   if (fused) {
     // one fused launch per sweep, out of place: ping-pong between phi and a second buffer
     if (!L.gs_tmp.ok()) L.gs_tmp.define(L.lev, IX_CELL, ncomp_, 1);
@@ -371,8 +371,10 @@ int NodeMG::smooth(int l, MF& phi, const MF& rhs, int nsweeps, cudaStream_t s) {
     }
     return IAMRX_OK;
   }
+  // decided from ALL boxes of the level (not just this rank's): the fused and the colour paths issue different
+  // numbers of ghost exchanges, so every rank must take the same one
   bool fused = true;
-  for (int il = 0; il < phi.n() && fused; ++il) fused = k::nodal_gs_sweep_ok(phi.vbox(il), wm);
+  for (size_t b = 0; b < L.lev->boxes.size() && fused; ++b) fused = k::nodal_gs_sweep_ok(ixbox(L.lev->boxes[b], IX_NODE), wm);
   if (fused) {
     // out-of-place fused sweeps ping-pong between phi and a second buffer.  Slabs (x and y wrapped in the kernel, z
     // exchanged): the even-plane phase reads the old odd ghost planes of `src`, the odd-plane phase the NEW even ghost

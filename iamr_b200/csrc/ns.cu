@@ -593,7 +593,8 @@ int iamrx_ns_step_host(iamrx_ns_t nsp, const double* const* host_in, double* con
   size_t maxpts = 0;
   for (int il = 0; il < L.nlocal(); ++il) maxpts = std::max(maxpts, (size_t)L.lbox(il).npts());
   const size_t need = maxpts * NUM_STATE;
-  double* dbuf = dev_alloc(need);
+  struct Guard { double* p; ~Guard() { dev_free(p); } } dg{dev_alloc(need)}, eg{nullptr};   // released on every exit path
+  double* dbuf = dg.p;
   if (!dbuf) return IAMRX_ERR_CUDA;
   for (int il = 0; il < L.nlocal(); ++il) {
     const size_t n = (size_t)L.lbox(il).npts() * NUM_STATE;
@@ -608,18 +609,18 @@ int iamrx_ns_step_host(iamrx_ns_t nsp, const double* const* host_in, double* con
       IX_CUDA(cudaStreamCreateWithFlags(&ns.s2, cudaStreamNonBlocking));
       IX_CUDA(cudaEventCreateWithFlags(&ns.ev_scal, cudaEventDisableTiming));
     }
-    ns.early_buf = dev_alloc(maxpts * NUM_SCALARS);
-    if (!ns.early_buf) { dev_free(dbuf); return IAMRX_ERR_CUDA; }
+    eg.p = ns.early_buf = dev_alloc(maxpts * NUM_SCALARS);
+    if (!ns.early_buf) return IAMRX_ERR_CUDA;
     ns.early_out = host_out[0] + (size_t)L.lbox(0).npts() * Density;
   }
 #endif
   int rc = iamrx_ns_step(nsp, dt_io);
   ns.early_out = nullptr;
+  ns.early_buf = nullptr;
   if (rc != IAMRX_OK) {
 #if !defined(IX_EMUL)
-    if (early) { cudaStreamSynchronize(ns.s2); dev_free(ns.early_buf); }
+    if (early) cudaStreamSynchronize(ns.s2);
 #endif
-    dev_free(dbuf);
     return rc;
   }
   const int nout = early ? Density : NUM_STATE;   // velocity only when the scalars already left
@@ -630,9 +631,8 @@ int iamrx_ns_step_host(iamrx_ns_t nsp, const double* const* host_in, double* con
   }
   IX_CUDA(cudaStreamSynchronize(ns.s));
 #if !defined(IX_EMUL)
-  if (early) { IX_CUDA(cudaStreamSynchronize(ns.s2)); dev_free(ns.early_buf); ns.early_buf = nullptr; }
+  if (early) IX_CUDA(cudaStreamSynchronize(ns.s2));
 #endif
-  dev_free(dbuf);
   return IAMRX_OK;
 }
 

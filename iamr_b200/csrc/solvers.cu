@@ -40,6 +40,16 @@ int mac_project(Level& L, LevelSolvers& sv, MF U[3], const MF& rho, const MF* rh
   return rc;
 }
 
+// Hydro::MacProjector::getFluxes (MacProj.cpp:1181-1183): F_d = -beta_d dphi/dx_d on the faces of every local box, with the
+// operator (beta) of the last mac_project on this level.  mac_sync_solve turns them into U_corr (MacProj.cpp:459-468).
+int mac_get_fluxes(Level& L, LevelSolvers& sv, MF F[3], MF& phi, cudaStream_t s) {
+  if (!sv.mac) { set_error("mac_get_fluxes: no MAC projection has been done on this level"); return IAMRX_ERR_ARG; }
+  IX_TRY(mf_fill_boundary(phi, 0, 1, 1, s));
+  for (int il = 0; il < phi.n(); ++il)
+    IX_TRY(k::abec_flux(L.lbox(il), F[0].v(il), F[1].v(il), F[2].v(il), phi.c(il), sv.mac->op_at(0, il), 0, s));
+  return IAMRX_OK;
+}
+
 // Projection::doMLMGNodalProjection (Projection.cpp:2385-2567) + Hydro::NodalProjector:
 //   rhs = FE divergence of vel on nodes; div(sigma grad phi) = rhs;
 //   vel -= sigma grad phi; gp (+)= grad phi

@@ -24,6 +24,7 @@ struct LevelSolvers {
 
 int mac_project(Level& L, LevelSolvers& sv, MF U[3], const MF& rho, const MF* rhs, MF& phi,
                 double rhs_scale, iamrx_mg_info* info, cudaStream_t s);
+int mac_get_fluxes(Level& L, LevelSolvers& sv, MF F[3], MF& phi, cudaStream_t s);
 int nodal_project(Level& L, LevelSolvers& sv, MF& vel, const MF& sigma, MF& phi, MF* gp,
                   int increment_gp, iamrx_mg_info* info, cudaStream_t s);
 int diffusion_apply(Level& L, LevelSolvers& sv, bool tensor, int ncomp, MF& out, MF& soln, double a,

@@ -79,12 +79,21 @@ enum {
   IAMRX_BC_HOEXTRAP = 4
 };
 
+/* amrex::BCRec of ONE component: math BC codes per direction, low and high side (what
+ * NavierStokesBase::fetchBCArray hands to the Godunov routines, NSB.cpp:4489,4645,4712). */
+typedef struct iamrx_bcrec {
+  int lo[3];
+  int hi[3];
+} iamrx_bcrec;
+
 /* amrex::LinOpBCType subset (MacProj.cpp:1187-1208, Projection.cpp:2436-2464,
  * Diffusion.cpp:1900-1938). */
 enum {
   IAMRX_LINOP_PERIODIC = 0,
   IAMRX_LINOP_DIRICHLET = 1,
-  IAMRX_LINOP_NEUMANN = 2
+  IAMRX_LINOP_NEUMANN = 2,
+  IAMRX_LINOP_REFLECT_ODD = 3,   /* cell-centred operators only (Diffusion.cpp:1921-1923) */
+  IAMRX_LINOP_INFLOW = 4         /* nodal projection only (Projection.cpp:2450,2458) */
 };
 
 /* flags of iamrx_compute_aofs_box (arguments of
@@ -95,8 +104,10 @@ enum {
   IAMRX_ADV_IS_VELOCITY = 4,
   IAMRX_ADV_WRITE_FLUXES = 8,      /* also store area-weighted fluxes + edge states */
   IAMRX_ADV_IS_SYNC = 16,          /* aofs -= update, fluxes from U_corr (NSB.cpp:4834) */
-  IAMRX_ADV_STAGED = 32            /* use the staged (global-scratch) kernels instead of the fused tile
+  IAMRX_ADV_STAGED = 32,           /* use the staged (global-scratch) kernels instead of the fused tile
                                       kernel: same algorithm, kept for cross-checks and partial tiles */
+  IAMRX_ADV_KNOWN_EDGE_STATE = 64  /* known_edge_state (NSB.cpp:4708; MacProj.cpp:776-785): xed/yed/zed are INPUTS,
+                                      only fluxes, divergence and the convective term are formed */
 };
 
 const char* iamrx_last_error(void);
@@ -106,6 +117,9 @@ int iamrx_version(void);
 int64_t iamrx_launch_count(void);
 void iamrx_launch_count_reset(void);
 int iamrx_device_ok(void);
+/* diagnostic: measured fp64 FMA issue rate of the device, in 1e9 thread-instructions/s (bench.py's second roofline
+ * for the Godunov kernels, which are FP64-pipe- rather than HBM-bound) */
+int iamrx_debug_fp64_peak(double* dp_ginstr_per_s, void* stream);
 
 /* Kernel timing for the roofline report (bench.py): when enabled, every launch of
  * the listed kernel classes that covers >= min_points points is bracketed by CUDA
@@ -175,30 +189,38 @@ int iamrx_tensor_cross_box(const iamrx_box* bx, iamrx_fab* out, const iamrx_fab*
                            const iamrx_fab* eta_z, double b, const double dxinv[3],
                            void* stream);
 
-/* Godunov::ExtrapVelToFaces (NSB.cpp:4487-4491), PLM, one box:
- * vel (3 comps, 3 ghost cells filled), force (3 comps, 1 ghost) ->
- * umac/vmac/wmac on the faces of bx. bc_lo/bc_hi: 3 comps x 3 dirs math BC
- * codes (only IAMRX_BC_INT_DIR, i.e. periodic / interior, is implemented in
- * this round). */
+/* Godunov::ExtrapVelToFaces(vel, forces, u_mac, v_mac, w_mac, h_bcrec, d_bcrec, geom, dt, use_ppm,
+ * use_forces_in_trans) (NSB.cpp:4487-4491), one box:
+ * vel (3 comps, 3 ghost cells filled incl. the physical-boundary fill), force (3 comps, 1 ghost) ->
+ * umac/vmac/wmac on the faces of bx.  bcrec: the BCRec of the three velocity components
+ * (h_bcrec/d_bcrec; NULL = interior / periodic everywhere); geom->domain locates the boundary.
+ * vel must cover grow(bx,3), force grow(bx,1), the outputs the faces of bx (else IAMRX_ERR_ARG). */
 int iamrx_extrap_vel_to_faces_box(const iamrx_box* bx, const iamrx_fab* vel,
                                   const iamrx_fab* force, iamrx_fab* umac,
                                   iamrx_fab* vmac, iamrx_fab* wmac,
+                                  const iamrx_bcrec* bcrec,
                                   const iamrx_geom* geom, double dt, int flags,
                                   void* stream);
 
-/* NavierStokesBase::ComputeAofs body for one box (NSB.cpp:4661-4845):
- * ComputeFluxesOnBoxFromState (Godunov edge states + fluxes) ->
- * ComputeDivergence(mult=-1) -> ComputeConvectiveTerm -> aofs = -update.
- * S: ncomp comps, 3 ghosts.  force: ncomp comps, 1 ghost.  divu may be NULL
- * (== 0).  umac..wmac: MAC velocities with 1 ghost face layer.  fx,fy,fz /
- * xed,yed,zed may be NULL unless IAMRX_ADV_WRITE_FLUXES. */
+/* NavierStokesBase::ComputeAofs body for one box (NSB.cpp:4661-4845), argument for argument the
+ * HydroUtils::ComputeFluxesOnBoxFromState call of NSB.cpp:4701-4717 followed by
+ * ComputeDivergence(mult=-1) -> ComputeConvectiveTerm -> aofs = -update (or aofs -= update, sync).
+ * S: ncomp comps, 3 ghosts.  force: ncomp comps, 1 ghost.  divu may be NULL (== 0).
+ * umac..wmac: the advecting MAC velocities (1 ghost face layer) that build the edge states;
+ * uflux..wflux: the velocities that multiply them into fluxes -- NULL = the MAC velocities, U_corr in
+ * the sync call (NSB.cpp:4672-4677).  fx,fy,fz / xed,yed,zed may be NULL unless
+ * IAMRX_ADV_WRITE_FLUXES; with IAMRX_ADV_KNOWN_EDGE_STATE xed,yed,zed are inputs.
+ * bcrec: BCRec of the ncomp components (NULL = interior).  S must cover grow(bx,3) (bx itself with
+ * known edge states), force / divu / the velocities grow(bx,1), aofs bx (else IAMRX_ERR_ARG). */
 int iamrx_compute_aofs_box(const iamrx_box* bx, iamrx_fab* aofs, int aofs_comp,
                            const iamrx_fab* S, int s_comp, int ncomp,
                            const iamrx_fab* force, int f_comp, const iamrx_fab* divu,
                            const iamrx_fab* umac, const iamrx_fab* vmac,
-                           const iamrx_fab* wmac, iamrx_fab* fx, iamrx_fab* fy,
+                           const iamrx_fab* wmac, const iamrx_fab* uflux,
+                           const iamrx_fab* vflux, const iamrx_fab* wflux,
+                           iamrx_fab* fx, iamrx_fab* fy,
                            iamrx_fab* fz, iamrx_fab* xed, iamrx_fab* yed,
-                           iamrx_fab* zed, const int* iconserv,
+                           iamrx_fab* zed, const int* iconserv, const iamrx_bcrec* bcrec,
                            const iamrx_geom* geom, double dt, int flags, void* stream);
 
 /* MLNodeLaplacian pieces on one box of NODES (Projection.cpp:2512-2542,
@@ -309,6 +331,12 @@ int iamrx_mac_project(iamrx_level_t lev, iamrx_fab* umac, iamrx_fab* vmac,
                       iamrx_fab* wmac, const iamrx_fab* rho, const iamrx_fab* rhs,
                       iamrx_fab* phi, double rhs_scale, const int lobc[3],
                       const int hibc[3], iamrx_mg_info* info, void* stream);
+
+/* Hydro::MacProjector::getFluxes (MacProj.cpp:1181-1183; "fluxes = -B grad phi"): face fluxes of the
+ * phi returned by the last iamrx_mac_project on this level, with that call's beta.  MacProj::mac_sync_solve
+ * turns them into U_corr (MacProj.cpp:459-468).  fx,fy,fz: face fabs of every local box; phi: 1 ghost. */
+int iamrx_mac_get_fluxes(iamrx_level_t lev, iamrx_fab* fx, iamrx_fab* fy, iamrx_fab* fz,
+                         iamrx_fab* phi, void* stream);
 
 /* Projection::doMLMGNodalProjection (Projection.cpp:2385-2567) =
  * Hydro::NodalProjector{ctor, setDomainBC, project, getGradPhi}: solve

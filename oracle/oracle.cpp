@@ -729,9 +729,12 @@ void edge_state_comp(const Arr& q, int c, const Arr* f, int fc, const Arr* divu,
   }
 }
 
-// NavierStokesBase::ComputeAofs body, non-EB, !is_sync (NSB.cpp:4661-4845)
+// NavierStokesBase::ComputeAofs body, non-EB (NSB.cpp:4661-4845).  uflux: the velocities that multiply the edge states into
+// fluxes (u_mac itself, or U_corr in the sync call :4672-4677); is_sync: aofs -= update and no convective term (:4784,4834);
+// known: eds[] are INPUT edge states (known_edge_state :4708), only fluxes / divergence / convective term are formed.
 void compute_aofs(const Arr& S, int ncomp, const Arr* force, const Arr* divu, Arr mac[3], const int* iconserv, AdvOpt fit,
-                  const double dx[3], double dt, Arr& aofs, int acomp, Arr* fl[3], Arr* eds[3]) {
+                  const double dx[3], double dt, Arr& aofs, int acomp, Arr* fl[3], Arr* eds[3], Arr* uflux = nullptr,
+                  bool is_sync = false, bool known = false) {
   const int* n = S.n;
   const Arr* macp[3] = {&mac[0], &mac[1], &mac[2]};
   const double area[3] = {dx[1] * dx[2], dx[0] * dx[2], dx[0] * dx[1]};
@@ -739,10 +742,11 @@ void compute_aofs(const Arr& S, int ncomp, const Arr* force, const Arr* divu, Ar
   for (int c = 0; c < ncomp; ++c) {
     Arr ed[3] = {Arr(n, 1, 1), Arr(n, 1, 1), Arr(n, 1, 1)};
     Arr* edp[3] = {&ed[0], &ed[1], &ed[2]};
-    edge_state_comp(S, c, force, c, divu, macp, iconserv[c] != 0, fit, dx, dt, edp);
+    if (known) { for (int d = 0; d < 3; ++d) ed[d].copy_from(*eds[d], c, 0, 1); }
+    else edge_state_comp(S, c, force, c, divu, macp, iconserv[c] != 0, fit, dx, dt, edp);
     Arr fx[3] = {Arr(n, 1, 1), Arr(n, 1, 1), Arr(n, 1, 1)};
     for (int d = 0; d < 3; ++d) {
-      Arr& F = fx[d]; const Arr& E = ed[d]; const Arr& M = mac[d];
+      Arr& F = fx[d]; const Arr& E = ed[d]; const Arr& M = uflux ? uflux[d] : mac[d];
       FOR_CELLS(F, i, j, k) F(i, j, k) = E(i, j, k) * M(i, j, k) * area[d];  // HydroUtils::ComputeFluxes, area-weighted (NSB.cpp:4651)
       F.fill_periodic(); ed[d].fill_periodic();
     }
@@ -750,17 +754,18 @@ void compute_aofs(const Arr& S, int ncomp, const Arr* force, const Arr* divu, Ar
     FOR_CELLS(aofs, i, j, k) {
       // ComputeDivergence(mult = -1, area-weighted fluxes) NSB.cpp:4753-4771
       double upd = -((fx[0](i + 1, j, k) - fx[0](i, j, k)) + (fx[1](i, j + 1, k) - fx[1](i, j, k)) + (fx[2](i, j, k + 1) - fx[2](i, j, k))) / vol;
-      if (!cons) {  // ComputeConvectiveTerm NSB.cpp:4809-4820
+      if (!cons && !is_sync) {  // ComputeConvectiveTerm NSB.cpp:4784,4809-4820 ("sync is always a conservative update")
         const double divum = (mac[0](i + 1, j, k) - mac[0](i, j, k)) / dx[0] + (mac[1](i, j + 1, k) - mac[1](i, j, k)) / dx[1] +
                              (mac[2](i, j, k + 1) - mac[2](i, j, k)) / dx[2];
         const double qavg = (ed[0](i, j, k) + ed[0](i + 1, j, k) + ed[1](i, j, k) + ed[1](i, j + 1, k) + ed[2](i, j, k) + ed[2](i, j, k + 1)) / 6.0;
         upd += qavg * divum;
       }
-      aofs(i, j, k, acomp + c) = -upd;  // NSB.cpp:4840
+      if (is_sync) aofs(i, j, k, acomp + c) -= upd;   // NSB.cpp:4834
+      else aofs(i, j, k, acomp + c) = -upd;            // NSB.cpp:4840
     }
     for (int d = 0; d < 3; ++d) {
       if (fl && fl[d]) fl[d]->copy_from(fx[d], 0, c, 1);
-      if (eds && eds[d]) eds[d]->copy_from(ed[d], 0, c, 1);
+      if (eds && eds[d] && !known) eds[d]->copy_from(ed[d], 0, c, 1);
     }
   }
 }
@@ -1130,9 +1135,17 @@ int orc_num_threads(void) {
 #endif
 }
 
+void orc_set_num_threads(int n) {   // torchrun exports OMP_NUM_THREADS=1: the CPU arm sets its thread count explicitly
+#ifdef _OPENMP
+  if (n > 0) omp_set_num_threads(n);
+#else
+  (void)n;
+#endif
+}
+
 void orc_mg_default(orc_mg* m) {
   m->rtol = 1e-12; m->atol = 1e-16; m->max_iter = 200; m->nu1 = 2; m->nu2 = 2; m->bottom_sweeps = 8; m->max_coarsening = 100;
-  m->omega = 1.0; m->iters = 0; m->resnorm0 = m->resnorm = m->rhsnorm = 0.0;
+  m->omega = 1.15; m->iters = 0; m->resnorm0 = m->resnorm = m->rhsnorm = 0.0;
 }
 
 static void load_faces(const int n[3], const double* bx, const double* by, const double* bz, int bn, Arr b[3]) {
@@ -1274,6 +1287,33 @@ void orc_compute_aofs(const int n[3], const double dx[3], double dt, int ncomp, 
   compute_aofs(q, ncomp, force ? &f : nullptr, divu ? &dv : nullptr, mac, iconserv, AdvOpt{(forces_in_trans & 1) != 0, (forces_in_trans & 2) != 0}, dx, dt, a, 0, flp, edp);
   a.store(aofs);
   for (int d = 0; d < 3; ++d) { if (fo[d]) fl[d].store(fo[d]); if (eo[d]) ed[d].store(eo[d]); }
+}
+
+/* the full argument list of the ComputeFluxesOnBoxFromState call site (NSB.cpp:4701-4717): separate flux velocities, the
+ * sync sign convention (aofs holds the running Sync on entry) and known edge states (xed..zed are inputs then) */
+void orc_compute_aofs2(const int n[3], const double dx[3], double dt, int ncomp, const double* S, const double* force,
+                       const double* divu, const double* umac, const double* vmac, const double* wmac, const double* uflux,
+                       const double* vflux, const double* wflux, const int* iconserv, int flags, int is_sync, int known,
+                       double* aofs, double* fx, double* fy, double* fz, double* xed, double* yed, double* zed) {
+  Arr q(n, ncomp, 3), f, dv; q.load(S); q.fill_periodic();
+  if (force) { f.define(n, ncomp, 1); f.load(force); f.fill_periodic(); }
+  if (divu) { dv.define(n, 1, 1); dv.load(divu); dv.fill_periodic(); }
+  Arr mac[3], ufl[3]; const double* m[3] = {umac, vmac, wmac}; const double* uf[3] = {uflux, vflux, wflux};
+  for (int d = 0; d < 3; ++d) {
+    mac[d].define(n, 1, 1); mac[d].load(m[d]); mac[d].fill_periodic();
+    if (uflux) { ufl[d].define(n, 1, 1); ufl[d].load(uf[d]); ufl[d].fill_periodic(); }
+  }
+  Arr a(n, ncomp, 0); a.load(aofs);
+  Arr fl[3], ed[3]; Arr* flp[3] = {nullptr, nullptr, nullptr}; Arr* edp[3] = {nullptr, nullptr, nullptr};
+  double* fo[3] = {fx, fy, fz}; double* eo[3] = {xed, yed, zed};
+  for (int d = 0; d < 3; ++d) {
+    if (fo[d]) { fl[d].define(n, ncomp, 0); flp[d] = &fl[d]; }
+    if (eo[d]) { ed[d].define(n, ncomp, 0); edp[d] = &ed[d]; if (known) ed[d].load(eo[d]); }
+  }
+  compute_aofs(q, ncomp, force ? &f : nullptr, divu ? &dv : nullptr, mac, iconserv, AdvOpt{(flags & 1) != 0, (flags & 2) != 0}, dx, dt, a, 0,
+               flp, edp, uflux ? ufl : nullptr, is_sync != 0, known != 0);
+  a.store(aofs);
+  for (int d = 0; d < 3; ++d) { if (fo[d]) fl[d].store(fo[d]); if (eo[d] && !known) ed[d].store(eo[d]); }
 }
 
 void orc_ns_params_default(orc_ns_params* p) {

@@ -81,6 +81,13 @@ void orc_compute_aofs(const int n[3], const double dx[3], double dt, int ncomp, 
                       const double* wmac, const int* iconserv, int forces_in_trans, double* aofs,
                       double* fx, double* fy, double* fz, double* xed, double* yed, double* zed);
 
+/* the same with the complete argument list of the call site NSB.cpp:4701-4717: flux velocities (NULL = the MAC velocities,
+ * U_corr in the sync call), is_sync (aofs in/out: aofs -= update, no convective term), known edge states (xed..zed inputs) */
+void orc_compute_aofs2(const int n[3], const double dx[3], double dt, int ncomp, const double* S, const double* force,
+                       const double* divu, const double* umac, const double* vmac, const double* wmac, const double* uflux,
+                       const double* vflux, const double* wflux, const int* iconserv, int flags, int is_sync, int known,
+                       double* aofs, double* fx, double* fy, double* fz, double* xed, double* yed, double* zed);
+
 /* NavierStokes::advance / post_init on one periodic box */
 typedef struct orc_ns_params {
   double cfl, visc_coef, be_cn_theta, change_max, init_shrink, fixed_dt, gravity, visc_tol;
@@ -104,6 +111,7 @@ void orc_ns_get(const orc_ns* ns, int which, double* out);
 void orc_ns_set_state(orc_ns* ns, const double* state5);
 void orc_ns_last_iters(const orc_ns* ns, int iters[3]);
 int orc_num_threads(void);
+void orc_set_num_threads(int n);
 
 #ifdef __cplusplus
 }

@@ -63,11 +63,11 @@ else:
         icons = (C.c_int * 3)(0, 0, 0)
         for _ in range(reps):
             lib.check(lib.iamrx_compute_aofs_box(C.byref(bx), C.byref(fA), 0, C.byref(fS), 0, 3, C.byref(fF), 0, None, C.byref(fum[0]), C.byref(fum[1]),
-                                                 C.byref(fum[2]), None, None, None, None, None, None, icons, C.byref(g), dt, 4, s))
+                                                 C.byref(fum[2]), None, None, None, None, None, None, None, None, None, icons, None, C.byref(g), dt, 4, s))
     else:
         tm = faces(1)
         fm = [f for _, f in tm]
         for _ in range(reps):
-            lib.check(lib.iamrx_extrap_vel_to_faces_box(C.byref(bx), C.byref(fS), C.byref(fF), C.byref(fm[0]), C.byref(fm[1]), C.byref(fm[2]), C.byref(g), dt, 0, s))
+            lib.check(lib.iamrx_extrap_vel_to_faces_box(C.byref(bx), C.byref(fS), C.byref(fF), C.byref(fm[0]), C.byref(fm[1]), C.byref(fm[2]), None, C.byref(g), dt, 0, s))
 torch.cuda.synchronize()
 print("done", what)

@@ -134,15 +134,15 @@ if spec:   # K2 of SURVEY.md 8d: Taylor-Green velocities at cell and face centre
     del k2
 timeit("ComputeAofs 3 comps (velocity)",
        lambda: lib.check(lib.iamrx_compute_aofs_box(C.byref(bx), C.byref(fA), 0, C.byref(fS), 0, 3, C.byref(fF), 0, None, C.byref(fum[0]), C.byref(fum[1]),
-                                                    C.byref(fum[2]), None, None, None, None, None, None, icons, C.byref(g), dt, ix.ADV_IS_VELOCITY if hasattr(ix, 'ADV_IS_VELOCITY') else 4, s)),
+                                                    C.byref(fum[2]), None, None, None, None, None, None, None, None, None, icons, None, C.byref(g), dt, ix.ADV_IS_VELOCITY if hasattr(ix, 'ADV_IS_VELOCITY') else 4, s)),
        104.0 * N, reps=5)
 timeit("ComputeAofs 3 comps staged kernels",
        lambda: lib.check(lib.iamrx_compute_aofs_box(C.byref(bx), C.byref(fA), 0, C.byref(fS), 0, 3, C.byref(fF), 0, None, C.byref(fum[0]), C.byref(fum[1]),
-                                                    C.byref(fum[2]), None, None, None, None, None, None, icons, C.byref(g), dt, 4 | 32, s)),
+                                                    C.byref(fum[2]), None, None, None, None, None, None, None, None, None, icons, None, C.byref(g), dt, 4 | 32, s)),
        104.0 * N, reps=3)
 tmac = [fab(tuple(m + (1 if d == q else 0) for q, m in enumerate(cells)), 1) for d in range(3)]
 fmac = [f for _, f in tmac]
 timeit("ExtrapVelToFaces",
        lambda: lib.check(lib.iamrx_extrap_vel_to_faces_box(C.byref(bx), C.byref(fS), C.byref(fF), C.byref(fmac[0]), C.byref(fmac[1]), C.byref(fmac[2]),
-                                                           C.byref(g), dt, 0, s)),
+                                                           None, C.byref(g), dt, 0, s)),
        72.0 * N, reps=5)

@@ -165,6 +165,21 @@ def compute_aofs(dx, dt, S, force, umac, vmac, wmac, iconserv, fit=0, divu=None,
     return (aofs, outs) if want_fluxes else aofs
 
 
+def compute_aofs2(dx, dt, S, force, umac, vmac, wmac, iconserv, fit=0, divu=None, ppm=0, uflux=None, is_sync=False,
+                  aofs_in=None, known_edges=None):
+    """Full call-site argument list: returns (aofs, fluxes[3], edges[3])."""
+    ncomp = S.shape[0]
+    aofs = np.zeros_like(S) if aofs_in is None else aofs_in.copy()
+    ic = (C.c_int * ncomp)(*iconserv)
+    fl = [np.empty_like(S) for _ in range(3)]
+    ed = [e.copy() for e in known_edges] if known_edges is not None else [np.empty_like(S) for _ in range(3)]
+    uf = uflux if uflux is not None else (None, None, None)
+    lib().orc_compute_aofs2(_i3(_n_of(S)), _d3(dx), C.c_double(dt), ncomp, _p(S), _p(force), _p(divu), _p(umac), _p(vmac), _p(wmac),
+                            _p(uf[0]), _p(uf[1]), _p(uf[2]), ic, int(fit) | (2 if ppm else 0), int(is_sync),
+                            int(known_edges is not None), _p(aofs), *[_p(o) for o in fl], *[_p(o) for o in ed])
+    return aofs, fl, ed
+
+
 class OracleNS:
     def __init__(self, n, prob_lo=(0, 0, 0), prob_hi=(1, 1, 1), **params):
         self.n = tuple(n)

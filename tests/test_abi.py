@@ -76,3 +76,41 @@ def test_level_argument_checks():
         ix.Level(lib, g, [((0, 0, 0), (8, 7, 7))])  # outside the domain
     with pytest.raises(ix.IamrxError):
         ix.Level(lib, g, [((0, 0, 0), (7, 7, 7))], owners=[3])  # rank out of range
+
+
+def _build_abi_check():
+    exe = os.path.join(ROOT, "tests", "abi", "_build", "abi_check")
+    os.makedirs(os.path.dirname(exe), exist_ok=True)
+    cxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
+    subprocess.check_call([cxx, "-std=c++17", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"),
+                           os.path.join(ROOT, "tests", "abi", "abi_check.cpp"), "-o", exe,
+                           "-L", os.path.join(ROOT, "iamr_b200"), "-liamrx",
+                           "-Wl,-rpath," + os.path.join(ROOT, "iamr_b200"), "-Wl,-rpath,/usr/local/cuda/lib64",
+                           "-Wl,--allow-shlib-undefined"])
+    return exe
+
+
+def test_cxx_program_links_against_the_header_and_library():
+    """include/iamrx.h as a C++ consumer sees it (not ctypes): compiled with -Wall -Werror, linked with libiamrx.so;
+    host-side entry points work, compute entries fail loudly without a device."""
+    exe = _build_abi_check()
+    out = subprocess.run([exe, "host"], capture_output=True, text=True)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert "abi_check host ok" in out.stdout
+
+
+@pytest.mark.gpu
+def test_cxx_program_runs_a_step_on_the_device():
+    exe = _build_abi_check()
+    out = subprocess.run([exe, "device"], capture_output=True, text=True)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert "abi_check device ok" in out.stdout
+
+
+def test_header_compiles_as_c():
+    """The ABI header is plain C (extern "C" guards only under __cplusplus)."""
+    src = os.path.join(ROOT, "tests", "abi", "_build", "hdr.c")
+    os.makedirs(os.path.dirname(src), exist_ok=True)
+    open(src, "w").write('#include "iamrx.h"\nint main(void) { iamrx_bcrec b; b.lo[0] = IAMRX_BC_EXT_DIR; return b.lo[0] == 3 ? 0 : 1; }\n')
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Werror", "-pedantic", "-I", os.path.join(ROOT, "include"), "-c", src,
+                           "-o", src + ".o"])

@@ -27,7 +27,8 @@ def test_oracle_matches_exact_taylor_vortex(oracle, n, tol):
     ex = g[f"state_{n}"].copy()
     ex[:2] *= math.exp(-8 * math.pi ** 2 * float(g["nu"]) * (t - float(g["time"])))
     assert np.abs(S[:2] - ex[:2]).max() < tol                 # O(h^2): 4x smaller at 32 than at 16
-    assert np.abs(S[2]).max() < 1e-13 and np.abs(S[3] - 1.0).max() < 1e-13
+    # rho sees dt * div(u_mac), which the MAC solve drives to mac_tol * |rhs| (1e-12 relative), not to rounding
+    assert np.abs(S[2]).max() < 1e-13 and np.abs(S[3] - 1.0).max() < 2e-12
     o.close()
 
 

@@ -281,7 +281,7 @@ def test_extrap_vel_to_faces(backend, oracle, nb, fit, ppm):
         macs = [to_fab(np.zeros((1, n[2], n[1], n[0])), box, 1, t, dev) for t in (ix.XFACE, ix.YFACE, ix.ZFACE)]
         bb = box_of(*box)
         lib.check(lib.iamrx_extrap_vel_to_faces_box(C.byref(bb), C.byref(fv), C.byref(ff), C.byref(macs[0][1]),
-                                                    C.byref(macs[1][1]), C.byref(macs[2][1]), C.byref(g), dt,
+                                                    C.byref(macs[1][1]), C.byref(macs[2][1]), None, C.byref(g), dt,
                                                     (2 if fit else 0) | (1 if ppm else 0), stream_of(dev)))
         for d in range(3):
             outs[d].append(macs[d][0])
@@ -316,10 +316,10 @@ def test_compute_aofs(backend, oracle, nb, ncomp, iconserv, fit, ppm):
         bb = box_of(*box)
         flags = (2 if fit else 0) | 8 | (1 if ppm else 0)
         lib.check(lib.iamrx_compute_aofs_box(C.byref(bb), C.byref(fa), 0, C.byref(fq), 0, ncomp, C.byref(ff), 0, None,
-                                             C.byref(macs[0][1]), C.byref(macs[1][1]), C.byref(macs[2][1]),
+                                             C.byref(macs[0][1]), C.byref(macs[1][1]), C.byref(macs[2][1]), None, None, None,
                                              C.byref(fl[0][1]), C.byref(fl[1][1]), C.byref(fl[2][1]),
                                              C.byref(ed[0][1]), C.byref(ed[1][1]), C.byref(ed[2][1]),
-                                             ic, C.byref(g), dt, flags, stream_of(dev)))
+                                             ic, None, C.byref(g), dt, flags, stream_of(dev)))
         out_a.append(ta)
         for d in range(3):
             out_f[d].append(fl[d][0]); out_e[d].append(ed[d][0])
@@ -366,10 +366,10 @@ def test_compute_aofs_fused_tile_vs_staged_gpu(cuda_lib, nb, ncomp, iconserv, fi
             flags = (2 if fit else 0) | 8 | sync_flag | staged
             lib.check(lib.iamrx_compute_aofs_box(C.byref(bb), C.byref(fa), 0, C.byref(fq), 0, ncomp, C.byref(ff), 0,
                                                  C.byref(fd) if with_divu else None,
-                                                 C.byref(macs[0][1]), C.byref(macs[1][1]), C.byref(macs[2][1]),
+                                                 C.byref(macs[0][1]), C.byref(macs[1][1]), C.byref(macs[2][1]), None, None, None,
                                                  C.byref(fl[0][1]), C.byref(fl[1][1]), C.byref(fl[2][1]),
                                                  C.byref(ed[0][1]), C.byref(ed[1][1]), C.byref(ed[2][1]),
-                                                 ic, C.byref(g), dt, flags, stream_of(dev)))
+                                                 ic, None, C.byref(g), dt, flags, stream_of(dev)))
             out_a.append(ta)
             for d in range(3):
                 out_f[d].append(fl[d][0]); out_e[d].append(ed[d][0])
@@ -397,5 +397,98 @@ def test_bad_arguments(backend):
     macs = [to_fab(z[:1], box, 1, t, dev) for t in (ix.XFACE, ix.YFACE, ix.ZFACE)]
     bb = box_of(*box)
     rc = lib.iamrx_extrap_vel_to_faces_box(C.byref(bb), C.byref(fv), None, C.byref(macs[0][1]), C.byref(macs[1][1]),
-                                           C.byref(macs[2][1]), C.byref(g), 0.1, 0, stream_of(dev))
+                                           C.byref(macs[2][1]), None, C.byref(g), 0.1, 0, stream_of(dev))
     assert rc == -1 and b"3 components" in lib.iamrx_last_error()
+
+
+@pytest.mark.parametrize("nb", [(1, 1, 1), (2, 2, 2)])   # whole 8^3 tiles -> fused tile kernel on the GPU; 8x8x4 boxes -> staged kernels
+@pytest.mark.parametrize("case", ["divu", "sync_ucorr", "known_edges", "sync_known"])
+def test_compute_aofs_callsite_arguments(backend, oracle, nb, case):
+    """The arguments of the ComputeFluxesOnBoxFromState call site (NSB.cpp:4701-4717) that a plain advection call does
+    not exercise, each against the ORACLE (not against another kernel variant): divu != 0 with conservative components
+    (edge-state -dt/2 q divu term), the sync call (is_sync: aofs -= update, fluxes built with a distinct U_corr while the
+    edge states still use u_mac, NSB.cpp:4672-4677,4834) and known_edge_state (MacProj.cpp:776-785)."""
+    lib, dev = backend
+    n = (16, 16, 8)
+    ncomp, iconserv = 2, (1, 0)
+    _, q, f, (um, vm, wm), dx = _adv_inputs(n, ncomp, 400)
+    dt = 0.5 * min(dx) / max(np.abs(um).max(), np.abs(vm).max(), np.abs(wm).max())
+    divu = smooth_field(n, 77, 1, amp=0.3) if case == "divu" else None
+    is_sync = case in ("sync_ucorr", "sync_known")
+    known = case in ("known_edges", "sync_known")
+    ucorr = [0.1 * smooth_field(n, 500 + d, 1)[0] for d in range(3)] if is_sync else None
+    aofs0 = 0.25 + 0.1 * smooth_field(n, 600, ncomp) if is_sync else None
+    edges = [q + 0.05 * smooth_field(n, 700 + d, ncomp) for d in range(3)] if known else None
+    ref, rfl, red = oracle.compute_aofs2(dx, dt, q, f[:ncomp].copy(), um, vm, wm, iconserv, fit=0, divu=divu, uflux=ucorr,
+                                         is_sync=is_sync, aofs_in=aofs0, known_edges=edges)
+    g = ix.Geom.make(n)
+    boxes = split_boxes(n, nb)
+    ic = (C.c_int * ncomp)(*iconserv)
+    out_a, out_f, out_e = [], [[], [], []], [[], [], []]
+    for box in boxes:
+        tq, fq = to_fab(q, box, 3, ix.CELL, dev)
+        tf, ff = to_fab(f[:ncomp], box, 1, ix.CELL, dev)
+        ta, fa = to_fab(aofs0 if is_sync else np.zeros_like(q), box, 0, ix.CELL, dev)
+        macs = [to_fab(m[None], box, 1, t, dev) for m, t in ((um, ix.XFACE), (vm, ix.YFACE), (wm, ix.ZFACE))]
+        ucs = [to_fab(m[None], box, 0, t, dev) for m, t in zip(ucorr, (ix.XFACE, ix.YFACE, ix.ZFACE))] if is_sync else None
+        fl = [to_fab(np.zeros_like(q), box, 0, t, dev) for t in (ix.XFACE, ix.YFACE, ix.ZFACE)]
+        ed = [to_fab(edges[d] if known else np.zeros_like(q), box, 0, t, dev) for d, t in enumerate((ix.XFACE, ix.YFACE, ix.ZFACE))]
+        td, fd = to_fab(divu, box, 1, ix.CELL, dev) if divu is not None else (None, None)
+        bb = box_of(*box)
+        flags = ix.ADV_WRITE_FLUXES | (ix.ADV_IS_SYNC if is_sync else 0) | (ix.ADV_KNOWN_EDGE_STATE if known else 0)
+        lib.check(lib.iamrx_compute_aofs_box(C.byref(bb), C.byref(fa), 0, C.byref(fq), 0, ncomp, C.byref(ff), 0,
+                                             C.byref(fd) if fd is not None else None,
+                                             C.byref(macs[0][1]), C.byref(macs[1][1]), C.byref(macs[2][1]),
+                                             *([C.byref(u[1]) for u in ucs] if is_sync else [None, None, None]),
+                                             C.byref(fl[0][1]), C.byref(fl[1][1]), C.byref(fl[2][1]),
+                                             C.byref(ed[0][1]), C.byref(ed[1][1]), C.byref(ed[2][1]),
+                                             ic, None, C.byref(g), dt, flags, stream_of(dev)))
+        out_a.append(ta)
+        for d in range(3):
+            out_f[d].append(fl[d][0]); out_e[d].append(ed[d][0])
+    sync(dev)
+    got, _ = from_fabs(out_a, boxes, 0, ix.CELL, n, ncomp)
+    assert np.abs(got - ref).max() <= 1e-12 * _scale(ref)
+    for d, t in enumerate((ix.XFACE, ix.YFACE, ix.ZFACE)):
+        gf, dup = from_fabs(out_f[d], boxes, 0, t, n, ncomp)
+        ge, dup2 = from_fabs(out_e[d], boxes, 0, t, n, ncomp)
+        assert dup == 0.0 and dup2 == 0.0
+        assert np.abs(gf - rfl[d]).max() <= RTOL * 10 and np.abs(ge - red[d]).max() <= RTOL * 10
+
+
+def test_advection_argument_checks(backend):
+    """Fabs that do not cover the stencil are rejected instead of read out of bounds (S needs 3 ghost cells,
+    force / the MAC velocities 1: NSB.cpp:4539-4552, NavierStokesBase.H:810)."""
+    lib, dev = backend
+    n = (8, 8, 8)
+    g = ix.Geom.make(n)
+    box = ((0, 0, 0), (7, 7, 7))
+    z = np.zeros((3, 8, 8, 8))
+    bb = box_of(*box)
+    ic = (C.c_int * 3)(0, 0, 0)
+    macs = [to_fab(z[:1], box, 1, t, dev) for t in (ix.XFACE, ix.YFACE, ix.ZFACE)]
+    ta, fa = to_fab(z, box, 0, ix.CELL, dev)
+    for ng_s, ng_f, ng_m, msg in ((2, 1, 1, b"grown by 3"), (3, 0, 1, b"force"), (3, 1, 0, b"ghost face layer")):
+        tq, fq = to_fab(z, box, ng_s, ix.CELL, dev)
+        tf, ff = to_fab(z, box, ng_f, ix.CELL, dev)
+        mm = [to_fab(z[:1], box, ng_m, t, dev) for t in (ix.XFACE, ix.YFACE, ix.ZFACE)]
+        rc = lib.iamrx_compute_aofs_box(C.byref(bb), C.byref(fa), 0, C.byref(fq), 0, 3, C.byref(ff), 0, None, C.byref(mm[0][1]),
+                                        C.byref(mm[1][1]), C.byref(mm[2][1]), None, None, None, None, None, None, None, None, None,
+                                        ic, None, C.byref(g), 0.1, 0, stream_of(dev))
+        assert rc == -1 and msg in lib.iamrx_last_error(), lib.iamrx_last_error()
+    tq, fq = to_fab(z, box, 2, ix.CELL, dev)
+    rc = lib.iamrx_extrap_vel_to_faces_box(C.byref(bb), C.byref(fq), None, C.byref(macs[0][1]), C.byref(macs[1][1]),
+                                           C.byref(macs[2][1]), None, C.byref(g), 0.1, 0, stream_of(dev))
+    assert rc == -1 and b"grown by 3" in lib.iamrx_last_error()
+    # one flux velocity without the others, an unknown BC code
+    tq, fq = to_fab(z, box, 3, ix.CELL, dev)
+    tf, ff = to_fab(z, box, 1, ix.CELL, dev)
+    rc = lib.iamrx_compute_aofs_box(C.byref(bb), C.byref(fa), 0, C.byref(fq), 0, 3, C.byref(ff), 0, None, C.byref(macs[0][1]),
+                                    C.byref(macs[1][1]), C.byref(macs[2][1]), C.byref(macs[0][1]), None, None, None, None, None, None, None,
+                                    None, ic, None, C.byref(g), 0.1, 0, stream_of(dev))
+    assert rc == -1 and b"all three" in lib.iamrx_last_error()
+    bad = (ix.BCRec * 3)(*[ix.BCRec.make((7, 0, 0), (0, 0, 0))] * 3)
+    rc = lib.iamrx_compute_aofs_box(C.byref(bb), C.byref(fa), 0, C.byref(fq), 0, 3, C.byref(ff), 0, None, C.byref(macs[0][1]),
+                                    C.byref(macs[1][1]), C.byref(macs[2][1]), None, None, None, None, None, None, None, None,
+                                    None, ic, bad, C.byref(g), 0.1, 0, stream_of(dev))
+    assert rc == -1 and b"BCRec" in lib.iamrx_last_error()

@@ -180,7 +180,8 @@ def test_tracer_diffusion_properties(oracle):
         o.close()
     for name in ("off", "on"):
         S4, s0 = res[name]
-        assert abs(S4.sum() - s0) <= 1e-12 * np.abs(S4).sum()   # the synthetic tracer has zero mean: absolute scale
+        # conserved up to the residual the diffusion solve leaves (visc_tol = 1e-10 per cell, summed); zero-mean tracer: absolute scale
+        assert abs(S4.sum() - s0) <= 1e-10 * np.abs(S4).sum()
     assert np.abs(res["off"][0] - res["zero"][0]).max() <= 1e-13   # same path (OpenMP reductions are not bit-reproducible)
     assert res["on"][0].var() < res["off"][0].var()
 

@@ -62,6 +62,15 @@ def test_mac_project(backend, oracle, nb):
     # phi is defined up to a constant on a periodic domain
     d = (gphi - gphi.mean()) - (rphi - rphi.mean())
     assert np.abs(d).max() < 1e-12
+    # MacProjector::getFluxes (MacProj.cpp:1181-1183): -beta grad phi; umac_in + flux == umac_out
+    F = [[to_fab(np.zeros_like(rho), b, 0, t, dev) for b in boxes] for t in (ix.XFACE, ix.YFACE, ix.ZFACE)]
+    lib.check(lib.iamrx_mac_get_fluxes(lev.h, fab_array([p[1] for p in F[0]]), fab_array([p[1] for p in F[1]]),
+                                       fab_array([p[1] for p in F[2]]), fab_array([p[1] for p in P]), stream_of(dev)))
+    sync(dev)
+    for fl, uin, uout, t in ((F[0], um, ru, ix.XFACE), (F[1], vm, rv, ix.YFACE), (F[2], wm, rw, ix.ZFACE)):
+        gf, dup = from_fabs([p[0] for p in fl], boxes, 0, t, N, 1)
+        assert dup < 1e-14
+        assert np.abs(uin[0] + gf[0] - uout).max() < 1e-12
     lev.close()
 
 
