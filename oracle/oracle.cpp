@@ -26,6 +26,22 @@
 
 namespace {
 
+// Periodicity of the problem the current extern "C" call works on (geometry.is_periodic).  Every entry point sets it
+// (PerScope); Arr::fill_periodic wraps only the periodic directions, physical boundaries are filled explicitly.
+int g_per[3] = {1, 1, 1};
+struct PerScope {
+  int old[3];
+  explicit PerScope(const int* per) { for (int d = 0; d < 3; ++d) { old[d] = g_per[d]; g_per[d] = per ? per[d] : 1; } }
+  ~PerScope() { for (int d = 0; d < 3; ++d) g_per[d] = old[d]; }
+};
+// amrex::BCType math codes (AMReX_BC_TYPES.H; NS_BC.H:7-55 maps the physical types onto them)
+enum { BC_INT_DIR = 0, BC_REFLECT_ODD = -1, BC_REFLECT_EVEN = 1, BC_FOEXTRAP = 2, BC_EXT_DIR = 3, BC_HOEXTRAP = 4 };
+// amrex::LinOpBCType subset (Diffusion.cpp:1887-1999, MacProj.cpp:1187-1208, Projection.cpp:2436-2464)
+enum { LO_PERIODIC = 0, LO_DIRICHLET = 1, LO_NEUMANN = 2, LO_REFLECT_ODD = 3, LO_INFLOW = 4 };
+// PhysBCType (inputs ns.lo_bc / ns.hi_bc, inputs.3d.taylorgreen:100-102)
+enum { PHYS_INTERIOR = 0, PHYS_INFLOW = 1, PHYS_OUTFLOW = 2, PHYS_SYMMETRY = 3, PHYS_SLIPWALL = 4, PHYS_NOSLIPWALL = 5 };
+struct BCRec { int lo[3] = {0, 0, 0}, hi[3] = {0, 0, 0}; };
+
 struct Arr {
   int n[3] = {0, 0, 0}, ng = 0, nc = 0;
   long sj = 0, sk = 0, sc = 0;
@@ -42,21 +58,31 @@ struct Arr {
   inline double operator()(int i, int j, int k, int c = 0) const { return d[(i + ng) + (j + ng) * sj + (k + ng) * sk + c * sc]; }
   void setval(double v) { std::fill(d.begin(), d.end(), v); }
   // FabArray::FillBoundary(periodicity) for a single box covering the domain
+  // (ghost cells beyond a NON-periodic side are left alone: the physical-boundary fills own them.  In a non-periodic
+  // direction d the index n[d] -- the high face / node of face- and node-centred data -- is ordinary data, so the loops
+  // over the other directions include it.)
   void fill_periodic() {
     if (ng == 0) return;
+    const int h0 = g_per[0] ? 0 : 1, h1 = g_per[1] ? 0 : 1, h2 = g_per[2] ? 0 : 1;   // extra high index of non-periodic dirs
     for (int c = 0; c < nc; ++c) {
+      if (g_per[0]) {
 #pragma omp parallel for
-      for (int k = 0; k < n[2]; ++k)
-        for (int j = 0; j < n[1]; ++j)
-          for (int g = 1; g <= ng; ++g) { (*this)(-g, j, k, c) = (*this)(n[0] - g, j, k, c); (*this)(n[0] - 1 + g, j, k, c) = (*this)(g - 1, j, k, c); }
+        for (int k = 0; k < n[2] + h2; ++k)
+          for (int j = 0; j < n[1] + h1; ++j)
+            for (int g = 1; g <= ng; ++g) { (*this)(-g, j, k, c) = (*this)(n[0] - g, j, k, c); (*this)(n[0] - 1 + g, j, k, c) = (*this)(g - 1, j, k, c); }
+      }
+      if (g_per[1]) {
 #pragma omp parallel for
-      for (int k = 0; k < n[2]; ++k)
-        for (int g = 1; g <= ng; ++g)
-          for (int i = -ng; i < n[0] + ng; ++i) { (*this)(i, -g, k, c) = (*this)(i, n[1] - g, k, c); (*this)(i, n[1] - 1 + g, k, c) = (*this)(i, g - 1, k, c); }
-      for (int g = 1; g <= ng; ++g) {
+        for (int k = 0; k < n[2] + h2; ++k)
+          for (int g = 1; g <= ng; ++g)
+            for (int i = (g_per[0] ? -ng : 0); i < n[0] + (g_per[0] ? ng : h0); ++i) { (*this)(i, -g, k, c) = (*this)(i, n[1] - g, k, c); (*this)(i, n[1] - 1 + g, k, c) = (*this)(i, g - 1, k, c); }
+      }
+      if (g_per[2]) {
+        for (int g = 1; g <= ng; ++g) {
 #pragma omp parallel for
-        for (int j = -ng; j < n[1] + ng; ++j)
-          for (int i = -ng; i < n[0] + ng; ++i) { (*this)(i, j, -g, c) = (*this)(i, j, n[2] - g, c); (*this)(i, j, n[2] - 1 + g, c) = (*this)(i, j, g - 1, c); }
+          for (int j = (g_per[1] ? -ng : 0); j < n[1] + (g_per[1] ? ng : h1); ++j)
+            for (int i = (g_per[0] ? -ng : 0); i < n[0] + (g_per[0] ? ng : h0); ++i) { (*this)(i, j, -g, c) = (*this)(i, j, n[2] - g, c); (*this)(i, j, n[2] - 1 + g, c) = (*this)(i, j, g - 1, c); }
+        }
       }
     }
   }
@@ -107,6 +133,145 @@ struct Arr {
     for (int j = 0; j < (A).n[1]; ++j)        \
       for (int i = 0; i < (A).n[0]; ++i)
 
+// faces of direction d (or nodes, d = 3): in a non-periodic direction the high face / node n[d] is ordinary data
+#define FOR_IDX(A, hx, hy, hz, i, j, k)                                   \
+  _Pragma("omp parallel for") for (int k = 0; k < (A).n[2] + (hz); ++k) \
+    for (int j = 0; j < (A).n[1] + (hy); ++j)                            \
+      for (int i = 0; i < (A).n[0] + (hx); ++i)
+inline int hi_ext(int d, int dir) { return (d == dir || dir == 3) && !g_per[d] ? 1 : 0; }   // dir = face direction, 3 = nodal
+#define FOR_FACES(A, dir, i, j, k) FOR_IDX(A, hi_ext(0, dir), hi_ext(1, dir), hi_ext(2, dir), i, j, k)
+#define FOR_NODES(A, i, j, k) FOR_IDX(A, hi_ext(0, 3), hi_ext(1, 3), hi_ext(2, 3), i, j, k)
+
+// ===========================================================================
+// Physical boundary fill of cell-centred state data: what AmrLevel::FillPatch does outside the domain
+// (amrex::GpuBndryFuncFab::ccfcdoit -> filcc_cell, then the user function for ext_dir: NS_bcfill.H:17-167 with the
+// constant face values bcv of NavierStokes::get_bc_values, NS.cpp:108-237).  Cells outside the domain in ONE
+// non-periodic direction first, then two (domain edges), then three (corners); in every cell the x, y, z rules are
+// applied in that order (a later direction overwrites an earlier one), and then the ext_dir values in the same order.
+// Ghost values of ext_dir faces therefore sit ON the face (Software.rst:206-213).
+// ===========================================================================
+void fill_physbc(Arr& a, int c0, int nc, const BCRec* bc, const double* bcv /* [6][nc] or null (= 0) */) {
+  if (a.ng == 0 || (g_per[0] && g_per[1] && g_per[2])) return;
+  const int ng = a.ng;
+  for (int pass = 1; pass <= 3; ++pass) {
+    for (int c = 0; c < nc; ++c) {
+      const BCRec& b = bc[c];
+#pragma omp parallel for
+      for (int k = -ng; k < a.n[2] + ng; ++k)
+        for (int j = -ng; j < a.n[1] + ng; ++j)
+          for (int i = -ng; i < a.n[0] + ng; ++i) {
+            const int idx[3] = {i, j, k};
+            int nout = 0, side[3] = {0, 0, 0};
+            for (int d = 0; d < 3; ++d)
+              if (!g_per[d]) { if (idx[d] < 0) { side[d] = -1; ++nout; } else if (idx[d] >= a.n[d]) { side[d] = 1; ++nout; } }
+            if (nout != pass) continue;
+            double v = a(i, j, k, c0 + c);
+            for (int d = 0; d < 3; ++d) {
+              if (!side[d]) continue;
+              const int code = side[d] < 0 ? b.lo[d] : b.hi[d];
+              const int e = side[d] < 0 ? 0 : a.n[d] - 1;        // first interior cell on that side
+              const int inw = side[d] < 0 ? 1 : -1;               // direction into the domain
+              auto at = [&](int m) { int q[3] = {i, j, k}; q[d] = m; return a(q[0], q[1], q[2], c0 + c); };
+              const int dist = side[d] < 0 ? -1 - idx[d] : idx[d] - a.n[d];   // 0 for the first ghost cell
+              switch (code) {
+                case BC_FOEXTRAP: v = at(e); break;
+                case BC_HOEXTRAP:
+                  if (dist > 0) v = at(e);
+                  else if (a.n[d] >= 3) v = 0.125 * (15.0 * at(e) - 10.0 * at(e + inw) + 3.0 * at(e + 2 * inw));
+                  else v = 0.5 * (3.0 * at(e) - at(e + inw));
+                  break;
+                case BC_REFLECT_EVEN: v = at(e + inw * dist); break;
+                case BC_REFLECT_ODD: v = -at(e + inw * dist); break;
+                default: break;   // int_dir: nothing; ext_dir: the user function below
+              }
+              a(i, j, k, c0 + c) = v;   // the next direction's rule may read this cell's row, not the cell itself
+            }
+            for (int d = 0; d < 3; ++d) {
+              if (!side[d]) continue;
+              const int code = side[d] < 0 ? b.lo[d] : b.hi[d];
+              if (code == BC_EXT_DIR) v = bcv ? bcv[(d + (side[d] > 0 ? 3 : 0)) * nc + c] : 0.0;
+            }
+            a(i, j, k, c0 + c) = v;
+          }
+    }
+  }
+}
+
+// Extrapolater::FirstOrderExtrap (NS.cpp:2046; also FillPatch of Gradp at walls = foextrap, NS_BC.H:27-38): every
+// ghost cell outside a non-periodic side copies the nearest valid cell
+void first_order_extrap(Arr& a, int c0, int nc) {
+  BCRec b; for (int d = 0; d < 3; ++d) { b.lo[d] = BC_FOEXTRAP; b.hi[d] = BC_FOEXTRAP; }
+  std::vector<BCRec> v(nc, b);
+  fill_physbc(a, c0, nc, v.data(), nullptr);
+}
+
+// ===========================================================================
+// Domain boundary conditions of the cell-centred linear operators (AMReX MLCellLinOp::applyBC ->
+// mllinop_apply_bc_{x,y,z}; A.6).  The ghost cell beyond a non-periodic side is a linear function of the boundary value
+// (ON the face) and of the first interior cells:
+//   Dirichlet   : Lagrange extrapolation through the face value and min(maxorder, n+1) - 1 interior cells
+//   Neumann     : ghost = first interior cell;   reflect_odd : ghost = -first interior cell
+// The coefficient of the first interior cell (f0) also enters the smoother's diagonal (the delta term of abec_gsrb).
+// ===========================================================================
+struct LinBC {
+  int lo[3][3], hi[3][3];   // [comp][dir]  LinOpBCType
+  int maxorder = 2;
+  LinBC() { for (int c = 0; c < 3; ++c) for (int d = 0; d < 3; ++d) { lo[c][d] = LO_PERIODIC; hi[c][d] = LO_PERIODIC; } }
+  int code(int c, int d, int side) const { return side < 0 ? lo[c < 3 ? c : 0][d] : hi[c < 3 ? c : 0][d]; }
+};
+// Lagrange weights at x = -1/2 (ghost centre, in cell widths from the face at 0) for nodes {0 (face), 1/2, 3/2, ...}:
+// w[0] multiplies the face value, w[m] the m-th interior cell
+inline void dirichlet_weights(int order, double w[5]) {
+  double x[5]; x[0] = 0.0; for (int m = 1; m < order; ++m) x[m] = m - 0.5;
+  const double xg = -0.5;
+  for (int m = 0; m < order; ++m) {
+    double num = 1.0, den = 1.0;
+    for (int q = 0; q < order; ++q) if (q != m) { num *= (xg - x[q]); den *= (x[m] - x[q]); }
+    w[m] = num / den;
+  }
+  for (int m = order; m < 5; ++m) w[m] = 0.0;
+}
+inline int bc_order(const LinBC& bc, int nlen) { return std::max(2, std::min(std::min(bc.maxorder, nlen + 1), 4)); }
+// coefficient of the first interior cell in the ghost-cell formula (the f0 of AMReX's undrrelxr)
+inline double bc_f0(const LinBC& bc, int c, int d, int side, int nlen) {
+  switch (bc.code(c, d, side)) {
+    case LO_NEUMANN: return 1.0;
+    case LO_REFLECT_ODD: return -1.0;
+    case LO_DIRICHLET: { double w[5]; dirichlet_weights(bc_order(bc, nlen), w); return w[1]; }
+    default: return 0.0;
+  }
+}
+// face ghost cells of phi (1 layer) beyond the non-periodic sides; bv = array whose ghost cells hold the Dirichlet face
+// values (inhomogeneous: MLLinOp::setLevelBC) or null (homogeneous: the multigrid corrections)
+void apply_linop_bc(Arr& phi, int ncomp, const LinBC& bc, const Arr* bv) {
+  for (int c = 0; c < ncomp; ++c)
+    for (int d = 0; d < 3; ++d) {
+      if (g_per[d]) continue;
+      const int nl = phi.n[d];
+      const int d1 = (d + 1) % 3, d2 = (d + 2) % 3;
+      double w[5]; dirichlet_weights(bc_order(bc, nl), w);
+      for (int side = -1; side <= 1; side += 2) {
+        const int code = bc.code(c, d, side);
+        const int g = side < 0 ? -1 : nl, e = side < 0 ? 0 : nl - 1, inw = side < 0 ? 1 : -1;
+#pragma omp parallel for
+        for (int b2 = 0; b2 < phi.n[d2]; ++b2)
+          for (int b1 = 0; b1 < phi.n[d1]; ++b1) {
+            int q[3]; q[d1] = b1; q[d2] = b2;
+            auto P = [&](int m) -> double& { q[d] = m; return phi(q[0], q[1], q[2], c); };
+            double v;
+            if (code == LO_NEUMANN) v = P(e);
+            else if (code == LO_REFLECT_ODD) v = -P(e);
+            else {
+              q[d] = g;
+              v = w[0] * (bv ? (*bv)(q[0], q[1], q[2], c) : 0.0);
+              for (int m = 1; m < 5; ++m) if (w[m] != 0.0) v += w[m] * P(e + inw * (m - 1));
+            }
+            P(g) = v;
+          }
+      }
+    }
+}
+
 // ===========================================================================
 // MLABecLaplacian  (AMReX MLABecLap_3D_K.H: mlabeclap_adotx / abec_gsrb; A.6)
 //   L phi = a*alpha*phi - b * sum_d [ beta_d(i+1)(phi(i+1)-phi(i)) - beta_d(i)(phi(i)-phi(i-1)) ] / h_d^2
@@ -117,10 +282,17 @@ struct AbecOp {
   const Arr* beta[3] = {nullptr, nullptr, nullptr};  // face arrays with >= 1 ghost (filled)
   int bncomp = 1;
   double dxinv[3];
+  const LinBC* bc = nullptr;   // domain BCs of the non-periodic sides (null: fully periodic)
+  const Arr* bv = nullptr;     // Dirichlet face values (ghost cells) for the inhomogeneous form, null = homogeneous
 };
 
-void abec_apply(const AbecOp& op, Arr& phi, Arr& out, int ncomp) {  // phi ghosts are filled here
+inline void abec_fill(const AbecOp& op, Arr& phi, int ncomp) {
   phi.fill_periodic();
+  if (op.bc) apply_linop_bc(phi, ncomp, *op.bc, op.bv);
+}
+
+void abec_apply(const AbecOp& op, Arr& phi, Arr& out, int ncomp) {  // phi ghosts are filled here
+  abec_fill(op, phi, ncomp);
   const double hx = op.b * op.dxinv[0] * op.dxinv[0], hy = op.b * op.dxinv[1] * op.dxinv[1], hz = op.b * op.dxinv[2] * op.dxinv[2];
   for (int c = 0; c < ncomp; ++c) {
     const int cb = op.bncomp > 1 ? c : 0;
@@ -138,7 +310,7 @@ void abec_apply(const AbecOp& op, Arr& phi, Arr& out, int ncomp) {  // phi ghost
 
 // one colour of red-black Gauss-Seidel (abec_gsrb): cells with (i+j+k+redblack) even
 void abec_gsrb(const AbecOp& op, Arr& phi, const Arr& rhs, int ncomp, double omega, int redblack) {
-  phi.fill_periodic();
+  abec_fill(op, phi, ncomp);   // AMReX fills the ghost cells (applyBC) before every colour
   const double hx = op.b * op.dxinv[0] * op.dxinv[0], hy = op.b * op.dxinv[1] * op.dxinv[1], hz = op.b * op.dxinv[2] * op.dxinv[2];
   for (int c = 0; c < ncomp; ++c) {
     const int cb = op.bncomp > 1 ? c : 0;
@@ -155,50 +327,87 @@ void abec_gsrb(const AbecOp& op, Arr& phi, const Arr& rhs, int ncomp, double ome
                              hy * (by(i, j, k, cb) * phi(i, j - 1, k, c) + by(i, j + 1, k, cb) * phi(i, j + 1, k, c)) +
                              hz * (bz(i, j, k, cb) * phi(i, j, k - 1, c) + bz(i, j, k + 1, cb) * phi(i, j, k + 1, c));
           const double res = rhs(i, j, k, c) - (gamma * phi(i, j, k, c) - rho);
-          phi(i, j, k, c) += omega / gamma * res;
+          // delta: the part of rho that depends on phi(i,j,k) itself through a boundary ghost cell (mlabeclap_gsrb cf0..cf5)
+          double delta = 0.0;
+          if (op.bc) {
+            const LinBC& B = *op.bc;
+            if (!g_per[0]) { if (i == 0) delta += hx * bx(i, j, k, cb) * bc_f0(B, c, 0, -1, phi.n[0]); if (i == phi.n[0] - 1) delta += hx * bx(i + 1, j, k, cb) * bc_f0(B, c, 0, 1, phi.n[0]); }
+            if (!g_per[1]) { if (j == 0) delta += hy * by(i, j, k, cb) * bc_f0(B, c, 1, -1, phi.n[1]); if (j == phi.n[1] - 1) delta += hy * by(i, j + 1, k, cb) * bc_f0(B, c, 1, 1, phi.n[1]); }
+            if (!g_per[2]) { if (k == 0) delta += hz * bz(i, j, k, cb) * bc_f0(B, c, 2, -1, phi.n[2]); if (k == phi.n[2] - 1) delta += hz * bz(i, j, k + 1, cb) * bc_f0(B, c, 2, 1, phi.n[2]); }
+          }
+          phi(i, j, k, c) += omega / (gamma - delta) * res;
         }
       }
   }
 }
 
+// periodic wrap over the FULL extent (ghost rows of the other directions included): extends wall ghost cells to the
+// transverse ghost positions at mixed periodic / physical edges
+void fill_periodic_all(Arr& a) {
+  const int ng = a.ng;
+  for (int c = 0; c < a.nc; ++c)
+    for (int d = 0; d < 3; ++d) {
+      if (!g_per[d]) continue;
+      const int d1 = (d + 1) % 3, d2 = (d + 2) % 3;
+#pragma omp parallel for
+      for (int b2 = -ng; b2 < a.n[d2] + ng; ++b2)
+        for (int b1 = -ng; b1 < a.n[d1] + ng; ++b1)
+          for (int g = 1; g <= ng; ++g) {
+            int q[3], r[3]; q[d1] = r[d1] = b1; q[d2] = r[d2] = b2;
+            q[d] = -g; r[d] = a.n[d] - g; a(q[0], q[1], q[2], c) = a(r[0], r[1], r[2], c);
+            q[d] = a.n[d] - 1 + g; r[d] = g - 1; a(q[0], q[1], q[2], c) = a(r[0], r[1], r[2], c);
+          }
+    }
+}
+
 // MLTensorOp cross terms (AMReX MLTensor_3D_K.H mltensor_cross_terms_f{x,y,z} with kappa = 0; A.8):
 // out += bscalar * div(F), F_x = (-eta*(-2/3)(dv/dy+dw/dz), -eta du/dy, -eta du/dz) on x-faces, etc.
-void tensor_cross(const double dxinv[3], double bscalar, const Arr& ex, const Arr& ey, const Arr& ez, Arr& vel, Arr& out) {
+// The transverse derivative of component c on a D-face is the mean of the two centred differences either side of the
+// face; ON a non-periodic domain face (mltensor_d?_on_?face with bct / bv?lo / bv?hi) it is taken from the boundary
+// data instead: Dirichlet -> centred difference of the FACE values (the ghost cells of the level-BC array; zero in
+// the homogeneous form), Neumann -> centred difference of the interior cell row, reflect_odd -> 0.
+void tensor_cross(const double dxinv[3], double bscalar, const Arr& ex, const Arr& ey, const Arr& ez, Arr& vel, Arr& out,
+                  const LinBC* bc = nullptr, const Arr* bv = nullptr) {
   vel.fill_periodic();
-  const double dxi = dxinv[0], dyi = dxinv[1], dzi = dxinv[2];
-  Arr fx(vel.n, 3, 1), fy(vel.n, 3, 1), fz(vel.n, 3, 1);
-  FOR_CELLS(out, i, j, k) {
-    auto ddy_x = [&](int c) { return (vel(i, j + 1, k, c) + vel(i - 1, j + 1, k, c) - vel(i, j - 1, k, c) - vel(i - 1, j - 1, k, c)) * (0.25 * dyi); };
-    auto ddz_x = [&](int c) { return (vel(i, j, k + 1, c) + vel(i - 1, j, k + 1, c) - vel(i, j, k - 1, c) - vel(i - 1, j, k - 1, c)) * (0.25 * dzi); };
-    auto ddx_y = [&](int c) { return (vel(i + 1, j, k, c) + vel(i + 1, j - 1, k, c) - vel(i - 1, j, k, c) - vel(i - 1, j - 1, k, c)) * (0.25 * dxi); };
-    auto ddz_y = [&](int c) { return (vel(i, j, k + 1, c) + vel(i, j - 1, k + 1, c) - vel(i, j, k - 1, c) - vel(i, j - 1, k - 1, c)) * (0.25 * dzi); };
-    auto ddx_z = [&](int c) { return (vel(i + 1, j, k, c) + vel(i + 1, j, k - 1, c) - vel(i - 1, j, k, c) - vel(i - 1, j, k - 1, c)) * (0.25 * dxi); };
-    auto ddy_z = [&](int c) { return (vel(i, j + 1, k, c) + vel(i, j + 1, k - 1, c) - vel(i, j - 1, k, c) - vel(i, j - 1, k - 1, c)) * (0.25 * dyi); };
-    const double twoThirds = 2.0 / 3.0;
-    {
-      const double mu = ex(i, j, k);
-      fx(i, j, k, 0) = -mu * (-twoThirds * (ddy_x(1) + ddz_x(2)));
-      fx(i, j, k, 1) = -mu * ddy_x(0);
-      fx(i, j, k, 2) = -mu * ddz_x(0);
+  if (bc) { apply_linop_bc(vel, 3, *bc, bv); fill_periodic_all(vel); }   // face ghosts, then their periodic images
+  Arr bvx;   // level-BC values with the periodic images of their wall ghost cells
+  if (bc && bv) { bvx = *bv; fill_periodic_all(bvx); }
+  const Arr* eta[3] = {&ex, &ey, &ez};
+  const int* n = vel.n;
+  // derivative along t of component c on the D-face whose upper cell is (i,j,k)
+  auto dt_on_face = [&](int D, int t, int c, int i, int j, int k) {
+    const double dti = dxinv[t];
+    int q[3] = {i, j, k};
+    auto V = [&](const Arr& A, int oD, int ot) { int r[3] = {q[0], q[1], q[2]}; r[D] += oD; r[t] += ot; return A(r[0], r[1], r[2], c); };
+    if (bc && !g_per[D] && (q[D] == 0 || q[D] == n[D])) {
+      const int side = q[D] == 0 ? -1 : 1;
+      const int code = bc->code(c, D, side);
+      const int og = side < 0 ? -1 : 0, oi = side < 0 ? 0 : -1;   // offsets of the ghost / interior cell along D
+      if (code == LO_DIRICHLET) return bv ? (V(bvx, og, 1) - V(bvx, og, -1)) * (0.5 * dti) : 0.0;
+      if (code == LO_NEUMANN) return (V(vel, oi, 1) - V(vel, oi, -1)) * (0.5 * dti);
+      return 0.0;   // reflect_odd
     }
-    {
-      const double mu = ey(i, j, k);
-      fy(i, j, k, 0) = -mu * ddx_y(1);
-      fy(i, j, k, 1) = -mu * (-twoThirds * (ddx_y(0) + ddz_y(2)));
-      fy(i, j, k, 2) = -mu * ddz_y(1);
+    return (V(vel, 0, 1) + V(vel, -1, 1) - V(vel, 0, -1) - V(vel, -1, -1)) * (0.25 * dti);
+  };
+  Arr fl[3] = {Arr(n, 3, 1), Arr(n, 3, 1), Arr(n, 3, 1)};
+  const double twoThirds = 2.0 / 3.0;
+  for (int D = 0; D < 3; ++D) {
+    const int t1 = (D + 1) % 3, t2 = (D + 2) % 3;
+    Arr& F = fl[D]; const Arr& E = *eta[D];
+    FOR_FACES(F, D, i, j, k) {
+      const double mu = E(i, j, k);
+      // normal component: -(2/3) eta (d u_t1/d t1 + d u_t2/d t2); tangential component t: eta d u_D / d t
+      F(i, j, k, D) = -mu * (-twoThirds * (dt_on_face(D, t1, t1, i, j, k) + dt_on_face(D, t2, t2, i, j, k)));
+      F(i, j, k, t1) = -mu * dt_on_face(D, t1, D, i, j, k);
+      F(i, j, k, t2) = -mu * dt_on_face(D, t2, D, i, j, k);
     }
-    {
-      const double mu = ez(i, j, k);
-      fz(i, j, k, 0) = -mu * ddx_z(2);
-      fz(i, j, k, 1) = -mu * ddy_z(2);
-      fz(i, j, k, 2) = -mu * (-twoThirds * (ddx_z(0) + ddy_z(1)));
-    }
+    F.fill_periodic();
   }
-  fx.fill_periodic(); fy.fill_periodic(); fz.fill_periodic();
+  const double dxi = dxinv[0], dyi = dxinv[1], dzi = dxinv[2];
   for (int c = 0; c < 3; ++c) {
     FOR_CELLS(out, i, j, k) {
-      out(i, j, k, c) += bscalar * (dxi * (fx(i + 1, j, k, c) - fx(i, j, k, c)) + dyi * (fy(i, j + 1, k, c) - fy(i, j, k, c)) +
-                                    dzi * (fz(i, j, k + 1, c) - fz(i, j, k, c)));
+      out(i, j, k, c) += bscalar * (dxi * (fl[0](i + 1, j, k, c) - fl[0](i, j, k, c)) + dyi * (fl[1](i, j + 1, k, c) - fl[1](i, j, k, c)) +
+                                    dzi * (fl[2](i, j, k + 1, c) - fl[2](i, j, k, c)));
     }
   }
 }
@@ -217,6 +426,9 @@ struct CellMG {
   const Arr* eta[3] = {nullptr, nullptr, nullptr};
   orc_mg mg;
   bool singular = false;
+  LinBC bc; bool has_bc = false;   // domain BCs (setDomainBC + setMaxOrder)
+  const Arr* bvals = nullptr;      // setLevelBC: array whose ghost cells hold the Dirichlet face values
+  void set_bc(const LinBC& b, const Arr* levelbc) { bc = b; has_bc = !(g_per[0] && g_per[1] && g_per[2]); bvals = levelbc; }
 
   CellMG(const int n[3], const double dx[3], int ncomp_, bool tensor_, int max_coarsening) : ncomp(ncomp_), tensor(tensor_) {
     bncomp = tensor ? ncomp : 1;
@@ -234,10 +446,11 @@ struct CellMG {
       for (int d = 0; d < 3; ++d) { cur[d] /= 2; h[d] *= 2.0; }
     }
   }
-  AbecOp op(int l) const {
+  AbecOp op(int l, bool inhomog = false) const {
     AbecOp o; o.a = a; o.b = b; o.alpha = (a != 0.0) ? &lv[l].alpha : nullptr;
     for (int d = 0; d < 3; ++d) { o.beta[d] = &lv[l].beta[d]; o.dxinv[d] = lv[l].dxinv[d]; }
     o.bncomp = bncomp;
+    if (has_bc) { o.bc = &bc; o.bv = (inhomog && l == 0) ? bvals : nullptr; }
     return o;
   }
   void set_coeffs(const Arr* alpha, const Arr* e[3]) {
@@ -249,7 +462,7 @@ struct CellMG {
       for (int c = 0; c < bncomp; ++c) {
         const double fac = (tensor && c == d) ? 4.0 / 3.0 : 1.0;  // MLTensorOp: (4/3)eta + kappa on the normal component
         Arr& B = F.beta[d]; const Arr& E = *e[d];
-        FOR_CELLS(B, i, j, k) B(i, j, k, c) = fac * E(i, j, k);
+        FOR_FACES(B, d, i, j, k) B(i, j, k, c) = fac * E(i, j, k);
       }
       F.beta[d].fill_periodic();
     }
@@ -267,7 +480,7 @@ struct CellMG {
         C.beta[d].define(C.n, bncomp, 1);
         Arr& cb = C.beta[d]; const Arr& fb = Fi.beta[d];
         for (int c = 0; c < bncomp; ++c) {
-          FOR_CELLS(cb, i, j, k) {
+          FOR_FACES(cb, d, i, j, k) {
             const int ii = 2 * i, jj = 2 * j, kk = 2 * k;
             double s;
             if (d == 0) s = fb(ii, jj, kk, c) + fb(ii, jj + 1, kk, c) + fb(ii, jj, kk + 1, c) + fb(ii, jj + 1, kk + 1, c);
@@ -279,21 +492,26 @@ struct CellMG {
         cb.fill_periodic();
       }
     }
-    singular = (a == 0.0);  // all-periodic: the operator annihilates constants
+    singular = (a == 0.0);  // periodic / Neumann everywhere: the operator annihilates constants
+    if (has_bc)
+      for (int c = 0; c < ncomp && c < 3; ++c) for (int d = 0; d < 3; ++d)
+        if (!g_per[d] && (bc.lo[c][d] == LO_DIRICHLET || bc.hi[c][d] == LO_DIRICHLET || bc.lo[c][d] == LO_REFLECT_ODD || bc.hi[c][d] == LO_REFLECT_ODD)) singular = false;
   }
   void smooth(int l, Arr& phi, const Arr& rhs, int nsweeps) {
     const AbecOp o = op(l);
     for (int s = 0; s < nsweeps; ++s)
       for (int rb = 0; rb < 2; ++rb) abec_gsrb(o, phi, rhs, ncomp, mg.omega, rb);
   }
+  // cross: the top-level residual of the solve (inhomogeneous BCs + tensor cross terms); the cycle's correction
+  // residuals are homogeneous and carry no cross terms
   void residual(int l, Arr& out, Arr& phi, const Arr& rhs, bool cross) {
-    abec_apply(op(l), phi, out, ncomp);
-    if (tensor && l == 0 && cross) tensor_cross(lv[0].dxinv, b, *eta[0], *eta[1], *eta[2], phi, out);
+    abec_apply(op(l, cross), phi, out, ncomp);
+    if (tensor && l == 0 && cross) tensor_cross(lv[0].dxinv, b, *eta[0], *eta[1], *eta[2], phi, out, has_bc ? &bc : nullptr, bvals);
     for (int c = 0; c < ncomp; ++c) { FOR_CELLS(out, i, j, k) out(i, j, k, c) = rhs(i, j, k, c) - out(i, j, k, c); }
   }
-  void apply(Arr& out, Arr& phi) {
-    abec_apply(op(0), phi, out, ncomp);
-    if (tensor) tensor_cross(lv[0].dxinv, b, *eta[0], *eta[1], *eta[2], phi, out);
+  void apply(Arr& out, Arr& phi) {   // MLMG::apply: inhomogeneous BCs
+    abec_apply(op(0, true), phi, out, ncomp);
+    if (tensor) tensor_cross(lv[0].dxinv, b, *eta[0], *eta[1], *eta[2], phi, out, has_bc ? &bc : nullptr, bvals);
   }
   void make_solvable(Arr& r) {
     for (int c = 0; c < ncomp; ++c) {
@@ -347,7 +565,7 @@ struct CellMG {
         if (r <= target) { rc = 0; break; }
       }
     }
-    sol.fill_periodic();
+    abec_fill(op(0, true), sol, ncomp);   // setFinalFillBC(true)
     mg.iters = it; mg.resnorm0 = r0; mg.resnorm = r; mg.rhsnorm = rhsnorm;
     return rc;
   }
@@ -390,38 +608,109 @@ inline double nodal_ax(const Q1& q, const Arr& sig, const Arr& phi, int i, int j
   return y;
 }
 
-void nodal_adotx(const double dxinv[3], Arr& sig, Arr& phi, Arr& out) {
+// Domain boundary conditions of the nodal operator (Projection.cpp:2436-2464: outflow -> Dirichlet, inflow -> inflow,
+// everything else -> Neumann).  AMReX MLNodeLaplacian (A.9): Neumann / inflow sides reflect the ghost node
+// (phi(lo-1) = phi(lo+1), mlndlap_applybc) and copy sigma into the ghost cell (mlndlap_fillbc_cc), the right-hand side
+// of nodes ON such a side is doubled once per direction (mlndlap_impose_neumann_bc), and nodes ON a Dirichlet side are
+// held at zero (dirichlet mask).  Node arrays carry 2 ghost layers: the ghost node of a high side is index n+1.
+struct NodalBC {
+  int lo[3] = {LO_PERIODIC, LO_PERIODIC, LO_PERIODIC}, hi[3] = {LO_PERIODIC, LO_PERIODIC, LO_PERIODIC};
+  bool neu(int d, int side) const { const int c = side < 0 ? lo[d] : hi[d]; return !g_per[d] && (c == LO_NEUMANN || c == LO_INFLOW); }
+  bool dir(int d, int side) const { const int c = side < 0 ? lo[d] : hi[d]; return !g_per[d] && c == LO_DIRICHLET; }
+};
+inline bool nodal_masked(const NodalBC& bc, const int n[3], int i, int j, int k) {   // node on a Dirichlet side
+  const int idx[3] = {i, j, k};
+  for (int d = 0; d < 3; ++d) if ((idx[d] == 0 && bc.dir(d, -1)) || (idx[d] == n[d] && bc.dir(d, 1))) return true;
+  return false;
+}
+inline double nodal_weight(const NodalBC& bc, const int n[3], int i, int j, int k) {   // mlndlap_set_dot_mask: 1/2 per Neumann side
+  const int idx[3] = {i, j, k};
+  double w = 1.0;
+  for (int d = 0; d < 3; ++d) if ((idx[d] == 0 && bc.neu(d, -1)) || (idx[d] == n[d] && bc.neu(d, 1))) w *= 0.5;
+  return w;
+}
+void nodal_fill_phi(Arr& phi, const NodalBC& bc) {
   phi.fill_periodic();
+  for (int d = 0; d < 3; ++d) {
+    if (g_per[d]) continue;
+    const int d1 = (d + 1) % 3, d2 = (d + 2) % 3, ng = phi.ng;
+#pragma omp parallel for
+    for (int b2 = -ng; b2 <= phi.n[d2] + ng - 1; ++b2)
+      for (int b1 = -ng; b1 <= phi.n[d1] + ng - 1; ++b1) {
+        int q[3], r[3]; q[d1] = r[d1] = b1; q[d2] = r[d2] = b2;
+        if (bc.neu(d, -1)) { q[d] = -1; r[d] = 1; phi(q[0], q[1], q[2]) = phi(r[0], r[1], r[2]); }
+        if (bc.neu(d, 1)) { q[d] = phi.n[d] + 1; r[d] = phi.n[d] - 1; phi(q[0], q[1], q[2]) = phi(r[0], r[1], r[2]); }
+      }
+  }
+}
+void nodal_fill_sigma(Arr& sig, const NodalBC& bc) {
+  sig.fill_periodic();
+  for (int d = 0; d < 3; ++d) {
+    if (g_per[d]) continue;
+    const int d1 = (d + 1) % 3, d2 = (d + 2) % 3, ng = sig.ng;
+#pragma omp parallel for
+    for (int b2 = -ng; b2 < sig.n[d2] + ng; ++b2)
+      for (int b1 = -ng; b1 < sig.n[d1] + ng; ++b1) {
+        int q[3], r[3]; q[d1] = r[d1] = b1; q[d2] = r[d2] = b2;
+        q[d] = -1; r[d] = 0; sig(q[0], q[1], q[2]) = bc.neu(d, -1) ? sig(r[0], r[1], r[2]) : 0.0;
+        q[d] = sig.n[d]; r[d] = sig.n[d] - 1; sig(q[0], q[1], q[2]) = bc.neu(d, 1) ? sig(r[0], r[1], r[2]) : 0.0;
+      }
+  }
+}
+const NodalBC PERIODIC_NBC;
+
+void nodal_adotx(const double dxinv[3], Arr& sig, Arr& phi, Arr& out, const NodalBC& bc = PERIODIC_NBC) {
+  nodal_fill_phi(phi, bc);
   const Q1 q(dxinv);
-  FOR_CELLS(out, i, j, k) { double dg; out(i, j, k) = nodal_ax(q, sig, phi, i, j, k, dg); }
+  FOR_NODES(out, i, j, k) {
+    double dg;
+    out(i, j, k) = nodal_masked(bc, out.n, i, j, k) ? 0.0 : nodal_ax(q, sig, phi, i, j, k, dg);
+  }
 }
 
 // multi-colour Gauss-Seidel: colour = (i&1) + 2(j&1) + 4(k&1); nodes of one colour are
 // mutually uncoupled under the 27-point stencil (even n per direction)
-void nodal_gs(const double dxinv[3], Arr& sig, const Arr& rhs, int color, Arr& phi) {
-  phi.fill_periodic();
+void nodal_gs(const double dxinv[3], Arr& sig, const Arr& rhs, int color, Arr& phi, const NodalBC& bc = PERIODIC_NBC) {
+  nodal_fill_phi(phi, bc);
   const Q1 q(dxinv);
   const int c0 = color & 1, c1 = (color >> 1) & 1, c2 = (color >> 2) & 1;
 #pragma omp parallel for
-  for (int k = c2; k < phi.n[2]; k += 2)
-    for (int j = c1; j < phi.n[1]; j += 2)
-      for (int i = c0; i < phi.n[0]; i += 2) {
+  for (int k = c2; k < phi.n[2] + hi_ext(2, 3); k += 2)
+    for (int j = c1; j < phi.n[1] + hi_ext(1, 3); j += 2)
+      for (int i = c0; i < phi.n[0] + hi_ext(0, 3); i += 2) {
+        if (nodal_masked(bc, phi.n, i, j, k)) continue;
         double dg; const double y = nodal_ax(q, sig, phi, i, j, k, dg);
         phi(i, j, k) += (rhs(i, j, k) - y) / dg;
       }
 }
 
-// FE divergence of a piecewise-constant velocity (NodalProjector computeRHS / mlndlap_divu)
-void nodal_divu(const double dxinv[3], Arr& vel, Arr& rhs) {
+// FE divergence of a piecewise-constant velocity (NodalProjector computeRHS / mlndlap_divu).  Beyond a Neumann / inflow
+// side the divergence does not see the TANGENTIAL velocities of the ghost cells (the zero_* factors of mlndlap_divu);
+// the normal component of the ghost cell is used as it is (zero at walls, the inflow value at inflow faces:
+// Projection::set_boundary_velocity, Projection.cpp:2570-2663).  Then mlndlap_impose_neumann_bc doubles the boundary rows.
+void nodal_divu(const double dxinv[3], Arr& vel, Arr& rhs, const NodalBC& bc = PERIODIC_NBC) {
   vel.fill_periodic();
-  FOR_CELLS(rhs, i, j, k) {
+  const int* n = rhs.n;
+  FOR_NODES(rhs, i, j, k) {
+    if (nodal_masked(bc, n, i, j, k)) { rhs(i, j, k) = 0.0; continue; }
+    const int idx[3] = {i, j, k};
     double r = 0.0;
     for (int cz = 0; cz < 2; ++cz) for (int cy = 0; cy < 2; ++cy) for (int cx = 0; cx < 2; ++cx) {
+      const int off[3] = {cx, cy, cz};
       const int ci = i - cx, cj = j - cy, ck = k - cz;
-      r += 0.25 * ((cx ? -1.0 : 1.0) * dxinv[0] * vel(ci, cj, ck, 0) + (cy ? -1.0 : 1.0) * dxinv[1] * vel(ci, cj, ck, 1) +
-                   (cz ? -1.0 : 1.0) * dxinv[2] * vel(ci, cj, ck, 2));
+      // is this cell outside a Neumann / inflow side in direction d?
+      bool outd[3];
+      for (int d = 0; d < 3; ++d) outd[d] = (idx[d] == 0 && off[d] == 1 && bc.neu(d, -1)) || (idx[d] == n[d] && off[d] == 0 && bc.neu(d, 1));
+      for (int c = 0; c < 3; ++c) {
+        bool tang_hidden = false;
+        for (int d = 0; d < 3; ++d) if (d != c && outd[d]) tang_hidden = true;
+        if (tang_hidden) continue;
+        r += 0.25 * (off[c] ? -1.0 : 1.0) * dxinv[c] * vel(ci, cj, ck, c);
+      }
     }
-    rhs(i, j, k) = r;
+    double fac = 1.0;
+    for (int d = 0; d < 3; ++d) if ((idx[d] == 0 && bc.neu(d, -1)) || (idx[d] == n[d] && bc.neu(d, 1))) fac *= 2.0;
+    rhs(i, j, k) = fac * r;
   }
 }
 
@@ -443,37 +732,48 @@ struct NodeMG {
   struct Lev { int n[3]; double dxinv[3]; Arr sig, cor, res, rescor; };
   std::vector<Lev> lv;
   orc_mg mg;
-  NodeMG(const int n[3], const double dx[3], int max_coarsening) {
+  NodalBC bc;
+  NodeMG(const int n[3], const double dx[3], int max_coarsening, const NodalBC& bc_ = PERIODIC_NBC) : bc(bc_) {
     orc_mg_default(&mg);
     int cur[3] = {n[0], n[1], n[2]}; double h[3] = {dx[0], dx[1], dx[2]};
     for (int l = 0; l <= max_coarsening; ++l) {
       lv.emplace_back();
       Lev& L = lv.back();
       for (int d = 0; d < 3; ++d) { L.n[d] = cur[d]; L.dxinv[d] = 1.0 / h[d]; }
-      L.sig.define(cur, 1, 1); L.cor.define(cur, 1, 1); L.res.define(cur, 1, 1); L.rescor.define(cur, 1, 1);
+      L.sig.define(cur, 1, 1); L.cor.define(cur, 1, 2); L.res.define(cur, 1, 2); L.rescor.define(cur, 1, 2);
       bool ok = true;
       for (int d = 0; d < 3; ++d) if (cur[d] % 2 != 0 || cur[d] / 2 < 2) ok = false;
       if (!ok) break;
       for (int d = 0; d < 3; ++d) { cur[d] /= 2; h[d] *= 2.0; }
     }
   }
+  bool singular() const { for (int d = 0; d < 3; ++d) if (bc.dir(d, -1) || bc.dir(d, 1)) return false; return true; }
+  static double norminf_nodes(const Arr& a) {
+    double m = 0.0;
+    const int n0 = a.n[0] + hi_ext(0, 3), n1 = a.n[1] + hi_ext(1, 3), n2 = a.n[2] + hi_ext(2, 3);
+#pragma omp parallel for reduction(max : m)
+    for (int k = 0; k < n2; ++k) for (int j = 0; j < n1; ++j) for (int i = 0; i < n0; ++i)
+      m = std::max(m, std::fabs(a(i, j, k)));
+    return m;
+  }
   void set_sigma(const Arr& s) {
-    lv[0].sig.copy_from(s, 0, 0, 1); lv[0].sig.fill_periodic();
+    lv[0].sig.copy_from(s, 0, 0, 1); nodal_fill_sigma(lv[0].sig, bc);
     for (size_t l = 1; l < lv.size(); ++l) {  // coarse sigma = mean of the 8 children
       Arr& c = lv[l].sig; const Arr& f = lv[l - 1].sig;
       FOR_CELLS(c, i, j, k) {
         double t = 0; for (int dk = 0; dk < 2; ++dk) for (int dj = 0; dj < 2; ++dj) for (int di = 0; di < 2; ++di) t += f(2 * i + di, 2 * j + dj, 2 * k + dk);
         c(i, j, k) = 0.125 * t;
       }
-      c.fill_periodic();
+      nodal_fill_sigma(c, bc);
     }
   }
   void smooth(int l, Arr& phi, const Arr& rhs, int ns) {
-    for (int s = 0; s < ns; ++s) for (int c = 0; c < 8; ++c) nodal_gs(lv[l].dxinv, lv[l].sig, rhs, c, phi);
+    for (int s = 0; s < ns; ++s) for (int c = 0; c < 8; ++c) nodal_gs(lv[l].dxinv, lv[l].sig, rhs, c, phi, bc);
   }
   void residual(int l, Arr& out, Arr& phi, const Arr& rhs) {
-    nodal_adotx(lv[l].dxinv, lv[l].sig, phi, out);
-    FOR_CELLS(out, i, j, k) out(i, j, k) = rhs(i, j, k) - out(i, j, k);
+    nodal_adotx(lv[l].dxinv, lv[l].sig, phi, out, bc);
+    const int* n = out.n;
+    FOR_NODES(out, i, j, k) out(i, j, k) = nodal_masked(bc, n, i, j, k) ? 0.0 : rhs(i, j, k) - out(i, j, k);
   }
   void vcycle() {
     const int nl = (int)lv.size();
@@ -482,13 +782,14 @@ struct NodeMG {
       L.cor.setval(0.0);
       smooth(l, L.cor, L.res, mg.nu1);
       residual(l, L.rescor, L.cor, L.res);
-      L.rescor.fill_periodic();
+      nodal_fill_phi(L.rescor, bc);   // MLNodeLaplacian::restriction: applyBC on the fine residual (periodic images, Neumann reflection)
       Arr& cr = lv[l + 1].res; const Arr& fr = L.rescor;
-      FOR_CELLS(cr, i, j, k) {  // full weighting (1,2,1)^3 / 64
+      const int* cn = cr.n;
+      FOR_NODES(cr, i, j, k) {  // full weighting (1,2,1)^3 / 64
         double s = 0;
         for (int dk = -1; dk <= 1; ++dk) for (int dj = -1; dj <= 1; ++dj) for (int di = -1; di <= 1; ++di)
           s += (double)((di ? 1 : 2) * (dj ? 1 : 2) * (dk ? 1 : 2)) * fr(2 * i + di, 2 * j + dj, 2 * k + dk);
-        cr(i, j, k) = s / 64.0;
+        cr(i, j, k) = nodal_masked(bc, cn, i, j, k) ? 0.0 : s / 64.0;
       }
     }
     Lev& B = lv[nl - 1];
@@ -497,7 +798,9 @@ struct NodeMG {
     for (int l = nl - 2; l >= 0; --l) {
       Arr& fc = lv[l].cor; Arr& cc = lv[l + 1].cor;
       cc.fill_periodic();
-      FOR_CELLS(fc, i, j, k) {  // trilinear interpolation
+      const int* fn = fc.n;
+      FOR_NODES(fc, i, j, k) {  // trilinear interpolation (Dirichlet nodes stay zero)
+        if (nodal_masked(bc, fn, i, j, k)) continue;
         const int ic = i / 2, jc = j / 2, kc = k / 2, ox = i & 1, oy = j & 1, oz = k & 1;
         double s = 0;
         for (int dk = 0; dk <= oz; ++dk) for (int dj = 0; dj <= oy; ++dj) for (int di = 0; di <= ox; ++di) s += cc(ic + di, jc + dj, kc + dk);
@@ -507,14 +810,22 @@ struct NodeMG {
     }
   }
   int solve(Arr& phi, Arr& rhs) {
-    {  // periodic => singular: remove the mean of the rhs
-      const double mean = rhs.sum(0) / (double)rhs.ncells();
-      FOR_CELLS(rhs, i, j, k) rhs(i, j, k) -= mean;
+    const int* n = lv[0].n;
+    if (singular()) {  // periodic / Neumann everywhere: make the rhs solvable (getSolvabilityOffset / fixSolvabilityByOffset:
+      double s1 = 0.0, s2 = 0.0;   // mean weighted with the dot mask, 1/2 per Neumann side, subtracted from every row)
+      const int n0 = n[0] + hi_ext(0, 3), n1 = n[1] + hi_ext(1, 3), n2 = n[2] + hi_ext(2, 3);
+#pragma omp parallel for reduction(+ : s1, s2)
+      for (int k = 0; k < n2; ++k) for (int j = 0; j < n1; ++j) for (int i = 0; i < n0; ++i) {
+        const double w = nodal_weight(bc, n, i, j, k);
+        s1 += w * rhs(i, j, k); s2 += w;
+      }
+      const double mean = s1 / s2;
+      FOR_NODES(rhs, i, j, k) rhs(i, j, k) -= mean;
     }
-    const double rhsnorm = rhs.norminf(0);
+    const double rhsnorm = norminf_nodes(rhs);
     Arr& res = lv[0].res;
     residual(0, res, phi, rhs);
-    const double r0 = res.norminf(0);
+    const double r0 = norminf_nodes(res);
     const double target = std::max(mg.atol, mg.rtol * std::max(rhsnorm, r0));
     double r = r0; int it = 0; int rc = 0;
     if (!(r0 <= target)) {
@@ -522,13 +833,13 @@ struct NodeMG {
       for (it = 1; it <= mg.max_iter; ++it) {
         vcycle();
         Arr& cor = lv[0].cor;
-        FOR_CELLS(phi, i, j, k) phi(i, j, k) += cor(i, j, k);
+        FOR_NODES(phi, i, j, k) phi(i, j, k) += cor(i, j, k);
         residual(0, res, phi, rhs);
-        r = res.norminf(0);
+        r = norminf_nodes(res);
         if (r <= target) { rc = 0; break; }
       }
     }
-    phi.fill_periodic();
+    nodal_fill_phi(phi, bc);
     mg.iters = it; mg.resnorm0 = r0; mg.resnorm = r; mg.rhsnorm = rhsnorm;
     return rc;
   }
@@ -576,7 +887,9 @@ inline double riemann_self(double lo, double hi) {  // normal velocity upwinded 
     for (int j = -1; j <= (A).n[1]; ++j)                          \
       for (int i = -1; i <= (A).n[0]; ++i)
 
-struct AdvOpt { bool fit; bool ppm; };   // godunov.use_forces_in_trans, advection_scheme == Godunov_PPM (NSB.cpp:4485)
+// godunov.use_forces_in_trans, advection_scheme == Godunov_PPM (NSB.cpp:4485); bc = BCRec of every advected component
+// (null: interior / periodic everywhere), is_velocity as in the ComputeFluxesOnBoxFromState call (NSB.cpp:4701-4717)
+struct AdvOpt { bool fit; bool ppm; const BCRec* bc = nullptr; bool is_velocity = false; };
 
 // PPM (AMReX-Hydro hydro_godunov_ppm.H, van Leer limited edges + Colella-Woodward monotonisation): parabola of one cell from
 // the five values along the direction; Im / Ip are its averages over the domain of dependence of the lower / upper face
@@ -605,15 +918,96 @@ inline double ppm_im(double s0, double sm, double sp, double v, double dtdx) {  
   return sm + 0.5 * sg * ((sp - sm) + (1.0 - (2.0 / 3.0) * sg) * s6);
 }
 
-void ppm_lohi(const Arr& q, int c, int d, double dtdx, const Arr* mac, const Arr* vcc, const Arr* f, int fc, bool fit, double dt,
-              Arr& lo, Arr& hi) {
-  Arr pm(q.n, 1, 1), pp(q.n, 1, 1);   // parabola edges of cells -1..n
+// ---- physical boundaries of the Godunov states (AMReX_Slopes_K.H amrex_calc_*slope_extdir, hydro_godunov_ppm.H SetXBCs,
+// hydro_bcs_K.H Set{X,Y,Z}EdgeBCs) ------------------------------------------------------------------------------------
+inline bool ed_or_ho(int code) { return code == BC_EXT_DIR || code == BC_HOEXTRAP; }
+inline double one_sided_lim(double dl2, double dr2, double val) {   // dl2, dr2 = 2 x the one-sided differences
+  const double lim = (dl2 * dr2 >= 0.0) ? std::min(std::fabs(dl2), std::fabs(dr2)) : 0.0;
+  return std::copysign(1.0, val) * std::min(lim, std::fabs(val));
+}
+// 4th-order limited slope of cell `idx` (0..nd-1 inside the domain) along a direction whose low / high side is an
+// ext_dir or hoextrap boundary: the ghost value sits ON the face, so the first cell uses the one-sided 4-point
+// difference and the second cell's formula takes that one-sided slope for its neighbour
+inline double slope_order4_bc(double qmm, double qm, double q0, double qp, double qpp, int idx, int nd, bool edlo, bool edhi) {
+  double dfm = limited2(qm - qmm, q0 - qm), dfp = limited2(qp - q0, qpp - qp);
+  const double dl = q0 - qm, dr = qp - q0, dc = 0.5 * (dl + dr);
+  const double lim = (dl * dr >= 0.0) ? 2.0 * std::min(std::fabs(dl), std::fabs(dr)) : 0.0;
+  auto combine = [&]() { return std::copysign(1.0, dc) * std::min(lim, std::fabs(4.0 / 3.0 * dc - 1.0 / 6.0 * (dfp + dfm))); };
+  double sl = combine();
+  if (edlo && idx == 0) sl = one_sided_lim(2.0 * (q0 - qm), 2.0 * (qp - q0), -16.0 / 15.0 * qm + 0.5 * q0 + 2.0 / 3.0 * qp - 0.1 * qpp);
+  else if (edlo && idx == 1) { dfm = one_sided_lim(2.0 * (qm - qmm), 2.0 * (q0 - qm), -16.0 / 15.0 * qmm + 0.5 * qm + 2.0 / 3.0 * q0 - 0.1 * qp); sl = combine(); }
+  if (edhi && idx == nd - 1) sl = one_sided_lim(2.0 * (q0 - qm), 2.0 * (qp - q0), 16.0 / 15.0 * qp - 0.5 * q0 - 2.0 / 3.0 * qm + 0.1 * qmm);
+  else if (edhi && idx == nd - 2) { dfp = one_sided_lim(2.0 * (qp - q0), 2.0 * (qpp - qp), 16.0 / 15.0 * qpp - 0.5 * qp - 2.0 / 3.0 * q0 + 0.1 * qm); sl = combine(); }
+  return sl;
+}
+inline double clampv(double v, double a, double b) { return std::min(std::max(v, std::min(a, b)), std::max(a, b)); }
+inline void ppm_monotone(double s0, double& sm, double& sp) {
+  if ((sp - s0) * (s0 - sm) <= 0.0) { sm = s0; sp = s0; }
+  else if (std::fabs(sp - s0) >= 2.0 * std::fabs(sm - s0)) sp = 3.0 * s0 - 2.0 * sm;
+  else if (std::fabs(sm - s0) >= 2.0 * std::fabs(sp - s0)) sm = 3.0 * s0 - 2.0 * sp;
+}
+inline void ppm_parabola_bc(double sm2, double sm1, double s0, double sp1, double sp2, int idx, int nd, bool edlo, bool edhi, double& sm, double& sp) {
+  ppm_parabola(sm2, sm1, s0, sp1, sp2, sm, sp);
+  if (edlo && idx == 0) { sp = clampv(-0.2 * sm1 + 0.75 * s0 + 0.5 * sp1 - 0.05 * sp2, sp1, s0); sm = sm1; }
+  else if (edlo && idx == 1) {
+    sm = clampv(-0.2 * sm2 + 0.75 * sm1 + 0.5 * s0 - 0.05 * sp1, s0, sm1);
+    sp = clampv(0.5 * (sp1 + s0) - (1.0 / 6.0) * (vanleer(sp1, sp2, s0) - vanleer(s0, sp1, sm1)), s0, sp1);
+    ppm_monotone(s0, sm, sp);
+  }
+  if (edhi && idx == nd - 1) { sm = clampv(-0.2 * sp1 + 0.75 * s0 + 0.5 * sm1 - 0.05 * sm2, sm1, s0); sp = sp1; }
+  else if (edhi && idx == nd - 2) {
+    sp = clampv(-0.2 * sp2 + 0.75 * sp1 + 0.5 * s0 - 0.05 * sm1, s0, sp1);
+    sm = clampv(0.5 * (s0 + sm1) - (1.0 / 6.0) * (vanleer(s0, sp1, sm1) - vanleer(sm1, s0, sm2)), s0, sm1);
+    ppm_monotone(s0, sm, sp);
+  }
+}
+// SetEdgeBCs on the pair (lo, hi) of the face with index f (0 = low domain face, nd = high domain face) along d;
+// qb / qa: the cell values below / above the face (the ghost value holds the face value at ext_dir sides)
+inline void edge_bcs(double& lo, double& hi, double qb, double qa, int f, int nd, int d, const BCRec& bc, bool normal_vel) {
+  if (g_per[d]) return;
+  if (f == 0) {
+    const int c = bc.lo[d];
+    if (c == BC_EXT_DIR) { lo = qb; if (normal_vel) hi = lo; }
+    else if (c == BC_FOEXTRAP || c == BC_HOEXTRAP || c == BC_REFLECT_EVEN) lo = hi;
+    else if (c == BC_REFLECT_ODD) { lo = 0.0; hi = 0.0; }
+  } else if (f == nd) {
+    const int c = bc.hi[d];
+    if (c == BC_EXT_DIR) { hi = qa; if (normal_vel) lo = hi; }
+    else if (c == BC_FOEXTRAP || c == BC_HOEXTRAP || c == BC_REFLECT_EVEN) hi = lo;
+    else if (c == BC_REFLECT_ODD) { lo = 0.0; hi = 0.0; }
+  }
+}
+// the outflow rule of the FINAL states: through a foextrap / hoextrap face nothing is advected into the domain
+inline void outflow_rule(double& lo, double& hi, int f, int nd, int d, const BCRec& bc, bool clip_lo, bool clip_hi) {
+  if (g_per[d]) return;
+  if (f == 0 && (bc.lo[d] == BC_FOEXTRAP || bc.lo[d] == BC_HOEXTRAP)) { if (clip_lo) hi = std::min(hi, 0.0); lo = hi; }
+  if (f == nd && (bc.hi[d] == BC_FOEXTRAP || bc.hi[d] == BC_HOEXTRAP)) { if (clip_hi) lo = std::max(lo, 0.0); hi = lo; }
+}
+inline int comp_of(int d, int i, int j, int k) { return d == 0 ? i : (d == 1 ? j : k); }
+
+// traced states on d-faces for component c: lo = Ip(cell below), hi = Im(cell above); PLM or PPM.
+// trace velocity: umac on the face (edge state) or the cell-centred normal velocity (vel prediction).
+void trace_lohi(bool ppm, const Arr& q, int c, int d, double dtdx, const Arr* mac, const Arr* vcc, const Arr* f, int fc, bool fit, double dt,
+                Arr& lo, Arr& hi, const BCRec* bc, bool normal_vel) {
+  const int nd = q.n[d];
+  const bool edlo = bc && !g_per[d] && ed_or_ho(bc->lo[d]), edhi = bc && !g_per[d] && ed_or_ho(bc->hi[d]);
+  Arr s(q.n, 1, 1), pm, pp;   // PLM slopes, or PPM parabola edges, of cells -1..n
+  if (ppm) { pm.define(q.n, 1, 1); pp.define(q.n, 1, 1); }
 #pragma omp parallel for
   for (int k = -1; k <= q.n[2]; ++k)
     for (int j = -1; j <= q.n[1]; ++j)
-      for (int i = -1; i <= q.n[0]; ++i)
-        ppm_parabola(q(i - 2 * e0(d), j - 2 * e1(d), k - 2 * e2(d), c), q(i - e0(d), j - e1(d), k - e2(d), c), q(i, j, k, c),
-                     q(i + e0(d), j + e1(d), k + e2(d), c), q(i + 2 * e0(d), j + 2 * e1(d), k + 2 * e2(d), c), pm(i, j, k), pp(i, j, k));
+      for (int i = -1; i <= q.n[0]; ++i) {
+        const double qmm = q(i - 2 * e0(d), j - 2 * e1(d), k - 2 * e2(d), c), qm = q(i - e0(d), j - e1(d), k - e2(d), c), q0 = q(i, j, k, c),
+                     qp = q(i + e0(d), j + e1(d), k + e2(d), c), qpp = q(i + 2 * e0(d), j + 2 * e1(d), k + 2 * e2(d), c);
+        const int idx = comp_of(d, i, j, k);
+        if (ppm) {
+          if (edlo || edhi) ppm_parabola_bc(qmm, qm, q0, qp, qpp, idx, nd, edlo, edhi, pm(i, j, k), pp(i, j, k));
+          else ppm_parabola(qmm, qm, q0, qp, qpp, pm(i, j, k), pp(i, j, k));
+        } else {
+          s(i, j, k) = (edlo || edhi) ? slope_order4_bc(qmm, qm, q0, qp, qpp, idx, nd, edlo, edhi) : slope_order4(qmm, qm, q0, qp, qpp);
+        }
+      }
+  // faces 0..n along d, -1..n in the transverse directions
 #pragma omp parallel for
   for (int k = -1 + e2(d); k <= q.n[2]; ++k)
     for (int j = -1 + e1(d); j <= q.n[1]; ++j)
@@ -622,44 +1016,24 @@ void ppm_lohi(const Arr& q, int c, int d, double dtdx, const Arr* mac, const Arr
     // trace velocities: the MAC velocity of THIS face for both sides (edge states), or each cell's own velocity (prediction)
     const double ul = mac ? (*mac)(i, j, k) : (*vcc)(im, jm, km, d);
     const double uh = mac ? (*mac)(i, j, k) : (*vcc)(i, j, k, d);
-    double l = ppm_ip(q(im, jm, km, c), pm(im, jm, km), pp(im, jm, km), ul, dtdx);
-    double h = ppm_im(q(i, j, k, c), pm(i, j, k), pp(i, j, k), uh, dtdx);
+    double l, h;
+    if (ppm) {
+      l = ppm_ip(q(im, jm, km, c), pm(im, jm, km), pp(im, jm, km), ul, dtdx);
+      h = ppm_im(q(i, j, k, c), pm(i, j, k), pp(i, j, k), uh, dtdx);
+    } else {
+      l = q(im, jm, km, c) + 0.5 * (1.0 - ul * dtdx) * s(im, jm, km);
+      h = q(i, j, k, c) + 0.5 * (-1.0 - uh * dtdx) * s(i, j, k);
+    }
     if (fit && f) { l += 0.5 * dt * (*f)(im, jm, km, fc); h += 0.5 * dt * (*f)(i, j, k, fc); }
-    lo(i, j, k) = l; hi(i, j, k) = h;
-  }
-}
-
-// PLM traced states on d-faces for component c: lo = Ip(cell below), hi = Im(cell above).
-// trace velocity: umac on the face (edge state) or the cell-centred normal velocity (vel prediction).
-void plm_lohi(const Arr& q, int c, int d, double dtdx, const Arr* mac, const Arr* vcc, const Arr* f, int fc, bool fit, double dt,
-              Arr& lo, Arr& hi) {
-  Arr s(q.n, 1, 1);
-  // slopes on cells -1..n (what the faces 0..n of direction d touch); needs q on -3..n+2
-#pragma omp parallel for
-  for (int k = -1; k <= q.n[2]; ++k)
-    for (int j = -1; j <= q.n[1]; ++j)
-      for (int i = -1; i <= q.n[0]; ++i)
-        s(i, j, k) = slope_order4(q(i - 2 * e0(d), j - 2 * e1(d), k - 2 * e2(d), c), q(i - e0(d), j - e1(d), k - e2(d), c), q(i, j, k, c),
-                                  q(i + e0(d), j + e1(d), k + e2(d), c), q(i + 2 * e0(d), j + 2 * e1(d), k + 2 * e2(d), c));
-  // faces 0..n along d, -1..n in the transverse directions
-#pragma omp parallel for
-  for (int k = -1 + e2(d); k <= q.n[2]; ++k)
-    for (int j = -1 + e1(d); j <= q.n[1]; ++j)
-      for (int i = -1 + e0(d); i <= q.n[0]; ++i) {
-    const int im = i - e0(d), jm = j - e1(d), km = k - e2(d);
-    const double ul = mac ? (*mac)(i, j, k) : (*vcc)(im, jm, km, d);
-    const double uh = mac ? (*mac)(i, j, k) : (*vcc)(i, j, k, d);
-    double l = q(im, jm, km, c) + 0.5 * (1.0 - ul * dtdx) * s(im, jm, km);
-    double h = q(i, j, k, c) + 0.5 * (-1.0 - uh * dtdx) * s(i, j, k);
-    if (fit && f) { l += 0.5 * dt * (*f)(im, jm, km, fc); h += 0.5 * dt * (*f)(i, j, k, fc); }
+    if (bc) edge_bcs(l, h, q(im, jm, km, c), q(i, j, k, c), comp_of(d, i, j, k), nd, d, *bc, normal_vel);
     lo(i, j, k) = l; hi(i, j, k) = h;
   }
 }
 
 // Godunov_corner_couple_<d1><d2>: d1-face lo/hi states corrected with the d2-derivative of the
-// (already upwinded) d2-edge state, then upwinded with the d1 face velocity
+// (already upwinded) d2-edge state, boundary conditions of the d1-face re-imposed, then upwinded with the d1 face velocity
 void corner_couple(const Arr& lo, const Arr& hi, int d1, int d2, double dt3dx, bool conserv, const Arr& q, int c, const Arr& mac2,
-                   const Arr& edge2, const Arr& mac1, Arr& out) {
+                   const Arr& edge2, const Arr& mac1, Arr& out, const BCRec* bc = nullptr, bool normal_vel = false) {
   const int n0 = q.n[0], n1 = q.n[1], n2 = q.n[2];
 #pragma omp parallel for
   for (int k = -1 + e2(d2); k <= n2 - e2(d2); ++k)
@@ -674,20 +1048,22 @@ void corner_couple(const Arr& lo, const Arr& hi, int d1, int d2, double dt3dx, b
           l += dt3dx * q(im, jm, km, c) * (mac2(im + ip, jm + jp, km + kp) - mac2(im, jm, km));
           h += dt3dx * q(i, j, k, c) * (mac2(i + ip, j + jp, k + kp) - mac2(i, j, k));
         }
+        if (bc) edge_bcs(l, h, q(im, jm, km, c), q(i, j, k, c), comp_of(d1, i, j, k), q.n[d1], d1, *bc, normal_vel);
         out(i, j, k) = upwind_by(l, h, mac1(i, j, k));
       }
 }
 
 // HydroUtils::ComputeFluxesOnBoxFromState -> Godunov::ComputeEdgeState for one component:
-// fills the final edge states edge[d] (1 comp) on the low faces of every cell
+// fills the final edge states edge[d] (1 comp) on the low faces of every cell (and the high domain face when not periodic)
 void edge_state_comp(const Arr& q, int c, const Arr* f, int fc, const Arr* divu, const Arr* mac[3], bool conserv, AdvOpt opt,
                      const double dx[3], double dt, Arr* edge[3]) {
   const bool fit = opt.fit;
   const int* n = q.n;
+  const BCRec* bc = opt.bc ? &opt.bc[c] : nullptr;
   Arr lo[3], hi[3], ed[3];
   for (int d = 0; d < 3; ++d) {
     lo[d].define(n, 1, 2); hi[d].define(n, 1, 2); ed[d].define(n, 1, 2);
-    (opt.ppm ? ppm_lohi : plm_lohi)(q, c, d, dt / dx[d], mac[d], nullptr, f, fc, fit, dt, lo[d], hi[d]);
+    trace_lohi(opt.ppm, q, c, d, dt / dx[d], mac[d], nullptr, f, fc, fit, dt, lo[d], hi[d], bc, opt.is_velocity && c == d);
     Arr& E = ed[d]; const Arr& M = *mac[d]; const Arr &L = lo[d], &H = hi[d];
     FOR_G1(E, i, j, k) E(i, j, k) = upwind_by(L(i, j, k), H(i, j, k), M(i, j, k));
   }
@@ -697,15 +1073,16 @@ void edge_state_comp(const Arr& q, int c, const Arr* f, int fc, const Arr* divu,
     for (int d2 = 0; d2 < 3; ++d2) {
       if (d1 == d2) continue;
       cc[d1][d2].define(n, 1, 2);
-      corner_couple(lo[d1], hi[d1], d1, d2, dt / (3.0 * dx[d2]), conserv, q, c, *mac[d2], ed[d2], *mac[d1], cc[d1][d2]);
+      corner_couple(lo[d1], hi[d1], d1, d2, dt / (3.0 * dx[d2]), conserv, q, c, *mac[d2], ed[d2], *mac[d1], cc[d1][d2], bc, opt.is_velocity && c == d1);
     }
   for (int d = 0; d < 3; ++d) {
     const int t1 = (d == 0) ? 1 : 0, t2 = (d == 2) ? 1 : 2;  // the two transverse directions
     // transverse d/dt1 uses the t1-face state that was corrected by the t2 derivative, and vice versa
     const Arr &A1 = cc[t1][t2], &A2 = cc[t2][t1], &M1 = *mac[t1], &M2 = *mac[t2], &M = *mac[d];
     const double dtd1 = dt / dx[t1], dtd2 = dt / dx[t2];
+    const bool nv = opt.is_velocity && c == d;
     Arr& E = *edge[d];
-    FOR_CELLS(E, i, j, k) {
+    FOR_FACES(E, d, i, j, k) {
       double st[2];
       for (int side = 0; side < 2; ++side) {  // 0: from the cell below (stl), 1: from the cell above (sth)
         const int ci = i - (side == 0 ? e0(d) : 0), cj = j - (side == 0 ? e1(d) : 0), ck = k - (side == 0 ? e2(d) : 0);
@@ -723,6 +1100,11 @@ void edge_state_comp(const Arr& q, int c, const Arr* f, int fc, const Arr* divu,
         }
         if (!fit && f) s += 0.5 * dt * (*f)(ci, cj, ck, fc);
         st[side] = s;
+      }
+      if (bc) {
+        const int fidx = comp_of(d, i, j, k);
+        edge_bcs(st[0], st[1], q(i - e0(d), j - e1(d), k - e2(d), c), q(i, j, k, c), fidx, n[d], d, *bc, nv);
+        outflow_rule(st[0], st[1], fidx, n[d], d, *bc, nv && M(i, j, k) >= 0.0, nv && M(i, j, k) <= 0.0);
       }
       E(i, j, k) = upwind_by(st[0], st[1], M(i, j, k));
     }
@@ -742,12 +1124,12 @@ void compute_aofs(const Arr& S, int ncomp, const Arr* force, const Arr* divu, Ar
   for (int c = 0; c < ncomp; ++c) {
     Arr ed[3] = {Arr(n, 1, 1), Arr(n, 1, 1), Arr(n, 1, 1)};
     Arr* edp[3] = {&ed[0], &ed[1], &ed[2]};
-    if (known) { for (int d = 0; d < 3; ++d) ed[d].copy_from(*eds[d], c, 0, 1); }
+    if (known) { for (int d = 0; d < 3; ++d) { Arr& E = ed[d]; const Arr& K = *eds[d]; FOR_FACES(E, d, i, j, k) E(i, j, k) = K(i, j, k, c); } }
     else edge_state_comp(S, c, force, c, divu, macp, iconserv[c] != 0, fit, dx, dt, edp);
     Arr fx[3] = {Arr(n, 1, 1), Arr(n, 1, 1), Arr(n, 1, 1)};
     for (int d = 0; d < 3; ++d) {
       Arr& F = fx[d]; const Arr& E = ed[d]; const Arr& M = uflux ? uflux[d] : mac[d];
-      FOR_CELLS(F, i, j, k) F(i, j, k) = E(i, j, k) * M(i, j, k) * area[d];  // HydroUtils::ComputeFluxes, area-weighted (NSB.cpp:4651)
+      FOR_FACES(F, d, i, j, k) F(i, j, k) = E(i, j, k) * M(i, j, k) * area[d];  // HydroUtils::ComputeFluxes, area-weighted (NSB.cpp:4651)
       F.fill_periodic(); ed[d].fill_periodic();
     }
     const bool cons = iconserv[c] != 0;
@@ -764,22 +1146,22 @@ void compute_aofs(const Arr& S, int ncomp, const Arr* force, const Arr* divu, Ar
       else aofs(i, j, k, acomp + c) = -upd;            // NSB.cpp:4840
     }
     for (int d = 0; d < 3; ++d) {
-      if (fl && fl[d]) fl[d]->copy_from(fx[d], 0, c, 1);
-      if (eds && eds[d] && !known) eds[d]->copy_from(ed[d], 0, c, 1);
+      if (fl && fl[d]) { Arr& O = *fl[d]; const Arr& F = fx[d]; FOR_FACES(O, d, i, j, k) O(i, j, k, c) = F(i, j, k); }
+      if (eds && eds[d] && !known) { Arr& O = *eds[d]; const Arr& E = ed[d]; FOR_FACES(O, d, i, j, k) O(i, j, k, c) = E(i, j, k); }
     }
   }
 }
 
-// Godunov::ExtrapVelToFaces (hydro_godunov_extrap_vel_to_faces_3D.cpp), PLM, periodic
+// Godunov::ExtrapVelToFaces (hydro_godunov_extrap_vel_to_faces_3D.cpp), PLM or PPM
 void extrap_vel_to_faces(const Arr& vel, const Arr* f, AdvOpt opt, const double dx[3], double dt, Arr umac[3]) {
   const bool fit = opt.fit;
   const int* n = vel.n;
-  // traced states of every component on every face direction
+  // traced states of every component on every face direction (boundary conditions applied: is_velocity = true)
   Arr lo[3][3], hi[3][3];  // [dir][comp]
   for (int d = 0; d < 3; ++d)
     for (int c = 0; c < 3; ++c) {
       lo[d][c].define(n, 1, 2); hi[d][c].define(n, 1, 2);
-      (opt.ppm ? ppm_lohi : plm_lohi)(vel, c, d, dt / dx[d], nullptr, &vel, f, c, fit, dt, lo[d][c], hi[d][c]);
+      trace_lohi(opt.ppm, vel, c, d, dt / dx[d], nullptr, &vel, f, c, fit, dt, lo[d][c], hi[d][c], opt.bc ? &opt.bc[c] : nullptr, c == d);
     }
   // advective velocities (ComputeAdvectiveVel) and transverse edge states upwinded by them
   Arr ad[3], ed[3][3];
@@ -795,13 +1177,14 @@ void extrap_vel_to_faces(const Arr& vel, const Arr* f, AdvOpt opt, const double 
   }
   for (int d = 0; d < 3; ++d) {
     const int t1 = (d == 0) ? 1 : 0, t2 = (d == 2) ? 1 : 2;
+    const BCRec* bcd = opt.bc ? &opt.bc[d] : nullptr;
     Arr a1(n, 1, 2), a2(n, 1, 2);  // t1-face state of comp d corrected by t2, and t2-face state corrected by t1
-    corner_couple(lo[t1][d], hi[t1][d], t1, t2, dt / (3.0 * dx[t2]), false, vel, d, ad[t2], ed[t2][d], ad[t1], a1);
-    corner_couple(lo[t2][d], hi[t2][d], t2, t1, dt / (3.0 * dx[t1]), false, vel, d, ad[t1], ed[t1][d], ad[t2], a2);
+    corner_couple(lo[t1][d], hi[t1][d], t1, t2, dt / (3.0 * dx[t2]), false, vel, d, ad[t2], ed[t2][d], ad[t1], a1, bcd, false);
+    corner_couple(lo[t2][d], hi[t2][d], t2, t1, dt / (3.0 * dx[t1]), false, vel, d, ad[t1], ed[t1][d], ad[t2], a2, bcd, false);
     const double dtd1 = dt / dx[t1], dtd2 = dt / dx[t2];
     const Arr &M1 = ad[t1], &M2 = ad[t2];
     Arr& U = umac[d];
-    FOR_CELLS(U, i, j, k) {
+    FOR_FACES(U, d, i, j, k) {
       double st[2];
       for (int side = 0; side < 2; ++side) {
         const int ci = i - (side == 0 ? e0(d) : 0), cj = j - (side == 0 ? e1(d) : 0), ck = k - (side == 0 ? e2(d) : 0);
@@ -811,6 +1194,11 @@ void extrap_vel_to_faces(const Arr& vel, const Arr* f, AdvOpt opt, const double 
              - (0.25 * dtd2) * (M2(i2, j2, k2) + M2(ci, cj, ck)) * (a2(i2, j2, k2) - a2(ci, cj, ck));
         if (!fit && f) s += 0.5 * dt * (*f)(ci, cj, ck, d);
         st[side] = s;
+      }
+      if (bcd) {
+        const int fidx = comp_of(d, i, j, k);
+        edge_bcs(st[0], st[1], vel(i - e0(d), j - e1(d), k - e2(d), d), vel(i, j, k, d), fidx, n[d], d, *bcd, true);
+        outflow_rule(st[0], st[1], fidx, n[d], d, *bcd, true, true);
       }
       U(i, j, k) = riemann_self(st[0], st[1]);
     }
