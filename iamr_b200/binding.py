@@ -80,8 +80,27 @@ class MGInfo(C.Structure):
     _fields_ = [("rtol", C.c_double), ("atol", C.c_double), ("max_iter", C.c_int),
                 ("max_coarsening", C.c_int), ("nu1", C.c_int), ("nu2", C.c_int),
                 ("bottom_sweeps", C.c_int), ("verbose", C.c_int), ("omega", C.c_double),
-                ("iters", C.c_int), ("pad_", C.c_int), ("resnorm0", C.c_double),
+                ("iters", C.c_int), ("maxorder", C.c_int), ("resnorm0", C.c_double),
                 ("resnorm", C.c_double), ("rhsnorm", C.c_double)]
+
+
+class LinopBC(C.Structure):
+    """iamrx_linop_bc: LinOpBCType [comp][dir] of the low / high sides + maxorder."""
+    _fields_ = [("lo", (C.c_int * 3) * 3), ("hi", (C.c_int * 3) * 3), ("maxorder", C.c_int), ("pad_", C.c_int)]
+
+    @staticmethod
+    def make(lo, hi, maxorder=2):
+        b = LinopBC()
+        for c in range(3):
+            cs = c if c < len(lo) else 0
+            for d in range(3):
+                b.lo[c][d] = int(lo[cs][d])
+                b.hi[c][d] = int(hi[cs][d])
+        b.maxorder = maxorder
+        return b
+
+
+LINOP_PERIODIC, LINOP_DIRICHLET, LINOP_NEUMANN, LINOP_REFLECT_ODD, LINOP_INFLOW = 0, 1, 2, 3, 4
 
 
 class NSParams(C.Structure):
@@ -144,6 +163,7 @@ SIGNATURES = {
     "iamrx_level_num_local": (C.c_int, [_vp]),
     "iamrx_level_local_box": (C.c_int, [_vp, C.c_int, _P(Box), _P(C.c_int)]),
     "iamrx_fill_boundary": (C.c_int, [_vp, _P(Fab), C.c_int, C.c_int, C.c_int, _vp]),
+    "iamrx_fill_physbc": (C.c_int, [_vp, _P(Fab), C.c_int, C.c_int, _P(BCRec), _P(C.c_double), _vp]),
     "iamrx_mg_info_default": (None, [_P(MGInfo)]),
     "iamrx_mac_project": (C.c_int, [_vp, _P(Fab), _P(Fab), _P(Fab), _P(Fab), _P(Fab), _P(Fab), C.c_double,
                                     _P(C.c_int), _P(C.c_int), _P(MGInfo), _vp]),
@@ -151,9 +171,9 @@ SIGNATURES = {
     "iamrx_nodal_project": (C.c_int, [_vp, _P(Fab), _P(Fab), _P(Fab), _P(Fab), C.c_int, _P(C.c_int), _P(C.c_int),
                                       _P(MGInfo), _vp]),
     "iamrx_diffusion_apply": (C.c_int, [_vp, C.c_int, C.c_int, _P(Fab), _P(Fab), C.c_double, C.c_double, _P(Fab),
-                                        _P(Fab), _P(Fab), _P(Fab), _vp]),
+                                        _P(Fab), _P(Fab), _P(Fab), _P(LinopBC), _vp]),
     "iamrx_diffusion_solve": (C.c_int, [_vp, C.c_int, C.c_int, _P(Fab), _P(Fab), C.c_double, C.c_double, _P(Fab),
-                                        _P(Fab), _P(Fab), _P(Fab), _P(MGInfo), _vp]),
+                                        _P(Fab), _P(Fab), _P(Fab), _P(LinopBC), _P(MGInfo), _vp]),
     "iamrx_ns_params_default": (None, [_P(NSParams)]),
     "iamrx_ns_create": (C.c_int, [_vp, _P(NSParams), _P(_vp)]),
     "iamrx_ns_destroy": (C.c_int, [_vp]),

@@ -43,9 +43,12 @@ inline AbecDev to_dev(const Abec& op) {
 constexpr int GS_TX = 64;
 constexpr int GS_TY = 4;
 
-template <int MINB>
+// HASBC: the box touches a non-periodic domain face.  The ghost cell behind such a face is a linear function of the interior
+// cells (MLCellLinOp::applyBC); f0 is the coefficient of the adjacent cell, and the smoother removes that self-dependence
+// from the diagonal (the delta of AMReX's abec_gsrb: phi += omega/(gamma - delta) * res).
+template <int MINB, bool HASBC>
 __global__ void __launch_bounds__(GS_TX* GS_TY, MINB)
-gsrb_kernel(Bx bx, V4 phi, C4 rhs, IX_KARG(AbecDev) op, double omega, int redblack, int nz, int wm) {
+gsrb_kernel(Bx bx, V4 phi, C4 rhs, IX_KARG(AbecDev) op, double omega, int redblack, int nz, int wm, IX_KARG(GsBC) gb) {
   const int kz = blockIdx.z % nz;
   const int n = blockIdx.z / nz;
   const int k = bx.lo[2] + kz;
@@ -77,7 +80,19 @@ gsrb_kernel(Bx bx, V4 phi, C4 rhs, IX_KARG(AbecDev) op, double omega, int redbla
                      op.dhy * (bym * pc[oym] + byp * pc[oyp]) +
                      op.dhz * (bzm * pc[ozm] + bzp * pc[ozp]);
   const double res = rhs(i, j, k, n) - (gamma * p0 - rho);
-  pc[0] = p0 + omega / gamma * res;
+  if (HASBC) {
+    const int nc = n < 3 ? n : 0;
+    double delta = 0.0;
+    if (i == bx.lo[0]) delta += op.dhx * bxm * gb.f0[nc][0];
+    if (i == bx.hi[0]) delta += op.dhx * bxp * gb.f0[nc][1];
+    if (j == bx.lo[1]) delta += op.dhy * bym * gb.f0[nc][2];
+    if (j == bx.hi[1]) delta += op.dhy * byp * gb.f0[nc][3];
+    if (k == bx.lo[2]) delta += op.dhz * bzm * gb.f0[nc][4];
+    if (k == bx.hi[2]) delta += op.dhz * bzp * gb.f0[nc][5];
+    pc[0] = p0 + omega / (gamma - delta) * res;
+  } else {
+    pc[0] = p0 + omega / gamma * res;
+  }
 }
 
 // ---- apply / residual ----------------------------------------------------
@@ -328,6 +343,56 @@ tensor_cross_kernel(Bx bx, V4 out, C4 vel, C4 ex, C4 ey, C4 ez, double b, double
   for (int n = 0; n < 3; ++n) out(i, j, k, n) += b * acc[n];
 }
 
+// tensor cross terms on a box that touches non-periodic domain faces (mltensor_cross_terms_f? with bct / bv?lo / bv?hi): ON such
+// a face the transverse derivative of component c comes from the boundary data -- Dirichlet: centred difference of the face
+// values (ghost cells of the level-BC fab bv; zero when homogeneous), Neumann: centred difference of the interior cell row,
+// reflect_odd: zero -- instead of the two-sided mean.
+struct CrossBC { int lo[3][3], hi[3][3]; int dlo[3], dhi[3]; int per[3]; };
+template <int D, int T>
+IX_D double d_on_face(const C4& vel, const C4& bv, const CrossBC& cb, int c, int i, int j, int k, double dti) {
+  const int q[3] = {i, j, k};
+  auto V = [&](const C4& A, int oD, int oT) {
+    return A(i + oD * (D == 0) + oT * (T == 0), j + oD * (D == 1) + oT * (T == 1), k + oD * (D == 2) + oT * (T == 2), c);
+  };
+  if (!cb.per[D] && (q[D] == cb.dlo[D] || q[D] == cb.dhi[D] + 1)) {
+    const bool low = q[D] == cb.dlo[D];
+    const int code = low ? cb.lo[c][D] : cb.hi[c][D];
+    const int og = low ? -1 : 0, oi = low ? 0 : -1;
+    if (code == IAMRX_LINOP_DIRICHLET) return bv.ok() ? (V(bv, og, 1) - V(bv, og, -1)) * (0.5 * dti) : 0.0;
+    if (code == IAMRX_LINOP_NEUMANN) return (V(vel, oi, 1) - V(vel, oi, -1)) * (0.5 * dti);
+    return 0.0;
+  }
+  return (V(vel, 0, 1) + V(vel, -1, 1) - V(vel, 0, -1) - V(vel, -1, -1)) * (0.25 * dti);
+}
+// cross flux of the D-face whose upper cell is (i,j,k): f[D] = (2/3) eta (d u_t1/d t1 + d u_t2/d t2), f[t] = -eta d u_D/d t
+template <int D>
+IX_D void cross_flux_bc(const C4& vel, const C4& bv, const C4& eta, const CrossBC& cb, int i, int j, int k, const double dxi[3], double f[3]) {
+  constexpr int T1 = (D + 1) % 3, T2 = (D + 2) % 3;
+  const double mu = eta(i, j, k);
+  f[D] = -mu * (-(2.0 / 3.0) * (d_on_face<D, T1>(vel, bv, cb, T1, i, j, k, dxi[T1]) + d_on_face<D, T2>(vel, bv, cb, T2, i, j, k, dxi[T2])));
+  f[T1] = -mu * d_on_face<D, T1>(vel, bv, cb, D, i, j, k, dxi[T1]);
+  f[T2] = -mu * d_on_face<D, T2>(vel, bv, cb, D, i, j, k, dxi[T2]);
+}
+__global__ void __launch_bounds__(AP_TX* AP_TY)
+tensor_cross_bc_kernel(Bx bx, V4 out, C4 vel, C4 bv, C4 ex, C4 ey, C4 ez, double b, double dxi0, double dxi1, double dxi2, IX_KARG(CrossBC) cb) {
+  const int k = bx.lo[2] + blockIdx.z;
+  const int j = bx.lo[1] + blockIdx.y * AP_TY + threadIdx.y;
+  const int i = bx.lo[0] + blockIdx.x * AP_TX + threadIdx.x;
+  if (j > bx.hi[1] || i > bx.hi[0]) return;
+  const double dxi[3] = {dxi0, dxi1, dxi2};
+  double fl[3], fh[3], acc[3];
+  cross_flux_bc<0>(vel, bv, ex, cb, i, j, k, dxi, fl);
+  cross_flux_bc<0>(vel, bv, ex, cb, i + 1, j, k, dxi, fh);
+  for (int n = 0; n < 3; ++n) acc[n] = dxi0 * (fh[n] - fl[n]);
+  cross_flux_bc<1>(vel, bv, ey, cb, i, j, k, dxi, fl);
+  cross_flux_bc<1>(vel, bv, ey, cb, i, j + 1, k, dxi, fh);
+  for (int n = 0; n < 3; ++n) acc[n] += dxi1 * (fh[n] - fl[n]);
+  cross_flux_bc<2>(vel, bv, ez, cb, i, j, k, dxi, fl);
+  cross_flux_bc<2>(vel, bv, ez, cb, i, j, k + 1, dxi, fh);
+  for (int n = 0; n < 3; ++n) acc[n] += dxi2 * (fh[n] - fl[n]);
+  for (int n = 0; n < 3; ++n) out(i, j, k, n) += b * acc[n];
+}
+
 #if !defined(IX_EMUL)
 // ---- fused red+black GSRB sweep (box spans the periodic domain) ------------------------------
 // One launch = one full sweep (colour `rb0` then the other), phi_in -> phi_out.  A CTA owns an xy tile
@@ -565,15 +630,17 @@ inline dim3 grid_for(const Bx& bx, int tx, int ty, int nz_total) {
 }  // namespace
 
 int abec_gsrb(const Bx& bx, V4 phi, C4 rhs, const Abec& op, double omega, int redblack, int ncomp,
-              cudaStream_t s, int wrapmask) {
+              cudaStream_t s, int wrapmask, const GsBC* gb) {
   if (!bx.ok()) return IAMRX_OK;
   ProfScope prof_(IAMRX_PROF_ABEC_GSRB, bx.npts(), (double)bx.npts() * ncomp * (op.a != 0.0 ? 56.0 : 48.0), s);
   dim3 blk(GS_TX, GS_TY, 1);
   dim3 grd(cdiv(bx.nx() + 1, 2 * GS_TX), cdiv(bx.ny(), GS_TY), bx.nz() * ncomp);
   static int minb = -1;
   if (minb < 0) { const char* e = getenv("IAMRX_GSRB_MINB"); minb = e ? atoi(e) : 6; }
-  if (minb >= 8) IX_LAUNCH(gsrb_kernel<8>, grd, blk, 0, s, bx, phi, rhs, to_dev(op), omega, redblack, bx.nz(), wrapmask);
-  else IX_LAUNCH(gsrb_kernel<6>, grd, blk, 0, s, bx, phi, rhs, to_dev(op), omega, redblack, bx.nz(), wrapmask);
+  const GsBC none{};
+  if (gb) IX_LAUNCH((gsrb_kernel<6, true>), grd, blk, 0, s, bx, phi, rhs, to_dev(op), omega, redblack, bx.nz(), wrapmask, *gb);
+  else if (minb >= 8) IX_LAUNCH((gsrb_kernel<8, false>), grd, blk, 0, s, bx, phi, rhs, to_dev(op), omega, redblack, bx.nz(), wrapmask, none);
+  else IX_LAUNCH((gsrb_kernel<6, false>), grd, blk, 0, s, bx, phi, rhs, to_dev(op), omega, redblack, bx.nz(), wrapmask, none);
   return check_launch("abec_gsrb");
 }
 
@@ -711,6 +778,20 @@ int mac_update(const Bx& bx, V4 u, V4 v, V4 w, C4 phi, const Abec& op, cudaStrea
   IX_LAUNCH(mac_update_kernel, grid_for(g, AP_TX, AP_TY, g.nz()), dim3(AP_TX, AP_TY, 1), 0, s, 
       bx, u, v, w, phi, to_dev(op), op.b * op.dxinv[0], op.b * op.dxinv[1], op.b * op.dxinv[2]);
   return check_launch("mac_update");
+}
+
+int tensor_cross_bc(const Bx& bx, V4 out, C4 vel, C4 bv, C4 ex, C4 ey, C4 ez, double b, const double dxinv[3], const LinBC& bc,
+                    const Bx& dom, const int per[3], cudaStream_t s) {
+  if (!bx.ok()) return IAMRX_OK;
+  bool touches = false;
+  for (int d = 0; d < 3; ++d) if (!per[d] && (bx.lo[d] == dom.lo[d] || bx.hi[d] == dom.hi[d])) touches = true;
+  if (!touches) return tensor_cross(bx, out, vel, ex, ey, ez, b, dxinv, s);
+  CrossBC cb;
+  for (int c = 0; c < 3; ++c) for (int d = 0; d < 3; ++d) { cb.lo[c][d] = bc.lo[c][d]; cb.hi[c][d] = bc.hi[c][d]; }
+  for (int d = 0; d < 3; ++d) { cb.dlo[d] = dom.lo[d]; cb.dhi[d] = dom.hi[d]; cb.per[d] = per[d]; }
+  IX_LAUNCH(tensor_cross_bc_kernel, grid_for(bx, AP_TX, AP_TY, bx.nz()), dim3(AP_TX, AP_TY, 1), 0, s,
+      bx, out, vel, bv, ex, ey, ez, b, dxinv[0], dxinv[1], dxinv[2], cb);
+  return check_launch("tensor_cross_bc");
 }
 
 int tensor_cross(const Bx& bx, V4 out, C4 vel, C4 ex, C4 ey, C4 ez, double b, const double dxinv[3],

@@ -349,6 +349,21 @@ int iamrx_fill_boundary(iamrx_level_t lev, iamrx_fab* fabs, int ixtype, int ncom
   IX_GUARD_END
 }
 
+int iamrx_fill_physbc(iamrx_level_t lev, iamrx_fab* fabs, int ncomp, int ngrow, const iamrx_bcrec* bcrec, const double* bcvals,
+                      void* stream) {
+  IX_GUARD_BEGIN
+  IX_NEED_DEVICE();
+  IX_ARG(lev && fabs && bcrec && ncomp >= 1 && ncomp <= 8 && ngrow >= 0, "fill_physbc arguments");
+  IX_ARG(bc_codes_ok(bcrec, ncomp), "unknown BCRec code");
+  k::PhysBC bc{};
+  for (int n = 0; n < ncomp; ++n)
+    for (int d = 0; d < 3; ++d) { bc.lo[n][d] = bcrec[n].lo[d]; bc.hi[n][d] = bcrec[n].hi[d]; }
+  if (bcvals) for (int f = 0; f < 6; ++f) for (int n = 0; n < ncomp; ++n) bc.val[f][n] = bcvals[f * ncomp + n];
+  MF m; m.alias(lev->lev.get(), IX_CELL, ncomp, ngrow, fabs);
+  return mf_fill_physbc(m, 0, ncomp, ngrow, bc, S(stream));
+  IX_GUARD_END
+}
+
 void iamrx_mg_info_default(iamrx_mg_info* info) {
   if (!info) return;
   memset(info, 0, sizeof(*info));
@@ -359,18 +374,46 @@ void iamrx_mg_info_default(iamrx_mg_info* info) {
   info->nu1 = 2; info->nu2 = 2;
   info->bottom_sweeps = 8;
   info->verbose = 0;
+  info->maxorder = 3;   // MLLinOp default; IAMR sets 4 for the MAC solve, 2 for diffusion
   info->omega = 1.15;   // AMReX abec_gsrb over-relaxation (AMReX_MLABecLap_3D_K.H); the UNVERIFIED-UPSTREAM table in DESIGN.md
 }
 
-static int check_periodic_bc(const Level& L, const int lobc[3], const int hibc[3]) {
+// lobc / hibc of a scalar operator -> LinBC; periodic directions must be declared periodic and vice versa
+static int make_linbc(const Level& L, const int lobc[3], const int hibc[3], int maxorder, bool nodal, k::LinBC* out) {
+  k::LinBC b = periodic_linbc();
+  b.maxorder = maxorder > 0 ? maxorder : 3;
   for (int d = 0; d < 3; ++d) {
     const int lo = lobc ? lobc[d] : IAMRX_LINOP_PERIODIC, hi = hibc ? hibc[d] : IAMRX_LINOP_PERIODIC;
     if (L.geom.periodic[d]) {
       IX_ARG(lo == IAMRX_LINOP_PERIODIC && hi == IAMRX_LINOP_PERIODIC, "periodic direction needs periodic BC");
     } else {
-      IX_ARG(false, "only periodic domain boundaries are implemented in this round");
+      for (int v : {lo, hi}) {
+        IX_ARG(v == IAMRX_LINOP_DIRICHLET || v == IAMRX_LINOP_NEUMANN || (!nodal && v == IAMRX_LINOP_REFLECT_ODD) || (nodal && v == IAMRX_LINOP_INFLOW),
+               "non-periodic direction needs Dirichlet / Neumann (cell: reflect_odd, nodal: inflow) boundary conditions");
+      }
+    }
+    for (int c = 0; c < 3; ++c) { b.lo[c][d] = lo; b.hi[c][d] = hi; }
+  }
+  *out = b;
+  return IAMRX_OK;
+}
+static int make_linbc3(const Level& L, const iamrx_linop_bc* bc, int ncomp, k::LinBC* out) {
+  k::LinBC b = periodic_linbc();
+  if (bc) {
+    b.maxorder = bc->maxorder > 0 ? bc->maxorder : 2;
+    for (int c = 0; c < 3; ++c) {
+      const int cs = c < ncomp ? c : 0;
+      for (int d = 0; d < 3; ++d) { b.lo[c][d] = bc->lo[cs][d]; b.hi[c][d] = bc->hi[cs][d]; }
     }
   }
+  for (int c = 0; c < ncomp && c < 3; ++c)
+    for (int d = 0; d < 3; ++d) {
+      if (L.geom.periodic[d]) IX_ARG(b.lo[c][d] == IAMRX_LINOP_PERIODIC && b.hi[c][d] == IAMRX_LINOP_PERIODIC, "periodic direction needs periodic BC");
+      else for (int v : {b.lo[c][d], b.hi[c][d]})
+        IX_ARG(v == IAMRX_LINOP_DIRICHLET || v == IAMRX_LINOP_NEUMANN || v == IAMRX_LINOP_REFLECT_ODD,
+               "non-periodic direction needs Dirichlet / Neumann / reflect_odd boundary conditions");
+    }
+  *out = b;
   return IAMRX_OK;
 }
 
@@ -382,14 +425,15 @@ int iamrx_mac_project(iamrx_level_t lev, iamrx_fab* umac, iamrx_fab* vmac, iamrx
   IX_ARG(lev && umac && vmac && wmac && rho && phi, "null argument");
   IX_ARG(rhs_scale != 0.0, "rhs_scale");
   Level* L = lev->lev.get();
-  IX_TRY(check_periodic_bc(*L, lobc, hibc));
+  k::LinBC bc;
+  IX_TRY(make_linbc(*L, lobc, hibc, info ? info->maxorder : 0, false, &bc));
   iamrx_fab* um[3] = {umac, vmac, wmac};
   MF U[3];
   for (int d = 0; d < 3; ++d) U[d].alias(L, IX_XFACE + d, 1, 0, um[d]);
   MF Rho; Rho.alias(L, IX_CELL, 1, 1, rho);
   MF Phi; Phi.alias(L, IX_CELL, 1, 1, phi);
   MF Rhs; if (rhs) Rhs.alias(L, IX_CELL, 1, 0, rhs);
-  return mac_project(*L, lev->solvers, U, Rho, rhs ? &Rhs : nullptr, Phi, rhs_scale, info, S(stream));
+  return mac_project(*L, lev->solvers, U, Rho, rhs ? &Rhs : nullptr, Phi, rhs_scale, info, S(stream), &bc);
   IX_GUARD_END
 }
 
@@ -413,18 +457,21 @@ int iamrx_nodal_project(iamrx_level_t lev, iamrx_fab* vel, const iamrx_fab* sigm
   IX_NEED_DEVICE();
   IX_ARG(lev && vel && sigma && phi, "null argument");
   Level* L = lev->lev.get();
-  IX_TRY(check_periodic_bc(*L, lobc, hibc));
+  k::LinBC lb;
+  IX_TRY(make_linbc(*L, lobc, hibc, 0, true, &lb));
+  k::NodalBC nb;
+  for (int d = 0; d < 3; ++d) { nb.lo[d] = lb.lo[0][d]; nb.hi[d] = lb.hi[0][d]; }
   MF Vel; Vel.alias(L, IX_CELL, 3, 1, vel);
   MF Sig; Sig.alias(L, IX_CELL, 1, 0, sigma);
   MF Phi; Phi.alias(L, IX_NODE, 1, 1, phi);
   MF Gp; if (gp) Gp.alias(L, IX_CELL, 3, 0, gp);
-  return nodal_project(*L, lev->solvers, Vel, Sig, Phi, gp ? &Gp : nullptr, increment_gp, info, S(stream));
+  return nodal_project(*L, lev->solvers, Vel, Sig, Phi, gp ? &Gp : nullptr, increment_gp, info, S(stream), &nb);
   IX_GUARD_END
 }
 
 int iamrx_diffusion_apply(iamrx_level_t lev, int tensor, int ncomp, iamrx_fab* out, iamrx_fab* soln, double a,
                           double b, const iamrx_fab* acoef, const iamrx_fab* eta_x, const iamrx_fab* eta_y,
-                          const iamrx_fab* eta_z, void* stream) {
+                          const iamrx_fab* eta_z, const iamrx_linop_bc* bcin, void* stream) {
   IX_GUARD_BEGIN
   IX_NEED_DEVICE();
   IX_ARG(lev && out && soln && eta_x && eta_y && eta_z, "null argument");
@@ -437,13 +484,15 @@ int iamrx_diffusion_apply(iamrx_level_t lev, int tensor, int ncomp, iamrx_fab* o
   MF E[3];
   const iamrx_fab* e[3] = {eta_x, eta_y, eta_z};
   for (int d = 0; d < 3; ++d) E[d].alias(L, IX_XFACE + d, 1, 0, e[d]);
-  return diffusion_apply(*L, lev->solvers, tensor != 0, ncomp, Out, Sol, a, b, acoef ? &A : nullptr, E, S(stream));
+  k::LinBC bc;
+  IX_TRY(make_linbc3(*L, bcin, ncomp, &bc));
+  return diffusion_apply(*L, lev->solvers, tensor != 0, ncomp, Out, Sol, a, b, acoef ? &A : nullptr, E, S(stream), &bc);
   IX_GUARD_END
 }
 
 int iamrx_diffusion_solve(iamrx_level_t lev, int tensor, int ncomp, iamrx_fab* soln, const iamrx_fab* rhs,
                           double a, double b, const iamrx_fab* acoef, const iamrx_fab* eta_x,
-                          const iamrx_fab* eta_y, const iamrx_fab* eta_z, iamrx_mg_info* info, void* stream) {
+                          const iamrx_fab* eta_y, const iamrx_fab* eta_z, const iamrx_linop_bc* bcin, iamrx_mg_info* info, void* stream) {
   IX_GUARD_BEGIN
   IX_NEED_DEVICE();
   IX_ARG(lev && soln && rhs && eta_x && eta_y && eta_z, "null argument");
@@ -456,8 +505,10 @@ int iamrx_diffusion_solve(iamrx_level_t lev, int tensor, int ncomp, iamrx_fab* s
   MF E[3];
   const iamrx_fab* e[3] = {eta_x, eta_y, eta_z};
   for (int d = 0; d < 3; ++d) E[d].alias(L, IX_XFACE + d, 1, 0, e[d]);
+  k::LinBC bc;
+  IX_TRY(make_linbc3(*L, bcin, ncomp, &bc));
   return diffusion_solve(*L, lev->solvers, tensor != 0, ncomp, Sol, Rhs, a, b, acoef ? &A : nullptr, E, info,
-                         S(stream));
+                         S(stream), &bc);
   IX_GUARD_END
 }
 

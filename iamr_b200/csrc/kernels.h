@@ -18,8 +18,11 @@ struct Abec {
 // --- cell-centred ABec (abec.cu) -----------------------------------------
 // wrapmask bit d: bx spans the periodic domain in direction d -> neighbours are read with
 // periodic wrap inside the kernel and phi's ghost cells in that direction are not touched.
+// gb (optional): the box touches non-periodic domain faces -- f0[comp][xlo,xhi,ylo,yhi,zlo,zhi] = coefficient of the adjacent
+// interior cell in the boundary ghost-cell formula (linop_bc_f0; 0 for sides that are not domain faces)
+struct GsBC { double f0[3][6]; };
 int abec_gsrb(const Bx& bx, V4 phi, C4 rhs, const Abec& op, double omega, int redblack,
-              int ncomp, cudaStream_t s, int wrapmask = 0);
+              int ncomp, cudaStream_t s, int wrapmask = 0, const GsBC* gb = nullptr);
 // one full red-black sweep (colour rb0, then the other) phi_in -> phi_out (different arrays) on a box that spans
 // the periodic domain in all directions with even extents; abec_gsrb_sweep_ok tells whether the box qualifies
 bool abec_gsrb_sweep_ok(const Bx& bx, int wrapmask);
@@ -47,6 +50,11 @@ int mac_update(const Bx& bx, V4 u, V4 v, V4 w, C4 phi, const Abec& op, cudaStrea
 // tensor cross terms: out += b*div(F_cross(eta, vel))
 int tensor_cross(const Bx& bx, V4 out, C4 vel, C4 ex, C4 ey, C4 ez, double b,
                  const double dxinv[3], cudaStream_t s);
+
+struct LinBC;
+// the same on a box that may touch non-periodic domain faces: boundary-aware transverse derivatives (bv: level-BC fab, may be null)
+int tensor_cross_bc(const Bx& bx, V4 out, C4 vel, C4 bv, C4 ex, C4 ey, C4 ez, double b, const double dxinv[3], const LinBC& bc,
+                    const Bx& dom, const int per[3], cudaStream_t s);
 
 // --- BLAS-1 style level ops (blas.cu) ------------------------------------
 int setval(const Bx& bx, V4 dst, int ncomp, double val, cudaStream_t s);
@@ -104,7 +112,8 @@ struct AofsArgs {
 int compute_aofs(const Bx& bx, const AofsArgs& a, const AdvGeom& g, cudaStream_t s);
 
 // --- nodal Laplacian (nodal.cu) ------------------------------------------
-int nodal_divu(const Bx& nbx, V4 rhs, C4 vel, const double dxinv[3], cudaStream_t s);
+// hide: bit 2d / 2d+1 = the low / high side of nbx in direction d is a Neumann / inflow domain side (tangential ghost velocities unseen)
+int nodal_divu(const Bx& nbx, V4 rhs, C4 vel, const double dxinv[3], cudaStream_t s, int hide = 0);
 int nodal_adotx(const Bx& nbx, V4 out, C4 phi, C4 rhs, C4 sig, const double dxinv[3], cudaStream_t s,
                 int wrapmask = 0);
 int nodal_gs_color(const Bx& nbx, V4 phi, C4 rhs, C4 sig, const double dxinv[3], int color,
@@ -123,6 +132,32 @@ int nodal_restrict(const Bx& cnbx, V4 crse, C4 fine, cudaStream_t s);
 int nodal_interp_add(const Bx& fnbx, V4 fine, C4 crse, cudaStream_t s);
 int nodal_mknewu(const Bx& bx, V4 vel, V4 gp, int increment_gp, C4 phi, C4 sig,
                  const double dxinv[3], cudaStream_t s);
+
+// --- physical domain boundaries (bc.cu) -----------------------------------
+// BCRec (IAMRX_BC_* codes) and ext_dir face values of up to 8 state components: what AmrLevel::FillPatch applies outside the domain
+struct PhysBC {
+  int lo[8][3], hi[8][3];
+  double val[6][8];   // [x lo, y lo, z lo, x hi, y hi, z hi][comp]  (NavierStokes::get_bc_values, NS.cpp:108-237)
+};
+// fill the cells of `fabbox` (the fab's allocated region) outside the non-periodic sides of the domain
+int fill_physbc(const Bx& fabbox, V4 a, int ncomp, const PhysBC& bc, const Bx& dom, const int per[3], cudaStream_t s);
+// LinOpBCType of every side for up to 3 components (MLTensorOp has one set per velocity component) + setMaxOrder
+struct LinBC {
+  int lo[3][3], hi[3][3];   // [comp][dir]
+  int maxorder;
+  bool any_nonperiodic() const { for (int c = 0; c < 3; ++c) for (int d = 0; d < 3; ++d) if (lo[c][d] != IAMRX_LINOP_PERIODIC || hi[c][d] != IAMRX_LINOP_PERIODIC) return true; return false; }
+};
+int linop_bc_order(int maxorder, int boxlen);
+double linop_bc_f0(int code, int maxorder, int boxlen);   // coefficient of the first interior cell in the ghost formula
+// MLCellLinOp::applyBC on the domain faces of box vbx: ghost layer of phi beyond every non-periodic side the box touches.
+// bv: fab whose ghost cells hold the Dirichlet face values (null: homogeneous).  grow_t: extra transverse cells (the tensor
+// cross terms read one cell sideways).  skipmask bit d: leave direction d alone.
+int linop_bc_fill(const Bx& vbx, V4 phi, int ncomp, const LinBC& bc, C4 bv, const Bx& dom, const int per[3], int grow_t, int skipmask,
+                  cudaStream_t s);
+struct NodalBC { int lo[3], hi[3]; };   // LinOpBCType per side (Projection.cpp:2436-2464)
+int nodal_bc_fill_phi(const Bx& nbx, V4 phi, const NodalBC& bc, const Bx& ndom, const int per[3], int skipmask, cudaStream_t s);
+int nodal_bc_fill_sigma(const Bx& cbx, V4 sig, const NodalBC& bc, const Bx& dom, const int per[3], cudaStream_t s);
+int nodal_bc_scale(const Bx& nbx, V4 a, const NodalBC& bc, const Bx& ndom, const int per[3], double f, cudaStream_t s);
 
 // --- pointwise IAMR glue (pointwise.cu) -----------------------------------
 // floor NSB.cpp:4530-4534: |v| > 1e-20 ? v : 0

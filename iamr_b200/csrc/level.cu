@@ -692,6 +692,16 @@ int mf_fill_boundary(MF& m, int comp, int ncomp, int ng, cudaStream_t s, int ski
   return IAMRX_OK;
 }
 
+// physical-boundary part of a FillPatch: cells of every local fab outside the non-periodic sides of the domain
+int mf_fill_physbc(MF& m, int comp, int ncomp, int ng, const k::PhysBC& bc, cudaStream_t s) {
+  const Level& L = *m.lev;
+  if (ng <= 0 || (L.geom.periodic[0] && L.geom.periodic[1] && L.geom.periodic[2])) return IAMRX_OK;
+  if (m.ixtype != IX_CELL) { set_error("mf_fill_physbc: cell-centred data only"); return IAMRX_ERR_ARG; }
+  for (int il = 0; il < m.n(); ++il)
+    IX_TRY(k::fill_physbc(m.gbox(il, ng), m.v(il, comp), ncomp, bc, L.domain, L.geom.periodic, s));
+  return IAMRX_OK;
+}
+
 // ---- gather into a replicated level ---------------------------------------------------
 GatherPlan::~GatherPlan() {
   if (d_pack) cudaFree(d_pack);

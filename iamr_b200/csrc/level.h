@@ -180,6 +180,9 @@ int mf_lincomb(MF& dst, int dcomp, double a, const MF& x, int xcomp, double b, c
                int ncomp, int ng, cudaStream_t s);
 int mf_scale(MF& m, double c, int comp, int ncomp, int ng, cudaStream_t s);
 int mf_fill_boundary(MF& m, int comp, int ncomp, int ng, cudaStream_t s, int skip = 0);
+// AmrLevel::FillPatch outside the domain: physical boundary conditions of cell data (after mf_fill_boundary); bc holds the
+// BCRec / ext_dir values of components comp .. comp+ncomp-1 in its slots 0 .. ncomp-1
+int mf_fill_physbc(MF& m, int comp, int ncomp, int ng, const k::PhysBC& bc, cudaStream_t s);
 // dst (one box covering the domain, on a replicated level) <- valid regions of every box of src (a distributed level
 // of the same resolution): local boxes by a copy kernel, remote ones by an all-to-all of packed boxes
 int mf_gather_replicate(MF& dst, const MF& src, int ncomp, cudaStream_t s);

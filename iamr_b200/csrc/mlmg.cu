@@ -100,6 +100,42 @@ CellMG::CellMG(Level* fine, int ncomp, bool tensor, int max_coarsening)
   }
 }
 
+void CellMG::set_bc(const k::LinBC& bc) {
+  bc_ = bc;
+  has_bc_ = !all_periodic(*lv_[0].lev);
+}
+
+bool CellMG::box_on_boundary(int l, int il) const {
+  const Level& L = *lv_[l].lev;
+  const Bx& b = L.lbox(il);
+  for (int d = 0; d < 3; ++d) if (!L.geom.periodic[d] && (b.lo[d] == L.domain.lo[d] || b.hi[d] == L.domain.hi[d])) return true;
+  return false;
+}
+
+k::GsBC CellMG::gsbc_of(int l, int il) const {
+  k::GsBC g{};
+  const Level& L = *lv_[l].lev;
+  const Bx& b = L.lbox(il);
+  for (int c = 0; c < 3; ++c)
+    for (int d = 0; d < 3; ++d) {
+      if (L.geom.periodic[d]) continue;
+      const int len = b.hi[d] - b.lo[d] + 1;
+      if (b.lo[d] == L.domain.lo[d]) g.f0[c][2 * d] = k::linop_bc_f0(bc_.lo[c][d], bc_.maxorder, len);
+      if (b.hi[d] == L.domain.hi[d]) g.f0[c][2 * d + 1] = k::linop_bc_f0(bc_.hi[c][d], bc_.maxorder, len);
+    }
+  return g;
+}
+
+int CellMG::fill_ghosts(int l, MF& phi, bool inhomog, int wm, int grow_t, cudaStream_t s) {
+  if (wm != 7) IX_TRY(mf_fill_boundary(phi, 0, ncomp_, 1, s, wm));
+  if (!has_bc_) return IAMRX_OK;
+  const Level& L = *lv_[l].lev;
+  const bool ih = inhomog && l == 0 && bvals_.ok();
+  for (int il = 0; il < phi.n(); ++il)
+    IX_TRY(k::linop_bc_fill(phi.vbox(il), phi.v(il), ncomp_, bc_, ih ? bvals_.c(il) : C4{}, L.domain, L.geom.periodic, grow_t, 0, s));
+  return IAMRX_OK;
+}
+
 k::Abec CellMG::op_at(int l, int il) const {
   const MGLevelCell& L = lv_[l];
   k::Abec op;
@@ -157,7 +193,15 @@ int CellMG::set_coeffs(const MF* acoef, const MF* bx, const MF* by, const MF* bz
       }
     }
   }
-  singular_ = (a_ == 0.0) && all_periodic(*lv_[0].lev);
+  // the operator annihilates constants when a = 0 and no side pins the solution (periodic / Neumann everywhere)
+  singular_ = (a_ == 0.0);
+  if (has_bc_)
+    for (int c = 0; c < ncomp_ && c < 3; ++c)
+      for (int d = 0; d < 3; ++d) {
+        if (lv_[0].lev->geom.periodic[d]) continue;
+        for (int code : {bc_.lo[c][d], bc_.hi[c][d]})
+          if (code == IAMRX_LINOP_DIRICHLET || code == IAMRX_LINOP_REFLECT_ODD) singular_ = false;
+      }
   return IAMRX_OK;
 }
 
@@ -183,35 +227,64 @@ int CellMG::smooth(int l, MF& phi, const MF& rhs, int nsweeps, bool /*zero_init*
   }
   for (int sw = 0; sw < nsweeps; ++sw) {
     for (int rb = 0; rb < 2; ++rb) {
-      if (!wrap) IX_TRY(mf_fill_boundary(phi, 0, ncomp_, 1, s, wm));
-      for (int il = 0; il < phi.n(); ++il)
-        IX_TRY(k::abec_gsrb(phi.vbox(il), phi.v(il), rhs.c(il), op_at(l, il), info_.omega, rb, ncomp_, s, wm));
+      IX_TRY(fill_ghosts(l, phi, false, wm, 0, s));   // corrections: homogeneous boundary conditions
+      for (int il = 0; il < phi.n(); ++il) {
+        const bool onb = has_bc_ && box_on_boundary(l, il);
+        const k::GsBC gb = onb ? gsbc_of(l, il) : k::GsBC{};
+        IX_TRY(k::abec_gsrb(phi.vbox(il), phi.v(il), rhs.c(il), op_at(l, il), info_.omega, rb, ncomp_, s, wm, onb ? &gb : nullptr));
+      }
     }
   }
   return IAMRX_OK;
 }
 
+// with_cross marks the top-level residual of a solve: inhomogeneous boundary conditions (+ the tensor cross terms)
 int CellMG::residual(int l, MF& out, MF& phi, const MF& rhs, bool with_cross, cudaStream_t s) {
   const bool cross = tensor_ && l == 0 && with_cross;  // the cross terms read edge/corner ghosts
   const int wm = cross ? 0 : lv_[l].lev->level_wrapmask();
-  if (wm != 7) IX_TRY(mf_fill_boundary(phi, 0, ncomp_, 1, s, wm));
+  IX_TRY(fill_ghosts(l, phi, with_cross, wm, cross ? 1 : 0, s));
+  const Level& L = *lv_[l].lev;
   for (int il = 0; il < phi.n(); ++il) {
     IX_TRY(k::abec_apply(phi.vbox(il), out.v(il), phi.c(il), rhs.c(il), op_at(l, il), ncomp_, s, wm));
-    if (tensor_ && l == 0 && with_cross)
-      IX_TRY(k::tensor_cross(phi.vbox(il), out.v(il), phi.c(il), eta_[0]->c(il), eta_[1]->c(il),
-                             eta_[2]->c(il), -b_, lv_[0].dxinv, s));
+    if (cross) {
+      if (has_bc_)
+        IX_TRY(k::tensor_cross_bc(phi.vbox(il), out.v(il), phi.c(il), bvals_.ok() ? bvals_.c(il) : C4{}, eta_[0]->c(il), eta_[1]->c(il),
+                                  eta_[2]->c(il), -b_, lv_[0].dxinv, bc_, L.domain, L.geom.periodic, s));
+      else
+        IX_TRY(k::tensor_cross(phi.vbox(il), out.v(il), phi.c(il), eta_[0]->c(il), eta_[1]->c(il),
+                               eta_[2]->c(il), -b_, lv_[0].dxinv, s));
+    }
   }
   return IAMRX_OK;
 }
 
+// the level BC of a solve / apply = the ghost cells of the MF handed in (MLLinOp::setLevelBC(0, &Soln), Diffusion.cpp:743-744,886-887;
+// MacProj.cpp:1168): keep a copy, the ghost cells themselves are overwritten by the extrapolated values
+static int save_level_bc(MF& bvals, MF& phi, int ncomp, bool needed, cudaStream_t s) {
+  if (!needed) { bvals.clear(); return IAMRX_OK; }
+  if (!bvals.ok() || bvals.lev != phi.lev || bvals.ncomp != ncomp) bvals.define(phi.lev, IX_CELL, ncomp, 1);
+  IX_TRY(mf_copy(bvals, phi, 0, 0, ncomp, 1, s));
+  return mf_fill_boundary(bvals, 0, ncomp, 1, s);   // periodic / interior images of the wall ghost cells (tensor: transverse neighbours)
+}
+
 int CellMG::apply(MF& out, MF& phi, cudaStream_t s) {
-  IX_TRY(mf_fill_boundary(phi, 0, ncomp_, 1, s));
+  bool dirichlet = false;
+  for (int c = 0; c < ncomp_ && c < 3; ++c) for (int d = 0; d < 3; ++d) if (bc_.lo[c][d] == IAMRX_LINOP_DIRICHLET || bc_.hi[c][d] == IAMRX_LINOP_DIRICHLET) dirichlet = true;
+  IX_TRY(save_level_bc(bvals_, phi, ncomp_, has_bc_ && dirichlet, s));
+  IX_TRY(fill_ghosts(0, phi, true, 0, tensor_ ? 1 : 0, s));
+  const Level& L = *lv_[0].lev;
   for (int il = 0; il < phi.n(); ++il) {
     IX_TRY(k::abec_apply(phi.vbox(il), out.v(il), phi.c(il), C4{}, op_at(0, il), ncomp_, s));
-    if (tensor_)
-      IX_TRY(k::tensor_cross(phi.vbox(il), out.v(il), phi.c(il), eta_[0]->c(il), eta_[1]->c(il),
-                             eta_[2]->c(il), b_, lv_[0].dxinv, s));
+    if (tensor_) {
+      if (has_bc_)
+        IX_TRY(k::tensor_cross_bc(phi.vbox(il), out.v(il), phi.c(il), bvals_.ok() ? bvals_.c(il) : C4{}, eta_[0]->c(il), eta_[1]->c(il),
+                                  eta_[2]->c(il), b_, lv_[0].dxinv, bc_, L.domain, L.geom.periodic, s));
+      else
+        IX_TRY(k::tensor_cross(phi.vbox(il), out.v(il), phi.c(il), eta_[0]->c(il), eta_[1]->c(il),
+                               eta_[2]->c(il), b_, lv_[0].dxinv, s));
+    }
   }
+  bvals_.clear();
   return IAMRX_OK;
 }
 
@@ -261,6 +334,11 @@ int CellMG::vcycle(cudaStream_t s) {
 int CellMG::solve(MF& sol, const MF& rhs_in, iamrx_mg_info* info, cudaStream_t s) {
   if (info) info_ = *info;
   MGLevelCell& L0 = lv_[0];
+  {
+    bool dirichlet = false;
+    for (int c = 0; c < ncomp_ && c < 3; ++c) for (int d = 0; d < 3; ++d) if (bc_.lo[c][d] == IAMRX_LINOP_DIRICHLET || bc_.hi[c][d] == IAMRX_LINOP_DIRICHLET) dirichlet = true;
+    IX_TRY(save_level_bc(bvals_, sol, ncomp_, has_bc_ && dirichlet, s));
+  }
   MF rhs(L0.lev, IX_CELL, ncomp_, 0);
   IX_TRY(mf_copy(rhs, rhs_in, 0, 0, ncomp_, 0, s));
   if (singular_) IX_TRY(make_solvable(0, rhs, s));
@@ -286,7 +364,8 @@ int CellMG::solve(MF& sol, const MF& rhs_in, iamrx_mg_info* info, cudaStream_t s
       if (resnorm <= target) { rc = IAMRX_OK; break; }
     }
   }
-  IX_TRY(mf_fill_boundary(sol, 0, ncomp_, 1, s));  // setFinalFillBC(true)
+  IX_TRY(fill_ghosts(0, sol, true, 0, 0, s));  // setFinalFillBC(true)
+  bvals_.clear();
   if (info_.verbose > 0)
     fprintf(stderr, "[iamrx] CellMG: %d iters, res0 %.3e -> %.3e (rhs %.3e, levels %d)\n", iters, resnorm0,
             resnorm, rhsnorm, nlevels());
@@ -323,13 +402,70 @@ NodeMG::NodeMG(Level* fine, int max_coarsening) {
     L.res.define(L.lev, IX_NODE, 1, 1);
     L.rescor.define(L.lev, IX_NODE, 1, 1);
     if (L.xfer_lev) L.xfer.define(L.xfer_lev.get(), IX_NODE, 1, 1);
+    // nodes ON Dirichlet sides are never written by the kernels (active_nbox): they must hold zero from the start
+    for (MF* m : {&L.cor, &L.res, &L.rescor, &L.xfer}) if (m->ok()) mf_setval(*m, 0.0, 0, 1, 1, nullptr);
   }
+  for (int d = 0; d < 3; ++d) { bc_.lo[d] = IAMRX_LINOP_PERIODIC; bc_.hi[d] = IAMRX_LINOP_PERIODIC; }
+}
+
+void NodeMG::set_bc(const k::NodalBC& bc) {
+  bc_ = bc;
+  has_bc_ = !all_periodic(*lv_[0].lev);
+}
+
+Bx NodeMG::active_nbox(int l, int il) const {
+  const Level& L = *lv_[l].lev;
+  Bx nb = ixbox(L.lbox(il), IX_NODE);
+  if (!has_bc_) return nb;
+  for (int d = 0; d < 3; ++d) {
+    if (L.geom.periodic[d]) continue;
+    if (bc_.lo[d] == IAMRX_LINOP_DIRICHLET && L.lbox(il).lo[d] == L.domain.lo[d]) nb.lo[d] += 1;
+    if (bc_.hi[d] == IAMRX_LINOP_DIRICHLET && L.lbox(il).hi[d] == L.domain.hi[d]) nb.hi[d] -= 1;
+  }
+  return nb;
+}
+
+int NodeMG::neumann_sides(int l, int il) const {
+  if (!has_bc_) return 0;
+  const Level& L = *lv_[l].lev;
+  int m = 0;
+  for (int d = 0; d < 3; ++d) {
+    if (L.geom.periodic[d]) continue;
+    if ((bc_.lo[d] == IAMRX_LINOP_NEUMANN || bc_.lo[d] == IAMRX_LINOP_INFLOW) && L.lbox(il).lo[d] == L.domain.lo[d]) m |= 1 << (2 * d);
+    if ((bc_.hi[d] == IAMRX_LINOP_NEUMANN || bc_.hi[d] == IAMRX_LINOP_INFLOW) && L.lbox(il).hi[d] == L.domain.hi[d]) m |= 1 << (2 * d + 1);
+  }
+  return m;
+}
+
+bool NodeMG::singular() const {
+  const Level& L = *lv_[0].lev;
+  for (int d = 0; d < 3; ++d)
+    if (!L.geom.periodic[d] && has_bc_ && (bc_.lo[d] == IAMRX_LINOP_DIRICHLET || bc_.hi[d] == IAMRX_LINOP_DIRICHLET)) return false;
+  return true;
+}
+
+int NodeMG::fill_ghosts(int l, MF& phi, int wm, cudaStream_t s) {
+  if (wm != 7) IX_TRY(mf_fill_boundary(phi, 0, 1, 1, s, wm));
+  if (!has_bc_) return IAMRX_OK;
+  const Level& L = *lv_[l].lev;
+  const Bx ndom = ixbox(L.domain, IX_NODE);
+  for (int il = 0; il < phi.n(); ++il)
+    IX_TRY(k::nodal_bc_fill_phi(phi.vbox(il), phi.v(il), bc_, ndom, L.geom.periodic, 0, s));
+  return IAMRX_OK;
 }
 
 int NodeMG::set_sigma(const MF& sigma, cudaStream_t s) {
+  auto sigma_bc = [&](MGLevelNode& M) -> int {   // mlndlap_fillbc_cc: the ghost layer beyond a Neumann / inflow side copies the interior
+    if (!has_bc_) return IAMRX_OK;
+    const Level& LL = *M.lev;
+    for (int il = 0; il < M.sigma.n(); ++il)
+      IX_TRY(k::nodal_bc_fill_sigma(M.sigma.vbox(il), M.sigma.v(il), bc_, LL.domain, LL.geom.periodic, s));
+    return IAMRX_OK;
+  };
   IX_TRY(mf_setval(lv_[0].sigma, 0.0, 0, 1, 1, s));
   IX_TRY(mf_copy(lv_[0].sigma, sigma, 0, 0, 1, 0, s));
   IX_TRY(mf_fill_boundary(lv_[0].sigma, 0, 1, 1, s));
+  IX_TRY(sigma_bc(lv_[0]));
   for (size_t l = 1; l < lv_.size(); ++l) {
     MGLevelNode& C = lv_[l];
     MGLevelNode& F = lv_[l - 1];
@@ -343,6 +479,7 @@ int NodeMG::set_sigma(const MF& sigma, cudaStream_t s) {
         IX_TRY(k::cc_restrict(C.sigma.vbox(il), C.sigma.v(il), F.sigma.c(il), 1, s));
     }
     IX_TRY(mf_fill_boundary(C.sigma, 0, 1, 1, s));
+    IX_TRY(sigma_bc(C));
   }
   return IAMRX_OK;
 }
@@ -363,9 +500,9 @@ int NodeMG::smooth(int l, MF& phi, const MF& rhs, int nsweeps, cudaStream_t s) {
   if (nodal_smoother_kind() == 1) {
     MF tmp(L.lev, IX_NODE, 1, 1);
     for (int sw = 0; sw < 2 * nsweeps; ++sw) {
-      IX_TRY(mf_fill_boundary(phi, 0, 1, 1, s));
+      IX_TRY(fill_ghosts(l, phi, 0, s));
       for (int il = 0; il < phi.n(); ++il)
-        IX_TRY(k::nodal_jacobi(phi.vbox(il), tmp.v(il), phi.c(il), rhs.c(il), L.sigma.c(il), L.dxinv,
+        IX_TRY(k::nodal_jacobi(active_nbox(l, il), tmp.v(il), phi.c(il), rhs.c(il), L.sigma.c(il), L.dxinv,
                                2.0 / 3.0, s));
       IX_TRY(mf_copy(phi, tmp, 0, 0, 1, 0, s));
     }
@@ -375,18 +512,23 @@ int NodeMG::smooth(int l, MF& phi, const MF& rhs, int nsweeps, cudaStream_t s) {
   // numbers of ghost exchanges, so every rank must take the same one
   bool fused = true;
   for (size_t b = 0; b < L.lev->boxes.size() && fused; ++b) fused = k::nodal_gs_sweep_ok(ixbox(L.lev->boxes[b], IX_NODE), wm);
+  // Dirichlet sides shorten the active node box; keep the fused sweep only if its plane pairing survives (both z sides or none)
+  if (fused && has_bc_)
+    for (int d = 0; d < 3; ++d)
+      if (!L.lev->geom.periodic[d] && ((bc_.lo[d] == IAMRX_LINOP_DIRICHLET) != (bc_.hi[d] == IAMRX_LINOP_DIRICHLET))) fused = false;
   if (fused) {
     // out-of-place fused sweeps ping-pong between phi and a second buffer.  Slabs (x and y wrapped in the kernel, z
     // exchanged): the even-plane phase reads the old odd ghost planes of `src`, the odd-plane phase the NEW even ghost
     // planes of `dst` -- two plane exchanges per sweep instead of eight colour fills.
     if (!L.gs_tmp.ok()) L.gs_tmp.define(L.lev, IX_NODE, 1, 1);
+    if (!L.gs_tmp.ok()) { L.gs_tmp.define(L.lev, IX_NODE, 1, 1); IX_TRY(mf_setval(L.gs_tmp, 0.0, 0, 1, 1, s)); }
     MF* src = &phi; MF* dst = &L.gs_tmp;
-    if (!wrap) IX_TRY(mf_fill_boundary(*src, 0, 1, 1, s, wm));
+    IX_TRY(fill_ghosts(l, *src, wm, s));
     for (int sw = 0; sw < nsweeps; ++sw) {
       for (int phase = 0; phase < 2; ++phase) {
         for (int il = 0; il < phi.n(); ++il)
-          IX_TRY(k::nodal_gs_sweep(phi.vbox(il), dst->v(il), src->c(il), rhs.c(il), L.sigma.c(il), L.dxinv, s, wm, phase));
-        if (!wrap) IX_TRY(mf_fill_boundary(*dst, 0, 1, 1, s, wm));
+          IX_TRY(k::nodal_gs_sweep(active_nbox(l, il), dst->v(il), src->c(il), rhs.c(il), L.sigma.c(il), L.dxinv, s, wm, phase));
+        IX_TRY(fill_ghosts(l, *dst, wm, s));
       }
       std::swap(src, dst);
     }
@@ -395,9 +537,9 @@ int NodeMG::smooth(int l, MF& phi, const MF& rhs, int nsweeps, cudaStream_t s) {
   }
   for (int sw = 0; sw < nsweeps; ++sw) {
     for (int color = 0; color < 8; ++color) {
-      if (!wrap) IX_TRY(mf_fill_boundary(phi, 0, 1, 1, s, wm));
+      IX_TRY(fill_ghosts(l, phi, wm, s));
       for (int il = 0; il < phi.n(); ++il)
-        IX_TRY(k::nodal_gs_color(phi.vbox(il), phi.v(il), rhs.c(il), L.sigma.c(il), L.dxinv, color, s, wm));
+        IX_TRY(k::nodal_gs_color(active_nbox(l, il), phi.v(il), rhs.c(il), L.sigma.c(il), L.dxinv, color, s, wm));
     }
   }
   return IAMRX_OK;
@@ -406,9 +548,9 @@ int NodeMG::smooth(int l, MF& phi, const MF& rhs, int nsweeps, cudaStream_t s) {
 int NodeMG::residual(int l, MF& out, MF& phi, const MF& rhs, cudaStream_t s) {
   MGLevelNode& L = lv_[l];
   const int wm = L.lev->level_wrapmask();
-  if (wm != 7) IX_TRY(mf_fill_boundary(phi, 0, 1, 1, s, wm));
+  IX_TRY(fill_ghosts(l, phi, wm, s));
   for (int il = 0; il < phi.n(); ++il)
-    IX_TRY(k::nodal_adotx(phi.vbox(il), out.v(il), phi.c(il), rhs.c(il), L.sigma.c(il), L.dxinv, s, wm));
+    IX_TRY(k::nodal_adotx(active_nbox(l, il), out.v(il), phi.c(il), rhs.c(il), L.sigma.c(il), L.dxinv, s, wm));
   return IAMRX_OK;
 }
 
@@ -419,15 +561,25 @@ int NodeMG::vcycle(cudaStream_t s) {
     IX_TRY(mf_setval(L.cor, 0.0, 0, 1, 1, s));
     IX_TRY(smooth(l, L.cor, L.res, info_.nu1, s));
     IX_TRY(residual(l, L.rescor, L.cor, L.res, s));
-    IX_TRY(mf_fill_boundary(L.rescor, 0, 1, 1, s));
+    IX_TRY(fill_ghosts(l, L.rescor, 0, s));   // MLNodeLaplacian::restriction: applyBC on the fine residual (Neumann sides mirrored)
     MGLevelNode& C = lv_[l + 1];
     if (C.xfer_lev) {
-      for (int il = 0; il < C.xfer.n(); ++il)
-        IX_TRY(k::nodal_restrict(C.xfer.vbox(il), C.xfer.v(il), L.rescor.c(il), s));
+      // (the transfer level shares the boundary flags of the coarse level: same domain, boxes tile it)
+      for (int il = 0; il < C.xfer.n(); ++il) {
+        Bx cb = C.xfer.vbox(il);
+        const Level& XL = *C.xfer_lev;
+        if (has_bc_)
+          for (int d = 0; d < 3; ++d) {
+            if (XL.geom.periodic[d]) continue;
+            if (bc_.lo[d] == IAMRX_LINOP_DIRICHLET && XL.lbox(il).lo[d] == XL.domain.lo[d]) cb.lo[d] += 1;
+            if (bc_.hi[d] == IAMRX_LINOP_DIRICHLET && XL.lbox(il).hi[d] == XL.domain.hi[d]) cb.hi[d] -= 1;
+          }
+        IX_TRY(k::nodal_restrict(cb, C.xfer.v(il), L.rescor.c(il), s));
+      }
       IX_TRY(mf_gather_replicate(C.res, C.xfer, 1, s));
     } else {
       for (int il = 0; il < C.res.n(); ++il)
-        IX_TRY(k::nodal_restrict(C.res.vbox(il), C.res.v(il), L.rescor.c(il), s));
+        IX_TRY(k::nodal_restrict(active_nbox(l + 1, il), C.res.v(il), L.rescor.c(il), s));
     }
   }
   {
@@ -439,7 +591,7 @@ int NodeMG::vcycle(cudaStream_t s) {
     MGLevelNode& L = lv_[l];
     MGLevelNode& C = lv_[l + 1];
     for (int il = 0; il < L.cor.n(); ++il)
-      IX_TRY(k::nodal_interp_add(L.cor.vbox(il), L.cor.v(il), C.cor.c(C.xfer_lev ? 0 : il), s));
+      IX_TRY(k::nodal_interp_add(active_nbox(l, il), L.cor.v(il), C.cor.c(C.xfer_lev ? 0 : il), s));
     IX_TRY(smooth(l, L.cor, L.res, info_.nu2, s));
   }
   return IAMRX_OK;
@@ -449,10 +601,21 @@ int NodeMG::solve(MF& phi, MF& rhs, iamrx_mg_info* info, cudaStream_t s) {
   if (info) info_ = *info;
   MGLevelNode& L0 = lv_[0];
   Level& lev = *L0.lev;
-  if (all_periodic(lev)) {  // singular: make rhs solvable (subtract the mean over unique nodes)
+  if (singular()) {
+    // periodic / Neumann everywhere: make rhs solvable (MLNodeLinOp::getSolvabilityOffset / fixSolvabilityByOffset): subtract the
+    // mean weighted with the dot mask -- unique nodes, 1/2 per Neumann side a node lies on.  The weights sum to the number of
+    // cells (a periodic direction has n unique nodes, a Neumann-Neumann one n + 1 with two halves).
     double sum = 0;
-    IX_TRY(mf_sum(rhs, 0, &sum, s, true));
-    const double mean = sum / (double)lev.ncells_global;  // #unique nodes == #cells when periodic
+    if (has_bc_) {
+      MF tmp(&lev, IX_NODE, 1, 0);
+      IX_TRY(mf_copy(tmp, rhs, 0, 0, 1, 0, s));
+      const Bx ndom = ixbox(lev.domain, IX_NODE);
+      for (int il = 0; il < tmp.n(); ++il) IX_TRY(k::nodal_bc_scale(tmp.vbox(il), tmp.v(il), bc_, ndom, lev.geom.periodic, 0.5, s));
+      IX_TRY(mf_sum(tmp, 0, &sum, s, true));
+    } else {
+      IX_TRY(mf_sum(rhs, 0, &sum, s, true));
+    }
+    const double mean = sum / (double)lev.ncells_global;
     for (int il = 0; il < rhs.n(); ++il) IX_TRY(k::addconst(rhs.vbox(il), rhs.v(il), -mean, 1, s));
   }
   double rhsnorm = 0, resnorm0 = 0, resnorm = 0;
@@ -477,7 +640,7 @@ int NodeMG::solve(MF& phi, MF& rhs, iamrx_mg_info* info, cudaStream_t s) {
       if (resnorm <= target) { rc = IAMRX_OK; break; }
     }
   }
-  IX_TRY(mf_fill_boundary(phi, 0, 1, 1, s));
+  IX_TRY(fill_ghosts(0, phi, 0, s));
   if (info_.verbose > 0)
     fprintf(stderr, "[iamrx] NodeMG: %d iters, res0 %.3e -> %.3e (rhs %.3e, levels %d)\n", iters, resnorm0,
             resnorm, rhsnorm, nlevels());

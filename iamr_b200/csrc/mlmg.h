@@ -29,6 +29,9 @@ class CellMG {
   // fine-level coefficient MFs are referenced, not copied (caller keeps them alive)
   CellMG(Level* fine, int ncomp, bool tensor, int max_coarsening);
   int set_scalars(double a, double b) { a_ = a; b_ = b; return 0; }
+  // MLLinOp::setDomainBC + setMaxOrder (MacProj.cpp:1164,1172; Diffusion.cpp:715-724).  The level BC (setLevelBC: the Dirichlet
+  // face values) is taken from the ghost cells of the solution / input MF at the start of solve() / apply().
+  void set_bc(const k::LinBC& bc);
   // acoef: cell MF (1 comp); eta[d]: face MFs with 1 comp.  For tensor the solver
   // builds per-component b = eta * (1 + 1/3 delta_{c,d}) (4/3 on the diagonal).
   int set_coeffs(const MF* acoef, const MF* bx, const MF* by, const MF* bz, cudaStream_t s,
@@ -45,6 +48,14 @@ class CellMG {
   int residual(int l, MF& out, MF& phi, const MF& rhs, bool with_cross, cudaStream_t s);
   int vcycle(cudaStream_t s);
   int make_solvable(int l, MF& rhs, cudaStream_t s);
+  // ghost cells of phi on level l: FillBoundary (interior / periodic, minus the in-kernel wrapped directions) then the domain
+  // boundary conditions; inhomog: Dirichlet values from bvals_ (finest level only), else homogeneous
+  int fill_ghosts(int l, MF& phi, bool inhomog, int wm, int grow_t, cudaStream_t s);
+  k::GsBC gsbc_of(int l, int il) const;
+  bool box_on_boundary(int l, int il) const;
+  k::LinBC bc_{};
+  bool has_bc_ = false;
+  MF bvals_;   // copy of the level-BC data (valid + 1 ghost) while a solve / apply is in flight
   std::vector<MGLevelCell> lv_;
   int ncomp_;
   bool tensor_;
@@ -68,6 +79,12 @@ struct MGLevelNode {
 class NodeMG {
  public:
   NodeMG(Level* fine, int max_coarsening);
+  void set_bc(const k::NodalBC& bc);   // NodalProjector::setDomainBC (Projection.cpp:2436-2464,2513)
+  const k::NodalBC& bc() const { return bc_; }
+  bool has_bc() const { return has_bc_; }
+  // node box of local box il on level l without the planes ON Dirichlet domain sides (those nodes are held at zero)
+  Bx active_nbox(int l, int il) const;
+  int neumann_sides(int l, int il) const;   // bit 2d / 2d+1: the low / high side of the box is a Neumann / inflow domain side
   int set_sigma(const MF& sigma, cudaStream_t s);  // copies + coarsens
   int solve(MF& phi, MF& rhs, iamrx_mg_info* info, cudaStream_t s);
   int nlevels() const { return (int)lv_.size(); }
@@ -77,8 +94,12 @@ class NodeMG {
   int smooth(int l, MF& phi, const MF& rhs, int nsweeps, cudaStream_t s);
   int residual(int l, MF& out, MF& phi, const MF& rhs, cudaStream_t s);
   int vcycle(cudaStream_t s);
+  int fill_ghosts(int l, MF& phi, int wm, cudaStream_t s);   // FillBoundary + mirrored ghost nodes of the Neumann sides
+  bool singular() const;
   std::vector<MGLevelNode> lv_;
   iamrx_mg_info info_;
+  k::NodalBC bc_{};
+  bool has_bc_ = false;
 };
 
 // coarsen a level by 2 (all boxes must be coarsenable); nullptr if not possible

@@ -161,6 +161,32 @@ divu_kernel(Bx bx, V4 rhs, C4 vel, double facx, double facy, double facz) {
   rhs(i, j, k) = dx + dy + dz;
 }
 
+// the same next to Neumann / inflow domain sides (mlndlap_divu's zero_* factors): bit 2d / 2d+1 of `hide` = the low / high
+// side of the node box in direction d is such a side; a node ON it does not see the TANGENTIAL velocities of the cells
+// beyond it (the normal component of those ghost cells is used as it is: zero at walls, the inflow value otherwise)
+__global__ void __launch_bounds__(TX* TY)
+divu_bc_kernel(Bx bx, V4 rhs, C4 vel, double facx, double facy, double facz, int hide) {
+  NIDX(bx)
+  const int idx[3] = {i, j, k};
+  const double fac[3] = {facx, facy, facz};
+  bool hlo[3], hhi[3];
+  for (int d = 0; d < 3; ++d) { hlo[d] = (hide >> (2 * d) & 1) && idx[d] == bx.lo[d]; hhi[d] = (hide >> (2 * d + 1) & 1) && idx[d] == bx.hi[d]; }
+  double r = 0.0;
+  for (int cz = 0; cz < 2; ++cz)
+    for (int cy = 0; cy < 2; ++cy)
+      for (int cx = 0; cx < 2; ++cx) {
+        const int off[3] = {cx, cy, cz};
+        bool outd[3];
+        for (int d = 0; d < 3; ++d) outd[d] = (off[d] == 1 && hlo[d]) || (off[d] == 0 && hhi[d]);
+        for (int c = 0; c < 3; ++c) {
+          bool hidden = false;
+          for (int d = 0; d < 3; ++d) if (d != c && outd[d]) hidden = true;
+          if (!hidden) r += (off[c] ? -1.0 : 1.0) * fac[c] * vel(i - cx, j - cy, k - cz, c);
+        }
+      }
+  rhs(i, j, k) = r;
+}
+
 __global__ void __launch_bounds__(TX* TY)
 mknewu_kernel(Bx bx, V4 vel, V4 gp, int incr, C4 p, C4 sig, double facx, double facy, double facz) {
   NIDX(bx)
@@ -588,8 +614,12 @@ inline void facs(const double dxinv[3], double f[3]) {
 
 }  // namespace
 
-int nodal_divu(const Bx& nbx, V4 rhs, C4 vel, const double dxinv[3], cudaStream_t s) {
+int nodal_divu(const Bx& nbx, V4 rhs, C4 vel, const double dxinv[3], cudaStream_t s, int hide) {
   if (!nbx.ok()) return IAMRX_OK;
+  if (hide) {
+    IX_LAUNCH(divu_bc_kernel, grid_for(nbx), dim3(TX, TY, 1), 0, s, nbx, rhs, vel, 0.25 * dxinv[0], 0.25 * dxinv[1], 0.25 * dxinv[2], hide);
+    return check_launch("nodal_divu_bc");
+  }
   IX_LAUNCH(divu_kernel, grid_for(nbx), dim3(TX, TY, 1), 0, s, nbx, rhs, vel, 0.25 * dxinv[0], 0.25 * dxinv[1],
                                                         0.25 * dxinv[2]);
   return check_launch("nodal_divu");

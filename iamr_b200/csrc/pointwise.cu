@@ -126,6 +126,32 @@ __global__ void init_kernel(Bx bx, V4 st, int probtype, ProbParams pp, iamrx_geo
     const double bx0 = pp.v[2], by0 = pp.v[3], bz0 = pp.v[4], br = pp.v[5];
     const double d = sqrt((x - bx0) * (x - bx0) + (y - by0) * (y - by0) + (z - bz0) * (z - bz0));
     st(i, j, k, 4) = (d < br) ? 1.0 : 0.0;
+  } else if (probtype == 10) {
+    // RayleighTaylor 3-D (prob_init.cpp:447-487): params = rho_1, rho_2, tra_1, tra_2, interface_width, perturbation_amplitude;
+    // velocity at rest, the hard-coded random phases of :465-467
+    const double pi = 0.5 * twopi;
+    const double Lx = (g.domain.hi[0] - g.domain.lo[0] + 1) * g.dx[0], Ly = (g.domain.hi[1] - g.domain.lo[1] + 1) * g.dx[1];
+    const double splitz = 0.5 * (g.prob_lo[2] + (g.prob_lo[2] + (g.domain.hi[2] - g.domain.lo[2] + 1) * g.dx[2]));
+    const double ranampl = 2. * (0.6544437533747718 - 0.5), ranphse1 = 2. * pi * 0.1556190326530211, ranphse2 = 2. * pi * 0.4196144025537369;
+    const double pert = ranampl * sin(2.0 * pi * x / Lx + ranphse1) * sin(2.0 * pi * y / Ly + ranphse2);
+    const double pertheight = splitz - pp.v[5] * pert;
+    st(i, j, k, 0) = 0.0; st(i, j, k, 1) = 0.0; st(i, j, k, 2) = 0.0;
+    st(i, j, k, 3) = pp.v[0] + ((pp.v[1] - pp.v[0]) / 2.0) * (1.0 + tanh((z - pertheight) / pp.v[4]));
+    st(i, j, k, 4) = pp.v[2] + ((pp.v[3] - pp.v[2]) / 2.0) * (1.0 + tanh((z - pertheight) / pp.v[4]));
+  } else if (probtype == 1) {
+    // LidDrivenCavity: start from rest, density 1 (prob_init.cpp:102-109)
+    st(i, j, k, 0) = 0.0; st(i, j, k, 1) = 0.0; st(i, j, k, 2) = 0.0; st(i, j, k, 3) = 1.0; st(i, j, k, 4) = 0.0;
+  } else if (probtype == 101) {
+    // synthetic wall-bounded test field (not in the reference): params = amplitude, density, density variation
+    const double pi = 0.5 * twopi, A = pp.v[0], dens = pp.v[1], vd = pp.v[2];
+    const double X = (x - g.prob_lo[0]) / ((g.domain.hi[0] - g.domain.lo[0] + 1) * g.dx[0]);
+    const double Y = (y - g.prob_lo[1]) / ((g.domain.hi[1] - g.domain.lo[1] + 1) * g.dx[1]);
+    const double Z = (z - g.prob_lo[2]) / ((g.domain.hi[2] - g.domain.lo[2] + 1) * g.dx[2]);
+    st(i, j, k, 0) = A * sin(pi * X) * cos(twopi * Y) * cos(pi * Z);
+    st(i, j, k, 1) = -A * cos(pi * X) * sin(twopi * Y) * cos(twopi * Z) * 0.5;
+    st(i, j, k, 2) = A * 0.3 * sin(twopi * X) * sin(twopi * Y) * sin(pi * Z);
+    st(i, j, k, 3) = dens * (1.0 + vd * cos(twopi * X) * cos(twopi * Y) * cos(pi * Z));
+    st(i, j, k, 4) = exp(-20.0 * ((X - 0.4) * (X - 0.4) + (Y - 0.5) * (Y - 0.5) + (Z - 0.6) * (Z - 0.6)));
   } else if (probtype == 20) {
     // HIT (Tutorials/HIT/prob_init.cpp:100-131): params = turb_scale, density [, amplitude of the synthetic density variation
     // of BASELINE.json's "variable-density HIT"; 0 = the reference's constant density].  Lz is measured from prob_lo[1] as

@@ -23,14 +23,16 @@ struct LevelSolvers {
 };
 
 int mac_project(Level& L, LevelSolvers& sv, MF U[3], const MF& rho, const MF* rhs, MF& phi,
-                double rhs_scale, iamrx_mg_info* info, cudaStream_t s);
+                double rhs_scale, iamrx_mg_info* info, cudaStream_t s, const k::LinBC* bc = nullptr);
 int mac_get_fluxes(Level& L, LevelSolvers& sv, MF F[3], MF& phi, cudaStream_t s);
 int nodal_project(Level& L, LevelSolvers& sv, MF& vel, const MF& sigma, MF& phi, MF* gp,
-                  int increment_gp, iamrx_mg_info* info, cudaStream_t s);
+                  int increment_gp, iamrx_mg_info* info, cudaStream_t s, const k::NodalBC* bc = nullptr);
 int diffusion_apply(Level& L, LevelSolvers& sv, bool tensor, int ncomp, MF& out, MF& soln, double a,
-                    double b, const MF* acoef, MF eta[3], cudaStream_t s);
+                    double b, const MF* acoef, MF eta[3], cudaStream_t s, const k::LinBC* bc = nullptr);
 int diffusion_solve(Level& L, LevelSolvers& sv, bool tensor, int ncomp, MF& soln, const MF& rhs,
-                    double a, double b, const MF* acoef, MF eta[3], iamrx_mg_info* info, cudaStream_t s);
+                    double a, double b, const MF* acoef, MF eta[3], iamrx_mg_info* info, cudaStream_t s,
+                    const k::LinBC* bc = nullptr);
+k::LinBC periodic_linbc();
 // MLNodeLaplacian::compGrad (NSB.cpp:4106-4118): gp = grad(p) on cell centres
 int comp_grad(Level& L, MF& gp, MF& p, cudaStream_t s);
 

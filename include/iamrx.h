@@ -303,6 +303,14 @@ int iamrx_debug_fb_plan(iamrx_level_t lev, int ixtype, int ng, int cap, int* dst
 int iamrx_fill_boundary(iamrx_level_t lev, iamrx_fab* fabs, int ixtype, int ncomp,
                         int ngrow, void* stream);
 
+/* The physical-boundary part of AmrLevel::FillPatch for cell-centred state data (NSB.cpp:4399,4435,3382; the fill
+ * functions of NS_bcfill.H:17-167 with the BCRec tables of NS_BC.H:7-55): cells outside the non-periodic sides of the
+ * domain.  Call after iamrx_fill_boundary.  bcrec: one BCRec per component; bcvals: the ext_dir face values
+ * [x lo, y lo, z lo, x hi, y hi, z hi][ncomp] (NavierStokes::get_bc_values; NULL = 0).  ext_dir ghost cells hold the
+ * value ON the face (Docs .../Software.rst:206-213). */
+int iamrx_fill_physbc(iamrx_level_t lev, iamrx_fab* fabs, int ncomp, int ngrow,
+                      const iamrx_bcrec* bcrec, const double* bcvals, void* stream);
+
 typedef struct iamrx_mg_info {
   double rtol;
   double atol;
@@ -314,7 +322,8 @@ typedef struct iamrx_mg_info {
   double omega;          /* GSRB over-relaxation (AMReX abec_gsrb: 1.15) */
   /* out */
   int iters;
-  int pad_;
+  int maxorder;          /* in: MLLinOp::setMaxOrder -- order of the Dirichlet ghost-cell extrapolation of the cell-centred
+                            operators (AMReX default 3; mac_proj.maxorder 4 MacProj.cpp:30; diffuse.max_order 2 Diffusion.cpp:95-96) */
   double resnorm0;
   double resnorm;
   double rhsnorm;
@@ -325,8 +334,11 @@ void iamrx_mg_info_default(iamrx_mg_info* info);
 /* MacProj::mlmg_mac_solve (MacProj.cpp:1084-1184) = Hydro::MacProjector
  * {ctor, setDomainBC, project}: beta_d = (1/rhs_scale)/avg(rho) on faces,
  * solve -div(beta grad phi) = -(div(umac) - rhs), umac -= beta grad phi.
- * rho: cell fabs with >=1 ghost (filled); umac[d]: face fabs; phi: cell fab,
- * 1 ghost; rhs may be NULL (divu == 0). */
+ * rho: cell fabs with >=1 ghost (filled, physical boundaries included); umac[d]: face fabs; phi: cell fab,
+ * 1 ghost; rhs may be NULL (divu == 0).  lobc/hibc: LinOpBCType of the six domain sides as set_mac_solve_bc
+ * builds them (MacProj.cpp:1187-1208: outflow -> Dirichlet, every other non-periodic side -> Neumann; NULL =
+ * periodic); the ghost cells of phi on entry are the level BC (setLevelBC(0, mac_phi), MacProj.cpp:1168) and
+ * info->maxorder the extrapolation order (setMaxOrder, :1172). */
 int iamrx_mac_project(iamrx_level_t lev, iamrx_fab* umac, iamrx_fab* vmac,
                       iamrx_fab* wmac, const iamrx_fab* rho, const iamrx_fab* rhs,
                       iamrx_fab* phi, double rhs_scale, const int lobc[3],
@@ -351,16 +363,27 @@ int iamrx_nodal_project(iamrx_level_t lev, iamrx_fab* vel, const iamrx_fab* sigm
 /* Diffusion: MLABecLaplacian / MLTensorOp solve and apply
  * (Diffusion.cpp:327-567, 715-768, 858-923, 1708-1757).
  *   (a*acoef - b*div(eta grad))soln = rhs   [+ tensor cross terms if tensor]
- * eta_[xyz]: face fabs, 1 comp.  soln: ncomp comps (3 if tensor), 1 ghost. */
+ * eta_[xyz]: face fabs, 1 comp.  soln: ncomp comps (3 if tensor), 1 ghost.
+ * bc: domain boundary conditions as Diffusion::setDomainBC builds them from the BCRec of each component
+ * (Diffusion.cpp:1887-1999: ext_dir -> Dirichlet, foextrap/hoextrap/reflect_even -> Neumann, reflect_odd ->
+ * reflect_odd), one set per component for the tensor operator (:711-724), plus setMaxOrder; NULL = periodic.
+ * The ghost cells of soln on entry are the level BC (setLevelBC(0, &Soln) :743-744, 886-887): the Dirichlet
+ * values ON the faces, as the FillPatch that precedes the call leaves them. */
+typedef struct iamrx_linop_bc {
+  int lo[3][3];   /* [component][direction] IAMRX_LINOP_* (component 0 only unless ncomp > 1) */
+  int hi[3][3];
+  int maxorder;   /* diffuse.max_order / diffuse.tensor_max_order = 2 (Diffusion.cpp:95-96,102-103) */
+  int pad_;
+} iamrx_linop_bc;
 int iamrx_diffusion_apply(iamrx_level_t lev, int tensor, int ncomp, iamrx_fab* out,
                           iamrx_fab* soln, double a, double b, const iamrx_fab* acoef,
                           const iamrx_fab* eta_x, const iamrx_fab* eta_y,
-                          const iamrx_fab* eta_z, void* stream);
+                          const iamrx_fab* eta_z, const iamrx_linop_bc* bc, void* stream);
 int iamrx_diffusion_solve(iamrx_level_t lev, int tensor, int ncomp, iamrx_fab* soln,
                           const iamrx_fab* rhs, double a, double b,
                           const iamrx_fab* acoef, const iamrx_fab* eta_x,
                           const iamrx_fab* eta_y, const iamrx_fab* eta_z,
-                          iamrx_mg_info* info, void* stream);
+                          const iamrx_linop_bc* bc, iamrx_mg_info* info, void* stream);
 
 /* ------------------------------------------------------------------------
  * 4. The level time step: NavierStokes::advance (NS.cpp:543-691) and the

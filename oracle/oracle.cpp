@@ -102,6 +102,10 @@ struct Arr {
         for (int j = 0; j < n[1]; ++j)
           for (int i = 0; i < n[0]; ++i) dst[i + (long)n[0] * (j + (long)n[1] * (k + (long)n[2] * c))] = (*this)(i, j, k, c0 + c);
   }
+  // "padded" exchange format of the non-periodic entry points: the whole array INCLUDING its ng ghost layers,
+  // [comp][nz+2ng][ny+2ng][nx+2ng] (the high face / node of a non-periodic direction lives at index n, inside the layer)
+  void load_padded(const double* src) { std::copy(src, src + d.size(), d.begin()); }
+  void store_padded(double* dst) const { std::copy(d.begin(), d.end(), dst); }
   void copy_from(const Arr& s, int sc0, int dc0, int ncopy) {  // interior only
     for (int c = 0; c < ncopy; ++c)
 #pragma omp parallel for
@@ -1208,20 +1212,26 @@ void extrap_vel_to_faces(const Arr& vel, const Arr* f, AdvOpt opt, const double 
 // ===========================================================================
 // level solvers
 // ===========================================================================
-int mac_project(const int n[3], const double dx[3], Arr mac[3], Arr& rho, const Arr* rhs_in, Arr& phi, double rhs_scale, orc_mg* mgp) {
+// MacProj::mlmg_mac_solve + Hydro::MacProjector (MacProj.cpp:1084-1184).  bc (null: periodic): the LinOpBCType of every
+// side from set_mac_solve_bc (:1187-1208) and mac_proj.maxorder (:30,75); phi's ghost cells hold the level BC
+// (setLevelBC(0, mac_phi) :1168; mac_phi = 0 on entry :253).  rho: 1 ghost cell, filled (foextrap at walls).
+int mac_project(const int n[3], const double dx[3], Arr mac[3], Arr& rho, const Arr* rhs_in, Arr& phi, double rhs_scale, orc_mg* mgp,
+                const LinBC* bc = nullptr) {
   // beta = (1/rhs_scale)/avg(rho)  MacProj.cpp:1115-1127
   rho.fill_periodic();
   Arr beta[3];
   for (int d = 0; d < 3; ++d) {
     beta[d].define(n, 1, 1);
     Arr& B = beta[d];
-    FOR_CELLS(B, i, j, k) B(i, j, k) = (1.0 / rhs_scale) / (0.5 * (rho(i - e0(d), j - e1(d), k - e2(d)) + rho(i, j, k)));
+    FOR_FACES(B, d, i, j, k) B(i, j, k) = (1.0 / rhs_scale) / (0.5 * (rho(i - e0(d), j - e1(d), k - e2(d)) + rho(i, j, k)));
     B.fill_periodic();
     mac[d].fill_periodic();
   }
   CellMG mg(n, dx, 1, false, mgp ? mgp->max_coarsening : 100);
   if (mgp) mg.mg = *mgp;
   mg.a = 0.0; mg.b = 1.0;
+  Arr levelbc;
+  if (bc) { levelbc = phi; mg.set_bc(*bc, &levelbc); }
   const Arr* e[3] = {&beta[0], &beta[1], &beta[2]};
   mg.set_coeffs(nullptr, e);
   Arr rhs(n, 1, 0);
@@ -1230,23 +1240,44 @@ int mac_project(const int n[3], const double dx[3], Arr mac[3], Arr& rho, const 
                 (mac[2](i, j, k + 1) - mac[2](i, j, k)) / dx[2];
     rhs(i, j, k) = -dv + (rhs_in ? (*rhs_in)(i, j, k) : 0.0);
   }
-  const int rc = mg.solve(phi, rhs);
+  const int rc = mg.solve(phi, rhs);   // ghost cells of phi are BC-filled on return (setFinalFillBC)
   if (mgp) *mgp = mg.mg;
-  for (int d = 0; d < 3; ++d) {  // umac -= beta grad phi
+  for (int d = 0; d < 3; ++d) {  // umac += fluxes = -beta grad phi; a Neumann face has zero flux (its ghost equals the interior cell)
     Arr& U = mac[d]; const Arr& B = beta[d];
-    FOR_CELLS(U, i, j, k) U(i, j, k) -= B(i, j, k) * (phi(i, j, k) - phi(i - e0(d), j - e1(d), k - e2(d))) / dx[d];
+    FOR_FACES(U, d, i, j, k) U(i, j, k) -= B(i, j, k) * (phi(i, j, k) - phi(i - e0(d), j - e1(d), k - e2(d))) / dx[d];
     U.fill_periodic();
   }
   return rc;
 }
 
-int nodal_project(const int n[3], const double dx[3], Arr& vel, Arr& sigma, Arr& phi, Arr* gp, bool increment, orc_mg* mgp) {
+// Projection::set_boundary_velocity (Projection.cpp:2570-2663): the normal velocity in the ghost cells beyond every
+// non-periodic side is zeroed unless that side is an inflow face (whose ghost cells carry the inflow velocity)
+void set_boundary_velocity(Arr& vel, const NodalBC& bc) {
+  for (int d = 0; d < 3; ++d) {
+    if (g_per[d]) continue;
+    const int d1 = (d + 1) % 3, d2 = (d + 2) % 3;
+    for (int side = -1; side <= 1; side += 2) {
+      if ((side < 0 ? bc.lo[d] : bc.hi[d]) == LO_INFLOW) continue;
+      const int g = side < 0 ? -1 : vel.n[d];
+#pragma omp parallel for
+      for (int b2 = -1; b2 <= vel.n[d2]; ++b2)
+        for (int b1 = -1; b1 <= vel.n[d1]; ++b1) { int q[3]; q[d] = g; q[d1] = b1; q[d2] = b2; vel(q[0], q[1], q[2], d) = 0.0; }
+    }
+  }
+}
+
+// Projection::doMLMGNodalProjection + Hydro::NodalProjector (Projection.cpp:2385-2567).  With a non-periodic side phi
+// carries 2 ghost layers (the ghost node of a high side is index n+1) and vel's ghost cells beyond inflow sides hold
+// the inflow velocity.
+int nodal_project(const int n[3], const double dx[3], Arr& vel, Arr& sigma, Arr& phi, Arr* gp, bool increment, orc_mg* mgp,
+                  const NodalBC& bc = PERIODIC_NBC) {
   const double dxinv[3] = {1.0 / dx[0], 1.0 / dx[1], 1.0 / dx[2]};
-  NodeMG mg(n, dx, mgp ? mgp->max_coarsening : 100);
+  NodeMG mg(n, dx, mgp ? mgp->max_coarsening : 100, bc);
   if (mgp) mg.mg = *mgp;
   mg.set_sigma(sigma);
-  Arr rhs(n, 1, 1);
-  nodal_divu(dxinv, vel, rhs);
+  set_boundary_velocity(vel, bc);
+  Arr rhs(n, 1, 2);
+  nodal_divu(dxinv, vel, rhs, bc);
   const int rc = mg.solve(phi, rhs);
   if (mgp) *mgp = mg.mg;
   Arr g(n, 3, 0);
@@ -1275,6 +1306,76 @@ struct orc_ns {
   int it[3] = {0, 0, 0};
   Arr force;  // velocity forcing from predict_velocity (1 ghost), reused by velocity_advection
   Arr seta[3];  // tracer diffusivity on faces (getDiffusivity: constant ns.scal_diff_coefs, NS.cpp:2051-2119)
+  // ---- physical boundaries (ns.lo_bc / ns.hi_bc, geometry.is_periodic; NS.cpp:90-237) --------------------------------
+  int per[3] = {1, 1, 1}, phys_lo[3] = {0, 0, 0}, phys_hi[3] = {0, 0, 0};
+  double bcv[6][5] = {};   // Dirichlet face values per face (x lo, y lo, z lo, x hi, y hi, z hi) and state component
+  bool has_walls() const { return !(per[0] && per[1] && per[2]); }
+  // NS_BC.H:7-38 : physical type -> math BC of every state component / of grad p
+  static int math_bc(const int* table, int phys) { return table[phys]; }
+  BCRec state_bc(int comp) const {
+    static const int norm_vel[6] = {BC_INT_DIR, BC_EXT_DIR, BC_FOEXTRAP, BC_REFLECT_ODD, BC_EXT_DIR, BC_EXT_DIR};
+    static const int tang_vel[6] = {BC_INT_DIR, BC_EXT_DIR, BC_FOEXTRAP, BC_REFLECT_EVEN, BC_HOEXTRAP, BC_EXT_DIR};
+    static const int scalar[6] = {BC_INT_DIR, BC_EXT_DIR, BC_FOEXTRAP, BC_REFLECT_EVEN, BC_FOEXTRAP, BC_FOEXTRAP};
+    BCRec b;
+    for (int d = 0; d < 3; ++d) {
+      const int* t = comp < 3 ? (comp == d ? norm_vel : tang_vel) : scalar;
+      b.lo[d] = per[d] ? BC_INT_DIR : t[phys_lo[d]]; b.hi[d] = per[d] ? BC_INT_DIR : t[phys_hi[d]];
+    }
+    return b;
+  }
+  BCRec gradp_bc(int comp) const {
+    static const int norm_gp[6] = {BC_INT_DIR, BC_FOEXTRAP, BC_FOEXTRAP, BC_REFLECT_ODD, BC_FOEXTRAP, BC_FOEXTRAP};
+    static const int tang_gp[6] = {BC_INT_DIR, BC_FOEXTRAP, BC_FOEXTRAP, BC_REFLECT_EVEN, BC_FOEXTRAP, BC_FOEXTRAP};
+    BCRec b;
+    for (int d = 0; d < 3; ++d) {
+      const int* t = comp == d ? norm_gp : tang_gp;
+      b.lo[d] = per[d] ? BC_INT_DIR : t[phys_lo[d]]; b.hi[d] = per[d] ? BC_INT_DIR : t[phys_hi[d]];
+    }
+    return b;
+  }
+  // AmrLevel::FillPatch of State_Type on one level: valid copy, periodic images, physical boundaries (NS_bcfill.H)
+  void fillpatch(Arr& dst, const Arr& src, int scomp, int ncomp) const {
+    dst.copy_from(src, scomp, 0, ncomp);
+    fill_state_bc(dst, scomp, ncomp);
+  }
+  void fill_state_bc(Arr& a, int scomp, int ncomp) const {
+    a.fill_periodic();
+    if (!has_walls()) return;
+    std::vector<BCRec> b(ncomp); std::vector<double> v(6 * ncomp);
+    for (int c = 0; c < ncomp; ++c) { b[c] = state_bc(scomp + c); for (int f = 0; f < 6; ++f) v[f * ncomp + c] = bcv[f][scomp + c]; }
+    fill_physbc(a, 0, ncomp, b.data(), v.data());
+  }
+  void fill_gradp(Arr& gp) const {   // FillPatch of Gradp_Type (NS_setup.cpp:339-360)
+    gp.fill_periodic();
+    if (!has_walls()) return;
+    BCRec b[3] = {gradp_bc(0), gradp_bc(1), gradp_bc(2)};
+    fill_physbc(gp, 0, 3, b, nullptr);
+  }
+  static int linop_of(int math) {   // Diffusion::setDomainBC (Diffusion.cpp:1887-1999)
+    return math == BC_EXT_DIR ? LO_DIRICHLET : (math == BC_REFLECT_ODD ? LO_REFLECT_ODD : (math == BC_INT_DIR ? LO_PERIODIC : LO_NEUMANN));
+  }
+  LinBC diff_bc(int scomp, int ncomp, int maxorder = 2) const {   // diffuse.max_order / tensor_max_order = 2 (Diffusion.cpp:95-96)
+    LinBC L; L.maxorder = maxorder;
+    for (int c = 0; c < ncomp && c < 3; ++c) { const BCRec b = state_bc(scomp + c); for (int d = 0; d < 3; ++d) { L.lo[c][d] = linop_of(b.lo[d]); L.hi[c][d] = linop_of(b.hi[d]); } }
+    return L;
+  }
+  LinBC mac_bc() const {   // set_mac_solve_bc (MacProj.cpp:1187-1208), mac_proj.maxorder = 4 (MacProj.cpp:30)
+    LinBC L; L.maxorder = 4;
+    for (int d = 0; d < 3; ++d) {
+      L.lo[0][d] = per[d] ? LO_PERIODIC : (phys_lo[d] == PHYS_OUTFLOW ? LO_DIRICHLET : LO_NEUMANN);
+      L.hi[0][d] = per[d] ? LO_PERIODIC : (phys_hi[d] == PHYS_OUTFLOW ? LO_DIRICHLET : LO_NEUMANN);
+    }
+    return L;
+  }
+  NodalBC nodal_bc() const {   // Projection.cpp:2436-2464
+    NodalBC B;
+    for (int d = 0; d < 3; ++d) {
+      B.lo[d] = per[d] ? LO_PERIODIC : (phys_lo[d] == PHYS_OUTFLOW ? LO_DIRICHLET : (phys_lo[d] == PHYS_INFLOW ? LO_INFLOW : LO_NEUMANN));
+      B.hi[d] = per[d] ? LO_PERIODIC : (phys_hi[d] == PHYS_OUTFLOW ? LO_DIRICHLET : (phys_hi[d] == PHYS_INFLOW ? LO_INFLOW : LO_NEUMANN));
+    }
+    return B;
+  }
+  std::vector<BCRec> adv_bc(int scomp, int ncomp) const { std::vector<BCRec> b(ncomp); for (int c = 0; c < ncomp; ++c) b[c] = state_bc(scomp + c); return b; }
 
   orc_mg mg(double rtol, double atol) const { orc_mg m; orc_mg_default(&m); m.rtol = rtol; m.atol = atol; return m; }
   bool diffusive() const { return p.visc_coef > 0.0; }
@@ -1284,49 +1385,55 @@ struct orc_ns {
   // getViscTerms -> getTensorViscTerms (Diffusion.cpp:1655-1777): a = 0, b = -1
   void visc_terms(const Arr& S, Arr& visc) {
     if (!diffusive()) { visc.setval(0.0); return; }
-    Arr u(n, 3, 1); u.copy_from(S, Xvel, 0, 3);
+    Arr u(n, 3, 1); fillpatch(u, S, Xvel, 3);     // Diffusion.cpp:1745: FillPatch'd Soln is the level BC
+    Arr lbc = u;
     CellMG op(n, dx, 3, true, 0);
     op.a = 0.0; op.b = -1.0;
+    if (has_walls()) op.set_bc(diff_bc(Xvel, 3), &lbc);
     const Arr* e[3] = {&eta[0], &eta[1], &eta[2]};
     op.set_coeffs(nullptr, e);
     op.apply(visc, u);
     visc.fill_periodic();
+    if (has_walls()) first_order_extrap(visc, 0, 3);   // NS.cpp:2045-2046
   }
   double ext_force(int c, double rho) const { return (c == 2 && std::fabs(p.gravity) > 1.0e-4) ? p.gravity * rho : 0.0; }  // NS_getForce.cpp:117-141
 
   int advance(double dt, double* dt_test) {
     // advance_setup NSB.cpp:613-741
     std::swap(S_old, S_new); std::swap(P_old, P_new); std::swap(Gp_old, Gp_new);
-    rho_p.copy_from(S_old, Density, 0, 1); rho_p.fill_periodic();
+    fillpatch(rho_p, S_old, Density, 1);
     // ---- predict_velocity NSB.cpp:4376-4512
-    Arr Umf(n, 3, 3); Umf.copy_from(S_old, Xvel, 0, 3); Umf.fill_periodic();
+    Arr Umf(n, 3, 3); fillpatch(Umf, S_old, Xvel, 3);
     for (double& v : Umf.d) v = (std::fabs(v) > 1.0e-20) ? v : 0.0;  // floor :4530-4534
     double cflmax = 0.0;
     for (int d = 0; d < 3; ++d) cflmax = std::max(cflmax, dt * Umf.norminf(d) / dx[d]);
     const double tempdt = (cflmax == 0.0) ? p.change_max : std::min(p.change_max, p.cfl / cflmax);
     Arr visc(n, 3, 1);
     if (p.be_cn_theta != 1.0) visc_terms(S_old, visc); else visc.setval(0.0);
-    Arr Smf(n, 2, 3); Smf.copy_from(S_old, Density, 0, 2); Smf.fill_periodic();
-    Gp_old.fill_periodic();
+    Arr Smf(n, 2, 3); fillpatch(Smf, S_old, Density, 2);
+    fill_gradp(Gp_old);
     force.define(n, 3, 1);
     for (int c = 0; c < 3; ++c) {
       FOR_G1(force, i, j, k) force(i, j, k, c) = (ext_force(c, Smf(i, j, k, 0)) + visc(i, j, k, c) - Gp_old(i, j, k, c)) / Smf(i, j, k, 0);  // :4466-4470
     }
-    const AdvOpt aopt{p.use_forces_in_trans != 0, p.use_ppm != 0};
+    const std::vector<BCRec> vbc = adv_bc(Xvel, 3), sbc = adv_bc(Density, 2);
+    const AdvOpt aopt{p.use_forces_in_trans != 0, p.use_ppm != 0, has_walls() ? vbc.data() : nullptr, true};
+    const AdvOpt sopt{p.use_forces_in_trans != 0, p.use_ppm != 0, has_walls() ? sbc.data() : nullptr, false};
     extrap_vel_to_faces(Umf, &force, aopt, dx, dt, umac);  // :4487
     *dt_test = dt * tempdt;
     // ---- mac_project NS.cpp:589-597, MacProj.cpp:225-353
     Arr mac_phi(n, 1, 1);
     orc_mg m1 = mg(p.mac_tol, p.mac_abs_tol);
-    int rc = mac_project(n, dx, umac, rho_p, nullptr, mac_phi, 2.0 / dt, &m1);
+    const LinBC mbc = mac_bc();
+    int rc = mac_project(n, dx, umac, rho_p, nullptr, mac_phi, 2.0 / dt, &m1, has_walls() ? &mbc : nullptr);
     it[0] = m1.iters;
     if (rc) return rc;
     // ---- velocity_advection NSB.cpp:3358-3470 (fresh un-floored FillPatch copy, same forcing); with do_mom_diff it runs AFTER
     //      rho^{n+1} exists (NS.cpp:606-623), advects the momentum rho^n u^n conservatively and its forcing is not divided by rho
     auto velocity_advection = [&]() {
-      Arr Umf2(n, 3, 3); Umf2.copy_from(S_old, Xvel, 0, 3); Umf2.fill_periodic();
+      Arr Umf2(n, 3, 3); fillpatch(Umf2, S_old, Xvel, 3);
       if (p.do_mom_diff) {
-        Arr rho3(n, 1, 3); rho3.copy_from(S_old, Density, 0, 1); rho3.fill_periodic();
+        Arr rho3(n, 1, 3); fillpatch(rho3, S_old, Density, 1);
         for (int c = 0; c < 3; ++c) {
 #pragma omp parallel for
           for (int k = -3; k < n[2] + 3; ++k) for (int j = -3; j < n[1] + 3; ++j) for (int i = -3; i < n[0] + 3; ++i) Umf2(i, j, k, c) *= rho3(i, j, k);
@@ -1346,26 +1453,29 @@ struct orc_ns {
     if (diffusive_tracer() && p.be_cn_theta != 1.0) {
       // NavierStokes::getViscTerms (NS.cpp:2012-2048) -> Diffusion::getViscTerms (Diffusion.cpp:1540-1652): a = 0, b = -1 applied to
       // S (rho_flag 0) or S/rho (rho_flag 2), then FillBoundary; tf = tf/rho + visc or tf + visc with zero body force (NS.cpp:774-804)
-      Arr s1(n, 1, 1); s1.copy_from(S_old, Tracer, 0, 1);
-      if (rho_flag() == 2) { FOR_CELLS(s1, i, j, k) s1(i, j, k) /= S_old(i, j, k, Density); }
+      Arr s1(n, 1, 1); fillpatch(s1, S_old, Tracer, 1);
+      if (rho_flag() == 2) { FOR_G1(s1, i, j, k) s1(i, j, k) /= rho_p(i, j, k); }
+      Arr lbc = s1;
       CellMG op(n, dx, 1, false, 0);
       op.a = 0.0; op.b = -1.0;
+      if (has_walls()) op.set_bc(diff_bc(Tracer, 1), &lbc);
       const Arr* e[3] = {&seta[0], &seta[1], &seta[2]};
       op.set_coeffs(nullptr, e);
       Arr sv(n, 1, 1);
       op.apply(sv, s1);
       sv.fill_periodic();
+      if (has_walls()) first_order_extrap(sv, 0, 1);
       FOR_G1(sforce, i, j, k) sforce(i, j, k, 1) = sv(i, j, k);
     }
     const int ic_scal[2] = {1, p.conservative_tracer ? 1 : 0};
-    compute_aofs(Smf, 2, &sforce, nullptr, umac, ic_scal, aopt, dx, dt, aofs, Density, nullptr, nullptr);
+    compute_aofs(Smf, 2, &sforce, nullptr, umac, ic_scal, sopt, dx, dt, aofs, Density, nullptr, nullptr);
     // ---- scalar updates NSB.cpp:2761-2765, 2887-2896
     FOR_CELLS(S_new, i, j, k) S_new(i, j, k, Density) = S_old(i, j, k, Density) - dt * aofs(i, j, k, Density);
-    rho_c.copy_from(S_new, Density, 0, 1); rho_c.fill_periodic();
+    fillpatch(rho_c, S_new, Density, 1);
     if (p.do_mom_diff) velocity_advection();
     FOR_CELLS(S_new, i, j, k) S_new(i, j, k, Tracer) = S_old(i, j, k, Tracer) - dt * aofs(i, j, k, Tracer);
     if (p.do_scalminmax) {   // NSB.cpp:2907-2935 -> Conservative / ConvectiveScalMinMax (:4256-4370) on an un-floored copy of the old scalars
-      Arr so(n, 2, 1); so.copy_from(S_old, Density, 0, 2); so.fill_periodic();
+      Arr so(n, 2, 1); fillpatch(so, S_old, Density, 2);
       const bool cons = p.conservative_tracer != 0;
       FOR_CELLS(S_new, i, j, k) {
         double smn = std::numeric_limits<double>::max(), smx = std::numeric_limits<double>::min();   // sic: smallest positive value
@@ -1406,24 +1516,26 @@ struct orc_ns {
     const Arr* e[3] = {&seta[0], &seta[1], &seta[2]};
     Arr rhs(n, 1, 0);
     if (th != 1.0) {   // :364-430: Rhs = -(b) div beta grad (old solution), a = 0, b = -(1-theta) dt
-      Arr so(n, 1, 1); so.copy_from(S_old, Tracer, 0, 1);
-      if (rf == 2) { FOR_CELLS(so, i, j, k) so(i, j, k) /= S_old(i, j, k, Density); }
+      Arr so(n, 1, 1); fillpatch(so, S_old, Tracer, 1);
+      if (rf == 2) { FOR_G1(so, i, j, k) so(i, j, k) /= rho_p(i, j, k); }
+      Arr lbc = so;
       CellMG ex(n, dx, 1, false, 0);
       ex.a = 0.0; ex.b = -(1.0 - th) * dt;
+      if (has_walls()) ex.set_bc(diff_bc(Tracer, 1), &lbc);
       ex.set_coeffs(nullptr, e);
       ex.apply(rhs, so);
     }
     FOR_CELLS(rhs, i, j, k) rhs(i, j, k) += S_new(i, j, k, Tracer);   // :465-490 (rho_flag 0 and 2: no scaling)
     Arr soln(n, 1, 1), alpha(n, 1, 0);
-    FOR_CELLS(soln, i, j, k) {   // :520-540 initial guess = new state (/ rho_new), :1355-1395 computeAlpha
-      const double r = S_new(i, j, k, Density);
-      soln(i, j, k) = (rf == 2) ? S_new(i, j, k, Tracer) / r : S_new(i, j, k, Tracer);
-      alpha(i, j, k) = (rf == 2) ? r : 1.0;
-    }
+    fillpatch(soln, S_new, Tracer, 1);   // :520-540 initial guess = FillPatch'd new state (/ rho_new) incl. its ghost cells = the level BC
+    if (rf == 2) { FOR_G1(soln, i, j, k) soln(i, j, k) /= rho_c(i, j, k); }
+    FOR_CELLS(alpha, i, j, k) alpha(i, j, k) = (rf == 2) ? S_new(i, j, k, Density) : 1.0;   // :1355-1395 computeAlpha
+    Arr lbc1 = soln;
     const double tol_abs = p.visc_tol * rhs.norminf(0);   // get_scaled_abs_tol :193-204
     CellMG im(n, dx, 1, false, 100);
     im.mg = mg(p.visc_tol, tol_abs);
     im.a = 1.0; im.b = th * dt;
+    if (has_walls()) im.set_bc(diff_bc(Tracer, 1), &lbc1);
     im.set_coeffs(&alpha, e);
     const int rc = im.solve(soln, rhs);
     FOR_CELLS(soln, i, j, k) S_new(i, j, k, Tracer) = (rf == 2) ? soln(i, j, k) * S_new(i, j, k, Density) : soln(i, j, k);   // :575-590
@@ -1437,9 +1549,11 @@ struct orc_ns {
     const Arr* e[3] = {&eta[0], &eta[1], &eta[2]};
     Arr rhs(n, 3, 0);
     if (th != 1.0) {
-      Arr u(n, 3, 1); u.copy_from(S_old, Xvel, 0, 3);
+      Arr u(n, 3, 1); fillpatch(u, S_old, Xvel, 3);   // Diffusion.cpp:742-743: FillPatch at prev_time = the level BC
+      Arr lbc = u;
       CellMG ex(n, dx, 3, true, 0);
       ex.a = 0.0; ex.b = -(1.0 - th) * dt;
+      if (has_walls()) ex.set_bc(diff_bc(Xvel, 3), &lbc);
       ex.set_coeffs(nullptr, e);
       ex.apply(rhs, u);
     }
@@ -1450,10 +1564,12 @@ struct orc_ns {
       }
     }
     const double tol_abs = p.visc_tol * (rhs.norminf(0) + rhs.norminf(1) + rhs.norminf(2)) / 3.0;  // get_scaled_abs_tol :193-204
-    Arr soln(n, 3, 1); soln.copy_from(S_new, Xvel, 0, 3);
+    Arr soln(n, 3, 1); fillpatch(soln, S_new, Xvel, 3);   // :885-886 FillPatch at cur_time (U_new holds rho U* by now) = the level BC
+    Arr lbc2 = soln;
     CellMG im(n, dx, 3, true, 100);
     im.mg = mg(p.visc_tol, tol_abs);
     im.a = 1.0; im.b = th * dt;
+    if (has_walls()) im.set_bc(diff_bc(Xvel, 3), &lbc2);
     Arr rho_n(n, 1, 0); rho_n.copy_from(S_new, Density, 0, 1);
     im.set_coeffs(p.do_mom_diff ? &rho_n : &rho_half, e);   // :893-897 alpha = rho_half or (rho_flag 3) the NEW density
     const int rc = im.solve(soln, rhs);
@@ -1483,10 +1599,10 @@ struct orc_ns {
     for (int c = 0; c < 3; ++c) { FOR_CELLS(vel, i, j, k) vel(i, j, k, c) = S_new(i, j, k, c) * (1.0 / dt) + Gp_old(i, j, k, c) / rho_half(i, j, k); }
     FOR_CELLS(sig, i, j, k) sig(i, j, k) = 1.0 / rho_half(i, j, k);
     orc_mg m = mg(p.proj_tol, p.proj_abs_tol);
-    const int rc = nodal_project(n, dx, vel, sig, P_new, &Gp_new, false, &m);
+    const int rc = nodal_project(n, dx, vel, sig, P_new, &Gp_new, false, &m, nodal_bc());
     it[2] = m.iters;
     if (rc) return rc;
-    Gp_new.fill_periodic();
+    fill_gradp(Gp_new);   // Projection.cpp:2565 FillPatch of Gradp
     for (int c = 0; c < 3; ++c) { FOR_CELLS(vel, i, j, k) S_new(i, j, k, c) = vel(i, j, k, c) * dt; }
     return 0;
   }
@@ -1704,6 +1820,118 @@ void orc_compute_aofs2(const int n[3], const double dx[3], double dt, int ncomp,
   for (int d = 0; d < 3; ++d) { if (fo[d]) fl[d].store(fo[d]); if (eo[d] && !known) ed[d].store(eo[d]); }
 }
 
+/* ------------------------------------------------------------------------------------------------------------------
+ * Non-periodic domains.  Arrays are exchanged "padded" (with their ghost layers, see Arr::load_padded); bclo / bchi are
+ * BCRec codes [ncomp][3], lobc / hibc LinOpBCType codes.
+ * ---------------------------------------------------------------------------------------------------------------- */
+static std::vector<BCRec> bcrecs(int ncomp, const int* bclo, const int* bchi) {
+  std::vector<BCRec> b(ncomp);
+  for (int c = 0; c < ncomp; ++c) for (int d = 0; d < 3; ++d) { b[c].lo[d] = bclo[3 * c + d]; b[c].hi[d] = bchi[3 * c + d]; }
+  return b;
+}
+void orc_fill_physbc(const int n[3], const int per[3], int ng, int ncomp, const int* bclo, const int* bchi, const double* bcv, double* a) {
+  PerScope ps(per);
+  Arr A(n, ncomp, ng); A.load_padded(a);
+  A.fill_periodic();
+  const std::vector<BCRec> b = bcrecs(ncomp, bclo, bchi);
+  fill_physbc(A, 0, ncomp, b.data(), bcv);
+  A.store_padded(a);
+}
+void orc_extrap_vel_to_faces_bc(const int n[3], const int per[3], const double dx[3], double dt, const double* vel /*ng 3*/,
+                                const double* force /*ng 1 or NULL*/, int flags, const int* bclo, const int* bchi,
+                                double* umac, double* vmac, double* wmac /*ng 1*/) {
+  PerScope ps(per);
+  Arr v(n, 3, 3), f; v.load_padded(vel);
+  if (force) { f.define(n, 3, 1); f.load_padded(force); }
+  const std::vector<BCRec> b = bcrecs(3, bclo, bchi);
+  Arr mac[3] = {Arr(n, 1, 1), Arr(n, 1, 1), Arr(n, 1, 1)};
+  extrap_vel_to_faces(v, force ? &f : nullptr, AdvOpt{(flags & 1) != 0, (flags & 2) != 0, b.data(), true}, dx, dt, mac);
+  mac[0].store_padded(umac); mac[1].store_padded(vmac); mac[2].store_padded(wmac);
+}
+void orc_compute_aofs_bc(const int n[3], const int per[3], const double dx[3], double dt, int ncomp, const double* S /*ng 3*/,
+                         const double* force /*ng 1*/, const double* divu /*ng 1*/, const double* umac, const double* vmac,
+                         const double* wmac /*ng 1*/, const int* iconserv, int flags /*1 fit, 2 ppm, 4 is_velocity*/, const int* bclo,
+                         const int* bchi, double* aofs /*dense*/, double* fx, double* fy, double* fz, double* xed, double* yed, double* zed /*ng 1 or NULL*/) {
+  PerScope ps(per);
+  Arr q(n, ncomp, 3), f, dv; q.load_padded(S);
+  if (force) { f.define(n, ncomp, 1); f.load_padded(force); }
+  if (divu) { dv.define(n, 1, 1); dv.load_padded(divu); }
+  Arr mac[3]; const double* m[3] = {umac, vmac, wmac};
+  for (int d = 0; d < 3; ++d) { mac[d].define(n, 1, 1); mac[d].load_padded(m[d]); }
+  const std::vector<BCRec> b = bcrecs(ncomp, bclo, bchi);
+  Arr a(n, ncomp, 0);
+  Arr fl[3], ed[3]; Arr* flp[3] = {nullptr, nullptr, nullptr}; Arr* edp[3] = {nullptr, nullptr, nullptr};
+  double* fo[3] = {fx, fy, fz}; double* eo[3] = {xed, yed, zed};
+  for (int d = 0; d < 3; ++d) {
+    if (fo[d]) { fl[d].define(n, ncomp, 1); flp[d] = &fl[d]; }
+    if (eo[d]) { ed[d].define(n, ncomp, 1); edp[d] = &ed[d]; }
+  }
+  compute_aofs(q, ncomp, force ? &f : nullptr, divu ? &dv : nullptr, mac, iconserv, AdvOpt{(flags & 1) != 0, (flags & 2) != 0, b.data(), (flags & 4) != 0},
+               dx, dt, a, 0, flp, edp);
+  a.store(aofs);
+  for (int d = 0; d < 3; ++d) { if (fo[d]) fl[d].store_padded(fo[d]); if (eo[d]) ed[d].store_padded(eo[d]); }
+}
+static LinBC linbc(int ncomp, const int* lobc, const int* hibc, int maxorder) {
+  LinBC L; L.maxorder = maxorder;
+  for (int c = 0; c < ncomp && c < 3; ++c) for (int d = 0; d < 3; ++d) { L.lo[c][d] = lobc[3 * c + d]; L.hi[c][d] = hibc[3 * c + d]; }
+  return L;
+}
+int orc_mac_project_bc(const int n[3], const int per[3], const double dx[3], double* umac, double* vmac, double* wmac /*ng 1*/,
+                       const double* rho /*ng 1, BC-filled*/, const double* rhs /*dense or NULL*/, double* phi /*ng 1; ghost = level BC*/,
+                       double rhs_scale, const int lobc[3], const int hibc[3], int maxorder, orc_mg* mg) {
+  PerScope ps(per);
+  Arr mac[3]; double* m[3] = {umac, vmac, wmac};
+  for (int d = 0; d < 3; ++d) { mac[d].define(n, 1, 1); mac[d].load_padded(m[d]); }
+  Arr r(n, 1, 1), p(n, 1, 1), rh; r.load_padded(rho); p.load_padded(phi);
+  if (rhs) { rh.define(n, 1, 0); rh.load(rhs); }
+  const LinBC L = linbc(1, lobc, hibc, maxorder);
+  const int rc = mac_project(n, dx, mac, r, rhs ? &rh : nullptr, p, rhs_scale, mg, &L);
+  for (int d = 0; d < 3; ++d) mac[d].store_padded(m[d]);
+  p.store_padded(phi);
+  return rc;
+}
+int orc_nodal_project_bc(const int n[3], const int per[3], const double dx[3], double* vel /*ng 1*/, const double* sigma /*dense*/,
+                         double* phi /*nodal, ng 2*/, double* gp /*dense, out*/, const int lobc[3], const int hibc[3], orc_mg* mg) {
+  PerScope ps(per);
+  Arr v(n, 3, 1), s(n, 1, 1), p(n, 1, 2), g(n, 3, 0); v.load_padded(vel); s.load(sigma); p.load_padded(phi);
+  NodalBC B; for (int d = 0; d < 3; ++d) { B.lo[d] = lobc[d]; B.hi[d] = hibc[d]; }
+  const int rc = nodal_project(n, dx, v, s, p, gp ? &g : nullptr, false, mg, B);
+  v.store_padded(vel); p.store_padded(phi);
+  if (gp) g.store(gp);
+  return rc;
+}
+/* (a alpha - b div eta grad [+ tensor cross terms]) with domain BCs; soln's ghost cells hold the level BC (Dirichlet face
+ * values).  solve != 0: multigrid solve of ... = rhs into soln; else out = L(soln). */
+int orc_diffusion_bc(const int n[3], const int per[3], const double dx[3], int solve, int tensor, int ncomp, double a, double b,
+                     const double* alpha /*dense*/, const double* ex, const double* ey, const double* ez /*ng 1*/, const double* rhs /*dense*/,
+                     double* soln /*ng 1*/, double* out /*dense*/, const int* lobc, const int* hibc, int maxorder, orc_mg* mgp) {
+  PerScope ps(per);
+  Arr e[3]; const double* es[3] = {ex, ey, ez};
+  for (int d = 0; d < 3; ++d) { e[d].define(n, 1, 1); e[d].load_padded(es[d]); }
+  Arr al; if (alpha) { al.define(n, 1, 0); al.load(alpha); }
+  CellMG mg(n, dx, ncomp, tensor != 0, solve ? (mgp ? mgp->max_coarsening : 100) : 0);
+  if (mgp) mg.mg = *mgp;
+  mg.a = a; mg.b = b;
+  Arr s(n, ncomp, 1); s.load_padded(soln);
+  Arr lbc = s;
+  const LinBC L = linbc(ncomp, lobc, hibc, maxorder);
+  mg.set_bc(L, &lbc);
+  const Arr* ep[3] = {&e[0], &e[1], &e[2]};
+  mg.set_coeffs(alpha ? &al : nullptr, ep);
+  int rc = 0;
+  if (solve) {
+    Arr r(n, ncomp, 0); r.load(rhs);
+    rc = mg.solve(s, r);
+    if (mgp) *mgp = mg.mg;
+    s.store_padded(soln);
+  } else {
+    Arr o(n, ncomp, 0);
+    mg.apply(o, s);
+    o.store(out);
+  }
+  return rc;
+}
+
 void orc_ns_params_default(orc_ns_params* p) {
   p->cfl = 0.7; p->visc_coef = 0.0; p->be_cn_theta = 0.5; p->change_max = 1.1; p->init_shrink = 1.0; p->fixed_dt = -1.0;
   p->gravity = 0.0; p->visc_tol = 1e-10; p->mac_tol = 1e-12; p->mac_abs_tol = 1e-16; p->proj_tol = 1e-12; p->proj_abs_tol = 1e-16;
@@ -1714,13 +1942,29 @@ orc_ns* orc_ns_create(const int n[3], const double prob_lo[3], const double prob
   orc_ns* ns = new orc_ns();
   for (int d = 0; d < 3; ++d) { ns->n[d] = n[d]; ns->prob_lo[d] = prob_lo[d]; ns->dx[d] = (prob_hi[d] - prob_lo[d]) / n[d]; }
   ns->p = *p;
-  ns->S_old.define(n, 5, 1); ns->S_new.define(n, 5, 1); ns->P_old.define(n, 1, 1); ns->P_new.define(n, 1, 1);
+  ns->S_old.define(n, 5, 1); ns->S_new.define(n, 5, 1); ns->P_old.define(n, 1, 2); ns->P_new.define(n, 1, 2);
   ns->Gp_old.define(n, 3, 1); ns->Gp_new.define(n, 3, 1); ns->aofs.define(n, 5, 0);
   ns->rho_p.define(n, 1, 1); ns->rho_c.define(n, 1, 1); ns->rho_half.define(n, 1, 1);
   for (int d = 0; d < 3; ++d) { ns->umac[d].define(n, 1, 1); ns->eta[d].define(n, 1, 1); ns->eta[d].setval(p->visc_coef); ns->seta[d].define(n, 1, 1); ns->seta[d].setval(p->scal_diff_coef); }
   return ns;
 }
+/* physical boundaries of the level (geometry.is_periodic, ns.lo_bc / ns.hi_bc, the Dirichlet face values of NS.cpp:108-237):
+ * call right after orc_ns_create.  Walls and symmetry planes only (inflow / outflow are exercised at operator level). */
+void orc_ns_set_bc(orc_ns* ns, const int per[3], const int phys_lo[3], const int phys_hi[3], const double* bcv /*[6][5]*/) {
+  for (int d = 0; d < 3; ++d) { ns->per[d] = per[d]; ns->phys_lo[d] = phys_lo[d]; ns->phys_hi[d] = phys_hi[d]; }
+  if (bcv) for (int f = 0; f < 6; ++f) for (int c = 0; c < 5; ++c) ns->bcv[f][c] = bcv[5 * f + c];
+}
 void orc_ns_destroy(orc_ns* ns) { delete ns; }
+/* which as orc_ns_get, padded: state ng 1, press ng 2 (nodal), gradp ng 1, umac ng 1 */
+void orc_ns_get_padded(const orc_ns* ns, int which, double* out) {
+  switch (which) {
+    case 0: ns->S_new.store_padded(out); break;
+    case 1: ns->P_new.store_padded(out); break;
+    case 2: ns->Gp_new.store_padded(out); break;
+    case 4: case 5: case 6: ns->umac[which - 4].store_padded(out); break;
+    default: break;
+  }
+}
 
 void orc_ns_init_prob(orc_ns* ns, int probtype, const double* pp, int npp) {
   // Source/prob/prob_init.cpp: 11 TaylorGreen :509-560, 5 DoubleShearLayer :346-405 (direction 1);
@@ -1740,6 +1984,25 @@ void orc_ns_init_prob(orc_ns* ns, int probtype, const double* pp, int npp) {
           S(i, j, k, 2) = 0.0;
           S(i, j, k, 3) = (probtype == 100) ? dens * (1.0 + 0.5 * std::sin(twopi * x) * std::sin(twopi * y) * std::sin(twopi * z)) : dens;
           S(i, j, k, 4) = (dens * vx * vx / 16.0) * (2.0 + std::cos(2.0 * c * twopi * z)) * (std::cos(2.0 * a * twopi * x) + std::cos(2.0 * b * twopi * y));
+        } else if (probtype == 10) {   // RayleighTaylor 3-D (prob_init.cpp:447-487): rho_1, rho_2, tra_1, tra_2, interface_width, pertamp
+          const double pi = 0.5 * twopi;
+          const double Lx = n[0] * ns->dx[0], Ly = n[1] * ns->dx[1], splitz = 0.5 * (ns->prob_lo[2] + (ns->prob_lo[2] + n[2] * ns->dx[2]));
+          const double ranampl = 2. * (0.6544437533747718 - 0.5), ranphse1 = 2. * pi * 0.1556190326530211, ranphse2 = 2. * pi * 0.4196144025537369;
+          const double pert = ranampl * std::sin(2.0 * pi * x / Lx + ranphse1) * std::sin(2.0 * pi * y / Ly + ranphse2);
+          const double pertheight = splitz - pp[5] * pert;
+          S(i, j, k, 0) = 0.0; S(i, j, k, 1) = 0.0; S(i, j, k, 2) = 0.0;
+          S(i, j, k, 3) = pp[0] + ((pp[1] - pp[0]) / 2.0) * (1.0 + std::tanh((z - pertheight) / pp[4]));
+          S(i, j, k, 4) = pp[2] + ((pp[3] - pp[2]) / 2.0) * (1.0 + std::tanh((z - pertheight) / pp[4]));
+        } else if (probtype == 1) {    // LidDrivenCavity: start from rest, density 1 (prob_init.cpp:102-109)
+          S(i, j, k, 0) = 0.0; S(i, j, k, 1) = 0.0; S(i, j, k, 2) = 0.0; S(i, j, k, 3) = 1.0; S(i, j, k, 4) = 0.0;
+        } else if (probtype == 101) {  // synthetic wall-bounded test field (not in the reference): pp = amplitude, density, density variation
+          const double pi = 0.5 * twopi, A = pp[0], dens = pp[1], vd = pp[2];
+          const double X = (x - ns->prob_lo[0]) / (n[0] * ns->dx[0]), Y = (y - ns->prob_lo[1]) / (n[1] * ns->dx[1]), Z = (z - ns->prob_lo[2]) / (n[2] * ns->dx[2]);
+          S(i, j, k, 0) = A * std::sin(pi * X) * std::cos(twopi * Y) * std::cos(pi * Z);
+          S(i, j, k, 1) = -A * std::cos(pi * X) * std::sin(twopi * Y) * std::cos(twopi * Z) * 0.5;
+          S(i, j, k, 2) = A * 0.3 * std::sin(twopi * X) * std::sin(twopi * Y) * std::sin(pi * Z);
+          S(i, j, k, 3) = dens * (1.0 + vd * std::cos(twopi * X) * std::cos(twopi * Y) * std::cos(pi * Z));
+          S(i, j, k, 4) = std::exp(-20.0 * ((X - 0.4) * (X - 0.4) + (Y - 0.5) * (Y - 0.5) + (Z - 0.6) * (Z - 0.6)));
         } else if (probtype == 20) {   // Tutorials/HIT/prob_init.cpp:100-131 (+ optional synthetic density variation pp[2])
           const double ts = pp[0], dens = pp[1], vd = npp > 2 ? pp[2] : 0.0;
           const double Lx = n[0] * ns->dx[0], Ly = n[1] * ns->dx[1], Lz = ns->prob_lo[2] + n[2] * ns->dx[2] - ns->prob_lo[1];   // :113
@@ -1763,19 +2026,34 @@ void orc_ns_init_prob(orc_ns* ns, int probtype, const double* pp, int npp) {
 }
 
 int orc_ns_post_init(orc_ns* ns, double* dt0) {
+  PerScope ps(ns->per);
   const int* n = ns->n;
   if (ns->p.do_init_proj) {  // initialVelocityProject Projection.cpp:615-838 (sigma = 1)
     for (int it = 0; it < ns->p.init_vel_iter; ++it) {
-      Arr vel(n, 3, 1), sig(n, 1, 1), phi(n, 1, 1);
+      Arr vel(n, 3, 1), sig(n, 1, 1), phi(n, 1, 2);
       vel.copy_from(ns->S_new, 0, 0, 3); sig.setval(1.0);
       orc_mg m = ns->mg(ns->p.proj_tol, ns->p.proj_abs_tol);
-      const int rc = nodal_project(n, ns->dx, vel, sig, phi, nullptr, false, &m);
+      const int rc = nodal_project(n, ns->dx, vel, sig, phi, nullptr, false, &m, ns->nodal_bc());
       if (rc) return rc;
       ns->S_new.copy_from(vel, 0, 0, 3);
       ns->P_old.setval(0); ns->P_new.setval(0); ns->Gp_old.setval(0); ns->Gp_new.setval(0);
     }
   }
   ns->initial_step = true;
+  if (ns->p.do_init_proj && std::fabs(ns->p.gravity) > 0.0 && ns->has_walls()) {
+    // initialPressureProject (NSB.cpp:2421-2431 -> Projection.cpp:841-960): the projection of the uniform gravity vector with
+    // sigma = 1/rho gives the hydrostatic pressure; P and Gradp old := new.  (On a fully periodic domain div(0,0,g) = 0.)
+    Arr vel(n, 3, 1), sig(n, 1, 1);
+    vel.setval(0.0);
+    { const double g = ns->p.gravity; for (int k = -1; k <= n[2]; ++k) for (int j = -1; j <= n[1]; ++j) for (int i = -1; i <= n[0]; ++i) vel(i, j, k, 2) = g; }
+    { const Arr& S = ns->S_new; FOR_CELLS(sig, i, j, k) sig(i, j, k) = 1.0 / S(i, j, k, orc_ns::Density); }
+    orc_mg m = ns->mg(ns->p.proj_tol, ns->p.proj_abs_tol);
+    ns->P_new.setval(0.0);
+    const int rc = nodal_project(n, ns->dx, vel, sig, ns->P_new, &ns->Gp_new, false, &m, ns->nodal_bc());
+    if (rc) return rc;
+    ns->fill_gradp(ns->Gp_new);
+    ns->P_old = ns->P_new; ns->Gp_old = ns->Gp_new;
+  }
   double est = 0;
   if (ns->est_time_step(&est)) return -1;
   const double dt_init = ns->p.init_shrink * est;  // post_init_estDT NSB.cpp:2307-2366
@@ -1786,15 +2064,15 @@ int orc_ns_post_init(orc_ns* ns, double* dt0) {
       int rc = ns->advance(dt_init, &dtt);
       if (rc) return rc;
       // initialSyncProject Projection.cpp:970-1185
-      Arr vel(n, 3, 1), sig(n, 1, 1), phi(n, 1, 1);
+      Arr vel(n, 3, 1), sig(n, 1, 1), phi(n, 1, 2);
       for (int c = 0; c < 3; ++c) { FOR_CELLS(vel, i, j, k) vel(i, j, k, c) = ns->S_new(i, j, k, c) * (1.0 / dt_init) + (-1.0 / dt_init) * ns->S_old(i, j, k, c); }
       FOR_CELLS(sig, i, j, k) sig(i, j, k) = 1.0 / ns->rho_half(i, j, k);
       orc_mg m = ns->mg(ns->p.proj_tol, ns->p.proj_abs_tol);
-      rc = nodal_project(n, ns->dx, vel, sig, phi, &ns->Gp_new, true, &m);
+      rc = nodal_project(n, ns->dx, vel, sig, phi, &ns->Gp_new, true, &m, ns->nodal_bc());
       ns->it[2] = m.iters;
       if (rc) return rc;
       { Arr& P = ns->P_new; FOR_G1(P, i, j, k) P(i, j, k) += phi(i, j, k); }
-      ns->Gp_new.fill_periodic();
+      ns->fill_gradp(ns->Gp_new);
       std::swap(ns->S_old, ns->S_new);  // resetState NSB.cpp:2643-2680
       ns->P_old = ns->P_new; ns->Gp_old = ns->Gp_new;
       ns->initial_iter = false;
@@ -1807,6 +2085,7 @@ int orc_ns_post_init(orc_ns* ns, double* dt0) {
 }
 
 int orc_ns_step(orc_ns* ns, double* dt_io) {
+  PerScope ps(ns->per);
   double dt = (dt_io && *dt_io > 0.0) ? *dt_io : -1.0;
   if (dt <= 0.0) {
     if (ns->p.fixed_dt > 0.0) dt = ns->p.fixed_dt;

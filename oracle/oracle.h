@@ -88,7 +88,26 @@ void orc_compute_aofs2(const int n[3], const double dx[3], double dt, int ncomp,
                        const double* vflux, const double* wflux, const int* iconserv, int flags, int is_sync, int known,
                        double* aofs, double* fx, double* fy, double* fz, double* xed, double* yed, double* zed);
 
-/* NavierStokes::advance / post_init on one periodic box */
+/* ---- non-periodic domains.  Arrays are exchanged "padded" = with their ghost layers, [comp][nz+2g][ny+2g][nx+2g]; the high
+ * face / node of a non-periodic direction sits at index n inside the layer.  bclo/bchi: amrex::BCType codes [ncomp][3]
+ * (int_dir 0, reflect_odd -1, reflect_even 1, foextrap 2, ext_dir 3, hoextrap 4); lobc/hibc: LinOpBCType (periodic 0,
+ * Dirichlet 1, Neumann 2, reflect_odd 3, inflow 4). ---- */
+/* AmrLevel::FillPatch's physical-boundary fill of cell data (filcc + NS_bcfill.H ext_dir values bcv[6][ncomp]) */
+void orc_fill_physbc(const int n[3], const int per[3], int ng, int ncomp, const int* bclo, const int* bchi, const double* bcv, double* a);
+void orc_extrap_vel_to_faces_bc(const int n[3], const int per[3], const double dx[3], double dt, const double* vel, const double* force,
+                                int flags, const int* bclo, const int* bchi, double* umac, double* vmac, double* wmac);
+void orc_compute_aofs_bc(const int n[3], const int per[3], const double dx[3], double dt, int ncomp, const double* S, const double* force,
+                         const double* divu, const double* umac, const double* vmac, const double* wmac, const int* iconserv, int flags,
+                         const int* bclo, const int* bchi, double* aofs, double* fx, double* fy, double* fz, double* xed, double* yed, double* zed);
+int orc_mac_project_bc(const int n[3], const int per[3], const double dx[3], double* umac, double* vmac, double* wmac, const double* rho,
+                       const double* rhs, double* phi, double rhs_scale, const int lobc[3], const int hibc[3], int maxorder, orc_mg* mg);
+int orc_nodal_project_bc(const int n[3], const int per[3], const double dx[3], double* vel, const double* sigma, double* phi, double* gp,
+                         const int lobc[3], const int hibc[3], orc_mg* mg);
+int orc_diffusion_bc(const int n[3], const int per[3], const double dx[3], int solve, int tensor, int ncomp, double a, double b,
+                     const double* alpha, const double* ex, const double* ey, const double* ez, const double* rhs, double* soln, double* out,
+                     const int* lobc, const int* hibc, int maxorder, orc_mg* mg);
+
+/* NavierStokes::advance / post_init on one box (periodic unless orc_ns_set_bc is called) */
 typedef struct orc_ns_params {
   double cfl, visc_coef, be_cn_theta, change_max, init_shrink, fixed_dt, gravity, visc_tol;
   double mac_tol, mac_abs_tol, proj_tol, proj_abs_tol;
@@ -101,6 +120,8 @@ typedef struct orc_ns_params {
 void orc_ns_params_default(orc_ns_params* p);
 typedef struct orc_ns orc_ns;
 orc_ns* orc_ns_create(const int n[3], const double prob_lo[3], const double prob_hi[3], const orc_ns_params* p);
+void orc_ns_set_bc(orc_ns* ns, const int per[3], const int phys_lo[3], const int phys_hi[3], const double* bcv);
+void orc_ns_get_padded(const orc_ns* ns, int which, double* out);
 void orc_ns_destroy(orc_ns* ns);
 void orc_ns_init_prob(orc_ns* ns, int probtype, const double* params, int nparams);
 int orc_ns_post_init(orc_ns* ns, double* dt0);

@@ -180,8 +180,75 @@ def compute_aofs2(dx, dt, S, force, umac, vmac, wmac, iconserv, fit=0, divu=None
     return aofs, fl, ed
 
 
+# ---- non-periodic domains: "padded" arrays carry their ghost layers -------------------------------------------------
+def _ia(a):
+    a = np.ascontiguousarray(np.asarray(a, dtype=np.int32))
+    return a.ctypes.data_as(C.POINTER(C.c_int)), a
+
+
+def padded_shape(n, ncomp, ng):
+    return (ncomp, n[2] + 2 * ng, n[1] + 2 * ng, n[0] + 2 * ng)
+
+
+def fill_physbc(n, per, ng, a, bclo, bchi, bcv=None):
+    """a: padded (ncomp, nz+2ng, ...) array with valid data inside; returns it with periodic + physical ghost cells filled."""
+    a = np.ascontiguousarray(a).copy()
+    plo, _k1 = _ia(bclo); phi, _k2 = _ia(bchi)
+    bv = None if bcv is None else np.ascontiguousarray(np.asarray(bcv, dtype=np.float64))
+    lib().orc_fill_physbc(_i3(n), _i3(per), int(ng), a.shape[0], plo, phi, _p(bv), _p(a))
+    return a
+
+
+def extrap_vel_to_faces_bc(n, per, dx, dt, vel, force, bclo, bchi, fit=0, ppm=0):
+    outs = [np.zeros(padded_shape(n, 1, 1)) for _ in range(3)]
+    plo, _k1 = _ia(bclo); phi, _k2 = _ia(bchi)
+    lib().orc_extrap_vel_to_faces_bc(_i3(n), _i3(per), _d3(dx), C.c_double(dt), _p(vel), _p(force), int(fit) | (2 if ppm else 0), plo, phi,
+                                     *[_p(o) for o in outs])
+    return outs
+
+
+def compute_aofs_bc(n, per, dx, dt, S, force, umac, vmac, wmac, iconserv, bclo, bchi, fit=0, ppm=0, is_velocity=0, divu=None):
+    ncomp = S.shape[0]
+    aofs = np.zeros((ncomp, n[2], n[1], n[0]))
+    fl = [np.zeros(padded_shape(n, ncomp, 1)) for _ in range(3)]
+    ed = [np.zeros(padded_shape(n, ncomp, 1)) for _ in range(3)]
+    ic = (C.c_int * ncomp)(*iconserv)
+    plo, _k1 = _ia(bclo); phi, _k2 = _ia(bchi)
+    lib().orc_compute_aofs_bc(_i3(n), _i3(per), _d3(dx), C.c_double(dt), ncomp, _p(S), _p(force), _p(divu), _p(umac), _p(vmac), _p(wmac), ic,
+                              int(fit) | (2 if ppm else 0) | (4 if is_velocity else 0), plo, phi, _p(aofs), *[_p(o) for o in fl], *[_p(o) for o in ed])
+    return aofs, fl, ed
+
+
+def mac_project_bc(n, per, dx, umac, vmac, wmac, rho, rhs, phi, rhs_scale, lobc, hibc, maxorder=4, mg=None):
+    mg = mg or mg_default()
+    u, v, w, phi = umac.copy(), vmac.copy(), wmac.copy(), phi.copy()
+    rc = lib().orc_mac_project_bc(_i3(n), _i3(per), _d3(dx), _p(u), _p(v), _p(w), _p(rho), _p(rhs), _p(phi), C.c_double(rhs_scale),
+                                  _i3(lobc), _i3(hibc), int(maxorder), C.byref(mg))
+    return u, v, w, phi, rc, mg
+
+
+def nodal_project_bc(n, per, dx, vel, sigma, phi, lobc, hibc, mg=None):
+    mg = mg or mg_default()
+    vel, phi = vel.copy(), phi.copy()
+    gp = np.zeros((3, n[2], n[1], n[0]))
+    rc = lib().orc_nodal_project_bc(_i3(n), _i3(per), _d3(dx), _p(vel), _p(sigma), _p(phi), _p(gp), _i3(lobc), _i3(hibc), C.byref(mg))
+    return vel, phi, gp, rc, mg
+
+
+def diffusion_bc(n, per, dx, solve, tensor, a, b, alpha, ex, ey, ez, rhs, soln, lobc, hibc, maxorder=2, mg=None):
+    """lobc/hibc: [ncomp][3] LinOpBCType.  solve: returns (soln padded, rc, mg); apply: returns out (dense)."""
+    mg = mg or mg_default()
+    ncomp = soln.shape[0]
+    soln = soln.copy()
+    out = np.zeros((ncomp, n[2], n[1], n[0]))
+    plo, _k1 = _ia(lobc); phi_, _k2 = _ia(hibc)
+    rc = lib().orc_diffusion_bc(_i3(n), _i3(per), _d3(dx), int(solve), int(tensor), ncomp, C.c_double(a), C.c_double(b), _p(alpha),
+                                _p(ex), _p(ey), _p(ez), _p(rhs), _p(soln), _p(out), plo, phi_, int(maxorder), C.byref(mg))
+    return (soln, rc, mg) if solve else out
+
+
 class OracleNS:
-    def __init__(self, n, prob_lo=(0, 0, 0), prob_hi=(1, 1, 1), **params):
+    def __init__(self, n, prob_lo=(0, 0, 0), prob_hi=(1, 1, 1), per=None, phys_lo=None, phys_hi=None, bcv=None, **params):
         self.n = tuple(n)
         p = OrcNSParams()
         lib().orc_ns_params_default(C.byref(p))
@@ -190,6 +257,15 @@ class OracleNS:
                 raise KeyError(k)
             setattr(p, k, v)
         self.h = C.c_void_p(lib().orc_ns_create(_i3(n), _d3(prob_lo), _d3(prob_hi), C.byref(p)))
+        if per is not None:
+            bv = None if bcv is None else np.ascontiguousarray(np.asarray(bcv, dtype=np.float64).reshape(6, 5))
+            lib().orc_ns_set_bc(self.h, _i3(per), _i3(phys_lo), _i3(phys_hi), _p(bv))
+
+    def get_padded(self, which):
+        nc, ng = {0: (5, 1), 1: (1, 2), 2: (3, 1), 4: (1, 1), 5: (1, 1), 6: (1, 1)}[which]
+        out = np.empty(padded_shape(self.n, nc, ng), dtype=np.float64)
+        lib().orc_ns_get_padded(self.h, which, _p(out))
+        return out
 
     def init_prob(self, probtype, params):
         arr = (C.c_double * len(params))(*params)

@@ -1,0 +1,414 @@
+"""Physical domain boundaries through the C ABI vs the oracle: the FillPatch boundary fill, the Godunov
+edge boundary conditions, Dirichlet / Neumann multigrid solves (MAC, diffusion incl. the tensor operator), the nodal
+projection with walls, and whole time steps on wall-bounded problems (RayleighTaylor, LidDrivenCavity)."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import iamr_b200 as ix
+from util import hash_uniform, smooth_field, split_boxes, fab_array, box_of, stream_of, sync
+
+INT, RODD, REVEN, FOEX, EXT, HOEX = 0, -1, 1, 2, 3, 4
+PER, DIR, NEU, LRODD, INFLOW = 0, 1, 2, 3, 4
+EXTENT = {ix.CELL: (0, 0, 0), ix.XFACE: (1, 0, 0), ix.YFACE: (0, 1, 0), ix.ZFACE: (0, 0, 1), ix.NODE: (1, 1, 1)}
+
+
+def pad(dense, ng):
+    """dense (ncomp, nz, ny, nx) -> padded array with ng zeroed ghost layers."""
+    return np.pad(dense, ((0, 0), (ng, ng), (ng, ng), (ng, ng)))
+
+
+def fab_from_padded(P, gng, box, ng, ixtype, dev):
+    """Per-box fab (valid + ng ghost layers, index type ixtype) cut out of the global padded array P (ghost width gng)."""
+    import torch
+    lo, hi = box
+    ext = EXTENT[ixtype]
+    sl = tuple(slice(lo[d] - ng + gng, hi[d] + ext[d] + ng + gng + 1) for d in (2, 1, 0))
+    t = torch.from_numpy(np.array(P[(slice(None),) + sl], order="C", copy=True)).to(dev)   # a private copy: the library writes into it
+    return t, ix.fab_of(t, [lo[d] - ng for d in range(3)])
+
+
+def scatter_valid(P, gng, tensors, boxes, ng, ixtype):
+    """Write the valid regions of per-box tensors back into (a copy of) the global padded array; returns it and the
+    largest disagreement on points shared between boxes."""
+    out = P.copy()
+    seen = np.zeros(P.shape[1:], dtype=bool)
+    dup = 0.0
+    ext = EXTENT[ixtype]
+    for t, (lo, hi) in zip(tensors, boxes):
+        a = t.detach().cpu().numpy()
+        v = a[:, ng:a.shape[1] - ng, ng:a.shape[2] - ng, ng:a.shape[3] - ng]
+        sl = tuple(slice(lo[d] + gng, hi[d] + ext[d] + gng + 1) for d in (2, 1, 0))
+        cur = out[(slice(None),) + sl]
+        m = seen[sl]
+        if m.any():
+            dup = max(dup, float(np.abs(cur[:, m] - v[:, m]).max()))
+        out[(slice(None),) + sl] = np.where(m[None], cur, v)
+        seen[sl] = True
+    return out, dup
+
+
+def orc_shape(n, ncomp, ng):
+    return (ncomp, n[2] + 2 * ng, n[1] + 2 * ng, n[0] + 2 * ng)
+
+
+def bcrec_array(bclo, bchi):
+    return (ix.BCRec * len(bclo))(*[ix.BCRec.make(l, h) for l, h in zip(bclo, bchi)])
+
+
+@pytest.mark.parametrize("per,nb", [((1, 1, 0), (2, 2, 2)), ((0, 0, 0), (2, 2, 2)), ((0, 1, 0), (1, 1, 1))])
+def test_fill_physbc(backend, oracle, per, nb):
+    """FillBoundary + the physical fill (filcc + NS_bcfill.H) on a multi-box level: every ghost cell of every box, edges and
+    corners included, against the oracle's fill of the whole domain."""
+    lib, dev = backend
+    n, ng, ncomp = (12, 8, 8), 3, 3
+    # one component per interesting rule; walls in z carry ext_dir / hoextrap / foextrap, x and y reflect / extrapolate
+    bclo = [(EXT, REVEN, EXT), (HOEX, FOEX, HOEX), (RODD, EXT, FOEX)]
+    bchi = [(FOEX, RODD, EXT), (EXT, HOEX, REVEN), (REVEN, FOEX, HOEX)]
+    bclo = [tuple(INT if per[d] else b[d] for d in range(3)) for b in bclo]
+    bchi = [tuple(INT if per[d] else b[d] for d in range(3)) for b in bchi]
+    bcv = 0.5 + hash_uniform(3, (6, ncomp))
+    dense = hash_uniform(1, (ncomp, n[2], n[1], n[0]))
+    P = pad(dense, ng)
+    ref = oracle.fill_physbc(n, per, ng, P, bclo, bchi, bcv)
+    g = ix.Geom.make(n, periodic=per)
+    boxes = split_boxes(n, nb)
+    lev = ix.Level(lib, g, boxes)
+    fabs = [fab_from_padded(P + 7.0e30 * (P == 0.0), ng, b, ng, ix.CELL, dev) for b in boxes]   # ghosts start as garbage
+    arr = fab_array([f[1] for f in fabs])
+    lib.check(lib.iamrx_fill_boundary(lev.h, arr, ix.CELL, ncomp, ng, stream_of(dev)))
+    lib.check(lib.iamrx_fill_physbc(lev.h, arr, ncomp, ng, bcrec_array(bclo, bchi), bcv.ctypes.data_as(C.POINTER(C.c_double)),
+                                    stream_of(dev)))
+    sync(dev)
+    for (t, _), (lo, hi) in zip(fabs, boxes):
+        sl = tuple(slice(lo[d], hi[d] + 2 * ng + 1) for d in (2, 1, 0))
+        want = ref[(slice(None),) + sl]
+        # copies and reflections are exact; the hoextrap cubic may differ in the last bit (FMA contraction)
+        assert np.abs(t.cpu().numpy() - want).max() <= 4e-16 * np.abs(want).max(), (lo, hi)
+    lev.close()
+
+
+def _wrap(oracle, n, per, ng, P):
+    """periodic images only (no physical fill)"""
+    z = [(INT, INT, INT)] * P.shape[0]
+    return oracle.fill_physbc(n, per, ng, P, z, z, None)
+
+
+def _vel_bcs(per, phys_lo, phys_hi):
+    """NS_BC.H:7-21: BCRec of the three velocity components from the physical boundary types"""
+    norm = {0: INT, 1: EXT, 2: FOEX, 3: RODD, 4: EXT, 5: EXT}
+    tang = {0: INT, 1: EXT, 2: FOEX, 3: REVEN, 4: HOEX, 5: EXT}
+    lo = [tuple(INT if per[d] else (norm if c == d else tang)[phys_lo[d]] for d in range(3)) for c in range(3)]
+    hi = [tuple(INT if per[d] else (norm if c == d else tang)[phys_hi[d]] for d in range(3)) for c in range(3)]
+    return lo, hi
+
+
+def _scal_bcs(per, phys_lo, phys_hi, ncomp):
+    sc = {0: INT, 1: EXT, 2: FOEX, 3: REVEN, 4: FOEX, 5: FOEX}
+    lo = [tuple(INT if per[d] else sc[phys_lo[d]] for d in range(3))] * ncomp
+    hi = [tuple(INT if per[d] else sc[phys_hi[d]] for d in range(3))] * ncomp
+    return lo, hi
+
+
+# (periodicity, ns.lo_bc, ns.hi_bc): RayleighTaylor's slip walls in z; a no-slip box; inflow / outflow in x with a symmetry plane
+BC_CASES = [((1, 1, 0), (0, 0, 4), (0, 0, 4)), ((0, 0, 0), (5, 5, 5), (5, 4, 5)), ((0, 1, 0), (1, 0, 3), (2, 0, 4))]
+
+
+@pytest.mark.parametrize("per,plo,phi", BC_CASES)
+@pytest.mark.parametrize("nb", [(1, 1, 1), (2, 2, 2)])
+@pytest.mark.parametrize("fit,ppm", [(0, 0), (1, 1)])
+def test_extrap_vel_to_faces_bc(backend, oracle, per, plo, phi, nb, fit, ppm):
+    lib, dev = backend
+    n = (16, 16, 8)
+    dx = tuple(1.0 / m for m in n)
+    bclo, bchi = _vel_bcs(per, plo, phi)
+    vel = smooth_field(n, 100, 3)
+    vel[2] += 0.2
+    bcv = 0.3 * hash_uniform(5, (6, 3))
+    V = oracle.fill_physbc(n, per, 3, pad(vel, 3), bclo, bchi, bcv)
+    fo = [tuple(FOEX if not per[d] else INT for d in range(3))] * 3
+    F = oracle.fill_physbc(n, per, 1, pad(smooth_field(n, 111, 3, amp=0.2), 1), fo, fo)
+    dt = 0.5 * min(dx) / np.abs(vel).max()
+    ref = oracle.extrap_vel_to_faces_bc(n, per, dx, dt, V, F, bclo, bchi, fit, ppm)
+    g = ix.Geom.make(n, periodic=per)
+    boxes = split_boxes(n, nb)
+    bcr = bcrec_array(bclo, bchi)
+    outs = [[], [], []]
+    for box in boxes:
+        tv, fv = fab_from_padded(V, 3, box, 3, ix.CELL, dev)
+        tf, ff = fab_from_padded(F, 1, box, 1, ix.CELL, dev)
+        macs = [fab_from_padded(np.zeros(orc_shape(n, 1, 2)), 2, box, 1, t, dev) for t in (ix.XFACE, ix.YFACE, ix.ZFACE)]
+        bb = box_of(*box)
+        lib.check(lib.iamrx_extrap_vel_to_faces_box(C.byref(bb), C.byref(fv), C.byref(ff), C.byref(macs[0][1]), C.byref(macs[1][1]),
+                                                    C.byref(macs[2][1]), bcr, C.byref(g), dt, (2 if fit else 0) | (1 if ppm else 0),
+                                                    stream_of(dev)))
+        for d in range(3):
+            outs[d].append(macs[d][0])
+    sync(dev)
+    for d, t in enumerate((ix.XFACE, ix.YFACE, ix.ZFACE)):
+        got, dup = scatter_valid(np.zeros_like(ref[d]), 1, outs[d], boxes, 1, t)
+        assert dup == 0.0
+        hi = [n[q] + (1 if (q == d and not per[q]) else 0) for q in range(3)]
+        sl = (slice(None), slice(1, 1 + hi[2]), slice(1, 1 + hi[1]), slice(1, 1 + hi[0]))
+        assert np.abs(got[sl] - ref[d][sl]).max() <= 1e-13
+        if not per[d] and plo[d] in (4, 5):   # walls: the normal MAC velocity on the wall is the wall velocity
+            wsl = [slice(None), slice(1, 1 + n[2]), slice(1, 1 + n[1]), slice(1, 1 + n[0])]
+            wsl[3 - d] = 1
+            assert np.abs(got[tuple(wsl)] - bcv[d, d]).max() <= 1e-15
+
+
+@pytest.mark.parametrize("per,plo,phi", BC_CASES)
+@pytest.mark.parametrize("nb", [(1, 1, 1), (2, 2, 2)])
+@pytest.mark.parametrize("kind,fit,ppm", [("vel", 0, 0), ("scal", 1, 0), ("scal", 0, 1)])
+def test_compute_aofs_bc(backend, oracle, per, plo, phi, nb, kind, fit, ppm):
+    lib, dev = backend
+    n = (16, 16, 8)
+    dx = tuple(1.0 / m for m in n)
+    if kind == "vel":
+        ncomp, iconserv, isvel = 3, (0, 0, 0), 1
+        bclo, bchi = _vel_bcs(per, plo, phi)
+    else:
+        ncomp, iconserv, isvel = 2, (1, 0), 0
+        bclo, bchi = _scal_bcs(per, plo, phi, 2)
+    q = smooth_field(n, 210, ncomp)
+    q[0] += 0.3 * np.sign(smooth_field(n, 219, 1)[0])
+    bcv = 0.3 * hash_uniform(6, (6, ncomp))
+    Q = oracle.fill_physbc(n, per, 3, pad(q, 3), bclo, bchi, bcv)
+    fo = [tuple(FOEX if not per[d] else INT for d in range(3))] * ncomp
+    F = oracle.fill_physbc(n, per, 1, pad(smooth_field(n, 211, ncomp, amp=0.2), 1), fo, fo)
+    DV = oracle.fill_physbc(n, per, 1, pad(smooth_field(n, 77, 1, amp=0.3), 1), fo[:1], fo[:1])
+    # MAC velocities on every face incl. the high domain faces; zero normal velocity on walls (as a MAC projection leaves them)
+    macs, macs2 = [], []   # ghost width 1 for the oracle, 2 for cutting per-box face fabs with one ghost face layer
+    for d in range(3):
+        M = 0.6 * hash_uniform(300 + d, orc_shape(n, 1, 2)) + 0.1
+        if not per[d] and plo[d] in (3, 4, 5):
+            idx = [slice(None)] * 4; idx[3 - d] = 2; M[tuple(idx)] = 0.0
+        if not per[d] and phi[d] in (3, 4, 5):
+            idx = [slice(None)] * 4; idx[3 - d] = n[d] + 2; M[tuple(idx)] = 0.0
+        M = _wrap(oracle, n, per, 2, M)
+        macs2.append(M)
+        macs.append(np.ascontiguousarray(M[:, 1:-1, 1:-1, 1:-1]))
+    dt = 0.4 * min(dx)
+    ref, rfl, red = oracle.compute_aofs_bc(n, per, dx, dt, Q, F, macs[0], macs[1], macs[2], iconserv, bclo, bchi, fit, ppm, isvel, divu=DV)
+    g = ix.Geom.make(n, periodic=per)
+    boxes = split_boxes(n, nb)
+    bcr = bcrec_array(bclo, bchi)
+    ic = (C.c_int * ncomp)(*iconserv)
+    out_a, out_f, out_e = [], [[], [], []], [[], [], []]
+    for box in boxes:
+        tq, fq = fab_from_padded(Q, 3, box, 3, ix.CELL, dev)
+        tf, ff = fab_from_padded(F, 1, box, 1, ix.CELL, dev)
+        td, fd = fab_from_padded(DV, 1, box, 1, ix.CELL, dev)
+        ta, fa = fab_from_padded(np.zeros((ncomp, n[2], n[1], n[0])), 0, box, 0, ix.CELL, dev)
+        mm = [fab_from_padded(macs2[d], 2, box, 1, t, dev) for d, t in enumerate((ix.XFACE, ix.YFACE, ix.ZFACE))]
+        fl = [fab_from_padded(np.zeros_like(rfl[0]), 1, box, 0, t, dev) for t in (ix.XFACE, ix.YFACE, ix.ZFACE)]
+        ed = [fab_from_padded(np.zeros_like(rfl[0]), 1, box, 0, t, dev) for t in (ix.XFACE, ix.YFACE, ix.ZFACE)]
+        bb = box_of(*box)
+        flags = (ix.ADV_FORCES_IN_TRANS if fit else 0) | ix.ADV_WRITE_FLUXES | (ix.ADV_PPM if ppm else 0) | (ix.ADV_IS_VELOCITY if isvel else 0)
+        lib.check(lib.iamrx_compute_aofs_box(C.byref(bb), C.byref(fa), 0, C.byref(fq), 0, ncomp, C.byref(ff), 0, C.byref(fd),
+                                             C.byref(mm[0][1]), C.byref(mm[1][1]), C.byref(mm[2][1]), None, None, None,
+                                             C.byref(fl[0][1]), C.byref(fl[1][1]), C.byref(fl[2][1]),
+                                             C.byref(ed[0][1]), C.byref(ed[1][1]), C.byref(ed[2][1]),
+                                             ic, bcr, C.byref(g), dt, flags, stream_of(dev)))
+        out_a.append(ta)
+        for d in range(3):
+            out_f[d].append(fl[d][0]); out_e[d].append(ed[d][0])
+    sync(dev)
+    got, _ = scatter_valid(np.zeros((ncomp, n[2], n[1], n[0])), 0, out_a, boxes, 0, ix.CELL)
+    assert np.abs(got - ref).max() <= 1e-12 * max(1.0, np.abs(ref).max())
+    for d, t in enumerate((ix.XFACE, ix.YFACE, ix.ZFACE)):
+        ge, dup = scatter_valid(np.zeros_like(red[d]), 1, out_e[d], boxes, 0, t)
+        gf, dup2 = scatter_valid(np.zeros_like(rfl[d]), 1, out_f[d], boxes, 0, t)
+        assert dup == 0.0 and dup2 == 0.0
+        hi = [n[q] + (1 if (q == d and not per[q]) else 0) for q in range(3)]
+        sl = (slice(None), slice(1, 1 + hi[2]), slice(1, 1 + hi[1]), slice(1, 1 + hi[0]))
+        assert np.abs(ge[sl] - red[d][sl]).max() <= 1e-13 and np.abs(gf[sl] - rfl[d][sl]).max() <= 1e-13
+
+
+def _mg(lib, **kw):
+    m = ix.MGInfo()
+    lib.iamrx_mg_info_default(C.byref(m))
+    for k, v in kw.items():
+        setattr(m, k, v)
+    return m
+
+
+def _rho(n):
+    z, y, x = [(np.arange(m) + 0.5) / m for m in (n[2], n[1], n[0])]
+    Z, Y, X = np.meshgrid(z, y, x, indexing="ij")
+    return (1.0 + 0.4 * np.sin(2 * np.pi * X) * np.cos(np.pi * Y) * np.sin(np.pi * Z + 0.3))[None]
+
+
+# (periodicity, lobc, hibc) of a scalar cell-centred solve: walls (all Neumann: singular), an outflow side (Dirichlet), mixed
+MAC_CASES = [((1, 1, 0), (PER, PER, NEU), (PER, PER, NEU)), ((0, 0, 0), (NEU, NEU, NEU), (DIR, NEU, NEU)),
+             ((0, 1, 0), (DIR, PER, NEU), (NEU, PER, DIR))]
+
+
+@pytest.mark.parametrize("per,lobc,hibc", MAC_CASES)
+@pytest.mark.parametrize("nb", [(1, 1, 1), (2, 2, 2)])
+def test_mac_project_bc(backend, oracle, per, lobc, hibc, nb):
+    """MacProj::mlmg_mac_solve with walls / outflow: Neumann and Dirichlet sides (maxorder 4, MacProj.cpp:30), variable density.
+    One box: iterate-for-iterate parity with the oracle; eight boxes: the converged fields (the extrapolation order follows the
+    box length, as in AMReX, so coarse multigrid levels differ between the two layouts)."""
+    lib, dev = backend
+    n = (16, 16, 16)
+    dx = tuple(1.0 / m for m in n)
+    fo = [tuple(FOEX if not per[d] else INT for d in range(3))]
+    RHO = oracle.fill_physbc(n, per, 1, pad(_rho(n), 1), fo, fo)
+    macs2 = []
+    for d in range(3):
+        M = hash_uniform(400 + d, orc_shape(n, 1, 2)) * 0.5
+        for side, code in ((2, lobc[d]), (n[d] + 2, hibc[d])):
+            if not per[d] and code == NEU:   # solid wall: zero normal velocity on the boundary face
+                idx = [slice(None)] * 4; idx[3 - d] = side; M[tuple(idx)] = 0.0
+        macs2.append(_wrap(oracle, n, per, 2, M))
+    macs = [np.ascontiguousarray(M[:, 1:-1, 1:-1, 1:-1]) for M in macs2]
+    dt = 0.7 / 16
+    mg = oracle.mg_default(rtol=1e-13)
+    ru, rv, rw, rphi, rc, mgo = oracle.mac_project_bc(n, per, dx, macs[0], macs[1], macs[2], RHO, None, np.zeros(orc_shape(n, 1, 1)),
+                                                      2.0 / dt, lobc, hibc, 4, mg)
+    assert rc == 0
+    # oracle identity: discretely divergence free, and the wall faces keep their zero velocity
+    div = ((ru[0, 1:-1, 1:-1, 2:] - ru[0, 1:-1, 1:-1, 1:-1]) / dx[0] + (rv[0, 1:-1, 2:, 1:-1] - rv[0, 1:-1, 1:-1, 1:-1]) / dx[1] +
+           (rw[0, 2:, 1:-1, 1:-1] - rw[0, 1:-1, 1:-1, 1:-1]) / dx[2])
+    assert np.abs(div).max() < 1e-9
+    g = ix.Geom.make(n, periodic=per)
+    boxes = split_boxes(n, nb)
+    lev = ix.Level(lib, g, boxes)
+    U = [[fab_from_padded(macs2[d], 2, b, 1, t, dev) for b in boxes] for d, t in enumerate((ix.XFACE, ix.YFACE, ix.ZFACE))]
+    R = [fab_from_padded(RHO, 1, b, 1, ix.CELL, dev) for b in boxes]
+    P = [fab_from_padded(np.zeros(orc_shape(n, 1, 1)), 1, b, 1, ix.CELL, dev) for b in boxes]
+    info = _mg(lib, rtol=1e-13, maxorder=4)
+    rc = lib.iamrx_mac_project(lev.h, fab_array([p[1] for p in U[0]]), fab_array([p[1] for p in U[1]]), fab_array([p[1] for p in U[2]]),
+                               fab_array([p[1] for p in R]), None, fab_array([p[1] for p in P]), 2.0 / dt,
+                               (C.c_int * 3)(*lobc), (C.c_int * 3)(*hibc), C.byref(info), stream_of(dev))
+    lib.check(rc)
+    sync(dev)
+    if nb == (1, 1, 1):
+        assert info.iters == mgo.iters
+    tol = 1e-12 if nb == (1, 1, 1) else 1e-9
+    for d, (ref, t) in enumerate(((ru, ix.XFACE), (rv, ix.YFACE), (rw, ix.ZFACE))):
+        got, dup = scatter_valid(np.zeros(orc_shape(n, 1, 1)), 1, [p[0] for p in U[d]], boxes, 1, t)
+        assert dup < 1e-14
+        hi = [n[q] + (1 if (q == d and not per[q]) else 0) for q in range(3)]
+        sl = (slice(None), slice(1, 1 + hi[2]), slice(1, 1 + hi[1]), slice(1, 1 + hi[0]))
+        assert np.abs(got[sl] - ref[sl]).max() < tol
+    gphi, _ = scatter_valid(np.zeros(orc_shape(n, 1, 1)), 1, [p[0] for p in P], boxes, 1, ix.CELL)
+    a, b = gphi[:, 1:-1, 1:-1, 1:-1], rphi[:, 1:-1, 1:-1, 1:-1]
+    if DIR not in lobc + hibc:   # singular: phi is defined up to a constant
+        a, b = a - a.mean(), b - b.mean()
+    assert np.abs(a - b).max() < tol
+    lev.close()
+
+
+NODAL_CASES = [((1, 1, 0), (PER, PER, NEU), (PER, PER, NEU)), ((0, 0, 0), (NEU, NEU, NEU), (NEU, NEU, NEU)),
+               ((0, 1, 0), (INFLOW, PER, NEU), (DIR, PER, NEU)), ((1, 0, 0), (PER, DIR, DIR), (PER, DIR, DIR))]
+
+
+@pytest.mark.parametrize("per,lobc,hibc", NODAL_CASES)
+@pytest.mark.parametrize("nb", [(1, 1, 1), (2, 2, 2)])
+def test_nodal_project_bc(backend, oracle, per, lobc, hibc, nb):
+    """Projection::doMLMGNodalProjection with walls (Neumann), an inflow face and outflow faces (Dirichlet): right-hand side with
+    the hidden tangential ghost velocities and the doubled wall rows, mirrored ghost nodes, held Dirichlet nodes."""
+    lib, dev = backend
+    n = (16, 16, 16)
+    dx = tuple(1.0 / m for m in n)
+    sig = 1.0 / _rho(n)
+    V = pad(smooth_field(n, 400, 3), 1)
+    V = _wrap(oracle, n, per, 1, V + 0.0)
+    for d in range(3):   # ghost cells beyond an inflow side carry the inflow velocity (everything else is zeroed by the projector)
+        if not per[d] and lobc[d] == INFLOW:
+            idx = [slice(None)] * 4; idx[3 - d] = 0; idx[0] = d; V[tuple(idx)] = 0.7
+    mg = oracle.mg_default(rtol=1e-13)
+    rvel, rphi, rgp, rc, mgo = oracle.nodal_project_bc(n, per, dx, V, sig, np.zeros(orc_shape(n, 1, 2)), lobc, hibc, mg)
+    assert rc == 0
+    g = ix.Geom.make(n, periodic=per)
+    boxes = split_boxes(n, nb)
+    lev = ix.Level(lib, g, boxes)
+    Vv = [fab_from_padded(V, 1, b, 1, ix.CELL, dev) for b in boxes]
+    Sg = [fab_from_padded(sig, 0, b, 0, ix.CELL, dev) for b in boxes]
+    Ph = [fab_from_padded(np.zeros(orc_shape(n, 1, 2)), 2, b, 1, ix.NODE, dev) for b in boxes]
+    Gp = [fab_from_padded(np.zeros((3, n[2], n[1], n[0])), 0, b, 0, ix.CELL, dev) for b in boxes]
+    info = _mg(lib, rtol=1e-13)
+    rc = lib.iamrx_nodal_project(lev.h, fab_array([p[1] for p in Vv]), fab_array([p[1] for p in Sg]), fab_array([p[1] for p in Ph]),
+                                 fab_array([p[1] for p in Gp]), 0, (C.c_int * 3)(*lobc), (C.c_int * 3)(*hibc), C.byref(info),
+                                 stream_of(dev))
+    lib.check(rc)
+    sync(dev)
+    if nb == (1, 1, 1):
+        assert info.iters == mgo.iters
+    gv, _ = scatter_valid(np.zeros(orc_shape(n, 3, 1)), 1, [p[0] for p in Vv], boxes, 1, ix.CELL)
+    assert np.abs(gv[:, 1:-1, 1:-1, 1:-1] - rvel[:, 1:-1, 1:-1, 1:-1]).max() < 1e-11
+    gg, _ = scatter_valid(np.zeros((3, n[2], n[1], n[0])), 0, [p[0] for p in Gp], boxes, 0, ix.CELL)
+    assert np.abs(gg - rgp).max() < 1e-10
+    gp_, dup = scatter_valid(np.zeros(orc_shape(n, 1, 2)), 2, [p[0] for p in Ph], boxes, 1, ix.NODE)
+    assert dup < 1e-12
+    hi = [n[q] + (0 if per[q] else 1) for q in range(3)]
+    sl = (slice(None), slice(2, 2 + hi[2]), slice(2, 2 + hi[1]), slice(2, 2 + hi[0]))
+    a, b = gp_[sl], rphi[sl]
+    if DIR not in lobc + hibc:
+        a, b = a - a.mean(), b - b.mean()
+    assert np.abs(a - b).max() < 1e-11
+    lev.close()
+
+
+# BCRec-derived boundary conditions of the velocity components (Diffusion::setDomainBC): no-slip box with a moving lid;
+# slip walls in z with periodic x, y (normal: Dirichlet, tangential: Neumann); a symmetry plane (reflect_odd / Neumann)
+def _tensor_bc(per, plo, phi):
+    blo, bhi = _vel_bcs(per, plo, phi)
+    m = {INT: PER, EXT: DIR, FOEX: NEU, HOEX: NEU, REVEN: NEU, RODD: LRODD}
+    return [tuple(m[v] for v in b) for b in blo], [tuple(m[v] for v in b) for b in bhi], blo, bhi
+
+
+@pytest.mark.parametrize("per,plo,phi", [((0, 0, 0), (5, 5, 5), (5, 5, 5)), ((1, 1, 0), (0, 0, 4), (0, 0, 4)), ((0, 1, 0), (3, 0, 5), (4, 0, 4))])
+@pytest.mark.parametrize("nb", [(1, 1, 1), (2, 2, 2)])
+@pytest.mark.parametrize("tensor", [1, 0])
+def test_diffusion_bc(backend, oracle, per, plo, phi, nb, tensor):
+    """Diffusion apply + solve with physical boundaries: MLTensorOp (per-component BCs, boundary-aware cross terms, the lid's
+    inhomogeneous Dirichlet data) and the scalar MLABecLaplacian (maxorder 2, Diffusion.cpp:95-96)."""
+    lib, dev = backend
+    n = (16, 16, 16)
+    dx = tuple(1.0 / m for m in n)
+    ncomp = 3 if tensor else 1
+    lobc, hibc, blo, bhi = _tensor_bc(per, plo, phi)
+    if not tensor:
+        lobc, hibc, blo, bhi = lobc[1:2], hibc[1:2], blo[1:2], bhi[1:2]   # the BCs of the v component for a scalar
+    bcv = np.zeros((6, ncomp)); bcv[5, 0] = 1.0   # zhi.velocity = 1 0 0 (the lid)
+    U = oracle.fill_physbc(n, per, 1, pad(smooth_field(n, 500, ncomp), 1), blo, bhi, bcv)
+    alpha = _rho(n)
+    eta = [0.05 * (1.0 + 0.3 * hash_uniform(600 + d, orc_shape(n, 1, 2))) for d in range(3)]
+    eta = [_wrap(oracle, n, per, 2, e) for e in eta]
+    eta1 = [np.ascontiguousarray(e[:, 1:-1, 1:-1, 1:-1]) for e in eta]
+    a, b = 1.0, 0.35
+    ref_ap = oracle.diffusion_bc(n, per, dx, 0, tensor, a, b, alpha, eta1[0], eta1[1], eta1[2], None, U, lobc, hibc, 2)
+    rhs = smooth_field(n, 510, ncomp)
+    mg = oracle.mg_default(rtol=1e-12)
+    ref_sol, rc, mgo = oracle.diffusion_bc(n, per, dx, 1, tensor, a, b, alpha, eta1[0], eta1[1], eta1[2], rhs, U, lobc, hibc, 2, mg)
+    assert rc == 0
+    g = ix.Geom.make(n, periodic=per)
+    boxes = split_boxes(n, nb)
+    lev = ix.Level(lib, g, boxes)
+    bc = ix.LinopBC.make(lobc, hibc, 2)
+    E = [[fab_from_padded(eta[d], 2, bx, 0, t, dev) for bx in boxes] for d, t in enumerate((ix.XFACE, ix.YFACE, ix.ZFACE))]
+    A = [fab_from_padded(alpha, 0, bx, 0, ix.CELL, dev) for bx in boxes]
+    Sol = [fab_from_padded(U, 1, bx, 1, ix.CELL, dev) for bx in boxes]
+    Out = [fab_from_padded(np.zeros((ncomp, n[2], n[1], n[0])), 0, bx, 0, ix.CELL, dev) for bx in boxes]
+    fa = lambda L: fab_array([p[1] for p in L])
+    lib.check(lib.iamrx_diffusion_apply(lev.h, tensor, ncomp, fa(Out), fa(Sol), a, b, fa(A), fa(E[0]), fa(E[1]), fa(E[2]), C.byref(bc),
+                                        stream_of(dev)))
+    sync(dev)
+    got, _ = scatter_valid(np.zeros((ncomp, n[2], n[1], n[0])), 0, [p[0] for p in Out], boxes, 0, ix.CELL)
+    assert np.abs(got - ref_ap).max() <= 1e-12 * np.abs(ref_ap).max()
+    Sol = [fab_from_padded(U, 1, bx, 1, ix.CELL, dev) for bx in boxes]   # fresh copy: level BC in the ghost cells, initial guess inside
+    Rhs = [fab_from_padded(rhs, 0, bx, 0, ix.CELL, dev) for bx in boxes]
+    info = _mg(lib, rtol=1e-12)
+    rc = lib.iamrx_diffusion_solve(lev.h, tensor, ncomp, fa(Sol), fa(Rhs), a, b, fa(A), fa(E[0]), fa(E[1]), fa(E[2]), C.byref(bc),
+                                   C.byref(info), stream_of(dev))
+    lib.check(rc)
+    sync(dev)
+    if nb == (1, 1, 1):
+        assert info.iters == mgo.iters
+    gs, _ = scatter_valid(np.zeros(orc_shape(n, ncomp, 1)), 1, [p[0] for p in Sol], boxes, 1, ix.CELL)
+    assert np.abs(gs[:, 1:-1, 1:-1, 1:-1] - ref_sol[:, 1:-1, 1:-1, 1:-1]).max() <= 1e-10
+    lev.close()

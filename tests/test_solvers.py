@@ -136,13 +136,13 @@ def test_diffusion_apply_and_solve(backend, oracle, nb, tensor, ncomp):
     _, Ez = fabs(eta[2], 0, ix.ZFACE)
     sol_p, Sol = fabs(u, 1, ix.CELL)
     out_p, Out = fabs(np.zeros_like(u), 0, ix.CELL)
-    lib.check(lib.iamrx_diffusion_apply(lev.h, tensor, ncomp, Out, Sol, a, b, A, Ex, Ey, Ez, stream_of(dev)))
+    lib.check(lib.iamrx_diffusion_apply(lev.h, tensor, ncomp, Out, Sol, a, b, A, Ex, Ey, Ez, None, stream_of(dev)))
     sync(dev)
     got, _ = from_fabs([p[0] for p in out_p], boxes, 0, ix.CELL, N, ncomp)
     assert np.abs(got - ref_apply).max() < 1e-12 * max(1.0, np.abs(ref_apply).max())
     _, Rhs = fabs(rhs, 0, ix.CELL)
     info = _mg(lib, rtol=1e-13, atol=1e-15)
-    lib.check(lib.iamrx_diffusion_solve(lev.h, tensor, ncomp, Sol, Rhs, a, b, A, Ex, Ey, Ez, C.byref(info), stream_of(dev)))
+    lib.check(lib.iamrx_diffusion_solve(lev.h, tensor, ncomp, Sol, Rhs, a, b, A, Ex, Ey, Ez, None, C.byref(info), stream_of(dev)))
     sync(dev)
     if nb == (1, 1, 1):  # same hierarchy depth as the oracle only when the box is the domain
         assert info.iters == mgo.iters
