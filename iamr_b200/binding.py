@@ -110,7 +110,8 @@ class NSParams(C.Structure):
                 ("mac_tol", C.c_double), ("mac_abs_tol", C.c_double), ("proj_tol", C.c_double),
                 ("proj_abs_tol", C.c_double), ("init_iter", C.c_int), ("init_vel_iter", C.c_int),
                 ("do_init_proj", C.c_int), ("use_forces_in_trans", C.c_int), ("verbose", C.c_int),
-                ("conservative_tracer", C.c_int), ("mg_verbose", C.c_int), ("godunov_ppm", C.c_int), ("do_scalminmax", C.c_int), ("do_mom_diff", C.c_int)]
+                ("conservative_tracer", C.c_int), ("mg_verbose", C.c_int), ("godunov_ppm", C.c_int), ("do_scalminmax", C.c_int), ("do_mom_diff", C.c_int),
+                ("lo_bc", C.c_int * 3), ("hi_bc", C.c_int * 3), ("bc_vals", (C.c_double * 5) * 6)]
 
 
 _P = C.POINTER
@@ -317,7 +318,15 @@ class NavierStokes:
         for k, v in params.items():
             if not hasattr(p, k):
                 raise KeyError(k)
-            setattr(p, k, v)
+            if k in ("lo_bc", "hi_bc"):
+                for d in range(3):
+                    getattr(p, k)[d] = int(v[d])
+            elif k == "bc_vals":
+                for f in range(6):
+                    for c in range(5):
+                        p.bc_vals[f][c] = float(v[f][c])
+            else:
+                setattr(p, k, v)
         self.params = p
         h = C.c_void_p()
         lib.check(lib.iamrx_ns_create(level.h, C.byref(p), C.byref(h)))

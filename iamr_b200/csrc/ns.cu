@@ -61,6 +61,84 @@ struct iamrx_ns_s {
   double* early_out = nullptr;   // host destination of comps Density.. (single local box), or null
   double* early_buf = nullptr;   // device staging of the packed scalars
 
+  // ---- physical boundaries (NS_BC.H:7-38: physical type -> math BC of every state component / of grad p) ----------------
+  bool walls = false;   // some direction is not periodic
+  void state_bc(int comp, int lo[3], int hi[3]) const {
+    static const int norm_vel[6] = {IAMRX_BC_INT_DIR, IAMRX_BC_EXT_DIR, IAMRX_BC_FOEXTRAP, IAMRX_BC_REFLECT_ODD, IAMRX_BC_EXT_DIR, IAMRX_BC_EXT_DIR};
+    static const int tang_vel[6] = {IAMRX_BC_INT_DIR, IAMRX_BC_EXT_DIR, IAMRX_BC_FOEXTRAP, IAMRX_BC_REFLECT_EVEN, IAMRX_BC_HOEXTRAP, IAMRX_BC_EXT_DIR};
+    static const int scalar[6] = {IAMRX_BC_INT_DIR, IAMRX_BC_EXT_DIR, IAMRX_BC_FOEXTRAP, IAMRX_BC_REFLECT_EVEN, IAMRX_BC_FOEXTRAP, IAMRX_BC_FOEXTRAP};
+    for (int d = 0; d < 3; ++d) {
+      const int* t = comp < 3 ? (comp == d ? norm_vel : tang_vel) : scalar;
+      lo[d] = L->geom.periodic[d] ? IAMRX_BC_INT_DIR : t[p.lo_bc[d]];
+      hi[d] = L->geom.periodic[d] ? IAMRX_BC_INT_DIR : t[p.hi_bc[d]];
+    }
+  }
+  k::PhysBC phys_bc(int scomp, int ncomp) const {   // BCRec + ext_dir values of state components scomp .. scomp+ncomp-1
+    k::PhysBC b{};
+    for (int c = 0; c < ncomp; ++c) {
+      state_bc(scomp + c, b.lo[c], b.hi[c]);
+      for (int f = 0; f < 6; ++f) b.val[f][c] = p.bc_vals[f][scomp + c];
+    }
+    return b;
+  }
+  k::PhysBC gradp_bc() const {   // norm_gradp_bc / tang_gradp_bc
+    static const int norm_gp[6] = {IAMRX_BC_INT_DIR, IAMRX_BC_FOEXTRAP, IAMRX_BC_FOEXTRAP, IAMRX_BC_REFLECT_ODD, IAMRX_BC_FOEXTRAP, IAMRX_BC_FOEXTRAP};
+    static const int tang_gp[6] = {IAMRX_BC_INT_DIR, IAMRX_BC_FOEXTRAP, IAMRX_BC_FOEXTRAP, IAMRX_BC_REFLECT_EVEN, IAMRX_BC_FOEXTRAP, IAMRX_BC_FOEXTRAP};
+    k::PhysBC b{};
+    for (int c = 0; c < 3; ++c)
+      for (int d = 0; d < 3; ++d) {
+        const int* t = c == d ? norm_gp : tang_gp;
+        b.lo[c][d] = L->geom.periodic[d] ? IAMRX_BC_INT_DIR : t[p.lo_bc[d]];
+        b.hi[c][d] = L->geom.periodic[d] ? IAMRX_BC_INT_DIR : t[p.hi_bc[d]];
+      }
+    return b;
+  }
+  k::PhysBC foextrap_bc(int ncomp) const {   // Extrapolater::FirstOrderExtrap
+    k::PhysBC b{};
+    for (int c = 0; c < ncomp; ++c)
+      for (int d = 0; d < 3; ++d) { b.lo[c][d] = b.hi[c][d] = L->geom.periodic[d] ? IAMRX_BC_INT_DIR : IAMRX_BC_FOEXTRAP; }
+    return b;
+  }
+  k::AdvBC adv_bc(int scomp, int ncomp) const {   // what fetchBCArray hands to the Godunov routines (NSB.cpp:4645)
+    k::AdvBC b{};
+    for (int d = 0; d < 3; ++d) { b.dlo[d] = L->domain.lo[d]; b.dhi[d] = L->domain.hi[d]; }
+    for (int c = 0; c < ncomp; ++c) state_bc(scomp + c, b.lo[c], b.hi[c]);
+    return b;
+  }
+  static int linop_of(int math) {   // Diffusion::setDomainBC (Diffusion.cpp:1887-1999)
+    return math == IAMRX_BC_EXT_DIR ? IAMRX_LINOP_DIRICHLET
+         : math == IAMRX_BC_REFLECT_ODD ? IAMRX_LINOP_REFLECT_ODD : math == IAMRX_BC_INT_DIR ? IAMRX_LINOP_PERIODIC : IAMRX_LINOP_NEUMANN;
+  }
+  k::LinBC diff_bc(int scomp, int ncomp) const {   // diffuse.max_order = diffuse.tensor_max_order = 2 (Diffusion.cpp:95-96,102-103)
+    k::LinBC b = periodic_linbc();
+    b.maxorder = 2;
+    for (int c = 0; c < 3; ++c) {
+      int lo[3], hi[3];
+      state_bc(scomp + (c < ncomp ? c : 0), lo, hi);
+      for (int d = 0; d < 3; ++d) { b.lo[c][d] = linop_of(lo[d]); b.hi[c][d] = linop_of(hi[d]); }
+    }
+    return b;
+  }
+  k::LinBC mac_bc() const {   // set_mac_solve_bc (MacProj.cpp:1187-1208); mac_proj.maxorder = 4 (MacProj.cpp:30)
+    k::LinBC b = periodic_linbc();
+    b.maxorder = 4;
+    for (int c = 0; c < 3; ++c)
+      for (int d = 0; d < 3; ++d) {
+        if (L->geom.periodic[d]) continue;
+        b.lo[c][d] = p.lo_bc[d] == 2 ? IAMRX_LINOP_DIRICHLET : IAMRX_LINOP_NEUMANN;
+        b.hi[c][d] = p.hi_bc[d] == 2 ? IAMRX_LINOP_DIRICHLET : IAMRX_LINOP_NEUMANN;
+      }
+    return b;
+  }
+  k::NodalBC nodal_bc() const {   // Projection.cpp:2436-2464
+    k::NodalBC b;
+    for (int d = 0; d < 3; ++d) {
+      b.lo[d] = L->geom.periodic[d] ? IAMRX_LINOP_PERIODIC : (p.lo_bc[d] == 2 ? IAMRX_LINOP_DIRICHLET : p.lo_bc[d] == 1 ? IAMRX_LINOP_INFLOW : IAMRX_LINOP_NEUMANN);
+      b.hi[d] = L->geom.periodic[d] ? IAMRX_LINOP_PERIODIC : (p.hi_bc[d] == 2 ? IAMRX_LINOP_DIRICHLET : p.hi_bc[d] == 1 ? IAMRX_LINOP_INFLOW : IAMRX_LINOP_NEUMANN);
+    }
+    return b;
+  }
+
   bool diffusive_vel() const { return p.visc_coef > 0.0; }
   bool diffusive_tracer() const { return p.scal_diff_coef > 0.0; }      // is_diffusive[Tracer], NS_setup.cpp:292-295
   int rho_flag() const { return p.conservative_tracer ? 2 : 0; }         // set_rho_flag(diffusionType[Tracer]), NS_setup.cpp:304-308
@@ -68,10 +146,26 @@ struct iamrx_ns_s {
 
 namespace {
 
+// AmrLevel::FillPatch of State_Type on one level: ghost cells of a state MF whose valid cells are in place
+int fill_state_ghosts(iamrx_ns_s& ns, MF& m, int mcomp, int scomp, int ncomp, int ng) {
+  IX_TRY(mf_fill_boundary(m, mcomp, ncomp, ng, ns.s));
+  if (ns.walls) IX_TRY(mf_fill_physbc(m, mcomp, ncomp, ng, ns.phys_bc(scomp, ncomp), ns.s));   // NS_bcfill.H
+  return IAMRX_OK;
+}
 int fillpatch(iamrx_ns_s& ns, MF& dst, const MF& src, int scomp, int ncomp) {
-  // single-level periodic FillPatch = copy of the valid region + FillBoundary
+  // single-level FillPatch = copy of the valid region + FillBoundary + the physical boundary fill
   IX_TRY(mf_copy(dst, src, scomp, 0, ncomp, 0, ns.s));
-  return mf_fill_boundary(dst, 0, ncomp, dst.ng, ns.s);
+  return fill_state_ghosts(ns, dst, 0, scomp, ncomp, dst.ng);
+}
+int fill_gradp(iamrx_ns_s& ns, MF& gp) {   // FillPatch of Gradp_Type (NS_setup.cpp:339-360)
+  IX_TRY(mf_fill_boundary(gp, 0, 3, 1, ns.s));
+  if (ns.walls) IX_TRY(mf_fill_physbc(gp, 0, 3, 1, ns.gradp_bc(), ns.s));
+  return IAMRX_OK;
+}
+int fill_extrap(iamrx_ns_s& ns, MF& m, int ncomp) {   // FillBoundary + Extrapolater::FirstOrderExtrap (NS.cpp:2045-2046)
+  IX_TRY(mf_fill_boundary(m, 0, ncomp, 1, ns.s));
+  if (ns.walls) IX_TRY(mf_fill_physbc(m, 0, ncomp, 1, ns.foextrap_bc(ncomp), ns.s));
+  return IAMRX_OK;
 }
 
 iamrx_mg_info mg_info(const iamrx_ns_s& ns, double rtol, double atol) {
@@ -87,8 +181,9 @@ iamrx_mg_info mg_info(const iamrx_ns_s& ns, double rtol, double atol) {
 int get_visc_terms(iamrx_ns_s& ns, MF& visc, const MF& S) {
   if (!ns.diffusive_vel()) return mf_setval(visc, 0.0, 0, 3, 1, ns.s);
   IX_TRY(fillpatch(ns, ns.soln, S, Xvel, 3));
-  IX_TRY(diffusion_apply(*ns.L, *ns.sv, true, 3, visc, ns.soln, 0.0, -1.0, nullptr, ns.eta, ns.s));
-  return mf_fill_boundary(visc, 0, 3, 1, ns.s);
+  const k::LinBC vbc = ns.diff_bc(Xvel, 3);
+  IX_TRY(diffusion_apply(*ns.L, *ns.sv, true, 3, visc, ns.soln, 0.0, -1.0, nullptr, ns.eta, ns.s, &vbc));
+  return fill_extrap(ns, visc, 3);
 }
 
 // velocity forcing on the 1-ghost box: tf = (getForce + visc - gp)/rho  (NSB.cpp:4456-4470 == 3445-3466)
@@ -114,9 +209,10 @@ int predict_velocity(iamrx_ns_s& ns, double dt, double* dt_test) {
   IX_TRY(fillpatch(ns, ns.Smf, ns.S_old, Density, NUM_SCALARS));           // :4435
   IX_TRY(vel_forcing(ns));                                                 // :4456-4470
   k::AdvGeom g; for (int d = 0; d < 3; ++d) g.dx[d] = L.geom.dx[d]; g.dt = dt;
+  const k::AdvBC vbc = ns.adv_bc(Xvel, 3);
   for (int il = 0; il < ns.Umf.n(); ++il)                                  // :4487-4491
     IX_TRY(k::extrap_vel_to_faces(L.lbox(il), ns.Umf.c(il), ns.force.c(il), ns.umac[0].v(il), ns.umac[1].v(il),
-                                  ns.umac[2].v(il), g, ns.p.use_forces_in_trans, ns.s, ns.p.godunov_ppm));
+                                  ns.umac[2].v(il), g, ns.p.use_forces_in_trans, ns.s, ns.p.godunov_ppm, ns.walls ? &vbc : nullptr));
   *dt_test = dt * tempdt;                                                  // :4511
   return IAMRX_OK;
 }
@@ -126,7 +222,8 @@ int predict_velocity(iamrx_ns_s& ns, double dt, double* dt_test) {
 int mac_project_step(iamrx_ns_s& ns, double dt) {
   IX_TRY(mf_setval(ns.mac_phi, 0.0, 0, 1, 1, ns.s));                       // MacProj.cpp:253
   iamrx_mg_info mi = mg_info(ns, ns.p.mac_tol, ns.p.mac_abs_tol);
-  IX_SOLVE(mac_project(*ns.L, *ns.sv, ns.umac, ns.rho_ptime, nullptr, ns.mac_phi, 2.0 / dt, &mi, ns.s));  // :272,294
+  const k::LinBC mbc = ns.mac_bc();
+  IX_SOLVE(mac_project(*ns.L, *ns.sv, ns.umac, ns.rho_ptime, nullptr, ns.mac_phi, 2.0 / dt, &mi, ns.s, ns.walls ? &mbc : nullptr));  // :272,294
   ns.it_mac = mi.iters;
   for (int d = 0; d < 3; ++d) IX_TRY(mf_fill_boundary(ns.umac[d], 0, 1, 1, ns.s));  // NSB.cpp:1102
   return IAMRX_OK;
@@ -155,6 +252,7 @@ int compute_aofs(iamrx_ns_s& ns, int state_comp, int ncomp, const MF& Sq, const 
     a.forces_in_trans = ns.p.use_forces_in_trans;
     a.ppm = ns.p.godunov_ppm;   // advection_scheme == Godunov_PPM (NSB.cpp:4609)
     a.is_velocity = is_velocity ? 1 : 0;
+    if (ns.walls) a.bc = ns.adv_bc(state_comp, ncomp);
     IX_TRY(k::compute_aofs(L.lbox(il), a, g, ns.s));
   }
   return IAMRX_OK;
@@ -188,8 +286,9 @@ int scalar_advection(iamrx_ns_s& ns, double dt) {
     IX_TRY(fillpatch(ns, ns.s1, ns.S_old, Tracer, 1));
     if (ns.rho_flag() == 2)
       for (int il = 0; il < ns.s1.n(); ++il) IX_TRY(k::divide(ns.s1.gbox(il, 1), ns.s1.v(il), ns.rho_ptime.c(il), 1, 1, ns.s));
-    IX_TRY(diffusion_apply(L, *ns.sv, false, 1, ns.svisc, ns.s1, 0.0, -1.0, nullptr, ns.seta, ns.s));
-    IX_TRY(mf_fill_boundary(ns.svisc, 0, 1, 1, ns.s));
+    const k::LinBC tbc = ns.diff_bc(Tracer, 1);
+    IX_TRY(diffusion_apply(L, *ns.sv, false, 1, ns.svisc, ns.s1, 0.0, -1.0, nullptr, ns.seta, ns.s, &tbc));
+    IX_TRY(fill_extrap(ns, ns.svisc, 1));
     IX_TRY(mf_copy(ns.sforce, ns.svisc, 0, Tracer - Density, 1, 1, ns.s));
   }
   return compute_aofs(ns, Density, NUM_SCALARS, ns.Smf, &ns.sforce, false, dt);  // :811
@@ -206,7 +305,8 @@ int tracer_diffusion_update(iamrx_ns_s& ns, double dt) {
     IX_TRY(fillpatch(ns, ns.s1, ns.S_old, Tracer, 1));
     if (rf == 2)
       for (int il = 0; il < ns.s1.n(); ++il) IX_TRY(k::divide(ns.s1.gbox(il, 1), ns.s1.v(il), ns.rho_ptime.c(il), 1, 1, ns.s));
-    IX_TRY(diffusion_apply(L, *ns.sv, false, 1, ns.r1, ns.s1, 0.0, -(1.0 - theta) * dt, nullptr, ns.seta, ns.s));
+    const k::LinBC tbc0 = ns.diff_bc(Tracer, 1);
+    IX_TRY(diffusion_apply(L, *ns.sv, false, 1, ns.r1, ns.s1, 0.0, -(1.0 - theta) * dt, nullptr, ns.seta, ns.s, &tbc0));
   } else {
     IX_TRY(mf_setval(ns.r1, 0.0, 0, 1, 0, ns.s));
   }
@@ -219,7 +319,8 @@ int tracer_diffusion_update(iamrx_ns_s& ns, double dt) {
     for (int il = 0; il < ns.s1.n(); ++il) IX_TRY(k::divide(ns.s1.gbox(il, 1), ns.s1.v(il), ns.rho_ctime.c(il), 1, 1, ns.s));
   iamrx_mg_info mi = mg_info(ns, ns.p.visc_tol, tol_abs);
   // computeAlpha (:1355-1395): alpha = 1 (rho_flag 0) or rho_new (rho_flag 2); a = 1, b = theta dt
-  IX_SOLVE(diffusion_solve(L, *ns.sv, false, 1, ns.s1, ns.r1, 1.0, theta * dt, rf == 2 ? &ns.rho_ctime : &ns.ones, ns.seta, &mi, ns.s));
+  const k::LinBC tbc = ns.diff_bc(Tracer, 1);
+  IX_SOLVE(diffusion_solve(L, *ns.sv, false, 1, ns.s1, ns.r1, 1.0, theta * dt, rf == 2 ? &ns.rho_ctime : &ns.ones, ns.seta, &mi, ns.s, &tbc));
   if (rf == 2)   // :575-590
     for (int il = 0; il < ns.s1.n(); ++il) IX_TRY(k::mult(L.lbox(il), ns.s1.v(il), ns.rho_ctime.c(il), 1, 1, ns.s));
   return mf_copy(ns.S_new, ns.s1, 0, Tracer, 1, 0, ns.s);
@@ -232,7 +333,8 @@ int velocity_diffusion_update(iamrx_ns_s& ns, double dt) {
   const double theta = ns.p.be_cn_theta;
   if (theta != 1.0) {
     IX_TRY(fillpatch(ns, ns.soln, ns.S_old, Xvel, 3));  // :742
-    IX_TRY(diffusion_apply(L, *ns.sv, true, 3, ns.rhs3, ns.soln, 0.0, -(1.0 - theta) * dt, nullptr, ns.eta, ns.s));  // :702-768
+    const k::LinBC vbc0 = ns.diff_bc(Xvel, 3);
+    IX_TRY(diffusion_apply(L, *ns.sv, true, 3, ns.rhs3, ns.soln, 0.0, -(1.0 - theta) * dt, nullptr, ns.eta, ns.s, &vbc0));  // :702-768
   } else {
     IX_TRY(mf_setval(ns.rhs3, 0.0, 0, 3, 0, ns.s));
   }
@@ -246,8 +348,9 @@ int velocity_diffusion_update(iamrx_ns_s& ns, double dt) {
   IX_TRY(fillpatch(ns, ns.soln, ns.S_new, Xvel, 3));  // :885 initial guess = new-time state
   iamrx_mg_info mi = mg_info(ns, ns.p.visc_tol, tol_abs);
   // :893-897 alpha = rho_half (rho_flag 1) or the NEW density (rho_flag 3, NS.cpp:1016)
+  const k::LinBC vbc = ns.diff_bc(Xvel, 3);
   IX_SOLVE(diffusion_solve(L, *ns.sv, true, 3, ns.soln, ns.rhs3, 1.0, theta * dt, ns.p.do_mom_diff ? &ns.rho_ctime : &ns.rho_half, ns.eta,
-                           &mi, ns.s));  // :895-923
+                           &mi, ns.s, &vbc));  // :895-923
   ns.it_visc = mi.iters;
   return mf_copy(ns.S_new, ns.soln, 0, Xvel, 3, 1, ns.s);  // :928
 }
@@ -286,9 +389,10 @@ int level_project(iamrx_ns_s& ns, double dt) {
     IX_TRY(k::invert(L.lbox(il), ns.sig.v(il), ns.rho_half.c(il), ns.s));
   MF vel; vel.alias(&L, IX_CELL, 3, 1, ns.S_new.fabs.data());  // comps 0..2 of the state
   iamrx_mg_info mi = mg_info(ns, ns.p.proj_tol, ns.p.proj_abs_tol);
-  IX_SOLVE(nodal_project(L, *ns.sv, vel, ns.sig, ns.P_new, &ns.Gp_new, 0, &mi, ns.s));  // :392 ; Gp = grad phi :2542-2563
+  const k::NodalBC nbc = ns.nodal_bc();
+  IX_SOLVE(nodal_project(L, *ns.sv, vel, ns.sig, ns.P_new, &ns.Gp_new, 0, &mi, ns.s, ns.walls ? &nbc : nullptr));  // :392 ; Gp = grad phi :2542-2563
   ns.it_nodal = mi.iters;
-  IX_TRY(mf_fill_boundary(ns.Gp_new, 0, 3, 1, ns.s));  // :2565
+  IX_TRY(fill_gradp(ns, ns.Gp_new));  // :2565
   return mf_scale(ns.S_new, dt, Xvel, 3, 0, ns.s);     // :438 (rescaleVar :434 restores rho_half: ns.sig is separate)
 }
 
@@ -362,7 +466,8 @@ int est_time_step(iamrx_ns_s& ns, double* out) {
 
 int project_simple(iamrx_ns_s& ns, MF& vel, const MF& sigma, MF& phi, MF* gp, int incr, int* iters) {
   iamrx_mg_info mi = mg_info(ns, ns.p.proj_tol, ns.p.proj_abs_tol);
-  IX_SOLVE(nodal_project(*ns.L, *ns.sv, vel, sigma, phi, gp, incr, &mi, ns.s));
+  const k::NodalBC nbc = ns.nodal_bc();
+  IX_SOLVE(nodal_project(*ns.L, *ns.sv, vel, sigma, phi, gp, incr, &mi, ns.s, ns.walls ? &nbc : nullptr));
   if (iters) *iters = mi.iters;
   return IAMRX_OK;
 }
@@ -405,9 +510,20 @@ int iamrx_ns_create(iamrx_level_t lev, const iamrx_ns_params* p, iamrx_ns_t* out
   IX_ARG(p->visc_coef >= 0.0, "ns.vel_visc_coef must be >= 0 (NS.cpp:2077)");
   IX_ARG(p->scal_diff_coef >= 0.0, "ns.scal_diff_coefs must be >= 0");
   Level* L = level_of(lev);
-  for (int d = 0; d < 3; ++d) IX_ARG(L->geom.periodic[d], "only fully periodic domains are implemented in this round");
+  bool walls = false;
+  for (int d = 0; d < 3; ++d) {
+    if (L->geom.periodic[d]) {
+      IX_ARG(p->lo_bc[d] == 0 && p->hi_bc[d] == 0, "ns.lo_bc / ns.hi_bc must be 0 (interior) in a periodic direction");
+    } else {
+      walls = true;
+      for (int v : {p->lo_bc[d], p->hi_bc[d]}) {
+        IX_ARG(v >= 1 && v <= 5, "ns.lo_bc / ns.hi_bc of a non-periodic direction must be 1..5 (inputs.3d.taylorgreen:100-102)");
+        IX_ARG(v >= 3, "the step driver implements symmetry (3), slip-wall (4) and no-slip-wall (5) boundaries; inflow / outflow only at operator level");
+      }
+    }
+  }
   auto* ns = new iamrx_ns_s();
-  ns->hlev = lev; ns->L = L; ns->sv = solvers_of(lev); ns->p = *p;
+  ns->hlev = lev; ns->L = L; ns->sv = solvers_of(lev); ns->p = *p; ns->walls = walls;
   ns->S_old.define(L, IX_CELL, NUM_STATE, 1); ns->S_new.define(L, IX_CELL, NUM_STATE, 1);
   ns->P_old.define(L, IX_NODE, 1, 1); ns->P_new.define(L, IX_NODE, 1, 1);
   ns->Gp_old.define(L, IX_CELL, 3, 1); ns->Gp_new.define(L, IX_CELL, 3, 1);
@@ -462,14 +578,15 @@ int iamrx_ns_destroy(iamrx_ns_t ns) {
 int iamrx_ns_init_prob(iamrx_ns_t ns, int probtype, const double* prob_params, int nparams) {
   IX_NEED_DEVICE();
   IX_ARG(ns && prob_params && nparams >= 0, "null argument");
-  IX_ARG(probtype == 11 || probtype == 100 || probtype == 5 || probtype == 20,
-         "probtype must be 11 (TaylorGreen), 5 (DoubleShearLayer), 20 (HIT) or 100");
-  IX_ARG((probtype == 5) ? nparams >= 6 : (probtype == 20 ? nparams >= 2 : nparams >= 5), "too few prob parameters");
+  IX_ARG(probtype == 11 || probtype == 100 || probtype == 5 || probtype == 20 || probtype == 10 || probtype == 1 || probtype == 101,
+         "probtype must be 11 (TaylorGreen), 5 (DoubleShearLayer), 10 (RayleighTaylor), 1 (LidDrivenCavity), 20 (HIT), 100 or 101");
+  IX_ARG((probtype == 5 || probtype == 10) ? nparams >= 6 : (probtype == 20 ? nparams >= 2 : (probtype == 1 ? nparams >= 0 : (probtype == 101 ? nparams >= 3 : nparams >= 5))),
+         "too few prob parameters");
   Level& L = *ns->L;
   // NavierStokes::initData (NS.cpp:335-460): S_new from prob_init, P_new = 0, Gp = 0
   for (int il = 0; il < ns->S_new.n(); ++il)
     IX_TRY(k::init_prob(L.lbox(il), ns->S_new.v(il), probtype, prob_params, nparams, L.geom, ns->s));
-  IX_TRY(mf_fill_boundary(ns->S_new, 0, NUM_STATE, 1, ns->s));
+  IX_TRY(fill_state_ghosts(*ns, ns->S_new, 0, 0, NUM_STATE, 1));
   IX_TRY(mf_setval(ns->P_new, 0.0, 0, 1, 1, ns->s));
   IX_TRY(mf_setval(ns->P_old, 0.0, 0, 1, 1, ns->s));
   IX_TRY(mf_setval(ns->Gp_new, 0.0, 0, 3, 1, ns->s));
@@ -499,6 +616,19 @@ int iamrx_ns_post_init(iamrx_ns_t nsp, double* dt0) {
     }
   }
   ns.initial_step = true;  // NSB.cpp:2403
+  if (ns.p.do_init_proj && std::fabs(ns.p.gravity) > 0.0 && ns.walls) {
+    // initialPressureProject (NSB.cpp:2421-2431 -> Projection.cpp:841-960): projecting the uniform gravity vector with sigma = 1/rho
+    // gives the hydrostatic pressure; P and Gradp old := new.  (On a fully periodic domain div(0,0,g) vanishes: nothing to do.)
+    MF gvel(&L, IX_CELL, 3, 1);
+    IX_TRY(mf_setval(gvel, 0.0, 0, 2, 1, ns.s));
+    IX_TRY(mf_setval(gvel, ns.p.gravity, 2, 1, 1, ns.s));
+    for (int il = 0; il < ns.sig.n(); ++il) IX_TRY(k::invert(L.lbox(il), ns.sig.v(il), ns.S_new.c(il, Density), ns.s));
+    IX_TRY(mf_setval(ns.P_new, 0.0, 0, 1, 1, ns.s));
+    IX_TRY(project_simple(ns, gvel, ns.sig, ns.P_new, &ns.Gp_new, 0, nullptr));
+    IX_TRY(fill_gradp(ns, ns.Gp_new));
+    IX_TRY(mf_copy(ns.P_old, ns.P_new, 0, 0, 1, 1, ns.s));
+    IX_TRY(mf_copy(ns.Gp_old, ns.Gp_new, 0, 0, 3, 1, ns.s));
+  }
   // --- post_init_estDT: dt_init = init_shrink * estTimeStep
   double est = 0.0;
   IX_TRY(est_time_step(ns, &est));
@@ -520,7 +650,7 @@ int iamrx_ns_post_init(iamrx_ns_t nsp, double* dt0) {
       MF vel; vel.alias(&L, IX_CELL, 3, 1, ns.S_new.fabs.data());
       IX_TRY(project_simple(ns, vel, ns.sig, ns.P_old, &ns.Gp_new, 1, &ns.it_nodal));
       IX_TRY(mf_lincomb(ns.P_new, 0, 1.0, ns.P_new, 0, 1.0, ns.P_old, 0, 1, 1, ns.s));  // :1166-1170
-      IX_TRY(mf_fill_boundary(ns.Gp_new, 0, 3, 1, ns.s));
+      IX_TRY(fill_gradp(ns, ns.Gp_new));
       // resetState (NSB.cpp:2643-2680): State new := the time-n state; P, Gp old := new
       std::swap(ns.S_old, ns.S_new);
       IX_TRY(mf_copy(ns.P_old, ns.P_new, 0, 0, 1, 1, ns.s));

@@ -416,6 +416,15 @@ typedef struct iamrx_ns_params {
   int godunov_ppm;       /* ns.advection_scheme = Godunov_PPM instead of the default Godunov_PLM (NSB.cpp:169,552-554) */
   int do_scalminmax;     /* ns.do_scalminmax (NSB.cpp:140,2907-2935): clamp the advected tracer to the old 3x3x3 range */
   int do_mom_diff;       /* ns.do_mom_diff (NSB.cpp:167,3358-3470,3609-3616; NS.cpp:606-623,1016): advect and diffuse momentum rho*u */
+  /* physical boundaries (ns.lo_bc / ns.hi_bc, NS.cpp:90-94; codes of inputs.3d.taylorgreen:100-102): 0 interior / periodic,
+   * 1 inflow, 2 outflow, 3 symmetry, 4 slip wall, 5 no-slip wall.  A periodic direction must carry 0, a non-periodic one must
+   * not.  The step driver implements walls and symmetry planes (3, 4, 5); inflow / outflow are available at the operator
+   * level (sections 1-3) but rejected here. */
+  int lo_bc[3];
+  int hi_bc[3];
+  /* Dirichlet face values [x lo, y lo, z lo, x hi, y hi, z hi][u, v, w, rho, tracer]: the xlo.velocity / xlo.density ...
+   * blocks of NS.cpp:108-237 (e.g. zhi.velocity = 1 0 0, the lid of Tutorials/LidDrivenCavity) */
+  double bc_vals[6][5];
 } iamrx_ns_params;
 
 void iamrx_ns_params_default(iamrx_ns_params* p);

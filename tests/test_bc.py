@@ -412,3 +412,103 @@ def test_diffusion_bc(backend, oracle, per, plo, phi, nb, tensor):
     gs, _ = scatter_valid(np.zeros(orc_shape(n, ncomp, 1)), 1, [p[0] for p in Sol], boxes, 1, ix.CELL)
     assert np.abs(gs[:, 1:-1, 1:-1, 1:-1] - ref_sol[:, 1:-1, 1:-1, 1:-1]).max() <= 1e-10
     lev.close()
+
+
+def _assemble_padded(ns, which, boxes, n, ncomp, ng, ixtype):
+    """Valid data of every local box -> the oracle's padded layout."""
+    out = np.zeros(orc_shape(n, ncomp, ng))
+    ext = EXTENT[ixtype]
+    for il, (lo, hi) in enumerate(boxes):
+        t = ns.field(which, il).cpu().numpy()
+        sl = tuple(slice(lo[d] + ng, hi[d] + ext[d] + ng + 1) for d in (2, 1, 0))
+        nz, ny, nx = (hi[2] - lo[2] + 1 + ext[2], hi[1] - lo[1] + 1 + ext[1], hi[0] - lo[0] + 1 + ext[0])
+        out[(slice(None),) + sl] = t[:, :nz, :ny, :nx]
+    return out
+
+
+LID = [[0.0] * 5 for _ in range(6)]
+LID[5][0] = 1.0   # zhi.velocity = 1 0 0 (Tutorials/LidDrivenCavity/inputs.3d.lid_driven_cavity)
+
+WALL_RUNS = [
+    # RayleighTaylor 3-D single level (regtest.3d.rayleightaylor:48-49 boundaries: periodic x, y, slip walls z; gravity, inviscid)
+    dict(n=(16, 16, 32), hi=(0.5, 0.5, 1.0), per=(1, 1, 0), lo_bc=(0, 0, 4), hi_bc=(0, 0, 4), probtype=10, pp=[1.0, 2.0, 1.0, 0.0, 0.05, 0.02],
+         kw=dict(visc_coef=0.0, cfl=0.7, gravity=-1.0)),
+    # ... with the regtest's options: momentum form, conservative tracer, PPM, forces in the transverse terms
+    dict(n=(16, 16, 32), hi=(0.5, 0.5, 1.0), per=(1, 1, 0), lo_bc=(0, 0, 4), hi_bc=(0, 0, 4), probtype=10, pp=[1.0, 2.0, 1.0, 0.0, 0.05, 0.02],
+         kw=dict(visc_coef=0.0, cfl=0.7, gravity=-1.0, do_mom_diff=1, conservative_tracer=1, godunov_ppm=1, use_forces_in_trans=1)),
+    # LidDrivenCavity (inputs.3d.lid_driven_cavity): no-slip box, moving lid, viscous (tensor solve with inhomogeneous Dirichlet data)
+    dict(n=(16, 16, 16), hi=(1.0, 1.0, 1.0), per=(0, 0, 0), lo_bc=(5, 5, 5), hi_bc=(5, 5, 5), probtype=1, pp=[0.0], bcv=LID,
+         kw=dict(visc_coef=0.01, cfl=0.7, init_shrink=0.3, init_iter=3, fixed_dt=0.0140625)),
+    # a wall-bounded 3-D flow with every wall type: no-slip x, slip y, slip / symmetry z; variable density, gravity, viscosity, diffusive tracer
+    dict(n=(16, 16, 16), hi=(1.0, 1.0, 1.0), per=(0, 0, 0), lo_bc=(5, 4, 4), hi_bc=(5, 4, 3), probtype=101, pp=[1.0, 1.0, 0.3],
+         kw=dict(visc_coef=0.01, cfl=0.5, gravity=-0.5, scal_diff_coef=5e-3)),
+]
+
+
+@pytest.mark.parametrize("run", WALL_RUNS, ids=["rayleigh_taylor", "rayleigh_taylor_regtest_options", "lid_driven_cavity", "mixed_walls"])
+@pytest.mark.parametrize("nb", [(1, 1, 1), (2, 2, 2)])
+def test_step_with_walls_matches_oracle(backend, oracle, run, nb):
+    """post_init (incl. the hydrostatic initialPressureProject when there is gravity) + 3 steps on wall-bounded domains:
+    velocity, scalars, pressure and grad(p) against the oracle, L-inf <= 1e-10."""
+    lib, dev = backend
+    n = run["n"]
+    g = ix.Geom.make(n, (0.0, 0.0, 0.0), run["hi"], periodic=run["per"])
+    boxes = split_boxes(n, nb)
+    lev = ix.Level(lib, g, boxes)
+    kw = dict(run["kw"])
+    bcv = run.get("bcv")
+    ns = ix.NavierStokes(lib, lev, dev, lo_bc=run["lo_bc"], hi_bc=run["hi_bc"], **(dict(bc_vals=bcv) if bcv else {}), **kw)
+    okw = {("use_ppm" if k == "godunov_ppm" else k): v for k, v in kw.items()}
+    o = oracle.OracleNS(n, (0, 0, 0), run["hi"], per=run["per"], phys_lo=run["lo_bc"], phys_hi=run["hi_bc"], bcv=bcv, **okw)
+    ns.init_prob(run["probtype"], run["pp"]); o.init_prob(run["probtype"], run["pp"])
+    d1, d2 = ns.post_init(), o.post_init()
+    assert abs(d1 - d2) <= 1e-12 * d2
+    for step in range(3):
+        a, b = ns.step(), o.step()
+        assert abs(a - b) <= 1e-11 * b
+    S = _assemble_padded(ns, 0, boxes, n, 5, 1, ix.CELL)[:, 1:-1, 1:-1, 1:-1]
+    So = o.get(0)
+    assert np.abs(S - So).max() <= 1e-10
+    G = _assemble_padded(ns, 2, boxes, n, 3, 1, ix.CELL)[:, 1:-1, 1:-1, 1:-1]
+    assert np.abs(G - o.get(2)).max() <= 1e-10 * max(1.0, np.abs(So[3]).max())
+    P = _assemble_padded(ns, 1, boxes, n, 1, 2, ix.NODE)
+    Po = o.get_padded(1)
+    hi = [n[q] + (0 if run["per"][q] else 1) for q in range(3)]
+    sl = (slice(None), slice(2, 2 + hi[2]), slice(2, 2 + hi[1]), slice(2, 2 + hi[0]))
+    a, b = P[sl], Po[sl]
+    assert np.abs((a - a.mean()) - (b - b.mean())).max() <= 1e-10 * max(1.0, np.abs(b).max())
+    if nb == (1, 1, 1):
+        assert ns.last_iters() == o.last_iters()
+    ns.close(); o.close(); lev.close()
+
+
+def test_hydrostatic_equilibrium_is_preserved(backend):
+    """Known answer (no oracle needed): a flat-interface RayleighTaylor stratification between slip walls with gravity is an
+    exact steady state; initialPressureProject must produce grad p = rho g and the velocity must stay zero."""
+    lib, dev = backend
+    n = (8, 8, 32)
+    g = ix.Geom.make(n, (0.0, 0.0, 0.0), (0.25, 0.25, 1.0), periodic=(1, 1, 0))
+    lev = ix.Level(lib, g, [((0, 0, 0), (7, 7, 15)), ((0, 0, 16), (7, 7, 31))])
+    ns = ix.NavierStokes(lib, lev, dev, lo_bc=(0, 0, 4), hi_bc=(0, 0, 4), visc_coef=0.0, gravity=-1.0, fixed_dt=0.01)
+    ns.init_prob(10, [1.0, 2.0, 1.0, 0.0, 0.05, 0.0])   # perturbation amplitude 0
+    ns.post_init()
+    for _ in range(3):
+        ns.step()
+    for il in range(2):
+        S, G = ns.field(0, il), ns.field(2, il)
+        assert float(S[:3].abs().max()) < 1e-12
+        assert float((G[2] + S[3]).abs().max()) < 1e-11   # dp/dz = rho * g with g = -1
+    ns.close(); lev.close()
+
+
+def test_driver_rejects_unsupported_boundaries(backend):
+    lib, dev = backend
+    g = ix.Geom.make((8, 8, 8), periodic=(0, 1, 1))
+    lev = ix.Level(lib, g, [((0, 0, 0), (7, 7, 7))])
+    with pytest.raises(ix.IamrxError, match="inflow / outflow"):
+        ix.NavierStokes(lib, lev, dev, lo_bc=(1, 0, 0), hi_bc=(2, 0, 0))
+    with pytest.raises(ix.IamrxError, match="non-periodic direction"):
+        ix.NavierStokes(lib, lev, dev)                       # lo_bc = 0 on a non-periodic side
+    with pytest.raises(ix.IamrxError, match="periodic direction"):
+        ix.NavierStokes(lib, lev, dev, lo_bc=(4, 4, 0), hi_bc=(4, 0, 0))
+    lev.close()
