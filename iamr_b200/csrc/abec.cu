@@ -73,12 +73,29 @@ gsrb_kernel(Bx bx, V4 phi, C4 rhs, IX_KARG(AbecDev) op, double omega, int redbla
   double gamma = op.dhx * (bxm + bxp) + op.dhy * (bym + byp) + op.dhz * (bzm + bzp);
   if (op.a != 0.0) gamma += op.a * op.acoef(i, j, k);
   // periodic wrap inside the kernel when the box spans the domain (no ghost fill needed)
-  const int oxm = ((wm & 1) && i == bx.lo[0]) ? bx.hi[0] - i : -1, oxp = ((wm & 1) && i == bx.hi[0]) ? bx.lo[0] - i : 1;
-  const int oym = (((wm & 2) && j == bx.lo[1]) ? bx.hi[1] - j : -1) * pjs, oyp = (((wm & 2) && j == bx.hi[1]) ? bx.lo[1] - j : 1) * pjs;
-  const int ozm = (((wm & 4) && k == bx.lo[2]) ? bx.hi[2] - k : -1) * pks, ozp = (((wm & 4) && k == bx.hi[2]) ? bx.lo[2] - k : 1) * pks;
-  const double rho = op.dhx * (bxm * pc[oxm] + bxp * pc[oxp]) +
-                     op.dhy * (bym * pc[oym] + byp * pc[oyp]) +
-                     op.dhz * (bzm * pc[ozm] + bzp * pc[ozp]);
+  int oxm = ((wm & 1) && i == bx.lo[0]) ? bx.hi[0] - i : -1, oxp = ((wm & 1) && i == bx.hi[0]) ? bx.lo[0] - i : 1;
+  int oym = (((wm & 2) && j == bx.lo[1]) ? bx.hi[1] - j : -1) * pjs, oyp = (((wm & 2) && j == bx.hi[1]) ? bx.lo[1] - j : 1) * pjs;
+  int ozm = (((wm & 4) && k == bx.lo[2]) ? bx.hi[2] - k : -1) * pks, ozp = (((wm & 4) && k == bx.hi[2]) ? bx.lo[2] - k : 1) * pks;
+  double rho;
+  if (HASBC) {
+    // sides whose homogeneous ghost cell is +/- the adjacent cell (Neumann, reflect_odd, order-2 Dirichlet) are evaluated
+    // in place: no ghost fill between the colours
+    const int nc = n < 3 ? n : 0;
+    const int mir = gb.even[nc] | gb.odd[nc], od = gb.odd[nc];
+    double sxm = 1.0, sxp = 1.0, sym = 1.0, syp = 1.0, szm = 1.0, szp = 1.0;
+    if ((mir & 1) && i == bx.lo[0]) { oxm = 0; if (od & 1) sxm = -1.0; }
+    if ((mir & 2) && i == bx.hi[0]) { oxp = 0; if (od & 2) sxp = -1.0; }
+    if ((mir & 4) && j == bx.lo[1]) { oym = 0; if (od & 4) sym = -1.0; }
+    if ((mir & 8) && j == bx.hi[1]) { oyp = 0; if (od & 8) syp = -1.0; }
+    if ((mir & 16) && k == bx.lo[2]) { ozm = 0; if (od & 16) szm = -1.0; }
+    if ((mir & 32) && k == bx.hi[2]) { ozp = 0; if (od & 32) szp = -1.0; }
+    rho = op.dhx * (bxm * (sxm * pc[oxm]) + bxp * (sxp * pc[oxp])) + op.dhy * (bym * (sym * pc[oym]) + byp * (syp * pc[oyp])) +
+          op.dhz * (bzm * (szm * pc[ozm]) + bzp * (szp * pc[ozp]));
+  } else {
+    rho = op.dhx * (bxm * pc[oxm] + bxp * pc[oxp]) +
+          op.dhy * (bym * pc[oym] + byp * pc[oyp]) +
+          op.dhz * (bzm * pc[ozm] + bzp * pc[ozp]);
+  }
   const double res = rhs(i, j, k, n) - (gamma * p0 - rho);
   if (HASBC) {
     const int nc = n < 3 ? n : 0;
@@ -99,8 +116,11 @@ gsrb_kernel(Bx bx, V4 phi, C4 rhs, IX_KARG(AbecDev) op, double omega, int redbla
 constexpr int AP_TX = 128;
 constexpr int AP_TY = 2;
 
+// mir: per component, bit s (xlo, xhi, ylo, yhi, zlo, zhi) of even / odd = the ghost cell beyond that side of the box is
+// + / - the adjacent cell (homogeneous Neumann / reflect_odd / order-2 Dirichlet): evaluated in place, no ghost fill
+struct MirBC { int even[3], odd[3]; };
 __global__ void __launch_bounds__(AP_TX* AP_TY)
-apply_kernel(Bx bx, V4 out, C4 phi, C4 rhs, IX_KARG(AbecDev) op, int nz, int wm) {
+apply_kernel(Bx bx, V4 out, C4 phi, C4 rhs, IX_KARG(AbecDev) op, int nz, int wm, IX_KARG(MirBC) mb) {
   const int kz = blockIdx.z % nz;
   const int n = blockIdx.z / nz;
   const int k = bx.lo[2] + kz;
@@ -114,12 +134,25 @@ apply_kernel(Bx bx, V4 out, C4 phi, C4 rhs, IX_KARG(AbecDev) op, int nz, int wm)
   const double* pc = phi.p + n * phi.ns + ((i - phi.l0) + (j - phi.l1) * phi.js + (k - phi.l2) * phi.ks);
   const int pjs = (int)phi.js, pks = (int)phi.ks;
   const double p0 = pc[0];
-  const int oxm = ((wm & 1) && i == bx.lo[0]) ? bx.hi[0] - i : -1, oxp = ((wm & 1) && i == bx.hi[0]) ? bx.lo[0] - i : 1;
-  const int oym = (((wm & 2) && j == bx.lo[1]) ? bx.hi[1] - j : -1) * pjs, oyp = (((wm & 2) && j == bx.hi[1]) ? bx.lo[1] - j : 1) * pjs;
-  const int ozm = (((wm & 4) && k == bx.lo[2]) ? bx.hi[2] - k : -1) * pks, ozp = (((wm & 4) && k == bx.hi[2]) ? bx.lo[2] - k : 1) * pks;
-  double y = -op.dhx * (bxc[1] * (pc[oxp] - p0) - bxc[0] * (p0 - pc[oxm])) -
-             op.dhy * (byc[(int)op.by.js] * (pc[oyp] - p0) - byc[0] * (p0 - pc[oym])) -
-             op.dhz * (bzc[(int)op.bz.ks] * (pc[ozp] - p0) - bzc[0] * (p0 - pc[ozm]));
+  int oxm = ((wm & 1) && i == bx.lo[0]) ? bx.hi[0] - i : -1, oxp = ((wm & 1) && i == bx.hi[0]) ? bx.lo[0] - i : 1;
+  int oym = (((wm & 2) && j == bx.lo[1]) ? bx.hi[1] - j : -1) * pjs, oyp = (((wm & 2) && j == bx.hi[1]) ? bx.lo[1] - j : 1) * pjs;
+  int ozm = (((wm & 4) && k == bx.lo[2]) ? bx.hi[2] - k : -1) * pks, ozp = (((wm & 4) && k == bx.hi[2]) ? bx.lo[2] - k : 1) * pks;
+  double sxm = 1.0, sxp = 1.0, sym = 1.0, syp = 1.0, szm = 1.0, szp = 1.0;
+  {
+    const int nc = n < 3 ? n : 0;
+    const int mir = mb.even[nc] | mb.odd[nc], od = mb.odd[nc];
+    if (mir) {
+      if ((mir & 1) && i == bx.lo[0]) { oxm = 0; if (od & 1) sxm = -1.0; }
+      if ((mir & 2) && i == bx.hi[0]) { oxp = 0; if (od & 2) sxp = -1.0; }
+      if ((mir & 4) && j == bx.lo[1]) { oym = 0; if (od & 4) sym = -1.0; }
+      if ((mir & 8) && j == bx.hi[1]) { oyp = 0; if (od & 8) syp = -1.0; }
+      if ((mir & 16) && k == bx.lo[2]) { ozm = 0; if (od & 16) szm = -1.0; }
+      if ((mir & 32) && k == bx.hi[2]) { ozp = 0; if (od & 32) szp = -1.0; }
+    }
+  }
+  double y = -op.dhx * (bxc[1] * (sxp * pc[oxp] - p0) - bxc[0] * (p0 - sxm * pc[oxm])) -
+             op.dhy * (byc[(int)op.by.js] * (syp * pc[oyp] - p0) - byc[0] * (p0 - sym * pc[oym])) -
+             op.dhz * (bzc[(int)op.bz.ks] * (szp * pc[ozp] - p0) - bzc[0] * (p0 - szm * pc[ozm]));
   if (op.a != 0.0) y += op.a * op.acoef(i, j, k) * p0;
   out(i, j, k, n) = rhs.ok() ? (rhs(i, j, k, n) - y) : y;
 }
@@ -342,6 +375,40 @@ tensor_cross_kernel(Bx bx, V4 out, C4 vel, C4 ex, C4 ey, C4 ez, double b, double
   for (int n = 0; n < 3; ++n) acc[n] += dzi * (fh[n] - fl[n]);
   for (int n = 0; n < 3; ++n) out(i, j, k, n) += b * acc[n];
 }
+
+#if !defined(IX_EMUL)
+// z-marching form of tensor_cross_kernel: a CTA owns a 32 x 8 column of cells and walks up in z.  Every thread computes only the
+// three LOW-face cross fluxes of its cell (the x / y neighbours' come through shared memory, the z one is carried in registers to
+// the next plane), i.e. each face flux is evaluated once instead of twice and the stencil loads per cell halve.
+constexpr int TC_X = 32, TC_Y = 8, TC_KB = 32;
+__global__ void __launch_bounds__((TC_X + 1) * (TC_Y + 1))
+tensor_cross_march_kernel(Bx bx, V4 out, C4 vel, C4 ex, C4 ey, C4 ez, double b, double dxi, double dyi, double dzi) {
+  __shared__ double sfx[3][TC_Y + 1][TC_X + 1], sfy[3][TC_Y + 1][TC_X + 1];
+  const int tx = threadIdx.x, ty = threadIdx.y;
+  const int i = bx.lo[0] + blockIdx.x * TC_X + tx, j = bx.lo[1] + blockIdx.y * TC_Y + ty;
+  const int k0 = bx.lo[2] + blockIdx.z * TC_KB, k1 = min(k0 + TC_KB - 1, bx.hi[2]);
+  // threads of the extra column / row only provide the x / y flux of the face beyond the tile
+  const bool in_x = tx < TC_X && i <= bx.hi[0], in_y = ty < TC_Y && j <= bx.hi[1];
+  const bool need_fx = i <= bx.hi[0] + 1 && in_y, need_fy = j <= bx.hi[1] + 1 && in_x, cell = in_x && in_y;
+  double fzl[3] = {0.0, 0.0, 0.0}, accxy[3] = {0.0, 0.0, 0.0};
+  if (cell) cross_fz(vel, ez, i, j, k0, dxi, dyi, fzl);
+  for (int k = k0; k <= k1; ++k) {
+    double f[3];
+    if (need_fx) { cross_fx(vel, ex, i, j, k, dyi, dzi, f); sfx[0][ty][tx] = f[0]; sfx[1][ty][tx] = f[1]; sfx[2][ty][tx] = f[2]; }
+    if (need_fy) { cross_fy(vel, ey, i, j, k, dxi, dzi, f); sfy[0][ty][tx] = f[0]; sfy[1][ty][tx] = f[1]; sfy[2][ty][tx] = f[2]; }
+    __syncthreads();
+    if (cell) {
+#pragma unroll
+      for (int n = 0; n < 3; ++n) accxy[n] = dxi * (sfx[n][ty][tx + 1] - sfx[n][ty][tx]) + dyi * (sfy[n][ty + 1][tx] - sfy[n][ty][tx]);
+      double fzh[3];
+      cross_fz(vel, ez, i, j, k + 1, dxi, dyi, fzh);
+#pragma unroll
+      for (int n = 0; n < 3; ++n) { out(i, j, k, n) += b * (accxy[n] + dzi * (fzh[n] - fzl[n])); fzl[n] = fzh[n]; }
+    }
+    __syncthreads();
+  }
+}
+#endif
 
 // tensor cross terms on a box that touches non-periodic domain faces (mltensor_cross_terms_f? with bct / bv?lo / bv?hi): ON such
 // a face the transverse derivative of component c comes from the boundary data -- Dirichlet: centred difference of the face
@@ -711,11 +778,14 @@ int abec_gsrb_sweep(const Bx& bx, V4 phi_out, C4 phi_in, C4 rhs, const Abec& op,
 #endif
 }
 
-int abec_apply(const Bx& bx, V4 out, C4 phi, C4 rhs, const Abec& op, int ncomp, cudaStream_t s, int wrapmask) {
+int abec_apply(const Bx& bx, V4 out, C4 phi, C4 rhs, const Abec& op, int ncomp, cudaStream_t s, int wrapmask, const GsBC* gb) {
   if (!bx.ok()) return IAMRX_OK;
+  MirBC mb{};
+  bool mirrored = false;
+  if (gb) for (int c = 0; c < 3; ++c) { mb.even[c] = gb->even[c]; mb.odd[c] = gb->odd[c]; if (mb.even[c] | mb.odd[c]) mirrored = true; }
   ProfScope prof_(IAMRX_PROF_ABEC_APPLY, bx.npts(), (double)bx.npts() * ncomp * ((op.a != 0.0 ? 56.0 : 48.0) + (rhs.ok() ? 0.0 : -8.0)), s);
 #if !defined(IX_EMUL)
-  if (bx.nx() % 2 == 0 && pairs_aligned(out, bx) && pairs_aligned(phi, bx) && pairs_aligned(rhs, bx) && pairs_aligned(op.acoef, bx) &&
+  if (!mirrored && bx.nx() % 2 == 0 && pairs_aligned(out, bx) && pairs_aligned(phi, bx) && pairs_aligned(rhs, bx) && pairs_aligned(op.acoef, bx) &&
       pairs_aligned(op.bx, bx) && pairs_aligned(op.by, bx) && pairs_aligned(op.bz, bx)) {
     const dim3 grd(cdiv(bx.nx() / 2, AP_TX), cdiv(bx.ny(), AP_TY), bx.nz() * ncomp);
     if (op.a != 0.0) IX_LAUNCH(apply2_kernel<true>, grd, dim3(AP_TX, AP_TY, 1), 0, s, bx, out, phi, rhs, to_dev(op), bx.nz(), wrapmask);
@@ -724,7 +794,7 @@ int abec_apply(const Bx& bx, V4 out, C4 phi, C4 rhs, const Abec& op, int ncomp, 
   }
 #endif
   IX_LAUNCH(apply_kernel, grid_for(bx, AP_TX, AP_TY, bx.nz() * ncomp), dim3(AP_TX, AP_TY, 1), 0, s, 
-      bx, out, phi, rhs, to_dev(op), bx.nz(), wrapmask);
+      bx, out, phi, rhs, to_dev(op), bx.nz(), wrapmask, mb);
   return check_launch("abec_apply");
 }
 
@@ -797,6 +867,19 @@ int tensor_cross_bc(const Bx& bx, V4 out, C4 vel, C4 bv, C4 ex, C4 ey, C4 ez, do
 int tensor_cross(const Bx& bx, V4 out, C4 vel, C4 ex, C4 ey, C4 ez, double b, const double dxinv[3],
                  cudaStream_t s) {
   if (!bx.ok()) return IAMRX_OK;
+#if !defined(IX_EMUL)
+  {
+    static int on = -1;
+    // measured on B200 (profiles/r02_notes.md): 1.22 ms vs 0.86 ms per launch at 256^3 -- the per-plane barriers cost more than the
+    // halved stencil loads save -- so the marching form is opt-in (IAMRX_TENSOR_MARCH=1)
+    if (on < 0) { const char* e = getenv("IAMRX_TENSOR_MARCH"); on = (e && e[0] == '1') ? 1 : 0; }
+    if (on && bx.nz() >= 8) {
+      const dim3 grd(cdiv(bx.nx(), TC_X), cdiv(bx.ny(), TC_Y), cdiv(bx.nz(), TC_KB));
+      IX_LAUNCH(tensor_cross_march_kernel, grd, dim3(TC_X + 1, TC_Y + 1, 1), 0, s, bx, out, vel, ex, ey, ez, b, dxinv[0], dxinv[1], dxinv[2]);
+      return check_launch("tensor_cross_march");
+    }
+  }
+#endif
   IX_LAUNCH(tensor_cross_kernel, grid_for(bx, AP_TX, AP_TY, bx.nz()), dim3(AP_TX, AP_TY, 1), 0, s, 
       bx, out, vel, ex, ey, ez, b, dxinv[0], dxinv[1], dxinv[2]);
   return check_launch("tensor_cross");

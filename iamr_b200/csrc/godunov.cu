@@ -107,20 +107,20 @@ enum { A_XE = 0, A_YE, A_ZE, A_XY, A_XZ, A_YX, A_YZ, A_ZX, A_ZY, A_FX, A_FY, A_F
 
 // lo/hi on the D-face of the cursor's cell, traced with the MAC velocity `u` of that face
 // Set{X,Y,Z}EdgeBCs on the states of the D-face with index c for component n
-template <int D, class A>
+template <int D, bool BC, class A>
 IX_D void edge_bc(const A& a, int n, const Cur& q, int c, double& lo, double& hi, bool normal_vel) {
-  if (!a.bc.any) return;
+  if (!BC) return;
   set_edge_bc(lo, hi, along<D>(q, -1), q(0, 0, 0), c, a.bc.dir(n, D), normal_vel);
 }
-template <int D>
+template <int D, bool BC>
 IX_D void es_lohi(const EsArgs& a, int n, int c, const Cur& q, const Cur& f, double u, double dtdx, double& lo, double& hi) {
-  const BcD b = a.bc.dir(n, D);
-  trace<D>(q, u, u, dtdx, lo, hi, a.ppm, c, a.bc.any ? &b : nullptr);
+  const BcD b = BC ? a.bc.dir(n, D) : BcD{};
+  trace<D>(q, u, u, dtdx, lo, hi, a.ppm, c, BC ? &b : nullptr);
   if (a.fit && f.ok()) {
     lo += 0.5 * a.dt * along<D>(f, -1);
     hi += 0.5 * a.dt * f(0, 0, 0);
   }
-  edge_bc<D>(a, n, q, c, lo, hi, a.is_velocity && n == D);
+  edge_bc<D, BC>(a, n, q, c, lo, hi, a.is_velocity && n == D);
 }
 
 struct EsCur {  // the cursors one thread needs
@@ -132,6 +132,7 @@ IX_D EsCur es_cursors(const EsArgs& a, const Scratch& sc, int n, int i, int j, i
                cur_at(a.vmac, 0, i, j, k), cur_at(a.wmac, 0, i, j, k), scur_at(sc, i, j, k)};
 }
 
+template <bool BC>
 __global__ void __launch_bounds__(TX* TY) es_edge_kernel(IX_KARG(EsArgs) a, IX_KARG(Scratch) sc, IX_KARG(Bx) R) {
   GIDX(R)
   const EsCur c = es_cursors(a, sc, n, i, j, k);
@@ -142,17 +143,17 @@ __global__ void __launch_bounds__(TX* TY) es_edge_kernel(IX_KARG(EsArgs) a, IX_K
   double lo, hi;
   if (i >= b.lo[0] && i <= b.hi[0] + 1 && iny && inz) {  // x-faces lo..hi+1
     const double u = c.u(0, 0, 0);
-    es_lohi<0>(a, n, i, c.q, c.f, u, a.dtdx, lo, hi);
+    es_lohi<0, BC>(a, n, i, c.q, c.f, u, a.dtdx, lo, hi);
     c.s(o + A_XE, 0, 0, 0) = upwind(lo, hi, u);
   }
   if (j >= b.lo[1] && j <= b.hi[1] + 1 && inx && inz) {
     const double v = c.v(0, 0, 0);
-    es_lohi<1>(a, n, j, c.q, c.f, v, a.dtdy, lo, hi);
+    es_lohi<1, BC>(a, n, j, c.q, c.f, v, a.dtdy, lo, hi);
     c.s(o + A_YE, 0, 0, 0) = upwind(lo, hi, v);
   }
   if (k >= b.lo[2] && k <= b.hi[2] + 1 && inx && iny) {
     const double w = c.w(0, 0, 0);
-    es_lohi<2>(a, n, k, c.q, c.f, w, a.dtdz, lo, hi);
+    es_lohi<2, BC>(a, n, k, c.q, c.f, w, a.dtdz, lo, hi);
     c.s(o + A_ZE, 0, 0, 0) = upwind(lo, hi, w);
   }
 }
@@ -173,6 +174,7 @@ IX_D void corner(double& lo1, double& hi1, double lo, double hi, const Cur& q, c
   }
 }
 
+template <bool BC>
 __global__ void __launch_bounds__(TX* TY) es_corner_kernel(IX_KARG(EsArgs) a, IX_KARG(Scratch) sc, IX_KARG(Bx) R) {
   GIDX(R)
   const EsCur c = es_cursors(a, sc, n, i, j, k);
@@ -190,15 +192,15 @@ __global__ void __launch_bounds__(TX* TY) es_corner_kernel(IX_KARG(EsArgs) a, IX
   if (fx && ((fy && cy && gz) || (gy && fz && cz))) {
     const double u = c.u(0, 0, 0);
     const bool nv = a.is_velocity && n == 0;
-    es_lohi<0>(a, n, i, c.q, c.f, u, a.dtdx, lo, hi);
+    es_lohi<0, BC>(a, n, i, c.q, c.f, u, a.dtdx, lo, hi);
     if (fy && cy && gz) {  // xy: needed for z-faces -> grown in z
       corner<0, 1>(l1, h1, lo, hi, c.q, c.v, ye, a.dtdy / 3.0, cs);
-      edge_bc<0>(a, n, c.q, i, l1, h1, nv);
+      edge_bc<0, BC>(a, n, c.q, i, l1, h1, nv);
       c.s(o + A_XY, 0, 0, 0) = upwind(l1, h1, u);
     }
     if (gy && fz && cz) {  // xz: needed for y-faces -> grown in y
       corner<0, 2>(l1, h1, lo, hi, c.q, c.w, ze, a.dtdz / 3.0, cs);
-      edge_bc<0>(a, n, c.q, i, l1, h1, nv);
+      edge_bc<0, BC>(a, n, c.q, i, l1, h1, nv);
       c.s(o + A_XZ, 0, 0, 0) = upwind(l1, h1, u);
     }
   }
@@ -206,15 +208,15 @@ __global__ void __launch_bounds__(TX* TY) es_corner_kernel(IX_KARG(EsArgs) a, IX
   if (fy && ((fx && cx && gz) || (gx && fz && cz))) {
     const double v = c.v(0, 0, 0);
     const bool nv = a.is_velocity && n == 1;
-    es_lohi<1>(a, n, j, c.q, c.f, v, a.dtdy, lo, hi);
+    es_lohi<1, BC>(a, n, j, c.q, c.f, v, a.dtdy, lo, hi);
     if (fx && cx && gz) {  // yx: needed for z-faces
       corner<1, 0>(l1, h1, lo, hi, c.q, c.u, xe, a.dtdx / 3.0, cs);
-      edge_bc<1>(a, n, c.q, j, l1, h1, nv);
+      edge_bc<1, BC>(a, n, c.q, j, l1, h1, nv);
       c.s(o + A_YX, 0, 0, 0) = upwind(l1, h1, v);
     }
     if (gx && fz && cz) {  // yz: needed for x-faces
       corner<1, 2>(l1, h1, lo, hi, c.q, c.w, ze, a.dtdz / 3.0, cs);
-      edge_bc<1>(a, n, c.q, j, l1, h1, nv);
+      edge_bc<1, BC>(a, n, c.q, j, l1, h1, nv);
       c.s(o + A_YZ, 0, 0, 0) = upwind(l1, h1, v);
     }
   }
@@ -222,15 +224,15 @@ __global__ void __launch_bounds__(TX* TY) es_corner_kernel(IX_KARG(EsArgs) a, IX
   if (fz && ((fx && cx && gy) || (gx && fy && cy))) {
     const double w = c.w(0, 0, 0);
     const bool nv = a.is_velocity && n == 2;
-    es_lohi<2>(a, n, k, c.q, c.f, w, a.dtdz, lo, hi);
+    es_lohi<2, BC>(a, n, k, c.q, c.f, w, a.dtdz, lo, hi);
     if (fx && cx && gy) {  // zx: needed for y-faces
       corner<2, 0>(l1, h1, lo, hi, c.q, c.u, xe, a.dtdx / 3.0, cs);
-      edge_bc<2>(a, n, c.q, k, l1, h1, nv);
+      edge_bc<2, BC>(a, n, c.q, k, l1, h1, nv);
       c.s(o + A_ZX, 0, 0, 0) = upwind(l1, h1, w);
     }
     if (gx && fy && cy) {  // zy: needed for x-faces
       corner<2, 1>(l1, h1, lo, hi, c.q, c.v, ye, a.dtdy / 3.0, cs);
-      edge_bc<2>(a, n, c.q, k, l1, h1, nv);
+      edge_bc<2, BC>(a, n, c.q, k, l1, h1, nv);
       c.s(o + A_ZY, 0, 0, 0) = upwind(l1, h1, w);
     }
   }
@@ -272,9 +274,9 @@ IX_D void es_finish(const EsArgs& a, const Cur& q, const Cur& f, const Cur& dv, 
 
 // boundary conditions of the final states: SetEdgeBCs, then the outflow rule (the normal velocity is not advected
 // INTO the domain through a foextrap / hoextrap face)
-template <int D>
+template <int D, bool BC>
 IX_D void es_final_bc(const EsArgs& a, int n, const Cur& q, int c, double mac, double& stl, double& sth) {
-  if (!a.bc.any) return;
+  if (!BC) return;
   const bool nv = a.is_velocity && n == D;
   set_edge_bc(stl, sth, along<D>(q, -1), q(0, 0, 0), c, a.bc.dir(n, D), nv);
   outflow_bc(stl, sth, c, a.bc.dir(n, D), nv && mac >= 0.0, nv && mac <= 0.0);
@@ -285,6 +287,7 @@ struct EsOut {
   double ax, ay, az;             // face areas
 };
 
+template <bool BC>
 __global__ void __launch_bounds__(TX* TY) es_final_kernel(IX_KARG(EsArgs) a, IX_KARG(Scratch) sc, IX_KARG(EsOut) out, IX_KARG(Bx) R) {
   GIDX(R)
   const EsCur c = es_cursors(a, sc, n, i, j, k);
@@ -296,10 +299,10 @@ __global__ void __launch_bounds__(TX* TY) es_final_kernel(IX_KARG(EsArgs) a, IX_
   double stl, sth;
   if (cy && cz) {  // x-face
     const double u = c.u(0, 0, 0);
-    es_lohi<0>(a, n, i, c.q, c.f, u, a.dtdx, stl, sth);
+    es_lohi<0, BC>(a, n, i, c.q, c.f, u, a.dtdx, stl, sth);
     transverse<0, 1, 2>(stl, sth, c.q, c.v, c.w, sarr(c.s, o + A_YZ), sarr(c.s, o + A_ZY), a.dtdy, a.dtdz, cs);
     es_finish<0>(a, c.q, c.f, dv, cs, stl, sth);
-    es_final_bc<0>(a, n, c.q, i, u, stl, sth);
+    es_final_bc<0, BC>(a, n, c.q, i, u, stl, sth);
     const double st = upwind(stl, sth, u);
     const double f = st * a.uflx(i, j, k) * out.ax;
     c.s(o + A_XE, 0, 0, 0) = st;
@@ -309,10 +312,10 @@ __global__ void __launch_bounds__(TX* TY) es_final_kernel(IX_KARG(EsArgs) a, IX_
   }
   if (cx && cz) {  // y-face
     const double v = c.v(0, 0, 0);
-    es_lohi<1>(a, n, j, c.q, c.f, v, a.dtdy, stl, sth);
+    es_lohi<1, BC>(a, n, j, c.q, c.f, v, a.dtdy, stl, sth);
     transverse<1, 0, 2>(stl, sth, c.q, c.u, c.w, sarr(c.s, o + A_XZ), sarr(c.s, o + A_ZX), a.dtdx, a.dtdz, cs);
     es_finish<1>(a, c.q, c.f, dv, cs, stl, sth);
-    es_final_bc<1>(a, n, c.q, j, v, stl, sth);
+    es_final_bc<1, BC>(a, n, c.q, j, v, stl, sth);
     const double st = upwind(stl, sth, v);
     const double f = st * a.vflx(i, j, k) * out.ay;
     c.s(o + A_YE, 0, 0, 0) = st;
@@ -322,10 +325,10 @@ __global__ void __launch_bounds__(TX* TY) es_final_kernel(IX_KARG(EsArgs) a, IX_
   }
   if (cx && cy) {  // z-face
     const double w = c.w(0, 0, 0);
-    es_lohi<2>(a, n, k, c.q, c.f, w, a.dtdz, stl, sth);
+    es_lohi<2, BC>(a, n, k, c.q, c.f, w, a.dtdz, stl, sth);
     transverse<2, 0, 1>(stl, sth, c.q, c.u, c.v, sarr(c.s, o + A_XY), sarr(c.s, o + A_YX), a.dtdx, a.dtdy, cs);
     es_finish<2>(a, c.q, c.f, dv, cs, stl, sth);
-    es_final_bc<2>(a, n, c.q, k, w, stl, sth);
+    es_final_bc<2, BC>(a, n, c.q, k, w, stl, sth);
     const double st = upwind(stl, sth, w);
     const double f = st * a.wflx(i, j, k) * out.az;
     c.s(o + A_ZE, 0, 0, 0) = st;
@@ -407,17 +410,18 @@ IX_D EvCur ev_cursors(const EvArgs& a, const Scratch& sc, int i, int j, int k) {
 }
 
 // lo/hi of component n on the D-face, traced with the cell-centred velocity component D
-template <int D>
+template <int D, bool BC>
 IX_D void ev_lohi(const EvArgs& a, const EvCur& c, int n, int ci, double dtdx, double& lo, double& hi) {
-  const BcD b = a.bc.dir(n, D);
-  trace<D>(c.q[n], along<D>(c.q[D], -1), c.q[D](0, 0, 0), dtdx, lo, hi, a.ppm, ci, a.bc.any ? &b : nullptr);
+  const BcD b = BC ? a.bc.dir(n, D) : BcD{};
+  trace<D>(c.q[n], along<D>(c.q[D], -1), c.q[D](0, 0, 0), dtdx, lo, hi, a.ppm, ci, BC ? &b : nullptr);
   if (a.fit && c.f[n].ok()) {
     lo += 0.5 * a.dt * along<D>(c.f[n], -1);
     hi += 0.5 * a.dt * c.f[n](0, 0, 0);
   }
-  edge_bc<D>(a, n, c.q[n], ci, lo, hi, n == D);
+  edge_bc<D, BC>(a, n, c.q[n], ci, lo, hi, n == D);
 }
 
+template <bool BC>
 __global__ void __launch_bounds__(TX* TY) ev_edge_kernel(IX_KARG(EvArgs) a, IX_KARG(Scratch) sc, IX_KARG(Bx) R) {
   GIDX(R)
   (void)n;
@@ -427,34 +431,35 @@ __global__ void __launch_bounds__(TX* TY) ev_edge_kernel(IX_KARG(EvArgs) a, IX_K
              inz = k >= b.lo[2] - 1 && k <= b.hi[2] + 1;
   double lo, hi;
   if (i >= b.lo[0] && i <= b.hi[0] + 1 && iny && inz) {
-    ev_lohi<0>(a, c, 0, i, a.dtdx, lo, hi);
+    ev_lohi<0, BC>(a, c, 0, i, a.dtdx, lo, hi);
     const double uad = riemann(lo, hi);
     c.s(B_UAD, 0, 0, 0) = uad;
-    ev_lohi<0>(a, c, 1, i, a.dtdx, lo, hi);
+    ev_lohi<0, BC>(a, c, 1, i, a.dtdx, lo, hi);
     c.s(B_XE_V, 0, 0, 0) = upwind(lo, hi, uad);
-    ev_lohi<0>(a, c, 2, i, a.dtdx, lo, hi);
+    ev_lohi<0, BC>(a, c, 2, i, a.dtdx, lo, hi);
     c.s(B_XE_W, 0, 0, 0) = upwind(lo, hi, uad);
   }
   if (j >= b.lo[1] && j <= b.hi[1] + 1 && inx && inz) {
-    ev_lohi<1>(a, c, 1, j, a.dtdy, lo, hi);
+    ev_lohi<1, BC>(a, c, 1, j, a.dtdy, lo, hi);
     const double vad = riemann(lo, hi);
     c.s(B_VAD, 0, 0, 0) = vad;
-    ev_lohi<1>(a, c, 0, j, a.dtdy, lo, hi);
+    ev_lohi<1, BC>(a, c, 0, j, a.dtdy, lo, hi);
     c.s(B_YE_U, 0, 0, 0) = upwind(lo, hi, vad);
-    ev_lohi<1>(a, c, 2, j, a.dtdy, lo, hi);
+    ev_lohi<1, BC>(a, c, 2, j, a.dtdy, lo, hi);
     c.s(B_YE_W, 0, 0, 0) = upwind(lo, hi, vad);
   }
   if (k >= b.lo[2] && k <= b.hi[2] + 1 && inx && iny) {
-    ev_lohi<2>(a, c, 2, k, a.dtdz, lo, hi);
+    ev_lohi<2, BC>(a, c, 2, k, a.dtdz, lo, hi);
     const double wad = riemann(lo, hi);
     c.s(B_WAD, 0, 0, 0) = wad;
-    ev_lohi<2>(a, c, 0, k, a.dtdz, lo, hi);
+    ev_lohi<2, BC>(a, c, 0, k, a.dtdz, lo, hi);
     c.s(B_ZE_U, 0, 0, 0) = upwind(lo, hi, wad);
-    ev_lohi<2>(a, c, 1, k, a.dtdz, lo, hi);
+    ev_lohi<2, BC>(a, c, 1, k, a.dtdz, lo, hi);
     c.s(B_ZE_V, 0, 0, 0) = upwind(lo, hi, wad);
   }
 }
 
+template <bool BC>
 __global__ void __launch_bounds__(TX* TY) ev_corner_kernel(IX_KARG(EvArgs) a, IX_KARG(Scratch) sc, IX_KARG(Bx) R) {
   GIDX(R)
   (void)n;
@@ -469,69 +474,70 @@ __global__ void __launch_bounds__(TX* TY) ev_corner_kernel(IX_KARG(EvArgs) a, IX
   double lo, hi, l1, h1;
   // x-face states: comp 2 coupled with y (for wmac), comp 1 coupled with z (for vmac)
   if (fx && fy && cy && gz) {
-    ev_lohi<0>(a, c, 2, i, a.dtdx, lo, hi);
+    ev_lohi<0, BC>(a, c, 2, i, a.dtdx, lo, hi);
     corner<0, 1>(l1, h1, lo, hi, c.q[2], vad, sarr(c.s, B_YE_W), a.dtdy / 3.0, false);
-    edge_bc<0>(a, 2, c.q[2], i, l1, h1, 2 == 0);
+    edge_bc<0, BC>(a, 2, c.q[2], i, l1, h1, 2 == 0);
     c.s(B_XY_W, 0, 0, 0) = upwind(l1, h1, uad(0, 0, 0));
   }
   if (fx && gy && fz && cz) {
-    ev_lohi<0>(a, c, 1, i, a.dtdx, lo, hi);
+    ev_lohi<0, BC>(a, c, 1, i, a.dtdx, lo, hi);
     corner<0, 2>(l1, h1, lo, hi, c.q[1], wad, sarr(c.s, B_ZE_V), a.dtdz / 3.0, false);
-    edge_bc<0>(a, 1, c.q[1], i, l1, h1, 1 == 0);
+    edge_bc<0, BC>(a, 1, c.q[1], i, l1, h1, 1 == 0);
     c.s(B_XZ_V, 0, 0, 0) = upwind(l1, h1, uad(0, 0, 0));
   }
   // y-face states: comp 2 coupled with x (for wmac), comp 0 coupled with z (for umac)
   if (fy && fx && cx && gz) {
-    ev_lohi<1>(a, c, 2, j, a.dtdy, lo, hi);
+    ev_lohi<1, BC>(a, c, 2, j, a.dtdy, lo, hi);
     corner<1, 0>(l1, h1, lo, hi, c.q[2], uad, sarr(c.s, B_XE_W), a.dtdx / 3.0, false);
-    edge_bc<1>(a, 2, c.q[2], j, l1, h1, 2 == 1);
+    edge_bc<1, BC>(a, 2, c.q[2], j, l1, h1, 2 == 1);
     c.s(B_YX_W, 0, 0, 0) = upwind(l1, h1, vad(0, 0, 0));
   }
   if (fy && gx && fz && cz) {
-    ev_lohi<1>(a, c, 0, j, a.dtdy, lo, hi);
+    ev_lohi<1, BC>(a, c, 0, j, a.dtdy, lo, hi);
     corner<1, 2>(l1, h1, lo, hi, c.q[0], wad, sarr(c.s, B_ZE_U), a.dtdz / 3.0, false);
-    edge_bc<1>(a, 0, c.q[0], j, l1, h1, 0 == 1);
+    edge_bc<1, BC>(a, 0, c.q[0], j, l1, h1, 0 == 1);
     c.s(B_YZ_U, 0, 0, 0) = upwind(l1, h1, vad(0, 0, 0));
   }
   // z-face states: comp 1 coupled with x (for vmac), comp 0 coupled with y (for umac)
   if (fz && fx && cx && gy) {
-    ev_lohi<2>(a, c, 1, k, a.dtdz, lo, hi);
+    ev_lohi<2, BC>(a, c, 1, k, a.dtdz, lo, hi);
     corner<2, 0>(l1, h1, lo, hi, c.q[1], uad, sarr(c.s, B_XE_V), a.dtdx / 3.0, false);
-    edge_bc<2>(a, 1, c.q[1], k, l1, h1, 1 == 2);
+    edge_bc<2, BC>(a, 1, c.q[1], k, l1, h1, 1 == 2);
     c.s(B_ZX_V, 0, 0, 0) = upwind(l1, h1, wad(0, 0, 0));
   }
   if (fz && gx && fy && cy) {
-    ev_lohi<2>(a, c, 0, k, a.dtdz, lo, hi);
+    ev_lohi<2, BC>(a, c, 0, k, a.dtdz, lo, hi);
     corner<2, 1>(l1, h1, lo, hi, c.q[0], vad, sarr(c.s, B_YE_U), a.dtdy / 3.0, false);
-    edge_bc<2>(a, 0, c.q[0], k, l1, h1, 0 == 2);
+    edge_bc<2, BC>(a, 0, c.q[0], k, l1, h1, 0 == 2);
     c.s(B_ZY_U, 0, 0, 0) = upwind(l1, h1, wad(0, 0, 0));
   }
 }
 
-template <int D, int D1, int D2>
+template <int D, int D1, int D2, bool BC>
 IX_D double ev_final(const EvArgs& a, const EvCur& c, int ci, int A1, int A2, int T1, int T2, double dtdx, double dtd1, double dtd2) {
   double stl, sth;
-  ev_lohi<D>(a, c, D, ci, dtdx, stl, sth);
+  ev_lohi<D, BC>(a, c, D, ci, dtdx, stl, sth);
   double fl = 0.0, fh = 0.0;
   if (!a.fit && c.f[D].ok()) { fl = 0.5 * a.dt * along<D>(c.f[D], -1); fh = 0.5 * a.dt * c.f[D](0, 0, 0); }
   transverse<D, D1, D2>(stl, sth, c.q[D], sarr(c.s, A1), sarr(c.s, A2), sarr(c.s, T1), sarr(c.s, T2), dtd1, dtd2, false);
   stl += fl; sth += fh;
-  if (a.bc.any) {
+  if (BC) {
     set_edge_bc(stl, sth, along<D>(c.q[D], -1), c.q[D](0, 0, 0), ci, a.bc.dir(D, D), true);
     outflow_bc(stl, sth, ci, a.bc.dir(D, D), true, true);
   }
   return riemann(stl, sth);
 }
 
+template <bool BC>
 __global__ void __launch_bounds__(TX* TY) ev_final_kernel(IX_KARG(EvArgs) a, IX_KARG(Scratch) sc, V4 umac, V4 vmac, V4 wmac, IX_KARG(Bx) R) {
   GIDX(R)
   (void)n;
   const EvCur c = ev_cursors(a, sc, i, j, k);
   const Bx& b = a.bx;
   const bool cx = i <= b.hi[0], cy = j <= b.hi[1], cz = k <= b.hi[2];
-  if (cy && cz) umac(i, j, k) = ev_final<0, 1, 2>(a, c, i, B_VAD, B_WAD, B_YZ_U, B_ZY_U, a.dtdx, a.dtdy, a.dtdz);
-  if (cx && cz) vmac(i, j, k) = ev_final<1, 0, 2>(a, c, j, B_UAD, B_WAD, B_XZ_V, B_ZX_V, a.dtdy, a.dtdx, a.dtdz);
-  if (cx && cy) wmac(i, j, k) = ev_final<2, 0, 1>(a, c, k, B_UAD, B_VAD, B_XY_W, B_YX_W, a.dtdz, a.dtdx, a.dtdy);
+  if (cy && cz) umac(i, j, k) = ev_final<0, 1, 2, BC>(a, c, i, B_VAD, B_WAD, B_YZ_U, B_ZY_U, a.dtdx, a.dtdy, a.dtdz);
+  if (cx && cz) vmac(i, j, k) = ev_final<1, 0, 2, BC>(a, c, j, B_UAD, B_WAD, B_XZ_V, B_ZX_V, a.dtdy, a.dtdx, a.dtdz);
+  if (cx && cy) wmac(i, j, k) = ev_final<2, 0, 1, BC>(a, c, k, B_UAD, B_VAD, B_XY_W, B_YX_W, a.dtdz, a.dtdx, a.dtdy);
 }
 
 #if !defined(IX_EMUL)
@@ -783,6 +789,34 @@ struct ScratchOwner {
 
 int compute_aofs(const Bx& bx, const AofsArgs& a, const AdvGeom& g, cudaStream_t s) {
   if (!bx.ok()) return IAMRX_OK;
+#if !defined(IX_EMUL)
+  // A box that touches non-interior domain sides: the 8-cell slabs next to those sides go through the staged kernels (which
+  // carry the boundary conditions), the rest of the box keeps the fused tile kernel.
+  if (!a.staged && !a.ppm && !a.known_edge_state && !a.bc.interior() && bx.nx() % tile::TB == 0 && bx.ny() % tile::TB == 0 && bx.nz() % tile::TB == 0) {
+    Bx rest = bx;
+    AofsArgs slab = a; slab.staged = 1;
+    for (int d = 0; d < 3; ++d) {
+      bool lo_bc = false, hi_bc = false;
+      for (int n = 0; n < a.ncomp; ++n) { lo_bc |= a.bc.lo[n][d] != IAMRX_BC_INT_DIR; hi_bc |= a.bc.hi[n][d] != IAMRX_BC_INT_DIR; }
+      if (lo_bc && rest.lo[d] - 4 <= a.bc.dlo[d] && rest.hi[d] - rest.lo[d] + 1 > tile::TB) {
+        Bx p = rest; p.hi[d] = p.lo[d] + tile::TB - 1; rest.lo[d] += tile::TB;
+        const int rc = compute_aofs(p, slab, g, s);
+        if (rc) return rc;
+      }
+      if (hi_bc && rest.hi[d] + 4 >= a.bc.dhi[d] && rest.hi[d] - rest.lo[d] + 1 > tile::TB) {
+        Bx p = rest; p.lo[d] = p.hi[d] - tile::TB + 1; rest.hi[d] -= tile::TB;
+        const int rc = compute_aofs(p, slab, g, s);
+        if (rc) return rc;
+      }
+    }
+    if (rest.lo[0] != bx.lo[0] || rest.hi[0] != bx.hi[0] || rest.lo[1] != bx.lo[1] || rest.hi[1] != bx.hi[1] || rest.lo[2] != bx.lo[2] || rest.hi[2] != bx.hi[2]) {
+      AofsArgs in = a;
+      if (to_bcall(&a.bc, rest, a.ncomp).any) in.staged = 1;   // still next to a boundary (thin box): staged as well
+      else in.bc = AdvBC{};                                      // interior stencil: no boundary logic
+      return compute_aofs(rest, in, g, s);
+    }
+  }
+#endif
   ProfScope prof_(IAMRX_PROF_AOFS, bx.npts(), (double)bx.npts() * (24.0 * a.ncomp + 32.0), s);
   EsArgs e{};
   e.bx = bx;
@@ -825,13 +859,16 @@ int compute_aofs(const Bx& bx, const AofsArgs& a, const AdvGeom& g, cudaStream_t
     rc = check_launch("es_known");
     if (rc) return rc;
   } else {
-    IX_LAUNCH(es_edge_kernel, grid_for(R1, a.ncomp), dim3(TX, TY, 1), 0, s, e, so.sc, R1);
+    if (e.bc.any) IX_LAUNCH(es_edge_kernel<true>, grid_for(R1, a.ncomp), dim3(TX, TY, 1), 0, s, e, so.sc, R1);
+    else IX_LAUNCH(es_edge_kernel<false>, grid_for(R1, a.ncomp), dim3(TX, TY, 1), 0, s, e, so.sc, R1);
     rc = check_launch("es_edge");
     if (rc) return rc;
-    IX_LAUNCH(es_corner_kernel, grid_for(R1, a.ncomp), dim3(TX, TY, 1), 0, s, e, so.sc, R1);
+    if (e.bc.any) IX_LAUNCH(es_corner_kernel<true>, grid_for(R1, a.ncomp), dim3(TX, TY, 1), 0, s, e, so.sc, R1);
+    else IX_LAUNCH(es_corner_kernel<false>, grid_for(R1, a.ncomp), dim3(TX, TY, 1), 0, s, e, so.sc, R1);
     rc = check_launch("es_corner");
     if (rc) return rc;
-    IX_LAUNCH(es_final_kernel, grid_for(R2, a.ncomp), dim3(TX, TY, 1), 0, s, e, so.sc, out, R2);
+    if (e.bc.any) IX_LAUNCH(es_final_kernel<true>, grid_for(R2, a.ncomp), dim3(TX, TY, 1), 0, s, e, so.sc, out, R2);
+    else IX_LAUNCH(es_final_kernel<false>, grid_for(R2, a.ncomp), dim3(TX, TY, 1), 0, s, e, so.sc, out, R2);
     rc = check_launch("es_final");
     if (rc) return rc;
   }
@@ -851,14 +888,17 @@ int extrap_vel_to_faces(const Bx& bx, C4 vel, C4 force, V4 umac, V4 vmac, V4 wma
   e.bc = to_bcall(bc, bx, 3);
   e.dt = g.dt; e.dtdx = g.dt / g.dx[0]; e.dtdy = g.dt / g.dx[1]; e.dtdz = g.dt / g.dx[2];
   Bx R1 = grow(bx, 1); R1.hi[0]++; R1.hi[1]++; R1.hi[2]++;
-  IX_LAUNCH(ev_edge_kernel, grid_for(R1, 1), dim3(TX, TY, 1), 0, s, e, so.sc, R1);
+  if (e.bc.any) IX_LAUNCH(ev_edge_kernel<true>, grid_for(R1, 1), dim3(TX, TY, 1), 0, s, e, so.sc, R1);
+    else IX_LAUNCH(ev_edge_kernel<false>, grid_for(R1, 1), dim3(TX, TY, 1), 0, s, e, so.sc, R1);
   int rc = check_launch("ev_edge");
   if (rc) return rc;
-  IX_LAUNCH(ev_corner_kernel, grid_for(R1, 1), dim3(TX, TY, 1), 0, s, e, so.sc, R1);
+  if (e.bc.any) IX_LAUNCH(ev_corner_kernel<true>, grid_for(R1, 1), dim3(TX, TY, 1), 0, s, e, so.sc, R1);
+    else IX_LAUNCH(ev_corner_kernel<false>, grid_for(R1, 1), dim3(TX, TY, 1), 0, s, e, so.sc, R1);
   rc = check_launch("ev_corner");
   if (rc) return rc;
   Bx R2 = bx; R2.hi[0]++; R2.hi[1]++; R2.hi[2]++;
-  IX_LAUNCH(ev_final_kernel, grid_for(R2, 1), dim3(TX, TY, 1), 0, s, e, so.sc, umac, vmac, wmac, R2);
+  if (e.bc.any) IX_LAUNCH(ev_final_kernel<true>, grid_for(R2, 1), dim3(TX, TY, 1), 0, s, e, so.sc, umac, vmac, wmac, R2);
+    else IX_LAUNCH(ev_final_kernel<false>, grid_for(R2, 1), dim3(TX, TY, 1), 0, s, e, so.sc, umac, vmac, wmac, R2);
   return check_launch("ev_final");
 }
 

@@ -20,7 +20,9 @@ struct Abec {
 // periodic wrap inside the kernel and phi's ghost cells in that direction are not touched.
 // gb (optional): the box touches non-periodic domain faces -- f0[comp][xlo,xhi,ylo,yhi,zlo,zhi] = coefficient of the adjacent
 // interior cell in the boundary ghost-cell formula (linop_bc_f0; 0 for sides that are not domain faces)
-struct GsBC { double f0[3][6]; };
+// even / odd[comp]: bit s = the HOMOGENEOUS ghost cell beyond side s is + / - the adjacent cell (Neumann / reflect_odd or order-2
+// Dirichlet): the kernels evaluate it in place and no ghost fill is needed for that side
+struct GsBC { double f0[3][6]; int even[3]; int odd[3]; };
 int abec_gsrb(const Bx& bx, V4 phi, C4 rhs, const Abec& op, double omega, int redblack,
               int ncomp, cudaStream_t s, int wrapmask = 0, const GsBC* gb = nullptr);
 // one full red-black sweep (colour rb0, then the other) phi_in -> phi_out (different arrays) on a box that spans
@@ -31,7 +33,7 @@ int abec_gsrb_sweep(const Bx& bx, V4 phi_out, C4 phi_in, C4 rhs, const Abec& op,
                     cudaStream_t s);
 // out = L phi (rhs null) or rhs - L phi
 int abec_apply(const Bx& bx, V4 out, C4 phi, C4 rhs, const Abec& op, int ncomp, cudaStream_t s,
-               int wrapmask = 0);
+               int wrapmask = 0, const GsBC* gb = nullptr);   // gb: in-place mirrored sides (homogeneous residuals)
 // face flux_d = -b * beta_d * dphi/dx_d on faces of bx (MLABecLaplacian FFlux)
 int abec_flux(const Bx& bx, V4 fx, V4 fy, V4 fz, C4 phi, const Abec& op, int comp, cudaStream_t s);
 // crse = mean of 2x2x2 fine (MLCellLinOp restriction / average_down)

@@ -112,16 +112,45 @@ bool CellMG::box_on_boundary(int l, int il) const {
   return false;
 }
 
+// the homogeneous ghost cell is +/- the adjacent cell: Neumann, reflect_odd, or Dirichlet extrapolated at order 2
+static int mirror_kind(int code, int maxorder, int len) {   // 0 no, 1 even, 2 odd
+  if (code == IAMRX_LINOP_NEUMANN) return 1;
+  if (code == IAMRX_LINOP_REFLECT_ODD) return 2;
+  if (code == IAMRX_LINOP_DIRICHLET && k::linop_bc_order(maxorder, len) == 2) return 2;
+  return 0;
+}
+
+bool CellMG::bc_in_kernel(int l) const {
+  if (!has_bc_) return true;
+  const Level& L = *lv_[l].lev;
+  for (const Bx& b : L.boxes)   // all boxes of the level: the same decision on every rank
+    for (int c = 0; c < ncomp_ && c < 3; ++c)
+      for (int d = 0; d < 3; ++d) {
+        if (L.geom.periodic[d]) continue;
+        const int len = b.hi[d] - b.lo[d] + 1;
+        if (b.lo[d] == L.domain.lo[d] && !mirror_kind(bc_.lo[c][d], bc_.maxorder, len)) return false;
+        if (b.hi[d] == L.domain.hi[d] && !mirror_kind(bc_.hi[c][d], bc_.maxorder, len)) return false;
+      }
+  return true;
+}
+
 k::GsBC CellMG::gsbc_of(int l, int il) const {
   k::GsBC g{};
   const Level& L = *lv_[l].lev;
   const Bx& b = L.lbox(il);
+  const bool ink = bc_in_kernel(l);
   for (int c = 0; c < 3; ++c)
     for (int d = 0; d < 3; ++d) {
       if (L.geom.periodic[d]) continue;
       const int len = b.hi[d] - b.lo[d] + 1;
-      if (b.lo[d] == L.domain.lo[d]) g.f0[c][2 * d] = k::linop_bc_f0(bc_.lo[c][d], bc_.maxorder, len);
-      if (b.hi[d] == L.domain.hi[d]) g.f0[c][2 * d + 1] = k::linop_bc_f0(bc_.hi[c][d], bc_.maxorder, len);
+      for (int side = 0; side < 2; ++side) {
+        if (side == 0 ? b.lo[d] != L.domain.lo[d] : b.hi[d] != L.domain.hi[d]) continue;
+        const int code = side == 0 ? bc_.lo[c][d] : bc_.hi[c][d];
+        g.f0[c][2 * d + side] = k::linop_bc_f0(code, bc_.maxorder, len);
+        const int mk = ink ? mirror_kind(code, bc_.maxorder, len) : 0;
+        if (mk == 1) g.even[c] |= 1 << (2 * d + side);
+        if (mk == 2) g.odd[c] |= 1 << (2 * d + side);
+      }
     }
   return g;
 }
@@ -129,6 +158,8 @@ k::GsBC CellMG::gsbc_of(int l, int il) const {
 int CellMG::fill_ghosts(int l, MF& phi, bool inhomog, int wm, int grow_t, cudaStream_t s) {
   if (wm != 7) IX_TRY(mf_fill_boundary(phi, 0, ncomp_, 1, s, wm));
   if (!has_bc_) return IAMRX_OK;
+  // homogeneous fills of sides the kernels mirror in place are not needed (grow_t > 0: the tensor cross terms read the cells)
+  if (!inhomog && grow_t == 0 && bc_in_kernel(l)) return IAMRX_OK;
   const Level& L = *lv_[l].lev;
   const bool ih = inhomog && l == 0 && bvals_.ok();
   for (int il = 0; il < phi.n(); ++il)
@@ -245,7 +276,9 @@ int CellMG::residual(int l, MF& out, MF& phi, const MF& rhs, bool with_cross, cu
   IX_TRY(fill_ghosts(l, phi, with_cross, wm, cross ? 1 : 0, s));
   const Level& L = *lv_[l].lev;
   for (int il = 0; il < phi.n(); ++il) {
-    IX_TRY(k::abec_apply(phi.vbox(il), out.v(il), phi.c(il), rhs.c(il), op_at(l, il), ncomp_, s, wm));
+    const bool mir = has_bc_ && !with_cross && box_on_boundary(l, il) && bc_in_kernel(l);
+    const k::GsBC gb = mir ? gsbc_of(l, il) : k::GsBC{};
+    IX_TRY(k::abec_apply(phi.vbox(il), out.v(il), phi.c(il), rhs.c(il), op_at(l, il), ncomp_, s, wm, mir ? &gb : nullptr));
     if (cross) {
       if (has_bc_)
         IX_TRY(k::tensor_cross_bc(phi.vbox(il), out.v(il), phi.c(il), bvals_.ok() ? bvals_.c(il) : C4{}, eta_[0]->c(il), eta_[1]->c(il),
@@ -444,9 +477,10 @@ bool NodeMG::singular() const {
   return true;
 }
 
-int NodeMG::fill_ghosts(int l, MF& phi, int wm, cudaStream_t s) {
+// bc_fill = false: the caller's kernels mirror the Neumann sides in place (wm | neumann_sides << 3), only the exchange is needed
+int NodeMG::fill_ghosts(int l, MF& phi, int wm, cudaStream_t s, bool bc_fill) {
   if (wm != 7) IX_TRY(mf_fill_boundary(phi, 0, 1, 1, s, wm));
-  if (!has_bc_) return IAMRX_OK;
+  if (!has_bc_ || !bc_fill) return IAMRX_OK;
   const Level& L = *lv_[l].lev;
   const Bx ndom = ixbox(L.domain, IX_NODE);
   for (int il = 0; il < phi.n(); ++il)
@@ -500,7 +534,7 @@ int NodeMG::smooth(int l, MF& phi, const MF& rhs, int nsweeps, cudaStream_t s) {
   if (nodal_smoother_kind() == 1) {
     MF tmp(L.lev, IX_NODE, 1, 1);
     for (int sw = 0; sw < 2 * nsweeps; ++sw) {
-      IX_TRY(fill_ghosts(l, phi, 0, s));
+      IX_TRY(fill_ghosts(l, phi, 0, s, true));
       for (int il = 0; il < phi.n(); ++il)
         IX_TRY(k::nodal_jacobi(active_nbox(l, il), tmp.v(il), phi.c(il), rhs.c(il), L.sigma.c(il), L.dxinv,
                                2.0 / 3.0, s));
@@ -523,12 +557,13 @@ int NodeMG::smooth(int l, MF& phi, const MF& rhs, int nsweeps, cudaStream_t s) {
     if (!L.gs_tmp.ok()) L.gs_tmp.define(L.lev, IX_NODE, 1, 1);
     if (!L.gs_tmp.ok()) { L.gs_tmp.define(L.lev, IX_NODE, 1, 1); IX_TRY(mf_setval(L.gs_tmp, 0.0, 0, 1, 1, s)); }
     MF* src = &phi; MF* dst = &L.gs_tmp;
-    IX_TRY(fill_ghosts(l, *src, wm, s));
+    IX_TRY(fill_ghosts(l, *src, wm, s, false));
     for (int sw = 0; sw < nsweeps; ++sw) {
       for (int phase = 0; phase < 2; ++phase) {
         for (int il = 0; il < phi.n(); ++il)
-          IX_TRY(k::nodal_gs_sweep(active_nbox(l, il), dst->v(il), src->c(il), rhs.c(il), L.sigma.c(il), L.dxinv, s, wm, phase));
-        IX_TRY(fill_ghosts(l, *dst, wm, s));
+          IX_TRY(k::nodal_gs_sweep(active_nbox(l, il), dst->v(il), src->c(il), rhs.c(il), L.sigma.c(il), L.dxinv, s,
+                                   wm | (neumann_sides(l, il) << 3), phase));
+        IX_TRY(fill_ghosts(l, *dst, wm, s, false));
       }
       std::swap(src, dst);
     }
@@ -537,9 +572,9 @@ int NodeMG::smooth(int l, MF& phi, const MF& rhs, int nsweeps, cudaStream_t s) {
   }
   for (int sw = 0; sw < nsweeps; ++sw) {
     for (int color = 0; color < 8; ++color) {
-      IX_TRY(fill_ghosts(l, phi, wm, s));
+      IX_TRY(fill_ghosts(l, phi, wm, s, false));
       for (int il = 0; il < phi.n(); ++il)
-        IX_TRY(k::nodal_gs_color(active_nbox(l, il), phi.v(il), rhs.c(il), L.sigma.c(il), L.dxinv, color, s, wm));
+        IX_TRY(k::nodal_gs_color(active_nbox(l, il), phi.v(il), rhs.c(il), L.sigma.c(il), L.dxinv, color, s, wm | (neumann_sides(l, il) << 3)));
     }
   }
   return IAMRX_OK;
@@ -548,9 +583,9 @@ int NodeMG::smooth(int l, MF& phi, const MF& rhs, int nsweeps, cudaStream_t s) {
 int NodeMG::residual(int l, MF& out, MF& phi, const MF& rhs, cudaStream_t s) {
   MGLevelNode& L = lv_[l];
   const int wm = L.lev->level_wrapmask();
-  IX_TRY(fill_ghosts(l, phi, wm, s));
+  IX_TRY(fill_ghosts(l, phi, wm, s, false));
   for (int il = 0; il < phi.n(); ++il)
-    IX_TRY(k::nodal_adotx(active_nbox(l, il), out.v(il), phi.c(il), rhs.c(il), L.sigma.c(il), L.dxinv, s, wm));
+    IX_TRY(k::nodal_adotx(active_nbox(l, il), out.v(il), phi.c(il), rhs.c(il), L.sigma.c(il), L.dxinv, s, wm | (neumann_sides(l, il) << 3)));
   return IAMRX_OK;
 }
 
@@ -561,7 +596,7 @@ int NodeMG::vcycle(cudaStream_t s) {
     IX_TRY(mf_setval(L.cor, 0.0, 0, 1, 1, s));
     IX_TRY(smooth(l, L.cor, L.res, info_.nu1, s));
     IX_TRY(residual(l, L.rescor, L.cor, L.res, s));
-    IX_TRY(fill_ghosts(l, L.rescor, 0, s));   // MLNodeLaplacian::restriction: applyBC on the fine residual (Neumann sides mirrored)
+    IX_TRY(fill_ghosts(l, L.rescor, 0, s, true));   // MLNodeLaplacian::restriction: applyBC on the fine residual (Neumann sides mirrored)
     MGLevelNode& C = lv_[l + 1];
     if (C.xfer_lev) {
       // (the transfer level shares the boundary flags of the coarse level: same domain, boxes tile it)
@@ -640,7 +675,7 @@ int NodeMG::solve(MF& phi, MF& rhs, iamrx_mg_info* info, cudaStream_t s) {
       if (resnorm <= target) { rc = IAMRX_OK; break; }
     }
   }
-  IX_TRY(fill_ghosts(0, phi, 0, s));
+  IX_TRY(fill_ghosts(0, phi, 0, s, true));
   if (info_.verbose > 0)
     fprintf(stderr, "[iamrx] NodeMG: %d iters, res0 %.3e -> %.3e (rhs %.3e, levels %d)\n", iters, resnorm0,
             resnorm, rhsnorm, nlevels());

@@ -52,6 +52,7 @@ class CellMG {
   // boundary conditions; inhomog: Dirichlet values from bvals_ (finest level only), else homogeneous
   int fill_ghosts(int l, MF& phi, bool inhomog, int wm, int grow_t, cudaStream_t s);
   k::GsBC gsbc_of(int l, int il) const;
+  bool bc_in_kernel(int l) const;   // every non-periodic side of every box of level l can be mirrored inside the kernels
   bool box_on_boundary(int l, int il) const;
   k::LinBC bc_{};
   bool has_bc_ = false;
@@ -94,7 +95,7 @@ class NodeMG {
   int smooth(int l, MF& phi, const MF& rhs, int nsweeps, cudaStream_t s);
   int residual(int l, MF& out, MF& phi, const MF& rhs, cudaStream_t s);
   int vcycle(cudaStream_t s);
-  int fill_ghosts(int l, MF& phi, int wm, cudaStream_t s);   // FillBoundary + mirrored ghost nodes of the Neumann sides
+  int fill_ghosts(int l, MF& phi, int wm, cudaStream_t s, bool bc_fill);   // FillBoundary + mirrored ghost nodes of the Neumann sides
   bool singular() const;
   std::vector<MGLevelNode> lv_;
   iamrx_mg_info info_;

@@ -70,10 +70,15 @@ IX_D double nodal_ax(C4 x, C4 sig, int i, int j, int k, int im, int ip, int jm, 
 
 // neighbour node indices; with wrap bit d set the node box [lo, hi] carries the periodic
 // duplicate (node hi == node lo), so lo-1 -> hi-1 and hi+1 -> lo+1
+// bits 3..8 of wm (x lo, x hi, y lo, y hi, z lo, z hi): that side of the node box is a Neumann / inflow domain side, whose ghost
+// node is the mirror image (lo-1 -> lo+1, hi+1 -> hi-1: mlndlap_applybc) -- evaluated in place, no ghost fill between the colours
 #define NWRAP(bx, wm)                                                                          \
-  const int im = (((wm) & 1) && i == bx.lo[0]) ? bx.hi[0] - 1 : i - 1, ip = (((wm) & 1) && i == bx.hi[0]) ? bx.lo[0] + 1 : i + 1; \
-  const int jm = (((wm) & 2) && j == bx.lo[1]) ? bx.hi[1] - 1 : j - 1, jp = (((wm) & 2) && j == bx.hi[1]) ? bx.lo[1] + 1 : j + 1; \
-  const int km = (((wm) & 4) && k == bx.lo[2]) ? bx.hi[2] - 1 : k - 1, kp = (((wm) & 4) && k == bx.hi[2]) ? bx.lo[2] + 1 : k + 1;
+  const int im = (((wm) & 1) && i == bx.lo[0]) ? bx.hi[0] - 1 : ((((wm) & 8) && i == bx.lo[0]) ? i + 1 : i - 1),       \
+            ip = (((wm) & 1) && i == bx.hi[0]) ? bx.lo[0] + 1 : ((((wm) & 16) && i == bx.hi[0]) ? i - 1 : i + 1);      \
+  const int jm = (((wm) & 2) && j == bx.lo[1]) ? bx.hi[1] - 1 : ((((wm) & 32) && j == bx.lo[1]) ? j + 1 : j - 1),      \
+            jp = (((wm) & 2) && j == bx.hi[1]) ? bx.lo[1] + 1 : ((((wm) & 64) && j == bx.hi[1]) ? j - 1 : j + 1);      \
+  const int km = (((wm) & 4) && k == bx.lo[2]) ? bx.hi[2] - 1 : ((((wm) & 128) && k == bx.lo[2]) ? k + 1 : k - 1),     \
+            kp = (((wm) & 4) && k == bx.hi[2]) ? bx.lo[2] + 1 : ((((wm) & 256) && k == bx.hi[2]) ? k - 1 : k + 1);
 
 #define NIDX(bx)                                                   \
   const int k = bx.lo[2] + blockIdx.z;                             \
@@ -450,7 +455,7 @@ IX_D void pass(double (*sp)[NR][NC], double (*ss)[NR][NC], int warp, int lane, d
 }
 
 __global__ void __launch_bounds__(NT, 4)
-gs_sweep_kernel(Bx bx, V4 out, C4 pin, C4 padj, C4 rhs, C4 sig, IX_KARG(Q1F) q, int k0, int zwrap) {
+gs_sweep_kernel(Bx bx, V4 out, C4 pin, C4 padj, C4 rhs, C4 sig, IX_KARG(Q1F) q, int k0, int zwrap, int zmir) {
   __shared__ double sp[3][NR][NC];
   __shared__ double ss[2][NR][NC];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -458,7 +463,9 @@ gs_sweep_kernel(Bx bx, V4 out, C4 pin, C4 padj, C4 rhs, C4 sig, IX_KARG(Q1F) q, 
   const int Y0 = (bx.lo[1] - (bx.lo[1] & 1)) + TYI * (int)blockIdx.y - 2;   // ... of tile row 0
   const int k = k0 + 2 * (int)blockIdx.z;
   // z neighbours: periodic images when the box spans the domain in z, else the (filled) ghost planes / ghost cells
-  const int km = (zwrap && k == bx.lo[2]) ? bx.hi[2] - 1 : k - 1, kp = (zwrap && k == bx.hi[2]) ? bx.lo[2] + 1 : k + 1;
+  // zmir bit 0 / 1: the low / high z side is a Neumann side (mirrored ghost plane, evaluated in place)
+  const int km = (zwrap && k == bx.lo[2]) ? bx.hi[2] - 1 : (((zmir & 1) && k == bx.lo[2]) ? k + 1 : k - 1),
+            kp = (zwrap && k == bx.hi[2]) ? bx.lo[2] + 1 : (((zmir & 2) && k == bx.hi[2]) ? k - 1 : k + 1);
   const int ckm = zwrap ? wrap_cell_any(k - 1, bx.lo[2], bx.hi[2]) : k - 1, ckp = zwrap ? wrap_cell_any(k, bx.lo[2], bx.hi[2]) : k;
   // stage phi (rows 1..17 of three planes) and sigma (cell rows 1..16 of planes k-1, k): a thread
   // always loads the same tile column, so the x wrap is done once
@@ -540,16 +547,20 @@ adotx_march_kernel(Bx bx, V4 out, C4 phi, C4 rhs, C4 sig, IX_KARG(fused::Q1F) q,
   const int kc1 = min(kc0 + KB - 1, bx.hi[2]);
   (void)nchunk;
   // neighbour columns / rows (periodic images when the box spans the domain: node hi duplicates node lo)
-  const int im = ((wm & 1) && i == bx.lo[0]) ? bx.hi[0] - 1 : i - 1, ip = ((wm & 1) && i == bx.hi[0]) ? bx.lo[0] + 1 : i + 1;
-  const int jm = ((wm & 2) && j == bx.lo[1]) ? bx.hi[1] - 1 : j - 1, jp = ((wm & 2) && j == bx.hi[1]) ? bx.lo[1] + 1 : j + 1;
+  const int im = ((wm & 1) && i == bx.lo[0]) ? bx.hi[0] - 1 : (((wm & 8) && i == bx.lo[0]) ? i + 1 : i - 1),
+            ip = ((wm & 1) && i == bx.hi[0]) ? bx.lo[0] + 1 : (((wm & 16) && i == bx.hi[0]) ? i - 1 : i + 1);
+  const int jm = ((wm & 2) && j == bx.lo[1]) ? bx.hi[1] - 1 : (((wm & 32) && j == bx.lo[1]) ? j + 1 : j - 1),
+            jp = ((wm & 2) && j == bx.hi[1]) ? bx.lo[1] + 1 : (((wm & 64) && j == bx.hi[1]) ? j - 1 : j + 1);
   const int pjs = (int)phi.js, sjs = (int)sig.js;
   const double* pcol = phi.p + (i - phi.l0);
   const int ox[3] = {im - i, 0, ip - i};
   const int oy[3] = {(jm - phi.l1) * pjs, (j - phi.l1) * pjs, (jp - phi.l1) * pjs};
   const double* scol = sig.p + (i - sig.l0) + (j - sig.l1) * sjs;
-  auto zplane = [&](int k) {  // node plane index with periodic image
-    if (!(wm & 4)) return k;
-    return k < bx.lo[2] ? bx.hi[2] - 1 : (k > bx.hi[2] ? bx.lo[2] + 1 : k);
+  auto zplane = [&](int k) {  // node plane index with periodic image / Neumann mirror image
+    if (wm & 4) return k < bx.lo[2] ? bx.hi[2] - 1 : (k > bx.hi[2] ? bx.lo[2] + 1 : k);
+    if ((wm & 128) && k < bx.lo[2]) return bx.lo[2] + 1;
+    if ((wm & 256) && k > bx.hi[2]) return bx.hi[2] - 1;
+    return k;
   };
   auto load_pl = [&](Pl& P, int k) {
     const double* b = pcol + (int64_t)(zplane(k) - phi.l2) * phi.ks;
@@ -630,7 +641,7 @@ int nodal_adotx(const Bx& nbx, V4 out, C4 phi, C4 rhs, C4 sig, const double dxin
   double f[3]; facs(dxinv, f);
   ProfScope prof_(IAMRX_PROF_NODAL_ADOTX, nbx.npts(), (double)nbx.npts() * (rhs.ok() ? 32.0 : 24.0), s);
 #if !defined(IX_EMUL)
-  if (use_tile_kernels() && nbx.nx() >= 32 && out.p != phi.p) {  // boxes wide enough to fill a CTA row
+  if (use_tile_kernels() && !(wrapmask >> 3) && nbx.nx() >= 32 && out.p != phi.p) {  // boxes wide enough to fill a CTA row
     using namespace tile;
     dim3 grd(cdiv(nbx.nx(), TXU), cdiv(nbx.ny(), TYU), nbx.nz());
     IX_LAUNCH((nodal_tile_kernel<1, false>), grd, dim3(TXU, TYU, 1), 0, s, nbx, out, phi, rhs, sig, f[0], f[1], f[2],
@@ -692,7 +703,7 @@ int nodal_gs_color(const Bx& nbx, V4 phi, C4 rhs, C4 sig, const double dxinv[3],
     static int use_vec = -1;
     if (use_vec < 0) { const char* e = getenv("IAMRX_GS_VEC"); use_vec = (e && e[0] == '0') ? 0 : 1; }
     // 16-byte loads need even row / plane strides and 8-byte aligned bases whose parity we can read off
-    const bool ok = use_vec && n[0] >= 32 && (phi.js % 2 == 0) && (phi.ks % 2 == 0) && (sig.js % 2 == 0) && (sig.ks % 2 == 0);
+    const bool ok = use_vec && !(wrapmask >> 3) && n[0] >= 32 && (phi.js % 2 == 0) && (phi.ks % 2 == 0) && (sig.js % 2 == 0) && (sig.ks % 2 == 0);
     if (ok) {
       const uintptr_t a_phi = (uintptr_t)(phi.p + ((o[0] - phi.l0) + (o[1] - phi.l1) * phi.js + (o[2] - phi.l2) * phi.ks));
       const uintptr_t a_sig = (uintptr_t)(sig.p + ((o[0] - sig.l0) + (o[1] - sig.l1) * sig.js + (o[2] - sig.l2) * sig.ks));
@@ -702,7 +713,7 @@ int nodal_gs_color(const Bx& nbx, V4 phi, C4 rhs, C4 sig, const double dxinv[3],
       return check_launch("nodal_gs_vec");
     }
   }
-  if (use_tile_kernels() && n[0] >= 16) {
+  if (use_tile_kernels() && !(wrapmask >> 3) && n[0] >= 16) {
     using namespace tile;
     dim3 tg(cdiv(n[0], TXU), cdiv(n[1], TYU), n[2]);
     C4 pin{phi.p, phi.l0, phi.l1, phi.l2, phi.js, phi.ks, phi.ns};
@@ -725,7 +736,7 @@ int nodal_gs_color(const Bx& nbx, V4 phi, C4 rhs, C4 sig, const double dxinv[3],
 bool nodal_gs_sweep_ok(const Bx& nbx, int wrapmask) {
   static int on = -1;
   if (on < 0) { const char* e = getenv("IAMRX_NODAL_FUSED"); on = (e && e[0] == '0') ? 0 : 1; }
-  if (!on || (wrapmask != 7 && wrapmask != 3)) return false;
+  if (!on || ((wrapmask & 7) != 7 && (wrapmask & 7) != 3)) return false;
   for (int d = 0; d < 3; ++d) if (((nbx.hi[d] - nbx.lo[d]) & 1) || nbx.hi[d] - nbx.lo[d] < 2) return false;
   return true;
 }
@@ -760,7 +771,7 @@ int nodal_gs_sweep(const Bx& nbx, V4 phi_out, C4 phi_in, C4 rhs, C4 sig, const d
     const int nk = (nbx.hi[2] - k0) / 2 + 1;
     // phase A (even planes): neighbours = old odd planes; phase B (odd planes): neighbours = new even planes
     IX_LAUNCH(gs_sweep_kernel, dim3(gx, gy, nk), dim3(NT, 1, 1), 0, s, nbx, phi_out, phi_in, cz == 0 ? phi_in : pout, rhs, sig,
-              q, k0, (wrapmask & 4) ? 1 : 0);
+              q, k0, (wrapmask & 4) ? 1 : 0, (wrapmask >> 7) & 3);
     const int rc = check_launch("nodal_gs_sweep");
     if (rc != IAMRX_OK) return rc;
   }

@@ -158,12 +158,19 @@ def test_extrap_vel_to_faces_bc(backend, oracle, per, plo, phi, nb, fit, ppm):
             assert np.abs(got[tuple(wsl)] - bcv[d, d]).max() <= 1e-15
 
 
+@pytest.mark.gpu
+@pytest.mark.parametrize("per,plo,phi", BC_CASES)
+@pytest.mark.parametrize("kind", ["vel", "scal"])
+def test_compute_aofs_bc_tile_split_gpu(cuda_lib, oracle, per, plo, phi, kind):
+    """32^3 box: the 8-cell slabs next to the walls take the staged kernels, the interior the fused tile kernel."""
+    test_compute_aofs_bc((cuda_lib, "cuda:0"), oracle, per, plo, phi, (1, 1, 1), kind, 0, 0, n=(32, 32, 32))
+
+
 @pytest.mark.parametrize("per,plo,phi", BC_CASES)
 @pytest.mark.parametrize("nb", [(1, 1, 1), (2, 2, 2)])
 @pytest.mark.parametrize("kind,fit,ppm", [("vel", 0, 0), ("scal", 1, 0), ("scal", 0, 1)])
-def test_compute_aofs_bc(backend, oracle, per, plo, phi, nb, kind, fit, ppm):
+def test_compute_aofs_bc(backend, oracle, per, plo, phi, nb, kind, fit, ppm, n=(16, 16, 8)):
     lib, dev = backend
-    n = (16, 16, 8)
     dx = tuple(1.0 / m for m in n)
     if kind == "vel":
         ncomp, iconserv, isvel = 3, (0, 0, 0), 1
