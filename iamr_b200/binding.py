@@ -185,6 +185,7 @@ SIGNATURES = {
     "iamrx_ns_nstep": (C.c_int, [_vp]),
     "iamrx_ns_field": (C.c_int, [_vp, C.c_int, C.c_int, _P(Fab)]),
     "iamrx_ns_step_host": (C.c_int, [_vp, _P(_vp), _P(_vp), _P(C.c_double)]),
+    "iamrx_ns_write_plotfile": (C.c_int, [_vp, C.c_char_p]),
     "iamrx_ns_last_iters": (C.c_int, [_vp, _P(C.c_int)]),
     "iamrx_ns_sum_integrated_quantities": (C.c_int, [_vp, _P(C.c_double)]),
 }
@@ -387,6 +388,9 @@ class NavierStokes:
         it = (C.c_int * 3)()
         self.lib.check(self.lib.iamrx_ns_last_iters(self.h, it))
         return tuple(it)
+
+    def write_plotfile(self, path):
+        self.lib.check(self.lib.iamrx_ns_write_plotfile(self.h, str(path).encode()))
 
     def sums(self):
         """(MASS, TRAC, KINETIC ENERGY) as NavierStokes::sum_integrated_quantities prints them."""

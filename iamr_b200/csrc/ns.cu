@@ -12,6 +12,9 @@
 namespace ix {
 Level* level_of(iamrx_level_t h);
 LevelSolvers* solvers_of(iamrx_level_t h);
+int write_plotfile(Level& L, const std::vector<const MF*>& mfs, const std::vector<int>& comp0, const std::vector<int>& ncomps,
+                   const std::vector<std::string>& names, const char* dir, const char* plot_type, double time, int level_steps,
+                   cudaStream_t s);
 }  // namespace ix
 
 using namespace ix;
@@ -764,6 +767,16 @@ int iamrx_ns_step_host(iamrx_ns_t nsp, const double* const* host_in, double* con
   if (early) IX_CUDA(cudaStreamSynchronize(ns.s2));
 #endif
   return IAMRX_OK;
+}
+
+// Amr::writePlotFile for the level (NavierStokesBase.cpp:3343-3352, NavierStokes.cpp:1080-1196): the cell-centred state components
+// AmrLevel::setPlotVariables registers (NS_setup.cpp:253-269 State_Type, :339-360 Gradp_Type), new-time data
+int iamrx_ns_write_plotfile(iamrx_ns_t nsp, const char* dir) {
+  IX_NEED_DEVICE();
+  IX_ARG(nsp && dir && dir[0], "null argument");
+  iamrx_ns_s& ns = *nsp;
+  const std::vector<std::string> names = {"x_velocity", "y_velocity", "z_velocity", "density", "tracer", "gradpx", "gradpy", "gradpz"};
+  return write_plotfile(*ns.L, {&ns.S_new, &ns.Gp_new}, {0, 0}, {NUM_STATE, 3}, names, dir, "NavierStokes-V1.1", ns.time, ns.nstep, ns.s);
 }
 
 int iamrx_ns_last_iters(iamrx_ns_t ns, int iters[3]) {

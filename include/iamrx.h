@@ -453,6 +453,11 @@ int iamrx_ns_field(iamrx_ns_t ns, int which, int ilocal, iamrx_fab* out);
  * device, advances, copies the new state back.  Both copies are inside. */
 int iamrx_ns_step_host(iamrx_ns_t ns, const double* const* host_state_in,
                        double* const* host_state_out, double* dt_io);
+/* Amr::writePlotFile (main.cpp:135; plotfile type "NavierStokes-V1.1", NavierStokesBase.cpp:3343-3352): the new-time cell-centred
+ * state (x_velocity y_velocity z_velocity density tracer gradpx gradpy gradpz) as an AMReX plotfile directory
+ * (Header, Level_0/Cell_H, Level_0/Cell_D_<rank>, job_info) that fcompare / yt / Amrvis read -- the way a site with an AMReX build
+ * can diff this library against IAMR.  Collective over the ranks of the level; every rank writes its own boxes. */
+int iamrx_ns_write_plotfile(iamrx_ns_t ns, const char* dir);
 /* solver statistics of the last step: iterations of {mac, visc, nodal}. */
 int iamrx_ns_last_iters(iamrx_ns_t ns, int iters[3]);
 /* NavierStokes::sum_integrated_quantities (NS.cpp:1046-1080): volume-weighted sums of the new state over the level, all
