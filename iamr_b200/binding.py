@@ -100,6 +100,7 @@ class LinopBC(C.Structure):
         return b
 
 
+OPT_SMALL_VEL, OPT_SLOPE_ORDER, OPT_CORNER_FORM, OPT_EXTDIR_BOTH = 0, 1, 2, 3
 LINOP_PERIODIC, LINOP_DIRICHLET, LINOP_NEUMANN, LINOP_REFLECT_ODD, LINOP_INFLOW = 0, 1, 2, 3, 4
 
 
@@ -122,6 +123,8 @@ _i3 = C.c_int * 3
 # name -> (restype, argtypes); every symbol include/iamrx.h declares
 SIGNATURES = {
     "iamrx_last_error": (C.c_char_p, []),
+    "iamrx_set_option": (C.c_int, [C.c_int, C.c_double]),
+    "iamrx_get_option": (C.c_double, [C.c_int]),
     "iamrx_version": (C.c_int, []),
     "iamrx_launch_count": (C.c_int64, []),
     "iamrx_launch_count_reset": (None, []),

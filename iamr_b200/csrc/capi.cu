@@ -56,6 +56,12 @@ static k::Abec make_abec(double a, double b, const iamrx_fab* acoef, const iamrx
 extern "C" {
 
 const char* iamrx_last_error(void) { return ix::last_error_cstr(); }
+int iamrx_set_option(int option, double value) {
+  const int rc = k::godunov_set_option(option, value);
+  if (rc == IAMRX_ERR_ARG) ix::set_error("bad argument: unknown option or value out of range");
+  return rc;
+}
+double iamrx_get_option(int option) { return k::godunov_get_option(option); }
 int iamrx_version(void) { return 100; }
 int64_t iamrx_launch_count(void) { return g_launches.load(); }
 void iamrx_launch_count_reset(void) { g_launches.store(0); }

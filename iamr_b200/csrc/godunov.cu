@@ -166,6 +166,11 @@ IX_D void corner(double& lo1, double& hi1, double lo, double hi, const Cur& q, c
                  double dt3dx, bool conserv) {
   const double mlo_p = rel2<D1, D2>(mac2, -1, 1), mlo_m = rel2<D1, D2>(mac2, -1, 0);
   const double mhi_p = rel2<D1, D2>(mac2, 0, 1), mhi_m = mac2(0, 0, 0);
+  if (!conserv && upopts().corner_adv) {   // UNVERIFIED-UPSTREAM alternative: advective form of the transverse derivative
+    lo1 = lo - dt3dx * 0.5 * (mlo_p + mlo_m) * (rel2<D1, D2>(edge2, -1, 1) - rel2<D1, D2>(edge2, -1, 0));
+    hi1 = hi - dt3dx * 0.5 * (mhi_p + mhi_m) * (rel2<D1, D2>(edge2, 0, 1) - edge2(0, 0, 0));
+    return;
+  }
   lo1 = lo - dt3dx * (rel2<D1, D2>(edge2, -1, 1) * mlo_p - rel2<D1, D2>(edge2, -1, 0) * mlo_m);
   hi1 = hi - dt3dx * (rel2<D1, D2>(edge2, 0, 1) * mhi_p - edge2(0, 0, 0) * mhi_m);
   if (!conserv) {
@@ -572,7 +577,7 @@ constexpr int SMEM_BYTES = (PAD + NQ + 12 * NS + PAD) * (int)sizeof(double);
 
 // upwind() as a select: identical value for finite inputs (fu is exactly 0 or 1 there), fewer DP instructions
 IX_D double upsel(double lo, double hi, double vel) {
-  return (fabs(vel) < SMALL_VEL) ? 0.5 * (hi + lo) : ((vel >= 0.0) ? lo : hi);
+  return (fabs(vel) < upopts().small_vel) ? 0.5 * (hi + lo) : ((vel >= 0.0) ? lo : hi);
 }
 // 32-bit element offset of (i,j,k) in a view (host checks that every fab has < 2^31 elements)
 template <class V> IX_D int off32(const V& v, int i, int j, int k) {
@@ -677,7 +682,10 @@ aofs_tile_kernel(IX_KARG(EsArgs) a, IX_KARG(EsOut) out, V4 aofs, double volinv, 
   __syncthreads();
   {  // stage 3: transverse derivative terms of this cell
     double Tx = AE[t + 1] * up - xe * um, Ty = AE[NS + t + G] * vp - ye * vm, Tz = AE[2 * NS + t + GG] * wp - ze * wm;
-    if (!cs) { Tx -= q0 * (up - um); Ty -= q0 * (vp - vm); Tz -= q0 * (wp - wm); }
+    if (!cs) {
+      if (upopts().corner_adv) { Tx = 0.5 * (up + um) * (AE[t + 1] - xe); Ty = 0.5 * (vp + vm) * (AE[NS + t + G] - ye); Tz = 0.5 * (wp + wm) * (AE[2 * NS + t + GG] - ze); }
+      else { Tx -= q0 * (up - um); Ty -= q0 * (vp - vm); Tz -= q0 * (wp - wm); }
+    }
     AT[t] = Tx; AT[NS + t] = Ty; AT[2 * NS + t] = Tz;
     __syncthreads();
     // stage 4: corner-coupled states on the low faces (AE is free: its last readers are behind the barrier)
@@ -875,6 +883,33 @@ int compute_aofs(const Bx& bx, const AofsArgs& a, const AdvGeom& g, cudaStream_t
   IX_LAUNCH(es_div_kernel, grid_for(bx, a.ncomp), dim3(TX, TY, 1), 0, s, e, so.sc, a.aofs,
             1.0 / (g.dx[0] * g.dx[1] * g.dx[2]), 1.0 / g.dx[0], 1.0 / g.dx[1], 1.0 / g.dx[2], a.is_sync, bx);
   return check_launch("es_div");
+}
+
+// UNVERIFIED-UPSTREAM switches (include/iamrx.h iamrx_set_option): host copy + the constant-memory copy the kernels read
+int godunov_set_option(int opt, double value) {
+  UpOpts o = g_upopts_host;
+  switch (opt) {
+    case IAMRX_OPT_SMALL_VEL: if (!(value >= 0.0)) return IAMRX_ERR_ARG; o.small_vel = value; break;
+    case IAMRX_OPT_SLOPE_ORDER: if (value != 2.0 && value != 4.0) return IAMRX_ERR_ARG; o.slope_order = (int)value; break;
+    case IAMRX_OPT_CORNER_FORM: if (value != 0.0 && value != 1.0) return IAMRX_ERR_ARG; o.corner_adv = (int)value; break;
+    case IAMRX_OPT_EXTDIR_BOTH: if (value != 0.0 && value != 1.0) return IAMRX_ERR_ARG; o.extdir_both = (int)value; break;
+    default: return IAMRX_ERR_ARG;
+  }
+  g_upopts_host = o;
+#if !defined(IX_EMUL)
+  if (device_ok()) IX_CUDA(cudaMemcpyToSymbol(c_upopts, &o, sizeof(o)));
+#endif
+  return IAMRX_OK;
+}
+double godunov_get_option(int opt) {
+  const UpOpts& o = g_upopts_host;
+  switch (opt) {
+    case IAMRX_OPT_SMALL_VEL: return o.small_vel;
+    case IAMRX_OPT_SLOPE_ORDER: return o.slope_order;
+    case IAMRX_OPT_CORNER_FORM: return o.corner_adv;
+    case IAMRX_OPT_EXTDIR_BOTH: return o.extdir_both;
+    default: return 0.0;
+  }
 }
 
 int extrap_vel_to_faces(const Bx& bx, C4 vel, C4 force, V4 umac, V4 vmac, V4 wmac, const AdvGeom& g,

@@ -18,6 +18,30 @@ namespace gd {
 
 constexpr double SMALL_VEL = 1.0e-8;
 
+// ---- UNVERIFIED-UPSTREAM switches (include/iamrx.h iamrx_set_option) -------------------------------
+// Details of AMReX-Hydro's Godunov that this repository restates from memory of the upstream sources and cannot check (they
+// are not vendored in the reference).  Each is a run-time switch, mirrored in the oracle, so that a site with the upstream
+// source can flip a choice instead of editing kernels.  Process-wide; device copy in constant memory.
+struct UpOpts {
+  double small_vel;   // |u| below which a face velocity counts as zero in the upwinding (hydro_constants: 1e-8)
+  int slope_order;    // 4 (Godunov default, AMReX_Slopes_K.H order 4) or 2 (monotonised central)
+  int corner_adv;     // corner coupling of non-conservative states: 0 flux form minus q div(u) (hydro_godunov_corner_couple.H as
+                      // restated), 1 advective form 1/2 (u+ + u-)(q+ - q-)
+  int extdir_both;    // ext_dir faces: 0 only the outside state takes the boundary value (tangential components keep the traced
+                      // interior state; hydro_bcs_K.H after the turbulent-inflow change), 1 both states take it
+};
+#if !defined(IX_EMUL)
+__constant__ UpOpts c_upopts = {1.0e-8, 4, 0, 0};
+#endif
+static UpOpts g_upopts_host = {1.0e-8, 4, 0, 0};
+IX_HD const UpOpts& upopts() {
+#if defined(__CUDA_ARCH__)
+  return c_upopts;
+#else
+  return g_upopts_host;
+#endif
+}
+
 template <int D> struct E {  // unit offset of direction D
   static constexpr int x = (D == 0), y = (D == 1), z = (D == 2);
 };
@@ -38,6 +62,7 @@ IX_HD double lim2(double dlft, double drgt) {  // limited 2nd-order difference
 // 4th-order limited slope from the five values q(i-2..i+2) along one direction
 // (amrex_calc_{x,y,z}slope, order 4)
 IX_HD double slope4_vals(double qm2, double qm, double q0, double qp, double qp2) {
+  if (upopts().slope_order == 2) return lim2(q0 - qm, qp - q0);
   const double dxl = lim2(qm - qm2, q0 - qm);
   const double dxr = lim2(qp - q0, qp2 - qp);
   const double dlft = q0 - qm, drgt = qp - q0;
@@ -100,12 +125,12 @@ IX_HD void ppm_parabola(double sm2, double sm1, double s0, double sp1, double sp
 }
 // averages of the parabola over the domain of dependence of the upper (Ip) / lower (Im) face for trace velocity v
 IX_HD double ppm_ip(double s0, double sm, double sp, double v, double dtdx) {
-  if (!(v > SMALL_VEL)) return s0;
+  if (!(v > upopts().small_vel)) return s0;
   const double sg = fabs(v) * dtdx, s6 = 6.0 * s0 - 3.0 * (sm + sp);
   return sp - 0.5 * sg * ((sp - sm) - (1.0 - (2.0 / 3.0) * sg) * s6);
 }
 IX_HD double ppm_im(double s0, double sm, double sp, double v, double dtdx) {
-  if (!(v < -SMALL_VEL)) return s0;
+  if (!(v < -upopts().small_vel)) return s0;
   const double sg = fabs(v) * dtdx, s6 = 6.0 * s0 - 3.0 * (sm + sp);
   return sm + 0.5 * sg * ((sp - sm) + (1.0 - (2.0 / 3.0) * sg) * s6);
 }
@@ -125,6 +150,11 @@ IX_HD double lim_os(double dl, double dr, double d) {   // one-sided limiter of 
 // one-sided 4-point formula in the first cell and the revised neighbour slope in the second.
 IX_HD double slope4_bc_vals(double qm2, double qm, double q0, double qp, double qp2, int c, const BcD& b) {
   const bool edlo = bc_extdir_or_ho(b.lo), edhi = bc_extdir_or_ho(b.hi);
+  if (upopts().slope_order == 2) {   // order 2 next to an ext_dir / hoextrap face: the wall value sits half a cell away
+    if (edlo && c == b.dlo) return lim_os(2.0 * (q0 - qm), 2.0 * (qp - q0), (qp + 3.0 * q0 - 4.0 * qm) / 3.0);
+    if (edhi && c == b.dhi) return lim_os(2.0 * (q0 - qm), 2.0 * (qp - q0), -(qm + 3.0 * q0 - 4.0 * qp) / 3.0);
+    return lim2(q0 - qm, qp - q0);
+  }
   if (!(edlo && (c == b.dlo || c == b.dlo + 1)) && !(edhi && (c == b.dhi || c == b.dhi - 1)))
     return slope4_vals(qm2, qm, q0, qp, qp2);
   double dfm = lim2(qm - qm2, q0 - qm), dfp = lim2(qp - q0, qp2 - qp);
@@ -182,11 +212,11 @@ IX_HD void ppm_parabola_bc(double sm2, double sm1, double s0, double sp1, double
 // both states, otherwise the interior state may still carry information out of the domain.
 IX_HD void set_edge_bc(double& lo, double& hi, double qbelow, double qabove, int f, const BcD& b, bool normal_vel) {
   if (f == b.dlo) {
-    if (b.lo == IAMRX_BC_EXT_DIR) { lo = qbelow; if (normal_vel) hi = lo; }
+    if (b.lo == IAMRX_BC_EXT_DIR) { lo = qbelow; if (normal_vel || upopts().extdir_both) hi = lo; }
     else if (b.lo == IAMRX_BC_FOEXTRAP || b.lo == IAMRX_BC_HOEXTRAP || b.lo == IAMRX_BC_REFLECT_EVEN) lo = hi;
     else if (b.lo == IAMRX_BC_REFLECT_ODD) { lo = 0.0; hi = 0.0; }
   } else if (f == b.dhi + 1) {
-    if (b.hi == IAMRX_BC_EXT_DIR) { hi = qabove; if (normal_vel) lo = hi; }
+    if (b.hi == IAMRX_BC_EXT_DIR) { hi = qabove; if (normal_vel || upopts().extdir_both) lo = hi; }
     else if (b.hi == IAMRX_BC_FOEXTRAP || b.hi == IAMRX_BC_HOEXTRAP || b.hi == IAMRX_BC_REFLECT_EVEN) hi = lo;
     else if (b.hi == IAMRX_BC_REFLECT_ODD) { lo = 0.0; hi = 0.0; }
   }
@@ -209,7 +239,7 @@ IX_HD void outflow_bc(double& lo, double& hi, int f, const BcD& b, bool clip_lo,
 // transverse states of ExtrapVelToFaces)
 IX_HD double upwind(double lo, double hi, double vel) {
   const double st = (vel >= 0.0) ? lo : hi;
-  const double fu = (fabs(vel) < SMALL_VEL) ? 0.0 : 1.0;
+  const double fu = (fabs(vel) < upopts().small_vel) ? 0.0 : 1.0;
   return fu * st + (1.0 - fu) * 0.5 * (hi + lo);
 }
 
@@ -217,7 +247,7 @@ IX_HD double upwind(double lo, double hi, double vel) {
 // ExtrapVelToFaces)
 IX_HD double riemann(double lo, double hi) {
   const double st = ((lo + hi) >= 0.0) ? lo : hi;
-  const bool ltm = ((lo <= 0.0 && hi >= 0.0) || (fabs(lo + hi) < SMALL_VEL));
+  const bool ltm = ((lo <= 0.0 && hi >= 0.0) || (fabs(lo + hi) < upopts().small_vel));
   return ltm ? 0.0 : st;
 }
 

@@ -83,6 +83,9 @@ int reduce_dot(const Bx& bx, C4 x, C4 y, C4 mask, double* result, cudaStream_t s
 // diagnostic: measured DFMA issue rate of the device in 1e9 instructions/s (thread-level; x2 = flop/s)
 int fp64_peak(double* dp_ginstr_per_s, cudaStream_t s);
 
+int godunov_set_option(int opt, double value);
+double godunov_get_option(int opt);
+
 // --- Godunov advection (godunov.cu) --------------------------------------
 struct AdvGeom { double dx[3]; double dt; };
 // physical boundaries seen by the Godunov kernels: the domain's cell bounds and the BCRec (IAMRX_BC_* codes) of every

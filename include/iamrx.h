@@ -110,6 +110,20 @@ enum {
                                       only fluxes, divergence and the convective term are formed */
 };
 
+/* UNVERIFIED-UPSTREAM switches.  The arithmetic of Godunov::ExtrapVelToFaces / ComputeEdgeState lives in
+ * AMReX-Hydro, which the reference does not vendor; where this library restates a detail from memory that a site with the
+ * upstream source might find different, the choice is a run-time switch (process-wide; mirrored by orc_set_option in the
+ * oracle) instead of a constant.  Defaults in brackets. */
+enum {
+  IAMRX_OPT_SMALL_VEL = 0,     /* [1e-8] |u| below which a face velocity counts as zero when upwinding */
+  IAMRX_OPT_SLOPE_ORDER = 1,   /* [4] order of the limited slopes of the PLM trace: 4 or 2 */
+  IAMRX_OPT_CORNER_FORM = 2,   /* [0] corner coupling of non-conservative states: 0 flux form - q div(u), 1 advective form */
+  IAMRX_OPT_EXTDIR_BOTH = 3    /* [0] ext_dir faces: 1 = both traced states take the boundary value (0: only the outside one,
+                                  except for the normal velocity) */
+};
+int iamrx_set_option(int option, double value);
+double iamrx_get_option(int option);
+
 const char* iamrx_last_error(void);
 int iamrx_version(void);
 /* number of kernels this library has launched since load (bench.py's

@@ -854,7 +854,12 @@ struct NodeMG {
 // hydro_godunov_extrap_vel_to_faces_3D.cpp, hydro_godunov_corner_couple.H,
 // AMReX_Slopes_K.H; A.2-A.5), periodic boundaries only.
 // ===========================================================================
-const double small_vel = 1.0e-8;
+// UNVERIFIED-UPSTREAM switches (orc_set_option; the library's iamrx_set_option mirrors them): details of AMReX-Hydro's Godunov
+// restated from memory of the upstream sources, kept switchable
+double small_vel = 1.0e-8;   // |u| below which a face velocity counts as zero in the upwinding
+int opt_slope_order = 4;     // limited slopes of the PLM trace: 4th order (Godunov default) or 2nd (monotonised central)
+int opt_corner_adv = 0;      // corner coupling of non-conservative states: 0 flux form minus q div u, 1 advective form
+int opt_extdir_both = 0;     // ext_dir faces: 1 = both traced states take the boundary value
 
 inline double limited2(double dl, double dr) {  // 2nd-order monotonised central difference
   const double dc = 0.5 * (dl + dr);
@@ -863,6 +868,7 @@ inline double limited2(double dl, double dr) {  // 2nd-order monotonised central
 }
 // amrex_calc_{x,y,z}slope, order 4: q values at i-2..i+2 along the direction
 inline double slope_order4(double qmm, double qm, double q0, double qp, double qpp) {
+  if (opt_slope_order == 2) return limited2(q0 - qm, qp - q0);
   const double dfm = limited2(qm - qmm, q0 - qm);
   const double dfp = limited2(qp - q0, qpp - qp);
   const double dl = q0 - qm, dr = qp - q0, dc = 0.5 * (dl + dr);
@@ -933,6 +939,11 @@ inline double one_sided_lim(double dl2, double dr2, double val) {   // dl2, dr2 
 // ext_dir or hoextrap boundary: the ghost value sits ON the face, so the first cell uses the one-sided 4-point
 // difference and the second cell's formula takes that one-sided slope for its neighbour
 inline double slope_order4_bc(double qmm, double qm, double q0, double qp, double qpp, int idx, int nd, bool edlo, bool edhi) {
+  if (opt_slope_order == 2) {   // A.2: dc = (q(i+1) + 3 q(i) - 4 q_wall)/3 in the first cell
+    if (edlo && idx == 0) return one_sided_lim(2.0 * (q0 - qm), 2.0 * (qp - q0), (qp + 3.0 * q0 - 4.0 * qm) / 3.0);
+    if (edhi && idx == nd - 1) return one_sided_lim(2.0 * (q0 - qm), 2.0 * (qp - q0), -(qm + 3.0 * q0 - 4.0 * qp) / 3.0);
+    return limited2(q0 - qm, qp - q0);
+  }
   double dfm = limited2(qm - qmm, q0 - qm), dfp = limited2(qp - q0, qpp - qp);
   const double dl = q0 - qm, dr = qp - q0, dc = 0.5 * (dl + dr);
   const double lim = (dl * dr >= 0.0) ? 2.0 * std::min(std::fabs(dl), std::fabs(dr)) : 0.0;
@@ -971,12 +982,12 @@ inline void edge_bcs(double& lo, double& hi, double qb, double qa, int f, int nd
   if (g_per[d]) return;
   if (f == 0) {
     const int c = bc.lo[d];
-    if (c == BC_EXT_DIR) { lo = qb; if (normal_vel) hi = lo; }
+    if (c == BC_EXT_DIR) { lo = qb; if (normal_vel || opt_extdir_both) hi = lo; }
     else if (c == BC_FOEXTRAP || c == BC_HOEXTRAP || c == BC_REFLECT_EVEN) lo = hi;
     else if (c == BC_REFLECT_ODD) { lo = 0.0; hi = 0.0; }
   } else if (f == nd) {
     const int c = bc.hi[d];
-    if (c == BC_EXT_DIR) { hi = qa; if (normal_vel) lo = hi; }
+    if (c == BC_EXT_DIR) { hi = qa; if (normal_vel || opt_extdir_both) lo = hi; }
     else if (c == BC_FOEXTRAP || c == BC_HOEXTRAP || c == BC_REFLECT_EVEN) hi = lo;
     else if (c == BC_REFLECT_ODD) { lo = 0.0; hi = 0.0; }
   }
@@ -1048,7 +1059,10 @@ void corner_couple(const Arr& lo, const Arr& hi, int d1, int d2, double dt3dx, b
         const int ip = e0(d2), jp = e1(d2), kp = e2(d2);
         double l = lo(i, j, k) - dt3dx * (edge2(im + ip, jm + jp, km + kp) * mac2(im + ip, jm + jp, km + kp) - edge2(im, jm, km) * mac2(im, jm, km));
         double h = hi(i, j, k) - dt3dx * (edge2(i + ip, j + jp, k + kp) * mac2(i + ip, j + jp, k + kp) - edge2(i, j, k) * mac2(i, j, k));
-        if (!conserv) {
+        if (!conserv && opt_corner_adv) {   // advective form of the transverse derivative
+          l = lo(i, j, k) - dt3dx * 0.5 * (mac2(im + ip, jm + jp, km + kp) + mac2(im, jm, km)) * (edge2(im + ip, jm + jp, km + kp) - edge2(im, jm, km));
+          h = hi(i, j, k) - dt3dx * 0.5 * (mac2(i + ip, j + jp, k + kp) + mac2(i, j, k)) * (edge2(i + ip, j + jp, k + kp) - edge2(i, j, k));
+        } else if (!conserv) {
           l += dt3dx * q(im, jm, km, c) * (mac2(im + ip, jm + jp, km + kp) - mac2(im, jm, km));
           h += dt3dx * q(i, j, k, c) * (mac2(i + ip, j + jp, k + kp) - mac2(i, j, k));
         }
@@ -1637,6 +1651,16 @@ int orc_num_threads(void) {
 #else
   return 1;
 #endif
+}
+
+int orc_set_option(int opt, double value) {   // same option ids as include/iamrx.h IAMRX_OPT_*
+  switch (opt) {
+    case 0: small_vel = value; return 0;
+    case 1: opt_slope_order = (int)value; return 0;
+    case 2: opt_corner_adv = (int)value; return 0;
+    case 3: opt_extdir_both = (int)value; return 0;
+    default: return -1;
+  }
 }
 
 void orc_set_num_threads(int n) {   // torchrun exports OMP_NUM_THREADS=1: the CPU arm sets its thread count explicitly

@@ -131,6 +131,8 @@ double orc_ns_time(const orc_ns* ns);
 void orc_ns_get(const orc_ns* ns, int which, double* out);
 void orc_ns_set_state(orc_ns* ns, const double* state5);
 void orc_ns_last_iters(const orc_ns* ns, int iters[3]);
+/* UNVERIFIED-UPSTREAM switches (ids = IAMRX_OPT_* of include/iamrx.h): 0 small_vel, 1 slope order (4|2), 2 corner form (0|1), 3 ext_dir both states */
+int orc_set_option(int opt, double value);
 int orc_num_threads(void);
 void orc_set_num_threads(int n);
 

@@ -58,6 +58,11 @@ def _d3(x):
     return (C.c_double * 3)(*[float(v) for v in x])
 
 
+def set_option(opt, value):
+    lib().orc_set_option.argtypes = [C.c_int, C.c_double]
+    assert lib().orc_set_option(int(opt), float(value)) == 0
+
+
 def mg_default(**kw):
     m = OrcMG()
     lib().orc_mg_default(C.byref(m))

@@ -519,3 +519,40 @@ def test_driver_rejects_unsupported_boundaries(backend):
     with pytest.raises(ix.IamrxError, match="periodic direction"):
         ix.NavierStokes(lib, lev, dev, lo_bc=(4, 4, 0), hi_bc=(4, 0, 0))
     lev.close()
+
+
+UPSTREAM_SWITCHES = [(ix.OPT_SLOPE_ORDER, 2.0, 4.0), (ix.OPT_SMALL_VEL, 1.0e-3, 1.0e-8), (ix.OPT_CORNER_FORM, 1.0, 0.0), (ix.OPT_EXTDIR_BOTH, 1.0, 0.0)]
+
+
+@pytest.mark.parametrize("opt,value,default", UPSTREAM_SWITCHES, ids=["slope_order_2", "small_vel_1e-3", "corner_advective", "extdir_both"])
+def test_unverified_upstream_switches(backend, oracle, opt, value, default):
+    """every UNVERIFIED-UPSTREAM choice of the Godunov restatement is a run-time switch in the library
+    (iamrx_set_option) and in the oracle (orc_set_option).  With a switch flipped on BOTH sides the two still agree -- on
+    periodic boxes (fused tile kernel on the GPU) and on wall-bounded ones -- and the result differs from the default's."""
+    lib, dev = backend
+    per, plo, phi = BC_CASES[1]
+    n = (16, 16, 8)
+    try:
+        lib.check(lib.iamrx_set_option(opt, value))
+        oracle.set_option(opt, value)
+        assert lib.iamrx_get_option(opt) == value
+        test_extrap_vel_to_faces_bc(backend, oracle, per, plo, phi, (2, 2, 2), 0, 0)
+        test_compute_aofs_bc(backend, oracle, per, plo, phi, (1, 1, 1), "vel", 0, 0)
+        test_compute_aofs_bc(backend, oracle, (1, 1, 1), (0, 0, 0), (0, 0, 0), (1, 1, 1), "vel", 0, 0)   # periodic: tile kernel on the GPU
+        test_compute_aofs_bc(backend, oracle, (1, 1, 1), (0, 0, 0), (0, 0, 0), (2, 2, 2), "scal", 1, 0)
+        # the switch is live: a flipped oracle differs from the default oracle on the same input
+        dx = tuple(1.0 / m for m in n)
+        bclo, bchi = _vel_bcs(per, plo, phi)
+        vel = smooth_field(n, 100, 3)
+        vel[2] += 0.2
+        V = oracle.fill_physbc(n, per, 3, pad(vel, 3), bclo, bchi, 0.3 * hash_uniform(5, (6, 3)))
+        dt = 0.5 * min(dx) / np.abs(vel).max()
+        flipped = oracle.extrap_vel_to_faces_bc(n, per, dx, dt, V, None, bclo, bchi)
+        oracle.set_option(opt, default)
+        base = oracle.extrap_vel_to_faces_bc(n, per, dx, dt, V, None, bclo, bchi)
+        assert max(np.abs(a - b).max() for a, b in zip(flipped, base)) > 1e-8
+    finally:
+        lib.iamrx_set_option(opt, default)
+        oracle.set_option(opt, default)
+    assert lib.iamrx_set_option(opt, -7.0) == -1 or opt == ix.OPT_SMALL_VEL
+    lib.iamrx_set_option(opt, default)
