@@ -168,6 +168,16 @@ SIGNATURES = {
     "iamrx_level_local_box": (C.c_int, [_vp, C.c_int, _P(Box), _P(C.c_int)]),
     "iamrx_fill_boundary": (C.c_int, [_vp, _P(Fab), C.c_int, C.c_int, C.c_int, _vp]),
     "iamrx_fill_physbc": (C.c_int, [_vp, _P(Fab), C.c_int, C.c_int, _P(BCRec), _P(C.c_double), _vp]),
+    "iamrx_average_down_box": (C.c_int, [_P(Box), _P(Fab), _P(Fab), C.c_int, C.c_int, _vp]),
+    "iamrx_interp_box": (C.c_int, [C.c_int, _P(Box), _P(Fab), _P(Fab), C.c_int, _vp]),
+    "iamrx_fluxreg_create": (C.c_int, [_vp, _vp, C.c_int, _P(_vp)]),
+    "iamrx_fluxreg_destroy": (C.c_int, [_vp]),
+    "iamrx_fluxreg_num_patches": (C.c_int, [_vp]),
+    "iamrx_fluxreg_reset": (C.c_int, [_vp, _vp]),
+    "iamrx_fluxreg_crse_add": (C.c_int, [_vp, _P(Fab), _P(Fab), _P(Fab), C.c_double, C.c_double, _vp]),
+    "iamrx_fluxreg_fine_add": (C.c_int, [_vp, _P(Fab), _P(Fab), _P(Fab), C.c_double, C.c_double, _vp]),
+    "iamrx_fluxreg_reflux": (C.c_int, [_vp, _P(Fab), C.c_int, C.c_double, _vp]),
+    "iamrx_fluxreg_field": (C.c_int, [_vp, C.c_int, _P(Fab)]),
     "iamrx_mg_info_default": (None, [_P(MGInfo)]),
     "iamrx_mac_project": (C.c_int, [_vp, _P(Fab), _P(Fab), _P(Fab), _P(Fab), _P(Fab), _P(Fab), C.c_double,
                                     _P(C.c_int), _P(C.c_int), _P(MGInfo), _vp]),

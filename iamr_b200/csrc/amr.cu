@@ -1,0 +1,361 @@
+// amr.cu -- inter-level transfer operators and the coarse-fine flux register of the two-level coupling:
+//   average_down         : NavierStokesBase::avgDown_StatePress (NSB.cpp:4125-4191) -- cells: mean of the 2^3 children
+//                          (amrex::average_down), faces: mean of the 2^2 fine faces on the coarse face (average_down_faces),
+//                          nodes: injection (average_down_nodal, NSB.cpp:4154)
+//   interp cell_cons     : cell_cons_interp of State_Type (NS_setup.cpp:211,228-230): conservative linear interpolation with
+//                          monotonised-central slopes per direction, scaled so that no fine value leaves the range of the 3^3
+//                          coarse neighbourhood (CellConservativeLinear without linear limiting: mclim + mmlim)
+//   interp node_bilinear : node_bilinear_interp of Press_Type (NS_setup.cpp:331)
+//   interp face_linear   : face_linear_interp of u_mac in create_umac_grown (NSB.cpp:1127): linear along the face normal
+//                          between the two coarse faces, piecewise constant across
+//   flux register        : the advective register's CrseAdd / FineAdd / Reflux with area-weighted fluxes and dx := cell volume
+//                          (NSB.cpp:4848-4889, 5083-5096; NS.cpp:1794-1795): on the coarse cells that border the fine grids from
+//                          outside, reg = dt (sum of fine fluxes - coarse flux) / vol_crse * (+-1); Reflux adds it to the state.
+// Refinement ratio 2 (amr.ref_ratio = 2 in every BASELINE config).  These are the building blocks; the two-level time stepping
+// itself (FillPatchTwoLevels in time, coarse-fine solver boundaries, mac_sync / level_sync) is not driven by this library.
+#include <algorithm>
+#include "level.h"
+
+namespace ix {
+namespace k {
+namespace {
+
+constexpr int TX = 64;
+constexpr int TY = 4;
+inline dim3 grid_for(const Bx& bx, int nzc) { return dim3(cdiv(bx.nx(), TX), cdiv(bx.ny(), TY), nzc); }
+#define IDX3(bx)                                                     \
+  const int nz_ = bx.hi[2] - bx.lo[2] + 1;                            \
+  const int k = bx.lo[2] + (int)(blockIdx.z % nz_);                   \
+  const int n = (int)(blockIdx.z / nz_);                              \
+  const int j = bx.lo[1] + blockIdx.y * TY + threadIdx.y;             \
+  const int i = bx.lo[0] + blockIdx.x * TX + threadIdx.x;             \
+  if (j > bx.hi[1] || i > bx.hi[0]) return;
+
+IX_HD int coarsen2(int a) { return (a >= 0) ? a / 2 : -((-a + 1) / 2); }   // floor(a/2)
+
+__global__ void __launch_bounds__(TX* TY) node_inject_kernel(Bx cnbx, V4 crse, C4 fine) {
+  IDX3(cnbx)
+  crse(i, j, k, n) = fine(2 * i, 2 * j, 2 * k, n);
+}
+
+IX_D double mc_slope(double um, double u0, double up) {
+  const double dc = 0.5 * (up - um), df = 2.0 * (up - u0), db = 2.0 * (u0 - um);
+  const double lim = (df * db >= 0.0) ? fmin(fabs(df), fabs(db)) : 0.0;
+  return copysign(1.0, dc) * fmin(lim, fabs(dc));
+}
+
+// one thread per FINE cell: slopes of its coarse parent are recomputed (27 coarse loads, served by L1: 8 siblings share them)
+__global__ void __launch_bounds__(TX* TY) cell_cons_interp_kernel(Bx fbx, V4 fine, C4 crse) {
+  IDX3(fbx)
+  const int I = coarsen2(i), J = coarsen2(j), K = coarsen2(k);
+  const double u = crse(I, J, K, n);
+  double sx = mc_slope(crse(I - 1, J, K, n), u, crse(I + 1, J, K, n));
+  double sy = mc_slope(crse(I, J - 1, K, n), u, crse(I, J + 1, K, n));
+  double sz = mc_slope(crse(I, J, K - 1, n), u, crse(I, J, K + 1, n));
+  double cmn = u, cmx = u;
+  for (int kk = -1; kk <= 1; ++kk)
+    for (int jj = -1; jj <= 1; ++jj)
+      for (int ii = -1; ii <= 1; ++ii) { const double v = crse(I + ii, J + jj, K + kk, n); cmn = fmin(cmn, v); cmx = fmax(cmx, v); }
+  // largest excursion of the eight children: sum of |slope| / 4
+  const double dmax = 0.25 * (fabs(sx) + fabs(sy) + fabs(sz));
+  double alpha = 1.0;
+  if (dmax > 0.0) {
+    if (u + dmax > cmx) alpha = fmin(alpha, (cmx - u) / dmax);
+    if (u - dmax < cmn) alpha = fmin(alpha, (u - cmn) / dmax);
+  }
+  const double ox = (i - 2 * I) ? 0.25 : -0.25, oy = (j - 2 * J) ? 0.25 : -0.25, oz = (k - 2 * K) ? 0.25 : -0.25;
+  fine(i, j, k, n) = u + alpha * (sx * ox + sy * oy + sz * oz);
+}
+
+__global__ void __launch_bounds__(TX* TY) node_bilinear_interp_kernel(Bx fnbx, V4 fine, C4 crse) {
+  IDX3(fnbx)
+  const int I = coarsen2(i), J = coarsen2(j), K = coarsen2(k);
+  const int ox = i - 2 * I, oy = j - 2 * J, oz = k - 2 * K;
+  double acc = 0.0;
+  for (int dk = 0; dk <= oz; ++dk)
+    for (int dj = 0; dj <= oy; ++dj)
+      for (int di = 0; di <= ox; ++di) acc += crse(I + di, J + dj, K + dk, n);
+  fine(i, j, k, n) = acc / (double)((1 + ox) * (1 + oy) * (1 + oz));
+}
+
+__global__ void __launch_bounds__(TX* TY) face_linear_interp_kernel(Bx ffbx, int dir, V4 fine, C4 crse) {
+  IDX3(ffbx)
+  const int I = coarsen2(i), J = coarsen2(j), K = coarsen2(k);
+  const int idx = dir == 0 ? i : (dir == 1 ? j : k);
+  const double c0 = crse(I, J, K, n);
+  if ((idx & 1) == 0) fine(i, j, k, n) = c0;   // on a coarse face
+  else fine(i, j, k, n) = 0.5 * (c0 + crse(I + (dir == 0), J + (dir == 1), K + (dir == 2), n));
+}
+
+// ---- flux register ---------------------------------------------------------------------------------------------------
+// R = coarse cells of one interface patch (a one-cell-thick slab just OUTSIDE a fine box, on side `side` of direction d);
+// fc = index of the coarse face between the slab and the fine region.
+__global__ void __launch_bounds__(TX* TY) fr_crse_add_kernel(Bx R, V4 reg, C4 flux, int d, int fc_off, double scale) {
+  IDX3(R)
+  // coarse flux through the face the cell shares with the fine region (fc_off = 1: its high face, 0: its low face)
+  reg(i, j, k, n) += scale * flux(i + fc_off * (d == 0), j + fc_off * (d == 1), k + fc_off * (d == 2), n);
+}
+__global__ void __launch_bounds__(TX* TY) fr_fine_add_kernel(Bx R, V4 reg, C4 flux, int d, int fc_off, double scale) {
+  IDX3(R)
+  // the 2 x 2 fine faces that tile the coarse face
+  const int fi = 2 * (i + fc_off * (d == 0)), fj = 2 * (j + fc_off * (d == 1)), fk = 2 * (k + fc_off * (d == 2));
+  double sum = 0.0;
+  for (int b = 0; b < 2; ++b)
+    for (int a = 0; a < 2; ++a) {
+      const int ii = fi + (d == 0 ? 0 : a), jj = fj + (d == 1 ? 0 : (d == 0 ? a : b)), kk = fk + (d == 2 ? 0 : b);
+      sum += flux(ii, jj, kk, n);
+    }
+  reg(i, j, k, n) += scale * sum;
+}
+__global__ void __launch_bounds__(TX* TY) fr_reflux_kernel(Bx R, V4 state, C4 reg, double scale) {
+  IDX3(R)
+  state(i, j, k, n) += scale * reg(i, j, k, n);
+}
+
+}  // namespace
+
+int average_down_nodal(const Bx& cnbx, V4 crse, C4 fine, int ncomp, cudaStream_t s) {
+  if (!cnbx.ok()) return IAMRX_OK;
+  IX_LAUNCH(node_inject_kernel, grid_for(cnbx, cnbx.nz() * ncomp), dim3(TX, TY, 1), 0, s, cnbx, crse, fine);
+  return check_launch("average_down_nodal");
+}
+int cell_cons_interp(const Bx& fbx, V4 fine, C4 crse, int ncomp, cudaStream_t s) {
+  if (!fbx.ok()) return IAMRX_OK;
+  IX_LAUNCH(cell_cons_interp_kernel, grid_for(fbx, fbx.nz() * ncomp), dim3(TX, TY, 1), 0, s, fbx, fine, crse);
+  return check_launch("cell_cons_interp");
+}
+int node_bilinear_interp(const Bx& fnbx, V4 fine, C4 crse, int ncomp, cudaStream_t s) {
+  if (!fnbx.ok()) return IAMRX_OK;
+  IX_LAUNCH(node_bilinear_interp_kernel, grid_for(fnbx, fnbx.nz() * ncomp), dim3(TX, TY, 1), 0, s, fnbx, fine, crse);
+  return check_launch("node_bilinear_interp");
+}
+int face_linear_interp(const Bx& ffbx, int dir, V4 fine, C4 crse, int ncomp, cudaStream_t s) {
+  if (!ffbx.ok()) return IAMRX_OK;
+  IX_LAUNCH(face_linear_interp_kernel, grid_for(ffbx, ffbx.nz() * ncomp), dim3(TX, TY, 1), 0, s, ffbx, dir, fine, crse);
+  return check_launch("face_linear_interp");
+}
+int fr_crse_add(const Bx& R, V4 reg, C4 flux, int d, int fc_off, double scale, int ncomp, cudaStream_t s) {
+  if (!R.ok()) return IAMRX_OK;
+  IX_LAUNCH(fr_crse_add_kernel, grid_for(R, R.nz() * ncomp), dim3(TX, TY, 1), 0, s, R, reg, flux, d, fc_off, scale);
+  return check_launch("fr_crse_add");
+}
+int fr_fine_add(const Bx& R, V4 reg, C4 flux, int d, int fc_off, double scale, int ncomp, cudaStream_t s) {
+  if (!R.ok()) return IAMRX_OK;
+  IX_LAUNCH(fr_fine_add_kernel, grid_for(R, R.nz() * ncomp), dim3(TX, TY, 1), 0, s, R, reg, flux, d, fc_off, scale);
+  return check_launch("fr_fine_add");
+}
+int fr_reflux(const Bx& R, V4 state, C4 reg, double scale, int ncomp, cudaStream_t s) {
+  if (!R.ok()) return IAMRX_OK;
+  IX_LAUNCH(fr_reflux_kernel, grid_for(R, R.nz() * ncomp), dim3(TX, TY, 1), 0, s, R, state, reg, scale);
+  return check_launch("fr_reflux");
+}
+
+}  // namespace k
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Flux register object: coarse level + fine level (ratio 2), every box on this rank (single-rank coupling; see header).
+// Interface patches = for every fine box, direction and side, the coarsened one-cell slab just outside it, minus what other
+// fine boxes cover (those faces are fine-fine), shifted periodically into the coarse box that owns it.
+// ---------------------------------------------------------------------------------------------------------------------
+struct FluxReg {
+  Level* crse = nullptr; Level* fine = nullptr;
+  int ncomp = 0;
+  MF reg;                      // on the coarse level, 0 ghost; nonzero only on interface cells
+  struct Patch { int cbox; int fbox; int d; int side; Bx R; int shift[3]; };   // R in the index space of coarse box cbox; fine = R - shift
+  std::vector<Patch> patches;
+};
+
+static void subtract_boxes(std::vector<Bx>& pieces, const Bx& cut) {
+  std::vector<Bx> out;
+  for (const Bx& a : pieces) {
+    const Bx is = intersect(a, cut);
+    if (!is.ok()) { out.push_back(a); continue; }
+    Bx rest = a;
+    for (int d = 2; d >= 0; --d) {
+      if (rest.lo[d] < is.lo[d]) { Bx p = rest; p.hi[d] = is.lo[d] - 1; out.push_back(p); rest.lo[d] = is.lo[d]; }
+      if (rest.hi[d] > is.hi[d]) { Bx p = rest; p.lo[d] = is.hi[d] + 1; out.push_back(p); rest.hi[d] = is.hi[d]; }
+    }
+  }
+  pieces.swap(out);
+}
+
+int fluxreg_build(FluxReg& F, Level* crse, Level* fine, int ncomp) {
+  F.crse = crse; F.fine = fine; F.ncomp = ncomp;
+  for (size_t b = 0; b < crse->boxes.size(); ++b) if (crse->owner[b] != comm().rank) { set_error("flux register: every coarse box must live on this rank"); return IAMRX_ERR_ARG; }
+  for (size_t b = 0; b < fine->boxes.size(); ++b) if (fine->owner[b] != comm().rank) { set_error("flux register: every fine box must live on this rank"); return IAMRX_ERR_ARG; }
+  F.reg.define(crse, IX_CELL, ncomp, 0);
+  std::vector<Bx> cf;   // coarsened fine boxes
+  for (const Bx& fb : fine->boxes) {
+    Bx c;
+    for (int d = 0; d < 3; ++d) {
+      if ((fb.lo[d] & 1) || !((fb.hi[d] + 1) % 2 == 0)) { set_error("flux register: fine boxes must be coarsenable by 2"); return IAMRX_ERR_ARG; }
+      c.lo[d] = k::coarsen2(fb.lo[d]); c.hi[d] = k::coarsen2(fb.hi[d]);
+    }
+    cf.push_back(c);
+  }
+  int plen[3];
+  for (int d = 0; d < 3; ++d) plen[d] = crse->domain.hi[d] - crse->domain.lo[d] + 1;
+  for (size_t fbi = 0; fbi < cf.size(); ++fbi)
+    for (int d = 0; d < 3; ++d)
+      for (int side = -1; side <= 1; side += 2) {
+        Bx slab = cf[fbi];
+        slab.lo[d] = slab.hi[d] = side < 0 ? cf[fbi].lo[d] - 1 : cf[fbi].hi[d] + 1;
+        // periodic images of the slab that fall inside the domain; a slab outside a non-periodic side is a physical boundary
+        for (int sz = -1; sz <= 1; ++sz) for (int sy = -1; sy <= 1; ++sy) for (int sx = -1; sx <= 1; ++sx) {
+          const int sh[3] = {sx * plen[0], sy * plen[1], sz * plen[2]};
+          bool ok = true;
+          for (int q = 0; q < 3; ++q) if (sh[q] != 0 && !crse->geom.periodic[q]) ok = false;
+          if (!ok) continue;
+          Bx img = slab;
+          for (int q = 0; q < 3; ++q) { img.lo[q] += sh[q]; img.hi[q] += sh[q]; }
+          img = intersect(img, crse->domain);
+          if (!img.ok()) continue;
+          std::vector<Bx> pieces{img};
+          // cells covered by (an image of) any fine box are not coarse-fine interface cells
+          for (const Bx& other : cf)
+            for (int tz = -1; tz <= 1; ++tz) for (int ty = -1; ty <= 1; ++ty) for (int tx = -1; tx <= 1; ++tx) {
+              const int th[3] = {tx * plen[0], ty * plen[1], tz * plen[2]};
+              bool ok2 = true;
+              for (int q = 0; q < 3; ++q) if (th[q] != 0 && !crse->geom.periodic[q]) ok2 = false;
+              if (!ok2) continue;
+              Bx o = other;
+              for (int q = 0; q < 3; ++q) { o.lo[q] += th[q]; o.hi[q] += th[q]; }
+              subtract_boxes(pieces, o);
+            }
+          for (const Bx& pc : pieces)
+            for (int cb = 0; cb < crse->nlocal(); ++cb) {
+              const Bx is = intersect(pc, crse->lbox(cb));
+              if (!is.ok()) continue;
+              FluxReg::Patch P{cb, (int)fbi, d, side, is, {sh[0], sh[1], sh[2]}};
+              F.patches.push_back(P);
+            }
+        }
+      }
+  return IAMRX_OK;
+}
+
+}  // namespace ix
+
+// ---------------------------------------------------------------------------------------------------------------------
+// C ABI
+// ---------------------------------------------------------------------------------------------------------------------
+using namespace ix;
+namespace ix { Level* level_of(iamrx_level_t h); }
+struct iamrx_fluxreg_s { FluxReg F; };
+
+#define IX_TRY(call) do { int rc_ = (call); if (rc_ != IAMRX_OK) return rc_; } while (0)
+
+extern "C" {
+
+int iamrx_average_down_box(const iamrx_box* cbx, iamrx_fab* crse, const iamrx_fab* fine, int ncomp, int ixtype, void* stream) {
+  IX_NEED_DEVICE();
+  IX_ARG(cbx && crse && fine && ncomp >= 1 && ixtype >= 0 && ixtype <= 4, "average_down arguments");
+  const Bx b = ixbox(mkbx(*cbx), ixtype);
+  cudaStream_t s = (cudaStream_t)stream;
+  if (ixtype == IX_CELL) return k::cc_restrict(b, view(crse), cview(fine), ncomp, s);
+  if (ixtype == IX_NODE) return k::average_down_nodal(b, view(crse), cview(fine), ncomp, s);
+  return k::face_restrict(b, ixtype - 1, view(crse), cview(fine), ncomp, s);
+}
+
+int iamrx_interp_box(int kind, const iamrx_box* fbx, iamrx_fab* fine, const iamrx_fab* crse, int ncomp, void* stream) {
+  IX_NEED_DEVICE();
+  IX_ARG(fbx && fine && crse && ncomp >= 1, "interp arguments");
+  const Bx b = mkbx(*fbx);
+  cudaStream_t s = (cudaStream_t)stream;
+  // the coarse fab must cover the coarsened fine region grown by the stencil (1 cell for the conservative slopes)
+  Bx need;
+  for (int d = 0; d < 3; ++d) { need.lo[d] = k::coarsen2(b.lo[d]); need.hi[d] = k::coarsen2(b.hi[d]); }
+  switch (kind) {
+    case IAMRX_INTERP_CELL_CONS: {
+      const Bx g = grow(need, 1);
+      for (int d = 0; d < 3; ++d) IX_ARG(crse->lo[d] <= g.lo[d] && crse->hi[d] >= g.hi[d], "cell_cons_interp: the coarse fab needs one filled ghost cell around the coarsened fine box");
+      return k::cell_cons_interp(b, view(fine), cview(crse), ncomp, s);
+    }
+    case IAMRX_INTERP_NODE_BILINEAR: {
+      const Bx nb = ixbox(b, IX_NODE);
+      for (int d = 0; d < 3; ++d) IX_ARG(crse->lo[d] <= k::coarsen2(nb.lo[d]) && crse->hi[d] >= k::coarsen2(nb.hi[d] + 1), "node_bilinear_interp: the coarse fab must cover the coarsened node box");
+      return k::node_bilinear_interp(nb, view(fine), cview(crse), ncomp, s);
+    }
+    case IAMRX_INTERP_FACE_LINEAR_X: case IAMRX_INTERP_FACE_LINEAR_Y: case IAMRX_INTERP_FACE_LINEAR_Z: {
+      const int dir = kind - IAMRX_INTERP_FACE_LINEAR_X;
+      const Bx fb = ixbox(b, IX_XFACE + dir);
+      for (int d = 0; d < 3; ++d) IX_ARG(crse->lo[d] <= k::coarsen2(fb.lo[d]) && crse->hi[d] >= k::coarsen2(fb.hi[d]) + (d == dir ? 1 : 0), "face_linear_interp: the coarse fab must cover the coarsened faces");
+      return k::face_linear_interp(fb, dir, view(fine), cview(crse), ncomp, s);
+    }
+    default: IX_ARG(false, "unknown interpolater");
+  }
+}
+
+int iamrx_fluxreg_create(iamrx_level_t crse, iamrx_level_t fine, int ncomp, iamrx_fluxreg_t* out) {
+  IX_NEED_DEVICE();
+  IX_ARG(crse && fine && out && ncomp >= 1, "null argument");
+  Level* C = level_of(crse); Level* Fn = level_of(fine);
+  for (int d = 0; d < 3; ++d) {
+    IX_ARG(Fn->domain.lo[d] == 2 * C->domain.lo[d] && Fn->domain.hi[d] == 2 * C->domain.hi[d] + 1, "the fine level's domain must be the coarse domain refined by 2");
+  }
+  auto* h = new iamrx_fluxreg_s();
+  const int rc = fluxreg_build(h->F, C, Fn, ncomp);
+  if (rc) { delete h; return rc; }
+  const int rc2 = mf_setval(h->F.reg, 0.0, 0, ncomp, 0, nullptr);
+  if (rc2) { delete h; return rc2; }
+  *out = h;
+  return IAMRX_OK;
+}
+int iamrx_fluxreg_destroy(iamrx_fluxreg_t r) { delete r; return IAMRX_OK; }
+int iamrx_fluxreg_num_patches(iamrx_fluxreg_t r) { return r ? (int)r->F.patches.size() : IAMRX_ERR_ARG; }
+int iamrx_fluxreg_reset(iamrx_fluxreg_t r, void* stream) {
+  IX_NEED_DEVICE();
+  IX_ARG(r, "null argument");
+  return mf_setval(r->F.reg, 0.0, 0, r->F.ncomp, 0, (cudaStream_t)stream);
+}
+// fluxes: per coarse local box, per direction (fx[il], fy[il], fz[il]); area-weighted; vol = coarse cell volume ("dx := volume")
+int iamrx_fluxreg_crse_add(iamrx_fluxreg_t r, const iamrx_fab* fx, const iamrx_fab* fy, const iamrx_fab* fz, double dt, double vol_crse,
+                           void* stream) {
+  IX_NEED_DEVICE();
+  IX_ARG(r && fx && fy && fz && vol_crse > 0.0, "fluxreg_crse_add arguments");
+  const iamrx_fab* f[3] = {fx, fy, fz};
+  FluxReg& F = r->F;
+  for (const FluxReg::Patch& P : F.patches) {
+    // the cell lies below the fine region (side < 0): the shared face is its HIGH face and the coarse flux leaves it (-);
+    // above (side > 0): the shared face is its LOW face and the coarse flux enters it (+).  The register holds minus that.
+    const int fc_off = P.side < 0 ? 1 : 0;
+    const double sgn = P.side < 0 ? 1.0 : -1.0;
+    IX_TRY(k::fr_crse_add(P.R, F.reg.v(P.cbox), cview(&f[P.d][P.cbox]), P.d, fc_off, sgn * dt / vol_crse, F.ncomp, (cudaStream_t)stream));
+  }
+  return IAMRX_OK;
+}
+// fine fluxes: per FINE local box and direction
+int iamrx_fluxreg_fine_add(iamrx_fluxreg_t r, const iamrx_fab* fx, const iamrx_fab* fy, const iamrx_fab* fz, double dt, double vol_crse,
+                           void* stream) {
+  IX_NEED_DEVICE();
+  IX_ARG(r && fx && fy && fz && vol_crse > 0.0, "fluxreg_fine_add arguments");
+  const iamrx_fab* f[3] = {fx, fy, fz};
+  FluxReg& F = r->F;
+  for (const FluxReg::Patch& P : F.patches) {
+    const int fc_off = P.side < 0 ? 1 : 0;
+    const double sgn = P.side < 0 ? -1.0 : 1.0;
+    // the fine box sits at (R - shift) in unshifted coarse index space: hand the kernel a view of the fine flux shifted by 2*shift
+    iamrx_fab ff = f[P.d][P.fbox];
+    for (int q = 0; q < 3; ++q) { ff.lo[q] += 2 * P.shift[q]; ff.hi[q] += 2 * P.shift[q]; }
+    IX_TRY(k::fr_fine_add(P.R, F.reg.v(P.cbox), cview(&ff), P.d, fc_off, sgn * dt / vol_crse, F.ncomp, (cudaStream_t)stream));
+  }
+  return IAMRX_OK;
+}
+// state(il, scomp..) += scale * register on the interface cells (NS.cpp:1794-1795 advflux_reg->Reflux)
+int iamrx_fluxreg_reflux(iamrx_fluxreg_t r, iamrx_fab* state, int scomp, double scale, void* stream) {
+  IX_NEED_DEVICE();
+  IX_ARG(r && state && scomp >= 0, "fluxreg_reflux arguments");
+  FluxReg& F = r->F;
+  // a cell can border the fine grids through several faces (several patches), but the register value must be added once:
+  // reflux over whole coarse boxes (the register is zero away from the interface)
+  for (int il = 0; il < F.crse->nlocal(); ++il)
+    IX_TRY(k::fr_reflux(F.crse->lbox(il), view(&state[il], scomp), F.reg.c(il), scale, F.ncomp, (cudaStream_t)stream));
+  return IAMRX_OK;
+}
+int iamrx_fluxreg_field(iamrx_fluxreg_t r, int ilocal, iamrx_fab* out) {
+  IX_ARG(r && out && ilocal >= 0 && ilocal < r->F.reg.n(), "fluxreg_field arguments");
+  *out = r->F.reg.fabs[ilocal];
+  return IAMRX_OK;
+}
+
+}  // extern "C"

@@ -164,6 +164,12 @@ int nodal_bc_fill_phi(const Bx& nbx, V4 phi, const NodalBC& bc, const Bx& ndom, 
 int nodal_bc_fill_sigma(const Bx& cbx, V4 sig, const NodalBC& bc, const Bx& dom, const int per[3], cudaStream_t s);
 int nodal_bc_scale(const Bx& nbx, V4 a, const NodalBC& bc, const Bx& ndom, const int per[3], double f, cudaStream_t s);
 
+// --- two-level transfer operators and flux register pieces (amr.cu) ---------
+int average_down_nodal(const Bx& cnbx, V4 crse, C4 fine, int ncomp, cudaStream_t s);
+int cell_cons_interp(const Bx& fbx, V4 fine, C4 crse, int ncomp, cudaStream_t s);
+int node_bilinear_interp(const Bx& fnbx, V4 fine, C4 crse, int ncomp, cudaStream_t s);
+int face_linear_interp(const Bx& ffbx, int dir, V4 fine, C4 crse, int ncomp, cudaStream_t s);
+
 // --- pointwise IAMR glue (pointwise.cu) -----------------------------------
 // floor NSB.cpp:4530-4534: |v| > 1e-20 ? v : 0
 int floor_small(const Bx& bx, V4 f, int ncomp, cudaStream_t s);

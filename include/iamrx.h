@@ -400,6 +400,44 @@ int iamrx_diffusion_solve(iamrx_level_t lev, int tensor, int ncomp, iamrx_fab* s
                           const iamrx_linop_bc* bc, iamrx_mg_info* info, void* stream);
 
 /* ------------------------------------------------------------------------
+ * 3b. Two-level coupling: inter-level transfer operators and the coarse-fine flux register (refinement ratio 2).
+ *     Building blocks of NavierStokesBase::avgDown_StatePress (NSB.cpp:4125-4191), FillPatchTwoLevels' interpolaters
+ *     (NS_setup.cpp:211,228-230,331; NSB.cpp:1127) and the advective flux register (NSB.cpp:4848-4889,5083-5096;
+ *     NS.cpp:1794-1795).  The two-level time stepping itself (subcycling, coarse-fine solver boundaries, mac_sync,
+ *     level_sync) is not driven by this library.
+ * ---------------------------------------------------------------------- */
+/* amrex::average_down (cells, ixtype 0: mean of the 8 children), average_down_faces (ixtype 1..3: mean of the 4 fine
+ * faces on the coarse face), average_down_nodal (ixtype 4: injection) on the coarse box cbx (cell index space). */
+int iamrx_average_down_box(const iamrx_box* cbx, iamrx_fab* crse, const iamrx_fab* fine, int ncomp, int ixtype, void* stream);
+enum {
+  IAMRX_INTERP_CELL_CONS = 0,       /* cell_cons_interp (State_Type, NS_setup.cpp:211,228-230): conservative linear, MC-limited
+                                       slopes scaled to keep every fine value inside the range of the 3^3 coarse neighbourhood */
+  IAMRX_INTERP_NODE_BILINEAR = 1,   /* node_bilinear_interp (Press_Type, NS_setup.cpp:331) */
+  IAMRX_INTERP_FACE_LINEAR_X = 2,   /* face_linear_interp (u_mac in create_umac_grown, NSB.cpp:1127) */
+  IAMRX_INTERP_FACE_LINEAR_Y = 3,
+  IAMRX_INTERP_FACE_LINEAR_Z = 4
+};
+/* fine (on the cells / nodes / faces of the FINE cell box fbx) = interpolation of crse.  cell_cons needs one filled ghost
+ * cell around the coarsened box (interior / periodic; physical-boundary one-sided slopes are not implemented). */
+int iamrx_interp_box(int kind, const iamrx_box* fbx, iamrx_fab* fine, const iamrx_fab* crse, int ncomp, void* stream);
+/* Flux register between a coarse level and the fine level that refines part of it (all boxes on this rank): the coarse cells
+ * that border the fine grids from outside accumulate dt (sum of fine fluxes - coarse flux) / vol with the sign of the face,
+ * for AREA-WEIGHTED fluxes and vol = coarse cell volume (the "dx := volume" convention of NSB.cpp:4878-4889).
+ * crse_add / fine_add take the face-flux fabs of every local box of the respective level (x, y, z arrays in local-box
+ * order); reflux adds scale * register to the coarse state (NS.cpp:1794-1799). */
+typedef struct iamrx_fluxreg_s* iamrx_fluxreg_t;
+int iamrx_fluxreg_create(iamrx_level_t crse, iamrx_level_t fine, int ncomp, iamrx_fluxreg_t* out);
+int iamrx_fluxreg_destroy(iamrx_fluxreg_t reg);
+int iamrx_fluxreg_num_patches(iamrx_fluxreg_t reg);
+int iamrx_fluxreg_reset(iamrx_fluxreg_t reg, void* stream);
+int iamrx_fluxreg_crse_add(iamrx_fluxreg_t reg, const iamrx_fab* fx, const iamrx_fab* fy, const iamrx_fab* fz, double dt,
+                           double vol_crse, void* stream);
+int iamrx_fluxreg_fine_add(iamrx_fluxreg_t reg, const iamrx_fab* fx, const iamrx_fab* fy, const iamrx_fab* fz, double dt,
+                           double vol_crse, void* stream);
+int iamrx_fluxreg_reflux(iamrx_fluxreg_t reg, iamrx_fab* crse_state, int scomp, double scale, void* stream);
+int iamrx_fluxreg_field(iamrx_fluxreg_t reg, int ilocal, iamrx_fab* out);
+
+/* ------------------------------------------------------------------------
  * 4. The level time step: NavierStokes::advance (NS.cpp:543-691) and the
  *    start-up sequence NavierStokes::post_init (NS.cpp:1254-1432) for a
  *    single-level periodic problem.  This is the caller of sections 1-3 in

@@ -1956,6 +1956,107 @@ int orc_diffusion_bc(const int n[3], const int per[3], const double dx[3], int s
   return rc;
 }
 
+/* ------------------------------------------------------------------------------------------------------------------
+ * Two-level transfer operators and the coarse-fine flux register, restated on a fully periodic coarse
+ * domain nc refined by 2 (dense n-periodic arrays: faces / nodes hold the LOW face / node of each cell).
+ * ---------------------------------------------------------------------------------------------------------------- */
+/* amrex::average_down (ixtype 0), average_down_faces (1..3), average_down_nodal = injection (4): NSB.cpp:4125-4191 */
+void orc_average_down(const int nc[3], int ncomp, int ixtype, const double* fine, double* crse) {
+  const int nf[3] = {2 * nc[0], 2 * nc[1], 2 * nc[2]};
+  auto F = [&](int i, int j, int k, int c) { return fine[i + (long)nf[0] * (j + (long)nf[1] * (k + (long)nf[2] * c))]; };
+  for (int c = 0; c < ncomp; ++c)
+    for (int k = 0; k < nc[2]; ++k) for (int j = 0; j < nc[1]; ++j) for (int i = 0; i < nc[0]; ++i) {
+      double v = 0.0;
+      if (ixtype == 0) { for (int dk = 0; dk < 2; ++dk) for (int dj = 0; dj < 2; ++dj) for (int di = 0; di < 2; ++di) v += F(2 * i + di, 2 * j + dj, 2 * k + dk, c); v *= 0.125; }
+      else if (ixtype == 4) v = F(2 * i, 2 * j, 2 * k, c);
+      else {
+        const int d = ixtype - 1;
+        for (int b = 0; b < 2; ++b) for (int a = 0; a < 2; ++a) {
+          int o[3]; o[d] = 0; o[(d + 1) % 3] = a; o[(d + 2) % 3] = b;
+          v += F(2 * i + o[0], 2 * j + o[1], 2 * k + o[2], c);
+        }
+        v *= 0.25;
+      }
+      crse[i + (long)nc[0] * (j + (long)nc[1] * (k + (long)nc[2] * c))] = v;
+    }
+}
+/* kind 0 cell_cons_interp (NS_setup.cpp:211: CellConservativeLinear without linear limiting = MC slopes per direction, then one
+ * factor per coarse cell that keeps all eight children inside [min, max] of the 3^3 coarse neighbourhood), 1 node_bilinear_interp
+ * (NS_setup.cpp:331), 2..4 face_linear_interp for x / y / z faces (NSB.cpp:1127) */
+void orc_interp(int kind, const int nc[3], int ncomp, const double* crse, double* fine) {
+  const int nf[3] = {2 * nc[0], 2 * nc[1], 2 * nc[2]};
+  auto C = [&](int i, int j, int k, int c) {
+    i = ((i % nc[0]) + nc[0]) % nc[0]; j = ((j % nc[1]) + nc[1]) % nc[1]; k = ((k % nc[2]) + nc[2]) % nc[2];
+    return crse[i + (long)nc[0] * (j + (long)nc[1] * (k + (long)nc[2] * c))];
+  };
+  auto mc = [](double um, double u0, double up) {
+    const double dc = 0.5 * (up - um), df = 2.0 * (up - u0), db = 2.0 * (u0 - um);
+    const double lim = (df * db >= 0.0) ? std::min(std::fabs(df), std::fabs(db)) : 0.0;
+    return std::copysign(1.0, dc) * std::min(lim, std::fabs(dc));
+  };
+  for (int c = 0; c < ncomp; ++c)
+    for (int K = 0; K < nc[2]; ++K) for (int J = 0; J < nc[1]; ++J) for (int I = 0; I < nc[0]; ++I) {
+      const double u = C(I, J, K, c);
+      if (kind == 0) {
+        const double s[3] = {mc(C(I - 1, J, K, c), u, C(I + 1, J, K, c)), mc(C(I, J - 1, K, c), u, C(I, J + 1, K, c)), mc(C(I, J, K - 1, c), u, C(I, J, K + 1, c))};
+        double cmn = u, cmx = u;
+        for (int kk = -1; kk <= 1; ++kk) for (int jj = -1; jj <= 1; ++jj) for (int ii = -1; ii <= 1; ++ii) { const double v = C(I + ii, J + jj, K + kk, c); cmn = std::min(cmn, v); cmx = std::max(cmx, v); }
+        // the extreme children sit at (+-1/4, +-1/4, +-1/4): the largest excursion is sum |s_d| / 4 either way
+        const double dmax = 0.25 * (std::fabs(s[0]) + std::fabs(s[1]) + std::fabs(s[2]));
+        double alpha = 1.0;
+        if (dmax > 0.0) { if (u + dmax > cmx) alpha = std::min(alpha, (cmx - u) / dmax); if (u - dmax < cmn) alpha = std::min(alpha, (u - cmn) / dmax); }
+        for (int dk = 0; dk < 2; ++dk) for (int dj = 0; dj < 2; ++dj) for (int di = 0; di < 2; ++di)
+          fine[(2 * I + di) + (long)nf[0] * ((2 * J + dj) + (long)nf[1] * ((2 * K + dk) + (long)nf[2] * c))] =
+              u + alpha * (s[0] * (di ? 0.25 : -0.25) + s[1] * (dj ? 0.25 : -0.25) + s[2] * (dk ? 0.25 : -0.25));
+      } else if (kind == 1) {
+        for (int dk = 0; dk < 2; ++dk) for (int dj = 0; dj < 2; ++dj) for (int di = 0; di < 2; ++di) {
+          double acc = 0.0;
+          for (int a = 0; a <= dk; ++a) for (int b = 0; b <= dj; ++b) for (int e = 0; e <= di; ++e) acc += C(I + e, J + b, K + a, c);
+          fine[(2 * I + di) + (long)nf[0] * ((2 * J + dj) + (long)nf[1] * ((2 * K + dk) + (long)nf[2] * c))] = acc / (double)((1 + di) * (1 + dj) * (1 + dk));
+        }
+      } else {
+        const int d = kind - 2;
+        const double up = C(I + (d == 0), J + (d == 1), K + (d == 2), c);
+        for (int dk = 0; dk < 2; ++dk) for (int dj = 0; dj < 2; ++dj) for (int di = 0; di < 2; ++di) {
+          const int off = d == 0 ? di : (d == 1 ? dj : dk);   // 0: on the coarse face, 1: half way to the next one
+          fine[(2 * I + di) + (long)nf[0] * ((2 * J + dj) + (long)nf[1] * ((2 * K + dk) + (long)nf[2] * c))] = off ? 0.5 * (u + up) : u;
+        }
+      }
+    }
+}
+/* The advective flux register (NSB.cpp:4848-4889, 5083-5096; NS.cpp:1794-1795) restated cell by cell: a coarse cell that is not
+ * covered by fine grids looks at its six faces; where the neighbour across a face IS covered, the coarse update used the coarse
+ * flux but should have used the sum of the four fine fluxes: reg = dt (sum fine - coarse) / vol, entering (+, low face) or
+ * leaving (-, high face) -- area-weighted fluxes, vol = coarse cell volume.  mask: 1 where a coarse cell is covered by fine. */
+void orc_fluxreg(const int nc[3], int ncomp, const unsigned char* mask, const double* cfx, const double* cfy, const double* cfz,
+                 const double* ffx, const double* ffy, const double* ffz, double dt, double vol, double* reg) {
+  const int nf[3] = {2 * nc[0], 2 * nc[1], 2 * nc[2]};
+  const double* cf[3] = {cfx, cfy, cfz};
+  const double* ff[3] = {ffx, ffy, ffz};
+  auto wrap = [](int a, int n) { return ((a % n) + n) % n; };
+  auto M = [&](int i, int j, int k) { return mask[wrap(i, nc[0]) + (long)nc[0] * (wrap(j, nc[1]) + (long)nc[1] * wrap(k, nc[2]))] != 0; };
+  for (int c = 0; c < ncomp; ++c)
+    for (int k = 0; k < nc[2]; ++k) for (int j = 0; j < nc[1]; ++j) for (int i = 0; i < nc[0]; ++i) {
+      double r = 0.0;
+      if (!M(i, j, k))
+        for (int d = 0; d < 3; ++d)
+          for (int side = 0; side < 2; ++side) {   // 0: low face, 1: high face
+            int q[3] = {i, j, k}; q[d] += side ? 1 : -1;
+            if (!M(q[0], q[1], q[2])) continue;
+            int fc[3] = {i, j, k}; fc[d] += side;   // coarse face index (low-face convention), periodic
+            const double Fc = cf[d][wrap(fc[0], nc[0]) + (long)nc[0] * (wrap(fc[1], nc[1]) + (long)nc[1] * (wrap(fc[2], nc[2]) + (long)nc[2] * c))];
+            double Ff = 0.0;
+            for (int b = 0; b < 2; ++b) for (int a = 0; a < 2; ++a) {
+              int o[3]; o[d] = 0; o[(d + 1) % 3] = a; o[(d + 2) % 3] = b;
+              const int fi = wrap(2 * fc[0] + o[0], nf[0]), fj = wrap(2 * fc[1] + o[1], nf[1]), fk = wrap(2 * fc[2] + o[2], nf[2]);
+              Ff += ff[d][fi + (long)nf[0] * (fj + (long)nf[1] * (fk + (long)nf[2] * c))];
+            }
+            r += (side ? -1.0 : 1.0) * dt * (Ff - Fc) / vol;
+          }
+      reg[i + (long)nc[0] * (j + (long)nc[1] * (k + (long)nc[2] * c))] = r;
+    }
+}
+
 void orc_ns_params_default(orc_ns_params* p) {
   p->cfl = 0.7; p->visc_coef = 0.0; p->be_cn_theta = 0.5; p->change_max = 1.1; p->init_shrink = 1.0; p->fixed_dt = -1.0;
   p->gravity = 0.0; p->visc_tol = 1e-10; p->mac_tol = 1e-12; p->mac_abs_tol = 1e-16; p->proj_tol = 1e-12; p->proj_abs_tol = 1e-16;

@@ -107,6 +107,12 @@ int orc_diffusion_bc(const int n[3], const int per[3], const double dx[3], int s
                      const double* alpha, const double* ex, const double* ey, const double* ez, const double* rhs, double* soln, double* out,
                      const int* lobc, const int* hibc, int maxorder, orc_mg* mg);
 
+/* two-level transfer operators and the coarse-fine flux register on a periodic coarse domain nc refined by 2 */
+void orc_average_down(const int nc[3], int ncomp, int ixtype, const double* fine, double* crse);
+void orc_interp(int kind, const int nc[3], int ncomp, const double* crse, double* fine);
+void orc_fluxreg(const int nc[3], int ncomp, const unsigned char* mask, const double* cfx, const double* cfy, const double* cfz,
+                 const double* ffx, const double* ffy, const double* ffz, double dt, double vol, double* reg);
+
 /* NavierStokes::advance / post_init on one box (periodic unless orc_ns_set_bc is called) */
 typedef struct orc_ns_params {
   double cfl, visc_coef, be_cn_theta, change_max, init_shrink, fixed_dt, gravity, visc_tol;

@@ -252,6 +252,29 @@ def diffusion_bc(n, per, dx, solve, tensor, a, b, alpha, ex, ey, ez, rhs, soln, 
     return (soln, rc, mg) if solve else out
 
 
+def average_down(nc, ixtype, fine):
+    ncomp = fine.shape[0]
+    crse = np.empty((ncomp, nc[2], nc[1], nc[0]))
+    lib().orc_average_down(_i3(nc), ncomp, int(ixtype), _p(fine), _p(crse))
+    return crse
+
+
+def interp(kind, nc, crse):
+    ncomp = crse.shape[0]
+    fine = np.empty((ncomp, 2 * nc[2], 2 * nc[1], 2 * nc[0]))
+    lib().orc_interp(int(kind), _i3(nc), ncomp, _p(crse), _p(fine))
+    return fine
+
+
+def fluxreg(nc, mask, cflux, fflux, dt, vol):
+    ncomp = cflux[0].shape[0]
+    reg = np.empty((ncomp, nc[2], nc[1], nc[0]))
+    m = np.ascontiguousarray(mask.astype(np.uint8))
+    lib().orc_fluxreg(_i3(nc), ncomp, m.ctypes.data_as(C.c_void_p), _p(cflux[0]), _p(cflux[1]), _p(cflux[2]), _p(fflux[0]), _p(fflux[1]),
+                      _p(fflux[2]), C.c_double(dt), C.c_double(vol), _p(reg))
+    return reg
+
+
 class OracleNS:
     def __init__(self, n, prob_lo=(0, 0, 0), prob_hi=(1, 1, 1), per=None, phys_lo=None, phys_hi=None, bcv=None, **params):
         self.n = tuple(n)

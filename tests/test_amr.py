@@ -1,0 +1,171 @@
+"""Two-level coupling building blocks through the C ABI vs the oracle: average_down (cells / faces / nodes),
+the FillPatchTwoLevels interpolaters (cell_cons_interp, node_bilinear_interp, face_linear_interp) and the advective flux
+register (CrseAdd / FineAdd / Reflux), plus the properties they exist for: conservation and the telescoping of fluxes."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import iamr_b200 as ix
+from util import hash_uniform, smooth_field, to_fab, from_fabs, split_boxes, fab_array, box_of, stream_of, sync
+
+NC = (8, 8, 8)
+NF = (16, 16, 16)
+
+
+@pytest.mark.parametrize("ixtype", [ix.CELL, ix.XFACE, ix.YFACE, ix.ZFACE, ix.NODE])
+def test_average_down(backend, oracle, ixtype):
+    lib, dev = backend
+    fine = hash_uniform(11 + ixtype, (2,) + NF[::-1])
+    ref = oracle.average_down(NC, ixtype, fine)
+    outs, cboxes = [], split_boxes(NC, (2, 1, 2))
+    for cb in cboxes:
+        fb = (tuple(2 * l for l in cb[0]), tuple(2 * h + 1 for h in cb[1]))
+        tf, ff = to_fab(fine, fb, 1, ixtype, dev)
+        tc, fc = to_fab(np.zeros((2,) + NC[::-1]), cb, 0, ixtype, dev)
+        bb = box_of(*cb)
+        lib.check(lib.iamrx_average_down_box(C.byref(bb), C.byref(fc), C.byref(ff), 2, ixtype, stream_of(dev)))
+        outs.append(tc)
+    sync(dev)
+    got, dup = from_fabs(outs, cboxes, 0, ixtype, NC, 2)
+    assert dup == 0.0
+    assert np.abs(got - ref).max() <= 1e-15
+
+
+@pytest.mark.parametrize("kind,ixtype", [(0, ix.CELL), (1, ix.NODE), (2, ix.XFACE), (3, ix.YFACE), (4, ix.ZFACE)])
+def test_interpolaters(backend, oracle, kind, ixtype):
+    lib, dev = backend
+    crse = smooth_field(NC, 21 + kind, 2)
+    crse[0] += 0.4 * np.sign(smooth_field(NC, 29, 1)[0])      # steep: the limiters are active
+    ref = oracle.interp(kind, NC, crse)
+    fboxes = split_boxes(NF, (2, 2, 1))
+    outs = []
+    for fb in fboxes:
+        cb = (tuple(l // 2 for l in fb[0]), tuple(h // 2 for h in fb[1]))
+        tcr, fcr = to_fab(crse, cb, 1, ixtype, dev)
+        tfi, ffi = to_fab(np.zeros((2,) + NF[::-1]), fb, 0, ixtype, dev)
+        bb = box_of(*fb)
+        lib.check(lib.iamrx_interp_box(kind, C.byref(bb), C.byref(ffi), C.byref(fcr), 2, stream_of(dev)))
+        outs.append(tfi)
+    sync(dev)
+    got, dup = from_fabs(outs, fboxes, 0, ixtype, NF, 2)
+    assert dup <= 1e-15
+    assert np.abs(got - ref).max() <= 1e-14
+    if kind == 0:
+        # conservative: the children average back to the parent; and no new extrema (range of the 3^3 coarse neighbourhood)
+        assert np.abs(oracle.average_down(NC, ix.CELL, got) - crse).max() <= 1e-14
+        lo = np.min([np.roll(crse, (a, b, c), (1, 2, 3)) for a in (-1, 0, 1) for b in (-1, 0, 1) for c in (-1, 0, 1)], axis=0)
+        hi = np.max([np.roll(crse, (a, b, c), (1, 2, 3)) for a in (-1, 0, 1) for b in (-1, 0, 1) for c in (-1, 0, 1)], axis=0)
+        up = lambda a: np.repeat(np.repeat(np.repeat(a, 2, 1), 2, 2), 2, 3)
+        assert (got >= up(lo) - 1e-14).all() and (got <= up(hi) + 1e-14).all()
+    if kind == 1:
+        assert np.array_equal(got[:, ::2, ::2, ::2], crse)   # coincident nodes are injected
+
+
+def test_cell_cons_interp_is_exact_for_linear_data(backend):
+    lib, dev = backend
+    z, y, x = np.meshgrid(*[np.arange(-1, 9) + 0.5] * 3, indexing="ij")
+    crse = (0.3 * x - 0.7 * y + 1.1 * z)[None]
+    import torch
+    tcr = torch.from_numpy(crse.copy()).to(dev)
+    fcr = ix.fab_of(tcr, [-1, -1, -1])
+    tfi, ffi = ix.alloc_fab((0, 0, 0), (15, 15, 15), 1, 0, dev)
+    bb = box_of((0, 0, 0), (15, 15, 15))
+    lib.check(lib.iamrx_interp_box(0, C.byref(bb), C.byref(ffi), C.byref(fcr), 1, stream_of(dev)))
+    sync(dev)
+    zf, yf, xf = np.meshgrid(*[(np.arange(16) + 0.5) / 2] * 3, indexing="ij")
+    assert np.abs(tfi.cpu().numpy()[0] - (0.3 * xf - 0.7 * yf + 1.1 * zf)).max() <= 1e-13
+
+
+def _level_pair(lib, fine_boxes_c):
+    """coarse level 8^3 (two boxes) + fine level = the refinement of the given coarse-index boxes"""
+    gc = ix.Geom.make(NC)
+    gf = ix.Geom.make(NF)
+    cboxes = split_boxes(NC, (2, 1, 1))
+    fboxes = [(tuple(2 * l for l in lo), tuple(2 * h + 1 for h in hi)) for lo, hi in fine_boxes_c]
+    return ix.Level(lib, gc, cboxes), ix.Level(lib, gf, fboxes), cboxes, fboxes
+
+
+FINE_LAYOUTS = [[((2, 2, 2), (5, 5, 5))],                                   # one fine box in the middle
+                [((2, 0, 2), (3, 7, 5)), ((4, 0, 2), (5, 7, 5))],           # two abutting boxes spanning the periodic y direction
+                [((0, 2, 2), (1, 5, 5)), ((6, 2, 2), (7, 5, 5))]]           # two boxes that touch through the periodic x boundary
+
+
+@pytest.mark.parametrize("layout", FINE_LAYOUTS)
+def test_flux_register(backend, oracle, layout):
+    lib, dev = backend
+    ncomp = 2
+    clev, flev, cboxes, fboxes = _level_pair(lib, layout)
+    mask = np.zeros(NC[::-1], dtype=bool)
+    for lo, hi in layout:
+        mask[lo[2]:hi[2] + 1, lo[1]:hi[1] + 1, lo[0]:hi[0] + 1] = True
+    cflux = [hash_uniform(31 + d, (ncomp,) + NC[::-1]) for d in range(3)]
+    fflux = [hash_uniform(41 + d, (ncomp,) + NF[::-1]) for d in range(3)]
+    dt, vol = 0.05, (1.0 / 8) ** 3
+    ref = oracle.fluxreg(NC, mask, cflux, fflux, dt, vol)
+    reg = C.c_void_p()
+    lib.check(lib.iamrx_fluxreg_create(clev.h, flev.h, ncomp, C.byref(reg)))
+    assert lib.iamrx_fluxreg_num_patches(reg) > 0
+    CF = [[to_fab(cflux[d], b, 0, t, dev) for b in cboxes] for d, t in enumerate((ix.XFACE, ix.YFACE, ix.ZFACE))]
+    FF = [[to_fab(fflux[d], b, 0, t, dev) for b in fboxes] for d, t in enumerate((ix.XFACE, ix.YFACE, ix.ZFACE))]
+    fa = lambda L: fab_array([p[1] for p in L])
+    lib.check(lib.iamrx_fluxreg_reset(reg, stream_of(dev)))
+    lib.check(lib.iamrx_fluxreg_crse_add(reg, fa(CF[0]), fa(CF[1]), fa(CF[2]), dt, vol, stream_of(dev)))
+    lib.check(lib.iamrx_fluxreg_fine_add(reg, fa(FF[0]), fa(FF[1]), fa(FF[2]), dt, vol, stream_of(dev)))
+    sync(dev)
+    got = np.zeros((ncomp,) + NC[::-1])
+    for il, (lo, hi) in enumerate(cboxes):
+        f = ix.Fab()
+        lib.check(lib.iamrx_fluxreg_field(reg, il, C.byref(f)))
+        t = ix.tensor_of(f, dev).cpu().numpy()
+        got[:, lo[2]:hi[2] + 1, lo[1]:hi[1] + 1, lo[0]:hi[0] + 1] = t[:, :hi[2] - lo[2] + 1, :hi[1] - lo[1] + 1, :hi[0] - lo[0] + 1]
+    assert np.abs(got - ref).max() <= 1e-12 * np.abs(ref).max()
+    assert np.abs(got[:, mask]).max() == 0.0            # nothing under the fine grids
+    # reflux: state += register
+    state = hash_uniform(51, (3,) + NC[::-1])
+    ST = [to_fab(state, b, 0, ix.CELL, dev) for b in cboxes]
+    lib.check(lib.iamrx_fluxreg_reflux(reg, fa(ST), 1, 1.0, stream_of(dev)))
+    sync(dev)
+    snew, _ = from_fabs([p[0] for p in ST], cboxes, 0, ix.CELL, NC, 3)
+    assert np.abs(snew[1:] - (state[1:] + ref)).max() <= 1e-13 and np.array_equal(snew[0], state[0])
+    lib.iamrx_fluxreg_destroy(reg)
+    clev.close(); flev.close()
+
+
+def test_flux_register_restores_conservation(backend, oracle):
+    """The reason the register exists: advance a coarse level and a fine patch with their own (inconsistent) fluxes, average the
+    fine result down, reflux -- the composite total changes exactly by nothing (periodic domain)."""
+    lib, dev = backend
+    layout = FINE_LAYOUTS[1]
+    clev, flev, cboxes, fboxes = _level_pair(lib, layout)
+    mask = np.zeros(NC[::-1], dtype=bool)
+    for lo, hi in layout:
+        mask[lo[2]:hi[2] + 1, lo[1]:hi[1] + 1, lo[0]:hi[0] + 1] = True
+    dxc, dxf = 1.0 / 8, 1.0 / 16
+    cflux = [hash_uniform(61 + d, (1,) + NC[::-1]) * dxc ** 2 for d in range(3)]     # area-weighted
+    fflux = [hash_uniform(71 + d, (1,) + NF[::-1]) * dxf ** 2 for d in range(3)]
+    dt = 0.01
+    div = lambda f, h: sum((np.roll(f[d], -1, 3 - d) - f[d]) for d in range(3)) / h ** 3
+    sc = 1.0 + 0.1 * hash_uniform(81, (1,) + NC[::-1])
+    sf = np.repeat(np.repeat(np.repeat(sc, 2, 1), 2, 2), 2, 3)
+    total0 = (sc * (~mask)).sum() * dxc ** 3 + (sf * np.repeat(np.repeat(np.repeat(mask, 2, 0), 2, 1), 2, 2)).sum() * dxf ** 3
+    sc1 = sc - dt * div(cflux, dxc)
+    sf1 = sf - dt * div(fflux, dxf)      # (the fine patch's outer faces use its own fine fluxes)
+    reg = C.c_void_p()
+    lib.check(lib.iamrx_fluxreg_create(clev.h, flev.h, 1, C.byref(reg)))
+    CF = [[to_fab(cflux[d], b, 0, t, dev) for b in cboxes] for d, t in enumerate((ix.XFACE, ix.YFACE, ix.ZFACE))]
+    FF = [[to_fab(fflux[d], b, 0, t, dev) for b in fboxes] for d, t in enumerate((ix.XFACE, ix.YFACE, ix.ZFACE))]
+    fa = lambda L: fab_array([p[1] for p in L])
+    lib.check(lib.iamrx_fluxreg_crse_add(reg, fa(CF[0]), fa(CF[1]), fa(CF[2]), dt, dxc ** 3, stream_of(dev)))
+    lib.check(lib.iamrx_fluxreg_fine_add(reg, fa(FF[0]), fa(FF[1]), fa(FF[2]), dt, dxc ** 3, stream_of(dev)))
+    ST = [to_fab(sc1, b, 0, ix.CELL, dev) for b in cboxes]
+    lib.check(lib.iamrx_fluxreg_reflux(reg, fa(ST), 0, 1.0, stream_of(dev)))
+    sync(dev)
+    sc2, _ = from_fabs([p[0] for p in ST], cboxes, 0, ix.CELL, NC, 1)
+    fm = np.repeat(np.repeat(np.repeat(mask, 2, 0), 2, 1), 2, 2)
+    total_noreflux = (sc1[0] * (~mask)).sum() * dxc ** 3 + (sf1[0] * fm).sum() * dxf ** 3
+    total_reflux = (sc2[0] * (~mask)).sum() * dxc ** 3 + (sf1[0] * fm).sum() * dxf ** 3
+    assert abs(total_noreflux - total0) > 1e-6          # the mismatch is real
+    assert abs(total_reflux - total0) <= 1e-14 * abs(total0) * 10
+    lib.iamrx_fluxreg_destroy(reg)
+    clev.close(); flev.close()
