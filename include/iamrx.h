@@ -312,6 +312,9 @@ int iamrx_debug_fb_plan(iamrx_level_t lev, int ixtype, int ng, int cap, int* dst
  *    LOCAL box in level order; the caller owns all field memory.
  * ---------------------------------------------------------------------- */
 
+/* amrex::IndexType of a field, as the `ixtype` arguments below take it */
+enum { IAMRX_IX_CELL = 0, IAMRX_IX_XFACE = 1, IAMRX_IX_YFACE = 2, IAMRX_IX_ZFACE = 3, IAMRX_IX_NODE = 4 };
+
 /* FabArray::FillBoundary(periodicity) on cell (ixtype 0), face-d (1+d) or
  * nodal (4) data (NSB.cpp:1171, MacProj.cpp:1127, Projection.cpp:338). */
 int iamrx_fill_boundary(iamrx_level_t lev, iamrx_fab* fabs, int ixtype, int ncomp,

@@ -114,3 +114,25 @@ def test_header_compiles_as_c():
     open(src, "w").write('#include "iamrx.h"\nint main(void) { iamrx_bcrec b; b.lo[0] = IAMRX_BC_EXT_DIR; return b.lo[0] == 3 ? 0 : 1; }\n')
     subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Werror", "-pedantic", "-I", os.path.join(ROOT, "include"), "-c", src,
                            "-o", src + ".o"])
+
+
+def test_integration_snippets_compile():
+    """INTEGRATION.md's call-site replacements are excerpts of tests/abi/adapter_sites.cpp, which compiles (-Wall -Werror)
+    against include/iamrx.h + include/IamrxAdapter.H and a stand-in with the shape of the AMReX classes, and links with the
+    library: the documented binding cannot drift from the ABI."""
+    import re
+    abi = os.path.join(ROOT, "tests", "abi")
+    exe = os.path.join(abi, "_build", "adapter_sites")
+    os.makedirs(os.path.dirname(exe), exist_ok=True)
+    subprocess.check_call(["g++", "-std=c++17", "-Wall", "-Wextra", "-Werror", "-I", os.path.join(ROOT, "include"),
+                           "-I", os.path.join(abi, "amrex_stub"), os.path.join(abi, "adapter_sites.cpp"), "-o", exe,
+                           "-L", os.path.join(ROOT, "iamr_b200"), "-liamrx", "-Wl,-rpath," + os.path.join(ROOT, "iamr_b200")])
+    md = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    src = open(os.path.join(abi, "adapter_sites.cpp")).read()
+    blocks = re.findall(r"// \[site (\d) begin\]\n(.*?)// \[site \1 end\]", src, re.S)
+    assert len(blocks) == 6
+    for n, body in blocks:
+        assert body in md, f"INTEGRATION.md section {n} differs from tests/abi/adapter_sites.cpp"
+    adapter = open(os.path.join(ROOT, "include", "IamrxAdapter.H")).read()
+    ns = re.search(r"(namespace iamrx_adapt \{.*?\n\}  // namespace iamrx_adapt)", adapter, re.S).group(1)
+    assert ns in md

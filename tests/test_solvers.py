@@ -168,3 +168,30 @@ def test_solver_reports_non_convergence(backend):
                                C.byref(info), stream_of(dev))
     assert rc == 3 and b"converge" in lib.iamrx_last_error()  # ">0 = solver did not converge (iterations done)"
     lev.close()
+
+
+@pytest.mark.parametrize("n", [(32, 32, 32), (16, 16, 32)])
+def test_bottom_sweeps_do_not_change_vcycles(backend, n):
+    """The bottom solve is `bottom_sweeps` smoother sweeps on the coarsest (2^3 .. 2x2x4) level, where IAMR's default asks
+    BiCGStab for a 1e-4 reduction.  Eight sweeps are already that accurate there: solving the bottom level
+    eight times harder changes neither the V-cycle count nor (beyond the tolerance) the answer."""
+    lib, dev = backend
+    x = [(np.arange(m) + 0.5) / m for m in n]
+    Z, Y, X = np.meshgrid(x[2], x[1], x[0], indexing="ij")
+    rho = (1.0 + 0.5 * np.sin(2 * np.pi * X) * np.sin(2 * np.pi * Y) * np.sin(2 * np.pi * Z))[None]
+    um, vm, wm = (smooth_field(n, 700 + d, 1) for d in range(3))
+    boxes = split_boxes(n, (1, 1, 1))
+    lev = ix.Level(lib, ix.Geom.make(n), boxes)
+    res = []
+    for sweeps in (8, 64):
+        U, V, W = (to_fab(f, boxes[0], 1, t, dev) for f, t in ((um, ix.XFACE), (vm, ix.YFACE), (wm, ix.ZFACE)))
+        R = to_fab(rho, boxes[0], 1, ix.CELL, dev)
+        P = to_fab(np.zeros_like(rho), boxes[0], 1, ix.CELL, dev)
+        info = _mg(lib, rtol=1e-12, bottom_sweeps=sweeps)
+        lib.check(lib.iamrx_mac_project(lev.h, fab_array([U[1]]), fab_array([V[1]]), fab_array([W[1]]), fab_array([R[1]]), None,
+                                        fab_array([P[1]]), 2.0 * n[0] / 0.7, None, None, C.byref(info), stream_of(dev)))
+        sync(dev)
+        res.append((info.iters, from_fabs([U[0]], boxes, 1, ix.XFACE, n, 1)[0]))
+    assert res[0][0] == res[1][0]
+    assert np.abs(res[0][1] - res[1][1]).max() < 1e-11
+    lev.close()
