@@ -196,13 +196,14 @@ int nodal_bc_fill_phi(const Bx& nbx, V4 phi, const NodalBC& bc, const Bx& ndom, 
 }
 
 // sigma ghost cell layer beyond a Neumann / inflow side = the first interior layer (mlndlap_fillbc_cc); zero beyond Dirichlet
-int nodal_bc_fill_sigma(const Bx& cbx, V4 sig, const NodalBC& bc, const Bx& dom, const int per[3], cudaStream_t s) {
+// ngt: width of the ghost plane in the tangential directions (the fab's ghost depth; deep-ghost multigrid levels: 4)
+int nodal_bc_fill_sigma(const Bx& cbx, V4 sig, const NodalBC& bc, const Bx& dom, const int per[3], cudaStream_t s, int ngt) {
   for (int d = 0; d < 3; ++d) {
     if (per[d]) continue;
     for (int side = -1; side <= 1; side += 2) {
       const int code = side < 0 ? bc.lo[d] : bc.hi[d];
       if (side < 0 ? cbx.lo[d] != dom.lo[d] : cbx.hi[d] != dom.hi[d]) continue;
-      Bx R = grow(cbx, 1);
+      Bx R = grow(cbx, ngt);
       R.lo[d] = R.hi[d] = side < 0 ? dom.lo[d] - 1 : dom.hi[d] + 1;
       if (code == IAMRX_LINOP_NEUMANN || code == IAMRX_LINOP_INFLOW) {
         IX_LAUNCH(mirror_kernel, grid_for(R, R.nz()), dim3(TX, TY, 1), 0, s, R, sig, d, side < 0 ? dom.lo[d] : dom.hi[d]);

@@ -126,6 +126,11 @@ int nodal_gs_color(const Bx& nbx, V4 phi, C4 rhs, C4 sig, const double dxinv[3],
 // full 8-colour Gauss-Seidel sweep phi_in -> phi_out on a box that spans the periodic domain
 // (one fused launch per plane parity); nodal_gs_sweep_ok tells whether the box qualifies
 bool nodal_gs_sweep_ok(const Bx& nbx, int wrapmask);
+// wrapmask flag of nodal_gs_sweep[_ok]: the x / y directions that are NOT wrapped have neighbouring boxes (same level or periodic
+// images) and phi_in, phi_out, rhs carry 4 filled ghost nodes, sigma 4 filled ghost cells there: the tiles take their
+// halos (and recompute the colour dependences) from the ghost layers, so a block-decomposed level smooths with two
+// launches + two ghost exchanges per sweep like a slab instead of eight colour launches + eight exchanges
+constexpr int NODAL_DEEP_GHOSTS = 512;
 // wrapmask 7 (box spans the periodic domain) or 3 (slab: x, y wrapped, z neighbours read from filled ghost planes).
 // phase 0 = even planes (colours 0-3), 1 = odd planes (colours 4-7), -1 = both; with wrapmask 3 the caller exchanges
 // the z ghost planes of phi_out between the phases.
@@ -161,7 +166,7 @@ int linop_bc_fill(const Bx& vbx, V4 phi, int ncomp, const LinBC& bc, C4 bv, cons
                   cudaStream_t s);
 struct NodalBC { int lo[3], hi[3]; };   // LinOpBCType per side (Projection.cpp:2436-2464)
 int nodal_bc_fill_phi(const Bx& nbx, V4 phi, const NodalBC& bc, const Bx& ndom, const int per[3], int skipmask, cudaStream_t s);
-int nodal_bc_fill_sigma(const Bx& cbx, V4 sig, const NodalBC& bc, const Bx& dom, const int per[3], cudaStream_t s);
+int nodal_bc_fill_sigma(const Bx& cbx, V4 sig, const NodalBC& bc, const Bx& dom, const int per[3], cudaStream_t s, int ngt = 1);
 int nodal_bc_scale(const Bx& nbx, V4 a, const NodalBC& bc, const Bx& ndom, const int per[3], double f, cudaStream_t s);
 
 // --- two-level transfer operators and flux register pieces (amr.cu) ---------

@@ -56,7 +56,7 @@ struct CopyDesc {
 };
 
 struct FabTable {  // passed by value to the batched copy kernel
-  static constexpr int MAXF = 48;
+  static constexpr int MAXF = 128;   // local boxes per rank (two tables = 11 KB of kernel parameters; sm_100 allows 32 KB)
   double* p[MAXF];
   int lo[MAXF][3];
   int64_t js[MAXF], ks[MAXF], ns[MAXF];

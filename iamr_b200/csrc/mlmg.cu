@@ -428,15 +428,26 @@ NodeMG::NodeMG(Level* fine, int max_coarsening) {
     lv_.back().lev = lv_.back().lev_owned.get();
     cur = lv_.back().lev;
   }
+  static int deep_on = -1;
+  if (deep_on < 0) { const char* e = getenv("IAMRX_NODAL_DEEP"); deep_on = (e && e[0] == '0') ? 0 : 1; }
   for (auto& L : lv_) {
     for (int d = 0; d < 3; ++d) L.dxinv[d] = L.lev->dxinv[d];
-    L.sigma.define(L.lev, IX_CELL, 1, 1);
-    L.cor.define(L.lev, IX_NODE, 1, 1);
-    L.res.define(L.lev, IX_NODE, 1, 1);
+    // deep-ghost level (decided from ALL boxes, the same on every rank): some x / y direction is not wrapped in the kernels,
+    // it is periodic (every box side has a neighbour or a periodic image; walls in x / y keep the colour path), and every box
+    // qualifies for the fused sweep with ghost-layer halos
+    const int wm = L.lev->level_wrapmask();
+    L.deep = deep_on && !L.lev->replicated && (wm & 3) != 3;
+    for (int d = 0; d < 2 && L.deep; ++d) if (!(wm & (1 << d)) && !L.lev->geom.periodic[d]) L.deep = false;
+    for (size_t b = 0; b < L.lev->boxes.size() && L.deep; ++b)
+      L.deep = k::nodal_gs_sweep_ok(ixbox(L.lev->boxes[b], IX_NODE), wm | k::NODAL_DEEP_GHOSTS);
+    L.ngd = L.deep ? 4 : 1;
+    L.sigma.define(L.lev, IX_CELL, 1, L.ngd);
+    L.cor.define(L.lev, IX_NODE, 1, L.ngd);
+    L.res.define(L.lev, IX_NODE, 1, L.ngd);
     L.rescor.define(L.lev, IX_NODE, 1, 1);
     if (L.xfer_lev) L.xfer.define(L.xfer_lev.get(), IX_NODE, 1, 1);
     // nodes ON Dirichlet sides are never written by the kernels (active_nbox): they must hold zero from the start
-    for (MF* m : {&L.cor, &L.res, &L.rescor, &L.xfer}) if (m->ok()) mf_setval(*m, 0.0, 0, 1, 1, nullptr);
+    for (MF* m : {&L.cor, &L.res, &L.rescor, &L.xfer}) if (m->ok()) mf_setval(*m, 0.0, 0, 1, m->ng, nullptr);
   }
   for (int d = 0; d < 3; ++d) { bc_.lo[d] = IAMRX_LINOP_PERIODIC; bc_.hi[d] = IAMRX_LINOP_PERIODIC; }
 }
@@ -478,8 +489,8 @@ bool NodeMG::singular() const {
 }
 
 // bc_fill = false: the caller's kernels mirror the Neumann sides in place (wm | neumann_sides << 3), only the exchange is needed
-int NodeMG::fill_ghosts(int l, MF& phi, int wm, cudaStream_t s, bool bc_fill) {
-  if (wm != 7) IX_TRY(mf_fill_boundary(phi, 0, 1, 1, s, wm));
+int NodeMG::fill_ghosts(int l, MF& phi, int wm, cudaStream_t s, bool bc_fill, int depth) {
+  if (wm != 7) IX_TRY(mf_fill_boundary(phi, 0, 1, depth, s, wm));
   if (!has_bc_ || !bc_fill) return IAMRX_OK;
   const Level& L = *lv_[l].lev;
   const Bx ndom = ixbox(L.domain, IX_NODE);
@@ -493,17 +504,17 @@ int NodeMG::set_sigma(const MF& sigma, cudaStream_t s) {
     if (!has_bc_) return IAMRX_OK;
     const Level& LL = *M.lev;
     for (int il = 0; il < M.sigma.n(); ++il)
-      IX_TRY(k::nodal_bc_fill_sigma(M.sigma.vbox(il), M.sigma.v(il), bc_, LL.domain, LL.geom.periodic, s));
+      IX_TRY(k::nodal_bc_fill_sigma(M.sigma.vbox(il), M.sigma.v(il), bc_, LL.domain, LL.geom.periodic, s, M.ngd));
     return IAMRX_OK;
   };
-  IX_TRY(mf_setval(lv_[0].sigma, 0.0, 0, 1, 1, s));
+  IX_TRY(mf_setval(lv_[0].sigma, 0.0, 0, 1, lv_[0].ngd, s));
   IX_TRY(mf_copy(lv_[0].sigma, sigma, 0, 0, 1, 0, s));
-  IX_TRY(mf_fill_boundary(lv_[0].sigma, 0, 1, 1, s));
+  IX_TRY(mf_fill_boundary(lv_[0].sigma, 0, 1, lv_[0].ngd, s));
   IX_TRY(sigma_bc(lv_[0]));
   for (size_t l = 1; l < lv_.size(); ++l) {
     MGLevelNode& C = lv_[l];
     MGLevelNode& F = lv_[l - 1];
-    IX_TRY(mf_setval(C.sigma, 0.0, 0, 1, 1, s));
+    IX_TRY(mf_setval(C.sigma, 0.0, 0, 1, C.ngd, s));
     if (C.xfer_lev) {
       MF tmp(C.xfer_lev.get(), IX_CELL, 1, 0);
       for (int il = 0; il < tmp.n(); ++il) IX_TRY(k::cc_restrict(tmp.vbox(il), tmp.v(il), F.sigma.c(il), 1, s));
@@ -512,7 +523,7 @@ int NodeMG::set_sigma(const MF& sigma, cudaStream_t s) {
       for (int il = 0; il < C.sigma.n(); ++il)
         IX_TRY(k::cc_restrict(C.sigma.vbox(il), C.sigma.v(il), F.sigma.c(il), 1, s));
     }
-    IX_TRY(mf_fill_boundary(C.sigma, 0, 1, 1, s));
+    IX_TRY(mf_fill_boundary(C.sigma, 0, 1, C.ngd, s));
     IX_TRY(sigma_bc(C));
   }
   return IAMRX_OK;
@@ -544,8 +555,12 @@ int NodeMG::smooth(int l, MF& phi, const MF& rhs, int nsweeps, cudaStream_t s) {
   }
   // decided from ALL boxes of the level (not just this rank's): the fused and the colour paths issue different
   // numbers of ghost exchanges, so every rank must take the same one
+  // deep-ghost levels (block decompositions): same fused sweep, halos from 4 ghost layers of phi / rhs / sigma instead of wraps
+  const bool deep = L.deep && phi.ng >= L.ngd && rhs.ng >= L.ngd;
+  const int wmk = deep ? (wm | k::NODAL_DEEP_GHOSTS) : wm;
+  const int gd = deep ? L.ngd : 1;
   bool fused = true;
-  for (size_t b = 0; b < L.lev->boxes.size() && fused; ++b) fused = k::nodal_gs_sweep_ok(ixbox(L.lev->boxes[b], IX_NODE), wm);
+  for (size_t b = 0; b < L.lev->boxes.size() && fused; ++b) fused = k::nodal_gs_sweep_ok(ixbox(L.lev->boxes[b], IX_NODE), wmk);
   // Dirichlet sides shorten the active node box; keep the fused sweep only if its plane pairing survives (both z sides or none)
   if (fused && has_bc_)
     for (int d = 0; d < 3; ++d)
@@ -554,16 +569,17 @@ int NodeMG::smooth(int l, MF& phi, const MF& rhs, int nsweeps, cudaStream_t s) {
     // out-of-place fused sweeps ping-pong between phi and a second buffer.  Slabs (x and y wrapped in the kernel, z
     // exchanged): the even-plane phase reads the old odd ghost planes of `src`, the odd-plane phase the NEW even ghost
     // planes of `dst` -- two plane exchanges per sweep instead of eight colour fills.
-    if (!L.gs_tmp.ok()) L.gs_tmp.define(L.lev, IX_NODE, 1, 1);
-    if (!L.gs_tmp.ok()) { L.gs_tmp.define(L.lev, IX_NODE, 1, 1); IX_TRY(mf_setval(L.gs_tmp, 0.0, 0, 1, 1, s)); }
+    if (!L.gs_tmp.ok()) { L.gs_tmp.define(L.lev, IX_NODE, 1, L.ngd); IX_TRY(mf_setval(L.gs_tmp, 0.0, 0, 1, L.ngd, s)); }
     MF* src = &phi; MF* dst = &L.gs_tmp;
-    IX_TRY(fill_ghosts(l, *src, wm, s, false));
+    // (the ghost layers of the right-hand side are scratch: filling them does not change the caller's data)
+    if (deep) IX_TRY(mf_fill_boundary(const_cast<MF&>(rhs), 0, 1, gd, s, wm));
+    IX_TRY(fill_ghosts(l, *src, wm, s, false, gd));
     for (int sw = 0; sw < nsweeps; ++sw) {
       for (int phase = 0; phase < 2; ++phase) {
         for (int il = 0; il < phi.n(); ++il)
           IX_TRY(k::nodal_gs_sweep(active_nbox(l, il), dst->v(il), src->c(il), rhs.c(il), L.sigma.c(il), L.dxinv, s,
-                                   wm | (neumann_sides(l, il) << 3), phase));
-        IX_TRY(fill_ghosts(l, *dst, wm, s, false));
+                                   wmk | (neumann_sides(l, il) << 3), phase));
+        IX_TRY(fill_ghosts(l, *dst, wm, s, false, gd));
       }
       std::swap(src, dst);
     }
@@ -677,8 +693,12 @@ int NodeMG::solve(MF& phi, MF& rhs, iamrx_mg_info* info, cudaStream_t s) {
   }
   IX_TRY(fill_ghosts(0, phi, 0, s, true));
   if (info_.verbose > 0)
-    fprintf(stderr, "[iamrx] NodeMG: %d iters, res0 %.3e -> %.3e (rhs %.3e, levels %d)\n", iters, resnorm0,
-            resnorm, rhsnorm, nlevels());
+  {
+    int ndeep = 0;
+    for (const auto& L : lv_) ndeep += L.deep ? 1 : 0;
+    fprintf(stderr, "[iamrx] NodeMG: %d iters, res0 %.3e -> %.3e (rhs %.3e, levels %d, deep-ghost levels %d)\n", iters, resnorm0,
+            resnorm, rhsnorm, nlevels(), ndeep);
+  }
   if (info) { info->iters = iters; info->resnorm0 = resnorm0; info->resnorm = resnorm; info->rhsnorm = rhsnorm; }
   if (rc > 0) set_error("NodeMG: failed to converge");
   return rc;

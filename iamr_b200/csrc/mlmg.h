@@ -75,6 +75,10 @@ struct MGLevelNode {
   MF cor, res, rescor; // nodal, 1 ghost
   MF gs_tmp;           // second phi buffer of the out-of-place fused Gauss-Seidel sweep (lazy)
   double dxinv[3];
+  // deep-ghost level: boxes have neighbours in x / y (block decomposition); sigma / cor / res / gs_tmp carry 4 ghost layers so
+  // that the fused two-phase Gauss-Seidel sweep can take its tile halos from them (k::NODAL_DEEP_GHOSTS)
+  bool deep = false;
+  int ngd = 1;         // ghost depth of sigma, cor, res, gs_tmp
 };
 
 class NodeMG {
@@ -95,7 +99,7 @@ class NodeMG {
   int smooth(int l, MF& phi, const MF& rhs, int nsweeps, cudaStream_t s);
   int residual(int l, MF& out, MF& phi, const MF& rhs, cudaStream_t s);
   int vcycle(cudaStream_t s);
-  int fill_ghosts(int l, MF& phi, int wm, cudaStream_t s, bool bc_fill);   // FillBoundary + mirrored ghost nodes of the Neumann sides
+  int fill_ghosts(int l, MF& phi, int wm, cudaStream_t s, bool bc_fill, int depth = 1);   // FillBoundary + mirrored ghost nodes of the Neumann sides
   bool singular() const;
   std::vector<MGLevelNode> lv_;
   iamrx_mg_info info_;

@@ -412,6 +412,12 @@ IX_D int wrap_cell_any(int c, int lo, int hi) {  // cells lo .. hi-1 (hi = node 
   return lo + m;
 }
 IX_D int col(int c) { return (c & 1) * HALF + (c >> 1); }
+// halo index of a tile: periodic image (the box spans the domain in this direction) or, for a box with neighbours
+// (ghost = 1), the node / cell itself inside the DEEP ghost layers (depth GD, filled by the caller); indices further out
+// only feed halo nodes outside the dependence cone of the box's own nodes, so they are clamped, not computed
+constexpr int GD = 4;
+IX_D int halo_node(int g, int lo, int hi, int ghost) { return ghost ? min(max(g, lo - GD), hi + GD) : wrap_node_any(g, lo, hi); }
+IX_D int halo_cell(int c, int lo, int hi, int ghost) { return ghost ? min(max(c, lo - GD), hi - 1 + GD) : wrap_cell_any(c, lo, hi); }
 
 struct Q1F { double f0c, f1c, f0j, f1j, f0k, f1k, f0jk, f1jk; };  // q1_factor by row kind
 
@@ -455,7 +461,7 @@ IX_D void pass(double (*sp)[NR][NC], double (*ss)[NR][NC], int warp, int lane, d
 }
 
 __global__ void __launch_bounds__(NT, 4)
-gs_sweep_kernel(Bx bx, V4 out, C4 pin, C4 padj, C4 rhs, C4 sig, IX_KARG(Q1F) q, int k0, int zwrap, int zmir) {
+gs_sweep_kernel(Bx bx, V4 out, C4 pin, C4 padj, C4 rhs, C4 sig, IX_KARG(Q1F) q, int k0, int zwrap, int zmir, int xyg) {
   __shared__ double sp[3][NR][NC];
   __shared__ double ss[2][NR][NC];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -474,8 +480,8 @@ gs_sweep_kernel(Bx bx, V4 out, C4 pin, C4 padj, C4 rhs, C4 sig, IX_KARG(Q1F) q, 
     // half-warp then writes 128 contiguous bytes of shared memory (no bank conflict in the de-interleaved
     // layout) while the warp still reads one contiguous 256-byte global segment
     const int c = (tid & 32) + 2 * (tid & 15) + ((tid >> 4) & 1), r0 = 1 + (tid >> 6), sc = col(c);
-    const int gi = wrap_node_any(X0 + c, bx.lo[0], bx.hi[0]);
-    const int ci = wrap_cell_any(X0 + c, bx.lo[0], bx.hi[0]);
+    const int gi = halo_node(X0 + c, bx.lo[0], bx.hi[0], xyg & 1);
+    const int ci = halo_cell(X0 + c, bx.lo[0], bx.hi[0], xyg & 1);
     const double* pk = pin.p + (gi - pin.l0) + (int64_t)(k - pin.l2) * pin.ks;
     const double* pm = padj.p + (gi - padj.l0) + (int64_t)(km - padj.l2) * padj.ks;
     const double* pp = padj.p + (gi - padj.l0) + (int64_t)(kp - padj.l2) * padj.ks;
@@ -486,12 +492,12 @@ gs_sweep_kernel(Bx bx, V4 out, C4 pin, C4 padj, C4 rhs, C4 sig, IX_KARG(Q1F) q, 
     for (int m = 0; m < 5; ++m) {
       const int r = r0 + 4 * m;
       if (r <= 17) {
-        const int gj = wrap_node_any(Y0 + r, bx.lo[1], bx.hi[1]);
+        const int gj = halo_node(Y0 + r, bx.lo[1], bx.hi[1], xyg & 2);
         tile::cp_async8(&sp[0][r][sc], pm + (gj - padj.l1) * ajs);
         tile::cp_async8(&sp[1][r][sc], pk + (gj - pin.l1) * pjs);
         tile::cp_async8(&sp[2][r][sc], pp + (gj - padj.l1) * ajs);
         if (r <= 16) {
-          const int cj = wrap_cell_any(Y0 + r, bx.lo[1], bx.hi[1]) - sig.l1;
+          const int cj = halo_cell(Y0 + r, bx.lo[1], bx.hi[1], xyg & 2) - sig.l1;
           tile::cp_async8(&ss[0][r][sc], s0p + cj * sjs);
           tile::cp_async8(&ss[1][r][sc], s1p + cj * sjs);
         }
@@ -505,7 +511,7 @@ gs_sweep_kernel(Bx bx, V4 out, C4 pin, C4 padj, C4 rhs, C4 sig, IX_KARG(Q1F) q, 
   for (int q = 0; q < 4; ++q) {
     const int cx = q & 1, cy = q >> 1;
     const int h = (cy == 0 ? 1 : 2) + lane, ty = 2 + cy + 2 * warp;
-    const int gi = wrap_node_any(X0 + 2 * h + cx, bx.lo[0], bx.hi[0]), gj = wrap_node_any(Y0 + ty, bx.lo[1], bx.hi[1]);
+    const int gi = halo_node(X0 + 2 * h + cx, bx.lo[0], bx.hi[0], xyg & 1), gj = halo_node(Y0 + ty, bx.lo[1], bx.hi[1], xyg & 2);
     rv[q] = (warp < 8 && ty < NR) ? rhs(gi, gj, k) : 0.0;
   }
   asm volatile("cp.async.wait_group 0;" ::: "memory");
@@ -736,7 +742,12 @@ int nodal_gs_color(const Bx& nbx, V4 phi, C4 rhs, C4 sig, const double dxinv[3],
 bool nodal_gs_sweep_ok(const Bx& nbx, int wrapmask) {
   static int on = -1;
   if (on < 0) { const char* e = getenv("IAMRX_NODAL_FUSED"); on = (e && e[0] == '0') ? 0 : 1; }
-  if (!on || ((wrapmask & 7) != 7 && (wrapmask & 7) != 3)) return false;
+  if (!on) return false;
+  if (wrapmask & NODAL_DEEP_GHOSTS) {   // x / y sides with neighbours: tile halos come from ghost layers of depth 4 (NodeMG deep levels)
+    for (int d = 0; d < 2; ++d) if (!(wrapmask & (1 << d)) && ((nbx.lo[d] & 1) || nbx.hi[d] - nbx.lo[d] < 8)) return false;
+  } else if ((wrapmask & 7) != 7 && (wrapmask & 7) != 3) {
+    return false;
+  }
   for (int d = 0; d < 3; ++d) if (((nbx.hi[d] - nbx.lo[d]) & 1) || nbx.hi[d] - nbx.lo[d] < 2) return false;
   return true;
 }
@@ -750,10 +761,23 @@ int nodal_gs_sweep(const Bx& nbx, V4 phi_out, C4 phi_in, C4 rhs, C4 sig, const d
   // host emulation (tests only): the same sweep as eight in-place colour passes on a copy (ghost planes of the
   // exchanged direction included: the even-plane colours read them as old values)
   int rc = IAMRX_OK;
-  if (phase != 1) rc = copy((wrapmask & 4) ? nbx : grow(nbx, 2, 1), phi_out, phi_in, 1, s);
+  const bool deep = (wrapmask & NODAL_DEEP_GHOSTS) != 0;
+  Bx cb = (wrapmask & 4) ? nbx : grow(nbx, 2, 1);
+  if (deep) for (int d = 0; d < 2; ++d) if (!(wrapmask & (1 << d))) cb = grow(cb, d, 4);
+  if (phase != 1) rc = copy(cb, phi_out, phi_in, 1, s);
   const int c0 = (phase == 1) ? 4 : 0, c1 = (phase == 0) ? 4 : 8;
   (void)pout;
-  for (int color = c0; color < c1 && rc == IAMRX_OK; ++color) rc = nodal_gs_color(nbx, phi_out, rhs, sig, dxinv, color, s, wrapmask);
+  for (int color = c0; color < c1 && rc == IAMRX_OK; ++color) {
+    // deep ghosts: the halo nodes the later colours depend on are recomputed redundantly, as the tiles of the CUDA kernel do
+    // (colour (cx, cy): 3 - cx - 2 cy ... nodes in x, 1 - cy in y; scratch values in the ghost layers, refilled by the caller)
+    Bx ub = nbx;
+    if (deep) {
+      const int cx = color & 1, cy = (color >> 1) & 1;
+      if (!(wrapmask & 1)) ub = grow(ub, 0, 3 - cx - 2 * cy);
+      if (!(wrapmask & 2)) ub = grow(ub, 1, 1 - cy);
+    }
+    rc = nodal_gs_color(ub, phi_out, rhs, sig, dxinv, color, s, wrapmask & ~NODAL_DEEP_GHOSTS);
+  }
   return rc;
 #else
   using namespace fused;
@@ -771,7 +795,8 @@ int nodal_gs_sweep(const Bx& nbx, V4 phi_out, C4 phi_in, C4 rhs, C4 sig, const d
     const int nk = (nbx.hi[2] - k0) / 2 + 1;
     // phase A (even planes): neighbours = old odd planes; phase B (odd planes): neighbours = new even planes
     IX_LAUNCH(gs_sweep_kernel, dim3(gx, gy, nk), dim3(NT, 1, 1), 0, s, nbx, phi_out, phi_in, cz == 0 ? phi_in : pout, rhs, sig,
-              q, k0, (wrapmask & 4) ? 1 : 0, (wrapmask >> 7) & 3);
+              q, k0, (wrapmask & 4) ? 1 : 0, (wrapmask >> 7) & 3,
+              (wrapmask & NODAL_DEEP_GHOSTS) ? (((wrapmask & 1) ? 0 : 1) | ((wrapmask & 2) ? 0 : 2)) : 0);
     const int rc = check_launch("nodal_gs_sweep");
     if (rc != IAMRX_OK) return rc;
   }
