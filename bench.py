@@ -289,14 +289,15 @@ def run_ours(args):
     g = ix.Geom.make(ncell, (0.0, 0.0, 0.0), prob_hi)
     lev = ix.Level(lib, g, boxes, owners)
     hit = args.problem == "hit"
+    bs = 1 if args.bottom_solver == "bicgstab" else 0
     if hit:   # BASELINE.json configs[4]: Tutorials/HIT initial field, nu = 1e-4, proj_tol 1e-10 (inputs.3d.forced:129), synthetic variable density.
         # mac_tol 1e-10: at 512^3 the fp64 round-off floor of the MAC residual is eps / (h k)^2 ~ 4e-12 of the right-hand side for
         # domain-scale modes (profiles/r02_notes.md: residual stalls at 3.7e-12 relative), above IAMR's default 1e-12 -- the
         # reference's MLMG would abort the same way; a site running this case sets mac_proj.mac_tol as here.
-        ns = ix.NavierStokes(lib, lev, dev, visc_coef=NU, cfl=CFL, proj_tol=1e-10, mac_tol=1e-10)
+        ns = ix.NavierStokes(lib, lev, dev, visc_coef=NU, cfl=CFL, proj_tol=1e-10, mac_tol=1e-10, bottom_solver=bs)
         ns.init_prob(20, [1.0, 1.0, 0.5])
     else:
-        ns = ix.NavierStokes(lib, lev, dev, visc_coef=NU, cfl=CFL)
+        ns = ix.NavierStokes(lib, lev, dev, visc_coef=NU, cfl=CFL, bottom_solver=bs)
         ns.init_prob(11, TG)
     ns.post_init()
     cells_total = ncell[0] * ncell[1] * ncell[2]
@@ -423,6 +424,7 @@ def run_ours(args):
             cfg["workload"] = (f"HIT 3D {nbox}^3 per GPU single-level variable-density (Tutorials/HIT/prob_init.cpp:100-131 field, nu=1e-4, "
                                f"proj_tol 1e-10, mac_tol 1e-10 (fp64 floor at 512^3), rho = 1 + 0.5 sin sin sin, forcing off), BASELINE.json configs[4]" + ("" if world == 1 else " weak-scaled"))
         cfg["mg_iters_last_step"] = {"mac": iters[-1][0], "visc": iters[-1][1], "nodal": iters[-1][2]}
+        cfg["bottom_solver"] = args.bottom_solver
         cfg["timing"] = "headline pass without per-launch events; roofline from a separate pass of %d steps" % args.prof_steps
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -460,6 +462,8 @@ def main():
     ap.add_argument("--n", type=int, default=256, help="box size per GPU")
     ap.add_argument("--cpu-n", type=int, default=0, help="box size of the CPU runs (0: --impl reference uses --n, the cpu_baseline leg 128)")
     ap.add_argument("--decomp", default="slabs", choices=["slabs", "blocks"], help="weak-scaling decomposition: z slabs or 3-D blocks")
+    ap.add_argument("--bottom-solver", default="smoother", choices=["smoother", "bicgstab"],
+                    help="multigrid bottom solver: smoother sweeps (default) or BiCGStab (IAMR's bicgcg)")
     ap.add_argument("--problem", default="tg", choices=["tg", "hit"], help="tg: BASELINE configs[1]; hit: configs[4] (HIT, variable density)")
     ap.add_argument("--prof-steps", type=int, default=3, help="steps of the separate roofline pass")
     ap.add_argument("--no-verify", action="store_true", help="skip the untimed multi-rank parity leg")

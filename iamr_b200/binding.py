@@ -81,7 +81,9 @@ class MGInfo(C.Structure):
                 ("max_coarsening", C.c_int), ("nu1", C.c_int), ("nu2", C.c_int),
                 ("bottom_sweeps", C.c_int), ("verbose", C.c_int), ("omega", C.c_double),
                 ("iters", C.c_int), ("maxorder", C.c_int), ("resnorm0", C.c_double),
-                ("resnorm", C.c_double), ("rhsnorm", C.c_double)]
+                ("resnorm", C.c_double), ("rhsnorm", C.c_double),
+                ("bottom_solver", C.c_int), ("bottom_maxiter", C.c_int), ("bottom_rtol", C.c_double),
+                ("bottom_iters", C.c_int), ("pad_", C.c_int)]
 
 
 class LinopBC(C.Structure):
@@ -111,7 +113,7 @@ class NSParams(C.Structure):
                 ("mac_tol", C.c_double), ("mac_abs_tol", C.c_double), ("proj_tol", C.c_double),
                 ("proj_abs_tol", C.c_double), ("init_iter", C.c_int), ("init_vel_iter", C.c_int),
                 ("do_init_proj", C.c_int), ("use_forces_in_trans", C.c_int), ("verbose", C.c_int),
-                ("conservative_tracer", C.c_int), ("mg_verbose", C.c_int), ("godunov_ppm", C.c_int), ("do_scalminmax", C.c_int), ("do_mom_diff", C.c_int),
+                ("conservative_tracer", C.c_int), ("mg_verbose", C.c_int), ("godunov_ppm", C.c_int), ("do_scalminmax", C.c_int), ("do_mom_diff", C.c_int), ("bottom_solver", C.c_int),
                 ("lo_bc", C.c_int * 3), ("hi_bc", C.c_int * 3), ("bc_vals", (C.c_double * 5) * 6)]
 
 

@@ -381,6 +381,7 @@ void iamrx_mg_info_default(iamrx_mg_info* info) {
   info->bottom_sweeps = 8;
   info->verbose = 0;
   info->maxorder = 3;   // MLLinOp default; IAMR sets 4 for the MAC solve, 2 for diffusion
+  info->bottom_solver = 0; info->bottom_maxiter = 200; info->bottom_rtol = 1.0e-4;
   info->omega = 1.15;   // AMReX abec_gsrb over-relaxation (AMReX_MLABecLap_3D_K.H); the UNVERIFIED-UPSTREAM table in DESIGN.md
 }
 

@@ -1,5 +1,6 @@
 // mlmg.cu -- see mlmg.h.  V-cycle drivers; every arithmetic step is one of the
 // kernels in abec.cu / nodal.cu / blas.cu launched over the rank's local boxes.
+#include <functional>
 #include "mlmg.h"
 #include <algorithm>
 #include <cmath>
@@ -331,6 +332,121 @@ int CellMG::make_solvable(int l, MF& rhs, cudaStream_t s) {
   return IAMRX_OK;
 }
 
+
+// ===========================================================================
+// BiCGStab bottom solver (AMReX MLCGSolver::solve_bicgstab, the first stage of IAMR's default "bicgcg" bottom solver):
+// unpreconditioned, zero initial guess, homogeneous boundary conditions, converged when |r|_inf <= rtol |r0|_inf.
+// Host-driven over the level operations (apply / dot / axpy), so it works on any layout and for both operators; the dot
+// products use the deterministic two-pass sum.  Returns 0 (converged), or the AMReX break-down code (1 rho = 0,
+// 2 <rh,v> = 0, 3 <t,t> = 0, 4 omega = 0, 8 iteration cap): the caller then falls back to the smoother as AMReX does.
+// ===========================================================================
+namespace {
+struct KrylovOps {
+  std::function<int(MF& out, MF& in)> apply;                       // out = A in (homogeneous BC; may fill in's ghosts)
+  std::function<int(const MF& a, const MF& b, double* r)> dot;
+  std::function<int(const MF& a, double* r)> norminf;
+  int ncomp = 1;
+};
+
+int bicgstab(const KrylovOps& op, MF& sol, const MF& rhs, double rtol, int maxiter, int* iters_out, cudaStream_t s) {
+  Level* lev = sol.lev;
+  const int nc = op.ncomp, it = sol.ixtype;
+  MF r(lev, it, nc, 0), rh(lev, it, nc, 0), p(lev, it, nc, sol.ng), v(lev, it, nc, 0), sv(lev, it, nc, sol.ng), t(lev, it, nc, 0);
+  IX_TRY(mf_setval(p, 0.0, 0, nc, p.ng, s));
+  IX_TRY(mf_setval(sv, 0.0, 0, nc, sv.ng, s));
+  IX_TRY(mf_copy(r, rhs, 0, 0, nc, 0, s));       // x0 = 0: r = b
+  IX_TRY(mf_copy(rh, r, 0, 0, nc, 0, s));
+  double rnorm0 = 0;
+  IX_TRY(op.norminf(r, &rnorm0));
+  *iters_out = 0;
+  if (rnorm0 == 0.0) return 0;
+  const double target = rtol * rnorm0;
+  double rho_1 = 0, alpha = 0, omega = 0;
+  int ret = 8;
+  for (int nit = 1; nit <= maxiter; ++nit) {
+    *iters_out = nit;
+    double rho = 0;
+    IX_TRY(op.dot(rh, r, &rho));
+    if (rho == 0.0) { ret = 1; break; }
+    if (nit == 1) {
+      IX_TRY(mf_copy(p, r, 0, 0, nc, 0, s));
+    } else {
+      const double beta = (rho / rho_1) * (alpha / omega);
+      IX_TRY(mf_lincomb(p, 0, 1.0, p, 0, -omega, v, 0, nc, 0, s));     // p = p - omega v
+      IX_TRY(mf_lincomb(p, 0, beta, p, 0, 1.0, r, 0, nc, 0, s));       // p = r + beta p
+    }
+    IX_TRY(op.apply(v, p));
+    double rhTv = 0;
+    IX_TRY(op.dot(rh, v, &rhTv));
+    if (rhTv == 0.0) { ret = 2; break; }
+    alpha = rho / rhTv;
+    IX_TRY(mf_lincomb(sol, 0, 1.0, sol, 0, alpha, p, 0, nc, 0, s));
+    IX_TRY(mf_lincomb(sv, 0, 1.0, r, 0, -alpha, v, 0, nc, 0, s));      // s = r - alpha v
+    double rnorm = 0;
+    IX_TRY(op.norminf(sv, &rnorm));
+    if (!(rnorm == rnorm)) { ret = 9; break; }
+    if (rnorm <= target) { ret = 0; break; }
+    IX_TRY(op.apply(t, sv));
+    double tt = 0, ts = 0;
+    IX_TRY(op.dot(t, t, &tt));
+    IX_TRY(op.dot(t, sv, &ts));
+    if (tt == 0.0) { ret = 3; break; }
+    omega = ts / tt;
+    IX_TRY(mf_lincomb(sol, 0, 1.0, sol, 0, omega, sv, 0, nc, 0, s));
+    IX_TRY(mf_lincomb(r, 0, 1.0, sv, 0, -omega, t, 0, nc, 0, s));      // r = s - omega t
+    IX_TRY(op.norminf(r, &rnorm));
+    if (!(rnorm == rnorm)) { ret = 9; break; }
+    if (rnorm <= target) { ret = 0; break; }
+    if (omega == 0.0) { ret = 4; break; }
+    rho_1 = rho;
+  }
+  return ret;
+}
+
+// <a, b> over all components: the product goes through a temporary and the deterministic sum (unique nodes for nodal data)
+int mf_dot(const MF& a, const MF& b, int ncomp, bool unique_nodes, double* out, cudaStream_t s) {
+  MF tmp(a.lev, a.ixtype, ncomp, 0);
+  IX_TRY(mf_copy(tmp, a, 0, 0, ncomp, 0, s));
+  for (int il = 0; il < tmp.n(); ++il) IX_TRY(k::mult(tmp.vbox(il), tmp.v(il), b.c(il), ncomp, ncomp, s));
+  double tot = 0;
+  for (int c = 0; c < ncomp; ++c) { double v = 0; IX_TRY(mf_sum(tmp, c, &v, s, unique_nodes)); tot += v; }
+  *out = tot;
+  return IAMRX_OK;
+}
+}  // namespace
+
+int CellMG::bottom_solve(cudaStream_t s) {
+  const int nl = (int)lv_.size();
+  MGLevelCell& B = lv_[nl - 1];
+  IX_TRY(mf_setval(B.cor, 0.0, 0, ncomp_, 1, s));
+  if (singular_ && nl > 1) IX_TRY(make_solvable(nl - 1, B.res, s));
+  const int nsm = nl == 1 ? info_.nu1 + info_.nu2 : info_.bottom_sweeps;
+  if (info_.bottom_solver != 1 || nl == 1) return smooth(nl - 1, B.cor, B.res, nsm, true, s);
+  KrylovOps op;
+  op.ncomp = ncomp_;
+  op.apply = [&](MF& out, MF& in) -> int {       // rhs - A in with no rhs = A in (homogeneous BC, no cross terms: a coarse level)
+    const int wm = B.lev->level_wrapmask();
+    IX_TRY(fill_ghosts(nl - 1, in, false, wm, 0, s));
+    for (int il = 0; il < in.n(); ++il) {
+      const bool mir = has_bc_ && box_on_boundary(nl - 1, il) && bc_in_kernel(nl - 1);
+      const k::GsBC gb = mir ? gsbc_of(nl - 1, il) : k::GsBC{};
+      IX_TRY(k::abec_apply(in.vbox(il), out.v(il), in.c(il), C4{}, op_at(nl - 1, il), ncomp_, s, wm, mir ? &gb : nullptr));
+    }
+    return IAMRX_OK;
+  };
+  op.dot = [&](const MF& a, const MF& b, double* r) { return mf_dot(a, b, ncomp_, false, r, s); };
+  op.norminf = [&](const MF& a, double* r) { return mf_norminf(a, 0, ncomp_, r, s); };
+  int its = 0;
+  const int ret = bicgstab(op, B.cor, B.res, info_.bottom_rtol, info_.bottom_maxiter, &its, s);
+  if (ret < 0) return ret;
+  info_.bottom_iters += its;
+  if (ret != 0) {   // MLMG::bottomSolve: a failed CG solve is discarded and replaced by smoothing
+    IX_TRY(mf_setval(B.cor, 0.0, 0, ncomp_, 1, s));
+    IX_TRY(smooth(nl - 1, B.cor, B.res, nsm, true, s));
+  }
+  return IAMRX_OK;
+}
+
 int CellMG::vcycle(cudaStream_t s) {
   const int nl = (int)lv_.size();
   for (int l = 0; l < nl - 1; ++l) {
@@ -348,12 +464,7 @@ int CellMG::vcycle(cudaStream_t s) {
         IX_TRY(k::cc_restrict(C.res.vbox(il), C.res.v(il), L.rescor.c(il), ncomp_, s));
     }
   }
-  {
-    MGLevelCell& B = lv_[nl - 1];
-    IX_TRY(mf_setval(B.cor, 0.0, 0, ncomp_, 1, s));
-    if (singular_ && nl > 1) IX_TRY(make_solvable(nl - 1, B.res, s));
-    IX_TRY(smooth(nl - 1, B.cor, B.res, nl == 1 ? info_.nu1 + info_.nu2 : info_.bottom_sweeps, true, s));
-  }
+  IX_TRY(bottom_solve(s));
   for (int l = nl - 2; l >= 0; --l) {
     MGLevelCell& L = lv_[l];
     MGLevelCell& C = lv_[l + 1];
@@ -366,6 +477,7 @@ int CellMG::vcycle(cudaStream_t s) {
 
 int CellMG::solve(MF& sol, const MF& rhs_in, iamrx_mg_info* info, cudaStream_t s) {
   if (info) info_ = *info;
+  info_.bottom_iters = 0;
   MGLevelCell& L0 = lv_[0];
   {
     bool dirichlet = false;
@@ -402,7 +514,7 @@ int CellMG::solve(MF& sol, const MF& rhs_in, iamrx_mg_info* info, cudaStream_t s
   if (info_.verbose > 0)
     fprintf(stderr, "[iamrx] CellMG: %d iters, res0 %.3e -> %.3e (rhs %.3e, levels %d)\n", iters, resnorm0,
             resnorm, rhsnorm, nlevels());
-  if (info) { info->iters = iters; info->resnorm0 = resnorm0; info->resnorm = resnorm; info->rhsnorm = rhsnorm; }
+  if (info) { info->iters = iters; info->resnorm0 = resnorm0; info->resnorm = resnorm; info->rhsnorm = rhsnorm; info->bottom_iters = info_.bottom_iters; }
   if (rc > 0) set_error("CellMG: failed to converge");
   return rc;
 }
@@ -605,6 +717,56 @@ int NodeMG::residual(int l, MF& out, MF& phi, const MF& rhs, cudaStream_t s) {
   return IAMRX_OK;
 }
 
+// periodic / Neumann everywhere: make rhs solvable (MLNodeLinOp::getSolvabilityOffset / fixSolvabilityByOffset): subtract the
+// mean weighted with the dot mask -- unique nodes, 1/2 per Neumann side a node lies on.  The weights sum to the number of
+// cells (a periodic direction has n unique nodes, a Neumann-Neumann one n + 1 with two halves).
+int NodeMG::make_solvable(int l, MF& rhs, cudaStream_t s) {
+  Level& lev = *lv_[l].lev;
+  double sum = 0;
+  if (has_bc_) {
+    MF tmp(&lev, IX_NODE, 1, 0);
+    IX_TRY(mf_copy(tmp, rhs, 0, 0, 1, 0, s));
+    const Bx ndom = ixbox(lev.domain, IX_NODE);
+    for (int il = 0; il < tmp.n(); ++il) IX_TRY(k::nodal_bc_scale(tmp.vbox(il), tmp.v(il), bc_, ndom, lev.geom.periodic, 0.5, s));
+    IX_TRY(mf_sum(tmp, 0, &sum, s, true));
+  } else {
+    IX_TRY(mf_sum(rhs, 0, &sum, s, true));
+  }
+  const double mean = sum / (double)lev.ncells_global;
+  for (int il = 0; il < rhs.n(); ++il) IX_TRY(k::addconst(rhs.vbox(il), rhs.v(il), -mean, 1, s));
+  return IAMRX_OK;
+}
+
+int NodeMG::bottom_solve(cudaStream_t s) {
+  const int nl = (int)lv_.size();
+  MGLevelNode& B = lv_[nl - 1];
+  IX_TRY(mf_setval(B.cor, 0.0, 0, 1, 1, s));
+  const int nsm = nl == 1 ? info_.nu1 + info_.nu2 : info_.bottom_sweeps;
+  if (info_.bottom_solver != 1 || nl == 1) return smooth(nl - 1, B.cor, B.res, nsm, s);
+  if (singular()) IX_TRY(make_solvable(nl - 1, B.res, s));   // MLMG::bottomSolve: a singular bottom problem is made solvable first
+  KrylovOps op;
+  op.ncomp = 1;
+  op.apply = [&](MF& out, MF& in) -> int {
+    const int wm = B.lev->level_wrapmask();
+    IX_TRY(fill_ghosts(nl - 1, in, wm, s, false));
+    IX_TRY(mf_setval(out, 0.0, 0, 1, 0, s));   // nodes ON Dirichlet sides stay zero (active_nbox)
+    for (int il = 0; il < in.n(); ++il)
+      IX_TRY(k::nodal_adotx(active_nbox(nl - 1, il), out.v(il), in.c(il), C4{}, B.sigma.c(il), B.dxinv, s, wm | (neumann_sides(nl - 1, il) << 3)));
+    return IAMRX_OK;
+  };
+  op.dot = [&](const MF& a, const MF& b, double* r) { return mf_dot(a, b, 1, true, r, s); };
+  op.norminf = [&](const MF& a, double* r) { return mf_norminf(a, 0, 1, r, s); };
+  int its = 0;
+  const int ret = bicgstab(op, B.cor, B.res, info_.bottom_rtol, info_.bottom_maxiter, &its, s);
+  if (ret < 0) return ret;
+  info_.bottom_iters += its;
+  if (ret != 0) {
+    IX_TRY(mf_setval(B.cor, 0.0, 0, 1, 1, s));
+    IX_TRY(smooth(nl - 1, B.cor, B.res, nsm, s));
+  }
+  return IAMRX_OK;
+}
+
 int NodeMG::vcycle(cudaStream_t s) {
   const int nl = (int)lv_.size();
   for (int l = 0; l < nl - 1; ++l) {
@@ -633,11 +795,7 @@ int NodeMG::vcycle(cudaStream_t s) {
         IX_TRY(k::nodal_restrict(active_nbox(l + 1, il), C.res.v(il), L.rescor.c(il), s));
     }
   }
-  {
-    MGLevelNode& B = lv_[nl - 1];
-    IX_TRY(mf_setval(B.cor, 0.0, 0, 1, 1, s));
-    IX_TRY(smooth(nl - 1, B.cor, B.res, nl == 1 ? info_.nu1 + info_.nu2 : info_.bottom_sweeps, s));
-  }
+  IX_TRY(bottom_solve(s));
   for (int l = nl - 2; l >= 0; --l) {
     MGLevelNode& L = lv_[l];
     MGLevelNode& C = lv_[l + 1];
@@ -650,25 +808,11 @@ int NodeMG::vcycle(cudaStream_t s) {
 
 int NodeMG::solve(MF& phi, MF& rhs, iamrx_mg_info* info, cudaStream_t s) {
   if (info) info_ = *info;
+  info_.bottom_iters = 0;
   MGLevelNode& L0 = lv_[0];
   Level& lev = *L0.lev;
-  if (singular()) {
-    // periodic / Neumann everywhere: make rhs solvable (MLNodeLinOp::getSolvabilityOffset / fixSolvabilityByOffset): subtract the
-    // mean weighted with the dot mask -- unique nodes, 1/2 per Neumann side a node lies on.  The weights sum to the number of
-    // cells (a periodic direction has n unique nodes, a Neumann-Neumann one n + 1 with two halves).
-    double sum = 0;
-    if (has_bc_) {
-      MF tmp(&lev, IX_NODE, 1, 0);
-      IX_TRY(mf_copy(tmp, rhs, 0, 0, 1, 0, s));
-      const Bx ndom = ixbox(lev.domain, IX_NODE);
-      for (int il = 0; il < tmp.n(); ++il) IX_TRY(k::nodal_bc_scale(tmp.vbox(il), tmp.v(il), bc_, ndom, lev.geom.periodic, 0.5, s));
-      IX_TRY(mf_sum(tmp, 0, &sum, s, true));
-    } else {
-      IX_TRY(mf_sum(rhs, 0, &sum, s, true));
-    }
-    const double mean = sum / (double)lev.ncells_global;
-    for (int il = 0; il < rhs.n(); ++il) IX_TRY(k::addconst(rhs.vbox(il), rhs.v(il), -mean, 1, s));
-  }
+  (void)lev;
+  if (singular()) IX_TRY(make_solvable(0, rhs, s));
   double rhsnorm = 0, resnorm0 = 0, resnorm = 0;
   IX_TRY(mf_norminf(rhs, 0, 1, &rhsnorm, s));
   IX_TRY(residual(0, L0.res, phi, rhs, s));
@@ -699,7 +843,7 @@ int NodeMG::solve(MF& phi, MF& rhs, iamrx_mg_info* info, cudaStream_t s) {
     fprintf(stderr, "[iamrx] NodeMG: %d iters, res0 %.3e -> %.3e (rhs %.3e, levels %d, deep-ghost levels %d)\n", iters, resnorm0,
             resnorm, rhsnorm, nlevels(), ndeep);
   }
-  if (info) { info->iters = iters; info->resnorm0 = resnorm0; info->resnorm = resnorm; info->rhsnorm = rhsnorm; }
+  if (info) { info->iters = iters; info->resnorm0 = resnorm0; info->resnorm = resnorm; info->rhsnorm = rhsnorm; info->bottom_iters = info_.bottom_iters; }
   if (rc > 0) set_error("NodeMG: failed to converge");
   return rc;
 }

@@ -47,6 +47,7 @@ class CellMG {
   int smooth(int l, MF& phi, const MF& rhs, int nsweeps, bool zero_init, cudaStream_t s);
   int residual(int l, MF& out, MF& phi, const MF& rhs, bool with_cross, cudaStream_t s);
   int vcycle(cudaStream_t s);
+  int bottom_solve(cudaStream_t s);   // smoother sweeps or BiCGStab (iamrx_mg_info.bottom_solver) on the coarsest level
   int make_solvable(int l, MF& rhs, cudaStream_t s);
   // ghost cells of phi on level l: FillBoundary (interior / periodic, minus the in-kernel wrapped directions) then the domain
   // boundary conditions; inhomog: Dirichlet values from bvals_ (finest level only), else homogeneous
@@ -99,6 +100,8 @@ class NodeMG {
   int smooth(int l, MF& phi, const MF& rhs, int nsweeps, cudaStream_t s);
   int residual(int l, MF& out, MF& phi, const MF& rhs, cudaStream_t s);
   int vcycle(cudaStream_t s);
+  int bottom_solve(cudaStream_t s);
+  int make_solvable(int l, MF& rhs, cudaStream_t s);
   int fill_ghosts(int l, MF& phi, int wm, cudaStream_t s, bool bc_fill, int depth = 1);   // FillBoundary + mirrored ghost nodes of the Neumann sides
   bool singular() const;
   std::vector<MGLevelNode> lv_;

@@ -175,6 +175,7 @@ iamrx_mg_info mg_info(const iamrx_ns_s& ns, double rtol, double atol) {
   iamrx_mg_info mi;
   iamrx_mg_info_default(&mi);
   mi.rtol = rtol; mi.atol = atol; mi.verbose = ns.p.mg_verbose;
+  mi.bottom_solver = ns.p.bottom_solver;
   return mi;
 }
 
@@ -503,6 +504,7 @@ void iamrx_ns_params_default(iamrx_ns_params* p) {
   p->godunov_ppm = 0;     // ns.advection_scheme = Godunov_PLM (NSB.cpp:169)
   p->do_scalminmax = 0;   // NSB.cpp:140
   p->do_mom_diff = 0;     // NSB.cpp:167
+  p->bottom_solver = 0;   // smoother sweeps; 1 = BiCGStab as IAMR's "bicgcg"
 }
 
 int iamrx_ns_create(iamrx_level_t lev, const iamrx_ns_params* p, iamrx_ns_t* out) {

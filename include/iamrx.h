@@ -344,6 +344,14 @@ typedef struct iamrx_mg_info {
   double resnorm0;
   double resnorm;
   double rhsnorm;
+  /* bottom solver (MLMG::setBottomSolver; IAMR's default is "bicgcg", Docs .../RunningProblems.rst:509-516): 0 = bottom_sweeps
+   * smoother sweeps [default: exact enough on the 2^3..4^3 coarsest boxes, DESIGN.md 4a], 1 = BiCGStab (MLCGSolver) run to
+   * bottom_rtol (AMReX default 1e-4) within bottom_maxiter (200), falling back to the smoother if it breaks down */
+  int bottom_solver;
+  int bottom_maxiter;
+  double bottom_rtol;
+  int bottom_iters;      /* out: BiCGStab iterations summed over the V-cycles of the solve */
+  int pad_;
 } iamrx_mg_info;
 
 void iamrx_mg_info_default(iamrx_mg_info* info);
@@ -471,6 +479,7 @@ typedef struct iamrx_ns_params {
   int godunov_ppm;       /* ns.advection_scheme = Godunov_PPM instead of the default Godunov_PLM (NSB.cpp:169,552-554) */
   int do_scalminmax;     /* ns.do_scalminmax (NSB.cpp:140,2907-2935): clamp the advected tracer to the old 3x3x3 range */
   int do_mom_diff;       /* ns.do_mom_diff (NSB.cpp:167,3358-3470,3609-3616; NS.cpp:606-623,1016): advect and diffuse momentum rho*u */
+  int bottom_solver;     /* bottom solver of all three multigrid solves: 0 smoother sweeps, 1 BiCGStab (iamrx_mg_info.bottom_solver) */
   /* physical boundaries (ns.lo_bc / ns.hi_bc, NS.cpp:90-94; codes of inputs.3d.taylorgreen:100-102): 0 interior / periodic,
    * 1 inflow, 2 outflow, 3 symmetry, 4 slip wall, 5 no-slip wall.  A periodic direction must carry 0, a non-periodic one must
    * not.  The step driver implements walls and symmetry planes (3, 4, 5); inflow / outflow are available at the operator

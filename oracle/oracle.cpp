@@ -421,6 +421,56 @@ void tensor_cross(const double dxinv[3], double bscalar, const Arr& ex, const Ar
 // mean of 8 children, interpolation = piecewise-constant add; coefficient coarsening =
 // average_down (alpha) / average_down_faces (beta))
 // ===========================================================================
+
+// ===========================================================================
+// BiCGStab (AMReX MLCGSolver::solve_bicgstab, first stage of the "bicgcg" bottom solver IAMR uses by default,
+// Docs/sphinx_documentation/source/RunningProblems.rst:509-516): unpreconditioned, x0 = 0, homogeneous BCs, stop when
+// |r|_inf <= rtol |r0|_inf.  Returns 0 or the break-down code (1 rho = 0, 2 <rh,v> = 0, 3 <t,t> = 0, 4 omega = 0, 8 cap).
+// The coarsest level is tiny: plain serial loops.  nodal: data lives on nodes (index n[d] of a non-periodic direction included).
+// ===========================================================================
+template <class Apply>
+static int bicgstab(Apply&& A, Arr& sol, const Arr& rhs, int ncomp, bool nodal, double rtol, int maxiter, int* iters) {
+  int ex[3];
+  for (int d = 0; d < 3; ++d) ex[d] = sol.n[d] + ((nodal && !g_per[d]) ? 1 : 0);
+  auto each = [&](auto&& f) {
+    for (int c = 0; c < ncomp; ++c) for (int k = 0; k < ex[2]; ++k) for (int j = 0; j < ex[1]; ++j) for (int i = 0; i < ex[0]; ++i) f(i, j, k, c);
+  };
+  auto dot = [&](const Arr& a, const Arr& b) { double s = 0; each([&](int i, int j, int k, int c) { s += a(i, j, k, c) * b(i, j, k, c); }); return s; };
+  auto nrm = [&](const Arr& a) { double m = 0; each([&](int i, int j, int k, int c) { m = std::max(m, std::fabs(a(i, j, k, c))); }); return m; };
+  Arr r(sol.n, ncomp, sol.ng), rh(sol.n, ncomp, sol.ng), p(sol.n, ncomp, sol.ng), v(sol.n, ncomp, sol.ng), sv(sol.n, ncomp, sol.ng), t(sol.n, ncomp, sol.ng);
+  each([&](int i, int j, int k, int c) { r(i, j, k, c) = rhs(i, j, k, c); rh(i, j, k, c) = rhs(i, j, k, c); });
+  *iters = 0;
+  const double rnorm0 = nrm(r);
+  if (rnorm0 == 0.0) return 0;
+  const double target = rtol * rnorm0;
+  double rho_1 = 0, alpha = 0, omega = 0;
+  for (int nit = 1; nit <= maxiter; ++nit) {
+    *iters = nit;
+    const double rho = dot(rh, r);
+    if (rho == 0.0) return 1;
+    if (nit == 1) each([&](int i, int j, int k, int c) { p(i, j, k, c) = r(i, j, k, c); });
+    else {
+      const double beta = (rho / rho_1) * (alpha / omega);
+      each([&](int i, int j, int k, int c) { const double q = p(i, j, k, c) - omega * v(i, j, k, c); p(i, j, k, c) = beta * q + r(i, j, k, c); });
+    }
+    A(v, p);
+    const double rhTv = dot(rh, v);
+    if (rhTv == 0.0) return 2;
+    alpha = rho / rhTv;
+    each([&](int i, int j, int k, int c) { sol(i, j, k, c) += alpha * p(i, j, k, c); sv(i, j, k, c) = r(i, j, k, c) - alpha * v(i, j, k, c); });
+    { const double q = nrm(sv); if (!(q == q)) return 9; if (q <= target) return 0; }
+    A(t, sv);
+    const double tt = dot(t, t), ts = dot(t, sv);
+    if (tt == 0.0) return 3;
+    omega = ts / tt;
+    each([&](int i, int j, int k, int c) { sol(i, j, k, c) += omega * sv(i, j, k, c); r(i, j, k, c) = sv(i, j, k, c) - omega * t(i, j, k, c); });
+    { const double q = nrm(r); if (!(q == q)) return 9; if (q <= target) return 0; }
+    if (omega == 0.0) return 4;
+    rho_1 = rho;
+  }
+  return 8;
+}
+
 struct CellMG {
   struct Lev { int n[3]; double dxinv[3]; Arr alpha, beta[3], cor, res, rescor; };
   std::vector<Lev> lv;
@@ -541,7 +591,16 @@ struct CellMG {
     Lev& B = lv[nl - 1];
     B.cor.setval(0.0);
     if (singular && nl > 1) make_solvable(B.res);
-    smooth(nl - 1, B.cor, B.res, nl == 1 ? mg.nu1 + mg.nu2 : mg.bottom_sweeps);
+    const int nsm = nl == 1 ? mg.nu1 + mg.nu2 : mg.bottom_sweeps;
+    if (mg.bottom_solver == 1 && nl > 1) {
+      int its = 0;
+      const int ret = bicgstab([&](Arr& out, Arr& in) { abec_apply(op(nl - 1, false), in, out, ncomp); }, B.cor, B.res, ncomp, false,
+                               mg.bottom_rtol, mg.bottom_maxiter, &its);
+      mg.bottom_iters += its;
+      if (ret != 0) { B.cor.setval(0.0); smooth(nl - 1, B.cor, B.res, nsm); }   // MLMG::bottomSolve falls back to smoothing
+    } else {
+      smooth(nl - 1, B.cor, B.res, nsm);
+    }
     for (int l = nl - 2; l >= 0; --l) {
       Arr& fc = lv[l].cor; const Arr& cc = lv[l + 1].cor;
       for (int c = 0; c < ncomp; ++c) { FOR_CELLS(fc, i, j, k) fc(i, j, k, c) += cc(i / 2, j / 2, k / 2, c); }
@@ -798,7 +857,20 @@ struct NodeMG {
     }
     Lev& B = lv[nl - 1];
     B.cor.setval(0.0);
-    smooth(nl - 1, B.cor, B.res, nl == 1 ? mg.nu1 + mg.nu2 : mg.bottom_sweeps);
+    const int nsm = nl == 1 ? mg.nu1 + mg.nu2 : mg.bottom_sweeps;
+    if (mg.bottom_solver == 1 && nl > 1) {
+      int its = 0;
+      const int* bn = B.cor.n;
+      if (singular()) make_solvable(B.res);   // MLMG::bottomSolve: a singular bottom problem is made solvable first
+      const int ret = bicgstab([&](Arr& out, Arr& in) {
+                                 nodal_adotx(lv[nl - 1].dxinv, lv[nl - 1].sig, in, out, bc);
+                                 FOR_NODES(out, i, j, k) if (nodal_masked(bc, bn, i, j, k)) out(i, j, k) = 0.0;
+                               }, B.cor, B.res, 1, true, mg.bottom_rtol, mg.bottom_maxiter, &its);
+      mg.bottom_iters += its;
+      if (ret != 0) { B.cor.setval(0.0); smooth(nl - 1, B.cor, B.res, nsm); }
+    } else {
+      smooth(nl - 1, B.cor, B.res, nsm);
+    }
     for (int l = nl - 2; l >= 0; --l) {
       Arr& fc = lv[l].cor; Arr& cc = lv[l + 1].cor;
       cc.fill_periodic();
@@ -813,19 +885,22 @@ struct NodeMG {
       smooth(l, fc, lv[l].res, mg.nu2);
     }
   }
-  int solve(Arr& phi, Arr& rhs) {
-    const int* n = lv[0].n;
-    if (singular()) {  // periodic / Neumann everywhere: make the rhs solvable (getSolvabilityOffset / fixSolvabilityByOffset:
-      double s1 = 0.0, s2 = 0.0;   // mean weighted with the dot mask, 1/2 per Neumann side, subtracted from every row)
-      const int n0 = n[0] + hi_ext(0, 3), n1 = n[1] + hi_ext(1, 3), n2 = n[2] + hi_ext(2, 3);
+  // periodic / Neumann everywhere: make a right-hand side solvable (getSolvabilityOffset / fixSolvabilityByOffset: mean weighted
+  // with the dot mask, 1/2 per Neumann side, subtracted from every row)
+  void make_solvable(Arr& rhs) {
+    const int* n = rhs.n;
+    double s1 = 0.0, s2 = 0.0;
+    const int n0 = n[0] + hi_ext(0, 3), n1 = n[1] + hi_ext(1, 3), n2 = n[2] + hi_ext(2, 3);
 #pragma omp parallel for reduction(+ : s1, s2)
-      for (int k = 0; k < n2; ++k) for (int j = 0; j < n1; ++j) for (int i = 0; i < n0; ++i) {
-        const double w = nodal_weight(bc, n, i, j, k);
-        s1 += w * rhs(i, j, k); s2 += w;
-      }
-      const double mean = s1 / s2;
-      FOR_NODES(rhs, i, j, k) rhs(i, j, k) -= mean;
+    for (int k = 0; k < n2; ++k) for (int j = 0; j < n1; ++j) for (int i = 0; i < n0; ++i) {
+      const double w = nodal_weight(bc, n, i, j, k);
+      s1 += w * rhs(i, j, k); s2 += w;
     }
+    const double mean = s1 / s2;
+    FOR_NODES(rhs, i, j, k) rhs(i, j, k) -= mean;
+  }
+  int solve(Arr& phi, Arr& rhs) {
+    if (singular()) make_solvable(rhs);
     const double rhsnorm = norminf_nodes(rhs);
     Arr& res = lv[0].res;
     residual(0, res, phi, rhs);
@@ -1391,7 +1466,7 @@ struct orc_ns {
   }
   std::vector<BCRec> adv_bc(int scomp, int ncomp) const { std::vector<BCRec> b(ncomp); for (int c = 0; c < ncomp; ++c) b[c] = state_bc(scomp + c); return b; }
 
-  orc_mg mg(double rtol, double atol) const { orc_mg m; orc_mg_default(&m); m.rtol = rtol; m.atol = atol; return m; }
+  orc_mg mg(double rtol, double atol) const { orc_mg m; orc_mg_default(&m); m.rtol = rtol; m.atol = atol; m.bottom_solver = p.bottom_solver; return m; }
   bool diffusive() const { return p.visc_coef > 0.0; }
   bool diffusive_tracer() const { return p.scal_diff_coef > 0.0; }   // is_diffusive[Tracer], NS_setup.cpp:292-295
   int rho_flag() const { return p.conservative_tracer ? 2 : 0; }      // Diffusion::set_rho_flag of diffusionType[Tracer], NS_setup.cpp:304-308
@@ -1674,6 +1749,7 @@ void orc_set_num_threads(int n) {   // torchrun exports OMP_NUM_THREADS=1: the C
 void orc_mg_default(orc_mg* m) {
   m->rtol = 1e-12; m->atol = 1e-16; m->max_iter = 200; m->nu1 = 2; m->nu2 = 2; m->bottom_sweeps = 8; m->max_coarsening = 100;
   m->omega = 1.15; m->iters = 0; m->resnorm0 = m->resnorm = m->rhsnorm = 0.0;
+  m->bottom_solver = 0; m->bottom_maxiter = 200; m->bottom_rtol = 1.0e-4; m->bottom_iters = 0; m->pad_ = 0;
 }
 
 static void load_faces(const int n[3], const double* bx, const double* by, const double* bz, int bn, Arr b[3]) {
@@ -2060,7 +2136,7 @@ void orc_fluxreg(const int nc[3], int ncomp, const unsigned char* mask, const do
 void orc_ns_params_default(orc_ns_params* p) {
   p->cfl = 0.7; p->visc_coef = 0.0; p->be_cn_theta = 0.5; p->change_max = 1.1; p->init_shrink = 1.0; p->fixed_dt = -1.0;
   p->gravity = 0.0; p->visc_tol = 1e-10; p->mac_tol = 1e-12; p->mac_abs_tol = 1e-16; p->proj_tol = 1e-12; p->proj_abs_tol = 1e-16;
-  p->init_iter = 2; p->init_vel_iter = 1; p->do_init_proj = 1; p->use_forces_in_trans = 0; p->conservative_tracer = 0; p->verbose = 0; p->scal_diff_coef = 0.0; p->use_ppm = 0; p->do_scalminmax = 0; p->do_mom_diff = 0;
+  p->init_iter = 2; p->init_vel_iter = 1; p->do_init_proj = 1; p->use_forces_in_trans = 0; p->conservative_tracer = 0; p->verbose = 0; p->scal_diff_coef = 0.0; p->use_ppm = 0; p->do_scalminmax = 0; p->do_mom_diff = 0; p->bottom_solver = 0;
 }
 
 orc_ns* orc_ns_create(const int n[3], const double prob_lo[3], const double prob_hi[3], const orc_ns_params* p) {

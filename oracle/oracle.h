@@ -38,6 +38,10 @@ typedef struct orc_mg {
   /* out */
   int iters;
   double resnorm0, resnorm, rhsnorm;
+  /* bottom solver: 0 = bottom_sweeps smoother sweeps, 1 = BiCGStab to bottom_rtol (MLCGSolver; IAMR's default "bicgcg") */
+  int bottom_solver, bottom_maxiter;
+  double bottom_rtol;
+  int bottom_iters, pad_;
 } orc_mg;
 void orc_mg_default(orc_mg* m);
 
@@ -121,7 +125,8 @@ typedef struct orc_ns_params {
   double scal_diff_coef;   /* ns.scal_diff_coefs of the tracer (0: non-diffusive) */
   int use_ppm;             /* ns.advection_scheme = Godunov_PPM (NSB.cpp:552-554, 4485) */
   int do_scalminmax;       /* ns.do_scalminmax (NSB.cpp:2907-2935) */
-  int do_mom_diff, pad_;   /* ns.do_mom_diff (NSB.cpp:3358-3470, 3609-3616; NS.cpp:606-623, 1016) */
+  int do_mom_diff;         /* ns.do_mom_diff (NSB.cpp:3358-3470, 3609-3616; NS.cpp:606-623, 1016) */
+  int bottom_solver;       /* orc_mg.bottom_solver of the three solves */
 } orc_ns_params;
 void orc_ns_params_default(orc_ns_params* p);
 typedef struct orc_ns orc_ns;

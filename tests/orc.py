@@ -13,7 +13,8 @@ _SO = os.path.join(_ROOT, "oracle", "_build", "liboracle.so")
 class OrcMG(C.Structure):
     _fields_ = [("rtol", C.c_double), ("atol", C.c_double), ("max_iter", C.c_int), ("nu1", C.c_int), ("nu2", C.c_int),
                 ("bottom_sweeps", C.c_int), ("max_coarsening", C.c_int), ("omega", C.c_double), ("iters", C.c_int),
-                ("resnorm0", C.c_double), ("resnorm", C.c_double), ("rhsnorm", C.c_double)]
+                ("resnorm0", C.c_double), ("resnorm", C.c_double), ("rhsnorm", C.c_double),
+                ("bottom_solver", C.c_int), ("bottom_maxiter", C.c_int), ("bottom_rtol", C.c_double), ("bottom_iters", C.c_int), ("pad_", C.c_int)]
 
 
 class OrcNSParams(C.Structure):
@@ -21,7 +22,7 @@ class OrcNSParams(C.Structure):
                 ("init_shrink", C.c_double), ("fixed_dt", C.c_double), ("gravity", C.c_double), ("visc_tol", C.c_double),
                 ("mac_tol", C.c_double), ("mac_abs_tol", C.c_double), ("proj_tol", C.c_double), ("proj_abs_tol", C.c_double),
                 ("init_iter", C.c_int), ("init_vel_iter", C.c_int), ("do_init_proj", C.c_int), ("use_forces_in_trans", C.c_int),
-                ("conservative_tracer", C.c_int), ("verbose", C.c_int), ("scal_diff_coef", C.c_double), ("use_ppm", C.c_int), ("do_scalminmax", C.c_int), ("do_mom_diff", C.c_int), ("pad_", C.c_int)]
+                ("conservative_tracer", C.c_int), ("verbose", C.c_int), ("scal_diff_coef", C.c_double), ("use_ppm", C.c_int), ("do_scalminmax", C.c_int), ("do_mom_diff", C.c_int), ("bottom_solver", C.c_int)]
 
 
 _lib = None

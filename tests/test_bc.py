@@ -449,10 +449,16 @@ WALL_RUNS = [
     # a wall-bounded 3-D flow with every wall type: no-slip x, slip y, slip / symmetry z; variable density, gravity, viscosity, diffusive tracer
     dict(n=(16, 16, 16), hi=(1.0, 1.0, 1.0), per=(0, 0, 0), lo_bc=(5, 4, 4), hi_bc=(5, 4, 3), probtype=101, pp=[1.0, 1.0, 0.3],
          kw=dict(visc_coef=0.01, cfl=0.5, gravity=-0.5, scal_diff_coef=5e-3)),
+    # the same two wall configurations with the BiCGStab bottom solver (Neumann / Dirichlet / reflect sides inside the Krylov operator)
+    dict(n=(16, 16, 32), hi=(0.5, 0.5, 1.0), per=(1, 1, 0), lo_bc=(0, 0, 4), hi_bc=(0, 0, 4), probtype=10, pp=[1.0, 2.0, 1.0, 0.0, 0.05, 0.02],
+         kw=dict(visc_coef=0.0, cfl=0.7, gravity=-1.0, bottom_solver=1)),
+    dict(n=(16, 16, 16), hi=(1.0, 1.0, 1.0), per=(0, 0, 0), lo_bc=(5, 4, 4), hi_bc=(5, 4, 3), probtype=101, pp=[1.0, 1.0, 0.3],
+         kw=dict(visc_coef=0.01, cfl=0.5, gravity=-0.5, scal_diff_coef=5e-3, bottom_solver=1)),
 ]
 
 
-@pytest.mark.parametrize("run", WALL_RUNS, ids=["rayleigh_taylor", "rayleigh_taylor_regtest_options", "lid_driven_cavity", "mixed_walls"])
+@pytest.mark.parametrize("run", WALL_RUNS, ids=["rayleigh_taylor", "rayleigh_taylor_regtest_options", "lid_driven_cavity", "mixed_walls",
+                                                 "rayleigh_taylor_bicgstab", "mixed_walls_bicgstab"])
 @pytest.mark.parametrize("nb", [(1, 1, 1), (2, 2, 2)])
 def test_step_with_walls_matches_oracle(backend, oracle, run, nb):
     """post_init (incl. the hydrostatic initialPressureProject when there is gravity) + 3 steps on wall-bounded domains:

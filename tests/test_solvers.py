@@ -195,3 +195,66 @@ def test_bottom_sweeps_do_not_change_vcycles(backend, n):
     assert res[0][0] == res[1][0]
     assert np.abs(res[0][1] - res[1][1]).max() < 1e-11
     lev.close()
+
+
+@pytest.mark.parametrize("nb", [(1, 1, 1), (2, 2, 2)])
+def test_bicgstab_bottom_solver(backend, oracle, nb):
+    """iamrx_mg_info.bottom_solver = 1: BiCGStab on the coarsest level (IAMR's default "bicgcg") instead of smoother sweeps, in
+    the cell-centred and the nodal multigrid, against the oracle's BiCGStab; and the V-cycle counts both ways."""
+    lib, dev = backend
+    rho = _rho()
+    um, vm, wm = (smooth_field(N, 300 + d, 1) for d in range(3))
+    dt = 0.7 / 16
+    boxes = split_boxes(N, nb)
+    lev = ix.Level(lib, ix.Geom.make(N), boxes)
+    its = {}
+    for bs in (0, 1):
+        mgo = oracle.mg_default(rtol=1e-13, bottom_solver=bs)
+        ru, rv, rw, rphi, rc, mgo = oracle.mac_project(DX, um[0], vm[0], wm[0], rho, None, np.zeros_like(rho), 2.0 / dt, mgo)
+        assert rc == 0
+        U = [to_fab(um, b, 1, ix.XFACE, dev) for b in boxes]
+        V = [to_fab(vm, b, 1, ix.YFACE, dev) for b in boxes]
+        W = [to_fab(wm, b, 1, ix.ZFACE, dev) for b in boxes]
+        R = [to_fab(rho, b, 1, ix.CELL, dev) for b in boxes]
+        P = [to_fab(np.zeros_like(rho), b, 1, ix.CELL, dev) for b in boxes]
+        info = _mg(lib, rtol=1e-13, bottom_solver=bs)
+        lib.check(lib.iamrx_mac_project(lev.h, fab_array([p[1] for p in U]), fab_array([p[1] for p in V]), fab_array([p[1] for p in W]),
+                                        fab_array([p[1] for p in R]), None, fab_array([p[1] for p in P]), 2.0 / dt, None, None,
+                                        C.byref(info), stream_of(dev)))
+        sync(dev)
+        got, _ = from_fabs([p[0] for p in U], boxes, 1, ix.XFACE, N, 1)
+        assert np.abs(got[0] - ru).max() < 1e-12
+        if bs == 1:
+            assert info.bottom_iters > 0 and mgo.bottom_iters > 0
+            if nb == (1, 1, 1):
+                assert info.bottom_iters == mgo.bottom_iters
+        else:
+            assert info.bottom_iters == 0
+        if nb == (1, 1, 1):
+            assert info.iters == mgo.iters
+        its[("mac", bs)] = info.iters
+    # nodal projection
+    sig = 1.0 / rho
+    vel = smooth_field(N, 400, 3)
+    for bs in (0, 1):
+        mgo = oracle.mg_default(rtol=1e-12, bottom_solver=bs)
+        rvel, rphi, rgp, rc, mgo = oracle.nodal_project(DX, vel, sig, np.zeros_like(sig), mgo)
+        assert rc == 0
+        Vf = [to_fab(vel, b, 1, ix.CELL, dev, fill_ghost=False) for b in boxes]
+        Sf = [to_fab(sig, b, 0, ix.CELL, dev) for b in boxes]
+        Pf = [to_fab(np.zeros_like(sig), b, 1, ix.NODE, dev) for b in boxes]
+        Gf = [to_fab(np.zeros_like(vel), b, 0, ix.CELL, dev) for b in boxes]
+        info = _mg(lib, rtol=1e-12, bottom_solver=bs)
+        lib.check(lib.iamrx_nodal_project(lev.h, fab_array([p[1] for p in Vf]), fab_array([p[1] for p in Sf]), fab_array([p[1] for p in Pf]),
+                                          fab_array([p[1] for p in Gf]), 0, None, None, C.byref(info), stream_of(dev)))
+        sync(dev)
+        got, _ = from_fabs([p[0] for p in Vf], boxes, 1, ix.CELL, N, 3)
+        assert np.abs(got - rvel).max() < 1e-11
+        if bs == 1:
+            assert info.bottom_iters > 0
+        if nb == (1, 1, 1):
+            assert info.iters == mgo.iters
+        its[("nodal", bs)] = info.iters
+    # the bottom level is 2^3: both bottom solvers are exact enough there, the V-cycle counts do not move
+    assert its[("mac", 0)] == its[("mac", 1)] and its[("nodal", 0)] == its[("nodal", 1)]
+    lev.close()

@@ -33,6 +33,7 @@ def _assemble(ns, which, boxes, n, ncomp, ext=(0, 0, 0)):
     (5, [1.0, 1.0, 0.0, 0.0, 0.0, 0.4], {"do_scalminmax": 1, "conservative_tracer": 1}),   # ConservativeScalMinMax
     (100, [1.0, 1.0, 1.0, 1.0, 1.0], {"do_mom_diff": 1, "gravity": -0.5}),                  # momentum form (NSB.cpp:3390-3414, 3609-3616)
     (100, [1.0, 1.0, 1.0, 1.0, 1.0], {"do_mom_diff": 1, "godunov_ppm": 1, "conservative_tracer": 1}),   # regtest.3d.rayleightaylor's options
+    (100, [1.0, 1.0, 1.0, 1.0, 1.0], {"bottom_solver": 1, "gravity": -0.5, "scal_diff_coef": 5e-3}),   # BiCGStab bottom solver in all four solves
     (20, [1.0, 1.0, 0.5], {}),   # Tutorials/HIT initial field on [-1/2, 1/2]^3 with the synthetic density variation (BASELINE configs[4])
 ])
 def test_step_matches_oracle(backend, oracle, nb, probtype, pp, extra):
