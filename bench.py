@@ -20,6 +20,7 @@ problem of Tutorials/TaylorGreen/inputs.3d.taylorgreen on a 256^3 box per GPU
 import argparse
 import ctypes as C
 import json
+import math
 import os
 import subprocess
 import sys
@@ -256,6 +257,29 @@ def verify_multirank(lib, ix, dev, rank, world, decomp):
             "n_cell": list(ncell), "dt_equal": bool(max(abs(a - b) for a, b in zip(dts[0], dts[1])) <= 1e-12 * dts[1][0])}
 
 
+def bind_to_gpu_numa_node(torch, local):
+    """Multi-rank runs: pin this rank's host threads (and hence its first-touch pinned staging buffers) to the NUMA node its GPU
+    hangs off, so that the e2e leg's host<->device copies of all ranks do not funnel through one socket.  Best effort: returns
+    the node or None."""
+    try:
+        p = torch.cuda.get_device_properties(local)
+        bdf = "%04x:%02x:%02x.0" % (p.pci_domain_id, p.pci_bus_id, p.pci_device_id)
+        node = int(open(f"/sys/bus/pci/devices/{bdf}/numa_node").read())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if not cpus:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return node
+    except Exception:
+        return None
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -268,6 +292,7 @@ def run_ours(args):
         raise SystemExit("bench.py: no CUDA device; iamr_b200 has no CPU path (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local)
     dev = f"cuda:{local}"
+    numa = bind_to_gpu_numa_node(torch, local) if world > 1 else None
     lib = ix.load()
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device(dev))
@@ -285,12 +310,25 @@ def run_ours(args):
     verify = verify_multirank(lib, ix, dev, rank, world, args.decomp) if (world > 1 and not args.no_verify) else None
 
     nbox = args.n
-    ncell, boxes, owners, prob_hi = domain_for(world, nbox, args.decomp)
-    g = ix.Geom.make(ncell, (0.0, 0.0, 0.0), prob_hi)
-    lev = ix.Level(lib, g, boxes, owners)
     hit = args.problem == "hit"
+    rt = args.problem == "rt"
     bs = 1 if args.bottom_solver == "bicgstab" else 0
-    if hit:   # BASELINE.json configs[4]: Tutorials/HIT initial field, nu = 1e-4, proj_tol 1e-10 (inputs.3d.forced:129), synthetic variable density.
+    if rt:
+        # BASELINE.json configs[3] geometry on ONE level: RayleighTaylor 256^2 x 512 (regtest.3d.rayleightaylor: periodic x / y, slip
+        # walls in z, gravity -1, inviscid, rho 1 -> 2), the fixed domain split into N z slabs (strong scaling: N must divide 512)
+        ncell = (nbox, nbox, 2 * nbox)
+        nzs = ncell[2] // world
+        boxes = [((0, 0, r * nzs), (nbox - 1, nbox - 1, (r + 1) * nzs - 1)) for r in range(world)]
+        owners = list(range(world))
+        g = ix.Geom.make(ncell, (0.0, 0.0, 0.0), (0.5, 0.5, 1.0), periodic=(1, 1, 0))
+    else:
+        ncell, boxes, owners, prob_hi = domain_for(world, nbox, args.decomp)
+        g = ix.Geom.make(ncell, (0.0, 0.0, 0.0), prob_hi)
+    lev = ix.Level(lib, g, boxes, owners)
+    if rt:
+        ns = ix.NavierStokes(lib, lev, dev, lo_bc=(0, 0, 4), hi_bc=(0, 0, 4), visc_coef=0.0, cfl=CFL, gravity=-1.0, bottom_solver=bs)
+        ns.init_prob(10, [1.0, 2.0, 1.0, 0.0, 0.01, 0.005])
+    elif hit:   # BASELINE.json configs[4]: Tutorials/HIT initial field, nu = 1e-4, proj_tol 1e-10 (inputs.3d.forced:129), synthetic variable density.
         # mac_tol 1e-10: at 512^3 the fp64 round-off floor of the MAC residual is eps / (h k)^2 ~ 4e-12 of the right-hand side for
         # domain-scale modes (profiles/r02_notes.md: residual stalls at 3.7e-12 relative), above IAMR's default 1e-12 -- the
         # reference's MLMG would abort the same way; a site running this case sets mac_proj.mac_tol as here.
@@ -356,10 +394,12 @@ def run_ours(args):
 
     # ---- end-to-end steps through the host-buffer entry ---------------------------
     nloc = lev.num_local()
-    e2e_value, state_bytes, checksum = None, 5 * nbox ** 3 * 8 * nloc, None
+    mine = [b for b, o in zip(boxes, owners) if o == rank]
+    shp = [(5,) + tuple(hi[d] - lo[d] + 1 for d in (2, 1, 0)) for lo, hi in mine]
+    e2e_value, state_bytes, checksum = None, sum(8 * math.prod(q) for q in shp), None
     if args.e2e_steps > 0:
-        hin = [torch.empty((5, nbox, nbox, nbox), dtype=torch.float64).pin_memory() for _ in range(nloc)]
-        hout = [torch.empty((5, nbox, nbox, nbox), dtype=torch.float64).pin_memory() for _ in range(nloc)]
+        hin = [torch.empty(q, dtype=torch.float64).pin_memory() for q in shp]
+        hout = [torch.empty(q, dtype=torch.float64).pin_memory() for q in shp]
         for il in range(nloc):
             hin[il].copy_(ns.field(0, il))
         ns.step_host(hin, hout)      # warm-up of the staging path
@@ -423,12 +463,18 @@ def run_ours(args):
         if hit:
             cfg["workload"] = (f"HIT 3D {nbox}^3 per GPU single-level variable-density (Tutorials/HIT/prob_init.cpp:100-131 field, nu=1e-4, "
                                f"proj_tol 1e-10, mac_tol 1e-10 (fp64 floor at 512^3), rho = 1 + 0.5 sin sin sin, forcing off), BASELINE.json configs[4]" + ("" if world == 1 else " weak-scaled"))
+        if rt:
+            cfg["workload"] = (f"RayleighTaylor 3D {ncell[0]}x{ncell[1]}x{ncell[2]} SINGLE level (BASELINE.json configs[3] geometry without the fine level: "
+                               f"periodic x/y, slip walls z, gravity, inviscid, rho 1->2), fixed domain in {world} z slab(s)")
+            cfg["parallelism"] = f"{world} z slab(s) of {ncell[2] // world} planes; x/y wrapped in-kernel, z ghost planes over NCCL, walls mirrored in the kernels"
         cfg["mg_iters_last_step"] = {"mac": iters[-1][0], "visc": iters[-1][1], "nodal": iters[-1][2]}
         cfg["bottom_solver"] = args.bottom_solver
+        if numa is not None:
+            cfg["host_numa_node_rank0"] = numa
         cfg["timing"] = "headline pass without per-launch events; roofline from a separate pass of %d steps" % args.prof_steps
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong" if rt else "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic", "config": cfg,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": state_bytes, "d2h_bytes_per_step": state_bytes,
                     "steps": args.e2e_steps, "api": "iamrx_ns_step_host (pinned host state in, new state out)",
@@ -464,7 +510,8 @@ def main():
     ap.add_argument("--decomp", default="slabs", choices=["slabs", "blocks"], help="weak-scaling decomposition: z slabs or 3-D blocks")
     ap.add_argument("--bottom-solver", default="smoother", choices=["smoother", "bicgstab"],
                     help="multigrid bottom solver: smoother sweeps (default) or BiCGStab (IAMR's bicgcg)")
-    ap.add_argument("--problem", default="tg", choices=["tg", "hit"], help="tg: BASELINE configs[1]; hit: configs[4] (HIT, variable density)")
+    ap.add_argument("--problem", default="tg", choices=["tg", "hit", "rt"],
+                    help="tg: BASELINE configs[1]; hit: configs[4] (HIT, variable density); rt: configs[3] geometry on one level (walls, gravity; strong-scaled)")
     ap.add_argument("--prof-steps", type=int, default=3, help="steps of the separate roofline pass")
     ap.add_argument("--no-verify", action="store_true", help="skip the untimed multi-rank parity leg")
     ap.add_argument("--e2e-steps", type=int, default=3)

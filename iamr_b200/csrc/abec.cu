@@ -726,6 +726,11 @@ bool abec_gsrb_sweep_ok(const Bx& bx, int wrapmask) {
   (void)bx;
   return wrapmask == 7;
 #else
+  // IAMRX_GSRB_FUSED_MIN=<cells>: only boxes at least this large take the fused sweep (it wins on HBM-resident levels and
+  // loses on the L2-resident coarser ones)
+  static int64_t min_cells = -1;
+  if (min_cells < 0) { const char* e = getenv("IAMRX_GSRB_FUSED_MIN"); min_cells = e ? atoll(e) : 0; }
+  if (bx.npts() < min_cells) return false;
   return sweep::gsrb_sweep_ok(bx, wrapmask);
 #endif
 }

@@ -137,8 +137,34 @@ def main():
             err2 = max(err2, np.abs(t - So[:, lo[2]:hi[2] + 1, lo[1]:hi[1] + 1, lo[0]:hi[0] + 1]).max())
         assert err2 <= 1e-10, err2
     o3.close()
-    # 5. reductions agree across ranks
-    t = torch.tensor([max(err, err2)])
+    # 5. walls across ranks: single-level RayleighTaylor (periodic x, y; slip walls in z; gravity, initialPressureProject) as two
+    #    z slabs (each rank owns one wall) and as 2 x 1 x 2 blocks (deep-ghost nodal sweep in x, walls in z), vs the oracle
+    nrt = (16, 16, 32)
+    grt = ix.Geom.make(nrt, (0.0, 0.0, 0.0), (0.5, 0.5, 1.0), periodic=(1, 1, 0))
+    kwrt = dict(visc_coef=1e-3, cfl=0.7, gravity=-1.0)
+    ppr = [1.0, 2.0, 1.0, 0.0, 0.05, 0.02]
+    ort = orc.OracleNS(nrt, (0, 0, 0), (0.5, 0.5, 1.0), per=(1, 1, 0), phys_lo=(0, 0, 4), phys_hi=(0, 0, 4), **kwrt)
+    ort.init_prob(10, ppr)
+    dto = [ort.post_init()] + [ort.step() for _ in range(2)]
+    Srt = ort.get(0)
+    err3 = 0.0
+    for nbk, own in (((1, 1, 2), [0, 1]), ((2, 1, 2), [0, 1, 1, 0])):
+        bxs = split_boxes(nrt, nbk)
+        lv = ix.Level(lib, grt, bxs, own)
+        nsr = ix.NavierStokes(lib, lv, "cpu", lo_bc=(0, 0, 4), hi_bc=(0, 0, 4), **kwrt)
+        nsr.init_prob(10, ppr)
+        dts = [nsr.post_init()] + [nsr.step() for _ in range(2)]
+        assert np.allclose(dts, dto, rtol=1e-11, atol=0), (dts, dto)
+        for il, gi in enumerate([i for i, o_ in enumerate(own) if o_ == rank]):
+            lo, hi = bxs[gi]
+            t = nsr.field(0, il).numpy()
+            nz, ny, nx = hi[2] - lo[2] + 1, hi[1] - lo[1] + 1, hi[0] - lo[0] + 1
+            err3 = max(err3, np.abs(t[:, :nz, :ny, :nx] - Srt[:, lo[2]:hi[2] + 1, lo[1]:hi[1] + 1, lo[0]:hi[0] + 1]).max())
+        nsr.close(); lv.close()
+    assert err3 <= 1e-10, err3
+    ort.close()
+    # 6. reductions agree across ranks
+    t = torch.tensor([max(err, err2, err3)])
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     print(f"rank {rank} ok max_err {t.item():.3e}", flush=True)
     ns.close(); lev.close()
