@@ -257,6 +257,44 @@ def verify_multirank(lib, ix, dev, rank, world, decomp):
             "n_cell": list(ncell), "dt_equal": bool(max(abs(a - b) for a, b in zip(dts[0], dts[1])) <= 1e-12 * dts[1][0])}
 
 
+def hit_forcedata(L, nmodes=4, seed=111397, array_size=33):
+    """A TurbulentForcing::forcedata table (17 x 33^3) with the structure TurbulentForcing_def.H:141-230 builds for
+    inputs.3d.forced (turb.nmodes = 4, mode_start 0, div_free_force, spectrum_type 2, moderate_zero_modes); the random
+    numbers come from numpy, not DepRand -- the table is an INPUT of the forcing kernel."""
+    import numpy as np
+    rng = np.random.default_rng(seed)
+    fd = np.zeros((17, array_size, array_size, array_size))
+    lmin = min(L)
+    step = [int(l / lmin + 0.5) for l in L]
+    kmax = nmodes / lmin + 1e-8
+
+    def fill(kx, ky, kz):
+        kappa = math.sqrt((kx / L[0]) ** 2 + (ky / L[1]) ** 2 + (kz / L[2]) ** 2)
+        if kappa > kmax:
+            return
+        fd[0, kz, ky, kx] = (1.0 + rng.random()) * 2 * math.pi
+        fd[1:5, kz, ky, kx] = rng.random(4) * 2 * math.pi
+        fd[8:17, kz, ky, kx] = rng.random(9) * 2 * math.pi
+        th, ph = rng.random() * 2 * math.pi, rng.random() * math.pi
+        p = np.array([math.cos(th) * math.sin(ph), math.sin(th) * math.sin(ph), math.cos(ph)])
+        if kappa < 1e-6:
+            return
+        e = 1.0 / kappa ** 3
+        for kk in (kx, ky, kz):
+            if kk == 0:
+                e /= 2.0
+        fd[5:8, kz, ky, kx] = p * e / float(p @ p)
+    for kz in range(0, nmodes * step[2] + 1, step[2]):
+        for ky in range(0, nmodes * step[1] + 1, step[1]):
+            for kx in range(0, nmodes * step[0] + 1, step[0]):
+                fill(kx, ky, kz)
+    for kz in range(1, step[2]):
+        for ky in range(0, nmodes * step[1] + 1):
+            for kx in range(0, nmodes * step[0] + 1):
+                fill(kx, ky, kz)
+    return fd
+
+
 def bind_to_gpu_numa_node(torch, local):
     """Multi-rank runs: pin this rank's host threads (and hence its first-touch pinned staging buffers) to the NUMA node its GPU
     hangs off, so that the e2e leg's host<->device copies of all ranks do not funnel through one socket.  Best effort: returns
@@ -333,6 +371,8 @@ def run_ours(args):
         # domain-scale modes (profiles/r02_notes.md: residual stalls at 3.7e-12 relative), above IAMR's default 1e-12 -- the
         # reference's MLMG would abort the same way; a site running this case sets mac_proj.mac_tol as here.
         ns = ix.NavierStokes(lib, lev, dev, visc_coef=NU, cfl=CFL, proj_tol=1e-10, mac_tol=1e-10, bottom_solver=bs)
+        if not args.no_forcing:   # USE_TURBULENT_FORCING = TRUE (Tutorials/HIT/GNUmakefile), turb.nmodes = 4 (inputs.3d.forced:110)
+            ns.set_turbulent_forcing(4, 0, 1, hit_forcedata(prob_hi))
         ns.init_prob(20, [1.0, 1.0, 0.5])
     else:
         ns = ix.NavierStokes(lib, lev, dev, visc_coef=NU, cfl=CFL, bottom_solver=bs)
@@ -462,7 +502,7 @@ def run_ours(args):
         cfg = workload_config(nbox, world, ncell, len(boxes), args.decomp)
         if hit:
             cfg["workload"] = (f"HIT 3D {nbox}^3 per GPU single-level variable-density (Tutorials/HIT/prob_init.cpp:100-131 field, nu=1e-4, "
-                               f"proj_tol 1e-10, mac_tol 1e-10 (fp64 floor at 512^3), rho = 1 + 0.5 sin sin sin, forcing off), BASELINE.json configs[4]" + ("" if world == 1 else " weak-scaled"))
+                               f"proj_tol 1e-10, mac_tol 1e-10 (fp64 floor at 512^3), rho = 1 + 0.5 sin sin sin, turbulent forcing {'off' if args.no_forcing else 'on: turb.nmodes 4, div-free, synthetic mode table'}), BASELINE.json configs[4]" + ("" if world == 1 else " weak-scaled"))
         if rt:
             cfg["workload"] = (f"RayleighTaylor 3D {ncell[0]}x{ncell[1]}x{ncell[2]} SINGLE level (BASELINE.json configs[3] geometry without the fine level: "
                                f"periodic x/y, slip walls z, gravity, inviscid, rho 1->2), fixed domain in {world} z slab(s)")
@@ -508,6 +548,7 @@ def main():
     ap.add_argument("--n", type=int, default=256, help="box size per GPU")
     ap.add_argument("--cpu-n", type=int, default=0, help="box size of the CPU runs (0: --impl reference uses --n, the cpu_baseline leg 128)")
     ap.add_argument("--decomp", default="slabs", choices=["slabs", "blocks"], help="weak-scaling decomposition: z slabs or 3-D blocks")
+    ap.add_argument("--no-forcing", action="store_true", help="--problem hit without the tutorial's turbulent forcing")
     ap.add_argument("--bottom-solver", default="smoother", choices=["smoother", "bicgstab"],
                     help="multigrid bottom solver: smoother sweeps (default) or BiCGStab (IAMR's bicgcg)")
     ap.add_argument("--problem", default="tg", choices=["tg", "hit", "rt"],

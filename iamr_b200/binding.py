@@ -194,6 +194,9 @@ SIGNATURES = {
     "iamrx_ns_create": (C.c_int, [_vp, _P(NSParams), _P(_vp)]),
     "iamrx_ns_destroy": (C.c_int, [_vp]),
     "iamrx_ns_init_prob": (C.c_int, [_vp, C.c_int, _P(C.c_double), C.c_int]),
+    "iamrx_ns_set_turbulent_forcing": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, C.c_int, _P(C.c_double)]),
+    "iamrx_turbulent_force_box": (C.c_int, [_P(Box), _P(Fab), _P(Fab), _P(Geom), C.c_double, C.c_int, C.c_int, C.c_int, C.c_int,
+                                            _P(C.c_double), _vp]),
     "iamrx_ns_post_init": (C.c_int, [_vp, _P(C.c_double)]),
     "iamrx_ns_step": (C.c_int, [_vp, _P(C.c_double)]),
     "iamrx_ns_time": (C.c_double, [_vp]),
@@ -347,6 +350,14 @@ class NavierStokes:
         h = C.c_void_p()
         lib.check(lib.iamrx_ns_create(level.h, C.byref(p), C.byref(h)))
         self.h = h
+
+    def set_turbulent_forcing(self, nmodes, mode_start, div_free_force, forcedata):
+        """forcedata: numpy float64 array [17, as, as, as] indexed [array, kz, ky, kx] (i fastest, TurbulentForcing::forcedata)."""
+        import numpy as np
+        fd = np.ascontiguousarray(forcedata, dtype=np.float64)
+        assert fd.ndim == 4 and fd.shape[0] == 17 and fd.shape[1] == fd.shape[2] == fd.shape[3]
+        self.lib.check(self.lib.iamrx_ns_set_turbulent_forcing(self.h, nmodes, mode_start, int(div_free_force), fd.shape[1],
+                                                              fd.ctypes.data_as(_P(C.c_double))))
 
     def init_prob(self, probtype, params):
         arr = (C.c_double * len(params))(*params)

@@ -370,6 +370,31 @@ int iamrx_fill_physbc(iamrx_level_t lev, iamrx_fab* fabs, int ncomp, int ngrow, 
   IX_GUARD_END
 }
 
+int iamrx_turbulent_force_box(const iamrx_box* bx, iamrx_fab* frc, const iamrx_fab* rho, const iamrx_geom* geom, double time,
+                              int nmodes, int mode_start, int div_free_force, int array_size, const double* forcedata, void* stream) {
+  IX_GUARD_BEGIN
+  IX_NEED_DEVICE();
+  IX_ARG(bx && frc && geom && forcedata, "null argument");
+  IX_ARG(nmodes > 0 && mode_start >= 0 && mode_start <= nmodes && array_size > 0, "bad turbulent forcing parameters");
+  const Bx b = mkbx(*bx);
+  IX_ARG(frc->ncomp >= 3 && covers(frc, b), "force array does not cover the box");
+  IX_ARG(!rho || covers(rho, b), "density array does not cover the box");
+  double len[3];
+  for (int d = 0; d < 3; ++d) len[d] = (geom->domain.hi[d] - geom->domain.lo[d] + 1) * geom->dx[d];
+  const k::TurbParams tp{nmodes, mode_start, div_free_force ? 1 : 0, array_size};
+  std::vector<k::TurbMode> modes;
+  if (k::turb_modes(tp, forcedata, len, time, modes) != IAMRX_OK) { set_error("turbulent forcing: mode index beyond array_size"); return IAMRX_ERR_ARG; }
+  const int nm = (int)modes.size();
+  const size_t md = (modes.size() * sizeof(k::TurbMode) + 7) / 8 + 8;
+  struct Guard { double* p; ~Guard() { dev_free(p); } } g{dev_alloc(md + k::turb_scratch_doubles(b, nm) + 8)};
+  if (!g.p) return IAMRX_ERR_CUDA;
+  if (nm > 0) IX_CUDA(cudaMemcpyAsync(g.p, modes.data(), modes.size() * sizeof(k::TurbMode), cudaMemcpyHostToDevice, S(stream)));
+  int rc = k::turb_force(b, view(frc, 0), rho ? cview(rho, 0) : C4{}, *geom, reinterpret_cast<const k::TurbMode*>(g.p), nm, tp.div_free, g.p + md, 1, S(stream));
+  IX_CUDA(cudaStreamSynchronize(S(stream)));   // the scratch and the host mode list are released on return
+  return rc;
+  IX_GUARD_END
+}
+
 void iamrx_mg_info_default(iamrx_mg_info* info) {
   if (!info) return;
   memset(info, 0, sizeof(*info));

@@ -181,11 +181,26 @@ int floor_small(const Bx& bx, V4 f, int ncomp, cudaStream_t s);
 // velocity forcing: tf_n = getForce_n + visc_n - gp_n, optionally / rho
 // (NSB.cpp:4456-4470, 3445-3466, 1411-1424); getForce = NS_getForce.cpp:117-141
 // (buoyancy grav*rho on the z component when |grav| > 1e-4).  visc / gp may be null.
-int force_vel(const Bx& bx, V4 tf, C4 visc, C4 gp, C4 rho, double grav, int div_rho, cudaStream_t s);
+// uf: optional user force per unit mass (the HIT turbulent forcing, 3 comps): f += rho * uf
+int force_vel(const Bx& bx, V4 tf, C4 visc, C4 gp, C4 rho, double grav, int div_rho, cudaStream_t s, C4 uf = C4{});
+
+// ---- HIT turbulent forcing (forcing.cu; Tutorials/HIT/NS_getForce.cpp:205-640) -----------------------------------------
+struct TurbParams { int nmodes, mode_start, div_free, array_size; };
+struct TurbMode { double w[3]; double ph[3][3]; double a[3]; };   // 2 pi k_d / L_d; phases [component][direction]; xT * amplitudes
+}  // namespace k
+}  // namespace ix
+#include <vector>
+namespace ix {
+namespace k {
+int turb_modes(const TurbParams& tp, const double* forcedata, const double L[3], double time, std::vector<TurbMode>& out);
+size_t turb_scratch_doubles(const Bx& bx, int nm);
+// frc (3 comps) = or += rho * f(x, t) on bx; d_modes / d_tab: device copies of the mode list / table scratch
+int turb_force(const Bx& bx, V4 frc, C4 rho, const iamrx_geom& g, const TurbMode* d_modes, int nm, int div_free, double* d_tab,
+               int accumulate, cudaStream_t s);
 // velocity update NSB.cpp:3607-3626; do_mom_diff when rho_old / rho_new are given (u_new = (rho_old u_old - dt aofs + dt f - dt gp) / rho_new):
 //   unew = uold - dt*aofs + dt*(getForce(rho_half) - gp)/rho_half
 int vel_update(const Bx& bx, V4 unew, C4 uold, C4 aofs, C4 gp, C4 rhohalf, double grav, double dt,
-               int zero_force, cudaStream_t s, C4 rho_old = C4{}, C4 rho_new = C4{});
+               int zero_force, cudaStream_t s, C4 rho_old = C4{}, C4 rho_new = C4{}, C4 uf = C4{});
 // scalar update NSB.cpp:2761-2765 / 2887-2896 with the default (zero) scalar forcing
 int scal_update(const Bx& bx, V4 snew, C4 sold, C4 aofs, double dt, int ncomp, cudaStream_t s);
 // ns.do_scalminmax: Conservative / ConvectiveScalMinMax (NSB.cpp:2907-2935, 4256-4370); sold / rhoold need 1 filled ghost cell

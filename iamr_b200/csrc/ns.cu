@@ -50,6 +50,13 @@ struct iamrx_ns_s {
   MF s1, r1, svisc, ones;  // tracer diffusion work: Soln (1 ghost), Rhs, visc term (1 ghost), alpha = 1
   MF smm;                  // old scalars (density, tracer) with 1 filled ghost for ns.do_scalminmax
 
+  // HIT turbulent forcing (Tutorials/HIT/NS_getForce.cpp:205-640): off unless iamrx_ns_set_turbulent_forcing was called
+  bool turb_on = false;
+  k::TurbParams turb{};
+  std::vector<double> turb_data;   // host copy of TurbulentForcing::forcedata
+  MF turbf;                        // f(x, t) per unit mass, 3 comps, 1 ghost
+  double* turb_dev = nullptr; size_t turb_dev_n = 0;   // device scratch: mode list + axis tables
+
   double time = 0.0, dt_level = 0.0, dt_min = 1.0e100;
   int nstep = 0;
   bool initial_step = false, initial_iter = false;
@@ -190,11 +197,38 @@ int get_visc_terms(iamrx_ns_s& ns, MF& visc, const MF& S) {
   return fill_extrap(ns, visc, 3);
 }
 
+// the user force of getForce at `time` on the ng-ghost boxes -> ns.turbf (per unit mass; the callers weight it with the density
+// getForce is handed at that call site)
+int turb_eval(iamrx_ns_s& ns, double time, int ng) {
+  if (!ns.turb_on) return IAMRX_OK;
+  Level& L = *ns.L;
+  double len[3];
+  for (int d = 0; d < 3; ++d) len[d] = (L.domain.hi[d] - L.domain.lo[d] + 1) * L.geom.dx[d];
+  std::vector<k::TurbMode> modes;
+  IX_TRY(k::turb_modes(ns.turb, ns.turb_data.data(), len, time, modes));
+  const int nm = (int)modes.size();
+  const size_t mode_doubles = (modes.size() * sizeof(k::TurbMode) + 7) / 8;
+  size_t need = mode_doubles + 16;
+  for (int il = 0; il < ns.turbf.n(); ++il) need = std::max(need, mode_doubles + 16 + k::turb_scratch_doubles(ns.turbf.gbox(il, ng), nm));
+  if (need > ns.turb_dev_n) {
+    if (ns.turb_dev) dev_free(ns.turb_dev);
+    ns.turb_dev = dev_alloc(need); ns.turb_dev_n = ns.turb_dev ? need : 0;
+    if (!ns.turb_dev) return IAMRX_ERR_CUDA;
+  }
+  if (nm > 0) IX_CUDA(cudaMemcpyAsync(ns.turb_dev, modes.data(), modes.size() * sizeof(k::TurbMode), cudaMemcpyHostToDevice, ns.s));
+  IX_CUDA(cudaStreamSynchronize(ns.s));   // `modes` is a local: the copy must have left it
+  for (int il = 0; il < ns.turbf.n(); ++il)
+    IX_TRY(k::turb_force(ns.turbf.gbox(il, ng), ns.turbf.v(il), C4{}, L.geom, reinterpret_cast<const k::TurbMode*>(ns.turb_dev), nm,
+                         ns.turb.div_free, ns.turb_dev + mode_doubles + 8, 0, ns.s));
+  return IAMRX_OK;
+}
+inline C4 turb_c(const iamrx_ns_s& ns, int il) { return ns.turb_on ? ns.turbf.c(il) : C4{}; }
+
 // velocity forcing on the 1-ghost box: tf = (getForce + visc - gp)/rho  (NSB.cpp:4456-4470 == 3445-3466)
 int vel_forcing(iamrx_ns_s& ns) {
   for (int il = 0; il < ns.force.n(); ++il)
     IX_TRY(k::force_vel(ns.force.gbox(il, 1), ns.force.v(il), ns.visc.c(il), ns.Gp_old.c(il), ns.Smf.c(il, 0),
-                        ns.p.gravity, 1, ns.s));
+                        ns.p.gravity, 1, ns.s, turb_c(ns, il)));
   return IAMRX_OK;
 }
 
@@ -270,7 +304,7 @@ int velocity_advection(iamrx_ns_s& ns, double dt) {
     // ns.Smf(0) is the old density with 3 filled ghosts (its floor at 1e-20 never bites a density); ns.visc still holds visc^n.
     for (int il = 0; il < ns.Umf.n(); ++il) {
       IX_TRY(k::mult(ns.Umf.gbox(il, 3), ns.Umf.v(il), ns.Smf.c(il, 0), 3, 1, ns.s));
-      IX_TRY(k::force_vel(ns.force.gbox(il, 1), ns.force.v(il), ns.visc.c(il), ns.Gp_old.c(il), ns.Smf.c(il, 0), ns.p.gravity, 0, ns.s));
+      IX_TRY(k::force_vel(ns.force.gbox(il, 1), ns.force.v(il), ns.visc.c(il), ns.Gp_old.c(il), ns.Smf.c(il, 0), ns.p.gravity, 0, ns.s, turb_c(ns, il)));
     }
     return compute_aofs(ns, Xvel, 3, ns.Umf, &ns.force, true, dt);  // conservative: advectionType[Xvel..] (NS_setup.cpp:297-299)
   }
@@ -360,15 +394,16 @@ int velocity_diffusion_update(iamrx_ns_s& ns, double dt) {
 }
 
 // NavierStokesBase::initial_velocity_diffusion_update (NSB.cpp:3658-3749)
-int initial_velocity_diffusion_update(iamrx_ns_s& ns, double dt) {
+int initial_velocity_diffusion_update(iamrx_ns_s& ns, double time, double dt) {
   if (!ns.diffusive_vel()) return IAMRX_OK;
   Level& L = *ns.L;
+  IX_TRY(turb_eval(ns, time, 0));   // getForce at prev_time (:3696)
   if (ns.p.be_cn_theta != 1.0) IX_TRY(get_visc_terms(ns, ns.visc, ns.S_old));
   else IX_TRY(mf_setval(ns.visc, 0.0, 0, 3, 1, ns.s));
   for (int il = 0; il < ns.tf0.n(); ++il) {
     // force = (getForce(rho_old) + visc - gp)/rho_half - aofs ; u_new = u_old + dt*force
     IX_TRY(k::force_vel(L.lbox(il), ns.tf0.v(il), ns.visc.c(il), ns.Gp_old.c(il), ns.S_old.c(il, Density),
-                        ns.p.gravity, 0, ns.s));
+                        ns.p.gravity, 0, ns.s, turb_c(ns, il)));
     if (!ns.p.do_mom_diff) IX_TRY(k::divide(L.lbox(il), ns.tf0.v(il), ns.rho_half.c(il), 3, 1, ns.s));
     IX_TRY(k::lincomb(L.lbox(il), ns.tf0.v(il), 1.0, ns.tf0.c(il), -1.0, ns.aofs.c(il, Xvel), 3, ns.s));
     if (ns.p.do_mom_diff) {   // :3743-3744 u_new = (force dt + u_old rho_old) / rho_new
@@ -402,8 +437,8 @@ int level_project(iamrx_ns_s& ns, double dt) {
 
 // NavierStokes::advance (NS.cpp:543-691)
 int advance(iamrx_ns_s& ns, double time, double dt, double* dt_test) {
-  (void)time;
   Level& L = *ns.L;
+  IX_TRY(turb_eval(ns, time, 1));   // getForce at prev_time for predict_velocity / velocity_advection (NSB.cpp:4453, 3448)
   // advance_setup (NSB.cpp:613-741): swap time levels, rho at the previous time
   std::swap(ns.S_old, ns.S_new);
   std::swap(ns.P_old, ns.P_new);
@@ -437,12 +472,14 @@ int advance(iamrx_ns_s& ns, double time, double dt, double* dt_test) {
 #endif
   // velocity_update :645 -> NSB.cpp:3487: rho_half (:1561-1565), advection update (:3523-3655), diffusion
   IX_TRY(mf_lincomb(ns.rho_half, 0, 0.5, ns.rho_ptime, 0, 0.5, ns.rho_ctime, 0, 1, 1, ns.s));
+  IX_TRY(turb_eval(ns, time + 0.5 * dt, 0));   // getForce at half_time with the half-time density (NSB.cpp:3581-3583)
   for (int il = 0; il < ns.S_new.n(); ++il)
     IX_TRY(k::vel_update(L.lbox(il), ns.S_new.v(il, Xvel), ns.S_old.c(il, Xvel), ns.aofs.c(il, Xvel), ns.Gp_old.c(il),
                          ns.rho_half.c(il), ns.p.gravity, dt, (ns.initial_iter && ns.diffusive_vel()) ? 1 : 0, ns.s,
-                         ns.p.do_mom_diff ? ns.S_old.c(il, Density) : C4{}, ns.p.do_mom_diff ? ns.S_new.c(il, Density) : C4{}));
+                         ns.p.do_mom_diff ? ns.S_old.c(il, Density) : C4{}, ns.p.do_mom_diff ? ns.S_new.c(il, Density) : C4{},
+                         turb_c(ns, il)));
   if (!ns.initial_iter) IX_TRY(velocity_diffusion_update(ns, dt));
-  else IX_TRY(initial_velocity_diffusion_update(ns, dt));
+  else IX_TRY(initial_velocity_diffusion_update(ns, time, dt));
   if (!ns.initial_step) IX_TRY(level_project(ns, dt));         // :650-670
   return IAMRX_OK;
 }
@@ -455,8 +492,9 @@ int est_time_step(iamrx_ns_s& ns, double* out) {
   double estdt = 1.0e20;
   double umax[3], fmax[3];
   IX_TRY(mf_norminf_each(ns.S_new, Xvel, 3, umax, ns.s));
+  IX_TRY(turb_eval(ns, ns.time, 0));   // getForce at cur_time (:1410)
   for (int il = 0; il < ns.tf0.n(); ++il)
-    IX_TRY(k::force_vel(L.lbox(il), ns.tf0.v(il), C4{}, ns.Gp_new.c(il), ns.S_new.c(il, Density), ns.p.gravity, 1, ns.s));
+    IX_TRY(k::force_vel(L.lbox(il), ns.tf0.v(il), C4{}, ns.Gp_new.c(il), ns.S_new.c(il, Density), ns.p.gravity, 1, ns.s, turb_c(ns, il)));
   IX_TRY(mf_norminf_each(ns.tf0, 0, 3, fmax, ns.s));
   for (int d = 0; d < 3; ++d) {
     if (umax[d] > small) estdt = std::min(estdt, L.geom.dx[d] / umax[d]);
@@ -573,10 +611,35 @@ int iamrx_ns_create(iamrx_level_t lev, const iamrx_ns_params* p, iamrx_ns_t* out
 
 int iamrx_ns_destroy(iamrx_ns_t ns) {
   if (ns && ns->stage) cudaFreeHost(ns->stage);
+  if (ns && ns->turb_dev) dev_free(ns->turb_dev);
 #if !defined(IX_EMUL)
   if (ns && ns->s2) { cudaStreamDestroy(ns->s2); cudaEventDestroy(ns->ev_scal); }
 #endif
   delete ns;
+  return IAMRX_OK;
+}
+
+int iamrx_ns_set_turbulent_forcing(iamrx_ns_t ns, int nmodes, int mode_start, int div_free_force, int array_size, const double* forcedata) {
+  IX_NEED_DEVICE();
+  IX_ARG(ns, "null argument");
+  if (!forcedata || nmodes <= 0) { ns->turb_on = false; return IAMRX_OK; }
+  IX_ARG(array_size > 0 && mode_start >= 0 && mode_start <= nmodes, "bad turbulent forcing parameters");
+  for (int d = 0; d < 3; ++d) IX_ARG(ns->L->geom.periodic[d], "turbulent forcing needs a triply periodic domain");
+  const size_t n = (size_t)17 * array_size * array_size * array_size;
+  ns->turb_data.resize(n);
+  // the table may live in host or device memory (TurbulentForcing_def.H:350-364 puts it in The_Arena on GPU builds)
+  IX_CUDA(cudaMemcpy(ns->turb_data.data(), forcedata, n * sizeof(double), cudaMemcpyDefault));
+  ns->turb = k::TurbParams{nmodes, mode_start, div_free_force ? 1 : 0, array_size};
+  if (!ns->turbf.ok()) { ns->turbf.define(ns->L, IX_CELL, 3, 1); IX_TRY(mf_setval(ns->turbf, 0.0, 0, 3, 1, ns->s)); }
+  // every mode index the loops can reach must lie inside the table
+  double len[3];
+  for (int d = 0; d < 3; ++d) len[d] = (ns->L->domain.hi[d] - ns->L->domain.lo[d] + 1) * ns->L->geom.dx[d];
+  std::vector<k::TurbMode> probe;
+  if (k::turb_modes(ns->turb, ns->turb_data.data(), len, 0.0, probe) != IAMRX_OK) {
+    set_error("turbulent forcing: mode index beyond array_size");
+    return IAMRX_ERR_ARG;
+  }
+  ns->turb_on = true;
   return IAMRX_OK;
 }
 

@@ -29,10 +29,11 @@ IX_D double ext_force(int n, double grav, double rho) {  // NS_getForce.cpp:117-
   return (n == 2 && fabs(grav) > 1.0e-4) ? grav * rho : 0.0;
 }
 
-__global__ void force_vel_kernel(Bx bx, V4 tf, C4 visc, C4 gp, C4 rho, double grav, int div_rho) {
+__global__ void force_vel_kernel(Bx bx, V4 tf, C4 visc, C4 gp, C4 rho, double grav, int div_rho, C4 uf) {
   IDX3(bx)
   const double r = rho(i, j, k);
   double f = ext_force(n, grav, r);
+  if (uf.ok()) f += r * uf(i, j, k, n);   // density-weighted user forcing (Tutorials/HIT/NS_getForce.cpp:540, 619-621)
   if (visc.ok()) f += visc(i, j, k, n);
   if (gp.ok()) f -= gp(i, j, k, n);
   if (div_rho) f /= r;
@@ -40,10 +41,10 @@ __global__ void force_vel_kernel(Bx bx, V4 tf, C4 visc, C4 gp, C4 rho, double gr
 }
 
 __global__ void vel_update_kernel(Bx bx, V4 unew, C4 uold, C4 aofs, C4 gp, C4 rh, double grav, double dt,
-                                  int zero_force, C4 rho_old, C4 rho_new) {
+                                  int zero_force, C4 rho_old, C4 rho_new, C4 uf) {
   IDX3(bx)
   const double r = rh(i, j, k);
-  const double force = zero_force ? 0.0 : ext_force(n, grav, r);
+  const double force = zero_force ? 0.0 : ext_force(n, grav, r) + (uf.ok() ? r * uf(i, j, k, n) : 0.0);
   if (rho_old.ok()) {  // do_mom_diff (NSB.cpp:3609-3616): momentum update, then back to velocity with the new density
     const double m = uold(i, j, k, n) * rho_old(i, j, k) - dt * aofs(i, j, k, n) + dt * force - dt * gp(i, j, k, n);
     unew(i, j, k, n) = m / rho_new(i, j, k);
@@ -177,12 +178,12 @@ __global__ void init_kernel(Bx bx, V4 st, int probtype, ProbParams pp, iamrx_geo
   } while (0)
 
 int floor_small(const Bx& bx, V4 f, int ncomp, cudaStream_t s) { LAUNCH3(floor_kernel, bx, ncomp, s, f); }
-int force_vel(const Bx& bx, V4 tf, C4 visc, C4 gp, C4 rho, double grav, int div_rho, cudaStream_t s) {
-  LAUNCH3(force_vel_kernel, bx, 3, s, tf, visc, gp, rho, grav, div_rho);
+int force_vel(const Bx& bx, V4 tf, C4 visc, C4 gp, C4 rho, double grav, int div_rho, cudaStream_t s, C4 uf) {
+  LAUNCH3(force_vel_kernel, bx, 3, s, tf, visc, gp, rho, grav, div_rho, uf);
 }
 int vel_update(const Bx& bx, V4 unew, C4 uold, C4 aofs, C4 gp, C4 rhohalf, double grav, double dt, int zero_force,
-               cudaStream_t s, C4 rho_old, C4 rho_new) {
-  LAUNCH3(vel_update_kernel, bx, 3, s, unew, uold, aofs, gp, rhohalf, grav, dt, zero_force, rho_old, rho_new);
+               cudaStream_t s, C4 rho_old, C4 rho_new, C4 uf) {
+  LAUNCH3(vel_update_kernel, bx, 3, s, unew, uold, aofs, gp, rhohalf, grav, dt, zero_force, rho_old, rho_new, uf);
 }
 int scal_update(const Bx& bx, V4 snew, C4 sold, C4 aofs, double dt, int ncomp, cudaStream_t s) {
   LAUNCH3(scal_update_kernel, bx, ncomp, s, snew, sold, aofs, dt);

@@ -320,6 +320,15 @@ enum { IAMRX_IX_CELL = 0, IAMRX_IX_XFACE = 1, IAMRX_IX_YFACE = 2, IAMRX_IX_ZFACE
 int iamrx_fill_boundary(iamrx_level_t lev, iamrx_fab* fabs, int ixtype, int ncomp,
                         int ngrow, void* stream);
 
+/* The HIT tutorial's turbulent forcing block of NavierStokesBase::getForce (Tutorials/HIT/NS_getForce.cpp:205-640, exact path):
+ * frc(i,j,k,0..2) += rho(i,j,k) * f(x, time), f = the sum over the low-wavenumber modes of TurbulentForcing::forcedata
+ * (17 arrays of array_size^3, TurbulentForcing_def.H:66-82; HOST pointer here), divergence free if div_free_force
+ * (turb.div_free_force), modes mode_start .. nmodes per direction (turb.mode_start, turb.nmodes) with kappa <= nmodes / Lmin.
+ * rho may be NULL (== 1).  geom: the level geometry (domain lengths and cell centres). */
+int iamrx_turbulent_force_box(const iamrx_box* bx, iamrx_fab* frc, const iamrx_fab* rho, const iamrx_geom* geom, double time,
+                              int nmodes, int mode_start, int div_free_force, int array_size, const double* forcedata,
+                              void* stream);
+
 /* The physical-boundary part of AmrLevel::FillPatch for cell-centred state data (NSB.cpp:4399,4435,3382; the fill
  * functions of NS_bcfill.H:17-167 with the BCRec tables of NS_BC.H:7-55): cells outside the non-periodic sides of the
  * domain.  Call after iamrx_fill_boundary.  bcrec: one BCRec per component; bcvals: the ext_dir face values
@@ -500,6 +509,12 @@ int iamrx_ns_destroy(iamrx_ns_t ns);
  * probtype 20 the HIT tutorial's field (Tutorials/HIT/prob_init.cpp:100-131; turb_scale, density [, amplitude of a
  * synthetic density variation]); probtype 100 a synthetic variable-density Taylor-Green field. */
 int iamrx_ns_init_prob(iamrx_ns_t ns, int probtype, const double* prob_params, int nparams);
+/* Switch on the HIT tutorial's turbulent forcing in the step driver (USE_TURBULENT_FORCING; inputs.3d.forced: turb.nmodes = 4):
+ * getForce adds rho * f(x, t) at prev_time (predict_velocity, velocity_advection, initial diffusion update), half_time
+ * (velocity update) and cur_time (estTimeStep).  forcedata: TurbulentForcing::forcedata (host or device memory; copied);
+ * NULL or nmodes <= 0 switches it off.  Triply periodic domains only. */
+int iamrx_ns_set_turbulent_forcing(iamrx_ns_t ns, int nmodes, int mode_start, int div_free_force, int array_size,
+                                   const double* forcedata);
 /* NavierStokes::post_init: initial velocity projection, initial dt, initial
  * pressure iterations. Returns dt for the first step in *dt0. */
 int iamrx_ns_post_init(iamrx_ns_t ns, double* dt0);

@@ -19,6 +19,7 @@
 #include <cstring>
 #include <limits>
 #include <memory>
+#include <array>
 #include <vector>
 #ifdef _OPENMP
 #include <omp.h>
@@ -1485,7 +1486,74 @@ struct orc_ns {
     visc.fill_periodic();
     if (has_walls()) first_order_extrap(visc, 0, 3);   // NS.cpp:2045-2046
   }
-  double ext_force(int c, double rho) const { return (c == 2 && std::fabs(p.gravity) > 1.0e-4) ? p.gravity * rho : 0.0; }  // NS_getForce.cpp:117-141
+  // ---- HIT turbulent forcing, the exact (all modes in every cell) path of Tutorials/HIT/NS_getForce.cpp:541-621 ------------
+  bool turb_on = false;
+  int turb_nmodes = 0, turb_mode_start = 0, turb_div_free = 1, turb_as = 33;
+  std::vector<double> turb_fd;                  // TurbulentForcing::forcedata: 17 arrays of as^3, kx fastest
+  std::vector<std::array<int, 3>> turb_k;       // the modes the two loops of :555-557 and :616-618 visit with kappa <= kappaMax
+  double turb_L[3] = {1, 1, 1};
+  double fd(int arr, int kx, int ky, int kz) const {
+    const size_t ne = (size_t)turb_as * turb_as * turb_as;
+    return turb_fd[(size_t)arr * ne + kx + (size_t)turb_as * (ky + (size_t)turb_as * kz)];
+  }
+  void set_turb(int nmodes, int mode_start, int div_free, int as, const double* data) {
+    turb_on = data != nullptr && nmodes > 0;
+    if (!turb_on) return;
+    turb_nmodes = nmodes; turb_mode_start = mode_start; turb_div_free = div_free; turb_as = as;
+    turb_fd.assign(data, data + (size_t)17 * as * as * as);
+    for (int d = 0; d < 3; ++d) turb_L[d] = n[d] * dx[d];
+    const double Lx = turb_L[0], Ly = turb_L[1], Lz = turb_L[2], Lmin = std::min(Lx, std::min(Ly, Lz));
+    const int xstep = (int)(Lx / Lmin + 0.5), ystep = (int)(Ly / Lmin + 0.5), zstep = (int)(Lz / Lmin + 0.5);
+    const double kappaMax = nmodes / Lmin + 1.0e-8;
+    turb_k.clear();
+    auto consider = [&](int kx, int ky, int kz) {
+      const double kappa = std::sqrt((kx * kx) / (Lx * Lx) + (ky * ky) / (Ly * Ly) + (kz * kz) / (Lz * Lz));
+      if (kappa <= kappaMax) turb_k.push_back({kx, ky, kz});
+    };
+    for (int kz = mode_start * zstep; kz <= nmodes * zstep; kz += zstep)
+      for (int ky = mode_start * ystep; ky <= nmodes * ystep; ky += ystep)
+        for (int kx = mode_start * xstep; kx <= nmodes * xstep; kx += xstep) consider(kx, ky, kz);
+    for (int kz = 1; kz <= zstep - 1; ++kz)      // high aspect ratio: extra symmetry-breaking modes
+      for (int ky = mode_start; ky <= nmodes * ystep; ++ky)
+        for (int kx = mode_start; kx <= nmodes * xstep; ++kx) consider(kx, ky, kz);
+  }
+  double turb(int c, int i, int j, int k, double t) const {   // component c of f at the centre of cell (i, j, k), per unit mass
+    const double TwoPi = 2.0 * M_PI, Lx = turb_L[0], Ly = turb_L[1], Lz = turb_L[2];
+    const double x = prob_lo[0] + dx[0] * (i + 0.5), y = prob_lo[1] + dx[1] * (j + 0.5), z = prob_lo[2] + dx[2] * (k + 0.5);
+    double f = 0.0;
+    for (const auto& m : turb_k) {
+      const int kx = m[0], ky = m[1], kz = m[2];
+      const double xT = std::cos(fd(0, kx, ky, kz) * t + fd(1, kx, ky, kz));
+      const double FAX = fd(5, kx, ky, kz), FAY = fd(6, kx, ky, kz), FAZ = fd(7, kx, ky, kz);
+      if (turb_div_free) {
+        const double FPXX = fd(8, kx, ky, kz), FPXY = fd(9, kx, ky, kz), FPXZ = fd(10, kx, ky, kz);
+        const double FPYX = fd(11, kx, ky, kz), FPYY = fd(12, kx, ky, kz), FPYZ = fd(13, kx, ky, kz);
+        const double FPZX = fd(14, kx, ky, kz), FPZY = fd(15, kx, ky, kz), FPZZ = fd(16, kx, ky, kz);
+        if (c == 0)
+          f += xT * (FAZ * TwoPi * (ky / Ly) * std::sin(TwoPi * kx * x / Lx + FPZX) * std::cos(TwoPi * ky * y / Ly + FPZY) * std::sin(TwoPi * kz * z / Lz + FPZZ)
+                     - FAY * TwoPi * (kz / Lz) * std::sin(TwoPi * kx * x / Lx + FPYX) * std::sin(TwoPi * ky * y / Ly + FPYY) * std::cos(TwoPi * kz * z / Lz + FPYZ));
+        else if (c == 1)
+          f += xT * (FAX * TwoPi * (kz / Lz) * std::sin(TwoPi * kx * x / Lx + FPXX) * std::sin(TwoPi * ky * y / Ly + FPXY) * std::cos(TwoPi * kz * z / Lz + FPXZ)
+                     - FAZ * TwoPi * (kx / Lx) * std::cos(TwoPi * kx * x / Lx + FPZX) * std::sin(TwoPi * ky * y / Ly + FPZY) * std::sin(TwoPi * kz * z / Lz + FPZZ));
+        else
+          f += xT * (FAY * TwoPi * (kx / Lx) * std::cos(TwoPi * kx * x / Lx + FPYX) * std::sin(TwoPi * ky * y / Ly + FPYY) * std::sin(TwoPi * kz * z / Lz + FPYZ)
+                     - FAX * TwoPi * (ky / Ly) * std::sin(TwoPi * kx * x / Lx + FPXX) * std::cos(TwoPi * ky * y / Ly + FPXY) * std::sin(TwoPi * kz * z / Lz + FPXZ));
+      } else {
+        const double FPX = fd(2, kx, ky, kz), FPY = fd(3, kx, ky, kz), FPZ = fd(4, kx, ky, kz);
+        const double ax = TwoPi * kx * x / Lx + FPX, ay = TwoPi * ky * y / Ly + FPY, az = TwoPi * kz * z / Lz + FPZ;
+        if (c == 0) f += xT * FAX * std::cos(ax) * std::sin(ay) * std::sin(az);
+        else if (c == 1) f += xT * FAY * std::sin(ax) * std::cos(ay) * std::sin(az);
+        else f += xT * FAZ * std::sin(ax) * std::sin(ay) * std::cos(az);
+      }
+    }
+    return f;
+  }
+  // NavierStokesBase::getForce for a velocity component (NS_getForce.cpp:117-141 gravity; Tutorials/HIT: + rho * turbulent force)
+  double ext_force(int c, double rho, int i, int j, int k, double t) const {
+    double f = (c == 2 && std::fabs(p.gravity) > 1.0e-4) ? p.gravity * rho : 0.0;
+    if (turb_on) f += rho * turb(c, i, j, k, t);
+    return f;
+  }
 
   int advance(double dt, double* dt_test) {
     // advance_setup NSB.cpp:613-741
@@ -1503,7 +1571,7 @@ struct orc_ns {
     fill_gradp(Gp_old);
     force.define(n, 3, 1);
     for (int c = 0; c < 3; ++c) {
-      FOR_G1(force, i, j, k) force(i, j, k, c) = (ext_force(c, Smf(i, j, k, 0)) + visc(i, j, k, c) - Gp_old(i, j, k, c)) / Smf(i, j, k, 0);  // :4466-4470
+      FOR_G1(force, i, j, k) force(i, j, k, c) = (ext_force(c, Smf(i, j, k, 0), i, j, k, time) + visc(i, j, k, c) - Gp_old(i, j, k, c)) / Smf(i, j, k, 0);  // :4466-4470
     }
     const std::vector<BCRec> vbc = adv_bc(Xvel, 3), sbc = adv_bc(Density, 2);
     const AdvOpt aopt{p.use_forces_in_trans != 0, p.use_ppm != 0, has_walls() ? vbc.data() : nullptr, true};
@@ -1526,7 +1594,7 @@ struct orc_ns {
         for (int c = 0; c < 3; ++c) {
 #pragma omp parallel for
           for (int k = -3; k < n[2] + 3; ++k) for (int j = -3; j < n[1] + 3; ++j) for (int i = -3; i < n[0] + 3; ++i) Umf2(i, j, k, c) *= rho3(i, j, k);
-          FOR_G1(force, i, j, k) force(i, j, k, c) = ext_force(c, rho3(i, j, k)) + visc(i, j, k, c) - Gp_old(i, j, k, c);   // :3459-3466
+          FOR_G1(force, i, j, k) force(i, j, k, c) = ext_force(c, rho3(i, j, k), i, j, k, time) + visc(i, j, k, c) - Gp_old(i, j, k, c);   // :3459-3466
         }
         const int ic_mom[3] = {1, 1, 1};   // NS_setup.cpp:297-299
         compute_aofs(Umf2, 3, &force, nullptr, umac, ic_mom, aopt, dx, dt, aofs, Xvel, nullptr, nullptr);
@@ -1584,7 +1652,7 @@ struct orc_ns {
     for (int c = 0; c < 3; ++c) {
       FOR_CELLS(S_new, i, j, k) {
         const double r = rho_half(i, j, k);
-        const double frc = zero_force ? 0.0 : ext_force(c, r);
+        const double frc = zero_force ? 0.0 : ext_force(c, r, i, j, k, time + 0.5 * dt);   // half_time (NSB.cpp:3581-3583)
         if (p.do_mom_diff)   // NSB.cpp:3609-3616
           S_new(i, j, k, c) = (S_old(i, j, k, c) * S_old(i, j, k, Density) - dt * aofs(i, j, k, c) + dt * frc - dt * Gp_old(i, j, k, c)) / S_new(i, j, k, Density);
         else
@@ -1673,7 +1741,7 @@ struct orc_ns {
     if (p.be_cn_theta != 1.0) visc_terms(S_old, visc); else visc.setval(0.0);
     for (int c = 0; c < 3; ++c) {
       FOR_CELLS(S_new, i, j, k) {
-        double f = ext_force(c, S_old(i, j, k, Density)) + visc(i, j, k, c) - Gp_old(i, j, k, c);
+        double f = ext_force(c, S_old(i, j, k, Density), i, j, k, time) + visc(i, j, k, c) - Gp_old(i, j, k, c);   // prev_time (:3696)
         if (!p.do_mom_diff) f /= rho_half(i, j, k);
         f -= aofs(i, j, k, c);
         if (p.do_mom_diff) S_new(i, j, k, c) = (f * dt + S_old(i, j, k, c) * S_old(i, j, k, Density)) / S_new(i, j, k, Density);   // :3743
@@ -1707,7 +1775,7 @@ struct orc_ns {
         for (int j = 0; j < n[1]; ++j)
           for (int i = 0; i < n[0]; ++i) {
             const double r = S_new(i, j, k, Density);
-            fm = std::max(fm, std::fabs((ext_force(d, r) - Gp_new(i, j, k, d)) / r));
+            fm = std::max(fm, std::fabs((ext_force(d, r, i, j, k, time) - Gp_new(i, j, k, d)) / r));   // cur_time (:1410)
           }
       if (um > 1.0e-8) est = std::min(est, dx[d] / um);
       if (fm > 1.0e-8) est = std::min(est, std::sqrt(2.0 * dx[d] / fm));
@@ -2131,6 +2199,10 @@ void orc_fluxreg(const int nc[3], int ncomp, const unsigned char* mask, const do
           }
       reg[i + (long)nc[0] * (j + (long)nc[1] * (k + (long)nc[2] * c))] = r;
     }
+}
+
+void orc_ns_set_turbulent_forcing(orc_ns* ns, int nmodes, int mode_start, int div_free_force, int array_size, const double* forcedata) {
+  ns->set_turb(nmodes, mode_start, div_free_force, array_size, forcedata);
 }
 
 void orc_ns_params_default(orc_ns_params* p) {

@@ -134,6 +134,8 @@ orc_ns* orc_ns_create(const int n[3], const double prob_lo[3], const double prob
 void orc_ns_set_bc(orc_ns* ns, const int per[3], const int phys_lo[3], const int phys_hi[3], const double* bcv);
 void orc_ns_get_padded(const orc_ns* ns, int which, double* out);
 void orc_ns_destroy(orc_ns* ns);
+/* Tutorials/HIT turbulent forcing (NS_getForce.cpp:205-640, exact path); forcedata = TurbulentForcing::forcedata (17 x as^3) */
+void orc_ns_set_turbulent_forcing(orc_ns* ns, int nmodes, int mode_start, int div_free_force, int array_size, const double* forcedata);
 void orc_ns_init_prob(orc_ns* ns, int probtype, const double* params, int nparams);
 int orc_ns_post_init(orc_ns* ns, double* dt0);
 int orc_ns_step(orc_ns* ns, double* dt_io);

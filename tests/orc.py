@@ -296,6 +296,10 @@ class OracleNS:
         lib().orc_ns_get_padded(self.h, which, _p(out))
         return out
 
+    def set_turbulent_forcing(self, nmodes, mode_start, div_free_force, forcedata):
+        fd = np.ascontiguousarray(forcedata, dtype=np.float64)
+        lib().orc_ns_set_turbulent_forcing(self.h, nmodes, mode_start, int(div_free_force), fd.shape[1], _p(fd))
+
     def init_prob(self, probtype, params):
         arr = (C.c_double * len(params))(*params)
         lib().orc_ns_init_prob(self.h, probtype, arr, len(params))
