@@ -351,7 +351,16 @@ def run_ours(args):
     hit = args.problem == "hit"
     rt = args.problem == "rt"
     bs = 1 if args.bottom_solver == "bicgstab" else 0
-    if rt:
+    dsl = args.problem == "dsl2d"
+    if dsl:
+        # BASELINE.json configs[2] on ONE level: DoubleShearLayer 2-D 1024^2 (inputs.2d.double_shear_layer-rotate: [-1,1]^2 periodic,
+        # inviscid, cfl 0.5), run as a two-layer 3-D problem (tests/test_twod.py): n = (1024, 1024, 2), z extent = x extent
+        if world != 1:
+            raise SystemExit("--problem dsl2d is a single-GPU configuration")
+        ncell = (4 * nbox, 4 * nbox, 2)
+        boxes, owners = [((0, 0, 0), (ncell[0] - 1, ncell[1] - 1, 1))], [0]
+        g = ix.Geom.make(ncell, (-1.0, -1.0, -1.0), (1.0, 1.0, 1.0))
+    elif rt:
         # BASELINE.json configs[3] geometry on ONE level: RayleighTaylor 256^2 x 512 (regtest.3d.rayleightaylor: periodic x / y, slip
         # walls in z, gravity -1, inviscid, rho 1 -> 2), the fixed domain split into N z slabs (strong scaling: N must divide 512)
         ncell = (nbox, nbox, 2 * nbox)
@@ -363,7 +372,10 @@ def run_ours(args):
         ncell, boxes, owners, prob_hi = domain_for(world, nbox, args.decomp)
         g = ix.Geom.make(ncell, (0.0, 0.0, 0.0), prob_hi)
     lev = ix.Level(lib, g, boxes, owners)
-    if rt:
+    if dsl:
+        ns = ix.NavierStokes(lib, lev, dev, visc_coef=0.0, cfl=0.5, bottom_solver=bs)
+        ns.init_prob(5, [1.0, 1.0, 0.0, 0.0, 0.0, 0.4])
+    elif rt:
         ns = ix.NavierStokes(lib, lev, dev, lo_bc=(0, 0, 4), hi_bc=(0, 0, 4), visc_coef=0.0, cfl=CFL, gravity=-1.0, bottom_solver=bs)
         ns.init_prob(10, [1.0, 2.0, 1.0, 0.0, 0.01, 0.005])
     elif hit:   # BASELINE.json configs[4]: Tutorials/HIT initial field, nu = 1e-4, proj_tol 1e-10 (inputs.3d.forced:129), synthetic variable density.
@@ -378,7 +390,7 @@ def run_ours(args):
         ns = ix.NavierStokes(lib, lev, dev, visc_coef=NU, cfl=CFL, bottom_solver=bs)
         ns.init_prob(11, TG)
     ns.post_init()
-    cells_total = ncell[0] * ncell[1] * ncell[2]
+    cells_total = ncell[0] * ncell[1] * (1 if dsl else ncell[2])   # dsl2d: 2-D cells (the second layer is a copy)
 
     def barrier():
         if world > 1:
@@ -503,6 +515,11 @@ def run_ours(args):
         if hit:
             cfg["workload"] = (f"HIT 3D {nbox}^3 per GPU single-level variable-density (Tutorials/HIT/prob_init.cpp:100-131 field, nu=1e-4, "
                                f"proj_tol 1e-10, mac_tol 1e-10 (fp64 floor at 512^3), rho = 1 + 0.5 sin sin sin, turbulent forcing {'off' if args.no_forcing else 'on: turb.nmodes 4, div-free, synthetic mode table'}), BASELINE.json configs[4]" + ("" if world == 1 else " weak-scaled"))
+        if dsl:
+            cfg["workload"] = (f"DoubleShearLayer 2D {ncell[0]}^2 SINGLE level (BASELINE.json configs[2] without the fine level; "
+                               f"inputs.2d.double_shear_layer-rotate: periodic, inviscid, cfl 0.5), run as a two-layer 3-D box "
+                               f"{ncell[0]}x{ncell[1]}x2 (z-uniform; value counts 2-D cells)")
+            cfg["parallelism"] = "one box; multigrid semi-coarsens x / y only"
         if rt:
             cfg["workload"] = (f"RayleighTaylor 3D {ncell[0]}x{ncell[1]}x{ncell[2]} SINGLE level (BASELINE.json configs[3] geometry without the fine level: "
                                f"periodic x/y, slip walls z, gravity, inviscid, rho 1->2), fixed domain in {world} z slab(s)")
@@ -551,8 +568,8 @@ def main():
     ap.add_argument("--no-forcing", action="store_true", help="--problem hit without the tutorial's turbulent forcing")
     ap.add_argument("--bottom-solver", default="smoother", choices=["smoother", "bicgstab"],
                     help="multigrid bottom solver: smoother sweeps (default) or BiCGStab (IAMR's bicgcg)")
-    ap.add_argument("--problem", default="tg", choices=["tg", "hit", "rt"],
-                    help="tg: BASELINE configs[1]; hit: configs[4] (HIT, variable density); rt: configs[3] geometry on one level (walls, gravity; strong-scaled)")
+    ap.add_argument("--problem", default="tg", choices=["tg", "hit", "rt", "dsl2d"],
+                    help="tg: BASELINE configs[1]; hit: configs[4] (HIT, variable density); rt: configs[3] geometry on one level (walls, gravity; strong-scaled); dsl2d: configs[2] on one level (2-D as two layers)")
     ap.add_argument("--prof-steps", type=int, default=3, help="steps of the separate roofline pass")
     ap.add_argument("--no-verify", action="store_true", help="skip the untimed multi-rank parity leg")
     ap.add_argument("--e2e-steps", type=int, default=3)

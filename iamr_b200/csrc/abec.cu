@@ -221,39 +221,61 @@ __global__ void flux_kernel(Bx bx, V4 fx, V4 fy, V4 fz, C4 phi, IX_KARG(AbecDev)
   if (fz.ok() && ii && jj) fz(i, j, k) = -fzs * op.bz(i, j, k, nb) * (p0 - phi(i, j, k - 1));
 }
 
-__global__ void restrict_kernel(Bx cbx, V4 crse, C4 fine, int nz) {
+// thin: bit d set = direction d is NOT coarsened between the two levels (semi-coarsening of thin, "2-D" domains: ratio 1)
+__global__ void restrict_kernel(Bx cbx, V4 crse, C4 fine, int nz, int thin) {
   const int kz = blockIdx.z % nz;
   const int n = blockIdx.z / nz;
   const int k = cbx.lo[2] + kz;
   const int j = cbx.lo[1] + blockIdx.y * AP_TY + threadIdx.y;
   const int i = cbx.lo[0] + blockIdx.x * AP_TX + threadIdx.x;
   if (j > cbx.hi[1] || i > cbx.hi[0]) return;
-  const int ii = 2 * i, jj = 2 * j, kk = 2 * k;
-  crse(i, j, k, n) = 0.125 * (fine(ii, jj, kk, n) + fine(ii + 1, jj, kk, n) + fine(ii, jj + 1, kk, n) +
-                              fine(ii + 1, jj + 1, kk, n) + fine(ii, jj, kk + 1, n) +
-                              fine(ii + 1, jj, kk + 1, n) + fine(ii, jj + 1, kk + 1, n) +
-                              fine(ii + 1, jj + 1, kk + 1, n));
+  if (thin == 0) {
+    const int ii = 2 * i, jj = 2 * j, kk = 2 * k;
+    crse(i, j, k, n) = 0.125 * (fine(ii, jj, kk, n) + fine(ii + 1, jj, kk, n) + fine(ii, jj + 1, kk, n) +
+                                fine(ii + 1, jj + 1, kk, n) + fine(ii, jj, kk + 1, n) +
+                                fine(ii + 1, jj, kk + 1, n) + fine(ii, jj + 1, kk + 1, n) +
+                                fine(ii + 1, jj + 1, kk + 1, n));
+    return;
+  }
+  const int r0 = (thin & 1) ? 1 : 2, r1 = (thin & 2) ? 1 : 2, r2 = (thin & 4) ? 1 : 2;
+  double acc = 0.0;
+  for (int dk = 0; dk < r2; ++dk) for (int dj = 0; dj < r1; ++dj) for (int di = 0; di < r0; ++di) acc += fine(r0 * i + di, r1 * j + dj, r2 * k + dk, n);
+  crse(i, j, k, n) = acc / (double)(r0 * r1 * r2);
 }
 
 IX_D int cdiv2(int a) { return (a >= 0) ? a / 2 : -((-a + 1) / 2); }  // floor(a/2)
 
-__global__ void prolong_kernel(Bx fbx, V4 fine, C4 crse, int nz) {
+__global__ void prolong_kernel(Bx fbx, V4 fine, C4 crse, int nz, int thin) {
   const int kz = blockIdx.z % nz;
   const int n = blockIdx.z / nz;
   const int k = fbx.lo[2] + kz;
   const int j = fbx.lo[1] + blockIdx.y * AP_TY + threadIdx.y;
   const int i = fbx.lo[0] + blockIdx.x * AP_TX + threadIdx.x;
   if (j > fbx.hi[1] || i > fbx.hi[0]) return;
-  fine(i, j, k, n) += crse(cdiv2(i), cdiv2(j), cdiv2(k), n);
+  fine(i, j, k, n) += crse((thin & 1) ? i : cdiv2(i), (thin & 2) ? j : cdiv2(j), (thin & 4) ? k : cdiv2(k), n);
 }
 
-__global__ void face_restrict_kernel(Bx cfbx, int dir, V4 crse, C4 fine, int nz) {
+__global__ void face_restrict_kernel(Bx cfbx, int dir, V4 crse, C4 fine, int nz, int thin) {
   const int kz = blockIdx.z % nz;
   const int n = blockIdx.z / nz;
   const int k = cfbx.lo[2] + kz;
   const int j = cfbx.lo[1] + blockIdx.y * AP_TY + threadIdx.y;
   const int i = cfbx.lo[0] + blockIdx.x * AP_TX + threadIdx.x;
   if (j > cfbx.hi[1] || i > cfbx.hi[0]) return;
+  if (thin != 0) {   // mean of the fine faces on the coarse face: the transverse directions that are coarsened contribute 2 each
+    const int r[3] = {(thin & 1) ? 1 : 2, (thin & 2) ? 1 : 2, (thin & 4) ? 1 : 2};
+    const int c[3] = {i, j, k};
+    const int t0 = (dir + 1) % 3, t1 = (dir + 2) % 3;
+    double acc = 0.0;
+    for (int b = 0; b < r[t1]; ++b)
+      for (int a_ = 0; a_ < r[t0]; ++a_) {
+        int f[3];
+        f[dir] = r[dir] * c[dir]; f[t0] = r[t0] * c[t0] + a_; f[t1] = r[t1] * c[t1] + b;
+        acc += fine(f[0], f[1], f[2], n);
+      }
+    crse(i, j, k, n) = acc / (double)(r[t0] * r[t1]);
+    return;
+  }
   const int ii = 2 * i, jj = 2 * j, kk = 2 * k;
   double v;
   if (dir == 0)
@@ -811,24 +833,24 @@ int abec_flux(const Bx& bx, V4 fx, V4 fy, V4 fz, C4 phi, const Abec& op, int com
   return check_launch("abec_flux");
 }
 
-int cc_restrict(const Bx& cbx, V4 crse, C4 fine, int ncomp, cudaStream_t s) {
+int cc_restrict(const Bx& cbx, V4 crse, C4 fine, int ncomp, cudaStream_t s, int thin) {
   if (!cbx.ok()) return IAMRX_OK;
   IX_LAUNCH(restrict_kernel, grid_for(cbx, AP_TX, AP_TY, cbx.nz() * ncomp), dim3(AP_TX, AP_TY, 1), 0, s, 
-      cbx, crse, fine, cbx.nz());
+      cbx, crse, fine, cbx.nz(), thin);
   return check_launch("cc_restrict");
 }
 
-int cc_prolong_add(const Bx& fbx, V4 fine, C4 crse, int ncomp, cudaStream_t s) {
+int cc_prolong_add(const Bx& fbx, V4 fine, C4 crse, int ncomp, cudaStream_t s, int thin) {
   if (!fbx.ok()) return IAMRX_OK;
   IX_LAUNCH(prolong_kernel, grid_for(fbx, AP_TX, AP_TY, fbx.nz() * ncomp), dim3(AP_TX, AP_TY, 1), 0, s, 
-      fbx, fine, crse, fbx.nz());
+      fbx, fine, crse, fbx.nz(), thin);
   return check_launch("cc_prolong_add");
 }
 
-int face_restrict(const Bx& cfbx, int dir, V4 crse, C4 fine, int ncomp, cudaStream_t s) {
+int face_restrict(const Bx& cfbx, int dir, V4 crse, C4 fine, int ncomp, cudaStream_t s, int thin) {
   if (!cfbx.ok()) return IAMRX_OK;
   IX_LAUNCH(face_restrict_kernel, grid_for(cfbx, AP_TX, AP_TY, cfbx.nz() * ncomp), dim3(AP_TX, AP_TY, 1), 0, s, 
-      cfbx, dir, crse, fine, cfbx.nz());
+      cfbx, dir, crse, fine, cfbx.nz(), thin);
   return check_launch("face_restrict");
 }
 

@@ -37,11 +37,12 @@ int abec_apply(const Bx& bx, V4 out, C4 phi, C4 rhs, const Abec& op, int ncomp, 
 // face flux_d = -b * beta_d * dphi/dx_d on faces of bx (MLABecLaplacian FFlux)
 int abec_flux(const Bx& bx, V4 fx, V4 fy, V4 fz, C4 phi, const Abec& op, int comp, cudaStream_t s);
 // crse = mean of 2x2x2 fine (MLCellLinOp restriction / average_down)
-int cc_restrict(const Bx& cbx, V4 crse, C4 fine, int ncomp, cudaStream_t s);
+// thin (all transfer operators): bit d set = direction d has ratio 1 between the two levels (semi-coarsening of thin domains)
+int cc_restrict(const Bx& cbx, V4 crse, C4 fine, int ncomp, cudaStream_t s, int thin = 0);
 // fine += crse(i/2,j/2,k/2) (MLCellLinOp piecewise-constant interpolation)
-int cc_prolong_add(const Bx& fbx, V4 fine, C4 crse, int ncomp, cudaStream_t s);
+int cc_prolong_add(const Bx& fbx, V4 fine, C4 crse, int ncomp, cudaStream_t s, int thin = 0);
 // crse face coefficient = mean of the 4 fine faces (average_down_faces)
-int face_restrict(const Bx& cfbx, int dir, V4 crse, C4 fine, int ncomp, cudaStream_t s);
+int face_restrict(const Bx& cfbx, int dir, V4 crse, C4 fine, int ncomp, cudaStream_t s, int thin = 0);
 // beta_d = scale / (0.5*(rho(i-1)+rho(i))) (average_cellcenter_to_face + invert)
 int rho_to_beta(const Bx& fbx, int dir, V4 beta, C4 rho, double scale, cudaStream_t s);
 // div = fac * sum_d (u_d(i+1)-u_d(i))*dxinv[d]   (computeDivergence)
@@ -138,8 +139,8 @@ int nodal_gs_sweep(const Bx& nbx, V4 phi_out, C4 phi_in, C4 rhs, C4 sig, const d
                    int wrapmask = 7, int phase = -1);
 int nodal_jacobi(const Bx& nbx, V4 out, C4 phi, C4 rhs, C4 sig, const double dxinv[3], double omega,
                  cudaStream_t s);
-int nodal_restrict(const Bx& cnbx, V4 crse, C4 fine, cudaStream_t s);
-int nodal_interp_add(const Bx& fnbx, V4 fine, C4 crse, cudaStream_t s);
+int nodal_restrict(const Bx& cnbx, V4 crse, C4 fine, cudaStream_t s, int thin = 0);
+int nodal_interp_add(const Bx& fnbx, V4 fine, C4 crse, cudaStream_t s, int thin = 0);
 int nodal_mknewu(const Bx& bx, V4 vel, V4 gp, int increment_gp, C4 phi, C4 sig,
                  const double dxinv[3], cudaStream_t s);
 

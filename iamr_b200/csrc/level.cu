@@ -432,9 +432,13 @@ void build_fb_regions(const Level& L, int ixtype, int ng, std::vector<int>& dst_
     // Candidate sources in a fixed order: (box index, shift).  The first source
     // covering a point wins; pieces already filled are removed, so every ghost
     // point is written exactly once (deterministic for face/nodal overlaps).
+    // periodic images up to the distance the ghost depth reaches: more than one period when the domain is thinner than the
+    // ghost layer (two-layer "2-D" domains with 3 ghost cells)
+    int smax[3];
+    for (int d = 0; d < 3; ++d) smax[d] = L.geom.periodic[d] ? (ng + plen[d] - 1) / plen[d] : 0;
     for (int bj = 0; bj < nb && !todo.empty(); ++bj) {
       const Bx vsrc = ixbox(L.boxes[bj], ixtype);
-      for (int sz = -1; sz <= 1; ++sz) for (int sy = -1; sy <= 1; ++sy) for (int sx = -1; sx <= 1; ++sx) {
+      for (int sz = -smax[2]; sz <= smax[2]; ++sz) for (int sy = -smax[1]; sy <= smax[1]; ++sy) for (int sx = -smax[0]; sx <= smax[0]; ++sx) {
         const int sh[3] = {sx, sy, sz};
         bool okp = true;
         for (int d = 0; d < 3; ++d) if (sh[d] != 0 && !L.geom.periodic[d]) okp = false;

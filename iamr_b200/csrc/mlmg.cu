@@ -26,11 +26,20 @@ std::unique_ptr<Level> make_level(const iamrx_geom& g, const std::vector<Bx>& bo
   return L;
 }
 
-std::unique_ptr<Level> coarsen_level(const Level& f, int min_width) {
+// thin: directions that are never coarsened (semi-coarsening: a domain two cells thick in z is a "2-D" problem whose multigrid
+// hierarchy coarsens x and y only; the transfer operators take the same mask)
+int thin_mask(const Level& f) {
+  int m = 0;
+  for (int d = 0; d < 3; ++d) if (f.geom.domain.hi[d] - f.geom.domain.lo[d] + 1 <= 2) m |= 1 << d;
+  return m == 7 ? 0 : m;
+}
+
+std::unique_ptr<Level> coarsen_level(const Level& f, int min_width, int thin) {
   std::vector<Bx> cb;
   for (const Bx& b : f.boxes) {
     Bx c;
     for (int d = 0; d < 3; ++d) {
+      if (thin & (1 << d)) { c.lo[d] = b.lo[d]; c.hi[d] = b.hi[d]; continue; }
       const int n = b.hi[d] - b.lo[d] + 1;
       if ((n % 2) != 0 || (b.lo[d] % 2) != 0 || n / 2 < min_width) return nullptr;
       c.lo[d] = b.lo[d] / 2;
@@ -40,6 +49,10 @@ std::unique_ptr<Level> coarsen_level(const Level& f, int min_width) {
   }
   iamrx_geom g = f.geom;
   for (int d = 0; d < 3; ++d) {
+    // a thin direction keeps its cells AND its spacing (the operator stays consistent for the mode that differs between the two
+    // layers).  For the point smoother not to meet a dominant coupling across the layers on coarse levels, such a "2-D" run
+    // makes the layers THICK: z extent about half the x extent, so dz >= dx on every level.
+    if (thin & (1 << d)) continue;
     const int n = f.geom.domain.hi[d] - f.geom.domain.lo[d] + 1;
     if ((n % 2) != 0 || (f.geom.domain.lo[d] % 2) != 0) return nullptr;
     g.domain.lo[d] = f.geom.domain.lo[d] / 2;
@@ -76,11 +89,12 @@ static bool all_periodic(const Level& L) {
 CellMG::CellMG(Level* fine, int ncomp, bool tensor, int max_coarsening)
     : ncomp_(ncomp), tensor_(tensor) {
   iamrx_mg_info_default(&info_);
+  thin_ = thin_mask(*fine);
   lv_.emplace_back();
   lv_[0].lev = fine;
   Level* cur = fine;
   for (int l = 1; l <= max_coarsening; ++l) {
-    auto c = coarsen_level(*cur, 2);
+    auto c = coarsen_level(*cur, 2, thin_);
     if (!c) break;
     lv_.emplace_back();
     if (auto r = consolidated_level(*c)) {   // from here down: one replicated box per rank, no ghost traffic
@@ -206,22 +220,22 @@ int CellMG::set_coeffs(const MF* acoef, const MF* bx, const MF* by, const MF* bz
       if (!C.acoef.ok()) C.acoef.define(C.lev, IX_CELL, 1, 0);
       if (C.xfer_lev) {   // restrict on the distributed layout, then gather into the replicated box
         MF tmp(C.xfer_lev.get(), IX_CELL, 1, 0);
-        for (int il = 0; il < tmp.n(); ++il) IX_TRY(k::cc_restrict(tmp.vbox(il), tmp.v(il), F.acoef.c(il), 1, s));
+        for (int il = 0; il < tmp.n(); ++il) IX_TRY(k::cc_restrict(tmp.vbox(il), tmp.v(il), F.acoef.c(il), 1, s, thin_));
         IX_TRY(mf_gather_replicate(C.acoef, tmp, 1, s));
       } else {
         for (int il = 0; il < C.acoef.n(); ++il)
-          IX_TRY(k::cc_restrict(C.acoef.vbox(il), C.acoef.v(il), F.acoef.c(il), 1, s));
+          IX_TRY(k::cc_restrict(C.acoef.vbox(il), C.acoef.v(il), F.acoef.c(il), 1, s, thin_));
       }
     }
     for (int d = 0; d < 3; ++d) {
       if (!C.b[d].ok()) C.b[d].define(C.lev, IX_XFACE + d, bn, 0);
       if (C.xfer_lev) {
         MF tmp(C.xfer_lev.get(), IX_XFACE + d, bn, 0);
-        for (int il = 0; il < tmp.n(); ++il) IX_TRY(k::face_restrict(tmp.vbox(il), d, tmp.v(il), F.b[d].c(il), bn, s));
+        for (int il = 0; il < tmp.n(); ++il) IX_TRY(k::face_restrict(tmp.vbox(il), d, tmp.v(il), F.b[d].c(il), bn, s, thin_));
         IX_TRY(mf_gather_replicate(C.b[d], tmp, bn, s));
       } else {
         for (int il = 0; il < C.b[d].n(); ++il)
-          IX_TRY(k::face_restrict(C.b[d].vbox(il), d, C.b[d].v(il), F.b[d].c(il), bn, s));
+          IX_TRY(k::face_restrict(C.b[d].vbox(il), d, C.b[d].v(il), F.b[d].c(il), bn, s, thin_));
       }
     }
   }
@@ -457,11 +471,11 @@ int CellMG::vcycle(cudaStream_t s) {
     MGLevelCell& C = lv_[l + 1];
     if (C.xfer_lev) {
       for (int il = 0; il < C.xfer.n(); ++il)
-        IX_TRY(k::cc_restrict(C.xfer.vbox(il), C.xfer.v(il), L.rescor.c(il), ncomp_, s));
+        IX_TRY(k::cc_restrict(C.xfer.vbox(il), C.xfer.v(il), L.rescor.c(il), ncomp_, s, thin_));
       IX_TRY(mf_gather_replicate(C.res, C.xfer, ncomp_, s));
     } else {
       for (int il = 0; il < C.res.n(); ++il)
-        IX_TRY(k::cc_restrict(C.res.vbox(il), C.res.v(il), L.rescor.c(il), ncomp_, s));
+        IX_TRY(k::cc_restrict(C.res.vbox(il), C.res.v(il), L.rescor.c(il), ncomp_, s, thin_));
     }
   }
   IX_TRY(bottom_solve(s));
@@ -469,7 +483,7 @@ int CellMG::vcycle(cudaStream_t s) {
     MGLevelCell& L = lv_[l];
     MGLevelCell& C = lv_[l + 1];
     for (int il = 0; il < L.cor.n(); ++il)
-      IX_TRY(k::cc_prolong_add(L.cor.vbox(il), L.cor.v(il), C.cor.c(C.xfer_lev ? 0 : il), ncomp_, s));   // replicated coarse box: read in place
+      IX_TRY(k::cc_prolong_add(L.cor.vbox(il), L.cor.v(il), C.cor.c(C.xfer_lev ? 0 : il), ncomp_, s, thin_));   // replicated coarse box: read in place
     IX_TRY(smooth(l, L.cor, L.res, info_.nu2, false, s));
   }
   return IAMRX_OK;
@@ -524,11 +538,12 @@ int CellMG::solve(MF& sol, const MF& rhs_in, iamrx_mg_info* info, cudaStream_t s
 // ===========================================================================
 NodeMG::NodeMG(Level* fine, int max_coarsening) {
   iamrx_mg_info_default(&info_);
+  thin_ = thin_mask(*fine);
   lv_.emplace_back();
   lv_[0].lev = fine;
   Level* cur = fine;
   for (int l = 1; l <= max_coarsening; ++l) {
-    auto c = coarsen_level(*cur, 2);
+    auto c = coarsen_level(*cur, 2, thin_);
     if (!c) break;
     lv_.emplace_back();
     if (auto r = consolidated_level(*c)) {   // from here down: one replicated box per rank, no ghost traffic
@@ -629,11 +644,11 @@ int NodeMG::set_sigma(const MF& sigma, cudaStream_t s) {
     IX_TRY(mf_setval(C.sigma, 0.0, 0, 1, C.ngd, s));
     if (C.xfer_lev) {
       MF tmp(C.xfer_lev.get(), IX_CELL, 1, 0);
-      for (int il = 0; il < tmp.n(); ++il) IX_TRY(k::cc_restrict(tmp.vbox(il), tmp.v(il), F.sigma.c(il), 1, s));
+      for (int il = 0; il < tmp.n(); ++il) IX_TRY(k::cc_restrict(tmp.vbox(il), tmp.v(il), F.sigma.c(il), 1, s, thin_));
       IX_TRY(mf_gather_replicate(C.sigma, tmp, 1, s));
     } else {
       for (int il = 0; il < C.sigma.n(); ++il)
-        IX_TRY(k::cc_restrict(C.sigma.vbox(il), C.sigma.v(il), F.sigma.c(il), 1, s));
+        IX_TRY(k::cc_restrict(C.sigma.vbox(il), C.sigma.v(il), F.sigma.c(il), 1, s, thin_));
     }
     IX_TRY(mf_fill_boundary(C.sigma, 0, 1, C.ngd, s));
     IX_TRY(sigma_bc(C));
@@ -787,12 +802,12 @@ int NodeMG::vcycle(cudaStream_t s) {
             if (bc_.lo[d] == IAMRX_LINOP_DIRICHLET && XL.lbox(il).lo[d] == XL.domain.lo[d]) cb.lo[d] += 1;
             if (bc_.hi[d] == IAMRX_LINOP_DIRICHLET && XL.lbox(il).hi[d] == XL.domain.hi[d]) cb.hi[d] -= 1;
           }
-        IX_TRY(k::nodal_restrict(cb, C.xfer.v(il), L.rescor.c(il), s));
+        IX_TRY(k::nodal_restrict(cb, C.xfer.v(il), L.rescor.c(il), s, thin_));
       }
       IX_TRY(mf_gather_replicate(C.res, C.xfer, 1, s));
     } else {
       for (int il = 0; il < C.res.n(); ++il)
-        IX_TRY(k::nodal_restrict(active_nbox(l + 1, il), C.res.v(il), L.rescor.c(il), s));
+        IX_TRY(k::nodal_restrict(active_nbox(l + 1, il), C.res.v(il), L.rescor.c(il), s, thin_));
     }
   }
   IX_TRY(bottom_solve(s));
@@ -800,7 +815,7 @@ int NodeMG::vcycle(cudaStream_t s) {
     MGLevelNode& L = lv_[l];
     MGLevelNode& C = lv_[l + 1];
     for (int il = 0; il < L.cor.n(); ++il)
-      IX_TRY(k::nodal_interp_add(active_nbox(l, il), L.cor.v(il), C.cor.c(C.xfer_lev ? 0 : il), s));
+      IX_TRY(k::nodal_interp_add(active_nbox(l, il), L.cor.v(il), C.cor.c(C.xfer_lev ? 0 : il), s, thin_));
     IX_TRY(smooth(l, L.cor, L.res, info_.nu2, s));
   }
   return IAMRX_OK;

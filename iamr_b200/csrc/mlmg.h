@@ -65,6 +65,7 @@ class CellMG {
   bool singular_ = false;
   const MF* eta_[3] = {nullptr, nullptr, nullptr};
   iamrx_mg_info info_;
+  int thin_ = 0;   // semi-coarsening mask (thin_mask of the finest level)
 };
 
 struct MGLevelNode {
@@ -106,12 +107,14 @@ class NodeMG {
   bool singular() const;
   std::vector<MGLevelNode> lv_;
   iamrx_mg_info info_;
+  int thin_ = 0;   // semi-coarsening mask (thin_mask of the finest level)
   k::NodalBC bc_{};
   bool has_bc_ = false;
 };
 
 // coarsen a level by 2 (all boxes must be coarsenable); nullptr if not possible
-std::unique_ptr<Level> coarsen_level(const Level& f, int min_width);
+int thin_mask(const Level& f);   // directions (bit mask) a multigrid hierarchy on this level never coarsens: <= 2 cells thick
+std::unique_ptr<Level> coarsen_level(const Level& f, int min_width, int thin = 0);
 // consolidation policy: given the distributed coarsening `c` of a level, return the replicated single-box level that
 // should replace it (small boxes: ghost exchanges are pure latency there), or nullptr to stay distributed
 std::unique_ptr<Level> consolidated_level(const Level& c);

@@ -121,28 +121,28 @@ gs_color_kernel(Bx bx, V4 phi, C4 rhs, C4 sig, double facx, double facy, double 
   phi(i, j, k) += (rhs(i, j, k) - y) / s0;
 }
 
-__global__ void __launch_bounds__(TX* TY) nd_restrict_kernel(Bx cbx, V4 crse, C4 fine) {
+__global__ void __launch_bounds__(TX* TY) nd_restrict_kernel(Bx cbx, V4 crse, C4 fine, int thin) {
   NIDX(cbx)
-  const int ii = 2 * i, jj = 2 * j, kk = 2 * k;
+  // full weighting (1, 2, 1) / 4 in every coarsened direction, injection in a direction with ratio 1 (thin bit set)
+  const int r0 = (thin & 1) ? 1 : 2, r1 = (thin & 2) ? 1 : 2, r2 = (thin & 4) ? 1 : 2;
+  const int ii = r0 * i, jj = r1 * j, kk = r2 * k;
+  const int e0 = r0 - 1, e1 = r1 - 1, e2 = r2 - 1;   // stencil half-width: 1 or 0
   double acc = 0.0;
-#pragma unroll
-  for (int dk = -1; dk <= 1; ++dk)
-#pragma unroll
-    for (int dj = -1; dj <= 1; ++dj)
-#pragma unroll
-      for (int di = -1; di <= 1; ++di) {
-        const double w = (double)((di == 0 ? 2 : 1) * (dj == 0 ? 2 : 1) * (dk == 0 ? 2 : 1));
+  for (int dk = -e2; dk <= e2; ++dk)
+    for (int dj = -e1; dj <= e1; ++dj)
+      for (int di = -e0; di <= e0; ++di) {
+        const double w = (double)(((di == 0 && e0) ? 2 : 1) * ((dj == 0 && e1) ? 2 : 1) * ((dk == 0 && e2) ? 2 : 1));
         acc += w * fine(ii + di, jj + dj, kk + dk);
       }
-  crse(i, j, k) = acc * (1.0 / 64.0);
+  crse(i, j, k) = acc / (double)((e0 ? 4 : 1) * (e1 ? 4 : 1) * (e2 ? 4 : 1));
 }
 
 IX_D int fl2(int a) { return (a >= 0) ? a / 2 : -((-a + 1) / 2); }
 
-__global__ void __launch_bounds__(TX* TY) nd_interp_kernel(Bx fbx, V4 fine, C4 crse) {
+__global__ void __launch_bounds__(TX* TY) nd_interp_kernel(Bx fbx, V4 fine, C4 crse, int thin) {
   NIDX(fbx)
-  const int ic = fl2(i), jc = fl2(j), kc = fl2(k);
-  const int ox = i - 2 * ic, oy = j - 2 * jc, oz = k - 2 * kc;  // 0 or 1
+  const int ic = (thin & 1) ? i : fl2(i), jc = (thin & 2) ? j : fl2(j), kc = (thin & 4) ? k : fl2(k);
+  const int ox = (thin & 1) ? 0 : i - 2 * ic, oy = (thin & 2) ? 0 : j - 2 * jc, oz = (thin & 4) ? 0 : k - 2 * kc;  // 0 or 1
   double acc = 0.0;
   for (int dk = 0; dk <= oz; ++dk)
     for (int dj = 0; dj <= oy; ++dj)
@@ -804,15 +804,15 @@ int nodal_gs_sweep(const Bx& nbx, V4 phi_out, C4 phi_in, C4 rhs, C4 sig, const d
 #endif
 }
 
-int nodal_restrict(const Bx& cnbx, V4 crse, C4 fine, cudaStream_t s) {
+int nodal_restrict(const Bx& cnbx, V4 crse, C4 fine, cudaStream_t s, int thin) {
   if (!cnbx.ok()) return IAMRX_OK;
-  IX_LAUNCH(nd_restrict_kernel, grid_for(cnbx), dim3(TX, TY, 1), 0, s, cnbx, crse, fine);
+  IX_LAUNCH(nd_restrict_kernel, grid_for(cnbx), dim3(TX, TY, 1), 0, s, cnbx, crse, fine, thin);
   return check_launch("nodal_restrict");
 }
 
-int nodal_interp_add(const Bx& fnbx, V4 fine, C4 crse, cudaStream_t s) {
+int nodal_interp_add(const Bx& fnbx, V4 fine, C4 crse, cudaStream_t s, int thin) {
   if (!fnbx.ok()) return IAMRX_OK;
-  IX_LAUNCH(nd_interp_kernel, grid_for(fnbx), dim3(TX, TY, 1), 0, s, fnbx, fine, crse);
+  IX_LAUNCH(nd_interp_kernel, grid_for(fnbx), dim3(TX, TY, 1), 0, s, fnbx, fine, crse, thin);
   return check_launch("nodal_interp_add");
 }
 
