@@ -44,6 +44,19 @@ __global__ void unpack_kernel(Bx bx, V4 d, const double* buf) {
   d(i, j, k, n) = buf[(i - bx.lo[0]) + nx * ((j - bx.lo[1]) + ny * ((k - bx.lo[2]) + (int64_t)nz_ * n))];
 }
 
+// max that PROPAGATES NaN (fmax drops it): a NaN anywhere in the data must reach the norm the solvers test, as a positive quiet
+// NaN whose bit pattern also wins the unsigned atomicMax below
+IX_HD double nanmax(double a, double b) {
+  if (a != a || b != b) {
+#if defined(__CUDA_ARCH__)
+    return __longlong_as_double(0x7ff8000000000000LL);
+#else
+    return fabs(a != a ? a : b);
+#endif
+  }
+  return a > b ? a : b;
+}
+
 #if defined(IX_EMUL)
 // tests-only serial stand-ins for the cooperative reduction kernels below
 static void reduce_serial(Bx bx, C4 src, int ncomp, int op, double* result) {
@@ -53,7 +66,7 @@ static void reduce_serial(Bx bx, C4 src, int ncomp, int op, double* result) {
       for (int j = bx.lo[1]; j <= bx.hi[1]; ++j)
         for (int i = bx.lo[0]; i <= bx.hi[0]; ++i) {
           const double v = src(i, j, k, n);
-          acc = (op == 0) ? acc + v : (op == 1 ? fmin(acc, v) : fmax(acc, fabs(v)));
+          acc = (op == 0) ? acc + v : (op == 1 ? fmin(acc, v) : nanmax(acc, fabs(v)));
         }
     result[n] = acc;
   }
@@ -77,7 +90,7 @@ static void dot_serial(Bx bx, C4 x, C4 y, C4 mask, double* result) {
 IX_D double warp_red(double v, int op) {
   for (int o = 16; o > 0; o >>= 1) {
     const double t = __shfl_xor_sync(0xffffffffu, v, o);
-    v = (op == 0) ? v + t : (op == 1 ? fmin(v, t) : fmax(v, t));
+    v = (op == 0) ? v + t : (op == 1 ? fmin(v, t) : nanmax(v, t));
   }
   return v;
 }
@@ -112,7 +125,7 @@ __global__ void __launch_bounds__(RT) reduce_kernel(Bx bx, C4 src, int op, doubl
     const int k = bx.lo[2] + (int)(r / ny);
     for (int ii = lane_x; ii < nx; ii += 64) {
       const double v = src(bx.lo[0] + ii, j, k, n);
-      acc = (op == 0) ? acc + v : (op == 1 ? fmin(acc, v) : fmax(acc, fabs(v)));
+      acc = (op == 0) ? acc + v : (op == 1 ? fmin(acc, v) : nanmax(acc, fabs(v)));
     }
   }
   __shared__ double sm[RT / 32];

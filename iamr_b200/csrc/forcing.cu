@@ -73,39 +73,69 @@ __global__ void turb_table_kernel(double* tab, const TurbMode* modes, int nm, in
   tab[(size_t)(row * 2 + 1) * pitch + q] = cv;
 }
 
-// frc(i,j,k,n) (+)= rho * f_n.  One thread per cell, all modes; T(d,m,c,s) = table row.
+// frc(i,j,k,n) (+)= rho * f_n.  One thread per (i, j) and KP consecutive planes, all modes: the x and y factors of a mode are
+// loaded once and combined into the six plane-independent products, each plane then costs five warp-uniform z loads and six
+// FMAs.  T(d,m,c,s) = table row.
+constexpr int KP = 4;
 template <bool DIVFREE>
 __global__ void __launch_bounds__(TX* TY)
 turb_force_kernel(Bx bx, V4 frc, C4 rho, const double* __restrict__ tab, const TurbMode* __restrict__ modes, int nm, int pitch, int accumulate) {
-  const int k = bx.lo[2] + (int)blockIdx.z;
+  const int k0 = bx.lo[2] + KP * (int)blockIdx.z;
   const int j = bx.lo[1] + blockIdx.y * TY + threadIdx.y;
   const int i = bx.lo[0] + blockIdx.x * TX + threadIdx.x;
   if (j > bx.hi[1] || i > bx.hi[0]) return;
-  const int qi = i - bx.lo[0], qj = j - bx.lo[1], qk = k - bx.lo[2];
-  double f1 = 0.0, f2 = 0.0, f3 = 0.0;
+  const int qi = i - bx.lo[0], qj = j - bx.lo[1], qk0 = k0 - bx.lo[2];
+  const int nk = (bx.hi[2] - k0 + 1 < KP) ? bx.hi[2] - k0 + 1 : KP;
+  double f1[KP], f2[KP], f3[KP];
+#pragma unroll
+  for (int p = 0; p < KP; ++p) { f1[p] = 0.0; f2[p] = 0.0; f3[p] = 0.0; }
   for (int m = 0; m < nm; ++m) {
 #define TT(d, c, s, q) tab[(size_t)((((d) * nm + m) * 3 + (c)) * 2 + (s)) * pitch + (q)]
     const double ax = modes[m].a[0], ay = modes[m].a[1], az = modes[m].a[2];
     if (DIVFREE) {
       const double wx = modes[m].w[0], wy = modes[m].w[1], wz = modes[m].w[2];
       // curl of the vector potential (A_x, A_y, A_z) sin sin sin with per-component phases (NS_getForce.cpp:376-401)
-      const double sXx = TT(0, 0, 0, qi), cXx = TT(0, 0, 1, qi), sXy = TT(1, 0, 0, qj), cXy = TT(1, 0, 1, qj), sXz = TT(2, 0, 0, qk), cXz = TT(2, 0, 1, qk);
-      const double sYx = TT(0, 1, 0, qi), cYx = TT(0, 1, 1, qi), sYy = TT(1, 1, 0, qj), cYy = TT(1, 1, 1, qj), sYz = TT(2, 1, 0, qk), cYz = TT(2, 1, 1, qk);
-      const double sZx = TT(0, 2, 0, qi), cZx = TT(0, 2, 1, qi), sZy = TT(1, 2, 0, qj), cZy = TT(1, 2, 1, qj), sZz = TT(2, 2, 0, qk), cZz = TT(2, 2, 1, qk);
-      f1 += az * wy * sZx * cZy * sZz - ay * wz * sYx * sYy * cYz;
-      f2 += ax * wz * sXx * sXy * cXz - az * wx * cZx * sZy * sZz;
-      f3 += ay * wx * cYx * sYy * sYz - ax * wy * sXx * cXy * sXz;
+      const double sXx = TT(0, 0, 0, qi), sXy = TT(1, 0, 0, qj), cXy = TT(1, 0, 1, qj);
+      const double sYx = TT(0, 1, 0, qi), cYx = TT(0, 1, 1, qi), sYy = TT(1, 1, 0, qj);
+      const double sZx = TT(0, 2, 0, qi), cZx = TT(0, 2, 1, qi), sZy = TT(1, 2, 0, qj), cZy = TT(1, 2, 1, qj);
+      const double p1a = az * wy * sZx * cZy, p1b = ay * wz * sYx * sYy;   // f1 = p1a sZz - p1b cYz
+      const double p2a = ax * wz * sXx * sXy, p2b = az * wx * cZx * sZy;   // f2 = p2a cXz - p2b sZz
+      const double p3a = ay * wx * cYx * sYy, p3b = ax * wy * sXx * cXy;   // f3 = p3a sYz - p3b sXz
+#pragma unroll
+      for (int p = 0; p < KP; ++p) {
+        if (p < nk) {
+          const int qk = qk0 + p;
+          const double sXz = TT(2, 0, 0, qk), cXz = TT(2, 0, 1, qk), sYz = TT(2, 1, 0, qk), cYz = TT(2, 1, 1, qk), sZz = TT(2, 2, 0, qk);
+          f1[p] += p1a * sZz - p1b * cYz;
+          f2[p] += p2a * cXz - p2b * sZz;
+          f3[p] += p3a * sYz - p3b * sXz;
+        }
+      }
     } else {
-      const double sx = TT(0, 0, 0, qi), cx = TT(0, 0, 1, qi), sy = TT(1, 0, 0, qj), cy = TT(1, 0, 1, qj), sz = TT(2, 0, 0, qk), cz = TT(2, 0, 1, qk);
-      f1 += ax * cx * sy * sz;
-      f2 += ay * sx * cy * sz;
-      f3 += az * sx * sy * cz;
+      const double sx = TT(0, 0, 0, qi), cx = TT(0, 0, 1, qi), sy = TT(1, 0, 0, qj), cy = TT(1, 0, 1, qj);
+      const double q1 = ax * cx * sy, q2 = ay * sx * cy, q3 = az * sx * sy;
+#pragma unroll
+      for (int p = 0; p < KP; ++p) {
+        if (p < nk) {
+          const int qk = qk0 + p;
+          const double sz = TT(2, 0, 0, qk), cz = TT(2, 0, 1, qk);
+          f1[p] += q1 * sz;
+          f2[p] += q2 * sz;
+          f3[p] += q3 * cz;
+        }
+      }
     }
 #undef TT
   }
-  const double r = rho.ok() ? rho(i, j, k) : 1.0;
-  if (accumulate) { frc(i, j, k, 0) += r * f1; frc(i, j, k, 1) += r * f2; frc(i, j, k, 2) += r * f3; }
-  else { frc(i, j, k, 0) = r * f1; frc(i, j, k, 1) = r * f2; frc(i, j, k, 2) = r * f3; }
+#pragma unroll
+  for (int p = 0; p < KP; ++p) {
+    if (p < nk) {
+      const int k = k0 + p;
+      const double r = rho.ok() ? rho(i, j, k) : 1.0;
+      if (accumulate) { frc(i, j, k, 0) += r * f1[p]; frc(i, j, k, 1) += r * f2[p]; frc(i, j, k, 2) += r * f3[p]; }
+      else { frc(i, j, k, 0) = r * f1[p]; frc(i, j, k, 1) = r * f2[p]; frc(i, j, k, 2) = r * f3[p]; }
+    }
+  }
 }
 }  // namespace
 
@@ -128,7 +158,7 @@ int turb_force(const Bx& bx, V4 frc, C4 rho, const iamrx_geom& g, const TurbMode
             g.prob_lo[0], g.prob_lo[1], g.prob_lo[2], g.dx[0], g.dx[1], g.dx[2]);
   int rc = check_launch("turb_table");
   if (rc) return rc;
-  const dim3 grd(cdiv(bx.nx(), TX), cdiv(bx.ny(), TY), bx.nz());
+  const dim3 grd(cdiv(bx.nx(), TX), cdiv(bx.ny(), TY), cdiv(bx.nz(), KP));
   if (div_free) IX_LAUNCH((turb_force_kernel<true>), grd, dim3(TX, TY, 1), 0, s, bx, frc, rho, d_tab, d_modes, nm, pitch, accumulate);
   else IX_LAUNCH((turb_force_kernel<false>), grd, dim3(TX, TY, 1), 0, s, bx, frc, rho, d_tab, d_modes, nm, pitch, accumulate);
   return check_launch("turb_force");

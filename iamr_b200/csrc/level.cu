@@ -827,7 +827,8 @@ int mf_norminf_each(const MF& m, int comp, int ncomp, double* out, cudaStream_t 
 int mf_norminf(const MF& m, int comp, int ncomp, double* out, cudaStream_t s) {
   double tmp[16];
   IX_TRY(reduce_common(m, comp, ncomp, 2, tmp, s, false));
-  double r = 0; for (int n = 0; n < ncomp; ++n) r = std::max(r, tmp[n]);
+  double r = 0;
+  for (int n = 0; n < ncomp; ++n) r = (tmp[n] != tmp[n] || r != r) ? std::nan("") : std::max(r, tmp[n]);   // a NaN component is a NaN norm
   *out = r;
   return IAMRX_OK;
 }

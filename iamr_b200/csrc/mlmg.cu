@@ -505,6 +505,7 @@ int CellMG::solve(MF& sol, const MF& rhs_in, iamrx_mg_info* info, cudaStream_t s
   IX_TRY(mf_norminf(rhs, 0, ncomp_, &rhsnorm, s));
   IX_TRY(residual(0, L0.res, sol, rhs, true, s));
   IX_TRY(mf_norminf(L0.res, 0, ncomp_, &resnorm0, s));
+  if (!std::isfinite(rhsnorm) || !std::isfinite(resnorm0)) { bvals_.clear(); set_error("CellMG: NaN in the right-hand side or the initial guess"); return IAMRX_ERR_NAN; }
   const double maxnorm = std::max(rhsnorm, resnorm0);
   const double target = std::max(info_.atol, info_.rtol * maxnorm);
   resnorm = resnorm0;
@@ -519,7 +520,7 @@ int CellMG::solve(MF& sol, const MF& rhs_in, iamrx_mg_info* info, cudaStream_t s
       IX_TRY(mf_norminf(L0.res, 0, ncomp_, &resnorm, s));
       if (info_.verbose > 1)
         fprintf(stderr, "[iamrx] CellMG iter %d resnorm %.6e (target %.3e)\n", iters, resnorm, target);
-      if (!(resnorm == resnorm)) { set_error("CellMG: NaN residual"); rc = IAMRX_ERR_NAN; break; }
+      if (!std::isfinite(resnorm)) { set_error("CellMG: NaN residual"); rc = IAMRX_ERR_NAN; break; }
       if (resnorm <= target) { rc = IAMRX_OK; break; }
     }
   }
@@ -832,6 +833,7 @@ int NodeMG::solve(MF& phi, MF& rhs, iamrx_mg_info* info, cudaStream_t s) {
   IX_TRY(mf_norminf(rhs, 0, 1, &rhsnorm, s));
   IX_TRY(residual(0, L0.res, phi, rhs, s));
   IX_TRY(mf_norminf(L0.res, 0, 1, &resnorm0, s));
+  if (!std::isfinite(rhsnorm) || !std::isfinite(resnorm0)) { set_error("NodeMG: NaN in the right-hand side or the initial guess"); return IAMRX_ERR_NAN; }
   const double maxnorm = std::max(rhsnorm, resnorm0);
   const double target = std::max(info_.atol, info_.rtol * maxnorm);
   resnorm = resnorm0;
@@ -846,7 +848,7 @@ int NodeMG::solve(MF& phi, MF& rhs, iamrx_mg_info* info, cudaStream_t s) {
       IX_TRY(mf_norminf(L0.res, 0, 1, &resnorm, s));
       if (info_.verbose > 1)
         fprintf(stderr, "[iamrx] NodeMG iter %d resnorm %.6e (target %.3e)\n", iters, resnorm, target);
-      if (!(resnorm == resnorm)) { set_error("NodeMG: NaN residual"); rc = IAMRX_ERR_NAN; break; }
+      if (!std::isfinite(resnorm)) { set_error("NodeMG: NaN residual"); rc = IAMRX_ERR_NAN; break; }
       if (resnorm <= target) { rc = IAMRX_OK; break; }
     }
   }

@@ -56,6 +56,7 @@ struct iamrx_ns_s {
   std::vector<double> turb_data;   // host copy of TurbulentForcing::forcedata
   MF turbf;                        // f(x, t) per unit mass, 3 comps, 1 ghost
   double* turb_dev = nullptr; size_t turb_dev_n = 0;   // device scratch: mode list + axis tables
+  double turb_time = 0.0; int turb_ng = -1; bool turb_time_ok = false;   // what turbf currently holds
 
   double time = 0.0, dt_level = 0.0, dt_min = 1.0e100;
   int nstep = 0;
@@ -201,6 +202,9 @@ int get_visc_terms(iamrx_ns_s& ns, MF& visc, const MF& S) {
 // getForce is handed at that call site)
 int turb_eval(iamrx_ns_s& ns, double time, int ng) {
   if (!ns.turb_on) return IAMRX_OK;
+  // estTimeStep's cur_time evaluation at the end of a step is the next step's prev_time evaluation: keep it
+  if (ns.turb_time_ok && time == ns.turb_time && ng <= ns.turb_ng) return IAMRX_OK;
+  ns.turb_time_ok = false;
   Level& L = *ns.L;
   double len[3];
   for (int d = 0; d < 3; ++d) len[d] = (L.domain.hi[d] - L.domain.lo[d] + 1) * L.geom.dx[d];
@@ -220,6 +224,7 @@ int turb_eval(iamrx_ns_s& ns, double time, int ng) {
   for (int il = 0; il < ns.turbf.n(); ++il)
     IX_TRY(k::turb_force(ns.turbf.gbox(il, ng), ns.turbf.v(il), C4{}, L.geom, reinterpret_cast<const k::TurbMode*>(ns.turb_dev), nm,
                          ns.turb.div_free, ns.turb_dev + mode_doubles + 8, 0, ns.s));
+  ns.turb_time = time; ns.turb_ng = ng; ns.turb_time_ok = true;
   return IAMRX_OK;
 }
 inline C4 turb_c(const iamrx_ns_s& ns, int il) { return ns.turb_on ? ns.turbf.c(il) : C4{}; }
@@ -492,7 +497,7 @@ int est_time_step(iamrx_ns_s& ns, double* out) {
   double estdt = 1.0e20;
   double umax[3], fmax[3];
   IX_TRY(mf_norminf_each(ns.S_new, Xvel, 3, umax, ns.s));
-  IX_TRY(turb_eval(ns, ns.time, 0));   // getForce at cur_time (:1410)
+  IX_TRY(turb_eval(ns, ns.time, 1));   // getForce at cur_time (:1410); with the ghost layer the next advance's prev_time call needs
   for (int il = 0; il < ns.tf0.n(); ++il)
     IX_TRY(k::force_vel(L.lbox(il), ns.tf0.v(il), C4{}, ns.Gp_new.c(il), ns.S_new.c(il, Density), ns.p.gravity, 1, ns.s, turb_c(ns, il)));
   IX_TRY(mf_norminf_each(ns.tf0, 0, 3, fmax, ns.s));
@@ -640,6 +645,7 @@ int iamrx_ns_set_turbulent_forcing(iamrx_ns_t ns, int nmodes, int mode_start, in
     return IAMRX_ERR_ARG;
   }
   ns->turb_on = true;
+  ns->turb_time_ok = false;
   return IAMRX_OK;
 }
 

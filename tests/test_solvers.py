@@ -258,3 +258,23 @@ def test_bicgstab_bottom_solver(backend, oracle, nb):
     # the bottom level is 2^3: both bottom solvers are exact enough there, the V-cycle counts do not move
     assert its[("mac", 0)] == its[("mac", 1)] and its[("nodal", 0)] == its[("nodal", 1)]
     lev.close()
+
+
+def test_solver_reports_nan(backend):
+    """A NaN in the data is reported as IAMRX_ERR_NAN (with a message), not iterated on until the cap and not returned as a result."""
+    lib, dev = backend
+    rho = _rho()
+    um, vm, wm = (smooth_field(N, 300 + d, 1) for d in range(3))
+    um = um.copy(); um[0, 3, 4, 5] = np.nan
+    boxes = split_boxes(N, (1, 1, 1))
+    lev = ix.Level(lib, ix.Geom.make(N), boxes)
+    U, V, W = (to_fab(f, boxes[0], 1, t, dev) for f, t in ((um, ix.XFACE), (vm, ix.YFACE), (wm, ix.ZFACE)))
+    R = to_fab(rho, boxes[0], 1, ix.CELL, dev)
+    P = to_fab(np.zeros_like(rho), boxes[0], 1, ix.CELL, dev)
+    info = _mg(lib)
+    rc = lib.iamrx_mac_project(lev.h, fab_array([U[1]]), fab_array([V[1]]), fab_array([W[1]]), fab_array([R[1]]), None,
+                               fab_array([P[1]]), 2.0 * 16 / 0.7, None, None, C.byref(info), stream_of(dev))
+    sync(dev)
+    assert rc == -5   # IAMRX_ERR_NAN
+    assert b"NaN" in lib.dll.iamrx_last_error()
+    lev.close()
