@@ -106,10 +106,17 @@ CellMG::CellMG(Level* fine, int ncomp, bool tensor, int max_coarsening)
     lv_.back().lev = lv_.back().lev_owned.get();
     cur = lv_.back().lev;
   }
+  // IAMRX_CELL_DEEP=0 / 1 forces the deep-ghost sweeps off / on; by default they are used when boxes live on several ranks (they
+  // trade a larger ghost copy and a grown red pass for one exchange instead of two: a loss when the exchange is a local copy --
+  // 155.5 vs 149.6 ms per step for 8 boxes on one GPU -- and a gain when it is an NCCL round trip)
+  static int deep_env = -2;
+  if (deep_env == -2) { const char* e = getenv("IAMRX_CELL_DEEP"); deep_env = e ? (e[0] == '0' ? 0 : 1) : -1; }
+  const int deep_on = deep_env >= 0 ? deep_env : (comm().nranks > 1 ? 1 : 0);
   for (auto& L : lv_) {
     for (int d = 0; d < 3; ++d) L.dxinv[d] = L.lev->dxinv[d];
-    L.cor.define(L.lev, IX_CELL, ncomp_, 1);
-    L.res.define(L.lev, IX_CELL, ncomp_, 0);
+    L.deep = deep_on && !L.lev->replicated && L.lev->level_wrapmask() != 7 && all_periodic(*L.lev);
+    L.cor.define(L.lev, IX_CELL, ncomp_, L.deep ? 2 : 1);
+    L.res.define(L.lev, IX_CELL, ncomp_, L.deep ? 1 : 0);
     L.rescor.define(L.lev, IX_CELL, ncomp_, 0);
     if (L.xfer_lev) L.xfer.define(L.xfer_lev.get(), IX_CELL, ncomp_, 0);
   }
@@ -202,22 +209,24 @@ int CellMG::set_coeffs(const MF* acoef, const MF* bx, const MF* by, const MF* bz
   {
     MGLevelCell& L = lv_[0];
     if (a_ != 0.0 && acoef) {
-      if (!L.acoef.ok()) L.acoef.define(L.lev, IX_CELL, 1, 0);
+      if (!L.acoef.ok()) L.acoef.define(L.lev, IX_CELL, 1, L.deep ? 1 : 0);
       IX_TRY(mf_copy(L.acoef, *acoef, 0, 0, 1, 0, s));
+      if (L.deep) IX_TRY(mf_fill_boundary(L.acoef, 0, 1, 1, s));
     }
     for (int d = 0; d < 3; ++d) {
-      if (!L.b[d].ok()) L.b[d].define(L.lev, IX_XFACE + d, bn, 0);
+      if (!L.b[d].ok()) L.b[d].define(L.lev, IX_XFACE + d, bn, L.deep ? 1 : 0);
       for (int c = 0; c < bn; ++c) {
         const double fac = (tensor_ && c == d) ? (4.0 / 3.0) : 1.0;
         IX_TRY(mf_lincomb(L.b[d], c, fac, *bin[d], 0, 0.0, *bin[d], 0, 1, 0, s));
       }
+      if (L.deep) IX_TRY(mf_fill_boundary(L.b[d], 0, bn, 1, s));   // deep-ghost sweeps relax the first ghost layer too
     }
   }
   for (size_t l = 1; l < lv_.size() && !finest_only; ++l) {
     MGLevelCell& C = lv_[l];
     MGLevelCell& F = lv_[l - 1];
     if (a_ != 0.0 && acoef) {
-      if (!C.acoef.ok()) C.acoef.define(C.lev, IX_CELL, 1, 0);
+      if (!C.acoef.ok()) C.acoef.define(C.lev, IX_CELL, 1, C.deep ? 1 : 0);
       if (C.xfer_lev) {   // restrict on the distributed layout, then gather into the replicated box
         MF tmp(C.xfer_lev.get(), IX_CELL, 1, 0);
         for (int il = 0; il < tmp.n(); ++il) IX_TRY(k::cc_restrict(tmp.vbox(il), tmp.v(il), F.acoef.c(il), 1, s, thin_));
@@ -226,9 +235,10 @@ int CellMG::set_coeffs(const MF* acoef, const MF* bx, const MF* by, const MF* bz
         for (int il = 0; il < C.acoef.n(); ++il)
           IX_TRY(k::cc_restrict(C.acoef.vbox(il), C.acoef.v(il), F.acoef.c(il), 1, s, thin_));
       }
+      if (C.deep) IX_TRY(mf_fill_boundary(C.acoef, 0, 1, 1, s));
     }
     for (int d = 0; d < 3; ++d) {
-      if (!C.b[d].ok()) C.b[d].define(C.lev, IX_XFACE + d, bn, 0);
+      if (!C.b[d].ok()) C.b[d].define(C.lev, IX_XFACE + d, bn, C.deep ? 1 : 0);
       if (C.xfer_lev) {
         MF tmp(C.xfer_lev.get(), IX_XFACE + d, bn, 0);
         for (int il = 0; il < tmp.n(); ++il) IX_TRY(k::face_restrict(tmp.vbox(il), d, tmp.v(il), F.b[d].c(il), bn, s, thin_));
@@ -237,6 +247,7 @@ int CellMG::set_coeffs(const MF* acoef, const MF* bx, const MF* by, const MF* bz
         for (int il = 0; il < C.b[d].n(); ++il)
           IX_TRY(k::face_restrict(C.b[d].vbox(il), d, C.b[d].v(il), F.b[d].c(il), bn, s, thin_));
       }
+      if (C.deep) IX_TRY(mf_fill_boundary(C.b[d], 0, bn, 1, s));
     }
   }
   // the operator annihilates constants when a = 0 and no side pins the solution (periodic / Neumann everywhere)
@@ -251,7 +262,7 @@ int CellMG::set_coeffs(const MF* acoef, const MF* bx, const MF* by, const MF* bz
   return IAMRX_OK;
 }
 
-int CellMG::smooth(int l, MF& phi, const MF& rhs, int nsweeps, bool /*zero_init*/, cudaStream_t s) {
+int CellMG::smooth(int l, MF& phi, const MF& rhs, int nsweeps, bool zero_init, cudaStream_t s) {
   MGLevelCell& L = lv_[l];
   // a box that spans the periodic domain wraps its neighbour indices inside the kernel:
   // no ghost fill (and no extra launch) per colour
@@ -269,6 +280,22 @@ int CellMG::smooth(int l, MF& phi, const MF& rhs, int nsweeps, bool /*zero_init*
       std::swap(src, dst);
     }
     if (src != &phi) IX_TRY(mf_copy(phi, *src, 0, 0, ncomp_, 0, s));
+    return IAMRX_OK;
+  }
+  if (L.deep && !has_bc_ && phi.ng >= 2 && rhs.ng >= 1) {
+    // deep-ghost sweep: one exchange of two ghost layers, the red pass on the box grown by one cell towards its neighbours (the
+    // same arithmetic on the same values as the neighbour's own red pass), the black pass on the box.  A zero initial guess
+    // (ghost layers included) needs no exchange before the first sweep.
+    if (!L.rhs_ghost_ok) { IX_TRY(mf_fill_boundary(const_cast<MF&>(rhs), 0, ncomp_, 1, s, wm)); L.rhs_ghost_ok = true; }
+    for (int sw = 0; sw < nsweeps; ++sw) {
+      if (!(zero_init && sw == 0)) IX_TRY(mf_fill_boundary(phi, 0, ncomp_, 2, s, wm));
+      for (int rb = 0; rb < 2; ++rb)
+        for (int il = 0; il < phi.n(); ++il) {
+          Bx b = phi.vbox(il);
+          if (rb == 0) for (int d = 0; d < 3; ++d) if (!(wm & (1 << d))) b = grow(b, d, 1);
+          IX_TRY(k::abec_gsrb(b, phi.v(il), rhs.c(il), op_at(l, il), info_.omega, rb, ncomp_, s, wm, nullptr));
+        }
+    }
     return IAMRX_OK;
   }
   for (int sw = 0; sw < nsweeps; ++sw) {
@@ -432,7 +459,8 @@ int mf_dot(const MF& a, const MF& b, int ncomp, bool unique_nodes, double* out, 
 int CellMG::bottom_solve(cudaStream_t s) {
   const int nl = (int)lv_.size();
   MGLevelCell& B = lv_[nl - 1];
-  IX_TRY(mf_setval(B.cor, 0.0, 0, ncomp_, 1, s));
+  IX_TRY(mf_setval(B.cor, 0.0, 0, ncomp_, B.cor.ng, s));
+  B.rhs_ghost_ok = false;
   if (singular_ && nl > 1) IX_TRY(make_solvable(nl - 1, B.res, s));
   const int nsm = nl == 1 ? info_.nu1 + info_.nu2 : info_.bottom_sweeps;
   if (info_.bottom_solver != 1 || nl == 1) return smooth(nl - 1, B.cor, B.res, nsm, true, s);
@@ -465,7 +493,8 @@ int CellMG::vcycle(cudaStream_t s) {
   const int nl = (int)lv_.size();
   for (int l = 0; l < nl - 1; ++l) {
     MGLevelCell& L = lv_[l];
-    IX_TRY(mf_setval(L.cor, 0.0, 0, ncomp_, 1, s));
+    IX_TRY(mf_setval(L.cor, 0.0, 0, ncomp_, L.cor.ng, s));
+    L.rhs_ghost_ok = false;   // L.res was just rewritten (top-level residual or restriction)
     IX_TRY(smooth(l, L.cor, L.res, info_.nu1, true, s));
     IX_TRY(residual(l, L.rescor, L.cor, L.res, false, s));
     MGLevelCell& C = lv_[l + 1];
@@ -699,6 +728,8 @@ int NodeMG::smooth(int l, MF& phi, const MF& rhs, int nsweeps, cudaStream_t s) {
     // planes of `dst` -- two plane exchanges per sweep instead of eight colour fills.
     if (!L.gs_tmp.ok()) { L.gs_tmp.define(L.lev, IX_NODE, 1, L.ngd); IX_TRY(mf_setval(L.gs_tmp, 0.0, 0, 1, L.ngd, s)); }
     MF* src = &phi; MF* dst = &L.gs_tmp;
+    bool zeven = true;   // every box starts (and, having an even extent, ends) on an even node plane
+    for (const Bx& b : L.lev->boxes) if (b.lo[2] & 1) zeven = false;
     // (the ghost layers of the right-hand side are scratch: filling them does not change the caller's data)
     if (deep) IX_TRY(mf_fill_boundary(const_cast<MF&>(rhs), 0, 1, gd, s, wm));
     IX_TRY(fill_ghosts(l, *src, wm, s, false, gd));
@@ -707,7 +738,10 @@ int NodeMG::smooth(int l, MF& phi, const MF& rhs, int nsweeps, cudaStream_t s) {
         for (int il = 0; il < phi.n(); ++il)
           IX_TRY(k::nodal_gs_sweep(active_nbox(l, il), dst->v(il), src->c(il), rhs.c(il), L.sigma.c(il), L.dxinv, s,
                                    wmk | (neumann_sides(l, il) << 3), phase));
-        IX_TRY(fill_ghosts(l, *dst, wm, s, false, gd));
+        // slabs (x, y wrapped; node boxes start and end on even planes): the ghost planes are ODD planes, which only the second
+        // phase changes, and the second phase reads nothing beyond the box's own even planes -- one exchange per sweep.  Boxes
+        // with x / y neighbours (deep-ghost halos) need the new even planes of their neighbours for the second phase.
+        if (phase == 1 || deep || !zeven) IX_TRY(fill_ghosts(l, *dst, wm, s, false, gd));
       }
       std::swap(src, dst);
     }

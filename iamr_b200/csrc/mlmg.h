@@ -22,6 +22,11 @@ struct MGLevelCell {
   MF cor, res, rescor; // ncomp
   MF gs_tmp;           // second phi buffer of the out-of-place fused red-black sweep (lazy)
   double dxinv[3];
+  // deep-ghost level (boxes with neighbours, fully periodic domain): cor carries 2 ghost layers, res / coefficients 1, so that a
+  // red-black sweep needs ONE ghost exchange (the red pass also updates the first ghost layer, redundantly with the
+  // neighbour) instead of one per colour; the right-hand side's ghost layer is exchanged once per V-cycle visit
+  bool deep = false;
+  bool rhs_ghost_ok = false;
 };
 
 class CellMG {

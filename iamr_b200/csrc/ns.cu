@@ -69,6 +69,12 @@ struct iamrx_ns_s {
   cudaStream_t s2 = nullptr;
   cudaEvent_t ev_scal = nullptr;
 #endif
+  // ... and the tracer is not read before scalar_advection (after the MAC projection): its host->device copy runs on the second
+  // stream underneath predict_velocity and the MAC solve; late_tracer marks a step whose tracer is still in flight
+  bool late_tracer = false;
+#if !defined(IX_EMUL)
+  cudaEvent_t ev_in = nullptr, ev_prev = nullptr;
+#endif
   double* early_out = nullptr;   // host destination of comps Density.. (single local box), or null
   double* early_buf = nullptr;   // device staging of the packed scalars
 
@@ -249,7 +255,7 @@ int predict_velocity(iamrx_ns_s& ns, double dt, double* dt_test) {
   const double tempdt = (cflmax == 0.0) ? ns.p.change_max : std::min(ns.p.change_max, ns.p.cfl / cflmax);  // :4413
   if (ns.p.be_cn_theta != 1.0) IX_TRY(get_visc_terms(ns, ns.visc, ns.S_old));   // :4426-4433
   else IX_TRY(mf_setval(ns.visc, 0.0, 0, 3, 1, ns.s));
-  IX_TRY(fillpatch(ns, ns.Smf, ns.S_old, Density, NUM_SCALARS));           // :4435
+  IX_TRY(fillpatch(ns, ns.Smf, ns.S_old, Density, ns.late_tracer ? 1 : NUM_SCALARS));   // :4435 (a tracer still in flight is patched in scalar_advection)
   IX_TRY(vel_forcing(ns));                                                 // :4456-4470
   k::AdvGeom g; for (int d = 0; d < 3; ++d) g.dx[d] = L.geom.dx[d]; g.dt = dt;
   const k::AdvBC vbc = ns.adv_bc(Xvel, 3);
@@ -320,6 +326,14 @@ int velocity_advection(iamrx_ns_s& ns, double dt) {
 
 // NavierStokes::scalar_advection (NS.cpp:698-812)
 int scalar_advection(iamrx_ns_s& ns, double dt) {
+#if !defined(IX_EMUL)
+  if (ns.late_tracer) {   // step_host: the tracer's upload ran underneath predict_velocity and the MAC solve; first use is here
+    IX_CUDA(cudaStreamWaitEvent(ns.s, ns.ev_in, 0));
+    IX_TRY(mf_copy(ns.Smf, ns.S_old, Tracer, Tracer - Density, 1, 0, ns.s));
+    IX_TRY(fill_state_ghosts(ns, ns.Smf, Tracer - Density, Tracer, 1, ns.Smf.ng));
+    ns.late_tracer = false;
+  }
+#endif
   for (int il = 0; il < ns.Smf.n(); ++il) IX_TRY(k::floor_small(ns.Smf.gbox(il, 3), ns.Smf.v(il), NUM_SCALARS, ns.s));  // :722
   IX_TRY(mf_setval(ns.sforce, 0.0, 0, NUM_SCALARS, 1, ns.s));  // getForce: zero scalar forcing (:755-760)
   if (ns.diffusive_tracer() && ns.p.be_cn_theta != 1.0) {
@@ -618,7 +632,7 @@ int iamrx_ns_destroy(iamrx_ns_t ns) {
   if (ns && ns->stage) cudaFreeHost(ns->stage);
   if (ns && ns->turb_dev) dev_free(ns->turb_dev);
 #if !defined(IX_EMUL)
-  if (ns && ns->s2) { cudaStreamDestroy(ns->s2); cudaEventDestroy(ns->ev_scal); }
+  if (ns && ns->s2) { cudaStreamDestroy(ns->s2); cudaEventDestroy(ns->ev_scal); cudaEventDestroy(ns->ev_in); cudaEventDestroy(ns->ev_prev); }
 #endif
   delete ns;
   return IAMRX_OK;
@@ -800,19 +814,37 @@ int iamrx_ns_step_host(iamrx_ns_t nsp, const double* const* host_in, double* con
   struct Guard { double* p; ~Guard() { dev_free(p); } } dg{dev_alloc(need)}, eg{nullptr};   // released on every exit path
   double* dbuf = dg.p;
   if (!dbuf) return IAMRX_ERR_CUDA;
-  for (int il = 0; il < L.nlocal(); ++il) {
-    const size_t n = (size_t)L.lbox(il).npts() * NUM_STATE;
-    IX_CUDA(cudaMemcpyAsync(dbuf, host_in[il], n * sizeof(double), cudaMemcpyHostToDevice, ns.s));
-    IX_TRY(k::unpack(L.lbox(il), ns.S_new.v(il), dbuf, NUM_STATE, ns.s));
-  }
   bool early = false;
 #if !defined(IX_EMUL)
   early = L.nlocal() == 1 && !ns.initial_step && !ns.initial_iter;
-  if (early) {
-    if (!ns.s2) {
-      IX_CUDA(cudaStreamCreateWithFlags(&ns.s2, cudaStreamNonBlocking));
-      IX_CUDA(cudaEventCreateWithFlags(&ns.ev_scal, cudaEventDisableTiming));
+  if (early && !ns.s2) {
+    IX_CUDA(cudaStreamCreateWithFlags(&ns.s2, cudaStreamNonBlocking));
+    IX_CUDA(cudaEventCreateWithFlags(&ns.ev_scal, cudaEventDisableTiming));
+    IX_CUDA(cudaEventCreateWithFlags(&ns.ev_in, cudaEventDisableTiming));
+    IX_CUDA(cudaEventCreateWithFlags(&ns.ev_prev, cudaEventDisableTiming));
+  }
+#endif
+  // scalminmax / a diffusive tracer / momentum form read the tracer no earlier either, but keep the overlap to the plain path
+  const bool late = early && Tracer == NUM_STATE - 1;
+  for (int il = 0; il < L.nlocal(); ++il) {
+    const size_t npts = (size_t)L.lbox(il).npts();
+    const int nfirst = late ? NUM_STATE - 1 : NUM_STATE;
+    IX_CUDA(cudaMemcpyAsync(dbuf, host_in[il], npts * nfirst * sizeof(double), cudaMemcpyHostToDevice, ns.s));
+    IX_TRY(k::unpack(L.lbox(il), ns.S_new.v(il), dbuf, nfirst, ns.s));
+#if !defined(IX_EMUL)
+    if (late) {   // the tracer follows on the second stream, after everything already queued on the main stream (previous readers)
+      double* tb = dbuf + npts * (NUM_STATE - 1);
+      IX_CUDA(cudaEventRecord(ns.ev_prev, ns.s));
+      IX_CUDA(cudaStreamWaitEvent(ns.s2, ns.ev_prev, 0));
+      IX_CUDA(cudaMemcpyAsync(tb, host_in[il] + npts * (NUM_STATE - 1), npts * sizeof(double), cudaMemcpyHostToDevice, ns.s2));
+      IX_TRY(k::unpack(L.lbox(il), ns.S_new.v(il, Tracer), tb, 1, ns.s2));
+      IX_CUDA(cudaEventRecord(ns.ev_in, ns.s2));
+      ns.late_tracer = true;
     }
+#endif
+  }
+#if !defined(IX_EMUL)
+  if (early) {
     eg.p = ns.early_buf = dev_alloc(maxpts * NUM_SCALARS);
     if (!ns.early_buf) return IAMRX_ERR_CUDA;
     ns.early_out = host_out[0] + (size_t)L.lbox(0).npts() * Density;
@@ -821,6 +853,7 @@ int iamrx_ns_step_host(iamrx_ns_t nsp, const double* const* host_in, double* con
   int rc = iamrx_ns_step(nsp, dt_io);
   ns.early_out = nullptr;
   ns.early_buf = nullptr;
+  ns.late_tracer = false;
   if (rc != IAMRX_OK) {
 #if !defined(IX_EMUL)
     if (early) cudaStreamSynchronize(ns.s2);

@@ -150,25 +150,38 @@ def test_sum_integrated_quantities(backend, nb):
     ns.close(); lev.close()
 
 
-def test_step_host_roundtrip(backend):
-    """The host-buffer entry (e2e path) gives the same state as the device-resident step."""
+@pytest.mark.parametrize("nb,probtype,pp,kw", [
+    ((2, 1, 1), 11, [1.0, 1.0, 1.0, 1.0, 1.0], {}),
+    # one local box: the scalars leave early and the tracer arrives late on the second stream (ns.cu step_host) -- a field with a
+    # non-trivial tracer, with and without the options that read the old tracer (scalminmax, tracer diffusion, momentum form)
+    ((1, 1, 1), 5, [1.0, 1.0, 0.0, 0.0, 0.0, 0.4], {}),
+    ((1, 1, 1), 5, [1.0, 1.0, 0.0, 0.0, 0.0, 0.4], {"scal_diff_coef": 5e-3, "do_scalminmax": 1, "conservative_tracer": 1}),
+    ((1, 1, 1), 100, [1.0, 1.0, 1.0, 1.0, 1.0], {"do_mom_diff": 1, "gravity": -0.5}),
+])
+def test_step_host_roundtrip(backend, nb, probtype, pp, kw):
+    """The host-buffer entry (e2e path) gives the same state as the device-resident step, over two chained calls."""
     lib, dev = backend
     n = (16, 16, 16)
-    g = ix.Geom.make(n)
-    boxes = split_boxes(n, (2, 1, 1))
+    lo, hi = ((-1.0, -1.0, -1.0), (1.0, 1.0, 1.0)) if probtype == 5 else ((0, 0, 0), (1, 1, 1))
+    g = ix.Geom.make(n, lo, hi)
+    boxes = split_boxes(n, nb)
     lev = ix.Level(lib, g, boxes)
-    a = ix.NavierStokes(lib, lev, dev, visc_coef=1e-3)
-    b = ix.NavierStokes(lib, lev, dev, visc_coef=1e-3)
+    a = ix.NavierStokes(lib, lev, dev, visc_coef=1e-3, **kw)
+    b = ix.NavierStokes(lib, lev, dev, visc_coef=1e-3, **kw)
     for ns in (a, b):
-        ns.init_prob(11, [1.0, 1.0, 1.0, 1.0, 1.0])
+        ns.init_prob(probtype, pp)
         ns.post_init()
     hin = [a.field(0, il).cpu().contiguous() for il in range(len(boxes))]
+    if dev != "cpu":
+        hin = [t.pin_memory() for t in hin]
     hout = [torch.empty_like(t) for t in hin]
-    dt = a.step()
-    dtb = b.step_host(hin, hout)
-    assert dt == dtb
-    for il in range(len(boxes)):
-        assert np.array_equal(hout[il].numpy(), a.field(0, il).cpu().numpy())
+    for _ in range(2):
+        dt = a.step()
+        dtb = b.step_host(hin, hout)
+        assert dt == dtb
+        for il in range(len(boxes)):
+            assert np.array_equal(hout[il].numpy(), a.field(0, il).cpu().numpy())
+        hin, hout = hout, hin
     a.close(); b.close(); lev.close()
 
 
