@@ -63,6 +63,9 @@ int iamrx_set_option(int option, double value) {
 }
 double iamrx_get_option(int option) { return k::godunov_get_option(option); }
 int iamrx_version(void) { return 100; }
+void iamrx_debug_fb_stats(int64_t out[4], int reset) {
+  for (int q = 0; q < 4; ++q) { if (out) out[q] = ix::g_fb_stats[q].load(); if (reset) ix::g_fb_stats[q].store(0); }
+}
 int64_t iamrx_launch_count(void) { return g_launches.load(); }
 void iamrx_launch_count_reset(void) { g_launches.store(0); }
 int iamrx_device_ok(void) { return device_ok() ? 1 : 0; }

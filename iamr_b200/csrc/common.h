@@ -105,6 +105,7 @@ inline Bx shift(Bx b, int d, int n) { b.lo[d] += n; b.hi[d] += n; return b; }
 // ---- errors / accounting -------------------------------------------------
 void set_error(const std::string& s);
 extern std::atomic<int64_t> g_launches;
+extern std::atomic<int64_t> g_fb_stats[4];   // ghost-fill counters (iamrx_debug_fb_stats)
 inline void count_launch(int n = 1) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 bool device_ok();
 

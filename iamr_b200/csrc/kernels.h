@@ -139,7 +139,8 @@ int nodal_gs_sweep(const Bx& nbx, V4 phi_out, C4 phi_in, C4 rhs, C4 sig, const d
                    int wrapmask = 7, int phase = -1);
 int nodal_jacobi(const Bx& nbx, V4 out, C4 phi, C4 rhs, C4 sig, const double dxinv[3], double omega,
                  cudaStream_t s);
-int nodal_restrict(const Bx& cnbx, V4 crse, C4 fine, cudaStream_t s, int thin = 0);
+// wm + fnb: wrap the stencil in the directions (bits) in which the fine node box fnb spans the periodic domain
+int nodal_restrict(const Bx& cnbx, V4 crse, C4 fine, cudaStream_t s, int thin = 0, int wm = 0, const Bx* fnb = nullptr);
 int nodal_interp_add(const Bx& fnbx, V4 fine, C4 crse, cudaStream_t s, int thin = 0);
 int nodal_mknewu(const Bx& bx, V4 vel, V4 gp, int increment_gp, C4 phi, C4 sig,
                  const double dxinv[3], cudaStream_t s);

@@ -419,7 +419,7 @@ static void box_diff(const Bx& a, const Bx& b, std::vector<Bx>& out) {
 }
 
 void build_fb_regions(const Level& L, int ixtype, int ng, std::vector<int>& dst_box,
-                      std::vector<int>& src_box, std::vector<Bx>& region, std::vector<int>& shift3) {
+                      std::vector<int>& src_box, std::vector<Bx>& region, std::vector<int>& shift3, int skip) {
   const int nb = (int)L.boxes.size();
   int plen[3];
   for (int d = 0; d < 3; ++d) plen[d] = L.geom.domain.hi[d] - L.geom.domain.lo[d] + 1;
@@ -442,6 +442,9 @@ void build_fb_regions(const Level& L, int ixtype, int ng, std::vector<int>& dst_
         const int sh[3] = {sx, sy, sz};
         bool okp = true;
         for (int d = 0; d < 3; ++d) if (sh[d] != 0 && !L.geom.periodic[d]) okp = false;
+        // a skipped direction needs no ghost points, and its valid range is covered by the unshifted sources: without this a
+        // periodic image would claim the shared node / face column of nodal and face data first and break up the plane
+        for (int d = 0; d < 3; ++d) if (sh[d] != 0 && (skip & (1 << d))) okp = false;
         if (!okp) continue;
         if (bj == bi && sx == 0 && sy == 0 && sz == 0) continue;
         Bx s = vsrc;  // source valid box shifted INTO dst index space
@@ -476,7 +479,7 @@ FBPlan& Level::plan(int ixtype, int ng, int skip) {
   auto P = std::make_unique<FBPlan>();
   P->ixtype = ixtype; P->ng = ng;
   std::vector<int> db, sb, sh; std::vector<Bx> rg;
-  build_fb_regions(*this, ixtype, ng, db, sb, rg, sh);
+  build_fb_regions(*this, ixtype, ng, db, sb, rg, sh, skip);
   if (skip) {  // clip every region to the valid range of the skipped directions; drop what is left empty
     std::vector<int> db2, sb2, sh2; std::vector<Bx> rg2;
     for (size_t r = 0; r < rg.size(); ++r) {
@@ -646,6 +649,8 @@ int mf_scale(MF& m, double c, int comp, int ncomp, int ng, cudaStream_t s) {
   return IAMRX_OK;
 }
 
+std::atomic<int64_t> g_fb_stats[4];   // fills: in-place exchanges, packed exchanges, local-copy launches, local-only fills
+
 int mf_fill_boundary(MF& m, int comp, int ncomp, int ng, cudaStream_t s, int skip) {
   if (ng <= 0 || m.n() == 0 || skip == 7) return IAMRX_OK;
   if (m.n() > FabTable::MAXF) { set_error("mf_fill_boundary: too many local boxes"); return IAMRX_ERR_ARG; }
@@ -654,6 +659,7 @@ int mf_fill_boundary(MF& m, int comp, int ncomp, int ng, cudaStream_t s, int ski
   FabTable t; fill_table(t, m, comp);
   if (P.peers.empty()) {
     if (P.local.empty()) return IAMRX_OK;
+    g_fb_stats[3]++;
     return k::copy_batch(P.d_local, (int)P.local.size(), P.max_local, t, t, nullptr, ncomp, 0, s);
   }
   bool owned = true;
@@ -678,9 +684,12 @@ int mf_fill_boundary(MF& m, int comp, int ncomp, int ng, cudaStream_t s, int ski
       }
     }
     IX_TRY(comm_exchange(pl, sb, sc, rb, rc, s));
-    if (!P.local.empty()) IX_TRY(k::copy_batch(P.d_local, (int)P.local.size(), P.max_local, t, t, nullptr, ncomp, 0, s));
+    g_fb_stats[0]++;
+    if (!P.local.empty()) { g_fb_stats[2]++; IX_TRY(k::copy_batch(P.d_local, (int)P.local.size(), P.max_local, t, t, nullptr, ncomp, 0, s)); }
     return IAMRX_OK;
   }
+  g_fb_stats[1]++;
+  { static const char* dbg = getenv("IAMRX_DEBUG_FB"); if (dbg) fprintf(stderr, "[iamrx] packed fill: ixtype %d ng %d skip %d ncomp %d owned %d direct %d\n", m.ixtype, ng, skip, ncomp, (int)owned, (int)P.direct); }
   DevBuf sb_((size_t)(P.send_total * ncomp + 1)), rb_((size_t)(P.recv_total * ncomp + 1));
   double* sbuf = sb_.p; double* rbuf = rb_.p;
   if (!sbuf || !rbuf) return IAMRX_ERR_CUDA;

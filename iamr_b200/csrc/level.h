@@ -146,7 +146,7 @@ struct Level {
 // iamrx_debug_fb_plan.
 void build_fb_regions(const Level& L, int ixtype, int ng,
                       std::vector<int>& dst_box, std::vector<int>& src_box,
-                      std::vector<Bx>& region, std::vector<int>& shift3);
+                      std::vector<Bx>& region, std::vector<int>& shift3, int skip = 0);
 
 // ---- local multifab ---------------------------------------------------------
 struct MF {

@@ -824,7 +824,10 @@ int NodeMG::vcycle(cudaStream_t s) {
     IX_TRY(mf_setval(L.cor, 0.0, 0, 1, 1, s));
     IX_TRY(smooth(l, L.cor, L.res, info_.nu1, s));
     IX_TRY(residual(l, L.rescor, L.cor, L.res, s));
-    IX_TRY(fill_ghosts(l, L.rescor, 0, s, true));   // MLNodeLaplacian::restriction: applyBC on the fine residual (Neumann sides mirrored)
+    // MLNodeLaplacian::restriction: applyBC on the fine residual (Neumann sides mirrored); directions every box spans are wrapped
+    // inside the restriction kernel, so a slab exchanges whole planes in place here too
+    const int rwm = L.lev->level_wrapmask();
+    IX_TRY(fill_ghosts(l, L.rescor, rwm, s, true));
     MGLevelNode& C = lv_[l + 1];
     if (C.xfer_lev) {
       // (the transfer level shares the boundary flags of the coarse level: same domain, boxes tile it)
@@ -837,12 +840,15 @@ int NodeMG::vcycle(cudaStream_t s) {
             if (bc_.lo[d] == IAMRX_LINOP_DIRICHLET && XL.lbox(il).lo[d] == XL.domain.lo[d]) cb.lo[d] += 1;
             if (bc_.hi[d] == IAMRX_LINOP_DIRICHLET && XL.lbox(il).hi[d] == XL.domain.hi[d]) cb.hi[d] -= 1;
           }
-        IX_TRY(k::nodal_restrict(cb, C.xfer.v(il), L.rescor.c(il), s, thin_));
+        const Bx fnb = L.rescor.vbox(il);
+        IX_TRY(k::nodal_restrict(cb, C.xfer.v(il), L.rescor.c(il), s, thin_, rwm, &fnb));
       }
       IX_TRY(mf_gather_replicate(C.res, C.xfer, 1, s));
     } else {
-      for (int il = 0; il < C.res.n(); ++il)
-        IX_TRY(k::nodal_restrict(active_nbox(l + 1, il), C.res.v(il), L.rescor.c(il), s, thin_));
+      for (int il = 0; il < C.res.n(); ++il) {
+        const Bx fnb = L.rescor.vbox(il);
+        IX_TRY(k::nodal_restrict(active_nbox(l + 1, il), C.res.v(il), L.rescor.c(il), s, thin_, rwm, &fnb));
+      }
     }
   }
   IX_TRY(bottom_solve(s));

@@ -121,7 +121,8 @@ gs_color_kernel(Bx bx, V4 phi, C4 rhs, C4 sig, double facx, double facy, double 
   phi(i, j, k) += (rhs(i, j, k) - y) / s0;
 }
 
-__global__ void __launch_bounds__(TX* TY) nd_restrict_kernel(Bx cbx, V4 crse, C4 fine, int thin) {
+// wm / fnb: directions in which the FINE node box fnb spans the periodic domain; the stencil wraps there instead of reading ghosts
+__global__ void __launch_bounds__(TX* TY) nd_restrict_kernel(Bx cbx, V4 crse, C4 fine, int thin, int wm, Bx fnb) {
   NIDX(cbx)
   // full weighting (1, 2, 1) / 4 in every coarsened direction, injection in a direction with ratio 1 (thin bit set)
   const int r0 = (thin & 1) ? 1 : 2, r1 = (thin & 2) ? 1 : 2, r2 = (thin & 4) ? 1 : 2;
@@ -132,7 +133,11 @@ __global__ void __launch_bounds__(TX* TY) nd_restrict_kernel(Bx cbx, V4 crse, C4
     for (int dj = -e1; dj <= e1; ++dj)
       for (int di = -e0; di <= e0; ++di) {
         const double w = (double)(((di == 0 && e0) ? 2 : 1) * ((dj == 0 && e1) ? 2 : 1) * ((dk == 0 && e2) ? 2 : 1));
-        acc += w * fine(ii + di, jj + dj, kk + dk);
+        int fi = ii + di, fj = jj + dj, fk = kk + dk;
+        if (wm & 1) fi = fi < fnb.lo[0] ? fi + (fnb.hi[0] - fnb.lo[0]) : (fi > fnb.hi[0] ? fi - (fnb.hi[0] - fnb.lo[0]) : fi);
+        if (wm & 2) fj = fj < fnb.lo[1] ? fj + (fnb.hi[1] - fnb.lo[1]) : (fj > fnb.hi[1] ? fj - (fnb.hi[1] - fnb.lo[1]) : fj);
+        if (wm & 4) fk = fk < fnb.lo[2] ? fk + (fnb.hi[2] - fnb.lo[2]) : (fk > fnb.hi[2] ? fk - (fnb.hi[2] - fnb.lo[2]) : fk);
+        acc += w * fine(fi, fj, fk);
       }
   crse(i, j, k) = acc / (double)((e0 ? 4 : 1) * (e1 ? 4 : 1) * (e2 ? 4 : 1));
 }
@@ -804,9 +809,9 @@ int nodal_gs_sweep(const Bx& nbx, V4 phi_out, C4 phi_in, C4 rhs, C4 sig, const d
 #endif
 }
 
-int nodal_restrict(const Bx& cnbx, V4 crse, C4 fine, cudaStream_t s, int thin) {
+int nodal_restrict(const Bx& cnbx, V4 crse, C4 fine, cudaStream_t s, int thin, int wm, const Bx* fnb) {
   if (!cnbx.ok()) return IAMRX_OK;
-  IX_LAUNCH(nd_restrict_kernel, grid_for(cnbx), dim3(TX, TY, 1), 0, s, cnbx, crse, fine, thin);
+  IX_LAUNCH(nd_restrict_kernel, grid_for(cnbx), dim3(TX, TY, 1), 0, s, cnbx, crse, fine, thin, fnb ? (wm & 7) : 0, fnb ? *fnb : Bx{});
   return check_launch("nodal_restrict");
 }
 

@@ -303,6 +303,9 @@ int iamrx_level_local_box(iamrx_level_t lev, int ilocal, iamrx_box* out, int* gl
 /* Test hook (pure host logic, no device needed): the FillBoundary copy plan of a
  * level.  Returns the number of regions; fills up to `cap` entries (6 ints per
  * region lo/hi in destination index space, 3 ints per shift: src = dst + shift). */
+/* counters of iamrx_fill_boundary-type ghost fills since the last reset: [0] in-place plane exchanges, [1] packed exchanges
+ * (pack + send/recv + unpack), [2] local-copy launches next to an in-place exchange, [3] fills with no remote part */
+void iamrx_debug_fb_stats(int64_t out[4], int reset);
 int iamrx_debug_fb_plan(iamrx_level_t lev, int ixtype, int ng, int cap, int* dst_box, int* src_box,
                         int* region6, int* shift3);
 
