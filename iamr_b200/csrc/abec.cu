@@ -25,6 +25,7 @@ struct AbecDev {
   C4 acoef, bx, by, bz;
   int bncomp;
   double dhx, dhy, dhz;  // b * dxinv^2
+  double cb[3][3], ca;   // constant-coefficient path (Abec::cc): values per component / direction
 };
 
 inline AbecDev to_dev(const Abec& op) {
@@ -34,6 +35,8 @@ inline AbecDev to_dev(const Abec& op) {
   d.dhx = op.b * op.dxinv[0] * op.dxinv[0];
   d.dhy = op.b * op.dxinv[1] * op.dxinv[1];
   d.dhz = op.b * op.dxinv[2] * op.dxinv[2];
+  for (int n = 0; n < 3; ++n) for (int e = 0; e < 3; ++e) d.cb[n][e] = op.cb[n][e];
+  d.ca = op.ca;
   return d;
 }
 
@@ -46,7 +49,9 @@ constexpr int GS_TY = 4;
 // HASBC: the box touches a non-periodic domain face.  The ghost cell behind such a face is a linear function of the interior
 // cells (MLCellLinOp::applyBC); f0 is the coefficient of the adjacent cell, and the smoother removes that self-dependence
 // from the diagonal (the delta of AMReX's abec_gsrb: phi += omega/(gamma - delta) * res).
-template <int MINB, bool HASBC>
+// CONSTB: constant coefficients (Abec::cc) -- the same expression on values taken from the kernel arguments: 24 B/cell per
+// colour pass (phi read + write, rhs) instead of 48 / 56.
+template <int MINB, bool HASBC, bool CONSTB>
 __global__ void __launch_bounds__(GS_TX* GS_TY, MINB)
 gsrb_kernel(Bx bx, V4 phi, C4 rhs, IX_KARG(AbecDev) op, double omega, int redblack, int nz, int wm, IX_KARG(GsBC) gb) {
   const int kz = blockIdx.z % nz;
@@ -61,17 +66,24 @@ gsrb_kernel(Bx bx, V4 phi, C4 rhs, IX_KARG(AbecDev) op, double omega, int redbla
   const int nb = (op.bncomp > 1) ? n : 0;
 
   // 32-bit element offsets from the cell's own address (one address computation per array)
-  const double* bxc = op.bx.p + nb * op.bx.ns + ((i - op.bx.l0) + (j - op.bx.l1) * op.bx.js + (k - op.bx.l2) * op.bx.ks);
-  const double* byc = op.by.p + nb * op.by.ns + ((i - op.by.l0) + (j - op.by.l1) * op.by.js + (k - op.by.l2) * op.by.ks);
-  const double* bzc = op.bz.p + nb * op.bz.ns + ((i - op.bz.l0) + (j - op.bz.l1) * op.bz.js + (k - op.bz.l2) * op.bz.ks);
-  const double bxm = bxc[0], bxp = bxc[1];
-  const double bym = byc[0], byp = byc[(int)op.by.js];
-  const double bzm = bzc[0], bzp = bzc[(int)op.bz.ks];
+  double bxm, bxp, bym, byp, bzm, bzp;
+  if (CONSTB) {
+    bxm = bxp = (nb == 0) ? op.cb[0][0] : (nb == 1 ? op.cb[1][0] : op.cb[2][0]);
+    bym = byp = (nb == 0) ? op.cb[0][1] : (nb == 1 ? op.cb[1][1] : op.cb[2][1]);
+    bzm = bzp = (nb == 0) ? op.cb[0][2] : (nb == 1 ? op.cb[1][2] : op.cb[2][2]);
+  } else {
+    const double* bxc = op.bx.p + nb * op.bx.ns + ((i - op.bx.l0) + (j - op.bx.l1) * op.bx.js + (k - op.bx.l2) * op.bx.ks);
+    const double* byc = op.by.p + nb * op.by.ns + ((i - op.by.l0) + (j - op.by.l1) * op.by.js + (k - op.by.l2) * op.by.ks);
+    const double* bzc = op.bz.p + nb * op.bz.ns + ((i - op.bz.l0) + (j - op.bz.l1) * op.bz.js + (k - op.bz.l2) * op.bz.ks);
+    bxm = bxc[0]; bxp = bxc[1];
+    bym = byc[0]; byp = byc[(int)op.by.js];
+    bzm = bzc[0]; bzp = bzc[(int)op.bz.ks];
+  }
   double* pc = phi.p + n * phi.ns + ((i - phi.l0) + (j - phi.l1) * phi.js + (k - phi.l2) * phi.ks);
   const int pjs = (int)phi.js, pks = (int)phi.ks;
   const double p0 = pc[0];
   double gamma = op.dhx * (bxm + bxp) + op.dhy * (bym + byp) + op.dhz * (bzm + bzp);
-  if (op.a != 0.0) gamma += op.a * op.acoef(i, j, k);
+  if (op.a != 0.0) gamma += op.a * (CONSTB ? op.ca : op.acoef(i, j, k));
   // periodic wrap inside the kernel when the box spans the domain (no ghost fill needed)
   int oxm = ((wm & 1) && i == bx.lo[0]) ? bx.hi[0] - i : -1, oxp = ((wm & 1) && i == bx.hi[0]) ? bx.lo[0] - i : 1;
   int oym = (((wm & 2) && j == bx.lo[1]) ? bx.hi[1] - j : -1) * pjs, oyp = (((wm & 2) && j == bx.hi[1]) ? bx.lo[1] - j : 1) * pjs;
@@ -119,6 +131,7 @@ constexpr int AP_TY = 2;
 // mir: per component, bit s (xlo, xhi, ylo, yhi, zlo, zhi) of even / odd = the ghost cell beyond that side of the box is
 // + / - the adjacent cell (homogeneous Neumann / reflect_odd / order-2 Dirichlet): evaluated in place, no ghost fill
 struct MirBC { int even[3], odd[3]; };
+template <bool CONSTB>
 __global__ void __launch_bounds__(AP_TX* AP_TY)
 apply_kernel(Bx bx, V4 out, C4 phi, C4 rhs, IX_KARG(AbecDev) op, int nz, int wm, IX_KARG(MirBC) mb) {
   const int kz = blockIdx.z % nz;
@@ -128,9 +141,19 @@ apply_kernel(Bx bx, V4 out, C4 phi, C4 rhs, IX_KARG(AbecDev) op, int nz, int wm,
   const int i = bx.lo[0] + blockIdx.x * AP_TX + threadIdx.x;
   if (j > bx.hi[1] || i > bx.hi[0]) return;
   const int nb = (op.bncomp > 1) ? n : 0;
-  const double* bxc = op.bx.p + nb * op.bx.ns + ((i - op.bx.l0) + (j - op.bx.l1) * op.bx.js + (k - op.bx.l2) * op.bx.ks);
-  const double* byc = op.by.p + nb * op.by.ns + ((i - op.by.l0) + (j - op.by.l1) * op.by.js + (k - op.by.l2) * op.by.ks);
-  const double* bzc = op.bz.p + nb * op.bz.ns + ((i - op.bz.l0) + (j - op.bz.l1) * op.bz.js + (k - op.bz.l2) * op.bz.ks);
+  double bxm, bxp, bym, byp, bzm, bzp;
+  if (CONSTB) {
+    bxm = bxp = (nb == 0) ? op.cb[0][0] : (nb == 1 ? op.cb[1][0] : op.cb[2][0]);
+    bym = byp = (nb == 0) ? op.cb[0][1] : (nb == 1 ? op.cb[1][1] : op.cb[2][1]);
+    bzm = bzp = (nb == 0) ? op.cb[0][2] : (nb == 1 ? op.cb[1][2] : op.cb[2][2]);
+  } else {
+    const double* bxc = op.bx.p + nb * op.bx.ns + ((i - op.bx.l0) + (j - op.bx.l1) * op.bx.js + (k - op.bx.l2) * op.bx.ks);
+    const double* byc = op.by.p + nb * op.by.ns + ((i - op.by.l0) + (j - op.by.l1) * op.by.js + (k - op.by.l2) * op.by.ks);
+    const double* bzc = op.bz.p + nb * op.bz.ns + ((i - op.bz.l0) + (j - op.bz.l1) * op.bz.js + (k - op.bz.l2) * op.bz.ks);
+    bxm = bxc[0]; bxp = bxc[1];
+    bym = byc[0]; byp = byc[(int)op.by.js];
+    bzm = bzc[0]; bzp = bzc[(int)op.bz.ks];
+  }
   const double* pc = phi.p + n * phi.ns + ((i - phi.l0) + (j - phi.l1) * phi.js + (k - phi.l2) * phi.ks);
   const int pjs = (int)phi.js, pks = (int)phi.ks;
   const double p0 = pc[0];
@@ -150,10 +173,10 @@ apply_kernel(Bx bx, V4 out, C4 phi, C4 rhs, IX_KARG(AbecDev) op, int nz, int wm,
       if ((mir & 32) && k == bx.hi[2]) { ozp = 0; if (od & 32) szp = -1.0; }
     }
   }
-  double y = -op.dhx * (bxc[1] * (sxp * pc[oxp] - p0) - bxc[0] * (p0 - sxm * pc[oxm])) -
-             op.dhy * (byc[(int)op.by.js] * (syp * pc[oyp] - p0) - byc[0] * (p0 - sym * pc[oym])) -
-             op.dhz * (bzc[(int)op.bz.ks] * (szp * pc[ozp] - p0) - bzc[0] * (p0 - szm * pc[ozm]));
-  if (op.a != 0.0) y += op.a * op.acoef(i, j, k) * p0;
+  double y = -op.dhx * (bxp * (sxp * pc[oxp] - p0) - bxm * (p0 - sxm * pc[oxm])) -
+             op.dhy * (byp * (syp * pc[oyp] - p0) - bym * (p0 - sym * pc[oym])) -
+             op.dhz * (bzp * (szp * pc[ozp] - p0) - bzm * (p0 - szm * pc[ozm]));
+  if (op.a != 0.0) y += op.a * (CONSTB ? op.ca : op.acoef(i, j, k)) * p0;
   out(i, j, k, n) = rhs.ok() ? (rhs(i, j, k, n) - y) : y;
 }
 
@@ -161,7 +184,7 @@ apply_kernel(Bx bx, V4 out, C4 phi, C4 rhs, IX_KARG(AbecDev) op, int nz, int wm,
 // apply / residual, two cells per thread with 128-bit loads and stores (same expression per cell as apply_kernel:
 // bit-identical).  Needs an even x extent and 16-byte aligned cell pairs in every array (checked by the launcher).
 IX_D double2 ld2(const double* p) { return *reinterpret_cast<const double2*>(p); }
-template <bool HASA>
+template <bool HASA, bool CONSTB>
 __global__ void __launch_bounds__(AP_TX* AP_TY)
 apply2_kernel(Bx bx, V4 out, C4 phi, C4 rhs, IX_KARG(AbecDev) op, int nz, int wm) {
   const int kz = blockIdx.z % nz;
@@ -171,9 +194,6 @@ apply2_kernel(Bx bx, V4 out, C4 phi, C4 rhs, IX_KARG(AbecDev) op, int nz, int wm
   const int i = bx.lo[0] + 2 * (blockIdx.x * AP_TX + threadIdx.x);
   if (j > bx.hi[1] || i > bx.hi[0]) return;
   const int nb = (op.bncomp > 1) ? n : 0;
-  const double* bxc = op.bx.p + nb * op.bx.ns + ((i - op.bx.l0) + (j - op.bx.l1) * op.bx.js + (k - op.bx.l2) * op.bx.ks);
-  const double* byc = op.by.p + nb * op.by.ns + ((i - op.by.l0) + (j - op.by.l1) * op.by.js + (k - op.by.l2) * op.by.ks);
-  const double* bzc = op.bz.p + nb * op.bz.ns + ((i - op.bz.l0) + (j - op.bz.l1) * op.bz.js + (k - op.bz.l2) * op.bz.ks);
   const double* pc = phi.p + n * phi.ns + ((i - phi.l0) + (j - phi.l1) * phi.js + (k - phi.l2) * phi.ks);
   const int pjs = (int)phi.js, pks = (int)phi.ks;
   const int oxm = ((wm & 1) && i == bx.lo[0]) ? bx.hi[0] - i : -1, oxp = ((wm & 1) && i + 1 == bx.hi[0]) ? bx.lo[0] - i : 2;
@@ -181,14 +201,29 @@ apply2_kernel(Bx bx, V4 out, C4 phi, C4 rhs, IX_KARG(AbecDev) op, int nz, int wm
   const int ozm = (((wm & 4) && k == bx.lo[2]) ? bx.hi[2] - k : -1) * pks, ozp = (((wm & 4) && k == bx.hi[2]) ? bx.lo[2] - k : 1) * pks;
   const double2 p0 = ld2(pc), pym = ld2(pc + oym), pyp = ld2(pc + oyp), pzm = ld2(pc + ozm), pzp = ld2(pc + ozp);
   const double pxm = pc[oxm], pxp = pc[oxp];
-  const double2 b01 = ld2(bxc); const double b2 = bxc[2];
-  const double2 bym = ld2(byc), byp = ld2(byc + (int)op.by.js), bzm = ld2(bzc), bzp = ld2(bzc + (int)op.bz.ks);
+  double2 b01, bym, byp, bzm, bzp;
+  double b2;
+  if (CONSTB) {
+    const double cx = (nb == 0) ? op.cb[0][0] : (nb == 1 ? op.cb[1][0] : op.cb[2][0]);
+    const double cy = (nb == 0) ? op.cb[0][1] : (nb == 1 ? op.cb[1][1] : op.cb[2][1]);
+    const double cz = (nb == 0) ? op.cb[0][2] : (nb == 1 ? op.cb[1][2] : op.cb[2][2]);
+    b01 = make_double2(cx, cx); b2 = cx;
+    bym = byp = make_double2(cy, cy);
+    bzm = bzp = make_double2(cz, cz);
+  } else {
+    const double* bxc = op.bx.p + nb * op.bx.ns + ((i - op.bx.l0) + (j - op.bx.l1) * op.bx.js + (k - op.bx.l2) * op.bx.ks);
+    const double* byc = op.by.p + nb * op.by.ns + ((i - op.by.l0) + (j - op.by.l1) * op.by.js + (k - op.by.l2) * op.by.ks);
+    const double* bzc = op.bz.p + nb * op.bz.ns + ((i - op.bz.l0) + (j - op.bz.l1) * op.bz.js + (k - op.bz.l2) * op.bz.ks);
+    b01 = ld2(bxc); b2 = bxc[2];
+    bym = ld2(byc); byp = ld2(byc + (int)op.by.js); bzm = ld2(bzc); bzp = ld2(bzc + (int)op.bz.ks);
+  }
   double y0 = -op.dhx * (b01.y * (p0.y - p0.x) - b01.x * (p0.x - pxm)) - op.dhy * (byp.x * (pyp.x - p0.x) - bym.x * (p0.x - pym.x)) -
               op.dhz * (bzp.x * (pzp.x - p0.x) - bzm.x * (p0.x - pzm.x));
   double y1 = -op.dhx * (b2 * (pxp - p0.y) - b01.y * (p0.y - p0.x)) - op.dhy * (byp.y * (pyp.y - p0.y) - bym.y * (p0.y - pym.y)) -
               op.dhz * (bzp.y * (pzp.y - p0.y) - bzm.y * (p0.y - pzm.y));
   if (HASA) {
-    const double2 ac = ld2(op.acoef.p + ((i - op.acoef.l0) + (j - op.acoef.l1) * op.acoef.js + (k - op.acoef.l2) * op.acoef.ks));
+    const double2 ac = CONSTB ? make_double2(op.ca, op.ca)
+                              : ld2(op.acoef.p + ((i - op.acoef.l0) + (j - op.acoef.l1) * op.acoef.js + (k - op.acoef.l2) * op.acoef.ks));
     y0 += op.a * ac.x * p0.x; y1 += op.a * ac.y * p0.y;
   }
   double2 r;
@@ -721,15 +756,19 @@ inline dim3 grid_for(const Bx& bx, int tx, int ty, int nz_total) {
 int abec_gsrb(const Bx& bx, V4 phi, C4 rhs, const Abec& op, double omega, int redblack, int ncomp,
               cudaStream_t s, int wrapmask, const GsBC* gb) {
   if (!bx.ok()) return IAMRX_OK;
-  ProfScope prof_(IAMRX_PROF_ABEC_GSRB, bx.npts(), (double)bx.npts() * ncomp * (op.a != 0.0 ? 56.0 : 48.0), s);
+  ProfScope prof_(IAMRX_PROF_ABEC_GSRB, bx.npts(),
+                  (double)bx.npts() * ncomp * (op.cc ? 24.0 : (op.a != 0.0 ? 56.0 : 48.0)), s);
   dim3 blk(GS_TX, GS_TY, 1);
   dim3 grd(cdiv(bx.nx() + 1, 2 * GS_TX), cdiv(bx.ny(), GS_TY), bx.nz() * ncomp);
   static int minb = -1;
   if (minb < 0) { const char* e = getenv("IAMRX_GSRB_MINB"); minb = e ? atoi(e) : 6; }
   const GsBC none{};
-  if (gb) IX_LAUNCH((gsrb_kernel<6, true>), grd, blk, 0, s, bx, phi, rhs, to_dev(op), omega, redblack, bx.nz(), wrapmask, *gb);
-  else if (minb >= 8) IX_LAUNCH((gsrb_kernel<8, false>), grd, blk, 0, s, bx, phi, rhs, to_dev(op), omega, redblack, bx.nz(), wrapmask, none);
-  else IX_LAUNCH((gsrb_kernel<6, false>), grd, blk, 0, s, bx, phi, rhs, to_dev(op), omega, redblack, bx.nz(), wrapmask, none);
+#define IX_GSRB(M, B, C, G) IX_LAUNCH((gsrb_kernel<M, B, C>), grd, blk, 0, s, bx, phi, rhs, to_dev(op), omega, redblack, bx.nz(), wrapmask, G)
+  if (op.cc) { if (gb) IX_GSRB(6, true, true, *gb); else IX_GSRB(6, false, true, none); }
+  else if (gb) IX_GSRB(6, true, false, *gb);
+  else if (minb >= 8) IX_GSRB(8, false, false, none);
+  else IX_GSRB(6, false, false, none);
+#undef IX_GSRB
   return check_launch("abec_gsrb");
 }
 
@@ -810,17 +849,21 @@ int abec_apply(const Bx& bx, V4 out, C4 phi, C4 rhs, const Abec& op, int ncomp, 
   MirBC mb{};
   bool mirrored = false;
   if (gb) for (int c = 0; c < 3; ++c) { mb.even[c] = gb->even[c]; mb.odd[c] = gb->odd[c]; if (mb.even[c] | mb.odd[c]) mirrored = true; }
-  ProfScope prof_(IAMRX_PROF_ABEC_APPLY, bx.npts(), (double)bx.npts() * ncomp * ((op.a != 0.0 ? 56.0 : 48.0) + (rhs.ok() ? 0.0 : -8.0)), s);
+  ProfScope prof_(IAMRX_PROF_ABEC_APPLY, bx.npts(), (double)bx.npts() * ncomp * ((op.cc ? 24.0 : (op.a != 0.0 ? 56.0 : 48.0)) + (rhs.ok() ? 0.0 : -8.0)), s);
 #if !defined(IX_EMUL)
   if (!mirrored && bx.nx() % 2 == 0 && pairs_aligned(out, bx) && pairs_aligned(phi, bx) && pairs_aligned(rhs, bx) && pairs_aligned(op.acoef, bx) &&
       pairs_aligned(op.bx, bx) && pairs_aligned(op.by, bx) && pairs_aligned(op.bz, bx)) {
     const dim3 grd(cdiv(bx.nx() / 2, AP_TX), cdiv(bx.ny(), AP_TY), bx.nz() * ncomp);
-    if (op.a != 0.0) IX_LAUNCH(apply2_kernel<true>, grd, dim3(AP_TX, AP_TY, 1), 0, s, bx, out, phi, rhs, to_dev(op), bx.nz(), wrapmask);
-    else IX_LAUNCH(apply2_kernel<false>, grd, dim3(AP_TX, AP_TY, 1), 0, s, bx, out, phi, rhs, to_dev(op), bx.nz(), wrapmask);
+#define IX_AP2(A, C) IX_LAUNCH((apply2_kernel<A, C>), grd, dim3(AP_TX, AP_TY, 1), 0, s, bx, out, phi, rhs, to_dev(op), bx.nz(), wrapmask)
+    if (op.cc) { if (op.a != 0.0) IX_AP2(true, true); else IX_AP2(false, true); }
+    else { if (op.a != 0.0) IX_AP2(true, false); else IX_AP2(false, false); }
+#undef IX_AP2
     return check_launch("abec_apply2");
   }
 #endif
-  IX_LAUNCH(apply_kernel, grid_for(bx, AP_TX, AP_TY, bx.nz() * ncomp), dim3(AP_TX, AP_TY, 1), 0, s, 
+  if (op.cc) IX_LAUNCH(apply_kernel<true>, grid_for(bx, AP_TX, AP_TY, bx.nz() * ncomp), dim3(AP_TX, AP_TY, 1), 0, s,
+      bx, out, phi, rhs, to_dev(op), bx.nz(), wrapmask, mb);
+  else IX_LAUNCH(apply_kernel<false>, grid_for(bx, AP_TX, AP_TY, bx.nz() * ncomp), dim3(AP_TX, AP_TY, 1), 0, s,
       bx, out, phi, rhs, to_dev(op), bx.nz(), wrapmask, mb);
   return check_launch("abec_apply");
 }

@@ -15,6 +15,7 @@
 // itself (FillPatchTwoLevels in time, coarse-fine solver boundaries, mac_sync / level_sync) is not driven by this library.
 #include <algorithm>
 #include "level.h"
+#include "mlmg.h"
 
 namespace ix {
 namespace k {
@@ -355,6 +356,75 @@ int iamrx_fluxreg_reflux(iamrx_fluxreg_t r, iamrx_fab* state, int scomp, double 
 int iamrx_fluxreg_field(iamrx_fluxreg_t r, int ilocal, iamrx_fab* out) {
   IX_ARG(r && out && ilocal >= 0 && ilocal < r->F.reg.n(), "fluxreg_field arguments");
   *out = r->F.reg.fabs[ilocal];
+  return IAMRX_OK;
+}
+
+// amrex::FillPatchTwoLevels for cell-centred data (what AmrLevel::FillPatch does on a level that does not cover the domain;
+// NSB.cpp:4399,4435 through FillPatchIterator with the cell_cons_interp interpolater of NS_setup.cpp:211): see iamrx.h.
+// The time-interpolated coarse data is gathered into ONE replicated box covering the coarse domain (ghost cells: periodic images
+// and the physical boundary fill), so every rank interpolates what its fine boxes need without a second parallel copy -- at 180 GB
+// per GPU a replicated coarse level is cheap next to the fine one it serves.
+int iamrx_fillpatch_two_levels(iamrx_level_t fine_lev, iamrx_level_t crse_lev, iamrx_fab* fine, const iamrx_fab* crse_old,
+                               const iamrx_fab* crse_new, double t_old, double t_new, double time, int ncomp, int ngrow,
+                               const iamrx_bcrec* bcrec, const double* bcvals, void* stream) {
+  IX_NEED_DEVICE();
+  IX_ARG(fine_lev && crse_lev && fine && crse_new && ncomp >= 1 && ncomp <= 8 && ngrow >= 1, "fillpatch_two_levels arguments");
+  Level* FL = level_of(fine_lev);
+  Level* CL = level_of(crse_lev);
+  cudaStream_t s = (cudaStream_t)stream;
+  for (int d = 0; d < 3; ++d) {
+    IX_ARG(FL->geom.domain.lo[d] == 2 * CL->geom.domain.lo[d] && FL->geom.domain.hi[d] == 2 * CL->geom.domain.hi[d] + 1,
+           "the fine level's domain must be the coarse one refined by 2");
+    IX_ARG(FL->geom.periodic[d] == CL->geom.periodic[d], "periodicity differs between the levels");
+  }
+  double w_new = 1.0;
+  if (crse_old && t_new != t_old) w_new = (time - t_old) / (t_new - t_old);
+  IX_ARG(w_new >= -1.0e-12 && w_new <= 1.0 + 1.0e-12, "time outside [t_old, t_new]");
+  // 1. coarse data at `time` on the coarse layout, gathered into a replicated box with enough ghost cells for the stencil
+  const int ngc = (ngrow + 1) / 2 + 1;
+  MF cn; cn.alias(CL, IX_CELL, ncomp, 0, const_cast<iamrx_fab*>(crse_new));
+  MF ct(CL, IX_CELL, ncomp, 0);
+  if (crse_old && w_new != 1.0) {
+    MF co; co.alias(CL, IX_CELL, ncomp, 0, const_cast<iamrx_fab*>(crse_old));
+    IX_TRY(mf_lincomb(ct, 0, 1.0 - w_new, co, 0, w_new, cn, 0, ncomp, 0, s));
+  } else {
+    IX_TRY(mf_copy(ct, cn, 0, 0, ncomp, 0, s));
+  }
+  std::vector<Bx> one{mkbx(CL->geom.domain)};
+  std::vector<int> own{comm().rank};
+  std::unique_ptr<Level> RL = make_level(CL->geom, one, own);
+  RL->replicated = true;
+  MF cr(RL.get(), IX_CELL, ncomp, ngc);
+  if (CL->replicated || (CL->boxes.size() == 1 && CL->nlocal() == 1)) IX_TRY(mf_copy(cr, ct, 0, 0, ncomp, 0, s));
+  else IX_TRY(mf_gather_replicate(cr, ct, ncomp, s));
+  IX_TRY(mf_fill_boundary(cr, 0, ncomp, ngc, s));
+  k::PhysBC bc{};
+  bool walls = false;
+  for (int d = 0; d < 3; ++d) if (!CL->geom.periodic[d]) walls = true;
+  if (walls) {
+    IX_ARG(bcrec != nullptr, "a non-periodic domain needs the BCRec of every component");
+    for (int n = 0; n < ncomp; ++n)
+      for (int d = 0; d < 3; ++d) { bc.lo[n][d] = bcrec[n].lo[d]; bc.hi[n][d] = bcrec[n].hi[d]; }
+    if (bcvals) for (int f = 0; f < 6; ++f) for (int n = 0; n < ncomp; ++n) bc.val[f][n] = bcvals[f * ncomp + n];
+    IX_TRY(mf_fill_physbc(cr, 0, ncomp, ngc, bc, s));
+  }
+  // 2. every ghost cell of every local fine box that lies inside the domain (periodic directions: anywhere) <- interpolation
+  MF fm; fm.alias(FL, IX_CELL, ncomp, ngrow, fine);
+  const Bx fdom = mkbx(FL->geom.domain);
+  for (int il = 0; il < fm.n(); ++il) {
+    const Bx vb = fm.vbox(il);
+    std::vector<Bx> shell{fm.gbox(il, ngrow)};
+    subtract_boxes(shell, vb);
+    for (Bx p : shell) {
+      for (int d = 0; d < 3; ++d)
+        if (!FL->geom.periodic[d]) { p.lo[d] = std::max(p.lo[d], fdom.lo[d]); p.hi[d] = std::min(p.hi[d], fdom.hi[d]); }
+      if (!p.ok()) continue;
+      IX_TRY(k::cell_cons_interp(p, fm.v(il), cr.c(0), ncomp, s));
+    }
+  }
+  // 3. fine data where fine neighbours (or their periodic images) exist, 4. the physical boundary of the fine level
+  IX_TRY(mf_fill_boundary(fm, 0, ncomp, ngrow, s));
+  if (walls) IX_TRY(mf_fill_physbc(fm, 0, ncomp, ngrow, bc, s));
   return IAMRX_OK;
 }
 

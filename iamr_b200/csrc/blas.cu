@@ -184,6 +184,26 @@ __global__ void __launch_bounds__(RT) dot_kernel(Bx bx, C4 x, C4 y, C4 mask, dou
   }
 }
 
+// every element of comp 0 equal to the first one?  (constant-coefficient detection of the cell-centred multigrid)
+__global__ void __launch_bounds__(RT) const_check_kernel(Bx bx, C4 src, double* result) {
+  const int nx = bx.nx(), ny = bx.ny(), nz = bx.nz();
+  const int64_t nrows = (int64_t)ny * nz;
+  const double ref = src(bx.lo[0], bx.lo[1], bx.lo[2]);
+  bool diff = false;
+  const int lane_x = threadIdx.x & 63;
+  const int rsub = threadIdx.x >> 6;
+  for (int64_t r = (int64_t)blockIdx.x * 4 + rsub; r < nrows; r += (int64_t)gridDim.x * 4) {
+    const int j = bx.lo[1] + (int)(r % ny);
+    const int k = bx.lo[2] + (int)(r / ny);
+    for (int ii = lane_x; ii < nx; ii += 64) diff |= (src(bx.lo[0] + ii, j, k) != ref);
+  }
+  if (__syncthreads_or(diff ? 1 : 0) && threadIdx.x == 0) result[0] = 1.0;
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    if (!(ref > 0.0)) result[0] = 1.0;
+    else { atomic_fmax_nonneg(result + 1, ref); atomic_fmin(result + 2, ref); }
+  }
+}
+
 #endif  // IX_EMUL
 
 __global__ void reduce_init_kernel(double* r, int n, int op) {
@@ -241,6 +261,28 @@ int reduce(const Bx& bx, C4 src, int ncomp, int op, double* result, cudaStream_t
   }
 #endif
   return check_launch("reduce");
+}
+
+// const_check: result[0] = 1 if some element of comp 0 over bx differs from the first one (or the value is not positive),
+// result[1] = max over the calls of the first element, result[2] = min of it.  The caller initialises result = {0, 0, 1e300};
+// after all boxes (and an allreduce) the data is one constant iff result[0] == 0 and result[1] == result[2].
+int const_check(const Bx& bx, C4 src, double* result, cudaStream_t s) {
+  if (!bx.ok()) return IAMRX_OK;
+#if defined(IX_EMUL)
+  const double ref = src(bx.lo[0], bx.lo[1], bx.lo[2]);
+  bool diff = !(ref > 0.0);
+  for (int k = bx.lo[2]; k <= bx.hi[2]; ++k)
+    for (int j = bx.lo[1]; j <= bx.hi[1]; ++j)
+      for (int i = bx.lo[0]; i <= bx.hi[0]; ++i) if (src(i, j, k) != ref) diff = true;
+  if (diff) result[0] = 1.0;
+  result[1] = fmax(result[1], ref); result[2] = fmin(result[2], ref);
+#else
+  const int64_t nrows = (int64_t)bx.ny() * bx.nz();
+  int nb = (int)((nrows + 3) / 4);
+  if (nb > 148 * 8) nb = 148 * 8;
+  IX_LAUNCH(const_check_kernel, nb, RT, 0, s, bx, src, result);
+#endif
+  return check_launch("const_check");
 }
 
 int reduce_dot(const Bx& bx, C4 x, C4 y, C4 mask, double* result, cudaStream_t s) {

@@ -13,6 +13,11 @@ struct Abec {
   C4 bx, by, bz;    // face coefficients; bncomp comps
   int bncomp;       // 1 or ncomp
   double dxinv[3];
+  // constant-coefficient fast path (CellMG detects it when the coefficients are set): every face coefficient of
+  // component n in direction d equals cb[n][d] and (a != 0) acoef equals ca -- the kernels then read no coefficient array
+  int cc = 0;
+  double cb[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
+  double ca = 0;
 };
 
 // --- cell-centred ABec (abec.cu) -----------------------------------------
@@ -80,6 +85,8 @@ int unpack(const Bx& bx, V4 dst, const double* buf, int ncomp, cudaStream_t s);
 int reduce_init(double* result, int n, int op, cudaStream_t s);
 int reduce(const Bx& bx, C4 src, int ncomp, int op, double* result, cudaStream_t s);
 int reduce_dot(const Bx& bx, C4 x, C4 y, C4 mask, double* result, cudaStream_t s);
+// constant-data detection (comp 0): see blas.cu; result = {differs, max first element, min first element}
+int const_check(const Bx& bx, C4 src, double* result, cudaStream_t s);
 
 // diagnostic: measured DFMA issue rate of the device in 1e9 instructions/s (thread-level; x2 = flop/s)
 int fp64_peak(double* dp_ginstr_per_s, cudaStream_t s);

@@ -197,7 +197,58 @@ k::Abec CellMG::op_at(int l, int il) const {
   op.bx = L.b[0].c(il); op.by = L.b[1].c(il); op.bz = L.b[2].c(il);
   op.bncomp = tensor_ ? ncomp_ : 1;
   for (int d = 0; d < 3; ++d) op.dxinv[d] = L.dxinv[d];
+  op.cc = cc_ ? 1 : 0;
+  for (int c = 0; c < 3; ++c) for (int d = 0; d < 3; ++d) op.cb[c][d] = cbv_[c][d];
+  op.ca = cav_;
   return op;
+}
+
+// Are the coefficients handed to set_coeffs constants (constant density / viscosity: TaylorGreen, HIT, DoubleShearLayer, the
+// viscous solves of every constant-mu run)?  One pass over each input array (compare with its first element) and one host
+// read-back; the ranks agree through max / min reductions.  IAMRX_CONST_COEF=0 switches the detection off.
+int CellMG::detect_constant(const MF* acoef, const MF* const bin[3], cudaStream_t s) {
+  cc_ = false;
+  static int enabled = -1;
+  if (enabled < 0) { const char* e = getenv("IAMRX_CONST_COEF"); enabled = (e && e[0] == '0') ? 0 : 1; }
+  if (!enabled) return IAMRX_OK;
+  const bool ha = a_ != 0.0 && acoef;
+  const int na = ha ? 4 : 3;
+  struct Guard { double* p; ~Guard() { dev_free(p); } } buf{dev_alloc(12)}, g{nullptr};
+  if (!buf.p) return IAMRX_ERR_CUDA;
+  const double init[12] = {0, 0, 1e300, 0, 0, 1e300, 0, 0, 1e300, 0, 0, 1e300};
+  IX_CUDA(cudaMemcpyAsync(buf.p, init, sizeof(init), cudaMemcpyHostToDevice, s));
+  for (int q = 0; q < na; ++q) {
+    const MF& m = q < 3 ? *bin[q] : *acoef;
+    for (int il = 0; il < m.n(); ++il) IX_TRY(k::const_check(m.vbox(il), m.c(il), buf.p + 3 * q, s));
+  }
+  double h[12];
+  if (!lv_[0].lev->replicated && comm().nranks > 1) {
+    // {differs, max} under MAX, {min} under MIN: regroup so that each reduction is one contiguous call
+    g.p = dev_alloc(12);
+    if (!g.p) return IAMRX_ERR_CUDA;
+    for (int q = 0; q < 4; ++q) {
+      IX_CUDA(cudaMemcpyAsync(g.p + 2 * q, buf.p + 3 * q, 2 * sizeof(double), cudaMemcpyDeviceToDevice, s));
+      IX_CUDA(cudaMemcpyAsync(g.p + 8 + q, buf.p + 3 * q + 2, sizeof(double), cudaMemcpyDeviceToDevice, s));
+    }
+    IX_TRY(comm_allreduce(g.p, 8, 2, s));
+    IX_TRY(comm_allreduce(g.p + 8, 4, 1, s));
+    double t[12];
+    IX_CUDA(cudaMemcpyAsync(t, g.p, sizeof(t), cudaMemcpyDeviceToHost, s));
+    IX_CUDA(cudaStreamSynchronize(s));
+    for (int q = 0; q < 4; ++q) { h[3 * q] = t[2 * q]; h[3 * q + 1] = t[2 * q + 1]; h[3 * q + 2] = t[8 + q]; }
+  } else {
+    IX_CUDA(cudaMemcpyAsync(h, buf.p, sizeof(h), cudaMemcpyDeviceToHost, s));
+    IX_CUDA(cudaStreamSynchronize(s));
+  }
+  for (int q = 0; q < na; ++q) if (h[3 * q] != 0.0 || h[3 * q + 1] != h[3 * q + 2]) return IAMRX_OK;
+  for (int c = 0; c < 3; ++c)
+    for (int d = 0; d < 3; ++d) {
+      const double fac = (tensor_ && c == d) ? (4.0 / 3.0) : 1.0;
+      cbv_[c][d] = fac * h[3 * d + 1];   // what mf_lincomb(fac, x, 0, x) stores
+    }
+  cav_ = ha ? h[3 * 3 + 1] : 0.0;
+  cc_ = true;
+  return IAMRX_OK;
 }
 
 int CellMG::set_coeffs(const MF* acoef, const MF* bx, const MF* by, const MF* bz, cudaStream_t s,
@@ -205,6 +256,7 @@ int CellMG::set_coeffs(const MF* acoef, const MF* bx, const MF* by, const MF* bz
   const MF* bin[3] = {bx, by, bz};
   for (int d = 0; d < 3; ++d) eta_[d] = bin[d];
   const int bn = tensor_ ? ncomp_ : 1;
+  IX_TRY(detect_constant(acoef, bin, s));
   // level 0
   {
     MGLevelCell& L = lv_[0];
@@ -222,7 +274,8 @@ int CellMG::set_coeffs(const MF* acoef, const MF* bx, const MF* by, const MF* bz
       if (L.deep) IX_TRY(mf_fill_boundary(L.b[d], 0, bn, 1, s));   // deep-ghost sweeps relax the first ghost layer too
     }
   }
-  for (size_t l = 1; l < lv_.size() && !finest_only; ++l) {
+  // constant coefficients: the coarse levels' arrays are never read (averages of a constant are that constant, exactly)
+  for (size_t l = 1; l < lv_.size() && !finest_only && !cc_; ++l) {
     MGLevelCell& C = lv_[l];
     MGLevelCell& F = lv_[l - 1];
     if (a_ != 0.0 && acoef) {

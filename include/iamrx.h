@@ -448,6 +448,17 @@ int iamrx_interp_box(int kind, const iamrx_box* fbx, iamrx_fab* fine, const iamr
  * for AREA-WEIGHTED fluxes and vol = coarse cell volume (the "dx := volume" convention of NSB.cpp:4878-4889).
  * crse_add / fine_add take the face-flux fabs of every local box of the respective level (x, y, z arrays in local-box
  * order); reflux adds scale * register to the coarse state (NS.cpp:1794-1799). */
+/* amrex::FillPatchTwoLevels for cell-centred data with the conservative linear interpolater: the ghost cells of every local fine
+ * box (ngrow layers) that no fine box covers are interpolated from the coarse level's data at `time` -- linear in time between
+ * crse_old (t_old) and crse_new (t_new); crse_old may be NULL -- ghost cells a fine neighbour (or its periodic image) covers get
+ * the fine data, cells outside a non-periodic domain the physical boundary fill (bcrec / bcvals as in iamrx_fill_physbc).  What
+ * AmrLevel::FillPatch does for State_Type on a level that does not cover the domain (NSB.cpp:4399,4435; NS_setup.cpp:211).  The
+ * valid cells of `fine` hold the fine data at `time` and are not touched.  fine: one fab per local fine box; crse_*: one per local
+ * coarse box.  Collective over the ranks of the communicator. */
+int iamrx_fillpatch_two_levels(iamrx_level_t fine_lev, iamrx_level_t crse_lev, iamrx_fab* fine, const iamrx_fab* crse_old,
+                               const iamrx_fab* crse_new, double t_old, double t_new, double time, int ncomp, int ngrow,
+                               const iamrx_bcrec* bcrec, const double* bcvals, void* stream);
+
 typedef struct iamrx_fluxreg_s* iamrx_fluxreg_t;
 int iamrx_fluxreg_create(iamrx_level_t crse, iamrx_level_t fine, int ncomp, iamrx_fluxreg_t* out);
 int iamrx_fluxreg_destroy(iamrx_fluxreg_t reg);

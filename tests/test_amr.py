@@ -169,3 +169,87 @@ def test_flux_register_restores_conservation(backend, oracle):
     assert abs(total_reflux - total0) <= 1e-14 * abs(total0) * 10
     lib.iamrx_fluxreg_destroy(reg)
     clev.close(); flev.close()
+
+
+@pytest.mark.parametrize("layout", FINE_LAYOUTS)
+@pytest.mark.parametrize("ngrow", [1, 3])
+def test_fillpatch_two_levels(backend, oracle, layout, ngrow):
+    """amrex::FillPatchTwoLevels (cell data, conservative linear interpolation, linear in time): ghost cells under a fine
+    neighbour (or its periodic image) take the fine data, the rest the interpolated coarse data at `time`.  Reference =
+    the oracle's whole-domain cell_cons_interp of the time-interpolated coarse field + the fine data where the fine level exists."""
+    lib, dev = backend
+    ncomp = 2
+    clev, flev, cboxes, fboxes = _level_pair(lib, layout)
+    cmask = np.zeros(NC[::-1], dtype=bool)
+    for lo, hi in layout:
+        cmask[lo[2]:hi[2] + 1, lo[1]:hi[1] + 1, lo[0]:hi[0] + 1] = True
+    fmask = np.repeat(np.repeat(np.repeat(cmask, 2, 0), 2, 1), 2, 2)
+    c_old = smooth_field(NC, 91, ncomp)
+    c_new = smooth_field(NC, 92, ncomp)
+    c_new[0] += 0.3 * np.sign(smooth_field(NC, 93, 1)[0])      # steep: limited slopes
+    fdat = hash_uniform(94, (ncomp,) + NF[::-1])
+    t_old, t_new, time = 0.5, 0.9, 0.62
+    w = (time - t_old) / (t_new - t_old)
+    interp = oracle.interp(0, NC, (1.0 - w) * c_old + w * c_new)
+    expect = np.where(fmask[None], fdat, interp)
+    CO = [to_fab(c_old, b, 0, ix.CELL, dev) for b in cboxes]
+    CN = [to_fab(c_new, b, 0, ix.CELL, dev) for b in cboxes]
+    FI = [to_fab(fdat, b, ngrow, ix.CELL, dev, fill_ghost=False) for b in fboxes]
+    fa = lambda L: fab_array([p[1] for p in L])
+    lib.check(lib.iamrx_fillpatch_two_levels(flev.h, clev.h, fa(FI), fa(CO), fa(CN), t_old, t_new, time, ncomp, ngrow,
+                                             None, None, stream_of(dev)))
+    sync(dev)
+    for (t, _), b in zip(FI, fboxes):
+        ref, _ = to_fab(expect, b, ngrow, ix.CELL, "cpu")
+        assert np.abs(t.cpu().numpy() - ref.numpy()).max() <= 1e-14
+    # crse_old = NULL: the new data as they are
+    FI = [to_fab(fdat, b, ngrow, ix.CELL, dev, fill_ghost=False) for b in fboxes]
+    lib.check(lib.iamrx_fillpatch_two_levels(flev.h, clev.h, fa(FI), None, fa(CN), t_old, t_new, t_new, ncomp, ngrow,
+                                             None, None, stream_of(dev)))
+    sync(dev)
+    expect = np.where(fmask[None], fdat, oracle.interp(0, NC, c_new))
+    for (t, _), b in zip(FI, fboxes):
+        ref, _ = to_fab(expect, b, ngrow, ix.CELL, "cpu")
+        assert np.abs(t.cpu().numpy() - ref.numpy()).max() <= 1e-14
+    clev.close(); flev.close()
+
+
+def test_fillpatch_two_levels_walls(backend, oracle):
+    """Non-periodic z (comp 0 reflect_even, comp 1 reflect_odd): a fine box on the low wall.  Cells outside the domain mirror the
+    filled interior (physical boundary fill after the interpolation); interior ghost cells away from the wall and from the
+    fine box's lateral neighbours equal the periodic-case interpolation two coarse cells away from the wall."""
+    lib, dev = backend
+    ncomp, ngrow = 2, 2
+    gc = ix.Geom.make(NC, periodic=(1, 1, 0))
+    gf = ix.Geom.make(NF, periodic=(1, 1, 0))
+    cboxes = split_boxes(NC, (2, 1, 1))
+    layout = [((2, 2, 0), (5, 5, 3))]
+    fboxes = [(tuple(2 * l for l in lo), tuple(2 * h + 1 for h in hi)) for lo, hi in layout]
+    clev, flev = ix.Level(lib, gc, cboxes), ix.Level(lib, gf, fboxes)
+    c_new = smooth_field(NC, 95, ncomp)
+    fdat = hash_uniform(96, (ncomp,) + NF[::-1])
+    CN = [to_fab(c_new, b, 0, ix.CELL, dev) for b in cboxes]
+    FI = [to_fab(fdat, b, ngrow, ix.CELL, dev, fill_ghost=False) for b in fboxes]
+    bcs = (ix.BCRec * ncomp)(ix.BCRec.make((0, 0, ix.BC_REFLECT_EVEN), (0, 0, ix.BC_REFLECT_EVEN)),
+                             ix.BCRec.make((0, 0, ix.BC_REFLECT_ODD), (0, 0, ix.BC_REFLECT_ODD)))
+    fa = lambda L: fab_array([p[1] for p in L])
+    lib.check(lib.iamrx_fillpatch_two_levels(flev.h, clev.h, fa(FI), None, fa(CN), 0.0, 1.0, 1.0, ncomp, ngrow,
+                                             bcs, None, stream_of(dev)))
+    sync(dev)
+    a = FI[0][0].cpu().numpy()                      # (ncomp, 8+4, 8+4, 8+4), origin (4-2, 4-2, 0-2)
+    assert np.abs(a).max() < 1e30                   # every ghost cell was written
+    g = ngrow
+    assert np.array_equal(a[:, g:-g, g:-g, g:-g], fdat[:, 0:8, 4:12, 4:12])
+    for m in range(g):                              # below the wall: mirror images (even / odd)
+        assert np.array_equal(a[0, g - 1 - m], a[0, g + m])
+        assert np.array_equal(a[1, g - 1 - m], -a[1, g + m])
+    # lateral ghost cells at z >= 4 fine cells from the wall: the coarse stencil there does not see the wall -> periodic interpolation
+    per = oracle.interp(0, NC, c_new)
+    ref, _ = to_fab(per, fboxes[0], ngrow, ix.CELL, "cpu")
+    r = ref.numpy()
+    lat = np.ones(a.shape[1:], dtype=bool)
+    lat[:, g:-g, g:-g] = False                      # x / y ghost columns only
+    lat[:g + 4] = False
+    lat[-g:] = False
+    assert lat.any() and np.abs(a[:, lat] - r[:, lat]).max() <= 1e-14
+    clev.close(); flev.close()
