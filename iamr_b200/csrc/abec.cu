@@ -25,7 +25,8 @@ struct AbecDev {
   C4 acoef, bx, by, bz;
   int bncomp;
   double dhx, dhy, dhz;  // b * dxinv^2
-  double cb[3][3], ca;   // constant-coefficient path (Abec::cc): values per component / direction
+  double cb[3][3], ca;   // constant-coefficient path (Abec::cc, cac): values per component / direction
+  int cac;
 };
 
 inline AbecDev to_dev(const Abec& op) {
@@ -36,7 +37,7 @@ inline AbecDev to_dev(const Abec& op) {
   d.dhy = op.b * op.dxinv[1] * op.dxinv[1];
   d.dhz = op.b * op.dxinv[2] * op.dxinv[2];
   for (int n = 0; n < 3; ++n) for (int e = 0; e < 3; ++e) d.cb[n][e] = op.cb[n][e];
-  d.ca = op.ca;
+  d.ca = op.ca; d.cac = op.cac;
   return d;
 }
 
@@ -51,7 +52,10 @@ constexpr int GS_TY = 4;
 // from the diagonal (the delta of AMReX's abec_gsrb: phi += omega/(gamma - delta) * res).
 // CONSTB: constant coefficients (Abec::cc) -- the same expression on values taken from the kernel arguments: 24 B/cell per
 // colour pass (phi read + write, rhs) instead of 48 / 56.
-template <int MINB, bool HASBC, bool CONSTB>
+// ZERO: first colour pass of a sweep on phi == 0 (ghost cells included: the multigrid correction with homogeneous boundary
+// conditions).  No phi is read -- phi = omega / (gamma - delta) * rhs, the value the general expression gives -- and the other
+// cell of the pair is set to zero, so the caller needs no setval before the sweep.
+template <int MINB, bool HASBC, bool CONSTB, bool ZERO>
 __global__ void __launch_bounds__(GS_TX* GS_TY, MINB)
 gsrb_kernel(Bx bx, V4 phi, C4 rhs, IX_KARG(AbecDev) op, double omega, int redblack, int nz, int wm, IX_KARG(GsBC) gb) {
   const int kz = blockIdx.z % nz;
@@ -60,8 +64,13 @@ gsrb_kernel(Bx bx, V4 phi, C4 rhs, IX_KARG(AbecDev) op, double omega, int redbla
   const int j = bx.lo[1] + blockIdx.y * GS_TY + threadIdx.y;
   if (j > bx.hi[1]) return;
   int i = bx.lo[0] + 2 * (blockIdx.x * GS_TX + threadIdx.x);
+  const int ipair = i;
   // make (i + j + k + redblack) even
   i += (i + j + k + redblack) & 1;
+  if (ZERO) {   // the pair's cell of the other colour (or both, if the coloured one lies beyond the box)
+    const int io = ipair + (1 - (i - ipair));
+    if (io <= bx.hi[0]) phi(io, j, k, n) = 0.0;
+  }
   if (i > bx.hi[0]) return;
   const int nb = (op.bncomp > 1) ? n : 0;
 
@@ -81,9 +90,23 @@ gsrb_kernel(Bx bx, V4 phi, C4 rhs, IX_KARG(AbecDev) op, double omega, int redbla
   }
   double* pc = phi.p + n * phi.ns + ((i - phi.l0) + (j - phi.l1) * phi.js + (k - phi.l2) * phi.ks);
   const int pjs = (int)phi.js, pks = (int)phi.ks;
-  const double p0 = pc[0];
   double gamma = op.dhx * (bxm + bxp) + op.dhy * (bym + byp) + op.dhz * (bzm + bzp);
-  if (op.a != 0.0) gamma += op.a * (CONSTB ? op.ca : op.acoef(i, j, k));
+  if (op.a != 0.0) gamma += op.a * ((CONSTB && op.cac) ? op.ca : op.acoef(i, j, k));
+  if (ZERO) {
+    double delta = 0.0;
+    if (HASBC) {
+      const int nc = n < 3 ? n : 0;
+      if (i == bx.lo[0]) delta += op.dhx * bxm * gb.f0[nc][0];
+      if (i == bx.hi[0]) delta += op.dhx * bxp * gb.f0[nc][1];
+      if (j == bx.lo[1]) delta += op.dhy * bym * gb.f0[nc][2];
+      if (j == bx.hi[1]) delta += op.dhy * byp * gb.f0[nc][3];
+      if (k == bx.lo[2]) delta += op.dhz * bzm * gb.f0[nc][4];
+      if (k == bx.hi[2]) delta += op.dhz * bzp * gb.f0[nc][5];
+    }
+    pc[0] = omega / (HASBC ? (gamma - delta) : gamma) * rhs(i, j, k, n);
+    return;
+  }
+  const double p0 = pc[0];
   // periodic wrap inside the kernel when the box spans the domain (no ghost fill needed)
   int oxm = ((wm & 1) && i == bx.lo[0]) ? bx.hi[0] - i : -1, oxp = ((wm & 1) && i == bx.hi[0]) ? bx.lo[0] - i : 1;
   int oym = (((wm & 2) && j == bx.lo[1]) ? bx.hi[1] - j : -1) * pjs, oyp = (((wm & 2) && j == bx.hi[1]) ? bx.lo[1] - j : 1) * pjs;
@@ -176,7 +199,7 @@ apply_kernel(Bx bx, V4 out, C4 phi, C4 rhs, IX_KARG(AbecDev) op, int nz, int wm,
   double y = -op.dhx * (bxp * (sxp * pc[oxp] - p0) - bxm * (p0 - sxm * pc[oxm])) -
              op.dhy * (byp * (syp * pc[oyp] - p0) - bym * (p0 - sym * pc[oym])) -
              op.dhz * (bzp * (szp * pc[ozp] - p0) - bzm * (p0 - szm * pc[ozm]));
-  if (op.a != 0.0) y += op.a * (CONSTB ? op.ca : op.acoef(i, j, k)) * p0;
+  if (op.a != 0.0) y += op.a * ((CONSTB && op.cac) ? op.ca : op.acoef(i, j, k)) * p0;
   out(i, j, k, n) = rhs.ok() ? (rhs(i, j, k, n) - y) : y;
 }
 
@@ -222,7 +245,7 @@ apply2_kernel(Bx bx, V4 out, C4 phi, C4 rhs, IX_KARG(AbecDev) op, int nz, int wm
   double y1 = -op.dhx * (b2 * (pxp - p0.y) - b01.y * (p0.y - p0.x)) - op.dhy * (byp.y * (pyp.y - p0.y) - bym.y * (p0.y - pym.y)) -
               op.dhz * (bzp.y * (pzp.y - p0.y) - bzm.y * (p0.y - pzm.y));
   if (HASA) {
-    const double2 ac = CONSTB ? make_double2(op.ca, op.ca)
+    const double2 ac = (CONSTB && op.cac) ? make_double2(op.ca, op.ca)
                               : ld2(op.acoef.p + ((i - op.acoef.l0) + (j - op.acoef.l1) * op.acoef.js + (k - op.acoef.l2) * op.acoef.ks));
     y0 += op.a * ac.x * p0.x; y1 += op.a * ac.y * p0.y;
   }
@@ -280,14 +303,22 @@ __global__ void restrict_kernel(Bx cbx, V4 crse, C4 fine, int nz, int thin) {
 
 IX_D int cdiv2(int a) { return (a >= 0) ? a / 2 : -((-a + 1) / 2); }  // floor(a/2)
 
-__global__ void prolong_kernel(Bx fbx, V4 fine, C4 crse, int nz, int thin) {
-  const int kz = blockIdx.z % nz;
-  const int n = blockIdx.z / nz;
-  const int k = fbx.lo[2] + kz;
+// two fine planes per thread (2 m, 2 m + 1 relative to the box: the same coarse plane unless z is not coarsened)
+__global__ void prolong_kernel(Bx fbx, V4 fine, C4 crse, int nzh, int thin) {
+  const int kz = blockIdx.z % nzh;
+  const int n = blockIdx.z / nzh;
   const int j = fbx.lo[1] + blockIdx.y * AP_TY + threadIdx.y;
   const int i = fbx.lo[0] + blockIdx.x * AP_TX + threadIdx.x;
   if (j > fbx.hi[1] || i > fbx.hi[0]) return;
-  fine(i, j, k, n) += crse((thin & 1) ? i : cdiv2(i), (thin & 2) ? j : cdiv2(j), (thin & 4) ? k : cdiv2(k), n);
+  const int ic = (thin & 1) ? i : cdiv2(i), jc = (thin & 2) ? j : cdiv2(j);
+  const int k0 = fbx.lo[2] + 2 * kz, k1 = k0 + 1;
+  const bool two = k1 <= fbx.hi[2];
+  const double c0 = crse(ic, jc, (thin & 4) ? k0 : cdiv2(k0), n);
+  const double c1 = two ? crse(ic, jc, (thin & 4) ? k1 : cdiv2(k1), n) : 0.0;
+  const double f0 = fine(i, j, k0, n);
+  const double f1 = two ? fine(i, j, k1, n) : 0.0;
+  fine(i, j, k0, n) = f0 + c0;
+  if (two) fine(i, j, k1, n) = f1 + c1;
 }
 
 __global__ void face_restrict_kernel(Bx cfbx, int dir, V4 crse, C4 fine, int nz, int thin) {
@@ -754,20 +785,24 @@ inline dim3 grid_for(const Bx& bx, int tx, int ty, int nz_total) {
 }  // namespace
 
 int abec_gsrb(const Bx& bx, V4 phi, C4 rhs, const Abec& op, double omega, int redblack, int ncomp,
-              cudaStream_t s, int wrapmask, const GsBC* gb) {
+              cudaStream_t s, int wrapmask, const GsBC* gb, bool zero_phi) {
   if (!bx.ok()) return IAMRX_OK;
   ProfScope prof_(IAMRX_PROF_ABEC_GSRB, bx.npts(),
-                  (double)bx.npts() * ncomp * (op.cc ? 24.0 : (op.a != 0.0 ? 56.0 : 48.0)), s);
+                  (double)bx.npts() * ncomp * ((op.cc ? 24.0 : 48.0) + ((op.a != 0.0 && !(op.cc && op.cac)) ? 8.0 : 0.0) - (zero_phi ? 8.0 : 0.0)), s);
   dim3 blk(GS_TX, GS_TY, 1);
   dim3 grd(cdiv(bx.nx() + 1, 2 * GS_TX), cdiv(bx.ny(), GS_TY), bx.nz() * ncomp);
   static int minb = -1;
   if (minb < 0) { const char* e = getenv("IAMRX_GSRB_MINB"); minb = e ? atoi(e) : 6; }
   const GsBC none{};
-#define IX_GSRB(M, B, C, G) IX_LAUNCH((gsrb_kernel<M, B, C>), grd, blk, 0, s, bx, phi, rhs, to_dev(op), omega, redblack, bx.nz(), wrapmask, G)
-  if (op.cc) { if (gb) IX_GSRB(6, true, true, *gb); else IX_GSRB(6, false, true, none); }
-  else if (gb) IX_GSRB(6, true, false, *gb);
-  else if (minb >= 8) IX_GSRB(8, false, false, none);
-  else IX_GSRB(6, false, false, none);
+#define IX_GSRB(M, B, C, Z, G) IX_LAUNCH((gsrb_kernel<M, B, C, Z>), grd, blk, 0, s, bx, phi, rhs, to_dev(op), omega, redblack, bx.nz(), wrapmask, G)
+  if (zero_phi) {
+    if (op.cc) { if (gb) IX_GSRB(6, true, true, true, *gb); else IX_GSRB(6, false, true, true, none); }
+    else { if (gb) IX_GSRB(6, true, false, true, *gb); else IX_GSRB(6, false, false, true, none); }
+  }
+  else if (op.cc) { if (gb) IX_GSRB(6, true, true, false, *gb); else IX_GSRB(6, false, true, false, none); }
+  else if (gb) IX_GSRB(6, true, false, false, *gb);
+  else if (minb >= 8) IX_GSRB(8, false, false, false, none);
+  else IX_GSRB(6, false, false, false, none);
 #undef IX_GSRB
   return check_launch("abec_gsrb");
 }
@@ -849,7 +884,7 @@ int abec_apply(const Bx& bx, V4 out, C4 phi, C4 rhs, const Abec& op, int ncomp, 
   MirBC mb{};
   bool mirrored = false;
   if (gb) for (int c = 0; c < 3; ++c) { mb.even[c] = gb->even[c]; mb.odd[c] = gb->odd[c]; if (mb.even[c] | mb.odd[c]) mirrored = true; }
-  ProfScope prof_(IAMRX_PROF_ABEC_APPLY, bx.npts(), (double)bx.npts() * ncomp * ((op.cc ? 24.0 : (op.a != 0.0 ? 56.0 : 48.0)) + (rhs.ok() ? 0.0 : -8.0)), s);
+  ProfScope prof_(IAMRX_PROF_ABEC_APPLY, bx.npts(), (double)bx.npts() * ncomp * ((op.cc ? 24.0 : 48.0) + ((op.a != 0.0 && !(op.cc && op.cac)) ? 8.0 : 0.0) + (rhs.ok() ? 0.0 : -8.0)), s);
 #if !defined(IX_EMUL)
   if (!mirrored && bx.nx() % 2 == 0 && pairs_aligned(out, bx) && pairs_aligned(phi, bx) && pairs_aligned(rhs, bx) && pairs_aligned(op.acoef, bx) &&
       pairs_aligned(op.bx, bx) && pairs_aligned(op.by, bx) && pairs_aligned(op.bz, bx)) {
@@ -885,8 +920,9 @@ int cc_restrict(const Bx& cbx, V4 crse, C4 fine, int ncomp, cudaStream_t s, int 
 
 int cc_prolong_add(const Bx& fbx, V4 fine, C4 crse, int ncomp, cudaStream_t s, int thin) {
   if (!fbx.ok()) return IAMRX_OK;
-  IX_LAUNCH(prolong_kernel, grid_for(fbx, AP_TX, AP_TY, fbx.nz() * ncomp), dim3(AP_TX, AP_TY, 1), 0, s, 
-      fbx, fine, crse, fbx.nz(), thin);
+  const int nzh = cdiv(fbx.nz(), 2);
+  IX_LAUNCH(prolong_kernel, grid_for(fbx, AP_TX, AP_TY, nzh * ncomp), dim3(AP_TX, AP_TY, 1), 0, s,
+      fbx, fine, crse, nzh, thin);
   return check_launch("cc_prolong_add");
 }
 

@@ -14,8 +14,10 @@ struct Abec {
   int bncomp;       // 1 or ncomp
   double dxinv[3];
   // constant-coefficient fast path (CellMG detects it when the coefficients are set): every face coefficient of
-  // component n in direction d equals cb[n][d] and (a != 0) acoef equals ca -- the kernels then read no coefficient array
-  int cc = 0;
+  // component n in direction d equals cb[n][d] (cc) -- the kernels then read no face-coefficient array; cac: acoef is the
+  // constant ca as well (constant viscosity is the rule in IAMR runs; a constant density stops being bitwise constant after
+  // the first conservative update)
+  int cc = 0, cac = 0;
   double cb[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
   double ca = 0;
 };
@@ -29,7 +31,9 @@ struct Abec {
 // Dirichlet): the kernels evaluate it in place and no ghost fill is needed for that side
 struct GsBC { double f0[3][6]; int even[3]; int odd[3]; };
 int abec_gsrb(const Bx& bx, V4 phi, C4 rhs, const Abec& op, double omega, int redblack,
-              int ncomp, cudaStream_t s, int wrapmask = 0, const GsBC* gb = nullptr);
+              int ncomp, cudaStream_t s, int wrapmask = 0, const GsBC* gb = nullptr, bool zero_phi = false);
+// zero_phi: phi (ghost cells included) is identically zero before this pass: phi is not read, the cells of the other colour are
+// set to zero (no setval needed before the first sweep of a multigrid correction)
 // one full red-black sweep (colour rb0, then the other) phi_in -> phi_out (different arrays) on a box that spans
 // the periodic domain in all directions with even extents; abec_gsrb_sweep_ok tells whether the box qualifies
 bool abec_gsrb_sweep_ok(const Bx& bx, int wrapmask);

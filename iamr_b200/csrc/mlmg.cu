@@ -197,7 +197,7 @@ k::Abec CellMG::op_at(int l, int il) const {
   op.bx = L.b[0].c(il); op.by = L.b[1].c(il); op.bz = L.b[2].c(il);
   op.bncomp = tensor_ ? ncomp_ : 1;
   for (int d = 0; d < 3; ++d) op.dxinv[d] = L.dxinv[d];
-  op.cc = cc_ ? 1 : 0;
+  op.cc = cc_ ? 1 : 0; op.cac = cac_ ? 1 : 0;
   for (int c = 0; c < 3; ++c) for (int d = 0; d < 3; ++d) op.cb[c][d] = cbv_[c][d];
   op.ca = cav_;
   return op;
@@ -207,7 +207,7 @@ k::Abec CellMG::op_at(int l, int il) const {
 // viscous solves of every constant-mu run)?  One pass over each input array (compare with its first element) and one host
 // read-back; the ranks agree through max / min reductions.  IAMRX_CONST_COEF=0 switches the detection off.
 int CellMG::detect_constant(const MF* acoef, const MF* const bin[3], cudaStream_t s) {
-  cc_ = false;
+  cc_ = false; cac_ = false;
   static int enabled = -1;
   if (enabled < 0) { const char* e = getenv("IAMRX_CONST_COEF"); enabled = (e && e[0] == '0') ? 0 : 1; }
   if (!enabled) return IAMRX_OK;
@@ -240,13 +240,15 @@ int CellMG::detect_constant(const MF* acoef, const MF* const bin[3], cudaStream_
     IX_CUDA(cudaMemcpyAsync(h, buf.p, sizeof(h), cudaMemcpyDeviceToHost, s));
     IX_CUDA(cudaStreamSynchronize(s));
   }
-  for (int q = 0; q < na; ++q) if (h[3 * q] != 0.0 || h[3 * q + 1] != h[3 * q + 2]) return IAMRX_OK;
+  cac_ = false;
+  for (int q = 0; q < 3; ++q) if (h[3 * q] != 0.0 || h[3 * q + 1] != h[3 * q + 2]) return IAMRX_OK;
+  cac_ = ha && h[9] == 0.0 && h[10] == h[11];
   for (int c = 0; c < 3; ++c)
     for (int d = 0; d < 3; ++d) {
       const double fac = (tensor_ && c == d) ? (4.0 / 3.0) : 1.0;
       cbv_[c][d] = fac * h[3 * d + 1];   // what mf_lincomb(fac, x, 0, x) stores
     }
-  cav_ = ha ? h[3 * 3 + 1] : 0.0;
+  cav_ = cac_ ? h[3 * 3 + 1] : 0.0;
   cc_ = true;
   return IAMRX_OK;
 }
@@ -267,7 +269,9 @@ int CellMG::set_coeffs(const MF* acoef, const MF* bx, const MF* by, const MF* bz
     }
     for (int d = 0; d < 3; ++d) {
       if (!L.b[d].ok()) L.b[d].define(L.lev, IX_XFACE + d, bn, L.deep ? 1 : 0);
-      for (int c = 0; c < bn; ++c) {
+      // the tensor operator's nine constant face arrays are never read on the constant-coefficient path (the MAC operator's
+      // are: mac_update / getFluxes take beta from them)
+      for (int c = 0; c < bn && !(tensor_ && cc_); ++c) {
         const double fac = (tensor_ && c == d) ? (4.0 / 3.0) : 1.0;
         IX_TRY(mf_lincomb(L.b[d], c, fac, *bin[d], 0, 0.0, *bin[d], 0, 1, 0, s));
       }
@@ -275,10 +279,10 @@ int CellMG::set_coeffs(const MF* acoef, const MF* bx, const MF* by, const MF* bz
     }
   }
   // constant coefficients: the coarse levels' arrays are never read (averages of a constant are that constant, exactly)
-  for (size_t l = 1; l < lv_.size() && !finest_only && !cc_; ++l) {
+  for (size_t l = 1; l < lv_.size() && !finest_only && !(cc_ && (cac_ || !(a_ != 0.0 && acoef))); ++l) {
     MGLevelCell& C = lv_[l];
     MGLevelCell& F = lv_[l - 1];
-    if (a_ != 0.0 && acoef) {
+    if (a_ != 0.0 && acoef && !cac_) {
       if (!C.acoef.ok()) C.acoef.define(C.lev, IX_CELL, 1, C.deep ? 1 : 0);
       if (C.xfer_lev) {   // restrict on the distributed layout, then gather into the replicated box
         MF tmp(C.xfer_lev.get(), IX_CELL, 1, 0);
@@ -292,6 +296,7 @@ int CellMG::set_coeffs(const MF* acoef, const MF* bx, const MF* by, const MF* bz
     }
     for (int d = 0; d < 3; ++d) {
       if (!C.b[d].ok()) C.b[d].define(C.lev, IX_XFACE + d, bn, C.deep ? 1 : 0);
+      if (cc_) continue;
       if (C.xfer_lev) {
         MF tmp(C.xfer_lev.get(), IX_XFACE + d, bn, 0);
         for (int il = 0; il < tmp.n(); ++il) IX_TRY(k::face_restrict(tmp.vbox(il), d, tmp.v(il), F.b[d].c(il), bn, s, thin_));
@@ -321,10 +326,12 @@ int CellMG::smooth(int l, MF& phi, const MF& rhs, int nsweeps, bool zero_init, c
   // no ghost fill (and no extra launch) per colour
   const int wm = L.lev->level_wrapmask();   // directions wrapped inside the kernels: no ghost traffic there
   const bool wrap = wm == 7;
+  if (zero_init && nsweeps <= 0) return mf_setval(phi, 0.0, 0, ncomp_, phi.ng, s);
   bool fused = wrap && k::abec_gsrb_sweep_enabled();
   for (size_t b = 0; b < L.lev->boxes.size() && fused; ++b) fused = k::abec_gsrb_sweep_ok(L.lev->boxes[b], 7);
   if (fused) {
     // one fused launch per sweep, out of place: ping-pong between phi and a second buffer
+    if (zero_init) IX_TRY(mf_setval(phi, 0.0, 0, ncomp_, phi.ng, s));
     if (!L.gs_tmp.ok()) L.gs_tmp.define(L.lev, IX_CELL, ncomp_, 1);
     MF* src = &phi; MF* dst = &L.gs_tmp;
     for (int sw = 0; sw < nsweeps; ++sw) {
@@ -339,6 +346,7 @@ int CellMG::smooth(int l, MF& phi, const MF& rhs, int nsweeps, bool zero_init, c
     // deep-ghost sweep: one exchange of two ghost layers, the red pass on the box grown by one cell towards its neighbours (the
     // same arithmetic on the same values as the neighbour's own red pass), the black pass on the box.  A zero initial guess
     // (ghost layers included) needs no exchange before the first sweep.
+    if (zero_init) IX_TRY(mf_setval(phi, 0.0, 0, ncomp_, phi.ng, s));
     if (!L.rhs_ghost_ok) { IX_TRY(mf_fill_boundary(const_cast<MF&>(rhs), 0, ncomp_, 1, s, wm)); L.rhs_ghost_ok = true; }
     for (int sw = 0; sw < nsweeps; ++sw) {
       if (!(zero_init && sw == 0)) IX_TRY(mf_fill_boundary(phi, 0, ncomp_, 2, s, wm));
@@ -353,11 +361,14 @@ int CellMG::smooth(int l, MF& phi, const MF& rhs, int nsweeps, bool zero_init, c
   }
   for (int sw = 0; sw < nsweeps; ++sw) {
     for (int rb = 0; rb < 2; ++rb) {
-      IX_TRY(fill_ghosts(l, phi, false, wm, 0, s));   // corrections: homogeneous boundary conditions
+      // zero_init: the caller did NOT clear phi -- the first colour pass writes every cell (the homogeneous ghost cells of a zero
+      // field are zero and are not read); the fill before the second colour refreshes all of them
+      const bool zero = zero_init && sw == 0 && rb == 0;
+      if (!zero) IX_TRY(fill_ghosts(l, phi, false, wm, 0, s));   // corrections: homogeneous boundary conditions
       for (int il = 0; il < phi.n(); ++il) {
         const bool onb = has_bc_ && box_on_boundary(l, il);
         const k::GsBC gb = onb ? gsbc_of(l, il) : k::GsBC{};
-        IX_TRY(k::abec_gsrb(phi.vbox(il), phi.v(il), rhs.c(il), op_at(l, il), info_.omega, rb, ncomp_, s, wm, onb ? &gb : nullptr));
+        IX_TRY(k::abec_gsrb(phi.vbox(il), phi.v(il), rhs.c(il), op_at(l, il), info_.omega, rb, ncomp_, s, wm, onb ? &gb : nullptr, zero));
       }
     }
   }
@@ -546,9 +557,8 @@ int CellMG::vcycle(cudaStream_t s) {
   const int nl = (int)lv_.size();
   for (int l = 0; l < nl - 1; ++l) {
     MGLevelCell& L = lv_[l];
-    IX_TRY(mf_setval(L.cor, 0.0, 0, ncomp_, L.cor.ng, s));
     L.rhs_ghost_ok = false;   // L.res was just rewritten (top-level residual or restriction)
-    IX_TRY(smooth(l, L.cor, L.res, info_.nu1, true, s));
+    IX_TRY(smooth(l, L.cor, L.res, info_.nu1, true, s));   // zero initial guess: smooth() clears or overwrites L.cor
     IX_TRY(residual(l, L.rescor, L.cor, L.res, false, s));
     MGLevelCell& C = lv_[l + 1];
     if (C.xfer_lev) {

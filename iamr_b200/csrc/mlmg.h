@@ -61,7 +61,7 @@ class CellMG {
   bool bc_in_kernel(int l) const;   // every non-periodic side of every box of level l can be mirrored inside the kernels
   bool box_on_boundary(int l, int il) const;
   int detect_constant(const MF* acoef, const MF* const bin[3], cudaStream_t s);
-  bool cc_ = false;               // constant-coefficient fast path (k::Abec::cc)
+  bool cc_ = false, cac_ = false;   // constant-coefficient fast path (k::Abec::cc, cac)
   double cbv_[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}}, cav_ = 0;
   k::LinBC bc_{};
   bool has_bc_ = false;

@@ -144,16 +144,33 @@ __global__ void __launch_bounds__(TX* TY) nd_restrict_kernel(Bx cbx, V4 crse, C4
 
 IX_D int fl2(int a) { return (a >= 0) ? a / 2 : -((-a + 1) / 2); }
 
-__global__ void __launch_bounds__(TX* TY) nd_interp_kernel(Bx fbx, V4 fine, C4 crse, int thin) {
-  NIDX(fbx)
-  const int ic = (thin & 1) ? i : fl2(i), jc = (thin & 2) ? j : fl2(j), kc = (thin & 4) ? k : fl2(k);
-  const int ox = (thin & 1) ? 0 : i - 2 * ic, oy = (thin & 2) ? 0 : j - 2 * jc, oz = (thin & 4) ? 0 : k - 2 * kc;  // 0 or 1
-  double acc = 0.0;
-  for (int dk = 0; dk <= oz; ++dk)
-    for (int dj = 0; dj <= oy; ++dj)
-      for (int di = 0; di <= ox; ++di) acc += crse(ic + di, jc + dj, kc + dk);
-  const double w = 1.0 / (double)((1 + ox) * (1 + oy) * (1 + oz));
-  fine(i, j, k) += w * acc;
+// two fine planes (k, k + nzh) per thread: all coarse and fine loads are issued before the stores; the weights are powers of two
+// (what 1 / ((1 + ox)(1 + oy)(1 + oz)) evaluates to, exactly)
+__global__ void __launch_bounds__(TX* TY) nd_interp_kernel(Bx fbx, V4 fine, C4 crse, int thin, int nzh) {
+  const int j = fbx.lo[1] + blockIdx.y * TY + threadIdx.y;
+  const int i = fbx.lo[0] + blockIdx.x * TX + threadIdx.x;
+  if (j > fbx.hi[1] || i > fbx.hi[0]) return;
+  const int ic = (thin & 1) ? i : fl2(i), jc = (thin & 2) ? j : fl2(j);
+  const int ox = (thin & 1) ? 0 : i - 2 * ic, oy = (thin & 2) ? 0 : j - 2 * jc;  // 0 or 1
+  double acc[2], old[2], w[2];
+  int kk[2];
+#pragma unroll
+  for (int q = 0; q < 2; ++q) {
+    const int k = fbx.lo[2] + (int)blockIdx.z + q * nzh;
+    kk[q] = k;
+    acc[q] = 0.0; old[q] = 0.0; w[q] = 0.0;
+    if (k > fbx.hi[2]) continue;
+    const int kc = (thin & 4) ? k : fl2(k);
+    const int oz = (thin & 4) ? 0 : k - 2 * kc;
+    for (int dk = 0; dk <= oz; ++dk)
+      for (int dj = 0; dj <= oy; ++dj)
+        for (int di = 0; di <= ox; ++di) acc[q] += crse(ic + di, jc + dj, kc + dk);
+    const int sh = ox + oy + oz;
+    w[q] = sh == 0 ? 1.0 : (sh == 1 ? 0.5 : (sh == 2 ? 0.25 : 0.125));
+    old[q] = fine(i, j, k);
+  }
+#pragma unroll
+  for (int q = 0; q < 2; ++q) if (kk[q] <= fbx.hi[2]) fine(i, j, kk[q]) = old[q] + w[q] * acc[q];
 }
 
 __global__ void __launch_bounds__(TX* TY)
@@ -423,6 +440,19 @@ IX_D int col(int c) { return (c & 1) * HALF + (c >> 1); }
 constexpr int GD = 4;
 IX_D int halo_node(int g, int lo, int hi, int ghost) { return ghost ? min(max(g, lo - GD), hi + GD) : wrap_node_any(g, lo, hi); }
 IX_D int halo_cell(int c, int lo, int hi, int ghost) { return ghost ? min(max(c, lo - GD), hi - 1 + GD) : wrap_cell_any(c, lo, hi); }
+// the same for boxes at least as wide as a tile (one period at most: no integer division; `big` is uniform per launch)
+IX_D int halo_node_f(int g, int lo, int hi, int ghost, bool big) {
+  if (!big) return halo_node(g, lo, hi, ghost);
+  if (ghost) return min(max(g, lo - GD), hi + GD);
+  const int n = hi - lo;
+  return g < lo ? g + n : (g > hi ? g - n : g);
+}
+IX_D int halo_cell_f(int c, int lo, int hi, int ghost, bool big) {
+  if (!big) return halo_cell(c, lo, hi, ghost);
+  if (ghost) return min(max(c, lo - GD), hi - 1 + GD);
+  const int n = hi - lo;
+  return c < lo ? c + n : (c >= hi ? c - n : c);
+}
 
 struct Q1F { double f0c, f1c, f0j, f1j, f0k, f1k, f0jk, f1jk; };  // q1_factor by row kind
 
@@ -465,11 +495,81 @@ IX_D void pass(double (*sp)[NR][NC], double (*ss)[NR][NC], int warp, int lane, d
   }
 }
 
+// ---- 2 x 2 node blocks (BLK = true) --------------------------------------------------------------------------------
+// The colour passes above read 27 phi + 8 sigma values per node from shared memory and the kernel sits on the shared-memory
+// pipe (ncu: l1tex 85 %).  Here a thread owns the 2 x 2 block of nodes (columns 2l, 2l+1; rows 2+2w, 3+2w) = one node of each
+// in-plane colour.  The two neighbouring planes never change during the four passes, so their part of A phi is computed ONCE
+// for the four nodes from the block's shared 4 x 4 neighbourhood (2 x 16 phi + 2 x 9 sigma loads instead of 4 x (18 + 8)); a
+// pass then reads only the node's 3 x 3 in-plane neighbourhood: 86 instead of 140 shared loads per four nodes.
+struct Blk {
+  double z[3][3];   // sigma summed over the two cell planes: rows b-1 .. b+1, columns a-1 .. a+1 (cells)
+  double r[4];      // rhs - (contribution of planes k-1, k+1) of node (cx, cy) at [cx + 2 cy]
+};
+
+// one neighbouring plane (phi rows b-1 .. b+2 = r[0..3] of sp, cell rows b-1 .. b+1 of ss) -> B.r, B.z
+IX_D void blk_adjacent(const double (*sp)[NC], const double (*ss)[NC], int b, int r3, int sA, int sB, int sC, int sD, const Q1F& q, Blk& B,
+                       bool first) {
+  double S[3][3];
+#pragma unroll
+  for (int j = 0; j < 3; ++j) {
+    S[j][0] = ss[b - 1 + j][sA]; S[j][1] = ss[b - 1 + j][sB]; S[j][2] = ss[b - 1 + j][sC];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) B.z[j][i] = first ? S[j][i] : B.z[j][i] + S[j][i];
+  }
+  // sums shared by the nodes of the block: H[j][cx] = cells (-x, +x) of node column cx in cell row j; V[cy][i] = cells (-y, +y)
+  // of node row cy in cell column i
+  double H[3][2], V[2][3];
+#pragma unroll
+  for (int j = 0; j < 3; ++j) { H[j][0] = S[j][0] + S[j][1]; H[j][1] = S[j][1] + S[j][2]; }
+#pragma unroll
+  for (int i = 0; i < 3; ++i) { V[0][i] = S[0][i] + S[1][i]; V[1][i] = S[1][i] + S[2][i]; }
+  const double n1jk = -q.f1jk, n0jk = -q.f0jk, n1k = -q.f1k, n0k = -q.f0k;
+#pragma unroll
+  for (int rr = 0; rr < 4; ++rr) {
+    const int row = (rr == 3) ? r3 : b - 1 + rr;
+    const double X[4] = {sp[row][sA], sp[row][sB], sp[row][sC], sp[row][sD]};
+#pragma unroll
+    for (int cy = 0; cy < 2; ++cy) {
+      const int dj = rr - cy - 1;   // this row's offset from the node row b + cy
+      if (dj < -1 || dj > 1) continue;
+#pragma unroll
+      for (int cx = 0; cx < 2; ++cx) {
+        const int n = cx + 2 * cy;
+        if (dj == 0) {
+          const double t1 = V[cy][cx] * X[cx] + V[cy][cx + 1] * X[cx + 2], t0 = (V[cy][cx] + V[cy][cx + 1]) * X[cx + 1];
+          B.r[n] = fma(n0k, t0, fma(n1k, t1, B.r[n]));
+        } else {
+          const int j = (dj < 0) ? cy : cy + 1;   // cell row on that side of the node
+          const double t1 = S[j][cx] * X[cx] + S[j][cx + 1] * X[cx + 2], t0 = H[j][cx] * X[cx + 1];
+          B.r[n] = fma(n0jk, t0, fma(n1jk, t1, B.r[n]));
+        }
+      }
+    }
+  }
+}
+
+// colour pass (CX, CY) of the block: node column slot c0 (neighbours cm, cp), row ty.  The update divides by the diagonal
+// through a correctly rounded reciprocal (a fraction of the instructions of an IEEE division; last-bit differences).
+template <int CX, int CY>
+IX_D void blk_pass(double (*sp)[NC], int ty, int cm, int c0, int cp, const Q1F& q, const Blk& B) {
+  const double mj0 = B.z[CY][CX], pj0 = B.z[CY][CX + 1], mj1 = B.z[CY + 1][CX], pj1 = B.z[CY + 1][CX + 1];
+  const double mc = mj0 + mj1, pc = pj0 + pj1;
+  const double s0 = q.f0c * (mc + pc);
+  const double x0 = sp[ty][c0];
+  const double a1c = mc * sp[ty][cm] + pc * sp[ty][cp];
+  const double a1j = mj0 * sp[ty - 1][cm] + pj0 * sp[ty - 1][cp] + mj1 * sp[ty + 1][cm] + pj1 * sp[ty + 1][cp];
+  const double a0j = (mj0 + pj0) * sp[ty - 1][c0] + (mj1 + pj1) * sp[ty + 1][c0];
+  const double y = s0 * x0 + q.f1c * a1c + q.f1j * a1j + q.f0j * a0j;
+  sp[ty][c0] = x0 + (B.r[CX + 2 * CY] - y) * __drcp_rn(s0);
+}
+
+template <bool BLK>
 __global__ void __launch_bounds__(NT, 4)
 gs_sweep_kernel(Bx bx, V4 out, C4 pin, C4 padj, C4 rhs, C4 sig, IX_KARG(Q1F) q, int k0, int zwrap, int zmir, int xyg) {
   __shared__ double sp[3][NR][NC];
   __shared__ double ss[2][NR][NC];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const bool bgx = bx.hi[0] - bx.lo[0] >= NC, bgy = bx.hi[1] - bx.lo[1] >= NC;   // a tile reaches less than one period beyond the box
   const int X0 = (bx.lo[0] - (bx.lo[0] & 1)) + TXI * (int)blockIdx.x - 4;   // global node index of tile column 0
   const int Y0 = (bx.lo[1] - (bx.lo[1] & 1)) + TYI * (int)blockIdx.y - 2;   // ... of tile row 0
   const int k = k0 + 2 * (int)blockIdx.z;
@@ -485,8 +585,8 @@ gs_sweep_kernel(Bx bx, V4 out, C4 pin, C4 padj, C4 rhs, C4 sig, IX_KARG(Q1F) q, 
     // half-warp then writes 128 contiguous bytes of shared memory (no bank conflict in the de-interleaved
     // layout) while the warp still reads one contiguous 256-byte global segment
     const int c = (tid & 32) + 2 * (tid & 15) + ((tid >> 4) & 1), r0 = 1 + (tid >> 6), sc = col(c);
-    const int gi = halo_node(X0 + c, bx.lo[0], bx.hi[0], xyg & 1);
-    const int ci = halo_cell(X0 + c, bx.lo[0], bx.hi[0], xyg & 1);
+    const int gi = halo_node_f(X0 + c, bx.lo[0], bx.hi[0], xyg & 1, bgx);
+    const int ci = halo_cell_f(X0 + c, bx.lo[0], bx.hi[0], xyg & 1, bgx);
     const double* pk = pin.p + (gi - pin.l0) + (int64_t)(k - pin.l2) * pin.ks;
     const double* pm = padj.p + (gi - padj.l0) + (int64_t)(km - padj.l2) * padj.ks;
     const double* pp = padj.p + (gi - padj.l0) + (int64_t)(kp - padj.l2) * padj.ks;
@@ -497,12 +597,12 @@ gs_sweep_kernel(Bx bx, V4 out, C4 pin, C4 padj, C4 rhs, C4 sig, IX_KARG(Q1F) q, 
     for (int m = 0; m < 5; ++m) {
       const int r = r0 + 4 * m;
       if (r <= 17) {
-        const int gj = halo_node(Y0 + r, bx.lo[1], bx.hi[1], xyg & 2);
+        const int gj = halo_node_f(Y0 + r, bx.lo[1], bx.hi[1], xyg & 2, bgy);
         tile::cp_async8(&sp[0][r][sc], pm + (gj - padj.l1) * ajs);
         tile::cp_async8(&sp[1][r][sc], pk + (gj - pin.l1) * pjs);
         tile::cp_async8(&sp[2][r][sc], pp + (gj - padj.l1) * ajs);
         if (r <= 16) {
-          const int cj = halo_cell(Y0 + r, bx.lo[1], bx.hi[1], xyg & 2) - sig.l1;
+          const int cj = halo_cell_f(Y0 + r, bx.lo[1], bx.hi[1], xyg & 2, bgy) - sig.l1;
           tile::cp_async8(&ss[0][r][sc], s0p + cj * sjs);
           tile::cp_async8(&ss[1][r][sc], s1p + cj * sjs);
         }
@@ -510,14 +610,45 @@ gs_sweep_kernel(Bx bx, V4 out, C4 pin, C4 padj, C4 rhs, C4 sig, IX_KARG(Q1F) q, 
     }
   }
   asm volatile("cp.async.commit_group;" ::: "memory");
+  if (BLK) {
+    // block (warp, lane): node columns a = 2 (lane + 1), a + 1; rows b = 2 + 2 warp, b + 1
+    const int lp = lane + 1, a = 2 * lp, b = 2 + 2 * warp;
+    const bool act = lane <= 30;
+    Blk B;
+    {
+      const int gi0 = halo_node_f(X0 + a, bx.lo[0], bx.hi[0], xyg & 1, bgx), gi1 = halo_node_f(X0 + min(a + 1, NC - 1), bx.lo[0], bx.hi[0], xyg & 1, bgx);
+      const int gj0 = halo_node_f(Y0 + b, bx.lo[1], bx.hi[1], xyg & 2, bgy), gj1 = halo_node_f(Y0 + b + 1, bx.lo[1], bx.hi[1], xyg & 2, bgy);
+      const double* rp = rhs.p + (int64_t)(k - rhs.l2) * rhs.ks - rhs.l0;
+      const int o0 = (gj0 - rhs.l1) * (int)rhs.js, o1 = (gj1 - rhs.l1) * (int)rhs.js;
+      B.r[0] = act ? rp[o0 + gi0] : 0.0; B.r[1] = act ? rp[o0 + gi1] : 0.0;
+      B.r[2] = act ? rp[o1 + gi0] : 0.0; B.r[3] = act ? rp[o1 + gi1] : 0.0;
+    }
+    // de-interleaved slots of columns a-1, a, a+1, a+2 (column 64 and row 18 only feed nodes that are never updated: clamped)
+    const int sA = HALF + lp - 1, sB = lp, sC = HALF + lp, sD = min(lp + 1, HALF - 1);
+    const int r3 = min(b + 2, NR - 1);
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncthreads();
+    if (act) {
+      blk_adjacent(sp[0], ss[0], b, r3, sA, sB, sC, sD, q, B, true);
+      blk_adjacent(sp[2], ss[1], b, r3, sA, sB, sC, sD, q, B, false);
+      blk_pass<0, 0>(sp[1], b, sA, sB, sC, q, B);                                  // columns 2 .. 62, rows 2 .. 16
+    }
+    __syncthreads();
+    if (lane <= 29) blk_pass<1, 0>(sp[1], b, sB, sC, sD, q, B);                    // columns 3 .. 61
+    __syncthreads();
+    if (lane >= 1 && lane <= 29 && warp <= 6) blk_pass<0, 1>(sp[1], b + 1, sA, sB, sC, q, B);   // columns 4 .. 60, rows 3 .. 15
+    __syncthreads();
+    if (lane >= 1 && lane <= 28 && warp <= 6) blk_pass<1, 1>(sp[1], b + 1, sB, sC, sD, q, B);   // columns 5 .. 59
+    __syncthreads();
+  } else {
   // right-hand sides of the (up to) four nodes this thread updates, one per colour
   double rv[4];
 #pragma unroll
-  for (int q = 0; q < 4; ++q) {
-    const int cx = q & 1, cy = q >> 1;
+  for (int qq = 0; qq < 4; ++qq) {
+    const int cx = qq & 1, cy = qq >> 1;
     const int h = (cy == 0 ? 1 : 2) + lane, ty = 2 + cy + 2 * warp;
     const int gi = halo_node(X0 + 2 * h + cx, bx.lo[0], bx.hi[0], xyg & 1), gj = halo_node(Y0 + ty, bx.lo[1], bx.hi[1], xyg & 2);
-    rv[q] = (warp < 8 && ty < NR) ? rhs(gi, gj, k) : 0.0;
+    rv[qq] = (warp < 8 && ty < NR) ? rhs(gi, gj, k) : 0.0;
   }
   asm volatile("cp.async.wait_group 0;" ::: "memory");
   __syncthreads();
@@ -529,6 +660,7 @@ gs_sweep_kernel(Bx bx, V4 out, C4 pin, C4 padj, C4 rhs, C4 sig, IX_KARG(Q1F) q, 
   __syncthreads();
   pass<1, 1>(sp, ss, warp, lane, rv[3], q);
   __syncthreads();
+  }
   for (int e = tid; e < TXI * TYI; e += NT) {
     const int tx = 4 + e % TXI, ty = 2 + e / TXI;
     const int gi = X0 + tx, gj = Y0 + ty;
@@ -799,9 +931,13 @@ int nodal_gs_sweep(const Bx& nbx, V4 phi_out, C4 phi_in, C4 rhs, C4 sig, const d
     if (k0 > nbx.hi[2]) continue;
     const int nk = (nbx.hi[2] - k0) / 2 + 1;
     // phase A (even planes): neighbours = old odd planes; phase B (odd planes): neighbours = new even planes
-    IX_LAUNCH(gs_sweep_kernel, dim3(gx, gy, nk), dim3(NT, 1, 1), 0, s, nbx, phi_out, phi_in, cz == 0 ? phi_in : pout, rhs, sig,
-              q, k0, (wrapmask & 4) ? 1 : 0, (wrapmask >> 7) & 3,
-              (wrapmask & NODAL_DEEP_GHOSTS) ? (((wrapmask & 1) ? 0 : 1) | ((wrapmask & 2) ? 0 : 2)) : 0);
+    static int blk = -1;   // IAMRX_NODAL_BLOCK=0: one node per thread and colour (the first fused kernel)
+    if (blk < 0) { const char* e = getenv("IAMRX_NODAL_BLOCK"); blk = (e && e[0] == '0') ? 0 : 1; }
+    const int xyg = (wrapmask & NODAL_DEEP_GHOSTS) ? (((wrapmask & 1) ? 0 : 1) | ((wrapmask & 2) ? 0 : 2)) : 0;
+    if (blk) IX_LAUNCH(gs_sweep_kernel<true>, dim3(gx, gy, nk), dim3(NT, 1, 1), 0, s, nbx, phi_out, phi_in, cz == 0 ? phi_in : pout, rhs, sig,
+                       q, k0, (wrapmask & 4) ? 1 : 0, (wrapmask >> 7) & 3, xyg);
+    else IX_LAUNCH(gs_sweep_kernel<false>, dim3(gx, gy, nk), dim3(NT, 1, 1), 0, s, nbx, phi_out, phi_in, cz == 0 ? phi_in : pout, rhs, sig,
+                   q, k0, (wrapmask & 4) ? 1 : 0, (wrapmask >> 7) & 3, xyg);
     const int rc = check_launch("nodal_gs_sweep");
     if (rc != IAMRX_OK) return rc;
   }
@@ -817,7 +953,8 @@ int nodal_restrict(const Bx& cnbx, V4 crse, C4 fine, cudaStream_t s, int thin, i
 
 int nodal_interp_add(const Bx& fnbx, V4 fine, C4 crse, cudaStream_t s, int thin) {
   if (!fnbx.ok()) return IAMRX_OK;
-  IX_LAUNCH(nd_interp_kernel, grid_for(fnbx), dim3(TX, TY, 1), 0, s, fnbx, fine, crse, thin);
+  const int nzh = cdiv(fnbx.nz(), 2);
+  IX_LAUNCH(nd_interp_kernel, dim3(cdiv(fnbx.nx(), TX), cdiv(fnbx.ny(), TY), nzh), dim3(TX, TY, 1), 0, s, fnbx, fine, crse, thin, nzh);
   return check_launch("nodal_interp_add");
 }
 

@@ -27,6 +27,11 @@ if what == 'adotx':
     tphi, fphi = fab(nodes, 1); tout, fout = fab(nodes, 1); trhs, frhs = fab(nodes, 1); tsig, fsig = fab(cells, 1)
     fn = lambda: lib.check(lib.iamrx_nodal_adotx_box(C.byref(nbx), C.byref(fout), C.byref(fphi), C.byref(frhs), C.byref(fsig), d3(DXINV), s))
     nbytes = 32.0 * (n + 1) ** 3
+elif what == 'gs_sweep':
+    tphi, fphi = fab(nodes, 1); tout, fout = fab(nodes, 1); trhs, frhs = fab(nodes, 1); tsig, fsig = fab(cells, 1)
+    tsig.add_(1.0)
+    fn = lambda: lib.check(lib.iamrx_nodal_gs_sweep_box(C.byref(nbx), C.byref(fout), C.byref(fphi), C.byref(frhs), C.byref(fsig), d3(DXINV), s))
+    nbytes = 32.0 * (n + 1) ** 3
 elif what in ('gsrb', 'gsrb_sweep'):
     tp, fp = fab(cells, 1); tp2, fp2 = fab(cells, 1); tr, fr = fab(cells, 0)
     tb = [fab(tuple(m + (1 if d == q else 0) for q, m in enumerate(cells)), 0) for d in range(3)]
