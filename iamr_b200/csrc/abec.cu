@@ -207,9 +207,11 @@ apply_kernel(Bx bx, V4 out, C4 phi, C4 rhs, IX_KARG(AbecDev) op, int nz, int wm,
 // apply / residual, two cells per thread with 128-bit loads and stores (same expression per cell as apply_kernel:
 // bit-identical).  Needs an even x extent and 16-byte aligned cell pairs in every array (checked by the launcher).
 IX_D double2 ld2(const double* p) { return *reinterpret_cast<const double2*>(p); }
-template <bool HASA, bool CONSTB>
+// NORM: also max |out| -> *norm (the residual norm of the multigrid iteration, fused: saves a pass over `out`).  Needs whole
+// warps (the launcher checks nx / 2 % 32 == 0); a NaN wins the unsigned atomicMax (blas.cu nanmax).
+template <bool HASA, bool CONSTB, bool NORM>
 __global__ void __launch_bounds__(AP_TX* AP_TY)
-apply2_kernel(Bx bx, V4 out, C4 phi, C4 rhs, IX_KARG(AbecDev) op, int nz, int wm) {
+apply2_kernel(Bx bx, V4 out, C4 phi, C4 rhs, IX_KARG(AbecDev) op, int nz, int wm, double* norm) {
   const int kz = blockIdx.z % nz;
   const int n = blockIdx.z / nz;
   const int k = bx.lo[2] + kz;
@@ -255,6 +257,17 @@ apply2_kernel(Bx bx, V4 out, C4 phi, C4 rhs, IX_KARG(AbecDev) op, int nz, int wm
     r.x = rh.x - y0; r.y = rh.y - y1;
   } else { r.x = y0; r.y = y1; }
   *reinterpret_cast<double2*>(out.p + n * out.ns + ((i - out.l0) + (j - out.l1) * out.js + (k - out.l2) * out.ks)) = r;
+  if (NORM) {
+    const double ax = fabs(r.x), ay = fabs(r.y);
+    const unsigned long long qnan = 0x7ff8000000000000ULL;
+    unsigned long long m = (ax != ax || ay != ay) ? qnan : (unsigned long long)__double_as_longlong(ax > ay ? ax : ay);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { const unsigned long long t = __shfl_xor_sync(0xffffffffu, m, o); m = t > m ? t : m; }   // non-negative doubles order like their bits
+    if ((threadIdx.x & 31) == 0) {
+      unsigned long long* a = reinterpret_cast<unsigned long long*>(norm);
+      if (m > *reinterpret_cast<volatile unsigned long long*>(a)) atomicMax(a, m);
+    }
+  }
 }
 
 // every (lo0 + 2m, j, k, n) element of the view is 16-byte aligned
@@ -879,7 +892,9 @@ int abec_gsrb_sweep(const Bx& bx, V4 phi_out, C4 phi_in, C4 rhs, const Abec& op,
 #endif
 }
 
-int abec_apply(const Bx& bx, V4 out, C4 phi, C4 rhs, const Abec& op, int ncomp, cudaStream_t s, int wrapmask, const GsBC* gb) {
+int abec_apply(const Bx& bx, V4 out, C4 phi, C4 rhs, const Abec& op, int ncomp, cudaStream_t s, int wrapmask, const GsBC* gb,
+               double* norm_dev, bool* norm_fused) {
+  if (norm_fused) *norm_fused = false;
   if (!bx.ok()) return IAMRX_OK;
   MirBC mb{};
   bool mirrored = false;
@@ -889,9 +904,16 @@ int abec_apply(const Bx& bx, V4 out, C4 phi, C4 rhs, const Abec& op, int ncomp, 
   if (!mirrored && bx.nx() % 2 == 0 && pairs_aligned(out, bx) && pairs_aligned(phi, bx) && pairs_aligned(rhs, bx) && pairs_aligned(op.acoef, bx) &&
       pairs_aligned(op.bx, bx) && pairs_aligned(op.by, bx) && pairs_aligned(op.bz, bx)) {
     const dim3 grd(cdiv(bx.nx() / 2, AP_TX), cdiv(bx.ny(), AP_TY), bx.nz() * ncomp);
-#define IX_AP2(A, C) IX_LAUNCH((apply2_kernel<A, C>), grd, dim3(AP_TX, AP_TY, 1), 0, s, bx, out, phi, rhs, to_dev(op), bx.nz(), wrapmask)
-    if (op.cc) { if (op.a != 0.0) IX_AP2(true, true); else IX_AP2(false, true); }
-    else { if (op.a != 0.0) IX_AP2(true, false); else IX_AP2(false, false); }
+    const bool nf = norm_dev != nullptr && (bx.nx() / 2) % 32 == 0;
+    if (norm_fused) *norm_fused = nf;
+#define IX_AP2(A, C, N) IX_LAUNCH((apply2_kernel<A, C, N>), grd, dim3(AP_TX, AP_TY, 1), 0, s, bx, out, phi, rhs, to_dev(op), bx.nz(), wrapmask, norm_dev)
+    if (nf) {
+      if (op.cc) { if (op.a != 0.0) IX_AP2(true, true, true); else IX_AP2(false, true, true); }
+      else { if (op.a != 0.0) IX_AP2(true, false, true); else IX_AP2(false, false, true); }
+    } else {
+      if (op.cc) { if (op.a != 0.0) IX_AP2(true, true, false); else IX_AP2(false, true, false); }
+      else { if (op.a != 0.0) IX_AP2(true, false, false); else IX_AP2(false, false, false); }
+    }
 #undef IX_AP2
     return check_launch("abec_apply2");
   }

@@ -42,7 +42,10 @@ int abec_gsrb_sweep(const Bx& bx, V4 phi_out, C4 phi_in, C4 rhs, const Abec& op,
                     cudaStream_t s);
 // out = L phi (rhs null) or rhs - L phi
 int abec_apply(const Bx& bx, V4 out, C4 phi, C4 rhs, const Abec& op, int ncomp, cudaStream_t s,
-               int wrapmask = 0, const GsBC* gb = nullptr);   // gb: in-place mirrored sides (homogeneous residuals)
+               int wrapmask = 0, const GsBC* gb = nullptr,    // gb: in-place mirrored sides (homogeneous residuals)
+               double* norm_dev = nullptr, bool* norm_fused = nullptr);
+// norm_dev (device scalar, initialised by the caller, e.g. reduce_init op 2): *norm_dev = max(*norm_dev, max |out|) in the same
+// launch when the fast kernel applies -- *norm_fused tells whether it did (otherwise reduce `out` afterwards)
 // face flux_d = -b * beta_d * dphi/dx_d on faces of bx (MLABecLaplacian FFlux)
 int abec_flux(const Bx& bx, V4 fx, V4 fy, V4 fz, C4 phi, const Abec& op, int comp, cudaStream_t s);
 // crse = mean of 2x2x2 fine (MLCellLinOp restriction / average_down)
@@ -132,7 +135,7 @@ int compute_aofs(const Bx& bx, const AofsArgs& a, const AdvGeom& g, cudaStream_t
 // hide: bit 2d / 2d+1 = the low / high side of nbx in direction d is a Neumann / inflow domain side (tangential ghost velocities unseen)
 int nodal_divu(const Bx& nbx, V4 rhs, C4 vel, const double dxinv[3], cudaStream_t s, int hide = 0);
 int nodal_adotx(const Bx& nbx, V4 out, C4 phi, C4 rhs, C4 sig, const double dxinv[3], cudaStream_t s,
-                int wrapmask = 0);
+                int wrapmask = 0, double* norm_dev = nullptr, bool* norm_fused = nullptr);   // norm_dev: as in abec_apply
 int nodal_gs_color(const Bx& nbx, V4 phi, C4 rhs, C4 sig, const double dxinv[3], int color,
                    cudaStream_t s, int wrapmask = 0);
 // full 8-colour Gauss-Seidel sweep phi_in -> phi_out on a box that spans the periodic domain

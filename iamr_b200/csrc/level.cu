@@ -830,6 +830,24 @@ static int reduce_common(const MF& m, int comp, int ncomp, int op, double* out, 
   return IAMRX_OK;
 }
 
+// max-norm accumulated by a producer kernel (abec_apply / nodal_adotx with norm_dev): begin hands out a zeroed device scalar,
+// end reduces it over the ranks and brings it to the host
+int norm_acc_begin(double** dev, cudaStream_t s) {
+  RedScratch& R = red();
+  IX_TRY(R.init());
+  IX_TRY(k::reduce_init(R.d + 32, 1, 2, s));
+  *dev = R.d + 32;
+  return IAMRX_OK;
+}
+int norm_acc_end(double* dev, bool replicated, double* out, cudaStream_t s) {
+  RedScratch& R = red();
+  if (!replicated) IX_TRY(comm_allreduce(dev, 1, 2, s));
+  IX_CUDA(cudaMemcpyAsync(R.h + 32, dev, sizeof(double), cudaMemcpyDeviceToHost, s));
+  IX_CUDA(cudaStreamSynchronize(s));
+  *out = R.h[32];
+  return IAMRX_OK;
+}
+
 int mf_norminf_each(const MF& m, int comp, int ncomp, double* out, cudaStream_t s) {
   return reduce_common(m, comp, ncomp, 2, out, s, false);
 }

@@ -190,6 +190,8 @@ int mf_gather_replicate(MF& dst, const MF& src, int ncomp, cudaStream_t s);
 // For face/nodal data shared points are counted once per owning box (norms only).
 int mf_norminf(const MF& m, int comp, int ncomp, double* out_host, cudaStream_t s);  // max over comps
 int mf_norminf_each(const MF& m, int comp, int ncomp, double* out_host, cudaStream_t s);
+int norm_acc_begin(double** dev, cudaStream_t s);   // max-norm accumulated inside a producer kernel: zeroed device scalar ...
+int norm_acc_end(double* dev, bool replicated, double* out_host, cudaStream_t s);   // ... reduced over the ranks, to the host
 int mf_sum(const MF& m, int comp, double* out_host, cudaStream_t s, bool unique_nodes = false);
 int mf_min(const MF& m, int comp, double* out_host, cudaStream_t s);
 

@@ -376,15 +376,23 @@ int CellMG::smooth(int l, MF& phi, const MF& rhs, int nsweeps, bool zero_init, c
 }
 
 // with_cross marks the top-level residual of a solve: inhomogeneous boundary conditions (+ the tensor cross terms)
-int CellMG::residual(int l, MF& out, MF& phi, const MF& rhs, bool with_cross, cudaStream_t s) {
+int CellMG::residual(int l, MF& out, MF& phi, const MF& rhs, bool with_cross, cudaStream_t s, double* norm) {
   const bool cross = tensor_ && l == 0 && with_cross;  // the cross terms read edge/corner ghosts
   const int wm = cross ? 0 : lv_[l].lev->level_wrapmask();
   IX_TRY(fill_ghosts(l, phi, with_cross, wm, cross ? 1 : 0, s));
   const Level& L = *lv_[l].lev;
+  double* nd = nullptr;
+  bool all_fused = norm != nullptr && !cross && phi.n() > 0;
+  if (all_fused) IX_TRY(norm_acc_begin(&nd, s));
   for (int il = 0; il < phi.n(); ++il) {
     const bool mir = has_bc_ && !with_cross && box_on_boundary(l, il) && bc_in_kernel(l);
     const k::GsBC gb = mir ? gsbc_of(l, il) : k::GsBC{};
-    IX_TRY(k::abec_apply(phi.vbox(il), out.v(il), phi.c(il), rhs.c(il), op_at(l, il), ncomp_, s, wm, mir ? &gb : nullptr));
+    bool nf = false;
+    IX_TRY(k::abec_apply(phi.vbox(il), out.v(il), phi.c(il), rhs.c(il), op_at(l, il), ncomp_, s, wm, mir ? &gb : nullptr, all_fused ? nd : nullptr, &nf));
+    if (all_fused && !nf) {   // this box took a kernel without the fused norm: reduce it into the same scalar
+      double* one = nd;
+      for (int c = 0; c < ncomp_; ++c) IX_TRY(k::reduce(phi.vbox(il), out.c(il, c), 1, 2, one, s));
+    }
     if (cross) {
       if (has_bc_)
         IX_TRY(k::tensor_cross_bc(phi.vbox(il), out.v(il), phi.c(il), bvals_.ok() ? bvals_.c(il) : C4{}, eta_[0]->c(il), eta_[1]->c(il),
@@ -393,6 +401,10 @@ int CellMG::residual(int l, MF& out, MF& phi, const MF& rhs, bool with_cross, cu
         IX_TRY(k::tensor_cross(phi.vbox(il), out.v(il), phi.c(il), eta_[0]->c(il), eta_[1]->c(il),
                                eta_[2]->c(il), -b_, lv_[0].dxinv, s));
     }
+  }
+  if (norm) {
+    if (all_fused) IX_TRY(norm_acc_end(nd, L.replicated, norm, s));
+    else IX_TRY(mf_norminf(out, 0, ncomp_, norm, s));
   }
   return IAMRX_OK;
 }
@@ -595,8 +607,7 @@ int CellMG::solve(MF& sol, const MF& rhs_in, iamrx_mg_info* info, cudaStream_t s
   if (singular_) IX_TRY(make_solvable(0, rhs, s));
   double rhsnorm = 0, resnorm0 = 0, resnorm = 0;
   IX_TRY(mf_norminf(rhs, 0, ncomp_, &rhsnorm, s));
-  IX_TRY(residual(0, L0.res, sol, rhs, true, s));
-  IX_TRY(mf_norminf(L0.res, 0, ncomp_, &resnorm0, s));
+  IX_TRY(residual(0, L0.res, sol, rhs, true, s, &resnorm0));
   if (!std::isfinite(rhsnorm) || !std::isfinite(resnorm0)) { bvals_.clear(); set_error("CellMG: NaN in the right-hand side or the initial guess"); return IAMRX_ERR_NAN; }
   const double maxnorm = std::max(rhsnorm, resnorm0);
   const double target = std::max(info_.atol, info_.rtol * maxnorm);
@@ -608,8 +619,7 @@ int CellMG::solve(MF& sol, const MF& rhs_in, iamrx_mg_info* info, cudaStream_t s
     for (iters = 1; iters <= info_.max_iter; ++iters) {
       IX_TRY(vcycle(s));
       IX_TRY(mf_lincomb(sol, 0, 1.0, sol, 0, 1.0, L0.cor, 0, ncomp_, 0, s));
-      IX_TRY(residual(0, L0.res, sol, rhs, true, s));
-      IX_TRY(mf_norminf(L0.res, 0, ncomp_, &resnorm, s));
+      IX_TRY(residual(0, L0.res, sol, rhs, true, s, &resnorm));
       if (info_.verbose > 1)
         fprintf(stderr, "[iamrx] CellMG iter %d resnorm %.6e (target %.3e)\n", iters, resnorm, target);
       if (!std::isfinite(resnorm)) { set_error("CellMG: NaN residual"); rc = IAMRX_ERR_NAN; break; }
@@ -821,12 +831,30 @@ int NodeMG::smooth(int l, MF& phi, const MF& rhs, int nsweeps, cudaStream_t s) {
   return IAMRX_OK;
 }
 
-int NodeMG::residual(int l, MF& out, MF& phi, const MF& rhs, cudaStream_t s) {
+int NodeMG::residual(int l, MF& out, MF& phi, const MF& rhs, cudaStream_t s, double* norm) {
   MGLevelNode& L = lv_[l];
   const int wm = L.lev->level_wrapmask();
   IX_TRY(fill_ghosts(l, phi, wm, s, false));
-  for (int il = 0; il < phi.n(); ++il)
-    IX_TRY(k::nodal_adotx(active_nbox(l, il), out.v(il), phi.c(il), rhs.c(il), L.sigma.c(il), L.dxinv, s, wm | (neumann_sides(l, il) << 3)));
+  // the norm is taken inside the residual kernel when every box's active nodes are all of its nodes (no Dirichlet planes whose
+  // entries of `out` the kernel does not write) and the kernel supports it
+  double* nd = nullptr;
+  bool fusedn = norm != nullptr && phi.n() > 0;
+  for (int il = 0; il < phi.n() && fusedn; ++il) {
+    const Bx a = active_nbox(l, il), v = phi.vbox(il);
+    for (int d = 0; d < 3; ++d) if (a.lo[d] != v.lo[d] || a.hi[d] != v.hi[d]) fusedn = false;
+  }
+  if (fusedn) IX_TRY(norm_acc_begin(&nd, s));
+  bool all = fusedn;
+  for (int il = 0; il < phi.n(); ++il) {
+    bool nf = false;
+    IX_TRY(k::nodal_adotx(active_nbox(l, il), out.v(il), phi.c(il), rhs.c(il), L.sigma.c(il), L.dxinv, s, wm | (neumann_sides(l, il) << 3),
+                          fusedn ? nd : nullptr, &nf));
+    if (fusedn && !nf) all = false;
+  }
+  if (norm) {
+    if (fusedn && all) IX_TRY(norm_acc_end(nd, L.lev->replicated, norm, s));
+    else IX_TRY(mf_norminf(out, 0, 1, norm, s));
+  }
   return IAMRX_OK;
 }
 
@@ -934,8 +962,7 @@ int NodeMG::solve(MF& phi, MF& rhs, iamrx_mg_info* info, cudaStream_t s) {
   if (singular()) IX_TRY(make_solvable(0, rhs, s));
   double rhsnorm = 0, resnorm0 = 0, resnorm = 0;
   IX_TRY(mf_norminf(rhs, 0, 1, &rhsnorm, s));
-  IX_TRY(residual(0, L0.res, phi, rhs, s));
-  IX_TRY(mf_norminf(L0.res, 0, 1, &resnorm0, s));
+  IX_TRY(residual(0, L0.res, phi, rhs, s, &resnorm0));
   if (!std::isfinite(rhsnorm) || !std::isfinite(resnorm0)) { set_error("NodeMG: NaN in the right-hand side or the initial guess"); return IAMRX_ERR_NAN; }
   const double maxnorm = std::max(rhsnorm, resnorm0);
   const double target = std::max(info_.atol, info_.rtol * maxnorm);
@@ -947,8 +974,7 @@ int NodeMG::solve(MF& phi, MF& rhs, iamrx_mg_info* info, cudaStream_t s) {
     for (iters = 1; iters <= info_.max_iter; ++iters) {
       IX_TRY(vcycle(s));
       IX_TRY(mf_lincomb(phi, 0, 1.0, phi, 0, 1.0, L0.cor, 0, 1, 0, s));
-      IX_TRY(residual(0, L0.res, phi, rhs, s));
-      IX_TRY(mf_norminf(L0.res, 0, 1, &resnorm, s));
+      IX_TRY(residual(0, L0.res, phi, rhs, s, &resnorm));
       if (info_.verbose > 1)
         fprintf(stderr, "[iamrx] NodeMG iter %d resnorm %.6e (target %.3e)\n", iters, resnorm, target);
       if (!std::isfinite(resnorm)) { set_error("NodeMG: NaN residual"); rc = IAMRX_ERR_NAN; break; }

@@ -50,7 +50,8 @@ class CellMG {
 
  private:
   int smooth(int l, MF& phi, const MF& rhs, int nsweeps, bool zero_init, cudaStream_t s);
-  int residual(int l, MF& out, MF& phi, const MF& rhs, bool with_cross, cudaStream_t s);
+  // norm (optional): max-norm of `out`, taken inside the residual kernel where it can be
+  int residual(int l, MF& out, MF& phi, const MF& rhs, bool with_cross, cudaStream_t s, double* norm = nullptr);
   int vcycle(cudaStream_t s);
   int bottom_solve(cudaStream_t s);   // smoother sweeps or BiCGStab (iamrx_mg_info.bottom_solver) on the coarsest level
   int make_solvable(int l, MF& rhs, cudaStream_t s);
@@ -107,7 +108,7 @@ class NodeMG {
 
  private:
   int smooth(int l, MF& phi, const MF& rhs, int nsweeps, cudaStream_t s);
-  int residual(int l, MF& out, MF& phi, const MF& rhs, cudaStream_t s);
+  int residual(int l, MF& out, MF& phi, const MF& rhs, cudaStream_t s, double* norm = nullptr);
   int vcycle(cudaStream_t s);
   int bottom_solve(cudaStream_t s);
   int make_solvable(int l, MF& rhs, cudaStream_t s);

@@ -144,33 +144,67 @@ __global__ void __launch_bounds__(TX* TY) nd_restrict_kernel(Bx cbx, V4 crse, C4
 
 IX_D int fl2(int a) { return (a >= 0) ? a / 2 : -((-a + 1) / 2); }
 
-// two fine planes (k, k + nzh) per thread: all coarse and fine loads are issued before the stores; the weights are powers of two
-// (what 1 / ((1 + ox)(1 + oy)(1 + oz)) evaluates to, exactly)
-__global__ void __launch_bounds__(TX* TY) nd_interp_kernel(Bx fbx, V4 fine, C4 crse, int thin, int nzh) {
-  const int j = fbx.lo[1] + blockIdx.y * TY + threadIdx.y;
-  const int i = fbx.lo[0] + blockIdx.x * TX + threadIdx.x;
-  if (j > fbx.hi[1] || i > fbx.hi[0]) return;
-  const int ic = (thin & 1) ? i : fl2(i), jc = (thin & 2) ? j : fl2(j);
-  const int ox = (thin & 1) ? 0 : i - 2 * ic, oy = (thin & 2) ? 0 : j - 2 * jc;  // 0 or 1
-  double acc[2], old[2], w[2];
-  int kk[2];
+__global__ void __launch_bounds__(TX* TY) nd_interp_kernel(Bx fbx, V4 fine, C4 crse, int thin) {
+  NIDX(fbx)
+  const int ic = (thin & 1) ? i : fl2(i), jc = (thin & 2) ? j : fl2(j), kc = (thin & 4) ? k : fl2(k);
+  const int ox = (thin & 1) ? 0 : i - 2 * ic, oy = (thin & 2) ? 0 : j - 2 * jc, oz = (thin & 4) ? 0 : k - 2 * kc;  // 0 or 1
+  double acc = 0.0;
+  for (int dk = 0; dk <= oz; ++dk)
+    for (int dj = 0; dj <= oy; ++dj)
+      for (int di = 0; di <= ox; ++di) acc += crse(ic + di, jc + dj, kc + dk);
+  const double w = 1.0 / (double)((1 + ox) * (1 + oy) * (1 + oz));
+  fine(i, j, k) += w * acc;
+}
+
+// The same with one thread per COARSE cell (all three directions coarsened): its eight coarse corner nodes are loaded once and
+// the 2 x 2 x 2 fine nodes (2 ic + {0,1}, ...) updated from registers; sums in the order of the loop above (bit-identical).
+__global__ void __launch_bounds__(TX* TY) nd_interp8_kernel(Bx fbx, Bx cbx, V4 fine, C4 crse) {
+  const int kc = cbx.lo[2] + blockIdx.z;
+  const int jc = cbx.lo[1] + blockIdx.y * TY + threadIdx.y;
+  const int ic = cbx.lo[0] + blockIdx.x * TX + threadIdx.x;
+  if (jc > cbx.hi[1] || ic > cbx.hi[0]) return;
+  const double* cp = crse.p + ((ic - crse.l0) + (jc - crse.l1) * crse.js + (kc - crse.l2) * crse.ks);
+  const int cjs = (int)crse.js, cks = (int)crse.ks;
+  // corner nodes beyond the fine box's coarsening are only read for fine nodes inside the box (guards below)
+  const int i0 = 2 * ic, j0 = 2 * jc, k0 = 2 * kc;
+  const bool xi[2] = {i0 >= fbx.lo[0] && i0 <= fbx.hi[0], i0 + 1 >= fbx.lo[0] && i0 + 1 <= fbx.hi[0]};
+  const bool yi[2] = {j0 >= fbx.lo[1] && j0 <= fbx.hi[1], j0 + 1 >= fbx.lo[1] && j0 + 1 <= fbx.hi[1]};
+  const bool zi[2] = {k0 >= fbx.lo[2] && k0 <= fbx.hi[2], k0 + 1 >= fbx.lo[2] && k0 + 1 <= fbx.hi[2]};
+  double C[2][2][2];
 #pragma unroll
-  for (int q = 0; q < 2; ++q) {
-    const int k = fbx.lo[2] + (int)blockIdx.z + q * nzh;
-    kk[q] = k;
-    acc[q] = 0.0; old[q] = 0.0; w[q] = 0.0;
-    if (k > fbx.hi[2]) continue;
-    const int kc = (thin & 4) ? k : fl2(k);
-    const int oz = (thin & 4) ? 0 : k - 2 * kc;
-    for (int dk = 0; dk <= oz; ++dk)
-      for (int dj = 0; dj <= oy; ++dj)
-        for (int di = 0; di <= ox; ++di) acc[q] += crse(ic + di, jc + dj, kc + dk);
-    const int sh = ox + oy + oz;
-    w[q] = sh == 0 ? 1.0 : (sh == 1 ? 0.5 : (sh == 2 ? 0.25 : 0.125));
-    old[q] = fine(i, j, k);
-  }
+  for (int dk = 0; dk < 2; ++dk)
 #pragma unroll
-  for (int q = 0; q < 2; ++q) if (kk[q] <= fbx.hi[2]) fine(i, j, kk[q]) = old[q] + w[q] * acc[q];
+    for (int dj = 0; dj < 2; ++dj)
+#pragma unroll
+      for (int di = 0; di < 2; ++di)
+        C[dk][dj][di] = ((di == 0 || xi[1]) && (dj == 0 || yi[1]) && (dk == 0 || zi[1])) ? cp[di + dj * cjs + dk * cks] : 0.0;
+  double* fp = fine.p + ((i0 - fine.l0) + (j0 - fine.l1) * fine.js + (k0 - fine.l2) * fine.ks);
+  const int fjs = (int)fine.js, fks = (int)fine.ks;
+  double F[2][2][2];
+#pragma unroll
+  for (int oz = 0; oz < 2; ++oz)
+#pragma unroll
+    for (int oy = 0; oy < 2; ++oy)
+#pragma unroll
+      for (int ox = 0; ox < 2; ++ox) F[oz][oy][ox] = (xi[ox] && yi[oy] && zi[oz]) ? fp[ox + oy * fjs + oz * fks] : 0.0;
+#pragma unroll
+  for (int oz = 0; oz < 2; ++oz)
+#pragma unroll
+    for (int oy = 0; oy < 2; ++oy)
+#pragma unroll
+      for (int ox = 0; ox < 2; ++ox) {
+        if (!(xi[ox] && yi[oy] && zi[oz])) continue;
+        double acc = 0.0;
+#pragma unroll
+        for (int dk = 0; dk <= oz; ++dk)
+#pragma unroll
+          for (int dj = 0; dj <= oy; ++dj)
+#pragma unroll
+            for (int di = 0; di <= ox; ++di) acc += C[dk][dj][di];
+        const int sh = ox + oy + oz;
+        const double w = sh == 0 ? 1.0 : (sh == 1 ? 0.5 : (sh == 2 ? 0.25 : 0.125));   // = 1 / ((1 + ox)(1 + oy)(1 + oz))
+        fp[ox + oy * fjs + oz * fks] = F[oz][oy][ox] + w * acc;
+      }
 }
 
 __global__ void __launch_bounds__(TX* TY)
@@ -682,7 +716,7 @@ struct Sg { double m0, m1, p0, p1; };   // cells (i-1, j-1), (i-1, j), (i, j-1),
 
 template <int KB, int MINB>
 __global__ void __launch_bounds__(TX* TY, MINB)
-adotx_march_kernel(Bx bx, V4 out, C4 phi, C4 rhs, C4 sig, IX_KARG(fused::Q1F) q, int wm, int nchunk) {
+adotx_march_kernel(Bx bx, V4 out, C4 phi, C4 rhs, C4 sig, IX_KARG(fused::Q1F) q, int wm, int nchunk, double* norm) {
   const int i = bx.lo[0] + blockIdx.x * TX + threadIdx.x;
   const int j = bx.lo[1] + blockIdx.y * TY + threadIdx.y;
   if (i > bx.hi[0] || j > bx.hi[1]) return;
@@ -735,6 +769,8 @@ adotx_march_kernel(Bx bx, V4 out, C4 phi, C4 rhs, C4 sig, IX_KARG(fused::Q1F) q,
     load_pl(C, kc0 + 1);
     D = C; S2 = S1;
     double ua = U(A, S0);
+    double nrm = 0.0;     // max |out| of this column (norm != nullptr: the residual norm, fused)
+    bool isnan_ = false;
     for (int k = kc0; k <= kc1; ++k) {
       if (k < kc1) { load_pl(D, k + 2); load_sg(S2, k + 1); }   // next iteration's plane and layer
       const double mj0 = S0.m0 + S1.m0, mj1 = S0.m1 + S1.m1, pj0 = S0.p0 + S1.p0, pj1 = S0.p1 + S1.p1;
@@ -744,9 +780,25 @@ adotx_march_kernel(Bx bx, V4 out, C4 phi, C4 rhs, C4 sig, IX_KARG(fused::Q1F) q,
       const double a1c = mc * B.v[1][0] + pc * B.v[1][2];
       const double s0 = q.f0c * (mc + pc);
       const double y = s0 * B.v[1][1] + q.f1c * a1c + q.f1j * a1j + q.f0j * a0j + ua + U(C, S1);
-      out(i, j, k) = rhs.ok() ? (rhs(i, j, k) - y) : y;
+      const double val = rhs.ok() ? (rhs(i, j, k) - y) : y;
+      out(i, j, k) = val;
+      isnan_ |= (val != val);
+      nrm = fmax(nrm, fabs(val));
       ua = U(B, S1);          // plane k seen from node k+1 through layer k
       B = C; C = D; S0 = S1; S1 = S2;
+    }
+    if (norm) {
+      // non-negative doubles order like their bit patterns; a quiet NaN wins (blas.cu nanmax)
+      unsigned long long m = isnan_ ? 0x7ff8000000000000ULL : (unsigned long long)__double_as_longlong(nrm);
+      const unsigned act = __activemask();
+      if (act == 0xffffffffu) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) { const unsigned long long t = __shfl_xor_sync(0xffffffffu, m, o); m = t > m ? t : m; }
+      }
+      if (act != 0xffffffffu || (threadIdx.x & 31) == 0) {
+        unsigned long long* a = reinterpret_cast<unsigned long long*>(norm);
+        if (m > *reinterpret_cast<volatile unsigned long long*>(a)) atomicMax(a, m);
+      }
     }
   }
 }
@@ -779,7 +831,9 @@ int nodal_divu(const Bx& nbx, V4 rhs, C4 vel, const double dxinv[3], cudaStream_
   return check_launch("nodal_divu");
 }
 
-int nodal_adotx(const Bx& nbx, V4 out, C4 phi, C4 rhs, C4 sig, const double dxinv[3], cudaStream_t s, int wrapmask) {
+int nodal_adotx(const Bx& nbx, V4 out, C4 phi, C4 rhs, C4 sig, const double dxinv[3], cudaStream_t s, int wrapmask,
+                double* norm_dev, bool* norm_fused) {
+  if (norm_fused) *norm_fused = false;
   if (!nbx.ok()) return IAMRX_OK;
   double f[3]; facs(dxinv, f);
   ProfScope prof_(IAMRX_PROF_NODAL_ADOTX, nbx.npts(), (double)nbx.npts() * (rhs.ok() ? 32.0 : 24.0), s);
@@ -809,10 +863,11 @@ int nodal_adotx(const Bx& nbx, V4 out, C4 phi, C4 rhs, C4 sig, const double dxin
       const int KBv = (kb >= 32) ? 32 : 16;
       const int nchunk = cdiv(nbx.nz(), KBv);
       const dim3 grd(cdiv(nbx.nx(), TX), cdiv(nbx.ny(), TY), nchunk), blk(TX, TY, 1);
-      if (KBv == 32 && minb >= 3) IX_LAUNCH((march::adotx_march_kernel<32, 3>), grd, blk, 0, s, nbx, out, phi, rhs, sig, q, wrapmask, nchunk);
-      else if (KBv == 32) IX_LAUNCH((march::adotx_march_kernel<32, 2>), grd, blk, 0, s, nbx, out, phi, rhs, sig, q, wrapmask, nchunk);
-      else if (minb >= 3) IX_LAUNCH((march::adotx_march_kernel<16, 3>), grd, blk, 0, s, nbx, out, phi, rhs, sig, q, wrapmask, nchunk);
-      else IX_LAUNCH((march::adotx_march_kernel<16, 2>), grd, blk, 0, s, nbx, out, phi, rhs, sig, q, wrapmask, nchunk);
+      if (KBv == 32 && minb >= 3) IX_LAUNCH((march::adotx_march_kernel<32, 3>), grd, blk, 0, s, nbx, out, phi, rhs, sig, q, wrapmask, nchunk, norm_dev);
+      else if (KBv == 32) IX_LAUNCH((march::adotx_march_kernel<32, 2>), grd, blk, 0, s, nbx, out, phi, rhs, sig, q, wrapmask, nchunk, norm_dev);
+      else if (minb >= 3) IX_LAUNCH((march::adotx_march_kernel<16, 3>), grd, blk, 0, s, nbx, out, phi, rhs, sig, q, wrapmask, nchunk, norm_dev);
+      else IX_LAUNCH((march::adotx_march_kernel<16, 2>), grd, blk, 0, s, nbx, out, phi, rhs, sig, q, wrapmask, nchunk, norm_dev);
+      if (norm_fused) *norm_fused = norm_dev != nullptr;
       return check_launch("nodal_adotx_march");
     }
   }
@@ -953,8 +1008,13 @@ int nodal_restrict(const Bx& cnbx, V4 crse, C4 fine, cudaStream_t s, int thin, i
 
 int nodal_interp_add(const Bx& fnbx, V4 fine, C4 crse, cudaStream_t s, int thin) {
   if (!fnbx.ok()) return IAMRX_OK;
-  const int nzh = cdiv(fnbx.nz(), 2);
-  IX_LAUNCH(nd_interp_kernel, dim3(cdiv(fnbx.nx(), TX), cdiv(fnbx.ny(), TY), nzh), dim3(TX, TY, 1), 0, s, fnbx, fine, crse, thin, nzh);
+  if (thin == 0) {
+    Bx cb;   // coarse cells whose 2 x 2 x 2 fine nodes meet the fine box
+    for (int d = 0; d < 3; ++d) { cb.lo[d] = fnbx.lo[d] >= 0 ? fnbx.lo[d] / 2 : -((-fnbx.lo[d] + 1) / 2); cb.hi[d] = fnbx.hi[d] >= 0 ? fnbx.hi[d] / 2 : -((-fnbx.hi[d] + 1) / 2); }
+    IX_LAUNCH(nd_interp8_kernel, grid_for(cb), dim3(TX, TY, 1), 0, s, fnbx, cb, fine, crse);
+    return check_launch("nodal_interp_add");
+  }
+  IX_LAUNCH(nd_interp_kernel, grid_for(fnbx), dim3(TX, TY, 1), 0, s, fnbx, fine, crse, thin);
   return check_launch("nodal_interp_add");
 }
 
