@@ -55,23 +55,9 @@ constexpr int GS_TY = 4;
 // ZERO: first colour pass of a sweep on phi == 0 (ghost cells included: the multigrid correction with homogeneous boundary
 // conditions).  No phi is read -- phi = omega / (gamma - delta) * rhs, the value the general expression gives -- and the other
 // cell of the pair is set to zero, so the caller needs no setval before the sweep.
-template <int MINB, bool HASBC, bool CONSTB, bool ZERO>
-__global__ void __launch_bounds__(GS_TX* GS_TY, MINB)
-gsrb_kernel(Bx bx, V4 phi, C4 rhs, IX_KARG(AbecDev) op, double omega, int redblack, int nz, int wm, IX_KARG(GsBC) gb) {
-  const int kz = blockIdx.z % nz;
-  const int n = blockIdx.z / nz;
-  const int k = bx.lo[2] + kz;
-  const int j = bx.lo[1] + blockIdx.y * GS_TY + threadIdx.y;
-  if (j > bx.hi[1]) return;
-  int i = bx.lo[0] + 2 * (blockIdx.x * GS_TX + threadIdx.x);
-  const int ipair = i;
-  // make (i + j + k + redblack) even
-  i += (i + j + k + redblack) & 1;
-  if (ZERO) {   // the pair's cell of the other colour (or both, if the coloured one lies beyond the box)
-    const int io = ipair + (1 - (i - ipair));
-    if (io <= bx.hi[0]) phi(io, j, k, n) = 0.0;
-  }
-  if (i > bx.hi[0]) return;
+// the relaxation of ONE cell (i, j, k, n) of the right colour (shared by the colour-pass kernel and the small-box sweep kernel)
+template <bool HASBC, bool CONSTB, bool ZERO>
+IX_D void gsrb_cell(const Bx& bx, const V4& phi, const C4& rhs, const AbecDev& op, double omega, int wm, const GsBC& gb, int i, int j, int k, int n) {
   const int nb = (op.bncomp > 1) ? n : 0;
 
   // 32-bit element offsets from the cell's own address (one address computation per array)
@@ -146,6 +132,58 @@ gsrb_kernel(Bx bx, V4 phi, C4 rhs, IX_KARG(AbecDev) op, double omega, int redbla
     pc[0] = p0 + omega / gamma * res;
   }
 }
+
+template <int MINB, bool HASBC, bool CONSTB, bool ZERO>
+__global__ void __launch_bounds__(GS_TX* GS_TY, MINB)
+gsrb_kernel(Bx bx, V4 phi, C4 rhs, IX_KARG(AbecDev) op, double omega, int redblack, int nz, int wm, IX_KARG(GsBC) gb) {
+  const int kz = blockIdx.z % nz;
+  const int n = blockIdx.z / nz;
+  const int k = bx.lo[2] + kz;
+  const int j = bx.lo[1] + blockIdx.y * GS_TY + threadIdx.y;
+  if (j > bx.hi[1]) return;
+  int i = bx.lo[0] + 2 * (blockIdx.x * GS_TX + threadIdx.x);
+  const int ipair = i;
+  // make (i + j + k + redblack) even
+  i += (i + j + k + redblack) & 1;
+  if (ZERO) {   // the pair's cell of the other colour (or both, if the coloured one lies beyond the box)
+    const int io = ipair + (1 - (i - ipair));
+    if (io <= bx.hi[0]) phi(io, j, k, n) = 0.0;
+  }
+  if (i > bx.hi[0]) return;
+  gsrb_cell<HASBC, CONSTB, ZERO>(bx, phi, rhs, op, omega, wm, gb, i, j, k, n);
+}
+
+// Small boxes (the coarse multigrid levels: a few thousand cells): ALL sweeps of a smoothing step in one launch of one CTA,
+// colours separated by __syncthreads -- 2 nsweeps launches of a few microseconds each become one.  Only for boxes whose
+// neighbours are all reached inside the kernel (periodic wrap / mirrored sides): no ghost exchange between the colours.
+#if !defined(IX_EMUL)
+constexpr int GS_SMALL_T = 512;
+template <bool HASBC, bool CONSTB>
+__global__ void __launch_bounds__(GS_SMALL_T)
+gsrb_small_kernel(Bx bx, V4 phi, C4 rhs, IX_KARG(AbecDev) op, double omega, int ncomp, int wm, IX_KARG(GsBC) gb, int nsweeps, int zero_first) {
+  const int hx = (bx.nx() + 1) / 2, ny = bx.ny(), nz = bx.nz();
+  const int npairs = hx * ny * nz * ncomp;
+  for (int sw = 0; sw < nsweeps; ++sw)
+    for (int rb = 0; rb < 2; ++rb) {
+      const bool zero = zero_first && sw == 0 && rb == 0;
+      for (int idx = threadIdx.x; idx < npairs; idx += GS_SMALL_T) {
+        const int ph = idx % hx, r1 = idx / hx;
+        const int j = bx.lo[1] + r1 % ny, r2 = r1 / ny;
+        const int k = bx.lo[2] + r2 % nz, n = r2 / nz;
+        const int ipair = bx.lo[0] + 2 * ph;
+        const int i = ipair + ((ipair + j + k + rb) & 1);
+        if (zero) {
+          const int io = ipair + (1 - (i - ipair));
+          if (io <= bx.hi[0]) phi(io, j, k, n) = 0.0;
+          if (i <= bx.hi[0]) gsrb_cell<HASBC, CONSTB, true>(bx, phi, rhs, op, omega, wm, gb, i, j, k, n);
+        } else if (i <= bx.hi[0]) {
+          gsrb_cell<HASBC, CONSTB, false>(bx, phi, rhs, op, omega, wm, gb, i, j, k, n);
+        }
+      }
+      __syncthreads();
+    }
+}
+#endif
 
 // ---- apply / residual ----------------------------------------------------
 constexpr int AP_TX = 128;
@@ -818,6 +856,28 @@ int abec_gsrb(const Bx& bx, V4 phi, C4 rhs, const Abec& op, double omega, int re
   else IX_GSRB(6, false, false, false, none);
 #undef IX_GSRB
   return check_launch("abec_gsrb");
+}
+
+bool abec_gsrb_small_ok(const Bx& bx, int ncomp) { return bx.npts() * ncomp <= 16384; }
+int abec_gsrb_small(const Bx& bx, V4 phi, C4 rhs, const Abec& op, double omega, int ncomp, int nsweeps, bool zero_phi, cudaStream_t s,
+                    int wrapmask, const GsBC* gb) {
+  if (!bx.ok() || nsweeps <= 0) return IAMRX_OK;
+#if defined(IX_EMUL)
+  // host emulation (tests only; no barriers there): the same sweeps as colour launches
+  for (int sw = 0; sw < nsweeps; ++sw)
+    for (int rb = 0; rb < 2; ++rb) {
+      const int rc = abec_gsrb(bx, phi, rhs, op, omega, rb, ncomp, s, wrapmask, gb, zero_phi && sw == 0 && rb == 0);
+      if (rc != IAMRX_OK) return rc;
+    }
+  return IAMRX_OK;
+#else
+  const GsBC none{};
+#define IX_GSS(B, C, G) IX_LAUNCH((gsrb_small_kernel<B, C>), 1, GS_SMALL_T, 0, s, bx, phi, rhs, to_dev(op), omega, ncomp, wrapmask, G, nsweeps, zero_phi ? 1 : 0)
+  if (op.cc) { if (gb) IX_GSS(true, true, *gb); else IX_GSS(false, true, none); }
+  else { if (gb) IX_GSS(true, false, *gb); else IX_GSS(false, false, none); }
+#undef IX_GSS
+  return check_launch("abec_gsrb_small");
+#endif
 }
 
 // Measured on B200 (profiles/r01_notes.md): the fused sweep halves the DRAM traffic (832 MB vs 1590 MB per sweep at 256^3)

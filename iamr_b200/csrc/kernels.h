@@ -37,6 +37,11 @@ int abec_gsrb(const Bx& bx, V4 phi, C4 rhs, const Abec& op, double omega, int re
 // one full red-black sweep (colour rb0, then the other) phi_in -> phi_out (different arrays) on a box that spans
 // the periodic domain in all directions with even extents; abec_gsrb_sweep_ok tells whether the box qualifies
 bool abec_gsrb_sweep_ok(const Bx& bx, int wrapmask);
+// all `nsweeps` red-black sweeps of a small box (coarse multigrid levels) in one single-CTA launch; only when every neighbour is
+// reached inside the kernel (wrapmask / mirrored sides of gb cover all sides of the box)
+bool abec_gsrb_small_ok(const Bx& bx, int ncomp);
+int abec_gsrb_small(const Bx& bx, V4 phi, C4 rhs, const Abec& op, double omega, int ncomp, int nsweeps, bool zero_phi, cudaStream_t s,
+                    int wrapmask, const GsBC* gb);
 bool abec_gsrb_sweep_enabled();  // multigrid uses the fused sweep only when IAMRX_GSRB_FUSED=1 (see abec.cu)
 int abec_gsrb_sweep(const Bx& bx, V4 phi_out, C4 phi_in, C4 rhs, const Abec& op, double omega, int rb0, int ncomp,
                     cudaStream_t s);

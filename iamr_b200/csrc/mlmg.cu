@@ -359,6 +359,11 @@ int CellMG::smooth(int l, MF& phi, const MF& rhs, int nsweeps, bool zero_init, c
     }
     return IAMRX_OK;
   }
+  // small single box whose neighbours are all periodic images: every sweep in one launch (IAMRX_GSRB_SMALL=0: colour launches)
+  static int small_on = -1;
+  if (small_on < 0) { const char* e = getenv("IAMRX_GSRB_SMALL"); small_on = (e && e[0] == '0') ? 0 : 1; }
+  if (small_on && wrap && !has_bc_ && phi.n() == 1 && L.lev->boxes.size() == 1 && k::abec_gsrb_small_ok(phi.vbox(0), ncomp_))
+    return k::abec_gsrb_small(phi.vbox(0), phi.v(0), rhs.c(0), op_at(l, 0), info_.omega, ncomp_, nsweeps, zero_init, s, wm, nullptr);
   for (int sw = 0; sw < nsweeps; ++sw) {
     for (int rb = 0; rb < 2; ++rb) {
       // zero_init: the caller did NOT clear phi -- the first colour pass writes every cell (the homogeneous ghost cells of a zero

@@ -803,6 +803,32 @@ int iamrx_ns_field(iamrx_ns_t ns, int which, int il, iamrx_fab* out) {
   return IAMRX_OK;
 }
 
+#if !defined(IX_EMUL)
+// dense host array (ncomp, nz, ny, nx) <-> the valid region of a ghosted device fab, as one strided DMA per component: no
+// staging buffer and no pack / unpack kernel between the PCIe copy and the state (IAMRX_E2E_3D=0: the staged path)
+static bool e2e_3d() {
+  static int on = -1;
+  if (on < 0) { const char* e = getenv("IAMRX_E2E_3D"); on = (e && e[0] == '0') ? 0 : 1; }
+  return on != 0;
+}
+static int copy3d(const Bx& b, V4 dev, int dcomp, double* host, int ncomp, bool to_device, cudaStream_t s) {
+  if (dev.js <= 0 || dev.ks % dev.js != 0) return IAMRX_ERR_ARG;
+  const size_t nx = (size_t)b.nx(), ny = (size_t)b.ny(), nz = (size_t)b.nz();
+  for (int n = 0; n < ncomp; ++n) {
+    double* d = dev.p + (dcomp + n) * dev.ns + ((b.lo[0] - dev.l0) + (b.lo[1] - dev.l1) * dev.js + (b.lo[2] - dev.l2) * dev.ks);
+    cudaMemcpy3DParms p{};
+    const cudaPitchedPtr hp = make_cudaPitchedPtr(host + (size_t)n * nx * ny * nz, nx * sizeof(double), nx * sizeof(double), ny);
+    const cudaPitchedPtr dp = make_cudaPitchedPtr(d, (size_t)dev.js * sizeof(double), (size_t)dev.js * sizeof(double), (size_t)(dev.ks / dev.js));
+    p.srcPtr = to_device ? hp : dp;
+    p.dstPtr = to_device ? dp : hp;
+    p.extent = make_cudaExtent(nx * sizeof(double), ny, nz);
+    p.kind = to_device ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToHost;
+    IX_CUDA(cudaMemcpy3DAsync(&p, s));
+  }
+  return IAMRX_OK;
+}
+#endif
+
 int iamrx_ns_step_host(iamrx_ns_t nsp, const double* const* host_in, double* const* host_out, double* dt_io) {
   IX_NEED_DEVICE();
   IX_ARG(nsp && host_in && host_out, "null argument");
@@ -829,15 +855,26 @@ int iamrx_ns_step_host(iamrx_ns_t nsp, const double* const* host_in, double* con
   for (int il = 0; il < L.nlocal(); ++il) {
     const size_t npts = (size_t)L.lbox(il).npts();
     const int nfirst = late ? NUM_STATE - 1 : NUM_STATE;
-    IX_CUDA(cudaMemcpyAsync(dbuf, host_in[il], npts * nfirst * sizeof(double), cudaMemcpyHostToDevice, ns.s));
-    IX_TRY(k::unpack(L.lbox(il), ns.S_new.v(il), dbuf, nfirst, ns.s));
+#if !defined(IX_EMUL)
+    if (e2e_3d()) {
+      IX_TRY(copy3d(L.lbox(il), ns.S_new.v(il), 0, const_cast<double*>(host_in[il]), nfirst, true, ns.s));
+    } else
+#endif
+    {
+      IX_CUDA(cudaMemcpyAsync(dbuf, host_in[il], npts * nfirst * sizeof(double), cudaMemcpyHostToDevice, ns.s));
+      IX_TRY(k::unpack(L.lbox(il), ns.S_new.v(il), dbuf, nfirst, ns.s));
+    }
 #if !defined(IX_EMUL)
     if (late) {   // the tracer follows on the second stream, after everything already queued on the main stream (previous readers)
       double* tb = dbuf + npts * (NUM_STATE - 1);
       IX_CUDA(cudaEventRecord(ns.ev_prev, ns.s));
       IX_CUDA(cudaStreamWaitEvent(ns.s2, ns.ev_prev, 0));
-      IX_CUDA(cudaMemcpyAsync(tb, host_in[il] + npts * (NUM_STATE - 1), npts * sizeof(double), cudaMemcpyHostToDevice, ns.s2));
-      IX_TRY(k::unpack(L.lbox(il), ns.S_new.v(il, Tracer), tb, 1, ns.s2));
+      if (e2e_3d()) {
+        IX_TRY(copy3d(L.lbox(il), ns.S_new.v(il), Tracer, const_cast<double*>(host_in[il]) + npts * (NUM_STATE - 1), 1, true, ns.s2));
+      } else {
+        IX_CUDA(cudaMemcpyAsync(tb, host_in[il] + npts * (NUM_STATE - 1), npts * sizeof(double), cudaMemcpyHostToDevice, ns.s2));
+        IX_TRY(k::unpack(L.lbox(il), ns.S_new.v(il, Tracer), tb, 1, ns.s2));
+      }
       IX_CUDA(cudaEventRecord(ns.ev_in, ns.s2));
       ns.late_tracer = true;
     }
@@ -863,6 +900,9 @@ int iamrx_ns_step_host(iamrx_ns_t nsp, const double* const* host_in, double* con
   const int nout = early ? Density : NUM_STATE;   // velocity only when the scalars already left
   for (int il = 0; il < L.nlocal(); ++il) {
     const size_t n = (size_t)L.lbox(il).npts() * nout;
+#if !defined(IX_EMUL)
+    if (e2e_3d()) { IX_TRY(copy3d(L.lbox(il), ns.S_new.v(il), 0, host_out[il], nout, false, ns.s)); continue; }
+#endif
     IX_TRY(k::pack(L.lbox(il), dbuf, ns.S_new.c(il), nout, ns.s));
     IX_CUDA(cudaMemcpyAsync(host_out[il], dbuf, n * sizeof(double), cudaMemcpyDeviceToHost, ns.s));
   }
