@@ -451,7 +451,7 @@ nodal_tile_kernel(Bx bx, V4 out, C4 phi, C4 rhs, C4 sig, double facx, double fac
 // (8-byte cp.async; columns stored de-interleaved, even | odd, so that the stride-2 accesses of one
 // colour are contiguous in shared memory).  One warp per tile row, one lane per node of the colour.
 namespace fused {
-constexpr int TXI = 56, TYI = 14, NC = 64, HALF = 32, NR = TYI + 4, NT = 256;
+constexpr int TXI = 56, TYI = 14, NC = 64, HALF = 32, NR = TYI + 4;
 
 IX_D int wrap_node_any(int g, int lo, int hi) {  // any distance; node hi duplicates node lo
   if (g >= lo && g <= hi) return g;
@@ -597,15 +597,20 @@ IX_D void blk_pass(double (*sp)[NC], int ty, int cm, int c0, int cp, const Q1F& 
   sp[ty][c0] = x0 + (B.r[CX + 2 * CY] - y) * __drcp_rn(s0);
 }
 
-template <bool BLK>
-__global__ void __launch_bounds__(NT, 4)
+// NRT = rows of the staged tile (NRT - 4 of them updated): 18 (8 warps, 46 KB, four CTAs per SM) or 34 (16 warps, 87 KB, two
+// CTAs per SM; 30 of 34 instead of 14 of 18 staged rows are useful).  Dynamic shared memory: 5 planes of NRT x NC doubles.
+template <bool BLK, int NRT>
+__global__ void __launch_bounds__(16 * (NRT - 2), NRT == NR ? 4 : 2)
 gs_sweep_kernel(Bx bx, V4 out, C4 pin, C4 padj, C4 rhs, C4 sig, IX_KARG(Q1F) q, int k0, int zwrap, int zmir, int xyg) {
-  __shared__ double sp[3][NR][NC];
-  __shared__ double ss[2][NR][NC];
+  static_assert(BLK || NRT == NR, "the one-node-per-thread passes are written for the 18-row tile");
+  constexpr int NTT = 16 * (NRT - 2), RPP = NTT / 64, TYT = NRT - 4, NWB = (NRT - 2) / 2;   // threads, rows per staging pass, updated rows, warps
+  extern __shared__ double smraw[];
+  double (*sp)[NRT][NC] = reinterpret_cast<double (*)[NRT][NC]>(smraw);
+  double (*ss)[NRT][NC] = sp + 3;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const bool bgx = bx.hi[0] - bx.lo[0] >= NC, bgy = bx.hi[1] - bx.lo[1] >= NC;   // a tile reaches less than one period beyond the box
   const int X0 = (bx.lo[0] - (bx.lo[0] & 1)) + TXI * (int)blockIdx.x - 4;   // global node index of tile column 0
-  const int Y0 = (bx.lo[1] - (bx.lo[1] & 1)) + TYI * (int)blockIdx.y - 2;   // ... of tile row 0
+  const int Y0 = (bx.lo[1] - (bx.lo[1] & 1)) + TYT * (int)blockIdx.y - 2;   // ... of tile row 0
   const int k = k0 + 2 * (int)blockIdx.z;
   // z neighbours: periodic images when the box spans the domain in z, else the (filled) ghost planes / ghost cells
   // zmir bit 0 / 1: the low / high z side is a Neumann side (mirrored ghost plane, evaluated in place)
@@ -628,14 +633,14 @@ gs_sweep_kernel(Bx bx, V4 out, C4 pin, C4 padj, C4 rhs, C4 sig, IX_KARG(Q1F) q, 
     const double* s1p = sig.p + (ci - sig.l0) + (int64_t)(ckp - sig.l2) * sig.ks;
     const int pjs = (int)pin.js, ajs = (int)padj.js, sjs = (int)sig.js;
 #pragma unroll
-    for (int m = 0; m < 5; ++m) {
-      const int r = r0 + 4 * m;
-      if (r <= 17) {
+    for (int m = 0; m < (NRT - 1 + RPP - 1) / RPP; ++m) {
+      const int r = r0 + RPP * m;
+      if (r <= NRT - 1) {
         const int gj = halo_node_f(Y0 + r, bx.lo[1], bx.hi[1], xyg & 2, bgy);
         tile::cp_async8(&sp[0][r][sc], pm + (gj - padj.l1) * ajs);
         tile::cp_async8(&sp[1][r][sc], pk + (gj - pin.l1) * pjs);
         tile::cp_async8(&sp[2][r][sc], pp + (gj - padj.l1) * ajs);
-        if (r <= 16) {
+        if (r <= NRT - 2) {
           const int cj = halo_cell_f(Y0 + r, bx.lo[1], bx.hi[1], xyg & 2, bgy) - sig.l1;
           tile::cp_async8(&ss[0][r][sc], s0p + cj * sjs);
           tile::cp_async8(&ss[1][r][sc], s1p + cj * sjs);
@@ -644,7 +649,7 @@ gs_sweep_kernel(Bx bx, V4 out, C4 pin, C4 padj, C4 rhs, C4 sig, IX_KARG(Q1F) q, 
     }
   }
   asm volatile("cp.async.commit_group;" ::: "memory");
-  if (BLK) {
+  if constexpr (BLK) {
     // block (warp, lane): node columns a = 2 (lane + 1), a + 1; rows b = 2 + 2 warp, b + 1
     const int lp = lane + 1, a = 2 * lp, b = 2 + 2 * warp;
     const bool act = lane <= 30;
@@ -659,7 +664,7 @@ gs_sweep_kernel(Bx bx, V4 out, C4 pin, C4 padj, C4 rhs, C4 sig, IX_KARG(Q1F) q, 
     }
     // de-interleaved slots of columns a-1, a, a+1, a+2 (column 64 and row 18 only feed nodes that are never updated: clamped)
     const int sA = HALF + lp - 1, sB = lp, sC = HALF + lp, sD = min(lp + 1, HALF - 1);
-    const int r3 = min(b + 2, NR - 1);
+    const int r3 = min(b + 2, NRT - 1);
     asm volatile("cp.async.wait_group 0;" ::: "memory");
     __syncthreads();
     if (act) {
@@ -670,9 +675,9 @@ gs_sweep_kernel(Bx bx, V4 out, C4 pin, C4 padj, C4 rhs, C4 sig, IX_KARG(Q1F) q, 
     __syncthreads();
     if (lane <= 29) blk_pass<1, 0>(sp[1], b, sB, sC, sD, q, B);                    // columns 3 .. 61
     __syncthreads();
-    if (lane >= 1 && lane <= 29 && warp <= 6) blk_pass<0, 1>(sp[1], b + 1, sA, sB, sC, q, B);   // columns 4 .. 60, rows 3 .. 15
+    if (lane >= 1 && lane <= 29 && warp <= NWB - 2) blk_pass<0, 1>(sp[1], b + 1, sA, sB, sC, q, B);   // columns 4 .. 60, rows 3 .. 15
     __syncthreads();
-    if (lane >= 1 && lane <= 28 && warp <= 6) blk_pass<1, 1>(sp[1], b + 1, sB, sC, sD, q, B);   // columns 5 .. 59
+    if (lane >= 1 && lane <= 28 && warp <= NWB - 2) blk_pass<1, 1>(sp[1], b + 1, sB, sC, sD, q, B);   // columns 5 .. 59
     __syncthreads();
   } else {
   // right-hand sides of the (up to) four nodes this thread updates, one per colour
@@ -686,16 +691,18 @@ gs_sweep_kernel(Bx bx, V4 out, C4 pin, C4 padj, C4 rhs, C4 sig, IX_KARG(Q1F) q, 
   }
   asm volatile("cp.async.wait_group 0;" ::: "memory");
   __syncthreads();
-  pass<0, 0>(sp, ss, warp, lane, rv[0], q);
+  double (*sp18)[NR][NC] = reinterpret_cast<double (*)[NR][NC]>(smraw);
+  double (*ss18)[NR][NC] = sp18 + 3;
+  pass<0, 0>(sp18, ss18, warp, lane, rv[0], q);
   __syncthreads();
-  pass<1, 0>(sp, ss, warp, lane, rv[1], q);
+  pass<1, 0>(sp18, ss18, warp, lane, rv[1], q);
   __syncthreads();
-  pass<0, 1>(sp, ss, warp, lane, rv[2], q);
+  pass<0, 1>(sp18, ss18, warp, lane, rv[2], q);
   __syncthreads();
-  pass<1, 1>(sp, ss, warp, lane, rv[3], q);
+  pass<1, 1>(sp18, ss18, warp, lane, rv[3], q);
   __syncthreads();
   }
-  for (int e = tid; e < TXI * TYI; e += NT) {
+  for (int e = tid; e < TXI * TYT; e += NTT) {
     const int tx = 4 + e % TXI, ty = 2 + e / TXI;
     const int gi = X0 + tx, gj = Y0 + ty;
     if (gi >= bx.lo[0] && gi <= bx.hi[0] && gj >= bx.lo[1] && gj <= bx.hi[1]) out(gi, gj, k) = sp[1][ty][col(tx)];
@@ -979,20 +986,32 @@ int nodal_gs_sweep(const Bx& nbx, V4 phi_out, C4 phi_in, C4 rhs, C4 sig, const d
   q.f0j = q1_factor(false, true, false, f[0], f[1], f[2]);  q.f1j = q1_factor(true, true, false, f[0], f[1], f[2]);
   q.f0k = q1_factor(false, false, true, f[0], f[1], f[2]);  q.f1k = q1_factor(true, false, true, f[0], f[1], f[2]);
   q.f0jk = q1_factor(false, true, true, f[0], f[1], f[2]);  q.f1jk = q1_factor(true, true, true, f[0], f[1], f[2]);
-  const int gx = cdiv(nbx.hi[0] - (nbx.lo[0] - (nbx.lo[0] & 1)) + 1, TXI), gy = cdiv(nbx.hi[1] - (nbx.lo[1] - (nbx.lo[1] & 1)) + 1, TYI);
+  static int blk = -1, tall = -1;   // IAMRX_NODAL_BLOCK=0: one node per thread and colour (the first fused kernel); IAMRX_NODAL_TALL=1: 34-row tiles
+  if (blk < 0) { const char* e = getenv("IAMRX_NODAL_BLOCK"); blk = (e && e[0] == '0') ? 0 : 1; }
+  if (tall < 0) { const char* e = getenv("IAMRX_NODAL_TALL"); tall = (e && e[0] == '1') ? 1 : 0; }   // measured slower (293 vs 278 us per 257^3 sweep): opt-in
+  constexpr int NRTALL = 34;
+  static bool attr_set = false;
+  if (!attr_set) {
+    IX_CUDA(cudaFuncSetAttribute(gs_sweep_kernel<true, NRTALL>, cudaFuncAttributeMaxDynamicSharedMemorySize, 5 * NRTALL * NC * (int)sizeof(double)));
+    attr_set = true;
+  }
+  const int ylen = nbx.hi[1] - (nbx.lo[1] - (nbx.lo[1] & 1)) + 1;
+  const bool use_tall = blk && tall && ylen >= 4 * (NRTALL - 4);
+  const int tyi = use_tall ? NRTALL - 4 : TYI;
+  const int gx = cdiv(nbx.hi[0] - (nbx.lo[0] - (nbx.lo[0] & 1)) + 1, TXI), gy = cdiv(ylen, tyi);
   for (int cz = 0; cz < 2; ++cz) {
     if (phase >= 0 && phase != cz) continue;
     const int k0 = nbx.lo[2] + ((cz - nbx.lo[2]) & 1);
     if (k0 > nbx.hi[2]) continue;
     const int nk = (nbx.hi[2] - k0) / 2 + 1;
     // phase A (even planes): neighbours = old odd planes; phase B (odd planes): neighbours = new even planes
-    static int blk = -1;   // IAMRX_NODAL_BLOCK=0: one node per thread and colour (the first fused kernel)
-    if (blk < 0) { const char* e = getenv("IAMRX_NODAL_BLOCK"); blk = (e && e[0] == '0') ? 0 : 1; }
     const int xyg = (wrapmask & NODAL_DEEP_GHOSTS) ? (((wrapmask & 1) ? 0 : 1) | ((wrapmask & 2) ? 0 : 2)) : 0;
-    if (blk) IX_LAUNCH(gs_sweep_kernel<true>, dim3(gx, gy, nk), dim3(NT, 1, 1), 0, s, nbx, phi_out, phi_in, cz == 0 ? phi_in : pout, rhs, sig,
-                       q, k0, (wrapmask & 4) ? 1 : 0, (wrapmask >> 7) & 3, xyg);
-    else IX_LAUNCH(gs_sweep_kernel<false>, dim3(gx, gy, nk), dim3(NT, 1, 1), 0, s, nbx, phi_out, phi_in, cz == 0 ? phi_in : pout, rhs, sig,
-                   q, k0, (wrapmask & 4) ? 1 : 0, (wrapmask >> 7) & 3, xyg);
+#define IX_GSW(B, R) IX_LAUNCH((gs_sweep_kernel<B, R>), dim3(gx, gy, nk), dim3(16 * (R - 2), 1, 1), 5 * R * NC * sizeof(double), s, nbx, phi_out, phi_in, \
+                               cz == 0 ? phi_in : pout, rhs, sig, q, k0, (wrapmask & 4) ? 1 : 0, (wrapmask >> 7) & 3, xyg)
+    if (use_tall) IX_GSW(true, NRTALL);
+    else if (blk) IX_GSW(true, NR);
+    else IX_GSW(false, NR);
+#undef IX_GSW
     const int rc = check_launch("nodal_gs_sweep");
     if (rc != IAMRX_OK) return rc;
   }
