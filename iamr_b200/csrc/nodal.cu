@@ -585,7 +585,7 @@ IX_D void blk_adjacent(const double (*sp)[NC], const double (*ss)[NC], int b, in
 // colour pass (CX, CY) of the block: node column slot c0 (neighbours cm, cp), row ty.  The update divides by the diagonal
 // through a correctly rounded reciprocal (a fraction of the instructions of an IEEE division; last-bit differences).
 template <int CX, int CY>
-IX_D void blk_pass(double (*sp)[NC], int ty, int cm, int c0, int cp, const Q1F& q, const Blk& B) {
+IX_D double blk_pass(double (*sp)[NC], int ty, int cm, int c0, int cp, const Q1F& q, const Blk& B) {
   const double mj0 = B.z[CY][CX], pj0 = B.z[CY][CX + 1], mj1 = B.z[CY + 1][CX], pj1 = B.z[CY + 1][CX + 1];
   const double mc = mj0 + mj1, pc = pj0 + pj1;
   const double s0 = q.f0c * (mc + pc);
@@ -594,12 +594,16 @@ IX_D void blk_pass(double (*sp)[NC], int ty, int cm, int c0, int cp, const Q1F& 
   const double a1j = mj0 * sp[ty - 1][cm] + pj0 * sp[ty - 1][cp] + mj1 * sp[ty + 1][cm] + pj1 * sp[ty + 1][cp];
   const double a0j = (mj0 + pj0) * sp[ty - 1][c0] + (mj1 + pj1) * sp[ty + 1][c0];
   const double y = s0 * x0 + q.f1c * a1c + q.f1j * a1j + q.f0j * a0j;
-  sp[ty][c0] = x0 + (B.r[CX + 2 * CY] - y) * __drcp_rn(s0);
+  const double v = x0 + (B.r[CX + 2 * CY] - y) * __drcp_rn(s0);
+  sp[ty][c0] = v;
+  return v;
 }
 
 // NRT = rows of the staged tile (NRT - 4 of them updated): 18 (8 warps, 46 KB, four CTAs per SM) or 34 (16 warps, 87 KB, two
 // CTAs per SM; 30 of 34 instead of 14 of 18 staged rows are useful).  Dynamic shared memory: 5 planes of NRT x NC doubles.
-template <bool BLK, int NRT>
+// FAST: the box is at least a tile wide in x and y and its tile halos are periodic images (no deep ghost layers): halo indices by
+// one compare-and-shift, no integer division and no per-variant branches in the staging code (half of the kernel's instructions).
+template <bool BLK, int NRT, bool FAST>
 __global__ void __launch_bounds__(16 * (NRT - 2), NRT == NR ? 4 : 2)
 gs_sweep_kernel(Bx bx, V4 out, C4 pin, C4 padj, C4 rhs, C4 sig, IX_KARG(Q1F) q, int k0, int zwrap, int zmir, int xyg) {
   static_assert(BLK || NRT == NR, "the one-node-per-thread passes are written for the 18-row tile");
@@ -608,7 +612,8 @@ gs_sweep_kernel(Bx bx, V4 out, C4 pin, C4 padj, C4 rhs, C4 sig, IX_KARG(Q1F) q, 
   double (*sp)[NRT][NC] = reinterpret_cast<double (*)[NRT][NC]>(smraw);
   double (*ss)[NRT][NC] = sp + 3;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const bool bgx = bx.hi[0] - bx.lo[0] >= NC, bgy = bx.hi[1] - bx.lo[1] >= NC;   // a tile reaches less than one period beyond the box
+  const bool bgx = FAST || bx.hi[0] - bx.lo[0] >= NC, bgy = FAST || bx.hi[1] - bx.lo[1] >= NC;   // a tile reaches less than one period beyond the box
+  if (FAST) xyg = 0;
   const int X0 = (bx.lo[0] - (bx.lo[0] & 1)) + TXI * (int)blockIdx.x - 4;   // global node index of tile column 0
   const int Y0 = (bx.lo[1] - (bx.lo[1] & 1)) + TYT * (int)blockIdx.y - 2;   // ... of tile row 0
   const int k = k0 + 2 * (int)blockIdx.z;
@@ -667,18 +672,31 @@ gs_sweep_kernel(Bx bx, V4 out, C4 pin, C4 padj, C4 rhs, C4 sig, IX_KARG(Q1F) q, 
     const int r3 = min(b + 2, NRT - 1);
     asm volatile("cp.async.wait_group 0;" ::: "memory");
     __syncthreads();
+    double v00 = 0.0, v10 = 0.0, v01 = 0.0, v11 = 0.0;   // the block's new values (every node is updated once: they are final)
     if (act) {
       blk_adjacent(sp[0], ss[0], b, r3, sA, sB, sC, sD, q, B, true);
       blk_adjacent(sp[2], ss[1], b, r3, sA, sB, sC, sD, q, B, false);
-      blk_pass<0, 0>(sp[1], b, sA, sB, sC, q, B);                                  // columns 2 .. 62, rows 2 .. 16
+      v00 = blk_pass<0, 0>(sp[1], b, sA, sB, sC, q, B);                                  // columns 2 .. 62, rows 2 .. 16
     }
     __syncthreads();
-    if (lane <= 29) blk_pass<1, 0>(sp[1], b, sB, sC, sD, q, B);                    // columns 3 .. 61
+    if (lane <= 29) v10 = blk_pass<1, 0>(sp[1], b, sB, sC, sD, q, B);                    // columns 3 .. 61
     __syncthreads();
-    if (lane >= 1 && lane <= 29 && warp <= NWB - 2) blk_pass<0, 1>(sp[1], b + 1, sA, sB, sC, q, B);   // columns 4 .. 60, rows 3 .. 15
+    if (lane >= 1 && lane <= 29 && warp <= NWB - 2) v01 = blk_pass<0, 1>(sp[1], b + 1, sA, sB, sC, q, B);   // columns 4 .. 60, rows 3 .. 15
     __syncthreads();
-    if (lane >= 1 && lane <= 28 && warp <= NWB - 2) blk_pass<1, 1>(sp[1], b + 1, sB, sC, sD, q, B);   // columns 5 .. 59
-    __syncthreads();
+    if (lane >= 1 && lane <= 28 && warp <= NWB - 2) v11 = blk_pass<1, 1>(sp[1], b + 1, sB, sC, sD, q, B);   // columns 5 .. 59
+    // the tile's interior (columns 4 .. 59, rows 2 .. NRT - 3) straight from the registers: the two stores of a row pair fill
+    // each other's sector halves
+    {
+      const int gi = X0 + a, gj = Y0 + b;
+      const bool c0 = lane >= 1 && lane <= 28 && gi >= bx.lo[0] && gi <= bx.hi[0], c1 = lane >= 1 && lane <= 28 && gi + 1 >= bx.lo[0] && gi + 1 <= bx.hi[0];
+      const bool r0 = warp <= NWB - 2 && gj >= bx.lo[1] && gj <= bx.hi[1], r1 = warp <= NWB - 2 && gj + 1 >= bx.lo[1] && gj + 1 <= bx.hi[1];
+      double* op = out.p + (gi - out.l0) + (int64_t)(gj - out.l1) * out.js + (int64_t)(k - out.l2) * out.ks;
+      if (r0 && c0) op[0] = v00;
+      if (r0 && c1) op[1] = v10;
+      if (r1 && c0) op[out.js] = v01;
+      if (r1 && c1) op[out.js + 1] = v11;
+    }
+    return;
   } else {
   // right-hand sides of the (up to) four nodes this thread updates, one per colour
   double rv[4];
@@ -701,11 +719,11 @@ gs_sweep_kernel(Bx bx, V4 out, C4 pin, C4 padj, C4 rhs, C4 sig, IX_KARG(Q1F) q, 
   __syncthreads();
   pass<1, 1>(sp18, ss18, warp, lane, rv[3], q);
   __syncthreads();
-  }
-  for (int e = tid; e < TXI * TYT; e += NTT) {
+  for (int e = tid; e < TXI * TYT; e += NTT) {   // the interior from shared memory
     const int tx = 4 + e % TXI, ty = 2 + e / TXI;
     const int gi = X0 + tx, gj = Y0 + ty;
     if (gi >= bx.lo[0] && gi <= bx.hi[0] && gj >= bx.lo[1] && gj <= bx.hi[1]) out(gi, gj, k) = sp[1][ty][col(tx)];
+  }
   }
 }
 }  // namespace fused
@@ -992,7 +1010,7 @@ int nodal_gs_sweep(const Bx& nbx, V4 phi_out, C4 phi_in, C4 rhs, C4 sig, const d
   constexpr int NRTALL = 34;
   static bool attr_set = false;
   if (!attr_set) {
-    IX_CUDA(cudaFuncSetAttribute(gs_sweep_kernel<true, NRTALL>, cudaFuncAttributeMaxDynamicSharedMemorySize, 5 * NRTALL * NC * (int)sizeof(double)));
+    IX_CUDA(cudaFuncSetAttribute(gs_sweep_kernel<true, NRTALL, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 5 * NRTALL * NC * (int)sizeof(double)));
     attr_set = true;
   }
   const int ylen = nbx.hi[1] - (nbx.lo[1] - (nbx.lo[1] & 1)) + 1;
@@ -1006,11 +1024,13 @@ int nodal_gs_sweep(const Bx& nbx, V4 phi_out, C4 phi_in, C4 rhs, C4 sig, const d
     const int nk = (nbx.hi[2] - k0) / 2 + 1;
     // phase A (even planes): neighbours = old odd planes; phase B (odd planes): neighbours = new even planes
     const int xyg = (wrapmask & NODAL_DEEP_GHOSTS) ? (((wrapmask & 1) ? 0 : 1) | ((wrapmask & 2) ? 0 : 2)) : 0;
-#define IX_GSW(B, R) IX_LAUNCH((gs_sweep_kernel<B, R>), dim3(gx, gy, nk), dim3(16 * (R - 2), 1, 1), 5 * R * NC * sizeof(double), s, nbx, phi_out, phi_in, \
-                               cz == 0 ? phi_in : pout, rhs, sig, q, k0, (wrapmask & 4) ? 1 : 0, (wrapmask >> 7) & 3, xyg)
-    if (use_tall) IX_GSW(true, NRTALL);
-    else if (blk) IX_GSW(true, NR);
-    else IX_GSW(false, NR);
+    const bool fast = xyg == 0 && nbx.hi[0] - nbx.lo[0] >= NC && nbx.hi[1] - nbx.lo[1] >= NC;
+#define IX_GSW(B, R, F) IX_LAUNCH((gs_sweep_kernel<B, R, F>), dim3(gx, gy, nk), dim3(16 * (R - 2), 1, 1), 5 * R * NC * sizeof(double), s, nbx, phi_out, phi_in, \
+                                  cz == 0 ? phi_in : pout, rhs, sig, q, k0, (wrapmask & 4) ? 1 : 0, (wrapmask >> 7) & 3, xyg)
+    if (use_tall) IX_GSW(true, NRTALL, false);
+    else if (blk && fast) IX_GSW(true, NR, true);
+    else if (blk) IX_GSW(true, NR, false);
+    else IX_GSW(false, NR, false);
 #undef IX_GSW
     const int rc = check_launch("nodal_gs_sweep");
     if (rc != IAMRX_OK) return rc;
