@@ -438,6 +438,7 @@ int initial_velocity_diffusion_update(iamrx_ns_s& ns, double time, double dt) {
 }
 
 // Projection::level_project (Projection.cpp:166-450) + doMLMGNodalProjection (:2385-2567)
+int inflow_ghost_velocity(iamrx_ns_s& ns, MF& vel, double scale);
 int level_project(iamrx_ns_s& ns, double dt) {
   Level& L = *ns.L;
   IX_TRY(mf_setval(ns.P_new, 0.0, 0, 1, 1, ns.s));   // :247-256
@@ -446,6 +447,7 @@ int level_project(iamrx_ns_s& ns, double dt) {
   for (int il = 0; il < ns.sig.n(); ++il)            // scaleVar :332, :1327-1349
     IX_TRY(k::invert(L.lbox(il), ns.sig.v(il), ns.rho_half.c(il), ns.s));
   MF vel; vel.alias(&L, IX_CELL, 3, 1, ns.S_new.fabs.data());  // comps 0..2 of the state
+  IX_TRY(inflow_ghost_velocity(ns, vel, 1.0 / dt));
   iamrx_mg_info mi = mg_info(ns, ns.p.proj_tol, ns.p.proj_abs_tol);
   const k::NodalBC nbc = ns.nodal_bc();
   IX_SOLVE(nodal_project(L, *ns.sv, vel, ns.sig, ns.P_new, &ns.Gp_new, 0, &mi, ns.s, ns.walls ? &nbc : nullptr));  // :392 ; Gp = grad phi :2542-2563
@@ -525,6 +527,35 @@ int est_time_step(iamrx_ns_s& ns, double* out) {
   return IAMRX_OK;
 }
 
+// Velocity ghost cells beyond INFLOW faces as the nodal projections see them: setPhysBoundaryValues (Projection.cpp:211-217,
+// 729, 1096-1097) puts the inflow velocity there and set_boundary_velocity(inflowCorner = true) (:2570-2663) keeps its normal
+// component on the face cells and their periodic / interior-neighbour extensions and zeroes it in the corners outside walls.
+// `scale`: 1 for initialVelocityProject, 1/dt for level_project (U_new.mult(dt_inv, ..., 1 ghost) :274), 0 for initialSyncProject
+// ((U_new - U_old)/dt of a steady inflow value, ConvertUnew on the grown box :1192-1232).
+int inflow_ghost_velocity(iamrx_ns_s& ns, MF& vel, double scale) {
+  Level& L = *ns.L;
+  for (int il = 0; il < vel.n(); ++il)
+    for (int d = 0; d < 3; ++d) {
+      if (L.geom.periodic[d]) continue;
+      for (int side = 0; side < 2; ++side) {
+        if ((side == 0 ? ns.p.lo_bc[d] : ns.p.hi_bc[d]) != 1) continue;
+        const Bx b = L.lbox(il);
+        if (side == 0 ? b.lo[d] != L.domain.lo[d] : b.hi[d] != L.domain.hi[d]) continue;
+        const int g = side == 0 ? L.domain.lo[d] - 1 : L.domain.hi[d] + 1;
+        Bx R = grow(b, 1); R.lo[d] = R.hi[d] = g;
+        IX_TRY(k::setval(R, vel.v(il, d), 1, 0.0, ns.s));
+        Bx P = b; P.lo[d] = P.hi[d] = g;
+        for (int o = 0; o < 3; ++o) {
+          if (o == d) continue;
+          if (L.geom.periodic[o] || b.lo[o] != L.domain.lo[o]) P.lo[o] -= 1;
+          if (L.geom.periodic[o] || b.hi[o] != L.domain.hi[o]) P.hi[o] += 1;
+        }
+        IX_TRY(k::setval(P, vel.v(il, d), 1, scale * ns.p.bc_vals[side == 0 ? d : 3 + d][d], ns.s));
+      }
+    }
+  return IAMRX_OK;
+}
+
 int project_simple(iamrx_ns_s& ns, MF& vel, const MF& sigma, MF& phi, MF* gp, int incr, int* iters) {
   iamrx_mg_info mi = mg_info(ns, ns.p.proj_tol, ns.p.proj_abs_tol);
   const k::NodalBC nbc = ns.nodal_bc();
@@ -580,7 +611,10 @@ int iamrx_ns_create(iamrx_level_t lev, const iamrx_ns_params* p, iamrx_ns_t* out
       walls = true;
       for (int v : {p->lo_bc[d], p->hi_bc[d]}) {
         IX_ARG(v >= 1 && v <= 5, "ns.lo_bc / ns.hi_bc of a non-periodic direction must be 1..5 (inputs.3d.taylorgreen:100-102)");
-        IX_ARG(v >= 3, "the step driver implements symmetry (3), slip-wall (4) and no-slip-wall (5) boundaries; inflow / outflow only at operator level");
+        // Projection::set_outflow_bcs / OutFlowBC (the outflow pressure profile under gravity or divu) is not restated: IAMR calls it
+        // only when have_divu or gravity != 0 (Projection.cpp:309-324,896-899; MacProj.cpp:265), so inflow / outflow runs without
+        // gravity take the plain path -- phi = 0 on the outflow face
+        IX_ARG(v >= 3 || p->gravity == 0.0, "inflow / outflow boundaries together with gravity need Projection::set_outflow_bcs, which is not implemented");
       }
     }
   }
@@ -696,6 +730,7 @@ int iamrx_ns_post_init(iamrx_ns_t nsp, double* dt0) {
       IX_TRY(mf_setval(ns.P_old, 0.0, 0, 1, 1, ns.s));
       IX_TRY(mf_setval(ns.sig, 1.0, 0, 1, 1, ns.s));
       MF vel; vel.alias(&L, IX_CELL, 3, 1, ns.S_new.fabs.data());
+      IX_TRY(inflow_ghost_velocity(ns, vel, 1.0));
       IX_TRY(project_simple(ns, vel, ns.sig, ns.P_old, nullptr, 0, nullptr));
       IX_TRY(mf_setval(ns.P_old, 0.0, 0, 1, 1, ns.s));
       IX_TRY(mf_setval(ns.P_new, 0.0, 0, 1, 1, ns.s));
@@ -736,6 +771,7 @@ int iamrx_ns_post_init(iamrx_ns_t nsp, double* dt0) {
                           ns.S_old.c(il, Xvel), 3, ns.s));
       for (int il = 0; il < ns.sig.n(); ++il) IX_TRY(k::invert(L.lbox(il), ns.sig.v(il), ns.rho_half.c(il), ns.s));
       MF vel; vel.alias(&L, IX_CELL, 3, 1, ns.S_new.fabs.data());
+      IX_TRY(inflow_ghost_velocity(ns, vel, 0.0));
       IX_TRY(project_simple(ns, vel, ns.sig, ns.P_old, &ns.Gp_new, 1, &ns.it_nodal));
       IX_TRY(mf_lincomb(ns.P_new, 0, 1.0, ns.P_new, 0, 1.0, ns.P_old, 0, 1, 1, ns.s));  // :1166-1170
       IX_TRY(fill_gradp(ns, ns.Gp_new));

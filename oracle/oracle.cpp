@@ -1749,12 +1749,34 @@ struct orc_ns {
       }
     }
   }
+  // Velocity ghost cells beyond INFLOW faces for the nodal projections: setPhysBoundaryValues (Projection.cpp:211-217, 729,
+  // 1096-1097) + set_boundary_velocity with inflowCorner = true (:2570-2663): normal component = scale * inflow value on the face
+  // cells and their periodic extensions, zero in the corners outside walls.  scale: 1 (initialVelocityProject), 1/dt
+  // (level_project: U_new.mult(dt_inv, 0, 3, 1) :274), 0 (initialSyncProject of a steady inflow value, ConvertUnew :1192-1232)
+  void inflow_ghost_velocity(Arr& vel, double scale) const {
+    for (int d = 0; d < 3; ++d) {
+      if (per[d]) continue;
+      const int d1 = (d + 1) % 3, d2 = (d + 2) % 3;
+      for (int side = 0; side < 2; ++side) {
+        if ((side == 0 ? phys_lo[d] : phys_hi[d]) != PHYS_INFLOW) continue;
+        const int g = side == 0 ? -1 : n[d];
+        const double v = scale * bcv[side == 0 ? d : 3 + d][d];
+        for (int b2 = -1; b2 <= n[d2]; ++b2)
+          for (int b1 = -1; b1 <= n[d1]; ++b1) {
+            const bool in1 = (b1 >= 0 && b1 < n[d1]) || per[d1], in2 = (b2 >= 0 && b2 < n[d2]) || per[d2];
+            int q[3]; q[d] = g; q[d1] = b1; q[d2] = b2;
+            vel(q[0], q[1], q[2], d) = (in1 && in2) ? v : 0.0;
+          }
+      }
+    }
+  }
   // Projection::level_project Projection.cpp:166-450
   int level_project(double dt) {
     P_new.setval(0.0);
     Arr vel(n, 3, 1), sig(n, 1, 1);
     for (int c = 0; c < 3; ++c) { FOR_CELLS(vel, i, j, k) vel(i, j, k, c) = S_new(i, j, k, c) * (1.0 / dt) + Gp_old(i, j, k, c) / rho_half(i, j, k); }
     FOR_CELLS(sig, i, j, k) sig(i, j, k) = 1.0 / rho_half(i, j, k);
+    inflow_ghost_velocity(vel, 1.0 / dt);
     orc_mg m = mg(p.proj_tol, p.proj_abs_tol);
     const int rc = nodal_project(n, dx, vel, sig, P_new, &Gp_new, false, &m, nodal_bc());
     it[2] = m.iters;
@@ -2222,7 +2244,7 @@ orc_ns* orc_ns_create(const int n[3], const double prob_lo[3], const double prob
   return ns;
 }
 /* physical boundaries of the level (geometry.is_periodic, ns.lo_bc / ns.hi_bc, the Dirichlet face values of NS.cpp:108-237):
- * call right after orc_ns_create.  Walls and symmetry planes only (inflow / outflow are exercised at operator level). */
+ * call right after orc_ns_create.  Walls, symmetry planes, inflow and (without gravity: no set_outflow_bcs) outflow. */
 void orc_ns_set_bc(orc_ns* ns, const int per[3], const int phys_lo[3], const int phys_hi[3], const double* bcv /*[6][5]*/) {
   for (int d = 0; d < 3; ++d) { ns->per[d] = per[d]; ns->phys_lo[d] = phys_lo[d]; ns->phys_hi[d] = phys_hi[d]; }
   if (bcv) for (int f = 0; f < 6; ++f) for (int c = 0; c < 5; ++c) ns->bcv[f][c] = bcv[5 * f + c];
@@ -2305,6 +2327,7 @@ int orc_ns_post_init(orc_ns* ns, double* dt0) {
     for (int it = 0; it < ns->p.init_vel_iter; ++it) {
       Arr vel(n, 3, 1), sig(n, 1, 1), phi(n, 1, 2);
       vel.copy_from(ns->S_new, 0, 0, 3); sig.setval(1.0);
+      ns->inflow_ghost_velocity(vel, 1.0);
       orc_mg m = ns->mg(ns->p.proj_tol, ns->p.proj_abs_tol);
       const int rc = nodal_project(n, ns->dx, vel, sig, phi, nullptr, false, &m, ns->nodal_bc());
       if (rc) return rc;

@@ -130,7 +130,8 @@ iamrx_adapt::check(rc);
 }
 
 // ---- AmrLevel::FillPatch physical fill (NS_bcfill.H:17-167) + two-level transfer (NSB.cpp:4125-4191, 4848-4889) --------------
-void site6_fill_and_transfer(iamrx_level_t Lc, iamrx_level_t Lf, MultiFab& S_fine, MultiFab& S_crse, Vector<BCRec> const& bcs,
+void site6_fill_and_transfer(iamrx_level_t Lc, iamrx_level_t Lf, MultiFab& S_fine, MultiFab& S_crse, MultiFab& S_crse_old,
+                             Real t_crse_old, Real t_crse_new, Real time, Vector<BCRec> const& bcs,
                              const double* bc_values, MultiFab* const* fine_fluxes, MultiFab* const* crse_fluxes, Real dt_fine,
                              Real dt_crse, int ncomp, Geometry const& crse_geom) {
 // [site 6 begin]
@@ -139,6 +140,10 @@ auto bc = iamrx_adapt::bcrecs(bcs);
 // same-level ghost exchange, then the physical-boundary fill of FillPatch (ext_dir values ON the face)
 iamrx_adapt::check(iamrx_fill_boundary(Lf, sf.data(), IAMRX_IX_CELL, ncomp, S_fine.nGrow(), Gpu::gpuStream()));
 iamrx_adapt::check(iamrx_fill_physbc(Lf, sf.data(), ncomp, S_fine.nGrow(), bc.data(), bc_values, Gpu::gpuStream()));
+// on a level that does not cover the domain: FillPatchTwoLevels (coarse data linear in time between the two coarse states)
+auto so = iamrx_adapt::fabs(S_crse_old);
+iamrx_adapt::check(iamrx_fillpatch_two_levels(Lf, Lc, sf.data(), so.data(), sc.data(), t_crse_old, t_crse_new, time, ncomp, S_fine.nGrow(),
+                                              bc.data(), bc_values, Gpu::gpuStream()));
 // advective flux register: CrseInit / FineAdd during the two advances, Reflux afterwards (NS.cpp:1713-1838)
 static iamrx_fluxreg_t reg = nullptr;
 if (!reg) iamrx_adapt::check(iamrx_fluxreg_create(Lc, Lf, ncomp, &reg));

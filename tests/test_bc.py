@@ -436,6 +436,9 @@ def _assemble_padded(ns, which, boxes, n, ncomp, ng, ixtype):
 LID = [[0.0] * 5 for _ in range(6)]
 LID[5][0] = 1.0   # zhi.velocity = 1 0 0 (Tutorials/LidDrivenCavity/inputs.3d.lid_driven_cavity)
 
+INFLOW = [[0.0] * 5 for _ in range(6)]
+INFLOW[0] = [1.0, 0.0, 0.0, 1.0, 0.5]   # xlo.velocity = 1 0 0, density 1, tracer 0.5 (ns.lo_bc = 1: inflow)
+
 WALL_RUNS = [
     # RayleighTaylor 3-D single level (regtest.3d.rayleightaylor:48-49 boundaries: periodic x, y, slip walls z; gravity, inviscid)
     dict(n=(16, 16, 32), hi=(0.5, 0.5, 1.0), per=(1, 1, 0), lo_bc=(0, 0, 4), hi_bc=(0, 0, 4), probtype=10, pp=[1.0, 2.0, 1.0, 0.0, 0.05, 0.02],
@@ -454,11 +457,18 @@ WALL_RUNS = [
          kw=dict(visc_coef=0.0, cfl=0.7, gravity=-1.0, bottom_solver=1)),
     dict(n=(16, 16, 16), hi=(1.0, 1.0, 1.0), per=(0, 0, 0), lo_bc=(5, 4, 4), hi_bc=(5, 4, 3), probtype=101, pp=[1.0, 1.0, 0.3],
          kw=dict(visc_coef=0.01, cfl=0.5, gravity=-0.5, scal_diff_coef=5e-3, bottom_solver=1)),
+    # channel: inflow at x lo (ext_dir velocity and scalars), outflow at x hi (phi = 0; no gravity, so IAMR does not call
+    # set_outflow_bcs: Projection.cpp:309-324), periodic y, no-slip walls z; viscous, diffusive tracer
+    dict(n=(32, 16, 16), hi=(2.0, 1.0, 1.0), per=(0, 1, 0), lo_bc=(1, 0, 5), hi_bc=(2, 0, 5), probtype=101, pp=[1.0, 1.0, 0.3], bcv=INFLOW, iters_slack=1,
+         kw=dict(visc_coef=0.01, cfl=0.5, scal_diff_coef=5e-3)),
+    # inviscid channel between slip walls with inflow and outflow on the y sides
+    dict(n=(16, 32, 16), hi=(1.0, 2.0, 1.0), per=(1, 0, 0), lo_bc=(0, 2, 4), hi_bc=(0, 1, 4), probtype=101, pp=[1.0, 1.0, 0.3],
+         bcv=[[0.0] * 5, [0.0] * 5, [0.0] * 5, [0.0] * 5, [0.0, -1.0, 0.0, 1.0, 0.0], [0.0] * 5], iters_slack=1, kw=dict(visc_coef=0.0, cfl=0.5)),
 ]
 
 
 @pytest.mark.parametrize("run", WALL_RUNS, ids=["rayleigh_taylor", "rayleigh_taylor_regtest_options", "lid_driven_cavity", "mixed_walls",
-                                                 "rayleigh_taylor_bicgstab", "mixed_walls_bicgstab"])
+                                                 "rayleigh_taylor_bicgstab", "mixed_walls_bicgstab", "channel_inflow_outflow", "channel_y_inviscid"])
 @pytest.mark.parametrize("nb", [(1, 1, 1), (2, 2, 2)])
 def test_step_with_walls_matches_oracle(backend, oracle, run, nb):
     """post_init (incl. the hydrostatic initialPressureProject when there is gravity) + 3 steps on wall-bounded domains:
@@ -490,8 +500,8 @@ def test_step_with_walls_matches_oracle(backend, oracle, run, nb):
     sl = (slice(None), slice(2, 2 + hi[2]), slice(2, 2 + hi[1]), slice(2, 2 + hi[0]))
     a, b = P[sl], Po[sl]
     assert np.abs((a - a.mean()) - (b - b.mean())).max() <= 1e-10 * max(1.0, np.abs(b).max())
-    if nb == (1, 1, 1):
-        assert ns.last_iters() == o.last_iters()
+    if nb == (1, 1, 1):   # (a residual that crosses the tolerance within rounding may cost one V-cycle more on one side)
+        assert all(abs(x - y) <= run.get("iters_slack", 0) for x, y in zip(ns.last_iters(), o.last_iters()))
     ns.close(); o.close(); lev.close()
 
 
@@ -519,7 +529,7 @@ def test_driver_rejects_unsupported_boundaries(backend):
     g = ix.Geom.make((8, 8, 8), periodic=(0, 1, 1))
     lev = ix.Level(lib, g, [((0, 0, 0), (7, 7, 7))])
     with pytest.raises(ix.IamrxError, match="inflow / outflow"):
-        ix.NavierStokes(lib, lev, dev, lo_bc=(1, 0, 0), hi_bc=(2, 0, 0))
+        ix.NavierStokes(lib, lev, dev, lo_bc=(1, 0, 0), hi_bc=(2, 0, 0), gravity=-1.0)   # needs set_outflow_bcs
     with pytest.raises(ix.IamrxError, match="non-periodic direction"):
         ix.NavierStokes(lib, lev, dev)                       # lo_bc = 0 on a non-periodic side
     with pytest.raises(ix.IamrxError, match="periodic direction"):
