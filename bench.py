@@ -543,7 +543,9 @@ def run_ours(args):
                          "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                          "traffic_note": f"DRAM bytes per finest-level launch ({nbox}^3, algorithmic {48 * nbox ** 3}); {traffic_src}",
                          "peak_source": peak_src, "launches_timed": nl, "ms_total": t, "ms_per_step": t / max(1, args.prof_steps),
-                         "algorithmic_bytes": "48 B/cell/colour pass (a=0), 56 with alpha (SURVEY.md 8d)",
+                         "algorithmic_bytes": "per colour pass and cell: 48 B (a=0), 56 with a variable alpha (SURVEY.md 8d); 24 (+8 with alpha) when the face "
+                                              "coefficients are constants taken from the kernel arguments (viscous solves); 8 less for the first pass of a "
+                                              "correction (zero initial guess: phi is not read).  achieved = sum of these per launch / sum of launch times",
                          "fp64_peak": fp64, "other_kernels": secondary},
             "clocks": clocks,
         }
