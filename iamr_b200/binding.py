@@ -194,6 +194,7 @@ SIGNATURES = {
     "iamrx_ns_create": (C.c_int, [_vp, _P(NSParams), _P(_vp)]),
     "iamrx_ns_destroy": (C.c_int, [_vp]),
     "iamrx_debug_fb_stats": (None, [_P(C.c_int64), C.c_int]),
+    "iamrx_diffusion_get_fluxes": (C.c_int, [_vp, C.c_int, _P(Fab), _P(Fab), _P(Fab), _P(Fab), C.c_double, _P(Fab), _P(Fab), _P(Fab), C.c_double, _vp]),
     "iamrx_fillpatch_two_levels": (C.c_int, [_vp, _vp, _P(Fab), _P(Fab), _P(Fab), C.c_double, C.c_double, C.c_double, C.c_int, C.c_int,
                                              _P(BCRec), _P(C.c_double), _vp]),
     "iamrx_ns_init_prob": (C.c_int, [_vp, C.c_int, _P(C.c_double), C.c_int]),

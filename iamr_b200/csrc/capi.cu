@@ -485,6 +485,38 @@ int iamrx_mac_get_fluxes(iamrx_level_t lev, iamrx_fab* fx, iamrx_fab* fy, iamrx_
   IX_GUARD_END
 }
 
+// Diffusion::computeExtensiveFluxes (Diffusion.cpp:1463-1537) for the scalar operator: MLMG::getFluxes (-b eta_d dphi/dx_d on the
+// faces, with the ghost cells of soln as the solve's final fill left them) times fac * face area -- what diffuse_scalar hands to the
+// viscous flux registers (Diffusion.cpp:560-566).
+int iamrx_diffusion_get_fluxes(iamrx_level_t lev, int ncomp, iamrx_fab* fx, iamrx_fab* fy, iamrx_fab* fz, iamrx_fab* soln, double b,
+                               const iamrx_fab* eta_x, const iamrx_fab* eta_y, const iamrx_fab* eta_z, double fac, void* stream) {
+  IX_GUARD_BEGIN
+  IX_NEED_DEVICE();
+  IX_ARG(lev && fx && fy && fz && soln && eta_x && eta_y && eta_z && ncomp >= 1, "null argument");
+  Level* L = lev->lev.get();
+  cudaStream_t s = S(stream);
+  iamrx_fab* ff[3] = {fx, fy, fz};
+  const iamrx_fab* e[3] = {eta_x, eta_y, eta_z};
+  MF F[3], E[3];
+  for (int d = 0; d < 3; ++d) { F[d].alias(L, IX_XFACE + d, ncomp, 0, ff[d]); E[d].alias(L, IX_XFACE + d, 1, 0, e[d]); }
+  MF Sol; Sol.alias(L, IX_CELL, ncomp, 1, soln);
+  IX_TRY(mf_fill_boundary(Sol, 0, ncomp, 1, s));   // interior / periodic ghost cells; physical sides keep the caller's (solve's) values
+  const double* dx = L->geom.dx;
+  const double area[3] = {dx[1] * dx[2], dx[0] * dx[2], dx[0] * dx[1]};
+  for (int il = 0; il < Sol.n(); ++il) {
+    k::Abec op{};
+    op.a = 0.0; op.b = b; op.bncomp = 1;
+    op.bx = E[0].c(il); op.by = E[1].c(il); op.bz = E[2].c(il);
+    for (int d = 0; d < 3; ++d) op.dxinv[d] = L->dxinv[d];
+    for (int n = 0; n < ncomp; ++n) {
+      IX_TRY(k::abec_flux(L->lbox(il), F[0].v(il, n), F[1].v(il, n), F[2].v(il, n), Sol.c(il, n), op, 0, s));
+      for (int d = 0; d < 3; ++d) IX_TRY(k::scale(F[d].vbox(il), F[d].v(il, n), fac * area[d], 1, s));
+    }
+  }
+  return IAMRX_OK;
+  IX_GUARD_END
+}
+
 int iamrx_nodal_project(iamrx_level_t lev, iamrx_fab* vel, const iamrx_fab* sigma, iamrx_fab* phi,
                         iamrx_fab* gp, int increment_gp, const int lobc[3], const int hibc[3],
                         iamrx_mg_info* info, void* stream) {

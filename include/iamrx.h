@@ -416,6 +416,12 @@ int iamrx_diffusion_apply(iamrx_level_t lev, int tensor, int ncomp, iamrx_fab* o
                           iamrx_fab* soln, double a, double b, const iamrx_fab* acoef,
                           const iamrx_fab* eta_x, const iamrx_fab* eta_y,
                           const iamrx_fab* eta_z, const iamrx_linop_bc* bc, void* stream);
+/* Diffusion::computeExtensiveFluxes (Diffusion.cpp:1463-1537) for the scalar operator: f_d = fac * area_d * (-b eta_d dsoln/dx_d) on the
+ * faces of every local box (MLMG::getFluxes, then the area weighting) -- the fluxes diffuse_scalar gives to the viscous flux
+ * registers (Diffusion.cpp:560-566).  soln: ncomp components, 1 ghost: the cells beyond physical sides as the solve left them
+ * (setFinalFillBC), interior / periodic ghost cells are refilled here.  fx, fy, fz: face fabs with ncomp components. */
+int iamrx_diffusion_get_fluxes(iamrx_level_t lev, int ncomp, iamrx_fab* fx, iamrx_fab* fy, iamrx_fab* fz, iamrx_fab* soln, double b,
+                               const iamrx_fab* eta_x, const iamrx_fab* eta_y, const iamrx_fab* eta_z, double fac, void* stream);
 int iamrx_diffusion_solve(iamrx_level_t lev, int tensor, int ncomp, iamrx_fab* soln,
                           const iamrx_fab* rhs, double a, double b,
                           const iamrx_fab* acoef, const iamrx_fab* eta_x,

@@ -278,3 +278,43 @@ def test_solver_reports_nan(backend):
     assert rc == -5   # IAMRX_ERR_NAN
     assert b"NaN" in lib.dll.iamrx_last_error()
     lev.close()
+
+
+@pytest.mark.parametrize("nb", [(1, 1, 1), (2, 2, 2)])
+def test_diffusion_extensive_fluxes(backend, nb):
+    """Diffusion::computeExtensiveFluxes (Diffusion.cpp:1463-1537): fac * area * (-b eta dphi/dx) on every face (MLABecLaplacian FFlux),
+    and the identity the flux registers rely on: the divergence of the fluxes is -fac * volume * b div(eta grad phi)."""
+    lib, dev = backend
+    ncomp, b, fac = 2, 0.02, 0.35
+    eta = [0.05 * (1.0 + 0.3 * smooth_field(N, 600 + d, 1)) for d in range(3)]
+    phi = smooth_field(N, 610, ncomp)
+    area = [DX[1] * DX[2], DX[0] * DX[2], DX[0] * DX[1]]
+    ref = [-fac * area[d] * b * eta[d] * (phi - np.roll(phi, 1, 3 - d)) / DX[d] for d in range(3)]
+    boxes = split_boxes(N, nb)
+    lev = ix.Level(lib, ix.Geom.make(N), boxes)
+    keep = []
+
+    def fabs(arr, ng, t):
+        prs = [to_fab(arr, bx, ng, t, dev) for bx in boxes]
+        keep.append(prs)
+        return prs, fab_array([p[1] for p in prs])
+    _, Ex = fabs(eta[0], 0, ix.XFACE)
+    _, Ey = fabs(eta[1], 0, ix.YFACE)
+    _, Ez = fabs(eta[2], 0, ix.ZFACE)
+    _, Sol = fabs(phi, 1, ix.CELL)
+    zf = np.zeros_like(phi)
+    fx_p, Fx = fabs(zf, 0, ix.XFACE)
+    fy_p, Fy = fabs(zf, 0, ix.YFACE)
+    fz_p, Fz = fabs(zf, 0, ix.ZFACE)
+    lib.check(lib.iamrx_diffusion_get_fluxes(lev.h, ncomp, Fx, Fy, Fz, Sol, b, Ex, Ey, Ez, fac, stream_of(dev)))
+    sync(dev)
+    got = []
+    for d, (prs, t) in enumerate(((fx_p, ix.XFACE), (fy_p, ix.YFACE), (fz_p, ix.ZFACE))):
+        g, dup = from_fabs([p[0] for p in prs], boxes, 0, t, N, ncomp)
+        assert dup <= 1e-18
+        assert np.abs(g - ref[d]).max() <= 1e-14 * np.abs(ref[d]).max()
+        got.append(g)
+    div = sum(np.roll(got[d], -1, 3 - d) - got[d] for d in range(3))
+    lap = sum((np.roll(eta[d], -1, 3 - d) * (np.roll(phi, -1, 3 - d) - phi) - eta[d] * (phi - np.roll(phi, 1, 3 - d))) / DX[d] ** 2 for d in range(3))
+    assert np.abs(div + fac * DX[0] * DX[1] * DX[2] * b * lap).max() <= 1e-13 * np.abs(div).max()
+    lev.close()
