@@ -296,6 +296,7 @@ int comm_set_transport(int rank, int nranks, iamrx_exchange_fn ex, iamrx_allredu
 int comm_finalize() {
   Comm& c = comm();
   c.ex = nullptr; c.ar = nullptr; c.ctx = nullptr;
+  p2p_finalize();
   if (c.nccl) { nccl().destroy(c.nccl); c.nccl = nullptr; }
   c.rank = 0; c.nranks = 1;
   return IAMRX_OK;
@@ -324,8 +325,17 @@ int comm_exchange(const std::vector<int>& peers, const std::vector<double*>& sbu
     return IAMRX_OK;
   }
   if (!c.nccl) { set_error("communicator not initialised"); return IAMRX_ERR_COMM; }
+  // peer-memory transport (p2p.cu) for the pairs it can carry; NCCL for the rest
+  std::vector<char> handled;
+  int prc = IAMRX_OK;
+  const bool p2p = p2p_try_exchange(peers, sbuf, scount, rbuf, rcount, s, handled, &prc);
+  if (prc != IAMRX_OK) return prc;
+  bool rest = !p2p;
+  if (p2p) for (size_t i = 0; i < peers.size(); ++i) if (!handled[i] && (scount[i] > 0 || rcount[i] > 0)) rest = true;
+  if (!rest) return IAMRX_OK;
   IX_NCCL(nccl().gstart());
   for (size_t i = 0; i < peers.size(); ++i) {
+    if (p2p && handled[i]) continue;
     if (scount[i] > 0) IX_NCCL(nccl().send(sbuf[i], (size_t)scount[i], NCCL_FLOAT64, peers[i], c.nccl, s));
     if (rcount[i] > 0) IX_NCCL(nccl().recv(rbuf[i], (size_t)rcount[i], NCCL_FLOAT64, peers[i], c.nccl, s));
   }

@@ -46,6 +46,12 @@ int comm_exchange(const std::vector<int>& peers, const std::vector<double*>& sbu
                   const std::vector<int64_t>& scount, const std::vector<double*>& rbuf,
                   const std::vector<int64_t>& rcount, cudaStream_t s);
 
+// peer-memory transport (p2p.cu): carries the entries of an exchange whose pair fits a mailbox slot over NVLink (CUDA IPC mapped
+// mailboxes + device-side sequence flags); handled[i] = 1 for those.  false: transport off (the default; IAMRX_P2P=1 turns it on).
+bool p2p_try_exchange(const std::vector<int>& peers, const std::vector<double*>& sbuf, const std::vector<int64_t>& scount,
+                      const std::vector<double*>& rbuf, const std::vector<int64_t>& rcount, cudaStream_t s, std::vector<char>& handled, int* rc);
+void p2p_finalize();
+
 // ---- copy descriptors (FillBoundary / ParallelCopy data movers) -----------
 struct CopyDesc {
   int kind;        // 0 fab->fab, 1 fab->buf, 2 buf->fab
