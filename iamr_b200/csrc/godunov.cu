@@ -747,6 +747,137 @@ aofs_tile_kernel(IX_KARG(EsArgs) a, IX_KARG(EsOut) out, V4 aofs, double volinv, 
   }  // components
 }
 
+// ===========================================================================
+// Fused ExtrapVelToFaces tile kernel
+// ===========================================================================
+// The same 8^3 tile / 10^3 site organisation as aofs_tile_kernel, for the whole velocity at once: the advective velocities
+// (u_ad, v_ad, w_ad = Riemann states of the NORMAL traces) upwind the transverse traces of the other components, so the three
+// components share one CTA.  Per site: 9 limited slopes (3 components x 3 directions, each evaluated once), the 9 high-face traces
+// L in shared memory and the 9 low-face traces H in registers; then per site the advective velocities and the 6 transverse edge
+// states of its low faces, the 6 transverse-derivative terms, the 6 corner-coupled states, the three normal corrections and the
+// three final Riemann states.  Global memory sees the velocity tile grown by 3 (three cp.async stages through one buffer), the
+// forcing, and the three face stores: the staged kernels move 5.7x the algorithmic bytes through 15 scratch arrays.
+// Interior boxes (no physical boundary within reach) and PLM only; everything else takes the staged kernels.
+constexpr int EV_SMEM_BYTES = (PAD + NQ + 18 * NS + PAD) * (int)sizeof(double);
+IX_D double riem(double lo, double hi) {
+  const double st = ((lo + hi) >= 0.0) ? lo : hi;
+  const bool ltm = ((lo <= 0.0 && hi >= 0.0) || (fabs(lo + hi) < upopts().small_vel));
+  return ltm ? 0.0 : st;
+}
+__global__ void __launch_bounds__(NT, 1)
+ev_tile_kernel(IX_KARG(EvArgs) a, V4 umac, V4 vmac, V4 wmac) {
+  extern __shared__ double sm_raw[];
+  double* const Q = sm_raw + PAD;
+  double* const AL = Q + NQ;        // L[n][d] at (3 n + d) NS; in stage 5 the slots (n, n) take the corrected normal states
+  double* const AB = AL + 9 * NS;   // u_ad, v_ad, w_ad; then 6 transverse edge states -> 6 T terms -> 6 corner states
+  const int tid = threadIdx.x;
+  const int l0 = a.bx.lo[0] + TB * (int)blockIdx.x, l1 = a.bx.lo[1] + TB * (int)blockIdx.y, l2 = a.bx.lo[2] + TB * (int)blockIdx.z;
+  const int sjs = (int)a.vel.js, sks = (int)a.vel.ks;
+  const double* Sp0 = a.vel.p + off32(a.vel, l0 - 3, l1 - 3, l2 - 3);
+  auto stage_q = [&](int n) {
+    const double* Sp = Sp0 + n * a.vel.ns;
+    const int x = tid & 15, r0 = tid >> 4;
+    if (x < QE) {
+#pragma unroll
+      for (int m = 0; m < 4; ++m) {
+        const int r = r0 + 64 * m;
+        if (r < QQ) {
+          const int z = r / QE, y = r - z * QE;
+          cp_async8(&Q[x + r * QE], Sp + x + y * sjs + z * sks);
+        }
+      }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  stage_q(0);
+  const bool act = tid < NS;
+  const int t = act ? tid : 0;
+  const int sk = t / GG, sj = (t - sk * GG) / G, si = t - sk * GG - sj * G;
+  const int i = l0 - 1 + si, j = l1 - 1 + sj, k = l2 - 1 + sk;
+  const bool fx = act && si >= 1, fy = act && sj >= 1, fz = act && sk >= 1;          // low face is a face of the tile
+  const bool inx = fx && si <= TB, iny = fy && sj <= TB, inz = fz && sk <= TB;      // cell index inside the tile
+  const bool hasf = a.force.ok();
+  // the cell's own velocity (the trace speeds) and forcing
+  const double* pv0 = a.vel.p + off32(a.vel, i, j, k);
+  const double cvel[3] = {pv0[0], pv0[a.vel.ns], pv0[2 * a.vel.ns]};
+  double frc[3] = {0.0, 0.0, 0.0};
+  if (hasf) { const double* pf = a.force.p + off32(a.force, i, j, k); frc[0] = pf[0]; frc[1] = pf[a.force.ns]; frc[2] = pf[2 * a.force.ns]; }
+  const double dtd[3] = {a.dtdx, a.dtdy, a.dtdz};
+  double H[3][3];   // [component][direction]
+#pragma unroll
+  for (int n = 0; n < 3; ++n) {
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncthreads();
+    {  // stage 1: slopes and the six traced states of component n
+      const int qi = (si + 2) + (sj + 2) * QE + (sk + 2) * QQ;
+      const double q0 = Q[qi];
+      const double sl[3] = {slope4_vals(Q[qi - 2], Q[qi - 1], q0, Q[qi + 1], Q[qi + 2]),
+                            slope4_vals(Q[qi - 2 * QE], Q[qi - QE], q0, Q[qi + QE], Q[qi + 2 * QE]),
+                            slope4_vals(Q[qi - 2 * QQ], Q[qi - QQ], q0, Q[qi + QQ], Q[qi + 2 * QQ])};
+      const double h = (a.fit && hasf) ? 0.5 * a.dt * frc[n] : 0.0;
+#pragma unroll
+      for (int d = 0; d < 3; ++d) {
+        double L = q0 + 0.5 * (1.0 - cvel[d] * dtd[d]) * sl[d];
+        double Hh = q0 + 0.5 * (-1.0 - cvel[d] * dtd[d]) * sl[d];
+        if (a.fit && hasf) { L += h; Hh += h; }
+        AL[(3 * n + d) * NS + t] = L;
+        H[n][d] = Hh;
+      }
+    }
+    __syncthreads();
+    if (n + 1 < 3) stage_q(n + 1);
+  }
+  // stage 2: advective velocities and transverse edge states on the low faces of this site
+  const int off[3] = {1, G, GG};
+#define EV_LO(n, d) AL[(3 * (n) + (d)) * NS + t - off[d]]
+  const double uad = riem(EV_LO(0, 0), H[0][0]), vad = riem(EV_LO(1, 1), H[1][1]), wad = riem(EV_LO(2, 2), H[2][2]);
+  {
+    const double xe_v = upsel(EV_LO(1, 0), H[1][0], uad), xe_w = upsel(EV_LO(2, 0), H[2][0], uad);
+    const double ye_u = upsel(EV_LO(0, 1), H[0][1], vad), ye_w = upsel(EV_LO(2, 1), H[2][1], vad);
+    const double ze_u = upsel(EV_LO(0, 2), H[0][2], wad), ze_v = upsel(EV_LO(1, 2), H[1][2], wad);
+    AB[t] = uad; AB[NS + t] = vad; AB[2 * NS + t] = wad;
+    AB[3 * NS + t] = xe_v; AB[4 * NS + t] = xe_w; AB[5 * NS + t] = ye_u; AB[6 * NS + t] = ye_w; AB[7 * NS + t] = ze_u; AB[8 * NS + t] = ze_v;
+    __syncthreads();
+    // stage 3: transverse-derivative terms of this CELL (non-conservative form; godunov.cu corner())
+    const double uadp = AB[t + 1], vadp = AB[NS + t + G], wadp = AB[2 * NS + t + GG];
+    auto T = [&](double ep, double e, double adp, double ad, double q) {
+      return upopts().corner_adv ? 0.5 * (adp + ad) * (ep - e) : (ep * adp - e * ad) - q * (adp - ad);
+    };
+    const double Tx1 = T(AB[3 * NS + t + 1], xe_v, uadp, uad, cvel[1]), Tx2 = T(AB[4 * NS + t + 1], xe_w, uadp, uad, cvel[2]);
+    const double Ty0 = T(AB[5 * NS + t + G], ye_u, vadp, vad, cvel[0]), Ty2 = T(AB[6 * NS + t + G], ye_w, vadp, vad, cvel[2]);
+    const double Tz0 = T(AB[7 * NS + t + GG], ze_u, wadp, wad, cvel[0]), Tz1 = T(AB[8 * NS + t + GG], ze_v, wadp, wad, cvel[1]);
+    __syncthreads();
+    AB[3 * NS + t] = Tx1; AB[4 * NS + t] = Tx2; AB[5 * NS + t] = Ty0; AB[6 * NS + t] = Ty2; AB[7 * NS + t] = Tz0; AB[8 * NS + t] = Tz1;
+    __syncthreads();
+    // stage 4: corner-coupled states on the low faces (for u_mac: u on y / z faces; v_mac: v on x / z; w_mac: w on x / y)
+    const double d3x = a.dtdx / 3.0, d3y = a.dtdy / 3.0, d3z = a.dtdz / 3.0;
+    const double yz_u = upsel(EV_LO(0, 1) - d3z * AB[7 * NS + t - G], H[0][1] - d3z * Tz0, vad);
+    const double zy_u = upsel(EV_LO(0, 2) - d3y * AB[5 * NS + t - GG], H[0][2] - d3y * Ty0, wad);
+    const double xz_v = upsel(EV_LO(1, 0) - d3z * AB[8 * NS + t - 1], H[1][0] - d3z * Tz1, uad);
+    const double zx_v = upsel(EV_LO(1, 2) - d3x * AB[3 * NS + t - GG], H[1][2] - d3x * Tx1, wad);
+    const double xy_w = upsel(EV_LO(2, 0) - d3y * AB[6 * NS + t - 1], H[2][0] - d3y * Ty2, uad);
+    const double yx_w = upsel(EV_LO(2, 1) - d3x * AB[4 * NS + t - G], H[2][1] - d3x * Tx2, vad);
+    __syncthreads();
+    AB[3 * NS + t] = yz_u; AB[4 * NS + t] = zy_u; AB[5 * NS + t] = xz_v; AB[6 * NS + t] = zx_v; AB[7 * NS + t] = xy_w; AB[8 * NS + t] = yx_w;
+    __syncthreads();
+    // stage 5: transverse (+ forcing) correction of the normal states of this cell
+    const double fb[3] = {(!a.fit && hasf) ? -0.5 * a.dt * frc[0] : 0.0, (!a.fit && hasf) ? -0.5 * a.dt * frc[1] : 0.0,
+                          (!a.fit && hasf) ? -0.5 * a.dt * frc[2] : 0.0};
+    const double Wx = fb[0] + (0.25 * a.dtdy) * (vadp + vad) * (AB[3 * NS + t + G] - yz_u) + (0.25 * a.dtdz) * (wadp + wad) * (AB[4 * NS + t + GG] - zy_u);
+    const double Wy = fb[1] + (0.25 * a.dtdx) * (uadp + uad) * (AB[5 * NS + t + 1] - xz_v) + (0.25 * a.dtdz) * (wadp + wad) * (AB[6 * NS + t + GG] - zx_v);
+    const double Wz = fb[2] + (0.25 * a.dtdx) * (uadp + uad) * (AB[7 * NS + t + 1] - xy_w) + (0.25 * a.dtdy) * (vadp + vad) * (AB[8 * NS + t + G] - yx_w);
+    // (each thread replaces ITS OWN normal L; the neighbours' reads of the old values are all behind the barriers above)
+    AL[0 * NS + t] -= Wx; AL[4 * NS + t] -= Wy; AL[8 * NS + t] -= Wz;
+    H[0][0] -= Wx; H[1][1] -= Wy; H[2][2] -= Wz;
+  }
+  __syncthreads();
+  // stage 6: final Riemann states = the face velocities; every face is written by exactly one tile
+  if (fx && iny && inz && (si <= TB || i == a.bx.hi[0] + 1)) umac.p[off32(umac, i, j, k)] = riem(AL[0 * NS + t - 1], H[0][0]);
+  if (fy && inx && inz && (sj <= TB || j == a.bx.hi[1] + 1)) vmac.p[off32(vmac, i, j, k)] = riem(AL[4 * NS + t - G], H[1][1]);
+  if (fz && inx && iny && (sk <= TB || k == a.bx.hi[2] + 1)) wmac.p[off32(wmac, i, j, k)] = riem(AL[8 * NS + t - GG], H[2][2]);
+#undef EV_LO
+}
+
 inline bool fits32(const C4& v, const Bx& bx, int ng) {  // offsets of grow(bx, ng+1) fit in 32 bits
   return !v.p || ((int64_t)(bx.nz() + 2 * ng + 2) * v.ks < (int64_t)1 << 31);
 }
@@ -886,6 +1017,9 @@ int compute_aofs(const Bx& bx, const AofsArgs& a, const AdvGeom& g, cudaStream_t
 }
 
 // UNVERIFIED-UPSTREAM switches (include/iamrx.h iamrx_set_option): host copy + the constant-memory copy the kernels read
+int extrap_vel_to_faces_staged(const Bx& bx, C4 vel, C4 force, V4 umac, V4 vmac, V4 wmac, const AdvGeom& g,
+                               int forces_in_trans, cudaStream_t s, int ppm, const AdvBC* bc);
+
 int godunov_set_option(int opt, double value) {
   UpOpts o = g_upopts_host;
   switch (opt) {
@@ -915,13 +1049,65 @@ double godunov_get_option(int opt) {
 int extrap_vel_to_faces(const Bx& bx, C4 vel, C4 force, V4 umac, V4 vmac, V4 wmac, const AdvGeom& g,
                         int forces_in_trans, cudaStream_t s, int ppm, const AdvBC* bc) {
   if (!bx.ok()) return IAMRX_OK;
+#if !defined(IX_EMUL)
+  // A box that touches non-interior domain sides: the 8-cell slabs next to those sides go through the staged kernels (which carry
+  // the boundary conditions), the rest of the box takes the fused tile kernel (as compute_aofs does).  The faces between a slab and
+  // the rest are computed by both; the later launch (the rest) stores last.
+  if (!ppm && bc && !bc->interior() && bx.nx() % tile::TB == 0 && bx.ny() % tile::TB == 0 && bx.nz() % tile::TB == 0 &&
+      to_bcall(bc, bx, 3).any) {
+    Bx rest = bx;
+    bool cut = false;
+    for (int d = 0; d < 3; ++d) {
+      bool lo_bc = false, hi_bc = false;
+      for (int n = 0; n < 3; ++n) { lo_bc |= bc->lo[n][d] != IAMRX_BC_INT_DIR; hi_bc |= bc->hi[n][d] != IAMRX_BC_INT_DIR; }
+      if (lo_bc && rest.lo[d] - 4 <= bc->dlo[d] && rest.hi[d] - rest.lo[d] + 1 > tile::TB) {
+        Bx p = rest; p.hi[d] = p.lo[d] + tile::TB - 1; rest.lo[d] += tile::TB; cut = true;
+        const int rc = extrap_vel_to_faces_staged(p, vel, force, umac, vmac, wmac, g, forces_in_trans, s, ppm, bc);
+        if (rc) return rc;
+      }
+      if (hi_bc && rest.hi[d] + 4 >= bc->dhi[d] && rest.hi[d] - rest.lo[d] + 1 > tile::TB) {
+        Bx p = rest; p.lo[d] = p.hi[d] - tile::TB + 1; rest.hi[d] -= tile::TB; cut = true;
+        const int rc = extrap_vel_to_faces_staged(p, vel, force, umac, vmac, wmac, g, forces_in_trans, s, ppm, bc);
+        if (rc) return rc;
+      }
+    }
+    if (cut) {
+      if (to_bcall(bc, rest, 3).any) return extrap_vel_to_faces_staged(rest, vel, force, umac, vmac, wmac, g, forces_in_trans, s, ppm, bc);
+      return extrap_vel_to_faces(rest, vel, force, umac, vmac, wmac, g, forces_in_trans, s, ppm, nullptr);
+    }
+  }
+#endif
+  return extrap_vel_to_faces_staged(bx, vel, force, umac, vmac, wmac, g, forces_in_trans, s, ppm, bc);
+}
+
+// one box: the fused tile kernel when it applies, else the three staged kernels
+int extrap_vel_to_faces_staged(const Bx& bx, C4 vel, C4 force, V4 umac, V4 vmac, V4 wmac, const AdvGeom& g,
+                               int forces_in_trans, cudaStream_t s, int ppm, const AdvBC* bc) {
+  if (!bx.ok()) return IAMRX_OK;
   ProfScope prof_(IAMRX_PROF_EXTRAP, bx.npts(), (double)bx.npts() * 72.0, s);
-  ScratchOwner so;
-  if (so.init(bx, B_N) != IAMRX_OK) return IAMRX_ERR_CUDA;
   EvArgs e{};
   e.bx = bx; e.vel = vel; e.force = force; e.fit = forces_in_trans; e.ppm = ppm;
   e.bc = to_bcall(bc, bx, 3);
   e.dt = g.dt; e.dtdx = g.dt / g.dx[0]; e.dtdy = g.dt / g.dx[1]; e.dtdz = g.dt / g.dx[2];
+#if !defined(IX_EMUL)
+  {
+    // fused tile kernel: boxes made of whole 8^3 tiles with no physical boundary within reach of the stencil, PLM
+    static int on = -1;
+    if (on < 0) { const char* ev = getenv("IAMRX_EV_TILE"); on = (ev && ev[0] == '0') ? 0 : 1; }
+    using namespace tile;
+    const C4 um{umac.p, umac.l0, umac.l1, umac.l2, umac.js, umac.ks, umac.ns}, vm{vmac.p, vmac.l0, vmac.l1, vmac.l2, vmac.js, vmac.ks, vmac.ns},
+        wm{wmac.p, wmac.l0, wmac.l1, wmac.l2, wmac.js, wmac.ks, wmac.ns};
+    if (on && !ppm && !e.bc.any && bx.nx() % TB == 0 && bx.ny() % TB == 0 && bx.nz() % TB == 0 && fits32(vel, bx, 3) && fits32(force, bx, 1) &&
+        fits32(um, bx, 1) && fits32(vm, bx, 1) && fits32(wm, bx, 1)) {
+      static bool attr = false;
+      if (!attr) { IX_CUDA(cudaFuncSetAttribute(ev_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, EV_SMEM_BYTES)); attr = true; }
+      IX_LAUNCH(ev_tile_kernel, dim3(bx.nx() / TB, bx.ny() / TB, bx.nz() / TB), dim3(NT, 1, 1), EV_SMEM_BYTES, s, e, umac, vmac, wmac);
+      return check_launch("ev_tile");
+    }
+  }
+#endif
+  ScratchOwner so;
+  if (so.init(bx, B_N) != IAMRX_OK) return IAMRX_ERR_CUDA;
   Bx R1 = grow(bx, 1); R1.hi[0]++; R1.hi[1]++; R1.hi[2]++;
   if (e.bc.any) IX_LAUNCH(ev_edge_kernel<true>, grid_for(R1, 1), dim3(TX, TY, 1), 0, s, e, so.sc, R1);
     else IX_LAUNCH(ev_edge_kernel<false>, grid_for(R1, 1), dim3(TX, TY, 1), 0, s, e, so.sc, R1);
