@@ -495,7 +495,10 @@ IX_D void cross_fz(C4 vel, C4 ez, int i, int j, int k, double dxi, double dyi, d
   f[2] = -mu * (-(2.0 / 3.0) * divu);
 }
 
-__global__ void __launch_bounds__(AP_TX* AP_TY)
+// MINB = resident CTAs per SM the kernel is compiled for: uncapped it takes 100 registers (two CTAs, 22 % of the warps) and is
+// latency-bound (ncu: issue 25 %, l1tex 25 %, 1.9 TB/s)
+template <int MINB>
+__global__ void __launch_bounds__(AP_TX* AP_TY, MINB)
 tensor_cross_kernel(Bx bx, V4 out, C4 vel, C4 ex, C4 ey, C4 ez, double b, double dxi, double dyi,
                     double dzi) {
   const int k = bx.lo[2] + blockIdx.z;
@@ -1068,8 +1071,11 @@ int tensor_cross(const Bx& bx, V4 out, C4 vel, C4 ex, C4 ey, C4 ez, double b, co
     }
   }
 #endif
-  IX_LAUNCH(tensor_cross_kernel, grid_for(bx, AP_TX, AP_TY, bx.nz()), dim3(AP_TX, AP_TY, 1), 0, s, 
-      bx, out, vel, ex, ey, ez, b, dxinv[0], dxinv[1], dxinv[2]);
+  static int minb = -1;
+  if (minb < 0) { const char* e = getenv("IAMRX_TC_MINB"); minb = e ? atoi(e) : 2; }   // measured per call at 256^3: 2 -> 0.62 ms, 3 -> 0.70, 4 -> 0.69 (uncapped: 0.85)
+#define IX_TC(M) IX_LAUNCH(tensor_cross_kernel<M>, grid_for(bx, AP_TX, AP_TY, bx.nz()), dim3(AP_TX, AP_TY, 1), 0, s, bx, out, vel, ex, ey, ez, b, dxinv[0], dxinv[1], dxinv[2])
+  if (minb >= 4) IX_TC(4); else if (minb == 3) IX_TC(3); else IX_TC(2);
+#undef IX_TC
   return check_launch("tensor_cross");
 }
 

@@ -51,12 +51,12 @@ IX_HD double sh(const A& a, int i, int j, int k, int o) {  // a(idx + o*e_D)
   return a(i + o * E<D>::x, j + o * E<D>::y, k + o * E<D>::z);
 }
 
+// (sign(dcen) * x for x >= 0 is written copysign(x, dcen): the same bits, signed zeros included, without the multiplication)
 IX_HD double lim2(double dlft, double drgt) {  // limited 2nd-order difference
   const double dcen = 0.5 * (dlft + drgt);
-  const double dsgn = copysign(1.0, dcen);
   const double slop = 2.0 * fmin(fabs(dlft), fabs(drgt));
   const double dlim = (dlft * drgt >= 0.0) ? slop : 0.0;
-  return dsgn * fmin(dlim, fabs(dcen));
+  return copysign(fmin(dlim, fabs(dcen)), dcen);
 }
 
 // 4th-order limited slope from the five values q(i-2..i+2) along one direction
@@ -67,10 +67,9 @@ IX_HD double slope4_vals(double qm2, double qm, double q0, double qp, double qp2
   const double dxr = lim2(qp - q0, qp2 - qp);
   const double dlft = q0 - qm, drgt = qp - q0;
   const double dcen = 0.5 * (dlft + drgt);
-  const double dsgn = copysign(1.0, dcen);
   const double slop = 2.0 * fmin(fabs(dlft), fabs(drgt));
   const double dlim = (dlft * drgt >= 0.0) ? slop : 0.0;
-  return dsgn * fmin(dlim, fabs((4.0 / 3.0) * dcen - (1.0 / 6.0) * (dxl + dxr)));
+  return copysign(fmin(dlim, fabs((4.0 / 3.0) * dcen - (1.0 / 6.0) * (dxl + dxr))), dcen);
 }
 
 // 4th-order limited slope of q along D at cell (i,j,k)
