@@ -141,6 +141,9 @@ int compute_aofs(const Bx& bx, const AofsArgs& a, const AdvGeom& g, cudaStream_t
 int nodal_divu(const Bx& nbx, V4 rhs, C4 vel, const double dxinv[3], cudaStream_t s, int hide = 0);
 int nodal_adotx(const Bx& nbx, V4 out, C4 phi, C4 rhs, C4 sig, const double dxinv[3], cudaStream_t s,
                 int wrapmask = 0, double* norm_dev = nullptr, bool* norm_fused = nullptr);   // norm_dev: as in abec_apply
+// all sweeps (8 colours each, in place) of a small single-box level in one single-CTA launch (see nodal.cu)
+bool nodal_gs_small_ok(const Bx& nbx);
+int nodal_gs_small(const Bx& nbx, V4 phi, C4 rhs, C4 sig, const double dxinv[3], int nsweeps, cudaStream_t s, int wrapmask);
 int nodal_gs_color(const Bx& nbx, V4 phi, C4 rhs, C4 sig, const double dxinv[3], int color,
                    cudaStream_t s, int wrapmask = 0);
 // full 8-colour Gauss-Seidel sweep phi_in -> phi_out on a box that spans the periodic domain

@@ -346,7 +346,6 @@ int CellMG::smooth(int l, MF& phi, const MF& rhs, int nsweeps, bool zero_init, c
     // deep-ghost sweep: one exchange of two ghost layers, the red pass on the box grown by one cell towards its neighbours (the
     // same arithmetic on the same values as the neighbour's own red pass), the black pass on the box.  A zero initial guess
     // (ghost layers included) needs no exchange before the first sweep.
-    if (zero_init) IX_TRY(mf_setval(phi, 0.0, 0, ncomp_, phi.ng, s));
     if (!L.rhs_ghost_ok) { IX_TRY(mf_fill_boundary(const_cast<MF&>(rhs), 0, ncomp_, 1, s, wm)); L.rhs_ghost_ok = true; }
     for (int sw = 0; sw < nsweeps; ++sw) {
       if (!(zero_init && sw == 0)) IX_TRY(mf_fill_boundary(phi, 0, ncomp_, 2, s, wm));
@@ -354,7 +353,9 @@ int CellMG::smooth(int l, MF& phi, const MF& rhs, int nsweeps, bool zero_init, c
         for (int il = 0; il < phi.n(); ++il) {
           Bx b = phi.vbox(il);
           if (rb == 0) for (int d = 0; d < 3; ++d) if (!(wm & (1 << d))) b = grow(b, d, 1);
-          IX_TRY(k::abec_gsrb(b, phi.v(il), rhs.c(il), op_at(l, il), info_.omega, rb, ncomp_, s, wm, nullptr));
+          // zero initial guess: the first red pass (on the grown box) writes every cell the black pass reads -- the coloured cells
+          // and zeros in between; the second ghost layer is refilled by the next sweep's exchange before anything reads it
+          IX_TRY(k::abec_gsrb(b, phi.v(il), rhs.c(il), op_at(l, il), info_.omega, rb, ncomp_, s, wm, nullptr, zero_init && sw == 0 && rb == 0));
         }
     }
     return IAMRX_OK;
@@ -792,6 +793,11 @@ int NodeMG::smooth(int l, MF& phi, const MF& rhs, int nsweeps, cudaStream_t s) {
   // numbers of ghost exchanges, so every rank must take the same one
   // deep-ghost levels (block decompositions): same fused sweep, halos from 4 ghost layers of phi / rhs / sigma instead of wraps
   const bool deep = L.deep && phi.ng >= L.ngd && rhs.ng >= L.ngd;
+  // a small level that is ONE box (the coarse levels; consolidated levels of multi-rank runs): every sweep in one launch
+  if (L.lev->boxes.size() == 1 && phi.n() == 1 && k::nodal_gs_small_ok(active_nbox(l, 0))) {
+    IX_TRY(fill_ghosts(l, phi, wm, s, false));
+    return k::nodal_gs_small(active_nbox(l, 0), phi.v(0), rhs.c(0), L.sigma.c(0), L.dxinv, nsweeps, s, wm | (neumann_sides(l, 0) << 3));
+  }
   const int wmk = deep ? (wm | k::NODAL_DEEP_GHOSTS) : wm;
   const int gd = deep ? L.ngd : 1;
   bool fused = true;
