@@ -72,6 +72,7 @@ class BCRec(C.Structure):
 
 # amrex::BCType math codes (include/iamrx.h IAMRX_BC_*)
 BC_INT_DIR, BC_REFLECT_ODD, BC_REFLECT_EVEN, BC_FOEXTRAP, BC_EXT_DIR, BC_HOEXTRAP = 0, -1, 1, 2, 3, 4
+SYNC_PC, SYNC_CELL_CONS = 0, 1   # NavierStokesBase::SyncInterpType subset (iamrx_sync_interp)
 # iamrx_compute_aofs_box flags
 ADV_PPM, ADV_FORCES_IN_TRANS, ADV_IS_VELOCITY, ADV_WRITE_FLUXES, ADV_IS_SYNC, ADV_STAGED, ADV_KNOWN_EDGE_STATE = 1, 2, 4, 8, 16, 32, 64
 
@@ -194,6 +195,8 @@ SIGNATURES = {
     "iamrx_ns_create": (C.c_int, [_vp, _P(NSParams), _P(_vp)]),
     "iamrx_ns_destroy": (C.c_int, [_vp]),
     "iamrx_debug_fb_stats": (None, [_P(C.c_int64), C.c_int]),
+    "iamrx_sync_interp": (C.c_int, [_vp, _vp, _P(Fab), C.c_int, _P(Fab), C.c_int, C.c_int, C.c_int, C.c_double, C.c_int, _P(BCRec), _vp]),
+    "iamrx_sync_proj_interp": (C.c_int, [_vp, _vp, _P(Fab), _P(Fab), _P(Fab), _vp]),
     "iamrx_diffusion_get_fluxes": (C.c_int, [_vp, C.c_int, _P(Fab), _P(Fab), _P(Fab), _P(Fab), C.c_double, _P(Fab), _P(Fab), _P(Fab), C.c_double, _vp]),
     "iamrx_fillpatch_two_levels": (C.c_int, [_vp, _vp, _P(Fab), _P(Fab), _P(Fab), C.c_double, C.c_double, C.c_double, C.c_int, C.c_int,
                                              _P(BCRec), _P(C.c_double), _vp]),

@@ -68,6 +68,17 @@ __global__ void __launch_bounds__(TX* TY) cell_cons_interp_kernel(Bx fbx, V4 fin
   fine(i, j, k, n) = u + alpha * (sx * ox + sy * oy + sz * oz);
 }
 
+// pc_interp (piecewise constant): every fine cell takes its parent's value
+__global__ void __launch_bounds__(TX* TY) pc_interp_kernel(Bx fbx, V4 fine, C4 crse, int nz) {
+  const int kz = blockIdx.z % nz, n = blockIdx.z / nz;
+  const int k = fbx.lo[2] + kz;
+  const int j = fbx.lo[1] + blockIdx.y * TY + threadIdx.y;
+  const int i = fbx.lo[0] + blockIdx.x * TX + threadIdx.x;
+  if (j > fbx.hi[1] || i > fbx.hi[0]) return;
+  auto fl = [](int a) { return (a >= 0) ? a / 2 : -((-a + 1) / 2); };
+  fine(i, j, k, n) = crse(fl(i), fl(j), fl(k), n);
+}
+
 __global__ void __launch_bounds__(TX* TY) node_bilinear_interp_kernel(Bx fnbx, V4 fine, C4 crse) {
   IDX3(fnbx)
   const int I = coarsen2(i), J = coarsen2(j), K = coarsen2(k);
@@ -124,6 +135,11 @@ int cell_cons_interp(const Bx& fbx, V4 fine, C4 crse, int ncomp, cudaStream_t s)
   if (!fbx.ok()) return IAMRX_OK;
   IX_LAUNCH(cell_cons_interp_kernel, grid_for(fbx, fbx.nz() * ncomp), dim3(TX, TY, 1), 0, s, fbx, fine, crse);
   return check_launch("cell_cons_interp");
+}
+int pc_interp(const Bx& fbx, V4 fine, C4 crse, int ncomp, cudaStream_t s) {
+  if (!fbx.ok()) return IAMRX_OK;
+  IX_LAUNCH(pc_interp_kernel, dim3(cdiv(fbx.nx(), TX), cdiv(fbx.ny(), TY), fbx.nz() * ncomp), dim3(TX, TY, 1), 0, s, fbx, fine, crse, fbx.nz());
+  return check_launch("pc_interp");
 }
 int node_bilinear_interp(const Bx& fnbx, V4 fine, C4 crse, int ncomp, cudaStream_t s) {
   if (!fnbx.ok()) return IAMRX_OK;
@@ -425,6 +441,93 @@ int iamrx_fillpatch_two_levels(iamrx_level_t fine_lev, iamrx_level_t crse_lev, i
   // 3. fine data where fine neighbours (or their periodic images) exist, 4. the physical boundary of the fine level
   IX_TRY(mf_fill_boundary(fm, 0, ncomp, ngrow, s));
   if (walls) IX_TRY(mf_fill_physbc(fm, 0, ncomp, ngrow, bc, s));
+  return IAMRX_OK;
+}
+
+
+// The coarse data of a two-level transfer as ONE replicated box over the coarse domain with ngc ghost layers: periodic images and,
+// on a non-periodic domain, the physical boundary fill (bc: BCRec + values of every component).
+static int replicated_coarse(Level* CL, const iamrx_fab* crse, int scomp, int ncomp, int ixtype, int ngc, const k::PhysBC* bc, cudaStream_t s,
+                             std::unique_ptr<Level>& RL, MF& cr) {
+  std::vector<Bx> one{mkbx(CL->geom.domain)};
+  std::vector<int> own{comm().rank};
+  RL = make_level(CL->geom, one, own);
+  RL->replicated = true;
+  MF cn; cn.alias(CL, ixtype, scomp + ncomp, 0, const_cast<iamrx_fab*>(crse));
+  MF ct(CL, ixtype, ncomp, 0);
+  IX_TRY(mf_copy(ct, cn, scomp, 0, ncomp, 0, s));
+  cr.define(RL.get(), ixtype, ncomp, ngc);
+  if (CL->replicated || (CL->boxes.size() == 1 && CL->nlocal() == 1)) IX_TRY(mf_copy(cr, ct, 0, 0, ncomp, 0, s));
+  else IX_TRY(mf_gather_replicate(cr, ct, ncomp, s));
+  if (ngc > 0) {
+    IX_TRY(mf_fill_boundary(cr, 0, ncomp, ngc, s));
+    if (bc) IX_TRY(mf_fill_physbc(cr, 0, ncomp, ngc, *bc, s));
+  }
+  return IAMRX_OK;
+}
+
+// NavierStokesBase::SyncInterp (NSB.cpp:3071-3255): see iamrx.h
+int iamrx_sync_interp(iamrx_level_t fine_lev, iamrx_level_t crse_lev, iamrx_fab* fine_sync, int dest_comp, const iamrx_fab* crse_sync,
+                      int src_comp, int ncomp, int increment, double dt_clev, int which_interp, const iamrx_bcrec* bcrec, void* stream) {
+  IX_NEED_DEVICE();
+  IX_ARG(fine_lev && crse_lev && fine_sync && crse_sync && ncomp >= 1 && ncomp <= 8 && dest_comp >= 0 && src_comp >= 0, "sync_interp arguments");
+  IX_ARG(which_interp == IAMRX_SYNC_PC || which_interp == IAMRX_SYNC_CELL_CONS, "sync_interp: PC_T and CellCons_T are implemented");
+  Level* FL = level_of(fine_lev);
+  Level* CL = level_of(crse_lev);
+  cudaStream_t s = (cudaStream_t)stream;
+  bool walls = false;
+  for (int d = 0; d < 3; ++d) {
+    IX_ARG(FL->geom.domain.lo[d] == 2 * CL->geom.domain.lo[d] && FL->geom.domain.hi[d] == 2 * CL->geom.domain.hi[d] + 1,
+           "the fine level's domain must be the coarse one refined by 2");
+    if (!CL->geom.periodic[d]) walls = true;
+  }
+  k::PhysBC bc{};   // HomExtDirFill: the BCRec of the original quantity with homogeneous ext_dir values
+  if (walls) {
+    IX_ARG(bcrec != nullptr, "a non-periodic domain needs the BCRec of every component (bc_orig_qty)");
+    for (int n = 0; n < ncomp; ++n) for (int d = 0; d < 3; ++d) { bc.lo[n][d] = bcrec[n].lo[d]; bc.hi[n][d] = bcrec[n].hi[d]; }
+  }
+  std::unique_ptr<Level> RL;
+  MF cr;
+  IX_TRY(replicated_coarse(CL, crse_sync, src_comp, ncomp, IX_CELL, which_interp == IAMRX_SYNC_PC ? 0 : 1, walls ? &bc : nullptr, s, RL, cr));
+  MF fm; fm.alias(FL, IX_CELL, dest_comp + ncomp, 0, fine_sync);
+  MF tmp(FL, IX_CELL, ncomp, 0);
+  for (int il = 0; il < fm.n(); ++il) {
+    const Bx vb = fm.vbox(il);
+    if (which_interp == IAMRX_SYNC_PC) IX_TRY(k::pc_interp(vb, tmp.v(il), cr.c(0), ncomp, s));
+    else IX_TRY(k::cell_cons_interp(vb, tmp.v(il), cr.c(0), ncomp, s));
+    if (increment) {   // finedata *= dt_clev; fsync += finedata (:3209-3236)
+      IX_TRY(k::scale(vb, tmp.v(il), dt_clev, ncomp, s));
+      IX_TRY(k::lincomb(vb, fm.v(il, dest_comp), 1.0, fm.c(il, dest_comp), 1.0, tmp.c(il), ncomp, s));
+    } else {
+      IX_TRY(k::copy(vb, fm.v(il, dest_comp), tmp.c(il), ncomp, s));
+    }
+  }
+  return IAMRX_OK;
+}
+
+// NavierStokesBase::SyncProjInterp (NSB.cpp:3258-3336): P_new += I(phi), P_old += I(phi) with node_bilinear_interp
+int iamrx_sync_proj_interp(iamrx_level_t fine_lev, iamrx_level_t crse_lev, iamrx_fab* p_new, iamrx_fab* p_old, const iamrx_fab* phi_crse,
+                           void* stream) {
+  IX_NEED_DEVICE();
+  IX_ARG(fine_lev && crse_lev && p_new && p_old && phi_crse, "sync_proj_interp arguments");
+  Level* FL = level_of(fine_lev);
+  Level* CL = level_of(crse_lev);
+  cudaStream_t s = (cudaStream_t)stream;
+  for (int d = 0; d < 3; ++d)
+    IX_ARG(FL->geom.domain.lo[d] == 2 * CL->geom.domain.lo[d] && FL->geom.domain.hi[d] == 2 * CL->geom.domain.hi[d] + 1,
+           "the fine level's domain must be the coarse one refined by 2");
+  std::unique_ptr<Level> RL;
+  MF cr;
+  IX_TRY(replicated_coarse(CL, phi_crse, 0, 1, IX_NODE, 0, nullptr, s, RL, cr));
+  MF pn; pn.alias(FL, IX_NODE, 1, 0, p_new);
+  MF po; po.alias(FL, IX_NODE, 1, 0, p_old);
+  MF tmp(FL, IX_NODE, 1, 0);
+  for (int il = 0; il < pn.n(); ++il) {
+    const Bx nb = pn.vbox(il);
+    IX_TRY(k::node_bilinear_interp(nb, tmp.v(il), cr.c(0), 1, s));
+    IX_TRY(k::lincomb(nb, pn.v(il), 1.0, pn.c(il), 1.0, tmp.c(il), 1, s));
+    IX_TRY(k::lincomb(nb, po.v(il), 1.0, po.c(il), 1.0, tmp.c(il), 1, s));
+  }
   return IAMRX_OK;
 }
 

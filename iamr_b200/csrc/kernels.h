@@ -196,6 +196,7 @@ int nodal_bc_scale(const Bx& nbx, V4 a, const NodalBC& bc, const Bx& ndom, const
 // --- two-level transfer operators and flux register pieces (amr.cu) ---------
 int average_down_nodal(const Bx& cnbx, V4 crse, C4 fine, int ncomp, cudaStream_t s);
 int cell_cons_interp(const Bx& fbx, V4 fine, C4 crse, int ncomp, cudaStream_t s);
+int pc_interp(const Bx& fbx, V4 fine, C4 crse, int ncomp, cudaStream_t s);   // piecewise constant
 int node_bilinear_interp(const Bx& fnbx, V4 fine, C4 crse, int ncomp, cudaStream_t s);
 int face_linear_interp(const Bx& ffbx, int dir, V4 fine, C4 crse, int ncomp, cudaStream_t s);
 

@@ -465,6 +465,19 @@ int iamrx_fillpatch_two_levels(iamrx_level_t fine_lev, iamrx_level_t crse_lev, i
                                const iamrx_fab* crse_new, double t_old, double t_new, double time, int ncomp, int ngrow,
                                const iamrx_bcrec* bcrec, const double* bcvals, void* stream);
 
+/* NavierStokesBase::SyncInterp (NSB.cpp:3071-3255): interpolate a coarse-level sync correction (Vsync / Ssync, or the velocity
+ * correction of level_sync) onto the fine level -- coarse data with periodic images and the HOMOGENEOUS ext_dir fill of the original
+ * quantity's BCRec (HomExtDirFill), interpolated with pc_interp or cell_cons_interp; increment != 0: fine[dest..] += dt_clev * I(crse)
+ * (:3209-3236), else fine[dest..] = I(crse).  fine_sync: one fab per local fine box with >= dest_comp + ncomp components; crse_sync: one
+ * per local coarse box with >= src_comp + ncomp.  Collective.  (CellConsLin_T / CellConsProt_T are not implemented.) */
+enum { IAMRX_SYNC_PC = 0, IAMRX_SYNC_CELL_CONS = 1 };
+int iamrx_sync_interp(iamrx_level_t fine_lev, iamrx_level_t crse_lev, iamrx_fab* fine_sync, int dest_comp, const iamrx_fab* crse_sync,
+                      int src_comp, int ncomp, int increment, double dt_clev, int which_interp, const iamrx_bcrec* bcrec, void* stream);
+/* NavierStokesBase::SyncProjInterp (NSB.cpp:3258-3336): the coarse sync-projection correction phi interpolated with
+ * node_bilinear_interp and added to BOTH pressure time levels of the fine level.  Nodal fabs, no ghost nodes needed.  Collective. */
+int iamrx_sync_proj_interp(iamrx_level_t fine_lev, iamrx_level_t crse_lev, iamrx_fab* p_new, iamrx_fab* p_old, const iamrx_fab* phi_crse,
+                           void* stream);
+
 typedef struct iamrx_fluxreg_s* iamrx_fluxreg_t;
 int iamrx_fluxreg_create(iamrx_level_t crse, iamrx_level_t fine, int ncomp, iamrx_fluxreg_t* out);
 int iamrx_fluxreg_destroy(iamrx_fluxreg_t reg);

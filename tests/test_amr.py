@@ -253,3 +253,86 @@ def test_fillpatch_two_levels_walls(backend, oracle):
     lat[-g:] = False
     assert lat.any() and np.abs(a[:, lat] - r[:, lat]).max() <= 1e-14
     clev.close(); flev.close()
+
+
+@pytest.mark.parametrize("layout", FINE_LAYOUTS)
+@pytest.mark.parametrize("which,increment", [(ix.SYNC_CELL_CONS, 1), (ix.SYNC_PC, 1), (ix.SYNC_CELL_CONS, 0)])
+def test_sync_interp(backend, oracle, layout, which, increment):
+    """NavierStokesBase::SyncInterp (NSB.cpp:3071-3255) on a periodic two-level hierarchy: fine[dest..] (+)= dt_clev * I(crse[src..]) with
+    pc_interp or cell_cons_interp; the other components of the fine fabs are left alone."""
+    lib, dev = backend
+    ncomp, src, dest, dt = 2, 1, 2, 0.37
+    clev, flev, cboxes, fboxes = _level_pair(lib, layout)
+    crse = smooth_field(NC, 101, src + ncomp)
+    crse[src] += 0.3 * np.sign(smooth_field(NC, 102, 1)[0])
+    fine = hash_uniform(103, (dest + ncomp,) + NF[::-1])
+    if which == ix.SYNC_PC:
+        interp = np.repeat(np.repeat(np.repeat(crse[src:src + ncomp], 2, 1), 2, 2), 2, 3)
+    else:
+        interp = oracle.interp(0, NC, crse[src:src + ncomp])
+    expect = fine.copy()
+    expect[dest:] = fine[dest:] + dt * interp if increment else interp
+    CS = [to_fab(crse, b, 0, ix.CELL, dev) for b in cboxes]
+    FS = [to_fab(fine, b, 0, ix.CELL, dev) for b in fboxes]
+    fa = lambda L: fab_array([p[1] for p in L])
+    lib.check(lib.iamrx_sync_interp(flev.h, clev.h, fa(FS), dest, fa(CS), src, ncomp, increment, dt, which, None, stream_of(dev)))
+    sync(dev)
+    for (t, _), b in zip(FS, fboxes):
+        ref, _ = to_fab(expect, b, 0, ix.CELL, "cpu")
+        assert np.abs(t.cpu().numpy() - ref.numpy()).max() <= 2e-15
+    if which == ix.SYNC_CELL_CONS and increment:
+        # conservative: the fine correction integrates to the coarse one under the fine grids
+        for (t, _), (lo, hi) in zip(FS, fboxes):
+            d = t.cpu().numpy()[dest:] - fine[dest:, lo[2]:hi[2] + 1, lo[1]:hi[1] + 1, lo[0]:hi[0] + 1]
+            c = crse[src:src + ncomp, lo[2] // 2:hi[2] // 2 + 1, lo[1] // 2:hi[1] // 2 + 1, lo[0] // 2:hi[0] // 2 + 1]
+            assert abs(d.sum() / 8.0 - dt * c.sum()) <= 1e-12 * max(1.0, abs(c.sum()))
+    clev.close(); flev.close()
+
+
+def test_sync_interp_walls_homogeneous_extdir(backend):
+    """Non-periodic z with an ext_dir component: SyncInterp fills the coarse ghost cells with the HOMOGENEOUS boundary value
+    (HomExtDirFill), so a constant correction is NOT constant in the fine cells next to the wall under cell_cons_interp ... it is:
+    ext_dir ghost = 0 gives a slope towards the wall, limited by the neighbours; piecewise-constant interpolation ignores ghosts."""
+    lib, dev = backend
+    gc = ix.Geom.make(NC, periodic=(1, 1, 0))
+    gf = ix.Geom.make(NF, periodic=(1, 1, 0))
+    cboxes = split_boxes(NC, (1, 1, 1))
+    fboxes = [((4, 4, 0), (11, 11, 7))]
+    clev, flev = ix.Level(lib, gc, cboxes), ix.Level(lib, gf, fboxes)
+    crse = np.ones((1,) + NC[::-1])
+    fine = np.zeros((1,) + NF[::-1])
+    bcs = (ix.BCRec * 1)(ix.BCRec.make((0, 0, ix.BC_EXT_DIR), (0, 0, ix.BC_EXT_DIR)))
+    fa = lambda L: fab_array([p[1] for p in L])
+    for which in (ix.SYNC_PC, ix.SYNC_CELL_CONS):
+        CS = [to_fab(crse, b, 0, ix.CELL, dev) for b in cboxes]
+        FS = [to_fab(fine, b, 0, ix.CELL, dev) for b in fboxes]
+        lib.check(lib.iamrx_sync_interp(flev.h, clev.h, fa(FS), 0, fa(CS), 0, 1, 0, 1.0, which, bcs, stream_of(dev)))
+        sync(dev)
+        a = FS[0][0].cpu().numpy()[0]
+        assert np.abs(a[2:] - 1.0).max() <= 1e-15          # away from the wall: the constant
+        pair = a[0:2].mean(axis=0)
+        assert np.abs(pair - 1.0).max() <= 1e-15           # conservative in the wall cells as well
+        if which == ix.SYNC_PC:
+            assert np.abs(a[0:2] - 1.0).max() == 0.0
+    clev.close(); flev.close()
+
+
+@pytest.mark.parametrize("layout", FINE_LAYOUTS)
+def test_sync_proj_interp(backend, oracle, layout):
+    """NavierStokesBase::SyncProjInterp (NSB.cpp:3258-3336): P_new += I(phi), P_old += I(phi), I = node_bilinear_interp."""
+    lib, dev = backend
+    clev, flev, cboxes, fboxes = _level_pair(lib, layout)
+    phi = smooth_field(NC, 111, 1)
+    pn, po = hash_uniform(112, (1,) + NF[::-1]), hash_uniform(113, (1,) + NF[::-1])
+    interp = oracle.interp(1, NC, phi)
+    PH = [to_fab(phi, b, 0, ix.NODE, dev) for b in cboxes]
+    PN = [to_fab(pn, b, 0, ix.NODE, dev) for b in fboxes]
+    PO = [to_fab(po, b, 0, ix.NODE, dev) for b in fboxes]
+    fa = lambda L: fab_array([p[1] for p in L])
+    lib.check(lib.iamrx_sync_proj_interp(flev.h, clev.h, fa(PN), fa(PO), fa(PH), stream_of(dev)))
+    sync(dev)
+    for arr, base in ((PN, pn), (PO, po)):
+        for (t, _), b in zip(arr, fboxes):
+            ref, _ = to_fab(base + interp, b, 0, ix.NODE, "cpu")
+            assert np.abs(t.cpu().numpy() - ref.numpy()).max() <= 2e-15
+    clev.close(); flev.close()
