@@ -441,23 +441,64 @@ __global__ void mac_update_kernel(Bx bx, V4 u, V4 v, V4 w, C4 phi, IX_KARG(AbecD
 // ---- tensor cross terms --------------------------------------------------
 // Transverse derivatives on faces (AMReX mltensor_d?_on_?face): average of the
 // two centred differences either side of the face.
-IX_D double dy_on_x(C4 v, int i, int j, int k, int n, double dyi) {
-  return (v(i, j + 1, k, n) + v(i - 1, j + 1, k, n) - v(i, j - 1, k, n) - v(i - 1, j - 1, k, n)) * (0.25 * dyi);
+// transverse derivatives on a face from the four cells around the face's edge mid-points; the two cells on either side of the
+// face along its normal (a = below, b = above) and the neighbour indices (m / p) are passed explicitly so that a caller can hand
+// in periodic images (in-kernel wrap) instead of ghost cells
+IX_D double dy_on_xw(C4 v, int ia, int ib, int jm, int jp, int k, int n, double dyi) {
+  return (v(ib, jp, k, n) + v(ia, jp, k, n) - v(ib, jm, k, n) - v(ia, jm, k, n)) * (0.25 * dyi);
 }
-IX_D double dz_on_x(C4 v, int i, int j, int k, int n, double dzi) {
-  return (v(i, j, k + 1, n) + v(i - 1, j, k + 1, n) - v(i, j, k - 1, n) - v(i - 1, j, k - 1, n)) * (0.25 * dzi);
+IX_D double dz_on_xw(C4 v, int ia, int ib, int j, int km, int kp, int n, double dzi) {
+  return (v(ib, j, kp, n) + v(ia, j, kp, n) - v(ib, j, km, n) - v(ia, j, km, n)) * (0.25 * dzi);
 }
-IX_D double dx_on_y(C4 v, int i, int j, int k, int n, double dxi) {
-  return (v(i + 1, j, k, n) + v(i + 1, j - 1, k, n) - v(i - 1, j, k, n) - v(i - 1, j - 1, k, n)) * (0.25 * dxi);
+IX_D double dx_on_yw(C4 v, int im, int ip, int ja, int jb, int k, int n, double dxi) {
+  return (v(ip, jb, k, n) + v(ip, ja, k, n) - v(im, jb, k, n) - v(im, ja, k, n)) * (0.25 * dxi);
 }
-IX_D double dz_on_y(C4 v, int i, int j, int k, int n, double dzi) {
-  return (v(i, j, k + 1, n) + v(i, j - 1, k + 1, n) - v(i, j, k - 1, n) - v(i, j - 1, k - 1, n)) * (0.25 * dzi);
+IX_D double dz_on_yw(C4 v, int i, int ja, int jb, int km, int kp, int n, double dzi) {
+  return (v(i, jb, kp, n) + v(i, ja, kp, n) - v(i, jb, km, n) - v(i, ja, km, n)) * (0.25 * dzi);
 }
-IX_D double dx_on_z(C4 v, int i, int j, int k, int n, double dxi) {
-  return (v(i + 1, j, k, n) + v(i + 1, j, k - 1, n) - v(i - 1, j, k, n) - v(i - 1, j, k - 1, n)) * (0.25 * dxi);
+IX_D double dx_on_zw(C4 v, int im, int ip, int j, int ka, int kb, int n, double dxi) {
+  return (v(ip, j, kb, n) + v(ip, j, ka, n) - v(im, j, kb, n) - v(im, j, ka, n)) * (0.25 * dxi);
 }
-IX_D double dy_on_z(C4 v, int i, int j, int k, int n, double dyi) {
-  return (v(i, j + 1, k, n) + v(i, j + 1, k - 1, n) - v(i, j - 1, k, n) - v(i, j - 1, k - 1, n)) * (0.25 * dyi);
+IX_D double dy_on_zw(C4 v, int i, int jm, int jp, int ka, int kb, int n, double dyi) {
+  return (v(i, jp, kb, n) + v(i, jp, ka, n) - v(i, jm, kb, n) - v(i, jm, ka, n)) * (0.25 * dyi);
+}
+IX_D double dy_on_x(C4 v, int i, int j, int k, int n, double dyi) { return dy_on_xw(v, i - 1, i, j - 1, j + 1, k, n, dyi); }
+IX_D double dz_on_x(C4 v, int i, int j, int k, int n, double dzi) { return dz_on_xw(v, i - 1, i, j, k - 1, k + 1, n, dzi); }
+IX_D double dx_on_y(C4 v, int i, int j, int k, int n, double dxi) { return dx_on_yw(v, i - 1, i + 1, j - 1, j, k, n, dxi); }
+IX_D double dz_on_y(C4 v, int i, int j, int k, int n, double dzi) { return dz_on_yw(v, i, j - 1, j, k - 1, k + 1, n, dzi); }
+IX_D double dx_on_z(C4 v, int i, int j, int k, int n, double dxi) { return dx_on_zw(v, i - 1, i + 1, j, k - 1, k, n, dxi); }
+IX_D double dy_on_z(C4 v, int i, int j, int k, int n, double dyi) { return dy_on_zw(v, i, j - 1, j + 1, k - 1, k, n, dyi); }
+
+// the cross fluxes with explicit neighbour indices: face between cells (ia, ib) along the normal; mu = the face coefficient
+IX_D void cross_fxw(C4 vel, double mu, int ia, int ib, int jm, int j, int jp, int km, int k, int kp, double dyi, double dzi, double f[3]) {
+  const double dudy = dy_on_xw(vel, ia, ib, jm, jp, k, 0, dyi);
+  const double dvdy = dy_on_xw(vel, ia, ib, jm, jp, k, 1, dyi);
+  const double dudz = dz_on_xw(vel, ia, ib, j, km, kp, 0, dzi);
+  const double dwdz = dz_on_xw(vel, ia, ib, j, km, kp, 2, dzi);
+  const double divu = dvdy + dwdz;
+  f[0] = -mu * (-(2.0 / 3.0) * divu);
+  f[1] = -mu * dudy;
+  f[2] = -mu * dudz;
+}
+IX_D void cross_fyw(C4 vel, double mu, int im, int i, int ip, int ja, int jb, int km, int k, int kp, double dxi, double dzi, double f[3]) {
+  const double dudx = dx_on_yw(vel, im, ip, ja, jb, k, 0, dxi);
+  const double dvdx = dx_on_yw(vel, im, ip, ja, jb, k, 1, dxi);
+  const double dvdz = dz_on_yw(vel, i, ja, jb, km, kp, 1, dzi);
+  const double dwdz = dz_on_yw(vel, i, ja, jb, km, kp, 2, dzi);
+  const double divu = dudx + dwdz;
+  f[0] = -mu * dvdx;
+  f[1] = -mu * (-(2.0 / 3.0) * divu);
+  f[2] = -mu * dvdz;
+}
+IX_D void cross_fzw(C4 vel, double mu, int im, int i, int ip, int jm, int j, int jp, int ka, int kb, double dxi, double dyi, double f[3]) {
+  const double dudx = dx_on_zw(vel, im, ip, j, ka, kb, 0, dxi);
+  const double dwdx = dx_on_zw(vel, im, ip, j, ka, kb, 2, dxi);
+  const double dvdy = dy_on_zw(vel, i, jm, jp, ka, kb, 1, dyi);
+  const double dwdy = dy_on_zw(vel, i, jm, jp, ka, kb, 2, dyi);
+  const double divu = dudx + dvdy;
+  f[0] = -mu * dwdx;
+  f[1] = -mu * dwdy;
+  f[2] = -mu * (-(2.0 / 3.0) * divu);
 }
 
 // cross flux through the x-face i (between cells i-1 and i), comps 0..2
@@ -500,20 +541,25 @@ IX_D void cross_fz(C4 vel, C4 ez, int i, int j, int k, double dxi, double dyi, d
 template <int MINB>
 __global__ void __launch_bounds__(AP_TX* AP_TY, MINB)
 tensor_cross_kernel(Bx bx, V4 out, C4 vel, C4 ex, C4 ey, C4 ez, double b, double dxi, double dyi,
-                    double dzi) {
+                    double dzi, int wm) {
   const int k = bx.lo[2] + blockIdx.z;
   const int j = bx.lo[1] + blockIdx.y * AP_TY + threadIdx.y;
   const int i = bx.lo[0] + blockIdx.x * AP_TX + threadIdx.x;
   if (j > bx.hi[1] || i > bx.hi[0]) return;
+  // wm bit d: the box spans the periodic domain in direction d -- the neighbours beyond it are its own cells on the other side
+  // (no ghost fill of edges and corners needed there)
+  const int im = ((wm & 1) && i == bx.lo[0]) ? bx.hi[0] : i - 1, ip = ((wm & 1) && i == bx.hi[0]) ? bx.lo[0] : i + 1;
+  const int jm = ((wm & 2) && j == bx.lo[1]) ? bx.hi[1] : j - 1, jp = ((wm & 2) && j == bx.hi[1]) ? bx.lo[1] : j + 1;
+  const int km = ((wm & 4) && k == bx.lo[2]) ? bx.hi[2] : k - 1, kp = ((wm & 4) && k == bx.hi[2]) ? bx.lo[2] : k + 1;
   double fl[3], fh[3], acc[3];
-  cross_fx(vel, ex, i, j, k, dyi, dzi, fl);
-  cross_fx(vel, ex, i + 1, j, k, dyi, dzi, fh);
+  cross_fxw(vel, ex(i, j, k), im, i, jm, j, jp, km, k, kp, dyi, dzi, fl);
+  cross_fxw(vel, ex(i + 1, j, k), i, ip, jm, j, jp, km, k, kp, dyi, dzi, fh);
   for (int n = 0; n < 3; ++n) acc[n] = dxi * (fh[n] - fl[n]);
-  cross_fy(vel, ey, i, j, k, dxi, dzi, fl);
-  cross_fy(vel, ey, i, j + 1, k, dxi, dzi, fh);
+  cross_fyw(vel, ey(i, j, k), im, i, ip, jm, j, km, k, kp, dxi, dzi, fl);
+  cross_fyw(vel, ey(i, j + 1, k), im, i, ip, j, jp, km, k, kp, dxi, dzi, fh);
   for (int n = 0; n < 3; ++n) acc[n] += dyi * (fh[n] - fl[n]);
-  cross_fz(vel, ez, i, j, k, dxi, dyi, fl);
-  cross_fz(vel, ez, i, j, k + 1, dxi, dyi, fh);
+  cross_fzw(vel, ez(i, j, k), im, i, ip, jm, j, jp, km, k, dxi, dyi, fl);
+  cross_fzw(vel, ez(i, j, k + 1), im, i, ip, jm, j, jp, k, kp, dxi, dyi, fh);
   for (int n = 0; n < 3; ++n) acc[n] += dzi * (fh[n] - fl[n]);
   for (int n = 0; n < 3; ++n) out(i, j, k, n) += b * acc[n];
 }
@@ -1056,7 +1102,7 @@ int tensor_cross_bc(const Bx& bx, V4 out, C4 vel, C4 bv, C4 ex, C4 ey, C4 ez, do
 }
 
 int tensor_cross(const Bx& bx, V4 out, C4 vel, C4 ex, C4 ey, C4 ez, double b, const double dxinv[3],
-                 cudaStream_t s) {
+                 cudaStream_t s, int wrapmask) {
   if (!bx.ok()) return IAMRX_OK;
 #if !defined(IX_EMUL)
   {
@@ -1064,7 +1110,7 @@ int tensor_cross(const Bx& bx, V4 out, C4 vel, C4 ex, C4 ey, C4 ez, double b, co
     // measured on B200 (profiles/r02_notes.md): 1.22 ms vs 0.86 ms per launch at 256^3 -- the per-plane barriers cost more than the
     // halved stencil loads save -- so the marching form is opt-in (IAMRX_TENSOR_MARCH=1)
     if (on < 0) { const char* e = getenv("IAMRX_TENSOR_MARCH"); on = (e && e[0] == '1') ? 1 : 0; }
-    if (on && bx.nz() >= 8) {
+    if (on && bx.nz() >= 8 && wrapmask == 0) {
       const dim3 grd(cdiv(bx.nx(), TC_X), cdiv(bx.ny(), TC_Y), cdiv(bx.nz(), TC_KB));
       IX_LAUNCH(tensor_cross_march_kernel, grd, dim3(TC_X + 1, TC_Y + 1, 1), 0, s, bx, out, vel, ex, ey, ez, b, dxinv[0], dxinv[1], dxinv[2]);
       return check_launch("tensor_cross_march");
@@ -1073,7 +1119,7 @@ int tensor_cross(const Bx& bx, V4 out, C4 vel, C4 ex, C4 ey, C4 ez, double b, co
 #endif
   static int minb = -1;
   if (minb < 0) { const char* e = getenv("IAMRX_TC_MINB"); minb = e ? atoi(e) : 2; }   // measured per call at 256^3: 2 -> 0.62 ms, 3 -> 0.70, 4 -> 0.69 (uncapped: 0.85)
-#define IX_TC(M) IX_LAUNCH(tensor_cross_kernel<M>, grid_for(bx, AP_TX, AP_TY, bx.nz()), dim3(AP_TX, AP_TY, 1), 0, s, bx, out, vel, ex, ey, ez, b, dxinv[0], dxinv[1], dxinv[2])
+#define IX_TC(M) IX_LAUNCH(tensor_cross_kernel<M>, grid_for(bx, AP_TX, AP_TY, bx.nz()), dim3(AP_TX, AP_TY, 1), 0, s, bx, out, vel, ex, ey, ez, b, dxinv[0], dxinv[1], dxinv[2], wrapmask)
   if (minb >= 4) IX_TC(4); else if (minb == 3) IX_TC(3); else IX_TC(2);
 #undef IX_TC
   return check_launch("tensor_cross");

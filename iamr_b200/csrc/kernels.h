@@ -69,7 +69,7 @@ int mac_divergence(const Bx& bx, V4 div, C4 u, C4 v, C4 w, const double dxinv[3]
 int mac_update(const Bx& bx, V4 u, V4 v, V4 w, C4 phi, const Abec& op, cudaStream_t s);
 // tensor cross terms: out += b*div(F_cross(eta, vel))
 int tensor_cross(const Bx& bx, V4 out, C4 vel, C4 ex, C4 ey, C4 ez, double b,
-                 const double dxinv[3], cudaStream_t s);
+                 const double dxinv[3], cudaStream_t s, int wrapmask = 0);   // wrapmask as for abec_apply: periodic images in-kernel
 
 struct LinBC;
 // the same on a box that may touch non-periodic domain faces: boundary-aware transverse derivatives (bv: level-BC fab, may be null)

@@ -383,8 +383,9 @@ int CellMG::smooth(int l, MF& phi, const MF& rhs, int nsweeps, bool zero_init, c
 
 // with_cross marks the top-level residual of a solve: inhomogeneous boundary conditions (+ the tensor cross terms)
 int CellMG::residual(int l, MF& out, MF& phi, const MF& rhs, bool with_cross, cudaStream_t s, double* norm) {
-  const bool cross = tensor_ && l == 0 && with_cross;  // the cross terms read edge/corner ghosts
-  const int wm = cross ? 0 : lv_[l].lev->level_wrapmask();
+  const bool cross = tensor_ && l == 0 && with_cross;  // the cross terms read edge / corner neighbours: periodic images in the
+  // wrapped directions (in-kernel), ghost cells elsewhere; a box on a physical boundary keeps the full ghost fill
+  const int wm = (cross && has_bc_) ? 0 : lv_[l].lev->level_wrapmask();
   IX_TRY(fill_ghosts(l, phi, with_cross, wm, cross ? 1 : 0, s));
   const Level& L = *lv_[l].lev;
   double* nd = nullptr;
@@ -405,7 +406,7 @@ int CellMG::residual(int l, MF& out, MF& phi, const MF& rhs, bool with_cross, cu
                                   eta_[2]->c(il), -b_, lv_[0].dxinv, bc_, L.domain, L.geom.periodic, s));
       else
         IX_TRY(k::tensor_cross(phi.vbox(il), out.v(il), phi.c(il), eta_[0]->c(il), eta_[1]->c(il),
-                               eta_[2]->c(il), -b_, lv_[0].dxinv, s));
+                               eta_[2]->c(il), -b_, lv_[0].dxinv, s, wm));
     }
   }
   if (norm) {
@@ -428,17 +429,19 @@ int CellMG::apply(MF& out, MF& phi, cudaStream_t s) {
   bool dirichlet = false;
   for (int c = 0; c < ncomp_ && c < 3; ++c) for (int d = 0; d < 3; ++d) if (bc_.lo[c][d] == IAMRX_LINOP_DIRICHLET || bc_.hi[c][d] == IAMRX_LINOP_DIRICHLET) dirichlet = true;
   IX_TRY(save_level_bc(bvals_, phi, ncomp_, has_bc_ && dirichlet, s));
-  IX_TRY(fill_ghosts(0, phi, true, 0, tensor_ ? 1 : 0, s));
+  // directions every box spans periodically are wrapped inside the kernels (cross terms included): no ghost traffic there
+  const int wm = has_bc_ ? 0 : lv_[0].lev->level_wrapmask();
+  IX_TRY(fill_ghosts(0, phi, true, wm, tensor_ ? 1 : 0, s));
   const Level& L = *lv_[0].lev;
   for (int il = 0; il < phi.n(); ++il) {
-    IX_TRY(k::abec_apply(phi.vbox(il), out.v(il), phi.c(il), C4{}, op_at(0, il), ncomp_, s));
+    IX_TRY(k::abec_apply(phi.vbox(il), out.v(il), phi.c(il), C4{}, op_at(0, il), ncomp_, s, wm));
     if (tensor_) {
       if (has_bc_)
         IX_TRY(k::tensor_cross_bc(phi.vbox(il), out.v(il), phi.c(il), bvals_.ok() ? bvals_.c(il) : C4{}, eta_[0]->c(il), eta_[1]->c(il),
                                   eta_[2]->c(il), b_, lv_[0].dxinv, bc_, L.domain, L.geom.periodic, s));
       else
         IX_TRY(k::tensor_cross(phi.vbox(il), out.v(il), phi.c(il), eta_[0]->c(il), eta_[1]->c(il),
-                               eta_[2]->c(il), b_, lv_[0].dxinv, s));
+                               eta_[2]->c(il), b_, lv_[0].dxinv, s, wm));
     }
   }
   bvals_.clear();
