@@ -472,6 +472,42 @@ int iamrx_mac_project(iamrx_level_t lev, iamrx_fab* umac, iamrx_fab* vmac, iamrx
   IX_GUARD_END
 }
 
+// MacProj::mac_sync_solve (MacProj.cpp:359-479): see iamrx.h
+int iamrx_mac_sync_solve(iamrx_level_t lev, iamrx_fluxreg_t mac_reg, const iamrx_fab* rho_half, const iamrx_fab* rhs_increment,
+                         iamrx_fab* ucorr, iamrx_fab* vcorr, iamrx_fab* wcorr, iamrx_fab* mac_sync_phi, double dt, const int lobc[3],
+                         const int hibc[3], iamrx_mg_info* info, void* stream) {
+  IX_GUARD_BEGIN
+  IX_NEED_DEVICE();
+  IX_ARG(lev && mac_reg && rho_half && ucorr && vcorr && wcorr && mac_sync_phi && dt > 0.0, "mac_sync_solve arguments");
+  Level* L = lev->lev.get();
+  cudaStream_t s = S(stream);
+  k::LinBC bc;
+  IX_TRY(make_linbc(*L, lobc, hibc, info ? info->maxorder : 0, false, &bc));
+  // Rhs = SUM{MR / VOL} over the faces of a coarse cell that adjoin the fine grids, sign opposite to a reflux (scale -1), zero
+  // elsewhere and under the fine grids (:385-418); + Rhs_increment (:420-423); negated (:445)
+  MF Rhs(L, IX_CELL, 1, 0);
+  IX_TRY(mf_setval(Rhs, 0.0, 0, 1, 0, s));
+  IX_TRY(iamrx_fluxreg_reflux(mac_reg, Rhs.fabs.data(), 0, -1.0, stream));
+  if (rhs_increment) {
+    MF Inc; Inc.alias(L, IX_CELL, 1, 0, const_cast<iamrx_fab*>(rhs_increment));
+    IX_TRY(mf_lincomb(Rhs, 0, 1.0, Rhs, 0, 1.0, Inc, 0, 1, 0, s));
+  }
+  IX_TRY(mf_scale(Rhs, -1.0, 0, 1, 0, s));
+  // mac_sync_phi = 0; solve with a null umac (no div(umac) in the right-hand side), rhs_scale = 2 / dt (:425-452)
+  iamrx_fab* um[3] = {ucorr, vcorr, wcorr};
+  MF U[3];
+  for (int d = 0; d < 3; ++d) { U[d].alias(L, IX_XFACE + d, 1, 0, um[d]); IX_TRY(mf_setval(U[d], 0.0, 0, 1, 0, s)); }
+  MF Rho; Rho.alias(L, IX_CELL, 1, 1, const_cast<iamrx_fab*>(rho_half));
+  MF Phi; Phi.alias(L, IX_CELL, 1, 1, mac_sync_phi);
+  IX_TRY(mf_setval(Phi, 0.0, 0, 1, 1, s));
+  const int rc = mac_project(*L, lev->solvers, U, Rho, &Rhs, Phi, 2.0 / dt, info, s, &bc);
+  if (rc < 0) return rc;
+  // U now holds 0 - beta grad phi = the fluxes "-B grad phi"; Ucorr = -fluxes (:454-459)
+  for (int d = 0; d < 3; ++d) IX_TRY(mf_scale(U[d], -1.0, 0, 1, 0, s));
+  return rc;
+  IX_GUARD_END
+}
+
 int iamrx_mac_get_fluxes(iamrx_level_t lev, iamrx_fab* fx, iamrx_fab* fy, iamrx_fab* fz, iamrx_fab* phi, void* stream) {
   IX_GUARD_BEGIN
   IX_NEED_DEVICE();

@@ -490,6 +490,15 @@ int iamrx_fluxreg_fine_add(iamrx_fluxreg_t reg, const iamrx_fab* fx, const iamrx
 int iamrx_fluxreg_reflux(iamrx_fluxreg_t reg, iamrx_fab* crse_state, int scomp, double scale, void* stream);
 int iamrx_fluxreg_field(iamrx_fluxreg_t reg, int ilocal, iamrx_fab* out);
 
+/* MacProj::mac_sync_solve (MacProj.cpp:359-479) on the coarse level of a pair: the right-hand side is the MAC register refluxed with
+ * scale -1 (SUM{MR / VOL} in the coarse cells next to the fine grids, zero elsewhere and under them; the register must have been
+ * filled with area-weighted face velocities: crse_add / fine_add with dt = 1 and vol = the coarse cell volume), plus the optional
+ * Rhs_increment, negated; mac_sync_phi is zeroed and solved for with rhs_scale = 2 / dt and no div(umac) term; Ucorr = -(-B grad phi).
+ * rho_half: >= 1 filled ghost cell; ucorr / vcorr / wcorr: face fabs of every local box; lobc / hibc / info as iamrx_mac_project. */
+int iamrx_mac_sync_solve(iamrx_level_t lev, iamrx_fluxreg_t mac_reg, const iamrx_fab* rho_half, const iamrx_fab* rhs_increment,
+                         iamrx_fab* ucorr, iamrx_fab* vcorr, iamrx_fab* wcorr, iamrx_fab* mac_sync_phi, double dt, const int lobc[3],
+                         const int hibc[3], iamrx_mg_info* info, void* stream);
+
 /* ------------------------------------------------------------------------
  * 4. The level time step: NavierStokes::advance (NS.cpp:543-691) and the
  *    start-up sequence NavierStokes::post_init (NS.cpp:1254-1432) for a

@@ -336,3 +336,54 @@ def test_sync_proj_interp(backend, oracle, layout):
             ref, _ = to_fab(base + interp, b, 0, ix.NODE, "cpu")
             assert np.abs(t.cpu().numpy() - ref.numpy()).max() <= 2e-15
     clev.close(); flev.close()
+
+
+def test_mac_sync_solve(backend, oracle):
+    """MacProj::mac_sync_solve (MacProj.cpp:359-479): right-hand side from the MAC register (reflux with scale -1) + increment, negated;
+    coarse-level MAC solve with rhs_scale 2/dt and no div(umac); Ucorr = -(-B grad phi).  Reference: the oracle's flux register and
+    MAC projection composed the same way."""
+    lib, dev = backend
+    layout = FINE_LAYOUTS[1]
+    clev, flev, cboxes, fboxes = _level_pair(lib, layout)
+    mask = np.zeros(NC[::-1], dtype=bool)
+    for lo, hi in layout:
+        mask[lo[2]:hi[2] + 1, lo[1]:hi[1] + 1, lo[0]:hi[0] + 1] = True
+    dxc, dxf, dt = 1.0 / 8, 1.0 / 16, 0.05
+    vol = dxc ** 3
+    cflux = [hash_uniform(121 + d, (1,) + NC[::-1]) * dxc ** 2 for d in range(3)]     # area-weighted face velocities
+    fflux = [hash_uniform(131 + d, (1,) + NF[::-1]) * dxf ** 2 for d in range(3)]
+    inc = 0.1 * smooth_field(NC, 141, 1)
+    rho = 1.0 + 0.3 * smooth_field(NC, 142, 1)
+    reg_ref = oracle.fluxreg(NC, mask, cflux, fflux, 1.0, vol)
+    rhs_neg = -(-reg_ref + inc)
+    z = np.zeros((1,) + NC[::-1])
+    mg = oracle.mg_default(rtol=1e-12, atol=1e-14)
+    u, v, w, phi, rc, _ = oracle.mac_project((dxc,) * 3, z[0], z[0], z[0], rho[0], rhs_neg[0], z[0], 2.0 / dt, mg)
+    assert rc == 0
+    reg = C.c_void_p()
+    lib.check(lib.iamrx_fluxreg_create(clev.h, flev.h, 1, C.byref(reg)))
+    CF = [[to_fab(cflux[d], b, 0, t, dev) for b in cboxes] for d, t in enumerate((ix.XFACE, ix.YFACE, ix.ZFACE))]
+    FF = [[to_fab(fflux[d], b, 0, t, dev) for b in fboxes] for d, t in enumerate((ix.XFACE, ix.YFACE, ix.ZFACE))]
+    fa = lambda L: fab_array([p[1] for p in L])
+    lib.check(lib.iamrx_fluxreg_reset(reg, stream_of(dev)))
+    lib.check(lib.iamrx_fluxreg_crse_add(reg, fa(CF[0]), fa(CF[1]), fa(CF[2]), 1.0, vol, stream_of(dev)))
+    lib.check(lib.iamrx_fluxreg_fine_add(reg, fa(FF[0]), fa(FF[1]), fa(FF[2]), 1.0, vol, stream_of(dev)))
+    RH = [to_fab(rho, b, 1, ix.CELL, dev) for b in cboxes]
+    IN = [to_fab(inc, b, 0, ix.CELL, dev) for b in cboxes]
+    PH = [to_fab(z, b, 1, ix.CELL, dev) for b in cboxes]
+    UC = [[to_fab(z, b, 0, t, dev) for b in cboxes] for t in (ix.XFACE, ix.YFACE, ix.ZFACE)]
+    info = ix.MGInfo()
+    lib.iamrx_mg_info_default(C.byref(info))
+    info.rtol, info.atol = 1e-12, 1e-14
+    rc = lib.iamrx_mac_sync_solve(clev.h, reg, fa(RH), fa(IN), fa(UC[0]), fa(UC[1]), fa(UC[2]), fa(PH), dt, None, None, C.byref(info),
+                                  stream_of(dev))
+    lib.check(rc)
+    sync(dev)
+    for d, (t, ref) in enumerate(zip((ix.XFACE, ix.YFACE, ix.ZFACE), (u, v, w))):
+        got, dup = from_fabs([p[0] for p in UC[d]], cboxes, 0, t, NC, 1)
+        assert dup <= 1e-12
+        assert np.abs(got[0] + ref).max() <= 1e-10 * max(1.0, np.abs(ref).max())       # Ucorr = -(0 - beta grad phi)
+    gp, _ = from_fabs([p[0] for p in PH], cboxes, 1, ix.CELL, NC, 1)
+    assert np.abs((gp[0] - gp[0].mean()) - (phi - phi.mean())).max() <= 1e-10 * max(1.0, np.abs(phi).max())
+    lib.iamrx_fluxreg_destroy(reg)
+    clev.close(); flev.close()
