@@ -847,7 +847,22 @@ static bool e2e_3d() {
   if (on < 0) { const char* e = getenv("IAMRX_E2E_3D"); on = (e && e[0] == '0') ? 0 : 1; }
   return on != 0;
 }
+// IAMRX_E2E_ZC=1: the pack / unpack kernels read and write the pinned host arrays directly over PCIe (zero copy) instead of the DMA
+// engines' strided copies -- only when the pointer is pinned memory the device can address
+static double* e2e_zero_copy(const void* host) {   // the device's address of the pinned host array, or nullptr
+  static int on = -1;
+  if (on < 0) { const char* e = getenv("IAMRX_E2E_ZC"); on = (e && e[0] == '1') ? 1 : 0; }
+  if (!on) return nullptr;
+  cudaPointerAttributes a{};
+  if (cudaPointerGetAttributes(&a, host) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+  return a.type == cudaMemoryTypeHost ? (double*)a.devicePointer : nullptr;
+}
 static int copy3d(const Bx& b, V4 dev, int dcomp, double* host, int ncomp, bool to_device, cudaStream_t s) {
+  if (double* hz = e2e_zero_copy(host)) {
+    V4 d = dev; d.p = dev.p + dcomp * dev.ns;
+    if (to_device) return k::unpack(b, d, hz, ncomp, s);
+    return k::pack(b, hz, C4{d.p, d.l0, d.l1, d.l2, d.js, d.ks, d.ns}, ncomp, s);
+  }
   if (dev.js <= 0 || dev.ks % dev.js != 0) return IAMRX_ERR_ARG;
   const size_t nx = (size_t)b.nx(), ny = (size_t)b.ny(), nz = (size_t)b.nz();
   for (int n = 0; n < ncomp; ++n) {
