@@ -115,8 +115,14 @@ CellMG::CellMG(Level* fine, int ncomp, bool tensor, int max_coarsening)
   for (auto& L : lv_) {
     for (int d = 0; d < 3; ++d) L.dxinv[d] = L.lev->dxinv[d];
     L.deep = deep_on && !L.lev->replicated && L.lev->level_wrapmask() != 7 && all_periodic(*L.lev);
-    L.cor.define(L.lev, IX_CELL, ncomp_, L.deep ? 2 : 1);
-    L.res.define(L.lev, IX_CELL, ncomp_, L.deep ? 1 : 0);
+    // deep levels: 2 m ghost layers of the correction, 2 m - 1 of the right-hand side and of the coefficients let m sweeps run on ONE
+    // exchange (red / black passes on boxes that shrink by one layer per pass, recomputing what the neighbour computes); m = 2 =
+    // the pre- or post-smoothing of a V-cycle (IAMRX_CELL_DEEP_SWEEPS=1: one sweep per exchange)
+    static int dsw = -1;
+    if (dsw < 0) { const char* e = getenv("IAMRX_CELL_DEEP_SWEEPS"); dsw = (e && atoi(e) == 1) ? 1 : 2; }
+    L.deep_sweeps = L.deep ? dsw : 0;
+    L.cor.define(L.lev, IX_CELL, ncomp_, L.deep ? 2 * dsw : 1);
+    L.res.define(L.lev, IX_CELL, ncomp_, L.deep ? 2 * dsw - 1 : 0);
     L.rescor.define(L.lev, IX_CELL, ncomp_, 0);
     if (L.xfer_lev) L.xfer.define(L.xfer_lev.get(), IX_CELL, ncomp_, 0);
   }
@@ -263,19 +269,19 @@ int CellMG::set_coeffs(const MF* acoef, const MF* bx, const MF* by, const MF* bz
   {
     MGLevelCell& L = lv_[0];
     if (a_ != 0.0 && acoef) {
-      if (!L.acoef.ok()) L.acoef.define(L.lev, IX_CELL, 1, L.deep ? 1 : 0);
+      if (!L.acoef.ok()) L.acoef.define(L.lev, IX_CELL, 1, L.deep ? 2 * L.deep_sweeps - 1 : 0);
       IX_TRY(mf_copy(L.acoef, *acoef, 0, 0, 1, 0, s));
-      if (L.deep) IX_TRY(mf_fill_boundary(L.acoef, 0, 1, 1, s));
+      if (L.deep) IX_TRY(mf_fill_boundary(L.acoef, 0, 1, L.acoef.ng, s));
     }
     for (int d = 0; d < 3; ++d) {
-      if (!L.b[d].ok()) L.b[d].define(L.lev, IX_XFACE + d, bn, L.deep ? 1 : 0);
+      if (!L.b[d].ok()) L.b[d].define(L.lev, IX_XFACE + d, bn, L.deep ? 2 * L.deep_sweeps - 1 : 0);
       // the tensor operator's nine constant face arrays are never read on the constant-coefficient path (the MAC operator's
       // are: mac_update / getFluxes take beta from them)
       for (int c = 0; c < bn && !(tensor_ && cc_); ++c) {
         const double fac = (tensor_ && c == d) ? (4.0 / 3.0) : 1.0;
         IX_TRY(mf_lincomb(L.b[d], c, fac, *bin[d], 0, 0.0, *bin[d], 0, 1, 0, s));
       }
-      if (L.deep) IX_TRY(mf_fill_boundary(L.b[d], 0, bn, 1, s));   // deep-ghost sweeps relax the first ghost layer too
+      if (L.deep) IX_TRY(mf_fill_boundary(L.b[d], 0, bn, L.b[d].ng, s));   // deep-ghost sweeps relax the ghost layers too
     }
   }
   // constant coefficients: the coarse levels' arrays are never read (averages of a constant are that constant, exactly)
@@ -283,7 +289,7 @@ int CellMG::set_coeffs(const MF* acoef, const MF* bx, const MF* by, const MF* bz
     MGLevelCell& C = lv_[l];
     MGLevelCell& F = lv_[l - 1];
     if (a_ != 0.0 && acoef && !cac_) {
-      if (!C.acoef.ok()) C.acoef.define(C.lev, IX_CELL, 1, C.deep ? 1 : 0);
+      if (!C.acoef.ok()) C.acoef.define(C.lev, IX_CELL, 1, C.deep ? 2 * C.deep_sweeps - 1 : 0);
       if (C.xfer_lev) {   // restrict on the distributed layout, then gather into the replicated box
         MF tmp(C.xfer_lev.get(), IX_CELL, 1, 0);
         for (int il = 0; il < tmp.n(); ++il) IX_TRY(k::cc_restrict(tmp.vbox(il), tmp.v(il), F.acoef.c(il), 1, s, thin_));
@@ -292,10 +298,10 @@ int CellMG::set_coeffs(const MF* acoef, const MF* bx, const MF* by, const MF* bz
         for (int il = 0; il < C.acoef.n(); ++il)
           IX_TRY(k::cc_restrict(C.acoef.vbox(il), C.acoef.v(il), F.acoef.c(il), 1, s, thin_));
       }
-      if (C.deep) IX_TRY(mf_fill_boundary(C.acoef, 0, 1, 1, s));
+      if (C.deep) IX_TRY(mf_fill_boundary(C.acoef, 0, 1, C.acoef.ng, s));
     }
     for (int d = 0; d < 3; ++d) {
-      if (!C.b[d].ok()) C.b[d].define(C.lev, IX_XFACE + d, bn, C.deep ? 1 : 0);
+      if (!C.b[d].ok()) C.b[d].define(C.lev, IX_XFACE + d, bn, C.deep ? 2 * C.deep_sweeps - 1 : 0);
       if (cc_) continue;
       if (C.xfer_lev) {
         MF tmp(C.xfer_lev.get(), IX_XFACE + d, bn, 0);
@@ -305,7 +311,7 @@ int CellMG::set_coeffs(const MF* acoef, const MF* bx, const MF* by, const MF* bz
         for (int il = 0; il < C.b[d].n(); ++il)
           IX_TRY(k::face_restrict(C.b[d].vbox(il), d, C.b[d].v(il), F.b[d].c(il), bn, s, thin_));
       }
-      if (C.deep) IX_TRY(mf_fill_boundary(C.b[d], 0, bn, 1, s));
+      if (C.deep) IX_TRY(mf_fill_boundary(C.b[d], 0, bn, C.b[d].ng, s));
     }
   }
   // the operator annihilates constants when a = 0 and no side pins the solution (periodic / Neumann everywhere)
@@ -343,19 +349,23 @@ int CellMG::smooth(int l, MF& phi, const MF& rhs, int nsweeps, bool zero_init, c
     return IAMRX_OK;
   }
   if (L.deep && !has_bc_ && phi.ng >= 2 && rhs.ng >= 1) {
-    // deep-ghost sweep: one exchange of two ghost layers, the red pass on the box grown by one cell towards its neighbours (the
-    // same arithmetic on the same values as the neighbour's own red pass), the black pass on the box.  A zero initial guess
-    // (ghost layers included) needs no exchange before the first sweep.
-    if (!L.rhs_ghost_ok) { IX_TRY(mf_fill_boundary(const_cast<MF&>(rhs), 0, ncomp_, 1, s, wm)); L.rhs_ghost_ok = true; }
-    for (int sw = 0; sw < nsweeps; ++sw) {
-      if (!(zero_init && sw == 0)) IX_TRY(mf_fill_boundary(phi, 0, ncomp_, 2, s, wm));
-      for (int rb = 0; rb < 2; ++rb)
+    // deep-ghost sweeps: ONE exchange of 2 c ghost layers for c sweeps; pass p of the batch (red, black, red, ...) runs on the box
+    // grown by 2 c - 1 - p cells towards its neighbours -- the same arithmetic on the same values as the neighbour's own passes --
+    // so the last black pass is on the box itself.  A zero initial guess (ghost layers included) needs no exchange for its batch.
+    const int cmax = std::max(1, std::min(std::min(phi.ng / 2, (rhs.ng + 1) / 2), L.deep_sweeps));
+    if (!L.rhs_ghost_ok) { IX_TRY(mf_fill_boundary(const_cast<MF&>(rhs), 0, ncomp_, std::min(rhs.ng, 2 * cmax - 1), s, wm)); L.rhs_ghost_ok = true; }
+    for (int s0 = 0; s0 < nsweeps; s0 += cmax) {
+      const int c = std::min(cmax, nsweeps - s0);
+      const bool zero = zero_init && s0 == 0;
+      if (!zero) IX_TRY(mf_fill_boundary(phi, 0, ncomp_, 2 * c, s, wm));
+      for (int p = 0; p < 2 * c; ++p)
         for (int il = 0; il < phi.n(); ++il) {
           Bx b = phi.vbox(il);
-          if (rb == 0) for (int d = 0; d < 3; ++d) if (!(wm & (1 << d))) b = grow(b, d, 1);
-          // zero initial guess: the first red pass (on the grown box) writes every cell the black pass reads -- the coloured cells
-          // and zeros in between; the second ghost layer is refilled by the next sweep's exchange before anything reads it
-          IX_TRY(k::abec_gsrb(b, phi.v(il), rhs.c(il), op_at(l, il), info_.omega, rb, ncomp_, s, wm, nullptr, zero_init && sw == 0 && rb == 0));
+          const int g = 2 * c - 1 - p;
+          for (int d = 0; d < 3; ++d) if (!(wm & (1 << d))) b = grow(b, d, g);
+          // zero initial guess: the first red pass (on the largest box) writes every cell the later passes read -- the coloured
+          // cells and zeros in between; the outermost ghost layer is refilled by the next exchange before anything reads it
+          IX_TRY(k::abec_gsrb(b, phi.v(il), rhs.c(il), op_at(l, il), info_.omega, p & 1, ncomp_, s, wm, nullptr, zero && p == 0));
         }
     }
     return IAMRX_OK;

@@ -26,6 +26,7 @@ struct MGLevelCell {
   // red-black sweep needs ONE ghost exchange (the red pass also updates the first ghost layer, redundantly with the
   // neighbour) instead of one per colour; the right-hand side's ghost layer is exchanged once per V-cycle visit
   bool deep = false;
+  int deep_sweeps = 0;   // sweeps per exchange on a deep level (ghost depths: cor 2 m, res / coefficients 2 m - 1)
   bool rhs_ghost_ok = false;
 };
 
