@@ -466,6 +466,62 @@ static int replicated_coarse(Level* CL, const iamrx_fab* crse, int scomp, int nc
   return IAMRX_OK;
 }
 
+// amrex::average_down between two levels (NavierStokesBase::avgDown, NSB.cpp:3913-3937 / average_down :3939-3990; avgDown of the
+// state and the pressure in NS.cpp:1840-1933): the fine data averaged onto the coarsened fine layout where they live, gathered into
+// one replicated coarse-domain box, and copied from there into every local coarse box where a fine box covers it.  Cells: mean of
+// the 8 children; nodes: injection (Press_Type, avgDown of the pressure); faces: mean of the 4 fine faces.
+int iamrx_average_down(iamrx_level_t fine_lev, iamrx_level_t crse_lev, const iamrx_fab* fine, iamrx_fab* crse, int scomp, int ncomp,
+                       int ixtype, void* stream) {
+  IX_NEED_DEVICE();
+  IX_ARG(fine_lev && crse_lev && fine && crse && ncomp >= 1 && scomp >= 0 && ixtype >= 0 && ixtype <= 4, "average_down arguments");
+  Level* FL = level_of(fine_lev);
+  Level* CL = level_of(crse_lev);
+  cudaStream_t s = (cudaStream_t)stream;
+  for (int d = 0; d < 3; ++d)
+    IX_ARG(FL->geom.domain.lo[d] == 2 * CL->geom.domain.lo[d] && FL->geom.domain.hi[d] == 2 * CL->geom.domain.hi[d] + 1,
+           "the fine level's domain must be the coarse one refined by 2");
+  // 1. coarsened fine layout (same owners): average where the fine data are
+  std::vector<Bx> cfb;
+  for (const Bx& b : FL->boxes) {
+    Bx c;
+    for (int d = 0; d < 3; ++d) {
+      IX_ARG((b.lo[d] & 1) == 0 && (b.hi[d] & 1) == 1, "fine boxes must be coarsenable by 2");
+      c.lo[d] = b.lo[d] / 2; c.hi[d] = (b.hi[d] - 1) / 2;   // (floor division for negative indices is not needed: lo even, hi odd)
+      if (b.lo[d] < 0) c.lo[d] = -((-b.lo[d] + 1) / 2);
+      if (b.hi[d] < 0) c.hi[d] = -((-b.hi[d] + 1) / 2);
+    }
+    cfb.push_back(c);
+  }
+  std::unique_ptr<Level> CFL = make_level(CL->geom, cfb, FL->owner);
+  MF fm; fm.alias(FL, ixtype, scomp + ncomp, 0, const_cast<iamrx_fab*>(fine));
+  MF cf(CFL.get(), ixtype, ncomp, 0);
+  for (int il = 0; il < cf.n(); ++il) {
+    const Bx b = cf.vbox(il);
+    if (ixtype == IX_CELL) IX_TRY(k::cc_restrict(b, cf.v(il), fm.c(il, scomp), ncomp, s));
+    else if (ixtype == IX_NODE) IX_TRY(k::average_down_nodal(b, cf.v(il), fm.c(il, scomp), ncomp, s));
+    else IX_TRY(k::face_restrict(b, ixtype - 1, cf.v(il), fm.c(il, scomp), ncomp, s));
+  }
+  // 2. one replicated box over the coarse domain
+  std::vector<Bx> one{mkbx(CL->geom.domain)};
+  std::vector<int> own{comm().rank};
+  std::unique_ptr<Level> RL = make_level(CL->geom, one, own);
+  RL->replicated = true;
+  MF cr(RL.get(), ixtype, ncomp, 0);
+  if (comm().nranks <= 1 && cf.n() == 0) return IAMRX_OK;
+  IX_TRY(mf_gather_replicate(cr, cf, ncomp, s));
+  // 3. into the coarse boxes, only where a fine box covers them
+  MF cm; cm.alias(CL, ixtype, scomp + ncomp, 0, crse);
+  for (int il = 0; il < cm.n(); ++il) {
+    const Bx vb = cm.vbox(il);
+    for (const Bx& c : cfb) {
+      Bx r = ixbox(c, ixtype);
+      for (int d = 0; d < 3; ++d) { r.lo[d] = std::max(r.lo[d], vb.lo[d]); r.hi[d] = std::min(r.hi[d], vb.hi[d]); }
+      if (r.ok()) IX_TRY(k::copy(r, cm.v(il, scomp), cr.c(0), ncomp, s));
+    }
+  }
+  return IAMRX_OK;
+}
+
 // NavierStokesBase::SyncInterp (NSB.cpp:3071-3255): see iamrx.h
 int iamrx_sync_interp(iamrx_level_t fine_lev, iamrx_level_t crse_lev, iamrx_fab* fine_sync, int dest_comp, const iamrx_fab* crse_sync,
                       int src_comp, int ncomp, int increment, double dt_clev, int which_interp, const iamrx_bcrec* bcrec, void* stream) {

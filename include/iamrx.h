@@ -465,6 +465,13 @@ int iamrx_fillpatch_two_levels(iamrx_level_t fine_lev, iamrx_level_t crse_lev, i
                                const iamrx_fab* crse_new, double t_old, double t_new, double time, int ncomp, int ngrow,
                                const iamrx_bcrec* bcrec, const double* bcvals, void* stream);
 
+/* amrex::average_down between two levels (NavierStokesBase::avgDown / average_down, NSB.cpp:3913-3990; NS.cpp:1840-1933 for the state and
+ * the pressure): crse[scomp .. scomp+ncomp) = average of fine[scomp ..) wherever a fine box covers the coarse level, untouched elsewhere.
+ * ixtype CELL: mean of the 8 children; NODE: injection; faces: mean of the 4 fine faces.  fine / crse: one fab per local box of the
+ * respective level (no ghost cells needed).  Collective (the fine and the coarse boxes of a region may live on different ranks). */
+int iamrx_average_down(iamrx_level_t fine_lev, iamrx_level_t crse_lev, const iamrx_fab* fine, iamrx_fab* crse, int scomp, int ncomp,
+                       int ixtype, void* stream);
+
 /* NavierStokesBase::SyncInterp (NSB.cpp:3071-3255): interpolate a coarse-level sync correction (Vsync / Ssync, or the velocity
  * correction of level_sync) onto the fine level -- coarse data with periodic images and the HOMOGENEOUS ext_dir fill of the original
  * quantity's BCRec (HomExtDirFill), interpolated with pc_interp or cell_cons_interp; increment != 0: fine[dest..] += dt_clev * I(crse)

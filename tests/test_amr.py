@@ -387,3 +387,36 @@ def test_mac_sync_solve(backend, oracle):
     assert np.abs((gp[0] - gp[0].mean()) - (phi - phi.mean())).max() <= 1e-10 * max(1.0, np.abs(phi).max())
     lib.iamrx_fluxreg_destroy(reg)
     clev.close(); flev.close()
+
+
+@pytest.mark.parametrize("layout", FINE_LAYOUTS)
+@pytest.mark.parametrize("ixtype", [ix.CELL, ix.NODE, ix.XFACE])
+def test_average_down_levels(backend, oracle, layout, ixtype):
+    """amrex::average_down between two levels (NavierStokesBase::avgDown): coarse data replaced by the averaged fine data under the
+    fine grids, untouched elsewhere; components outside [scomp, scomp + ncomp) untouched."""
+    lib, dev = backend
+    scomp, ncomp = 1, 2
+    clev, flev, cboxes, fboxes = _level_pair(lib, layout)
+    fine = hash_uniform(151 + ixtype, (scomp + ncomp,) + NF[::-1])
+    crse = hash_uniform(161 + ixtype, (scomp + ncomp,) + NC[::-1])
+    ref_avg = oracle.average_down(NC, ixtype, fine[scomp:])
+    ext = {ix.CELL: (0, 0, 0), ix.NODE: (1, 1, 1), ix.XFACE: (1, 0, 0)}[ixtype]
+    FI = [to_fab(fine, b, 0, ixtype, dev) for b in fboxes]
+    CR = [to_fab(crse, b, 0, ixtype, dev) for b in cboxes]
+    fa = lambda L: fab_array([p[1] for p in L])
+    lib.check(lib.iamrx_average_down(flev.h, clev.h, fa(FI), fa(CR), scomp, ncomp, ixtype, stream_of(dev)))
+    sync(dev)
+    for (t, _), (blo, bhi) in zip(CR, cboxes):
+        a = t.cpu().numpy()
+        exp, _ = to_fab(crse, (blo, bhi), 0, ixtype, "cpu")
+        exp = exp.numpy().copy()
+        for lo, hi in layout:     # covered region (points of the coarsened fine box), clipped to this coarse box (periodic images not needed here)
+            r_lo = [max(lo[d], blo[d]) for d in range(3)]
+            r_hi = [min(hi[d] + ext[d], bhi[d] + ext[d]) for d in range(3)]
+            if any(r_hi[d] < r_lo[d] for d in range(3)):
+                continue
+            sl_loc = tuple(slice(r_lo[d] - blo[d], r_hi[d] - blo[d] + 1) for d in (2, 1, 0))
+            idx = [np.arange(r_lo[d], r_hi[d] + 1) % NC[d] for d in (2, 1, 0)]
+            exp[(slice(scomp, None),) + sl_loc] = ref_avg[:, idx[0]][:, :, idx[1]][:, :, :, idx[2]]
+        assert np.abs(a - exp).max() <= 1e-15
+    clev.close(); flev.close()
