@@ -126,6 +126,38 @@ __global__ void __launch_bounds__(TX* TY) fr_reflux_kernel(Bx R, V4 state, C4 re
 
 }  // namespace
 
+// create_umac_grown's divergence correction (NSB.cpp:1203-1308, the non-RZ branch): a ghost cell that the fine level does not cover
+// and that has exactly ONE face neighbour in the valid / covered region gets its OUTER face velocity from the divergence constraint.
+// mask: 0 interior (valid cells of this box), 1 covered by another fine box, 2 not covered, 3 outside a physical boundary.
+__global__ void __launch_bounds__(TX* TY) umac_divfix_kernel(Bx g1, Bx vb, C4 mask, V4 u, V4 v, V4 w, C4 divu, double dx0, double dx1,
+                                                             double dx2) {
+  const int k = g1.lo[2] + blockIdx.z;
+  const int j = g1.lo[1] + blockIdx.y * TY + threadIdx.y;
+  const int i = g1.lo[0] + blockIdx.x * TX + threadIdx.x;
+  if (j > g1.hi[1] || i > g1.hi[0]) return;
+  if (mask(i, j, k) != 2.0) return;
+  auto inside = [&](int ii, int jj, int kk) { const double m = mask(ii, jj, kk); return m == 0.0 || m == 1.0; };
+  const int count = (int)inside(i - 1, j, k) + (int)inside(i + 1, j, k) + (int)inside(i, j - 1, k) + (int)inside(i, j + 1, k) +
+                    (int)inside(i, j, k - 1) + (int)inside(i, j, k + 1);
+  if (count != 1) return;
+  const double div = divu.ok() ? divu(i, j, k) : 0.0;
+  const double dux = (1.0 / dx0) * (u(i + 1, j, k) - u(i, j, k));
+  const double duy = (1.0 / dx1) * (v(i, j + 1, k) - v(i, j, k));
+  const double duz = (1.0 / dx2) * (w(i, j, k + 1) - w(i, j, k));
+  if (i < vb.lo[0] && mask(i + 1, j, k) != 2.0) u(i, j, k) = u(i + 1, j, k) + dx0 * (duy + duz - div);
+  else if (i > vb.hi[0] && mask(i - 1, j, k) != 2.0) u(i + 1, j, k) = u(i, j, k) - dx0 * (duy + duz - div);
+  if (j < vb.lo[1] && mask(i, j + 1, k) != 2.0) v(i, j, k) = v(i, j + 1, k) + dx1 * (dux + duz - div);
+  else if (j > vb.hi[1] && mask(i, j - 1, k) != 2.0) v(i, j + 1, k) = v(i, j, k) - dx1 * (dux + duz - div);
+  if (k < vb.lo[2] && mask(i, j, k + 1) != 2.0) w(i, j, k) = w(i, j, k + 1) + dx2 * (dux + duy - div);
+  else if (k > vb.hi[2] && mask(i, j, k - 1) != 2.0) w(i, j, k + 1) = w(i, j, k) - dx2 * (dux + duy - div);
+}
+int umac_divfix(const Bx& vb, C4 mask, V4 u, V4 v, V4 w, C4 divu, const double dx[3], cudaStream_t s) {
+  const Bx g1 = grow(vb, 1);
+  IX_LAUNCH(umac_divfix_kernel, dim3(cdiv(g1.nx(), TX), cdiv(g1.ny(), TY), g1.nz()), dim3(TX, TY, 1), 0, s, g1, vb, mask, u, v, w, divu,
+            dx[0], dx[1], dx[2]);
+  return check_launch("umac_divfix");
+}
+
 int average_down_nodal(const Bx& cnbx, V4 crse, C4 fine, int ncomp, cudaStream_t s) {
   if (!cnbx.ok()) return IAMRX_OK;
   IX_LAUNCH(node_inject_kernel, grid_for(cnbx, cnbx.nz() * ncomp), dim3(TX, TY, 1), 0, s, cnbx, crse, fine);
@@ -519,6 +551,73 @@ int iamrx_average_down(iamrx_level_t fine_lev, iamrx_level_t crse_lev, const iam
       if (r.ok()) IX_TRY(k::copy(r, cm.v(il, scomp), cr.c(0), ncomp, s));
     }
   }
+  return IAMRX_OK;
+}
+
+// NavierStokesBase::create_umac_grown on a level > 0 (NSB.cpp:1108-1310): see iamrx.h
+int iamrx_create_umac_grown(iamrx_level_t fine_lev, iamrx_level_t crse_lev, iamrx_fab* umac_f, iamrx_fab* vmac_f, iamrx_fab* wmac_f,
+                            const iamrx_fab* umac_c, const iamrx_fab* vmac_c, const iamrx_fab* wmac_c, const iamrx_fab* divu, void* stream) {
+  IX_NEED_DEVICE();
+  IX_ARG(fine_lev && crse_lev && umac_f && vmac_f && wmac_f && umac_c && vmac_c && wmac_c, "create_umac_grown arguments");
+  Level* FL = level_of(fine_lev);
+  Level* CL = level_of(crse_lev);
+  cudaStream_t s = (cudaStream_t)stream;
+  for (int d = 0; d < 3; ++d)
+    IX_ARG(FL->geom.domain.lo[d] == 2 * CL->geom.domain.lo[d] && FL->geom.domain.hi[d] == 2 * CL->geom.domain.hi[d] + 1,
+           "the fine level's domain must be the coarse one refined by 2");
+  const Bx fdom = mkbx(FL->geom.domain);
+  iamrx_fab* uf[3] = {umac_f, vmac_f, wmac_f};
+  const iamrx_fab* uc[3] = {umac_c, vmac_c, wmac_c};
+  // 1. FillPatchTwoLevels of the face velocities with face_linear_interp (piecewise constant in time), one ghost cell: every face
+  //    of the grown box from the coarse level, then the box's own faces, then the fine neighbours' (and their periodic images)
+  for (int d = 0; d < 3; ++d) {
+    std::unique_ptr<Level> RL;
+    MF cr;
+    IX_TRY(replicated_coarse(CL, uc[d], 0, 1, IX_XFACE + d, 1, nullptr, s, RL, cr));
+    MF um; um.alias(FL, IX_XFACE + d, 1, 1, uf[d]);
+    MF tmp(FL, IX_XFACE + d, 1, 1);
+    for (int il = 0; il < um.n(); ++il) {
+      Bx gb = grow(FL->lbox(il), 1);
+      for (int q = 0; q < 3; ++q)
+        if (!FL->geom.periodic[q]) { gb.lo[q] = std::max(gb.lo[q], fdom.lo[q]); gb.hi[q] = std::min(gb.hi[q], fdom.hi[q]); }
+      IX_TRY(k::copy(um.gbox(il, 1), tmp.v(il), um.c(il), 1, s));                       // (cells outside a physical boundary keep the caller's values)
+      IX_TRY(k::face_linear_interp(ixbox(gb, IX_XFACE + d), d, tmp.v(il), cr.c(0), 1, s));
+      IX_TRY(k::copy(um.vbox(il), tmp.v(il), um.c(il), 1, s));
+    }
+    IX_TRY(mf_fill_boundary(tmp, 0, 1, 1, s));
+    for (int il = 0; il < um.n(); ++il) IX_TRY(k::copy(um.gbox(il, 1), um.v(il), tmp.c(il), 1, s));
+  }
+  // 2. the coarse-fine mask on the boxes grown by 2 (iMultiFab::BuildMask: interior / covered / not covered / physical boundary)
+  MF mask(FL, IX_CELL, 1, 2);
+  IX_TRY(mf_setval(mask, 3.0, 0, 1, 2, s));
+  for (int il = 0; il < mask.n(); ++il) {
+    const Bx vb = FL->lbox(il), g2 = grow(vb, 2);
+    Bx in = g2;
+    for (int q = 0; q < 3; ++q)
+      if (!FL->geom.periodic[q]) { in.lo[q] = std::max(in.lo[q], fdom.lo[q]); in.hi[q] = std::min(in.hi[q], fdom.hi[q]); }
+    IX_TRY(k::setval(in, mask.v(il), 1, 2.0, s));
+    int sh[3];
+    for (sh[2] = -1; sh[2] <= 1; ++sh[2])
+      for (sh[1] = -1; sh[1] <= 1; ++sh[1])
+        for (sh[0] = -1; sh[0] <= 1; ++sh[0]) {
+          bool okshift = true;
+          for (int q = 0; q < 3; ++q) if (sh[q] != 0 && !FL->geom.periodic[q]) okshift = false;
+          if (!okshift) continue;
+          for (const Bx& ob : FL->boxes) {
+            Bx r = ob;
+            for (int q = 0; q < 3; ++q) { const int n = fdom.hi[q] - fdom.lo[q] + 1; r.lo[q] += sh[q] * n; r.hi[q] += sh[q] * n; }
+            for (int q = 0; q < 3; ++q) { r.lo[q] = std::max(r.lo[q], g2.lo[q]); r.hi[q] = std::min(r.hi[q], g2.hi[q]); }
+            if (r.ok()) IX_TRY(k::setval(r, mask.v(il), 1, 1.0, s));
+          }
+        }
+    IX_TRY(k::setval(vb, mask.v(il), 1, 0.0, s));
+  }
+  // 3. the divergence correction of the one-cell halo
+  MF U[3];
+  for (int d = 0; d < 3; ++d) U[d].alias(FL, IX_XFACE + d, 1, 1, uf[d]);
+  MF Dv; if (divu) Dv.alias(FL, IX_CELL, 1, 1, const_cast<iamrx_fab*>(divu));
+  for (int il = 0; il < mask.n(); ++il)
+    IX_TRY(k::umac_divfix(FL->lbox(il), mask.c(il), U[0].v(il), U[1].v(il), U[2].v(il), divu ? Dv.c(il) : C4{}, FL->geom.dx, s));
   return IAMRX_OK;
 }
 

@@ -197,6 +197,8 @@ int nodal_bc_scale(const Bx& nbx, V4 a, const NodalBC& bc, const Bx& ndom, const
 int average_down_nodal(const Bx& cnbx, V4 crse, C4 fine, int ncomp, cudaStream_t s);
 int cell_cons_interp(const Bx& fbx, V4 fine, C4 crse, int ncomp, cudaStream_t s);
 int pc_interp(const Bx& fbx, V4 fine, C4 crse, int ncomp, cudaStream_t s);   // piecewise constant
+// create_umac_grown's divergence correction on the one-cell halo of a fine box (mask: 0 interior, 1 covered, 2 not covered, 3 physbnd)
+int umac_divfix(const Bx& vb, C4 mask, V4 u, V4 v, V4 w, C4 divu, const double dx[3], cudaStream_t s);
 int node_bilinear_interp(const Bx& fnbx, V4 fine, C4 crse, int ncomp, cudaStream_t s);
 int face_linear_interp(const Bx& ffbx, int dir, V4 fine, C4 crse, int ncomp, cudaStream_t s);
 

@@ -472,6 +472,16 @@ int iamrx_fillpatch_two_levels(iamrx_level_t fine_lev, iamrx_level_t crse_lev, i
 int iamrx_average_down(iamrx_level_t fine_lev, iamrx_level_t crse_lev, const iamrx_fab* fine, iamrx_fab* crse, int scomp, int ncomp,
                        int ixtype, void* stream);
 
+/* NavierStokesBase::create_umac_grown on a level > 0 (NSB.cpp:1108-1310): the ghost faces (one ghost cell) of the fine MAC velocities from
+ * FillPatchTwoLevels with face_linear_interp -- coarse values on coincident faces, the mean of the two coarse faces in between; faces a
+ * fine neighbour (or its periodic image) owns take its values -- then the divergence correction: a ghost cell the fine level does not
+ * cover and with exactly one face neighbour in the valid / covered region gets its OUTER face velocity from div(u_mac) = divu
+ * (0 if divu is NULL); grid edges and corners are left as interpolated.  u/v/wmac_f: face fabs of every local fine box with ONE
+ * ghost cell; u/v/wmac_c: face fabs of every local coarse box; divu: fine cell fabs with one ghost cell, or NULL.  Cells outside a
+ * non-periodic domain are not touched.  Collective. */
+int iamrx_create_umac_grown(iamrx_level_t fine_lev, iamrx_level_t crse_lev, iamrx_fab* umac_f, iamrx_fab* vmac_f, iamrx_fab* wmac_f,
+                            const iamrx_fab* umac_c, const iamrx_fab* vmac_c, const iamrx_fab* wmac_c, const iamrx_fab* divu, void* stream);
+
 /* NavierStokesBase::SyncInterp (NSB.cpp:3071-3255): interpolate a coarse-level sync correction (Vsync / Ssync, or the velocity
  * correction of level_sync) onto the fine level -- coarse data with periodic images and the HOMOGENEOUS ext_dir fill of the original
  * quantity's BCRec (HomExtDirFill), interpolated with pc_interp or cell_cons_interp; increment != 0: fine[dest..] += dt_clev * I(crse)

@@ -420,3 +420,76 @@ def test_average_down_levels(backend, oracle, layout, ixtype):
             exp[(slice(scomp, None),) + sl_loc] = ref_avg[:, idx[0]][:, :, idx[1]][:, :, :, idx[2]]
         assert np.abs(a - exp).max() <= 1e-15
     clev.close(); flev.close()
+
+
+@pytest.mark.parametrize("layout", FINE_LAYOUTS)
+@pytest.mark.parametrize("with_divu", [0, 1])
+def test_create_umac_grown(backend, oracle, layout, with_divu):
+    """NavierStokesBase::create_umac_grown on the fine level (NSB.cpp:1108-1310): FillPatchTwoLevels of the MAC velocities with
+    face_linear_interp into one ghost cell, then the divergence correction of the halo cells with exactly one valid / covered
+    neighbour (numpy restatement of the reference loop); afterwards those cells satisfy div(u_mac) = divu."""
+    lib, dev = backend
+    clev, flev, cboxes, fboxes = _level_pair(lib, layout)
+    types = (ix.XFACE, ix.YFACE, ix.ZFACE)
+    cmask = np.zeros(NC[::-1], dtype=bool)
+    for lo, hi in layout:
+        cmask[lo[2]:hi[2] + 1, lo[1]:hi[1] + 1, lo[0]:hi[0] + 1] = True
+    fmask = np.repeat(np.repeat(np.repeat(cmask, 2, 0), 2, 1), 2, 2)
+    uc = [smooth_field(NC, 171 + d, 1) for d in range(3)]
+    uf = [hash_uniform(181 + d, (1,) + NF[::-1]) for d in range(3)]
+    divu = 0.3 * smooth_field(NF, 191, 1) if with_divu else None
+    dx = 1.0 / NF[0]
+    filled = []
+    for d in range(3):
+        interp = oracle.interp(2 + d, NC, uc[d])
+        fface = fmask | np.roll(fmask, 1, 2 - d)            # faces of fine cells: the cell above or below the face is fine
+        filled.append(np.where(fface[None], uf[d], interp))
+    UC = [[to_fab(uc[d], b, 0, types[d], dev) for b in cboxes] for d in range(3)]
+    UF = [[to_fab(uf[d], b, 1, types[d], dev, fill_ghost=False) for b in fboxes] for d in range(3)]
+    DV = [to_fab(divu, b, 1, ix.CELL, dev) for b in fboxes] if with_divu else None
+    fa = lambda L: fab_array([p[1] for p in L])
+    lib.check(lib.iamrx_create_umac_grown(flev.h, clev.h, fa(UF[0]), fa(UF[1]), fa(UF[2]), fa(UC[0]), fa(UC[1]), fa(UC[2]),
+                                          fa(DV) if with_divu else None, stream_of(dev)))
+    sync(dev)
+    n = NF
+    for ib, (lo, hi) in enumerate(fboxes):
+        exp = [to_fab(filled[d], (lo, hi), 1, types[d], "cpu")[0].numpy()[0].copy() for d in range(3)]   # [k][j][i], origin lo - 1
+        U, V, W = exp
+        def m(i, j, k):   # 0 interior, 1 covered, 2 not covered (global cell index, periodic)
+            if all(lo[q] <= (i, j, k)[q] <= hi[q] for q in range(3)):
+                return 0
+            return 1 if fmask[k % n[2], j % n[1], i % n[0]] else 2
+        fixed = 0
+        for k in range(lo[2] - 1, hi[2] + 2):
+            for j in range(lo[1] - 1, hi[1] + 2):
+                for i in range(lo[0] - 1, hi[0] + 2):
+                    if m(i, j, k) != 2:
+                        continue
+                    nb = [(i - 1, j, k), (i + 1, j, k), (i, j - 1, k), (i, j + 1, k), (i, j, k - 1), (i, j, k + 1)]
+                    if sum(m(*c) in (0, 1) for c in nb) != 1:
+                        continue
+                    a, b, c = i - (lo[0] - 1), j - (lo[1] - 1), k - (lo[2] - 1)      # local cell index in the grown box
+                    dv = divu[0, k % n[2], j % n[1], i % n[0]] if with_divu else 0.0
+                    dux = (U[c, b, a + 1] - U[c, b, a]) / dx
+                    duy = (V[c, b + 1, a] - V[c, b, a]) / dx
+                    duz = (W[c + 1, b, a] - W[c, b, a]) / dx
+                    if i < lo[0] and m(i + 1, j, k) != 2:
+                        U[c, b, a] = U[c, b, a + 1] + dx * (duy + duz - dv)
+                    elif i > hi[0] and m(i - 1, j, k) != 2:
+                        U[c, b, a + 1] = U[c, b, a] - dx * (duy + duz - dv)
+                    if j < lo[1] and m(i, j + 1, k) != 2:
+                        V[c, b, a] = V[c, b + 1, a] + dx * (dux + duz - dv)
+                    elif j > hi[1] and m(i, j - 1, k) != 2:
+                        V[c, b + 1, a] = V[c, b, a] - dx * (dux + duz - dv)
+                    if k < lo[2] and m(i, j, k + 1) != 2:
+                        W[c, b, a] = W[c + 1, b, a] + dx * (dux + duy - dv)
+                    elif k > hi[2] and m(i, j, k - 1) != 2:
+                        W[c + 1, b, a] = W[c, b, a] - dx * (dux + duy - dv)
+                    fixed += 1
+                    div = (U[c, b, a + 1] - U[c, b, a] + V[c, b + 1, a] - V[c, b, a] + W[c + 1, b, a] - W[c, b, a]) / dx
+                    assert abs(div - dv) <= 1e-12 * max(1.0, abs(dv)) * NF[0]
+        assert fixed > 0
+        for d in range(3):
+            got = UF[d][ib][0].cpu().numpy()[0]
+            assert np.abs(got - exp[d]).max() <= 1e-13, (d, ib)
+    clev.close(); flev.close()
