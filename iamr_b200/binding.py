@@ -195,6 +195,7 @@ SIGNATURES = {
     "iamrx_ns_create": (C.c_int, [_vp, _P(NSParams), _P(_vp)]),
     "iamrx_ns_destroy": (C.c_int, [_vp]),
     "iamrx_debug_fb_stats": (None, [_P(C.c_int64), C.c_int]),
+    "iamrx_ns_mac_sync_compute": (C.c_int, [_vp, _P(Fab), _P(Fab), _P(Fab), _P(Fab), _P(Fab), C.c_double]),
     "iamrx_create_umac_grown": (C.c_int, [_vp, _vp, _P(Fab), _P(Fab), _P(Fab), _P(Fab), _P(Fab), _P(Fab), _P(Fab), _vp]),
     "iamrx_average_down": (C.c_int, [_vp, _vp, _P(Fab), _P(Fab), C.c_int, C.c_int, C.c_int, _vp]),
     "iamrx_mac_sync_solve": (C.c_int, [_vp, _vp, _P(Fab), _P(Fab), _P(Fab), _P(Fab), _P(Fab), _P(Fab), C.c_double, _P(C.c_int), _P(C.c_int),

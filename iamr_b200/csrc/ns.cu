@@ -278,19 +278,22 @@ int mac_project_step(iamrx_ns_s& ns, double dt) {
   return IAMRX_OK;
 }
 
+// sync_out / sync_comp / ucorr: the is_sync call of MacProj::mac_sync_compute (MacProj.cpp:681-707) -- the update accumulates into
+// sync_out[sync_comp ..] and the fluxes are taken with the correction velocities Ucorr instead of u_mac (NSB.cpp:4672-4677)
 int compute_aofs(iamrx_ns_s& ns, int state_comp, int ncomp, const MF& Sq, const MF* forcing, bool is_velocity,
-                 double dt) {
+                 double dt, MF* sync_out = nullptr, int sync_comp = 0, const MF* ucorr = nullptr) {
   // NavierStokesBase::ComputeAofs (NSB.cpp:4555-4591 wrapper, :4594-4845 body)
   Level& L = *ns.L;
   k::AdvGeom g; for (int d = 0; d < 3; ++d) g.dx[d] = L.geom.dx[d]; g.dt = dt;
   for (int il = 0; il < ns.aofs.n(); ++il) {
     k::AofsArgs a{};
-    a.aofs = ns.aofs.v(il, state_comp);
+    a.aofs = sync_out ? sync_out->v(il, sync_comp) : ns.aofs.v(il, state_comp);
     a.S = Sq.c(il);
     a.force = forcing ? forcing->c(il) : C4{};
     a.divu = C4{};  // have_divu == 0: getDivCond returns zeros (NSB.cpp:1577-1590)
     a.umac = ns.umac[0].c(il); a.vmac = ns.umac[1].c(il); a.wmac = ns.umac[2].c(il);
     a.uflx = a.umac; a.vflx = a.vmac; a.wflx = a.wmac;
+    if (sync_out) { a.is_sync = 1; a.uflx = ucorr[0].c(il); a.vflx = ucorr[1].c(il); a.wflx = ucorr[2].c(il); }
     a.ncomp = ncomp;
     for (int n = 0; n < ncomp; ++n) {
       const int sc = state_comp + n;
@@ -972,6 +975,28 @@ int iamrx_ns_write_plotfile(iamrx_ns_t nsp, const char* dir) {
   iamrx_ns_s& ns = *nsp;
   const std::vector<std::string> names = {"x_velocity", "y_velocity", "z_velocity", "density", "tracer", "gradpx", "gradpy", "gradpz"};
   return write_plotfile(*ns.L, {&ns.S_new, &ns.Gp_new}, {0, 0}, {NUM_STATE, 3}, names, dir, "NavierStokes-V1.1", ns.time, ns.nstep, ns.s);
+}
+
+// MacProj::mac_sync_compute (MacProj.cpp:505-731) for the level this object advances, right after iamrx_ns_step: see iamrx.h
+int iamrx_ns_mac_sync_compute(iamrx_ns_t nsp, const iamrx_fab* ucorr, const iamrx_fab* vcorr, const iamrx_fab* wcorr, iamrx_fab* vsync,
+                              iamrx_fab* ssync, double dt) {
+  IX_NEED_DEVICE();
+  IX_ARG(nsp && ucorr && vcorr && wcorr && vsync && dt > 0.0, "mac_sync_compute arguments");
+  iamrx_ns_s& ns = *nsp;
+  IX_ARG(ns.nstep > 0, "mac_sync_compute follows a time step (it reuses that step's FillPatched state and forcing)");
+  Level& L = *ns.L;
+  const iamrx_fab* uc[3] = {ucorr, vcorr, wcorr};
+  MF U[3];
+  for (int d = 0; d < 3; ++d) U[d].alias(&L, IX_XFACE + d, 1, 0, const_cast<iamrx_fab*>(uc[d]));
+  // the state at prev_time, its forcing (visc - grad p + body force, /rho unless do_mom_diff; scalar forcing) and u_mac are the
+  // ones the step's own advection calls used: ns.Umf / ns.Smf / ns.force / ns.sforce / ns.umac still hold them (:519-660)
+  MF Vs; Vs.alias(&L, IX_CELL, 3, 0, vsync);
+  IX_TRY(compute_aofs(ns, Xvel, 3, ns.Umf, &ns.force, true, dt, &Vs, 0, U));                       // :681-691
+  if (ssync) {
+    MF Ss; Ss.alias(&L, IX_CELL, NUM_SCALARS, 0, ssync);
+    IX_TRY(compute_aofs(ns, Density, NUM_SCALARS, ns.Smf, &ns.sforce, false, dt, &Ss, 0, U));    // :695-707
+  }
+  return IAMRX_OK;
 }
 
 int iamrx_ns_last_iters(iamrx_ns_t ns, int iters[3]) {

@@ -586,6 +586,14 @@ int iamrx_ns_nstep(iamrx_ns_t ns);
  * (nodal, 1 ghost), 2 Gradp_new (3 comps, 1 ghost), 3 State_old,
  * 4..6 u_mac (face x,y,z), 7 aofs. */
 int iamrx_ns_field(iamrx_ns_t ns, int which, int ilocal, iamrx_fab* out);
+/* MacProj::mac_sync_compute (MacProj.cpp:505-731) on the level this object advances, to be called right after iamrx_ns_step: the sync
+ * advection with the correction velocities of iamrx_mac_sync_solve -- ComputeAofs(is_sync = true, Ucorr) of the velocity (momenta with
+ * do_mom_diff) and of the scalars on the state at prev_time with the forcing of the step, edge states upwinded with the step's u_mac,
+ * fluxes taken with Ucorr; the results ACCUMULATE into vsync (3 components) and ssync (density, tracer; may be NULL).  ucorr / vcorr /
+ * wcorr: face fabs of every local box; vsync / ssync: cell fabs, no ghost cells.  (The mac-register update of level > 0, :712-730, is
+ * the caller's iamrx_fluxreg_fine_add.) */
+int iamrx_ns_mac_sync_compute(iamrx_ns_t ns, const iamrx_fab* ucorr, const iamrx_fab* vcorr, const iamrx_fab* wcorr, iamrx_fab* vsync,
+                              iamrx_fab* ssync, double dt);
 /* Host-buffer variant of one step (the e2e path): copies the caller's HOST
  * valid-region state (5 comps, no ghosts, box order = local boxes) to the
  * device, advances, copies the new state back.  Both copies are inside. */

@@ -421,3 +421,45 @@ def test_one_step_256_matches_oracle_gpu(cuda_lib, oracle):
     assert np.abs(G - o.get(2)).max() <= 1e-10
     del S, So, G
     ns.close(); o.close(); lev.close()
+
+
+@pytest.mark.parametrize("nb", [(1, 1, 1), (2, 1, 2)])
+def test_mac_sync_compute_identities(backend, nb):
+    """MacProj::mac_sync_compute (MacProj.cpp:505-731) through iamrx_ns_mac_sync_compute, right after a step.  Known answers: for a
+    CONSERVATIVELY advected component the sync update with Ucorr = u_mac is that step's own advective update (the fluxes are the
+    edge states times the flux velocity), so Vsync / Ssync grow by exactly aofs; the update is linear in Ucorr and accumulates."""
+    lib, dev = backend
+    n = (16, 16, 16)
+    boxes = split_boxes(n, nb)
+    lev = ix.Level(lib, ix.Geom.make(n), boxes)
+    ns = ix.NavierStokes(lib, lev, dev, visc_coef=1e-3, cfl=0.5, do_mom_diff=1, conservative_tracer=1)
+    ns.init_prob(100, [1.0, 1.0, 1.0, 1.0, 1.0])
+    ns.post_init()
+    dt = ns.step()
+    import torch
+    from util import fab_array
+    for scale in (1.0, -0.5):
+        UC, VS, SS, keep = [[], [], []], [], [], []
+        for il, (lo, hi) in enumerate(boxes):
+            for d in range(3):
+                t = (scale * ns.field(4 + d, il)).contiguous().clone()          # a COPY of u_mac: the kernels see distinct flux velocities
+                keep.append(t)
+                flo = list(lo)
+                UC[d].append(ix.fab_of(t, flo))
+            shape = tuple(hi[q] - lo[q] + 1 for q in (2, 1, 0))
+            tv = torch.full((3,) + shape, 0.25, dtype=torch.float64, device=dev)
+            ts = torch.full((2,) + shape, -0.75, dtype=torch.float64, device=dev)
+            keep += [tv, ts]
+            VS.append((tv, ix.fab_of(tv, list(lo)))); SS.append((ts, ix.fab_of(ts, list(lo))))
+        lib.check(lib.iamrx_ns_mac_sync_compute(ns.h, fab_array(UC[0]), fab_array(UC[1]), fab_array(UC[2]), fab_array([p[1] for p in VS]),
+                                                fab_array([p[1] for p in SS]), dt))
+        if torch.device(dev).type == "cuda":
+            torch.cuda.synchronize()
+        for il in range(len(boxes)):
+            aofs = ns.field(7, il)
+            ref_v = 0.25 + scale * aofs[0:3]
+            ref_s = -0.75 + scale * aofs[3:5]
+            tol = 1e-12 * max(1.0, float(aofs.abs().max()))
+            assert float((VS[il][0] - ref_v).abs().max()) <= tol
+            assert float((SS[il][0] - ref_s).abs().max()) <= tol
+    ns.close(); lev.close()
