@@ -1,0 +1,137 @@
+"""Worker of tests/test_multirank.py::test_two_level_blocks_two_ranks: one rank of a world_size-2 gloo job.  The collective two-level
+building blocks (FillPatchTwoLevels, average_down, SyncInterp, SyncProjInterp, create_umac_grown) with the coarse and the fine boxes
+owned by DIFFERENT ranks, against the same references the single-rank tests use (oracle interpolaters + numpy)."""
+import ctypes as C
+import os
+import sys
+
+import numpy as np
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+import iamr_b200 as ix  # noqa: E402
+import orc  # noqa: E402
+from mr_worker import EXCH, ARED, exchange, allreduce  # noqa: E402
+from util import split_boxes, hash_uniform, smooth_field, to_fab, fab_array, stream_of  # noqa: E402
+
+NC, NF = (8, 8, 8), (16, 16, 16)
+
+
+def main():
+    rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    lib = ix.load(os.path.join(ROOT, "tests", "emul", "_build", "libiamrx_emul.so"))
+    ex, ar = EXCH(exchange), ARED(allreduce)
+    lib.check(lib.iamrx_comm_set_transport(rank, world, C.cast(ex, C.c_void_p), C.cast(ar, C.c_void_p), None))
+    orc.lib()
+    st = stream_of("cpu")
+    # coarse level: two boxes, rank 0 / rank 1; fine level: two abutting boxes spanning periodic y, owned the OTHER way round
+    cboxes = split_boxes(NC, (2, 1, 1)); cown = [0, 1]
+    layout = [((2, 0, 2), (3, 7, 5)), ((4, 0, 2), (5, 7, 5))]
+    fboxes = [(tuple(2 * l for l in lo), tuple(2 * h + 1 for h in hi)) for lo, hi in layout]; fown = [1, 0]
+    clev = ix.Level(lib, ix.Geom.make(NC), cboxes, cown)
+    flev = ix.Level(lib, ix.Geom.make(NF), fboxes, fown)
+    cmine = [i for i, o in enumerate(cown) if o == rank]
+    fmine = [i for i, o in enumerate(fown) if o == rank]
+    cmask = np.zeros(NC[::-1], dtype=bool)
+    for lo, hi in layout:
+        cmask[lo[2]:hi[2] + 1, lo[1]:hi[1] + 1, lo[0]:hi[0] + 1] = True
+    fmask = np.repeat(np.repeat(np.repeat(cmask, 2, 0), 2, 1), 2, 2)
+    fa = lambda L: fab_array([p[1] for p in L])
+
+    # 1. FillPatchTwoLevels
+    ncomp, ngrow = 2, 3
+    c_old, c_new = smooth_field(NC, 91, ncomp), smooth_field(NC, 92, ncomp)
+    fdat = hash_uniform(94, (ncomp,) + NF[::-1])
+    w = 0.3
+    expect = np.where(fmask[None], fdat, orc.interp(0, NC, (1.0 - w) * c_old + w * c_new))
+    CO = [to_fab(c_old, cboxes[i], 0, ix.CELL, "cpu") for i in cmine]
+    CN = [to_fab(c_new, cboxes[i], 0, ix.CELL, "cpu") for i in cmine]
+    FI = [to_fab(fdat, fboxes[i], ngrow, ix.CELL, "cpu", fill_ghost=False) for i in fmine]
+    lib.check(lib.iamrx_fillpatch_two_levels(flev.h, clev.h, fa(FI), fa(CO), fa(CN), 0.0, 1.0, w, ncomp, ngrow, None, None, st))
+    for (t, _), i in zip(FI, fmine):
+        ref, _ = to_fab(expect, fboxes[i], ngrow, ix.CELL, "cpu")
+        assert np.abs(t.numpy() - ref.numpy()).max() <= 1e-14, ("fillpatch", rank)
+
+    # 2. average_down (cells and nodes)
+    for ixtype in (ix.CELL, ix.NODE):
+        fine = hash_uniform(151 + ixtype, (2,) + NF[::-1])
+        crse = hash_uniform(161 + ixtype, (2,) + NC[::-1])
+        avg = orc.average_down(NC, ixtype, fine)
+        ext = 1 if ixtype == ix.NODE else 0
+        FI = [to_fab(fine, fboxes[i], 0, ixtype, "cpu") for i in fmine]
+        CR = [to_fab(crse, cboxes[i], 0, ixtype, "cpu") for i in cmine]
+        lib.check(lib.iamrx_average_down(flev.h, clev.h, fa(FI), fa(CR), 0, 2, ixtype, st))
+        for (t, _), i in zip(CR, cmine):
+            blo, bhi = cboxes[i]
+            exp = to_fab(crse, cboxes[i], 0, ixtype, "cpu")[0].numpy().copy()
+            for lo, hi in layout:
+                r_lo = [max(lo[d], blo[d]) for d in range(3)]
+                r_hi = [min(hi[d] + ext, bhi[d] + ext) for d in range(3)]
+                if any(r_hi[d] < r_lo[d] for d in range(3)):
+                    continue
+                sl = tuple(slice(r_lo[d] - blo[d], r_hi[d] - blo[d] + 1) for d in (2, 1, 0))
+                idx = [np.arange(r_lo[d], r_hi[d] + 1) % NC[d] for d in (2, 1, 0)]
+                exp[(slice(None),) + sl] = avg[:, idx[0]][:, :, idx[1]][:, :, :, idx[2]]
+            assert np.abs(t.numpy() - exp).max() <= 1e-15, ("average_down", ixtype, rank)
+
+    # 3. SyncInterp (cell-conservative, increment) and SyncProjInterp
+    crse = smooth_field(NC, 101, 2)
+    fine = hash_uniform(103, (2,) + NF[::-1])
+    dt = 0.37
+    expect = fine + dt * orc.interp(0, NC, crse)
+    CS = [to_fab(crse, cboxes[i], 0, ix.CELL, "cpu") for i in cmine]
+    FS = [to_fab(fine, fboxes[i], 0, ix.CELL, "cpu") for i in fmine]
+    lib.check(lib.iamrx_sync_interp(flev.h, clev.h, fa(FS), 0, fa(CS), 0, 2, 1, dt, ix.SYNC_CELL_CONS, None, st))
+    for (t, _), i in zip(FS, fmine):
+        ref, _ = to_fab(expect, fboxes[i], 0, ix.CELL, "cpu")
+        assert np.abs(t.numpy() - ref.numpy()).max() <= 2e-15, ("sync_interp", rank)
+    phi = smooth_field(NC, 111, 1)
+    pn, po = hash_uniform(112, (1,) + NF[::-1]), hash_uniform(113, (1,) + NF[::-1])
+    interp = orc.interp(1, NC, phi)
+    PH = [to_fab(phi, cboxes[i], 0, ix.NODE, "cpu") for i in cmine]
+    PN = [to_fab(pn, fboxes[i], 0, ix.NODE, "cpu") for i in fmine]
+    PO = [to_fab(po, fboxes[i], 0, ix.NODE, "cpu") for i in fmine]
+    lib.check(lib.iamrx_sync_proj_interp(flev.h, clev.h, fa(PN), fa(PO), fa(PH), st))
+    for arr, base in ((PN, pn), (PO, po)):
+        for (t, _), i in zip(arr, fmine):
+            ref, _ = to_fab(base + interp, fboxes[i], 0, ix.NODE, "cpu")
+            assert np.abs(t.numpy() - ref.numpy()).max() <= 2e-15, ("sync_proj_interp", rank)
+
+    # 4. create_umac_grown: the FillPatchTwoLevels part (ghost faces owned by the fine neighbour on the other rank / interpolated from
+    #    coarse data on the other rank); the halo correction itself is local and covered by tests/test_amr.py -- here the cells it
+    #    fixes must come out divergence-free
+    types = (ix.XFACE, ix.YFACE, ix.ZFACE)
+    uc = [smooth_field(NC, 171 + d, 1) for d in range(3)]
+    uf = [hash_uniform(181 + d, (1,) + NF[::-1]) for d in range(3)]
+    UC = [[to_fab(uc[d], cboxes[i], 0, types[d], "cpu") for i in cmine] for d in range(3)]
+    UF = [[to_fab(uf[d], fboxes[i], 1, types[d], "cpu", fill_ghost=False) for i in fmine] for d in range(3)]
+    lib.check(lib.iamrx_create_umac_grown(flev.h, clev.h, fa(UF[0]), fa(UF[1]), fa(UF[2]), fa(UC[0]), fa(UC[1]), fa(UC[2]), None, st))
+    dx = 1.0 / NF[0]
+    for q, i in enumerate(fmine):
+        lo, hi = fboxes[i]
+        U, V, W = (UF[d][q][0].numpy()[0] for d in range(3))
+        assert max(np.abs(U).max(), np.abs(V).max(), np.abs(W).max()) < 1e30, ("create_umac_grown: unfilled ghost faces", rank)
+        # valid faces untouched
+        for d in range(3):
+            ref = to_fab(uf[d], fboxes[i], 0, types[d], "cpu")[0].numpy()[0]
+            got = UF[d][q][0].numpy()[0][1:-1, 1:-1, 1:-1]
+            assert np.array_equal(got, ref), ("create_umac_grown: valid faces", rank)
+        # ghost cells beyond the x faces of the pair that the fine level does not cover (x = lo-1 of the first box / hi+1 of the second):
+        # exactly one valid neighbour -> divergence-free after the correction
+        a = 0 if i == 0 else U.shape[2] - 2        # local cell index of the ghost column on the uncovered x side
+        c, b = slice(1, W.shape[0] - 2), slice(1, V.shape[1] - 2)
+        div = (U[c, b, a + 1] - U[c, b, a]) / dx + (V[c, 2:V.shape[1] - 1, a] - V[c, 1:V.shape[1] - 2, a]) / dx \
+            + (W[2:W.shape[0] - 1, b, a] - W[1:W.shape[0] - 2, b, a]) / dx
+        assert np.abs(div).max() <= 1e-11, ("create_umac_grown: divergence of the corrected halo", rank, float(np.abs(div).max()))
+
+    clev.close(); flev.close()
+    dist.barrier()
+    print(f"rank {rank} ok", flush=True)
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -36,3 +36,26 @@ def test_two_ranks_gloo(emul_lib):
     for r, (p, out) in enumerate(zip(procs, outs)):
         assert p.returncode == 0, f"rank {r} failed:\n{out}"
         assert f"rank {r} ok" in out
+
+
+def test_two_level_blocks_two_ranks(emul_lib):
+    """The collective two-level building blocks with coarse and fine boxes on different ranks (tests/amr_worker.py)."""
+    port = _free_port()
+    procs = []
+    for r in range(2):
+        env = dict(os.environ, RANK=str(r), WORLD_SIZE="2", MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port),
+                   OMP_NUM_THREADS="2", OMP_WAIT_POLICY="passive")
+        procs.append(subprocess.Popen([sys.executable, os.path.join(ROOT, "tests", "amr_worker.py")], env=env,
+                                      stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True))
+    outs = []
+    for p in procs:
+        try:
+            out, _ = p.communicate(timeout=600)
+        except subprocess.TimeoutExpired:
+            for q in procs:
+                q.kill()
+            raise
+        outs.append(out)
+    for r, (p, out) in enumerate(zip(procs, outs)):
+        assert p.returncode == 0, f"rank {r} failed:\n{out}"
+        assert f"rank {r} ok" in out
