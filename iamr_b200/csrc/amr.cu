@@ -99,6 +99,46 @@ __global__ void __launch_bounds__(TX* TY) face_linear_interp_kernel(Bx ffbx, int
   else fine(i, j, k, n) = 0.5 * (c0 + crse(I + (dir == 0), J + (dir == 1), K + (dir == 2), n));
 }
 
+// ---- coarse-fine boundary values of a fine-level solve (InterpBndryData::setBndryValues, order 3) ---------------------------------
+// R = the one-cell layer of fine ghost cells beyond side d of a fine box.  The value of each cell is the coarse field at the fine
+// cell's TANGENTIAL position in the plane of the coarse cell centres: c0 + y dy + y^2 d2y + z dz + z^2 d2z + y z dyz, with
+// centred differences where both tangential coarse neighbours are usable (mask: inside the domain and not under the fine level),
+// one-sided first differences where one is, and the mixed term where all four diagonal neighbours are.
+__global__ void __launch_bounds__(TX* TY) cf_bndry_kernel(Bx R, V4 fine, C4 crse, C4 mask, int d) {
+  IDX3(R)
+  const int f[3] = {i, j, k};
+  const int I[3] = {coarsen2(i), coarsen2(j), coarsen2(k)};
+  if (mask(I[0], I[1], I[2]) == 0.0) return;   // beyond a physical side, or under another fine box
+  const int t[2] = {(d + 1) % 3, (d + 2) % 3};
+  const double c0 = crse(I[0], I[1], I[2], n);
+  double v = c0, off[2];
+  for (int q = 0; q < 2; ++q) {
+    int m[3] = {I[0], I[1], I[2]}, p[3] = {I[0], I[1], I[2]};
+    m[t[q]] -= 1; p[t[q]] += 1;
+    const bool um = mask(m[0], m[1], m[2]) != 0.0, up = mask(p[0], p[1], p[2]) != 0.0;
+    const double x = (f[t[q]] - 2 * I[t[q]]) ? 0.25 : -0.25;
+    off[q] = x;
+    double d1 = 0.0, d2 = 0.0;
+    if (um && up) {
+      const double cm = crse(m[0], m[1], m[2], n), cp = crse(p[0], p[1], p[2], n);
+      d1 = 0.5 * (cp - cm);
+      d2 = 0.5 * (cp - 2.0 * c0 + cm);
+    } else if (up) d1 = crse(p[0], p[1], p[2], n) - c0;
+    else if (um) d1 = c0 - crse(m[0], m[1], m[2], n);
+    v += x * d1 + x * x * d2;
+  }
+  bool all = true;
+  double cr[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
+  for (int sb = 0; sb < 2; ++sb)
+    for (int sa = 0; sa < 2; ++sa) {
+      int q[3] = {I[0], I[1], I[2]};
+      q[t[0]] += sa ? 1 : -1; q[t[1]] += sb ? 1 : -1;
+      if (mask(q[0], q[1], q[2]) == 0.0) all = false; else cr[sb][sa] = crse(q[0], q[1], q[2], n);
+    }
+  if (all) v += off[0] * off[1] * 0.25 * (cr[1][1] - cr[1][0] - cr[0][1] + cr[0][0]);
+  fine(i, j, k, n) = v;
+}
+
 // ---- flux register ---------------------------------------------------------------------------------------------------
 // R = coarse cells of one interface patch (a one-cell-thick slab just OUTSIDE a fine box, on side `side` of direction d);
 // fc = index of the coarse face between the slab and the fine region.
@@ -172,6 +212,11 @@ int pc_interp(const Bx& fbx, V4 fine, C4 crse, int ncomp, cudaStream_t s) {
   if (!fbx.ok()) return IAMRX_OK;
   IX_LAUNCH(pc_interp_kernel, dim3(cdiv(fbx.nx(), TX), cdiv(fbx.ny(), TY), fbx.nz() * ncomp), dim3(TX, TY, 1), 0, s, fbx, fine, crse, fbx.nz());
   return check_launch("pc_interp");
+}
+int cf_bndry_interp(const Bx& R, int d, V4 fine, C4 crse, C4 mask, int ncomp, cudaStream_t s) {
+  if (!R.ok()) return IAMRX_OK;
+  IX_LAUNCH(cf_bndry_kernel, grid_for(R, R.nz() * ncomp), dim3(TX, TY, 1), 0, s, R, fine, crse, mask, d);
+  return check_launch("cf_bndry_interp");
 }
 int node_bilinear_interp(const Bx& fnbx, V4 fine, C4 crse, int ncomp, cudaStream_t s) {
   if (!fnbx.ok()) return IAMRX_OK;
@@ -618,6 +663,48 @@ int iamrx_create_umac_grown(iamrx_level_t fine_lev, iamrx_level_t crse_lev, iamr
   MF Dv; if (divu) Dv.alias(FL, IX_CELL, 1, 1, const_cast<iamrx_fab*>(divu));
   for (int il = 0; il < mask.n(); ++il)
     IX_TRY(k::umac_divfix(FL->lbox(il), mask.c(il), U[0].v(il), U[1].v(il), U[2].v(il), divu ? Dv.c(il) : C4{}, FL->geom.dx, s));
+  return IAMRX_OK;
+}
+
+// MLLinOp::setCoarseFineBC(crse, ratio) (MacProj.cpp:1164-1167): see iamrx.h
+int iamrx_set_coarse_fine_bc(iamrx_level_t fine_lev, iamrx_level_t crse_lev, iamrx_fab* fine, const iamrx_fab* crse, int ncomp, void* stream) {
+  IX_NEED_DEVICE();
+  IX_ARG(fine_lev && crse_lev && fine && crse && ncomp >= 1 && ncomp <= 8, "set_coarse_fine_bc arguments");
+  Level* FL = level_of(fine_lev);
+  Level* CL = level_of(crse_lev);
+  cudaStream_t s = (cudaStream_t)stream;
+  for (int d = 0; d < 3; ++d) {
+    IX_ARG(FL->geom.domain.lo[d] == 2 * CL->geom.domain.lo[d] && FL->geom.domain.hi[d] == 2 * CL->geom.domain.hi[d] + 1,
+           "the fine level's domain must be the coarse one refined by 2");
+    IX_ARG(FL->geom.periodic[d] == CL->geom.periodic[d], "periodicity differs between the levels");
+  }
+  // 1. the coarse data as one replicated box with two ghost layers (periodic images; nothing beyond physical sides is read)
+  std::unique_ptr<Level> RL;
+  MF cr;
+  IX_TRY(replicated_coarse(CL, crse, 0, ncomp, IX_CELL, 2, nullptr, s, RL, cr));
+  // 2. usable coarse cells: inside the domain (periodic images included) and not under the fine level
+  MF mask(RL.get(), IX_CELL, 1, 2);
+  IX_TRY(mf_setval(mask, 0.0, 0, 1, 2, s));
+  IX_TRY(k::setval(mkbx(CL->geom.domain), mask.v(0), 1, 1.0, s));
+  for (const Bx& fb : FL->boxes) {
+    Bx cb;
+    for (int d = 0; d < 3; ++d) { cb.lo[d] = k::coarsen2(fb.lo[d]); cb.hi[d] = k::coarsen2(fb.hi[d]); }
+    IX_TRY(k::setval(cb, mask.v(0), 1, 0.0, s));
+  }
+  IX_TRY(mf_fill_boundary(mask, 0, 1, 2, s));
+  // 3. the layer beyond every side of every local fine box
+  MF fm; fm.alias(FL, IX_CELL, ncomp, 1, fine);
+  const Bx fdom = mkbx(FL->geom.domain);
+  for (int il = 0; il < fm.n(); ++il) {
+    const Bx vb = fm.vbox(il);
+    for (int d = 0; d < 3; ++d)
+      for (int side = 0; side < 2; ++side) {
+        Bx R = vb;
+        R.lo[d] = R.hi[d] = side == 0 ? vb.lo[d] - 1 : vb.hi[d] + 1;
+        if (!FL->geom.periodic[d] && (R.lo[d] < fdom.lo[d] || R.hi[d] > fdom.hi[d])) continue;
+        IX_TRY(k::cf_bndry_interp(R, d, fm.v(il), cr.c(0), mask.c(0), ncomp, s));
+      }
+  }
   return IAMRX_OK;
 }
 

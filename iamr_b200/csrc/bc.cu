@@ -72,9 +72,11 @@ physbc_kernel(Bx R, V4 a, IX_KARG(PhysBC) bc, Bx dom, int p0, int p1, int p2, in
 // ---- cell-centred linear operators -----------------------------------------------------------------------------------
 // Lagrange weights at the ghost centre (-1/2 cell from the face) for the nodes {face, 1/2, 3/2, ...}
 struct DirW { double w[5]; };
-inline DirW dirichlet_weights(int order) {
+// x0: location of the Dirichlet value in cell widths from the face (0: on the face; -ratio/2 scaled to the multigrid level: the
+// coarse-fine sides of a fine AMR level, whose data sit at the coarse cell centres)
+inline DirW dirichlet_weights(int order, double x0 = 0.0) {
   DirW r;
-  double x[5]; x[0] = 0.0;
+  double x[5]; x[0] = x0;
   for (int m = 1; m < order; ++m) x[m] = m - 0.5;
   for (int m = 0; m < order; ++m) {
     double num = 1.0, den = 1.0;
@@ -174,6 +176,30 @@ int linop_bc_fill(const Bx& vbx, V4 phi, int ncomp, const LinBC& bc, C4 bv, cons
       if (rc) return rc;
     }
   }
+  return IAMRX_OK;
+}
+
+// ---- coarse-fine sides of a fine AMR level (MLCellLinOp with setCoarseFineBC, MacProj.cpp:1164-1167) -------------------------
+// AMReX (MLMGBndry::setBoxBC) treats a box side that is not a domain face as Dirichlet with the value half a COARSE cell beyond the
+// face; the ghost cell is the Lagrange extrapolation through that value and the first interior cells, as on a Dirichlet domain side.
+double linop_cf_f0(int maxorder, int boxlen, double x0) { return dirichlet_weights(linop_bc_order(maxorder, boxlen), x0).w[1]; }
+
+// cfmask bit 2 d + side: that side of vbx is a coarse-fine side; the whole one-cell layer beyond it is written (the caller's
+// FillBoundary then overwrites the cells a fine neighbour covers).  bv: fab whose ghost cells hold the coarse-fine boundary
+// values (iamrx_set_coarse_fine_bc); null: homogeneous.
+int linop_cf_fill(const Bx& vbx, V4 phi, int ncomp, int maxorder, C4 bv, int cfmask, const double x0[3], cudaStream_t s) {
+  for (int d = 0; d < 3; ++d)
+    for (int side = 0; side < 2; ++side) {
+      if (!(cfmask & (1 << (2 * d + side)))) continue;
+      Bx R = vbx;
+      R.lo[d] = R.hi[d] = side == 0 ? vbx.lo[d] - 1 : vbx.hi[d] + 1;
+      const int e = side == 0 ? vbx.lo[d] : vbx.hi[d];
+      const DirW w = dirichlet_weights(linop_bc_order(maxorder, vbx.hi[d] - vbx.lo[d] + 1), x0[d]);
+      IX_LAUNCH(linop_bc_kernel, grid_for(R, R.nz() * ncomp), dim3(TX, TY, 1), 0, s, R, phi, bv, d, side == 0 ? -1 : 1, e,
+                IAMRX_LINOP_DIRICHLET, IAMRX_LINOP_DIRICHLET, IAMRX_LINOP_DIRICHLET, w);
+      const int rc = check_launch("linop_cf_fill");
+      if (rc) return rc;
+    }
   return IAMRX_OK;
 }
 

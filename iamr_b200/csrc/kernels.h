@@ -188,6 +188,9 @@ double linop_bc_f0(int code, int maxorder, int boxlen);   // coefficient of the 
 // cross terms read one cell sideways).  skipmask bit d: leave direction d alone.
 int linop_bc_fill(const Bx& vbx, V4 phi, int ncomp, const LinBC& bc, C4 bv, const Bx& dom, const int per[3], int grow_t, int skipmask,
                   cudaStream_t s);
+// coarse-fine sides of a fine AMR level (bc.cu): Dirichlet data x0 cell widths from the face (x0 < 0: beyond it)
+double linop_cf_f0(int maxorder, int boxlen, double x0);
+int linop_cf_fill(const Bx& vbx, V4 phi, int ncomp, int maxorder, C4 bv, int cfmask, const double x0[3], cudaStream_t s);
 struct NodalBC { int lo[3], hi[3]; };   // LinOpBCType per side (Projection.cpp:2436-2464)
 int nodal_bc_fill_phi(const Bx& nbx, V4 phi, const NodalBC& bc, const Bx& ndom, const int per[3], int skipmask, cudaStream_t s);
 int nodal_bc_fill_sigma(const Bx& cbx, V4 sig, const NodalBC& bc, const Bx& dom, const int per[3], cudaStream_t s, int ngt = 1);
@@ -197,6 +200,8 @@ int nodal_bc_scale(const Bx& nbx, V4 a, const NodalBC& bc, const Bx& ndom, const
 int average_down_nodal(const Bx& cnbx, V4 crse, C4 fine, int ncomp, cudaStream_t s);
 int cell_cons_interp(const Bx& fbx, V4 fine, C4 crse, int ncomp, cudaStream_t s);
 int pc_interp(const Bx& fbx, V4 fine, C4 crse, int ncomp, cudaStream_t s);   // piecewise constant
+// InterpBndryData (order 3): coarse-fine boundary values in the ghost layer R beyond side d of a fine box (mask: usable coarse cells)
+int cf_bndry_interp(const Bx& R, int d, V4 fine, C4 crse, C4 mask, int ncomp, cudaStream_t s);
 // create_umac_grown's divergence correction on the one-cell halo of a fine box (mask: 0 interior, 1 covered, 2 not covered, 3 physbnd)
 int umac_divfix(const Bx& vb, C4 mask, V4 u, V4 v, V4 w, C4 divu, const double dx[3], cudaStream_t s);
 int node_bilinear_interp(const Bx& fnbx, V4 fine, C4 crse, int ncomp, cudaStream_t s);

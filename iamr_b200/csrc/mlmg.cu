@@ -79,6 +79,36 @@ std::unique_ptr<Level> consolidated_level(const Level& c) {
   return L;
 }
 
+// Sides of box b of level L that border COARSE cells: the one-cell layer beyond the side is inside the domain (or a periodic
+// direction) and not completely covered by the boxes of the level and their periodic images.  Bit 2 d + side.
+static int coarse_fine_sides(const Level& L, const Bx& b) {
+  int mask = 0;
+  const Bx dom = L.domain;
+  for (int d = 0; d < 3; ++d)
+    for (int side = 0; side < 2; ++side) {
+      Bx S = b;
+      S.lo[d] = S.hi[d] = side == 0 ? b.lo[d] - 1 : b.hi[d] + 1;
+      if (!L.geom.periodic[d] && (S.lo[d] < dom.lo[d] || S.hi[d] > dom.hi[d])) continue;   // a physical side
+      int64_t covered = 0;
+      int sh[3];
+      for (sh[2] = -1; sh[2] <= 1; ++sh[2])
+        for (sh[1] = -1; sh[1] <= 1; ++sh[1])
+          for (sh[0] = -1; sh[0] <= 1; ++sh[0]) {
+            bool ok = true;
+            for (int q = 0; q < 3; ++q) if (sh[q] != 0 && !L.geom.periodic[q]) ok = false;
+            if (!ok) continue;
+            for (const Bx& o : L.boxes) {
+              Bx t = o;
+              for (int q = 0; q < 3; ++q) { const int len = dom.hi[q] - dom.lo[q] + 1; t.lo[q] += sh[q] * len; t.hi[q] += sh[q] * len; }
+              const Bx x = intersect(S, t);
+              if (x.ok()) covered += x.npts();
+            }
+          }
+      if (covered < S.npts()) mask |= 1 << (2 * d + side);
+    }
+  return mask;
+}
+
 static bool all_periodic(const Level& L) {
   return L.geom.periodic[0] && L.geom.periodic[1] && L.geom.periodic[2];
 }
@@ -126,16 +156,30 @@ CellMG::CellMG(Level* fine, int ncomp, bool tensor, int max_coarsening)
     L.rescor.define(L.lev, IX_CELL, ncomp_, 0);
     if (L.xfer_lev) L.xfer.define(L.xfer_lev.get(), IX_CELL, ncomp_, 0);
   }
+  // a level that does not tile its domain is a fine AMR level: find the coarse-fine sides of every box on every multigrid level
+  if (!fine->replicated && fine->ncells_global != mkbx(fine->geom.domain).npts()) {
+    cfmask_.resize(lv_.size());
+    for (size_t l = 0; l < lv_.size(); ++l) {
+      const Level& L = *lv_[l].lev;
+      for (int il = 0; il < L.nlocal(); ++il) {
+        cfmask_[l].push_back(coarse_fine_sides(L, L.lbox(il)));
+        if (cfmask_[l].back()) cf_ = true;
+      }
+      // every rank must take the same path: look at the boxes of the other ranks too
+      for (const Bx& b : L.boxes) if (!cf_ && coarse_fine_sides(L, b)) cf_ = true;
+    }
+  }
 }
 
 void CellMG::set_bc(const k::LinBC& bc) {
   bc_ = bc;
-  has_bc_ = !all_periodic(*lv_[0].lev);
+  has_bc_ = !all_periodic(*lv_[0].lev) || cf_;
 }
 
 bool CellMG::box_on_boundary(int l, int il) const {
   const Level& L = *lv_[l].lev;
   const Bx& b = L.lbox(il);
+  if (cf_ && cfmask_[l][il]) return true;
   for (int d = 0; d < 3; ++d) if (!L.geom.periodic[d] && (b.lo[d] == L.domain.lo[d] || b.hi[d] == L.domain.hi[d])) return true;
   return false;
 }
@@ -150,6 +194,7 @@ static int mirror_kind(int code, int maxorder, int len) {   // 0 no, 1 even, 2 o
 
 bool CellMG::bc_in_kernel(int l) const {
   if (!has_bc_) return true;
+  if (cf_) return false;   // coarse-fine sides: ghost cells are extrapolated between the colours
   const Level& L = *lv_[l].lev;
   for (const Bx& b : L.boxes)   // all boxes of the level: the same decision on every rank
     for (int c = 0; c < ncomp_ && c < 3; ++c)
@@ -180,10 +225,21 @@ k::GsBC CellMG::gsbc_of(int l, int il) const {
         if (mk == 2) g.odd[c] |= 1 << (2 * d + side);
       }
     }
+  if (cf_)
+    for (int d = 0; d < 3; ++d)
+      for (int side = 0; side < 2; ++side)
+        if (cfmask_[l][il] & (1 << (2 * d + side)))
+          for (int c = 0; c < 3; ++c) g.f0[c][2 * d + side] = k::linop_cf_f0(bc_.maxorder, b.hi[d] - b.lo[d] + 1, cf_x0(l, d));
   return g;
 }
 
 int CellMG::fill_ghosts(int l, MF& phi, bool inhomog, int wm, int grow_t, cudaStream_t s) {
+  if (cf_) {   // coarse-fine sides first: the exchange below overwrites the ghost cells that fine neighbours cover
+    const bool ihc = inhomog && l == 0 && bvals_.ok();
+    const double x0[3] = {cf_x0(l, 0), cf_x0(l, 1), cf_x0(l, 2)};
+    for (int il = 0; il < phi.n(); ++il)
+      IX_TRY(k::linop_cf_fill(phi.vbox(il), phi.v(il), ncomp_, bc_.maxorder, ihc ? bvals_.c(il) : C4{}, cfmask_[l][il], x0, s));
+  }
   if (wm != 7) IX_TRY(mf_fill_boundary(phi, 0, ncomp_, 1, s, wm));
   if (!has_bc_) return IAMRX_OK;
   // homogeneous fills of sides the kernels mirror in place are not needed (grow_t > 0: the tensor cross terms read the cells)
@@ -200,7 +256,9 @@ k::Abec CellMG::op_at(int l, int il) const {
   k::Abec op;
   op.a = a_; op.b = b_;
   op.acoef = (a_ != 0.0 && L.acoef.ok()) ? L.acoef.c(il) : C4{};
-  op.bx = L.b[0].c(il); op.by = L.b[1].c(il); op.bz = L.b[2].c(il);
+  // constant coefficients: the coarse levels' face arrays are never built (set_coeffs) nor read (k::Abec::cc)
+  const bool hb = L.b[0].n() > il;
+  op.bx = hb ? L.b[0].c(il) : C4{}; op.by = hb ? L.b[1].c(il) : C4{}; op.bz = hb ? L.b[2].c(il) : C4{};
   op.bncomp = tensor_ ? ncomp_ : 1;
   for (int d = 0; d < 3; ++d) op.dxinv[d] = L.dxinv[d];
   op.cc = cc_ ? 1 : 0; op.cac = cac_ ? 1 : 0;
@@ -323,6 +381,7 @@ int CellMG::set_coeffs(const MF* acoef, const MF* bx, const MF* by, const MF* bz
         for (int code : {bc_.lo[c][d], bc_.hi[c][d]})
           if (code == IAMRX_LINOP_DIRICHLET || code == IAMRX_LINOP_REFLECT_ODD) singular_ = false;
       }
+  if (cf_) singular_ = false;   // coarse-fine sides pin the solution
   return IAMRX_OK;
 }
 
@@ -436,9 +495,10 @@ static int save_level_bc(MF& bvals, MF& phi, int ncomp, bool needed, cudaStream_
 }
 
 int CellMG::apply(MF& out, MF& phi, cudaStream_t s) {
+  if (cf_ && tensor_) { set_error("CellMG: the tensor operator on a level with coarse-fine sides is not implemented"); return IAMRX_ERR_ARG; }
   bool dirichlet = false;
   for (int c = 0; c < ncomp_ && c < 3; ++c) for (int d = 0; d < 3; ++d) if (bc_.lo[c][d] == IAMRX_LINOP_DIRICHLET || bc_.hi[c][d] == IAMRX_LINOP_DIRICHLET) dirichlet = true;
-  IX_TRY(save_level_bc(bvals_, phi, ncomp_, has_bc_ && dirichlet, s));
+  IX_TRY(save_level_bc(bvals_, phi, ncomp_, has_bc_ && (dirichlet || cf_), s));
   // directions every box spans periodically are wrapped inside the kernels (cross terms included): no ghost traffic there
   const int wm = has_bc_ ? 0 : lv_[0].lev->level_wrapmask();
   IX_TRY(fill_ghosts(0, phi, true, wm, tensor_ ? 1 : 0, s));
@@ -613,13 +673,14 @@ int CellMG::vcycle(cudaStream_t s) {
 }
 
 int CellMG::solve(MF& sol, const MF& rhs_in, iamrx_mg_info* info, cudaStream_t s) {
+  if (cf_ && tensor_) { set_error("CellMG: the tensor operator on a level with coarse-fine sides is not implemented"); return IAMRX_ERR_ARG; }
   if (info) info_ = *info;
   info_.bottom_iters = 0;
   MGLevelCell& L0 = lv_[0];
   {
     bool dirichlet = false;
     for (int c = 0; c < ncomp_ && c < 3; ++c) for (int d = 0; d < 3; ++d) if (bc_.lo[c][d] == IAMRX_LINOP_DIRICHLET || bc_.hi[c][d] == IAMRX_LINOP_DIRICHLET) dirichlet = true;
-    IX_TRY(save_level_bc(bvals_, sol, ncomp_, has_bc_ && dirichlet, s));
+    IX_TRY(save_level_bc(bvals_, sol, ncomp_, has_bc_ && (dirichlet || cf_), s));
   }
   MF rhs(L0.lev, IX_CELL, ncomp_, 0);
   IX_TRY(mf_copy(rhs, rhs_in, 0, 0, ncomp_, 0, s));

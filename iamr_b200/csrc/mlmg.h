@@ -48,8 +48,15 @@ class CellMG {
   const MF& bcoef(int d) const { return lv_[0].b[d]; }
   double bscalar() const { return b_; }
   k::Abec op_at(int mglev, int il) const;
+  // the level does not tile its domain (a fine AMR level): box sides that are neither domain faces nor covered by other boxes
+  // are coarse-fine sides -- Dirichlet, data half a coarse cell beyond the face (MLCellLinOp with setCoarseFineBC,
+  // MacProj.cpp:1164-1167); the values are the ghost cells of the solution on entry (iamrx_set_coarse_fine_bc)
+  bool has_coarse_fine() const { return cf_; }
 
  private:
+  bool cf_ = false;
+  std::vector<std::vector<int>> cfmask_;   // [mg level][local box]: bit 2 d + side
+  double cf_x0(int l, int d) const { return -0.5 * 2.0 * lv_[l].dxinv[d] / lv_[0].dxinv[d]; }   // refinement ratio 2
   int smooth(int l, MF& phi, const MF& rhs, int nsweeps, bool zero_init, cudaStream_t s);
   // norm (optional): max-norm of `out`, taken inside the residual kernel where it can be
   int residual(int l, MF& out, MF& phi, const MF& rhs, bool with_cross, cudaStream_t s, double* norm = nullptr);

@@ -482,6 +482,21 @@ int iamrx_average_down(iamrx_level_t fine_lev, iamrx_level_t crse_lev, const iam
 int iamrx_create_umac_grown(iamrx_level_t fine_lev, iamrx_level_t crse_lev, iamrx_fab* umac_f, iamrx_fab* vmac_f, iamrx_fab* wmac_f,
                             const iamrx_fab* umac_c, const iamrx_fab* vmac_c, const iamrx_fab* wmac_c, const iamrx_fab* divu, void* stream);
 
+/* MLLinOp::setCoarseFineBC(crse, ratio) as MacProj::mlmg_mac_solve calls it on a level > 0 (MacProj.cpp:1164-1167;
+ * Diffusion.cpp:395,518 for the scalar viscous solves, :1608 for getViscTerms; ratio 2): the boundary values of a fine-level cell-centred solve along
+ * the coarse-fine interface, InterpBndryData::setBndryValues at order 3 -- the coarse field interpolated quadratically in the two
+ * tangential directions (centred differences where the tangential coarse neighbours are neither under the fine level nor outside
+ * the domain, one-sided otherwise, plus the mixed term) -- written into the ONE ghost-cell layer of `fine` beyond every box side
+ * that touches coarse cells.  A value stands for the coarse cell-centre plane, i.e. one FINE cell beyond the face.  Pass `fine`
+ * on to iamrx_mac_project / iamrx_diffusion_solve / iamrx_diffusion_apply on the fine level (setLevelBC(0, phi): "the ghost cells
+ * of phi on entry are the level BC"): on a level whose boxes do not tile the domain those solvers treat every box side that is
+ * neither a domain face nor covered by another fine box as a coarse-fine Dirichlet side (Lagrange extrapolation of order
+ * maxorder through that value and the interior cells, the location fixed in physical space on the coarser multigrid levels),
+ * and the operator is non-singular.  fine: cell fabs of every local fine box, >= 1 ghost; crse: cell fabs of every local coarse
+ * box (cells under the fine level are never read).  The tensor operator on such a level is not implemented.  Collective. */
+int iamrx_set_coarse_fine_bc(iamrx_level_t fine_lev, iamrx_level_t crse_lev, iamrx_fab* fine, const iamrx_fab* crse, int ncomp,
+                             void* stream);
+
 /* NavierStokesBase::SyncInterp (NSB.cpp:3071-3255): interpolate a coarse-level sync correction (Vsync / Ssync, or the velocity
  * correction of level_sync) onto the fine level -- coarse data with periodic images and the HOMOGENEOUS ext_dir fill of the original
  * quantity's BCRec (HomExtDirFill), interpolated with pc_interp or cell_cons_interp; increment != 0: fine[dest..] += dt_clev * I(crse)

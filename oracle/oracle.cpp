@@ -38,7 +38,8 @@ struct PerScope {
 // amrex::BCType math codes (AMReX_BC_TYPES.H; NS_BC.H:7-55 maps the physical types onto them)
 enum { BC_INT_DIR = 0, BC_REFLECT_ODD = -1, BC_REFLECT_EVEN = 1, BC_FOEXTRAP = 2, BC_EXT_DIR = 3, BC_HOEXTRAP = 4 };
 // amrex::LinOpBCType subset (Diffusion.cpp:1887-1999, MacProj.cpp:1187-1208, Projection.cpp:2436-2464)
-enum { LO_PERIODIC = 0, LO_DIRICHLET = 1, LO_NEUMANN = 2, LO_REFLECT_ODD = 3, LO_INFLOW = 4 };
+enum { LO_PERIODIC = 0, LO_DIRICHLET = 1, LO_NEUMANN = 2, LO_REFLECT_ODD = 3, LO_INFLOW = 4,
+       LO_COARSE_FINE = 5 };   // a side of a fine AMR level that borders coarse cells: Dirichlet data half a COARSE cell beyond the face
 // PhysBCType (inputs ns.lo_bc / ns.hi_bc, inputs.3d.taylorgreen:100-102)
 enum { PHYS_INTERIOR = 0, PHYS_INFLOW = 1, PHYS_OUTFLOW = 2, PHYS_SYMMETRY = 3, PHYS_SLIPWALL = 4, PHYS_NOSLIPWALL = 5 };
 struct BCRec { int lo[3] = {0, 0, 0}, hi[3] = {0, 0, 0}; };
@@ -221,13 +222,18 @@ void first_order_extrap(Arr& a, int c0, int nc) {
 struct LinBC {
   int lo[3][3], hi[3][3];   // [comp][dir]  LinOpBCType
   int maxorder = 2;
+  // coarse-fine sides (MLCellLinOp with setCoarseFineBC; AMReX MLMGBndry::setBoxBC: a side that is not a domain face is
+  // Dirichlet with bcloc = ratio * dx / 2): the Dirichlet value sits at x0 cell widths from the face, x0 = -ratio / 2 on the
+  // level of the solve and -ratio / 2^(l+1) on multigrid level l (the location is a fixed physical distance: setLOBndryConds
+  // is given the finest dx on every multigrid level)
+  double cf_x0[3] = {-1.0, -1.0, -1.0};
   LinBC() { for (int c = 0; c < 3; ++c) for (int d = 0; d < 3; ++d) { lo[c][d] = LO_PERIODIC; hi[c][d] = LO_PERIODIC; } }
   int code(int c, int d, int side) const { return side < 0 ? lo[c < 3 ? c : 0][d] : hi[c < 3 ? c : 0][d]; }
 };
 // Lagrange weights at x = -1/2 (ghost centre, in cell widths from the face at 0) for nodes {0 (face), 1/2, 3/2, ...}:
 // w[0] multiplies the face value, w[m] the m-th interior cell
-inline void dirichlet_weights(int order, double w[5]) {
-  double x[5]; x[0] = 0.0; for (int m = 1; m < order; ++m) x[m] = m - 0.5;
+inline void dirichlet_weights(int order, double w[5], double x0 = 0.0) {
+  double x[5]; x[0] = x0; for (int m = 1; m < order; ++m) x[m] = m - 0.5;
   const double xg = -0.5;
   for (int m = 0; m < order; ++m) {
     double num = 1.0, den = 1.0;
@@ -243,6 +249,7 @@ inline double bc_f0(const LinBC& bc, int c, int d, int side, int nlen) {
     case LO_NEUMANN: return 1.0;
     case LO_REFLECT_ODD: return -1.0;
     case LO_DIRICHLET: { double w[5]; dirichlet_weights(bc_order(bc, nlen), w); return w[1]; }
+    case LO_COARSE_FINE: { double w[5]; dirichlet_weights(bc_order(bc, nlen), w, bc.cf_x0[d]); return w[1]; }
     default: return 0.0;
   }
 }
@@ -254,9 +261,12 @@ void apply_linop_bc(Arr& phi, int ncomp, const LinBC& bc, const Arr* bv) {
       if (g_per[d]) continue;
       const int nl = phi.n[d];
       const int d1 = (d + 1) % 3, d2 = (d + 2) % 3;
-      double w[5]; dirichlet_weights(bc_order(bc, nl), w);
+      double w[5], wd[5], wcf[5];
+      dirichlet_weights(bc_order(bc, nl), wd);
+      dirichlet_weights(bc_order(bc, nl), wcf, bc.cf_x0[d]);
       for (int side = -1; side <= 1; side += 2) {
         const int code = bc.code(c, d, side);
+        for (int m = 0; m < 5; ++m) w[m] = code == LO_COARSE_FINE ? wcf[m] : wd[m];
         const int g = side < 0 ? -1 : nl, e = side < 0 ? 0 : nl - 1, inw = side < 0 ? 1 : -1;
 #pragma omp parallel for
         for (int b2 = 0; b2 < phi.n[d2]; ++b2)
@@ -473,7 +483,7 @@ static int bicgstab(Apply&& A, Arr& sol, const Arr& rhs, int ncomp, bool nodal, 
 }
 
 struct CellMG {
-  struct Lev { int n[3]; double dxinv[3]; Arr alpha, beta[3], cor, res, rescor; };
+  struct Lev { int n[3]; double dxinv[3]; Arr alpha, beta[3], cor, res, rescor; LinBC bc; };
   std::vector<Lev> lv;
   int ncomp, bncomp;
   bool tensor;
@@ -483,7 +493,13 @@ struct CellMG {
   bool singular = false;
   LinBC bc; bool has_bc = false;   // domain BCs (setDomainBC + setMaxOrder)
   const Arr* bvals = nullptr;      // setLevelBC: array whose ghost cells hold the Dirichlet face values
-  void set_bc(const LinBC& b, const Arr* levelbc) { bc = b; has_bc = !(g_per[0] && g_per[1] && g_per[2]); bvals = levelbc; }
+  void set_bc(const LinBC& b, const Arr* levelbc) {
+    bc = b; has_bc = !(g_per[0] && g_per[1] && g_per[2]); bvals = levelbc;
+    for (Lev& L : lv) {   // the coarse-fine Dirichlet location in cell widths of each multigrid level (ratio 2)
+      L.bc = b;
+      for (int d = 0; d < 3; ++d) L.bc.cf_x0[d] = -0.5 * 2.0 * L.dxinv[d] / lv[0].dxinv[d];
+    }
+  }
 
   CellMG(const int n[3], const double dx[3], int ncomp_, bool tensor_, int max_coarsening) : ncomp(ncomp_), tensor(tensor_) {
     bncomp = tensor ? ncomp : 1;
@@ -505,7 +521,7 @@ struct CellMG {
     AbecOp o; o.a = a; o.b = b; o.alpha = (a != 0.0) ? &lv[l].alpha : nullptr;
     for (int d = 0; d < 3; ++d) { o.beta[d] = &lv[l].beta[d]; o.dxinv[d] = lv[l].dxinv[d]; }
     o.bncomp = bncomp;
-    if (has_bc) { o.bc = &bc; o.bv = (inhomog && l == 0) ? bvals : nullptr; }
+    if (has_bc) { o.bc = &lv[l].bc; o.bv = (inhomog && l == 0) ? bvals : nullptr; }
     return o;
   }
   void set_coeffs(const Arr* alpha, const Arr* e[3]) {
@@ -550,7 +566,8 @@ struct CellMG {
     singular = (a == 0.0);  // periodic / Neumann everywhere: the operator annihilates constants
     if (has_bc)
       for (int c = 0; c < ncomp && c < 3; ++c) for (int d = 0; d < 3; ++d)
-        if (!g_per[d] && (bc.lo[c][d] == LO_DIRICHLET || bc.hi[c][d] == LO_DIRICHLET || bc.lo[c][d] == LO_REFLECT_ODD || bc.hi[c][d] == LO_REFLECT_ODD)) singular = false;
+        if (!g_per[d] && (bc.lo[c][d] == LO_DIRICHLET || bc.hi[c][d] == LO_DIRICHLET || bc.lo[c][d] == LO_REFLECT_ODD || bc.hi[c][d] == LO_REFLECT_ODD ||
+                          bc.lo[c][d] == LO_COARSE_FINE || bc.hi[c][d] == LO_COARSE_FINE)) singular = false;
   }
   void smooth(int l, Arr& phi, const Arr& rhs, int nsweeps) {
     const AbecOp o = op(l);
@@ -2145,6 +2162,76 @@ void orc_average_down(const int nc[3], int ncomp, int ixtype, const double* fine
       }
       crse[i + (long)nc[0] * (j + (long)nc[1] * (k + (long)nc[2] * c))] = v;
     }
+}
+/* The coarse-fine boundary values of a fine-level solve: what MLLinOp::setCoarseFineBC(crse, ratio) (MacProj.cpp:1164-1167) makes
+ * MLCellLinOp compute with InterpBndryData::setBndryValues (order 3).  Restated from memory of AMReX_InterpBndryData_3D_K.H
+ * interpbndrydata_{x,y,z}_o3 -- AMReX is not in the reference tree: PARITY UNPINNED.  For every ghost cell of the fine box
+ * [flo, fhi] (fine indices) that lies in the one-cell layer beyond one of its six sides, is inside the domain (periodic
+ * directions: anywhere) and whose coarse parent is not under the fine level:
+ *     v = c0 + y dy + y^2 d2y + z dz + z^2 d2z + y z dyz
+ * (y, z = the offset of the fine cell centre from the coarse cell centre in coarse cell widths: -1/4 or +1/4 for ratio 2; dy: the
+ * centred first difference over the two tangential coarse neighbours when both are usable, the one-sided difference when one is,
+ * 0 when none is; d2y: half the second difference, centred stencils only; dyz: a quarter of the mixed difference when all four
+ * diagonal neighbours are usable.  usable = inside the domain (periodic wrap) and not covered by the fine level.)
+ * The value belongs to the coarse cell-centre plane, i.e. ratio/2 fine cells beyond the face.  crse: dense (ncomp, nc) array;
+ * covered: nc bytes, 1 = coarse cell under the fine level; out: (ncomp, fn + 2) padded fine box, only the face ghost cells written. */
+void orc_interp_bndry(const int nc[3], const int per[3], int ncomp, const double* crse, const unsigned char* covered, const int flo[3],
+                      const int fhi[3], double* out) {
+  const int fn[3] = {fhi[0] - flo[0] + 1, fhi[1] - flo[1] + 1, fhi[2] - flo[2] + 1};
+  auto wrap = [&](int q[3]) {
+    for (int d = 0; d < 3; ++d) {
+      if (q[d] < 0 || q[d] >= nc[d]) { if (!per[d]) return false; q[d] = ((q[d] % nc[d]) + nc[d]) % nc[d]; }
+    }
+    return true;
+  };
+  auto usable = [&](int i, int j, int k) { int q[3] = {i, j, k}; if (!wrap(q)) return false; return covered[q[0] + (long)nc[0] * (q[1] + (long)nc[1] * q[2])] == 0; };
+  auto fl2 = [](int a) { return a >= 0 ? a / 2 : -((-a + 1) / 2); };
+  for (int c = 0; c < ncomp; ++c) {
+    auto CV = [&](int i, int j, int k) { int q[3] = {i, j, k}; wrap(q); return crse[q[0] + (long)nc[0] * (q[1] + (long)nc[1] * (q[2] + (long)nc[2] * c))]; };
+    auto O = [&](int i, int j, int k) -> double& {
+      return out[(i - flo[0] + 1) + (long)(fn[0] + 2) * ((j - flo[1] + 1) + (long)(fn[1] + 2) * ((k - flo[2] + 1) + (long)(fn[2] + 2) * c))];
+    };
+    for (int d = 0; d < 3; ++d) {
+      const int t1 = (d + 1) % 3, t2 = (d + 2) % 3;
+      for (int side = 0; side < 2; ++side) {
+        const int g = side == 0 ? flo[d] - 1 : fhi[d] + 1;
+        for (int b = flo[t2]; b <= fhi[t2]; ++b)
+          for (int a = flo[t1]; a <= fhi[t1]; ++a) {
+            int f[3]; f[d] = g; f[t1] = a; f[t2] = b;
+            const int I[3] = {fl2(f[0]), fl2(f[1]), fl2(f[2])};
+            if (!usable(I[0], I[1], I[2])) continue;   // outside a physical side, or under another fine box
+            const double c0 = CV(I[0], I[1], I[2]);
+            double v = c0;
+            double off[2]; bool um[2], up[2];
+            const int tt[2] = {t1, t2};
+            for (int q = 0; q < 2; ++q) {
+              const int t = tt[q];
+              int m[3] = {I[0], I[1], I[2]}, pq[3] = {I[0], I[1], I[2]};
+              m[t] -= 1; pq[t] += 1;
+              um[q] = usable(m[0], m[1], m[2]); up[q] = usable(pq[0], pq[1], pq[2]);
+              const double x = (f[t] - 2 * I[t]) ? 0.25 : -0.25;
+              off[q] = x;
+              double d1 = 0.0, d2 = 0.0;
+              if (um[q] && up[q]) {
+                d1 = 0.5 * (CV(pq[0], pq[1], pq[2]) - CV(m[0], m[1], m[2]));
+                d2 = 0.5 * (CV(pq[0], pq[1], pq[2]) - 2.0 * c0 + CV(m[0], m[1], m[2]));
+              } else if (up[q]) d1 = CV(pq[0], pq[1], pq[2]) - c0;
+              else if (um[q]) d1 = c0 - CV(m[0], m[1], m[2]);
+              v += x * d1 + x * x * d2;
+            }
+            {
+              bool all = true; double cr[2][2];
+              for (int sb = 0; sb < 2; ++sb) for (int sa = 0; sa < 2; ++sa) {
+                int q[3] = {I[0], I[1], I[2]}; q[t1] += sa ? 1 : -1; q[t2] += sb ? 1 : -1;
+                if (!usable(q[0], q[1], q[2])) all = false; else cr[sb][sa] = CV(q[0], q[1], q[2]);
+              }
+              if (all) v += off[0] * off[1] * 0.25 * (cr[1][1] - cr[1][0] - cr[0][1] + cr[0][0]);
+            }
+            O(f[0], f[1], f[2]) = v;
+          }
+      }
+    }
+  }
 }
 /* kind 0 cell_cons_interp (NS_setup.cpp:211: CellConservativeLinear without linear limiting = MC slopes per direction, then one
  * factor per coarse cell that keeps all eight children inside [min, max] of the 3^3 coarse neighbourhood), 1 node_bilinear_interp

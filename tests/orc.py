@@ -267,6 +267,15 @@ def interp(kind, nc, crse):
     return fine
 
 
+def interp_bndry(nc, per, crse, covered, flo, fhi, out):
+    """InterpBndryData (order 3) into the face ghost cells of the padded fine box array `out` (ncomp, fn + 2); returns it."""
+    out = np.ascontiguousarray(out.copy())
+    m = np.ascontiguousarray(covered.astype(np.uint8))
+    lib().orc_interp_bndry(_i3(nc), _i3(per), int(crse.shape[0]), _p(np.ascontiguousarray(crse)), m.ctypes.data_as(C.c_void_p), _i3(flo), _i3(fhi),
+                           _p(out))
+    return out
+
+
 def fluxreg(nc, mask, cflux, fflux, dt, vol):
     ncomp = cflux[0].shape[0]
     reg = np.empty((ncomp, nc[2], nc[1], nc[0]))

@@ -1,0 +1,302 @@
+"""The coarse-fine boundary of fine-level cell-centred solves (MacProj.cpp:1164-1168 setCoarseFineBC + setLevelBC,
+Diffusion.cpp:395,518): iamrx_set_coarse_fine_bc (InterpBndryData, order 3) and iamrx_mac_project / iamrx_diffusion_solve on a level
+whose boxes do not tile the domain, through the C ABI vs the oracle (which solves on the fine PATCH as its own domain with
+coarse-fine Dirichlet sides) and vs analytic fields."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import iamr_b200 as ix
+from util import hash_uniform, smooth_field, fab_array, stream_of, sync
+from test_bc import fab_from_padded, scatter_valid, _mg
+
+PER, DIR, NEU, CF = 0, 1, 2, 5   # LinOpBCType codes of the oracle (CF: coarse-fine side, oracle-internal)
+
+
+def _patch_boxes(clo, chi, nb):
+    """fine boxes of the patch that refines coarse cells clo..chi, split nb ways per direction"""
+    flo = [2 * c for c in clo]
+    fn = [2 * (h - l + 1) for l, h in zip(clo, chi)]
+    boxes = []
+    for kz in range(nb[2]):
+        for jy in range(nb[1]):
+            for ixx in range(nb[0]):
+                q = (ixx, jy, kz)
+                lo = tuple(flo[d] + q[d] * (fn[d] // nb[d]) for d in range(3))
+                hi = tuple(lo[d] + fn[d] // nb[d] - 1 for d in range(3))
+                boxes.append((lo, hi))
+    return boxes
+
+
+def _covered(nc, clo, chi):
+    m = np.zeros(nc[::-1], dtype=bool)
+    m[clo[2]:chi[2] + 1, clo[1]:chi[1] + 1, clo[0]:chi[0] + 1] = True
+    return m
+
+
+def _wrap_pad(dense, ng):
+    return np.pad(dense, ((0, 0), (ng, ng), (ng, ng), (ng, ng)), mode="wrap")
+
+
+def _cut(P, gng, lo, hi, ng):
+    """the box lo..hi with ng ghost layers out of the global array P padded by gng"""
+    sl = tuple(slice(lo[d] - ng + gng, hi[d] + ng + gng + 1) for d in (2, 1, 0))
+    return np.ascontiguousarray(P[(slice(None),) + sl])
+
+
+def _coarse_fabs(cdat, nc, dev):
+    import torch
+    t = torch.from_numpy(np.ascontiguousarray(cdat)).to(dev)
+    return [(t, ix.fab_of(t, [0, 0, 0]))]
+
+
+CASES = [((1, 1, 1), (4, 0, 4), (11, 15, 11)),     # periodic domain, the patch spans y
+         ((0, 0, 0), (4, 4, 4), (11, 11, 11)),     # walls, interior patch
+         ((0, 1, 0), (0, 0, 4), (7, 15, 15))]      # the patch touches the low x and the high z wall
+
+
+@pytest.mark.parametrize("per,clo,chi", CASES)
+@pytest.mark.parametrize("nb", [(1, 1, 1), (2, 1, 2)])
+def test_set_coarse_fine_bc(backend, oracle, per, clo, chi, nb):
+    """InterpBndryData into the ghost layer of every fine box: vs the oracle's restatement, box by box; ghost cells under other fine
+    boxes or outside the domain are left alone."""
+    lib, dev = backend
+    nc, nf = (16, 16, 16), (32, 32, 32)
+    ncomp = 2
+    cphi = smooth_field(nc, 31, ncomp) + 0.1 * hash_uniform(32, (ncomp,) + nc[::-1])
+    cov = _covered(nc, clo, chi)
+    cphi_in = np.where(cov[None], 1.0e30, cphi)   # cells under the fine level must never be read
+    boxes = _patch_boxes(clo, chi, nb)
+    clev = ix.Level(lib, ix.Geom.make(nc, periodic=per), [((0, 0, 0), tuple(m - 1 for m in nc))])
+    flev = ix.Level(lib, ix.Geom.make(nf, periodic=per), boxes)
+    CP = _coarse_fabs(cphi_in, nc, dev)
+    sentinel = np.full((ncomp, nf[2] + 2, nf[1] + 2, nf[0] + 2), -7.0)
+    P = [fab_from_padded(sentinel, 1, b, 1, ix.CELL, dev) for b in boxes]
+    lib.check(lib.iamrx_set_coarse_fine_bc(flev.h, clev.h, fab_array([p[1] for p in P]), fab_array([p[1] for p in CP]), ncomp, stream_of(dev)))
+    sync(dev)
+    nset = 0
+    for (t, _), (lo, hi) in zip(P, boxes):
+        fn = tuple(hi[d] - lo[d] + 1 for d in range(3))
+        ref = oracle.interp_bndry(nc, per, cphi_in, cov, lo, hi, np.full((ncomp, fn[2] + 2, fn[1] + 2, fn[0] + 2), -7.0))
+        got = t.detach().cpu().numpy()
+        assert np.abs(ref).max() < 1.0e20
+        assert np.abs(got - ref).max() <= 1e-14
+        nset += int((ref != -7.0).sum())
+    assert nset > 0
+    clev.close(); flev.close()
+
+
+def test_set_coarse_fine_bc_is_exact_for_quadratics(backend):
+    """A field that is quadratic in the tangential coordinates (cross term included) is reproduced exactly at the fine cells'
+    tangential positions in the plane of the coarse cell centres -- independent of the oracle."""
+    lib, dev = backend
+    nc, nf = (16, 16, 16), (32, 32, 32)
+    per = (0, 0, 0)
+    clo, chi = (4, 4, 4), (11, 11, 11)
+    f = lambda x, y, z: 1.0 + 2.0 * x + 3.0 * y - z + 0.5 * x * x - 0.7 * y * y + 0.3 * z * z + 0.9 * x * y - 0.4 * y * z + 0.6 * x * z
+    zc, yc, xc = [(np.arange(m) + 0.5) / m for m in nc[::-1]]
+    Z, Y, X = np.meshgrid(zc, yc, xc, indexing="ij")
+    cphi = f(X, Y, Z)[None]
+    boxes = _patch_boxes(clo, chi, (1, 1, 1))
+    clev = ix.Level(lib, ix.Geom.make(nc, periodic=per), [((0, 0, 0), tuple(m - 1 for m in nc))])
+    flev = ix.Level(lib, ix.Geom.make(nf, periodic=per), boxes)
+    CP = _coarse_fabs(cphi, nc, dev)
+    P = [fab_from_padded(np.zeros((1, nf[2] + 2, nf[1] + 2, nf[0] + 2)), 1, b, 1, ix.CELL, dev) for b in boxes]
+    lib.check(lib.iamrx_set_coarse_fine_bc(flev.h, clev.h, fab_array([p[1] for p in P]), fab_array([p[1] for p in CP]), 1, stream_of(dev)))
+    sync(dev)
+    got = P[0][0].detach().cpu().numpy()[0]
+    lo, hi = boxes[0]
+    hf = 1.0 / nf[0]
+    fc = lambda i: (i + 0.5) * hf                       # fine cell centre
+    cc = lambda i: (np.floor(i / 2.0) + 0.5) * 2.0 * hf   # centre of the coarse parent
+    idx = [np.arange(lo[d], hi[d] + 1) for d in range(3)]
+    for d in range(3):
+        for g, a in ((lo[d] - 1, 0), (hi[d] + 1, got.shape[2 - d] - 1)):
+            co = [fc(idx[0]), fc(idx[1]), fc(idx[2])]
+            co[d] = np.array([cc(g)])
+            Zg, Yg, Xg = np.meshgrid(co[2], co[1], co[0], indexing="ij")
+            exact = f(Xg, Yg, Zg)
+            sl = [slice(1, -1)] * 3
+            sl[2 - d] = slice(a, a + 1)
+            assert np.abs(got[tuple(sl)] - exact).max() <= 1e-13
+    clev.close(); flev.close()
+
+
+def _patch_problem(oracle, per, clo, chi, seed):
+    """global fine fields (periodic images in the padding) for a fine-level MAC solve on the patch"""
+    nc, nf = (16, 16, 16), (32, 32, 32)
+    z, y, x = [(np.arange(m) + 0.5) / m for m in nf[::-1]]
+    Z, Y, X = np.meshgrid(z, y, x, indexing="ij")
+    rho = (1.0 + 0.4 * np.sin(2 * np.pi * X) * np.cos(2 * np.pi * Y) * np.sin(2 * np.pi * Z + 0.3))[None]
+    macs = [0.5 * hash_uniform(seed + d, (1,) + nf[::-1]) + smooth_field(nf, seed + 10 + d, 1) for d in range(3)]
+    cphi = 0.05 * smooth_field(nc, seed + 20, 1)
+    return nc, nf, rho, macs, cphi
+
+
+@pytest.mark.parametrize("nb", [(1, 1, 1), (2, 1, 2), (2, 2, 2)])
+def test_mac_project_coarse_fine(backend, oracle, nb):
+    """MacProj::mlmg_mac_solve on a level > 0 (MacProj.cpp:1164-1168: setCoarseFineBC(cphi, 2), setLevelBC(0, mac_phi), maxorder 4):
+    a fine patch inside a periodic domain, spanning y.  The oracle solves on the patch as its own domain (periodic in y, coarse-fine
+    Dirichlet sides in x and z).  One box: iterate-for-iterate parity; several boxes: the converged fields (fine-fine sides inside
+    the patch are plain neighbour exchanges)."""
+    lib, dev = backend
+    per = (1, 1, 1)
+    clo, chi = (4, 0, 4), (11, 15, 11)
+    nc, nf, rho, macs, cphi = _patch_problem(oracle, per, clo, chi, 700)
+    flo, fhi = tuple(2 * c for c in clo), tuple(2 * c + 1 for c in chi)
+    n = tuple(fhi[d] - flo[d] + 1 for d in range(3))
+    dx = tuple(1.0 / m for m in nf)
+    cov = _covered(nc, clo, chi)
+    RHO, M2 = _wrap_pad(rho, 1), [_wrap_pad(m, 2) for m in macs]
+    pper = (0, 1, 0)
+    lobc, hibc = (CF, PER, CF), (CF, PER, CF)
+    dt = 0.7 / 32
+    phi0 = oracle.interp_bndry(nc, per, cphi, cov, flo, fhi, np.zeros((1, n[2] + 2, n[1] + 2, n[0] + 2)))
+    mg = oracle.mg_default(rtol=1e-12)
+    ru, rv, rw, rphi, rc, mgo = oracle.mac_project_bc(n, pper, dx, _cut(M2[0], 2, flo, fhi, 1), _cut(M2[1], 2, flo, fhi, 1), _cut(M2[2], 2, flo, fhi, 1),
+                                                      _cut(RHO, 1, flo, fhi, 1), None, phi0, 2.0 / dt, lobc, hibc, 4, mg)
+    assert rc == 0
+    # the oracle's result is discretely divergence free on the patch
+    div = ((ru[0, 1:-1, 1:-1, 2:] - ru[0, 1:-1, 1:-1, 1:-1]) / dx[0] + (rv[0, 1:-1, 2:, 1:-1] - rv[0, 1:-1, 1:-1, 1:-1]) / dx[1] +
+           (rw[0, 2:, 1:-1, 1:-1] - rw[0, 1:-1, 1:-1, 1:-1]) / dx[2])
+    scale = max(np.abs(m).max() for m in macs) / dx[0]
+    assert np.abs(div).max() < 1e-10 * scale
+    boxes = _patch_boxes(clo, chi, nb)
+    clev = ix.Level(lib, ix.Geom.make(nc, periodic=per), [((0, 0, 0), tuple(m - 1 for m in nc))])
+    flev = ix.Level(lib, ix.Geom.make(nf, periodic=per), boxes)
+    U = [[fab_from_padded(M2[d], 2, b, 1, t, dev) for b in boxes] for d, t in enumerate((ix.XFACE, ix.YFACE, ix.ZFACE))]
+    R = [fab_from_padded(RHO, 1, b, 1, ix.CELL, dev) for b in boxes]
+    P = [fab_from_padded(np.zeros((1, nf[2] + 2, nf[1] + 2, nf[0] + 2)), 1, b, 1, ix.CELL, dev) for b in boxes]
+    CP = _coarse_fabs(np.where(cov[None], 1.0e30, cphi), nc, dev)
+    fa = lambda L: fab_array([p[1] for p in L])
+    lib.check(lib.iamrx_set_coarse_fine_bc(flev.h, clev.h, fa(P), fa(CP), 1, stream_of(dev)))
+    info = _mg(lib, rtol=1e-12, maxorder=4)
+    rc = lib.iamrx_mac_project(flev.h, fa(U[0]), fa(U[1]), fa(U[2]), fa(R), None, fa(P), 2.0 / dt, None, None, C.byref(info), stream_of(dev))
+    lib.check(rc)
+    sync(dev)
+    if nb == (1, 1, 1):
+        assert info.iters == mgo.iters
+    tol = 1e-12 if nb == (1, 1, 1) else 2e-10
+    gshape = (1, nf[2] + 2, nf[1] + 2, nf[0] + 2)
+    for d, (ref, t) in enumerate(((ru, ix.XFACE), (rv, ix.YFACE), (rw, ix.ZFACE))):
+        got, dup = scatter_valid(np.zeros(gshape), 1, [p[0] for p in U[d]], boxes, 1, t)
+        assert dup < 1e-13
+        ext = [1 if q == d else 0 for q in range(3)]
+        g = _cut(got, 1, flo, tuple(fhi[q] + ext[q] for q in range(3)), 0)
+        r = ref[:, 1:1 + n[2] + ext[2], 1:1 + n[1] + ext[1], 1:1 + n[0] + ext[0]]
+        assert np.abs(g - r).max() < tol * max(1.0, np.abs(r).max())
+    gphi, _ = scatter_valid(np.zeros(gshape), 1, [p[0] for p in P], boxes, 1, ix.CELL)
+    assert np.abs(_cut(gphi, 1, flo, fhi, 0) - rphi[:, 1:-1, 1:-1, 1:-1]).max() < tol
+    clev.close(); flev.close()
+
+
+@pytest.mark.parametrize("nb", [(1, 1, 1), (2, 1, 2)])
+def test_diffusion_solve_coarse_fine(backend, oracle, nb):
+    """Diffusion::diffuse_scalar on a level > 0 (Diffusion.cpp:395,417 / 518,543: setCoarseFineBC(Solnc, 2), setLevelBC(0, &Soln),
+    maxorder 2): (a alpha - b div eta grad) S = rhs on the patch with variable eta, and the operator itself (MLMG::apply)."""
+    lib, dev = backend
+    per = (1, 1, 1)
+    clo, chi = (4, 0, 4), (11, 15, 11)
+    nc, nf = (16, 16, 16), (32, 32, 32)
+    flo, fhi = tuple(2 * c for c in clo), tuple(2 * c + 1 for c in chi)
+    n = tuple(fhi[d] - flo[d] + 1 for d in range(3))
+    dx = tuple(1.0 / m for m in nf)
+    cov = _covered(nc, clo, chi)
+    csol = smooth_field(nc, 801, 1)
+    alpha = 1.0 + 0.3 * hash_uniform(802, (1,) + nf[::-1])
+    eta = [_wrap_pad(0.05 * (1.0 + 0.3 * hash_uniform(810 + d, (1,) + nf[::-1])), 2) for d in range(3)]
+    rhs = smooth_field(nf, 803, 1)
+    guess = _wrap_pad(smooth_field(nf, 804, 1), 1)
+    a, b = 1.0, 0.35
+    pper = (0, 1, 0)
+    lobc, hibc = [(CF, PER, CF)], [(CF, PER, CF)]
+    s0 = oracle.interp_bndry(nc, per, csol, cov, flo, fhi, _cut(guess, 1, flo, fhi, 1))
+    e1 = [_cut(eta[d], 2, flo, fhi, 1) for d in range(3)]
+    al, rh = _cut(alpha, 0, flo, fhi, 0), _cut(rhs, 0, flo, fhi, 0)
+    ref_ap = oracle.diffusion_bc(n, pper, dx, 0, 0, a, b, al, e1[0], e1[1], e1[2], None, s0, lobc, hibc, 2)
+    mg = oracle.mg_default(rtol=1e-12)
+    ref_sol, rc, mgo = oracle.diffusion_bc(n, pper, dx, 1, 0, a, b, al, e1[0], e1[1], e1[2], rh, s0, lobc, hibc, 2, mg)
+    assert rc == 0
+    boxes = _patch_boxes(clo, chi, nb)
+    clev = ix.Level(lib, ix.Geom.make(nc, periodic=per), [((0, 0, 0), tuple(m - 1 for m in nc))])
+    flev = ix.Level(lib, ix.Geom.make(nf, periodic=per), boxes)
+    bc = ix.LinopBC.make([(PER, PER, PER)], [(PER, PER, PER)], 2)
+    E = [[fab_from_padded(eta[d], 2, bx, 0, t, dev) for bx in boxes] for d, t in enumerate((ix.XFACE, ix.YFACE, ix.ZFACE))]
+    A = [fab_from_padded(alpha, 0, bx, 0, ix.CELL, dev) for bx in boxes]
+    CS = _coarse_fabs(np.where(cov[None], 1.0e30, csol), nc, dev)
+    fa = lambda L: fab_array([p[1] for p in L])
+    gshape0, gshape1 = (1,) + nf[::-1], (1, nf[2] + 2, nf[1] + 2, nf[0] + 2)
+    # apply
+    Sol = [fab_from_padded(guess, 1, bx, 1, ix.CELL, dev) for bx in boxes]
+    Out = [fab_from_padded(np.zeros(gshape0), 0, bx, 0, ix.CELL, dev) for bx in boxes]
+    lib.check(lib.iamrx_set_coarse_fine_bc(flev.h, clev.h, fa(Sol), fa(CS), 1, stream_of(dev)))
+    lib.check(lib.iamrx_diffusion_apply(flev.h, 0, 1, fa(Out), fa(Sol), a, b, fa(A), fa(E[0]), fa(E[1]), fa(E[2]), C.byref(bc), stream_of(dev)))
+    sync(dev)
+    got, _ = scatter_valid(np.zeros(gshape0), 0, [p[0] for p in Out], boxes, 0, ix.CELL)
+    assert np.abs(_cut(got, 0, flo, fhi, 0) - ref_ap).max() <= 1e-12 * np.abs(ref_ap).max()
+    # solve
+    Sol = [fab_from_padded(guess, 1, bx, 1, ix.CELL, dev) for bx in boxes]
+    Rhs = [fab_from_padded(rhs, 0, bx, 0, ix.CELL, dev) for bx in boxes]
+    lib.check(lib.iamrx_set_coarse_fine_bc(flev.h, clev.h, fa(Sol), fa(CS), 1, stream_of(dev)))
+    info = _mg(lib, rtol=1e-12)
+    rc = lib.iamrx_diffusion_solve(flev.h, 0, 1, fa(Sol), fa(Rhs), a, b, fa(A), fa(E[0]), fa(E[1]), fa(E[2]), C.byref(bc), C.byref(info),
+                                   stream_of(dev))
+    lib.check(rc)
+    sync(dev)
+    if nb == (1, 1, 1):
+        assert info.iters == mgo.iters
+    gs, _ = scatter_valid(np.zeros(gshape1), 1, [p[0] for p in Sol], boxes, 1, ix.CELL)
+    assert np.abs(_cut(gs, 1, flo, fhi, 0) - ref_sol[:, 1:-1, 1:-1, 1:-1]).max() <= 1e-10
+    # the tensor operator on such a level is refused, not mis-solved
+    V = [fab_from_padded(np.zeros((3, nf[2] + 2, nf[1] + 2, nf[0] + 2)), 1, bx, 1, ix.CELL, dev) for bx in boxes]
+    O3 = [fab_from_padded(np.zeros((3,) + nf[::-1]), 0, bx, 0, ix.CELL, dev) for bx in boxes]
+    bc3 = ix.LinopBC.make([(PER, PER, PER)] * 3, [(PER, PER, PER)] * 3, 2)
+    assert lib.iamrx_diffusion_apply(flev.h, 1, 3, fa(O3), fa(V), a, b, fa(A), fa(E[0]), fa(E[1]), fa(E[2]), C.byref(bc3), stream_of(dev)) == -1   # IAMRX_ERR_ARG
+    clev.close(); flev.close()
+
+
+@pytest.mark.parametrize("nb", [(1, 1, 1), (2, 2, 2)])
+def test_coarse_fine_solve_converges_at_second_order(backend, nb):
+    """No oracle: the fine-level MAC solve with coarse-fine data taken from an analytic potential reproduces that potential to
+    O(h^2) -- the location of the coarse-fine Dirichlet value (half a coarse cell beyond the face), the extrapolation weights and
+    the tangential interpolation are all exercised by the error's convergence rate."""
+    lib, dev = backend
+    per = (1, 1, 1)
+    errs = []
+    for m in (8, 16):
+        nc, nf = (m, m, m), (2 * m, 2 * m, 2 * m)
+        clo, chi = (m // 4, m // 4, m // 4), (3 * m // 4 - 1, 3 * m // 4 - 1, 3 * m // 4 - 1)
+        flo, fhi = tuple(2 * c for c in clo), tuple(2 * c + 1 for c in chi)
+        h = 1.0 / nf[0]
+        pe = lambda x, y, z: np.sin(2 * np.pi * x) * np.cos(2 * np.pi * y) * np.sin(2 * np.pi * z + 0.4) + 0.3 * np.cos(2 * np.pi * (x + z))
+        cen = lambda k: (np.arange(k) + 0.5) / k
+        edg = lambda k: np.arange(k) / float(k)
+        Zc, Yc, Xc = np.meshgrid(cen(m), cen(m), cen(m), indexing="ij")
+        cphi = pe(Xc, Yc, Zc)[None]
+        # u_mac = the exact differences of the potential across the faces / h: div(u_mac) is then the discrete Laplacian of pe
+        Z, Y, X = np.meshgrid(cen(nf[2]), cen(nf[1]), edg(nf[0]), indexing="ij"); um = (pe(X + 0.5 * h, Y, Z) - pe(X - 0.5 * h, Y, Z)) / h
+        Z, Y, X = np.meshgrid(cen(nf[2]), edg(nf[1]), cen(nf[0]), indexing="ij"); vm = (pe(X, Y + 0.5 * h, Z) - pe(X, Y - 0.5 * h, Z)) / h
+        Z, Y, X = np.meshgrid(edg(nf[2]), cen(nf[1]), cen(nf[0]), indexing="ij"); wm = (pe(X, Y, Z + 0.5 * h) - pe(X, Y, Z - 0.5 * h)) / h
+        M2 = [_wrap_pad(q[None], 2) for q in (um, vm, wm)]
+        RHO = np.ones((1, nf[2] + 2, nf[1] + 2, nf[0] + 2))
+        boxes = _patch_boxes(clo, chi, nb)
+        clev = ix.Level(lib, ix.Geom.make(nc, periodic=per), [((0, 0, 0), tuple(q - 1 for q in nc))])
+        flev = ix.Level(lib, ix.Geom.make(nf, periodic=per), boxes)
+        U = [[fab_from_padded(M2[d], 2, b, 1, t, dev) for b in boxes] for d, t in enumerate((ix.XFACE, ix.YFACE, ix.ZFACE))]
+        R = [fab_from_padded(RHO, 1, b, 1, ix.CELL, dev) for b in boxes]
+        gshape = (1, nf[2] + 2, nf[1] + 2, nf[0] + 2)
+        P = [fab_from_padded(np.zeros(gshape), 1, b, 1, ix.CELL, dev) for b in boxes]
+        CP = _coarse_fabs(cphi, nc, dev)
+        fa = lambda L: fab_array([p[1] for p in L])
+        lib.check(lib.iamrx_set_coarse_fine_bc(flev.h, clev.h, fa(P), fa(CP), 1, stream_of(dev)))
+        info = _mg(lib, rtol=1e-11, maxorder=4)
+        lib.check(lib.iamrx_mac_project(flev.h, fa(U[0]), fa(U[1]), fa(U[2]), fa(R), None, fa(P), 1.0, None, None, C.byref(info), stream_of(dev)))
+        sync(dev)
+        gphi, _ = scatter_valid(np.zeros(gshape), 1, [p[0] for p in P], boxes, 1, ix.CELL)
+        Zf, Yf, Xf = np.meshgrid(cen(nf[2]), cen(nf[1]), cen(nf[0]), indexing="ij")
+        exact = pe(Xf, Yf, Zf)[None]
+        errs.append(float(np.abs(_cut(gphi, 1, flo, fhi, 0) - _cut(exact, 0, flo, fhi, 0)).max()))
+        clev.close(); flev.close()
+    assert errs[1] < 0.02
+    assert errs[0] / errs[1] > 3.0, errs
