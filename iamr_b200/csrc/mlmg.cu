@@ -760,17 +760,36 @@ NodeMG::NodeMG(Level* fine, int max_coarsening) {
     for (MF* m : {&L.cor, &L.res, &L.rescor, &L.xfer}) if (m->ok()) mf_setval(*m, 0.0, 0, 1, m->ng, nullptr);
   }
   for (int d = 0; d < 3; ++d) { bc_.lo[d] = IAMRX_LINOP_PERIODIC; bc_.hi[d] = IAMRX_LINOP_PERIODIC; }
+  // a level that does not tile its domain is a fine AMR level: the sides of the patch that border coarse cells carry Dirichlet nodes
+  if (!fine->replicated && fine->ncells_global != mkbx(fine->geom.domain).npts()) {
+    cfmask_.resize(lv_.size());
+    for (size_t l = 0; l < lv_.size(); ++l) {
+      const Level& L = *lv_[l].lev;
+      for (int il = 0; il < L.nlocal(); ++il) cfmask_[l].push_back(coarse_fine_sides(L, L.lbox(il)));
+      for (const Bx& b : L.boxes) if (coarse_fine_sides(L, b)) cf_ = true;
+    }
+    // the boundary nodes are found side by side: the boxes must form ONE rectangular patch (no re-entrant edges, no partly
+    // covered sides)
+    Bx u = fine->boxes[0];
+    for (const Bx& b : fine->boxes) for (int d = 0; d < 3; ++d) { u.lo[d] = std::min(u.lo[d], b.lo[d]); u.hi[d] = std::max(u.hi[d], b.hi[d]); }
+    cf_rect_ = u.npts() == fine->ncells_global;
+  }
 }
 
 void NodeMG::set_bc(const k::NodalBC& bc) {
   bc_ = bc;
-  has_bc_ = !all_periodic(*lv_[0].lev);
+  has_bc_ = !all_periodic(*lv_[0].lev) || cf_;
 }
 
-Bx NodeMG::active_nbox(int l, int il) const {
+Bx NodeMG::active_nbox(int l, int il, bool with_cf) const {
   const Level& L = *lv_[l].lev;
   Bx nb = ixbox(L.lbox(il), IX_NODE);
   if (!has_bc_) return nb;
+  if (cf_ && with_cf)
+    for (int d = 0; d < 3; ++d) {
+      if (cfmask_[l][il] & (1 << (2 * d))) nb.lo[d] += 1;
+      if (cfmask_[l][il] & (1 << (2 * d + 1))) nb.hi[d] -= 1;
+    }
   for (int d = 0; d < 3; ++d) {
     if (L.geom.periodic[d]) continue;
     if (bc_.lo[d] == IAMRX_LINOP_DIRICHLET && L.lbox(il).lo[d] == L.domain.lo[d]) nb.lo[d] += 1;
@@ -792,6 +811,7 @@ int NodeMG::neumann_sides(int l, int il) const {
 }
 
 bool NodeMG::singular() const {
+  if (cf_) return false;   // the coarse-fine boundary nodes pin the solution
   const Level& L = *lv_[0].lev;
   for (int d = 0; d < 3; ++d)
     if (!L.geom.periodic[d] && has_bc_ && (bc_.lo[d] == IAMRX_LINOP_DIRICHLET || bc_.hi[d] == IAMRX_LINOP_DIRICHLET)) return false;
@@ -877,6 +897,7 @@ int NodeMG::smooth(int l, MF& phi, const MF& rhs, int nsweeps, cudaStream_t s) {
   bool fused = true;
   for (size_t b = 0; b < L.lev->boxes.size() && fused; ++b) fused = k::nodal_gs_sweep_ok(ixbox(L.lev->boxes[b], IX_NODE), wmk);
   // Dirichlet sides shorten the active node box; keep the fused sweep only if its plane pairing survives (both z sides or none)
+  if (cf_) fused = false;   // coarse-fine Dirichlet planes shorten the active boxes side by side: colour passes
   if (fused && has_bc_)
     for (int d = 0; d < 3; ++d)
       if (!L.lev->geom.periodic[d] && ((bc_.lo[d] == IAMRX_LINOP_DIRICHLET) != (bc_.hi[d] == IAMRX_LINOP_DIRICHLET))) fused = false;
@@ -1039,6 +1060,10 @@ int NodeMG::vcycle(cudaStream_t s) {
 }
 
 int NodeMG::solve(MF& phi, MF& rhs, iamrx_mg_info* info, cudaStream_t s) {
+  if (!coarse_fine_supported()) {
+    set_error("NodeMG: the boxes of a level with coarse-fine sides must form one rectangular patch");
+    return IAMRX_ERR_ARG;
+  }
   if (info) info_ = *info;
   info_.bottom_iters = 0;
   MGLevelNode& L0 = lv_[0];

@@ -107,7 +107,13 @@ class NodeMG {
   const k::NodalBC& bc() const { return bc_; }
   bool has_bc() const { return has_bc_; }
   // node box of local box il on level l without the planes ON Dirichlet domain sides (those nodes are held at zero)
-  Bx active_nbox(int l, int il) const;
+  // with_cf = false: only the Dirichlet DOMAIN sides are removed (their nodes are held at zero; the nodes ON coarse-fine sides keep
+  // the values handed in -- the interpolated coarse pressure, Projection.cpp:236-239)
+  Bx active_nbox(int l, int il, bool with_cf = true) const;
+  // a fine AMR level (one rectangular patch of boxes that does not tile the domain): the nodes on the patch boundary are Dirichlet
+  // nodes of the single-level solve (MLNodeLaplacian: coarse-fine boundary nodes of the coarsest AMR level of a solve)
+  bool has_coarse_fine() const { return cf_; }
+  bool coarse_fine_supported() const { return !cf_ || cf_rect_; }
   int neumann_sides(int l, int il) const;   // bit 2d / 2d+1: the low / high side of the box is a Neumann / inflow domain side
   int set_sigma(const MF& sigma, cudaStream_t s);  // copies + coarsens
   int solve(MF& phi, MF& rhs, iamrx_mg_info* info, cudaStream_t s);
@@ -127,6 +133,8 @@ class NodeMG {
   int thin_ = 0;   // semi-coarsening mask (thin_mask of the finest level)
   k::NodalBC bc_{};
   bool has_bc_ = false;
+  bool cf_ = false, cf_rect_ = true;
+  std::vector<std::vector<int>> cfmask_;   // [mg level][local box]: bit 2 d + side = that side of the box is a coarse-fine side
 };
 
 // coarsen a level by 2 (all boxes must be coarsenable); nullptr if not possible

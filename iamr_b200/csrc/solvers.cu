@@ -98,7 +98,7 @@ int nodal_project(Level& L, LevelSolvers& sv, MF& vel, const MF& sigma, MF& phi,
   }
   if (mg.has_bc()) {   // nodes ON Dirichlet sides are held at zero
     for (int il = 0; il < phi.n(); ++il) {
-      const Bx full = phi.vbox(il), act = mg.active_nbox(0, il);
+      const Bx full = phi.vbox(il), act = mg.active_nbox(0, il, /*with_cf=*/false);   // coarse-fine boundary nodes keep their values
       for (int d = 0; d < 3; ++d) {
         if (act.lo[d] > full.lo[d]) { Bx R = full; R.hi[d] = full.lo[d]; IX_TRY(k::setval(R, phi.v(il), 1, 0.0, s)); }
         if (act.hi[d] < full.hi[d]) { Bx R = full; R.lo[d] = full.hi[d]; IX_TRY(k::setval(R, phi.v(il), 1, 0.0, s)); }

@@ -375,7 +375,9 @@ void iamrx_mg_info_default(iamrx_mg_info* info);
  * 1 ghost; rhs may be NULL (divu == 0).  lobc/hibc: LinOpBCType of the six domain sides as set_mac_solve_bc
  * builds them (MacProj.cpp:1187-1208: outflow -> Dirichlet, every other non-periodic side -> Neumann; NULL =
  * periodic); the ghost cells of phi on entry are the level BC (setLevelBC(0, mac_phi), MacProj.cpp:1168) and
- * info->maxorder the extrapolation order (setMaxOrder, :1172). */
+ * info->maxorder the extrapolation order (setMaxOrder, :1172).
+ * On a level > 0 (boxes that do not tile the domain) call iamrx_set_coarse_fine_bc(lev, crse_lev, phi, cphi, 1, stream) first
+ * (setCoarseFineBC(cphi, ratio) :1164-1167): every box side that borders coarse cells is then a coarse-fine Dirichlet side. */
 int iamrx_mac_project(iamrx_level_t lev, iamrx_fab* umac, iamrx_fab* vmac,
                       iamrx_fab* wmac, const iamrx_fab* rho, const iamrx_fab* rhs,
                       iamrx_fab* phi, double rhs_scale, const int lobc[3],
@@ -391,7 +393,10 @@ int iamrx_mac_get_fluxes(iamrx_level_t lev, iamrx_fab* fx, iamrx_fab* fy, iamrx_
  * Hydro::NodalProjector{ctor, setDomainBC, project, getGradPhi}: solve
  * div(sigma grad phi) = div(vel) on nodes, vel -= sigma grad phi,
  * gp (=|+=) grad phi.  vel: 3 comps >=1 ghost; sigma: 1 comp 1 ghost;
- * phi: nodal 1 ghost (initial guess in, solution out); gp: 3 comps. */
+ * phi: nodal 1 ghost (initial guess in, solution out); gp: 3 comps.
+ * On a level > 0 (Projection::level_project :236-257): the boxes must form ONE rectangular patch; the nodes on the sides of the
+ * patch that border coarse cells are Dirichlet nodes and KEEP the values of phi on entry (the coarse pressure interpolated by
+ * FillCoarsePatch -- iamrx_interp_box with node_bilinear), the interior nodes are the initial guess (IAMR zeroes them). */
 int iamrx_nodal_project(iamrx_level_t lev, iamrx_fab* vel, const iamrx_fab* sigma,
                         iamrx_fab* phi, iamrx_fab* gp, int increment_gp,
                         const int lobc[3], const int hibc[3], iamrx_mg_info* info,

@@ -60,7 +60,7 @@ for (MFIter mfi(advc); mfi.isValid(); ++mfi) {
 
 // ---- MacProj.cpp:1084-1184 ----------------------------------------------------------------------------------------------------
 void site3_mlmg_mac_solve(int level, Geometry const& geom, BoxArray const& ba, DistributionMapping const& dm, MultiFab* const* u_mac,
-                          MultiFab const& rho_half, MultiFab const* Rhs, MultiFab* mac_phi, MultiFab* const* fluxes, Real rhs_scale,
+                          MultiFab const* cphi, MultiFab const& rho_half, MultiFab const* Rhs, MultiFab* mac_phi, MultiFab* const* fluxes, Real rhs_scale,
                           Real a_mac_tol, Real a_mac_abs_tol, int max_order, int verbose,
                           Array<LinOpBCType, 3> const& mlmg_lobc, Array<LinOpBCType, 3> const& mlmg_hibc) {
 // [site 3 begin]
@@ -74,6 +74,10 @@ int lobc[3], hibc[3];
 iamrx_adapt::linop_bc(mlmg_lobc, mlmg_hibc, lobc, hibc);   // as set_mac_solve_bc filled them (:1187-1208)
 iamrx_mg_info info; iamrx_mg_info_default(&info);
 info.rtol = a_mac_tol; info.atol = a_mac_abs_tol; info.maxorder = max_order; info.verbose = verbose;
+if (level > 0 && cphi) {                                    // macproj.setCoarseFineBC(cphi, ratio) (:1164-1167)
+  auto cp = iamrx_adapt::fabs(*cphi);                       // -> coarse-fine boundary values in the ghost cells of mac_phi
+  iamrx_adapt::check(iamrx_set_coarse_fine_bc(L, lev_cache.at(level - 1), phi.data(), cp.data(), 1, Gpu::gpuStream()));
+}
 int rc = iamrx_mac_project(L, um.data(), vm.data(), wm.data(), rho.data(), Rhs ? rhs.data() : nullptr, phi.data(), rhs_scale,
                            lobc, hibc, &info, Gpu::gpuStream());
 if (rc > 0) Abort("MLMG failed to converge");               // reference behaviour

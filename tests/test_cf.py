@@ -300,3 +300,77 @@ def test_coarse_fine_solve_converges_at_second_order(backend, nb):
         clev.close(); flev.close()
     assert errs[1] < 0.02
     assert errs[0] / errs[1] > 3.0, errs
+
+
+@pytest.mark.parametrize("nb", [(1, 1, 1), (2, 1, 2), (2, 2, 2)])
+def test_nodal_project_coarse_fine(backend, oracle, nb):
+    """Projection::level_project on a level > 0 (Projection.cpp:236-257, 2385-2567): the nodes on the coarse-fine boundary hold the
+    coarse pressure interpolated by FillCoarsePatch and are Dirichlet nodes of the single-level nodal solve (inhomogeneous); the
+    interior starts from zero.  The oracle solves on the patch as its own domain with Dirichlet sides in x and z."""
+    lib, dev = backend
+    per = (1, 1, 1)
+    nf = (32, 32, 32)
+    clo, chi = (4, 0, 4), (11, 15, 11)
+    flo, fhi = tuple(2 * c for c in clo), tuple(2 * c + 1 for c in chi)
+    n = tuple(fhi[d] - flo[d] + 1 for d in range(3))
+    dx = tuple(1.0 / m for m in nf)
+    z, y, x = [(np.arange(m) + 0.5) / m for m in nf[::-1]]
+    Z, Y, X = np.meshgrid(z, y, x, indexing="ij")
+    sig = (1.0 / (1.0 + 0.4 * np.sin(2 * np.pi * X) * np.cos(2 * np.pi * Y) * np.sin(2 * np.pi * Z + 0.3)))[None]
+    V = _wrap_pad(smooth_field(nf, 900, 3) + 0.2 * hash_uniform(901, (3,) + nf[::-1]), 1)
+    # nodal boundary data: any field on the nodes of the fine index space; only the coarse-fine boundary planes of the patch matter
+    G = _wrap_pad(0.02 * smooth_field(nf, 902, 1), 2)      # node (i, j, k) = low corner of cell (i, j, k)
+    Pg = np.zeros_like(G)
+    ilo, ihi = [flo[d] + 2 for d in range(3)], [fhi[d] + 1 + 2 for d in range(3)]   # node index range of the patch inside the padded array
+    for d in (0, 2):   # the patch spans y
+        for pl in (ilo[d], ihi[d]):
+            sl = [slice(None), slice(ilo[2], ihi[2] + 1), slice(ilo[1], ihi[1] + 1), slice(ilo[0], ihi[0] + 1)]
+            sl[3 - d] = slice(pl, pl + 1)
+            Pg[tuple(sl)] = G[tuple(sl)]
+    pper = (0, 1, 0)
+    lobc, hibc = (DIR, PER, DIR), (DIR, PER, DIR)
+    mg = oracle.mg_default(rtol=1e-12)
+    rvel, rphi, rgp, rc, mgo = oracle.nodal_project_bc(n, pper, dx, _cut(V, 1, flo, fhi, 1), _cut(sig, 0, flo, fhi, 0), _cut(Pg, 2, flo, fhi, 2),
+                                                       lobc, hibc, mg)
+    assert rc == 0
+    boxes = _patch_boxes(clo, chi, nb)
+    flev = ix.Level(lib, ix.Geom.make(nf, periodic=per), boxes)
+    Vv = [fab_from_padded(V, 1, b, 1, ix.CELL, dev) for b in boxes]
+    Sg = [fab_from_padded(sig, 0, b, 0, ix.CELL, dev) for b in boxes]
+    Ph = [fab_from_padded(Pg, 2, b, 1, ix.NODE, dev) for b in boxes]
+    Gp = [fab_from_padded(np.zeros((3,) + nf[::-1]), 0, b, 0, ix.CELL, dev) for b in boxes]
+    fa = lambda L: fab_array([p[1] for p in L])
+    info = _mg(lib, rtol=1e-12)
+    rc = lib.iamrx_nodal_project(flev.h, fa(Vv), fa(Sg), fa(Ph), fa(Gp), 0, None, None, C.byref(info), stream_of(dev))
+    lib.check(rc)
+    sync(dev)
+    if nb == (1, 1, 1):
+        assert info.iters == mgo.iters
+    gv, _ = scatter_valid(np.zeros((3, nf[2] + 2, nf[1] + 2, nf[0] + 2)), 1, [p[0] for p in Vv], boxes, 1, ix.CELL)
+    assert np.abs(_cut(gv, 1, flo, fhi, 0) - rvel[:, 1:-1, 1:-1, 1:-1]).max() < 1e-10
+    gg, _ = scatter_valid(np.zeros((3,) + nf[::-1]), 0, [p[0] for p in Gp], boxes, 0, ix.CELL)
+    assert np.abs(_cut(gg, 0, flo, fhi, 0) - rgp).max() < 1e-9
+    gp_, dup = scatter_valid(np.zeros(Pg.shape), 2, [p[0] for p in Ph], boxes, 1, ix.NODE)
+    assert dup < 1e-11
+    got = gp_[:, ilo[2]:ihi[2] + 1, ilo[1]:ihi[1], ilo[0]:ihi[0] + 1]            # y: the n unique nodes of the periodic direction
+    ref = rphi[:, 2:2 + n[2] + 1, 2:2 + n[1], 2:2 + n[0] + 1]
+    assert np.abs(got - ref).max() < 1e-11
+    # the boundary nodes still hold the data handed in
+    assert np.array_equal(gp_[:, ilo[2]:ihi[2] + 1, ilo[1]:ihi[1], ilo[0]], Pg[:, ilo[2]:ihi[2] + 1, ilo[1]:ihi[1], ilo[0]])
+    flev.close()
+
+
+def test_nodal_project_refuses_non_rectangular_patch(backend):
+    """An L-shaped fine level has boundary nodes on a re-entrant edge that the side-by-side bookkeeping does not see: refused."""
+    lib, dev = backend
+    nf = (32, 32, 32)
+    boxes = [((8, 8, 8), (15, 15, 15)), ((16, 8, 8), (23, 15, 15)), ((8, 16, 8), (15, 23, 15))]
+    flev = ix.Level(lib, ix.Geom.make(nf, periodic=(1, 1, 1)), boxes)
+    Vv = [fab_from_padded(np.zeros((3, 34, 34, 34)), 1, b, 1, ix.CELL, dev) for b in boxes]
+    Sg = [fab_from_padded(np.ones((1,) + nf[::-1]), 0, b, 0, ix.CELL, dev) for b in boxes]
+    Ph = [fab_from_padded(np.zeros((1, 36, 36, 36)), 2, b, 1, ix.NODE, dev) for b in boxes]
+    fa = lambda L: fab_array([p[1] for p in L])
+    info = _mg(lib)
+    rc = lib.iamrx_nodal_project(flev.h, fa(Vv), fa(Sg), fa(Ph), None, 0, None, None, C.byref(info), stream_of(dev))
+    assert rc == -1   # IAMRX_ERR_ARG
+    flev.close()
