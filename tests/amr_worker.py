@@ -127,6 +127,37 @@ def main():
             + (W[2:W.shape[0] - 1, b, a] - W[1:W.shape[0] - 2, b, a]) / dx
         assert np.abs(div).max() <= 1e-11, ("create_umac_grown: divergence of the corrected halo", rank, float(np.abs(div).max()))
 
+    # 5. the level > 0 MAC solve: setCoarseFineBC (collective: coarse data on the other rank) + coarse-fine Dirichlet sides in the
+    #    multigrid, fine boxes on different ranks, against the oracle solving on the patch as its own domain (tests/test_cf.py)
+    from test_bc import _mg
+    CF, PER_ = 5, 0
+    flo, fhi = (4, 0, 4), (11, 15, 11)
+    n = tuple(fhi[d] - flo[d] + 1 for d in range(3))
+    dxf = tuple(1.0 / m for m in NF)
+    cov = cmask
+    cphi = 0.05 * smooth_field(NC, 191, 1)
+    rho = 1.0 + 0.3 * hash_uniform(192, (1,) + NF[::-1])
+    macs = [smooth_field(NF, 193 + d, 1) + 0.3 * hash_uniform(196 + d, (1,) + NF[::-1]) for d in range(3)]
+    wp = lambda a, g: np.pad(a, ((0, 0), (g, g), (g, g), (g, g)), mode="wrap")
+    cut = lambda P, g, ng: np.ascontiguousarray(P[:, flo[2] - ng + g:fhi[2] + ng + g + 1, flo[1] - ng + g:fhi[1] + ng + g + 1, flo[0] - ng + g:fhi[0] + ng + g + 1])
+    phi0 = orc.interp_bndry(NC, (1, 1, 1), cphi, cov, flo, fhi, np.zeros((1, n[2] + 2, n[1] + 2, n[0] + 2)))
+    mgo = orc.mg_default(rtol=1e-12)
+    ru, rv, rw, rphi, rc, mgo = orc.mac_project_bc(n, (0, 1, 0), dxf, cut(wp(macs[0], 2), 2, 1), cut(wp(macs[1], 2), 2, 1), cut(wp(macs[2], 2), 2, 1),
+                                                   cut(wp(rho, 1), 1, 1), None, phi0, 3.0, (CF, PER_, CF), (CF, PER_, CF), 4, mgo)
+    assert rc == 0
+    CP = [to_fab(np.where(cov[None], 1.0e30, cphi), cboxes[i], 0, ix.CELL, "cpu") for i in cmine]
+    UF = [[to_fab(macs[d], fboxes[i], 1, types[d], "cpu") for i in fmine] for d in range(3)]
+    RH = [to_fab(rho, fboxes[i], 1, ix.CELL, "cpu") for i in fmine]
+    PH = [to_fab(np.zeros((1,) + NF[::-1]), fboxes[i], 1, ix.CELL, "cpu") for i in fmine]
+    lib.check(lib.iamrx_set_coarse_fine_bc(flev.h, clev.h, fa(PH), fa(CP), 1, st))
+    info = _mg(lib, rtol=1e-12, maxorder=4)
+    lib.check(lib.iamrx_mac_project(flev.h, fa(UF[0]), fa(UF[1]), fa(UF[2]), fa(RH), None, fa(PH), 3.0, None, None, C.byref(info), st))
+    for (t, _), i in zip(PH, fmine):
+        lo, hi = fboxes[i]
+        got = t.numpy()[:, 1:-1, 1:-1, 1:-1]
+        ref = rphi[:, 1 + lo[2] - flo[2]:2 + hi[2] - flo[2], 1 + lo[1] - flo[1]:2 + hi[1] - flo[1], 1 + lo[0] - flo[0]:2 + hi[0] - flo[0]]
+        assert np.abs(got - ref).max() <= 2e-10, ("coarse-fine mac_project", rank, float(np.abs(got - ref).max()))
+
     clev.close(); flev.close()
     dist.barrier()
     print(f"rank {rank} ok", flush=True)
