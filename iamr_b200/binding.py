@@ -203,6 +203,7 @@ SIGNATURES = {
     "iamrx_sync_interp": (C.c_int, [_vp, _vp, _P(Fab), C.c_int, _P(Fab), C.c_int, C.c_int, C.c_int, C.c_double, C.c_int, _P(BCRec), _vp]),
     "iamrx_sync_proj_interp": (C.c_int, [_vp, _vp, _P(Fab), _P(Fab), _P(Fab), _vp]),
     "iamrx_set_coarse_fine_bc": (C.c_int, [_vp, _vp, _P(Fab), _P(Fab), C.c_int, _vp]),
+    "iamrx_fill_coarse_patch_nodal": (C.c_int, [_vp, _vp, _P(Fab), _P(Fab), _P(Fab), C.c_double, C.c_double, C.c_double, _vp]),
     "iamrx_diffusion_get_fluxes": (C.c_int, [_vp, C.c_int, _P(Fab), _P(Fab), _P(Fab), _P(Fab), C.c_double, _P(Fab), _P(Fab), _P(Fab), C.c_double, _vp]),
     "iamrx_fillpatch_two_levels": (C.c_int, [_vp, _vp, _P(Fab), _P(Fab), _P(Fab), C.c_double, C.c_double, C.c_double, C.c_int, C.c_int,
                                              _P(BCRec), _P(C.c_double), _vp]),

@@ -773,4 +773,35 @@ int iamrx_sync_proj_interp(iamrx_level_t fine_lev, iamrx_level_t crse_lev, iamrx
   return IAMRX_OK;
 }
 
+// AmrLevel::FillCoarsePatch of Press_Type (Projection.cpp:236-239): see iamrx.h
+int iamrx_fill_coarse_patch_nodal(iamrx_level_t fine_lev, iamrx_level_t crse_lev, iamrx_fab* fine, const iamrx_fab* crse_old,
+                                  const iamrx_fab* crse_new, double t_old, double t_new, double time, void* stream) {
+  IX_NEED_DEVICE();
+  IX_ARG(fine_lev && crse_lev && fine && crse_new, "fill_coarse_patch_nodal arguments");
+  Level* FL = level_of(fine_lev);
+  Level* CL = level_of(crse_lev);
+  cudaStream_t s = (cudaStream_t)stream;
+  for (int d = 0; d < 3; ++d)
+    IX_ARG(FL->geom.domain.lo[d] == 2 * CL->geom.domain.lo[d] && FL->geom.domain.hi[d] == 2 * CL->geom.domain.hi[d] + 1,
+           "the fine level's domain must be the coarse one refined by 2");
+  double w_new = 1.0;
+  if (crse_old && t_new != t_old) w_new = (time - t_old) / (t_new - t_old);
+  IX_ARG(w_new >= -1.0e-12 && w_new <= 1.0 + 1.0e-12, "time outside [t_old, t_new]");
+  // the coarse pressure at `time` (linear between the two time levels: StateData's interpolation of a point-in-time quantity)
+  MF cn; cn.alias(CL, IX_NODE, 1, 0, const_cast<iamrx_fab*>(crse_new));
+  MF ct(CL, IX_NODE, 1, 0);
+  if (crse_old && w_new != 1.0) {
+    MF co; co.alias(CL, IX_NODE, 1, 0, const_cast<iamrx_fab*>(crse_old));
+    IX_TRY(mf_lincomb(ct, 0, 1.0 - w_new, co, 0, w_new, cn, 0, 1, 0, s));
+  } else {
+    IX_TRY(mf_copy(ct, cn, 0, 0, 1, 0, s));
+  }
+  std::unique_ptr<Level> RL;
+  MF cr;
+  IX_TRY(replicated_coarse(CL, ct.fabs.data(), 0, 1, IX_NODE, 0, nullptr, s, RL, cr));
+  MF fm; fm.alias(FL, IX_NODE, 1, 0, fine);
+  for (int il = 0; il < fm.n(); ++il) IX_TRY(k::node_bilinear_interp(fm.vbox(il), fm.v(il), cr.c(0), 1, s));
+  return IAMRX_OK;
+}
+
 }  // extern "C"

@@ -320,11 +320,15 @@ def test_nodal_project_coarse_fine(backend, oracle, nb):
     Z, Y, X = np.meshgrid(z, y, x, indexing="ij")
     sig = (1.0 / (1.0 + 0.4 * np.sin(2 * np.pi * X) * np.cos(2 * np.pi * Y) * np.sin(2 * np.pi * Z + 0.3)))[None]
     V = _wrap_pad(smooth_field(nf, 900, 3) + 0.2 * hash_uniform(901, (3,) + nf[::-1]), 1)
-    # nodal boundary data: any field on the nodes of the fine index space; only the coarse-fine boundary planes of the patch matter
-    G = _wrap_pad(0.02 * smooth_field(nf, 902, 1), 2)      # node (i, j, k) = low corner of cell (i, j, k)
+    # Projection.cpp:236-257: P_new = FillCoarsePatch(coarse pressure), then the interior nodes of every grid are zeroed -- the
+    # coarse-fine boundary nodes keep the interpolated coarse pressure (in y, the periodic direction the patch spans, the kept
+    # plane is just part of the initial guess)
+    nc = (16, 16, 16)
+    cpress = 0.02 * smooth_field(nc, 902, 1)
+    G = _wrap_pad(oracle.interp(1, nc, cpress), 2)          # node (i, j, k) = low corner of cell (i, j, k)
     Pg = np.zeros_like(G)
     ilo, ihi = [flo[d] + 2 for d in range(3)], [fhi[d] + 1 + 2 for d in range(3)]   # node index range of the patch inside the padded array
-    for d in (0, 2):   # the patch spans y
+    for d in range(3):
         for pl in (ilo[d], ihi[d]):
             sl = [slice(None), slice(ilo[2], ihi[2] + 1), slice(ilo[1], ihi[1] + 1), slice(ilo[0], ihi[0] + 1)]
             sl[3 - d] = slice(pl, pl + 1)
@@ -339,9 +343,17 @@ def test_nodal_project_coarse_fine(backend, oracle, nb):
     flev = ix.Level(lib, ix.Geom.make(nf, periodic=per), boxes)
     Vv = [fab_from_padded(V, 1, b, 1, ix.CELL, dev) for b in boxes]
     Sg = [fab_from_padded(sig, 0, b, 0, ix.CELL, dev) for b in boxes]
-    Ph = [fab_from_padded(Pg, 2, b, 1, ix.NODE, dev) for b in boxes]
+    Ph = [fab_from_padded(np.zeros_like(Pg), 2, b, 1, ix.NODE, dev) for b in boxes]
     Gp = [fab_from_padded(np.zeros((3,) + nf[::-1]), 0, b, 0, ix.CELL, dev) for b in boxes]
     fa = lambda L: fab_array([p[1] for p in L])
+    clev = ix.Level(lib, ix.Geom.make(nc, periodic=per), [((0, 0, 0), tuple(m - 1 for m in nc))])
+    from util import to_fab
+    CPN = [to_fab(cpress, ((0, 0, 0), tuple(m - 1 for m in nc)), 0, ix.NODE, dev)]
+    lib.check(lib.iamrx_fill_coarse_patch_nodal(flev.h, clev.h, fa(Ph), None, fa(CPN), 0.0, 0.0, 0.0, stream_of(dev)))
+    sync(dev)
+    for t, _ in Ph:
+        t[:, 2:-2, 2:-2, 2:-2] = 0.0     # growntilebox(-1) of the node box (the fabs carry one ghost node layer)
+    clev.close()
     info = _mg(lib, rtol=1e-12)
     rc = lib.iamrx_nodal_project(flev.h, fa(Vv), fa(Sg), fa(Ph), fa(Gp), 0, None, None, C.byref(info), stream_of(dev))
     lib.check(rc)
@@ -358,7 +370,7 @@ def test_nodal_project_coarse_fine(backend, oracle, nb):
     ref = rphi[:, 2:2 + n[2] + 1, 2:2 + n[1], 2:2 + n[0] + 1]
     assert np.abs(got - ref).max() < 1e-11
     # the boundary nodes still hold the data handed in
-    assert np.array_equal(gp_[:, ilo[2]:ihi[2] + 1, ilo[1]:ihi[1], ilo[0]], Pg[:, ilo[2]:ihi[2] + 1, ilo[1]:ihi[1], ilo[0]])
+    assert np.abs(gp_[:, ilo[2]:ihi[2] + 1, ilo[1]:ihi[1], ilo[0]] - Pg[:, ilo[2]:ihi[2] + 1, ilo[1]:ihi[1], ilo[0]]).max() <= 1e-15
     flev.close()
 
 
