@@ -203,6 +203,12 @@ SIGNATURES = {
     "iamrx_sync_interp": (C.c_int, [_vp, _vp, _P(Fab), C.c_int, _P(Fab), C.c_int, C.c_int, C.c_int, C.c_double, C.c_int, _P(BCRec), _vp]),
     "iamrx_sync_proj_interp": (C.c_int, [_vp, _vp, _P(Fab), _P(Fab), _P(Fab), _vp]),
     "iamrx_set_coarse_fine_bc": (C.c_int, [_vp, _vp, _P(Fab), _P(Fab), C.c_int, _vp]),
+    "iamrx_syncreg_create": (C.c_int, [_vp, _vp, C.c_double, _P(_vp)]),
+    "iamrx_syncreg_destroy": (C.c_int, [_vp]),
+    "iamrx_syncreg_crse_init": (C.c_int, [_vp, _P(Fab), C.c_double, _vp]),
+    "iamrx_syncreg_fine_add": (C.c_int, [_vp, _P(Fab), C.c_double, _vp]),
+    "iamrx_syncreg_init_rhs": (C.c_int, [_vp, _P(Fab), _P(C.c_int), _P(C.c_int), _vp]),
+    "iamrx_syncreg_field": (C.c_int, [_vp, C.c_int, C.c_int, _P(Fab)]),
     "iamrx_fill_coarse_patch_nodal": (C.c_int, [_vp, _vp, _P(Fab), _P(Fab), _P(Fab), C.c_double, C.c_double, C.c_double, _vp]),
     "iamrx_diffusion_get_fluxes": (C.c_int, [_vp, C.c_int, _P(Fab), _P(Fab), _P(Fab), _P(Fab), C.c_double, _P(Fab), _P(Fab), _P(Fab), C.c_double, _vp]),
     "iamrx_fillpatch_two_levels": (C.c_int, [_vp, _vp, _P(Fab), _P(Fab), _P(Fab), C.c_double, C.c_double, C.c_double, C.c_int, C.c_int,

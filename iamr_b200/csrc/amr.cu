@@ -139,6 +139,72 @@ __global__ void __launch_bounds__(TX* TY) cf_bndry_kernel(Bx R, V4 fine, C4 crse
   fine(i, j, k, n) = v;
 }
 
+// ---- sync register (SyncRegister.cpp) ---------------------------------------------------------------------------------------
+// mask of InitRHS (SyncRegister.cpp:126-285): 0 on coarse nodes whose eight surrounding coarse cells are all under the fine level
+// (cells beyond a non-periodic side count as their mirror images: the "double the cell contributions" step), 1 elsewhere
+__global__ void __launch_bounds__(TX* TY) sync_mask_kernel(Bx nbx, V4 mask, C4 covered, double maxcount) {
+  IDX3(nbx)
+  double sum = 0.0;
+  for (int dk = -1; dk <= 0; ++dk) for (int dj = -1; dj <= 0; ++dj) for (int di = -1; di <= 0; ++di) sum += covered(i + di, j + dj, k + dk);
+  mask(i, j, k, n) = sum > maxcount ? 0.0 : 1.0;
+}
+// FineAdd (SyncRegister.cpp:351-607): the coarse nodes of ONE boundary plane (normal `dir`) of a coarsened fine node box take the
+// fine residual restricted with the tent weights of the two tangential directions, (r - m)(r - n) r_dir / prod(r^2), halved on
+// the centre lines; fine nodes on the edges of the fine box count half and on its corners a third (0.5 * 2/3), nodes outside the
+// fine box are zero (the residual's ghost nodes); nodes on non-periodic domain planes are doubled once per such direction.
+__global__ void __launch_bounds__(TX* TY) sync_fine_add_kernel(Bx R, V4 acc, C4 fine, Bx fnb, int dir, double mult, Bx cnd, int p0, int p1, int p2) {
+  IDX3(R)
+  const int dim1 = dir != 0 ? 0 : 1, dim2 = dir != 0 ? (dir == 2 ? 1 : 2) : 2;
+  const int ic[3] = {i, j, k};
+  const double denom = 2.0 / 64.0;
+  auto F = [&](int a, int b, int c) -> double {
+    if (a < fnb.lo[0] || a > fnb.hi[0] || b < fnb.lo[1] || b > fnb.hi[1] || c < fnb.lo[2] || c > fnb.hi[2]) return 0.0;
+    const int nb = (a == fnb.lo[0] || a == fnb.hi[0]) + (b == fnb.lo[1] || b == fnb.hi[1]) + (c == fnb.lo[2] || c == fnb.hi[2]);
+    const double w = nb >= 3 ? 0.5 * (2.0 / 3.0) : (nb == 2 ? 0.5 : 1.0);
+    return w * fine(a, b, c, n);
+  };
+  double v = 0.0;
+  for (int nn = 0; nn < 2; ++nn)
+    for (int m = 0; m < 2; ++m) {
+      double coeff = (2 - m) * (2 - nn) * denom;
+      if (nn == 0) coeff *= 0.5;
+      if (m == 0) coeff *= 0.5;
+      int f0[3] = {2 * ic[0], 2 * ic[1], 2 * ic[2]}, f1[3] = {2 * ic[0], 2 * ic[1], 2 * ic[2]}, f2[3] = {2 * ic[0], 2 * ic[1], 2 * ic[2]},
+          f3[3] = {2 * ic[0], 2 * ic[1], 2 * ic[2]};
+      f0[dim1] += m; f0[dim2] += nn;
+      f1[dim1] -= m; f1[dim2] += nn;
+      f2[dim1] += m; f2[dim2] -= nn;
+      f3[dim1] -= m; f3[dim2] -= nn;
+      v += coeff * (F(f0[0], f0[1], f0[2]) + F(f1[0], f1[1], f1[2]) + F(f2[0], f2[1], f2[2]) + F(f3[0], f3[1], f3[2]));
+    }
+  const int per[3] = {p0, p1, p2};
+  for (int q = 0; q < 3; ++q) if (!per[q] && (ic[q] == cnd.lo[q] || ic[q] == cnd.hi[q])) v *= 2.0;
+  acc(i, j, k, n) += mult * v;
+}
+// reg(p) += onB(p) * sum over the periodic images of p inside the node domain of acc(image)  (FabSet::plusFrom with periodicity)
+__global__ void __launch_bounds__(TX* TY) sync_gather_kernel(Bx nbx, V4 reg, C4 onb, C4 acc, Bx cnd, int l0, int l1, int l2) {
+  IDX3(nbx)
+  if (onb(i, j, k) == 0.0) return;
+  double s = 0.0;
+  for (int sz = -1; sz <= 1; ++sz) {
+    if (sz != 0 && l2 == 0) continue;
+    const int kk = k + sz * l2;
+    if (kk < cnd.lo[2] || kk > cnd.hi[2]) continue;
+    for (int sy = -1; sy <= 1; ++sy) {
+      if (sy != 0 && l1 == 0) continue;
+      const int jj = j + sy * l1;
+      if (jj < cnd.lo[1] || jj > cnd.hi[1]) continue;
+      for (int sx = -1; sx <= 1; ++sx) {
+        if (sx != 0 && l0 == 0) continue;
+        const int ii = i + sx * l0;
+        if (ii < cnd.lo[0] || ii > cnd.hi[0]) continue;
+        s += acc(ii, jj, kk, n);
+      }
+    }
+  }
+  reg(i, j, k, n) += s;
+}
+
 // ---- flux register ---------------------------------------------------------------------------------------------------
 // R = coarse cells of one interface patch (a one-cell-thick slab just OUTSIDE a fine box, on side `side` of direction d);
 // fc = index of the coarse face between the slab and the fine region.
@@ -212,6 +278,19 @@ int pc_interp(const Bx& fbx, V4 fine, C4 crse, int ncomp, cudaStream_t s) {
   if (!fbx.ok()) return IAMRX_OK;
   IX_LAUNCH(pc_interp_kernel, dim3(cdiv(fbx.nx(), TX), cdiv(fbx.ny(), TY), fbx.nz() * ncomp), dim3(TX, TY, 1), 0, s, fbx, fine, crse, fbx.nz());
   return check_launch("pc_interp");
+}
+int sync_mask(const Bx& nbx, V4 mask, C4 covered, double maxcount, cudaStream_t s) {
+  IX_LAUNCH(sync_mask_kernel, grid_for(nbx, nbx.nz()), dim3(TX, TY, 1), 0, s, nbx, mask, covered, maxcount);
+  return check_launch("sync_mask");
+}
+int sync_fine_add(const Bx& R, V4 acc, C4 fine, const Bx& fnb, int dir, double mult, const Bx& cnd, const int per[3], cudaStream_t s) {
+  if (!R.ok()) return IAMRX_OK;
+  IX_LAUNCH(sync_fine_add_kernel, grid_for(R, R.nz()), dim3(TX, TY, 1), 0, s, R, acc, fine, fnb, dir, mult, cnd, per[0], per[1], per[2]);
+  return check_launch("sync_fine_add");
+}
+int sync_gather(const Bx& nbx, V4 reg, C4 onb, C4 acc, const Bx& cnd, const int plen[3], cudaStream_t s) {
+  IX_LAUNCH(sync_gather_kernel, grid_for(nbx, nbx.nz()), dim3(TX, TY, 1), 0, s, nbx, reg, onb, acc, cnd, plen[0], plen[1], plen[2]);
+  return check_launch("sync_gather");
 }
 int cf_bndry_interp(const Bx& R, int d, V4 fine, C4 crse, C4 mask, int ncomp, cudaStream_t s) {
   if (!R.ok()) return IAMRX_OK;
@@ -336,6 +415,14 @@ int fluxreg_build(FluxReg& F, Level* crse, Level* fine, int ncomp) {
 using namespace ix;
 namespace ix { Level* level_of(iamrx_level_t h); }
 struct iamrx_fluxreg_s { FluxReg F; };
+
+// SyncRegister (SyncRegister.cpp): held densely on the coarse level's nodes -- `reg` is zero off the register's node set B (the
+// six boundary planes of every coarsened fine grid: the FabSets bndry[face]), `onb` marks B, `mask` is InitRHS's interior mask.
+struct iamrx_syncreg_s {
+  Level* crse = nullptr; Level* fine = nullptr;
+  MF reg, onb, mask;
+  std::vector<Bx> cnb;   // coarsened fine node boxes, one per fine box of the level
+};
 
 #define IX_TRY(call) do { int rc_ = (call); if (rc_ != IAMRX_OK) return rc_; } while (0)
 
@@ -770,6 +857,155 @@ int iamrx_sync_proj_interp(iamrx_level_t fine_lev, iamrx_level_t crse_lev, iamrx
     IX_TRY(k::lincomb(nb, pn.v(il), 1.0, pn.c(il), 1.0, tmp.c(il), 1, s));
     IX_TRY(k::lincomb(nb, po.v(il), 1.0, po.c(il), 1.0, tmp.c(il), 1, s));
   }
+  return IAMRX_OK;
+}
+
+// SyncRegister::SyncRegister (SyncRegister.cpp:20-47) + the mask of InitRHS (:126-272, which depends on the grids only)
+int iamrx_syncreg_create(iamrx_level_t crse_lev, iamrx_level_t fine_lev, double mask_maxcount, iamrx_syncreg_t* out) {
+  IX_NEED_DEVICE();
+  IX_ARG(crse_lev && fine_lev && out, "syncreg_create arguments");
+  Level* CL = level_of(crse_lev); Level* FL = level_of(fine_lev);
+  for (int d = 0; d < 3; ++d)
+    IX_ARG(FL->domain.lo[d] == 2 * CL->domain.lo[d] && FL->domain.hi[d] == 2 * CL->domain.hi[d] + 1, "the fine level's domain must be the coarse domain refined by 2");
+  auto h = std::make_unique<iamrx_syncreg_s>();
+  h->crse = CL; h->fine = FL;
+  std::vector<Bx> ccb;   // coarsened fine cell boxes
+  for (const Bx& fb : FL->boxes) {
+    Bx c;
+    for (int d = 0; d < 3; ++d) {
+      IX_ARG(!(fb.lo[d] & 1) && ((fb.hi[d] + 1) % 2 == 0), "sync register: fine boxes must be coarsenable by 2");
+      c.lo[d] = k::coarsen2(fb.lo[d]); c.hi[d] = k::coarsen2(fb.hi[d]);
+    }
+    ccb.push_back(c);
+    h->cnb.push_back(ixbox(c, IX_NODE));
+  }
+  h->reg.define(CL, IX_NODE, 1, 0); h->onb.define(CL, IX_NODE, 1, 0); h->mask.define(CL, IX_NODE, 1, 0);
+  cudaStream_t s = nullptr;
+  IX_TRY(mf_setval(h->reg, 0.0, 0, 1, 0, s));
+  IX_TRY(mf_setval(h->onb, 0.0, 0, 1, 0, s));
+  int plen[3];
+  for (int d = 0; d < 3; ++d) plen[d] = CL->domain.hi[d] - CL->domain.lo[d] + 1;
+  // B: the boundary planes of the coarsened fine node boxes and their periodic images
+  for (const Bx& nb : h->cnb)
+    for (int d = 0; d < 3; ++d)
+      for (int side = 0; side < 2; ++side) {
+        Bx pl = nb;
+        pl.lo[d] = pl.hi[d] = side == 0 ? nb.lo[d] : nb.hi[d];
+        for (int sz = -1; sz <= 1; ++sz) for (int sy = -1; sy <= 1; ++sy) for (int sx = -1; sx <= 1; ++sx) {
+          const int sh[3] = {sx * plen[0], sy * plen[1], sz * plen[2]};
+          bool ok = true;
+          for (int q = 0; q < 3; ++q) if (sh[q] != 0 && !CL->geom.periodic[q]) ok = false;
+          if (!ok) continue;
+          Bx img = pl;
+          for (int q = 0; q < 3; ++q) { img.lo[q] += sh[q]; img.hi[q] += sh[q]; }
+          for (int il = 0; il < h->onb.n(); ++il) {
+            const Bx is = intersect(img, h->onb.vbox(il));
+            if (is.ok()) IX_TRY(k::setval(is, h->onb.v(il), 1, 1.0, s));
+          }
+        }
+      }
+  // covered coarse cells with one ghost layer: periodic images, mirror images beyond non-periodic sides
+  MF cov(CL, IX_CELL, 1, 1);
+  IX_TRY(mf_setval(cov, 0.0, 0, 1, 1, s));
+  for (const Bx& c : ccb)
+    for (int il = 0; il < cov.n(); ++il) {
+      const Bx is = intersect(c, cov.vbox(il));
+      if (is.ok()) IX_TRY(k::setval(is, cov.v(il), 1, 1.0, s));
+    }
+  IX_TRY(mf_fill_boundary(cov, 0, 1, 1, s));
+  bool walls = false;
+  for (int d = 0; d < 3; ++d) if (!CL->geom.periodic[d]) walls = true;
+  if (walls) {
+    k::PhysBC bc{};
+    for (int d = 0; d < 3; ++d) { bc.lo[0][d] = IAMRX_BC_REFLECT_EVEN; bc.hi[0][d] = IAMRX_BC_REFLECT_EVEN; }
+    IX_TRY(mf_fill_physbc(cov, 0, 1, 1, bc, s));
+  }
+  for (int il = 0; il < h->mask.n(); ++il) IX_TRY(k::sync_mask(h->mask.vbox(il), h->mask.v(il), cov.c(il), mask_maxcount > 0.0 ? mask_maxcount : 26.5, s));
+  IX_CUDA(cudaStreamSynchronize(s));
+  *out = h.release();
+  return IAMRX_OK;
+}
+int iamrx_syncreg_destroy(iamrx_syncreg_t r) { delete r; return IAMRX_OK; }
+
+// SyncRegister::CrseInit (SyncRegister.cpp:288-300)
+int iamrx_syncreg_crse_init(iamrx_syncreg_t r, const iamrx_fab* sync_resid_crse, double mult, void* stream) {
+  IX_NEED_DEVICE();
+  IX_ARG(r && sync_resid_crse, "syncreg_crse_init arguments");
+  cudaStream_t s = (cudaStream_t)stream;
+  MF src; src.alias(r->crse, IX_NODE, 1, 0, const_cast<iamrx_fab*>(sync_resid_crse));
+  for (int il = 0; il < r->reg.n(); ++il) {
+    const Bx nb = r->reg.vbox(il);
+    IX_TRY(k::lincomb(nb, r->reg.v(il), mult, src.c(il), 0.0, src.c(il), 1, s));
+    IX_TRY(k::mult(nb, r->reg.v(il), r->onb.c(il), 1, 1, s));
+  }
+  return IAMRX_OK;
+}
+
+// SyncRegister::FineAdd (SyncRegister.cpp:351-607)
+int iamrx_syncreg_fine_add(iamrx_syncreg_t r, const iamrx_fab* sync_resid_fine, double mult, void* stream) {
+  IX_NEED_DEVICE();
+  IX_ARG(r && sync_resid_fine, "syncreg_fine_add arguments");
+  cudaStream_t s = (cudaStream_t)stream;
+  Level* CL = r->crse; Level* FL = r->fine;
+  // the restricted planes of every local fine box, summed into one replicated array over the coarse node domain
+  std::vector<Bx> one{mkbx(CL->geom.domain)};
+  std::vector<int> own{comm().rank};
+  std::unique_ptr<Level> RL = make_level(CL->geom, one, own);
+  RL->replicated = true;
+  MF acc(RL.get(), IX_NODE, 1, 0);
+  IX_TRY(mf_setval(acc, 0.0, 0, 1, 0, s));
+  const Bx cnd = ixbox(CL->domain, IX_NODE);
+  MF fm; fm.alias(FL, IX_NODE, 1, 0, const_cast<iamrx_fab*>(sync_resid_fine));
+  for (int il = 0; il < fm.n(); ++il) {
+    const Bx fnb = fm.vbox(il);
+    const Bx nb = r->cnb[FL->local[il]];
+    for (int d = 0; d < 3; ++d)
+      for (int side = 0; side < 2; ++side) {
+        Bx pl = nb;
+        pl.lo[d] = pl.hi[d] = side == 0 ? nb.lo[d] : nb.hi[d];
+        IX_TRY(k::sync_fine_add(pl, acc.v(0), fm.c(il), fnb, d, mult, cnd, CL->geom.periodic, s));
+      }
+  }
+  if (comm().nranks > 1) {
+    const Bx ab = acc.vbox(0);
+    IX_TRY(comm_allreduce(acc.fabs[0].p, (int)(acc.fabs[0].kstride * ab.nz()), 0, s));
+  }
+  int plen[3];
+  for (int d = 0; d < 3; ++d) plen[d] = CL->geom.periodic[d] ? CL->domain.hi[d] - CL->domain.lo[d] + 1 : 0;
+  for (int il = 0; il < r->reg.n(); ++il)
+    IX_TRY(k::sync_gather(r->reg.vbox(il), r->reg.v(il), r->onb.c(il), acc.c(0), cnd, plen, s));
+  return IAMRX_OK;
+}
+
+// SyncRegister::InitRHS (SyncRegister.cpp:49-285)
+int iamrx_syncreg_init_rhs(iamrx_syncreg_t r, iamrx_fab* rhs, const int phys_lo[3], const int phys_hi[3], void* stream) {
+  IX_NEED_DEVICE();
+  IX_ARG(r && rhs, "syncreg_init_rhs arguments");
+  cudaStream_t s = (cudaStream_t)stream;
+  Level* CL = r->crse;
+  const Bx cnd = ixbox(CL->domain, IX_NODE);
+  MF out; out.alias(CL, IX_NODE, 1, 0, rhs);
+  for (int il = 0; il < out.n(); ++il) {
+    const Bx nb = out.vbox(il);
+    IX_TRY(k::copy(nb, out.v(il), r->reg.c(il), 1, s));
+    for (int d = 0; d < 3; ++d) {
+      if (CL->geom.periodic[d]) continue;
+      for (int side = 0; side < 2; ++side) {
+        const int code = side == 0 ? (phys_lo ? phys_lo[d] : 0) : (phys_hi ? phys_hi[d] : 0);
+        if (code != 2) continue;   // PhysBCType::outflow (the ns.lo_bc / ns.hi_bc code, iamrx_ns_params.lo_bc)
+        Bx pl = cnd;
+        pl.lo[d] = pl.hi[d] = side == 0 ? cnd.lo[d] : cnd.hi[d];
+        const Bx is = intersect(pl, nb);
+        if (is.ok()) IX_TRY(k::setval(is, out.v(il), 1, 0.0, s));
+      }
+    }
+    IX_TRY(k::mult(nb, out.v(il), r->mask.c(il), 1, 1, s));
+  }
+  return IAMRX_OK;
+}
+int iamrx_syncreg_field(iamrx_syncreg_t r, int which, int ilocal, iamrx_fab* out) {
+  IX_ARG(r && out && ilocal >= 0 && ilocal < r->reg.n() && which >= 0 && which <= 2, "syncreg_field arguments");
+  *out = (which == 0 ? r->reg : (which == 1 ? r->onb : r->mask)).fabs[ilocal];
   return IAMRX_OK;
 }
 

@@ -202,6 +202,10 @@ int cell_cons_interp(const Bx& fbx, V4 fine, C4 crse, int ncomp, cudaStream_t s)
 int pc_interp(const Bx& fbx, V4 fine, C4 crse, int ncomp, cudaStream_t s);   // piecewise constant
 // InterpBndryData (order 3): coarse-fine boundary values in the ghost layer R beyond side d of a fine box (mask: usable coarse cells)
 int cf_bndry_interp(const Bx& R, int d, V4 fine, C4 crse, C4 mask, int ncomp, cudaStream_t s);
+// SyncRegister pieces (SyncRegister.cpp): InitRHS's interior mask, FineAdd's restriction of one boundary plane, the periodic gather
+int sync_mask(const Bx& nbx, V4 mask, C4 covered, double maxcount, cudaStream_t s);
+int sync_fine_add(const Bx& R, V4 acc, C4 fine, const Bx& fnb, int dir, double mult, const Bx& cnd, const int per[3], cudaStream_t s);
+int sync_gather(const Bx& nbx, V4 reg, C4 onb, C4 acc, const Bx& cnd, const int plen[3], cudaStream_t s);
 // create_umac_grown's divergence correction on the one-cell halo of a fine box (mask: 0 interior, 1 covered, 2 not covered, 3 physbnd)
 int umac_divfix(const Bx& vb, C4 mask, V4 u, V4 v, V4 w, C4 divu, const double dx[3], cudaStream_t s);
 int node_bilinear_interp(const Bx& fnbx, V4 fine, C4 crse, int ncomp, cudaStream_t s);

@@ -535,6 +535,36 @@ int iamrx_fluxreg_fine_add(iamrx_fluxreg_t reg, const iamrx_fab* fx, const iamrx
 int iamrx_fluxreg_reflux(iamrx_fluxreg_t reg, iamrx_fab* crse_state, int scomp, double scale, void* stream);
 int iamrx_fluxreg_field(iamrx_fluxreg_t reg, int ilocal, iamrx_fab* out);
 
+/* SyncRegister (Source/SyncRegister.cpp; used by Projection::level_project :399-426 and Projection::MLsyncProject): the nodal
+ * register between a coarse level and the next finer one that collects the divergence residuals of the two level projections
+ * and hands their sum to the sync projection as its right-hand side.  Held on the nodes of the coarse level; the register's node
+ * set B is the six boundary planes of every coarsened fine grid (the FabSets bndry[face], :20-47) and their periodic images.
+ *   crse_init : CrseInit (:288-300)  reg = mult * sync_resid_crse on B (the register is reset first).
+ *   fine_add  : FineAdd (:351-607)   reg += on B: for every fine grid, on each boundary plane of its coarsened node box, the fine
+ *               residual restricted with the tent weights (r - m)(r - n) r_dir / prod(r^2) of the two tangential directions
+ *               (halved on the centre lines); fine nodes on the edges of the grid count 1/2 and on its corners 1/3 (the planes of a
+ *               grid overlap there); nodes outside the grid are zero (the residual's ghost nodes, Projection.cpp:375-376);
+ *               coarse nodes on non-periodic domain planes are doubled once per direction; periodic images add
+ *               (FabSet::plusFrom with periodicity).  mult = 1 / crse_dt_ratio (Projection.cpp:424-425).
+ *   init_rhs  : InitRHS (:49-285)    rhs = reg, zero on the node planes of outflow sides (phys_lo / phys_hi: the ns.lo_bc / hi_bc
+ *               codes, 2 = outflow; NULL = none) and on nodes whose eight surrounding coarse cells all lie under the fine level
+ *               (cells beyond a non-periodic side counted as their mirror images) -- IF that count of covered cells exceeds
+ *               mask_maxcount.  The reference's threshold is AMREX_D_TERM(SPACEDIM, *SPACEDIM, *SPACEDIM) - 0.5 (:265): 3.5 in
+ *               2-D (all four cells covered) but 26.5 in 3-D, which a count of at most 8 never exceeds, so in 3-D the reference's
+ *               mask is all ones.  mask_maxcount <= 0 selects that reference behaviour (26.5); 7.5 is what the 2-D expression
+ *               generalises to (nodes interior to the fine level are zeroed).
+ * sync_resid_crse / rhs: nodal fabs of every local coarse box; sync_resid_fine: nodal fabs of every local fine box.  Unlike the
+ * reference the residual arrays are NOT scaled in place by mult.  Coarse boxes that share nodes must hold the same residual there
+ * (each node of B takes it once).  CompAdd (three or more levels) is not implemented.  create / fine_add are collective. */
+typedef struct iamrx_syncreg_s* iamrx_syncreg_t;
+int iamrx_syncreg_create(iamrx_level_t crse_lev, iamrx_level_t fine_lev, double mask_maxcount, iamrx_syncreg_t* out);
+int iamrx_syncreg_destroy(iamrx_syncreg_t reg);
+int iamrx_syncreg_crse_init(iamrx_syncreg_t reg, const iamrx_fab* sync_resid_crse, double mult, void* stream);
+int iamrx_syncreg_fine_add(iamrx_syncreg_t reg, const iamrx_fab* sync_resid_fine, double mult, void* stream);
+int iamrx_syncreg_init_rhs(iamrx_syncreg_t reg, iamrx_fab* rhs, const int phys_lo[3], const int phys_hi[3], void* stream);
+/* which: 0 the register, 1 the indicator of B, 2 the InitRHS mask (nodal fab of local coarse box ilocal; for inspection) */
+int iamrx_syncreg_field(iamrx_syncreg_t reg, int which, int ilocal, iamrx_fab* out);
+
 /* MacProj::mac_sync_solve (MacProj.cpp:359-479) on the coarse level of a pair: the right-hand side is the MAC register refluxed with
  * scale -1 (SUM{MR / VOL} in the coarse cells next to the fine grids, zero elsewhere and under them; the register must have been
  * filled with area-weighted face velocities: crse_add / fine_add with dt = 1 and vol = the coarse cell volume), plus the optional

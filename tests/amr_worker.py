@@ -158,6 +158,37 @@ def main():
         ref = rphi[:, 1 + lo[2] - flo[2]:2 + hi[2] - flo[2], 1 + lo[1] - flo[1]:2 + hi[1] - flo[1], 1 + lo[0] - flo[0]:2 + hi[0] - flo[0]]
         assert np.abs(got - ref).max() <= 2e-10, ("coarse-fine mac_project", rank, float(np.abs(got - ref).max()))
 
+    # 6. SyncRegister: CrseInit on the coarse boxes of both ranks, FineAdd from fine boxes on both ranks (one replicated accumulation
+    #    + all-reduce), InitRHS -- against oracle/syncreg.py
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import syncreg as orc_syncreg
+    import torch
+    rc_full = hash_uniform(201, (NC[2] + 1, NC[1] + 1, NC[0] + 1)) - 0.5
+    for d in range(3):
+        hi_, lo_ = [slice(None)] * 3, [slice(None)] * 3
+        hi_[2 - d], lo_[2 - d] = NC[d], 0
+        rc_full[tuple(hi_)] = rc_full[tuple(lo_)]
+    rf = [hash_uniform(210 + g, (hi[2] - lo[2] + 2, hi[1] - lo[1] + 2, hi[0] - lo[0] + 2)) - 0.5 for g, (lo, hi) in enumerate(fboxes)]
+    ref = orc_syncreg.SyncRegister(NC, (1, 1, 1), fboxes)
+    ref.crse_init(rc_full, 1.0)
+    ref.fine_add(fboxes, rf, 0.5)
+    expect = ref.init_rhs((0, 0, 0), (0, 0, 0), 7.5)
+    def nfab(arr, lo):
+        t = torch.from_numpy(np.ascontiguousarray(arr[None]))
+        return t, ix.fab_of(t, list(lo))
+    h = C.c_void_p()
+    lib.check(lib.iamrx_syncreg_create(clev.h, flev.h, 7.5, C.byref(h)))
+    CR = [nfab(rc_full[cboxes[i][0][2]:cboxes[i][1][2] + 2, cboxes[i][0][1]:cboxes[i][1][1] + 2, cboxes[i][0][0]:cboxes[i][1][0] + 2], cboxes[i][0]) for i in cmine]
+    FR = [nfab(rf[i], fboxes[i][0]) for i in fmine]
+    RH = [nfab(np.zeros((cboxes[i][1][2] - cboxes[i][0][2] + 2, cboxes[i][1][1] - cboxes[i][0][1] + 2, cboxes[i][1][0] - cboxes[i][0][0] + 2)), cboxes[i][0]) for i in cmine]
+    lib.check(lib.iamrx_syncreg_crse_init(h, fa(CR), 1.0, st))
+    lib.check(lib.iamrx_syncreg_fine_add(h, fa(FR), 0.5, st))
+    lib.check(lib.iamrx_syncreg_init_rhs(h, fa(RH), None, None, st))
+    for (t, _), i in zip(RH, cmine):
+        lo, hi = cboxes[i]
+        assert np.abs(t.numpy()[0] - expect[lo[2]:hi[2] + 2, lo[1]:hi[1] + 2, lo[0]:hi[0] + 2]).max() <= 1e-14, ("sync register", rank)
+    lib.check(lib.iamrx_syncreg_destroy(h))
+
     clev.close(); flev.close()
     dist.barrier()
     print(f"rank {rank} ok", flush=True)
