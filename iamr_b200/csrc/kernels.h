@@ -245,6 +245,11 @@ int scal_minmax(const Bx& bx, V4 snew, C4 rhonew, C4 sold, C4 rhoold, int conser
 int diff_rhs(const Bx& bx, V4 rhs, V4 unew, C4 rho, int ncomp, cudaStream_t s);
 // level_project pre: u = u*dt_inv + gp/rho  (Projection.cpp:273,296-300)
 int proj_pre(const Bx& bx, V4 u, C4 gp, C4 rho, double dt_inv, cudaStream_t s);
+// Projection::computeRhoG (Projection.cpp:1933-2379) on the part `strip` of an outflow face's node plane: d = direction of the face,
+// t = the other horizontal direction, c1 / c2 = the first / second cell layer inside the face, tlo / thi = the transverse node range
+// of the domain, code_lo / code_hi = the density's BCRec on the transverse sides, ztop = the top cell layer of the domain
+struct OutflowRhoG { int d, t, c1, c2, tlo, thi, code_lo, code_hi, ztop; double gravity, dz; };
+int outflow_rhog(const Bx& strip, V4 phi, C4 rho, const OutflowRhoG& a, cudaStream_t s);
 // scaleVar: sig = 1/rho (Projection.cpp:1327-1349)
 int invert(const Bx& bx, V4 sig, C4 rho, cudaStream_t s);
 // prob_init.cpp initial conditions (state: u,v,w,rho,tracer) on bx

@@ -442,9 +442,61 @@ int initial_velocity_diffusion_update(iamrx_ns_s& ns, double time, double dt) {
 
 // Projection::level_project (Projection.cpp:166-450) + doMLMGNodalProjection (:2385-2567)
 int inflow_ghost_velocity(iamrx_ns_s& ns, MF& vel, double scale);
+
+// Projection::set_outflow_bcs for LEVEL_PROJ / INITIAL_PRESS without divu (Projection.cpp:1721-1931 -> computeRhoG :1933-2379): under
+// gravity the nodes of an outflow face in x or y take the hydrostatic pressure of the density next to the face, integrated down
+// from the top of the domain; an outflow face on top keeps phi = 0, one at the bottom is refused (the reference aborts, :1957).
+// rho: the density the projection uses (rho_half / the new density), valid cells; its ghost cells are refilled here on a copy.
+bool outflow_with_gravity(const iamrx_ns_s& ns) {
+  if (std::fabs(ns.p.gravity) == 0.0) return false;
+  for (int d = 0; d < 3; ++d) if (!ns.L->geom.periodic[d] && (ns.p.lo_bc[d] == 2 || ns.p.hi_bc[d] == 2)) return true;
+  return false;
+}
+int set_outflow_bcs(iamrx_ns_s& ns, MF& phi, const MF& rho, int rho_comp) {
+  if (!outflow_with_gravity(ns)) return IAMRX_OK;
+  Level& L = *ns.L;
+  // the density as ONE box over the domain with a filled ghost layer (the reference copies a two-cell strip to one FAB, :1891-1893)
+  std::vector<Bx> one{L.domain};
+  std::vector<int> own{comm().rank};
+  std::unique_ptr<Level> RL = make_level(L.geom, one, own);
+  RL->replicated = true;
+  MF rr(RL.get(), IX_CELL, 1, 1);
+  MF rv(&L, IX_CELL, 1, 0);
+  IX_TRY(mf_copy(rv, rho, rho_comp, 0, 1, 0, ns.s));
+  if (L.replicated || (L.boxes.size() == 1 && L.nlocal() == 1)) IX_TRY(mf_copy(rr, rv, 0, 0, 1, 0, ns.s));
+  else IX_TRY(mf_gather_replicate(rr, rv, 1, ns.s));
+  IX_TRY(mf_fill_boundary(rr, 0, 1, 1, ns.s));
+  const k::PhysBC dbc = ns.phys_bc(Density, 1);
+  IX_TRY(mf_fill_physbc(rr, 0, 1, 1, dbc, ns.s));
+  for (int d = 0; d < 2; ++d) {
+    if (L.geom.periodic[d]) continue;
+    for (int side = 0; side < 2; ++side) {
+      if ((side == 0 ? ns.p.lo_bc[d] : ns.p.hi_bc[d]) != 2) continue;
+      k::OutflowRhoG a{};
+      a.d = d; a.t = 1 - d;
+      a.c1 = side == 0 ? L.domain.lo[d] : L.domain.hi[d];
+      a.c2 = side == 0 ? a.c1 + 1 : a.c1 - 1;
+      a.tlo = L.domain.lo[a.t]; a.thi = L.domain.hi[a.t] + 1;
+      a.code_lo = L.geom.periodic[a.t] ? IAMRX_BC_INT_DIR : dbc.lo[0][a.t];
+      a.code_hi = L.geom.periodic[a.t] ? IAMRX_BC_INT_DIR : dbc.hi[0][a.t];
+      a.ztop = L.domain.hi[2];
+      a.gravity = ns.p.gravity; a.dz = L.geom.dx[2];
+      const int plane = side == 0 ? L.domain.lo[d] : L.domain.hi[d] + 1;
+      for (int il = 0; il < phi.n(); ++il) {
+        Bx strip = phi.vbox(il);
+        if (plane < strip.lo[d] || plane > strip.hi[d]) continue;
+        strip.lo[d] = strip.hi[d] = plane;
+        IX_TRY(k::outflow_rhog(strip, phi.v(il), rr.c(0), a, ns.s));
+      }
+    }
+  }
+  return IAMRX_OK;
+}
+
 int level_project(iamrx_ns_s& ns, double dt) {
   Level& L = *ns.L;
   IX_TRY(mf_setval(ns.P_new, 0.0, 0, 1, 1, ns.s));   // :247-256
+  IX_TRY(set_outflow_bcs(ns, ns.P_new, ns.rho_half, 0));   // :304-324
   for (int il = 0; il < ns.S_new.n(); ++il)          // :273, :296-300
     IX_TRY(k::proj_pre(L.lbox(il), ns.S_new.v(il, Xvel), ns.Gp_old.c(il), ns.rho_half.c(il), 1.0 / dt, ns.s));
   for (int il = 0; il < ns.sig.n(); ++il)            // scaleVar :332, :1327-1349
@@ -453,7 +505,7 @@ int level_project(iamrx_ns_s& ns, double dt) {
   IX_TRY(inflow_ghost_velocity(ns, vel, 1.0 / dt));
   iamrx_mg_info mi = mg_info(ns, ns.p.proj_tol, ns.p.proj_abs_tol);
   const k::NodalBC nbc = ns.nodal_bc();
-  IX_SOLVE(nodal_project(L, *ns.sv, vel, ns.sig, ns.P_new, &ns.Gp_new, 0, &mi, ns.s, ns.walls ? &nbc : nullptr));  // :392 ; Gp = grad phi :2542-2563
+  IX_SOLVE(nodal_project(L, *ns.sv, vel, ns.sig, ns.P_new, &ns.Gp_new, 0, &mi, ns.s, ns.walls ? &nbc : nullptr, outflow_with_gravity(ns)));  // :392 ; Gp = grad phi :2542-2563
   ns.it_nodal = mi.iters;
   IX_TRY(fill_gradp(ns, ns.Gp_new));  // :2565
   return mf_scale(ns.S_new, dt, Xvel, 3, 0, ns.s);     // :438 (rescaleVar :434 restores rho_half: ns.sig is separate)
@@ -559,10 +611,10 @@ int inflow_ghost_velocity(iamrx_ns_s& ns, MF& vel, double scale) {
   return IAMRX_OK;
 }
 
-int project_simple(iamrx_ns_s& ns, MF& vel, const MF& sigma, MF& phi, MF* gp, int incr, int* iters) {
+int project_simple(iamrx_ns_s& ns, MF& vel, const MF& sigma, MF& phi, MF* gp, int incr, int* iters, bool keep_dirichlet = false) {
   iamrx_mg_info mi = mg_info(ns, ns.p.proj_tol, ns.p.proj_abs_tol);
   const k::NodalBC nbc = ns.nodal_bc();
-  IX_SOLVE(nodal_project(*ns.L, *ns.sv, vel, sigma, phi, gp, incr, &mi, ns.s, ns.walls ? &nbc : nullptr));
+  IX_SOLVE(nodal_project(*ns.L, *ns.sv, vel, sigma, phi, gp, incr, &mi, ns.s, ns.walls ? &nbc : nullptr, keep_dirichlet));
   if (iters) *iters = mi.iters;
   return IAMRX_OK;
 }
@@ -614,10 +666,10 @@ int iamrx_ns_create(iamrx_level_t lev, const iamrx_ns_params* p, iamrx_ns_t* out
       walls = true;
       for (int v : {p->lo_bc[d], p->hi_bc[d]}) {
         IX_ARG(v >= 1 && v <= 5, "ns.lo_bc / ns.hi_bc of a non-periodic direction must be 1..5 (inputs.3d.taylorgreen:100-102)");
-        // Projection::set_outflow_bcs / OutFlowBC (the outflow pressure profile under gravity or divu) is not restated: IAMR calls it
-        // only when have_divu or gravity != 0 (Projection.cpp:309-324,896-899; MacProj.cpp:265), so inflow / outflow runs without
-        // gravity take the plain path -- phi = 0 on the outflow face
-        IX_ARG(v >= 3 || p->gravity == 0.0, "inflow / outflow boundaries together with gravity need Projection::set_outflow_bcs, which is not implemented");
+        // Projection::set_outflow_bcs (the hydrostatic pressure on outflow faces under gravity, Projection.cpp:1721-2379; called only
+        // when gravity != 0 or have_divu: :309-324, 896-899) is implemented for side and top faces; like the reference (:1957) an
+        // outflow face at the bottom under gravity is refused
+        IX_ARG(!(d == 2 && p->lo_bc[2] == 2 && p->gravity != 0.0), "outflow at the bottom of the domain together with gravity (Projection::computeRhoG aborts)");
       }
     }
   }
@@ -750,7 +802,8 @@ int iamrx_ns_post_init(iamrx_ns_t nsp, double* dt0) {
     IX_TRY(mf_setval(gvel, ns.p.gravity, 2, 1, 1, ns.s));
     for (int il = 0; il < ns.sig.n(); ++il) IX_TRY(k::invert(L.lbox(il), ns.sig.v(il), ns.S_new.c(il, Density), ns.s));
     IX_TRY(mf_setval(ns.P_new, 0.0, 0, 1, 1, ns.s));
-    IX_TRY(project_simple(ns, gvel, ns.sig, ns.P_new, &ns.Gp_new, 0, nullptr));
+    IX_TRY(set_outflow_bcs(ns, ns.P_new, ns.S_new, Density));   // Projection.cpp:893-903 (INITIAL_PRESS)
+    IX_TRY(project_simple(ns, gvel, ns.sig, ns.P_new, &ns.Gp_new, 0, nullptr, outflow_with_gravity(ns)));
     IX_TRY(fill_gradp(ns, ns.Gp_new));
     IX_TRY(mf_copy(ns.P_old, ns.P_new, 0, 0, 1, 1, ns.s));
     IX_TRY(mf_copy(ns.Gp_old, ns.Gp_new, 0, 0, 3, 1, ns.s));

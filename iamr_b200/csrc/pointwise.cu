@@ -19,6 +19,36 @@ inline dim3 grid_for(const Bx& bx, int nzc) { return dim3(cdiv(bx.nx(), TX), cdi
   const int i = bx.lo[0] + blockIdx.x * TX + threadIdx.x;             \
   if (j > bx.hi[1] || i > bx.hi[0]) return;
 
+// Projection::computeRhoG (Projection.cpp:1933-2379): the hydrostatic pressure on the node plane of an outflow face in x or y,
+// phi(node, k) = sum over the cell layers k' >= k of -gravity * rhoExt(k') * dz, rhoExt = (3 rho_1 - rho_2) / 2 the density
+// extrapolated to the face from the two cell layers next to it, taken at the node's transverse position: the mean of the two
+// cell columns beside it, or at the domain's transverse edges what the density's BCRec says (ext_dir: the ghost column,
+// hoextrap: linear extrapolation, foextrap: the first column).  One thread per node column, marching down from the top of the
+// domain (the reference integrates serially too); only the nodes of the strip (this box's share of the plane) are written.
+__global__ void outflow_rhog_kernel(Bx T, int ktop_node, V4 phi, C4 rho, IX_KARG(OutflowRhoG) a) {
+  IDX3(T)
+  (void)n;
+  int q[3] = {i, j, k};
+  const int jt = q[a.t];   // transverse node index
+  auto R = [&](int c, int jj, int kk) { int p[3]; p[a.d] = c; p[a.t] = jj; p[2] = kk; return rho(p[0], p[1], p[2]); };
+  auto col = [&](int c, int kk) -> double {
+    if (jt == a.tlo && a.code_lo == IAMRX_BC_EXT_DIR) return R(c, jt - 1, kk);
+    if (jt == a.tlo && a.code_lo == IAMRX_BC_HOEXTRAP) return 0.5 * (3.0 * R(c, jt, kk) - R(c, jt + 1, kk));
+    if (jt == a.tlo && a.code_lo == IAMRX_BC_FOEXTRAP) return R(c, jt, kk);
+    if (jt == a.thi && a.code_hi == IAMRX_BC_EXT_DIR) return R(c, jt, kk);
+    if (jt == a.thi && a.code_hi == IAMRX_BC_HOEXTRAP) return 0.5 * (3.0 * R(c, jt - 1, kk) - R(c, jt - 2, kk));
+    if (jt == a.thi && a.code_hi == IAMRX_BC_FOEXTRAP) return R(c, jt - 1, kk);
+    return 0.5 * (R(c, jt, kk) + R(c, jt - 1, kk));
+  };
+  double rhog = 0.0;
+  for (int kk = a.ztop; kk >= k; --kk) {   // cell layers from the top of the domain down to the bottom of the strip
+    const double rho_ext = 0.5 * (3.0 * col(a.c1, kk) - col(a.c2, kk));
+    rhog -= a.gravity * rho_ext * a.dz;
+    if (kk <= ktop_node) phi(i, j, kk) = rhog;
+  }
+  if (ktop_node == a.ztop + 1) phi(i, j, ktop_node) = 0.0;   // the top node: the strip starts from zero (Projection.cpp:1888-1889)
+}
+
 __global__ void floor_kernel(Bx bx, V4 f) {
   IDX3(bx)
   const double v = f(i, j, k, n);
@@ -193,6 +223,12 @@ int scal_minmax(const Bx& bx, V4 snew, C4 rhonew, C4 sold, C4 rhoold, int conser
 }
 int diff_rhs(const Bx& bx, V4 rhs, V4 unew, C4 rho, int ncomp, cudaStream_t s) {
   LAUNCH3(diff_rhs_kernel, bx, ncomp, s, rhs, unew, rho);
+}
+int outflow_rhog(const Bx& strip, V4 phi, C4 rho, const OutflowRhoG& a, cudaStream_t s) {
+  Bx T = strip;   // one thread per node column of the strip
+  T.lo[2] = T.hi[2] = strip.lo[2];
+  IX_LAUNCH(outflow_rhog_kernel, grid_for(T, 1), dim3(TX, TY, 1), 0, s, T, strip.hi[2], phi, rho, a);
+  return check_launch("outflow_rhog");
 }
 int proj_pre(const Bx& bx, V4 u, C4 gp, C4 rho, double dt_inv, cudaStream_t s) {
   LAUNCH3(proj_pre_kernel, bx, 3, s, u, gp, rho, dt_inv);

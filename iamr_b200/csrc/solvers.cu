@@ -62,7 +62,7 @@ int mac_get_fluxes(Level& L, LevelSolvers& sv, MF F[3], MF& phi, cudaStream_t s)
 //   rhs = FE divergence of vel on nodes; div(sigma grad phi) = rhs;
 //   vel -= sigma grad phi; gp (+)= grad phi
 int nodal_project(Level& L, LevelSolvers& sv, MF& vel, const MF& sigma, MF& phi, MF* gp, int increment_gp,
-                  iamrx_mg_info* info, cudaStream_t s, const k::NodalBC* bc) {
+                  iamrx_mg_info* info, cudaStream_t s, const k::NodalBC* bc, bool keep_dirichlet) {
   iamrx_mg_info mi = info_or_default(info);
   if (!sv.nodal || sv.nodal_mc != mi.max_coarsening) {
     sv.nodal = std::make_unique<NodeMG>(&L, mi.max_coarsening);
@@ -96,7 +96,7 @@ int nodal_project(Level& L, LevelSolvers& sv, MF& vel, const MF& sigma, MF& phi,
     // mlndlap_impose_neumann_bc: rows ON Neumann / inflow sides are doubled, once per direction
     if (mg.has_bc()) IX_TRY(k::nodal_bc_scale(sv.nodal_rhs.vbox(il), sv.nodal_rhs.v(il), mg.bc(), ndom, L.geom.periodic, 2.0, s));
   }
-  if (mg.has_bc()) {   // nodes ON Dirichlet sides are held at zero
+  if (mg.has_bc() && !keep_dirichlet) {   // nodes ON Dirichlet sides are held at zero
     for (int il = 0; il < phi.n(); ++il) {
       const Bx full = phi.vbox(il), act = mg.active_nbox(0, il, /*with_cf=*/false);   // coarse-fine boundary nodes keep their values
       for (int d = 0; d < 3; ++d) {

@@ -25,8 +25,10 @@ struct LevelSolvers {
 int mac_project(Level& L, LevelSolvers& sv, MF U[3], const MF& rho, const MF* rhs, MF& phi,
                 double rhs_scale, iamrx_mg_info* info, cudaStream_t s, const k::LinBC* bc = nullptr);
 int mac_get_fluxes(Level& L, LevelSolvers& sv, MF F[3], MF& phi, cudaStream_t s);
+// keep_dirichlet: the nodes ON Dirichlet domain sides keep the values of phi on entry (Projection::set_outflow_bcs has put the
+// hydrostatic pressure there) instead of being held at zero
 int nodal_project(Level& L, LevelSolvers& sv, MF& vel, const MF& sigma, MF& phi, MF* gp,
-                  int increment_gp, iamrx_mg_info* info, cudaStream_t s, const k::NodalBC* bc = nullptr);
+                  int increment_gp, iamrx_mg_info* info, cudaStream_t s, const k::NodalBC* bc = nullptr, bool keep_dirichlet = false);
 int diffusion_apply(Level& L, LevelSolvers& sv, bool tensor, int ncomp, MF& out, MF& soln, double a,
                     double b, const MF* acoef, MF eta[3], cudaStream_t s, const k::LinBC* bc = nullptr);
 int diffusion_solve(Level& L, LevelSolvers& sv, bool tensor, int ncomp, MF& soln, const MF& rhs,

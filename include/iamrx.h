@@ -608,8 +608,9 @@ typedef struct iamrx_ns_params {
   int bottom_solver;     /* bottom solver of all three multigrid solves: 0 smoother sweeps, 1 BiCGStab (iamrx_mg_info.bottom_solver) */
   /* physical boundaries (ns.lo_bc / ns.hi_bc, NS.cpp:90-94; codes of inputs.3d.taylorgreen:100-102): 0 interior / periodic,
    * 1 inflow, 2 outflow, 3 symmetry, 4 slip wall, 5 no-slip wall.  A periodic direction must carry 0, a non-periodic one must
-   * not.  The step driver implements walls and symmetry planes (3, 4, 5); inflow / outflow are available at the operator
-   * level (sections 1-3) but rejected here. */
+   * not.  The step driver implements all of them: walls and symmetry planes (3, 4, 5), inflow (ext_dir values below) and outflow,
+   * under gravity with Projection::set_outflow_bcs / computeRhoG (Projection.cpp:1721-2379) for outflow faces in x, y or on top;
+   * an outflow face at the bottom together with gravity is refused (the reference aborts, :1957). */
   int lo_bc[3];
   int hi_bc[3];
   /* Dirichlet face values [x lo, y lo, z lo, x hi, y hi, z hi][u, v, w, rho, tracer]: the xlo.velocity / xlo.density ...

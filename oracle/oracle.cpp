@@ -1788,8 +1788,61 @@ struct orc_ns {
     }
   }
   // Projection::level_project Projection.cpp:166-450
+  // Projection::set_outflow_bcs for LEVEL_PROJ / INITIAL_PRESS under gravity (Projection.cpp:1721-1931) -> computeRhoG (:1933-2379),
+  // kept in the reference's loop structure: interior node columns first, then the two transverse edges by the density's BCRec.
+  // rho_valid: component rc of an array whose valid cells hold the density the projection uses.
+  void set_outflow_bcs(Arr& phi, const Arr& rho_valid, int rc) const {
+    if (!(std::fabs(p.gravity) > 0.0) || !has_walls()) return;
+    Arr rho(n, 1, 1);
+    rho.copy_from(rho_valid, rc, 0, 1);
+    fill_state_bc(rho, Density, 1);   // the one-cell transverse growth of the state strip (:1784-1786, 1891-1893)
+    const BCRec db = state_bc(Density);
+    const double dh = dx[2];
+    for (int od = 0; od < 2; ++od) {       // outDir x or y (top: nothing to do; bottom: the reference aborts, :1949-1958)
+      if (per[od]) continue;
+      const int td = 1 - od;
+      for (int side = 0; side < 2; ++side) {
+        if ((side == 0 ? phys_lo[od] : phys_hi[od]) != PHYS_OUTFLOW) continue;
+        const int pl = side == 0 ? 0 : n[od];                       // node plane of the face
+        const int c1 = side == 0 ? 0 : n[od] - 1, c2 = side == 0 ? 1 : n[od] - 2;   // rho(i), rho(i+1)  /  rho(i-1), rho(i-2)
+        auto RHO = [&](int c, int jj, int kk) { return od == 0 ? rho(c, jj, kk) : rho(jj, c, kk); };
+        auto PHI = [&](int jj, int kk) -> double& { return od == 0 ? phi(pl, jj, kk) : phi(jj, pl, kk); };
+        const int lo_code = per[td] ? BC_INT_DIR : db.lo[td], hi_code = per[td] ? BC_INT_DIR : db.hi[td];
+        auto special = [](int code) { return code == BC_EXT_DIR || code == BC_HOEXTRAP || code == BC_FOEXTRAP; };
+        const int jlo = special(lo_code) ? 1 : 0, jhi = special(hi_code) ? n[td] - 1 : n[td];
+        auto add_rhog = [&](double rho1, double rho2, double& rhog, double& phi_i) {
+          const double rhoExt = 0.5 * (3.0 * rho1 - rho2);
+          rhog -= p.gravity * rhoExt * dh;
+          phi_i += rhog;
+        };
+        for (int jj = 0; jj <= n[td]; ++jj) for (int kk = 0; kk <= n[2]; ++kk) PHI(jj, kk) = 0.0;   // phi_fine_strip.setVal(0)
+        for (int jj = jlo; jj <= jhi; ++jj) {
+          double rhog = 0.0;
+          for (int kk = n[2] - 1; kk >= 0; --kk)
+            add_rhog(0.5 * (RHO(c1, jj, kk) + RHO(c1, jj - 1, kk)), 0.5 * (RHO(c2, jj, kk) + RHO(c2, jj - 1, kk)), rhog, PHI(jj, kk));
+        }
+        if (special(lo_code)) {
+          const int jj = 0; double rhog = 0.0;
+          for (int kk = n[2] - 1; kk >= 0; --kk) {
+            if (lo_code == BC_EXT_DIR) add_rhog(RHO(c1, jj - 1, kk), RHO(c2, jj - 1, kk), rhog, PHI(jj, kk));
+            else if (lo_code == BC_HOEXTRAP) add_rhog(0.5 * (3.0 * RHO(c1, jj, kk) - RHO(c1, jj + 1, kk)), 0.5 * (3.0 * RHO(c2, jj, kk) - RHO(c2, jj + 1, kk)), rhog, PHI(jj, kk));
+            else add_rhog(RHO(c1, jj, kk), RHO(c2, jj, kk), rhog, PHI(jj, kk));
+          }
+        }
+        if (special(hi_code)) {
+          const int jj = n[td]; double rhog = 0.0;
+          for (int kk = n[2] - 1; kk >= 0; --kk) {
+            if (hi_code == BC_EXT_DIR) add_rhog(RHO(c1, jj, kk), RHO(c2, jj, kk), rhog, PHI(jj, kk));
+            else if (hi_code == BC_HOEXTRAP) add_rhog(0.5 * (3.0 * RHO(c1, jj - 1, kk) - RHO(c1, jj - 2, kk)), 0.5 * (3.0 * RHO(c2, jj - 1, kk) - RHO(c2, jj - 2, kk)), rhog, PHI(jj, kk));
+            else add_rhog(RHO(c1, jj - 1, kk), RHO(c2, jj - 1, kk), rhog, PHI(jj, kk));
+          }
+        }
+      }
+    }
+  }
   int level_project(double dt) {
     P_new.setval(0.0);
+    set_outflow_bcs(P_new, rho_half, 0);   // Projection.cpp:304-324
     Arr vel(n, 3, 1), sig(n, 1, 1);
     for (int c = 0; c < 3; ++c) { FOR_CELLS(vel, i, j, k) vel(i, j, k, c) = S_new(i, j, k, c) * (1.0 / dt) + Gp_old(i, j, k, c) / rho_half(i, j, k); }
     FOR_CELLS(sig, i, j, k) sig(i, j, k) = 1.0 / rho_half(i, j, k);
@@ -2432,6 +2485,7 @@ int orc_ns_post_init(orc_ns* ns, double* dt0) {
     { const Arr& S = ns->S_new; FOR_CELLS(sig, i, j, k) sig(i, j, k) = 1.0 / S(i, j, k, orc_ns::Density); }
     orc_mg m = ns->mg(ns->p.proj_tol, ns->p.proj_abs_tol);
     ns->P_new.setval(0.0);
+    ns->set_outflow_bcs(ns->P_new, ns->S_new, orc_ns::Density);   // Projection.cpp:893-903
     const int rc = nodal_project(n, ns->dx, vel, sig, ns->P_new, &ns->Gp_new, false, &m, ns->nodal_bc());
     if (rc) return rc;
     ns->fill_gradp(ns->Gp_new);
