@@ -388,3 +388,80 @@ def test_nodal_project_refuses_non_rectangular_patch(backend):
     rc = lib.iamrx_nodal_project(flev.h, fa(Vv), fa(Sg), fa(Ph), None, 0, None, None, C.byref(info), stream_of(dev))
     assert rc == -1   # IAMRX_ERR_ARG
     flev.close()
+
+
+@pytest.mark.parametrize("nb", [(1, 1, 1), (2, 1, 2)])
+def test_fine_level_predict_velocity_and_mac_project(backend, oracle, nb):
+    """The first half of NavierStokes::advance on a level > 0, strung together from the building blocks as the reference does it:
+    FillPatch of the velocity from both levels (NSB.cpp:4399: FillPatchTwoLevels, cell_cons_interp) -> Godunov::ExtrapVelToFaces per
+    box with interior (int_dir) BCRecs on the coarse-fine sides (:4487-4491) -> MacProj::mac_project with setCoarseFineBC from the
+    coarse level's MAC potential (MacProj.cpp:225-353, 1164-1168).  Reference: the oracle's pieces composed the same way on the
+    patch as its own domain."""
+    lib, dev = backend
+    from util import box_of
+    from test_bc import bcrec_array
+    per = (1, 1, 1)
+    nc, nf = (16, 16, 16), (32, 32, 32)
+    clo, chi = (4, 0, 4), (11, 15, 11)
+    flo, fhi = tuple(2 * c for c in clo), tuple(2 * c + 1 for c in chi)
+    n = tuple(fhi[d] - flo[d] + 1 for d in range(3))
+    dx = tuple(1.0 / m for m in nf)
+    cov = _covered(nc, clo, chi)
+    fmask = np.repeat(np.repeat(np.repeat(cov, 2, 0), 2, 1), 2, 2)
+    uc = smooth_field(nc, 950, 3)
+    uf = smooth_field(nf, 951, 3) + 0.05 * hash_uniform(952, (3,) + nf[::-1])
+    rho = 1.0 + 0.3 * hash_uniform(953, (1,) + nf[::-1])
+    cphi = 0.01 * smooth_field(nc, 954, 1)
+    dt = 0.4 * dx[0] / max(np.abs(uc).max(), np.abs(uf).max())
+    INT = 0
+    bclo = bchi = [(INT, INT, INT)] * 3
+    pper = (0, 1, 0)
+    # ---- the oracle's pieces, composed
+    ug = np.where(fmask[None], uf, oracle.interp(0, nc, uc))               # FillPatchTwoLevels: fine data where it exists, else interpolated
+    V = _cut(_wrap_pad(ug, 3), 3, flo, fhi, 3)
+    F = np.zeros((3, n[2] + 2, n[1] + 2, n[0] + 2))
+    macs = oracle.extrap_vel_to_faces_bc(n, pper, dx, dt, V, F, bclo, bchi, 0, 0)
+    phi0 = oracle.interp_bndry(nc, per, cphi, cov, flo, fhi, np.zeros((1, n[2] + 2, n[1] + 2, n[0] + 2)))
+    mg = oracle.mg_default(rtol=1e-12)
+    ru, rv, rw, rphi, rc, mgo = oracle.mac_project_bc(n, pper, dx, macs[0], macs[1], macs[2], _cut(_wrap_pad(rho, 1), 1, flo, fhi, 1), None, phi0,
+                                                      2.0 / dt, (CF, PER, CF), (CF, PER, CF), 4, mg)
+    assert rc == 0
+    # ---- the library
+    boxes = _patch_boxes(clo, chi, nb)
+    clev = ix.Level(lib, ix.Geom.make(nc, periodic=per), [((0, 0, 0), tuple(m - 1 for m in nc))])
+    fgeom = ix.Geom.make(nf, periodic=per)
+    flev = ix.Level(lib, fgeom, boxes)
+    fa = lambda L: fab_array([p[1] for p in L])
+    st = stream_of(dev)
+    sentinel = np.where(np.pad(fmask, 3, mode="wrap")[None], _wrap_pad(uf, 3), 1.0e30)      # ghost cells outside the patch: unfilled
+    VF = [fab_from_padded(sentinel, 3, b, 3, ix.CELL, dev) for b in boxes]
+    UC = _coarse_fabs(uc, nc, dev)
+    lib.check(lib.iamrx_fillpatch_two_levels(flev.h, clev.h, fa(VF), None, fa(UC), 0.0, 1.0, 1.0, 3, 3, None, None, st))
+    bcr = bcrec_array(bclo, bchi)
+    U = [[], [], []]
+    for (tv, fv), b in zip(VF, boxes):
+        tf, ff = fab_from_padded(np.zeros((3, nf[2] + 2, nf[1] + 2, nf[0] + 2)), 1, b, 1, ix.CELL, dev)
+        mm = [fab_from_padded(np.zeros((1, nf[2] + 4, nf[1] + 4, nf[0] + 4)), 2, b, 1, t, dev) for t in (ix.XFACE, ix.YFACE, ix.ZFACE)]
+        bb = box_of(*b)
+        lib.check(lib.iamrx_extrap_vel_to_faces_box(C.byref(bb), C.byref(fv), C.byref(ff), C.byref(mm[0][1]), C.byref(mm[1][1]), C.byref(mm[2][1]),
+                                                    bcr, C.byref(fgeom), dt, 0, st))
+        for d in range(3):
+            U[d].append(mm[d])
+    R = [fab_from_padded(_wrap_pad(rho, 1), 1, b, 1, ix.CELL, dev) for b in boxes]
+    P = [fab_from_padded(np.zeros((1, nf[2] + 2, nf[1] + 2, nf[0] + 2)), 1, b, 1, ix.CELL, dev) for b in boxes]
+    CP = _coarse_fabs(np.where(cov[None], 1.0e30, cphi), nc, dev)
+    lib.check(lib.iamrx_set_coarse_fine_bc(flev.h, clev.h, fa(P), fa(CP), 1, st))
+    info = _mg(lib, rtol=1e-12, maxorder=4)
+    lib.check(lib.iamrx_mac_project(flev.h, fa(U[0]), fa(U[1]), fa(U[2]), fa(R), None, fa(P), 2.0 / dt, None, None, C.byref(info), st))
+    sync(dev)
+    if nb == (1, 1, 1):
+        assert info.iters == mgo.iters
+    gshape = (1, nf[2] + 2, nf[1] + 2, nf[0] + 2)
+    for d, (ref, t) in enumerate(((ru, ix.XFACE), (rv, ix.YFACE), (rw, ix.ZFACE))):
+        got, dup = scatter_valid(np.zeros(gshape), 1, [p[0] for p in U[d]], boxes, 1, t)
+        assert dup < 1e-12
+        ext = [1 if q == d else 0 for q in range(3)]
+        g = _cut(got, 1, flo, tuple(fhi[q] + ext[q] for q in range(3)), 0)
+        r = ref[:, 1:1 + n[2] + ext[2], 1:1 + n[1] + ext[1], 1:1 + n[0] + ext[0]]
+        assert np.abs(g - r).max() < 1e-10 * max(1.0, np.abs(r).max())
+    clev.close(); flev.close()
