@@ -450,6 +450,51 @@ def test_average_down_levels(backend, oracle, layout, ixtype):
     clev.close(); flev.close()
 
 
+def umac_grown_expected(filled, fmask, box, n, dx, divu=None):
+    """numpy restatement of create_umac_grown's divergence correction (NSB.cpp:1203-1308) on one fine box: `filled` = the three
+    face arrays of the whole fine index space after the face_linear FillPatchTwoLevels; returns the box's face arrays with one
+    ghost cell ([k][j][i], origin lo - 1) and the number of corrected halo cells."""
+    types = (ix.XFACE, ix.YFACE, ix.ZFACE)
+    lo, hi = box
+    exp = [to_fab(filled[d], (lo, hi), 1, types[d], "cpu")[0].numpy()[0].copy() for d in range(3)]   # [k][j][i], origin lo - 1
+    U, V, W = exp
+    with_divu = divu is not None
+    def m(i, j, k):   # 0 interior, 1 covered, 2 not covered (global cell index, periodic)
+        if all(lo[q] <= (i, j, k)[q] <= hi[q] for q in range(3)):
+            return 0
+        return 1 if fmask[k % n[2], j % n[1], i % n[0]] else 2
+    fixed = 0
+    for k in range(lo[2] - 1, hi[2] + 2):
+        for j in range(lo[1] - 1, hi[1] + 2):
+            for i in range(lo[0] - 1, hi[0] + 2):
+                if m(i, j, k) != 2:
+                    continue
+                nb = [(i - 1, j, k), (i + 1, j, k), (i, j - 1, k), (i, j + 1, k), (i, j, k - 1), (i, j, k + 1)]
+                if sum(m(*c) in (0, 1) for c in nb) != 1:
+                    continue
+                a, b, c = i - (lo[0] - 1), j - (lo[1] - 1), k - (lo[2] - 1)      # local cell index in the grown box
+                dv = divu[0, k % n[2], j % n[1], i % n[0]] if with_divu else 0.0
+                dux = (U[c, b, a + 1] - U[c, b, a]) / dx
+                duy = (V[c, b + 1, a] - V[c, b, a]) / dx
+                duz = (W[c + 1, b, a] - W[c, b, a]) / dx
+                if i < lo[0] and m(i + 1, j, k) != 2:
+                    U[c, b, a] = U[c, b, a + 1] + dx * (duy + duz - dv)
+                elif i > hi[0] and m(i - 1, j, k) != 2:
+                    U[c, b, a + 1] = U[c, b, a] - dx * (duy + duz - dv)
+                if j < lo[1] and m(i, j + 1, k) != 2:
+                    V[c, b, a] = V[c, b + 1, a] + dx * (dux + duz - dv)
+                elif j > hi[1] and m(i, j - 1, k) != 2:
+                    V[c, b + 1, a] = V[c, b, a] - dx * (dux + duz - dv)
+                if k < lo[2] and m(i, j, k + 1) != 2:
+                    W[c, b, a] = W[c + 1, b, a] + dx * (dux + duy - dv)
+                elif k > hi[2] and m(i, j, k - 1) != 2:
+                    W[c + 1, b, a] = W[c, b, a] - dx * (dux + duy - dv)
+                fixed += 1
+                div = (U[c, b, a + 1] - U[c, b, a] + V[c, b + 1, a] - V[c, b, a] + W[c + 1, b, a] - W[c, b, a]) / dx
+                assert abs(div - dv) <= 1e-12 * max(1.0, abs(dv)) * n[0]
+    return exp, fixed
+
+
 @pytest.mark.parametrize("layout", FINE_LAYOUTS)
 @pytest.mark.parametrize("with_divu", [0, 1])
 def test_create_umac_grown(backend, oracle, layout, with_divu):
@@ -479,43 +524,8 @@ def test_create_umac_grown(backend, oracle, layout, with_divu):
     lib.check(lib.iamrx_create_umac_grown(flev.h, clev.h, fa(UF[0]), fa(UF[1]), fa(UF[2]), fa(UC[0]), fa(UC[1]), fa(UC[2]),
                                           fa(DV) if with_divu else None, stream_of(dev)))
     sync(dev)
-    n = NF
     for ib, (lo, hi) in enumerate(fboxes):
-        exp = [to_fab(filled[d], (lo, hi), 1, types[d], "cpu")[0].numpy()[0].copy() for d in range(3)]   # [k][j][i], origin lo - 1
-        U, V, W = exp
-        def m(i, j, k):   # 0 interior, 1 covered, 2 not covered (global cell index, periodic)
-            if all(lo[q] <= (i, j, k)[q] <= hi[q] for q in range(3)):
-                return 0
-            return 1 if fmask[k % n[2], j % n[1], i % n[0]] else 2
-        fixed = 0
-        for k in range(lo[2] - 1, hi[2] + 2):
-            for j in range(lo[1] - 1, hi[1] + 2):
-                for i in range(lo[0] - 1, hi[0] + 2):
-                    if m(i, j, k) != 2:
-                        continue
-                    nb = [(i - 1, j, k), (i + 1, j, k), (i, j - 1, k), (i, j + 1, k), (i, j, k - 1), (i, j, k + 1)]
-                    if sum(m(*c) in (0, 1) for c in nb) != 1:
-                        continue
-                    a, b, c = i - (lo[0] - 1), j - (lo[1] - 1), k - (lo[2] - 1)      # local cell index in the grown box
-                    dv = divu[0, k % n[2], j % n[1], i % n[0]] if with_divu else 0.0
-                    dux = (U[c, b, a + 1] - U[c, b, a]) / dx
-                    duy = (V[c, b + 1, a] - V[c, b, a]) / dx
-                    duz = (W[c + 1, b, a] - W[c, b, a]) / dx
-                    if i < lo[0] and m(i + 1, j, k) != 2:
-                        U[c, b, a] = U[c, b, a + 1] + dx * (duy + duz - dv)
-                    elif i > hi[0] and m(i - 1, j, k) != 2:
-                        U[c, b, a + 1] = U[c, b, a] - dx * (duy + duz - dv)
-                    if j < lo[1] and m(i, j + 1, k) != 2:
-                        V[c, b, a] = V[c, b + 1, a] + dx * (dux + duz - dv)
-                    elif j > hi[1] and m(i, j - 1, k) != 2:
-                        V[c, b + 1, a] = V[c, b, a] - dx * (dux + duz - dv)
-                    if k < lo[2] and m(i, j, k + 1) != 2:
-                        W[c, b, a] = W[c + 1, b, a] + dx * (dux + duy - dv)
-                    elif k > hi[2] and m(i, j, k - 1) != 2:
-                        W[c + 1, b, a] = W[c, b, a] - dx * (dux + duy - dv)
-                    fixed += 1
-                    div = (U[c, b, a + 1] - U[c, b, a] + V[c, b + 1, a] - V[c, b, a] + W[c + 1, b, a] - W[c, b, a]) / dx
-                    assert abs(div - dv) <= 1e-12 * max(1.0, abs(dv)) * NF[0]
+        exp, fixed = umac_grown_expected(filled, fmask, (lo, hi), NF, dx, divu)
         assert fixed > 0
         for d in range(3):
             got = UF[d][ib][0].cpu().numpy()[0]

@@ -391,12 +391,13 @@ def test_nodal_project_refuses_non_rectangular_patch(backend):
 
 
 @pytest.mark.parametrize("nb", [(1, 1, 1), (2, 1, 2)])
-def test_fine_level_predict_velocity_and_mac_project(backend, oracle, nb):
+def test_fine_level_advance_first_half(backend, oracle, nb):
     """The first half of NavierStokes::advance on a level > 0, strung together from the building blocks as the reference does it:
     FillPatch of the velocity from both levels (NSB.cpp:4399: FillPatchTwoLevels, cell_cons_interp) -> Godunov::ExtrapVelToFaces per
     box with interior (int_dir) BCRecs on the coarse-fine sides (:4487-4491) -> MacProj::mac_project with setCoarseFineBC from the
-    coarse level's MAC potential (MacProj.cpp:225-353, 1164-1168).  Reference: the oracle's pieces composed the same way on the
-    patch as its own domain."""
+    coarse level's MAC potential (MacProj.cpp:225-353, 1164-1168) -> create_umac_grown (ghost faces from the coarse MAC velocities +
+    the divergence fix, NSB.cpp:1108-1310) -> the velocity advection ComputeAofs per box (NSB.cpp:3358-3470).  Reference: the
+    oracle's pieces (and the numpy restatement of create_umac_grown) composed the same way on the patch as its own domain."""
     lib, dev = backend
     from util import box_of
     from test_bc import bcrec_array
@@ -457,6 +458,7 @@ def test_fine_level_predict_velocity_and_mac_project(backend, oracle, nb):
     if nb == (1, 1, 1):
         assert info.iters == mgo.iters if dev == "cpu" else abs(info.iters - mgo.iters) <= 1   # (GPU: FMA contraction may move a residual across the tolerance)
     gshape = (1, nf[2] + 2, nf[1] + 2, nf[0] + 2)
+    proj = []
     for d, (ref, t) in enumerate(((ru, ix.XFACE), (rv, ix.YFACE), (rw, ix.ZFACE))):
         got, dup = scatter_valid(np.zeros(gshape), 1, [p[0] for p in U[d]], boxes, 1, t)
         assert dup < 1e-12
@@ -464,4 +466,46 @@ def test_fine_level_predict_velocity_and_mac_project(backend, oracle, nb):
         g = _cut(got, 1, flo, tuple(fhi[q] + ext[q] for q in range(3)), 0)
         r = ref[:, 1:1 + n[2] + ext[2], 1:1 + n[1] + ext[1], 1:1 + n[0] + ext[0]]
         assert np.abs(g - r).max() < 1e-10 * max(1.0, np.abs(r).max())
+        proj.append(r)
+    # ---- second half: create_umac_grown (NSB.cpp:1108-1310) and the velocity advection ComputeAofs (NSB.cpp:3358-3470, 4594-4845)
+    from test_amr import umac_grown_expected
+    types = (ix.XFACE, ix.YFACE, ix.ZFACE)
+    ucm = [0.3 * smooth_field(nc, 960 + d, 1) for d in range(3)]            # the coarse level's MAC velocities
+    filled = []
+    for d in range(3):
+        interp = oracle.interp(2 + d, nc, ucm[d])
+        fface = fmask | np.roll(fmask, 1, 2 - d)
+        mine = np.zeros((1,) + nf[::-1])
+        ext = [1 if q == d else 0 for q in range(3)]
+        # the oracle's projected faces of the patch, written into the periodic fine face array (low faces; y is periodic: the
+        # patch's high y face is its low one)
+        sl = [slice(None), slice(flo[2], fhi[2] + 1 + ext[2]), slice(flo[1], fhi[1] + 1), slice(flo[0], fhi[0] + 1 + ext[0])]
+        mine[tuple(sl)] = proj[d][:, :, :n[1], :]
+        filled.append(np.where(fface[None], mine, interp))
+    expm, nfix = umac_grown_expected(filled, fmask, (flo, fhi), nf, dx[0])
+    assert nfix > 0
+    Vq = _cut(_wrap_pad(ug, 3), 3, flo, fhi, 3)
+    # the oracle's face layout: cell-shaped with one ghost layer, faces -1 .. n (the outer face of the high ghost cell is not held)
+    om = [np.ascontiguousarray(np.delete(expm[d], -1, axis=2 - d)[None]) for d in range(3)]
+    aofs_ref, _, _ = oracle.compute_aofs_bc(n, pper, dx, dt, Vq, F, om[0], om[1], om[2], (0, 0, 0), bclo, bchi, 0, 0, 1)
+    UCM = [[(lambda tt: (tt, ix.fab_of(tt, [0, 0, 0])))(__import__("torch").from_numpy(np.ascontiguousarray(
+        np.pad(ucm[d], ((0, 0),) + tuple((0, 1 if q == 2 - d else 0) for q in range(3)), mode="wrap"))).to(dev))] for d in range(3)]
+    lib.check(lib.iamrx_create_umac_grown(flev.h, clev.h, fa(U[0]), fa(U[1]), fa(U[2]), fa(UCM[0]), fa(UCM[1]), fa(UCM[2]), None, st))
+    sync(dev)
+    if nb == (1, 1, 1):
+        for d in range(3):
+            assert np.abs(U[d][0][0].cpu().numpy()[0] - expm[d]).max() <= 1e-10, ("create_umac_grown vs the numpy restatement", d)
+    ic = (C.c_int * 3)(0, 0, 0)
+    outs = []
+    for il, ((tv, fv), b) in enumerate(zip(VF, boxes)):
+        tf, ff = fab_from_padded(np.zeros((3, nf[2] + 2, nf[1] + 2, nf[0] + 2)), 1, b, 1, ix.CELL, dev)
+        ta, fa_ = fab_from_padded(np.zeros((3,) + nf[::-1]), 0, b, 0, ix.CELL, dev)
+        bb = box_of(*b)
+        lib.check(lib.iamrx_compute_aofs_box(C.byref(bb), C.byref(fa_), 0, C.byref(fv), 0, 3, C.byref(ff), 0, None,
+                                             C.byref(U[0][il][1]), C.byref(U[1][il][1]), C.byref(U[2][il][1]), None, None, None,
+                                             None, None, None, None, None, None, ic, bcr, C.byref(fgeom), dt, ix.ADV_IS_VELOCITY, st))
+        outs.append(ta)
+    sync(dev)
+    ga, _ = scatter_valid(np.zeros((3,) + nf[::-1]), 0, outs, boxes, 0, ix.CELL)
+    assert np.abs(_cut(ga, 0, flo, fhi, 0) - aofs_ref).max() <= 1e-9 * max(1.0, np.abs(aofs_ref).max())
     clev.close(); flev.close()
