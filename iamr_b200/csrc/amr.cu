@@ -1011,7 +1011,7 @@ int iamrx_syncreg_field(iamrx_syncreg_t r, int which, int ilocal, iamrx_fab* out
 
 // AmrLevel::FillCoarsePatch of Press_Type (Projection.cpp:236-239): see iamrx.h
 int iamrx_fill_coarse_patch_nodal(iamrx_level_t fine_lev, iamrx_level_t crse_lev, iamrx_fab* fine, const iamrx_fab* crse_old,
-                                  const iamrx_fab* crse_new, double t_old, double t_new, double time, void* stream) {
+                                  const iamrx_fab* crse_new, double t_new_start, double t_new_stop, double time, void* stream) {
   IX_NEED_DEVICE();
   IX_ARG(fine_lev && crse_lev && fine && crse_new, "fill_coarse_patch_nodal arguments");
   Level* FL = level_of(fine_lev);
@@ -1020,18 +1020,15 @@ int iamrx_fill_coarse_patch_nodal(iamrx_level_t fine_lev, iamrx_level_t crse_lev
   for (int d = 0; d < 3; ++d)
     IX_ARG(FL->geom.domain.lo[d] == 2 * CL->geom.domain.lo[d] && FL->geom.domain.hi[d] == 2 * CL->geom.domain.hi[d] + 1,
            "the fine level's domain must be the coarse one refined by 2");
-  double w_new = 1.0;
-  if (crse_old && t_new != t_old) w_new = (time - t_old) / (t_new - t_old);
-  IX_ARG(w_new >= -1.0e-12 && w_new <= 1.0 + 1.0e-12, "time outside [t_old, t_new]");
-  // the coarse pressure at `time` (linear between the two time levels: StateData's interpolation of a point-in-time quantity)
-  MF cn; cn.alias(CL, IX_NODE, 1, 0, const_cast<iamrx_fab*>(crse_new));
+  // Press_Type is an Interval quantity (NS_setup.cpp:329-331): StateData hands out the data of the time interval that contains
+  // `time` -- no interpolation in time.  New interval [t_new_start, t_new_stop], old interval ending at t_new_start; the new one is
+  // tried first, with AMReX's tolerance of 1e-3 of its length.
+  const double teps = 1.0e-3 * (t_new_stop - t_new_start);
+  const bool use_new = time > t_new_start - teps && time < t_new_stop + teps;
+  IX_ARG(use_new || (crse_old != nullptr && time <= t_new_start + teps), "time lies in neither pressure interval");
+  MF cn; cn.alias(CL, IX_NODE, 1, 0, const_cast<iamrx_fab*>(use_new ? crse_new : crse_old));
   MF ct(CL, IX_NODE, 1, 0);
-  if (crse_old && w_new != 1.0) {
-    MF co; co.alias(CL, IX_NODE, 1, 0, const_cast<iamrx_fab*>(crse_old));
-    IX_TRY(mf_lincomb(ct, 0, 1.0 - w_new, co, 0, w_new, cn, 0, 1, 0, s));
-  } else {
-    IX_TRY(mf_copy(ct, cn, 0, 0, 1, 0, s));
-  }
+  IX_TRY(mf_copy(ct, cn, 0, 0, 1, 0, s));
   std::unique_ptr<Level> RL;
   MF cr;
   IX_TRY(replicated_coarse(CL, ct.fabs.data(), 0, 1, IX_NODE, 0, nullptr, s, RL, cr));

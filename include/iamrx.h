@@ -504,11 +504,12 @@ int iamrx_set_coarse_fine_bc(iamrx_level_t fine_lev, iamrx_level_t crse_lev, iam
 
 /* AmrLevel::FillCoarsePatch of Press_Type as Projection::level_project calls it on a level > 0 (Projection.cpp:236-239:
  * LevelData[level]->FillCoarsePatch(P_new, 0, cur_pres_time, Press_Type, 0, 1)): EVERY node of every local fine box takes the coarse
- * pressure, linear in time between crse_old (t_old) and crse_new (t_new; crse_old may be NULL), interpolated with
- * node_bilinear_interp (NS_setup.cpp:331).  level_project then zeroes the interior nodes of each grid (:241-257), which leaves the
+ * pressure of the time INTERVAL that contains `time` -- Press_Type is a StateDescriptor::Interval quantity (NS_setup.cpp:329-331), so
+ * StateData picks crse_new if time lies in [t_new_start, t_new_stop] (within 1e-3 of its length), else crse_old (whose interval ends
+ * at t_new_start; may be NULL), and does not interpolate in time -- interpolated in space with node_bilinear_interp (NS_setup.cpp:331).  level_project then zeroes the interior nodes of each grid (:241-257), which leaves the
  * coarse-fine boundary data iamrx_nodal_project keeps.  Nodal fabs, no ghost nodes needed.  Collective. */
 int iamrx_fill_coarse_patch_nodal(iamrx_level_t fine_lev, iamrx_level_t crse_lev, iamrx_fab* fine, const iamrx_fab* crse_old,
-                                  const iamrx_fab* crse_new, double t_old, double t_new, double time, void* stream);
+                                  const iamrx_fab* crse_new, double t_new_start, double t_new_stop, double time, void* stream);
 
 /* NavierStokesBase::SyncInterp (NSB.cpp:3071-3255): interpolate a coarse-level sync correction (Vsync / Ssync, or the velocity
  * correction of level_sync) onto the fine level -- coarse data with periodic images and the HOMOGENEOUS ext_dir fill of the original

@@ -340,29 +340,25 @@ def test_sync_proj_interp(backend, oracle, layout):
 
 @pytest.mark.parametrize("layout", FINE_LAYOUTS)
 def test_fill_coarse_patch_nodal(backend, oracle, layout):
-    """AmrLevel::FillCoarsePatch of Press_Type (Projection.cpp:236-239): every fine node = node_bilinear_interp of the coarse pressure,
-    linear in time between the two coarse time levels."""
+    """AmrLevel::FillCoarsePatch of Press_Type (Projection.cpp:236-239): every fine node = node_bilinear_interp of the coarse pressure of
+    the time interval that contains `time` (Press_Type is an Interval quantity: no interpolation in time)."""
     lib, dev = backend
     clev, flev, cboxes, fboxes = _level_pair(lib, layout)
     p0, p1 = smooth_field(NC, 121, 1), smooth_field(NC, 122, 1)
-    t0, t1, t = 0.3, 0.5, 0.35
-    w = (t - t0) / (t1 - t0)
-    expect = oracle.interp(1, NC, (1.0 - w) * p0 + w * p1)
     P0 = [to_fab(p0, b, 0, ix.NODE, dev) for b in cboxes]
     P1 = [to_fab(p1, b, 0, ix.NODE, dev) for b in cboxes]
     PF = [to_fab(hash_uniform(123, (1,) + NF[::-1]), b, 0, ix.NODE, dev) for b in fboxes]
     fa = lambda L: fab_array([p[1] for p in L])
-    lib.check(lib.iamrx_fill_coarse_patch_nodal(flev.h, clev.h, fa(PF), fa(P0), fa(P1), t0, t1, t, stream_of(dev)))
-    sync(dev)
-    for (tt, _), b in zip(PF, fboxes):
-        ref, _ = to_fab(expect, b, 0, ix.NODE, "cpu")
-        assert np.abs(tt.cpu().numpy() - ref.numpy()).max() <= 2e-15
-    lib.check(lib.iamrx_fill_coarse_patch_nodal(flev.h, clev.h, fa(PF), None, fa(P1), 0.0, 0.0, 0.0, stream_of(dev)))
-    sync(dev)
-    expect = oracle.interp(1, NC, p1)
-    for (tt, _), b in zip(PF, fboxes):
-        ref, _ = to_fab(expect, b, 0, ix.NODE, "cpu")
-        assert np.abs(tt.cpu().numpy() - ref.numpy()).max() <= 2e-15
+    t0, t1 = 0.3, 0.5                                   # the coarse pressure's new interval; the old one ends at t0
+    for t, src in ((0.35, p1), (0.45, p1), (0.3, p1), (0.25, p0)):
+        lib.check(lib.iamrx_fill_coarse_patch_nodal(flev.h, clev.h, fa(PF), fa(P0), fa(P1), t0, t1, t, stream_of(dev)))
+        sync(dev)
+        expect = oracle.interp(1, NC, src)
+        for (tt, _), b in zip(PF, fboxes):
+            ref, _ = to_fab(expect, b, 0, ix.NODE, "cpu")
+            assert np.abs(tt.cpu().numpy() - ref.numpy()).max() <= 2e-15
+    assert lib.iamrx_fill_coarse_patch_nodal(flev.h, clev.h, fa(PF), None, fa(P1), t0, t1, 0.25, stream_of(dev)) == -1   # no old data
+    assert lib.iamrx_fill_coarse_patch_nodal(flev.h, clev.h, fa(PF), fa(P0), fa(P1), t0, t1, 0.7, stream_of(dev)) == -1  # beyond the new interval
     clev.close(); flev.close()
 
 

@@ -349,7 +349,7 @@ def test_nodal_project_coarse_fine(backend, oracle, nb):
     clev = ix.Level(lib, ix.Geom.make(nc, periodic=per), [((0, 0, 0), tuple(m - 1 for m in nc))])
     from util import to_fab
     CPN = [to_fab(cpress, ((0, 0, 0), tuple(m - 1 for m in nc)), 0, ix.NODE, dev)]
-    lib.check(lib.iamrx_fill_coarse_patch_nodal(flev.h, clev.h, fa(Ph), None, fa(CPN), 0.0, 0.0, 0.0, stream_of(dev)))
+    lib.check(lib.iamrx_fill_coarse_patch_nodal(flev.h, clev.h, fa(Ph), None, fa(CPN), 0.0, 1.0, 0.5, stream_of(dev)))
     sync(dev)
     for t, _ in Ph:
         t[:, 2:-2, 2:-2, 2:-2] = 0.0     # growntilebox(-1) of the node box (the fabs carry one ghost node layer)
