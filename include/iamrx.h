@@ -465,7 +465,9 @@ int iamrx_interp_box(int kind, const iamrx_box* fbx, iamrx_fab* fine, const iamr
  * the fine data, cells outside a non-periodic domain the physical boundary fill (bcrec / bcvals as in iamrx_fill_physbc).  What
  * AmrLevel::FillPatch does for State_Type on a level that does not cover the domain (NSB.cpp:4399,4435; NS_setup.cpp:211).  The
  * valid cells of `fine` hold the fine data at `time` and are not touched.  fine: one fab per local fine box; crse_*: one per local
- * coarse box.  Collective over the ranks of the communicator. */
+ * coarse box.  Collective over the ranks of the communicator.  (State_Type is a Point-in-time quantity; for an Interval quantity
+ * such as Gradp_Type, NS_setup.cpp:339-341, StateData does not interpolate in time: pass crse_old = NULL and the data of the
+ * interval that contains `time` as crse_new.) */
 int iamrx_fillpatch_two_levels(iamrx_level_t fine_lev, iamrx_level_t crse_lev, iamrx_fab* fine, const iamrx_fab* crse_old,
                                const iamrx_fab* crse_new, double t_old, double t_new, double time, int ncomp, int ngrow,
                                const iamrx_bcrec* bcrec, const double* bcvals, void* stream);
