@@ -134,23 +134,31 @@ def _patch_problem(oracle, per, clo, chi, seed):
     return nc, nf, rho, macs, cphi
 
 
+# (domain periodicity, coarse cells of the patch, domain lobc / hibc of the MAC solve, the patch's own periodicity and lobc / hibc for the oracle)
+MAC_CF_CASES = [
+    ((1, 1, 1), (4, 0, 4), (11, 15, 11), None, None, (0, 1, 0), (CF, PER, CF), (CF, PER, CF)),          # periodic domain, the patch spans y
+    # walls: the patch sits against the low x wall (Neumann) and the high z outflow side (Dirichlet); the other sides border coarse cells
+    ((0, 1, 0), (0, 0, 8), (7, 15, 15), (NEU, PER, NEU), (NEU, PER, DIR), (0, 1, 0), (NEU, PER, CF), (CF, PER, DIR)),
+]
+
+
+@pytest.mark.parametrize("per,clo,chi,dlobc,dhibc,pper,lobc,hibc", MAC_CF_CASES, ids=["periodic", "walls"])
 @pytest.mark.parametrize("nb", [(1, 1, 1), (2, 1, 2), (2, 2, 2)])
-def test_mac_project_coarse_fine(backend, oracle, nb):
+def test_mac_project_coarse_fine(backend, oracle, nb, per, clo, chi, dlobc, dhibc, pper, lobc, hibc):
     """MacProj::mlmg_mac_solve on a level > 0 (MacProj.cpp:1164-1168: setCoarseFineBC(cphi, 2), setLevelBC(0, mac_phi), maxorder 4):
     a fine patch inside a periodic domain, spanning y.  The oracle solves on the patch as its own domain (periodic in y, coarse-fine
     Dirichlet sides in x and z).  One box: iterate-for-iterate parity; several boxes: the converged fields (fine-fine sides inside
     the patch are plain neighbour exchanges)."""
     lib, dev = backend
-    per = (1, 1, 1)
-    clo, chi = (4, 0, 4), (11, 15, 11)
     nc, nf, rho, macs, cphi = _patch_problem(oracle, per, clo, chi, 700)
     flo, fhi = tuple(2 * c for c in clo), tuple(2 * c + 1 for c in chi)
     n = tuple(fhi[d] - flo[d] + 1 for d in range(3))
     dx = tuple(1.0 / m for m in nf)
     cov = _covered(nc, clo, chi)
     RHO, M2 = _wrap_pad(rho, 1), [_wrap_pad(m, 2) for m in macs]
-    pper = (0, 1, 0)
-    lobc, hibc = (CF, PER, CF), (CF, PER, CF)
+    for d in range(3):   # solid walls: zero normal velocity on the wall faces (the patch's wall faces are the low faces of its first cells)
+        if dlobc is not None and not per[d] and dlobc[d] == NEU and flo[d] == 0:
+            sl = [slice(None)] * 4; sl[3 - d] = 2; M2[d][tuple(sl)] = 0.0
     dt = 0.7 / 32
     phi0 = oracle.interp_bndry(nc, per, cphi, cov, flo, fhi, np.zeros((1, n[2] + 2, n[1] + 2, n[0] + 2)))
     mg = oracle.mg_default(rtol=1e-12)
@@ -172,7 +180,9 @@ def test_mac_project_coarse_fine(backend, oracle, nb):
     fa = lambda L: fab_array([p[1] for p in L])
     lib.check(lib.iamrx_set_coarse_fine_bc(flev.h, clev.h, fa(P), fa(CP), 1, stream_of(dev)))
     info = _mg(lib, rtol=1e-12, maxorder=4)
-    rc = lib.iamrx_mac_project(flev.h, fa(U[0]), fa(U[1]), fa(U[2]), fa(R), None, fa(P), 2.0 / dt, None, None, C.byref(info), stream_of(dev))
+    bcl = (C.c_int * 3)(*dlobc) if dlobc is not None else None
+    bch = (C.c_int * 3)(*dhibc) if dhibc is not None else None
+    rc = lib.iamrx_mac_project(flev.h, fa(U[0]), fa(U[1]), fa(U[2]), fa(R), None, fa(P), 2.0 / dt, bcl, bch, C.byref(info), stream_of(dev))
     lib.check(rc)
     sync(dev)
     if nb == (1, 1, 1):
