@@ -117,7 +117,18 @@ __global__ void __launch_bounds__(TX* TY) scale_plane_kernel(Bx R, V4 a, double 
   a(i, j, k, n) *= f;
 }
 
+// a(node) = 0 where m(node) != 0 (the Dirichlet nodes of a nodal solve on a fine AMR level of general shape)
+__global__ void __launch_bounds__(TX* TY) mask_zero_kernel(Bx R, V4 a, C4 m) {
+  IDX3(R)
+  if (m(i, j, k) != 0.0) a(i, j, k, n) = 0.0;
+}
+
 }  // namespace
+
+int mask_zero(const Bx& R, V4 a, C4 m, cudaStream_t s) {
+  IX_LAUNCH(mask_zero_kernel, grid_for(R, R.nz()), dim3(TX, TY, 1), 0, s, R, a, m);
+  return check_launch("mask_zero");
+}
 
 int fill_physbc(const Bx& fabbox, V4 a, int ncomp, const PhysBC& bc, const Bx& dom, const int per[3], cudaStream_t s) {
   int nnp = 0;

@@ -191,6 +191,7 @@ int linop_bc_fill(const Bx& vbx, V4 phi, int ncomp, const LinBC& bc, C4 bv, cons
 // coarse-fine sides of a fine AMR level (bc.cu): Dirichlet data x0 cell widths from the face (x0 < 0: beyond it)
 double linop_cf_f0(int maxorder, int boxlen, double x0);
 int linop_cf_fill(const Bx& vbx, V4 phi, int ncomp, int maxorder, C4 bv, int cfmask, const double x0[3], cudaStream_t s);
+int mask_zero(const Bx& R, V4 a, C4 m, cudaStream_t s);   // a = 0 where m != 0
 struct NodalBC { int lo[3], hi[3]; };   // LinOpBCType per side (Projection.cpp:2436-2464)
 int nodal_bc_fill_phi(const Bx& nbx, V4 phi, const NodalBC& bc, const Bx& ndom, const int per[3], int skipmask, cudaStream_t s);
 int nodal_bc_fill_sigma(const Bx& cbx, V4 sig, const NodalBC& bc, const Bx& dom, const int per[3], cudaStream_t s, int ngt = 1);

@@ -773,7 +773,39 @@ NodeMG::NodeMG(Level* fine, int max_coarsening) {
     Bx u = fine->boxes[0];
     for (const Bx& b : fine->boxes) for (int d = 0; d < 3; ++d) { u.lo[d] = std::min(u.lo[d], b.lo[d]); u.hi[d] = std::max(u.hi[d], b.hi[d]); }
     cf_rect_ = u.npts() == fine->ncells_global;
+    static int force_mask = -1;   // IAMRX_NODAL_CF_MASK=1: the node-mask path on rectangular patches too (cross-check)
+    if (force_mask < 0) { const char* e = getenv("IAMRX_NODAL_CF_MASK"); force_mask = (e && e[0] == '1') ? 1 : 0; }
+    cf_mask_ = cf_ && (!cf_rect_ || force_mask);
+    if (cf_mask_) {
+      // dmask = 1 on nodes with an uncovered cell among the cells around them that lie inside the domain (periodic images count)
+      for (auto& M : lv_) {
+        Level* LL = M.lev;
+        MF cov(LL, IX_CELL, 1, 1);
+        mf_setval(cov, 0.0, 0, 1, 1, nullptr);
+        for (int il = 0; il < cov.n(); ++il) k::setval(cov.vbox(il), cov.v(il), 1, 1.0, nullptr);
+        mf_fill_boundary(cov, 0, 1, 1, nullptr);
+        for (int il = 0; il < cov.n(); ++il)
+          for (int d = 0; d < 3; ++d) {
+            if (LL->geom.periodic[d]) continue;
+            for (int side = 0; side < 2; ++side) {   // cells beyond a physical side do not exist: they never make a node a coarse-fine node
+              Bx R = grow(cov.vbox(il), 1);
+              if (side == 0) R.hi[d] = std::min(R.hi[d], LL->domain.lo[d] - 1); else R.lo[d] = std::max(R.lo[d], LL->domain.hi[d] + 1);
+              if (R.ok()) k::setval(R, cov.v(il), 1, 1.0, nullptr);
+            }
+          }
+        M.dmask.define(LL, IX_NODE, 1, 0);
+        for (int il = 0; il < M.dmask.n(); ++il) k::sync_mask(M.dmask.vbox(il), M.dmask.v(il), cov.c(il), 7.5, nullptr);
+      }
+      cudaStreamSynchronize(nullptr);
+    }
   }
+}
+
+int NodeMG::apply_node_mask(int l, MF& a, cudaStream_t s) const {
+  if (!cf_mask_) return IAMRX_OK;
+  const MGLevelNode& M = lv_[l];
+  for (int il = 0; il < a.n(); ++il) IX_TRY(k::mask_zero(a.vbox(il), a.v(il), M.dmask.c(il), s));
+  return IAMRX_OK;
 }
 
 void NodeMG::set_bc(const k::NodalBC& bc) {
@@ -785,7 +817,7 @@ Bx NodeMG::active_nbox(int l, int il, bool with_cf) const {
   const Level& L = *lv_[l].lev;
   Bx nb = ixbox(L.lbox(il), IX_NODE);
   if (!has_bc_) return nb;
-  if (cf_ && with_cf)
+  if (cf_ && with_cf && !cf_mask_)
     for (int d = 0; d < 3; ++d) {
       if (cfmask_[l][il] & (1 << (2 * d))) nb.lo[d] += 1;
       if (cfmask_[l][il] & (1 << (2 * d + 1))) nb.hi[d] -= 1;
@@ -880,6 +912,7 @@ int NodeMG::smooth(int l, MF& phi, const MF& rhs, int nsweeps, cudaStream_t s) {
         IX_TRY(k::nodal_jacobi(active_nbox(l, il), tmp.v(il), phi.c(il), rhs.c(il), L.sigma.c(il), L.dxinv,
                                2.0 / 3.0, s));
       IX_TRY(mf_copy(phi, tmp, 0, 0, 1, 0, s));
+      IX_TRY(apply_node_mask(l, phi, s));
     }
     return IAMRX_OK;
   }
@@ -888,7 +921,7 @@ int NodeMG::smooth(int l, MF& phi, const MF& rhs, int nsweeps, cudaStream_t s) {
   // deep-ghost levels (block decompositions): same fused sweep, halos from 4 ghost layers of phi / rhs / sigma instead of wraps
   const bool deep = L.deep && phi.ng >= L.ngd && rhs.ng >= L.ngd;
   // a small level that is ONE box (the coarse levels; consolidated levels of multi-rank runs): every sweep in one launch
-  if (L.lev->boxes.size() == 1 && phi.n() == 1 && k::nodal_gs_small_ok(active_nbox(l, 0))) {
+  if (!cf_mask_ && L.lev->boxes.size() == 1 && phi.n() == 1 && k::nodal_gs_small_ok(active_nbox(l, 0))) {
     IX_TRY(fill_ghosts(l, phi, wm, s, false));
     return k::nodal_gs_small(active_nbox(l, 0), phi.v(0), rhs.c(0), L.sigma.c(0), L.dxinv, nsweeps, s, wm | (neumann_sides(l, 0) << 3));
   }
@@ -932,6 +965,7 @@ int NodeMG::smooth(int l, MF& phi, const MF& rhs, int nsweeps, cudaStream_t s) {
       IX_TRY(fill_ghosts(l, phi, wm, s, false));
       for (int il = 0; il < phi.n(); ++il)
         IX_TRY(k::nodal_gs_color(active_nbox(l, il), phi.v(il), rhs.c(il), L.sigma.c(il), L.dxinv, color, s, wm | (neumann_sides(l, il) << 3)));
+      IX_TRY(apply_node_mask(l, phi, s));   // (the smoother only ever works on corrections: their Dirichlet nodes are zero)
     }
   }
   return IAMRX_OK;
@@ -944,7 +978,7 @@ int NodeMG::residual(int l, MF& out, MF& phi, const MF& rhs, cudaStream_t s, dou
   // the norm is taken inside the residual kernel when every box's active nodes are all of its nodes (no Dirichlet planes whose
   // entries of `out` the kernel does not write) and the kernel supports it
   double* nd = nullptr;
-  bool fusedn = norm != nullptr && phi.n() > 0;
+  bool fusedn = norm != nullptr && phi.n() > 0 && !cf_mask_;
   for (int il = 0; il < phi.n() && fusedn; ++il) {
     const Bx a = active_nbox(l, il), v = phi.vbox(il);
     for (int d = 0; d < 3; ++d) if (a.lo[d] != v.lo[d] || a.hi[d] != v.hi[d]) fusedn = false;
@@ -957,6 +991,7 @@ int NodeMG::residual(int l, MF& out, MF& phi, const MF& rhs, cudaStream_t s, dou
                           fusedn ? nd : nullptr, &nf));
     if (fusedn && !nf) all = false;
   }
+  IX_TRY(apply_node_mask(l, out, s));
   if (norm) {
     if (fusedn && all) IX_TRY(norm_acc_end(nd, L.lev->replicated, norm, s));
     else IX_TRY(mf_norminf(out, 0, 1, norm, s));
@@ -999,6 +1034,7 @@ int NodeMG::bottom_solve(cudaStream_t s) {
     IX_TRY(mf_setval(out, 0.0, 0, 1, 0, s));   // nodes ON Dirichlet sides stay zero (active_nbox)
     for (int il = 0; il < in.n(); ++il)
       IX_TRY(k::nodal_adotx(active_nbox(nl - 1, il), out.v(il), in.c(il), C4{}, B.sigma.c(il), B.dxinv, s, wm | (neumann_sides(nl - 1, il) << 3)));
+    IX_TRY(apply_node_mask(nl - 1, out, s));
     return IAMRX_OK;
   };
   op.dot = [&](const MF& a, const MF& b, double* r) { return mf_dot(a, b, 1, true, r, s); };
@@ -1046,6 +1082,7 @@ int NodeMG::vcycle(cudaStream_t s) {
         const Bx fnb = L.rescor.vbox(il);
         IX_TRY(k::nodal_restrict(active_nbox(l + 1, il), C.res.v(il), L.rescor.c(il), s, thin_, rwm, &fnb));
       }
+      IX_TRY(apply_node_mask(l + 1, C.res, s));
     }
   }
   IX_TRY(bottom_solve(s));
@@ -1054,16 +1091,13 @@ int NodeMG::vcycle(cudaStream_t s) {
     MGLevelNode& C = lv_[l + 1];
     for (int il = 0; il < L.cor.n(); ++il)
       IX_TRY(k::nodal_interp_add(active_nbox(l, il), L.cor.v(il), C.cor.c(C.xfer_lev ? 0 : il), s, thin_));
+    IX_TRY(apply_node_mask(l, L.cor, s));
     IX_TRY(smooth(l, L.cor, L.res, info_.nu2, s));
   }
   return IAMRX_OK;
 }
 
 int NodeMG::solve(MF& phi, MF& rhs, iamrx_mg_info* info, cudaStream_t s) {
-  if (!coarse_fine_supported()) {
-    set_error("NodeMG: the boxes of a level with coarse-fine sides must form one rectangular patch");
-    return IAMRX_ERR_ARG;
-  }
   if (info) info_ = *info;
   info_.bottom_iters = 0;
   MGLevelNode& L0 = lv_[0];

@@ -86,6 +86,7 @@ class CellMG {
 };
 
 struct MGLevelNode {
+  MF dmask;            // nodal: 1 on the coarse-fine boundary nodes of a fine AMR level (NodeMG::node_mask() only)
   std::unique_ptr<Level> lev_owned;
   Level* lev = nullptr;
   std::unique_ptr<Level> xfer_lev;   // see MGLevelCell
@@ -113,7 +114,10 @@ class NodeMG {
   // a fine AMR level (one rectangular patch of boxes that does not tile the domain): the nodes on the patch boundary are Dirichlet
   // nodes of the single-level solve (MLNodeLaplacian: coarse-fine boundary nodes of the coarsest AMR level of a solve)
   bool has_coarse_fine() const { return cf_; }
-  bool coarse_fine_supported() const { return !cf_ || cf_rect_; }
+  // a fine level of general shape (re-entrant edges, partly covered sides): the boundary nodes are found node by node (dmask) and
+  // reset to zero after every kernel that may have written them, instead of being cut off side by side
+  bool node_mask() const { return cf_mask_; }
+  int apply_node_mask(int l, MF& a, cudaStream_t s) const;
   int neumann_sides(int l, int il) const;   // bit 2d / 2d+1: the low / high side of the box is a Neumann / inflow domain side
   int set_sigma(const MF& sigma, cudaStream_t s);  // copies + coarsens
   int solve(MF& phi, MF& rhs, iamrx_mg_info* info, cudaStream_t s);
@@ -133,7 +137,7 @@ class NodeMG {
   int thin_ = 0;   // semi-coarsening mask (thin_mask of the finest level)
   k::NodalBC bc_{};
   bool has_bc_ = false;
-  bool cf_ = false, cf_rect_ = true;
+  bool cf_ = false, cf_rect_ = true, cf_mask_ = false;
   std::vector<std::vector<int>> cfmask_;   // [mg level][local box]: bit 2 d + side = that side of the box is a coarse-fine side
 };
 

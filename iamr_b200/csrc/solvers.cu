@@ -96,6 +96,7 @@ int nodal_project(Level& L, LevelSolvers& sv, MF& vel, const MF& sigma, MF& phi,
     // mlndlap_impose_neumann_bc: rows ON Neumann / inflow sides are doubled, once per direction
     if (mg.has_bc()) IX_TRY(k::nodal_bc_scale(sv.nodal_rhs.vbox(il), sv.nodal_rhs.v(il), mg.bc(), ndom, L.geom.periodic, 2.0, s));
   }
+  IX_TRY(mg.apply_node_mask(0, sv.nodal_rhs, s));   // a fine level of general shape: no equation on its coarse-fine boundary nodes
   if (mg.has_bc() && !keep_dirichlet) {   // nodes ON Dirichlet sides are held at zero
     for (int il = 0; il < phi.n(); ++il) {
       const Bx full = phi.vbox(il), act = mg.active_nbox(0, il, /*with_cf=*/false);   // coarse-fine boundary nodes keep their values

@@ -394,9 +394,12 @@ int iamrx_mac_get_fluxes(iamrx_level_t lev, iamrx_fab* fx, iamrx_fab* fy, iamrx_
  * div(sigma grad phi) = div(vel) on nodes, vel -= sigma grad phi,
  * gp (=|+=) grad phi.  vel: 3 comps >=1 ghost; sigma: 1 comp 1 ghost;
  * phi: nodal 1 ghost (initial guess in, solution out); gp: 3 comps.
- * On a level > 0 (Projection::level_project :236-257): the boxes must form ONE rectangular patch; the nodes on the sides of the
- * patch that border coarse cells are Dirichlet nodes and KEEP the values of phi on entry (the coarse pressure interpolated by
- * FillCoarsePatch -- iamrx_interp_box with node_bilinear), the interior nodes are the initial guess (IAMR zeroes them). */
+ * On a level > 0 (Projection::level_project :236-257; boxes that do not tile the domain): the nodes on the boundary of the fine
+ * region that border coarse cells are Dirichlet nodes and KEEP the values of phi on entry (the coarse pressure interpolated by
+ * FillCoarsePatch: iamrx_fill_coarse_patch_nodal), the interior nodes are the initial guess (IAMR zeroes them).  One rectangular
+ * patch of boxes: the boundary planes are cut off the boxes' active node ranges; any other shape (re-entrant edges, partly covered
+ * sides): the boundary nodes are found node by node and reset after every kernel that may write them (IAMRX_NODAL_CF_MASK=1 forces
+ * this path for rectangular patches too). */
 int iamrx_nodal_project(iamrx_level_t lev, iamrx_fab* vel, const iamrx_fab* sigma,
                         iamrx_fab* phi, iamrx_fab* gp, int increment_gp,
                         const int lobc[3], const int hibc[3], iamrx_mg_info* info,

@@ -384,20 +384,72 @@ def test_nodal_project_coarse_fine(backend, oracle, nb):
     flev.close()
 
 
-def test_nodal_project_refuses_non_rectangular_patch(backend):
-    """An L-shaped fine level has boundary nodes on a re-entrant edge that the side-by-side bookkeeping does not see: refused."""
+def test_nodal_project_coarse_fine_node_mask_path():
+    """The node-mask bookkeeping of fine levels of general shape (boundary nodes found node by node and reset after every kernel),
+    forced onto the rectangular patches of test_nodal_project_coarse_fine, where the oracle is the reference: a fresh process with
+    IAMRX_NODAL_CF_MASK=1 (the switch is read once per process)."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, IAMRX_NODAL_CF_MASK="1")
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(root, "tests", "test_cf.py"), "-q", "-x", "-m", "not gpu", "-k",
+                        "test_nodal_project_coarse_fine and emul"], env=env, capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0 and "3 passed" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+
+
+L_SHAPES = [
+    [((8, 8, 8), (15, 15, 23)), ((16, 8, 8), (23, 15, 23)), ((8, 16, 8), (15, 23, 23))],
+    [((8, 8, 8), (15, 15, 15)), ((8, 8, 16), (15, 15, 23)), ((16, 8, 8), (23, 15, 23)), ((8, 16, 8), (15, 19, 23)), ((8, 20, 8), (15, 23, 23))],
+]
+
+
+def test_nodal_project_on_an_l_shaped_level(backend):
+    """A fine level whose boxes form an L: the nodes on its re-entrant edge are coarse-fine boundary nodes that no box SIDE reveals
+    (both sides of the corner box are covered by neighbours).  No oracle twin exists for this shape; checked here: the solve
+    converges, every boundary node of the union (re-entrant edge included) keeps the data handed in, and the result does not depend
+    on how the L is cut into boxes (3 boxes vs 5 with a partly covered side)."""
     lib, dev = backend
     nf = (32, 32, 32)
-    boxes = [((8, 8, 8), (15, 15, 15)), ((16, 8, 8), (23, 15, 15)), ((8, 16, 8), (15, 23, 15))]
-    flev = ix.Level(lib, ix.Geom.make(nf, periodic=(1, 1, 1)), boxes)
-    Vv = [fab_from_padded(np.zeros((3, 34, 34, 34)), 1, b, 1, ix.CELL, dev) for b in boxes]
-    Sg = [fab_from_padded(np.ones((1,) + nf[::-1]), 0, b, 0, ix.CELL, dev) for b in boxes]
-    Ph = [fab_from_padded(np.zeros((1, 36, 36, 36)), 2, b, 1, ix.NODE, dev) for b in boxes]
-    fa = lambda L: fab_array([p[1] for p in L])
-    info = _mg(lib)
-    rc = lib.iamrx_nodal_project(flev.h, fa(Vv), fa(Sg), fa(Ph), None, 0, None, None, C.byref(info), stream_of(dev))
-    assert rc == -1   # IAMRX_ERR_ARG
-    flev.close()
+    per = (1, 1, 1)
+    z, y, x = [(np.arange(m) + 0.5) / m for m in nf[::-1]]
+    Z, Y, X = np.meshgrid(z, y, x, indexing="ij")
+    sig = (1.0 / (1.0 + 0.4 * np.sin(2 * np.pi * X) * np.cos(2 * np.pi * Y) * np.sin(2 * np.pi * Z + 0.3)))[None]
+    V = _wrap_pad(smooth_field(nf, 970, 3) + 0.2 * hash_uniform(971, (3,) + nf[::-1]), 1)
+    G = _wrap_pad(0.02 * smooth_field(nf, 972, 1), 2)
+    cells = np.zeros(nf[::-1], dtype=bool)
+    for lo, hi in L_SHAPES[0]:
+        cells[lo[2]:hi[2] + 1, lo[1]:hi[1] + 1, lo[0]:hi[0] + 1] = True
+    # nodes of the union (low corner of cell (i, j, k) = node (i, j, k)) and its boundary nodes: not all eight cells around them are fine
+    pc = np.pad(cells, 1)
+    cnt = sum(pc[1 - dk:pc.shape[0] - dk, 1 - dj:pc.shape[1] - dj, 1 - di:pc.shape[2] - di].astype(int) for dk in (0, 1) for dj in (0, 1) for di in (0, 1))
+    cnt = cnt[:nf[2] + 1, :nf[1] + 1, :nf[0] + 1]          # cnt[k, j, i] = fine cells among the eight around node (i, j, k)
+    bnd = (cnt > 0) & (cnt < 8)
+    assert bnd[16, 16, 16] and cnt[16, 16, 16] == 6        # a node of the re-entrant edge
+    Pg = np.zeros_like(G)
+    Pg[0, 2:2 + nf[2] + 1, 2:2 + nf[1] + 1, 2:2 + nf[0] + 1][bnd] = G[0, 2:2 + nf[2] + 1, 2:2 + nf[1] + 1, 2:2 + nf[0] + 1][bnd]
+    results = []
+    for boxes in L_SHAPES:
+        flev = ix.Level(lib, ix.Geom.make(nf, periodic=per), boxes)
+        Vv = [fab_from_padded(V, 1, b, 1, ix.CELL, dev) for b in boxes]
+        Sg = [fab_from_padded(sig, 0, b, 0, ix.CELL, dev) for b in boxes]
+        Ph = [fab_from_padded(Pg, 2, b, 1, ix.NODE, dev) for b in boxes]
+        fa = lambda L: fab_array([p[1] for p in L])
+        info = _mg(lib, rtol=1e-12)
+        rc = lib.iamrx_nodal_project(flev.h, fa(Vv), fa(Sg), fa(Ph), None, 0, None, None, C.byref(info), stream_of(dev))
+        lib.check(rc)
+        sync(dev)
+        assert rc == 0 and info.iters < 30 and info.resnorm <= 1e-12 * max(info.rhsnorm, info.resnorm0)
+        gp_, dup = scatter_valid(np.zeros(Pg.shape), 2, [p[0] for p in Ph], boxes, 1, ix.NODE)
+        assert dup < 1e-11
+        phi = gp_[0, 2:2 + nf[2] + 1, 2:2 + nf[1] + 1, 2:2 + nf[0] + 1]
+        assert np.array_equal(phi[bnd], Pg[0, 2:2 + nf[2] + 1, 2:2 + nf[1] + 1, 2:2 + nf[0] + 1][bnd])
+        gv, _ = scatter_valid(np.zeros((3, nf[2] + 2, nf[1] + 2, nf[0] + 2)), 1, [p[0] for p in Vv], boxes, 1, ix.CELL)
+        results.append((phi.copy(), gv[:, 1:-1, 1:-1, 1:-1][:, cells].copy()))
+        flev.close()
+    assert np.abs(results[0][0] - results[1][0]).max() <= 1e-10
+    assert np.abs(results[0][1] - results[1][1]).max() <= 1e-9
+    assert np.abs(results[0][0][cnt == 8]).max() > 1e-4    # something was solved for in the interior
 
 
 @pytest.mark.parametrize("nb", [(1, 1, 1), (2, 1, 2)])
