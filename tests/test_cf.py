@@ -258,6 +258,23 @@ def test_diffusion_solve_coarse_fine(backend, oracle, nb):
         assert info.iters == mgo.iters if dev == "cpu" else abs(info.iters - mgo.iters) <= 1   # (GPU: FMA contraction may move a residual across the tolerance)
     gs, _ = scatter_valid(np.zeros(gshape1), 1, [p[0] for p in Sol], boxes, 1, ix.CELL)
     assert np.abs(_cut(gs, 1, flo, fhi, 0) - ref_sol[:, 1:-1, 1:-1, 1:-1]).max() <= 1e-10
+    # Diffusion::computeExtensiveFluxes on the fine level (the FineAdd of the viscous flux register): the fluxes through the
+    # coarse-fine faces use the ghost cells the solve left (setFinalFillBC) -- expected from the ORACLE's solution and ghost cells
+    fac = 0.35
+    area = [dx[1] * dx[2], dx[0] * dx[2], dx[0] * dx[1]]
+    FL = [[fab_from_padded(np.zeros(gshape1), 1, bx, 0, t, dev) for bx in boxes] for t in (ix.XFACE, ix.YFACE, ix.ZFACE)]
+    lib.check(lib.iamrx_diffusion_get_fluxes(flev.h, 1, fa(FL[0]), fa(FL[1]), fa(FL[2]), fa(Sol), b, fa(E[0]), fa(E[1]), fa(E[2]), fac, stream_of(dev)))
+    sync(dev)
+    for d, t in enumerate((ix.XFACE, ix.YFACE, ix.ZFACE)):
+        gf, dup = scatter_valid(np.zeros(gshape1), 1, [p[0] for p in FL[d]], boxes, 0, t)
+        assert dup < 1e-12
+        ext = [1 if q == d else 0 for q in range(3)]
+        got_f = _cut(gf, 1, flo, tuple(fhi[q] + ext[q] for q in range(3)), 0)
+        hi_sl = [slice(None), slice(1, 1 + n[2] + ext[2]), slice(1, 1 + n[1] + ext[1]), slice(1, 1 + n[0] + ext[0])]
+        lo_sl = list(hi_sl); lo_sl[3 - d] = slice(0, n[d] + 1)
+        et = _cut(eta[d], 2, flo, tuple(fhi[q] + ext[q] for q in range(3)), 0)
+        exp_f = -fac * area[d] * b * et * (ref_sol[tuple(hi_sl)] - ref_sol[tuple(lo_sl)]) / dx[d]
+        assert np.abs(got_f - exp_f).max() <= 1e-9 * max(1.0, np.abs(exp_f).max()), d
     # the tensor operator on such a level is refused, not mis-solved
     V = [fab_from_padded(np.zeros((3, nf[2] + 2, nf[1] + 2, nf[0] + 2)), 1, bx, 1, ix.CELL, dev) for bx in boxes]
     O3 = [fab_from_padded(np.zeros((3,) + nf[::-1]), 0, bx, 0, ix.CELL, dev) for bx in boxes]
