@@ -610,3 +610,101 @@ def test_fine_level_advance_first_half(backend, oracle, nb):
     ga, _ = scatter_valid(np.zeros((3,) + nf[::-1]), 0, outs, boxes, 0, ix.CELL)
     assert np.abs(_cut(ga, 0, flo, fhi, 0) - aofs_ref).max() <= 1e-9 * max(1.0, np.abs(aofs_ref).max())
     clev.close(); flev.close()
+
+
+@pytest.mark.parametrize("nb", [(1, 1, 1), (2, 1, 1)])
+def test_two_level_subcycled_scalar_advection_conserves(backend, nb):
+    """One coarse step and two subcycled fine steps of the conservative scalar advection, in the reference's order and with the real
+    Godunov fluxes: coarse ComputeAofs with its fluxes into the advective register (CrseInit, NSB.cpp:4848-4889), on the fine level
+    FillPatch in time from both levels (NS.cpp:719-728), ComputeAofs, FineAdd -- twice --, then reflux (NS.cpp:1713-1838) and
+    avgDown (NSB.cpp:4125-4191).  No oracle needed: the composite total of the scalar is conserved to round-off, and is NOT
+    without the reflux."""
+    lib, dev = backend
+    from util import box_of, to_fab
+    from test_bc import bcrec_array
+    per = (1, 1, 1)
+    nc, nf = (16, 16, 16), (32, 32, 32)
+    clo, chi = (4, 4, 4), (11, 11, 11)
+    flo, fhi = tuple(2 * c for c in clo), tuple(2 * c + 1 for c in chi)
+    dxc, dxf = 1.0 / nc[0], 1.0 / nf[0]
+    cbox = ((0, 0, 0), tuple(m - 1 for m in nc))
+    boxes = _patch_boxes(clo, chi, nb)
+    clev = ix.Level(lib, ix.Geom.make(nc, periodic=per), [cbox])
+    cgeom, fgeom = ix.Geom.make(nc, periodic=per), ix.Geom.make(nf, periodic=per)
+    flev = ix.Level(lib, fgeom, boxes)
+    cov = _covered(nc, clo, chi)
+    fmask = np.repeat(np.repeat(np.repeat(cov, 2, 0), 2, 1), 2, 2)
+    types = (ix.XFACE, ix.YFACE, ix.ZFACE)
+    fa = lambda L: fab_array([p[1] for p in L])
+    st = stream_of(dev)
+    sc0 = 1.0 + 0.3 * smooth_field(nc, 981, 1) + 0.05 * hash_uniform(982, (1,) + nc[::-1])
+    sf0 = 1.0 + 0.3 * smooth_field(nf, 983, 1) + 0.05 * hash_uniform(984, (1,) + nf[::-1])
+    ucm = [0.5 * smooth_field(nc, 985 + d, 1) for d in range(3)]
+    ufm = [0.5 * smooth_field(nf, 988 + d, 1) for d in range(3)]          # the fine level's own MAC velocities (valid faces)
+    dt_c = 0.4 * dxc / max(np.abs(u).max() for u in ucm + ufm)
+    dt_f = 0.5 * dt_c
+    vol_c = dxc ** 3
+    bcr = bcrec_array([(0, 0, 0)], [(0, 0, 0)])
+    ic = (C.c_int * 1)(1)
+    flags = ix.ADV_WRITE_FLUXES
+
+    def advect(geom, box, S, U, dt):
+        """ComputeAofs on one box: returns (aofs tensor, [flux fabs])"""
+        ta, fab_a = to_fab(np.zeros_like(sc0 if geom is cgeom else sf0), box, 0, ix.CELL, dev)
+        FLX = [to_fab(np.zeros_like(sc0 if geom is cgeom else sf0), box, 0, t, dev) for t in types]
+        EDG = [to_fab(np.zeros_like(sc0 if geom is cgeom else sf0), box, 0, t, dev) for t in types]
+        bb = box_of(*box)
+        lib.check(lib.iamrx_compute_aofs_box(C.byref(bb), C.byref(fab_a), 0, C.byref(S[1]), 0, 1, None, 0, None,
+                                             C.byref(U[0][1]), C.byref(U[1][1]), C.byref(U[2][1]), None, None, None,
+                                             C.byref(FLX[0][1]), C.byref(FLX[1][1]), C.byref(FLX[2][1]),
+                                             C.byref(EDG[0][1]), C.byref(EDG[1][1]), C.byref(EDG[2][1]), ic, bcr, C.byref(geom), dt, flags, st))
+        return ta, FLX
+
+    # ---- coarse level: one step
+    SC = to_fab(sc0, cbox, 3, ix.CELL, dev)
+    UC = [to_fab(ucm[d], cbox, 1, types[d], dev) for d in range(3)]
+    aofs_c, FC = advect(cgeom, cbox, SC, UC, dt_c)
+    sync(dev)
+    sc1 = sc0 - dt_c * aofs_c.cpu().numpy()
+    reg = C.c_void_p()
+    lib.check(lib.iamrx_fluxreg_create(clev.h, flev.h, 1, C.byref(reg)))
+    lib.check(lib.iamrx_fluxreg_crse_add(reg, fa([FC[0]]), fa([FC[1]]), fa([FC[2]]), dt_c, vol_c, st))
+    # ---- fine level: two steps
+    UF = [[to_fab(ufm[d], b, 1, types[d], dev, fill_ghost=False) for b in boxes] for d in range(3)]
+    UC0 = [[to_fab(ucm[d], cbox, 0, types[d], dev)] for d in range(3)]
+    lib.check(lib.iamrx_create_umac_grown(flev.h, clev.h, fa(UF[0]), fa(UF[1]), fa(UF[2]), fa(UC0[0]), fa(UC0[1]), fa(UC0[2]), None, st))
+    C_OLD, C_NEW = [to_fab(sc0, cbox, 0, ix.CELL, dev)], [to_fab(sc1, cbox, 0, ix.CELL, dev)]
+    sf = sf0.copy()
+    for step in range(2):
+        SF = [to_fab(sf, b, 3, ix.CELL, dev, fill_ghost=False) for b in boxes]
+        lib.check(lib.iamrx_fillpatch_two_levels(flev.h, clev.h, fa(SF), fa(C_OLD), fa(C_NEW), 0.0, dt_c, step * dt_f, 1, 3, None, None, st))
+        outs, FX = [], [[], [], []]
+        for il, b in enumerate(boxes):
+            ta, FLX = advect(fgeom, b, SF[il], [UF[0][il], UF[1][il], UF[2][il]], dt_f)
+            outs.append(ta)
+            for d in range(3):
+                FX[d].append(FLX[d])
+        lib.check(lib.iamrx_fluxreg_fine_add(reg, fa(FX[0]), fa(FX[1]), fa(FX[2]), dt_f, vol_c, st))
+        sync(dev)
+        aofs_f = np.zeros_like(sf)
+        for t, (lo, hi) in zip(outs, boxes):
+            aofs_f[:, lo[2]:hi[2] + 1, lo[1]:hi[1] + 1, lo[0]:hi[0] + 1] = t.cpu().numpy()
+        sf = np.where(fmask[None], sf - dt_f * aofs_f, sf)
+    # ---- reflux and average down
+    ST = [to_fab(sc1, cbox, 0, ix.CELL, dev)]
+    lib.check(lib.iamrx_fluxreg_reflux(reg, fa(ST), 0, 1.0, st))
+    FS = [to_fab(sf, b, 0, ix.CELL, dev) for b in boxes]
+    sync(dev)
+    sc_refluxed = ST[0][0].cpu().numpy().copy()
+    lib.check(lib.iamrx_average_down(flev.h, clev.h, fa(FS), fa(ST), 0, 1, ix.CELL, st))
+    sync(dev)
+    sc2 = ST[0][0].cpu().numpy()
+    avg = sf.reshape(1, nc[2], 2, nc[1], 2, nc[0], 2).mean(axis=(2, 4, 6))
+    assert np.abs(sc2[:, cov] - avg[:, cov]).max() <= 1e-14
+    total = lambda c, f: (c[0] * (~cov)).sum() * dxc ** 3 + (f[0] * fmask).sum() * dxf ** 3
+    t0, t_noreflux, t1 = total(sc0, sf0), total(sc1, sf), total(sc_refluxed, sf)
+    assert abs(t_noreflux - t0) > 1e-7 * abs(t0)         # the coarse and the fine fluxes through the interface do differ
+    assert abs(t1 - t0) <= 2e-14 * abs(t0)
+    assert abs(total(sc2, sf) - t0) <= 2e-14 * abs(t0)
+    lib.iamrx_fluxreg_destroy(reg)
+    clev.close(); flev.close()
