@@ -708,3 +708,70 @@ def test_two_level_subcycled_scalar_advection_conserves(backend, nb):
     assert abs(total(sc2, sf) - t0) <= 2e-14 * abs(t0)
     lib.iamrx_fluxreg_destroy(reg)
     clev.close(); flev.close()
+
+
+def test_two_level_implicit_diffusion_conserves(backend):
+    """The viscous counterpart: a backward-Euler diffusion step of a scalar on the coarse level (whole domain) and two subcycled ones on
+    the fine level, whose solves take their coarse-fine boundary values from the new coarse solution (setCoarseFineBC, Diffusion.cpp:
+    518,543); the extensive fluxes of every solve (computeExtensiveFluxes, Diffusion.cpp:1463-1537, 560-566) go through the viscous
+    flux register; reflux + avgDown.  The composite total is conserved to solver tolerance, and is not without the reflux."""
+    lib, dev = backend
+    from util import to_fab
+    per = (1, 1, 1)
+    nc, nf = (16, 16, 16), (32, 32, 32)
+    clo, chi = (4, 4, 4), (11, 11, 11)
+    dxc, dxf = 1.0 / nc[0], 1.0 / nf[0]
+    cbox = ((0, 0, 0), tuple(m - 1 for m in nc))
+    boxes = _patch_boxes(clo, chi, (2, 1, 1))
+    clev = ix.Level(lib, ix.Geom.make(nc, periodic=per), [cbox])
+    flev = ix.Level(lib, ix.Geom.make(nf, periodic=per), boxes)
+    cov = _covered(nc, clo, chi)
+    fmask = np.repeat(np.repeat(np.repeat(cov, 2, 0), 2, 1), 2, 2)
+    types = (ix.XFACE, ix.YFACE, ix.ZFACE)
+    fa = lambda L: fab_array([p[1] for p in L])
+    st = stream_of(dev)
+    sf0 = 1.0 + 0.5 * smooth_field(nf, 991, 1) + 0.2 * hash_uniform(992, (1,) + nf[::-1])
+    sc0 = sf0.reshape(1, nc[2], 2, nc[1], 2, nc[0], 2).mean(axis=(2, 4, 6))         # consistent levels to start from
+    eta_c = [0.02 * (1.0 + 0.3 * smooth_field(nc, 993 + d, 1)) for d in range(3)]
+    eta_f = [0.02 * (1.0 + 0.3 * smooth_field(nf, 996 + d, 1)) for d in range(3)]
+    dt_c, dt_f = 0.05, 0.025
+    bc = ix.LinopBC.make([(PER, PER, PER)], [(PER, PER, PER)], 2)
+    vol_c = dxc ** 3
+
+    def implicit_step(lev, bxs, n, s_old, eta, dt, crse_sol=None):
+        """(1 - dt div eta grad) S = S_old on one level; returns (new dense array, flux fabs)"""
+        E = [[to_fab(eta[d], b, 0, types[d], dev) for b in bxs] for d in range(3)]
+        A = [to_fab(np.ones((1,) + n[::-1]), b, 0, ix.CELL, dev) for b in bxs]
+        Sol = [to_fab(s_old, b, 1, ix.CELL, dev) for b in bxs]
+        Rhs = [to_fab(s_old, b, 0, ix.CELL, dev) for b in bxs]
+        if crse_sol is not None:
+            lib.check(lib.iamrx_set_coarse_fine_bc(flev.h, clev.h, fa(Sol), fa(crse_sol), 1, st))
+        info = _mg(lib, rtol=1e-13)
+        lib.check(lib.iamrx_diffusion_solve(lev.h, 0, 1, fa(Sol), fa(Rhs), 1.0, dt, fa(A), fa(E[0]), fa(E[1]), fa(E[2]), C.byref(bc), C.byref(info), st))
+        FL = [[to_fab(np.zeros((1,) + n[::-1]), b, 0, t, dev) for b in bxs] for t in types]
+        lib.check(lib.iamrx_diffusion_get_fluxes(lev.h, 1, fa(FL[0]), fa(FL[1]), fa(FL[2]), fa(Sol), dt, fa(E[0]), fa(E[1]), fa(E[2]), 1.0, st))
+        sync(dev)
+        new = s_old.copy()
+        for (t, _), (lo, hi) in zip(Sol, bxs):
+            new[:, lo[2]:hi[2] + 1, lo[1]:hi[1] + 1, lo[0]:hi[0] + 1] = t.cpu().numpy()[:, 1:-1, 1:-1, 1:-1]
+        return new, FL
+
+    sc1, FC = implicit_step(clev, [cbox], nc, sc0, eta_c, dt_c)
+    reg = C.c_void_p()
+    lib.check(lib.iamrx_fluxreg_create(clev.h, flev.h, 1, C.byref(reg)))
+    lib.check(lib.iamrx_fluxreg_crse_add(reg, fa(FC[0]), fa(FC[1]), fa(FC[2]), 1.0, vol_c, st))
+    CS = [to_fab(sc1, cbox, 0, ix.CELL, dev)]
+    sf = sf0
+    for step in range(2):
+        sf, FF = implicit_step(flev, boxes, nf, sf, eta_f, dt_f, crse_sol=CS)
+        lib.check(lib.iamrx_fluxreg_fine_add(reg, fa(FF[0]), fa(FF[1]), fa(FF[2]), 1.0, vol_c, st))
+    ST = [to_fab(sc1, cbox, 0, ix.CELL, dev)]
+    lib.check(lib.iamrx_fluxreg_reflux(reg, fa(ST), 0, 1.0, st))
+    sync(dev)
+    sc2 = ST[0][0].cpu().numpy()
+    total = lambda c, f: (c[0] * (~cov)).sum() * dxc ** 3 + (f[0] * fmask).sum() * dxf ** 3
+    t0, t_noreflux, t1 = total(sc0, sf0), total(sc1, sf), total(sc2, sf)
+    assert abs(t_noreflux - t0) > 1e-7 * abs(t0)
+    assert abs(t1 - t0) <= 1e-11 * abs(t0)
+    lib.iamrx_fluxreg_destroy(reg)
+    clev.close(); flev.close()
