@@ -158,6 +158,39 @@ def main():
         ref = rphi[:, 1 + lo[2] - flo[2]:2 + hi[2] - flo[2], 1 + lo[1] - flo[1]:2 + hi[1] - flo[1], 1 + lo[0] - flo[0]:2 + hi[0] - flo[0]]
         assert np.abs(got - ref).max() <= 2e-10, ("coarse-fine mac_project", rank, float(np.abs(got - ref).max()))
 
+    # 5b. the level > 0 nodal projection with the fine boxes on different ranks: FillCoarsePatch of the pressure (coarse data on the
+    #     other rank), interior zeroed, coarse-fine boundary nodes kept as Dirichlet data -- against the oracle on the patch
+    DIR_ = 1
+    cpress = 0.02 * smooth_field(NC, 221, 1)
+    velg = smooth_field(NF, 222, 3) + 0.2 * hash_uniform(223, (3,) + NF[::-1])
+    sigg = 1.0 / (1.0 + 0.3 * hash_uniform(224, (1,) + NF[::-1]))
+    Gn = wp(orc.interp(1, NC, cpress), 2)
+    Pg = np.zeros_like(Gn)
+    ilo, ihi = [flo[d] + 2 for d in range(3)], [fhi[d] + 1 + 2 for d in range(3)]
+    for d in range(3):
+        for pl in (ilo[d], ihi[d]):
+            sl = [slice(None), slice(ilo[2], ihi[2] + 1), slice(ilo[1], ihi[1] + 1), slice(ilo[0], ihi[0] + 1)]
+            sl[3 - d] = slice(pl, pl + 1)
+            Pg[tuple(sl)] = Gn[tuple(sl)]
+    cutg = lambda P, g, ng: np.ascontiguousarray(P[:, flo[2] - ng + g:fhi[2] + ng + g + 1, flo[1] - ng + g:fhi[1] + ng + g + 1, flo[0] - ng + g:fhi[0] + ng + g + 1])
+    mgn = orc.mg_default(rtol=1e-12)
+    rvel, rphi_n, rgp, rcn, mgn = orc.nodal_project_bc(n, (0, 1, 0), dxf, cutg(wp(velg, 1), 1, 1), cutg(sigg, 0, 0), cutg(Pg, 2, 2), (DIR_, PER_, DIR_), (DIR_, PER_, DIR_), mgn)
+    assert rcn == 0
+    VV = [to_fab(velg, fboxes[i], 1, ix.CELL, "cpu") for i in fmine]
+    SG = [to_fab(sigg, fboxes[i], 0, ix.CELL, "cpu") for i in fmine]
+    PN = [to_fab(np.zeros((1,) + NF[::-1]), fboxes[i], 1, ix.NODE, "cpu") for i in fmine]
+    CPN = [to_fab(cpress, cboxes[i], 0, ix.NODE, "cpu") for i in cmine]
+    lib.check(lib.iamrx_fill_coarse_patch_nodal(flev.h, clev.h, fa(PN), None, fa(CPN), 0.0, 1.0, 0.5, st))
+    for t, _ in PN:
+        t[:, 2:-2, 2:-2, 2:-2] = 0.0
+    infon = _mg(lib, rtol=1e-12)
+    lib.check(lib.iamrx_nodal_project(flev.h, fa(VV), fa(SG), fa(PN), None, 0, None, None, C.byref(infon), st))
+    for (t, _), i in zip(VV, fmine):
+        lo, hi = fboxes[i]
+        got = t.numpy()[:, 1:-1, 1:-1, 1:-1]
+        ref = rvel[:, 1 + lo[2] - flo[2]:2 + hi[2] - flo[2], 1 + lo[1] - flo[1]:2 + hi[1] - flo[1], 1 + lo[0] - flo[0]:2 + hi[0] - flo[0]]
+        assert np.abs(got - ref).max() <= 1e-9, ("coarse-fine nodal_project", rank, float(np.abs(got - ref).max()))
+
     # 6. SyncRegister: CrseInit on the coarse boxes of both ranks, FineAdd from fine boxes on both ranks (one replicated accumulation
     #    + all-reduce), InitRHS -- against oracle/syncreg.py
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
