@@ -90,12 +90,18 @@ static int coarse_fine_sides(const Level& L, const Bx& b) {
       S.lo[d] = S.hi[d] = side == 0 ? b.lo[d] - 1 : b.hi[d] + 1;
       if (!L.geom.periodic[d] && (S.lo[d] < dom.lo[d] || S.hi[d] > dom.hi[d])) continue;   // a physical side
       int64_t covered = 0;
+      const int64_t need = S.npts();
       int sh[3];
-      for (sh[2] = -1; sh[2] <= 1; ++sh[2])
-        for (sh[1] = -1; sh[1] <= 1; ++sh[1])
-          for (sh[0] = -1; sh[0] <= 1; ++sh[0]) {
+      for (sh[2] = -1; sh[2] <= 1 && covered < need; ++sh[2])
+        for (sh[1] = -1; sh[1] <= 1 && covered < need; ++sh[1])
+          for (sh[0] = -1; sh[0] <= 1 && covered < need; ++sh[0]) {
             bool ok = true;
-            for (int q = 0; q < 3; ++q) if (sh[q] != 0 && !L.geom.periodic[q]) ok = false;
+            for (int q = 0; q < 3; ++q) {
+              if (sh[q] != 0 && !L.geom.periodic[q]) ok = false;
+              // an image shifted by a whole period can only reach the slab if the slab lies at that end of the domain
+              if (sh[q] > 0 && S.hi[q] <= dom.hi[q]) ok = false;
+              if (sh[q] < 0 && S.lo[q] >= dom.lo[q]) ok = false;
+            }
             if (!ok) continue;
             for (const Bx& o : L.boxes) {
               Bx t = o;
