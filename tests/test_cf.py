@@ -775,3 +775,49 @@ def test_two_level_implicit_diffusion_conserves(backend):
     assert abs(t1 - t0) <= 1e-11 * abs(t0)
     lib.iamrx_fluxreg_destroy(reg)
     clev.close(); flev.close()
+
+
+@pytest.mark.parametrize("nb", [(1, 1, 1), (2, 2, 2)])
+def test_coarse_fine_solve_reproduces_quadratic_potentials(backend, nb):
+    """Exactness (no oracle): for a quadratic potential the face differences are the exact gradients, the 7-point operator is exact,
+    the tangential interpolation of the coarse data is exact (test_set_coarse_fine_bc_is_exact_for_quadratics) and so is the order-4
+    extrapolation into the ghost cells -- the fine-level MAC solve must return the potential itself, to solver tolerance."""
+    lib, dev = backend
+    per = (0, 0, 0)
+    nc, nf = (16, 16, 16), (32, 32, 32)
+    clo, chi = (4, 4, 4), (11, 11, 11)
+    flo, fhi = tuple(2 * c for c in clo), tuple(2 * c + 1 for c in chi)
+    h = 1.0 / nf[0]
+    pe = lambda x, y, z: 0.3 + 1.1 * x - 0.7 * y + 0.4 * z + 0.9 * x * x - 1.3 * y * y + 0.6 * z * z + 0.8 * x * y - 0.5 * y * z + 0.7 * x * z
+    cen = lambda k: (np.arange(k) + 0.5) / k
+    edg = lambda k: np.arange(k) / float(k)
+    Zc, Yc, Xc = np.meshgrid(cen(nc[2]), cen(nc[1]), cen(nc[0]), indexing="ij")
+    cphi = pe(Xc, Yc, Zc)[None]
+    Z, Y, X = np.meshgrid(cen(nf[2]), cen(nf[1]), edg(nf[0]), indexing="ij"); um = (pe(X + 0.5 * h, Y, Z) - pe(X - 0.5 * h, Y, Z)) / h
+    Z, Y, X = np.meshgrid(cen(nf[2]), edg(nf[1]), cen(nf[0]), indexing="ij"); vm = (pe(X, Y + 0.5 * h, Z) - pe(X, Y - 0.5 * h, Z)) / h
+    Z, Y, X = np.meshgrid(edg(nf[2]), cen(nf[1]), cen(nf[0]), indexing="ij"); wm = (pe(X, Y, Z + 0.5 * h) - pe(X, Y, Z - 0.5 * h)) / h
+    M2 = [_wrap_pad(q[None], 2) for q in (um, vm, wm)]     # (the wrapped padding is never read: the patch is interior)
+    boxes = _patch_boxes(clo, chi, nb)
+    clev = ix.Level(lib, ix.Geom.make(nc, periodic=per), [((0, 0, 0), tuple(q - 1 for q in nc))])
+    flev = ix.Level(lib, ix.Geom.make(nf, periodic=per), boxes)
+    gshape = (1, nf[2] + 2, nf[1] + 2, nf[0] + 2)
+    U = [[fab_from_padded(M2[d], 2, b, 1, t, dev) for b in boxes] for d, t in enumerate((ix.XFACE, ix.YFACE, ix.ZFACE))]
+    R = [fab_from_padded(np.ones(gshape), 1, b, 1, ix.CELL, dev) for b in boxes]
+    P = [fab_from_padded(np.zeros(gshape), 1, b, 1, ix.CELL, dev) for b in boxes]
+    CP = _coarse_fabs(cphi, nc, dev)
+    fa = lambda L: fab_array([p[1] for p in L])
+    lib.check(lib.iamrx_set_coarse_fine_bc(flev.h, clev.h, fa(P), fa(CP), 1, stream_of(dev)))
+    info = _mg(lib, rtol=1e-13, maxorder=4)
+    neu = (C.c_int * 3)(NEU, NEU, NEU)
+    lib.check(lib.iamrx_mac_project(flev.h, fa(U[0]), fa(U[1]), fa(U[2]), fa(R), None, fa(P), 1.0, neu, neu, C.byref(info), stream_of(dev)))
+    sync(dev)
+    gphi, _ = scatter_valid(np.zeros(gshape), 1, [p[0] for p in P], boxes, 1, ix.CELL)
+    Zf, Yf, Xf = np.meshgrid(cen(nf[2]), cen(nf[1]), cen(nf[0]), indexing="ij")
+    exact = pe(Xf, Yf, Zf)[None]
+    assert np.abs(_cut(gphi, 1, flo, fhi, 0) - _cut(exact, 0, flo, fhi, 0)).max() <= 1e-10
+    # and the projected MAC velocities vanish: u_mac - grad(phi) = 0
+    for d, t in enumerate((ix.XFACE, ix.YFACE, ix.ZFACE)):
+        got, _ = scatter_valid(np.zeros(gshape), 1, [p[0] for p in U[d]], boxes, 1, t)
+        ext = [1 if q == d else 0 for q in range(3)]
+        assert np.abs(_cut(got, 1, flo, tuple(fhi[q] + ext[q] for q in range(3)), 0)).max() <= 1e-8
+    clev.close(); flev.close()
