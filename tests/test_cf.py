@@ -821,3 +821,55 @@ def test_coarse_fine_solve_reproduces_quadratic_potentials(backend, nb):
         ext = [1 if q == d else 0 for q in range(3)]
         assert np.abs(_cut(got, 1, flo, tuple(fhi[q] + ext[q] for q in range(3)), 0)).max() <= 1e-8
     clev.close(); flev.close()
+
+
+@pytest.mark.parametrize("shape", ["patch", "L3", "L5"])
+def test_nodal_coarse_fine_projection_reproduces_harmonic_q1_fields(backend, shape):
+    """Exactness (no oracle): with sigma = 1 and a constant velocity the nodal right-hand side vanishes at interior nodes, and the
+    Q1 operator annihilates every harmonic function of its own space (1, x, y, z, xy, xz, yz, xyz).  Given such a function on the
+    coarse-fine boundary nodes -- of a rectangular patch or of an L-shaped level with its re-entrant edge -- the level > 0 nodal
+    projection must return it on all nodes, and the velocity must come out as the constant minus its exact gradient."""
+    lib, dev = backend
+    nf = (32, 32, 32)
+    per = (1, 1, 1)
+    boxes = {"patch": _patch_boxes((4, 4, 4), (11, 11, 11), (2, 1, 1)), "L3": L_SHAPES[0], "L5": L_SHAPES[1]}[shape]
+    pe = lambda x, y, z: 0.3 + 1.1 * x - 0.7 * y + 0.4 * z + 0.8 * x * y - 0.5 * y * z + 0.7 * x * z + 0.9 * x * y * z
+    gx = lambda x, y, z: 1.1 + 0.8 * y + 0.7 * z + 0.9 * y * z
+    gy = lambda x, y, z: -0.7 + 0.8 * x - 0.5 * z + 0.9 * x * z
+    gz = lambda x, y, z: 0.4 - 0.5 * y + 0.7 * x + 0.9 * x * y
+    cells = np.zeros(nf[::-1], dtype=bool)
+    for lo, hi in boxes:
+        cells[lo[2]:hi[2] + 1, lo[1]:hi[1] + 1, lo[0]:hi[0] + 1] = True
+    pc = np.pad(cells, 1)
+    cnt = sum(pc[1 - dk:pc.shape[0] - dk, 1 - dj:pc.shape[1] - dj, 1 - di:pc.shape[2] - di].astype(int) for dk in (0, 1) for dj in (0, 1) for di in (0, 1))
+    cnt = cnt[:nf[2] + 1, :nf[1] + 1, :nf[0] + 1]
+    bnd, inner = (cnt > 0) & (cnt < 8), cnt == 8
+    nod = np.arange(nf[0] + 1) / float(nf[0])
+    Zn, Yn, Xn = np.meshgrid(nod, nod, nod, indexing="ij")
+    exact = pe(Xn, Yn, Zn)
+    Pg = np.zeros((1, nf[2] + 5, nf[1] + 5, nf[0] + 5))
+    view = Pg[0, 2:2 + nf[2] + 1, 2:2 + nf[1] + 1, 2:2 + nf[0] + 1]
+    view[bnd] = exact[bnd]
+    vconst = np.array([0.6, -0.4, 0.2])
+    V = np.broadcast_to(vconst[:, None, None, None], (3, nf[2] + 2, nf[1] + 2, nf[0] + 2)).copy()
+    flev = ix.Level(lib, ix.Geom.make(nf, periodic=per), boxes)
+    Vv = [fab_from_padded(V, 1, b, 1, ix.CELL, dev) for b in boxes]
+    Sg = [fab_from_padded(np.ones((1,) + nf[::-1]), 0, b, 0, ix.CELL, dev) for b in boxes]
+    Ph = [fab_from_padded(Pg, 2, b, 1, ix.NODE, dev) for b in boxes]
+    Gp = [fab_from_padded(np.zeros((3,) + nf[::-1]), 0, b, 0, ix.CELL, dev) for b in boxes]
+    fa = lambda L: fab_array([p[1] for p in L])
+    info = _mg(lib, rtol=1e-13)
+    lib.check(lib.iamrx_nodal_project(flev.h, fa(Vv), fa(Sg), fa(Ph), fa(Gp), 0, None, None, C.byref(info), stream_of(dev)))
+    sync(dev)
+    gp_, dup = scatter_valid(np.zeros(Pg.shape), 2, [p[0] for p in Ph], boxes, 1, ix.NODE)
+    phi = gp_[0, 2:2 + nf[2] + 1, 2:2 + nf[1] + 1, 2:2 + nf[0] + 1]
+    assert inner.sum() > 1000
+    assert np.abs(phi[inner] - exact[inner]).max() <= 1e-10
+    cen = (np.arange(nf[0]) + 0.5) / nf[0]
+    Zc, Yc, Xc = np.meshgrid(cen, cen, cen, indexing="ij")
+    gv, _ = scatter_valid(np.zeros((3, nf[2] + 2, nf[1] + 2, nf[0] + 2)), 1, [p[0] for p in Vv], boxes, 1, ix.CELL)
+    gg, _ = scatter_valid(np.zeros((3,) + nf[::-1]), 0, [p[0] for p in Gp], boxes, 0, ix.CELL)
+    for c, g in enumerate((gx, gy, gz)):
+        assert np.abs(gg[c][cells] - g(Xc, Yc, Zc)[cells]).max() <= 1e-8
+        assert np.abs(gv[c, 1:-1, 1:-1, 1:-1][cells] - (vconst[c] - g(Xc, Yc, Zc))[cells]).max() <= 1e-8
+    flev.close()
