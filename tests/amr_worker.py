@@ -128,7 +128,7 @@ def main():
         assert np.abs(div).max() <= 1e-11, ("create_umac_grown: divergence of the corrected halo", rank, float(np.abs(div).max()))
 
     # 5. the level > 0 MAC solve: setCoarseFineBC (collective: coarse data on the other rank) + coarse-fine Dirichlet sides in the
-    #    multigrid, fine boxes on different ranks, against the oracle solving on the patch as its own domain (tests/test_cf.py)
+    #    multigrid, fine boxes on different ranks, against the oracle solving on the patch as its own domain (tests/test_twolevel.py)
     from test_bc import _mg
     CF, PER_ = 5, 0
     flo, fhi = (4, 0, 4), (11, 15, 11)

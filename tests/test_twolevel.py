@@ -432,7 +432,7 @@ def test_nodal_project_coarse_fine_node_mask_path():
     import sys
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     env = dict(os.environ, IAMRX_NODAL_CF_MASK="1")
-    r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(root, "tests", "test_cf.py"), "-q", "-x", "-m", "not gpu", "-k",
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(root, "tests", "test_twolevel.py"), "-q", "-x", "-m", "not gpu", "-k",
                         "test_nodal_project_coarse_fine and emul"], env=env, capture_output=True, text=True, timeout=900)
     assert r.returncode == 0 and "3 passed" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
 
