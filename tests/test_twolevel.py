@@ -882,3 +882,81 @@ def test_nodal_coarse_fine_projection_reproduces_harmonic_q1_fields(backend, sha
         assert np.abs(gg[c][cells] - g(Xc, Yc, Zc)[cells]).max() <= 1e-8
         assert np.abs(gv[c, 1:-1, 1:-1, 1:-1][cells] - (vconst[c] - g(Xc, Yc, Zc))[cells]).max() <= 1e-8
     flev.close()
+
+
+def test_fine_level_chain_preserves_a_free_stream(backend):
+    """Free-stream preservation through the level > 0 chain (no oracle): a uniform velocity with constant density on both levels.
+    FillPatchTwoLevels must hand back the same constants in the ghost cells (conservative interpolation of a constant), ExtrapVelToFaces
+    the same face velocities, the coarse-fine MAC projection (coarse potential zero) no correction, create_umac_grown no change in
+    the halo, ComputeAofs zero, and the coarse-fine nodal projection (coarse pressure zero) no pressure and no velocity change."""
+    lib, dev = backend
+    from util import box_of
+    from test_bc import bcrec_array
+    per = (1, 1, 1)
+    nc, nf = (16, 16, 16), (32, 32, 32)
+    clo, chi = (4, 4, 4), (11, 11, 11)
+    boxes = _patch_boxes(clo, chi, (2, 1, 2))
+    u0 = np.array([0.7, -0.4, 0.25])
+    dx = 1.0 / nf[0]
+    dt = 0.4 * dx / 0.7
+    clev = ix.Level(lib, ix.Geom.make(nc, periodic=per), [((0, 0, 0), tuple(m - 1 for m in nc))])
+    fgeom = ix.Geom.make(nf, periodic=per)
+    flev = ix.Level(lib, fgeom, boxes)
+    fa = lambda L: fab_array([p[1] for p in L])
+    st = stream_of(dev)
+    const = lambda shape: np.broadcast_to(u0[:, None, None, None], (3,) + shape).copy()
+    cov = _covered(nc, clo, chi)
+    fmask = np.repeat(np.repeat(np.repeat(cov, 2, 0), 2, 1), 2, 2)
+    sentinel = np.where(np.pad(fmask, 3, mode="wrap")[None], const((nf[2] + 6, nf[1] + 6, nf[0] + 6)), 1.0e30)
+    VF = [fab_from_padded(sentinel, 3, b, 3, ix.CELL, dev) for b in boxes]
+    UC = _coarse_fabs(const(nc[::-1]), nc, dev)
+    lib.check(lib.iamrx_fillpatch_two_levels(flev.h, clev.h, fa(VF), None, fa(UC), 0.0, 1.0, 1.0, 3, 3, None, None, st))
+    sync(dev)
+    for t, _ in VF:
+        assert np.abs(t.cpu().numpy() - u0[:, None, None, None]).max() <= 1e-15
+    bcr = bcrec_array([(0, 0, 0)] * 3, [(0, 0, 0)] * 3)
+    types = (ix.XFACE, ix.YFACE, ix.ZFACE)
+    U = [[], [], []]
+    for (tv, fv), b in zip(VF, boxes):
+        tf, ff = fab_from_padded(np.zeros((3, nf[2] + 2, nf[1] + 2, nf[0] + 2)), 1, b, 1, ix.CELL, dev)
+        mm = [fab_from_padded(np.full((1, nf[2] + 4, nf[1] + 4, nf[0] + 4), 1.0e30), 2, b, 1, t, dev) for t in types]
+        bb = box_of(*b)
+        lib.check(lib.iamrx_extrap_vel_to_faces_box(C.byref(bb), C.byref(fv), C.byref(ff), C.byref(mm[0][1]), C.byref(mm[1][1]), C.byref(mm[2][1]),
+                                                    bcr, C.byref(fgeom), dt, 0, st))
+        for d in range(3):
+            U[d].append(mm[d])
+    gs = (1, nf[2] + 2, nf[1] + 2, nf[0] + 2)
+    R = [fab_from_padded(np.ones(gs), 1, b, 1, ix.CELL, dev) for b in boxes]
+    P = [fab_from_padded(np.zeros(gs), 1, b, 1, ix.CELL, dev) for b in boxes]
+    CP = _coarse_fabs(np.zeros((1,) + nc[::-1]), nc, dev)
+    lib.check(lib.iamrx_set_coarse_fine_bc(flev.h, clev.h, fa(P), fa(CP), 1, st))
+    info = _mg(lib, rtol=1e-12, atol=1e-9, maxorder=4)   # (atol: a round-off sized residual must not be iterated on)
+    lib.check(lib.iamrx_mac_project(flev.h, fa(U[0]), fa(U[1]), fa(U[2]), fa(R), None, fa(P), 2.0 / dt, None, None, C.byref(info), st))
+    assert info.iters == 0                        # already divergence free
+    UCM = [[(lambda tt: (tt, ix.fab_of(tt, [0, 0, 0])))(__import__("torch").from_numpy(np.full(
+        (1,) + tuple(nc[2 - q] + (1 if q == 2 - d else 0) for q in range(3)), u0[d])).to(dev))] for d in range(3)]
+    lib.check(lib.iamrx_create_umac_grown(flev.h, clev.h, fa(U[0]), fa(U[1]), fa(U[2]), fa(UCM[0]), fa(UCM[1]), fa(UCM[2]), None, st))
+    sync(dev)
+    for d in range(3):
+        for t, _ in U[d]:
+            assert np.abs(t.cpu().numpy() - u0[d]).max() <= 1e-13      # valid faces and the whole ghost layer
+    ic = (C.c_int * 3)(0, 0, 0)
+    for il, ((tv, fv), b) in enumerate(zip(VF, boxes)):
+        ta, fa_ = fab_from_padded(np.full((3,) + nf[::-1], 9.0), 0, b, 0, ix.CELL, dev)
+        bb = box_of(*b)
+        lib.check(lib.iamrx_compute_aofs_box(C.byref(bb), C.byref(fa_), 0, C.byref(fv), 0, 3, None, 0, None,
+                                             C.byref(U[0][il][1]), C.byref(U[1][il][1]), C.byref(U[2][il][1]), None, None, None,
+                                             None, None, None, None, None, None, ic, bcr, C.byref(fgeom), dt, ix.ADV_IS_VELOCITY, st))
+        sync(dev)
+        assert np.abs(ta.cpu().numpy()).max() <= 1e-11
+    # nodal projection of U0 / dt with a zero coarse pressure on the boundary nodes
+    Vv = [fab_from_padded(const((nf[2] + 2, nf[1] + 2, nf[0] + 2)) / dt, 1, b, 1, ix.CELL, dev) for b in boxes]
+    Sg = [fab_from_padded(np.ones((1,) + nf[::-1]), 0, b, 0, ix.CELL, dev) for b in boxes]
+    Ph = [fab_from_padded(np.zeros((1, nf[2] + 5, nf[1] + 5, nf[0] + 5)), 2, b, 1, ix.NODE, dev) for b in boxes]
+    infon = _mg(lib, rtol=1e-12, atol=1e-9)
+    lib.check(lib.iamrx_nodal_project(flev.h, fa(Vv), fa(Sg), fa(Ph), None, 0, None, None, C.byref(infon), st))
+    sync(dev)
+    for (t, _), (p, _) in zip(Vv, Ph):
+        assert np.abs(p.cpu().numpy()).max() <= 1e-9 * 0.7 / dt * dx
+        assert np.abs(t.cpu().numpy()[:, 1:-1, 1:-1, 1:-1] * dt - u0[:, None, None, None]).max() <= 1e-10
+    clev.close(); flev.close()
