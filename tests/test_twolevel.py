@@ -746,7 +746,7 @@ def test_two_level_implicit_diffusion_conserves(backend):
         Rhs = [to_fab(s_old, b, 0, ix.CELL, dev) for b in bxs]
         if crse_sol is not None:
             lib.check(lib.iamrx_set_coarse_fine_bc(flev.h, clev.h, fa(Sol), fa(crse_sol), 1, st))
-        info = _mg(lib, rtol=1e-13)
+        info = _mg(lib, rtol=1e-12)
         lib.check(lib.iamrx_diffusion_solve(lev.h, 0, 1, fa(Sol), fa(Rhs), 1.0, dt, fa(A), fa(E[0]), fa(E[1]), fa(E[2]), C.byref(bc), C.byref(info), st))
         FL = [[to_fab(np.zeros((1,) + n[::-1]), b, 0, t, dev) for b in bxs] for t in types]
         lib.check(lib.iamrx_diffusion_get_fluxes(lev.h, 1, fa(FL[0]), fa(FL[1]), fa(FL[2]), fa(Sol), dt, fa(E[0]), fa(E[1]), fa(E[2]), 1.0, st))
@@ -772,7 +772,7 @@ def test_two_level_implicit_diffusion_conserves(backend):
     total = lambda c, f: (c[0] * (~cov)).sum() * dxc ** 3 + (f[0] * fmask).sum() * dxf ** 3
     t0, t_noreflux, t1 = total(sc0, sf0), total(sc1, sf), total(sc2, sf)
     assert abs(t_noreflux - t0) > 1e-7 * abs(t0)
-    assert abs(t1 - t0) <= 1e-11 * abs(t0)
+    assert abs(t1 - t0) <= 1e-10 * abs(t0)
     lib.iamrx_fluxreg_destroy(reg)
     clev.close(); flev.close()
 
@@ -816,19 +816,19 @@ def test_coarse_fine_solve_reproduces_quadratic_potentials(backend, nb):
     CP = _coarse_fabs(cphi, nc, dev)
     fa = lambda L: fab_array([p[1] for p in L])
     lib.check(lib.iamrx_set_coarse_fine_bc(flev.h, clev.h, fa(P), fa(CP), 1, stream_of(dev)))
-    info = _mg(lib, rtol=1e-13, maxorder=4)
+    info = _mg(lib, rtol=1e-12, maxorder=4)
     neu = (C.c_int * 3)(NEU, NEU, NEU)
     lib.check(lib.iamrx_mac_project(flev.h, fa(U[0]), fa(U[1]), fa(U[2]), fa(R), None, fa(P), 1.0, neu, neu, C.byref(info), stream_of(dev)))
     sync(dev)
     gphi, _ = scatter_valid(np.zeros(gshape), 1, [p[0] for p in P], boxes, 1, ix.CELL)
     Zf, Yf, Xf = np.meshgrid(cen(nf[2]), cen(nf[1]), cen(nf[0]), indexing="ij")
     exact = pe(Xf, Yf, Zf)[None]
-    assert np.abs(gphi[:, 1:-1, 1:-1, 1:-1] - exact)[:, fcells].max() <= 1e-10
+    assert np.abs(gphi[:, 1:-1, 1:-1, 1:-1] - exact)[:, fcells].max() <= 1e-9
     # and the projected MAC velocities vanish: u_mac - grad(phi) = 0
     for d, t in enumerate((ix.XFACE, ix.YFACE, ix.ZFACE)):
         got, _ = scatter_valid(np.zeros(gshape), 1, [p[0] for p in U[d]], boxes, 1, t)
         ffaces = fcells | np.roll(fcells, 1, 2 - d)      # the faces of the fine cells
-        assert np.abs(got[:, 1:-1, 1:-1, 1:-1][:, ffaces]).max() <= 1e-8
+        assert np.abs(got[:, 1:-1, 1:-1, 1:-1][:, ffaces]).max() <= 1e-7
     clev.close(); flev.close()
 
 
@@ -867,20 +867,20 @@ def test_nodal_coarse_fine_projection_reproduces_harmonic_q1_fields(backend, sha
     Ph = [fab_from_padded(Pg, 2, b, 1, ix.NODE, dev) for b in boxes]
     Gp = [fab_from_padded(np.zeros((3,) + nf[::-1]), 0, b, 0, ix.CELL, dev) for b in boxes]
     fa = lambda L: fab_array([p[1] for p in L])
-    info = _mg(lib, rtol=1e-13)
+    info = _mg(lib, rtol=1e-12)
     lib.check(lib.iamrx_nodal_project(flev.h, fa(Vv), fa(Sg), fa(Ph), fa(Gp), 0, None, None, C.byref(info), stream_of(dev)))
     sync(dev)
     gp_, dup = scatter_valid(np.zeros(Pg.shape), 2, [p[0] for p in Ph], boxes, 1, ix.NODE)
     phi = gp_[0, 2:2 + nf[2] + 1, 2:2 + nf[1] + 1, 2:2 + nf[0] + 1]
     assert inner.sum() > 1000
-    assert np.abs(phi[inner] - exact[inner]).max() <= 1e-10
+    assert np.abs(phi[inner] - exact[inner]).max() <= 1e-9
     cen = (np.arange(nf[0]) + 0.5) / nf[0]
     Zc, Yc, Xc = np.meshgrid(cen, cen, cen, indexing="ij")
     gv, _ = scatter_valid(np.zeros((3, nf[2] + 2, nf[1] + 2, nf[0] + 2)), 1, [p[0] for p in Vv], boxes, 1, ix.CELL)
     gg, _ = scatter_valid(np.zeros((3,) + nf[::-1]), 0, [p[0] for p in Gp], boxes, 0, ix.CELL)
     for c, g in enumerate((gx, gy, gz)):
-        assert np.abs(gg[c][cells] - g(Xc, Yc, Zc)[cells]).max() <= 1e-8
-        assert np.abs(gv[c, 1:-1, 1:-1, 1:-1][cells] - (vconst[c] - g(Xc, Yc, Zc))[cells]).max() <= 1e-8
+        assert np.abs(gg[c][cells] - g(Xc, Yc, Zc)[cells]).max() <= 1e-7
+        assert np.abs(gv[c, 1:-1, 1:-1, 1:-1][cells] - (vconst[c] - g(Xc, Yc, Zc))[cells]).max() <= 1e-7
     flev.close()
 
 
