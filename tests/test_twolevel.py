@@ -1,7 +1,14 @@
-"""The coarse-fine boundary of fine-level cell-centred solves (MacProj.cpp:1164-1168 setCoarseFineBC + setLevelBC,
-Diffusion.cpp:395,518): iamrx_set_coarse_fine_bc (InterpBndryData, order 3) and iamrx_mac_project / iamrx_diffusion_solve on a level
-whose boxes do not tile the domain, through the C ABI vs the oracle (which solves on the fine PATCH as its own domain with
-coarse-fine Dirichlet sides) and vs analytic fields."""
+"""Level > 0 of a two-level hierarchy through the C ABI.
+  * the coarse-fine boundary of the cell-centred solves: iamrx_set_coarse_fine_bc (setCoarseFineBC: InterpBndryData, order 3;
+    MacProj.cpp:1164-1168, Diffusion.cpp:395,518) and iamrx_mac_project / iamrx_diffusion_solve on a level whose boxes do not tile the
+    domain -- vs the oracle (which solves on the fine PATCH as its own domain with coarse-fine Dirichlet sides), vs analytic fields
+    (accuracy, exactness for quadratics / linears), on rectangular patches, against walls, and on L-shaped levels;
+  * the coarse-fine Dirichlet nodes of the nodal projection (Projection.cpp:236-257) after FillCoarsePatch -- vs the oracle, the
+    node-mask bookkeeping for levels of general shape, exactness for harmonic Q1 fields;
+  * compositions in the reference's order: the first half of a fine-level advance vs the oracle's pieces, two-level subcycled
+    conservative advection and implicit diffusion with flux registers / reflux / avgDown (composite conservation), free-stream
+    preservation through the whole fine-level chain.
+These tests were added after the round's GPU budget was spent: they have run through the host-emulation build only."""
 import ctypes as C
 
 import numpy as np
