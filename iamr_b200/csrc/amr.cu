@@ -335,7 +335,11 @@ struct FluxReg {
   int ncomp = 0;
   MF reg;                      // on the coarse level, 0 ghost; nonzero only on interface cells
   struct Patch { int cbox; int fbox; int d; int side; Bx R; int shift[3]; };   // R in the index space of coarse box cbox; fine = R - shift
-  std::vector<Patch> patches;
+  std::vector<Patch> patches;       // cbox = LOCAL index of a coarse box of this rank; fbox = index into fine->boxes
+  // several ranks: the interface regions of ALL coarse boxes (FineAdd goes through one replicated array over the coarse domain:
+  // every rank adds the contributions of its own fine boxes, an all-reduce sums them, each rank keeps what lies in its coarse boxes)
+  std::vector<Patch> all_patches;   // cbox unused
+  std::vector<int> fine_local;      // index into fine->boxes -> local index on this rank, or -1
 };
 
 static void subtract_boxes(std::vector<Bx>& pieces, const Bx& cut) {
@@ -354,8 +358,9 @@ static void subtract_boxes(std::vector<Bx>& pieces, const Bx& cut) {
 
 int fluxreg_build(FluxReg& F, Level* crse, Level* fine, int ncomp) {
   F.crse = crse; F.fine = fine; F.ncomp = ncomp;
-  for (size_t b = 0; b < crse->boxes.size(); ++b) if (crse->owner[b] != comm().rank) { set_error("flux register: every coarse box must live on this rank"); return IAMRX_ERR_ARG; }
-  for (size_t b = 0; b < fine->boxes.size(); ++b) if (fine->owner[b] != comm().rank) { set_error("flux register: every fine box must live on this rank"); return IAMRX_ERR_ARG; }
+  F.fine_local.assign(fine->boxes.size(), -1);
+  for (int il = 0; il < fine->nlocal(); ++il) F.fine_local[fine->local[il]] = il;
+  const bool distributed = comm().nranks > 1 && !crse->replicated;
   F.reg.define(crse, IX_CELL, ncomp, 0);
   std::vector<Bx> cf;   // coarsened fine boxes
   for (const Bx& fb : fine->boxes) {
@@ -395,13 +400,18 @@ int fluxreg_build(FluxReg& F, Level* crse, Level* fine, int ncomp) {
               for (int q = 0; q < 3; ++q) { o.lo[q] += th[q]; o.hi[q] += th[q]; }
               subtract_boxes(pieces, o);
             }
-          for (const Bx& pc : pieces)
+          for (const Bx& pc : pieces) {
             for (int cb = 0; cb < crse->nlocal(); ++cb) {
               const Bx is = intersect(pc, crse->lbox(cb));
               if (!is.ok()) continue;
               FluxReg::Patch P{cb, (int)fbi, d, side, is, {sh[0], sh[1], sh[2]}};
               F.patches.push_back(P);
             }
+            if (distributed && F.fine_local[fbi] >= 0) {   // the coarse boxes tile the domain: the whole piece belongs to some rank
+              FluxReg::Patch P{-1, (int)fbi, d, side, pc, {sh[0], sh[1], sh[2]}};
+              F.all_patches.push_back(P);
+            }
+          }
         }
       }
   return IAMRX_OK;
@@ -512,6 +522,27 @@ int iamrx_fluxreg_fine_add(iamrx_fluxreg_t r, const iamrx_fab* fx, const iamrx_f
   IX_ARG(r && fx && fy && fz && vol_crse > 0.0, "fluxreg_fine_add arguments");
   const iamrx_fab* f[3] = {fx, fy, fz};
   FluxReg& F = r->F;
+  if (comm().nranks > 1 && !F.crse->replicated) {
+    // fine and coarse boxes of an interface may live on different ranks
+    cudaStream_t s = (cudaStream_t)stream;
+    std::vector<Bx> one{F.crse->domain};
+    std::vector<int> own{comm().rank};
+    std::unique_ptr<Level> RL = make_level(F.crse->geom, one, own);
+    RL->replicated = true;
+    MF acc(RL.get(), IX_CELL, F.ncomp, 0);
+    IX_TRY(mf_setval(acc, 0.0, 0, F.ncomp, 0, s));
+    for (const FluxReg::Patch& P : F.all_patches) {
+      const int fc_off = P.side < 0 ? 1 : 0;
+      const double sgn = P.side < 0 ? -1.0 : 1.0;
+      iamrx_fab ff = f[P.d][F.fine_local[P.fbox]];
+      for (int q = 0; q < 3; ++q) { ff.lo[q] += 2 * P.shift[q]; ff.hi[q] += 2 * P.shift[q]; }
+      IX_TRY(k::fr_fine_add(P.R, acc.v(0), cview(&ff), P.d, fc_off, sgn * dt / vol_crse, F.ncomp, s));
+    }
+    IX_TRY(comm_allreduce(acc.fabs[0].p, (int)(acc.fabs[0].nstride * F.ncomp), 0, s));
+    for (int il = 0; il < F.reg.n(); ++il)
+      IX_TRY(k::lincomb(F.reg.vbox(il), F.reg.v(il), 1.0, F.reg.c(il), 1.0, acc.c(0), F.ncomp, s));
+    return IAMRX_OK;
+  }
   for (const FluxReg::Patch& P : F.patches) {
     const int fc_off = P.side < 0 ? 1 : 0;
     const double sgn = P.side < 0 ? -1.0 : 1.0;

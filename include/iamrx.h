@@ -457,7 +457,8 @@ enum {
 /* fine (on the cells / nodes / faces of the FINE cell box fbx) = interpolation of crse.  cell_cons needs one filled ghost
  * cell around the coarsened box (interior / periodic; physical-boundary one-sided slopes are not implemented). */
 int iamrx_interp_box(int kind, const iamrx_box* fbx, iamrx_fab* fine, const iamrx_fab* crse, int ncomp, void* stream);
-/* Flux register between a coarse level and the fine level that refines part of it (all boxes on this rank): the coarse cells
+/* Flux register between a coarse level and the fine level that refines part of it (with several ranks the coarse and the fine
+ * side of an interface may live on different ones: fine_add then sums through one replicated array + all-reduce and is collective): the coarse cells
  * that border the fine grids from outside accumulate dt (sum of fine fluxes - coarse flux) / vol with the sign of the face,
  * for AREA-WEIGHTED fluxes and vol = coarse cell volume (the "dx := volume" convention of NSB.cpp:4878-4889).
  * crse_add / fine_add take the face-flux fabs of every local box of the respective level (x, y, z arrays in local-box

@@ -191,6 +191,29 @@ def main():
         ref = rvel[:, 1 + lo[2] - flo[2]:2 + hi[2] - flo[2], 1 + lo[1] - flo[1]:2 + hi[1] - flo[1], 1 + lo[0] - flo[0]:2 + hi[0] - flo[0]]
         assert np.abs(got - ref).max() <= 1e-9, ("coarse-fine nodal_project", rank, float(np.abs(got - ref).max()))
 
+    # 5c. the flux register with the coarse and the fine side of the interface on different ranks: CrseAdd is local, FineAdd goes
+    #     through one replicated accumulation + all-reduce, Reflux is local -- against the oracle's register
+    cflux = [hash_uniform(231 + d, (2,) + NC[::-1]) for d in range(3)]
+    fflux = [hash_uniform(241 + d, (2,) + NF[::-1]) for d in range(3)]
+    dtr, volr = 0.05, (1.0 / NC[0]) ** 3
+    refreg = orc.fluxreg(NC, cmask, cflux, fflux, dtr, volr)
+    freg = C.c_void_p()
+    lib.check(lib.iamrx_fluxreg_create(clev.h, flev.h, 2, C.byref(freg)))
+    CFX = [[to_fab(cflux[d], cboxes[i], 0, types[d], "cpu") for i in cmine] for d in range(3)]
+    FFX = [[to_fab(fflux[d], fboxes[i], 0, types[d], "cpu") for i in fmine] for d in range(3)]
+    lib.check(lib.iamrx_fluxreg_reset(freg, st))
+    lib.check(lib.iamrx_fluxreg_crse_add(freg, fa(CFX[0]), fa(CFX[1]), fa(CFX[2]), dtr, volr, st))
+    lib.check(lib.iamrx_fluxreg_fine_add(freg, fa(FFX[0]), fa(FFX[1]), fa(FFX[2]), dtr, volr, st))
+    state = hash_uniform(251, (2,) + NC[::-1])
+    STR = [to_fab(state, cboxes[i], 0, ix.CELL, "cpu") for i in cmine]
+    lib.check(lib.iamrx_fluxreg_reflux(freg, fa(STR), 0, 1.0, st))
+    for (t, _), i in zip(STR, cmine):
+        lo, hi = cboxes[i]
+        exp = (state + refreg)[:, lo[2]:hi[2] + 1, lo[1]:hi[1] + 1, lo[0]:hi[0] + 1]
+        assert np.abs(t.numpy() - exp).max() <= 1e-12 * max(1.0, np.abs(refreg).max()), ("flux register across ranks", rank)
+    assert np.abs(refreg).max() > 0.1
+    lib.iamrx_fluxreg_destroy(freg)
+
     # 6. SyncRegister: CrseInit on the coarse boxes of both ranks, FineAdd from fine boxes on both ranks (one replicated accumulation
     #    + all-reduce), InitRHS -- against oracle/syncreg.py
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
