@@ -163,6 +163,29 @@ def main():
         nsr.close(); lv.close()
     assert err3 <= 1e-10, err3
     ort.close()
+    # 5b. outflow under gravity across ranks: Projection::set_outflow_bcs gathers the density next to the outflow face from both ranks
+    #     (the hydrostatic integral runs down through both z slabs), vs the oracle
+    nch = (16, 8, 16)
+    gch = ix.Geom.make(nch, (0.0, 0.0, 0.0), (2.0, 1.0, 2.0), periodic=(0, 1, 0))
+    kwch = dict(visc_coef=0.01, cfl=0.5, gravity=-0.5)
+    bcv = [[0.0] * 5 for _ in range(6)]
+    bcv[0] = [1.0, 0.0, 0.0, 1.0, 0.5]
+    och = orc.OracleNS(nch, (0, 0, 0), (2.0, 1.0, 2.0), per=(0, 1, 0), phys_lo=(1, 0, 4), phys_hi=(2, 0, 4), bcv=bcv, **kwch)
+    och.init_prob(101, [1.0, 1.0, 0.3])
+    dto = [och.post_init()] + [och.step() for _ in range(2)]
+    Sch = och.get(0)
+    bxs = split_boxes(nch, (1, 1, 2))
+    lv = ix.Level(lib, gch, bxs, [0, 1])
+    nsc = ix.NavierStokes(lib, lv, "cpu", lo_bc=(1, 0, 4), hi_bc=(2, 0, 4), bc_vals=bcv, **kwch)
+    nsc.init_prob(101, [1.0, 1.0, 0.3])
+    dts = [nsc.post_init()] + [nsc.step() for _ in range(2)]
+    assert np.allclose(dts, dto, rtol=1e-10, atol=0), (dts, dto)
+    lo, hi = bxs[rank]
+    t = nsc.field(0, 0).numpy()
+    nz, ny, nx = hi[2] - lo[2] + 1, hi[1] - lo[1] + 1, hi[0] - lo[0] + 1
+    err4 = np.abs(t[:, :nz, :ny, :nx] - Sch[:, lo[2]:hi[2] + 1, lo[1]:hi[1] + 1, lo[0]:hi[0] + 1]).max()
+    assert err4 <= 1e-10, err4
+    nsc.close(); lv.close(); och.close()
     # 6. reductions agree across ranks
     t = torch.tensor([max(err, err2, err3)])
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
