@@ -661,7 +661,8 @@ def test_two_level_subcycled_scalar_advection_conserves(backend, nb):
         FLX = [to_fab(np.zeros_like(sc0 if geom is cgeom else sf0), box, 0, t, dev) for t in types]
         EDG = [to_fab(np.zeros_like(sc0 if geom is cgeom else sf0), box, 0, t, dev) for t in types]
         bb = box_of(*box)
-        lib.check(lib.iamrx_compute_aofs_box(C.byref(bb), C.byref(fab_a), 0, C.byref(S[1]), 0, 1, None, 0, None,
+        FZ = to_fab(np.zeros_like(sc0 if geom is cgeom else sf0), box, 1, ix.CELL, dev)      # no forcing
+        lib.check(lib.iamrx_compute_aofs_box(C.byref(bb), C.byref(fab_a), 0, C.byref(S[1]), 0, 1, C.byref(FZ[1]), 0, None,
                                              C.byref(U[0][1]), C.byref(U[1][1]), C.byref(U[2][1]), None, None, None,
                                              C.byref(FLX[0][1]), C.byref(FLX[1][1]), C.byref(FLX[2][1]),
                                              C.byref(EDG[0][1]), C.byref(EDG[1][1]), C.byref(EDG[2][1]), ic, bcr, C.byref(geom), dt, flags, st))
@@ -950,8 +951,9 @@ def test_fine_level_chain_preserves_a_free_stream(backend):
     ic = (C.c_int * 3)(0, 0, 0)
     for il, ((tv, fv), b) in enumerate(zip(VF, boxes)):
         ta, fa_ = fab_from_padded(np.full((3,) + nf[::-1], 9.0), 0, b, 0, ix.CELL, dev)
+        tz, fz_ = fab_from_padded(np.zeros((3, nf[2] + 2, nf[1] + 2, nf[0] + 2)), 1, b, 1, ix.CELL, dev)      # no forcing
         bb = box_of(*b)
-        lib.check(lib.iamrx_compute_aofs_box(C.byref(bb), C.byref(fa_), 0, C.byref(fv), 0, 3, None, 0, None,
+        lib.check(lib.iamrx_compute_aofs_box(C.byref(bb), C.byref(fa_), 0, C.byref(fv), 0, 3, C.byref(fz_), 0, None,
                                              C.byref(U[0][il][1]), C.byref(U[1][il][1]), C.byref(U[2][il][1]), None, None, None,
                                              None, None, None, None, None, None, ic, bcr, C.byref(fgeom), dt, ix.ADV_IS_VELOCITY, st))
         sync(dev)
